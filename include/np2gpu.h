@@ -1,0 +1,138 @@
+/*
+ * np2gpu.h — C ABI of libnp2gpu.so, the B200-native (sm_100a) implementation of the
+ * NextPolish2 per-contig polish path.
+ *
+ * The reference (Nextomics/NextPolish2 @ 283dc5a) has no plugin / FFI interface
+ * (SURVEY.md §8b); the seams this library replaces are function-level:
+ *
+ *   np2_yak_load / np2_yak_from_arrays   <- KmerInfo::new            src/utils/kmer.rs:72-100
+ *                                           (+ one-time staging of the whole dump into HBM,
+ *                                            file format yak/htab.c:190-211)
+ *   np2_yak_lookup[_device]              <- KmerInfo::{insert,retrieve_kmers,get}
+ *                                                                      src/utils/kmer.rs:113-170
+ *   np2_seq_kscore                       <- iter2kmer + to_hash + get + min
+ *                                                                      src/utils/kmer.rs:255-314,
+ *                                                                      src/main.rs:761-769,1300-1315
+ *   np2_polish_contig                    <- the worker closure        src/main.rs:1726-1838
+ *   np2_job_* (staged form + stage dumps) <- the same closure, split at the points the
+ *                                            parity tests and bench.py need
+ *   np2_format_fasta                     <- display_consensusbase_vec src/main.rs:607-645
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  The caller owns every
+ * host buffer it passes in; the library owns device memory and the buffers returned by
+ * np2_job_get_* (valid until np2_job_destroy).  All functions return 0 on success or a
+ * negative NP2_ERR_* code; np2_last_error() returns the message of the calling thread's
+ * last failure.  The library never aborts: conditions on which the reference panics
+ * (unsorted BAM, unknown CIGAR op, bad yak magic ...) are reported as errors and the CLI
+ * maps them to the reference's exit behaviour.  One context per GPU; calls on one
+ * context must be serialised by the caller, contexts are independent.
+ */
+#ifndef NP2GPU_H
+#define NP2GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NP2_OK 0
+#define NP2_ERR_CUDA (-1)        /* CUDA runtime failure / no device */
+#define NP2_ERR_ARG (-2)         /* bad argument */
+#define NP2_ERR_IO (-3)          /* file missing / unreadable */
+#define NP2_ERR_FORMAT (-4)      /* reference would panic while parsing (bad magic, BAM parse, unknown CIGAR, unsorted input) */
+#define NP2_ERR_UNSUPPORTED (-5) /* valid for the reference but outside this library's scope (-S, k>=32 as smallest table ...) */
+#define NP2_ERR_INTERNAL (-6)
+
+/* CLI options that reach the hot path (src/utils/option.rs:15-41, defaults 267-292). */
+typedef struct np2_opts {
+    uint32_t min_kmer_count;    /* -k 5 */
+    uint32_t iter_count;        /* -i 2 */
+    uint32_t model;             /* -m: 0 = "ref", 1 = "len" */
+    uint32_t min_read_len;      /* -l 1000 */
+    uint64_t min_ctg_len;       /* -L 1000000 */
+    int32_t  max_indel_len;     /* -n 20 */
+    uint32_t use_supplementary; /* -s */
+    uint32_t use_secondary;     /* -S (NP2_ERR_UNSUPPORTED when set) */
+    uint32_t use_all_reads;     /* -r */
+    uint32_t min_map_len;       /* integer part of -a 500.5 */
+    float    min_map_fra;       /* fractional part of -a 500.5 */
+    int32_t  min_map_qual;      /* -q 1 */
+    uint32_t max_clip_len;      /* -c 100 */
+    uint32_t uppercase;         /* -u (np2_format_fasta only) */
+    uint32_t out_pos;           /* --out_pos (np2_format_fasta only) */
+    uint32_t reserved;
+} np2_opts;
+
+typedef struct np2_ctx np2_ctx;
+typedef struct np2_table np2_table;
+typedef struct np2_job np2_job;
+
+const char *np2_last_error(void);
+void np2_opts_default(np2_opts *o); /* option.rs:267-292 */
+
+int np2_ctx_create(int device, np2_ctx **out);
+void np2_ctx_destroy(np2_ctx *ctx);
+
+/* ---- yak tables, staged once into HBM ---- */
+int np2_yak_load(np2_ctx *ctx, const char *path, np2_table **out);
+/* hashes: full 64-bit yak hashes (low 10 bits = sub-table id), counts: 10-bit counts */
+int np2_yak_from_arrays(np2_ctx *ctx, uint32_t k, const uint64_t *hashes, const uint16_t *counts, uint64_t n,
+                        np2_table **out);
+void np2_yak_free(np2_table *t);
+uint32_t np2_yak_k(const np2_table *t);
+uint64_t np2_yak_size(const np2_table *t);
+uint64_t np2_yak_device_bytes(const np2_table *t);
+/* counts[i] = stored count of hashes[i] if present and >= min_count, else 0.  Host buffers. */
+int np2_yak_lookup(np2_ctx *ctx, const np2_table *t, const uint64_t *hashes, uint64_t n, uint32_t min_count,
+                   uint16_t *counts);
+/* Same with DEVICE buffers (inputs resident in HBM); *ms (optional) = kernel time from CUDA events on the
+ * library's stream, averaged over `repeat` back-to-back launches. */
+int np2_yak_lookup_device(np2_ctx *ctx, const np2_table *t, const uint64_t *d_hashes, uint64_t n, uint32_t min_count,
+                          uint16_t *d_counts, uint32_t repeat, float *ms);
+/* kscore of each byte string: min over its canonical k-mers of the filtered count, 0 if it has none
+ * (retrieve_kmer_count main.rs:761-769; reupdate main.rs:1300-1315).  seq_off has n+1 entries.  Host buffers. */
+int np2_seq_kscore(np2_ctx *ctx, const np2_table *t, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n,
+                   uint32_t min_count, uint16_t *kscore);
+
+/* ---- per-contig polish ----
+ * tseq/tlen : contig sequence (raw FASTA bytes, case preserved)
+ * bam       : this contig's BAM alignment records, concatenated in file order, each with its block_size prefix
+ * tables    : one or more tables (sorted by k internally, option.rs:238)
+ * The consensus comes back as parallel arrays (pos, base) = Vec<ConsensusBase> (main.rs:591-596). */
+int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
+                      np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out);
+
+/* staged form: create parses + filters the records on the host (main.rs:1758-1771), upload puts the inputs
+ * into HBM, run executes the device pipeline + host phases from resident inputs. */
+int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
+                   np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out);
+int np2_job_upload(np2_job *job);
+/* dump_iter >= 0: keep that iteration's intermediates on the host for the np2_job_get_* stage getters */
+int np2_job_run(np2_job *job, int32_t dump_iter);
+void np2_job_destroy(np2_job *job);
+
+uint64_t np2_job_get_consensus(np2_job *job, const uint32_t **pos, const uint8_t **base);
+/* stage dumps (same shapes as the oracle's getters) */
+uint64_t np2_job_get_reads(np2_job *job, const int32_t **rec_idx, const uint32_t **t_s, const uint32_t **t_e,
+                           const uint64_t **nib_off, const uint8_t **nib, const uint8_t **blank_after_clip);
+uint64_t np2_job_get_msa(np2_job *job, const uint64_t **off, const uint16_t **bases, const uint16_t **delta,
+                         const uint32_t **count, const uint32_t **besti);
+uint64_t np2_job_get_dp_consensus(np2_job *job, const uint32_t **pos, const uint8_t **base, const uint8_t **flags);
+uint64_t np2_job_get_regions(np2_job *job, const uint32_t **start, const uint32_t **end, const uint8_t **lable);
+uint64_t np2_job_get_candidates(np2_job *job, const uint64_t **roff, const uint32_t **order, const uint16_t **kscore,
+                                const uint64_t **kmer, const uint64_t **seq_off, const uint8_t **seq);
+uint64_t np2_job_get_dropped(np2_job *job, const uint32_t **ids);
+
+/* measurement: per-stage device time of the last np2_job_run (CUDA events on the library's stream), kernel
+ * launch count, bytes moved.  names: NUL-separated stage names; returns the number of stages. */
+uint32_t np2_job_get_timings(np2_job *job, const char **names, const float **ms, const uint32_t **launches);
+void np2_job_get_traffic(np2_job *job, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *n_kernel_launches,
+                         uint64_t *n_alignment_columns, uint64_t *n_probes);
+
+/* FASTA record exactly as display_consensusbase_vec prints it (main.rs:607-645); returns bytes needed. */
+uint64_t np2_format_fasta(const char *tid, const uint32_t *pos, const uint8_t *base, uint64_t n, int uppercase,
+                          int out_pos, uint8_t *out, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

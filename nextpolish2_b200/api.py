@@ -1,0 +1,310 @@
+"""ctypes mirror of include/np2gpu.h.
+
+Names follow the reference's seams: Table ~ KmerInfo (src/utils/kmer.rs:62-221),
+polish_contig ~ the worker closure (src/main.rs:1726-1838), Opts ~ Option (src/utils/option.rs:15-41).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "libnp2gpu.so")
+
+
+class Np2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("np2gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Opts(C.Structure):
+    """np2_opts; defaults = reference src/utils/option.rs:267-292."""
+    _fields_ = [("min_kmer_count", C.c_uint32), ("iter_count", C.c_uint32), ("model", C.c_uint32),
+                ("min_read_len", C.c_uint32), ("min_ctg_len", C.c_uint64), ("max_indel_len", C.c_int32),
+                ("use_supplementary", C.c_uint32), ("use_secondary", C.c_uint32), ("use_all_reads", C.c_uint32),
+                ("min_map_len", C.c_uint32), ("min_map_fra", C.c_float), ("min_map_qual", C.c_int32),
+                ("max_clip_len", C.c_uint32), ("uppercase", C.c_uint32), ("out_pos", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+    def __init__(self, **kw):
+        super().__init__(min_kmer_count=5, iter_count=2, model=0, min_read_len=1000, min_ctg_len=1000000,
+                         max_indel_len=20, use_supplementary=0, use_secondary=0, use_all_reads=0, min_map_len=500,
+                         min_map_fra=0.5, min_map_qual=1, max_clip_len=100, uppercase=0, out_pos=0, reserved=0)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+EXPORTS = [
+    "np2_last_error", "np2_opts_default", "np2_ctx_create", "np2_ctx_destroy", "np2_yak_load", "np2_yak_from_arrays",
+    "np2_yak_free", "np2_yak_k", "np2_yak_size", "np2_yak_device_bytes", "np2_yak_lookup", "np2_yak_lookup_device",
+    "np2_seq_kscore", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
+    "np2_job_get_consensus", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
+    "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
+]
+
+
+def load_library():
+    """Loads libnp2gpu.so (no CUDA call is made).  Raises if the extension has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nextpolish2_b200 has no CPU fallback)" % p)
+    L = C.CDLL(p)
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    L.np2_last_error.restype = C.c_char_p
+    L.np2_opts_default.argtypes = [vp]
+    L.np2_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.np2_ctx_destroy.argtypes = [vp]
+    L.np2_yak_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.np2_yak_from_arrays.argtypes = [vp, u32, vp, vp, u64, C.POINTER(vp)]
+    L.np2_yak_free.argtypes = [vp]
+    L.np2_yak_k.restype = u32
+    L.np2_yak_k.argtypes = [vp]
+    L.np2_yak_size.restype = u64
+    L.np2_yak_size.argtypes = [vp]
+    L.np2_yak_device_bytes.restype = u64
+    L.np2_yak_device_bytes.argtypes = [vp]
+    L.np2_yak_lookup.argtypes = [vp, vp, vp, u64, u32, vp]
+    L.np2_yak_lookup_device.argtypes = [vp, vp, vp, u64, u32, vp, u32, C.POINTER(C.c_float)]
+    L.np2_seq_kscore.argtypes = [vp, vp, vp, vp, u64, u32, vp]
+    L.np2_polish_contig.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
+    L.np2_job_create.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
+    L.np2_job_upload.argtypes = [vp]
+    L.np2_job_run.argtypes = [vp, C.c_int32]
+    L.np2_job_destroy.argtypes = [vp]
+    for name, n in [("np2_job_get_consensus", 2), ("np2_job_get_reads", 6), ("np2_job_get_msa", 5),
+                    ("np2_job_get_dp_consensus", 3), ("np2_job_get_regions", 3), ("np2_job_get_candidates", 6),
+                    ("np2_job_get_dropped", 1)]:
+        f = getattr(L, name)
+        f.restype = u64
+        f.argtypes = [vp] + [C.POINTER(vp)] * n
+    L.np2_job_get_timings.restype = u32
+    L.np2_job_get_timings.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
+    L.np2_format_fasta.restype = u64
+    L.np2_format_fasta.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int, vp, u64]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise Np2Error(rc, load_library().np2_last_error().decode())
+
+
+def _arr(ptr, n, dtype):
+    dt = np.dtype(dtype)
+    if n == 0 or not ptr.value:
+        return np.empty(0, dt)
+    return np.frombuffer(C.string_at(ptr.value, n * dt.itemsize), dtype=dt).copy()
+
+
+class Context:
+    """One GPU + one stream (np2_ctx)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(load_library().np2_ctx_create(device, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            load_library().np2_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Table:
+    """A yak k-mer count table staged in HBM (KmerInfo, src/utils/kmer.rs:62-221)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.h = handle
+
+    @classmethod
+    def load(cls, ctx, path):
+        h = C.c_void_p()
+        _check(load_library().np2_yak_load(ctx.h, path.encode(), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_arrays(cls, ctx, k, hashes, counts):
+        hashes = np.ascontiguousarray(hashes, np.uint64)
+        counts = np.ascontiguousarray(counts, np.uint16)
+        h = C.c_void_p()
+        _check(load_library().np2_yak_from_arrays(ctx.h, k, hashes.ctypes.data, counts.ctypes.data, len(hashes), C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def k(self):
+        return load_library().np2_yak_k(self.h)
+
+    def __len__(self):
+        return load_library().np2_yak_size(self.h)
+
+    @property
+    def device_bytes(self):
+        return load_library().np2_yak_device_bytes(self.h)
+
+    def lookup(self, hashes, min_count=5):
+        """insert + retrieve_kmers + get (kmer.rs:113-170) for a batch: count if present and >= min_count else 0."""
+        hashes = np.ascontiguousarray(hashes, np.uint64)
+        out = np.empty(len(hashes), np.uint16)
+        _check(load_library().np2_yak_lookup(self.ctx.h, self.h, hashes.ctypes.data, len(hashes), min_count, out.ctypes.data))
+        return out
+
+    def lookup_device(self, d_hashes_ptr, n, d_out_ptr, min_count=5, repeat=1):
+        """Device-resident batch; returns the mean kernel time in ms (CUDA events on the library stream)."""
+        ms = C.c_float()
+        _check(load_library().np2_yak_lookup_device(self.ctx.h, self.h, d_hashes_ptr, n, min_count, d_out_ptr, repeat, C.byref(ms)))
+        return ms.value
+
+    def seq_kscore(self, seqs, min_count=5):
+        """kscore of byte strings: min filtered count over their canonical k-mers (main.rs:761-769)."""
+        off = np.zeros(len(seqs) + 1, np.uint64)
+        off[1:] = np.cumsum([len(s) for s in seqs])
+        pool = np.frombuffer(b"".join(bytes(s) for s in seqs) + b"\0", np.uint8).copy()
+        out = np.empty(len(seqs), np.uint16)
+        _check(load_library().np2_seq_kscore(self.ctx.h, self.h, pool.ctypes.data, off.ctypes.data, len(seqs), min_count, out.ctypes.data))
+        return out
+
+    def free(self):
+        if self.h:
+            load_library().np2_yak_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Job:
+    """One contig (np2_job): create -> upload -> run, with stage dumps for the parity tests."""
+
+    def __init__(self, ctx, contig, bam, tables, opts=None):
+        self.ctx = ctx
+        self.contig = np.ascontiguousarray(contig, np.uint8)
+        self.bam = np.ascontiguousarray(bam, np.uint8)
+        self.tables = list(tables)
+        self.opts = opts or Opts()
+        tp = (C.c_void_p * len(self.tables))(*[t.h for t in self.tables])
+        self.h = C.c_void_p()
+        _check(load_library().np2_job_create(ctx.h, self.contig.ctypes.data, len(self.contig), self.bam.ctypes.data,
+                                             len(self.bam), tp, len(self.tables), C.byref(self.opts), C.byref(self.h)))
+
+    def upload(self):
+        _check(load_library().np2_job_upload(self.h))
+        return self
+
+    def run(self, dump_iter=-1):
+        _check(load_library().np2_job_run(self.h, dump_iter))
+        return self
+
+    def _get(self, name, n):
+        ptrs = [C.c_void_p() for _ in range(n)]
+        cnt = getattr(load_library(), name)(self.h, *[C.byref(p) for p in ptrs])
+        return cnt, ptrs
+
+    def consensus(self):
+        n, p = self._get("np2_job_get_consensus", 2)
+        return _arr(p[0], n, np.uint32), _arr(p[1], n, np.uint8)
+
+    def reads(self):
+        n, p = self._get("np2_job_get_reads", 6)
+        nib_off = _arr(p[3], n + 1 if n else 0, np.uint64)
+        return {"rec_idx": _arr(p[0], n, np.int32), "t_s": _arr(p[1], n, np.uint32), "t_e": _arr(p[2], n, np.uint32),
+                "nib_off": nib_off, "nib": _arr(p[4], int(nib_off[-1]) if n else 0, np.uint8),
+                "blank": _arr(p[5], n, np.uint8)}
+
+    def msa(self):
+        n, p = self._get("np2_job_get_msa", 5)
+        return {"off": _arr(p[0], len(self.contig) + 1 if n else 0, np.uint64), "bases": _arr(p[1], n, np.uint16),
+                "delta": _arr(p[2], n, np.uint16), "count": _arr(p[3], n, np.uint32), "besti": _arr(p[4], n, np.uint32)}
+
+    def dp_consensus(self):
+        n, p = self._get("np2_job_get_dp_consensus", 3)
+        return {"pos": _arr(p[0], n, np.uint32), "base": _arr(p[1], n, np.uint8), "flags": _arr(p[2], n, np.uint8)}
+
+    def regions(self):
+        n, p = self._get("np2_job_get_regions", 3)
+        lab = _arr(p[2], n, np.uint8)
+        return {"start": _arr(p[0], n, np.uint32), "end": _arr(p[1], n, np.uint32), "lable": lab}
+
+    def candidates(self):
+        nreg = len(self.regions()["start"])
+        n, p = self._get("np2_job_get_candidates", 6)
+        seq_off = _arr(p[4], n + 1 if nreg else 0, np.uint64)
+        return {"roff": _arr(p[0], nreg + 1 if nreg else 0, np.uint64), "order": _arr(p[1], n, np.uint32),
+                "kscore": _arr(p[2], n, np.uint16), "kmer": _arr(p[3], n, np.uint64), "seq_off": seq_off,
+                "seq": _arr(p[5], int(seq_off[-1]) if len(seq_off) else 0, np.uint8)}
+
+    def dropped(self):
+        n, p = self._get("np2_job_get_dropped", 1)
+        return _arr(p[0], n, np.uint32)
+
+    def timings(self):
+        names, ms, ln = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = load_library().np2_job_get_timings(self.h, C.byref(names), C.byref(ms), C.byref(ln))
+        if n == 0:
+            return {}
+        msv = _arr(ms, n, np.float32)
+        lnv = _arr(ln, n, np.uint32)
+        out, off = {}, 0
+        raw = C.string_at(names.value, 4096)
+        for i in range(n):
+            end = raw.index(b"\0", off)
+            out[raw[off:end].decode()] = (float(msv[i]), int(lnv[i]))
+            off = end + 1
+        return out
+
+    def traffic(self):
+        v = [C.c_uint64() for _ in range(5)]
+        load_library().np2_job_get_traffic(self.h, *[C.byref(x) for x in v])
+        return dict(zip(["h2d_bytes", "d2h_bytes", "kernel_launches", "alignment_columns", "probes"], [x.value for x in v]))
+
+    def destroy(self):
+        if self.h:
+            load_library().np2_job_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def polish_contig(ctx, contig, bam, tables, opts=None):
+    """The worker closure (main.rs:1726-1838): host buffers in, consensus (pos, base) out."""
+    j = Job(ctx, contig, bam, tables, opts)
+    try:
+        j.upload().run(-1)
+        return j.consensus()
+    finally:
+        j.destroy()
+
+
+def format_fasta(tid, pos, base, uppercase=False, out_pos=False):
+    """display_consensusbase_vec (main.rs:607-645)."""
+    pos = np.ascontiguousarray(pos, np.uint32)
+    base = np.ascontiguousarray(base, np.uint8)
+    L = load_library()
+    n = L.np2_format_fasta(tid.encode(), pos.ctypes.data, base.ctypes.data, len(base), int(uppercase), int(out_pos), None, 0)
+    out = np.empty(n, np.uint8)
+    L.np2_format_fasta(tid.encode(), pos.ctypes.data, base.ctypes.data, len(base), int(uppercase), int(out_pos), out.ctypes.data, n)
+    return bytes(out)

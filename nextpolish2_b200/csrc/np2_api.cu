@@ -1,0 +1,1293 @@
+// np2_api.cu — C ABI (include/np2gpu.h) and the per-contig pipeline that strings the kernels and host
+// phases together.  One np2_ctx = one GPU + one stream; all device work of a job is enqueued on that stream.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/np2gpu.h"
+#include "np2_host.h"
+#include "np2_kernels.cuh"
+
+using namespace np2;
+
+namespace {
+thread_local std::string g_err;
+
+template <class F>
+int guard(F f) {
+    try {
+        f();
+        return NP2_OK;
+    } catch (const np2::Error &e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return NP2_ERR_INTERNAL;
+    }
+}
+
+template <class T>
+struct DBuf {  // stream-ordered device buffer
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DBuf() {}
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    void alloc(size_t count, cudaStream_t st) {
+        release();
+        s = st;
+        n = count;
+        if (count) NP2_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), st));
+    }
+    void zero() {
+        if (n) NP2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void upload(const T *h, size_t count) { NP2_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
+    void download(T *h, size_t count) const { NP2_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    ~DBuf() { release(); }
+};
+
+template <class T>
+struct PBuf {  // pinned host buffer
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    void resize(size_t count) {
+        if (count > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = std::max(count, cap * 2);
+            NP2_CUDA(cudaMallocHost((void **)&p, cap * sizeof(T)));
+        }
+        n = count;
+    }
+    ~PBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
+struct StageTimer {
+    struct Rec {
+        cudaEvent_t a, b;
+        int stage;
+    };
+    std::vector<std::string> names;
+    std::vector<float> ms;
+    std::vector<uint32_t> launches;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaStream_t s = nullptr;
+    int id(const char *name) {
+        for (size_t i = 0; i < names.size(); i++)
+            if (names[i] == name) return (int)i;
+        names.push_back(name);
+        ms.push_back(0);
+        launches.push_back(0);
+        return (int)names.size() - 1;
+    }
+    cudaEvent_t ev() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        NP2_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+    int begin(const char *name, uint32_t n_launch) {
+        Rec r;
+        r.stage = id(name);
+        r.a = ev();
+        r.b = ev();
+        launches[r.stage] += n_launch;
+        NP2_CUDA(cudaEventRecord(r.a, s));
+        recs.push_back(r);
+        return (int)recs.size() - 1;
+    }
+    void end(int h) { NP2_CUDA(cudaEventRecord(recs[h].b, s)); }
+    void collect() {  // after a stream sync
+        for (auto &r : recs) {
+            float t = 0;
+            cudaEventElapsedTime(&t, r.a, r.b);
+            ms[r.stage] += t;
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    void reset() {
+        std::fill(ms.begin(), ms.end(), 0.f);
+        std::fill(launches.begin(), launches.end(), 0u);
+    }
+    ~StageTimer() {
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+}  // namespace
+
+struct np2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+};
+
+struct np2_table {
+    np2_ctx *ctx = nullptr;
+    TableDev dev;
+    uint64_t bytes = 0;
+};
+
+static void table_alloc(np2_ctx *ctx, np2_table *t, uint32_t k, uint64_t n, uint64_t max_sub) {
+    t->ctx = ctx;
+    t->dev.k = k;
+    t->dev.n = n;
+    // buckets of 4 slots, load factor <= 0.6 in the fullest sub-table
+    uint64_t nb = (uint64_t)((double)max_sub / (kBucketSlots * 0.6)) + 2;
+    if (nb >= (1ull << 32)) throw np2::Error(NP2_ERR_UNSUPPORTED, "table too large");
+    t->dev.nb = (uint32_t)nb;
+    t->bytes = 1024ull * nb * kBucketSlots * 8;
+    NP2_CUDA(cudaMalloc((void **)&t->dev.slots, t->bytes));
+    NP2_CUDA(cudaMemsetAsync(t->dev.slots, 0, t->bytes, ctx->stream));
+}
+
+struct np2_job {
+    np2_ctx *ctx = nullptr;
+    np2_opts opt;
+    std::vector<np2_table *> tables;  // sorted by k
+    std::vector<uint8_t> tseq;
+    const uint8_t *bam = nullptr;
+    uint64_t bam_len = 0;
+    Ingest ing;
+    bool uploaded = false;
+
+    // device inputs
+    DBuf<uint8_t> d_ref, d_code, d_blob, d_nib, d_blank;
+    DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off, d_op_col, d_op_q, d_op_t, d_op_cig;
+    DBuf<uint64_t> d_seq_off, d_nib_off;
+    DBuf<uint32_t> d_ts, d_te, d_n, d_ck_tpos, d_ck_read;
+    DBuf<uint16_t> d_ck_delta;
+    ReadsDev R;
+
+    // host state
+    std::vector<uint32_t> h_ts, h_te, h_n;
+    std::vector<uint8_t> h_blank;          // per candidate read
+    std::vector<int32_t> as_read;          // alignseq index -> candidate read (-1 = ref)
+    std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
+
+    Cns result;
+    StageTimer timer;
+    uint64_t h2d = 0, d2h = 0, n_launch = 0, n_probes = 0;
+    std::string timing_names;
+
+    // dumps
+    int32_t dump_iter = -1;
+    std::vector<int32_t> d_rec_idx;
+    std::vector<uint32_t> dm_ts, dm_te;
+    std::vector<uint64_t> dm_nib_off;
+    std::vector<uint8_t> dm_nib, dm_blank;
+    std::vector<uint64_t> dm_msa_off;
+    std::vector<uint16_t> dm_msa_bases, dm_msa_delta;
+    std::vector<uint32_t> dm_msa_count, dm_msa_besti;
+    std::vector<uint32_t> dm_dp_pos;
+    std::vector<uint8_t> dm_dp_base, dm_dp_flags;
+    std::vector<uint32_t> dm_reg_start, dm_reg_end;
+    std::vector<uint8_t> dm_reg_lable;
+    std::vector<uint64_t> dm_can_roff, dm_can_kmer, dm_can_seq_off;
+    std::vector<uint32_t> dm_can_order;
+    std::vector<uint16_t> dm_can_kscore;
+    std::vector<uint8_t> dm_can_seq;
+    std::vector<uint32_t> dm_dropped;
+
+    void upload();
+    void run(int32_t dump_iter);
+    void ingest_finish();
+    void iteration(uint32_t iter, bool final_iter, bool dump);
+    void launches(uint32_t n) { n_launch += n; }
+};
+
+/* ================================================================= pipeline */
+
+void np2_job::upload() {
+    cudaStream_t s = ctx->stream;
+    const uint32_t L = (uint32_t)tseq.size();
+    const uint32_t n = (uint32_t)ing.pos.size();
+    d_ref.alloc(L, s);
+    d_ref.upload(tseq.data(), L);
+    d_code.alloc(L, s);
+    d_blob.alloc(bam_len ? bam_len : 1, s);
+    if (bam_len) d_blob.upload(bam, bam_len);
+    auto up32 = [&](DBuf<uint32_t> &d, const std::vector<uint32_t> &h) {
+        d.alloc(std::max<size_t>(h.size(), 1), s);
+        if (!h.empty()) d.upload(h.data(), h.size());
+        h2d += h.size() * 4;
+    };
+    up32(d_pos, ing.pos);
+    up32(d_op_off, ing.op_off);
+    up32(d_ncols, ing.ncols);
+    up32(d_ck_off, ing.ck_off);
+    up32(d_op_col, ing.op_col);
+    up32(d_op_q, ing.op_q);
+    up32(d_op_t, ing.op_t);
+    up32(d_op_cig, ing.op_cig);
+    d_seq_off.alloc(std::max<size_t>(n, 1), s);
+    if (n) d_seq_off.upload(ing.seq_off.data(), n);
+    d_nib_off.alloc(n + 1, s);
+    d_nib_off.upload(ing.nib_off.data(), n + 1);
+    h2d += L + bam_len + (uint64_t)n * 8 * 2;
+    const uint32_t nck = ing.ck_off.back();
+    d_nib.alloc(ing.nib_off.back() + 16, s);
+    d_ts.alloc(std::max(n, 1u), s);
+    d_te.alloc(std::max(n, 1u), s);
+    d_n.alloc(std::max(n, 1u), s);
+    d_ck_tpos.alloc(std::max(nck, 1u), s);
+    d_ck_delta.alloc(std::max(nck, 1u), s);
+    d_ck_read.alloc(std::max(nck, 1u), s);
+    d_blank.alloc(std::max(n, 1u), s);
+    R.n_reads = n;
+    R.pos = d_pos.p;
+    R.op_off = d_op_off.p;
+    R.seq_off = d_seq_off.p;
+    R.ncols = d_ncols.p;
+    R.nib_off = d_nib_off.p;
+    R.ck_off = d_ck_off.p;
+    R.op_col = d_op_col.p;
+    R.op_q = d_op_q.p;
+    R.op_t = d_op_t.p;
+    R.op_cig = d_op_cig.p;
+    R.blob = d_blob.p;
+    R.t_s = d_ts.p;
+    R.t_e = d_te.p;
+    R.n = d_n.p;
+    R.nib = d_nib.p;
+    R.ck_tpos = d_ck_tpos.p;
+    R.ck_delta = d_ck_delta.p;
+    R.ck_read = d_ck_read.p;
+    NP2_CUDA(cudaStreamSynchronize(s));
+    uploaded = true;
+}
+
+// after K1: which candidate reads become alignseqs (main.rs:1800-1813), clip filter (main.rs:531-574)
+void np2_job::ingest_finish() {
+    const uint32_t n = R.n_reads;
+    const uint32_t L = (uint32_t)tseq.size();
+    h_blank.assign(std::max(n, 1u), 1);
+    read_order.assign(n, 0);
+    as_read.clear();
+    as_read.push_back(-1);
+    std::vector<uint32_t> as_ts{0}, as_te{L - 1};
+    std::vector<uint8_t> as_lab{0};
+    for (uint32_t i = 0; i < n; i++) {
+        if (h_n[i] <= opt.min_map_len) continue;
+        if (ing.is_clip[i] && L < 500000) continue;
+        read_order[i] = (uint32_t)as_read.size();
+        as_read.push_back((int32_t)i);
+        as_ts.push_back(h_ts[i]);
+        as_te.push_back(h_te[i]);
+        as_lab.push_back(ing.is_clip[i]);
+        h_blank[i] = 0;
+    }
+    // merged [t_s + 50, t_e - 50] of unlabelled reads; labelled reads inside a range are blanked
+    std::vector<std::pair<uint32_t, uint32_t>> ranges;
+    uint32_t s = 0, e = 0;
+    for (size_t a = 0; a < as_read.size(); a++) {
+        if (as_lab[a]) continue;
+        const uint32_t x = as_ts[a] + 50, y = as_te[a] - 50;
+        if (s == e) {
+            s = x;
+            e = y;
+        } else if (x > e) {
+            ranges.emplace_back(s, e);
+            s = x;
+            e = y;
+        } else if (e < y) {
+            e = y;
+        }
+    }
+    if (s != e) ranges.emplace_back(s, e);
+    for (size_t a = 0; a < as_read.size(); a++) {
+        if (!as_lab[a]) continue;
+        for (auto &r : ranges) {
+            if (r.first <= as_ts[a] && as_te[a] <= r.second) {
+                h_blank[as_read[a]] = 1;
+                break;
+            } else if (as_te[a] < r.first) {
+                break;
+            }
+        }
+    }
+}
+
+void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t L = (uint32_t)tseq.size();
+    const uint32_t n_reads = R.n_reads;
+    const uint32_t n_blocks = ing.ck_off.back();
+    int h;
+
+    /* ---------------- K2: pileup */
+    DBuf<int32_t> d_cover;
+    d_cover.alloc(L + 1, s);
+    DBuf<uint32_t> d_cta_cnt, d_cta_off;
+    const uint32_t n_cta = std::max(1u, pileup_ctas(n_blocks));
+    d_cta_cnt.alloc(n_cta + 1, s);
+    d_cta_off.alloc(n_cta + 1, s);
+    DBuf<uint8_t> d_tmp;
+    size_t tmp_bytes = 0;
+
+    h = timer.begin("pileup_scan", 4);
+    d_cover.zero();
+    {
+        int32_t one = 1;  // the ref read spans [0, L-1]
+        NP2_CUDA(cudaMemcpyAsync(d_cover.p, &one, 4, cudaMemcpyHostToDevice, s));
+    }
+    cover_diff(R, d_blank.p, d_cover.p, s);
+    {
+        size_t tb = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, tb, d_cover.p, d_cover.p, L + 1, s);
+        d_tmp.alloc(tb, s);
+        cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_cover.p, d_cover.p, L + 1, s);
+    }
+    d_cta_cnt.zero();
+    pileup_count(R, n_blocks, d_blank.p, d_code.p, L, d_cta_cnt.p, s);
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cta_cnt.p, d_cta_off.p, n_cta + 1, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_cta_cnt.p, d_cta_off.p, n_cta + 1, s);
+    }
+    timer.end(h);
+    uint32_t n_rec = 0;
+    NP2_CUDA(cudaMemcpyAsync(&n_rec, d_cta_off.p + n_cta, 4, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    n_rec += 2;
+    launches(6);
+
+    DBuf<uint64_t> d_key, d_key2;
+    DBuf<uint32_t> d_rd, d_rd2, d_head, d_gidx;
+    d_key.alloc(n_rec, s);
+    d_key2.alloc(n_rec, s);
+    d_rd.alloc(n_rec, s);
+    d_rd2.alloc(n_rec, s);
+    d_head.alloc(n_rec + 1, s);
+    d_gidx.alloc(n_rec + 1, s);
+    h = timer.begin("pileup_emit", 1);
+    pileup_emit(R, n_blocks, d_blank.p, d_code.p, L, d_cta_off.p, d_key.p, d_rd.p, s);
+    timer.end(h);
+    int pbits = 1;
+    while ((1ull << pbits) < (uint64_t)L) pbits++;
+    h = timer.begin("pileup_sort", 8);
+    {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)n_rec, 0, 32 + pbits, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)n_rec, 0, 32 + pbits, s);
+    }
+    timer.end(h);
+    h = timer.begin("pileup_group", 3);
+    mark_heads(d_key2.p, n_rec, d_head.p, s);
+    NP2_CUDA(cudaMemsetAsync(d_head.p + n_rec, 0, 4, s));
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_head.p, d_gidx.p, n_rec + 1, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_head.p, d_gidx.p, n_rec + 1, s);
+    }
+    timer.end(h);
+    uint32_t G = 0;
+    NP2_CUDA(cudaMemcpyAsync(&G, d_gidx.p + n_rec, 4, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    launches(13);
+
+    MsaDev m;
+    m.L = L;
+    m.G = G;
+    DBuf<uint32_t> d_sp_off, d_gcount, d_gfirst, d_gbesti, d_gstart, d_gpos, d_dense_cnt, d_dense_besti, d_n_emit,
+        d_emit_off;
+    DBuf<uint16_t> d_gbases, d_gdelta;
+    DBuf<int64_t> d_gscore, d_dense_score;
+    DBuf<uint8_t> d_multi, d_flag;
+    d_sp_off.alloc(L + 1, s);
+    d_gcount.alloc(G, s);
+    d_gfirst.alloc(G, s);
+    d_gbesti.alloc(G, s);
+    d_gstart.alloc(G, s);
+    d_gpos.alloc(G, s);
+    d_gbases.alloc(G, s);
+    d_gdelta.alloc(G, s);
+    d_gscore.alloc(G, s);
+    d_dense_cnt.alloc(L, s);
+    d_dense_besti.alloc(L, s);
+    d_dense_score.alloc(L, s);
+    d_multi.alloc(L, s);
+    d_flag.alloc(L, s);
+    d_n_emit.alloc(L + 1, s);
+    d_emit_off.alloc(L + 1, s);
+    m.sp_off = d_sp_off.p;
+    m.g_bases = d_gbases.p;
+    m.g_delta = d_gdelta.p;
+    m.g_count = d_gcount.p;
+    m.g_first = d_gfirst.p;
+    m.g_besti = d_gbesti.p;
+    m.g_score = d_gscore.p;
+    m.cover = d_cover.p;
+    m.dense_cnt = d_dense_cnt.p;
+    m.dense_besti = d_dense_besti.p;
+    m.dense_score = d_dense_score.p;
+    m.multi = d_multi.p;
+    m.code = d_code.p;
+
+    h = timer.begin("pileup_finalize", 4);
+    d_sp_off.zero();
+    d_dense_besti.zero();
+    groups_fill(d_key2.p, d_rd2.p, d_head.p, d_gidx.p, n_rec, G, d_gstart.p, d_gpos.p, m, s);
+    groups_finish(d_gstart.p, d_gpos.p, n_rec, m, s);
+    NP2_CUDA(cudaMemsetAsync(d_n_emit.p + L, 0, 4, s));
+    pos_finalize(m, d_n_emit.p, s);
+    timer.end(h);
+    launches(6);
+
+    /* ---------------- K3: DP over runs, backtrack, consensus */
+    DBuf<uint32_t> d_run_start, d_nruns, d_best_last;
+    DBuf<unsigned long long> d_total;
+    d_run_start.alloc(L, s);
+    d_nruns.alloc(1, s);
+    d_best_last.alloc(1, s);
+    d_total.alloc(1, s);
+    d_best_last.zero();
+    d_total.zero();
+    h = timer.begin("dp_runs_select", 2);
+    run_flags(d_multi.p, L, d_flag.p, s);
+    {
+        size_t tb = 0;
+        cub::CountingInputIterator<uint32_t> it(0);
+        cub::DeviceSelect::Flagged(nullptr, tb, it, d_flag.p, d_run_start.p, d_nruns.p, (int)L, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_flag.p, d_run_start.p, d_nruns.p, (int)L, s);
+    }
+    timer.end(h);
+    uint32_t n_runs = 0;
+    NP2_CUDA(cudaMemcpyAsync(&n_runs, d_nruns.p, 4, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    DpOut dpo;
+    dpo.best_last = d_best_last.p;
+    dpo.score_total = d_total.p;
+    h = timer.begin("dp_runs", 1);
+    dp_runs(m, d_run_start.p, n_runs, dpo, s);
+    timer.end(h);
+    h = timer.begin("consensus_emit", 5);
+    emit_count_runs(m, d_run_start.p, n_runs, dpo, d_n_emit.p, s);
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_n_emit.p, d_emit_off.p, L + 1, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_n_emit.p, d_emit_off.p, L + 1, s);
+    }
+    timer.end(h);
+    uint32_t N = 0;
+    NP2_CUDA(cudaMemcpyAsync(&N, d_emit_off.p + L, 4, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    DBuf<uint32_t> d_cpos, d_events, d_nev;
+    DBuf<uint8_t> d_cbase, d_cflags;
+    d_cpos.alloc(N, s);
+    d_cbase.alloc(N, s);
+    d_cflags.alloc(N, s);
+    d_events.alloc(N, s);
+    d_nev.alloc(1, s);
+    h = timer.begin("consensus_emit", 0);
+    emit_write(m, d_run_start.p, n_runs, dpo, d_n_emit.p, d_emit_off.p, d_cpos.p, d_cbase.p, d_cflags.p, s);
+    {
+        size_t tb = 0;
+        cub::CountingInputIterator<uint32_t> it(0);
+        cub::DeviceSelect::Flagged(nullptr, tb, it, d_cflags.p, d_events.p, d_nev.p, (int)N, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_cflags.p, d_events.p, d_nev.p, (int)N, s);
+    }
+    timer.end(h);
+    launches(12);
+    Cns cns;
+    cns.pos.resize(N);
+    cns.base.resize(N);
+    std::vector<uint8_t> cflags(N);
+    uint32_t n_ev = 0;
+    long long total = 0;
+    d_cpos.download(cns.pos.data(), N);
+    d_cbase.download(cns.base.data(), N);
+    d_cflags.download(cflags.data(), N);
+    NP2_CUDA(cudaMemcpyAsync(&n_ev, d_nev.p, 4, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    d2h += (uint64_t)N * 6;
+    if (total < 0)
+        throw np2::Error(NP2_ERR_UNSUPPORTED,
+                         "best path has a negative total score (main.rs:1680 picks the default 3-mer): not supported");
+    std::vector<uint32_t> events(n_ev);
+    if (n_ev) {
+        d_events.download(events.data(), n_ev);
+        NP2_CUDA(cudaStreamSynchronize(s));
+    }
+
+    if (dump) {
+        // Msa in the reference's order: reference 3-mer first (p >= 2), then the sorted sparse ones
+        std::vector<uint32_t> sp_off(L + 1), gc(G), gb(G), dc(L), db(L);
+        std::vector<uint16_t> gba(G), gde(G);
+        std::vector<uint8_t> code(L);
+        d_sp_off.download(sp_off.data(), L + 1);
+        d_gcount.download(gc.data(), G);
+        d_gbesti.download(gb.data(), G);
+        d_gbases.download(gba.data(), G);
+        d_gdelta.download(gde.data(), G);
+        d_dense_cnt.download(dc.data(), L);
+        d_dense_besti.download(db.data(), L);
+        d_code.download(code.data(), L);
+        NP2_CUDA(cudaStreamSynchronize(s));
+        dm_msa_off.assign(1, 0);
+        for (uint32_t p = 0; p < L; p++) {
+            if (p >= 2) {
+                dm_msa_bases.push_back((uint16_t)(code[p - 2] << 8 | code[p - 1] << 4 | code[p]));
+                dm_msa_delta.push_back(0);
+                dm_msa_count.push_back(dc[p]);
+                dm_msa_besti.push_back(db[p]);
+            }
+            for (uint32_t g = sp_off[p]; g < sp_off[p + 1]; g++) {
+                dm_msa_bases.push_back(gba[g]);
+                dm_msa_delta.push_back(gde[g]);
+                dm_msa_count.push_back(gc[g]);
+                dm_msa_besti.push_back(gb[g]);
+            }
+            dm_msa_off.push_back(dm_msa_bases.size());
+        }
+        dm_dp_pos = cns.pos;
+        dm_dp_base = cns.base;
+        dm_dp_flags = cflags;
+    }
+
+    /* ---------------- LQ regions (host, sparse events) */
+    Regions rg;
+    find_regions(cns.pos.data(), cns.base.data(), cflags.data(), N, events.data(), n_ev, rg);
+    const uint32_t nreg = (uint32_t)rg.start.size();
+    if (dump) {
+        dm_reg_start = rg.start;
+        dm_reg_end = rg.end;
+    }
+    if (nreg == 0) {  // main.rs:1638-1640
+        if (final_iter) result = std::move(cns);
+        return;
+    }
+
+    /* ---------------- K4: candidates */
+    np2_table *t0 = tables[0];
+    const uint32_t k0 = t0->dev.k;
+    if (k0 >= 32) throw np2::Error(NP2_ERR_UNSUPPORTED, "the smallest yak table must have k < 32 (main.rs:1432-1434)");
+    // read -> region ranges with the reference's monotone cursor (main.rs:1446-1460)
+    std::vector<uint32_t> pr_read, pr_reg, pr_limit;
+    {
+        size_t sidx = nreg - 1;
+        for (size_t a = 1; a < as_read.size(); a++) {
+            const uint32_t i = (uint32_t)as_read[a];
+            if (h_blank[i]) continue;
+            const uint32_t ts = h_ts[i], te = h_te[i];
+            while (sidx > 0 && rg.start[sidx] < ts) sidx--;
+            if (rg.start[sidx] < ts || rg.end[sidx] > te) continue;
+            size_t j = sidx;
+            while (j > 0 && rg.end[j] <= te) j--;
+            if (rg.end[j] > te) j++;
+            const uint32_t limit = rg.end[j] + k0;
+            for (size_t ri = j; ri <= sidx; ri++) {
+                pr_read.push_back(i);
+                pr_reg.push_back((uint32_t)ri);
+                pr_limit.push_back(limit);
+            }
+        }
+    }
+    const uint32_t n_pairs = (uint32_t)pr_read.size();
+    // the ref read's candidates are computed here: it is never trimmed, dropped or stored on the device.
+    // NOTE its cursor state is the first one of the loop above in the reference (idx 0): with t_s = 0 and
+    // t_e = L - 1 it covers regions [0, nreg - 1] and leaves s = nreg - 1, which is how the loop above starts.
+    const uint64_t mask0 = (1ULL << (2 * k0)) - 1;
+    std::vector<uint32_t> len_all(nreg + n_pairs);
+    std::vector<uint64_t> kmer_all(nreg + n_pairs);
+    std::vector<std::string> ref_seq(nreg);
+    {
+        const uint32_t limit = rg.end[0] + k0;
+        for (uint32_t ri = 0; ri < nreg; ri++) {
+            uint64_t f = 0, rv = 0;
+            uint32_t l = 0;
+            std::string sq;
+            for (uint32_t p = rg.start[ri]; p < L; p++) {
+                const uint32_t q = seq_code(tseq[p]);
+                if (q != 4) {
+                    if (p <= rg.end[ri]) sq.push_back((char)code_char(q));
+                    if (l < k0) {
+                        f = (f << 2 | (uint64_t)q) & mask0;
+                        rv = (rv >> 2) | (uint64_t)(3 ^ q) << (2 * (k0 - 1));
+                        l++;
+                    }
+                    if (p > rg.end[ri] && l >= k0) break;
+                }
+                if (p > limit) break;
+            }
+            len_all[ri] = (uint32_t)sq.size();
+            kmer_all[ri] = l >= k0 ? yak_hash64(f < rv ? f : rv, mask0) : UINT64_MAX;
+            ref_seq[ri] = std::move(sq);
+        }
+    }
+    DBuf<uint32_t> d_pr_read, d_pr_start, d_pr_end, d_pr_limit, d_len;
+    DBuf<uint64_t> d_kmer, d_soff;
+    DBuf<uint16_t> d_ks;
+    d_pr_read.alloc(std::max(n_pairs, 1u), s);
+    d_pr_start.alloc(std::max(n_pairs, 1u), s);
+    d_pr_end.alloc(std::max(n_pairs, 1u), s);
+    d_pr_limit.alloc(std::max(n_pairs, 1u), s);
+    d_len.alloc(nreg + n_pairs, s);
+    d_kmer.alloc(nreg + n_pairs, s);
+    d_soff.alloc(nreg + n_pairs + 1, s);
+    d_ks.alloc(nreg + n_pairs, s);
+    {
+        std::vector<uint32_t> st(n_pairs), en(n_pairs);
+        for (uint32_t i = 0; i < n_pairs; i++) {
+            st[i] = rg.start[pr_reg[i]];
+            en[i] = rg.end[pr_reg[i]];
+        }
+        if (n_pairs) {
+            d_pr_read.upload(pr_read.data(), n_pairs);
+            d_pr_start.upload(st.data(), n_pairs);
+            d_pr_end.upload(en.data(), n_pairs);
+            d_pr_limit.upload(pr_limit.data(), n_pairs);
+        }
+        d_kmer.upload(kmer_all.data(), nreg);
+        h2d += (uint64_t)n_pairs * 16 + nreg * 8;
+        CandDev c;
+        c.n_pairs = n_pairs;
+        c.pair_read = d_pr_read.p;
+        c.pair_start = d_pr_start.p;
+        c.pair_end = d_pr_end.p;
+        c.pair_limit = d_pr_limit.p;
+        c.len = d_len.p + nreg;
+        c.kmer = d_kmer.p + nreg;
+        h = timer.begin("cand_scan", 1);
+        cand_scan(R, c, k0, false, s);
+        timer.end(h);
+        h = timer.begin("yak_probe", 1);
+        table_probe(t0->dev, d_kmer.p, nreg + n_pairs, opt.min_kmer_count, d_ks.p, s);
+        timer.end(h);
+        n_probes += nreg + n_pairs;
+        launches(2);
+        if (n_pairs) d_len.download(len_all.data() + nreg, n_pairs), d_kmer.download(kmer_all.data() + nreg, n_pairs);
+        NP2_CUDA(cudaStreamSynchronize(s));  // also orders the pageable st/en uploads before they go out of scope
+        d2h += (uint64_t)n_pairs * 12;
+    }
+    // sequence pool: ref candidates first, then the device-extracted ones
+    std::vector<uint64_t> soff(nreg + n_pairs + 1);
+    soff[0] = 0;
+    for (uint32_t i = 0; i < nreg + n_pairs; i++) soff[i + 1] = soff[i] + len_all[i];
+    const uint64_t pool_bytes = soff.back();
+    DBuf<uint8_t> d_pool;
+    d_pool.alloc(pool_bytes + 1, s);
+    std::vector<uint8_t> pool(pool_bytes + 1);
+    for (uint32_t ri = 0; ri < nreg; ri++) memcpy(pool.data() + soff[ri], ref_seq[ri].data(), ref_seq[ri].size());
+    d_pool.upload(pool.data(), soff[nreg]);
+    d_soff.upload(soff.data(), nreg + n_pairs + 1);
+    h2d += soff[nreg] + (uint64_t)(nreg + n_pairs + 1) * 8;
+    {
+        CandDev c;
+        c.n_pairs = n_pairs;
+        c.pair_read = d_pr_read.p;
+        c.pair_start = d_pr_start.p;
+        c.pair_end = d_pr_end.p;
+        c.pair_limit = d_pr_limit.p;
+        c.seq_off = d_soff.p + nreg;
+        c.seq = d_pool.p;
+        h = timer.begin("cand_scan", 1);
+        cand_scan(R, c, k0, true, s);
+        timer.end(h);
+        launches(1);
+    }
+    // candidates longer than k are scored over all their k-mers (main.rs:746-749, 760-769)
+    std::vector<uint32_t> longsel;
+    for (uint32_t i = 0; i < nreg + n_pairs; i++)
+        if (len_all[i] > k0) longsel.push_back(i);
+    std::vector<uint16_t> ks_all(nreg + n_pairs), ks_long(longsel.size());
+    DBuf<uint32_t> d_sel;
+    DBuf<uint16_t> d_ks_long;
+    if (!longsel.empty()) {
+        d_sel.alloc(longsel.size(), s);
+        d_ks_long.alloc(longsel.size(), s);
+        d_sel.upload(longsel.data(), longsel.size());
+        h = timer.begin("yak_seq_kscore", 1);
+        seq_kscore(t0->dev, d_pool.p, d_soff.p, d_sel.p, longsel.size(), opt.min_kmer_count, d_ks_long.p, s);
+        timer.end(h);
+        launches(1);
+        d_ks_long.download(ks_long.data(), longsel.size());
+    }
+    d_ks.download(ks_all.data(), nreg + n_pairs);
+    if (pool_bytes > soff[nreg]) {
+        NP2_CUDA(cudaMemcpyAsync(pool.data() + soff[nreg], d_pool.p + soff[nreg], pool_bytes - soff[nreg],
+                                 cudaMemcpyDeviceToHost, s));
+    }
+    NP2_CUDA(cudaStreamSynchronize(s));
+    d2h += pool_bytes + (uint64_t)(nreg + n_pairs) * 2;
+    for (uint32_t i = 0; i < nreg + n_pairs; i++)
+        if (kmer_all[i] == UINT64_MAX) ks_all[i] = 0;  // INVALID_KMER keeps kscore 0 (main.rs:750,770)
+    for (size_t x = 0; x < longsel.size(); x++) ks_all[longsel[x]] = ks_long[x];
+
+    // per region, candidates in read order, first 60 non-empty (main.rs:1474,1509)
+    CandSet cs;
+    cs.pool = pool.data();
+    cs.roff.assign(nreg + 1, 0);
+    {
+        std::vector<uint32_t> cnt(nreg, 0);
+        for (uint32_t i = 0; i < n_pairs; i++) cnt[pr_reg[i]]++;
+        std::vector<uint32_t> first(nreg + 1, 0);
+        for (uint32_t r = 0; r < nreg; r++) first[r + 1] = first[r] + cnt[r];
+        std::vector<uint32_t> bucket(n_pairs);
+        std::vector<uint32_t> cur(first.begin(), first.end() - 1);
+        for (uint32_t i = 0; i < n_pairs; i++) bucket[cur[pr_reg[i]]++] = i;
+        for (uint32_t r = 0; r < nreg; r++) {
+            uint32_t taken = 0;
+            auto take = [&](uint32_t id, uint32_t order) {
+                cs.order.push_back(order);
+                cs.kscore.push_back(ks_all[id]);
+                cs.kmer.push_back(kmer_all[id]);
+                cs.seq_off.push_back(soff[id]);
+                cs.seq_len.push_back(len_all[id]);
+                taken++;
+            };
+            if (len_all[r] > 0) take(r, 0);
+            for (uint32_t x = first[r]; x < first[r + 1] && taken < 60; x++) {
+                const uint32_t id = nreg + bucket[x];
+                if (len_all[id] > 0) take(id, read_order[pr_read[bucket[x]]]);
+            }
+            cs.roff[r + 1] = (uint32_t)cs.order.size();
+        }
+    }
+    if (dump) {
+        dm_can_roff.assign(cs.roff.begin(), cs.roff.end());
+        dm_can_order = cs.order;
+        dm_can_kscore = cs.kscore;
+        dm_can_kmer = cs.kmer;
+        dm_can_seq_off.assign(1, 0);
+        for (size_t c = 0; c < cs.order.size(); c++) {
+            dm_can_seq.insert(dm_can_seq.end(), pool.data() + cs.seq_off[c], pool.data() + cs.seq_off[c] + cs.seq_len[c]);
+            dm_can_seq_off.push_back(dm_can_seq.size());
+        }
+    }
+    std::vector<RegionState> rs(nreg);
+    for (uint32_t r = 0; r < nreg; r++)
+        for (uint32_t c = cs.roff[r]; c < cs.roff[r + 1]; c++) rs[r].cand.push_back(c);
+
+    if (!final_iter) {
+        /* ---------------- phasing (main.rs:1544-1552) */
+        mark_hete(cs, rs);
+        std::vector<uint32_t> drop = phase_reads(cs, rs, opt.model == 0, opt.use_all_reads != 0);
+        for (uint32_t a : drop) {
+            if (a == 0 || a >= as_read.size()) throw np2::Error(NP2_ERR_INTERNAL, "phasing returned a bad read index");
+            h_blank[as_read[a]] = 1;
+            dm_dropped.push_back(a);
+        }
+        d_blank.upload(h_blank.data(), n_reads);
+        NP2_CUDA(cudaStreamSynchronize(s));
+        if (dump)
+            for (auto &r : rs) dm_reg_lable.push_back(r.lable);
+        return;
+    }
+
+    /* ---------------- final: seed alleles, splice, re-check with every table (main.rs:1527-1543) */
+    fill_seed(cs, rs, opt.max_indel_len);
+    Cns cur, nxt;
+    splice(rg, rs, LABLE_SUCC, cns, cur);
+    for (size_t ti = 0; ti < tables.size(); ti++) {
+        Reupdate ru;
+        reupdate_build(rg, cs, rs, cur, tables[ti]->dev.k, ru);
+        const size_t ns = ru.off.size() - 1;
+        std::vector<uint16_t> ks(ns);
+        if (ns) {
+            DBuf<uint8_t> d_rp;
+            DBuf<uint64_t> d_ro;
+            DBuf<uint16_t> d_rk;
+            d_rp.alloc(ru.pool.size() + 1, s);
+            d_ro.alloc(ns + 1, s);
+            d_rk.alloc(ns, s);
+            d_rp.upload(ru.pool.data(), ru.pool.size());
+            d_ro.upload(ru.off.data(), ns + 1);
+            h = timer.begin("yak_seq_kscore", 1);
+            seq_kscore(tables[ti]->dev, d_rp.p, d_ro.p, nullptr, ns, opt.min_kmer_count, d_rk.p, s);
+            timer.end(h);
+            launches(1);
+            d_rk.download(ks.data(), ns);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            h2d += ru.pool.size() + (ns + 1) * 8;
+            d2h += ns * 2;
+        }
+        reupdate_apply(rg, cs, rs, ru, ks.data(), (uint32_t)ti + 1, cur, nxt);
+        cur.pos.swap(nxt.pos);
+        cur.base.swap(nxt.base);
+    }
+    if (dump)
+        for (auto &r : rs) dm_reg_lable.push_back(r.lable);
+    result = std::move(cur);
+}
+
+void np2_job::run(int32_t dump_it) {
+    dump_iter = dump_it;
+    cudaStream_t s = ctx->stream;
+    const uint32_t L = (uint32_t)tseq.size();
+    result.pos.clear();
+    result.base.clear();
+    timer.s = s;
+    timer.reset();
+    n_launch = 0;
+    n_probes = 0;
+    dm_dropped.clear();
+    if (L < opt.min_ctg_len) {  // main.rs:1727-1730
+        result.pos.resize(L);
+        result.base.assign(tseq.begin(), tseq.end());
+        for (uint32_t p = 0; p < L; p++) result.pos[p] = p;
+        return;
+    }
+    if (!uploaded) upload();
+    const uint32_t n = R.n_reads;
+    int h = timer.begin("expand_trim_pack", 2);
+    ref_codes(d_ref.p, L, d_code.p, s);
+    expand_trim_pack(R, d_ref.p, L, s);
+    timer.end(h);
+    launches(2);
+    h_ts.resize(n);
+    h_te.resize(n);
+    h_n.resize(n);
+    if (n) {
+        d_ts.download(h_ts.data(), n);
+        d_te.download(h_te.data(), n);
+        d_n.download(h_n.data(), n);
+    }
+    NP2_CUDA(cudaStreamSynchronize(s));
+    d2h += (uint64_t)n * 12;
+    ingest_finish();
+    d_blank.upload(h_blank.data(), std::max(n, 1u));
+
+    if (dump_iter >= 0) {  // reads as the oracle reports them (after the clip filter)
+        std::vector<uint8_t> nib(ing.nib_off.back() + 16);
+        d_nib.download(nib.data(), nib.size());
+        NP2_CUDA(cudaStreamSynchronize(s));
+        d_rec_idx.clear();
+        dm_ts.clear();
+        dm_te.clear();
+        dm_blank.clear();
+        dm_nib.clear();
+        dm_nib_off.assign(1, 0);
+        for (size_t a = 0; a < as_read.size(); a++) {
+            if (a == 0) {
+                d_rec_idx.push_back(-1);
+                dm_ts.push_back(0);
+                dm_te.push_back(L - 1);
+                dm_blank.push_back(0);
+            } else {
+                const uint32_t i = (uint32_t)as_read[a];
+                d_rec_idx.push_back(ing.rec_idx[i]);
+                dm_ts.push_back(h_ts[i]);
+                dm_te.push_back(h_te[i]);
+                dm_blank.push_back(h_blank[i]);
+                if (!h_blank[i]) {
+                    const uint32_t nn = h_n[i];
+                    const uint8_t *src = nib.data() + ing.nib_off[i];
+                    const size_t bytes = ((size_t)nn + 1) / 2 + 1;
+                    size_t o = dm_nib.size();
+                    dm_nib.insert(dm_nib.end(), src, src + bytes);
+                    if (nn & 1) dm_nib[o + bytes - 1] = 0;  // Vec is zero-initialised past the terminator nibble
+                }
+            }
+            dm_nib_off.push_back(dm_nib.size());
+        }
+    }
+    for (uint32_t it = 0; it < opt.iter_count; it++) iteration(it, it + 1 == opt.iter_count, (int32_t)it == dump_iter);
+    NP2_CUDA(cudaStreamSynchronize(s));
+    timer.collect();
+}
+
+/* ================================================================= C ABI */
+
+extern "C" {
+
+const char *np2_last_error(void) { return g_err.c_str(); }
+
+void np2_opts_default(np2_opts *o) {
+    memset(o, 0, sizeof *o);
+    o->min_kmer_count = 5;
+    o->iter_count = 2;
+    o->model = 0;
+    o->min_read_len = 1000;
+    o->min_ctg_len = 1000000;
+    o->max_indel_len = 20;
+    o->min_map_len = 500;
+    o->min_map_fra = 0.5f;
+    o->min_map_qual = 1;
+    o->max_clip_len = 100;
+}
+
+int np2_ctx_create(int device, np2_ctx **out) {
+    return guard([&] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw np2::Error(NP2_ERR_CUDA, std::string("no CUDA device: libnp2gpu has no CPU fallback (") +
+                                               cudaGetErrorString(e) + ")");
+        if (device < 0 || device >= n) throw np2::Error(NP2_ERR_ARG, "bad device index");
+        NP2_CUDA(cudaSetDevice(device));
+        np2_ctx *c = new np2_ctx();
+        c->device = device;
+        NP2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        // keep freed blocks in the pool: per-iteration scratch is re-used instead of going back to the driver
+        cudaMemPool_t pool;
+        NP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        NP2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        *out = c;
+    });
+}
+void np2_ctx_destroy(np2_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int np2_yak_load(np2_ctx *ctx, const char *path, np2_table **out) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        FILE *fp = fopen(path, "rb");
+        if (!fp) throw np2::Error(NP2_ERR_IO, std::string("cannot open ") + path);
+        std::unique_ptr<FILE, int (*)(FILE *)> fc(fp, fclose);
+        uint8_t hdr[16];
+        if (fread(hdr, 1, 16, fp) != 16 || memcmp(hdr, "YAK\2", 4) != 0)
+            throw np2::Error(NP2_ERR_FORMAT, "The input binary k-mer dump file is incompatible.");  // kmer.rs:76-80
+        uint32_t k, pre, cb;
+        memcpy(&k, hdr + 4, 4);
+        memcpy(&pre, hdr + 8, 4);
+        memcpy(&cb, hdr + 12, 4);
+        if (cb != 10) throw np2::Error(NP2_ERR_FORMAT, "different YAK_COUNTER_BITS");  // kmer.rs:90
+        if (pre != 10) throw np2::Error(NP2_ERR_UNSUPPORTED, "yak prefix bits must be 10 (kmer.rs:52-54 vs htab.c:59)");
+        if (k == 0 || k > 63) throw np2::Error(NP2_ERR_FORMAT, "bad k in yak header");
+        fseek(fp, 0, SEEK_END);
+        const uint64_t fsz = (uint64_t)ftell(fp);
+        fseek(fp, 16, SEEK_SET);
+        std::vector<uint64_t> keys;
+        keys.reserve(fsz / 8);
+        std::vector<uint32_t> sub_off(1025, 0);
+        uint64_t max_sub = 0;
+        for (uint32_t b = 0; b < 1024; b++) {
+            uint32_t cs[2];
+            if (fread(cs, 4, 2, fp) != 2) throw np2::Error(NP2_ERR_FORMAT, "Failed to parse the dump file");
+            size_t o = keys.size();
+            keys.resize(o + cs[1]);
+            if (cs[1] && fread(keys.data() + o, 8, cs[1], fp) != cs[1])
+                throw np2::Error(NP2_ERR_FORMAT, "Failed to parse the dump file");
+            if (keys.size() >= (1ull << 32)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^32 keys: use np2_yak_from_arrays in chunks");
+            sub_off[b + 1] = (uint32_t)keys.size();
+            max_sub = std::max<uint64_t>(max_sub, cs[1]);
+        }
+        std::unique_ptr<np2_table> t(new np2_table());
+        table_alloc(ctx, t.get(), k, keys.size(), max_sub);
+        DBuf<uint64_t> d_keys;
+        DBuf<uint32_t> d_off;
+        DBuf<int> d_err;
+        d_keys.alloc(std::max<size_t>(keys.size(), 1), ctx->stream);
+        d_off.alloc(1025, ctx->stream);
+        d_err.alloc(1, ctx->stream);
+        d_err.zero();
+        if (!keys.empty()) d_keys.upload(keys.data(), keys.size());
+        d_off.upload(sub_off.data(), 1025);
+        table_insert_filekeys(t->dev, d_keys.p, d_off.p, keys.size(), d_err.p, ctx->stream);
+        int err = 0;
+        d_err.download(&err, 1);
+        NP2_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (err) throw np2::Error(NP2_ERR_INTERNAL, "table insertion overflow");
+        *out = t.release();
+    });
+}
+
+int np2_yak_from_arrays(np2_ctx *ctx, uint32_t k, const uint64_t *hashes, const uint16_t *counts, uint64_t n,
+                        np2_table **out) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        if (k == 0 || k > 63) throw np2::Error(NP2_ERR_ARG, "bad k");
+        std::vector<uint64_t> cnt(1024, 0);
+        for (uint64_t i = 0; i < n; i++) cnt[hashes[i] & 1023]++;
+        uint64_t max_sub = *std::max_element(cnt.begin(), cnt.end());
+        std::unique_ptr<np2_table> t(new np2_table());
+        table_alloc(ctx, t.get(), k, n, max_sub);
+        DBuf<uint64_t> d_h;
+        DBuf<uint16_t> d_c;
+        DBuf<int> d_err;
+        d_h.alloc(std::max<uint64_t>(n, 1), ctx->stream);
+        d_c.alloc(std::max<uint64_t>(n, 1), ctx->stream);
+        d_err.alloc(1, ctx->stream);
+        d_err.zero();
+        if (n) {
+            d_h.upload(hashes, n);
+            d_c.upload(counts, n);
+        }
+        table_insert(t->dev, d_h.p, d_c.p, n, d_err.p, ctx->stream);
+        int err = 0;
+        d_err.download(&err, 1);
+        NP2_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (err) throw np2::Error(NP2_ERR_INTERNAL, "table insertion overflow");
+        *out = t.release();
+    });
+}
+
+void np2_yak_free(np2_table *t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->dev.slots);
+    delete t;
+}
+uint32_t np2_yak_k(const np2_table *t) { return t->dev.k; }
+uint64_t np2_yak_size(const np2_table *t) { return t->dev.n; }
+uint64_t np2_yak_device_bytes(const np2_table *t) { return t->bytes; }
+
+int np2_yak_lookup(np2_ctx *ctx, const np2_table *t, const uint64_t *hashes, uint64_t n, uint32_t min_count,
+                   uint16_t *counts) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        if (!n) return;
+        DBuf<uint64_t> d_h;
+        DBuf<uint16_t> d_c;
+        d_h.alloc(n, ctx->stream);
+        d_c.alloc(n, ctx->stream);
+        d_h.upload(hashes, n);
+        table_probe(t->dev, d_h.p, n, min_count, d_c.p, ctx->stream);
+        d_c.download(counts, n);
+        NP2_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int np2_yak_lookup_device(np2_ctx *ctx, const np2_table *t, const uint64_t *d_hashes, uint64_t n, uint32_t min_count,
+                          uint16_t *d_counts, uint32_t repeat, float *ms) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        if (repeat == 0) repeat = 1;
+        cudaEvent_t a, b;
+        NP2_CUDA(cudaEventCreate(&a));
+        NP2_CUDA(cudaEventCreate(&b));
+        NP2_CUDA(cudaEventRecord(a, ctx->stream));
+        for (uint32_t r = 0; r < repeat; r++) table_probe(t->dev, d_hashes, n, min_count, d_counts, ctx->stream);
+        NP2_CUDA(cudaEventRecord(b, ctx->stream));
+        NP2_CUDA(cudaStreamSynchronize(ctx->stream));
+        float t_ms = 0;
+        cudaEventElapsedTime(&t_ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        NP2_CUDA(cudaGetLastError());
+        if (ms) *ms = t_ms / repeat;
+    });
+}
+
+int np2_seq_kscore(np2_ctx *ctx, const np2_table *t, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n,
+                   uint32_t min_count, uint16_t *kscore) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        if (!n) return;
+        DBuf<uint8_t> d_s;
+        DBuf<uint64_t> d_o;
+        DBuf<uint16_t> d_k;
+        d_s.alloc(seq_off[n] + 1, ctx->stream);
+        d_o.alloc(n + 1, ctx->stream);
+        d_k.alloc(n, ctx->stream);
+        if (seq_off[n]) d_s.upload(seqs, seq_off[n]);
+        d_o.upload(seq_off, n + 1);
+        seq_kscore(t->dev, d_s.p, d_o.p, nullptr, n, min_count, d_k.p, ctx->stream);
+        d_k.download(kscore, n);
+        NP2_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
+                   np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out) {
+    return guard([&] {
+        if (!ctx || !tseq || !opts || !out) throw np2::Error(NP2_ERR_ARG, "null argument");
+        if (opts->use_secondary) throw np2::Error(NP2_ERR_UNSUPPORTED, "-S / use_secondary is out of scope");
+        if (n_tables == 0) throw np2::Error(NP2_ERR_ARG, "Missing yak file!");
+        if (opts->iter_count == 0) throw np2::Error(NP2_ERR_ARG, "iter_count must be >= 1");
+        std::unique_ptr<np2_job> j(new np2_job());
+        j->ctx = ctx;
+        j->opt = *opts;
+        for (uint32_t i = 0; i < n_tables; i++) j->tables.push_back(tables[i]);
+        std::stable_sort(j->tables.begin(), j->tables.end(),
+                         [](np2_table *a, np2_table *b) { return a->dev.k < b->dev.k; });  // option.rs:238
+        j->tseq.assign(tseq, tseq + tlen);
+        j->bam = bam;
+        j->bam_len = bam_len;
+        if (tlen >= opts->min_ctg_len) {
+            if (tlen < 16) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig shorter than 16 bp");
+            if (tlen >= (1u << 30)) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig >= 2^30 bp (main.rs:270)");
+            for (uint32_t i = 0; i < tlen; i++)
+                if (tseq[i] >= 128 || tseq[i] == '-')
+                    throw np2::Error(NP2_ERR_FORMAT, "contig holds a byte the reference cannot index (>= 128 or '-')");
+            parse_records(bam, bam_len, tlen, *opts, j->ing);
+        }
+        *out = j.release();
+    });
+}
+
+int np2_job_upload(np2_job *job) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(job->ctx->device));
+        if (job->tseq.size() >= job->opt.min_ctg_len) job->upload();
+    });
+}
+
+int np2_job_run(np2_job *job, int32_t dump_iter) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(job->ctx->device));
+        job->run(dump_iter);
+    });
+}
+
+void np2_job_destroy(np2_job *job) {
+    if (!job) return;
+    cudaSetDevice(job->ctx->device);
+    cudaStreamSynchronize(job->ctx->stream);
+    delete job;
+}
+
+int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
+                      np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out) {
+    np2_job *j = nullptr;
+    int rc = np2_job_create(ctx, tseq, tlen, bam, bam_len, tables, n_tables, opts, &j);
+    if (rc == NP2_OK) rc = np2_job_upload(j);
+    if (rc == NP2_OK) rc = np2_job_run(j, -1);
+    if (rc != NP2_OK) {
+        np2_job_destroy(j);
+        return rc;
+    }
+    *out = j;
+    return NP2_OK;
+}
+
+uint64_t np2_job_get_consensus(np2_job *j, const uint32_t **pos, const uint8_t **base) {
+    *pos = j->result.pos.data();
+    *base = j->result.base.data();
+    return j->result.pos.size();
+}
+uint64_t np2_job_get_reads(np2_job *j, const int32_t **rec_idx, const uint32_t **t_s, const uint32_t **t_e,
+                           const uint64_t **nib_off, const uint8_t **nib, const uint8_t **blank) {
+    *rec_idx = j->d_rec_idx.data();
+    *t_s = j->dm_ts.data();
+    *t_e = j->dm_te.data();
+    *nib_off = j->dm_nib_off.data();
+    *nib = j->dm_nib.data();
+    *blank = j->dm_blank.data();
+    return j->d_rec_idx.size();
+}
+uint64_t np2_job_get_msa(np2_job *j, const uint64_t **off, const uint16_t **bases, const uint16_t **delta,
+                         const uint32_t **count, const uint32_t **besti) {
+    *off = j->dm_msa_off.data();
+    *bases = j->dm_msa_bases.data();
+    *delta = j->dm_msa_delta.data();
+    *count = j->dm_msa_count.data();
+    *besti = j->dm_msa_besti.data();
+    return j->dm_msa_bases.size();
+}
+uint64_t np2_job_get_dp_consensus(np2_job *j, const uint32_t **pos, const uint8_t **base, const uint8_t **flags) {
+    *pos = j->dm_dp_pos.data();
+    *base = j->dm_dp_base.data();
+    *flags = j->dm_dp_flags.data();
+    return j->dm_dp_pos.size();
+}
+uint64_t np2_job_get_regions(np2_job *j, const uint32_t **start, const uint32_t **end, const uint8_t **lable) {
+    *start = j->dm_reg_start.data();
+    *end = j->dm_reg_end.data();
+    *lable = j->dm_reg_lable.data();
+    return j->dm_reg_start.size();
+}
+uint64_t np2_job_get_candidates(np2_job *j, const uint64_t **roff, const uint32_t **order, const uint16_t **kscore,
+                                const uint64_t **kmer, const uint64_t **seq_off, const uint8_t **seq) {
+    *roff = j->dm_can_roff.data();
+    *order = j->dm_can_order.data();
+    *kscore = j->dm_can_kscore.data();
+    *kmer = j->dm_can_kmer.data();
+    *seq_off = j->dm_can_seq_off.data();
+    *seq = j->dm_can_seq.data();
+    return j->dm_can_order.size();
+}
+uint64_t np2_job_get_dropped(np2_job *j, const uint32_t **ids) {
+    *ids = j->dm_dropped.data();
+    return j->dm_dropped.size();
+}
+
+uint32_t np2_job_get_timings(np2_job *j, const char **names, const float **ms, const uint32_t **launches) {
+    j->timing_names.clear();
+    for (auto &n : j->timer.names) {
+        j->timing_names += n;
+        j->timing_names.push_back('\0');
+    }
+    *names = j->timing_names.data();
+    *ms = j->timer.ms.data();
+    *launches = j->timer.launches.data();
+    return (uint32_t)j->timer.names.size();
+}
+void np2_job_get_traffic(np2_job *j, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *n_kernel_launches,
+                         uint64_t *n_alignment_columns, uint64_t *n_probes) {
+    if (h2d_bytes) *h2d_bytes = j->h2d;
+    if (d2h_bytes) *d2h_bytes = j->d2h;
+    if (n_kernel_launches) *n_kernel_launches = j->n_launch;
+    if (n_alignment_columns) *n_alignment_columns = j->ing.total_cols;
+    if (n_probes) *n_probes = j->n_probes;
+}
+
+uint64_t np2_format_fasta(const char *tid, const uint32_t *pos, const uint8_t *base, uint64_t n, int uppercase,
+                          int out_pos, uint8_t *out, uint64_t cap) {
+    // display_consensusbase_vec main.rs:607-645
+    auto up = [&](uint8_t c) -> uint8_t { return (uppercase && c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; };
+    uint64_t w = 0;
+    auto put = [&](const char *s, size_t len) {
+        if (w + len <= cap) memcpy(out + w, s, len);
+        w += len;
+    };
+    char num[32];
+    const size_t tl = strlen(tid);
+    if (out_pos) {
+        for (uint64_t i = 0; i < n; i++) {
+            put(tid, tl);
+            char b[3] = {'\t', (char)up(base[i]), '\t'};
+            put(b, 3);
+            int l = snprintf(num, sizeof num, "%u\n", pos[i]);
+            put(num, (size_t)l);
+        }
+    } else if (n) {
+        put(">", 1);
+        put(tid, tl);
+        int l = snprintf(num, sizeof num, " start:%u", pos[0]);
+        put(num, (size_t)l);
+        l = snprintf(num, sizeof num, " end:%u\n", pos[n - 1]);
+        put(num, (size_t)l);
+        if (w + n <= cap) {
+            if (uppercase)
+                for (uint64_t i = 0; i < n; i++) out[w + i] = up(base[i]);
+            else
+                memcpy(out + w, base, n);
+        }
+        w += n;
+        put("\n", 1);
+    }
+    return w;
+}
+
+}  // extern "C"

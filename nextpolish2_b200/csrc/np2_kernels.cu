@@ -1,0 +1,879 @@
+// np2_kernels.cu — hand-written sm_100a kernels of the polish path.
+//
+//   K5  table_insert / table_probe / seq_kscore   yak k-mer table in HBM (kmer.rs:113-170, 255-314)
+//   K0  ref_codes                                  SEQ_NUM codes of the contig (kmer.rs:11-22)
+//   K1  expand_trim_pack                           fill_with_cigar + trim(8) + AlignSeq::new (main.rs:386-513, 279-312)
+//   K2  cover_diff / pileup_count / pileup_emit    update_msas + Msa::push/sort/coverage (main.rs:576-589, 193-241)
+//       mark_heads / groups_* / pos_finalize
+//   K3  dp_runs / emit_*                           get_cns_from_align_tags + backtrack (main.rs:1645-1687, 1572-1634)
+//   K4  cand_scan                                  generate_lqseqs_from_tags_kmer (main.rs:1462-1521)
+//
+// All of this is integer / byte work bound by HBM traffic and latency; there is no tensor-core term.
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
+
+#include "np2_kernels.cuh"
+
+namespace np2 {
+
+namespace {
+constexpr int kThreads = 256;
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+}  // namespace
+
+/* =============================================================== K5: yak table */
+
+__device__ __forceinline__ uint32_t bucket_of(uint64_t tag, uint32_t nb) {
+    uint32_t m = (uint32_t)((tag * 0x9E3779B97F4A7C15ULL) >> 32);
+    return (uint32_t)(((uint64_t)m * nb) >> 32);
+}
+
+__device__ __forceinline__ void insert_key(uint64_t *slots, uint32_t nb, uint32_t sub, uint64_t v, int *err) {
+    const uint64_t tag = v >> 10;
+    uint32_t b = bucket_of(tag, nb);
+    for (uint32_t step = 0; step < nb; step++) {
+        unsigned long long *bp = (unsigned long long *)(slots + ((uint64_t)sub * nb + b) * kBucketSlots);
+#pragma unroll
+        for (int j = 0; j < kBucketSlots; j++) {
+            unsigned long long old = atomicCAS(bp + j, 0ULL, (unsigned long long)v);
+            if (old == 0ULL || (old >> 10) == tag) return;
+        }
+        b = b + 1 == nb ? 0 : b + 1;
+    }
+    atomicExch(err, 1);
+}
+
+__global__ void k_table_insert(uint64_t *slots, uint32_t nb, const uint64_t *__restrict__ hashes,
+                               const uint16_t *__restrict__ counts, uint64_t n, int *err) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t h = hashes[i];
+        insert_key(slots, nb, (uint32_t)(h & 1023), (h >> 10) << 10 | (counts[i] & 1023), err);
+    }
+}
+
+__global__ void k_table_insert_filekeys(uint64_t *slots, uint32_t nb, const uint64_t *__restrict__ keys,
+                                        const uint32_t *__restrict__ sub_off, uint64_t n, int *err) {
+    __shared__ uint32_t s_off[1025];
+    for (int i = threadIdx.x; i < 1025; i += blockDim.x) s_off[i] = sub_off[i];
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = 1024;  // largest sub with s_off[sub] <= i
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= i) lo = mid;
+            else hi = mid;
+        }
+        insert_key(slots, nb, lo, keys[i], err);
+    }
+}
+
+// One probe = one 32-byte sector: 8 B query in, 32 B bucket, 2 B out.  Each thread keeps kProbeIlp
+// independent probes in flight so that DRAM latency is covered by memory-level parallelism.
+constexpr int kProbeIlp = 4;
+__device__ __forceinline__ uint16_t probe_finish(const uint64_t *__restrict__ slots, uint32_t nb, uint32_t sub,
+                                                 uint32_t b, uint64_t tag, ulonglong2 lo, ulonglong2 hi,
+                                                 uint32_t min_count) {
+    for (uint32_t step = 0;; step++) {
+        uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
+        bool empty = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((v[j] >> 10) == tag && v[j] != 0) {
+                uint32_t c = (uint32_t)(v[j] & 1023);
+                return c >= min_count ? (uint16_t)c : (uint16_t)0;
+            }
+            empty |= (v[j] == 0);
+        }
+        if (empty || step + 1 >= nb) return 0;
+        b = b + 1 == nb ? 0 : b + 1;
+        const ulonglong2 *bp = (const ulonglong2 *)(slots + ((uint64_t)sub * nb + b) * kBucketSlots);
+        lo = __ldg(bp);
+        hi = __ldg(bp + 1);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_table_probe(const uint64_t *__restrict__ slots, uint32_t nb,
+                                                          const uint64_t *__restrict__ hashes, uint64_t n,
+                                                          uint32_t min_count, uint16_t *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (; i0 < n; i0 += stride * kProbeIlp) {
+        uint64_t tag[kProbeIlp];
+        uint32_t sub[kProbeIlp], b[kProbeIlp];
+        ulonglong2 lo[kProbeIlp], hi[kProbeIlp];
+#pragma unroll
+        for (int u = 0; u < kProbeIlp; u++) {
+            uint64_t i = i0 + u * stride;
+            uint64_t h = i < n ? hashes[i] : 0;
+            sub[u] = (uint32_t)(h & 1023);
+            tag[u] = h >> 10;
+            b[u] = bucket_of(tag[u], nb);
+        }
+#pragma unroll
+        for (int u = 0; u < kProbeIlp; u++) {
+            const ulonglong2 *bp = (const ulonglong2 *)(slots + ((uint64_t)sub[u] * nb + b[u]) * kBucketSlots);
+            lo[u] = __ldg(bp);
+            hi[u] = __ldg(bp + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < kProbeIlp; u++) {
+            uint64_t i = i0 + u * stride;
+            if (i < n) out[i] = probe_finish(slots, nb, sub[u], b[u], tag[u], lo[u], hi[u], min_count);
+        }
+    }
+}
+
+__device__ __forceinline__ uint16_t probe_one(const uint64_t *__restrict__ slots, uint32_t nb, uint64_t h,
+                                              uint32_t min_count) {
+    uint32_t sub = (uint32_t)(h & 1023);
+    uint64_t tag = h >> 10;
+    uint32_t b = bucket_of(tag, nb);
+    const ulonglong2 *bp = (const ulonglong2 *)(slots + ((uint64_t)sub * nb + b) * kBucketSlots);
+    return probe_finish(slots, nb, sub, b, tag, __ldg(bp), __ldg(bp + 1), min_count);
+}
+
+// kscore of a byte string: one warp per string, one lane per k-mer end position (iter2kmer kmer.rs:255-314,
+// to_hash 102-110, min main.rs:761-769).  A window containing a non-ACGT code has no k-mer.
+__global__ void __launch_bounds__(kThreads) k_seq_kscore(const uint64_t *__restrict__ slots, uint32_t nb, uint32_t k,
+                                                         const uint8_t *__restrict__ seqs,
+                                                         const uint64_t *__restrict__ off,
+                                                         const uint32_t *__restrict__ sel, uint64_t n,
+                                                         uint32_t min_count, uint16_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (; w < n; w += nw) {
+        const uint64_t si = sel ? sel[w] : w;
+        const uint8_t *s = seqs + off[si];
+        const uint32_t len = (uint32_t)(off[si + 1] - off[si]);
+        uint32_t mn = 0xFFFFFFFFu;
+        for (uint32_t e = k - 1 + lane; e < len; e += 32) {  // k-mer occupying [e-k+1, e]
+            bool ok = true;
+            uint64_t hsh;
+            if (k < 32) {
+                const uint64_t mask = (1ULL << (2 * k)) - 1;
+                uint64_t f = 0, r = 0;
+                for (uint32_t x = e + 1 - k; x <= e; x++) {
+                    uint32_t c = seq_code(s[x]);
+                    ok &= c < 4;
+                    f = (f << 2 | c) & mask;
+                    r = (r >> 2) | (uint64_t)(3 ^ c) << (2 * (k - 1));
+                }
+                hsh = yak_hash64(f < r ? f : r, mask);
+            } else {
+                const uint64_t mask = (1ULL << k) - 1;
+                uint64_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+                for (uint32_t x = e + 1 - k; x <= e; x++) {
+                    uint64_t c = seq_code(s[x]);
+                    ok &= c < 4;
+                    x0 = (x0 << 1 | (c & 1)) & mask;
+                    x1 = (x1 << 1 | (c >> 1)) & mask;
+                    x2 = x2 >> 1 | (1 - (c & 1)) << (k - 1);
+                    x3 = x3 >> 1 | (1 - (c >> 1)) << (k - 1);
+                }
+                hsh = x1 < x3 ? yak_hash64_64(x0) + yak_hash64_64(x1) : yak_hash64_64(x2) + yak_hash64_64(x3);
+            }
+            if (ok) mn = min(mn, (uint32_t)probe_one(slots, nb, hsh, min_count));
+        }
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+        if (lane == 0) out[w] = mn == 0xFFFFFFFFu ? 0 : (uint16_t)mn;
+    }
+}
+
+void table_insert(const TableDev &t, const uint64_t *d_hashes, const uint16_t *d_counts, uint64_t n, int *d_err,
+                  cudaStream_t s) {
+    if (!n) return;
+    k_table_insert<<<min(cdiv(n, kThreads), 148u * 32u), kThreads, 0, s>>>(t.slots, t.nb, d_hashes, d_counts, n, d_err);
+}
+void table_insert_filekeys(const TableDev &t, const uint64_t *d_keys, const uint32_t *d_sub_off, uint64_t n,
+                           int *d_err, cudaStream_t s) {
+    if (!n) return;
+    k_table_insert_filekeys<<<min(cdiv(n, kThreads), 148u * 32u), kThreads, 0, s>>>(t.slots, t.nb, d_keys, d_sub_off, n,
+                                                                                   d_err);
+}
+void table_probe(const TableDev &t, const uint64_t *d_hashes, uint64_t n, uint32_t min_count, uint16_t *d_out,
+                 cudaStream_t s) {
+    if (!n) return;
+    // persistent-style grid: a multiple of the 148 SMs x 8 resident CTAs of 256 threads
+    uint32_t grid = min(cdiv(n, (uint64_t)kThreads * kProbeIlp), 148u * 8u);
+    k_table_probe<<<grid, kThreads, 0, s>>>(t.slots, t.nb, d_hashes, n, min_count, d_out);
+}
+void seq_kscore(const TableDev &t, const uint8_t *d_seqs, const uint64_t *d_off, const uint32_t *d_sel, uint64_t n,
+                uint32_t min_count, uint16_t *d_out, cudaStream_t s) {
+    if (!n) return;
+    uint32_t grid = min(cdiv(n * 32, kThreads), 148u * 8u);
+    k_seq_kscore<<<grid, kThreads, 0, s>>>(t.slots, t.nb, t.k, d_seqs, d_off, d_sel, n, min_count, d_out);
+}
+
+/* =============================================================== K0: reference codes */
+
+__global__ void k_ref_codes(const uint8_t *__restrict__ ref, uint32_t L, uint8_t *__restrict__ code) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L) code[i] = (uint8_t)seq_code(ref[i]);
+}
+void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, cudaStream_t s) {
+    k_ref_codes<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_ref, L, d_code);
+}
+
+/* =============================================================== K1: expand + trim + pack */
+
+struct OpCur {
+    uint32_t i, i_end;        // current op, one past the read's last op
+    uint32_t c_beg, c_end;    // columns covered by the op
+    uint32_t q, t, op;
+};
+__device__ __forceinline__ void op_load(const ReadsDev &R, OpCur &c) {
+    uint32_t cig = R.op_cig[c.i];
+    c.op = cig & 15;
+    c.c_beg = R.op_col[c.i];
+    c.c_end = c.c_beg + (cig >> 4);
+    c.q = R.op_q[c.i];
+    c.t = R.op_t[c.i];
+}
+// position the cursor on the op containing column col (col < total columns)
+__device__ __forceinline__ void op_seek(const ReadsDev &R, uint32_t r, uint32_t col, OpCur &c) {
+    uint32_t lo = R.op_off[r], hi = R.op_off[r + 1];
+    c.i_end = hi;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (R.op_col[mid] <= col) lo = mid;
+        else hi = mid;
+    }
+    c.i = lo;
+    op_load(R, c);
+}
+// column -> (match?, nibble).  M/=/X compare raw bytes like trim() (main.rs:454); the nibble is
+// SEQ_NUM[q] | 8 for an insertion column (main.rs:292-294).
+__device__ __forceinline__ void col_eval(const ReadsDev &R, const uint8_t *__restrict__ ref, uint32_t pos,
+                                         const uint8_t *__restrict__ seq4, const OpCur &c, uint32_t col, bool &match,
+                                         uint32_t &nib) {
+    uint32_t off = col - c.c_beg;
+    if (c.op == 2) {  // D
+        match = false;
+        nib = 4;
+        return;
+    }
+    uint32_t qi = c.q + off;
+    uint32_t byte = seq4[qi >> 1];
+    uint32_t b4 = (qi & 1) ? (byte & 15) : (byte >> 4);
+    if (c.op == 1) {  // I
+        match = false;
+        nib = bam4_code(b4) | 8;
+    } else {
+        match = ref[pos + c.t + off] == bam4_char(b4);
+        nib = bam4_code(b4);
+    }
+}
+__device__ __forceinline__ uint32_t block_mask16(const ReadsDev &R, const uint8_t *ref, uint32_t r, uint32_t pos,
+                                                 const uint8_t *seq4, uint32_t blk, uint32_t C) {
+    uint32_t c0 = blk * 16;
+    if (c0 >= C) return 0;
+    OpCur cur;
+    op_seek(R, r, c0, cur);
+    uint32_t m = 0;
+    uint32_t c1 = min(c0 + 16, C);
+    for (uint32_t c = c0; c < c1; c++) {
+        while (c >= cur.c_end) {
+            cur.i++;
+            op_load(R, cur);
+        }
+        bool match;
+        uint32_t nib;
+        col_eval(R, ref, pos, seq4, cur, c, match, nib);
+        m |= (uint32_t)match << (c - c0);
+    }
+    return m;
+}
+__device__ __forceinline__ uint32_t run8_starts(uint32_t x) {  // bit j set iff x[j..j+7] are all ones
+    x &= x >> 1;
+    x &= x >> 2;
+    x &= x >> 4;
+    return x;
+}
+// (t_pos, delta) of a column, from its op (get_align_tag main.rs:314-338 read forwards gives the same)
+__device__ __forceinline__ void col_tpos(const ReadsDev &R, uint32_t r, uint32_t pos, const OpCur &c, uint32_t col,
+                                         uint32_t &tpos, uint32_t &delta) {
+    uint32_t off = col - c.c_beg;
+    if (c.op == 1) {
+        tpos = pos + c.t - 1;
+        delta = off + 1;
+        uint32_t i = c.i;
+        while (i > R.op_off[r] && (R.op_cig[i - 1] & 15) == 1) {
+            delta += R.op_cig[i - 1] >> 4;
+            i--;
+        }
+    } else {
+        tpos = pos + c.t + off;
+        delta = 0;
+    }
+}
+
+// One warp per read.
+__global__ void __launch_bounds__(128) k_expand_trim_pack(ReadsDev R, const uint8_t *__restrict__ ref, uint32_t L) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R.n_reads) return;
+    const uint32_t pos = R.pos[r];
+    const uint32_t C = R.ncols[r];
+    const uint8_t *seq4 = R.blob + R.seq_off[r];
+    const uint32_t nb16 = (C + 15) >> 4;
+    const uint32_t ck0 = R.ck_off[r], nck = R.ck_off[r + 1] - ck0;
+    for (uint32_t b = lane; b < nck; b += 32) R.ck_read[ck0 + b] = r;
+
+    // ---- trim start: first run of 8 matching columns (main.rs:453-476)
+    uint32_t shift = 0xFFFFFFFFu;
+    for (uint32_t base = 0; base < nb16; base += 31) {
+        uint32_t m = block_mask16(R, ref, r, pos, seq4, base + lane, C);
+        uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, m, 1);
+        uint32_t st = lane < 31 ? (run8_starts(m | nxt << 16) & 0xFFFFu) : 0;
+        uint32_t bal = __ballot_sync(0xFFFFFFFFu, st != 0);
+        if (bal) {
+            uint32_t src = __ffs(bal) - 1;
+            uint32_t st0 = __shfl_sync(0xFFFFFFFFu, st, src);
+            shift = (base + src) * 16 + (__ffs(st0) - 1);
+            break;
+        }
+    }
+    if (shift == 0xFFFFFFFFu) {  // no anchor: shift = len, aln_len = 0 (main.rs:510-512)
+        if (lane == 0) {
+            R.n[r] = 0;
+            R.t_s[r] = pos;
+            R.t_e[r] = pos;
+        }
+        return;
+    }
+    // ---- trim end: last run of 8 (main.rs:479-509)
+    uint32_t new_len = 0;
+    for (int64_t base = (int64_t)nb16 - 31;; base -= 31) {
+        int64_t blk = base + lane;
+        uint32_t m = (blk >= 0 && blk < (int64_t)nb16) ? block_mask16(R, ref, r, pos, seq4, (uint32_t)blk, C) : 0;
+        uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, m, 1);
+        uint32_t st = lane < 31 ? (run8_starts(m | nxt << 16) & 0xFFFFu) : 0;
+        uint32_t bal = __ballot_sync(0xFFFFFFFFu, st != 0);
+        if (bal) {
+            uint32_t src = 31 - __clz(bal);
+            uint32_t st0 = __shfl_sync(0xFFFFFFFFu, st, src);
+            new_len = (uint32_t)(base + src) * 16 + (31 - __clz(st0)) + 8;
+            break;
+        }
+        if (base + 30 < 0) break;
+    }
+    const uint32_t n = new_len - shift;
+    if (lane == 0) {
+        OpCur cur;
+        uint32_t tp, dl;
+        op_seek(R, r, shift, cur);
+        col_tpos(R, r, pos, cur, shift, tp, dl);
+        R.t_s[r] = tp;
+        op_seek(R, r, new_len - 1, cur);
+        col_tpos(R, r, pos, cur, new_len - 1, tp, dl);
+        R.t_e[r] = tp;
+        R.n[r] = n;
+    }
+    // ---- pack columns [shift, new_len) into nibbles + terminator (main.rs:287-310), write checkpoints
+    uint8_t *out = R.nib + R.nib_off[r];
+    for (uint32_t o0 = lane * 16; o0 <= n; o0 += 512) {
+        uint64_t word = 0;
+        OpCur cur;
+        if (o0 < n) {
+            op_seek(R, r, shift + o0, cur);
+            if ((o0 & 31) == 0) {
+                uint32_t tp, dl;
+                col_tpos(R, r, pos, cur, shift + o0, tp, dl);
+                R.ck_tpos[ck0 + (o0 >> 5)] = tp;
+                R.ck_delta[ck0 + (o0 >> 5)] = (uint16_t)dl;
+            }
+        }
+#pragma unroll
+        for (uint32_t x = 0; x < 16; x++) {
+            uint32_t o = o0 + x, nib = 15;
+            if (o < n) {
+                uint32_t c = shift + o;
+                while (c >= cur.c_end) {
+                    cur.i++;
+                    op_load(R, cur);
+                }
+                bool match;
+                col_eval(R, ref, pos, seq4, cur, c, match, nib);
+            }
+            // column o -> byte o/2, high nibble when o is even
+            word |= (uint64_t)nib << (8 * (x >> 1) + ((x & 1) ? 0 : 4));
+        }
+        *(uint64_t *)(out + (o0 >> 1)) = word;
+    }
+}
+void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
+    if (!r.n_reads) return;
+    k_expand_trim_pack<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
+}
+
+/* =============================================================== K2: pileup */
+
+__global__ void k_cover_diff(ReadsDev R, const uint8_t *__restrict__ blank, int32_t *diff) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R.n_reads || blank[r] || R.n[r] == 0) return;
+    atomicAdd(&diff[R.t_s[r]], 1);
+    atomicAdd(&diff[R.t_e[r] + 1], -1);
+}
+void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s) {
+    if (!r.n_reads) return;
+    k_cover_diff<<<cdiv(r.n_reads, kThreads), kThreads, 0, s>>>(r, d_blank, d_diff);
+}
+
+__device__ __forceinline__ uint32_t nib_at(const uint8_t *__restrict__ nib, uint32_t o) {
+    uint32_t b = nib[o >> 1];
+    return (o & 1) ? (b & 15) : (b >> 4);
+}
+// delta of column o = number of consecutive insertion columns ending at o
+__device__ __forceinline__ uint32_t delta_scanback(const uint8_t *__restrict__ nib, uint32_t o) {
+    uint32_t d = 0;
+    while ((nib_at(nib, o) & 8) && o > 0) {
+        d++;
+        o--;
+    }
+    return d;
+}
+
+// Walks the 32 columns of global block g and calls f(p, bases, delta1) for every 3-mer that is NOT the
+// reference 3-mer of its position (those are counted as cover[p] - #others, see pos_finalize).
+template <class F>
+__device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, const uint8_t *__restrict__ blank,
+                                             const uint8_t *__restrict__ code, F f) {
+    const uint32_t r = R.ck_read[g];
+    if (blank[r]) return;
+    const uint32_t n = R.n[r];
+    const uint32_t o0 = (g - R.ck_off[r]) * 32;
+    if (o0 >= n) return;
+    const uint8_t *nib = R.nib + R.nib_off[r];
+    const uint4 w4 = *reinterpret_cast<const uint4 *>(nib + (o0 >> 1));
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    uint32_t tpos = R.ck_tpos[g], delta = R.ck_delta[g];
+    uint32_t q1 = 15, q2 = 15, ins1 = 0, ins2 = 0, d1 = 0, d2 = 1;  // heads (main.rs:579-580)
+    if (o0 > 0) {
+        uint32_t pb = nib[(o0 >> 1) - 1];
+        uint32_t v2 = pb & 15, v1 = pb >> 4;  // columns o0-1, o0-2
+        q2 = v2 & 7;
+        ins2 = v2 >> 3;
+        q1 = v1 & 7;
+        ins1 = v1 >> 3;
+        uint32_t first = (w[0] >> 4) & 15;  // column o0
+        if (first & 8) d2 = delta - 1;
+        else d2 = ins2 ? delta_scanback(nib, o0 - 1) : 0;
+        if (ins2) d1 = d2 - 1;
+        else d1 = ins1 ? delta_scanback(nib, o0 - 2) : 0;
+    }
+    uint32_t rc0 = code[tpos], rc1 = tpos >= 1 ? code[tpos - 1] : 255u, rc2 = tpos >= 2 ? code[tpos - 2] : 255u;
+    const uint32_t cnt = min(32u, n - o0);
+#pragma unroll
+    for (uint32_t i = 0; i < 32; i++) {
+        if (i >= cnt) break;
+        const uint32_t byte = (w[i >> 3] >> (8 * ((i >> 1) & 3))) & 255;
+        const uint32_t v = (i & 1) ? (byte & 15) : (byte >> 4);
+        const uint32_t q3 = v & 7, ins3 = v >> 3;
+        if (i > 0) {
+            if (ins3) delta++;
+            else {
+                delta = 0;
+                tpos++;
+                rc2 = rc1;
+                rc1 = rc0;
+                rc0 = code[tpos];
+            }
+        }
+        const uint32_t o = o0 + i;
+        uint32_t bases, dl1;
+        bool dense = false;
+        if (o == 0) {
+            bases = 0x4000u | 15u << 8 | 15u << 4 | q3;
+            dl1 = 0;
+        } else if (o == 1) {
+            bases = (ins3 ? 0x1000u : 0u) | 15u << 8 | q2 << 4 | q3;
+            dl1 = 1;
+        } else {
+            bases = (ins2 ? 0x4000u : 0u) | (ins3 ? 0x1000u : 0u) | q1 << 8 | q2 << 4 | q3;
+            dl1 = d1;
+            dense = !(ins1 | ins2 | ins3) && q1 == rc2 && q2 == rc1 && q3 == rc0;
+        }
+        if (!dense) f(tpos, bases, dl1 & 0xFFFFu);
+        q1 = q2;
+        ins1 = ins2;
+        d1 = d2;
+        q2 = q3;
+        ins2 = ins3;
+        d2 = delta;
+    }
+}
+
+constexpr int kPileThreads = 128;
+uint32_t pileup_ctas(uint32_t n_blocks) { return cdiv(n_blocks, kPileThreads); }
+
+__global__ void __launch_bounds__(kPileThreads) k_pileup_count(ReadsDev R, uint32_t n_blocks,
+                                                               const uint8_t *__restrict__ blank,
+                                                               const uint8_t *__restrict__ code,
+                                                               uint32_t *__restrict__ cta_count) {
+    typedef cub::BlockReduce<uint32_t, kPileThreads> BR;
+    __shared__ typename BR::TempStorage tmp;
+    uint32_t g = blockIdx.x * kPileThreads + threadIdx.x;
+    uint32_t c = 0;
+    if (g < n_blocks) scan_block32(R, g, blank, code, [&](uint32_t, uint32_t, uint32_t) { c++; });
+    uint32_t tot = BR(tmp).Sum(c);
+    if (threadIdx.x == 0) cta_count[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32_t n_blocks,
+                                                              const uint8_t *__restrict__ blank,
+                                                              const uint8_t *__restrict__ code,
+                                                              const uint32_t *__restrict__ cta_off,
+                                                              uint64_t *__restrict__ key, uint32_t *__restrict__ rd) {
+    typedef cub::BlockScan<uint32_t, kPileThreads> BS;
+    __shared__ typename BS::TempStorage tmp;
+    uint32_t g = blockIdx.x * kPileThreads + threadIdx.x;
+    uint32_t c = 0;
+    if (g < n_blocks) scan_block32(R, g, blank, code, [&](uint32_t, uint32_t, uint32_t) { c++; });
+    uint32_t off;
+    BS(tmp).ExclusiveSum(c, off);
+    if (c) {
+        // +2: records 0 and 1 are the reference read's two head 3-mers (main.rs:1732-1739, 579-584)
+        uint32_t w = cta_off[blockIdx.x] + off + 2;
+        const uint32_t order = R.ck_read[g] + 1;
+        scan_block32(R, g, blank, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) {
+            key[w] = (uint64_t)p << 32 | (uint64_t)bases << 16 | dl1;
+            rd[w] = order;
+            w++;
+        });
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        key[0] = (uint64_t)0 << 32 | (uint64_t)(0x4000u | 15u << 8 | 15u << 4 | code[0]) << 16 | 0;
+        rd[0] = 0;
+        key[1] = (uint64_t)1 << 32 | (uint64_t)(15u << 8 | (uint32_t)code[0] << 4 | code[1]) << 16 | 1;
+        rd[1] = 0;
+    }
+}
+void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
+                  uint32_t *d_cta_count, cudaStream_t s) {
+    k_pileup_count<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_count);
+}
+void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
+                 const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read, cudaStream_t s) {
+    k_pileup_emit<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_off, d_key,
+                                                                         d_read);
+}
+
+__global__ void k_mark_heads(const uint64_t *__restrict__ key, uint32_t n, uint32_t *__restrict__ head) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+}
+void mark_heads(const uint64_t *d_key, uint32_t n, uint32_t *d_head, cudaStream_t s) {
+    k_mark_heads<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, n, d_head);
+}
+__global__ void k_groups_fill(const uint64_t *__restrict__ key, const uint32_t *__restrict__ rd,
+                              const uint32_t *__restrict__ head, const uint32_t *__restrict__ gidx, uint32_t n,
+                              uint32_t *__restrict__ gstart, uint32_t *__restrict__ gpos, MsaDev m) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    uint32_t g = gidx[i];
+    uint64_t k = key[i];
+    gstart[g] = i;
+    gpos[g] = (uint32_t)(k >> 32);
+    m.g_bases[g] = (uint16_t)(k >> 16);
+    m.g_delta[g] = (uint16_t)k;
+    m.g_first[g] = rd[i];  // records were emitted in read order and the radix sort is stable
+}
+void groups_fill(const uint64_t *d_key, const uint32_t *d_read, const uint32_t *d_head, const uint32_t *d_gidx,
+                 uint32_t n, uint32_t G, uint32_t *d_gstart, uint32_t *d_gpos, MsaDev m, cudaStream_t s) {
+    k_groups_fill<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, d_read, d_head, d_gidx, n, d_gstart, d_gpos, m);
+}
+__global__ void k_groups_finish(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ gpos, uint32_t n,
+                                MsaDev m) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= m.G) return;
+    m.g_count[g] = (g + 1 < m.G ? gstart[g + 1] : n) - gstart[g];
+    uint32_t p = gpos[g];
+    uint32_t from = g ? gpos[g - 1] + 1 : 0;
+    for (uint32_t q = from; q <= p; q++) m.sp_off[q] = g;
+    if (g + 1 == m.G)
+        for (uint32_t q = p + 1; q <= m.L; q++) m.sp_off[q] = m.G;
+}
+void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t n, MsaDev m, cudaStream_t s) {
+    if (!m.G) return;
+    k_groups_finish<<<cdiv(m.G, kThreads), kThreads, 0, s>>>(d_gstart, d_gpos, n, m);
+}
+
+// Per position: order the sparse 3-mers like Msa::sort after first-seen pushes (main.rs:193-229): by b3.delta,
+// then by the first read that carried them; derive the reference 3-mer's count and the articulation flag.
+__global__ void k_pos_finalize(MsaDev m, uint32_t *__restrict__ n_emit) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m.L) return;
+    const uint32_t lo = m.sp_off[p], hi = m.sp_off[p + 1];
+    uint32_t sum0 = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        uint16_t bs = m.g_bases[i], dl = m.g_delta[i];
+        uint32_t cn = m.g_count[i], fr = m.g_first[i];
+        uint32_t kd = kmer_b3delta(bs, dl);
+        if (kd == 0) sum0 += cn;
+        uint32_t j = i;
+        while (j > lo) {
+            uint32_t kd2 = kmer_b3delta(m.g_bases[j - 1], m.g_delta[j - 1]);
+            if (kd2 < kd || (kd2 == kd && m.g_first[j - 1] <= fr)) break;
+            m.g_bases[j] = m.g_bases[j - 1];
+            m.g_delta[j] = m.g_delta[j - 1];
+            m.g_count[j] = m.g_count[j - 1];
+            m.g_first[j] = m.g_first[j - 1];
+            j--;
+        }
+        if (j != i) {
+            m.g_bases[j] = bs;
+            m.g_delta[j] = dl;
+            m.g_count[j] = cn;
+            m.g_first[j] = fr;
+        }
+    }
+    m.dense_cnt[p] = p >= 2 ? (uint32_t)m.cover[p] - sum0 : 0;
+    const bool multi = p < 2 || hi > lo;
+    m.multi[p] = multi;
+    n_emit[p] = multi ? 0 : (m.code[p] != 4);
+}
+void pos_finalize(MsaDev m, uint32_t *d_n_emit, cudaStream_t s) {
+    k_pos_finalize<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_n_emit);
+}
+
+/* =============================================================== K3: DP over runs + consensus */
+
+__global__ void k_run_flags(const uint8_t *__restrict__ multi, uint32_t L, uint8_t *__restrict__ flag) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < L) flag[p] = multi[p] && (p == 0 || !multi[p - 1]);
+}
+void run_flags(const uint8_t *d_multi, uint32_t L, uint8_t *d_flag, cudaStream_t s) {
+    k_run_flags<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_multi, L, d_flag);
+}
+
+struct Entry {
+    uint16_t bases, delta;
+    uint32_t count;
+    uint32_t g;  // sparse index or 0xFFFFFFFF for the reference 3-mer
+};
+__device__ __forceinline__ uint32_t n_ent(const MsaDev &m, uint32_t p) {
+    return (p >= 2 ? 1u : 0u) + m.sp_off[p + 1] - m.sp_off[p];
+}
+__device__ __forceinline__ Entry get_entry(const MsaDev &m, uint32_t p, uint32_t idx) {
+    Entry e;
+    if (p >= 2 && idx == 0) {
+        e.bases = (uint16_t)((uint32_t)m.code[p - 2] << 8 | (uint32_t)m.code[p - 1] << 4 | m.code[p]);
+        e.delta = 0;
+        e.count = m.dense_cnt[p];
+        e.g = 0xFFFFFFFFu;
+    } else {
+        e.g = m.sp_off[p] + idx - (p >= 2 ? 1 : 0);
+        e.bases = m.g_bases[e.g];
+        e.delta = m.g_delta[e.g];
+        e.count = m.g_count[e.g];
+    }
+    return e;
+}
+constexpr int64_t kDead = INT64_MIN >> 1;  // main.rs:1661
+
+// One thread per run of multi-entry positions [s, e); e is the next articulation position (single entry,
+// every path passes through it), so scores can be kept relative to the articulation before s.
+__global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, uint32_t n_runs, DpOut o) {
+    uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= n_runs) return;
+    const uint32_t s = run_start[ri], L = m.L;
+    int64_t best = 0;
+    uint32_t best_idx = 0;
+    for (uint32_t p = s; p < L; p++) {
+        const bool single = !m.multi[p];
+        const uint32_t ne = n_ent(m, p);
+        const int64_t cov = m.cover[p];
+        for (uint32_t idx = 0; idx < ne; idx++) {
+            const Entry x = get_entry(m, p, idx);
+            ABase b1, b2, b3;
+            kmer_bases(x.bases, x.delta, p, b1, b2, b3);
+            const int64_t inc = 10 * (int64_t)x.count - 4 * cov;
+            uint32_t besti = 0;
+            int64_t score;
+            if (b2.q == 15) {
+                score = inc;
+            } else {
+                score = kDead;
+                const uint32_t pp = b2.t_pos;
+                const uint32_t base23 = ((uint32_t)b1.q << 4 | b2.q) & 255u;
+                const uint32_t delta23 = b1.t_pos == b2.t_pos ? 1u : 0u;
+                const bool boundary = pp < s;  // the articulation before the run: one entry, local score 0
+                const uint32_t npe = boundary ? 1u : (pp == p ? idx : n_ent(m, pp));
+                for (uint32_t pi = 0; pi < npe; pi++) {
+                    const Entry v = get_entry(m, pp, pi);
+                    if ((v.bases & 255u) != base23 || ((v.bases >> 12) & 1u) != delta23) continue;
+                    ABase v1, v2, v3;
+                    kmer_bases(v.bases, v.delta, pp, v1, v2, v3);
+                    if (!(v2.eq(b1) && v3.eq(b2))) continue;
+                    if (pp >= 3 && v1.q == 15) continue;  // main.rs:1666-1668
+                    const int64_t vs = boundary ? 0 : (v.g == 0xFFFFFFFFu ? m.dense_score[pp] : m.g_score[v.g]);
+                    const int64_t sc = vs + inc;
+                    if (sc > score || (sc == score && v1.q != 4)) {  // main.rs:1670
+                        score = sc;
+                        besti = pi;
+                    }
+                }
+            }
+            if (x.g == 0xFFFFFFFFu) {
+                m.dense_besti[p] = besti;
+                if (!single) m.dense_score[p] = score;
+            } else {
+                m.g_besti[x.g] = besti;
+                m.g_score[x.g] = score;
+            }
+            if (p == L - 1 && (idx == 0 || score >= best)) {  // main.rs:1680, offset-invariant form
+                best = score;
+                best_idx = idx;
+            }
+        }
+        if (single) return;
+    }
+    *o.best_last = best_idx;  // the run reached the contig end
+}
+void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, cudaStream_t s) {
+    if (!n_runs) return;
+    k_dp_runs<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o);
+}
+
+// Backtrack of one run (main.rs:1572-1634 without the LQ state machine).  WRITE = false: count emitted
+// bases per position; WRITE = true: write them at the scanned offsets (ascending order == reversed vec).
+template <bool WRITE>
+__global__ void k_emit_runs(MsaDev m, const uint32_t *__restrict__ run_start, uint32_t n_runs, DpOut o,
+                            uint32_t *__restrict__ n_emit, const uint32_t *__restrict__ emit_off,
+                            uint32_t *__restrict__ out_pos, uint8_t *__restrict__ out_base,
+                            uint8_t *__restrict__ out_flags) {
+    uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    long long sum = 0;
+    if (ri < n_runs) {
+        const uint32_t s = run_start[ri], L = m.L;
+        uint32_t e = s;
+        while (e < L && m.multi[e]) e++;
+        uint32_t p, idx;
+        if (e < L) {
+            p = e - 1;  // b2 of the reference 3-mer at e sits at e - 1
+            idx = m.dense_besti[e];
+        } else {
+            p = L - 1;
+            idx = *o.best_last;
+        }
+        uint32_t cur_p = 0xFFFFFFFFu, cur_n = 0, cur_w = 0;
+        for (;;) {
+            if (s > 0 && p < s) break;  // reached the articulation before the run
+            const Entry x = get_entry(m, p, idx);
+            ABase b1, b2, b3;
+            kmer_bases(x.bases, x.delta, p, b1, b2, b3);
+            const int64_t cov = m.cover[p];
+            if (!WRITE) sum += 10 * (long long)x.count - 4 * cov;
+            if (p != cur_p) {
+                if (!WRITE && cur_p != 0xFFFFFFFFu) n_emit[cur_p] = cur_n;
+                cur_p = p;
+                cur_n = 0;
+                if (WRITE) cur_w = emit_off[p] + n_emit[p];
+            }
+            if (b3.q != 4) {
+                cur_n++;
+                if (WRITE) {
+                    cur_w--;
+                    out_pos[cur_w] = p;
+                    out_base[cur_w] = code_char(b3.q);
+                    const int64_t qv = (int64_t)x.count * 100 / cov;  // main.rs:1576
+                    out_flags[cur_w] = (uint8_t)((qv < 95 ? 1 : 0) | (cov < 2 ? 2 : 0));
+                }
+            }
+            if (b2.q == 15) break;  // main.rs:1629
+            idx = x.g == 0xFFFFFFFFu ? m.dense_besti[p] : m.g_besti[x.g];
+            p = b2.t_pos;
+        }
+        if (!WRITE && cur_p != 0xFFFFFFFFu) n_emit[cur_p] = cur_n;
+    }
+    if (!WRITE) {
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if ((threadIdx.x & 31) == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
+    }
+}
+__global__ void k_emit_singles(MsaDev m, const uint32_t *__restrict__ emit_off, uint32_t *__restrict__ out_pos,
+                               uint8_t *__restrict__ out_base, uint8_t *__restrict__ out_flags, DpOut o) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    long long sum = 0;
+    if (p < m.L && !m.multi[p]) {
+        const int64_t cov = m.cover[p], cnt = m.dense_cnt[p];
+        sum = 10 * cnt - 4 * cov;
+        if (m.code[p] != 4) {
+            uint32_t w = emit_off[p];
+            out_pos[w] = p;
+            out_base[w] = code_char(m.code[p]);
+            out_flags[w] = (uint8_t)((cnt * 100 / cov < 95 ? 1 : 0) | (cov < 2 ? 2 : 0));
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if ((threadIdx.x & 31) == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
+}
+void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, uint32_t *d_n_emit,
+                     cudaStream_t s) {
+    if (!n_runs) return;
+    k_emit_runs<false><<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, d_n_emit, nullptr, nullptr, nullptr,
+                                                       nullptr);
+}
+void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, const uint32_t *d_n_emit,
+                const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s) {
+    k_emit_singles<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags, o);
+    if (n_runs)
+        k_emit_runs<true><<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, const_cast<uint32_t *>(d_n_emit),
+                                                          d_emit_off, d_pos, d_base, d_flags);
+}
+
+/* =============================================================== K4: candidate alleles */
+
+// One thread per (read, LQ region) pair: the read's bases over [start, end] and its first-k canonical k-mer from
+// `start` on (main.rs:1478-1521).  The read is only decoded up to the first column whose t_pos exceeds
+// pair_limit (main.rs:1465-1471).
+template <bool WRITE>
+__global__ void k_cand_scan(ReadsDev R, CandDev c, uint32_t k) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n_pairs) return;
+    const uint32_t r = c.pair_read[i], start = c.pair_start[i], end = c.pair_end[i], limit = c.pair_limit[i];
+    const uint32_t n = R.n[r];
+    const uint8_t *nib = R.nib + R.nib_off[r];
+    const uint32_t *ck = R.ck_tpos + R.ck_off[r];
+    uint32_t lo = 0, hi = (n + 31) >> 5;  // last 32-column block whose first t_pos is < start (or block 0)
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (ck[mid] < start) lo = mid;
+        else hi = mid;
+    }
+    uint32_t tpos = ck[lo];
+    const uint64_t mask = (1ULL << (2 * k)) - 1;
+    const uint32_t sh = 2 * (k - 1);
+    uint64_t k0 = 0, k1 = 0;
+    uint32_t l = 0, len = 0;
+    uint8_t *out = WRITE ? c.seq + c.seq_off[i] : nullptr;
+    for (uint32_t o = lo * 32; o < n; o++) {
+        const uint32_t v = nib_at(nib, o);
+        if (o != lo * 32 && !(v & 8)) tpos++;
+        const uint32_t q = v & 7;
+        if (tpos >= start && q != 4) {
+            if (tpos <= end) {
+                if (WRITE) out[len] = code_char(q);
+                len++;
+            }
+            if (l < k) {
+                k0 = (k0 << 2 | (uint64_t)q) & mask;
+                k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
+                l++;
+            }
+            if (tpos > end && l >= k) break;
+        }
+        if (tpos > limit) break;
+    }
+    if (!WRITE) {
+        c.len[i] = len;
+        c.kmer[i] = l >= k ? yak_hash64(k0 < k1 ? k0 : k1, mask) : 0xFFFFFFFFFFFFFFFFULL;
+    }
+}
+void cand_scan(const ReadsDev &r, CandDev c, uint32_t k, bool write, cudaStream_t s) {
+    if (!c.n_pairs) return;
+    if (write) k_cand_scan<true><<<cdiv(c.n_pairs, 128), 128, 0, s>>>(r, c, k);
+    else k_cand_scan<false><<<cdiv(c.n_pairs, 128), 128, 0, s>>>(r, c, k);
+}
+
+}  // namespace np2

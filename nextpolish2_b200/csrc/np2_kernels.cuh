@@ -1,0 +1,105 @@
+// np2_kernels.cuh — launch wrappers of the sm_100a kernels (definitions in np2_kernels.cu).
+#pragma once
+#include "np2_common.cuh"
+
+namespace np2 {
+
+/* ------------------------------------------------------------------ yak table (K5) */
+constexpr int kBucketSlots = 4;  // 4 x u64 = one 32-byte DRAM sector per probe
+
+struct TableDev {
+    uint64_t *slots = nullptr;  // 1024 sub-tables x nb buckets x 4 slots; slot = (h >> 10) << 10 | count, 0 = empty
+    uint32_t nb = 0;            // buckets per sub-table
+    uint32_t k = 0;
+    uint64_t n = 0;
+};
+
+void table_insert(const TableDev &t, const uint64_t *d_hashes, const uint16_t *d_counts, uint64_t n, int *d_err,
+                  cudaStream_t s);
+// keys in yak file layout: key = (h >> 10) << 10 | count, sub-table id given per range
+void table_insert_filekeys(const TableDev &t, const uint64_t *d_keys, const uint32_t *d_sub_off /*1025*/, uint64_t n,
+                           int *d_err, cudaStream_t s);
+void table_probe(const TableDev &t, const uint64_t *d_hashes, uint64_t n, uint32_t min_count, uint16_t *d_out,
+                 cudaStream_t s);
+void seq_kscore(const TableDev &t, const uint8_t *d_seqs, const uint64_t *d_off, const uint32_t *d_sel, uint64_t n,
+                uint32_t min_count, uint16_t *d_out, cudaStream_t s);
+
+/* ------------------------------------------------------------------ K0/K1 ingest */
+void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, cudaStream_t s);
+
+struct ReadsDev {
+    uint32_t n_reads = 0;  // kept reads, index 0 = first BAM read (the ref read is implicit)
+    // inputs (host-built)
+    const uint32_t *pos = nullptr;
+    const uint32_t *op_off = nullptr;   // n_reads + 1
+    const uint64_t *seq_off = nullptr;  // byte offset of the 4-bit SEQ inside the blob
+    const uint32_t *ncols = nullptr;    // alignment columns before trimming
+    const uint64_t *nib_off = nullptr;  // byte offset into nib (16-B aligned), n_reads + 1
+    const uint32_t *ck_off = nullptr;   // first 32-column block of the read, n_reads + 1
+    const uint32_t *op_col = nullptr, *op_q = nullptr, *op_t = nullptr, *op_cig = nullptr;
+    const uint8_t *blob = nullptr;
+    // outputs
+    uint32_t *t_s = nullptr, *t_e = nullptr, *n = nullptr;  // trimmed start / inclusive end / column count (0 = no anchor)
+    uint8_t *nib = nullptr;
+    uint32_t *ck_tpos = nullptr;
+    uint16_t *ck_delta = nullptr;
+    uint32_t *ck_read = nullptr;
+};
+void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s);
+
+/* ------------------------------------------------------------------ K2 pileup */
+void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);
+// pass 1: per-CTA count of non-reference 3-mers; pass 2: write (key, read) records at the scanned offsets
+void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
+                  uint32_t *d_cta_count, cudaStream_t s);
+void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
+                 const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read, cudaStream_t s);
+uint32_t pileup_ctas(uint32_t n_blocks);
+
+struct MsaDev {
+    uint32_t L = 0;
+    uint32_t G = 0;             // sparse groups
+    uint32_t *sp_off = nullptr;  // L + 1
+    uint16_t *g_bases = nullptr, *g_delta = nullptr;
+    uint32_t *g_count = nullptr, *g_first = nullptr, *g_besti = nullptr;
+    int64_t *g_score = nullptr;
+    int32_t *cover = nullptr;        // L (+1): reads (incl. ref) spanning p == Msa::coverage()
+    uint32_t *dense_cnt = nullptr;   // L: count of the reference 3-mer (entry 0 for p >= 2)
+    uint32_t *dense_besti = nullptr; // L
+    int64_t *dense_score = nullptr;  // L
+    uint8_t *multi = nullptr;        // L: more than one entry (or p < 2)
+    const uint8_t *code = nullptr;   // ref codes
+};
+void mark_heads(const uint64_t *d_key, uint32_t n, uint32_t *d_head, cudaStream_t s);
+void groups_fill(const uint64_t *d_key, const uint32_t *d_read, const uint32_t *d_head, const uint32_t *d_gidx,
+                 uint32_t n, uint32_t G, uint32_t *d_gstart, uint32_t *d_gpos, MsaDev m, cudaStream_t s);
+void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t n, MsaDev m, cudaStream_t s);
+void pos_finalize(MsaDev m, uint32_t *d_n_emit, cudaStream_t s);
+
+/* ------------------------------------------------------------------ K3 DP + consensus */
+void run_flags(const uint8_t *d_multi, uint32_t L, uint8_t *d_flag, cudaStream_t s);
+struct DpOut {
+    uint32_t *best_last = nullptr;   // entry index chosen at p = L - 1 when L - 1 is inside a run
+    unsigned long long *score_total = nullptr;
+};
+void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, cudaStream_t s);
+void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, uint32_t *d_n_emit,
+                     cudaStream_t s);
+void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, const uint32_t *d_n_emit,
+                const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s);
+
+/* ------------------------------------------------------------------ K4 candidates */
+struct CandDev {
+    uint32_t n_pairs = 0;
+    const uint32_t *pair_read = nullptr;   // index into ReadsDev
+    const uint32_t *pair_start = nullptr;  // region start / end (inclusive)
+    const uint32_t *pair_end = nullptr;
+    const uint32_t *pair_limit = nullptr;  // decode limit of the read: lqseqs[j].end + k
+    uint32_t *len = nullptr;
+    uint64_t *kmer = nullptr;              // hashed first-k canonical k-mer or UINT64_MAX
+    const uint64_t *seq_off = nullptr;     // exclusive scan of len (pass 2)
+    uint8_t *seq = nullptr;
+};
+void cand_scan(const ReadsDev &r, CandDev c, uint32_t k, bool write, cudaStream_t s);
+
+}  // namespace np2

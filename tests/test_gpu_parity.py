@@ -1,0 +1,125 @@
+"""-m gpu: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs, stage by stage and
+end to end.  Everything here is integer/byte work: the bar is bit-exact equality."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import common
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(ctx, name, dump_iter, ks=common.KS, **optkw):
+    import nextpolish2_b200 as np2
+    ds = common.dataset(name)
+    oo, go = common.same_opts(**optkw)
+    oj = O.Job(ds["contig"], ds["bam"], common.oracle_tables(ds, ks), oo, dump_iter=dump_iter)
+    gt = common.gpu_tables(ctx, ds, ks)
+    gj = np2.Job(ctx, ds["contig"], ds["bam"], gt, go).upload().run(dump_iter)
+    return ds, oj, gj
+
+
+@pytest.mark.parametrize("name", ["tiny20k", "hap300k", "clip120k", "dip600k"])
+def test_stage_reads(ctx, name):
+    """K1: filter + fill_with_cigar + trim(8) + AlignSeq::new + clip filter (main.rs:1758-1817)."""
+    ds, oj, gj = _run_both(ctx, name, 0)
+    common.assert_same_dict("reads", oj.reads(), gj.reads(), ["rec_idx", "t_s", "t_e", "blank", "nib_off", "nib"])
+
+
+@pytest.mark.parametrize("name,it", [("tiny20k", 0), ("hap300k", 0), ("clip120k", 0), ("dip600k", 0), ("dip600k", 1),
+                                      ("tandem200k", 0), ("tandem200k", 1)])
+def test_stage_msa_dp(ctx, name, it):
+    """K2 + K3: per-position 3-mer lists in Msa order with counts, besti, consensus, qv/cov flags."""
+    ds, oj, gj = _run_both(ctx, name, it)
+    om, gm = oj.msa(), gj.msa()
+    common.assert_same_dict("msa", om, gm, ["off", "bases", "delta", "count"])
+    # besti is only defined by the reference where a predecessor exists; dead entries keep 0 in both
+    common.assert_same("msa.besti", om["besti"], gm["besti"])
+    common.assert_same_dict("dp", oj.dp_consensus(), gj.dp_consensus())
+
+
+@pytest.mark.parametrize("name,it", [("tiny20k", 0), ("hap300k", 1), ("clip120k", 0), ("dip600k", 0), ("dip600k", 1),
+                                      ("deep80k", 0), ("tandem200k", 1)])
+def test_stage_regions_candidates(ctx, name, it):
+    """LQ regions, K4 candidates (order, seq, first-k k-mer hash) and K5 kscore."""
+    ds, oj, gj = _run_both(ctx, name, it)
+    common.assert_same_dict("regions", oj.regions(), gj.regions(), ["start", "end"])
+    common.assert_same_dict("cand", oj.candidates(), gj.candidates(), ["roff", "order", "seq_off", "seq", "kmer", "kscore"])
+    common.assert_same("regions.lable", oj.regions()["lable"], gj.regions()["lable"])
+    common.assert_same("dropped", oj.dropped(), gj.dropped())
+
+
+CASES = [
+    ("tiny20k", common.KS, {}),
+    ("hap300k", common.KS, {}),
+    ("clip120k", common.KS, {}),
+    ("dip600k", common.KS, {}),
+    ("tandem200k", common.KS, {}),
+    ("deep80k", common.KS, {}),
+    ("dip600k", (21,), {"iter_count": 1}),
+    ("clip120k", (21, 31, 51), {"iter_count": 3}),
+    ("dip600k", (31,), {"use_all_reads": 1}),
+    ("dip600k", common.KS, {"model": 1}),
+    ("dip600k", common.KS, {"use_supplementary": 1, "min_map_qual": -1, "max_clip_len": 1000}),
+    ("hap300k", common.KS, {"min_kmer_count": 40}),
+    ("deep80k", (21, 51), {"max_indel_len": 1}),
+]
+
+
+@pytest.mark.parametrize("name,ks,optkw", CASES, ids=[f"{c[0]}-k{'_'.join(map(str, c[1]))}-{'_'.join(c[2]) or 'default'}" for c in CASES])
+def test_polish_fasta_identical(ctx, name, ks, optkw):
+    """End to end through np2_polish_contig: FASTA bytes identical to the oracle (= reference -t 1)."""
+    import nextpolish2_b200 as np2
+    ds = common.dataset(name)
+    oo, go = common.same_opts(**optkw)
+    oj = O.Job(ds["contig"], ds["bam"], common.oracle_tables(ds, ks), oo, dump_iter=-1)
+    opos, obase = oj.consensus()
+    gpos, gbase = np2.polish_contig(ctx, ds["contig"], ds["bam"], common.gpu_tables(ctx, ds, ks), go)
+    common.assert_same("consensus.base", obase, gbase)
+    common.assert_same("consensus.pos", opos, gpos)
+    fo = O.format_fasta("ctg1", opos, obase)
+    fg = np2.format_fasta("ctg1", gpos, gbase)
+    assert hashlib.sha256(fo).hexdigest() == hashlib.sha256(fg).hexdigest()
+    # sanity property of the domain: the polish does something (consensus differs from the draft assembly)
+    assert bytes(gbase) != bytes(ds["contig"])
+
+
+def test_passthrough_and_errors(ctx):
+    """Short contigs are echoed (main.rs:1727-1730); reference panics come back as error codes."""
+    import nextpolish2_b200 as np2
+    from nextpolish2_b200 import synth
+    ds = common.dataset("tiny20k")
+    gt = common.gpu_tables(ctx, ds)
+    pos, base = np2.polish_contig(ctx, ds["contig"], ds["bam"], gt, np2.Opts())  # default -L 1000000
+    assert bytes(base) == bytes(ds["contig"]) and pos[0] == 0 and pos[-1] == len(base) - 1
+    seq = "ACGT" * 600
+    bad = synth.bam_record(0, 10, [("M", 1200), ("N", 50), ("M", 1200)], seq)
+    with pytest.raises(np2.Np2Error) as e:
+        np2.polish_contig(ctx, ds["contig"], bad, gt, np2.Opts(min_ctg_len=0))
+    assert e.value.code == -4 and "Unknown cigar" in str(e.value)
+    r1 = synth.bam_record(0, 500, [("M", 2400)], seq)
+    r0 = synth.bam_record(0, 100, [("M", 2400)], seq)
+    with pytest.raises(np2.Np2Error) as e:
+        np2.polish_contig(ctx, ds["contig"], np.concatenate([r1, r0]), gt, np2.Opts(min_ctg_len=0))
+    assert "Unsorted" in str(e.value)
+    with pytest.raises(O.OracleError):
+        O.Job(ds["contig"], np.concatenate([r1, r0]), common.oracle_tables(ds), O.Opts(min_ctg_len=0))
+    with pytest.raises(np2.Np2Error):
+        np2.polish_contig(ctx, ds["contig"], ds["bam"], gt, np2.Opts(min_ctg_len=0, use_secondary=1))
+
+
+def test_no_reads(ctx):
+    """A contig without any alignment: consensus == the contig's own codes (upper-cased ACGT)."""
+    import nextpolish2_b200 as np2
+    ds = common.dataset("tiny20k")
+    empty = np.empty(0, np.uint8)
+    contig = ds["contig"].copy()
+    contig[100:200] |= 0x20  # lower-case stretch comes back upper-case (SEQ_NUM round trip)
+    oj = O.Job(contig, empty, common.oracle_tables(ds), O.Opts(min_ctg_len=0))
+    gpos, gbase = np2.polish_contig(ctx, contig, empty, common.gpu_tables(ctx, ds), np2.Opts(min_ctg_len=0))
+    opos, obase = oj.consensus()
+    common.assert_same("base", obase, gbase)
+    common.assert_same("pos", opos, gpos)
+    assert bytes(gbase) == bytes(ds["contig"])
