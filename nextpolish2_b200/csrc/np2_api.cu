@@ -49,7 +49,14 @@ struct DBuf {  // stream-ordered device buffer
         release();
         s = st;
         n = count;
-        if (count) NP2_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), st));
+        if (count) {
+            cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), st);
+            if (e != cudaSuccess) {
+                p = nullptr;
+                throw np2::Error(NP2_ERR_CUDA, std::string("cudaMallocAsync of ") + std::to_string(count) + " x " +
+                                                   std::to_string(sizeof(T)) + " bytes: " + cudaGetErrorString(e));
+            }
+        }
     }
     void zero() {
         if (n) NP2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
@@ -145,16 +152,26 @@ struct StageTimer {
 struct np2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    int refs = 1;  // tables and jobs keep their context alive (np2_ctx_destroy only drops the caller's reference)
 };
+static void ctx_release(np2_ctx *ctx) {
+    if (--ctx->refs > 0) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
 
 struct np2_table {
     np2_ctx *ctx = nullptr;
     TableDev dev;
     uint64_t bytes = 0;
 };
+static void ctx_release(np2_ctx *ctx);
 
 static void table_alloc(np2_ctx *ctx, np2_table *t, uint32_t k, uint64_t n, uint64_t max_sub) {
     t->ctx = ctx;
+    ctx->refs++;
     t->dev.k = k;
     t->dev.n = n;
     // buckets of 4 slots, load factor <= 0.6 in the fullest sub-table
@@ -292,6 +309,22 @@ void np2_job::ingest_finish() {
     as_read.push_back(-1);
     std::vector<uint32_t> as_ts{0}, as_te{L - 1};
     std::vector<uint8_t> as_lab{0};
+    // "Unsorted input file!" (main.rs:1753-1756): every record is compared with the last PUSHED read
+    {
+        int64_t pre_tid = 0, pre_pos = 0;
+        size_t c = 0;
+        for (size_t rec = 0; rec < ing.all_tid.size(); rec++) {
+            if (!(ing.all_tid[rec] > pre_tid || (int64_t)ing.all_pos[rec] >= pre_pos))
+                throw np2::Error(NP2_ERR_FORMAT, "Unsorted input file!");
+            if (c < n && ing.rec_idx[c] == (int32_t)rec) {
+                if (h_n[c] > opt.min_map_len && !(ing.is_clip[c] && L < 500000)) {
+                    pre_tid = ing.all_tid[rec];
+                    pre_pos = ing.all_pos[rec];
+                }
+                c++;
+            }
+        }
+    }
     for (uint32_t i = 0; i < n; i++) {
         if (h_n[i] <= opt.min_map_len) continue;
         if (ing.is_clip[i] && L < 500000) continue;
@@ -688,7 +721,10 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         timer.end(h);
         n_probes += nreg + n_pairs;
         launches(2);
-        if (n_pairs) d_len.download(len_all.data() + nreg, n_pairs), d_kmer.download(kmer_all.data() + nreg, n_pairs);
+        if (n_pairs) {
+            NP2_CUDA(cudaMemcpyAsync(len_all.data() + nreg, d_len.p + nreg, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaMemcpyAsync(kmer_all.data() + nreg, d_kmer.p + nreg, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, s));
+        }
         NP2_CUDA(cudaStreamSynchronize(s));  // also orders the pageable st/en uploads before they go out of scope
         d2h += (uint64_t)n_pairs * 12;
     }
@@ -862,6 +898,7 @@ void np2_job::run(int32_t dump_it) {
     }
     if (!uploaded) upload();
     const uint32_t n = R.n_reads;
+    const int h_total = timer.begin("total", 0);
     int h = timer.begin("expand_trim_pack", 2);
     ref_codes(d_ref.p, L, d_code.p, s);
     expand_trim_pack(R, d_ref.p, L, s);
@@ -915,6 +952,7 @@ void np2_job::run(int32_t dump_it) {
         }
     }
     for (uint32_t it = 0; it < opt.iter_count; it++) iteration(it, it + 1 == opt.iter_count, (int32_t)it == dump_iter);
+    timer.end(h_total);
     NP2_CUDA(cudaStreamSynchronize(s));
     timer.collect();
 }
@@ -960,11 +998,7 @@ int np2_ctx_create(int device, np2_ctx **out) {
     });
 }
 void np2_ctx_destroy(np2_ctx *ctx) {
-    if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    if (ctx) ctx_release(ctx);
 }
 
 int np2_yak_load(np2_ctx *ctx, const char *path, np2_table **out) {
@@ -1056,7 +1090,9 @@ void np2_yak_free(np2_table *t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->dev.slots);
+    np2_ctx *c = t->ctx;
     delete t;
+    ctx_release(c);
 }
 uint32_t np2_yak_k(const np2_table *t) { return t->dev.k; }
 uint64_t np2_yak_size(const np2_table *t) { return t->dev.n; }
@@ -1127,6 +1163,7 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
         if (opts->iter_count == 0) throw np2::Error(NP2_ERR_ARG, "iter_count must be >= 1");
         std::unique_ptr<np2_job> j(new np2_job());
         j->ctx = ctx;
+        ctx->refs++;
         j->opt = *opts;
         for (uint32_t i = 0; i < n_tables; i++) j->tables.push_back(tables[i]);
         std::stable_sort(j->tables.begin(), j->tables.end(),
@@ -1164,7 +1201,9 @@ void np2_job_destroy(np2_job *job) {
     if (!job) return;
     cudaSetDevice(job->ctx->device);
     cudaStreamSynchronize(job->ctx->stream);
+    np2_ctx *c = job->ctx;
     delete job;
+    ctx_release(c);
 }
 
 int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,

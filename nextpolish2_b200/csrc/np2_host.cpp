@@ -22,7 +22,6 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
     out.op_off.push_back(0);
     out.nib_off.push_back(0);
     out.ck_off.push_back(0);
-    int64_t pre_tid = 0, pre_pos = 0;
     uint64_t off = 0;
     int32_t rec = -1;
     while (off + 4 <= bam_len) {
@@ -43,7 +42,8 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
         memcpy(&l_seq, r + 16, 4);
         if (l_seq < 0 || 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 > (uint64_t)bs)
             herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
-        if (!(ref_id > pre_tid || (int64_t)pos >= pre_pos)) herr(NP2_ERR_FORMAT, "Unsorted input file!");  // main.rs:1753
+        out.all_tid.push_back(ref_id);
+        out.all_pos.push_back(pos);
         const uint8_t *cg = r + 32 + l_name;
         // seq_len_from_cigar(true), bam_endpos
         uint64_t rlen = 0, rspan = 0;
@@ -106,8 +106,6 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
         out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)col / 16 + 1) * 8 + 15) & ~15ull));
         out.ck_off.push_back(out.ck_off.back() + (col + 31) / 32);
         out.total_cols += col;
-        pre_tid = ref_id;
-        pre_pos = pos;
     }
     if (off != bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
 }

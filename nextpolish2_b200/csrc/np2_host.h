@@ -14,6 +14,7 @@ namespace np2 {
 /* ---------------------------------------------------------------- ingest */
 struct Ingest {
     // candidate reads = records that pass the record-level filter (main.rs:1758-1771)
+    std::vector<int32_t> all_tid, all_pos;  // every record, for the sortedness assertion (main.rs:1753-1756)
     std::vector<int32_t> rec_idx;
     std::vector<uint32_t> pos, ncols, rlen;
     std::vector<uint8_t> is_clip;

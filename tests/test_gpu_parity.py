@@ -99,13 +99,19 @@ def test_passthrough_and_errors(ctx):
     with pytest.raises(np2.Np2Error) as e:
         np2.polish_contig(ctx, ds["contig"], bad, gt, np2.Opts(min_ctg_len=0))
     assert e.value.code == -4 and "Unknown cigar" in str(e.value)
-    r1 = synth.bam_record(0, 500, [("M", 2400)], seq)
-    r0 = synth.bam_record(0, 100, [("M", 2400)], seq)
+    ref = bytes(ds["contig"])
+    r1 = synth.bam_record(0, 500, [("M", 2400)], ref[500:2900].decode())  # pushed reads: exact copies of the contig
+    r0 = synth.bam_record(0, 100, [("M", 2400)], ref[100:2500].decode())
     with pytest.raises(np2.Np2Error) as e:
         np2.polish_contig(ctx, ds["contig"], np.concatenate([r1, r0]), gt, np2.Opts(min_ctg_len=0))
     assert "Unsorted" in str(e.value)
     with pytest.raises(O.OracleError):
         O.Job(ds["contig"], np.concatenate([r1, r0]), common.oracle_tables(ds), O.Opts(min_ctg_len=0))
+    # a read that is never pushed (no 8-mer anchor) does not advance the sortedness cursor (main.rs:1814-1815)
+    j1 = synth.bam_record(0, 500, [("M", 2400)], seq)
+    mixed = np.concatenate([j1, r0])
+    common.assert_same("unsorted-but-unpushed", O.Job(ds["contig"], mixed, common.oracle_tables(ds), O.Opts(min_ctg_len=0)).consensus()[1],
+                       np2.polish_contig(ctx, ds["contig"], mixed, gt, np2.Opts(min_ctg_len=0))[1])
     with pytest.raises(np2.Np2Error):
         np2.polish_contig(ctx, ds["contig"], ds["bam"], gt, np2.Opts(min_ctg_len=0, use_secondary=1))
 
