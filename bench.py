@@ -249,10 +249,15 @@ def yak_bench(ctx, np2, torch, peak):
     exp = torch.where(cnt[perm] >= 5, cnt[perm], torch.zeros_like(cnt[perm]))
     ok = bool((tab.lookup(keys[perm].cpu().numpy().view(np.uint64), 5) == exp.cpu().numpy().view(np.uint16)).all())
     probes = q.numel()
+    from nextpolish2_b200.api import bench_gather32
+    g_ms = bench_gather32(ctx, tab.device_bytes, probes, repeat=10)
+    gather_gbs = probes * 32 / g_ms / 1e6
     res = {"probes": probes, "table_keys": nk, "table_bytes": tab.device_bytes, "ms": round(ms, 4),
            "gprobes_per_s": round(probes / ms / 1e6, 3),
            "sector_GBps": round(probes * 32 / ms / 1e6, 1), "algorithmic_GBps": round(probes * 42 / ms / 1e6, 1),
-           "frac_of_stream_peak": round(probes * 42 / ms / 1e6 / peak, 4), "correct": ok}
+           "frac_of_stream_peak": round(probes * 42 / ms / 1e6 / peak, 4),
+           "random_gather_peak_GBps": round(gather_gbs, 1), "frac_of_random_gather_peak": round(probes * 32 / ms / 1e6 / gather_gbs, 4),
+           "correct": ok}
     tab.free()
     return res
 

@@ -93,6 +93,10 @@ int np2_yak_lookup_device(np2_ctx *ctx, const np2_table *t, const uint64_t *d_ha
 int np2_seq_kscore(np2_ctx *ctx, const np2_table *t, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n,
                    uint32_t min_count, uint16_t *kscore);
 
+/* measurement aid (bench.py): mean time of n_loads independent uniformly random 32-byte sector reads over a
+ * scratch buffer of buf_bytes — the measured random-read peak K5 is compared with. */
+int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms);
+
 /* ---- per-contig polish ----
  * tseq/tlen : contig sequence (raw FASTA bytes, case preserved)
  * bam       : this contig's BAM alignment records, concatenated in file order, each with its block_size prefix

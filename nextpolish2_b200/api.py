@@ -42,7 +42,7 @@ class Opts(C.Structure):
 EXPORTS = [
     "np2_last_error", "np2_opts_default", "np2_ctx_create", "np2_ctx_destroy", "np2_yak_load", "np2_yak_from_arrays",
     "np2_yak_free", "np2_yak_k", "np2_yak_size", "np2_yak_device_bytes", "np2_yak_lookup", "np2_yak_lookup_device",
-    "np2_seq_kscore", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
+    "np2_seq_kscore", "np2_bench_gather32", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
     "np2_job_get_consensus", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
 ]
@@ -75,6 +75,7 @@ def load_library():
     L.np2_yak_lookup.argtypes = [vp, vp, vp, u64, u32, vp]
     L.np2_yak_lookup_device.argtypes = [vp, vp, vp, u64, u32, vp, u32, C.POINTER(C.c_float)]
     L.np2_seq_kscore.argtypes = [vp, vp, vp, vp, u64, u32, vp]
+    L.np2_bench_gather32.argtypes = [vp, u64, u64, u32, C.POINTER(C.c_float)]
     L.np2_polish_contig.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_job_create.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_job_upload.argtypes = [vp]
@@ -125,6 +126,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def bench_gather32(ctx, buf_bytes, n_loads, repeat=5):
+    """Measured random 32-byte-sector read rate (ms per n_loads loads): K5's roofline denominator."""
+    ms = C.c_float()
+    _check(load_library().np2_bench_gather32(ctx.h, buf_bytes, n_loads, repeat, C.byref(ms)))
+    return ms.value
 
 
 class Table:

@@ -139,6 +139,14 @@ struct StageTimer {
         }
         recs.clear();
     }
+    // host phases: wall clock, reported as "host:<name>"
+    std::chrono::steady_clock::time_point h0;
+    void hbegin() { h0 = std::chrono::steady_clock::now(); }
+    void hend(const char *name) {
+        auto t = std::chrono::steady_clock::now();
+        ms[id(name)] += std::chrono::duration<float, std::milli>(t - h0).count();
+        h0 = t;
+    }
     void reset() {
         std::fill(ms.begin(), ms.end(), 0.f);
         std::fill(launches.begin(), launches.end(), 0u);
@@ -410,6 +418,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     NP2_CUDA(cudaStreamSynchronize(s));
     n_rec += 2;
     launches(6);
+    timer.hbegin();
 
     DBuf<uint64_t> d_key, d_key2;
     DBuf<uint32_t> d_rd, d_rd2, d_head, d_gidx;
@@ -419,6 +428,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     d_rd2.alloc(n_rec, s);
     d_head.alloc(n_rec + 1, s);
     d_gidx.alloc(n_rec + 1, s);
+    timer.hend("host:alloc_records");
     h = timer.begin("pileup_emit", 1);
     pileup_emit(R, n_blocks, d_blank.p, d_code.p, L, d_cta_off.p, d_key.p, d_rd.p, s);
     timer.end(h);
@@ -553,6 +563,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     }
     timer.end(h);
     launches(12);
+    timer.hbegin();
     Cns cns;
     cns.pos.resize(N);
     cns.base.resize(N);
@@ -575,6 +586,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         NP2_CUDA(cudaStreamSynchronize(s));
     }
 
+    timer.hend("host:d2h_consensus");
     if (dump) {
         // Msa in the reference's order: reference 3-mer first (p >= 2), then the sorted sparse ones
         std::vector<uint32_t> sp_off(L + 1), gc(G), gb(G), dc(L), db(L);
@@ -611,9 +623,11 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     }
 
     /* ---------------- LQ regions (host, sparse events) */
+    timer.hbegin();
     Regions rg;
     find_regions(cns.pos.data(), cns.base.data(), cflags.data(), N, events.data(), n_ev, rg);
     const uint32_t nreg = (uint32_t)rg.start.size();
+    timer.hend("host:find_regions");
     if (dump) {
         dm_reg_start = rg.start;
         dm_reg_end = rg.end;
@@ -649,6 +663,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         }
     }
     const uint32_t n_pairs = (uint32_t)pr_read.size();
+    timer.hend("host:pairs");
     // the ref read's candidates are computed here: it is never trimmed, dropped or stored on the device.
     // NOTE its cursor state is the first one of the loop above in the reference (idx 0): with t_s = 0 and
     // t_e = L - 1 it covers regions [0, nreg - 1] and leaves s = nreg - 1, which is how the loop above starts.
@@ -680,6 +695,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             ref_seq[ri] = std::move(sq);
         }
     }
+    timer.hend("host:ref_candidates");
     DBuf<uint32_t> d_pr_read, d_pr_start, d_pr_end, d_pr_limit, d_len;
     DBuf<uint64_t> d_kmer, d_soff;
     DBuf<uint16_t> d_ks;
@@ -728,6 +744,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         NP2_CUDA(cudaStreamSynchronize(s));  // also orders the pageable st/en uploads before they go out of scope
         d2h += (uint64_t)n_pairs * 12;
     }
+    timer.hend("host:cand_pass1_sync");
     // sequence pool: ref candidates first, then the device-extracted ones
     std::vector<uint64_t> soff(nreg + n_pairs + 1);
     soff[0] = 0;
@@ -782,6 +799,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         if (kmer_all[i] == UINT64_MAX) ks_all[i] = 0;  // INVALID_KMER keeps kscore 0 (main.rs:750,770)
     for (size_t x = 0; x < longsel.size(); x++) ks_all[longsel[x]] = ks_long[x];
 
+    timer.hend("host:cand_pass2_sync");
     // per region, candidates in read order, first 60 non-empty (main.rs:1474,1509)
     CandSet cs;
     cs.pool = pool.data();
@@ -827,9 +845,11 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     for (uint32_t r = 0; r < nreg; r++)
         for (uint32_t c = cs.roff[r]; c < cs.roff[r + 1]; c++) rs[r].cand.push_back(c);
 
+    timer.hend("host:cand_select");
     if (!final_iter) {
         /* ---------------- phasing (main.rs:1544-1552) */
         mark_hete(cs, rs);
+        timer.hend("host:mark_hete");
         std::vector<uint32_t> drop = phase_reads(cs, rs, opt.model == 0, opt.use_all_reads != 0);
         for (uint32_t a : drop) {
             if (a == 0 || a >= as_read.size()) throw np2::Error(NP2_ERR_INTERNAL, "phasing returned a bad read index");
@@ -838,6 +858,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         }
         d_blank.upload(h_blank.data(), n_reads);
         NP2_CUDA(cudaStreamSynchronize(s));
+        timer.hend("host:phase_reads");
         if (dump)
             for (auto &r : rs) dm_reg_lable.push_back(r.lable);
         return;
@@ -845,11 +866,14 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
 
     /* ---------------- final: seed alleles, splice, re-check with every table (main.rs:1527-1543) */
     fill_seed(cs, rs, opt.max_indel_len);
+    timer.hend("host:fill_seed");
     Cns cur, nxt;
     splice(rg, rs, LABLE_SUCC, cns, cur);
+    timer.hend("host:splice");
     for (size_t ti = 0; ti < tables.size(); ti++) {
         Reupdate ru;
         reupdate_build(rg, cs, rs, cur, tables[ti]->dev.k, ru);
+        timer.hend("host:reupdate_build");
         const size_t ns = ru.off.size() - 1;
         std::vector<uint16_t> ks(ns);
         if (ns) {
@@ -870,7 +894,9 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             h2d += ru.pool.size() + (ns + 1) * 8;
             d2h += ns * 2;
         }
+        timer.hend("host:reupdate_score_sync");
         reupdate_apply(rg, cs, rs, ru, ks.data(), (uint32_t)ti + 1, cur, nxt);
+        timer.hend("host:reupdate_apply");
         cur.pos.swap(nxt.pos);
         cur.base.swap(nxt.base);
     }
@@ -914,7 +940,9 @@ void np2_job::run(int32_t dump_it) {
     }
     NP2_CUDA(cudaStreamSynchronize(s));
     d2h += (uint64_t)n * 12;
+    timer.hbegin();
     ingest_finish();
+    timer.hend("host:ingest_finish");
     d_blank.upload(h_blank.data(), std::max(n, 1u));
 
     if (dump_iter >= 0) {  // reads as the oracle reports them (after the clip filter)
@@ -1132,6 +1160,32 @@ int np2_yak_lookup_device(np2_ctx *ctx, const np2_table *t, const uint64_t *d_ha
         cudaEventDestroy(b);
         NP2_CUDA(cudaGetLastError());
         if (ms) *ms = t_ms / repeat;
+    });
+}
+
+int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        if (repeat == 0) repeat = 1;
+        DBuf<uint64_t> buf, sink;
+        const uint64_t n_sectors = buf_bytes / 32;
+        buf.alloc(n_sectors * 4, ctx->stream);
+        sink.alloc(1, ctx->stream);
+        NP2_CUDA(cudaMemsetAsync(buf.p, 0x5A, n_sectors * 32, ctx->stream));
+        gather32(buf.p, n_sectors, n_loads, 1, sink.p, ctx->stream);  // warm-up
+        cudaEvent_t a, b;
+        NP2_CUDA(cudaEventCreate(&a));
+        NP2_CUDA(cudaEventCreate(&b));
+        NP2_CUDA(cudaEventRecord(a, ctx->stream));
+        for (uint32_t r = 0; r < repeat; r++) gather32(buf.p, n_sectors, n_loads, 7 + r * n_loads, sink.p, ctx->stream);
+        NP2_CUDA(cudaEventRecord(b, ctx->stream));
+        NP2_CUDA(cudaStreamSynchronize(ctx->stream));
+        float t = 0;
+        cudaEventElapsedTime(&t, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        NP2_CUDA(cudaGetLastError());
+        *ms = t / repeat;
     });
 }
 

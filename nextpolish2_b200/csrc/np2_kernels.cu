@@ -205,6 +205,37 @@ void seq_kscore(const TableDev &t, const uint8_t *d_seqs, const uint64_t *d_off,
     k_seq_kscore<<<grid, kThreads, 0, s>>>(t.slots, t.nb, t.k, d_seqs, d_off, d_sel, n, min_count, d_out);
 }
 
+/* --------------------------------------------------------------- measurement: random 32-B sector gather
+ * The denominator for K5's roofline: independent uniformly random 32-byte sector reads over a buffer far larger
+ * than L2, same ILP and grid shape as k_table_probe but no hashing, no compare, no dependent second probe. */
+__global__ void __launch_bounds__(kThreads) k_gather32(const uint64_t *__restrict__ buf, uint64_t n_sectors,
+                                                       uint64_t n_loads, uint64_t seed, uint64_t *__restrict__ sink) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc = 0;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < n_loads; i0 += stride * kProbeIlp) {
+        ulonglong2 lo[kProbeIlp], hi[kProbeIlp];
+#pragma unroll
+        for (int u = 0; u < kProbeIlp; u++) {
+            uint64_t x = (i0 + u * stride + seed) * 0x9E3779B97F4A7C15ULL;
+            x ^= x >> 29;
+            x *= 0xBF58476D1CE4E5B9ULL;
+            x ^= x >> 32;
+            const uint64_t sct = (uint64_t)(((unsigned __int128)x * n_sectors) >> 64);
+            const ulonglong2 *bp = (const ulonglong2 *)(buf + sct * 4);
+            lo[u] = __ldg(bp);
+            hi[u] = __ldg(bp + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < kProbeIlp; u++) acc ^= lo[u].x ^ lo[u].y ^ hi[u].x ^ hi[u].y;
+    }
+    if (acc == 0x123456789ABCDEFULL) *sink = acc;  // keeps the loads alive
+}
+void gather32(const uint64_t *d_buf, uint64_t n_sectors, uint64_t n_loads, uint64_t seed, uint64_t *d_sink,
+              cudaStream_t s) {
+    uint32_t grid = min(cdiv(n_loads, (uint64_t)kThreads * kProbeIlp), 148u * 8u);
+    k_gather32<<<grid, kThreads, 0, s>>>(d_buf, n_sectors, n_loads, seed, d_sink);
+}
+
 /* =============================================================== K0: reference codes */
 
 __global__ void k_ref_codes(const uint8_t *__restrict__ ref, uint32_t L, uint8_t *__restrict__ code) {
