@@ -114,7 +114,10 @@ int np2_job_upload(np2_job *job);
 int np2_job_run(np2_job *job, int32_t dump_iter);
 void np2_job_destroy(np2_job *job);
 
+/* pos may be NULL: the per-base positions (40 MB for a 10 Mbp contig) are only built when asked for;
+ * np2_job_get_span gives the first/last position the FASTA header prints (main.rs:627-632). */
 uint64_t np2_job_get_consensus(np2_job *job, const uint32_t **pos, const uint8_t **base);
+uint64_t np2_job_get_span(np2_job *job, uint32_t *first_pos, uint32_t *last_pos);
 /* stage dumps (same shapes as the oracle's getters) */
 uint64_t np2_job_get_reads(np2_job *job, const int32_t **rec_idx, const uint32_t **t_s, const uint32_t **t_e,
                            const uint64_t **nib_off, const uint8_t **nib, const uint8_t **blank_after_clip);

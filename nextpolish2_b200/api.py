@@ -43,7 +43,7 @@ EXPORTS = [
     "np2_last_error", "np2_opts_default", "np2_ctx_create", "np2_ctx_destroy", "np2_yak_load", "np2_yak_from_arrays",
     "np2_yak_free", "np2_yak_k", "np2_yak_size", "np2_yak_device_bytes", "np2_yak_lookup", "np2_yak_lookup_device",
     "np2_seq_kscore", "np2_bench_gather32", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
-    "np2_job_get_consensus", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
+    "np2_job_get_consensus", "np2_job_get_span", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
 ]
 
@@ -87,6 +87,8 @@ def load_library():
         f = getattr(L, name)
         f.restype = u64
         f.argtypes = [vp] + [C.POINTER(vp)] * n
+    L.np2_job_get_span.restype = u64
+    L.np2_job_get_span.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.np2_job_get_timings.restype = u32
     L.np2_job_get_timings.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
@@ -231,6 +233,14 @@ class Job:
     def consensus(self):
         n, p = self._get("np2_job_get_consensus", 2)
         return _arr(p[0], n, np.uint32), _arr(p[1], n, np.uint8)
+
+    def bases(self):
+        """(first_pos, last_pos, bases): all the FASTA record needs, without materialising per-base positions."""
+        base = C.c_void_p()
+        n = load_library().np2_job_get_consensus(self.h, None, C.byref(base))
+        f, l = C.c_uint32(), C.c_uint32()
+        load_library().np2_job_get_span(self.h, C.byref(f), C.byref(l))
+        return f.value, l.value, _arr(base, n, np.uint8)
 
     def reads(self):
         n, p = self._get("np2_job_get_reads", 6)

@@ -1,6 +1,7 @@
 // np2_api.cu — C ABI (include/np2gpu.h) and the per-contig pipeline that strings the kernels and host
 // phases together.  One np2_ctx = one GPU + one stream; all device work of a job is enqueued on that stream.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
@@ -215,7 +216,17 @@ struct np2_job {
     std::vector<int32_t> as_read;          // alignseq index -> candidate read (-1 = ref)
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
-    Cns result;
+    // result: bases always; positions are materialised on request (np2_job_get_consensus with pos != NULL)
+    std::vector<uint8_t> res_base;
+    std::vector<uint32_t> res_pos;
+    uint32_t res_first = 0, res_last = 0;
+    bool res_pos_valid = false;
+    Patched res_patch;                       // kept so that positions can be produced lazily
+    std::vector<uint8_t> res_pool;           // candidate strings the patches point into
+    PBuf<uint32_t> p_cpos;
+    PBuf<uint8_t> p_cbase, p_cflags;
+    DBuf<uint32_t> d_order;
+    uint32_t max_span = 0;
     StageTimer timer;
     uint64_t h2d = 0, d2h = 0, n_launch = 0, n_probes = 0;
     std::string timing_names;
@@ -564,15 +575,14 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     timer.end(h);
     launches(12);
     timer.hbegin();
-    Cns cns;
-    cns.pos.resize(N);
-    cns.base.resize(N);
-    std::vector<uint8_t> cflags(N);
+    p_cpos.resize(std::max(N, 1u));
+    p_cbase.resize(std::max(N, 1u));
+    p_cflags.resize(std::max(N, 1u));
     uint32_t n_ev = 0;
     long long total = 0;
-    d_cpos.download(cns.pos.data(), N);
-    d_cbase.download(cns.base.data(), N);
-    d_cflags.download(cflags.data(), N);
+    d_cpos.download(p_cpos.p, N);
+    d_cbase.download(p_cbase.p, N);
+    d_cflags.download(p_cflags.p, N);
     NP2_CUDA(cudaMemcpyAsync(&n_ev, d_nev.p, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
@@ -585,8 +595,10 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         d_events.download(events.data(), n_ev);
         NP2_CUDA(cudaStreamSynchronize(s));
     }
-
+    const uint32_t *cpos = p_cpos.p;
+    const uint8_t *cbase = p_cbase.p, *cflags = p_cflags.p;
     timer.hend("host:d2h_consensus");
+
     if (dump) {
         // Msa in the reference's order: reference 3-mer first (p >= 2), then the sorted sparse ones
         std::vector<uint32_t> sp_off(L + 1), gc(G), gb(G), dc(L), db(L);
@@ -617,240 +629,247 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             }
             dm_msa_off.push_back(dm_msa_bases.size());
         }
-        dm_dp_pos = cns.pos;
-        dm_dp_base = cns.base;
-        dm_dp_flags = cflags;
+        dm_dp_pos.assign(cpos, cpos + N);
+        dm_dp_base.assign(cbase, cbase + N);
+        dm_dp_flags.assign(cflags, cflags + N);
     }
 
     /* ---------------- LQ regions (host, sparse events) */
     timer.hbegin();
     Regions rg;
-    find_regions(cns.pos.data(), cns.base.data(), cflags.data(), N, events.data(), n_ev, rg);
+    find_regions(cpos, cbase, cflags, N, events.data(), n_ev, rg);
     const uint32_t nreg = (uint32_t)rg.start.size();
     timer.hend("host:find_regions");
     if (dump) {
         dm_reg_start = rg.start;
         dm_reg_end = rg.end;
     }
-    if (nreg == 0) {  // main.rs:1638-1640
-        if (final_iter) result = std::move(cns);
+    auto finish_plain = [&]() {  // main.rs:1638-1640: no LQ region, the DP consensus is the answer
+        res_patch = Patched();
+        res_base.assign(cbase, cbase + N);
+        res_pos.assign(cpos, cpos + N);
+        res_pos_valid = true;
+        res_first = N ? cpos[0] : 0;
+        res_last = N ? cpos[N - 1] : 0;
+    };
+    if (nreg == 0) {
+        if (final_iter) finish_plain();
         return;
     }
 
-    /* ---------------- K4: candidates */
+    /* ---------------- K4: which reads cover which region, candidates, kscore — all on the device */
     np2_table *t0 = tables[0];
     const uint32_t k0 = t0->dev.k;
     if (k0 >= 32) throw np2::Error(NP2_ERR_UNSUPPORTED, "the smallest yak table must have k < 32 (main.rs:1432-1434)");
-    // read -> region ranges with the reference's monotone cursor (main.rs:1446-1460)
-    std::vector<uint32_t> pr_read, pr_reg, pr_limit;
+    GenoDev g;
+    g.nreg = nreg;
+    DBuf<uint32_t> d_rstart, d_rend, d_rd_s, d_rd_j, d_rd_np, d_rd_poff;
+    d_rstart.alloc(nreg, s);
+    d_rend.alloc(nreg, s);
+    d_rd_s.alloc(n_reads + 1, s);
+    d_rd_j.alloc(n_reads + 1, s);
+    d_rd_np.alloc(n_reads + 1, s);
+    d_rd_poff.alloc(n_reads + 1, s);
+    d_rstart.upload(rg.start.data(), nreg);
+    d_rend.upload(rg.end.data(), nreg);
+    h2d += (uint64_t)nreg * 8;
+    g.start = d_rstart.p;
+    g.end = d_rend.p;
+    g.rd_s = d_rd_s.p;
+    g.rd_j = d_rd_j.p;
+    g.rd_np = d_rd_np.p;
+    g.rd_poff = d_rd_poff.p;
+    g.rd_order = d_order.p;
+    h = timer.begin("read_ranges", 4);
+    geno_read_cursor(g, R, d_blank.p, s);
+    if (n_reads) {  // the cursor only ever moves down: prefix-min in read order (main.rs:1446-1448)
+        size_t tb = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, tb, d_rd_s.p, d_rd_s.p, cub::Min(), (int)n_reads, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceScan::InclusiveScan(d_tmp.p, tb, d_rd_s.p, d_rd_s.p, cub::Min(), (int)n_reads, s);
+    }
+    geno_read_ranges(g, R, d_blank.p, k0, s);
+    NP2_CUDA(cudaMemsetAsync(d_rd_np.p + n_reads, 0, 4, s));
     {
-        size_t sidx = nreg - 1;
-        for (size_t a = 1; a < as_read.size(); a++) {
-            const uint32_t i = (uint32_t)as_read[a];
-            if (h_blank[i]) continue;
-            const uint32_t ts = h_ts[i], te = h_te[i];
-            while (sidx > 0 && rg.start[sidx] < ts) sidx--;
-            if (rg.start[sidx] < ts || rg.end[sidx] > te) continue;
-            size_t j = sidx;
-            while (j > 0 && rg.end[j] <= te) j--;
-            if (rg.end[j] > te) j++;
-            const uint32_t limit = rg.end[j] + k0;
-            for (size_t ri = j; ri <= sidx; ri++) {
-                pr_read.push_back(i);
-                pr_reg.push_back((uint32_t)ri);
-                pr_limit.push_back(limit);
-            }
-        }
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_rd_np.p, d_rd_poff.p, (int)n_reads + 1, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_rd_np.p, d_rd_poff.p, (int)n_reads + 1, s);
     }
-    const uint32_t n_pairs = (uint32_t)pr_read.size();
-    timer.hend("host:pairs");
-    // the ref read's candidates are computed here: it is never trimmed, dropped or stored on the device.
-    // NOTE its cursor state is the first one of the loop above in the reference (idx 0): with t_s = 0 and
-    // t_e = L - 1 it covers regions [0, nreg - 1] and leaves s = nreg - 1, which is how the loop above starts.
-    const uint64_t mask0 = (1ULL << (2 * k0)) - 1;
-    std::vector<uint32_t> len_all(nreg + n_pairs);
-    std::vector<uint64_t> kmer_all(nreg + n_pairs);
-    std::vector<std::string> ref_seq(nreg);
-    {
-        const uint32_t limit = rg.end[0] + k0;
-        for (uint32_t ri = 0; ri < nreg; ri++) {
-            uint64_t f = 0, rv = 0;
-            uint32_t l = 0;
-            std::string sq;
-            for (uint32_t p = rg.start[ri]; p < L; p++) {
-                const uint32_t q = seq_code(tseq[p]);
-                if (q != 4) {
-                    if (p <= rg.end[ri]) sq.push_back((char)code_char(q));
-                    if (l < k0) {
-                        f = (f << 2 | (uint64_t)q) & mask0;
-                        rv = (rv >> 2) | (uint64_t)(3 ^ q) << (2 * (k0 - 1));
-                        l++;
-                    }
-                    if (p > rg.end[ri] && l >= k0) break;
-                }
-                if (p > limit) break;
-            }
-            len_all[ri] = (uint32_t)sq.size();
-            kmer_all[ri] = l >= k0 ? yak_hash64(f < rv ? f : rv, mask0) : UINT64_MAX;
-            ref_seq[ri] = std::move(sq);
-        }
-    }
-    timer.hend("host:ref_candidates");
-    DBuf<uint32_t> d_pr_read, d_pr_start, d_pr_end, d_pr_limit, d_len;
-    DBuf<uint64_t> d_kmer, d_soff;
-    DBuf<uint16_t> d_ks;
-    d_pr_read.alloc(std::max(n_pairs, 1u), s);
-    d_pr_start.alloc(std::max(n_pairs, 1u), s);
-    d_pr_end.alloc(std::max(n_pairs, 1u), s);
-    d_pr_limit.alloc(std::max(n_pairs, 1u), s);
-    d_len.alloc(nreg + n_pairs, s);
-    d_kmer.alloc(nreg + n_pairs, s);
-    d_soff.alloc(nreg + n_pairs + 1, s);
-    d_ks.alloc(nreg + n_pairs, s);
-    {
-        std::vector<uint32_t> st(n_pairs), en(n_pairs);
-        for (uint32_t i = 0; i < n_pairs; i++) {
-            st[i] = rg.start[pr_reg[i]];
-            en[i] = rg.end[pr_reg[i]];
-        }
-        if (n_pairs) {
-            d_pr_read.upload(pr_read.data(), n_pairs);
-            d_pr_start.upload(st.data(), n_pairs);
-            d_pr_end.upload(en.data(), n_pairs);
-            d_pr_limit.upload(pr_limit.data(), n_pairs);
-        }
-        d_kmer.upload(kmer_all.data(), nreg);
-        h2d += (uint64_t)n_pairs * 16 + nreg * 8;
-        CandDev c;
-        c.n_pairs = n_pairs;
-        c.pair_read = d_pr_read.p;
-        c.pair_start = d_pr_start.p;
-        c.pair_end = d_pr_end.p;
-        c.pair_limit = d_pr_limit.p;
-        c.len = d_len.p + nreg;
-        c.kmer = d_kmer.p + nreg;
-        h = timer.begin("cand_scan", 1);
-        cand_scan(R, c, k0, false, s);
-        timer.end(h);
-        h = timer.begin("yak_probe", 1);
-        table_probe(t0->dev, d_kmer.p, nreg + n_pairs, opt.min_kmer_count, d_ks.p, s);
-        timer.end(h);
-        n_probes += nreg + n_pairs;
-        launches(2);
-        if (n_pairs) {
-            NP2_CUDA(cudaMemcpyAsync(len_all.data() + nreg, d_len.p + nreg, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, s));
-            NP2_CUDA(cudaMemcpyAsync(kmer_all.data() + nreg, d_kmer.p + nreg, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, s));
-        }
-        NP2_CUDA(cudaStreamSynchronize(s));  // also orders the pageable st/en uploads before they go out of scope
-        d2h += (uint64_t)n_pairs * 12;
-    }
-    timer.hend("host:cand_pass1_sync");
-    // sequence pool: ref candidates first, then the device-extracted ones
-    std::vector<uint64_t> soff(nreg + n_pairs + 1);
-    soff[0] = 0;
-    for (uint32_t i = 0; i < nreg + n_pairs; i++) soff[i + 1] = soff[i] + len_all[i];
-    const uint64_t pool_bytes = soff.back();
-    DBuf<uint8_t> d_pool;
-    d_pool.alloc(pool_bytes + 1, s);
-    std::vector<uint8_t> pool(pool_bytes + 1);
-    for (uint32_t ri = 0; ri < nreg; ri++) memcpy(pool.data() + soff[ri], ref_seq[ri].data(), ref_seq[ri].size());
-    d_pool.upload(pool.data(), soff[nreg]);
-    d_soff.upload(soff.data(), nreg + n_pairs + 1);
-    h2d += soff[nreg] + (uint64_t)(nreg + n_pairs + 1) * 8;
-    {
-        CandDev c;
-        c.n_pairs = n_pairs;
-        c.pair_read = d_pr_read.p;
-        c.pair_start = d_pr_start.p;
-        c.pair_end = d_pr_end.p;
-        c.pair_limit = d_pr_limit.p;
-        c.seq_off = d_soff.p + nreg;
-        c.seq = d_pool.p;
-        h = timer.begin("cand_scan", 1);
-        cand_scan(R, c, k0, true, s);
-        timer.end(h);
-        launches(1);
-    }
-    // candidates longer than k are scored over all their k-mers (main.rs:746-749, 760-769)
-    std::vector<uint32_t> longsel;
-    for (uint32_t i = 0; i < nreg + n_pairs; i++)
-        if (len_all[i] > k0) longsel.push_back(i);
-    std::vector<uint16_t> ks_all(nreg + n_pairs), ks_long(longsel.size());
-    DBuf<uint32_t> d_sel;
-    DBuf<uint16_t> d_ks_long;
-    if (!longsel.empty()) {
-        d_sel.alloc(longsel.size(), s);
-        d_ks_long.alloc(longsel.size(), s);
-        d_sel.upload(longsel.data(), longsel.size());
-        h = timer.begin("yak_seq_kscore", 1);
-        seq_kscore(t0->dev, d_pool.p, d_soff.p, d_sel.p, longsel.size(), opt.min_kmer_count, d_ks_long.p, s);
-        timer.end(h);
-        launches(1);
-        d_ks_long.download(ks_long.data(), longsel.size());
-    }
-    d_ks.download(ks_all.data(), nreg + n_pairs);
-    if (pool_bytes > soff[nreg]) {
-        NP2_CUDA(cudaMemcpyAsync(pool.data() + soff[nreg], d_pool.p + soff[nreg], pool_bytes - soff[nreg],
-                                 cudaMemcpyDeviceToHost, s));
-    }
+    timer.end(h);
+    uint32_t n_pairs = 0;
+    NP2_CUDA(cudaMemcpyAsync(&n_pairs, d_rd_poff.p + n_reads, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
-    d2h += pool_bytes + (uint64_t)(nreg + n_pairs) * 2;
-    for (uint32_t i = 0; i < nreg + n_pairs; i++)
-        if (kmer_all[i] == UINT64_MAX) ks_all[i] = 0;  // INVALID_KMER keeps kscore 0 (main.rs:750,770)
-    for (size_t x = 0; x < longsel.size(); x++) ks_all[longsel[x]] = ks_long[x];
+    g.n_pairs = n_pairs;
+    launches(4);
 
-    timer.hend("host:cand_pass2_sync");
-    // per region, candidates in read order, first 60 non-empty (main.rs:1474,1509)
-    CandSet cs;
-    cs.pool = pool.data();
-    cs.roff.assign(nreg + 1, 0);
-    {
-        std::vector<uint32_t> cnt(nreg, 0);
-        for (uint32_t i = 0; i < n_pairs; i++) cnt[pr_reg[i]]++;
-        std::vector<uint32_t> first(nreg + 1, 0);
-        for (uint32_t r = 0; r < nreg; r++) first[r + 1] = first[r] + cnt[r];
-        std::vector<uint32_t> bucket(n_pairs);
-        std::vector<uint32_t> cur(first.begin(), first.end() - 1);
-        for (uint32_t i = 0; i < n_pairs; i++) bucket[cur[pr_reg[i]]++] = i;
-        for (uint32_t r = 0; r < nreg; r++) {
-            uint32_t taken = 0;
-            auto take = [&](uint32_t id, uint32_t order) {
-                cs.order.push_back(order);
-                cs.kscore.push_back(ks_all[id]);
-                cs.kmer.push_back(kmer_all[id]);
-                cs.seq_off.push_back(soff[id]);
-                cs.seq_len.push_back(len_all[id]);
-                taken++;
-            };
-            if (len_all[r] > 0) take(r, 0);
-            for (uint32_t x = first[r]; x < first[r + 1] && taken < 60; x++) {
-                const uint32_t id = nreg + bucket[x];
-                if (len_all[id] > 0) take(id, read_order[pr_read[bucket[x]]]);
-            }
-            cs.roff[r + 1] = (uint32_t)cs.order.size();
-        }
+    const uint64_t nslot = (uint64_t)nreg * kMaxCand;
+    DBuf<uint32_t> d_p_len, d_c_src, d_c_len, d_c_order, d_r_ncand, d_r_bytes, d_r_nedge, d_r_seed_len, d_r_nsurv;
+    DBuf<uint64_t> d_p_kmer, d_c_kmer, d_c_off, d_r_pool_off, d_r_edge_off, d_r_seed_off;
+    DBuf<uint16_t> d_c_ks;
+    DBuf<uint8_t> d_c_rep, d_r_lable, d_r_surv, d_gpool;
+    d_p_len.alloc(std::max(n_pairs, 1u), s);
+    d_p_kmer.alloc(std::max(n_pairs, 1u), s);
+    d_c_src.alloc(nslot, s);
+    d_c_len.alloc(nslot, s);
+    d_c_order.alloc(nslot, s);
+    d_c_kmer.alloc(nslot, s);
+    d_c_off.alloc(nslot, s);
+    d_c_ks.alloc(nslot, s);
+    d_c_rep.alloc(nslot, s);
+    d_r_ncand.alloc(nreg + 1, s);
+    d_r_bytes.alloc(nreg + 1, s);
+    d_r_nedge.alloc(nreg + 1, s);
+    d_r_seed_len.alloc(nreg, s);
+    d_r_nsurv.alloc(nreg, s);
+    d_r_pool_off.alloc(nreg + 1, s);
+    d_r_edge_off.alloc(nreg + 1, s);
+    d_r_seed_off.alloc(nreg, s);
+    d_r_lable.alloc(nreg, s);
+    d_r_surv.alloc(nslot, s);
+    g.p_len = d_p_len.p;
+    g.p_kmer = d_p_kmer.p;
+    g.c_src = d_c_src.p;
+    g.c_len = d_c_len.p;
+    g.c_order = d_c_order.p;
+    g.c_kmer = d_c_kmer.p;
+    g.c_off = d_c_off.p;
+    g.c_kscore = d_c_ks.p;
+    g.c_rep = d_c_rep.p;
+    g.r_ncand = d_r_ncand.p;
+    g.r_bytes = d_r_bytes.p;
+    g.r_nedge = d_r_nedge.p;
+    g.r_seed_len = d_r_seed_len.p;
+    g.r_nsurv = d_r_nsurv.p;
+    g.r_pool_off = d_r_pool_off.p;
+    g.r_edge_off = d_r_edge_off.p;
+    g.r_seed_off = d_r_seed_off.p;
+    g.r_lable = d_r_lable.p;
+    g.r_surv = d_r_surv.p;
+
+    h = timer.begin("cand_scan", 1);
+    geno_pair_scan(g, R, k0, s);
+    timer.end(h);
+    h = timer.begin("region_select", 2);
+    geno_region_select(g, R, d_blank.p, d_code.p, L, k0, max_span, s);
+    NP2_CUDA(cudaMemsetAsync(d_r_bytes.p + nreg, 0, 4, s));
+    {  // 64-bit offsets out of 32-bit per-region byte counts
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_r_bytes.p, d_r_pool_off.p, (int)nreg + 1, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_r_bytes.p, d_r_pool_off.p, (int)nreg + 1, s);
     }
-    if (dump) {
-        dm_can_roff.assign(cs.roff.begin(), cs.roff.end());
-        dm_can_order = cs.order;
-        dm_can_kscore = cs.kscore;
-        dm_can_kmer = cs.kmer;
+    timer.end(h);
+    uint64_t pool_bytes = 0;
+    NP2_CUDA(cudaMemcpyAsync(&pool_bytes, d_r_pool_off.p + nreg, 8, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    d_gpool.alloc(pool_bytes + 16, s);
+    g.pool = d_gpool.p;
+    h = timer.begin("cand_write", 1);
+    geno_cand_write(g, R, d_code.p, L, k0, s);
+    timer.end(h);
+    h = timer.begin("yak_probe", 2);
+    geno_cand_kscore(g, t0->dev, opt.min_kmer_count, s);
+    timer.end(h);
+    n_probes += n_pairs;
+    launches(6);
+
+    auto dump_candidates = [&](bool with_lable) {
+        std::vector<uint32_t> ncand(nreg), clen(nslot), cord(nslot);
+        std::vector<uint64_t> ckm(nslot), coff(nslot);
+        std::vector<uint16_t> cks(nslot);
+        std::vector<uint8_t> pool(pool_bytes + 16), lab(nreg);
+        d_r_ncand.download(ncand.data(), nreg);
+        d_c_len.download(clen.data(), nslot);
+        d_c_order.download(cord.data(), nslot);
+        d_c_kmer.download(ckm.data(), nslot);
+        d_c_off.download(coff.data(), nslot);
+        d_c_ks.download(cks.data(), nslot);
+        d_gpool.download(pool.data(), pool_bytes);
+        if (with_lable) d_r_lable.download(lab.data(), nreg);
+        NP2_CUDA(cudaStreamSynchronize(s));
+        if (with_lable) {
+            dm_reg_lable = lab;
+            return;
+        }
+        dm_can_roff.assign(1, 0);
         dm_can_seq_off.assign(1, 0);
-        for (size_t c = 0; c < cs.order.size(); c++) {
-            dm_can_seq.insert(dm_can_seq.end(), pool.data() + cs.seq_off[c], pool.data() + cs.seq_off[c] + cs.seq_len[c]);
-            dm_can_seq_off.push_back(dm_can_seq.size());
+        for (uint32_t r = 0; r < nreg; r++) {
+            for (uint32_t c = 0; c < ncand[r]; c++) {
+                const uint64_t sl = (uint64_t)r * kMaxCand + c;
+                dm_can_order.push_back(cord[sl]);
+                dm_can_kscore.push_back(cks[sl]);
+                dm_can_kmer.push_back(ckm[sl]);
+                dm_can_seq.insert(dm_can_seq.end(), pool.data() + coff[sl], pool.data() + coff[sl] + clen[sl]);
+                dm_can_seq_off.push_back(dm_can_seq.size());
+            }
+            dm_can_roff.push_back(dm_can_order.size());
         }
-    }
-    std::vector<RegionState> rs(nreg);
-    for (uint32_t r = 0; r < nreg; r++)
-        for (uint32_t c = cs.roff[r]; c < cs.roff[r + 1]; c++) rs[r].cand.push_back(c);
+    };
+    if (dump) dump_candidates(false);
 
-    timer.hend("host:cand_select");
     if (!final_iter) {
-        /* ---------------- phasing (main.rs:1544-1552) */
-        mark_hete(cs, rs);
-        timer.hend("host:mark_hete");
-        std::vector<uint32_t> drop = phase_reads(cs, rs, opt.model == 0, opt.use_all_reads != 0);
+        /* ---------------- heterozygous regions, agreement edges (device); Louvain (host) — main.rs:1544-1552 */
+        h = timer.begin("region_hete", 2);
+        geno_region_hete(g, s);
+        NP2_CUDA(cudaMemsetAsync(d_r_nedge.p + nreg, 0, 4, s));
+        {
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, d_r_nedge.p, d_r_edge_off.p, (int)nreg + 1, s);
+            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+            cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_r_nedge.p, d_r_edge_off.p, (int)nreg + 1, s);
+        }
+        timer.end(h);
+        uint64_t n_edges = 0;
+        NP2_CUDA(cudaMemcpyAsync(&n_edges, d_r_edge_off.p + nreg, 8, cudaMemcpyDeviceToHost, s));
+        NP2_CUDA(cudaStreamSynchronize(s));
+        launches(2);
+        if (dump) dump_candidates(true);
+        std::vector<uint64_t> ukeys;
+        std::vector<long long> uvals;
+        if (n_edges) {
+            if (n_edges >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^31 read-pair observations");
+            DBuf<uint64_t> d_ek, d_ek2, d_uk;
+            DBuf<long long> d_ev, d_ev2, d_uv;
+            DBuf<uint32_t> d_nu;
+            d_ek.alloc(n_edges, s);
+            d_ek2.alloc(n_edges, s);
+            d_uk.alloc(n_edges, s);
+            d_ev.alloc(n_edges, s);
+            d_ev2.alloc(n_edges, s);
+            d_uv.alloc(n_edges, s);
+            d_nu.alloc(1, s);
+            h = timer.begin("pair_edges", 6);
+            geno_edges_emit(g, d_ek.p, d_ev.p, s);
+            {
+                size_t tb = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 64, s);
+                if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+                cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 64, s);
+                tb = 0;
+                cub::DeviceReduce::ReduceByKey(nullptr, tb, d_ek2.p, d_uk.p, d_ev2.p, d_uv.p, d_nu.p, cub::Sum(),
+                                               (int)n_edges, s);
+                if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+                cub::DeviceReduce::ReduceByKey(d_tmp.p, tb, d_ek2.p, d_uk.p, d_ev2.p, d_uv.p, d_nu.p, cub::Sum(),
+                                               (int)n_edges, s);
+            }
+            timer.end(h);
+            launches(1);
+            uint32_t nu = 0;
+            d_nu.download(&nu, 1);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            ukeys.resize(nu);
+            uvals.resize(nu);
+            if (nu) {
+                d_uk.download(ukeys.data(), nu);
+                d_uv.download(uvals.data(), nu);
+                NP2_CUDA(cudaStreamSynchronize(s));
+            }
+            d2h += (uint64_t)nu * 16;
+        }
+        timer.hbegin();
+        std::vector<uint32_t> drop = phase_reads(ukeys.data(), uvals.data(), ukeys.size(), opt.model == 0,
+                                                 opt.use_all_reads != 0);
         for (uint32_t a : drop) {
             if (a == 0 || a >= as_read.size()) throw np2::Error(NP2_ERR_INTERNAL, "phasing returned a bad read index");
             h_blank[as_read[a]] = 1;
@@ -859,20 +878,84 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         d_blank.upload(h_blank.data(), n_reads);
         NP2_CUDA(cudaStreamSynchronize(s));
         timer.hend("host:phase_reads");
-        if (dump)
-            for (auto &r : rs) dm_reg_lable.push_back(r.lable);
         return;
     }
 
-    /* ---------------- final: seed alleles, splice, re-check with every table (main.rs:1527-1543) */
-    fill_seed(cs, rs, opt.max_indel_len);
-    timer.hend("host:fill_seed");
-    Cns cur, nxt;
-    splice(rg, rs, LABLE_SUCC, cns, cur);
-    timer.hend("host:splice");
+    /* ---------------- final: seed alleles (device), then re-check with every table (main.rs:1527-1543) */
+    DBuf<int> d_err;
+    d_err.alloc(1, s);
+    d_err.zero();
+    h = timer.begin("region_seed", 1);
+    geno_region_seed(g, opt.max_indel_len, d_err.p, s);
+    timer.end(h);
+    launches(1);
+    timer.hbegin();
+    std::vector<uint8_t> lab(nreg), surv;
+    std::vector<uint32_t> seed_len(nreg), nsurv(nreg);
+    std::vector<uint64_t> seed_off(nreg);
+    int gerr = 0;
+    d_err.download(&gerr, 1);
+    d_r_lable.download(lab.data(), nreg);
+    d_r_seed_len.download(seed_len.data(), nreg);
+    d_r_seed_off.download(seed_off.data(), nreg);
+    d_r_nsurv.download(nsurv.data(), nreg);
+    res_pool.resize(pool_bytes + 16);
+    d_gpool.download(res_pool.data(), pool_bytes);
+    NP2_CUDA(cudaStreamSynchronize(s));
+    d2h += pool_bytes + (uint64_t)nreg * 17;
+    if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
+    if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
+    if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
+    // patched view, regions in ascending position (q = nreg - 1 - r)
+    Patched &pc = res_patch;
+    pc = Patched();
+    pc.cbase = cbase;
+    pc.cpos = cpos;
+    pc.N = N;
+    pc.start.resize(nreg);
+    pc.end.resize(nreg);
+    pc.a.resize(nreg);
+    pc.b.resize(nreg);
+    pc.lable.resize(nreg);
+    pc.seed.resize(nreg);
+    pc.cand.resize(nreg);
+    std::vector<uint32_t> rech_regions;
+    for (uint32_t r = 0; r < nreg; r++) {
+        const uint32_t q = nreg - 1 - r;
+        pc.start[q] = rg.start[r];
+        pc.end[q] = rg.end[r];
+        pc.a[q] = rg.a[r];
+        pc.b[q] = rg.b[r];
+        pc.lable[q] = lab[r];
+        pc.seed[q].s = res_pool.data() + seed_off[r];
+        pc.seed[q].len = seed_len[r];
+        if (nsurv[r]) rech_regions.push_back(r);
+    }
+    if (!rech_regions.empty()) {  // survivors of the (few) regions that stay RECH: slot-level detail on demand
+        for (uint32_t r : rech_regions) {
+            const uint64_t base = (uint64_t)r * kMaxCand;
+            uint8_t sv[kMaxCand];
+            uint32_t cl[kMaxCand], co[kMaxCand];
+            uint64_t cf[kMaxCand];
+            NP2_CUDA(cudaMemcpyAsync(sv, d_r_surv.p + base, nsurv[r], cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaMemcpyAsync(cl, d_c_len.p + base, kMaxCand * 4, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaMemcpyAsync(co, d_c_order.p + base, kMaxCand * 4, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaMemcpyAsync(cf, d_c_off.p + base, kMaxCand * 8, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaStreamSynchronize(s));
+            auto &cd = pc.cand[nreg - 1 - r];
+            for (uint32_t x = 0; x < nsurv[r]; x++) {
+                Allele al;
+                al.s = res_pool.data() + cf[sv[x]];
+                al.len = cl[sv[x]];
+                al.order = co[sv[x]];
+                cd.push_back(al);
+            }
+        }
+    }
+    timer.hend("host:seed_download");
     for (size_t ti = 0; ti < tables.size(); ti++) {
         Reupdate ru;
-        reupdate_build(rg, cs, rs, cur, tables[ti]->dev.k, ru);
+        reupdate_build(pc, tables[ti]->dev.k, ru);
         timer.hend("host:reupdate_build");
         const size_t ns = ru.off.size() - 1;
         std::vector<uint16_t> ks(ns);
@@ -893,33 +976,41 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             NP2_CUDA(cudaStreamSynchronize(s));
             h2d += ru.pool.size() + (ns + 1) * 8;
             d2h += ns * 2;
+            n_probes += ru.pool.size();
         }
         timer.hend("host:reupdate_score_sync");
-        reupdate_apply(rg, cs, rs, ru, ks.data(), (uint32_t)ti + 1, cur, nxt);
+        reupdate_apply(pc, ru, ks.data(), (uint32_t)ti + 1);
         timer.hend("host:reupdate_apply");
-        cur.pos.swap(nxt.pos);
-        cur.base.swap(nxt.base);
     }
-    if (dump)
-        for (auto &r : rs) dm_reg_lable.push_back(r.lable);
-    result = std::move(cur);
+    if (dump) {
+        dm_reg_lable.resize(nreg);
+        for (uint32_t r = 0; r < nreg; r++) dm_reg_lable[r] = pc.lable[nreg - 1 - r];
+    }
+    assemble(pc, res_base, nullptr, &res_first, &res_last);
+    res_pos_valid = false;
+    timer.hend("host:assemble");
 }
 
 void np2_job::run(int32_t dump_it) {
     dump_iter = dump_it;
     cudaStream_t s = ctx->stream;
     const uint32_t L = (uint32_t)tseq.size();
-    result.pos.clear();
-    result.base.clear();
+    res_base.clear();
+    res_pos.clear();
+    res_pos_valid = false;
+    res_patch = Patched();
     timer.s = s;
     timer.reset();
     n_launch = 0;
     n_probes = 0;
     dm_dropped.clear();
     if (L < opt.min_ctg_len) {  // main.rs:1727-1730
-        result.pos.resize(L);
-        result.base.assign(tseq.begin(), tseq.end());
-        for (uint32_t p = 0; p < L; p++) result.pos[p] = p;
+        res_base.assign(tseq.begin(), tseq.end());
+        res_pos.resize(L);
+        for (uint32_t p = 0; p < L; p++) res_pos[p] = p;
+        res_pos_valid = true;
+        res_first = 0;
+        res_last = L ? L - 1 : 0;
         return;
     }
     if (!uploaded) upload();
@@ -944,6 +1035,10 @@ void np2_job::run(int32_t dump_it) {
     ingest_finish();
     timer.hend("host:ingest_finish");
     d_blank.upload(h_blank.data(), std::max(n, 1u));
+    d_order.alloc(std::max(n, 1u), s);
+    if (n) d_order.upload(read_order.data(), n);
+    max_span = 0;
+    for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
 
     if (dump_iter >= 0) {  // reads as the oracle reports them (after the clip filter)
         std::vector<uint8_t> nib(ing.nib_off.back() + 16);
@@ -1275,9 +1370,22 @@ int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const ui
 }
 
 uint64_t np2_job_get_consensus(np2_job *j, const uint32_t **pos, const uint8_t **base) {
-    *pos = j->result.pos.data();
-    *base = j->result.base.data();
-    return j->result.pos.size();
+    if (pos) {  // ConsensusBase.pos is materialised on request; the FASTA record only needs first/last
+        if (!j->res_pos_valid) {
+            std::vector<uint8_t> tmp;
+            uint32_t f, l;
+            assemble(j->res_patch, tmp, &j->res_pos, &f, &l);
+            j->res_pos_valid = true;
+        }
+        *pos = j->res_pos.data();
+    }
+    if (base) *base = j->res_base.data();
+    return j->res_base.size();
+}
+uint64_t np2_job_get_span(np2_job *j, uint32_t *first_pos, uint32_t *last_pos) {
+    *first_pos = j->res_first;
+    *last_pos = j->res_last;
+    return j->res_base.size();
 }
 uint64_t np2_job_get_reads(np2_job *j, const int32_t **rec_idx, const uint32_t **t_s, const uint32_t **t_e,
                            const uint64_t **nib_off, const uint8_t **nib, const uint8_t **blank) {

@@ -1,0 +1,593 @@
+// np2_geno.cu — per-region kernels: which reads cover which LQ region, candidate selection (first 60 non-empty in
+// read order), candidate k-mer scoring, the genotype rules and the read x read agreement edges.
+//
+//   k_read_ranges      the monotone region cursor of generate_lqseqs_from_tags_kmer (main.rs:1446-1460)
+//   k_region_select    per-region candidate list in read order with the 60 cap (main.rs:1473-1521)
+//   k_cand_write       candidate strings into a compact pool
+//   k_cand_kscore_*    retrieve_kmer_count (main.rs:740-778)
+//   k_region_hete      fill_order_stat + mark_hete_lqseqs (main.rs:813-849, 916-946) + edge counts
+//   k_edges_emit       the pair loop of phase_reads_by_lqseqs (main.rs:953-992)
+//   k_region_seed      fill_order_stat + fill_seed_lqseqs + retain_sort_seqs (main.rs:862-914, 714-726)
+#include "np2_kernels.cuh"
+
+namespace np2 {
+
+namespace {
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+constexpr int kWarpsPerCta = 4;
+}  // namespace
+
+/* ---------------------------------------------------------------- read -> region ranges */
+
+// g[i] = the cursor position read i would move an unconstrained cursor to: the largest region index whose start
+// is >= t_s (regions are stored in descending position), 0 if there is none.  Blank reads do not move the cursor.
+__global__ void k_read_cursor(GenoDev g, ReadsDev R, const uint8_t *__restrict__ blank) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n_reads) return;
+    uint32_t v = g.nreg - 1;
+    if (!blank[i]) {
+        const uint32_t ts = R.t_s[i];
+        uint32_t lo = 0, hi = g.nreg;  // count of regions with start >= ts
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (g.start[mid] >= ts) lo = mid + 1;
+            else hi = mid;
+        }
+        v = lo ? lo - 1 : 0;
+    }
+    g.rd_s[i] = v;
+}
+// after the prefix-min over reads: j, pair count and decode limit of every read (main.rs:1449-1471)
+__global__ void k_read_ranges(GenoDev g, ReadsDev R, const uint8_t *__restrict__ blank, uint32_t k) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n_reads) return;
+    uint32_t np = 0, j = 0;
+    if (!blank[i]) {
+        const uint32_t s = g.rd_s[i], ts = R.t_s[i], te = R.t_e[i];
+        if (!(g.start[s] < ts || g.end[s] > te)) {
+            uint32_t lo = 0, hi = g.nreg;  // count of regions with end > te
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (g.end[mid] > te) lo = mid + 1;
+                else hi = mid;
+            }
+            j = lo;
+            np = s - j + 1;
+        }
+    }
+    g.rd_j[i] = j;
+    g.rd_np[i] = np;
+}
+
+/* ---------------------------------------------------------------- candidate scan (one thread per pair) */
+
+struct ScanOut {
+    uint32_t len;
+    uint64_t kmer;
+};
+// The read's bases over [start, end] and its first-k canonical k-mer from `start` on (main.rs:1478-1521); the read
+// is only decoded up to the first column whose t_pos exceeds `limit` (main.rs:1465-1471).
+template <bool WRITE>
+__device__ __forceinline__ ScanOut scan_read_region(const ReadsDev &R, uint32_t r, uint32_t start, uint32_t end,
+                                                    uint32_t limit, uint32_t k, uint8_t *out) {
+    const uint32_t n = R.n[r];
+    const uint8_t *nib = R.nib + R.nib_off[r];
+    const uint32_t *ck = R.ck_tpos + R.ck_off[r];
+    uint32_t lo = 0, hi = (n + 31) >> 5;  // last 32-column block whose first t_pos is < start (or block 0)
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (ck[mid] < start) lo = mid;
+        else hi = mid;
+    }
+    uint32_t tpos = ck[lo];
+    const uint64_t mask = (1ULL << (2 * k)) - 1;
+    const uint32_t sh = 2 * (k - 1);
+    uint64_t k0 = 0, k1 = 0;
+    uint32_t l = 0, len = 0;
+    for (uint32_t o = lo * 32; o < n; o++) {
+        const uint32_t b = nib[o >> 1];
+        const uint32_t v = (o & 1) ? (b & 15) : (b >> 4);
+        if (o != lo * 32 && !(v & 8)) tpos++;
+        const uint32_t q = v & 7;
+        if (tpos >= start && q != 4) {
+            if (tpos <= end) {
+                if (WRITE) out[len] = code_char(q);
+                len++;
+            }
+            if (l < k) {
+                k0 = (k0 << 2 | (uint64_t)q) & mask;
+                k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
+                l++;
+            }
+            if (tpos > end && l >= k) break;
+        }
+        if (tpos > limit) break;
+    }
+    ScanOut so;
+    so.len = len;
+    so.kmer = l >= k ? yak_hash64(k0 < k1 ? k0 : k1, mask) : 0xFFFFFFFFFFFFFFFFULL;
+    return so;
+}
+// the ref read is alignseq 0: never trimmed, stored or dropped; its columns are the contig's codes
+template <bool WRITE>
+__device__ __forceinline__ ScanOut scan_ref_region(const uint8_t *__restrict__ code, uint32_t L, uint32_t start,
+                                                   uint32_t end, uint32_t limit, uint32_t k, uint8_t *out) {
+    const uint64_t mask = (1ULL << (2 * k)) - 1;
+    const uint32_t sh = 2 * (k - 1);
+    uint64_t k0 = 0, k1 = 0;
+    uint32_t l = 0, len = 0;
+    for (uint32_t p = start; p < L; p++) {
+        const uint32_t q = code[p];
+        if (q != 4) {
+            if (p <= end) {
+                if (WRITE) out[len] = code_char(q);
+                len++;
+            }
+            if (l < k) {
+                k0 = (k0 << 2 | (uint64_t)q) & mask;
+                k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
+                l++;
+            }
+            if (p > end && l >= k) break;
+        }
+        if (p > limit) break;
+    }
+    ScanOut so;
+    so.len = len;
+    so.kmer = l >= k ? yak_hash64(k0 < k1 ? k0 : k1, mask) : 0xFFFFFFFFFFFFFFFFULL;
+    return so;
+}
+
+__global__ void k_pair_scan(GenoDev g, ReadsDev R, uint32_t k) {
+    uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= g.n_pairs) return;
+    uint32_t lo = 0, hi = R.n_reads;  // read owning pair pi: largest i with rd_poff[i] <= pi
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (g.rd_poff[mid] <= pi) lo = mid;
+        else hi = mid;
+    }
+    const uint32_t i = lo, j = g.rd_j[i], reg = j + (pi - g.rd_poff[i]);
+    ScanOut so = scan_read_region<false>(R, i, g.start[reg], g.end[reg], g.end[j] + k, k, nullptr);
+    g.p_len[pi] = so.len;
+    g.p_kmer[pi] = so.kmer;
+}
+
+/* ---------------------------------------------------------------- per-region candidate selection */
+
+// One warp per region.  Reads are in BAM order (sorted by pos <= t_s), so the reads that can cover the region sit
+// in the window pos in [start - max_span, start]; inside it a read covers region r iff j <= r <= s.
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_select(GenoDev g, ReadsDev R,
+                                                                     const uint8_t *__restrict__ blank,
+                                                                     const uint8_t *__restrict__ code, uint32_t L,
+                                                                     uint32_t k, uint32_t max_span) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= g.nreg) return;
+    const uint32_t start = g.start[r], end = g.end[r];
+    const uint32_t base = r * kMaxCand;
+    uint32_t ncand = 0, bytes = 0;
+    if (lane == 0) {  // ref candidate (order 0); its decode limit is that of region 0 (main.rs:1467 with j = 0)
+        ScanOut so = scan_ref_region<false>(code, L, start, end, g.end[0] + k, k, nullptr);
+        if (so.len) {
+            g.c_src[base] = 0xFFFFFFFFu;
+            g.c_len[base] = so.len;
+            g.c_order[base] = 0;
+            g.c_kmer[base] = so.kmer;
+        }
+        ncand = so.len ? 1 : 0;
+        bytes = so.len;
+    }
+    ncand = __shfl_sync(0xFFFFFFFFu, ncand, 0);
+    bytes = __shfl_sync(0xFFFFFFFFu, bytes, 0);
+    const uint32_t lo_pos = start > max_span ? start - max_span : 0;
+    uint32_t lo = 0, hi = R.n_reads;  // first read with pos >= lo_pos
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (R.pos[mid] < lo_pos) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t first = lo;
+    hi = R.n_reads;  // first read with pos > start
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (R.pos[mid] <= start) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t last = lo;
+    for (uint32_t i0 = first; i0 < last && ncand < kMaxCand; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint32_t len = 0, pair = 0;
+        if (i < last && !blank[i] && g.rd_np[i]) {
+            const uint32_t j = g.rd_j[i];
+            if (j <= r && r < j + g.rd_np[i]) {
+                pair = g.rd_poff[i] + (r - j);
+                len = g.p_len[pair];
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, len > 0);  // empty candidates are not pushed (main.rs:1509)
+        const uint32_t slot = ncand + __popc(bal & ((1u << lane) - 1));
+        if (len > 0 && slot < kMaxCand) {
+            g.c_src[base + slot] = pair;
+            g.c_len[base + slot] = len;
+            g.c_order[base + slot] = g.rd_order[i];
+            g.c_kmer[base + slot] = g.p_kmer[pair];
+        }
+        uint32_t add = (len > 0 && slot < kMaxCand) ? len : 0;
+        for (int d = 16; d > 0; d >>= 1) add += __shfl_xor_sync(0xFFFFFFFFu, add, d);
+        bytes += add;
+        ncand = min(ncand + __popc(bal), (uint32_t)kMaxCand);
+    }
+    if (lane == 0) {
+        g.r_ncand[r] = ncand;
+        g.r_bytes[r] = bytes;
+    }
+}
+
+// One warp per region: candidate offsets inside the region's slice of the pool, then the bytes.
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_cand_write(GenoDev g, ReadsDev R,
+                                                                  const uint8_t *__restrict__ code, uint32_t L,
+                                                                  uint32_t k) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= g.nreg) return;
+    const uint32_t n = g.r_ncand[r], base = r * kMaxCand;
+    const uint32_t start = g.start[r], end = g.end[r];
+    uint64_t run = g.r_pool_off[r];
+    for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const uint32_t len = c < n ? g.c_len[base + c] : 0;
+        uint32_t incl = len;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint64_t off = run + incl - len;
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (c < n) {
+            g.c_off[base + c] = off;
+            const uint32_t src = g.c_src[base + c];
+            if (src == 0xFFFFFFFFu) {
+                scan_ref_region<true>(code, L, start, end, g.end[0] + k, k, g.pool + off);
+            } else {
+                uint32_t lo = 0, hi = R.n_reads;  // read owning the pair
+                while (hi - lo > 1) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (g.rd_poff[mid] <= src) lo = mid;
+                    else hi = mid;
+                }
+                scan_read_region<true>(R, lo, start, end, g.end[g.rd_j[lo]] + k, k, g.pool + off);
+            }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------- candidate kscore */
+
+__device__ __forceinline__ uint32_t g_bucket_of(uint64_t tag, uint32_t nb) {
+    uint32_t m = (uint32_t)((tag * 0x9E3779B97F4A7C15ULL) >> 32);
+    return (uint32_t)(((uint64_t)m * nb) >> 32);
+}
+__device__ __forceinline__ uint32_t g_probe(const TableDev &t, uint64_t h, uint32_t min_count) {
+    const uint32_t sub = (uint32_t)(h & 1023);
+    const uint64_t tag = h >> 10;
+    uint32_t b = g_bucket_of(tag, t.nb);
+    for (uint32_t step = 0; step < t.nb; step++) {
+        const ulonglong2 *bp = (const ulonglong2 *)(t.slots + ((uint64_t)sub * t.nb + b) * kBucketSlots);
+        const ulonglong2 lo = __ldg(bp), hi = __ldg(bp + 1);
+        const uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
+        bool empty = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((v[j] >> 10) == tag && v[j] != 0) {
+                const uint32_t c = (uint32_t)(v[j] & 1023);
+                return c >= min_count ? c : 0;
+            }
+            empty |= v[j] == 0;
+        }
+        if (empty) return 0;
+        b = b + 1 == t.nb ? 0 : b + 1;
+    }
+    return 0;
+}
+// candidates no longer than k: the single pre-computed first-k k-mer (main.rs:770-774); INVALID_KMER keeps 0
+__global__ void k_cand_kscore_short(GenoDev g, TableDev t, uint32_t min_count) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.nreg * kMaxCand) return;
+    const uint32_t r = s / kMaxCand, c = s - r * kMaxCand;
+    if (c >= g.r_ncand[r]) return;
+    if (g.c_len[s] > t.k) return;
+    const uint64_t h = g.c_kmer[s];
+    g.c_kscore[s] = h == 0xFFFFFFFFFFFFFFFFULL ? 0 : (uint16_t)g_probe(t, h, min_count);
+}
+// candidates longer than k: min over all their k-mers (main.rs:760-769); one warp per candidate, k < 32 here
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_cand_kscore_long(GenoDev g, TableDev t, uint32_t min_count) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= g.nreg * kMaxCand) return;
+    const uint32_t r = s / kMaxCand, c = s - r * kMaxCand;
+    if (c >= g.r_ncand[r]) return;
+    const uint32_t len = g.c_len[s], k = t.k;
+    if (len <= k) return;
+    const uint8_t *sq = g.pool + g.c_off[s];
+    const uint64_t mask = (1ULL << (2 * k)) - 1;
+    uint32_t mn = 0xFFFFFFFFu;
+    for (uint32_t e = k - 1 + lane; e < len; e += 32) {
+        bool ok = true;
+        uint64_t f = 0, rv = 0;
+        for (uint32_t x = e + 1 - k; x <= e; x++) {
+            const uint32_t cd = seq_code(sq[x]);
+            ok &= cd < 4;
+            f = (f << 2 | cd) & mask;
+            rv = (rv >> 2) | (uint64_t)(3 ^ cd) << (2 * (k - 1));
+        }
+        if (ok) mn = min(mn, g_probe(t, yak_hash64(f < rv ? f : rv, mask), min_count));
+    }
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    if (lane == 0) g.c_kscore[s] = mn == 0xFFFFFFFFu ? 0 : (uint16_t)mn;
+}
+
+/* ---------------------------------------------------------------- genotype rules (one warp per region) */
+
+struct RegionSmem {
+    uint32_t len[kMaxCand];
+    uint32_t order[kMaxCand];
+    uint64_t off[kMaxCand];
+    uint16_t kscore[kMaxCand];
+    uint8_t rep[kMaxCand];      // first candidate holding the same string
+    uint8_t per_pos[kMaxCand];  // group size as fill_order_stat leaves it in `stats`
+    uint8_t ostat[kMaxCand];    // order_stat value of the candidate's own order (0 = absent)
+    uint8_t surv[kMaxCand];
+    uint32_t max1_c, max1_p, max2_c, max2_p;
+};
+
+__device__ __forceinline__ void region_load(const GenoDev &g, uint32_t r, uint32_t n, uint32_t lane, RegionSmem &sm) {
+    const uint32_t base = r * kMaxCand;
+    for (uint32_t c = lane; c < n; c += 32) {
+        sm.len[c] = g.c_len[base + c];
+        sm.order[c] = g.c_order[base + c];
+        sm.off[c] = g.c_off[base + c];
+        sm.kscore[c] = g.c_kscore[base + c];
+    }
+    __syncwarp();
+    // rep[c] = first index holding the same string (exact byte comparison)
+    for (uint32_t c = lane; c < n; c += 32) {
+        uint32_t rp = c;
+        const uint8_t *a = g.pool + sm.off[c];
+        const uint32_t la = sm.len[c];
+        for (uint32_t d = 0; d < c; d++) {
+            if (sm.len[d] != la) continue;
+            const uint8_t *b = g.pool + sm.off[d];
+            bool eq = true;
+            for (uint32_t x = 0; x < la; x++)
+                if (a[x] != b[x]) {
+                    eq = false;
+                    break;
+                }
+            if (eq) {
+                rp = d;
+                break;
+            }
+        }
+        sm.rep[c] = (uint8_t)rp;
+    }
+    __syncwarp();
+}
+// fill_order_stat (main.rs:813-849), run by lane 0
+__device__ __forceinline__ void region_order_stat(uint32_t n, RegionSmem &sm) {
+    uint32_t max1_c = 0, max1_p = 0, max2_c = 0, max2_p = 0;
+    for (uint32_t c = 0; c < n; c++) {
+        sm.per_pos[c] = 0;
+        sm.ostat[c] = 0;
+    }
+    for (uint32_t p1 = 0; p1 < n; p1++) {
+        if (sm.kscore[p1] == 0 || sm.per_pos[p1] > 0) continue;
+        uint32_t c = 0;
+        for (uint32_t x = p1; x < n; x++) c += sm.rep[x] == sm.rep[p1];
+        sm.ostat[p1] = (uint8_t)c;
+        for (uint32_t x = p1; x < n; x++)
+            if (sm.rep[x] == sm.rep[p1]) sm.per_pos[x] = (uint8_t)c;
+        if (c > max1_c || (c == max1_c && sm.order[p1] == 0)) {
+            max2_c = max1_c;
+            max2_p = max1_p;
+            max1_c = c;
+            max1_p = p1;
+        } else if (max1_p == max2_p || c > max2_c) {
+            max2_c = c;
+            max2_p = p1;
+        }
+    }
+    sm.max1_c = max1_c;
+    sm.max1_p = max1_p;
+    sm.max2_c = max2_c;
+    sm.max2_p = max2_p;
+}
+__device__ __forceinline__ uint32_t min_count_for(uint32_t c) { return c >= 9 ? 3 : (c >= 6 ? 2 : 1); }  // main.rs:803
+// is_valid_snp (main.rs:780-801)
+__device__ __forceinline__ bool hp_differ(const uint8_t *a, uint32_t na, const uint8_t *b, uint32_t nb) {
+    uint32_t i = 0, j = 0;
+    while (i < na && j < nb) {
+        if (a[i] != b[j]) return true;
+        while (i + 1 < na && a[i] == a[i + 1]) i++;
+        while (j + 1 < nb && b[j] == b[j + 1]) j++;
+        i++;
+        j++;
+    }
+    return false;
+}
+
+// mark_hete_lqseqs (main.rs:916-946) + the number of agreement edges the region will emit
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_hete(GenoDev g) {
+    __shared__ RegionSmem smem[kWarpsPerCta];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= g.nreg) return;
+    RegionSmem &sm = smem[threadIdx.x >> 5];
+    const uint32_t n = g.r_ncand[r];
+    region_load(g, r, n, lane, sm);
+    if (lane == 0) {
+        uint8_t lable = 0;
+        uint32_t nedge = 0;
+        if (n) {
+            region_order_stat(n, sm);
+            const uint32_t min_c = min_count_for(n);
+            const uint32_t a = sm.max1_p, b = sm.max2_p;
+            if (sm.max2_c >= min_c && (sm.len[a] == sm.len[b] || (n >= 6 && sm.max2_c >= sm.max1_c / 2)) &&
+                hp_differ(g.pool + sm.off[a], sm.len[a], g.pool + sm.off[b], sm.len[b])) {
+                lable = 0x40;
+                uint32_t m = 0;
+                for (uint32_t p = 0; p < n; p++) {
+                    if (sm.kscore[p] > 0 && sm.per_pos[p] < min_c) {
+                        sm.kscore[p] = 0;
+                        g.c_kscore[r * kMaxCand + p] = 0;
+                    }
+                    m += sm.kscore[p] > 0;
+                }
+                nedge = m * (m - 1) / 2;
+            }
+        }
+        g.r_lable[r] = lable;
+        g.r_nedge[r] = nedge;
+    }
+    // rep is needed again by k_edges_emit
+    for (uint32_t c = lane; c < n; c += 32) g.c_rep[r * kMaxCand + c] = sm.rep[c];
+}
+
+// all pairs (i < j) of supported candidates of a heterozygous region: key = (min order, max order), value +1 when
+// the strings agree, -1 (and one "differs" count in the high half) when they do not (main.rs:953-992)
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_emit(GenoDev g, uint64_t *__restrict__ ekey,
+                                                                  long long *__restrict__ eval) {
+    __shared__ uint8_t s_valid[kWarpsPerCta][kMaxCand];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= g.nreg) return;
+    const uint32_t ne = g.r_nedge[r];
+    if (!ne) return;
+    uint8_t *valid = s_valid[threadIdx.x >> 5];
+    const uint32_t n = g.r_ncand[r], base = r * kMaxCand;
+    uint32_t m = 0;
+    if (lane == 0) {
+        for (uint32_t p = 0; p < n; p++)
+            if (g.c_kscore[base + p] > 0) valid[m++] = (uint8_t)p;
+    }
+    m = __shfl_sync(0xFFFFFFFFu, m, 0);
+    __syncwarp();
+    const uint64_t w0 = g.r_edge_off[r];
+    for (uint32_t a = 0; a + 1 < m; a++) {
+        // edges of row a start after rows 0..a-1: sum_{x<a} (m-1-x)
+        const uint32_t row0 = a * (m - 1) - a * (a - 1) / 2;
+        const uint32_t pa = valid[a];
+        const uint32_t oa = g.c_order[base + pa], ra = g.c_rep[base + pa];
+        for (uint32_t b = a + 1 + lane; b < m; b += 32) {
+            const uint32_t pb = valid[b];
+            const uint32_t ob = g.c_order[base + pb];
+            const bool same = g.c_rep[base + pb] == ra;
+            const uint32_t x = min(oa, ob), y = max(oa, ob);
+            ekey[w0 + row0 + (b - a - 1)] = (uint64_t)x << 32 | y;
+            eval[w0 + row0 + (b - a - 1)] = same ? 1LL : (-1LL + (1LL << 32));
+        }
+    }
+}
+
+// fill_seed_lqseqs (main.rs:862-914) with retain_sort_seqs (714-726)
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, int32_t max_indel_len, int *err) {
+    __shared__ RegionSmem smem[kWarpsPerCta];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= g.nreg) return;
+    RegionSmem &sm = smem[threadIdx.x >> 5];
+    const uint32_t n = g.r_ncand[r];
+    region_load(g, r, n, lane, sm);
+    if (lane != 0) return;
+    if (n == 0 || sm.order[0] != 0) {  // reference would panic: no candidate / "the first lqseq is not ref."
+        atomicExch(err, n == 0 ? 1 : 2);
+        return;
+    }
+    region_order_stat(n, sm);
+    uint32_t seed = sm.max1_p;
+    const uint32_t min_c = min_count_for(n), max1_c = sm.max1_c, max1_p = sm.max1_p;
+    if (sm.ostat[0]) {  // keep the reference allele when it has support (main.rs:876-890)
+        if (sm.ostat[0] > 1 && sm.ostat[0] < min_c) sm.ostat[0] = (uint8_t)min_c;
+    } else {
+        uint32_t c = 0;
+        for (uint32_t x = 0; x < n; x++) c += sm.rep[x] == 0;
+        if (c > 1) sm.ostat[0] = (uint8_t)min_c;
+    }
+    bool no_dup = true;  // no_dupseq_lqseq main.rs:851-860: no two equal strings among candidates 1..n-1
+    for (uint32_t p1 = 1; p1 < n && no_dup; p1++)
+        for (uint32_t p2 = p1 + 1; p2 < n; p2++)
+            if (sm.rep[p1] == sm.rep[p2]) {
+                no_dup = false;
+                break;
+            }
+    if (max1_p != 0 && max1_c < min_c && (max1_c > 1 || no_dup)) {
+        sm.ostat[max1_p] = (uint8_t)min_c;
+        sm.ostat[0] = (uint8_t)min_c;
+    } else if (max1_c < min_c) {
+        sm.ostat[0] = (uint8_t)min_c;
+    }
+    // stable sort by order_stat descending, keep those >= min_c
+    uint32_t ns = 0;
+    for (uint32_t p = 0; p < n; p++) {
+        if (sm.ostat[p] < min_c) continue;  // everything below min_c sorts after the cut anyway
+        uint32_t q = ns++;
+        while (q > 0 && sm.ostat[sm.surv[q - 1]] < sm.ostat[p]) {
+            sm.surv[q] = sm.surv[q - 1];
+            q--;
+        }
+        sm.surv[q] = (uint8_t)p;
+    }
+    if (ns == 0) {
+        atomicExch(err, 3);
+        return;
+    }
+    uint8_t lable = 0x80 | 0x20;
+    const int32_t dl = (int32_t)sm.len[seed] - (int32_t)sm.len[sm.surv[0]];
+    const bool skip_long = (dl < 0 ? -dl : dl) > max_indel_len;
+    if (ns <= 1 || skip_long) {
+        seed = sm.surv[0];
+        lable ^= 0x20;
+        ns = 0;
+    }
+    g.r_lable[r] = lable;
+    g.r_seed_off[r] = sm.off[seed];
+    g.r_seed_len[r] = sm.len[seed];
+    g.r_nsurv[r] = ns;
+    for (uint32_t q = 0; q < ns; q++) g.r_surv[r * kMaxCand + q] = sm.surv[q];
+}
+
+/* ---------------------------------------------------------------- launch wrappers */
+
+void geno_read_cursor(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, cudaStream_t s) {
+    if (R.n_reads) k_read_cursor<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank);
+}
+void geno_read_ranges(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, uint32_t k, cudaStream_t s) {
+    if (R.n_reads) k_read_ranges<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank, k);
+}
+void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, cudaStream_t s) {
+    if (g.n_pairs) k_pair_scan<<<cdiv(g.n_pairs, 128), 128, 0, s>>>(g, R, k);
+}
+void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
+                        uint32_t k, uint32_t max_span, cudaStream_t s) {
+    k_region_select<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_blank, d_code, L,
+                                                                                               k, max_span);
+}
+void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s) {
+    k_cand_write<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_code, L, k);
+}
+void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s) {
+    const uint64_t slots = (uint64_t)g.nreg * kMaxCand;
+    k_cand_kscore_short<<<cdiv(slots, 256), 256, 0, s>>>(g, t, min_count);
+    k_cand_kscore_long<<<cdiv(slots * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, t, min_count);
+}
+void geno_region_hete(GenoDev g, cudaStream_t s) {
+    k_region_hete<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g);
+}
+void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, cudaStream_t s) {
+    k_edges_emit<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_key, d_val);
+}
+void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s) {
+    k_region_seed<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, d_err);
+}
+
+}  // namespace np2

@@ -100,6 +100,7 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
         out.pos.push_back((uint32_t)pos);
         out.ncols.push_back(col);
         out.rlen.push_back((uint32_t)rlen);
+        out.rspan.push_back((uint32_t)rspan);
         out.is_clip.push_back((uint32_t)(aln_q_e - aln_q_s + opt.max_clip_len) < (uint32_t)rlen ? 1 : 0);  // main.rs:1796
         out.seq_off.push_back(rec_off + 32 + l_name + 4ull * n_cig);
         out.op_off.push_back((uint32_t)out.op_col.size());
@@ -114,8 +115,7 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
 
 void find_regions(const uint32_t *cpos, const uint8_t *cbase, const uint8_t *cflags, uint64_t n, const uint32_t *events,
                   uint64_t n_events, Regions &out) {
-    out.start.clear();
-    out.end.clear();
+    out = Regions();
     if (n == 0) return;
     // reversed indexing: rp = n - 1 - i is the index the reference uses while backtracking (main.rs:1570-1626)
     auto P = [&](uint64_t rp) { return cpos[n - 1 - rp]; };
@@ -123,6 +123,7 @@ void find_regions(const uint32_t *cpos, const uint8_t *cbase, const uint8_t *cfl
     const uint64_t NONE = UINT64_MAX;
     bool has_lq = false;
     uint64_t lq_s = NONE, lq_e = 0;
+    std::vector<uint64_t> i_start, i_end;  // consensus index of one base carrying region.start / region.end
     auto try_close = [&](uint64_t from, uint64_t to) {  // HQ bases rp in [from, to)
         for (uint64_t rp = std::max(from, lq_e + 5); rp < to; rp++) {
             if (P(rp - 1) != P(rp - 2) && B(rp - 1) != B(rp - 2)) {
@@ -131,9 +132,12 @@ void find_regions(const uint32_t *cpos, const uint8_t *cbase, const uint8_t *cfl
                 while (lq_s > 1 && (P(lq_s - 1) == P(lq_s) || B(lq_s - 1) == B(lq_s))) lq_s--;
                 if (!out.start.empty() && P(lq_s) >= out.start.back()) {
                     out.start.back() = P(lq_e);
+                    i_start.back() = n - 1 - lq_e;
                 } else {
                     out.end.push_back(P(lq_s));
                     out.start.push_back(P(lq_e));
+                    i_end.push_back(n - 1 - lq_s);
+                    i_start.push_back(n - 1 - lq_e);
                 }
                 has_lq = false;
                 lq_s = NONE;
@@ -157,148 +161,16 @@ void find_regions(const uint32_t *cpos, const uint8_t *cbase, const uint8_t *cfl
         next_rp = rp + 1;
     }
     if (has_lq) try_close(next_rp, n);
-}
-
-/* ================================================================= genotype rules */
-
-namespace {
-
-inline bool seq_eq(const CandSet &cs, uint32_t a, uint32_t b) {
-    return cs.seq_len[a] == cs.seq_len[b] &&
-           memcmp(cs.pool + cs.seq_off[a], cs.pool + cs.seq_off[b], cs.seq_len[a]) == 0;
-}
-inline size_t min_count_for(size_t c) { return c >= 9 ? 3 : (c >= 6 ? 2 : 1); }  // main.rs:803-811
-
-struct Stat {
-    size_t max1_c = 0, max1_p = 0, max2_c = 0, max2_p = 0;
-    size_t per_pos[64];                                  // group size seen from the group's first scored member
-    std::vector<std::pair<uint32_t, size_t>> by_order;  // order of a group's first scored member -> size
-    size_t *find(uint32_t order) {
-        for (auto &x : by_order)
-            if (x.first == order) return &x.second;
-        return nullptr;
-    }
-    size_t get(uint32_t order) {
-        size_t *p = find(order);
-        return p ? *p : 0;
-    }
-    void set(uint32_t order, size_t v) {
-        size_t *p = find(order);
-        if (p) *p = v;
-        else by_order.emplace_back(order, v);
-    }
-};
-
-// fill_order_stat (main.rs:813-849)
-void order_stat(const CandSet &cs, const std::vector<uint32_t> &cand, Stat &st) {
-    const size_t n = cand.size();
-    st = Stat();
-    std::fill(st.per_pos, st.per_pos + 64, 0);
-    // first index holding the same string
-    uint32_t rep[64];
-    for (size_t i = 0; i < n; i++) {
-        rep[i] = (uint32_t)i;
-        for (size_t j = 0; j < i; j++)
-            if (rep[j] == j && seq_eq(cs, cand[i], cand[j])) {
-                rep[i] = (uint32_t)j;
-                break;
-            }
-    }
-    for (size_t p1 = 0; p1 < n; p1++) {
-        if (cs.kscore[cand[p1]] == 0 || st.per_pos[p1] > 0) continue;
-        size_t c = 0;
-        for (size_t x = p1; x < n; x++) c += rep[x] == rep[p1];
-        st.set(cs.order[cand[p1]], c);
-        for (size_t x = p1; x < n; x++)
-            if (rep[x] == rep[p1]) st.per_pos[x] = c;
-        if (c > st.max1_c || (c == st.max1_c && cs.order[cand[p1]] == 0)) {
-            st.max2_c = st.max1_c;
-            st.max2_p = st.max1_p;
-            st.max1_c = c;
-            st.max1_p = p1;
-        } else if (st.max1_p == st.max2_p || c > st.max2_c) {
-            st.max2_c = c;
-            st.max2_p = p1;
-        }
-    }
-}
-
-// is_valid_snp (main.rs:780-801): do the homopolymer-compressed strings differ?
-bool hp_compressed_differ(const uint8_t *a, size_t na, const uint8_t *b, size_t nb) {
-    size_t i = 0, j = 0;
-    while (i < na && j < nb) {
-        if (a[i] != b[j]) return true;
-        while (i + 1 < na && a[i] == a[i + 1]) i++;
-        while (j + 1 < nb && b[j] == b[j + 1]) j++;
-        i++;
-        j++;
-    }
-    return false;
-}
-
-}  // namespace
-
-void mark_hete(CandSet &cs, std::vector<RegionState> &rs) {
-    Stat st;
-    for (auto &r : rs) {
-        if (r.cand.empty()) continue;
-        order_stat(cs, r.cand, st);
-        const size_t min_c = min_count_for(r.cand.size());
-        const uint32_t a = r.cand[st.max1_p], b = r.cand[st.max2_p];
-        if (st.max2_c >= min_c &&
-            (cs.seq_len[a] == cs.seq_len[b] || (r.cand.size() >= 6 && st.max2_c >= st.max1_c / 2)) &&
-            hp_compressed_differ(cs.pool + cs.seq_off[a], cs.seq_len[a], cs.pool + cs.seq_off[b], cs.seq_len[b])) {
-            r.lable |= LABLE_HETE;
-            for (size_t p = 0; p < r.cand.size(); p++)
-                if (cs.kscore[r.cand[p]] > 0 && st.per_pos[p] < min_c) cs.kscore[r.cand[p]] = 0;
-        }
-    }
-}
-
-void fill_seed(const CandSet &cs, std::vector<RegionState> &rs, long max_indel_len) {
-    Stat st;
-    for (auto &r : rs) {
-        if (r.cand.empty()) herr(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
-        order_stat(cs, r.cand, st);
-        auto str = [&](uint32_t c) { return std::string((const char *)cs.pool + cs.seq_off[c], cs.seq_len[c]); };
-        r.sudoseed = str(r.cand[st.max1_p]);
-        r.lable |= LABLE_SUCC | LABLE_RECH;
-        const size_t min_c = min_count_for(r.cand.size());
-        if (cs.order[r.cand[0]] != 0) herr(NP2_ERR_FORMAT, "the first lqseq is not ref.");
-        // keep the reference allele when it has support (main.rs:876-890)
-        if (size_t *v = st.find(0)) {
-            if (*v > 1 && *v < min_c) *v = min_c;
-        } else {
-            size_t c = 0;
-            for (uint32_t x : r.cand) c += seq_eq(cs, x, r.cand[0]);
-            if (c > 1) st.set(0, min_c);
-        }
-        bool no_dup = true;  // no_dupseq_lqseq main.rs:851-860
-        for (size_t p1 = 1; p1 < r.cand.size() && no_dup; p1++)
-            for (size_t p2 = p1 + 1; p2 < r.cand.size(); p2++)
-                if (seq_eq(cs, r.cand[p1], r.cand[p2])) {
-                    no_dup = false;
-                    break;
-                }
-        if (st.max1_p != 0 && st.max1_c < min_c && (st.max1_c > 1 || no_dup)) {
-            st.set(cs.order[r.cand[st.max1_p]], min_c);
-            st.set(0, min_c);
-        } else if (st.max1_c < min_c) {
-            st.set(0, min_c);
-        }
-        // retain_sort_seqs main.rs:714-726
-        std::stable_sort(r.cand.begin(), r.cand.end(),
-                         [&](uint32_t x, uint32_t y) { return st.get(cs.order[x]) > st.get(cs.order[y]); });
-        size_t keep = 0;
-        while (keep < r.cand.size() && st.get(cs.order[r.cand[keep]]) >= min_c) keep++;
-        r.cand.resize(keep);
-        if (r.cand.empty()) herr(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
-        const bool skip_long = std::labs((long)r.sudoseed.size() - (long)cs.seq_len[r.cand[0]]) > max_indel_len;
-        if (r.cand.size() <= 1 || skip_long) {
-            r.sudoseed = str(r.cand[0]);
-            r.lable ^= LABLE_RECH;
-            r.cand.clear();
-        }
+    // index ranges: positions are non-decreasing, insertions share their anchor's position
+    const size_t nr = out.start.size();
+    out.a.resize(nr);
+    out.b.resize(nr);
+    for (size_t r = 0; r < nr; r++) {
+        uint64_t a = i_start[r], b = i_end[r] + 1;
+        while (a > 0 && cpos[a - 1] == out.start[r]) a--;
+        while (b < n && cpos[b] <= out.end[r]) b++;
+        out.a[r] = (uint32_t)a;
+        out.b[r] = (uint32_t)b;
     }
 }
 
@@ -473,63 +345,28 @@ struct Community {
 
 }  // namespace
 
-std::vector<uint32_t> phase_reads(const CandSet &cs, const std::vector<RegionState> &rs, bool asref,
+std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
                                   bool use_all_reads) {
-    // ---- pair agreement over heterozygous regions (main.rs:953-992)
-    struct Edge {
-        uint32_t a, b;
-        int32_t w;
-    };
-    std::vector<Edge> edges;
     std::map<uint32_t, float> ref_w;
     bool have_ref = false;
     std::set<uint32_t> invalid;
-    for (auto &r : rs) {
-        if (!(r.lable & LABLE_HETE)) continue;
-        const size_t n = r.cand.size();
-        uint32_t rep[64];
-        for (size_t i = 0; i < n; i++) {
-            rep[i] = (uint32_t)i;
-            for (size_t j = 0; j < i; j++)
-                if (rep[j] == j && seq_eq(cs, r.cand[i], r.cand[j])) {
-                    rep[i] = (uint32_t)j;
-                    break;
-                }
-        }
-        for (size_t i = 0; i < n; i++) {
-            if (cs.kscore[r.cand[i]] == 0) continue;
-            const uint32_t oi = cs.order[r.cand[i]];
-            for (size_t j = i + 1; j < n; j++) {
-                if (cs.kscore[r.cand[j]] == 0) continue;
-                const uint32_t oj = cs.order[r.cand[j]];
-                const int32_t w = rep[i] == rep[j] ? 1 : -1;
-                if (oi == 0) {
-                    if (asref) {
-                        ref_w[oj] += (float)w;
-                        have_ref = true;
-                    }
-                    if (w < 0 && !use_all_reads) invalid.insert(oj);
-                    continue;
-                }
-                if (oj == 0) herr(NP2_ERR_FORMAT, "seq2 order is equal to 0");
-                edges.push_back({std::min(oi, oj), std::max(oi, oj), w});
-            }
-        }
-    }
-    std::sort(edges.begin(), edges.end(), [](const Edge &x, const Edge &y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
     Level lv;
-    for (size_t i = 0; i < edges.size();) {
-        size_t j = i;
-        int32_t sum = 0, ndif = 0;
-        while (j < edges.size() && edges[j].a == edges[i].a && edges[j].b == edges[i].b) {
-            sum += edges[j].w;
-            ndif += edges[j].w < 0 ? -1 : 0;
-            j++;
+    for (uint64_t e = 0; e < n_edges; e++) {
+        const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+        const long long v = vals[e];
+        const long long ndif = (v + (1LL << 31)) >> 32;  // number of disagreeing sites
+        const long long sum = v - (ndif << 32);          // sum of +-1 over shared heterozygous regions
+        if (a == 0) {  // pairs with the ref read (main.rs:972-980)
+            if (asref) {
+                ref_w[b] = (float)sum;
+                have_ref = true;
+            }
+            if (ndif > 0 && !use_all_reads) invalid.insert(b);
+            continue;
         }
-        const float w = ndif <= -3 ? (float)ndif : (float)sum;  // main.rs:996-1002
-        lv.data[edges[i].a][edges[i].b] = w;
-        lv.data[edges[i].b][edges[i].a] = w;
-        i = j;
+        const float w = ndif >= 3 ? -(float)ndif : (float)sum;  // main.rs:996-1002
+        lv.data[a][b] = w;
+        lv.data[b][a] = w;
     }
     if (!use_all_reads) {  // main.rs:1004-1010
         for (uint32_t x : invalid) lv.data.erase(x);
@@ -619,51 +456,7 @@ std::vector<uint32_t> phase_reads(const CandSet &cs, const std::vector<RegionSta
 
 /* ================================================================= consensus patching */
 
-void splice(const Regions &rg, const std::vector<RegionState> &rs, uint8_t lable, const Cns &in, Cns &out) {
-    out.pos.clear();
-    out.base.clear();
-    out.pos.reserve(in.pos.size());
-    out.base.reserve(in.pos.size());
-    const size_t nr = rs.size();
-    // regions are stored in descending position; walk them from the last (lowest position) to the first
-    auto next = [&](size_t i) {  // get_lqseqs_next_idx_by_lable main.rs:1017-1025
-        i -= 1;
-        while (i < nr && !(rs[i].lable & lable)) i -= 1;
-        return i;
-    };
-    size_t ri = next(nr);
-    const size_t n = in.pos.size();
-    size_t i = 0;
-    while (i < n) {
-        const uint32_t p = in.pos[i];
-        if (ri < nr && p == rg.start[ri]) {
-            for (char b : rs[ri].sudoseed) {
-                out.pos.push_back(p);
-                out.base.push_back((uint8_t)b);
-            }
-            while (i < n && in.pos[i] <= rg.end[ri]) i++;
-            ri = next(ri);
-        } else {
-            // copy the stretch up to the next region start in one go
-            size_t j = i + 1;
-            if (ri < nr) {
-                const uint32_t stop = rg.start[ri];
-                while (j < n && in.pos[j] != stop) j++;
-            } else {
-                j = n;
-            }
-            out.pos.insert(out.pos.end(), in.pos.begin() + i, in.pos.begin() + j);
-            out.base.insert(out.base.end(), in.base.begin() + i, in.base.begin() + j);
-            i = j;
-        }
-    }
-}
-
 namespace {
-// first index with pos >= p / first index with pos > p (consensus positions are non-decreasing)
-inline size_t lb(const Cns &c, uint32_t p) { return std::lower_bound(c.pos.begin(), c.pos.end(), p) - c.pos.begin(); }
-inline size_t ub(const Cns &c, uint32_t p) { return std::upper_bound(c.pos.begin(), c.pos.end(), p) - c.pos.begin(); }
-
 template <class F>
 void for_each_choice(const std::vector<uint32_t> &lens, F f) {  // itertools::multi_cartesian_product order
     std::vector<uint32_t> ch(lens.size(), 0);
@@ -679,59 +472,95 @@ void for_each_choice(const std::vector<uint32_t> &lens, F f) {  // itertools::mu
         if (d == (size_t)-1) break;
     }
 }
+// the `need` bases that precede region q in the current (patched) consensus, in forward order
+void take_left(const Patched &pc, size_t q, size_t need, std::vector<uint8_t> &out) {
+    std::vector<uint8_t> rev;
+    uint64_t i = pc.a[q];  // exclusive end of the DP stretch before the region
+    size_t rq = q;
+    while (rev.size() < need) {
+        const uint64_t lo = rq > 0 ? pc.b[rq - 1] : 0;
+        while (i > lo && rev.size() < need) rev.push_back(pc.cbase[--i]);
+        if (rev.size() >= need || rq == 0) break;
+        rq--;
+        const Allele &al = pc.seed[rq];
+        for (uint32_t x = al.len; x-- > 0 && rev.size() < need;) rev.push_back(al.s[x]);
+        i = pc.a[rq];
+    }
+    out.insert(out.end(), rev.rbegin(), rev.rend());
+}
+void take_right(const Patched &pc, size_t q, size_t need, std::vector<uint8_t> &out) {
+    size_t got = 0;
+    uint64_t i = pc.b[q];
+    size_t rq = q;
+    const size_t nr = pc.a.size();
+    while (got < need) {
+        const uint64_t hi = rq + 1 < nr ? pc.a[rq + 1] : pc.N;
+        while (i < hi && got < need) {
+            out.push_back(pc.cbase[i++]);
+            got++;
+        }
+        if (got >= need || rq + 1 >= nr) break;
+        rq++;
+        const Allele &al = pc.seed[rq];
+        for (uint32_t x = 0; x < al.len && got < need; x++) {
+            out.push_back(al.s[x]);
+            got++;
+        }
+        i = pc.b[rq];
+    }
+}
 }  // namespace
 
-void reupdate_build(const Regions &rg, const CandSet &cs, const std::vector<RegionState> &rs, const Cns &cns, uint32_t k,
-                    Reupdate &ru) {
+void reupdate_build(const Patched &pc, uint32_t k, Reupdate &ru) {
     ru = Reupdate();
-    for (size_t i = rs.size(); i-- > 0;)
-        if (rs[i].lable & LABLE_RECH) ru.rech.push_back((uint32_t)i);
+    for (size_t q = 0; q < pc.lable.size(); q++)
+        if (pc.lable[q] & LABLE_RECH) ru.rech.push_back((uint32_t)q);
     ru.off.push_back(0);
-    const size_t N = cns.pos.size();
-    auto put_cns = [&](size_t a, size_t b) {
-        if (a < b) ru.pool.insert(ru.pool.end(), cns.base.begin() + a, cns.base.begin() + b);
-    };
-    auto put_cand = [&](uint32_t c) {
-        ru.pool.insert(ru.pool.end(), cs.pool + cs.seq_off[c], cs.pool + cs.seq_off[c] + cs.seq_len[c]);
-    };
+    auto put = [&](const Allele &al) { ru.pool.insert(ru.pool.end(), al.s, al.s + al.len); };
+    std::vector<uint8_t> left, right;
     size_t sj = 0;
     while (sj < ru.rech.size()) {
         size_t ej = sj + 1;  // chain regions closer than k, at most 6 per group (main.rs:1197-1206)
-        while (ej < ru.rech.size() && rg.start[ru.rech[ej]] < rg.end[ru.rech[ej - 1]] + k) {
+        while (ej < ru.rech.size() && pc.start[ru.rech[ej]] < pc.end[ru.rech[ej - 1]] + k) {
             ej++;
             if (ej > sj + 5) break;
         }
-        // flanks: k-1 consensus bases on either side (iter_consensus_extend main.rs:1100-1139)
-        const size_t li = lb(cns, rg.start[ru.rech[sj]]);
-        const size_t l0 = li > k - 1 ? li - (k - 1) : 0;
-        const size_t rl = ub(cns, rg.end[ru.rech[ej - 1]]);  // index after the last base with pos <= end
-        if (li >= N || rl == 0 || rl >= N + 1) herr(NP2_ERR_FORMAT, "consensus index out of range in reupdate");
-        const size_t r1 = std::min(N, rl + (k - 1));
+        // flanks: k-1 bases of the current consensus on either side (iter_consensus_extend main.rs:1100-1139)
+        left.clear();
+        right.clear();
+        take_left(pc, ru.rech[sj], k - 1, left);
+        take_right(pc, ru.rech[ej - 1], k - 1, right);
         Reupdate::Group g{(uint32_t)sj, (uint32_t)ej, ru.off.size() - 1};
         if (ej == sj + 1) {
-            for (uint32_t c : rs[ru.rech[sj]].cand) {
-                put_cns(l0, li);
-                put_cand(c);
-                put_cns(rl, r1);
+            for (const Allele &al : pc.cand[ru.rech[sj]]) {
+                ru.pool.insert(ru.pool.end(), left.begin(), left.end());
+                put(al);
+                ru.pool.insert(ru.pool.end(), right.begin(), right.end());
                 ru.off.push_back(ru.pool.size());
             }
         } else {
             std::vector<uint32_t> lens;
-            for (size_t x = sj; x < ej; x++) lens.push_back((uint32_t)rs[ru.rech[x]].cand.size());
-            // consensus between consecutive regions of the chain (iter_consensus_region main.rs:1068-1097)
-            std::vector<std::pair<size_t, size_t>> mid;
-            for (size_t x = sj; x + 1 < ej; x++) {
-                const uint32_t s = rg.end[ru.rech[x]], e = rg.start[ru.rech[x + 1]];
-                if (s + 1 == e) mid.emplace_back(0, 0);
-                else mid.emplace_back(ub(cns, s), lb(cns, e));
-            }
+            for (size_t x = sj; x < ej; x++) lens.push_back((uint32_t)pc.cand[ru.rech[x]].size());
             for_each_choice(lens, [&](const std::vector<uint32_t> &ch) {
-                put_cns(l0, li);
+                ru.pool.insert(ru.pool.end(), left.begin(), left.end());
                 for (size_t x = 0; x < ch.size(); x++) {
-                    put_cand(rs[ru.rech[sj + x]].cand[ch[x]]);
-                    if (x + 1 < ch.size()) put_cns(mid[x].first, mid[x].second);
+                    const uint32_t q = ru.rech[sj + x];
+                    put(pc.cand[q][ch[x]]);
+                    if (x + 1 < ch.size()) {
+                        // consensus strictly between the two regions (iter_consensus_region main.rs:1068-1097):
+                        // the DP stretch between their index ranges, plus any non-RECH regions' alleles inside it
+                        const uint32_t qn = ru.rech[sj + x + 1];
+                        uint64_t i = pc.b[q];
+                        for (uint32_t m = q + 1; m <= qn; m++) {
+                            ru.pool.insert(ru.pool.end(), pc.cbase + i, pc.cbase + pc.a[m]);
+                            if (m < qn) {
+                                ru.pool.insert(ru.pool.end(), pc.seed[m].s, pc.seed[m].s + pc.seed[m].len);
+                                i = pc.b[m];
+                            }
+                        }
+                    }
                 }
-                put_cns(rl, r1);
+                ru.pool.insert(ru.pool.end(), right.begin(), right.end());
                 ru.off.push_back(ru.pool.size());
                 if (ru.pool.size() > (1ull << 32)) herr(NP2_ERR_UNSUPPORTED, "cartesian re-check group too large");
             });
@@ -741,53 +570,74 @@ void reupdate_build(const Regions &rg, const CandSet &cs, const std::vector<Regi
     }
 }
 
-void reupdate_apply(const Regions &rg, CandSet &cs, std::vector<RegionState> &rs, const Reupdate &ru,
-                    const uint16_t *ks, uint32_t iter_count, const Cns &in, Cns &out) {
+void reupdate_apply(Patched &pc, const Reupdate &ru, const uint16_t *ks, uint32_t iter_count) {
     for (auto &g : ru.groups) {
         uint64_t si = g.first_string;
         if (g.ej == g.sj + 1) {
-            for (uint32_t c : rs[ru.rech[g.sj]].cand) cs.kscore[c] = ks[si++];
+            for (Allele &al : pc.cand[ru.rech[g.sj]]) al.kscore = ks[si++];
         } else {
             std::vector<uint32_t> lens;
-            for (size_t x = g.sj; x < g.ej; x++) lens.push_back((uint32_t)rs[ru.rech[x]].cand.size());
+            for (size_t x = g.sj; x < g.ej; x++) lens.push_back((uint32_t)pc.cand[ru.rech[x]].size());
             for (size_t x = g.sj; x < g.ej; x++)
-                for (uint32_t c : rs[ru.rech[x]].cand) cs.kscore[c] = 0;
+                for (Allele &al : pc.cand[ru.rech[x]]) al.kscore = 0;
             // later combinations overwrite earlier ones (main.rs:1351-1366)
             for_each_choice(lens, [&](const std::vector<uint32_t> &ch) {
                 const uint16_t s = ks[si++];
                 if (s > 0)
-                    for (size_t x = 0; x < ch.size(); x++) cs.kscore[rs[ru.rech[g.sj + x]].cand[ch[x]]] = s;
+                    for (size_t x = 0; x < ch.size(); x++) pc.cand[ru.rech[g.sj + x]][ch[x]].kscore = s;
             });
         }
     }
-    // choose the allele (main.rs:1371-1406)
-    for (auto &r : rs) {
-        if (!(r.lable & LABLE_RECH)) continue;
+    // choose the allele (main.rs:1371-1406), then the lable bookkeeping (main.rs:1411-1417)
+    for (uint32_t q : ru.rech) {
+        auto &cd = pc.cand[q];
         size_t c = 0, valid = 0;
-        for (size_t p = 0; p < r.cand.size(); p++)
-            if (cs.kscore[r.cand[p]] != 0) {
-                if (c == 0 || cs.order[r.cand[p]] == 0) c = p + 1;
+        for (size_t p = 0; p < cd.size(); p++)
+            if (cd[p].kscore != 0) {
+                if (c == 0 || cd[p].order == 0) c = p + 1;
                 valid++;
             }
-        if (valid > 1) r.lable |= LABLE_TEMP;
-        auto str = [&](uint32_t x) { return std::string((const char *)cs.pool + cs.seq_off[x], cs.seq_len[x]); };
         if (c != 0) {
-            r.sudoseed = str(r.cand[c - 1]);
+            pc.seed[q] = cd[c - 1];
         } else if (iter_count == 1) {
             size_t i = 0;
-            for (size_t p = 0; p < r.cand.size(); p++)
-                if (cs.order[r.cand[p]] == 0) {
+            for (size_t p = 0; p < cd.size(); p++)
+                if (cd[p].order == 0) {
                     i = p;
                     break;
                 }
-            r.sudoseed = str(r.cand[i]);
+            pc.seed[q] = cd[i];
         }
+        if (valid <= 1) pc.lable[q] ^= LABLE_RECH;
     }
-    splice(rg, rs, LABLE_RECH, in, out);
-    for (auto &r : rs) {  // main.rs:1411-1417
-        if (!(r.lable & LABLE_RECH)) continue;
-        if (r.lable & LABLE_TEMP) r.lable ^= LABLE_TEMP;
-        else r.lable ^= LABLE_RECH;
+}
+
+void assemble(const Patched &pc, std::vector<uint8_t> &base, std::vector<uint32_t> *pos, uint32_t *first_pos,
+              uint32_t *last_pos) {
+    const size_t nr = pc.a.size();
+    uint64_t total = pc.N;
+    for (size_t q = 0; q < nr; q++) total = total - (pc.b[q] - pc.a[q]) + pc.seed[q].len;
+    base.resize(total);
+    if (pos) pos->resize(total);
+    uint64_t w = 0, i = 0;
+    for (size_t q = 0; q <= nr; q++) {
+        const uint64_t hi = q < nr ? pc.a[q] : pc.N;
+        if (hi > i) {
+            memcpy(base.data() + w, pc.cbase + i, hi - i);
+            if (pos) memcpy(pos->data() + w, pc.cpos + i, (hi - i) * 4);
+            w += hi - i;
+        }
+        if (q == nr) break;
+        memcpy(base.data() + w, pc.seed[q].s, pc.seed[q].len);
+        if (pos) std::fill(pos->begin() + w, pos->begin() + w + pc.seed[q].len, pc.start[q]);
+        w += pc.seed[q].len;
+        i = pc.b[q];
+    }
+    if (total) {
+        // first / last ConsensusBase.pos for the FASTA header (main.rs:627-632)
+        *first_pos = (nr && pc.a[0] == 0 && pc.seed[0].len) ? pc.start[0] : pc.cpos[0];
+        bool tail_is_region = nr && pc.b[nr - 1] == pc.N;
+        *last_pos = (tail_is_region && pc.seed[nr - 1].len) ? pc.start[nr - 1] : pc.cpos[pc.N - 1];
     }
 }
 

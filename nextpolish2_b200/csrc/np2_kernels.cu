@@ -6,7 +6,7 @@
 //   K2  cover_diff / pileup_count / pileup_emit    update_msas + Msa::push/sort/coverage (main.rs:576-589, 193-241)
 //       mark_heads / groups_* / pos_finalize
 //   K3  dp_runs / emit_*                           get_cns_from_align_tags + backtrack (main.rs:1645-1687, 1572-1634)
-//   K4  cand_scan                                  generate_lqseqs_from_tags_kmer (main.rs:1462-1521)
+//   (K4/K6 and the genotype kernels live in np2_geno.cu)
 //
 // All of this is integer / byte work bound by HBM traffic and latency; there is no tensor-core term.
 #include <cub/block/block_reduce.cuh>
@@ -851,60 +851,6 @@ void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o,
     if (n_runs)
         k_emit_runs<true><<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, const_cast<uint32_t *>(d_n_emit),
                                                           d_emit_off, d_pos, d_base, d_flags);
-}
-
-/* =============================================================== K4: candidate alleles */
-
-// One thread per (read, LQ region) pair: the read's bases over [start, end] and its first-k canonical k-mer from
-// `start` on (main.rs:1478-1521).  The read is only decoded up to the first column whose t_pos exceeds
-// pair_limit (main.rs:1465-1471).
-template <bool WRITE>
-__global__ void k_cand_scan(ReadsDev R, CandDev c, uint32_t k) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n_pairs) return;
-    const uint32_t r = c.pair_read[i], start = c.pair_start[i], end = c.pair_end[i], limit = c.pair_limit[i];
-    const uint32_t n = R.n[r];
-    const uint8_t *nib = R.nib + R.nib_off[r];
-    const uint32_t *ck = R.ck_tpos + R.ck_off[r];
-    uint32_t lo = 0, hi = (n + 31) >> 5;  // last 32-column block whose first t_pos is < start (or block 0)
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (ck[mid] < start) lo = mid;
-        else hi = mid;
-    }
-    uint32_t tpos = ck[lo];
-    const uint64_t mask = (1ULL << (2 * k)) - 1;
-    const uint32_t sh = 2 * (k - 1);
-    uint64_t k0 = 0, k1 = 0;
-    uint32_t l = 0, len = 0;
-    uint8_t *out = WRITE ? c.seq + c.seq_off[i] : nullptr;
-    for (uint32_t o = lo * 32; o < n; o++) {
-        const uint32_t v = nib_at(nib, o);
-        if (o != lo * 32 && !(v & 8)) tpos++;
-        const uint32_t q = v & 7;
-        if (tpos >= start && q != 4) {
-            if (tpos <= end) {
-                if (WRITE) out[len] = code_char(q);
-                len++;
-            }
-            if (l < k) {
-                k0 = (k0 << 2 | (uint64_t)q) & mask;
-                k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
-                l++;
-            }
-            if (tpos > end && l >= k) break;
-        }
-        if (tpos > limit) break;
-    }
-    if (!WRITE) {
-        c.len[i] = len;
-        c.kmer[i] = l >= k ? yak_hash64(k0 < k1 ? k0 : k1, mask) : 0xFFFFFFFFFFFFFFFFULL;
-    }
-}
-void cand_scan(const ReadsDev &r, CandDev c, uint32_t k, bool write, cudaStream_t s) {
-    if (!c.n_pairs) return;
-    if (write) k_cand_scan<true><<<cdiv(c.n_pairs, 128), 128, 0, s>>>(r, c, k);
-    else k_cand_scan<false><<<cdiv(c.n_pairs, 128), 128, 0, s>>>(r, c, k);
 }
 
 }  // namespace np2

@@ -91,18 +91,37 @@ void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpO
 void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, const uint32_t *d_n_emit,
                 const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s);
 
-/* ------------------------------------------------------------------ K4 candidates */
-struct CandDev {
-    uint32_t n_pairs = 0;
-    const uint32_t *pair_read = nullptr;   // index into ReadsDev
-    const uint32_t *pair_start = nullptr;  // region start / end (inclusive)
-    const uint32_t *pair_end = nullptr;
-    const uint32_t *pair_limit = nullptr;  // decode limit of the read: lqseqs[j].end + k
-    uint32_t *len = nullptr;
-    uint64_t *kmer = nullptr;              // hashed first-k canonical k-mer or UINT64_MAX
-    const uint64_t *seq_off = nullptr;     // exclusive scan of len (pass 2)
-    uint8_t *seq = nullptr;
+/* ------------------------------------------------------------------ per-region pipeline (np2_geno.cu) */
+constexpr int kMaxCand = 60;  // LQSEQ_MAX_CAN_COUNT main.rs:30
+struct GenoDev {
+    uint32_t nreg = 0, n_pairs = 0;
+    const uint32_t *start = nullptr, *end = nullptr;  // regions, descending position (reference order)
+    // per candidate read
+    uint32_t *rd_s = nullptr, *rd_j = nullptr, *rd_np = nullptr, *rd_poff = nullptr;
+    const uint32_t *rd_order = nullptr;  // alignseq index of the read
+    // per (read, region) pair
+    uint32_t *p_len = nullptr;
+    uint64_t *p_kmer = nullptr;
+    // per selected candidate: slot = region * kMaxCand + rank
+    uint32_t *c_src = nullptr, *c_len = nullptr, *c_order = nullptr;
+    uint64_t *c_kmer = nullptr, *c_off = nullptr;
+    uint16_t *c_kscore = nullptr;
+    uint8_t *c_rep = nullptr;
+    uint8_t *pool = nullptr;
+    // per region
+    uint32_t *r_ncand = nullptr, *r_bytes = nullptr, *r_nedge = nullptr, *r_seed_len = nullptr, *r_nsurv = nullptr;
+    uint64_t *r_pool_off = nullptr, *r_edge_off = nullptr, *r_seed_off = nullptr;
+    uint8_t *r_lable = nullptr, *r_surv = nullptr;
 };
-void cand_scan(const ReadsDev &r, CandDev c, uint32_t k, bool write, cudaStream_t s);
+void geno_read_cursor(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, cudaStream_t s);
+void geno_read_ranges(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, uint32_t k, cudaStream_t s);
+void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, cudaStream_t s);
+void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
+                        uint32_t k, uint32_t max_span, cudaStream_t s);
+void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s);
+void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s);
+void geno_region_hete(GenoDev g, cudaStream_t s);
+void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, cudaStream_t s);
+void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s);
 
 }  // namespace np2
