@@ -217,8 +217,12 @@ struct np2_job {
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
     // result: bases always; positions are materialised on request (np2_job_get_consensus with pos != NULL)
-    std::vector<uint8_t> res_base;
+    PBuf<uint8_t> res_base;
     std::vector<uint32_t> res_pos;
+    DBuf<uint32_t> jd_cpos;                  // DP consensus of the last iteration stays on the device
+    DBuf<uint8_t> jd_cbase, jd_cflags;
+    uint32_t res_N = 0;
+    std::vector<uint8_t> h_seeds, h_rech_pool;
     uint32_t res_first = 0, res_last = 0;
     bool res_pos_valid = false;
     Patched res_patch;                       // kept so that positions can be produced lazily
@@ -556,13 +560,15 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     uint32_t N = 0;
     NP2_CUDA(cudaMemcpyAsync(&N, d_emit_off.p + L, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
-    DBuf<uint32_t> d_cpos, d_events, d_nev;
-    DBuf<uint8_t> d_cbase, d_cflags;
-    d_cpos.alloc(N, s);
-    d_cbase.alloc(N, s);
-    d_cflags.alloc(N, s);
-    d_events.alloc(N, s);
+    DBuf<uint32_t> &d_cpos = jd_cpos;
+    DBuf<uint8_t> &d_cbase = jd_cbase, &d_cflags = jd_cflags;
+    DBuf<uint32_t> d_events, d_nev;
+    d_cpos.alloc(std::max(N, 1u), s);
+    d_cbase.alloc(std::max(N, 1u), s);
+    d_cflags.alloc(std::max(N, 1u), s);
+    d_events.alloc(std::max(N, 1u), s);
     d_nev.alloc(1, s);
+    res_N = N;
     h = timer.begin("consensus_emit", 0);
     emit_write(m, d_run_start.p, n_runs, dpo, d_n_emit.p, d_emit_off.p, d_cpos.p, d_cbase.p, d_cflags.p, s);
     {
@@ -574,30 +580,104 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     }
     timer.end(h);
     launches(12);
-    timer.hbegin();
-    p_cpos.resize(std::max(N, 1u));
-    p_cbase.resize(std::max(N, 1u));
-    p_cflags.resize(std::max(N, 1u));
     uint32_t n_ev = 0;
     long long total = 0;
-    d_cpos.download(p_cpos.p, N);
-    d_cbase.download(p_cbase.p, N);
-    d_cflags.download(p_cflags.p, N);
     NP2_CUDA(cudaMemcpyAsync(&n_ev, d_nev.p, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
-    d2h += (uint64_t)N * 6;
     if (total < 0)
         throw np2::Error(NP2_ERR_UNSUPPORTED,
                          "best path has a negative total score (main.rs:1680 picks the default 3-mer): not supported");
-    std::vector<uint32_t> events(n_ev);
+
+    /* ---------------- LQ regions on the device (np2_regions.cu) */
+    RegionDev rd;
+    rd.N = N;
+    rd.n_ev = n_ev;
+    rd.events = d_events.p;
+    rd.cflags = d_cflags.p;
+    rd.cbase = d_cbase.p;
+    rd.cpos = d_cpos.p;
+    DBuf<uint32_t> d_ev_close, d_c_t, d_c_start, d_c_end, d_c_a, d_c_b, d_c_head, d_c_hrank, d_ncand;
+    DBuf<uint8_t> d_ev_boundary, d_ev_closes;
+    DBuf<uint32_t> d_rstart, d_rend, d_ra, d_rb;
+    d_ev_close.alloc(std::max(n_ev, 1u), s);
+    d_ev_boundary.alloc(std::max(n_ev, 1u), s);
+    d_ev_closes.alloc(std::max(n_ev, 1u), s);
+    d_c_t.alloc(std::max(n_ev, 1u), s);
+    d_ncand.alloc(1, s);
+    rd.ev_close = d_ev_close.p;
+    rd.ev_boundary = d_ev_boundary.p;
+    rd.ev_closes = d_ev_closes.p;
+    rd.c_t = d_c_t.p;
+    uint32_t n_cand = 0, nreg = 0;
     if (n_ev) {
-        d_events.download(events.data(), n_ev);
+        h = timer.begin("regions", 2);
+        regions_event_close(rd, s);
+        {
+            size_t tb = 0;
+            cub::CountingInputIterator<uint32_t> it(0);
+            cub::DeviceSelect::Flagged(nullptr, tb, it, d_ev_closes.p, d_c_t.p, d_ncand.p, (int)n_ev, s);
+            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+            cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_ev_closes.p, d_c_t.p, d_ncand.p, (int)n_ev, s);
+        }
+        timer.end(h);
+        NP2_CUDA(cudaMemcpyAsync(&n_cand, d_ncand.p, 4, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaStreamSynchronize(s));
+        launches(1);
     }
-    const uint32_t *cpos = p_cpos.p;
-    const uint8_t *cbase = p_cbase.p, *cflags = p_cflags.p;
-    timer.hend("host:d2h_consensus");
+    if (n_cand) {
+        d_c_start.alloc(n_cand, s);
+        d_c_end.alloc(n_cand, s);
+        d_c_a.alloc(n_cand, s);
+        d_c_b.alloc(n_cand, s);
+        d_c_head.alloc(n_cand + 1, s);
+        d_c_hrank.alloc(n_cand + 1, s);
+        rd.c_start = d_c_start.p;
+        rd.c_end = d_c_end.p;
+        rd.c_a = d_c_a.p;
+        rd.c_b = d_c_b.p;
+        rd.c_head = d_c_head.p;
+        rd.c_hrank = d_c_hrank.p;
+        h = timer.begin("regions", 3);
+        regions_make(rd, n_cand, s);
+        NP2_CUDA(cudaMemsetAsync(d_c_head.p + n_cand, 0, 4, s));
+        {
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, d_c_head.p, d_c_hrank.p, (int)n_cand + 1, s);
+            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+            cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_c_head.p, d_c_hrank.p, (int)n_cand + 1, s);
+        }
+        timer.end(h);
+        NP2_CUDA(cudaMemcpyAsync(&nreg, d_c_hrank.p + n_cand, 4, cudaMemcpyDeviceToHost, s));
+        NP2_CUDA(cudaStreamSynchronize(s));
+        d_rstart.alloc(nreg, s);
+        d_rend.alloc(nreg, s);
+        d_ra.alloc(nreg, s);
+        d_rb.alloc(nreg, s);
+        rd.r_start = d_rstart.p;
+        rd.r_end = d_rend.p;
+        rd.r_a = d_ra.p;
+        rd.r_b = d_rb.p;
+        h = timer.begin("regions", 1);
+        regions_out(rd, n_cand, nreg, s);
+        timer.end(h);
+        launches(3);
+    }
+    Regions rg;  // host copy only when needed (dump, final iteration)
+    auto fetch_regions = [&]() {
+        rg.start.resize(nreg);
+        rg.end.resize(nreg);
+        rg.a.resize(nreg);
+        rg.b.resize(nreg);
+        if (nreg) {
+            d_rstart.download(rg.start.data(), nreg);
+            d_rend.download(rg.end.data(), nreg);
+            d_ra.download(rg.a.data(), nreg);
+            d_rb.download(rg.b.data(), nreg);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            d2h += (uint64_t)nreg * 16;
+        }
+    };
 
     if (dump) {
         // Msa in the reference's order: reference 3-mer first (p >= 2), then the sorted sparse ones
@@ -612,6 +692,12 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         d_dense_cnt.download(dc.data(), L);
         d_dense_besti.download(db.data(), L);
         d_code.download(code.data(), L);
+        dm_dp_pos.resize(N);
+        dm_dp_base.resize(N);
+        dm_dp_flags.resize(N);
+        d_cpos.download(dm_dp_pos.data(), N);
+        d_cbase.download(dm_dp_base.data(), N);
+        d_cflags.download(dm_dp_flags.data(), N);
         NP2_CUDA(cudaStreamSynchronize(s));
         dm_msa_off.assign(1, 0);
         for (uint32_t p = 0; p < L; p++) {
@@ -629,31 +715,27 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             }
             dm_msa_off.push_back(dm_msa_bases.size());
         }
-        dm_dp_pos.assign(cpos, cpos + N);
-        dm_dp_base.assign(cbase, cbase + N);
-        dm_dp_flags.assign(cflags, cflags + N);
-    }
-
-    /* ---------------- LQ regions (host, sparse events) */
-    timer.hbegin();
-    Regions rg;
-    find_regions(cpos, cbase, cflags, N, events.data(), n_ev, rg);
-    const uint32_t nreg = (uint32_t)rg.start.size();
-    timer.hend("host:find_regions");
-    if (dump) {
+        fetch_regions();
         dm_reg_start = rg.start;
         dm_reg_end = rg.end;
     }
-    auto finish_plain = [&]() {  // main.rs:1638-1640: no LQ region, the DP consensus is the answer
-        res_patch = Patched();
-        res_base.assign(cbase, cbase + N);
-        res_pos.assign(cpos, cpos + N);
-        res_pos_valid = true;
-        res_first = N ? cpos[0] : 0;
-        res_last = N ? cpos[N - 1] : 0;
-    };
-    if (nreg == 0) {
-        if (final_iter) finish_plain();
+    uint32_t edge_pos[2] = {0, 0};  // ConsensusBase.pos of the first / last DP base (FASTA header)
+    if (final_iter && N) {
+        NP2_CUDA(cudaMemcpyAsync(&edge_pos[0], d_cpos.p, 4, cudaMemcpyDeviceToHost, s));
+        NP2_CUDA(cudaMemcpyAsync(&edge_pos[1], d_cpos.p + (N - 1), 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (nreg == 0) {  // main.rs:1638-1640: no LQ region, the DP consensus is the answer
+        if (final_iter) {
+            res_patch = Patched();
+            res_base.resize(std::max(N, 1u));
+            res_base.n = N;
+            d_cbase.download(res_base.p, N);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            d2h += N;
+            res_first = edge_pos[0];
+            res_last = edge_pos[1];
+            res_pos_valid = false;
+        }
         return;
     }
 
@@ -663,16 +745,11 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     if (k0 >= 32) throw np2::Error(NP2_ERR_UNSUPPORTED, "the smallest yak table must have k < 32 (main.rs:1432-1434)");
     GenoDev g;
     g.nreg = nreg;
-    DBuf<uint32_t> d_rstart, d_rend, d_rd_s, d_rd_j, d_rd_np, d_rd_poff;
-    d_rstart.alloc(nreg, s);
-    d_rend.alloc(nreg, s);
+    DBuf<uint32_t> d_rd_s, d_rd_j, d_rd_np, d_rd_poff;
     d_rd_s.alloc(n_reads + 1, s);
     d_rd_j.alloc(n_reads + 1, s);
     d_rd_np.alloc(n_reads + 1, s);
     d_rd_poff.alloc(n_reads + 1, s);
-    d_rstart.upload(rg.start.data(), nreg);
-    d_rend.upload(rg.end.data(), nreg);
-    h2d += (uint64_t)nreg * 8;
     g.start = d_rstart.p;
     g.end = d_rend.p;
     g.rd_s = d_rd_s.p;
@@ -889,28 +966,99 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     geno_region_seed(g, opt.max_indel_len, d_err.p, s);
     timer.end(h);
     launches(1);
+    /* ---- what the host needs for the re-check: regions, every region's seed string, the survivors of the regions
+     *      that stay RECH, and the DP bases (flanks).  Everything else stays on the device. */
+    AssembleDev ad;
+    ad.nreg = nreg;
+    ad.N = N;
+    ad.cbase = d_cbase.p;
+    ad.pool = d_gpool.p;
+    ad.r_a = d_ra.p;
+    ad.r_b = d_rb.p;
+    ad.r_seed_len = d_r_seed_len.p;
+    ad.r_seed_off = d_r_seed_off.p;
+    DBuf<long long> d_q_delta, d_q_shift;
+    DBuf<uint32_t> d_q_seedlen, d_rech_bytes, d_ent_off;
+    DBuf<uint64_t> d_q_seedoff, d_rech_boff;
+    d_q_delta.alloc(nreg + 1, s);
+    d_q_shift.alloc(nreg + 1, s);
+    d_q_seedlen.alloc(nreg + 1, s);
+    d_q_seedoff.alloc(nreg + 1, s);
+    d_rech_bytes.alloc(nreg + 1, s);
+    d_rech_boff.alloc(nreg + 1, s);
+    d_ent_off.alloc(nreg + 1, s);
+    ad.q_delta = d_q_delta.p;
+    ad.q_shift = d_q_shift.p;
+    ad.q_seedlen = d_q_seedlen.p;
+    ad.q_seedoff = d_q_seedoff.p;
+    auto scan = [&](auto *in, auto *out, int n) {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s);
+        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, in, out, n, s);
+    };
+    h = timer.begin("seed_gather", 4);
+    assemble_sizes(ad, s);
+    NP2_CUDA(cudaMemsetAsync(d_q_seedlen.p + nreg, 0, 4, s));
+    scan(d_q_seedlen.p, d_q_seedoff.p, (int)nreg + 1);
+    rech_sizes(g, d_rech_bytes.p, s);
+    NP2_CUDA(cudaMemsetAsync(d_rech_bytes.p + nreg, 0, 4, s));
+    scan(d_rech_bytes.p, d_rech_boff.p, (int)nreg + 1);
+    scan(d_r_nsurv.p, d_ent_off.p, (int)nreg);  // last entry handled below
+    timer.end(h);
     timer.hbegin();
-    std::vector<uint8_t> lab(nreg), surv;
-    std::vector<uint32_t> seed_len(nreg), nsurv(nreg);
-    std::vector<uint64_t> seed_off(nreg);
+    std::vector<uint8_t> lab(nreg);
+    std::vector<uint32_t> seed_len(nreg), nsurv(nreg), ent_off(nreg);
+    std::vector<uint64_t> seed_off(nreg), q_seedoff(nreg + 1);
+    uint64_t rech_bytes = 0;
     int gerr = 0;
     d_err.download(&gerr, 1);
     d_r_lable.download(lab.data(), nreg);
     d_r_seed_len.download(seed_len.data(), nreg);
     d_r_seed_off.download(seed_off.data(), nreg);
     d_r_nsurv.download(nsurv.data(), nreg);
-    res_pool.resize(pool_bytes + 16);
-    d_gpool.download(res_pool.data(), pool_bytes);
-    NP2_CUDA(cudaStreamSynchronize(s));
-    d2h += pool_bytes + (uint64_t)nreg * 17;
+    d_ent_off.download(ent_off.data(), nreg);
+    d_q_seedoff.download(q_seedoff.data(), nreg + 1);
+    NP2_CUDA(cudaMemcpyAsync(&rech_bytes, d_rech_boff.p + nreg, 8, cudaMemcpyDeviceToHost, s));
+    fetch_regions();  // synchronises
     if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
     if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
     if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
+    const uint32_t n_ent = nreg ? ent_off[nreg - 1] + nsurv[nreg - 1] : 0;
+    const uint64_t seeds_bytes = q_seedoff[nreg];
+    DBuf<uint8_t> d_seeds, d_rech_pool;
+    DBuf<uint32_t> d_ent_order, d_ent_len;
+    DBuf<uint64_t> d_ent_poff;
+    d_seeds.alloc(seeds_bytes + 1, s);
+    d_rech_pool.alloc(rech_bytes + 1, s);
+    d_ent_order.alloc(std::max(n_ent, 1u), s);
+    d_ent_len.alloc(std::max(n_ent, 1u), s);
+    d_ent_poff.alloc(std::max(n_ent, 1u), s);
+    h = timer.begin("seed_gather", 2);
+    assemble_seed_gather(ad, d_seeds.p, s);
+    rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
+    timer.end(h);
+    launches(6);
+    h_seeds.resize(seeds_bytes + 1);
+    h_rech_pool.resize(rech_bytes + 1);
+    std::vector<uint32_t> ent_order(n_ent), ent_len(n_ent);
+    std::vector<uint64_t> ent_poff(n_ent);
+    p_cbase.resize(std::max(N, 1u));
+    d_seeds.download(h_seeds.data(), seeds_bytes);
+    d_rech_pool.download(h_rech_pool.data(), rech_bytes);
+    if (n_ent) {
+        d_ent_order.download(ent_order.data(), n_ent);
+        d_ent_len.download(ent_len.data(), n_ent);
+        d_ent_poff.download(ent_poff.data(), n_ent);
+    }
+    d_cbase.download(p_cbase.p, N);
+    NP2_CUDA(cudaStreamSynchronize(s));
+    d2h += (uint64_t)N + seeds_bytes + rech_bytes + (uint64_t)nreg * 33 + (uint64_t)n_ent * 16;
     // patched view, regions in ascending position (q = nreg - 1 - r)
     Patched &pc = res_patch;
     pc = Patched();
-    pc.cbase = cbase;
-    pc.cpos = cpos;
+    pc.cbase = p_cbase.p;
+    pc.cpos = nullptr;
     pc.N = N;
     pc.start.resize(nreg);
     pc.end.resize(nreg);
@@ -919,40 +1067,31 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     pc.lable.resize(nreg);
     pc.seed.resize(nreg);
     pc.cand.resize(nreg);
-    std::vector<uint32_t> rech_regions;
-    for (uint32_t r = 0; r < nreg; r++) {
-        const uint32_t q = nreg - 1 - r;
-        pc.start[q] = rg.start[r];
-        pc.end[q] = rg.end[r];
-        pc.a[q] = rg.a[r];
-        pc.b[q] = rg.b[r];
-        pc.lable[q] = lab[r];
-        pc.seed[q].s = res_pool.data() + seed_off[r];
-        pc.seed[q].len = seed_len[r];
-        if (nsurv[r]) rech_regions.push_back(r);
-    }
-    if (!rech_regions.empty()) {  // survivors of the (few) regions that stay RECH: slot-level detail on demand
-        for (uint32_t r : rech_regions) {
-            const uint64_t base = (uint64_t)r * kMaxCand;
-            uint8_t sv[kMaxCand];
-            uint32_t cl[kMaxCand], co[kMaxCand];
-            uint64_t cf[kMaxCand];
-            NP2_CUDA(cudaMemcpyAsync(sv, d_r_surv.p + base, nsurv[r], cudaMemcpyDeviceToHost, s));
-            NP2_CUDA(cudaMemcpyAsync(cl, d_c_len.p + base, kMaxCand * 4, cudaMemcpyDeviceToHost, s));
-            NP2_CUDA(cudaMemcpyAsync(co, d_c_order.p + base, kMaxCand * 4, cudaMemcpyDeviceToHost, s));
-            NP2_CUDA(cudaMemcpyAsync(cf, d_c_off.p + base, kMaxCand * 8, cudaMemcpyDeviceToHost, s));
-            NP2_CUDA(cudaStreamSynchronize(s));
-            auto &cd = pc.cand[nreg - 1 - r];
-            for (uint32_t x = 0; x < nsurv[r]; x++) {
+    {
+        uint64_t rb = 0;
+        for (uint32_t r = 0; r < nreg; r++) {
+            const uint32_t q = nreg - 1 - r;
+            pc.start[q] = rg.start[r];
+            pc.end[q] = rg.end[r];
+            pc.a[q] = rg.a[r];
+            pc.b[q] = rg.b[r];
+            pc.lable[q] = lab[r];
+            pc.seed[q].s = h_seeds.data() + q_seedoff[q];
+            pc.seed[q].len = seed_len[r];
+            pc.seed[q].dev_off = seed_off[r];
+            for (uint32_t x = 0; x < nsurv[r]; x++) {  // rech pool is laid out in r order, survivors in rank order
                 Allele al;
-                al.s = res_pool.data() + cf[sv[x]];
-                al.len = cl[sv[x]];
-                al.order = co[sv[x]];
-                cd.push_back(al);
+                al.s = h_rech_pool.data() + rb;
+                al.len = ent_len[ent_off[r] + x];
+                al.order = ent_order[ent_off[r] + x];
+                al.dev_off = ent_poff[ent_off[r] + x];
+                rb += al.len;
+                pc.cand[q].push_back(al);
             }
         }
     }
     timer.hend("host:seed_download");
+    bool changed = false;
     for (size_t ti = 0; ti < tables.size(); ti++) {
         Reupdate ru;
         reupdate_build(pc, tables[ti]->dev.k, ru);
@@ -977,6 +1116,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             h2d += ru.pool.size() + (ns + 1) * 8;
             d2h += ns * 2;
             n_probes += ru.pool.size();
+            changed = true;
         }
         timer.hend("host:reupdate_score_sync");
         reupdate_apply(pc, ru, ks.data(), (uint32_t)ti + 1);
@@ -986,7 +1126,38 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         dm_reg_lable.resize(nreg);
         for (uint32_t r = 0; r < nreg; r++) dm_reg_lable[r] = pc.lable[nreg - 1 - r];
     }
-    assemble(pc, res_base, nullptr, &res_first, &res_last);
+    /* ---- final consensus assembled on the device from the (possibly re-chosen) seeds */
+    if (changed) {
+        for (uint32_t r = 0; r < nreg; r++) {
+            const Allele &al = pc.seed[nreg - 1 - r];
+            seed_off[r] = al.dev_off;
+            seed_len[r] = al.len;
+        }
+        d_r_seed_off.upload(seed_off.data(), nreg);
+        d_r_seed_len.upload(seed_len.data(), nreg);
+        h2d += (uint64_t)nreg * 12;
+    }
+    h = timer.begin("assemble", 3);
+    assemble_sizes(ad, s);
+    NP2_CUDA(cudaMemsetAsync(d_q_delta.p + nreg, 0, 8, s));
+    scan(d_q_delta.p, d_q_shift.p, (int)nreg + 1);
+    long long total_shift = 0;
+    NP2_CUDA(cudaMemcpyAsync(&total_shift, d_q_shift.p + nreg, 8, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    const uint64_t out_n = (uint64_t)((long long)N + total_shift);
+    DBuf<uint8_t> d_out;
+    d_out.alloc(out_n + 1, s);
+    assemble_final(ad, d_out.p, s);
+    timer.end(h);
+    launches(3);
+    res_base.resize(std::max<uint64_t>(out_n, 1));
+    res_base.n = out_n;
+    d_out.download(res_base.p, out_n);
+    NP2_CUDA(cudaStreamSynchronize(s));
+    d2h += out_n;
+    // FASTA header span (main.rs:627-632)
+    res_first = (pc.a[0] == 0) ? pc.start[0] : edge_pos[0];
+    res_last = (pc.b[nreg - 1] == N) ? pc.start[nreg - 1] : edge_pos[1];
     res_pos_valid = false;
     timer.hend("host:assemble");
 }
@@ -995,7 +1166,7 @@ void np2_job::run(int32_t dump_it) {
     dump_iter = dump_it;
     cudaStream_t s = ctx->stream;
     const uint32_t L = (uint32_t)tseq.size();
-    res_base.clear();
+    res_base.n = 0;
     res_pos.clear();
     res_pos_valid = false;
     res_patch = Patched();
@@ -1005,7 +1176,9 @@ void np2_job::run(int32_t dump_it) {
     n_probes = 0;
     dm_dropped.clear();
     if (L < opt.min_ctg_len) {  // main.rs:1727-1730
-        res_base.assign(tseq.begin(), tseq.end());
+        res_base.resize(std::max(L, 1u));
+        res_base.n = L;
+        memcpy(res_base.p, tseq.data(), L);
         res_pos.resize(L);
         for (uint32_t p = 0; p < L; p++) res_pos[p] = p;
         res_pos_valid = true;
@@ -1372,20 +1545,24 @@ int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const ui
 uint64_t np2_job_get_consensus(np2_job *j, const uint32_t **pos, const uint8_t **base) {
     if (pos) {  // ConsensusBase.pos is materialised on request; the FASTA record only needs first/last
         if (!j->res_pos_valid) {
-            std::vector<uint8_t> tmp;
-            uint32_t f, l;
-            assemble(j->res_patch, tmp, &j->res_pos, &f, &l);
+            cudaSetDevice(j->ctx->device);
+            j->p_cpos.resize(std::max(j->res_N, 1u));
+            cudaMemcpyAsync(j->p_cpos.p, j->jd_cpos.p, (size_t)j->res_N * 4, cudaMemcpyDeviceToHost, j->ctx->stream);
+            cudaStreamSynchronize(j->ctx->stream);
+            j->res_patch.cpos = j->p_cpos.p;
+            j->res_patch.N = j->res_N;
+            positions(j->res_patch, j->res_pos);
             j->res_pos_valid = true;
         }
         *pos = j->res_pos.data();
     }
-    if (base) *base = j->res_base.data();
-    return j->res_base.size();
+    if (base) *base = j->res_base.p;
+    return j->res_base.n;
 }
 uint64_t np2_job_get_span(np2_job *j, uint32_t *first_pos, uint32_t *last_pos) {
     *first_pos = j->res_first;
     *last_pos = j->res_last;
-    return j->res_base.size();
+    return j->res_base.n;
 }
 uint64_t np2_job_get_reads(np2_job *j, const int32_t **rec_idx, const uint32_t **t_s, const uint32_t **t_e,
                            const uint64_t **nib_off, const uint8_t **nib, const uint8_t **blank) {

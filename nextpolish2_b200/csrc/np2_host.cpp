@@ -111,69 +111,6 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
     if (off != bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
 }
 
-/* ================================================================= regions */
-
-void find_regions(const uint32_t *cpos, const uint8_t *cbase, const uint8_t *cflags, uint64_t n, const uint32_t *events,
-                  uint64_t n_events, Regions &out) {
-    out = Regions();
-    if (n == 0) return;
-    // reversed indexing: rp = n - 1 - i is the index the reference uses while backtracking (main.rs:1570-1626)
-    auto P = [&](uint64_t rp) { return cpos[n - 1 - rp]; };
-    auto B = [&](uint64_t rp) { return cbase[n - 1 - rp]; };
-    const uint64_t NONE = UINT64_MAX;
-    bool has_lq = false;
-    uint64_t lq_s = NONE, lq_e = 0;
-    std::vector<uint64_t> i_start, i_end;  // consensus index of one base carrying region.start / region.end
-    auto try_close = [&](uint64_t from, uint64_t to) {  // HQ bases rp in [from, to)
-        for (uint64_t rp = std::max(from, lq_e + 5); rp < to; rp++) {
-            if (P(rp - 1) != P(rp - 2) && B(rp - 1) != B(rp - 2)) {
-                lq_e = rp - 2;
-                lq_s = lq_s > 2 ? lq_s - 2 : 1;
-                while (lq_s > 1 && (P(lq_s - 1) == P(lq_s) || B(lq_s - 1) == B(lq_s))) lq_s--;
-                if (!out.start.empty() && P(lq_s) >= out.start.back()) {
-                    out.start.back() = P(lq_e);
-                    i_start.back() = n - 1 - lq_e;
-                } else {
-                    out.end.push_back(P(lq_s));
-                    out.start.push_back(P(lq_e));
-                    i_end.push_back(n - 1 - lq_s);
-                    i_start.push_back(n - 1 - lq_e);
-                }
-                has_lq = false;
-                lq_s = NONE;
-                return;
-            }
-        }
-    };
-    uint64_t next_rp = 0;
-    for (uint64_t e = n_events; e-- > 0;) {
-        const uint64_t rp = n - 1 - events[e];
-        if (has_lq) try_close(next_rp, rp);
-        const uint8_t f = cflags[events[e]];
-        if (f & 2) {
-            has_lq = false;
-            lq_s = NONE;
-        } else if (f & 1) {
-            if (lq_s == NONE) lq_s = rp;
-            lq_e = rp;
-            has_lq = true;
-        }
-        next_rp = rp + 1;
-    }
-    if (has_lq) try_close(next_rp, n);
-    // index ranges: positions are non-decreasing, insertions share their anchor's position
-    const size_t nr = out.start.size();
-    out.a.resize(nr);
-    out.b.resize(nr);
-    for (size_t r = 0; r < nr; r++) {
-        uint64_t a = i_start[r], b = i_end[r] + 1;
-        while (a > 0 && cpos[a - 1] == out.start[r]) a--;
-        while (b < n && cpos[b] <= out.end[r]) b++;
-        out.a[r] = (uint32_t)a;
-        out.b[r] = (uint32_t)b;
-    }
-}
-
 /* ================================================================= phasing: graph + Louvain */
 
 namespace {
@@ -612,32 +549,22 @@ void reupdate_apply(Patched &pc, const Reupdate &ru, const uint16_t *ks, uint32_
     }
 }
 
-void assemble(const Patched &pc, std::vector<uint8_t> &base, std::vector<uint32_t> *pos, uint32_t *first_pos,
-              uint32_t *last_pos) {
+void positions(const Patched &pc, std::vector<uint32_t> &pos) {
     const size_t nr = pc.a.size();
     uint64_t total = pc.N;
     for (size_t q = 0; q < nr; q++) total = total - (pc.b[q] - pc.a[q]) + pc.seed[q].len;
-    base.resize(total);
-    if (pos) pos->resize(total);
+    pos.resize(total);
     uint64_t w = 0, i = 0;
     for (size_t q = 0; q <= nr; q++) {
         const uint64_t hi = q < nr ? pc.a[q] : pc.N;
         if (hi > i) {
-            memcpy(base.data() + w, pc.cbase + i, hi - i);
-            if (pos) memcpy(pos->data() + w, pc.cpos + i, (hi - i) * 4);
+            memcpy(pos.data() + w, pc.cpos + i, (hi - i) * 4);
             w += hi - i;
         }
         if (q == nr) break;
-        memcpy(base.data() + w, pc.seed[q].s, pc.seed[q].len);
-        if (pos) std::fill(pos->begin() + w, pos->begin() + w + pc.seed[q].len, pc.start[q]);
+        std::fill(pos.begin() + w, pos.begin() + w + pc.seed[q].len, pc.start[q]);
         w += pc.seed[q].len;
         i = pc.b[q];
-    }
-    if (total) {
-        // first / last ConsensusBase.pos for the FASTA header (main.rs:627-632)
-        *first_pos = (nr && pc.a[0] == 0 && pc.seed[0].len) ? pc.start[0] : pc.cpos[0];
-        bool tail_is_region = nr && pc.b[nr - 1] == pc.N;
-        *last_pos = (tail_is_region && pc.seed[nr - 1].len) ? pc.start[nr - 1] : pc.cpos[pc.N - 1];
     }
 }
 

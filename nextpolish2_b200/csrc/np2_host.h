@@ -1,6 +1,6 @@
 // np2_host.h — host phases of the polish path that stay on the CPU by design (small, sequential, irregular):
-// record parsing/filtering, the LQ-region state machine over sparse events, genotype rules, the phasing graph and
-// Louvain clustering, consensus splicing.  Everything works on flat arrays produced/consumed by the kernels.
+// record parsing/filtering, the Louvain clustering of the read agreement graph, and the k-mer re-check of the few
+// regions with more than one supported allele.  Everything works on flat arrays produced/consumed by the kernels.
 #pragma once
 #include <stdint.h>
 
@@ -33,11 +33,6 @@ struct Regions {
     std::vector<uint32_t> start, end;  // reference order: descending position
     std::vector<uint32_t> a, b;        // DP-consensus index range [a, b) of the bases with start <= pos <= end
 };
-// LQ state machine of generate_cns_from_best_score_lq (main.rs:1586-1625) driven by the sparse list of
-// consensus indices whose flags != 0 (ascending); flags: bit0 qv<95, bit1 cov<2.
-void find_regions(const uint32_t *cpos, const uint8_t *cbase, const uint8_t *cflags, uint64_t n, const uint32_t *events,
-                  uint64_t n_events, Regions &out);
-
 /* ---------------------------------------------------------------- phasing */
 // phase_reads_by_lqseqs (main.rs:994-1015) + louvain.rs on the reduced agreement edges produced on the device:
 // key = (min order << 32 | max order), val = sum of +-1 in the low 32 bits (signed) + number of disagreements << 32.
@@ -53,6 +48,7 @@ struct Allele {
     uint32_t len = 0;
     uint32_t order = 0;
     uint16_t kscore = 0;
+    uint64_t dev_off = 0;  // where the same string lives in the device candidate pool
 };
 // The consensus is never rebuilt base by base: it is the DP consensus (cbase, N bases) with the index range
 // [a, b) of every region replaced by that region's current sudoseed (update_consensus_with_lqseqs
@@ -79,8 +75,8 @@ struct Reupdate {
 };
 void reupdate_build(const Patched &pc, uint32_t k, Reupdate &ru);
 void reupdate_apply(Patched &pc, const Reupdate &ru, const uint16_t *kscores, uint32_t iter_count);
-// final Vec<ConsensusBase>: bases always, positions only when asked for
-void assemble(const Patched &pc, std::vector<uint8_t> &base, std::vector<uint32_t> *pos, uint32_t *first_pos,
-              uint32_t *last_pos);
+// ConsensusBase.pos of the final consensus (the bases are assembled on the device): DP positions outside the
+// regions, region.start for every base of a patched region (main.rs:1039-1045)
+void positions(const Patched &pc, std::vector<uint32_t> &pos);
 
 }  // namespace np2

@@ -124,4 +124,36 @@ void geno_region_hete(GenoDev g, cudaStream_t s);
 void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, cudaStream_t s);
 void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s);
 
+/* ------------------------------------------------------------------ regions + assembly (np2_regions.cu) */
+struct RegionDev {
+    uint32_t N = 0, n_ev = 0;
+    const uint32_t *events = nullptr;  // consensus indices with flags != 0, ascending
+    const uint8_t *cflags = nullptr, *cbase = nullptr;
+    const uint32_t *cpos = nullptr;
+    uint32_t *ev_close = nullptr;
+    uint8_t *ev_boundary = nullptr, *ev_closes = nullptr;
+    uint32_t *c_t = nullptr, *c_start = nullptr, *c_end = nullptr, *c_a = nullptr, *c_b = nullptr;
+    uint32_t *c_head = nullptr, *c_hrank = nullptr;
+    uint32_t *r_start = nullptr, *r_end = nullptr, *r_a = nullptr, *r_b = nullptr;
+};
+void regions_event_close(RegionDev d, cudaStream_t s);
+void regions_make(RegionDev d, uint32_t n_cand, cudaStream_t s);
+void regions_out(RegionDev d, uint32_t n_cand, uint32_t n_heads, cudaStream_t s);
+
+struct AssembleDev {
+    uint32_t nreg = 0, N = 0;
+    const uint8_t *cbase = nullptr, *pool = nullptr;
+    const uint32_t *r_a = nullptr, *r_b = nullptr, *r_seed_len = nullptr;
+    const uint64_t *r_seed_off = nullptr;
+    long long *q_delta = nullptr, *q_shift = nullptr;  // q_shift: nreg + 1
+    uint32_t *q_seedlen = nullptr;
+    uint64_t *q_seedoff = nullptr;                      // nreg + 1
+};
+void assemble_sizes(AssembleDev a, cudaStream_t s);
+void assemble_seed_gather(AssembleDev a, uint8_t *d_out, cudaStream_t s);
+void rech_sizes(GenoDev g, uint32_t *d_bytes, cudaStream_t s);
+void rech_gather(GenoDev g, const uint32_t *d_ent_off, const uint64_t *d_byte_off, uint32_t *d_order, uint32_t *d_len,
+                 uint64_t *d_pool_off, uint8_t *d_out, cudaStream_t s);
+void assemble_final(AssembleDev a, uint8_t *d_out, cudaStream_t s);
+
 }  // namespace np2

@@ -1,0 +1,186 @@
+// np2_regions.cu — LQ-region detection and final consensus assembly on the device.
+//
+// The reference finds LQ regions with a sequential state machine while it backtracks (main.rs:1586-1625).  Only the
+// sparse "events" (bases with qv < 95 or coverage < 2) change its state, and the three sequential dependencies it
+// has are all local, so it parallelises exactly:
+//   1. whether an open LQ run closes after a low-qv event depends only on the consensus between that event and the
+//      next one (first HQ base >= 5 later whose two predecessors differ in pos and base)      -> k_event_close
+//   2. the run's first event is found by walking back to the previous closing / low-coverage event -> k_region_make
+//   3. a new region is merged into the previous one iff its end reaches the previous candidate's start, which is
+//      a property of adjacent candidates only (main.rs:1613-1614)                             -> k_region_heads/out
+// Indices: "rp" is the reference's index into the reversed consensus (rp = N - 1 - i).
+#include "np2_kernels.cuh"
+
+namespace np2 {
+
+namespace {
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+}  // namespace
+
+// events[t] ascending consensus index => descending rp.  The next event in the reference's scan order is t - 1.
+__global__ void k_event_close(RegionDev d) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.n_ev) return;
+    const uint32_t N = d.N;
+    const uint32_t idx = d.events[t];
+    const uint32_t f = d.cflags[idx];
+    uint32_t close_rp = kNone;
+    uint8_t boundary = 0;
+    if (f & 2) {
+        boundary = 1;  // coverage < 2 drops the open run (main.rs:1586-1588)
+    } else {
+        const uint32_t rp = N - 1 - idx;
+        const uint32_t nx = t > 0 ? N - 1 - d.events[t - 1] : N;
+        // HQ bases rp' in [rp + 5, nx): closes at the first one whose predecessors differ in pos and base
+        for (uint64_t x = (uint64_t)rp + 5; x < nx; x++) {
+            const uint32_t i1 = N - 1 - (uint32_t)(x - 1), i2 = N - 1 - (uint32_t)(x - 2);
+            if (d.cpos[i1] != d.cpos[i2] && d.cbase[i1] != d.cbase[i2]) {
+                close_rp = (uint32_t)x;
+                boundary = 1;
+                break;
+            }
+        }
+    }
+    d.ev_close[t] = close_rp;
+    d.ev_boundary[t] = boundary;
+    d.ev_closes[t] = close_rp != kNone;
+}
+
+// one thread per closing event (candidate region); c_t[c] = event index, ascending
+__global__ void k_region_make(RegionDev d, uint32_t n_cand) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand) return;
+    const uint32_t N = d.N;
+    const uint32_t t = d.c_t[c];
+    uint32_t lq_e = d.ev_close[t] - 2;  // main.rs:1600
+    // first low-qv event of the run: walk towards smaller rp (larger t) until the previous boundary
+    uint32_t tf = t;
+    while (tf + 1 < d.n_ev && !d.ev_boundary[tf + 1]) tf++;
+    uint32_t lq_s = N - 1 - d.events[tf];
+    lq_s = lq_s > 2 ? lq_s - 2 : 1;  // main.rs:1601-1605
+    auto P = [&](uint32_t rp) { return d.cpos[N - 1 - rp]; };
+    auto B = [&](uint32_t rp) { return d.cbase[N - 1 - rp]; };
+    while (lq_s > 1 && (P(lq_s - 1) == P(lq_s) || B(lq_s - 1) == B(lq_s))) lq_s--;  // main.rs:1606-1611
+    const uint32_t start_pos = P(lq_e), end_pos = P(lq_s);
+    uint32_t a = N - 1 - lq_e, b = N - 1 - lq_s + 1;
+    while (a > 0 && d.cpos[a - 1] == start_pos) a--;
+    while (b < N && d.cpos[b] <= end_pos) b++;
+    d.c_start[c] = start_pos;
+    d.c_end[c] = end_pos;
+    d.c_a[c] = a;
+    d.c_b[c] = b;
+}
+// candidate c (larger c = earlier in the reference's scan) is merged into c + 1 when its end reaches that start
+__global__ void k_region_heads(RegionDev d, uint32_t n_cand) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand) return;
+    const bool merged = c + 1 < n_cand && d.c_end[c] >= d.c_start[c + 1];
+    d.c_head[c] = merged ? 0 : 1;
+}
+// heads in ascending c with exclusive rank hr; the reference's region order is descending c
+__global__ void k_region_out(RegionDev d, uint32_t n_cand, uint32_t n_heads) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand || !d.c_head[c]) return;
+    uint32_t lo = c;
+    while (lo > 0 && !d.c_head[lo - 1]) lo--;  // candidates lo..c-1 were merged into c
+    const uint32_t r = n_heads - 1 - d.c_hrank[c];
+    d.r_start[r] = d.c_start[lo];
+    d.r_a[r] = d.c_a[lo];
+    d.r_end[r] = d.c_end[c];
+    d.r_b[r] = d.c_b[c];
+}
+
+void regions_event_close(RegionDev d, cudaStream_t s) {
+    if (d.n_ev) k_event_close<<<cdiv(d.n_ev, 128), 128, 0, s>>>(d);
+}
+void regions_make(RegionDev d, uint32_t n_cand, cudaStream_t s) {
+    if (!n_cand) return;
+    k_region_make<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand);
+    k_region_heads<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand);
+}
+void regions_out(RegionDev d, uint32_t n_cand, uint32_t n_heads, cudaStream_t s) {
+    if (n_cand) k_region_out<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand, n_heads);
+}
+
+/* ---------------------------------------------------------------- seeds / survivors / assembly */
+
+// per region in ASCENDING position q = nreg - 1 - r: length change of the patch and seed length
+__global__ void k_patch_sizes(AssembleDev a) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.nreg) return;
+    const uint32_t r = a.nreg - 1 - q;
+    a.q_delta[q] = (long long)a.r_seed_len[r] - (long long)(a.r_b[r] - a.r_a[r]);
+    a.q_seedlen[q] = a.r_seed_len[r];
+}
+// compact copy of every region's seed string (for the host's flank extraction), q order
+__global__ void k_seed_gather(AssembleDev a, uint8_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= a.nreg) return;
+    const uint32_t r = a.nreg - 1 - q;
+    const uint8_t *src = a.pool + a.r_seed_off[r];
+    uint8_t *dst = out + a.q_seedoff[q];
+    for (uint32_t x = lane; x < a.r_seed_len[r]; x += 32) dst[x] = src[x];
+}
+// survivors of the regions that stay RECH: (order, len) entries + strings, in retain_sort_seqs order
+__global__ void k_rech_sizes(GenoDev g, uint32_t *__restrict__ bytes) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.nreg) return;
+    uint32_t b = 0;
+    for (uint32_t x = 0; x < g.r_nsurv[r]; x++) b += g.c_len[r * kMaxCand + g.r_surv[r * kMaxCand + x]];
+    bytes[r] = b;
+}
+__global__ void k_rech_gather(GenoDev g, const uint32_t *__restrict__ ent_off, const uint64_t *__restrict__ byte_off,
+                              uint32_t *__restrict__ ent_order, uint32_t *__restrict__ ent_len,
+                              uint64_t *__restrict__ ent_pool_off, uint8_t *__restrict__ out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.nreg) return;
+    uint64_t w = byte_off[r];
+    for (uint32_t x = 0; x < g.r_nsurv[r]; x++) {
+        const uint32_t sl = r * kMaxCand + g.r_surv[r * kMaxCand + x];
+        const uint32_t len = g.c_len[sl];
+        ent_order[ent_off[r] + x] = g.c_order[sl];
+        ent_len[ent_off[r] + x] = len;
+        ent_pool_off[ent_off[r] + x] = g.c_off[sl];  // offset in the device pool (for the final seed override)
+        const uint8_t *src = g.pool + g.c_off[sl];
+        for (uint32_t i = 0; i < len; i++) out[w + i] = src[i];
+        w += len;
+    }
+}
+// final consensus = DP consensus with [a, b) of every region replaced by its seed (main.rs:1027-1058).
+// One warp per region q (ascending position) copies the DP stretch before it and its seed; warp nreg copies the tail.
+__global__ void __launch_bounds__(128) k_assemble(AssembleDev a, uint8_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q > a.nreg) return;
+    const long long shift = a.q_shift[q];  // sum of deltas of the regions before q
+    const uint32_t lo = q ? a.r_b[a.nreg - q] : 0;              // region q - 1 is r = nreg - q
+    const uint32_t hi = q < a.nreg ? a.r_a[a.nreg - 1 - q] : a.N;
+    for (uint32_t i = lo + lane; i < hi; i += 32) out[(long long)i + shift] = a.cbase[i];
+    if (q < a.nreg) {
+        const uint32_t r = a.nreg - 1 - q;
+        const uint8_t *src = a.pool + a.r_seed_off[r];
+        uint8_t *dst = out + ((long long)hi + shift);
+        for (uint32_t x = lane; x < a.r_seed_len[r]; x += 32) dst[x] = src[x];
+    }
+}
+
+void assemble_sizes(AssembleDev a, cudaStream_t s) {
+    if (a.nreg) k_patch_sizes<<<cdiv(a.nreg, 128), 128, 0, s>>>(a);
+}
+void assemble_seed_gather(AssembleDev a, uint8_t *d_out, cudaStream_t s) {
+    if (a.nreg) k_seed_gather<<<cdiv((uint64_t)a.nreg * 32, 128), 128, 0, s>>>(a, d_out);
+}
+void rech_sizes(GenoDev g, uint32_t *d_bytes, cudaStream_t s) {
+    if (g.nreg) k_rech_sizes<<<cdiv(g.nreg, 128), 128, 0, s>>>(g, d_bytes);
+}
+void rech_gather(GenoDev g, const uint32_t *d_ent_off, const uint64_t *d_byte_off, uint32_t *d_order, uint32_t *d_len,
+                 uint64_t *d_pool_off, uint8_t *d_out, cudaStream_t s) {
+    if (g.nreg) k_rech_gather<<<cdiv(g.nreg, 128), 128, 0, s>>>(g, d_ent_off, d_byte_off, d_order, d_len, d_pool_off, d_out);
+}
+void assemble_final(AssembleDev a, uint8_t *d_out, cudaStream_t s) {
+    k_assemble<<<cdiv((uint64_t)(a.nreg + 1) * 32, 128), 128, 0, s>>>(a, d_out);
+}
+
+}  // namespace np2
