@@ -158,15 +158,32 @@ struct StageTimer {
 };
 }  // namespace
 
+// Host-side buffers a job needs, pooled per context: pinned allocations (cudaMallocHost) and first-touch page
+// faults of fresh vectors cost milliseconds each, far more than the kernels they feed.
+struct JobScratch {
+    Ingest ing;
+    std::vector<uint8_t> tseq, h_seeds, h_rech_pool;
+    PBuf<uint8_t> res_base, p_cbase, p_cflags;
+    PBuf<uint32_t> p_cpos;
+    StageTimer timer;
+};
 struct np2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int refs = 1;  // tables and jobs keep their context alive (np2_ctx_destroy only drops the caller's reference)
+    std::vector<JobScratch *> scratch_pool;
+    JobScratch *take_scratch() {
+        if (scratch_pool.empty()) return new JobScratch();
+        JobScratch *sc = scratch_pool.back();
+        scratch_pool.pop_back();
+        return sc;
+    }
 };
 static void ctx_release(np2_ctx *ctx) {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (JobScratch *sc : ctx->scratch_pool) delete sc;
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -194,13 +211,19 @@ static void table_alloc(np2_ctx *ctx, np2_table *t, uint32_t k, uint64_t n, uint
 
 struct np2_job {
     np2_ctx *ctx = nullptr;
+    JobScratch *sc = nullptr;
     np2_opts opt;
     std::vector<np2_table *> tables;  // sorted by k
-    std::vector<uint8_t> tseq;
+    std::vector<uint8_t> &tseq;
     const uint8_t *bam = nullptr;
     uint64_t bam_len = 0;
-    Ingest ing;
-    bool uploaded = false;
+    Ingest &ing;
+    bool uploaded = false, blob_sent = false;
+    explicit np2_job(np2_ctx *c)
+        : ctx(c), sc(c->take_scratch()), tseq(sc->tseq), ing(sc->ing), res_base(sc->res_base), p_cpos(sc->p_cpos),
+          p_cbase(sc->p_cbase), p_cflags(sc->p_cflags), timer(sc->timer), h_seeds(sc->h_seeds),
+          h_rech_pool(sc->h_rech_pool) {}
+    ~np2_job() { ctx->scratch_pool.push_back(sc); }
 
     // device inputs
     DBuf<uint8_t> d_ref, d_code, d_blob, d_nib, d_blank;
@@ -217,21 +240,20 @@ struct np2_job {
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
     // result: bases always; positions are materialised on request (np2_job_get_consensus with pos != NULL)
-    PBuf<uint8_t> res_base;
+    PBuf<uint8_t> &res_base;
     std::vector<uint32_t> res_pos;
     DBuf<uint32_t> jd_cpos;                  // DP consensus of the last iteration stays on the device
     DBuf<uint8_t> jd_cbase, jd_cflags;
     uint32_t res_N = 0;
-    std::vector<uint8_t> h_seeds, h_rech_pool;
+    std::vector<uint8_t> &h_seeds, &h_rech_pool;
     uint32_t res_first = 0, res_last = 0;
     bool res_pos_valid = false;
     Patched res_patch;                       // kept so that positions can be produced lazily
-    std::vector<uint8_t> res_pool;           // candidate strings the patches point into
-    PBuf<uint32_t> p_cpos;
-    PBuf<uint8_t> p_cbase, p_cflags;
+    PBuf<uint32_t> &p_cpos;
+    PBuf<uint8_t> &p_cbase, &p_cflags;
     DBuf<uint32_t> d_order;
     uint32_t max_span = 0;
-    StageTimer timer;
+    StageTimer &timer;
     uint64_t h2d = 0, d2h = 0, n_launch = 0, n_probes = 0;
     std::string timing_names;
 
@@ -270,8 +292,10 @@ void np2_job::upload() {
     d_ref.alloc(L, s);
     d_ref.upload(tseq.data(), L);
     d_code.alloc(L, s);
-    d_blob.alloc(bam_len ? bam_len : 1, s);
-    if (bam_len) d_blob.upload(bam, bam_len);
+    if (!blob_sent) {
+        d_blob.alloc(bam_len ? bam_len : 1, s);
+        if (bam_len) d_blob.upload(bam, bam_len);
+    }
     auto up32 = [&](DBuf<uint32_t> &d, const std::vector<uint32_t> &h) {
         d.alloc(std::max<size_t>(h.size(), 1), s);
         if (!h.empty()) d.upload(h.data(), h.size());
@@ -1190,9 +1214,14 @@ void np2_job::run(int32_t dump_it) {
     const uint32_t n = R.n_reads;
     const int h_total = timer.begin("total", 0);
     int h = timer.begin("expand_trim_pack", 2);
-    ref_codes(d_ref.p, L, d_code.p, s);
+    DBuf<int> d_bad;
+    d_bad.alloc(1, s);
+    d_bad.zero();
+    ref_codes(d_ref.p, L, d_code.p, d_bad.p, s);
     expand_trim_pack(R, d_ref.p, L, s);
     timer.end(h);
+    int bad_ref = 0;
+    d_bad.download(&bad_ref, 1);
     launches(2);
     h_ts.resize(n);
     h_te.resize(n);
@@ -1204,6 +1233,7 @@ void np2_job::run(int32_t dump_it) {
     }
     NP2_CUDA(cudaStreamSynchronize(s));
     d2h += (uint64_t)n * 12;
+    if (bad_ref) throw np2::Error(NP2_ERR_FORMAT, "contig holds a byte the reference cannot index (>= 128 or '-')");
     timer.hbegin();
     ingest_finish();
     timer.hend("host:ingest_finish");
@@ -1483,9 +1513,7 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
         if (opts->use_secondary) throw np2::Error(NP2_ERR_UNSUPPORTED, "-S / use_secondary is out of scope");
         if (n_tables == 0) throw np2::Error(NP2_ERR_ARG, "Missing yak file!");
         if (opts->iter_count == 0) throw np2::Error(NP2_ERR_ARG, "iter_count must be >= 1");
-        std::unique_ptr<np2_job> j(new np2_job());
-        j->ctx = ctx;
-        ctx->refs++;
+        std::unique_ptr<np2_job> j(new np2_job(ctx));
         j->opt = *opts;
         for (uint32_t i = 0; i < n_tables; i++) j->tables.push_back(tables[i]);
         std::stable_sort(j->tables.begin(), j->tables.end(),
@@ -1496,11 +1524,14 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
         if (tlen >= opts->min_ctg_len) {
             if (tlen < 16) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig shorter than 16 bp");
             if (tlen >= (1u << 30)) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig >= 2^30 bp (main.rs:270)");
-            for (uint32_t i = 0; i < tlen; i++)
-                if (tseq[i] >= 128 || tseq[i] == '-')
-                    throw np2::Error(NP2_ERR_FORMAT, "contig holds a byte the reference cannot index (>= 128 or '-')");
+            // start moving the records to the device before parsing them: the DMA overlaps the host walk
+            NP2_CUDA(cudaSetDevice(ctx->device));
+            j->d_blob.alloc(bam_len ? bam_len : 1, ctx->stream);
+            if (bam_len) j->d_blob.upload(bam, bam_len);
+            j->blob_sent = true;
             parse_records(bam, bam_len, tlen, *opts, j->ing);
         }
+        ctx->refs++;
         *out = j.release();
     });
 }

@@ -9,6 +9,7 @@
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 
 namespace np2 {
@@ -17,98 +18,254 @@ namespace np2 {
 
 /* ================================================================= ingest */
 
+namespace {
+typedef Ingest::RecOut RecOut;
+struct ParseErr {
+    int64_t rec = INT64_MAX;
+    std::string msg;
+};
+}  // namespace
+
+// Record-level filter (main.rs:1758-1771) and fill_with_cigar bookkeeping (main.rs:386-440) without materialising
+// the gapped strings.  Pass 1 walks the block_size chain (sequential by nature); pass 2 processes the records'
+// CIGARs on all host threads; pass 3 concatenates.  The first failing record in file order decides the error,
+// like the reference's sequential loop would.
+void Ingest::clear() {
+    all_tid.clear();
+    all_pos.clear();
+    rec_idx.clear();
+    pos.clear();
+    ncols.clear();
+    rlen.clear();
+    rspan.clear();
+    is_clip.clear();
+    seq_off.clear();
+    op_off.clear();
+    op_col.clear();
+    op_q.clear();
+    op_t.clear();
+    op_cig.clear();
+    nib_off.clear();
+    ck_off.clear();
+    total_cols = 0;
+    rec_off.clear();
+    ro.clear();
+}
+
 void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out) {
-    out = Ingest();
+    out.clear();
+    std::vector<uint64_t> &rec_off = out.rec_off;
+    {
+        uint64_t off = 0;
+        while (off + 4 <= bam_len) {
+            int32_t bs;
+            memcpy(&bs, bam + off, 4);
+            if (bs < 32 || off + 4 + (uint64_t)bs > bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+            rec_off.push_back(off + 4);
+            off += 4 + (uint64_t)bs;
+        }
+        if (off != bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+    }
+    const size_t nrec = rec_off.size();
+    out.all_tid.resize(nrec);
+    out.all_pos.resize(nrec);
+    std::vector<RecOut> &ro = out.ro;
+    ro.assign(nrec, RecOut());
+    unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (nrec < 2048) T = 1;
+    auto &t_col = out.t_col, &t_q = out.t_q, &t_t = out.t_t, &t_cig = out.t_cig;
+    if (t_col.size() < T) {
+        t_col.resize(T);
+        t_q.resize(T);
+        t_t.resize(T);
+        t_cig.resize(T);
+    }
+    std::vector<ParseErr> t_err(T);
+    auto work = [&](unsigned ti) {
+        const size_t b = nrec * ti / T, e = nrec * (ti + 1) / T;
+        // thread-local vectors: the shared arrays of vector headers would false-share on every push_back
+        std::vector<uint32_t> vcol, vq, vt, vcig;
+        vcol.swap(t_col[ti]);  // take last job's capacity
+        vq.swap(t_q[ti]);
+        vt.swap(t_t[ti]);
+        vcig.swap(t_cig[ti]);
+        vcol.clear();
+        vq.clear();
+        vt.clear();
+        vcig.clear();
+        const size_t guess = (e - b) * 64;
+        vcol.reserve(guess);
+        vq.reserve(guess);
+        vt.reserve(guess);
+        vcig.reserve(guess);
+        struct Publish {
+            std::vector<uint32_t> &a, &b, &c, &d, &A, &B, &C, &D;
+            ~Publish() {
+                A.swap(a);
+                B.swap(b);
+                C.swap(c);
+                D.swap(d);
+            }
+        } publish{vcol, vq, vt, vcig, t_col[ti], t_q[ti], t_t[ti], t_cig[ti]};
+        ParseErr my_err;
+        struct PublishErr {
+            ParseErr &src, &dst;
+            ~PublishErr() { dst = src; }
+        } publish_err{my_err, t_err[ti]};
+        auto fail = [&](size_t rec, const char *m) {
+            if ((int64_t)rec < my_err.rec) {
+                my_err.rec = (int64_t)rec;
+                my_err.msg = m;
+            }
+        };
+        for (size_t rec = b; rec < e; rec++) {
+            const uint8_t *r = bam + rec_off[rec];
+            int32_t bs, ref_id, pos, l_seq;
+            uint16_t n_cig, flag;
+            memcpy(&bs, r - 4, 4);
+            memcpy(&ref_id, r, 4);
+            memcpy(&pos, r + 4, 4);
+            const uint32_t l_name = r[8], mapq = r[9];
+            memcpy(&n_cig, r + 12, 2);
+            memcpy(&flag, r + 14, 2);
+            memcpy(&l_seq, r + 16, 4);
+            out.all_tid[rec] = ref_id;
+            out.all_pos[rec] = pos;
+            if (l_seq < 0 || 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 > (uint64_t)bs) {
+                fail(rec, "BAM/SAM parsing failed!");
+                return;  // a sequential reader stops here
+            }
+            const uint8_t *cg = r + 32 + l_name;
+            // seq_len_from_cigar(true), bam_endpos
+            uint64_t rlen = 0, rspan = 0;
+            for (uint32_t i = 0; i < n_cig; i++) {
+                uint32_t c;
+                memcpy(&c, cg + 4 * i, 4);
+                const uint32_t l = c >> 4, op = c & 15;
+                if (op == 0 || op == 1 || op == 4 || op == 5 || op == 7 || op == 8) rlen += l;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rspan += l;
+            }
+            const int64_t span = ((flag & 4) || n_cig == 0 || rspan == 0) ? 1 : (int64_t)rspan;
+            const int64_t need = std::max<int64_t>((int64_t)opt.min_map_len, (int64_t)((float)rlen * opt.min_map_fra));
+            if ((flag & 0x404) || (int16_t)mapq <= (int16_t)opt.min_map_qual || rlen <= opt.min_read_len ||
+                ((flag & 0x100) && !opt.use_secondary) || ((flag & 0x800) && !opt.use_supplementary) || span < need)
+                continue;
+            if (pos < 0 || (uint64_t)pos > tlen) {
+                fail(rec, "alignment starts outside the contig");
+                return;
+            }
+            uint32_t qs = 0, ts = 0, col = 0, aln_q_s = 0, aln_q_e = 0, n_ops = 0;
+            bool first = true;
+            const char *bad = nullptr;
+            for (uint32_t i = 0; i < n_cig && !bad; i++) {
+                uint32_t c;
+                memcpy(&c, cg + 4 * i, 4);
+                const uint32_t l = c >> 4, op = c & 15;
+                switch (op) {
+                    case 4:
+                        qs += l;
+                        if (first) aln_q_s = qs;
+                        else aln_q_e = qs - l;
+                        break;
+                    case 0: case 7: case 8: case 1: case 2:
+                        if (op != 2 && (uint64_t)qs + l > (uint64_t)l_seq) {
+                            bad = "CIGAR consumes more query bases than SEQ holds";
+                            break;
+                        }
+                        if (op != 1 && (uint64_t)pos + ts + l > tlen) {
+                            bad = "alignment runs past the end of the contig";
+                            break;
+                        }
+                        if (l) {
+                            vcol.push_back(col);
+                            vq.push_back(qs);
+                            vt.push_back(ts);
+                            vcig.push_back(c);
+                            n_ops++;
+                        }
+                        col += l;
+                        if (op != 2) qs += l;
+                        if (op != 1) ts += l;
+                        break;
+                    case 5:
+                        break;
+                    default:
+                        bad = "Unknown cigar";
+                }
+                first = false;
+            }
+            if (bad) {
+                fail(rec, bad);
+                return;
+            }
+            if (aln_q_e == 0) aln_q_e = qs;
+            RecOut &o = ro[rec];
+            o.kept = 1;
+            o.is_clip = (uint32_t)(aln_q_e - aln_q_s + opt.max_clip_len) < (uint32_t)rlen ? 1 : 0;  // main.rs:1796
+            o.ncols = col;
+            o.rlen = (uint32_t)rlen;
+            o.rspan = (uint32_t)rspan;
+            o.n_ops = n_ops;
+            o.seq_off = rec_off[rec] + 32 + l_name + 4ull * n_cig;
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned ti = 0; ti < T; ti++) th.emplace_back(work, ti);
+        for (auto &t : th) t.join();
+    }
+    const ParseErr *first_err = nullptr;
+    for (auto &e : t_err)
+        if (e.rec != INT64_MAX && (!first_err || e.rec < first_err->rec)) first_err = &e;
+    if (first_err) herr(NP2_ERR_FORMAT, first_err->msg);
+    // pass 3: compact the kept records, concatenate the per-thread op lists (already in record order)
+    size_t nk = 0, nops = 0;
+    for (auto &o : ro) nk += o.kept, nops += o.n_ops;
+    out.rec_idx.reserve(nk);
+    out.pos.reserve(nk);
+    out.ncols.reserve(nk);
+    out.rlen.reserve(nk);
+    out.rspan.reserve(nk);
+    out.is_clip.reserve(nk);
+    out.seq_off.reserve(nk);
+    out.op_off.reserve(nk + 1);
+    out.nib_off.reserve(nk + 1);
+    out.ck_off.reserve(nk + 1);
     out.op_off.push_back(0);
     out.nib_off.push_back(0);
     out.ck_off.push_back(0);
-    uint64_t off = 0;
-    int32_t rec = -1;
-    while (off + 4 <= bam_len) {
-        rec++;
-        int32_t bs;
-        memcpy(&bs, bam + off, 4);
-        if (bs < 32 || off + 4 + (uint64_t)bs > bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
-        const uint8_t *r = bam + off + 4;
-        const uint64_t rec_off = off + 4;
-        off += 4 + (uint64_t)bs;
-        int32_t ref_id, pos, l_seq;
-        uint16_t n_cig, flag;
-        memcpy(&ref_id, r, 4);
-        memcpy(&pos, r + 4, 4);
-        const uint32_t l_name = r[8], mapq = r[9];
-        memcpy(&n_cig, r + 12, 2);
-        memcpy(&flag, r + 14, 2);
-        memcpy(&l_seq, r + 16, 4);
-        if (l_seq < 0 || 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 > (uint64_t)bs)
-            herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
-        out.all_tid.push_back(ref_id);
-        out.all_pos.push_back(pos);
-        const uint8_t *cg = r + 32 + l_name;
-        // seq_len_from_cigar(true), bam_endpos
-        uint64_t rlen = 0, rspan = 0;
-        for (uint32_t i = 0; i < n_cig; i++) {
-            uint32_t c;
-            memcpy(&c, cg + 4 * i, 4);
-            const uint32_t l = c >> 4, op = c & 15;
-            if (op == 0 || op == 1 || op == 4 || op == 5 || op == 7 || op == 8) rlen += l;
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rspan += l;
-        }
-        const int64_t span = ((flag & 4) || n_cig == 0 || rspan == 0) ? 1 : (int64_t)rspan;
-        const int64_t need = std::max<int64_t>((int64_t)opt.min_map_len, (int64_t)((float)rlen * opt.min_map_fra));
-        if ((flag & 0x404) || (int16_t)mapq <= (int16_t)opt.min_map_qual || rlen <= opt.min_read_len ||
-            ((flag & 0x100) && !opt.use_secondary) || ((flag & 0x800) && !opt.use_supplementary) || span < need)
-            continue;
-        if (pos < 0 || (uint64_t)pos > tlen) herr(NP2_ERR_FORMAT, "alignment starts outside the contig");
-        // fill_with_cigar bookkeeping (main.rs:386-440) without materialising the strings
-        uint32_t qs = 0, ts = 0, col = 0, aln_q_s = 0, aln_q_e = 0;
-        bool first = true;
-        for (uint32_t i = 0; i < n_cig; i++) {
-            uint32_t c;
-            memcpy(&c, cg + 4 * i, 4);
-            const uint32_t l = c >> 4, op = c & 15;
-            switch (op) {
-                case 4:
-                    qs += l;
-                    if (first) aln_q_s = qs;
-                    else aln_q_e = qs - l;
-                    break;
-                case 0: case 7: case 8: case 1: case 2:
-                    if (op != 2 && (uint64_t)qs + l > (uint64_t)l_seq)
-                        herr(NP2_ERR_FORMAT, "CIGAR consumes more query bases than SEQ holds");
-                    if (op != 1 && (uint64_t)pos + ts + l > tlen)
-                        herr(NP2_ERR_FORMAT, "alignment runs past the end of the contig");
-                    if (l) {
-                        out.op_col.push_back(col);
-                        out.op_q.push_back(qs);
-                        out.op_t.push_back(ts);
-                        out.op_cig.push_back(c);
-                    }
-                    col += l;
-                    if (op != 2) qs += l;
-                    if (op != 1) ts += l;
-                    break;
-                case 5:
-                    break;
-                default:
-                    herr(NP2_ERR_FORMAT, "Unknown cigar");
-            }
-            first = false;
-        }
-        if (aln_q_e == 0) aln_q_e = qs;
-        out.rec_idx.push_back(rec);
-        out.pos.push_back((uint32_t)pos);
-        out.ncols.push_back(col);
-        out.rlen.push_back((uint32_t)rlen);
-        out.rspan.push_back((uint32_t)rspan);
-        out.is_clip.push_back((uint32_t)(aln_q_e - aln_q_s + opt.max_clip_len) < (uint32_t)rlen ? 1 : 0);  // main.rs:1796
-        out.seq_off.push_back(rec_off + 32 + l_name + 4ull * n_cig);
-        out.op_off.push_back((uint32_t)out.op_col.size());
-        out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)col / 16 + 1) * 8 + 15) & ~15ull));
-        out.ck_off.push_back(out.ck_off.back() + (col + 31) / 32);
-        out.total_cols += col;
+    for (size_t rec = 0; rec < nrec; rec++) {
+        const RecOut &o = ro[rec];
+        if (!o.kept) continue;
+        out.rec_idx.push_back((int32_t)rec);
+        out.pos.push_back((uint32_t)out.all_pos[rec]);
+        out.ncols.push_back(o.ncols);
+        out.rlen.push_back(o.rlen);
+        out.rspan.push_back(o.rspan);
+        out.is_clip.push_back(o.is_clip);
+        out.seq_off.push_back(o.seq_off);
+        out.op_off.push_back(out.op_off.back() + o.n_ops);
+        out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)o.ncols / 16 + 1) * 8 + 15) & ~15ull));
+        out.ck_off.push_back(out.ck_off.back() + (o.ncols + 31) / 32);
+        out.total_cols += o.ncols;
     }
-    if (off != bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+    out.op_col.resize(nops);
+    out.op_q.resize(nops);
+    out.op_t.resize(nops);
+    out.op_cig.resize(nops);
+    size_t w = 0;
+    for (unsigned ti = 0; ti < T; ti++) {
+        const size_t n = t_col[ti].size();
+        if (n) {
+            memcpy(out.op_col.data() + w, t_col[ti].data(), n * 4);
+            memcpy(out.op_q.data() + w, t_q[ti].data(), n * 4);
+            memcpy(out.op_t.data() + w, t_t[ti].data(), n * 4);
+            memcpy(out.op_cig.data() + w, t_cig[ti].data(), n * 4);
+        }
+        w += n;
+    }
 }
 
 /* ================================================================= phasing: graph + Louvain */

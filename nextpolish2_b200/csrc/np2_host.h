@@ -24,6 +24,16 @@ struct Ingest {
     std::vector<uint64_t> nib_off;      // n + 1, bytes, 16-B aligned
     std::vector<uint32_t> ck_off;       // n + 1, 32-column blocks
     uint64_t total_cols = 0;
+    // scratch kept between jobs (capacity reuse: fresh host pages are expensive to fault in)
+    struct RecOut {
+        uint8_t kept = 0, is_clip = 0;
+        uint32_t ncols = 0, rlen = 0, rspan = 0, n_ops = 0;
+        uint64_t seq_off = 0;
+    };
+    std::vector<uint64_t> rec_off;
+    std::vector<RecOut> ro;
+    std::vector<std::vector<uint32_t>> t_col, t_q, t_t, t_cig;
+    void clear();
 };
 // throws np2::Error(NP2_ERR_FORMAT) where the reference panics
 void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out);

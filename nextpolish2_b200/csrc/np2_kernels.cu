@@ -238,12 +238,16 @@ void gather32(const uint64_t *d_buf, uint64_t n_sectors, uint64_t n_loads, uint6
 
 /* =============================================================== K0: reference codes */
 
-__global__ void k_ref_codes(const uint8_t *__restrict__ ref, uint32_t L, uint8_t *__restrict__ code) {
+// also flags the bytes the reference cannot index (>= 128 panics in SEQ_NUM[..]; '-' would read as a gap column)
+__global__ void k_ref_codes(const uint8_t *__restrict__ ref, uint32_t L, uint8_t *__restrict__ code, int *bad) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < L) code[i] = (uint8_t)seq_code(ref[i]);
+    if (i >= L) return;
+    const uint32_t c = ref[i];
+    code[i] = (uint8_t)seq_code(c);
+    if (c >= 128 || c == '-') atomicExch(bad, 1);
 }
-void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, cudaStream_t s) {
-    k_ref_codes<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_ref, L, d_code);
+void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, int *d_bad, cudaStream_t s) {
+    k_ref_codes<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_ref, L, d_code, d_bad);
 }
 
 /* =============================================================== K1: expand + trim + pack */

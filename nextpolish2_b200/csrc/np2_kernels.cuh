@@ -28,7 +28,7 @@ void gather32(const uint64_t *d_buf, uint64_t n_sectors, uint64_t n_loads, uint6
               cudaStream_t s);
 
 /* ------------------------------------------------------------------ K0/K1 ingest */
-void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, cudaStream_t s);
+void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, int *d_bad, cudaStream_t s);
 
 struct ReadsDev {
     uint32_t n_reads = 0;  // kept reads, index 0 = first BAM read (the ref read is implicit)
