@@ -279,8 +279,7 @@ struct np2_job {
     void upload();
     void run(int32_t dump_iter);
     void ingest_finish();
-    void iteration(uint32_t iter, bool final_iter, bool dump);
-    void launches(uint32_t n) { n_launch += n; }
+    uint32_t iteration(uint32_t iter0);
 };
 
 /* ================================================================= pipeline */
@@ -413,7 +412,10 @@ void np2_job::ingest_finish() {
     }
 }
 
-void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
+// Runs iteration iter0 of the reference's loop (main.rs:1819-1836).  When a non-final iteration blanks no read, the
+// next iteration would rebuild exactly the same Msa, consensus, regions and candidates, so it is served from the
+// state already on the device instead of being recomputed.  Returns the next iteration that needs a fresh build.
+uint32_t np2_job::iteration(uint32_t iter0) {
     cudaStream_t s = ctx->stream;
     const uint32_t L = (uint32_t)tseq.size();
     const uint32_t n_reads = R.n_reads;
@@ -456,7 +458,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     NP2_CUDA(cudaMemcpyAsync(&n_rec, d_cta_off.p + n_cta, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
     n_rec += 2;
-    launches(6);
     timer.hbegin();
 
     DBuf<uint64_t> d_key, d_key2;
@@ -494,7 +495,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     uint32_t G = 0;
     NP2_CUDA(cudaMemcpyAsync(&G, d_gidx.p + n_rec, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
-    launches(13);
 
     MsaDev m;
     m.L = L;
@@ -542,7 +542,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     NP2_CUDA(cudaMemsetAsync(d_n_emit.p + L, 0, 4, s));
     pos_finalize(m, d_n_emit.p, s);
     timer.end(h);
-    launches(6);
 
     /* ---------------- K3: DP over runs, backtrack, consensus */
     DBuf<uint32_t> d_run_start, d_nruns, d_best_last;
@@ -603,7 +602,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_cflags.p, d_events.p, d_nev.p, (int)N, s);
     }
     timer.end(h);
-    launches(12);
     uint32_t n_ev = 0;
     long long total = 0;
     NP2_CUDA(cudaMemcpyAsync(&n_ev, d_nev.p, 4, cudaMemcpyDeviceToHost, s));
@@ -647,7 +645,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         timer.end(h);
         NP2_CUDA(cudaMemcpyAsync(&n_cand, d_ncand.p, 4, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaStreamSynchronize(s));
-        launches(1);
     }
     if (n_cand) {
         d_c_start.alloc(n_cand, s);
@@ -685,7 +682,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         h = timer.begin("regions", 1);
         regions_out(rd, n_cand, nreg, s);
         timer.end(h);
-        launches(3);
     }
     Regions rg;  // host copy only when needed (dump, final iteration)
     auto fetch_regions = [&]() {
@@ -703,7 +699,7 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         }
     };
 
-    if (dump) {
+    auto dump_stage1 = [&]() {
         // Msa in the reference's order: reference 3-mer first (p >= 2), then the sorted sparse ones
         std::vector<uint32_t> sp_off(L + 1), gc(G), gb(G), dc(L), db(L);
         std::vector<uint16_t> gba(G), gde(G);
@@ -742,14 +738,20 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         fetch_regions();
         dm_reg_start = rg.start;
         dm_reg_end = rg.end;
-    }
+    };
     uint32_t edge_pos[2] = {0, 0};  // ConsensusBase.pos of the first / last DP base (FASTA header)
-    if (final_iter && N) {
+    auto fetch_edge_pos = [&]() {
+        if (!N) return;
         NP2_CUDA(cudaMemcpyAsync(&edge_pos[0], d_cpos.p, 4, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaMemcpyAsync(&edge_pos[1], d_cpos.p + (N - 1), 4, cudaMemcpyDeviceToHost, s));
-    }
-    if (nreg == 0) {  // main.rs:1638-1640: no LQ region, the DP consensus is the answer
-        if (final_iter) {
+        NP2_CUDA(cudaStreamSynchronize(s));
+    };
+    uint32_t iter = iter0;
+    if (nreg == 0) {  // main.rs:1638-1640: no LQ region; nothing can be dropped, the DP consensus is the answer
+        for (;; iter++) {
+            if ((int32_t)iter == dump_iter) dump_stage1();
+            if (iter + 1 < opt.iter_count) continue;
+            fetch_edge_pos();
             res_patch = Patched();
             res_base.resize(std::max(N, 1u));
             res_base.n = N;
@@ -759,8 +761,8 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             res_first = edge_pos[0];
             res_last = edge_pos[1];
             res_pos_valid = false;
+            return iter + 1;
         }
-        return;
     }
 
     /* ---------------- K4: which reads cover which region, candidates, kscore — all on the device */
@@ -802,7 +804,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     NP2_CUDA(cudaMemcpyAsync(&n_pairs, d_rd_poff.p + n_reads, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
     g.n_pairs = n_pairs;
-    launches(4);
 
     const uint64_t nslot = (uint64_t)nreg * kMaxCand;
     DBuf<uint32_t> d_p_len, d_c_src, d_c_len, d_c_order, d_r_ncand, d_r_bytes, d_r_nedge, d_r_seed_len, d_r_nsurv;
@@ -828,6 +829,11 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     d_r_seed_off.alloc(nreg, s);
     d_r_lable.alloc(nreg, s);
     d_r_surv.alloc(nslot, s);
+    DBuf<uint32_t> d_long_list, d_long_count;
+    d_long_list.alloc(nslot, s);
+    d_long_count.alloc(1, s);
+    g.long_list = d_long_list.p;
+    g.long_count = d_long_count.p;
     g.p_len = d_p_len.p;
     g.p_kmer = d_p_kmer.p;
     g.c_src = d_c_src.p;
@@ -873,7 +879,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     geno_cand_kscore(g, t0->dev, opt.min_kmer_count, s);
     timer.end(h);
     n_probes += n_pairs;
-    launches(6);
 
     auto dump_candidates = [&](bool with_lable) {
         std::vector<uint32_t> ncand(nreg), clen(nslot), cord(nslot);
@@ -907,6 +912,15 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             dm_can_roff.push_back(dm_can_order.size());
         }
     };
+    // mark_hete_lqseqs zeroes kscores in place: keep the retrieve_kmer_count values for a re-used iteration
+    DBuf<uint16_t> d_c_ks_orig;
+    d_c_ks_orig.alloc(nslot, s);
+    NP2_CUDA(cudaMemcpyAsync(d_c_ks_orig.p, d_c_ks.p, nslot * 2, cudaMemcpyDeviceToDevice, s));
+  for (;; iter++) {
+    const bool final_iter = iter + 1 == opt.iter_count;
+    const bool dump = (int32_t)iter == dump_iter;
+    if (iter > iter0) NP2_CUDA(cudaMemcpyAsync(d_c_ks.p, d_c_ks_orig.p, nslot * 2, cudaMemcpyDeviceToDevice, s));
+    if (dump) dump_stage1();
     if (dump) dump_candidates(false);
 
     if (!final_iter) {
@@ -924,7 +938,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
         uint64_t n_edges = 0;
         NP2_CUDA(cudaMemcpyAsync(&n_edges, d_r_edge_off.p + nreg, 8, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaStreamSynchronize(s));
-        launches(2);
         if (dump) dump_candidates(true);
         std::vector<uint64_t> ukeys;
         std::vector<long long> uvals;
@@ -955,7 +968,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
                                                (int)n_edges, s);
             }
             timer.end(h);
-            launches(1);
             uint32_t nu = 0;
             d_nu.download(&nu, 1);
             NP2_CUDA(cudaStreamSynchronize(s));
@@ -976,11 +988,13 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             h_blank[as_read[a]] = 1;
             dm_dropped.push_back(a);
         }
+        timer.hend("host:phase_reads");
+        if (drop.empty()) continue;  // same reads => the next iteration is this one again
         d_blank.upload(h_blank.data(), n_reads);
         NP2_CUDA(cudaStreamSynchronize(s));
-        timer.hend("host:phase_reads");
-        return;
+        return iter + 1;
     }
+    fetch_edge_pos();
 
     /* ---------------- final: seed alleles (device), then re-check with every table (main.rs:1527-1543) */
     DBuf<int> d_err;
@@ -989,7 +1003,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     h = timer.begin("region_seed", 1);
     geno_region_seed(g, opt.max_indel_len, d_err.p, s);
     timer.end(h);
-    launches(1);
     /* ---- what the host needs for the re-check: regions, every region's seed string, the survivors of the regions
      *      that stay RECH, and the DP bases (flanks).  Everything else stays on the device. */
     AssembleDev ad;
@@ -1062,7 +1075,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     assemble_seed_gather(ad, d_seeds.p, s);
     rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
     timer.end(h);
-    launches(6);
     h_seeds.resize(seeds_bytes + 1);
     h_rech_pool.resize(rech_bytes + 1);
     std::vector<uint32_t> ent_order(n_ent), ent_len(n_ent);
@@ -1134,7 +1146,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
             h = timer.begin("yak_seq_kscore", 1);
             seq_kscore(tables[ti]->dev, d_rp.p, d_ro.p, nullptr, ns, opt.min_kmer_count, d_rk.p, s);
             timer.end(h);
-            launches(1);
             d_rk.download(ks.data(), ns);
             NP2_CUDA(cudaStreamSynchronize(s));
             h2d += ru.pool.size() + (ns + 1) * 8;
@@ -1173,7 +1184,6 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     d_out.alloc(out_n + 1, s);
     assemble_final(ad, d_out.p, s);
     timer.end(h);
-    launches(3);
     res_base.resize(std::max<uint64_t>(out_n, 1));
     res_base.n = out_n;
     d_out.download(res_base.p, out_n);
@@ -1184,6 +1194,8 @@ void np2_job::iteration(uint32_t iter, bool final_iter, bool dump) {
     res_last = (pc.b[nreg - 1] == N) ? pc.start[nreg - 1] : edge_pos[1];
     res_pos_valid = false;
     timer.hend("host:assemble");
+    return iter + 1;
+  }
 }
 
 void np2_job::run(int32_t dump_it) {
@@ -1196,9 +1208,24 @@ void np2_job::run(int32_t dump_it) {
     res_patch = Patched();
     timer.s = s;
     timer.reset();
+    const unsigned long long launches0 = launch_counter();
     n_launch = 0;
     n_probes = 0;
     dm_dropped.clear();
+    dm_msa_off.clear();
+    dm_msa_bases.clear();
+    dm_msa_delta.clear();
+    dm_msa_count.clear();
+    dm_msa_besti.clear();
+    dm_can_roff.clear();
+    dm_can_order.clear();
+    dm_can_kscore.clear();
+    dm_can_kmer.clear();
+    dm_can_seq_off.clear();
+    dm_can_seq.clear();
+    dm_reg_start.clear();
+    dm_reg_end.clear();
+    dm_reg_lable.clear();
     if (L < opt.min_ctg_len) {  // main.rs:1727-1730
         res_base.resize(std::max(L, 1u));
         res_base.n = L;
@@ -1222,7 +1249,6 @@ void np2_job::run(int32_t dump_it) {
     timer.end(h);
     int bad_ref = 0;
     d_bad.download(&bad_ref, 1);
-    launches(2);
     h_ts.resize(n);
     h_te.resize(n);
     h_n.resize(n);
@@ -1277,8 +1303,9 @@ void np2_job::run(int32_t dump_it) {
             dm_nib_off.push_back(dm_nib.size());
         }
     }
-    for (uint32_t it = 0; it < opt.iter_count; it++) iteration(it, it + 1 == opt.iter_count, (int32_t)it == dump_iter);
+    for (uint32_t it = 0; it < opt.iter_count;) it = iteration(it);
     timer.end(h_total);
+    n_launch = launch_counter() - launches0;
     NP2_CUDA(cudaStreamSynchronize(s));
     timer.collect();
 }

@@ -9,6 +9,15 @@
 
 namespace np2 {
 
+// launch accounting for bench.py's "gpu_launches": every launch of one of OUR kernels goes through NP2_K(...)
+unsigned long long &launch_counter();
+template <class F>
+inline F *count_launch(F *f) {
+    ++launch_counter();
+    return f;
+}
+#define NP2_K(k) (*np2::count_launch(k))
+
 #define NP2_CUDA(call)                                                                                  \
     do {                                                                                                \
         cudaError_t e_ = (call);                                                                        \

@@ -290,41 +290,45 @@ __device__ __forceinline__ uint32_t g_probe(const TableDev &t, uint64_t h, uint3
     }
     return 0;
 }
-// candidates no longer than k: the single pre-computed first-k k-mer (main.rs:770-774); INVALID_KMER keeps 0
+// candidates no longer than k: the single pre-computed first-k k-mer (main.rs:770-774); INVALID_KMER keeps 0.
+// The (rare) longer ones are queued for the warp-per-candidate kernel below.
 __global__ void k_cand_kscore_short(GenoDev g, TableDev t, uint32_t min_count) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= g.nreg * kMaxCand) return;
     const uint32_t r = s / kMaxCand, c = s - r * kMaxCand;
     if (c >= g.r_ncand[r]) return;
-    if (g.c_len[s] > t.k) return;
+    if (g.c_len[s] > t.k) {
+        g.long_list[atomicAdd(g.long_count, 1u)] = s;
+        return;
+    }
     const uint64_t h = g.c_kmer[s];
     g.c_kscore[s] = h == 0xFFFFFFFFFFFFFFFFULL ? 0 : (uint16_t)g_probe(t, h, min_count);
 }
-// candidates longer than k: min over all their k-mers (main.rs:760-769); one warp per candidate, k < 32 here
+// candidates longer than k: min over all their k-mers (main.rs:760-769); warps stride over the queue, k < 32 here
 __global__ void __launch_bounds__(32 * kWarpsPerCta) k_cand_kscore_long(GenoDev g, TableDev t, uint32_t min_count) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (s >= g.nreg * kMaxCand) return;
-    const uint32_t r = s / kMaxCand, c = s - r * kMaxCand;
-    if (c >= g.r_ncand[r]) return;
-    const uint32_t len = g.c_len[s], k = t.k;
-    if (len <= k) return;
-    const uint8_t *sq = g.pool + g.c_off[s];
-    const uint64_t mask = (1ULL << (2 * k)) - 1;
-    uint32_t mn = 0xFFFFFFFFu;
-    for (uint32_t e = k - 1 + lane; e < len; e += 32) {
-        bool ok = true;
-        uint64_t f = 0, rv = 0;
-        for (uint32_t x = e + 1 - k; x <= e; x++) {
-            const uint32_t cd = seq_code(sq[x]);
-            ok &= cd < 4;
-            f = (f << 2 | cd) & mask;
-            rv = (rv >> 2) | (uint64_t)(3 ^ cd) << (2 * (k - 1));
+    const uint32_t n_long = *g.long_count;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_long; w += nw) {
+        const uint32_t s = g.long_list[w];
+        const uint32_t len = g.c_len[s], k = t.k;
+        const uint8_t *sq = g.pool + g.c_off[s];
+        const uint64_t mask = (1ULL << (2 * k)) - 1;
+        uint32_t mn = 0xFFFFFFFFu;
+        for (uint32_t e = k - 1 + lane; e < len; e += 32) {
+            bool ok = true;
+            uint64_t f = 0, rv = 0;
+            for (uint32_t x = e + 1 - k; x <= e; x++) {
+                const uint32_t cd = seq_code(sq[x]);
+                ok &= cd < 4;
+                f = (f << 2 | cd) & mask;
+                rv = (rv >> 2) | (uint64_t)(3 ^ cd) << (2 * (k - 1));
+            }
+            if (ok) mn = min(mn, g_probe(t, yak_hash64(f < rv ? f : rv, mask), min_count));
         }
-        if (ok) mn = min(mn, g_probe(t, yak_hash64(f < rv ? f : rv, mask), min_count));
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+        if (lane == 0) g.c_kscore[s] = mn == 0xFFFFFFFFu ? 0 : (uint16_t)mn;
     }
-    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-    if (lane == 0) g.c_kscore[s] = mn == 0xFFFFFFFFu ? 0 : (uint16_t)mn;
 }
 
 /* ---------------------------------------------------------------- genotype rules (one warp per region) */
@@ -559,35 +563,36 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, in
 /* ---------------------------------------------------------------- launch wrappers */
 
 void geno_read_cursor(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, cudaStream_t s) {
-    if (R.n_reads) k_read_cursor<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank);
+    if (R.n_reads) NP2_K(k_read_cursor)<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank);
 }
 void geno_read_ranges(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, uint32_t k, cudaStream_t s) {
-    if (R.n_reads) k_read_ranges<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank, k);
+    if (R.n_reads) NP2_K(k_read_ranges)<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank, k);
 }
 void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, cudaStream_t s) {
-    if (g.n_pairs) k_pair_scan<<<cdiv(g.n_pairs, 128), 128, 0, s>>>(g, R, k);
+    if (g.n_pairs) NP2_K(k_pair_scan)<<<cdiv(g.n_pairs, 128), 128, 0, s>>>(g, R, k);
 }
 void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
                         uint32_t k, uint32_t max_span, cudaStream_t s) {
-    k_region_select<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_blank, d_code, L,
+    NP2_K(k_region_select)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_blank, d_code, L,
                                                                                                k, max_span);
 }
 void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s) {
-    k_cand_write<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_code, L, k);
+    NP2_K(k_cand_write)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_code, L, k);
 }
 void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s) {
     const uint64_t slots = (uint64_t)g.nreg * kMaxCand;
-    k_cand_kscore_short<<<cdiv(slots, 256), 256, 0, s>>>(g, t, min_count);
-    k_cand_kscore_long<<<cdiv(slots * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, t, min_count);
+    cudaMemsetAsync(g.long_count, 0, 4, s);
+    NP2_K(k_cand_kscore_short)<<<cdiv(slots, 256), 256, 0, s>>>(g, t, min_count);
+    NP2_K(k_cand_kscore_long)<<<148 * 4, 32 * kWarpsPerCta, 0, s>>>(g, t, min_count);
 }
 void geno_region_hete(GenoDev g, cudaStream_t s) {
-    k_region_hete<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g);
+    NP2_K(k_region_hete)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g);
 }
 void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, cudaStream_t s) {
-    k_edges_emit<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_key, d_val);
+    NP2_K(k_edges_emit)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_key, d_val);
 }
 void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s) {
-    k_region_seed<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, d_err);
+    NP2_K(k_region_seed)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, d_err);
 }
 
 }  // namespace np2

@@ -16,6 +16,11 @@
 
 namespace np2 {
 
+unsigned long long &launch_counter() {
+    static unsigned long long c = 0;
+    return c;
+}
+
 namespace {
 constexpr int kThreads = 256;
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
@@ -183,12 +188,12 @@ __global__ void __launch_bounds__(kThreads) k_seq_kscore(const uint64_t *__restr
 void table_insert(const TableDev &t, const uint64_t *d_hashes, const uint16_t *d_counts, uint64_t n, int *d_err,
                   cudaStream_t s) {
     if (!n) return;
-    k_table_insert<<<min(cdiv(n, kThreads), 148u * 32u), kThreads, 0, s>>>(t.slots, t.nb, d_hashes, d_counts, n, d_err);
+    NP2_K(k_table_insert)<<<min(cdiv(n, kThreads), 148u * 32u), kThreads, 0, s>>>(t.slots, t.nb, d_hashes, d_counts, n, d_err);
 }
 void table_insert_filekeys(const TableDev &t, const uint64_t *d_keys, const uint32_t *d_sub_off, uint64_t n,
                            int *d_err, cudaStream_t s) {
     if (!n) return;
-    k_table_insert_filekeys<<<min(cdiv(n, kThreads), 148u * 32u), kThreads, 0, s>>>(t.slots, t.nb, d_keys, d_sub_off, n,
+    NP2_K(k_table_insert_filekeys)<<<min(cdiv(n, kThreads), 148u * 32u), kThreads, 0, s>>>(t.slots, t.nb, d_keys, d_sub_off, n,
                                                                                    d_err);
 }
 void table_probe(const TableDev &t, const uint64_t *d_hashes, uint64_t n, uint32_t min_count, uint16_t *d_out,
@@ -196,13 +201,13 @@ void table_probe(const TableDev &t, const uint64_t *d_hashes, uint64_t n, uint32
     if (!n) return;
     // persistent-style grid: a multiple of the 148 SMs x 8 resident CTAs of 256 threads
     uint32_t grid = min(cdiv(n, (uint64_t)kThreads * kProbeIlp), 148u * 8u);
-    k_table_probe<<<grid, kThreads, 0, s>>>(t.slots, t.nb, d_hashes, n, min_count, d_out);
+    NP2_K(k_table_probe)<<<grid, kThreads, 0, s>>>(t.slots, t.nb, d_hashes, n, min_count, d_out);
 }
 void seq_kscore(const TableDev &t, const uint8_t *d_seqs, const uint64_t *d_off, const uint32_t *d_sel, uint64_t n,
                 uint32_t min_count, uint16_t *d_out, cudaStream_t s) {
     if (!n) return;
     uint32_t grid = min(cdiv(n * 32, kThreads), 148u * 8u);
-    k_seq_kscore<<<grid, kThreads, 0, s>>>(t.slots, t.nb, t.k, d_seqs, d_off, d_sel, n, min_count, d_out);
+    NP2_K(k_seq_kscore)<<<grid, kThreads, 0, s>>>(t.slots, t.nb, t.k, d_seqs, d_off, d_sel, n, min_count, d_out);
 }
 
 /* --------------------------------------------------------------- measurement: random 32-B sector gather
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kThreads) k_gather32(const uint64_t *__restric
 void gather32(const uint64_t *d_buf, uint64_t n_sectors, uint64_t n_loads, uint64_t seed, uint64_t *d_sink,
               cudaStream_t s) {
     uint32_t grid = min(cdiv(n_loads, (uint64_t)kThreads * kProbeIlp), 148u * 8u);
-    k_gather32<<<grid, kThreads, 0, s>>>(d_buf, n_sectors, n_loads, seed, d_sink);
+    NP2_K(k_gather32)<<<grid, kThreads, 0, s>>>(d_buf, n_sectors, n_loads, seed, d_sink);
 }
 
 /* =============================================================== K0: reference codes */
@@ -247,7 +252,7 @@ __global__ void k_ref_codes(const uint8_t *__restrict__ ref, uint32_t L, uint8_t
     if (c >= 128 || c == '-') atomicExch(bad, 1);
 }
 void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, int *d_bad, cudaStream_t s) {
-    k_ref_codes<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_ref, L, d_code, d_bad);
+    NP2_K(k_ref_codes)<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_ref, L, d_code, d_bad);
 }
 
 /* =============================================================== K1: expand + trim + pack */
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(128) k_expand_trim_pack(ReadsDev R, const uint
 }
 void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
     if (!r.n_reads) return;
-    k_expand_trim_pack<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
+    NP2_K(k_expand_trim_pack)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
 }
 
 /* =============================================================== K2: pileup */
@@ -452,7 +457,7 @@ __global__ void k_cover_diff(ReadsDev R, const uint8_t *__restrict__ blank, int3
 }
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s) {
     if (!r.n_reads) return;
-    k_cover_diff<<<cdiv(r.n_reads, kThreads), kThreads, 0, s>>>(r, d_blank, d_diff);
+    NP2_K(k_cover_diff)<<<cdiv(r.n_reads, kThreads), kThreads, 0, s>>>(r, d_blank, d_diff);
 }
 
 __device__ __forceinline__ uint32_t nib_at(const uint8_t *__restrict__ nib, uint32_t o) {
@@ -585,11 +590,11 @@ __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32
 }
 void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
                   uint32_t *d_cta_count, cudaStream_t s) {
-    k_pileup_count<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_count);
+    NP2_K(k_pileup_count)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_count);
 }
 void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
                  const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read, cudaStream_t s) {
-    k_pileup_emit<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_off, d_key,
+    NP2_K(k_pileup_emit)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_off, d_key,
                                                                          d_read);
 }
 
@@ -598,7 +603,7 @@ __global__ void k_mark_heads(const uint64_t *__restrict__ key, uint32_t n, uint3
     if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
 }
 void mark_heads(const uint64_t *d_key, uint32_t n, uint32_t *d_head, cudaStream_t s) {
-    k_mark_heads<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, n, d_head);
+    NP2_K(k_mark_heads)<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, n, d_head);
 }
 __global__ void k_groups_fill(const uint64_t *__restrict__ key, const uint32_t *__restrict__ rd,
                               const uint32_t *__restrict__ head, const uint32_t *__restrict__ gidx, uint32_t n,
@@ -615,7 +620,7 @@ __global__ void k_groups_fill(const uint64_t *__restrict__ key, const uint32_t *
 }
 void groups_fill(const uint64_t *d_key, const uint32_t *d_read, const uint32_t *d_head, const uint32_t *d_gidx,
                  uint32_t n, uint32_t G, uint32_t *d_gstart, uint32_t *d_gpos, MsaDev m, cudaStream_t s) {
-    k_groups_fill<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, d_read, d_head, d_gidx, n, d_gstart, d_gpos, m);
+    NP2_K(k_groups_fill)<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, d_read, d_head, d_gidx, n, d_gstart, d_gpos, m);
 }
 __global__ void k_groups_finish(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ gpos, uint32_t n,
                                 MsaDev m) {
@@ -630,7 +635,7 @@ __global__ void k_groups_finish(const uint32_t *__restrict__ gstart, const uint3
 }
 void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t n, MsaDev m, cudaStream_t s) {
     if (!m.G) return;
-    k_groups_finish<<<cdiv(m.G, kThreads), kThreads, 0, s>>>(d_gstart, d_gpos, n, m);
+    NP2_K(k_groups_finish)<<<cdiv(m.G, kThreads), kThreads, 0, s>>>(d_gstart, d_gpos, n, m);
 }
 
 // Per position: order the sparse 3-mers like Msa::sort after first-seen pushes (main.rs:193-229): by b3.delta,
@@ -668,7 +673,7 @@ __global__ void k_pos_finalize(MsaDev m, uint32_t *__restrict__ n_emit) {
     n_emit[p] = multi ? 0 : (m.code[p] != 4);
 }
 void pos_finalize(MsaDev m, uint32_t *d_n_emit, cudaStream_t s) {
-    k_pos_finalize<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_n_emit);
+    NP2_K(k_pos_finalize)<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_n_emit);
 }
 
 /* =============================================================== K3: DP over runs + consensus */
@@ -678,7 +683,7 @@ __global__ void k_run_flags(const uint8_t *__restrict__ multi, uint32_t L, uint8
     if (p < L) flag[p] = multi[p] && (p == 0 || !multi[p - 1]);
 }
 void run_flags(const uint8_t *d_multi, uint32_t L, uint8_t *d_flag, cudaStream_t s) {
-    k_run_flags<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_multi, L, d_flag);
+    NP2_K(k_run_flags)<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_multi, L, d_flag);
 }
 
 struct Entry {
@@ -767,7 +772,7 @@ __global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, uint
 }
 void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, cudaStream_t s) {
     if (!n_runs) return;
-    k_dp_runs<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o);
+    NP2_K(k_dp_runs)<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o);
 }
 
 // Backtrack of one run (main.rs:1572-1634 without the LQ state machine).  WRITE = false: count emitted
@@ -846,14 +851,14 @@ __global__ void k_emit_singles(MsaDev m, const uint32_t *__restrict__ emit_off, 
 void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, uint32_t *d_n_emit,
                      cudaStream_t s) {
     if (!n_runs) return;
-    k_emit_runs<false><<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, d_n_emit, nullptr, nullptr, nullptr,
+    NP2_K(k_emit_runs<false>)<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, d_n_emit, nullptr, nullptr, nullptr,
                                                        nullptr);
 }
 void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, const uint32_t *d_n_emit,
                 const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s) {
-    k_emit_singles<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags, o);
+    NP2_K(k_emit_singles)<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags, o);
     if (n_runs)
-        k_emit_runs<true><<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, const_cast<uint32_t *>(d_n_emit),
+        NP2_K(k_emit_runs<true>)<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, const_cast<uint32_t *>(d_n_emit),
                                                           d_emit_off, d_pos, d_base, d_flags);
 }
 

@@ -108,6 +108,7 @@ struct GenoDev {
     uint16_t *c_kscore = nullptr;
     uint8_t *c_rep = nullptr;
     uint8_t *pool = nullptr;
+    uint32_t *long_list = nullptr, *long_count = nullptr;  // candidates longer than k (scored over all their k-mers)
     // per region
     uint32_t *r_ncand = nullptr, *r_bytes = nullptr, *r_nedge = nullptr, *r_seed_len = nullptr, *r_nsurv = nullptr;
     uint64_t *r_pool_off = nullptr, *r_edge_off = nullptr, *r_seed_off = nullptr;

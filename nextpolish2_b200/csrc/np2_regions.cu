@@ -92,15 +92,15 @@ __global__ void k_region_out(RegionDev d, uint32_t n_cand, uint32_t n_heads) {
 }
 
 void regions_event_close(RegionDev d, cudaStream_t s) {
-    if (d.n_ev) k_event_close<<<cdiv(d.n_ev, 128), 128, 0, s>>>(d);
+    if (d.n_ev) NP2_K(k_event_close)<<<cdiv(d.n_ev, 128), 128, 0, s>>>(d);
 }
 void regions_make(RegionDev d, uint32_t n_cand, cudaStream_t s) {
     if (!n_cand) return;
-    k_region_make<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand);
-    k_region_heads<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand);
+    NP2_K(k_region_make)<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand);
+    NP2_K(k_region_heads)<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand);
 }
 void regions_out(RegionDev d, uint32_t n_cand, uint32_t n_heads, cudaStream_t s) {
-    if (n_cand) k_region_out<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand, n_heads);
+    if (n_cand) NP2_K(k_region_out)<<<cdiv(n_cand, 128), 128, 0, s>>>(d, n_cand, n_heads);
 }
 
 /* ---------------------------------------------------------------- seeds / survivors / assembly */
@@ -167,20 +167,20 @@ __global__ void __launch_bounds__(128) k_assemble(AssembleDev a, uint8_t *__rest
 }
 
 void assemble_sizes(AssembleDev a, cudaStream_t s) {
-    if (a.nreg) k_patch_sizes<<<cdiv(a.nreg, 128), 128, 0, s>>>(a);
+    if (a.nreg) NP2_K(k_patch_sizes)<<<cdiv(a.nreg, 128), 128, 0, s>>>(a);
 }
 void assemble_seed_gather(AssembleDev a, uint8_t *d_out, cudaStream_t s) {
-    if (a.nreg) k_seed_gather<<<cdiv((uint64_t)a.nreg * 32, 128), 128, 0, s>>>(a, d_out);
+    if (a.nreg) NP2_K(k_seed_gather)<<<cdiv((uint64_t)a.nreg * 32, 128), 128, 0, s>>>(a, d_out);
 }
 void rech_sizes(GenoDev g, uint32_t *d_bytes, cudaStream_t s) {
-    if (g.nreg) k_rech_sizes<<<cdiv(g.nreg, 128), 128, 0, s>>>(g, d_bytes);
+    if (g.nreg) NP2_K(k_rech_sizes)<<<cdiv(g.nreg, 128), 128, 0, s>>>(g, d_bytes);
 }
 void rech_gather(GenoDev g, const uint32_t *d_ent_off, const uint64_t *d_byte_off, uint32_t *d_order, uint32_t *d_len,
                  uint64_t *d_pool_off, uint8_t *d_out, cudaStream_t s) {
-    if (g.nreg) k_rech_gather<<<cdiv(g.nreg, 128), 128, 0, s>>>(g, d_ent_off, d_byte_off, d_order, d_len, d_pool_off, d_out);
+    if (g.nreg) NP2_K(k_rech_gather)<<<cdiv(g.nreg, 128), 128, 0, s>>>(g, d_ent_off, d_byte_off, d_order, d_len, d_pool_off, d_out);
 }
 void assemble_final(AssembleDev a, uint8_t *d_out, cudaStream_t s) {
-    k_assemble<<<cdiv((uint64_t)(a.nreg + 1) * 32, 128), 128, 0, s>>>(a, d_out);
+    NP2_K(k_assemble)<<<cdiv((uint64_t)(a.nreg + 1) * 32, 128), 128, 0, s>>>(a, d_out);
 }
 
 }  // namespace np2
