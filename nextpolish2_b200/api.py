@@ -107,7 +107,8 @@ def _arr(ptr, n, dtype):
     dt = np.dtype(dtype)
     if n == 0 or not ptr.value:
         return np.empty(0, dt)
-    return np.frombuffer(C.string_at(ptr.value, n * dt.itemsize), dtype=dt).copy()
+    src = (C.c_char * (n * dt.itemsize)).from_address(ptr.value)
+    return np.frombuffer(src, dtype=dt).copy()  # one copy out of library-owned memory
 
 
 class Context:

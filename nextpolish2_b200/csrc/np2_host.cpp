@@ -272,26 +272,27 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
 
 namespace {
 
-typedef std::map<uint32_t, std::map<uint32_t, float>> Adj;  // ordered: ascending-id iteration (SURVEY hard part 3)
-
-struct LNode {
-    uint32_t id;
-    float weight;
-    std::vector<uint32_t> members;  // sorted original vertices
-};
+// louvain.rs with flat arrays.  Vertex / community ids are alignseq indices (plus the few ids the decluster step
+// invents), so everything is indexed by id; iteration is always in ascending id (SURVEY hard part 3: the reference
+// iterates FxHashMaps, whose order is not reproducible here).
+typedef std::vector<std::pair<uint32_t, float>> AdjList;  // sorted by neighbour id
 
 struct Level {
-    Adj data;
-    std::map<uint32_t, std::set<uint32_t>> comm;
-    std::map<uint32_t, LNode> node;
+    std::vector<uint32_t> ids;                     // vertices of this level (keys of `data`), ascending
+    std::vector<AdjList> adj;                      // indexed by id
+    std::vector<uint32_t> cid;                     // vertex -> community id (Node.id)
+    std::vector<float> nweight;                    // Node.weight
+    std::vector<std::vector<uint32_t>> members;    // Node.nodes (original vertices, sorted)
+    std::map<uint32_t, std::set<uint32_t>> comm;   // community id -> vertices (may hold empty sets)
+    void grow(uint32_t id) {
+        if (id >= adj.size()) {
+            adj.resize(id + 1);
+            cid.resize(id + 1, 0);
+            nweight.resize(id + 1, 0.f);
+            members.resize(id + 1);
+        }
+    }
 };
-
-void add_w(Adj &a, uint32_t x, uint32_t y, float w) {
-    auto &m = a[x];
-    auto it = m.find(y);
-    if (it == m.end()) m.emplace(y, w);
-    else it->second += w;
-}
 
 // louvain.rs:72-117
 bool move_vertices(Level &lv) {
@@ -299,12 +300,11 @@ bool move_vertices(Level &lv) {
     std::vector<std::pair<uint32_t, float>> acc;
     for (;;) {
         bool stop = true;
-        for (auto &kv : lv.data) {
-            const uint32_t v = kv.first;
-            const uint32_t cur = lv.node.at(v).id;
+        for (uint32_t v : lv.ids) {
+            const uint32_t cur = lv.cid[v];
             acc.clear();
-            for (auto &e : kv.second) {
-                const uint32_t c = lv.node.at(e.first).id;
+            for (auto &e : lv.adj[v]) {
+                const uint32_t c = lv.cid[e.first];
                 bool found = false;
                 for (auto &a : acc)
                     if (a.first == c) {
@@ -318,14 +318,14 @@ bool move_vertices(Level &lv) {
             uint32_t bid = acc[0].first;
             float bw = acc[0].second;
             for (auto &a : acc)
-                if (a.second > bw || (a.second == bw && a.first < bid)) {
+                if (a.second > bw || (a.second == bw && a.first < bid)) {  // max weight, ties -> smaller id
                     bid = a.first;
                     bw = a.second;
                 }
             if (bw > 0.0f && bid != cur) {
-                lv.node.at(v).id = bid;
-                lv.comm.at(bid).insert(v);
-                lv.comm.at(cur).erase(v);
+                lv.cid[v] = bid;
+                lv.comm[bid].insert(v);
+                lv.comm[cur].erase(v);
                 stop = false;
                 moved_any = true;
             }
@@ -335,14 +335,13 @@ bool move_vertices(Level &lv) {
     return moved_any;
 }
 
+// weight of a community: its vertices' own weights + half of every internal edge seen from both ends
 float internal_weight(const Level &lv, const std::set<uint32_t> &nodes) {
     float w = 0.f;
     for (uint32_t n : nodes) {
-        w += lv.node.at(n).weight;
-        auto it = lv.data.find(n);
-        if (it != lv.data.end())
-            for (auto &e : it->second)
-                if (nodes.count(e.first)) w += e.second / 2.0f;
+        w += lv.nweight[n];
+        for (auto &e : lv.adj[n])
+            if (nodes.count(e.first)) w += e.second / 2.0f;
     }
     return w;
 }
@@ -350,64 +349,66 @@ float internal_weight(const Level &lv, const std::set<uint32_t> &nodes) {
 // louvain.rs:119-195
 Level aggregate(Level &lv) {
     Level nx;
+    std::set<uint32_t> nx_keys;  // `communities` / `node` keys of the next level
     std::vector<uint32_t> decluster;
     for (auto &kv : lv.comm) {
         if (kv.second.empty()) continue;
-        LNode nn;
-        nn.id = kv.first;
-        nn.weight = internal_weight(lv, kv.second);
+        const uint32_t id = kv.first;
+        float w = 0.f;
+        const bool fast = true;
+        (void)fast;
         for (uint32_t n : kv.second) {
-            const auto &mm = lv.node.at(n).members;
-            nn.members.insert(nn.members.end(), mm.begin(), mm.end());
+            w += lv.nweight[n];
+            for (auto &e : lv.adj[n])
+                if (lv.cid[e.first] == id && kv.second.count(e.first)) w += e.second / 2.0f;
         }
-        std::sort(nn.members.begin(), nn.members.end());
-        nn.members.erase(std::unique(nn.members.begin(), nn.members.end()), nn.members.end());
-        if (nn.weight < 0.f) decluster.push_back(kv.first);
-        else {
-            nx.comm[kv.first] = {kv.first};
-            nx.node[kv.first] = std::move(nn);
+        if (w < 0.f) {
+            decluster.push_back(id);
+            continue;
         }
+        nx.grow(id);
+        nx.cid[id] = id;
+        nx.nweight[id] = w;
+        auto &mm = nx.members[id];
+        for (uint32_t n : kv.second) mm.insert(mm.end(), lv.members[n].begin(), lv.members[n].end());
+        std::sort(mm.begin(), mm.end());
+        mm.erase(std::unique(mm.begin(), mm.end()), mm.end());
+        nx.comm[id] = {id};
+        nx_keys.insert(id);
     }
-    for (uint32_t cid : decluster) {  // communities with negative internal weight fall apart again
-        auto it = lv.comm.find(cid);
+    for (uint32_t id : decluster) {  // communities with negative internal weight fall apart again
+        auto it = lv.comm.find(id);
         if (it == lv.comm.end()) herr(NP2_ERR_FORMAT, "louvain: declustered community vanished (reference would panic)");
         std::set<uint32_t> nodes = std::move(it->second);
         lv.comm.erase(it);
         for (uint32_t nid : nodes) {
             uint32_t nn = nid;
-            while (nx.comm.count(nn) || nx.node.count(nn)) nn++;
+            while (nx_keys.count(nn)) nn++;
+            nx.grow(nn);
+            nx.cid[nn] = nn;
+            nx.nweight[nn] = lv.nweight[nid];
+            nx.members[nn] = lv.members[nid];
             nx.comm[nn] = {nn};
-            LNode x;
-            x.id = nn;
-            x.weight = lv.node.at(nid).weight;
-            x.members = lv.node.at(nid).members;
-            nx.node[nn] = std::move(x);
+            nx_keys.insert(nn);
             lv.comm[nn] = {nid};
         }
     }
-    // edges between the (possibly re-keyed) communities: one pass over the old edges via member -> community
-    std::unordered_map<uint32_t, uint32_t> owner;
+    // edges between the (possibly re-keyed) communities: one pass over the old edges via vertex -> owner
+    std::vector<uint32_t> owner(lv.adj.size(), 0xFFFFFFFFu);
     bool clean = true;
     for (auto &kv : lv.comm)
-        for (uint32_t n : kv.second)
-            if (!owner.emplace(n, kv.first).second) clean = false;
+        for (uint32_t n : kv.second) {
+            if (owner[n] != 0xFFFFFFFFu) clean = false;
+            owner[n] = kv.first;
+        }
+    std::map<std::pair<uint32_t, uint32_t>, float> sum;
     if (clean) {
-        Adj sum;
         for (auto &kv : lv.comm)
-            for (uint32_t v : kv.second) {
-                auto it = lv.data.find(v);
-                if (it == lv.data.end()) continue;
-                for (auto &e : it->second) {
-                    auto ow = owner.find(e.first);
-                    if (ow == owner.end() || !(ow->second > kv.first)) continue;
-                    add_w(sum, kv.first, ow->second, e.second);
-                }
-            }
-        for (auto &a : sum)
-            for (auto &b : a.second)
-                if (b.second != 0.f) {
-                    add_w(nx.data, a.first, b.first, b.second);
-                    add_w(nx.data, b.first, a.first, b.second);
+            for (uint32_t v : kv.second)
+                for (auto &e : lv.adj[v]) {
+                    const uint32_t o = owner[e.first];
+                    if (o == 0xFFFFFFFFu || !(o > kv.first)) continue;
+                    sum[{kv.first, o}] += e.second;
                 }
     } else {  // a vertex listed in two communities (reference quirk): literal pairwise form
         for (auto &c1 : lv.comm) {
@@ -415,19 +416,30 @@ Level aggregate(Level &lv) {
             for (auto &c2 : lv.comm) {
                 if (!(c2.first > c1.first) || c2.second.empty()) continue;
                 float w = 0.f;
-                for (uint32_t v : c1.second) {
-                    auto it = lv.data.find(v);
-                    if (it != lv.data.end())
-                        for (auto &e : it->second)
-                            if (c2.second.count(e.first)) w += e.second;
-                }
-                if (w != 0.f) {
-                    add_w(nx.data, c1.first, c2.first, w);
-                    add_w(nx.data, c2.first, c1.first, w);
-                }
+                bool any = false;
+                for (uint32_t v : c1.second)
+                    for (auto &e : lv.adj[v])
+                        if (c2.second.count(e.first)) {
+                            w += e.second;
+                            any = true;
+                        }
+                if (any) sum[{c1.first, c2.first}] = w;
             }
         }
     }
+    for (uint32_t id : nx_keys) nx.grow(id);
+    for (auto &kv : sum) {
+        if (kv.second == 0.f) continue;
+        nx.grow(std::max(kv.first.first, kv.first.second));
+        nx.adj[kv.first.first].emplace_back(kv.first.second, kv.second);
+        nx.adj[kv.first.second].emplace_back(kv.first.first, kv.second);
+    }
+    // `data` keys of the next level = communities that have at least one non-zero edge (louvain.rs:183-186)
+    for (uint32_t id = 0; id < nx.adj.size(); id++)
+        if (!nx.adj[id].empty()) {
+            std::sort(nx.adj[id].begin(), nx.adj[id].end());
+            nx.ids.push_back(id);
+        }
     return nx;
 }
 
@@ -444,33 +456,49 @@ std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, u
     std::map<uint32_t, float> ref_w;
     bool have_ref = false;
     std::set<uint32_t> invalid;
-    Level lv;
+    uint32_t max_id = 0;
+    for (uint64_t e = 0; e < n_edges; e++) max_id = std::max(max_id, (uint32_t)keys[e]);  // b > a
+    // pass 1: ref pairs (main.rs:972-980)
     for (uint64_t e = 0; e < n_edges; e++) {
         const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+        if (a != 0) break;  // keys are sorted: ref pairs come first
+        const long long v = vals[e];
+        const long long ndif = (v + (1LL << 31)) >> 32;
+        const long long sum = v - (ndif << 32);
+        if (asref) {
+            ref_w[b] = (float)sum;
+            have_ref = true;
+        }
+        if (ndif > 0 && !use_all_reads) invalid.insert(b);
+    }
+    std::vector<uint8_t> bad_v(max_id + 1, 0), has(max_id + 1, 0);
+    for (uint32_t x : invalid) bad_v[x] = 1;
+    Level lv;
+    lv.grow(max_id);
+    for (uint64_t e = 0; e < n_edges; e++) {
+        const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+        if (a == 0) continue;
         const long long v = vals[e];
         const long long ndif = (v + (1LL << 31)) >> 32;  // number of disagreeing sites
         const long long sum = v - (ndif << 32);          // sum of +-1 over shared heterozygous regions
-        if (a == 0) {  // pairs with the ref read (main.rs:972-980)
-            if (asref) {
-                ref_w[b] = (float)sum;
-                have_ref = true;
-            }
-            if (ndif > 0 && !use_all_reads) invalid.insert(b);
+        const float w = ndif >= 3 ? -(float)ndif : (float)sum;  // main.rs:996-1002
+        // main.rs:1004-1010: invalid reads leave the graph, their partners stay (possibly without edges)
+        if (!use_all_reads && (bad_v[a] || bad_v[b])) {
+            if (!bad_v[a]) has[a] = 1;
+            if (!bad_v[b]) has[b] = 1;
             continue;
         }
-        const float w = ndif >= 3 ? -(float)ndif : (float)sum;  // main.rs:996-1002
-        lv.data[a][b] = w;
-        lv.data[b][a] = w;
-    }
-    if (!use_all_reads) {  // main.rs:1004-1010
-        for (uint32_t x : invalid) lv.data.erase(x);
-        for (auto &kv : lv.data)
-            for (uint32_t x : invalid) kv.second.erase(x);
+        has[a] = has[b] = 1;
+        lv.adj[a].emplace_back(b, w);  // sorted keys keep every list ascending (smaller neighbours arrive first)
+        lv.adj[b].emplace_back(a, w);
     }
     // ---- Louvain (louvain.rs:59-257)
-    for (auto &kv : lv.data) {
-        lv.comm[kv.first] = {kv.first};
-        lv.node[kv.first] = LNode{kv.first, 0.f, {kv.first}};
+    for (uint32_t v = 0; v <= max_id; v++) {
+        if (!has[v]) continue;
+        lv.ids.push_back(v);
+        lv.cid[v] = v;
+        lv.members[v] = {v};
+        lv.comm[v] = {v};
     }
     while (move_vertices(lv)) lv = aggregate(lv);
     std::vector<Community> comms;
@@ -479,31 +507,27 @@ std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, u
         Community c;
         c.id = kv.first;
         c.weight = internal_weight(lv, kv.second);
-        for (uint32_t n : kv.second) {
-            const auto &mm = lv.node.at(n).members;
-            c.members.insert(c.members.end(), mm.begin(), mm.end());
-        }
+        for (uint32_t n : kv.second) c.members.insert(c.members.end(), lv.members[n].begin(), lv.members[n].end());
         comms.push_back(std::move(c));
     }
-    Adj conflict;
-    for (auto &c1 : comms)
-        for (auto &c2 : comms) {
-            if (!(c2.id > c1.id)) continue;
-            float w = 0.f;
-            for (uint32_t n1 : lv.comm.at(c1.id)) {
-                auto it = lv.data.find(n1);
-                if (it == lv.data.end()) continue;
-                for (uint32_t n2 : lv.comm.at(c2.id)) {
-                    auto jt = it->second.find(n2);
-                    if (jt != it->second.end()) w += jt->second;
-                }
+    // weights between communities: sum of the edges from the smaller id's vertices to the larger id's
+    std::vector<uint32_t> owner(lv.adj.size(), 0xFFFFFFFFu);
+    for (auto &kv : lv.comm)
+        for (uint32_t n : kv.second) owner[n] = kv.first;
+    std::map<std::pair<uint32_t, uint32_t>, float> between;
+    for (auto &kv : lv.comm)
+        for (uint32_t n1 : kv.second)
+            for (auto &e : lv.adj[n1]) {
+                const uint32_t o = owner[e.first];
+                if (o != 0xFFFFFFFFu && o > kv.first) between[{kv.first, o}] += e.second;
             }
-            if (w != 0.f) {
-                if (!(w < 0.f)) herr(NP2_ERR_FORMAT, "the weight of two conflicting community is not less than 0");
-                add_w(conflict, c1.id, c2.id, w);
-                add_w(conflict, c2.id, c1.id, w);
-            }
-        }
+    std::map<uint32_t, std::set<uint32_t>> conflict;
+    for (auto &kv : between) {
+        if (kv.second == 0.f) continue;
+        if (!(kv.second < 0.f)) herr(NP2_ERR_FORMAT, "the weight of two conflicting community is not less than 0");
+        conflict[kv.first.first].insert(kv.first.second);
+        conflict[kv.first.second].insert(kv.first.first);
+    }
     // ---- phase_communities louvain.rs:290-356
     if (have_ref) {
         std::vector<std::pair<std::pair<int32_t, float>, size_t>> key;
