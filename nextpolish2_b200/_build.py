@@ -24,3 +24,15 @@ def build_gpu_lib(force=False, verbose=False):
               [os.path.join(CSRC, s) for s in SOURCES]
         subprocess.check_call(cmd)
     return LIB
+
+
+CLI = os.path.join(HERE, "nextPolish2")
+
+
+def build_cli(force=False):
+    """The nextPolish2-compatible command line (C++ host + libnp2gpu)."""
+    src = os.path.join(CSRC, "np2_cli.cpp")
+    if force or _stale(CLI, [src, LIB]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", CLI, src, "-L" + HERE, "-lnp2gpu", "-lz", "-lpthread",
+                               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + "/usr/local/cuda/lib64"])
+    return CLI

@@ -1,0 +1,480 @@
+// np2_cli.cpp — `nextPolish2` command line on top of libnp2gpu (C ABI in include/np2gpu.h).
+//
+// Same surface as the reference CLI (src/utils/option.rs:45-225): positional <sorted.bam> <genome.fa[.gz]>
+// <k1.yak> [k2.yak ...], options -o -u --out_pos -k -t -i -m -l -L -n -s -S -a -q -c -r --min_base_cov, same
+// defaults (option.rs:267-292).  Extensions: -g/--gpus N (GPUs to use, default all visible).
+//
+// This file is the caller side of the hot path: hand-written BGZF/BAM/BAI and FASTA(.gz) readers
+// (zlib only) that hand each contig's raw alignment records to np2_polish_contig, and the orchestration
+// the reference does with three thread stages (main.rs:1698-1853): contigs are LPT-partitioned over the GPUs, one host
+// thread per GPU, records are printed in INPUT order (= the reference with -t 1).
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/np2gpu.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string &m) {
+    fprintf(stderr, "%s\n", m.c_str());
+    exit(101);  // the reference aborts with a panic message
+}
+
+/* ---------------------------------------------------------------- FASTA (kseq semantics) */
+struct Contig {
+    std::string name;  // first word of the header (kseq head())
+    std::string seq;
+};
+std::vector<Contig> read_fasta(const std::string &path) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) die("\"" + path + "\" does not exist!");
+    gzbuffer(f, 1 << 20);
+    std::vector<Contig> out;
+    std::vector<char> buf(1 << 20);
+    std::string line;
+    bool in_header = false, bol = true;
+    auto end_header = [&]() {
+        size_t e = 0;
+        while (e < line.size() && !isspace((unsigned char)line[e])) e++;
+        out.push_back(Contig{line.substr(1, e - 1), std::string()});
+        line.clear();
+    };
+    for (;;) {
+        int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n <= 0) break;
+        for (int i = 0; i < n; i++) {
+            const char c = buf[i];
+            if (in_header) {
+                if (c == '\n') {
+                    end_header();
+                    in_header = false;
+                } else if (c != '\r') line.push_back(c);
+            } else if (c == '>' && bol) {
+                in_header = true;
+                line.assign(1, '>');
+            } else if (c != '\n' && c != '\r') {
+                if (out.empty()) die("FASTA parsing failed!");
+                out.back().seq.push_back(c);
+            }
+            bol = c == '\n';
+        }
+    }
+    if (in_header) end_header();
+    gzclose(f);
+    return out;
+}
+
+/* ---------------------------------------------------------------- BGZF / BAM / BAI */
+struct BamFile {
+    FILE *fp = nullptr;
+    std::vector<std::string> ref_names;
+    std::vector<uint32_t> ref_lens;
+    std::vector<uint64_t> ref_voff;  // virtual offset of the first record of each reference (UINT64_MAX = none / unknown)
+    uint64_t first_rec_voff = 0;
+    bool have_index = false;
+    int threads = 1;
+};
+
+struct RawBlock {
+    uint64_t coff;
+    std::vector<uint8_t> cdata;  // deflate payload
+    uint32_t isize;
+};
+// reads the next BGZF member; returns false at EOF
+bool read_block(FILE *fp, RawBlock &b) {
+    uint8_t h[18];
+    b.coff = (uint64_t)ftello(fp);
+    size_t n = fread(h, 1, 18, fp);
+    if (n == 0) return false;
+    if (n != 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) die("BAM/SAM parsing failed!");
+    const uint32_t xlen = h[10] | h[11] << 8;
+    uint32_t bsize = 0;
+    std::vector<uint8_t> extra(xlen);
+    memcpy(extra.data(), h + 12, std::min<uint32_t>(6, xlen));
+    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fp) != xlen - 6) die("BAM/SAM parsing failed!");
+    for (uint32_t o = 0; o + 4 <= xlen;) {
+        const uint32_t slen = extra[o + 2] | extra[o + 3] << 8;
+        if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2) bsize = (extra[o + 4] | extra[o + 5] << 8) + 1;
+        o += 4 + slen;
+    }
+    if (!bsize || bsize < 12 + xlen + 8) die("BAM/SAM parsing failed!");
+    const uint32_t clen = bsize - 12 - xlen - 8;
+    b.cdata.resize(clen);
+    uint8_t tail[8];
+    if (fread(b.cdata.data(), 1, clen, fp) != clen || fread(tail, 1, 8, fp) != 8) die("BAM/SAM parsing failed!");
+    memcpy(&b.isize, tail + 4, 4);
+    return true;
+}
+void inflate_block(const RawBlock &b, uint8_t *out) {
+    if (!b.isize) return;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) die("BAM/SAM parsing failed!");
+    zs.next_in = (Bytef *)b.cdata.data();
+    zs.avail_in = (uInt)b.cdata.size();
+    zs.next_out = out;
+    zs.avail_out = b.isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END || zs.total_out != b.isize) die("BAM/SAM parsing failed!");
+}
+// inflates a batch of blocks in parallel into one contiguous buffer
+void inflate_batch(const std::vector<RawBlock> &blocks, std::vector<uint8_t> &out, std::vector<uint64_t> &uoff,
+                   int threads) {
+    uoff.assign(blocks.size() + 1, 0);
+    for (size_t i = 0; i < blocks.size(); i++) uoff[i + 1] = uoff[i] + blocks[i].isize;
+    out.resize(uoff.back());
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (size_t i; (i = next.fetch_add(1)) < blocks.size();) inflate_block(blocks[i], out.data() + uoff[i]);
+    };
+    const int T = std::max(1, std::min<int>(threads, (int)blocks.size()));
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
+void open_bam(const std::string &path, BamFile &bf) {
+    bf.fp = fopen(path.c_str(), "rb");
+    if (!bf.fp) die("\"" + path + "\" does not exist!");
+    // header: sequential blocks until the reference dictionary is complete
+    std::vector<uint8_t> u;
+    std::vector<uint64_t> blk_coff, blk_uoff;
+    auto need = [&](size_t n) {
+        while (u.size() < n) {
+            RawBlock b;
+            if (!read_block(bf.fp, b)) die("BAM/SAM parsing failed!");
+            blk_coff.push_back(b.coff);
+            blk_uoff.push_back(u.size());
+            size_t o = u.size();
+            u.resize(o + b.isize);
+            inflate_block(b, u.data() + o);
+        }
+    };
+    need(12);
+    if (memcmp(u.data(), "BAM\1", 4) != 0) die("BAM/SAM parsing failed!");
+    int32_t l_text, n_ref;
+    memcpy(&l_text, u.data() + 4, 4);
+    need(12 + (size_t)l_text);
+    memcpy(&n_ref, u.data() + 8 + l_text, 4);
+    size_t o = 12 + (size_t)l_text;
+    for (int32_t i = 0; i < n_ref; i++) {
+        need(o + 4);
+        int32_t l_name;
+        memcpy(&l_name, u.data() + o, 4);
+        need(o + 4 + l_name + 4);
+        bf.ref_names.emplace_back((const char *)u.data() + o + 4);
+        uint32_t l_ref;
+        memcpy(&l_ref, u.data() + o + 4 + l_name, 4);
+        bf.ref_lens.push_back(l_ref);
+        o += 8 + l_name;
+    }
+    // virtual offset of the first alignment record
+    size_t bi = blk_uoff.size() - 1;
+    while (blk_uoff[bi] > o) bi--;
+    if (o == u.size()) bf.first_rec_voff = (uint64_t)ftello(bf.fp) << 16;
+    else bf.first_rec_voff = blk_coff[bi] << 16 | (o - blk_uoff[bi]);
+    bf.ref_voff.assign(n_ref, UINT64_MAX);
+    // BAI: smallest chunk start of each reference
+    for (const std::string &ip : {path + ".bai", path.substr(0, path.size() > 4 ? path.size() - 4 : 0) + ".bai"}) {
+        FILE *fi = fopen(ip.c_str(), "rb");
+        if (!fi) continue;
+        char magic[4];
+        int32_t nr;
+        if (fread(magic, 1, 4, fi) != 4 || memcmp(magic, "BAI\1", 4) != 0 || fread(&nr, 4, 1, fi) != 1) die("bad BAI");
+        for (int32_t r = 0; r < nr && r < n_ref; r++) {
+            int32_t n_bin;
+            if (fread(&n_bin, 4, 1, fi) != 1) die("bad BAI");
+            uint64_t best = UINT64_MAX;
+            for (int32_t b = 0; b < n_bin; b++) {
+                uint32_t bin;
+                int32_t n_chunk;
+                if (fread(&bin, 4, 1, fi) != 1 || fread(&n_chunk, 4, 1, fi) != 1) die("bad BAI");
+                for (int32_t c = 0; c < n_chunk; c++) {
+                    uint64_t be[2];
+                    if (fread(be, 8, 2, fi) != 2) die("bad BAI");
+                    if (bin != 37450) best = std::min(best, be[0]);
+                }
+            }
+            int32_t n_intv;
+            if (fread(&n_intv, 4, 1, fi) != 1) die("bad BAI");
+            fseeko(fi, (off_t)n_intv * 8, SEEK_CUR);
+            bf.ref_voff[r] = best;
+        }
+        fclose(fi);
+        bf.have_index = true;
+        break;
+    }
+    if (!bf.have_index) die("Faield random access BAM/SAM!");  // IndexedReader needs the index (main.rs:1745-1747)
+}
+
+// IndexedReader::fetch((tid, 0, len)) + read loop (main.rs:1745-1751): every record of that reference, file order
+void fetch_records(BamFile &bf, int tid, std::vector<uint8_t> &blob) {
+    blob.clear();
+    if (tid < 0 || bf.ref_voff[tid] == UINT64_MAX) return;
+    const uint64_t voff = bf.ref_voff[tid];
+    fseeko(bf.fp, (off_t)(voff >> 16), SEEK_SET);
+    size_t skip = voff & 0xFFFF;
+    std::vector<uint8_t> carry, u;
+    std::vector<uint64_t> uoff;
+    std::vector<RawBlock> batch;
+    bool done = false, eof = false;
+    while (!done && !eof) {
+        batch.clear();
+        const size_t want = (size_t)std::max(64, bf.threads * 16);
+        for (size_t i = 0; i < want; i++) {
+            RawBlock b;
+            if (!read_block(bf.fp, b)) {
+                eof = true;
+                break;
+            }
+            batch.push_back(std::move(b));
+        }
+        inflate_batch(batch, u, uoff, bf.threads);
+        size_t o = std::min(skip, u.size());
+        skip -= o;
+        // stitch the partial record left over from the previous batch
+        carry.insert(carry.end(), u.begin() + o, u.end());
+        size_t p = 0;
+        while (p + 8 <= carry.size()) {
+            int32_t bs, ref_id;
+            memcpy(&bs, carry.data() + p, 4);
+            if (bs < 32) die("BAM/SAM parsing failed!");
+            if (p + 4 + (size_t)bs > carry.size()) break;
+            memcpy(&ref_id, carry.data() + p + 4, 4);
+            if (ref_id != tid) {
+                done = true;
+                break;
+            }
+            p += 4 + (size_t)bs;
+        }
+        blob.insert(blob.end(), carry.begin(), carry.begin() + p);
+        carry.erase(carry.begin(), carry.begin() + p);
+    }
+}
+
+/* ---------------------------------------------------------------- options (option.rs:45-292) */
+struct Cli {
+    std::string bam, fa, out = "stdout";
+    std::vector<std::string> yaks;
+    np2_opts o;
+    int threads = 1, gpus = 0;
+};
+void usage() {
+    fprintf(stderr,
+            "Usage: nextPolish2 [OPTIONS] <HiFi.map.bam> <genome.fa[.gz]> <short.read.yak>...\n"
+            "  -o, --out <FILE>            output file [default: stdout]\n"
+            "  -u, --uppercase             output in uppercase sequences\n"
+            "      --out_pos               output each base and its position\n"
+            "  -k, --min_kmer_count <INT>  filter kmers in k-mer dataset with count <= INT [default: 5]\n"
+            "  -t, --thread <INT>          number of (host) threads [default: 1]\n"
+            "  -i, --iter_count <INT>      number of iterations to attempt phasing [default: 2]\n"
+            "  -m, --model <ref|len>       phasing model [default: ref]\n"
+            "  -l, --min_read_len <INT>    filter reads with length <= INT [default: 1000]\n"
+            "  -L, --min_ctg_len <INT>     don't correct reference sequences with length <= INT [default: 1000000]\n"
+            "  -n, --max_indel_len <INT>   ignore indel errors with length > INT [default: 20]\n"
+            "  -s, --use_supplementary     use supplementary alignments\n"
+            "  -S, --use_secondary         use secondary alignments (not supported by this build)\n"
+            "  -a, --min_map_len <FLOAT>   filter alignments with alignment length <= min(INT, FLOAT * read_length) [default: 500.5]\n"
+            "  -q, --min_map_qual <INT>    filter alignments with mapping quality <= INT [default: 1]\n"
+            "  -c, --max_clip_len <INT>    filter alignments with unaligned length >= INT [default: 100]\n"
+            "  -r, --use_all_reads         use all unfiltered reads\n"
+            "      --min_base_cov <INT>    accepted for compatibility (unused by the reference as well)\n"
+            "  -g, --gpus <INT>            GPUs to use [default: all visible]\n");
+}
+Cli parse_args(int argc, char **argv) {
+    Cli c;
+    np2_opts_default(&c.o);
+    std::vector<std::string> pos;
+    auto val = [&](int &i) -> std::string {
+        if (i + 1 >= argc) {
+            usage();
+            exit(2);
+        }
+        return argv[++i];
+    };
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "-h" || a == "--help") {
+            usage();
+            exit(0);
+        } else if (a == "-o" || a == "--out") c.out = val(i);
+        else if (a == "-u" || a == "--uppercase") c.o.uppercase = 1;
+        else if (a == "--out_pos") c.o.out_pos = 1;
+        else if (a == "-k" || a == "--min_kmer_count") c.o.min_kmer_count = (uint32_t)atoi(val(i).c_str());
+        else if (a == "-t" || a == "--thread") c.threads = std::max(1, atoi(val(i).c_str()));
+        else if (a == "-i" || a == "--iter_count") c.o.iter_count = (uint32_t)atoi(val(i).c_str());
+        else if (a == "-m" || a == "--model") {
+            std::string m = val(i);
+            if (m != "ref" && m != "len") die("invalid value for --model");
+            c.o.model = m == "len";
+        } else if (a == "-l" || a == "--min_read_len") c.o.min_read_len = (uint32_t)atoi(val(i).c_str());
+        else if (a == "-L" || a == "--min_ctg_len") c.o.min_ctg_len = (uint64_t)atoll(val(i).c_str());
+        else if (a == "-n" || a == "--max_indel_len") c.o.max_indel_len = atoi(val(i).c_str());
+        else if (a == "-s" || a == "--use_supplementary") c.o.use_supplementary = 1;
+        else if (a == "-S" || a == "--use_secondary") c.o.use_secondary = 1;
+        else if (a == "-a" || a == "--min_map_len") {
+            const float f = (float)atof(val(i).c_str());  // option.rs:232,258-259
+            c.o.min_map_len = (uint32_t)f;
+            c.o.min_map_fra = f - (float)(uint32_t)f;
+        } else if (a == "-q" || a == "--min_map_qual") c.o.min_map_qual = atoi(val(i).c_str());
+        else if (a == "-c" || a == "--max_clip_len") c.o.max_clip_len = (uint32_t)atoi(val(i).c_str());
+        else if (a == "-r" || a == "--use_all_reads") c.o.use_all_reads = 1;
+        else if (a == "--min_base_cov") val(i);
+        else if (a == "-g" || a == "--gpus") c.gpus = atoi(val(i).c_str());
+        else if (!a.empty() && a[0] == '-' && a.size() > 1) {
+            fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str());
+            usage();
+            exit(2);
+        } else pos.push_back(a);
+    }
+    if (pos.size() < 3) {
+        usage();
+        exit(2);
+    }
+    c.bam = pos[0];
+    c.fa = pos[1];
+    c.yaks.assign(pos.begin() + 2, pos.end());
+    return c;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Cli cli = parse_args(argc, argv);
+    FILE *out = stdout;
+    if (cli.out != "stdout") {  // option.rs:308-328: refuse to overwrite
+        if (FILE *t = fopen(cli.out.c_str(), "rb")) {
+            fclose(t);
+            die("\"" + cli.out + "\" already exists!");
+        }
+        out = fopen(cli.out.c_str(), "wb");
+        if (!out) die("Failed to freopen: \"" + cli.out + "\"");
+    }
+    std::vector<Contig> contigs = read_fasta(cli.fa);
+    const size_t n = contigs.size();
+    for (auto &c : contigs)
+        if (c.seq.size() >= 0xFFFFFFFFull) die(c.name + " is too long!");  // main.rs:1707-1711
+    std::vector<std::vector<uint8_t>> results(n);
+    std::vector<uint8_t> done(n, 0);
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < n; i++) {
+        if (contigs[i].seq.size() < cli.o.min_ctg_len) {  // main.rs:1727-1730, no GPU involved
+            std::vector<uint32_t> pos(contigs[i].seq.size());
+            for (size_t p = 0; p < pos.size(); p++) pos[p] = (uint32_t)p;
+            const uint8_t *b = (const uint8_t *)contigs[i].seq.data();
+            uint64_t need = np2_format_fasta(contigs[i].name.c_str(), pos.data(), b, pos.size(), cli.o.uppercase,
+                                             cli.o.out_pos, nullptr, 0);
+            results[i].resize(need);
+            np2_format_fasta(contigs[i].name.c_str(), pos.data(), b, pos.size(), cli.o.uppercase, cli.o.out_pos,
+                             results[i].data(), need);
+            done[i] = 1;
+        } else todo.push_back(i);
+    }
+    if (!todo.empty()) {
+        BamFile bf;
+        bf.threads = cli.threads;
+        open_bam(cli.bam, bf);
+        int n_gpu = cli.gpus;
+        if (n_gpu <= 0) {
+            // probe: contexts are created until one fails
+            n_gpu = 0;
+            for (int d = 0; d < 16; d++) {
+                np2_ctx *c = nullptr;
+                if (np2_ctx_create(d, &c) != NP2_OK) break;
+                np2_ctx_destroy(c);
+                n_gpu++;
+            }
+            if (n_gpu == 0) die(std::string("no usable GPU: ") + np2_last_error());
+        }
+        n_gpu = (int)std::min<size_t>(n_gpu, todo.size());
+        // LPT partition by contig length (weight ~ length x depth)
+        std::vector<size_t> order = todo;
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            return contigs[a].seq.size() != contigs[b].seq.size() ? contigs[a].seq.size() > contigs[b].seq.size() : a < b;
+        });
+        std::vector<std::vector<size_t>> share(n_gpu);
+        std::vector<uint64_t> load(n_gpu, 0);
+        for (size_t i : order) {
+            int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            share[g].push_back(i);
+            load[g] += contigs[i].seq.size();
+        }
+        std::mutex bam_mu, err_mu;
+        std::string first_err;
+        auto worker = [&](int g) {
+            np2_ctx *ctx = nullptr;
+            auto fail = [&](const std::string &m) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (first_err.empty()) first_err = m;
+            };
+            if (np2_ctx_create(g, &ctx) != NP2_OK) return fail(np2_last_error());
+            std::vector<np2_table *> tabs;
+            for (auto &y : cli.yaks) {
+                np2_table *t = nullptr;
+                if (np2_yak_load(ctx, y.c_str(), &t) != NP2_OK) return fail(np2_last_error());
+                tabs.push_back(t);
+            }
+            std::sort(share[g].begin(), share[g].end());
+            std::vector<uint8_t> blob;
+            for (size_t i : share[g]) {
+                {
+                    std::lock_guard<std::mutex> lk(bam_mu);
+                    int tid = -1;
+                    for (size_t r = 0; r < bf.ref_names.size(); r++)
+                        if (bf.ref_names[r] == contigs[i].name) tid = (int)r;
+                    if (tid < 0) return fail("Faield random access BAM/SAM!");
+                    fetch_records(bf, tid, blob);
+                }
+                np2_job *job = nullptr;
+                if (np2_polish_contig(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(),
+                                      blob.data(), blob.size(), tabs.data(), (uint32_t)tabs.size(), &cli.o,
+                                      &job) != NP2_OK)
+                    return fail(np2_last_error());
+                const uint32_t *pos;
+                const uint8_t *base;
+                uint64_t nb = np2_job_get_consensus(job, cli.o.out_pos ? &pos : nullptr, &base);
+                if (cli.o.out_pos) {
+                    uint64_t need = np2_format_fasta(contigs[i].name.c_str(), pos, base, nb, cli.o.uppercase, 1, nullptr, 0);
+                    results[i].resize(need);
+                    np2_format_fasta(contigs[i].name.c_str(), pos, base, nb, cli.o.uppercase, 1, results[i].data(), need);
+                } else {
+                    uint32_t span[2];
+                    np2_job_get_span(job, &span[0], &span[1]);
+                    // header needs the first / last position only: format with a two-entry position view
+                    std::string hdr = ">" + contigs[i].name + " start:" + std::to_string(span[0]) +
+                                      " end:" + std::to_string(span[1]) + "\n";
+                    results[i].assign(hdr.begin(), hdr.end());
+                    size_t o = results[i].size();
+                    results[i].resize(o + nb + 1);
+                    if (cli.o.uppercase)
+                        for (uint64_t x = 0; x < nb; x++) results[i][o + x] = (uint8_t)toupper(base[x]);
+                    else memcpy(results[i].data() + o, base, nb);
+                    results[i][o + nb] = '\n';
+                }
+                np2_job_destroy(job);
+                done[i] = 1;
+            }
+            for (auto t : tabs) np2_yak_free(t);
+            np2_ctx_destroy(ctx);
+        };
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_gpu; g++) th.emplace_back(worker, g);
+        for (auto &t : th) t.join();
+        if (!first_err.empty()) die(first_err);
+    }
+    for (size_t i = 0; i < n; i++) fwrite(results[i].data(), 1, results[i].size(), out);
+    if (out != stdout) fclose(out);
+    return 0;
+}
