@@ -227,6 +227,7 @@ struct np2_job {
 
     // device inputs
     DBuf<uint8_t> d_ref, d_code, d_blob, d_nib, d_blank;
+    DBuf<uint32_t> d_refpk;
     DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off, d_op_col, d_op_q, d_op_t, d_op_cig;
     DBuf<uint64_t> d_seq_off, d_nib_off;
     DBuf<uint32_t> d_ts, d_te, d_n, d_ck_tpos, d_ck_read;
@@ -291,6 +292,7 @@ void np2_job::upload() {
     d_ref.alloc(L, s);
     d_ref.upload(tseq.data(), L);
     d_code.alloc(L, s);
+    d_refpk.alloc(L / 8 + 8, s);
     if (!blob_sent) {
         d_blob.alloc(bam_len ? bam_len : 1, s);
         if (bam_len) d_blob.upload(bam, bam_len);
@@ -446,7 +448,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_cover.p, d_cover.p, L + 1, s);
     }
     d_cta_cnt.zero();
-    pileup_count(R, n_blocks, d_blank.p, d_code.p, L, d_cta_cnt.p, s);
+    pileup_count(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, d_cta_cnt.p, s);
     {
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cta_cnt.p, d_cta_off.p, n_cta + 1, s);
@@ -470,7 +472,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     d_gidx.alloc(n_rec + 1, s);
     timer.hend("host:alloc_records");
     h = timer.begin("pileup_emit", 1);
-    pileup_emit(R, n_blocks, d_blank.p, d_code.p, L, d_cta_off.p, d_key.p, d_rd.p, s);
+    pileup_emit(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, d_cta_off.p, d_key.p, d_rd.p, s);
     timer.end(h);
     int pbits = 1;
     while ((1ull << pbits) < (uint64_t)L) pbits++;
@@ -1244,7 +1246,7 @@ void np2_job::run(int32_t dump_it) {
     DBuf<int> d_bad;
     d_bad.alloc(1, s);
     d_bad.zero();
-    ref_codes(d_ref.p, L, d_code.p, d_bad.p, s);
+    ref_codes(d_ref.p, L, d_code.p, d_refpk.p, d_bad.p, s);
     expand_trim_pack(R, d_ref.p, L, s);
     timer.end(h);
     int bad_ref = 0;

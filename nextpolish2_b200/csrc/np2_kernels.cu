@@ -251,8 +251,23 @@ __global__ void k_ref_codes(const uint8_t *__restrict__ ref, uint32_t L, uint8_t
     code[i] = (uint8_t)seq_code(c);
     if (c >= 128 || c == '-') atomicExch(bad, 1);
 }
-void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, int *d_bad, cudaStream_t s) {
+// 8 codes per u32, position 8w in the most significant nibble: a read block's 32 plain columns can then be compared
+// with the reference in four word operations (scan_block32 fast path).  The array is padded with 0xF nibbles.
+__global__ void k_ref_pack(const uint8_t *__restrict__ code, uint32_t L, uint32_t n_words, uint32_t *__restrict__ pk) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t v = 0;
+#pragma unroll
+    for (uint32_t x = 0; x < 8; x++) {
+        const uint32_t p = w * 8 + x;
+        v = v << 4 | (p < L ? code[p] : 15u);
+    }
+    pk[w] = v;
+}
+void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, uint32_t *d_refpk, int *d_bad, cudaStream_t s) {
     NP2_K(k_ref_codes)<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_ref, L, d_code, d_bad);
+    const uint32_t nw = L / 8 + 8;
+    NP2_K(k_ref_pack)<<<cdiv(nw, kThreads), kThreads, 0, s>>>(d_code, L, nw, d_refpk);
 }
 
 /* =============================================================== K1: expand + trim + pack */
@@ -410,20 +425,21 @@ __global__ void __launch_bounds__(128) k_expand_trim_pack(ReadsDev R, const uint
         R.t_e[r] = tp;
         R.n[r] = n;
     }
-    // ---- pack columns [shift, new_len) into nibbles + terminator (main.rs:287-310), write checkpoints
+    // ---- pack columns [shift, new_len) into nibbles + terminator (main.rs:287-310), write checkpoints.
+    // A lane packs 16 columns per step.  Blocks that lie inside one M/=/X op (~95 %) take a word-parallel path;
+    // the others (op boundaries, indels, the terminator) are queued per warp and packed later by densely filled
+    // warps, so that one odd block does not drag 31 idle lanes through the column-by-column code.
+    __shared__ uint32_t s_slow[4][64];
+    uint32_t *slow = s_slow[(threadIdx.x >> 5) & 3];
+    uint32_t n_slow = 0;
     uint8_t *out = R.nib + R.nib_off[r];
-    for (uint32_t o0 = lane * 16; o0 <= n; o0 += 512) {
+    const uint64_t lut = (4ULL << 0) | (0ULL << 4) | (1ULL << 8) | (6ULL << 12) | (2ULL << 16) | (4ULL << 20) |
+                         (4ULL << 24) | (4ULL << 28) | (3ULL << 32) | (4ULL << 36) | (4ULL << 40) | (4ULL << 44) |
+                         (4ULL << 48) | (4ULL << 52) | (4ULL << 56) | (5ULL << 60);
+    auto pack_slow = [&](uint32_t o0) {
         uint64_t word = 0;
         OpCur cur;
-        if (o0 < n) {
-            op_seek(R, r, shift + o0, cur);
-            if ((o0 & 31) == 0) {
-                uint32_t tp, dl;
-                col_tpos(R, r, pos, cur, shift + o0, tp, dl);
-                R.ck_tpos[ck0 + (o0 >> 5)] = tp;
-                R.ck_delta[ck0 + (o0 >> 5)] = (uint16_t)dl;
-            }
-        }
+        if (o0 < n) op_seek(R, r, shift + o0, cur);
 #pragma unroll
         for (uint32_t x = 0; x < 16; x++) {
             uint32_t o = o0 + x, nib = 15;
@@ -440,7 +456,52 @@ __global__ void __launch_bounds__(128) k_expand_trim_pack(ReadsDev R, const uint
             word |= (uint64_t)nib << (8 * (x >> 1) + ((x & 1) ? 0 : 4));
         }
         *(uint64_t *)(out + (o0 >> 1)) = word;
+    };
+    auto drain = [&](bool all) {
+        while (n_slow >= 32 || (all && n_slow > 0)) {
+            const uint32_t m = min(32u, n_slow);
+            __syncwarp();
+            if (lane < m) pack_slow(slow[n_slow - m + lane]);
+            n_slow -= m;
+            __syncwarp();
+        }
+    };
+    for (uint32_t base = 0; base <= n; base += 512) {
+        const uint32_t o0 = base + lane * 16;
+        bool is_slow = o0 <= n;
+        if (o0 < n) {
+            OpCur cur;
+            op_seek(R, r, shift + o0, cur);
+            if ((o0 & 31) == 0) {
+                uint32_t tp, dl;
+                col_tpos(R, r, pos, cur, shift + o0, tp, dl);
+                R.ck_tpos[ck0 + (o0 >> 5)] = tp;
+                R.ck_delta[ck0 + (o0 >> 5)] = (uint16_t)dl;
+            }
+            if (o0 + 16 <= n && cur.op != 1 && cur.op != 2 && shift + o0 + 16 <= cur.c_end) {
+                // 16 consecutive SEQ nibbles mapped through the code table
+                const uint32_t qi = cur.q + (shift + o0 - cur.c_beg);
+                const uint8_t *sp = seq4 + (qi >> 1);
+                uint64_t v = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) v = v << 8 | sp[j];
+                if (qi & 1) v = v << 4 | (sp[8] >> 4);
+                uint64_t codes = 0;  // column x at bits 60 - 4x
+#pragma unroll
+                for (int x = 0; x < 16; x++) codes = codes << 4 | ((lut >> (4 * ((v >> (60 - 4 * x)) & 15))) & 15);
+                // memory order: byte j holds columns 2j (high nibble), 2j+1 -> byte-reverse the numeric word
+                const uint32_t hi = (uint32_t)(codes >> 32), lo = (uint32_t)codes;
+                *(uint64_t *)(out + (o0 >> 1)) =
+                    (uint64_t)__byte_perm(hi, 0, 0x0123) | (uint64_t)__byte_perm(lo, 0, 0x0123) << 32;
+                is_slow = false;
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, is_slow);
+        if (is_slow) slow[n_slow + __popc(bal & ((1u << lane) - 1))] = o0;
+        n_slow += __popc(bal);
+        drain(false);
     }
+    drain(true);
 }
 void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
     if (!r.n_reads) return;
@@ -474,16 +535,42 @@ __device__ __forceinline__ uint32_t delta_scanback(const uint8_t *__restrict__ n
     return d;
 }
 
+// Fast check (the overwhelmingly common block): 32 plain columns (codes 0-3, no insertion, no gap) that equal the
+// reference, preceded by two plain matching columns => every 3-mer of the block is the reference 3-mer and nothing
+// has to be emitted.  Four word compares instead of 32 column steps.  Also true for blocks that hold no columns.
+__device__ __forceinline__ bool block_all_reference(const ReadsDev &R, uint32_t g, const uint8_t *__restrict__ blank,
+                                                    const uint8_t *__restrict__ code,
+                                                    const uint32_t *__restrict__ refpk) {
+    const uint32_t r = R.ck_read[g];
+    if (blank[r]) return true;
+    const uint32_t n = R.n[r];
+    const uint32_t o0 = (g - R.ck_off[r]) * 32;
+    if (o0 >= n) return true;
+    if (o0 == 0 || o0 + 32 > n) return false;
+    const uint8_t *nib = R.nib + R.nib_off[r];
+    const uint4 w4 = *reinterpret_cast<const uint4 *>(nib + (o0 >> 1));
+    if (((w4.x | w4.y | w4.z | w4.w) & 0xCCCCCCCCu) != 0) return false;
+    const uint32_t tpos = R.ck_tpos[g];
+    const uint32_t pb = nib[(o0 >> 1) - 1];
+    if ((pb & 0xCCu) != 0 || (pb >> 4) != code[tpos - 2] || (pb & 15u) != code[tpos - 1]) return false;
+    const uint32_t k = tpos >> 3, sh = (tpos & 7) * 4;
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    uint32_t diff = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t rj = __byte_perm(w[j], 0, 0x0123);  // column 8j in the most significant nibble
+        diff |= rj ^ __funnelshift_l(refpk[k + j + 1], refpk[k + j], sh);
+    }
+    return diff == 0;
+}
+
 // Walks the 32 columns of global block g and calls f(p, bases, delta1) for every 3-mer that is NOT the
 // reference 3-mer of its position (those are counted as cover[p] - #others, see pos_finalize).
 template <class F>
-__device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, const uint8_t *__restrict__ blank,
-                                             const uint8_t *__restrict__ code, F f) {
+__device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, const uint8_t *__restrict__ code, F f) {
     const uint32_t r = R.ck_read[g];
-    if (blank[r]) return;
     const uint32_t n = R.n[r];
     const uint32_t o0 = (g - R.ck_off[r]) * 32;
-    if (o0 >= n) return;
     const uint8_t *nib = R.nib + R.nib_off[r];
     const uint4 w4 = *reinterpret_cast<const uint4 *>(nib + (o0 >> 1));
     const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -544,38 +631,64 @@ __device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, cons
     }
 }
 
-constexpr int kPileThreads = 128;
-uint32_t pileup_ctas(uint32_t n_blocks) { return cdiv(n_blocks, kPileThreads); }
+constexpr int kPileThreads = 256;
+constexpr int kPilePerThread = 4;  // 32-column blocks examined per thread in the fast pass
+constexpr int kPileCta = kPileThreads * kPilePerThread;
+uint32_t pileup_ctas(uint32_t n_blocks) { return cdiv(n_blocks, kPileCta); }
 
+// Both passes: (1) every thread checks kPilePerThread blocks against the reference with word compares and queues the
+// few that hold something else in shared memory; (2) the queued blocks are walked column by column by densely packed
+// threads (without the queue, one odd block per warp would drag 31 idle lanes through the slow loop).
+__device__ __forceinline__ uint32_t pile_queue(const ReadsDev &R, uint32_t n_blocks, const uint8_t *__restrict__ blank,
+                                               const uint8_t *__restrict__ code, const uint32_t *__restrict__ refpk,
+                                               uint32_t *q, uint32_t *qn) {
+    if (threadIdx.x == 0) *qn = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPilePerThread; u++) {
+        const uint32_t g = blockIdx.x * kPileCta + u * kPileThreads + threadIdx.x;
+        if (g < n_blocks && !block_all_reference(R, g, blank, code, refpk)) q[atomicAdd(qn, 1u)] = g;
+    }
+    __syncthreads();
+    return *qn;
+}
 __global__ void __launch_bounds__(kPileThreads) k_pileup_count(ReadsDev R, uint32_t n_blocks,
                                                                const uint8_t *__restrict__ blank,
                                                                const uint8_t *__restrict__ code,
+                                                               const uint32_t *__restrict__ refpk,
                                                                uint32_t *__restrict__ cta_count) {
     typedef cub::BlockReduce<uint32_t, kPileThreads> BR;
     __shared__ typename BR::TempStorage tmp;
-    uint32_t g = blockIdx.x * kPileThreads + threadIdx.x;
+    __shared__ uint32_t q[kPileCta], qn;
+    const uint32_t nq = pile_queue(R, n_blocks, blank, code, refpk, q, &qn);
     uint32_t c = 0;
-    if (g < n_blocks) scan_block32(R, g, blank, code, [&](uint32_t, uint32_t, uint32_t) { c++; });
+    for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads)
+        scan_block32(R, q[i], code, [&](uint32_t, uint32_t, uint32_t) { c++; });
     uint32_t tot = BR(tmp).Sum(c);
     if (threadIdx.x == 0) cta_count[blockIdx.x] = tot;
 }
 __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32_t n_blocks,
                                                               const uint8_t *__restrict__ blank,
                                                               const uint8_t *__restrict__ code,
+                                                              const uint32_t *__restrict__ refpk,
                                                               const uint32_t *__restrict__ cta_off,
                                                               uint64_t *__restrict__ key, uint32_t *__restrict__ rd) {
     typedef cub::BlockScan<uint32_t, kPileThreads> BS;
     __shared__ typename BS::TempStorage tmp;
-    uint32_t g = blockIdx.x * kPileThreads + threadIdx.x;
+    __shared__ uint32_t q[kPileCta], qn;
+    const uint32_t nq = pile_queue(R, n_blocks, blank, code, refpk, q, &qn);
     uint32_t c = 0;
-    if (g < n_blocks) scan_block32(R, g, blank, code, [&](uint32_t, uint32_t, uint32_t) { c++; });
+    for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads)
+        scan_block32(R, q[i], code, [&](uint32_t, uint32_t, uint32_t) { c++; });
     uint32_t off;
     BS(tmp).ExclusiveSum(c, off);
-    if (c) {
-        // +2: records 0 and 1 are the reference read's two head 3-mers (main.rs:1732-1739, 579-584)
-        uint32_t w = cta_off[blockIdx.x] + off + 2;
+    // +2: records 0 and 1 are the reference read's two head 3-mers (main.rs:1732-1739, 579-584).  Record order inside
+    // the buffer is arbitrary: the first read of a 3-mer is taken as a minimum over its records (k_groups_fill).
+    uint32_t w = cta_off[blockIdx.x] + off + 2;
+    for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads) {
+        const uint32_t g = q[i];
         const uint32_t order = R.ck_read[g] + 1;
-        scan_block32(R, g, blank, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) {
+        scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) {
             key[w] = (uint64_t)p << 32 | (uint64_t)bases << 16 | dl1;
             rd[w] = order;
             w++;
@@ -588,14 +701,16 @@ __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32
         rd[1] = 0;
     }
 }
-void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                  uint32_t *d_cta_count, cudaStream_t s) {
-    NP2_K(k_pileup_count)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_count);
+void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
+                  const uint32_t *d_refpk, uint32_t L, uint32_t *d_cta_count, cudaStream_t s) {
+    NP2_K(k_pileup_count)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk,
+                                                                                  d_cta_count);
 }
-void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                 const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read, cudaStream_t s) {
-    NP2_K(k_pileup_emit)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_cta_off, d_key,
-                                                                         d_read);
+void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
+                 const uint32_t *d_refpk, uint32_t L, const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read,
+                 cudaStream_t s) {
+    NP2_K(k_pileup_emit)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk,
+                                                                                 d_cta_off, d_key, d_read);
 }
 
 __global__ void k_mark_heads(const uint64_t *__restrict__ key, uint32_t n, uint32_t *__restrict__ head) {
@@ -616,7 +731,9 @@ __global__ void k_groups_fill(const uint64_t *__restrict__ key, const uint32_t *
     gpos[g] = (uint32_t)(k >> 32);
     m.g_bases[g] = (uint16_t)(k >> 16);
     m.g_delta[g] = (uint16_t)k;
-    m.g_first[g] = rd[i];  // records were emitted in read order and the radix sort is stable
+    uint32_t first = rd[i];  // first read that carried this 3-mer = minimum over its records
+    for (uint32_t j = i + 1; j < n && key[j] == k; j++) first = min(first, rd[j]);
+    m.g_first[g] = first;
 }
 void groups_fill(const uint64_t *d_key, const uint32_t *d_read, const uint32_t *d_head, const uint32_t *d_gidx,
                  uint32_t n, uint32_t G, uint32_t *d_gstart, uint32_t *d_gpos, MsaDev m, cudaStream_t s) {

@@ -28,7 +28,8 @@ void gather32(const uint64_t *d_buf, uint64_t n_sectors, uint64_t n_loads, uint6
               cudaStream_t s);
 
 /* ------------------------------------------------------------------ K0/K1 ingest */
-void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, int *d_bad, cudaStream_t s);
+void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, uint32_t *d_refpk /* L/8 + 8 words */, int *d_bad,
+               cudaStream_t s);
 
 struct ReadsDev {
     uint32_t n_reads = 0;  // kept reads, index 0 = first BAM read (the ref read is implicit)
@@ -53,10 +54,11 @@ void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaS
 /* ------------------------------------------------------------------ K2 pileup */
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);
 // pass 1: per-CTA count of non-reference 3-mers; pass 2: write (key, read) records at the scanned offsets
-void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                  uint32_t *d_cta_count, cudaStream_t s);
-void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                 const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read, cudaStream_t s);
+void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
+                  const uint32_t *d_refpk, uint32_t L, uint32_t *d_cta_count, cudaStream_t s);
+void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
+                 const uint32_t *d_refpk, uint32_t L, const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read,
+                 cudaStream_t s);
 uint32_t pileup_ctas(uint32_t n_blocks);
 
 struct MsaDev {
