@@ -163,9 +163,26 @@ struct StageTimer {
 struct JobScratch {
     Ingest ing;
     std::vector<uint8_t> tseq, h_seeds, h_rech_pool;
-    PBuf<uint8_t> res_base, p_cbase, p_cflags;
+    PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage;
     PBuf<uint32_t> p_cpos;
     StageTimer timer;
+};
+// bump allocator over a pinned staging buffer: many small device arrays come back with one synchronisation and
+// without the implicit host-side staging of pageable destinations
+struct Stager {
+    PBuf<uint8_t> &buf;
+    cudaStream_t s;
+    size_t used = 0;
+    Stager(PBuf<uint8_t> &b, cudaStream_t st, size_t cap) : buf(b), s(st) { buf.resize(std::max<size_t>(cap, 64)); }
+    template <class T>
+    T *fetch(const T *dev, size_t n) {
+        used = (used + 15) & ~(size_t)15;
+        if (used + n * sizeof(T) > buf.cap) throw np2::Error(NP2_ERR_INTERNAL, "staging buffer overflow");
+        T *dst = reinterpret_cast<T *>(buf.p + used);
+        if (n) NP2_CUDA(cudaMemcpyAsync(dst, dev, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+        used += n * sizeof(T);
+        return dst;
+    }
 };
 struct np2_ctx {
     int device = 0;
@@ -1046,23 +1063,34 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     scan(d_r_nsurv.p, d_ent_off.p, (int)nreg);  // last entry handled below
     timer.end(h);
     timer.hbegin();
-    std::vector<uint8_t> lab(nreg);
-    std::vector<uint32_t> seed_len(nreg), nsurv(nreg), ent_off(nreg);
-    std::vector<uint64_t> seed_off(nreg), q_seedoff(nreg + 1);
-    uint64_t rech_bytes = 0;
-    int gerr = 0;
-    d_err.download(&gerr, 1);
-    d_r_lable.download(lab.data(), nreg);
-    d_r_seed_len.download(seed_len.data(), nreg);
-    d_r_seed_off.download(seed_off.data(), nreg);
-    d_r_nsurv.download(nsurv.data(), nreg);
-    d_ent_off.download(ent_off.data(), nreg);
-    d_q_seedoff.download(q_seedoff.data(), nreg + 1);
-    NP2_CUDA(cudaMemcpyAsync(&rech_bytes, d_rech_boff.p + nreg, 8, cudaMemcpyDeviceToHost, s));
-    fetch_regions();  // synchronises
+    // round 1: everything whose size is known (one synchronisation, pinned destinations)
+    p_cbase.resize(std::max(N, 1u));
+    d_cbase.download(p_cbase.p, N);
+    Stager st1(sc->p_stage, s, (size_t)nreg * 64 + 4096);
+    const int *h_gerr = st1.fetch(d_err.p, 1);
+    const uint64_t *h_rech_bytes = st1.fetch(d_rech_boff.p + nreg, 1);
+    const uint8_t *lab = st1.fetch(d_r_lable.p, nreg);
+    uint32_t *seed_len = st1.fetch(d_r_seed_len.p, nreg);
+    uint64_t *seed_off = st1.fetch(d_r_seed_off.p, nreg);
+    const uint32_t *nsurv = st1.fetch(d_r_nsurv.p, nreg);
+    const uint32_t *ent_off = st1.fetch(d_ent_off.p, nreg);
+    const uint64_t *q_seedoff = st1.fetch(d_q_seedoff.p, nreg + 1);
+    rg.start.resize(nreg);
+    rg.end.resize(nreg);
+    rg.a.resize(nreg);
+    rg.b.resize(nreg);
+    const uint32_t *h_rs = st1.fetch(d_rstart.p, nreg), *h_re = st1.fetch(d_rend.p, nreg);
+    const uint32_t *h_ra = st1.fetch(d_ra.p, nreg), *h_rb = st1.fetch(d_rb.p, nreg);
+    NP2_CUDA(cudaStreamSynchronize(s));
+    const int gerr = *h_gerr;
+    const uint64_t rech_bytes = *h_rech_bytes;
     if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
     if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
     if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
+    memcpy(rg.start.data(), h_rs, (size_t)nreg * 4);
+    memcpy(rg.end.data(), h_re, (size_t)nreg * 4);
+    memcpy(rg.a.data(), h_ra, (size_t)nreg * 4);
+    memcpy(rg.b.data(), h_rb, (size_t)nreg * 4);
     const uint32_t n_ent = nreg ? ent_off[nreg - 1] + nsurv[nreg - 1] : 0;
     const uint64_t seeds_bytes = q_seedoff[nreg];
     DBuf<uint8_t> d_seeds, d_rech_pool;
@@ -1075,23 +1103,22 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     d_ent_poff.alloc(std::max(n_ent, 1u), s);
     h = timer.begin("seed_gather", 2);
     assemble_seed_gather(ad, d_seeds.p, s);
-    rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
+    if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
     timer.end(h);
-    h_seeds.resize(seeds_bytes + 1);
-    h_rech_pool.resize(rech_bytes + 1);
+    // round 2: the seed strings and the survivors of the RECH regions
+    h_seeds.resize(seeds_bytes + 16);
+    h_rech_pool.resize(rech_bytes + 16);
+    d_seeds.download(h_seeds.data(), seeds_bytes);
+    if (rech_bytes) d_rech_pool.download(h_rech_pool.data(), rech_bytes);
     std::vector<uint32_t> ent_order(n_ent), ent_len(n_ent);
     std::vector<uint64_t> ent_poff(n_ent);
-    p_cbase.resize(std::max(N, 1u));
-    d_seeds.download(h_seeds.data(), seeds_bytes);
-    d_rech_pool.download(h_rech_pool.data(), rech_bytes);
     if (n_ent) {
         d_ent_order.download(ent_order.data(), n_ent);
         d_ent_len.download(ent_len.data(), n_ent);
         d_ent_poff.download(ent_poff.data(), n_ent);
     }
-    d_cbase.download(p_cbase.p, N);
     NP2_CUDA(cudaStreamSynchronize(s));
-    d2h += (uint64_t)N + seeds_bytes + rech_bytes + (uint64_t)nreg * 33 + (uint64_t)n_ent * 16;
+    d2h += (uint64_t)N + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
     // patched view, regions in ascending position (q = nreg - 1 - r)
     Patched &pc = res_patch;
     pc = Patched();
@@ -1170,24 +1197,23 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             seed_off[r] = al.dev_off;
             seed_len[r] = al.len;
         }
-        d_r_seed_off.upload(seed_off.data(), nreg);
-        d_r_seed_len.upload(seed_len.data(), nreg);
+        d_r_seed_off.upload(seed_off, nreg);
+        d_r_seed_len.upload(seed_len, nreg);
         h2d += (uint64_t)nreg * 12;
     }
+    long long total_shift = 0;
+    for (uint32_t q = 0; q < nreg; q++) total_shift += (long long)pc.seed[q].len - (long long)(pc.b[q] - pc.a[q]);
+    const uint64_t out_n = (uint64_t)((long long)N + total_shift);
+    DBuf<uint8_t> d_out;
+    d_out.alloc(out_n + 1, s);
+    res_base.resize(std::max<uint64_t>(out_n, 1));
+    res_base.n = out_n;
     h = timer.begin("assemble", 3);
     assemble_sizes(ad, s);
     NP2_CUDA(cudaMemsetAsync(d_q_delta.p + nreg, 0, 8, s));
     scan(d_q_delta.p, d_q_shift.p, (int)nreg + 1);
-    long long total_shift = 0;
-    NP2_CUDA(cudaMemcpyAsync(&total_shift, d_q_shift.p + nreg, 8, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
-    const uint64_t out_n = (uint64_t)((long long)N + total_shift);
-    DBuf<uint8_t> d_out;
-    d_out.alloc(out_n + 1, s);
     assemble_final(ad, d_out.p, s);
     timer.end(h);
-    res_base.resize(std::max<uint64_t>(out_n, 1));
-    res_base.n = out_n;
     d_out.download(res_base.p, out_n);
     NP2_CUDA(cudaStreamSynchronize(s));
     d2h += out_n;
