@@ -129,3 +129,30 @@ def test_no_reads(ctx):
     common.assert_same("base", obase, gbase)
     common.assert_same("pos", opos, gpos)
     assert bytes(gbase) == bytes(ds["contig"])
+
+
+@pytest.mark.parametrize("optkw", [{}, {"use_supplementary": 1, "min_map_qual": -1}, {"max_clip_len": 1000, "iter_count": 1},
+                                   {"iter_count": 3, "use_all_reads": 1}])
+def test_exotic_alignments(ctx, optkw):
+    """IUPAC/N bases, lower-case and N stretches in the contig, H/S clip mixes, indels at read ends, long indels,
+    =/X mixed with M, reads without an anchor, flagged records, zero-length ops (tests/exotic.py): every stage."""
+    import exotic
+    import nextpolish2_b200 as np2
+    from nextpolish2_b200 import synth
+    ref, blob = exotic.make()
+    up = np.char.upper(ref.view("S1")).view(np.uint8)
+    tabs = {k: synth.make_table(5, k, [up]) for k in (21, 31)}
+    oo, go = common.same_opts(**optkw)
+    for it in range(oo.iter_count):
+        oj = O.Job(ref, blob, [O.Table.from_arrays(k, *tabs[k]) for k in (21, 31)], oo, dump_iter=it)
+        gj = np2.Job(ctx, ref, blob, [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in (21, 31)], go).upload().run(it)
+        common.assert_same_dict("reads", oj.reads(), gj.reads(), ["rec_idx", "t_s", "t_e", "blank", "nib_off", "nib"])
+        common.assert_same_dict("msa", oj.msa(), gj.msa(), ["off", "bases", "delta", "count", "besti"])
+        common.assert_same_dict("dp", oj.dp_consensus(), gj.dp_consensus())
+        common.assert_same_dict("regions", oj.regions(), gj.regions(), ["start", "end", "lable"])
+        common.assert_same_dict("cand", oj.candidates(), gj.candidates(), ["roff", "order", "seq_off", "seq", "kmer", "kscore"])
+        common.assert_same("dropped", oj.dropped(), gj.dropped())
+        opos, obase = oj.consensus()
+        gpos, gbase = gj.consensus()
+        common.assert_same("final.base", obase, gbase)
+        common.assert_same("final.pos", opos, gpos)
