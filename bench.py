@@ -92,6 +92,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+# (profiles/r01_pipeline_full.txt was taken at 4 Mbp; scaled x2.5 to the 10 Mbp launch), bytes
+NCU_TRAFFIC = {"expand_trim_pack": None, "pileup_emit": None, "pileup_scan": None}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -155,7 +160,6 @@ def run_ours(args):
         launches += job.traffic()["kernel_launches"]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
     barrier()
     traffic = job.traffic()
     _, _, gbase = job.bases()
@@ -177,6 +181,7 @@ def run_ours(args):
         if i >= args.warmup:
             e2e_t.append(t2 - t1)
     e2e_time = sum(e2e_t)
+    clocks = sampler.stop()  # sampled over both timed regions (device-resident steps and end-to-end steps)
 
     t_dev = torch.tensor([dev_time, e2e_time, wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -198,7 +203,7 @@ def run_ours(args):
             per_launch_ms = stages[dom] / n_launch
             achieved = stage_bytes(dom, st) / (per_launch_ms * 1e-3) / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+                        "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_kind,
                         "launch_ms": round(per_launch_ms, 4), "share_of_step": round(stages[dom] / stages["total"], 4)}
         line = {
             "metric": "polished Mbp/s", "value": round(mbp_total / dev_time, 3), "unit": "Mbp/s", "n_gpus": world,
@@ -318,8 +323,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--length", type=int, default=10_000_000, help="contig length per GPU (configs[1] = 10 Mbp)")
     ap.add_argument("--cpu-contig", type=int, default=1_000_000)

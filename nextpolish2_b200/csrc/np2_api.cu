@@ -247,7 +247,7 @@ struct np2_job {
     DBuf<uint32_t> d_refpk;
     DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off, d_op_col, d_op_q, d_op_t, d_op_cig;
     DBuf<uint64_t> d_seq_off, d_nib_off;
-    DBuf<uint32_t> d_ts, d_te, d_n, d_ck_tpos, d_ck_read;
+    DBuf<uint32_t> d_ts, d_te, d_n, d_shift, d_ck_tpos, d_ck_read;
     DBuf<uint16_t> d_ck_delta;
     ReadsDev R;
 
@@ -337,6 +337,7 @@ void np2_job::upload() {
     d_ts.alloc(std::max(n, 1u), s);
     d_te.alloc(std::max(n, 1u), s);
     d_n.alloc(std::max(n, 1u), s);
+    d_shift.alloc(std::max(n, 1u), s);
     d_ck_tpos.alloc(std::max(nck, 1u), s);
     d_ck_delta.alloc(std::max(nck, 1u), s);
     d_ck_read.alloc(std::max(nck, 1u), s);
@@ -356,6 +357,7 @@ void np2_job::upload() {
     R.t_s = d_ts.p;
     R.t_e = d_te.p;
     R.n = d_n.p;
+    R.shift = d_shift.p;
     R.nib = d_nib.p;
     R.ck_tpos = d_ck_tpos.p;
     R.ck_delta = d_ck_delta.p;
@@ -1273,7 +1275,7 @@ void np2_job::run(int32_t dump_it) {
     d_bad.alloc(1, s);
     d_bad.zero();
     ref_codes(d_ref.p, L, d_code.p, d_refpk.p, d_bad.p, s);
-    expand_trim_pack(R, d_ref.p, L, s);
+    expand_trim_pack(R, d_ref.p, L, ing.ck_off.back(), s);
     timer.end(h);
     int bad_ref = 0;
     d_bad.download(&bad_ref, 1);

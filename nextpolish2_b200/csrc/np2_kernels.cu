@@ -425,87 +425,111 @@ __global__ void __launch_bounds__(128) k_expand_trim_pack(ReadsDev R, const uint
         R.t_e[r] = tp;
         R.n[r] = n;
     }
-    // ---- pack columns [shift, new_len) into nibbles + terminator (main.rs:287-310), write checkpoints.
-    // A lane packs 16 columns per step.  Blocks that lie inside one M/=/X op (~95 %) take a word-parallel path;
-    // the others (op boundaries, indels, the terminator) are queued per warp and packed later by densely filled
-    // warps, so that one odd block does not drag 31 idle lanes through the column-by-column code.
-    __shared__ uint32_t s_slow[4][64];
-    uint32_t *slow = s_slow[(threadIdx.x >> 5) & 3];
-    uint32_t n_slow = 0;
-    uint8_t *out = R.nib + R.nib_off[r];
+    // the packing itself is a separate, perfectly parallel kernel (k_pack_columns); when the terminator falls on a
+    // 32-column boundary no pack thread owns its word, so it is written here
+    if (lane == 0) {
+        R.shift[r] = shift;
+        if ((n & 31) == 0) *(uint64_t *)(R.nib + R.nib_off[r] + (n >> 1)) = 0xFFFFFFFFFFFFFFFFULL;
+    }
+}
+
+// ---- pack columns [shift, shift + n) into nibbles + terminator (main.rs:287-310) and write the checkpoints.
+// One thread per 32-column output block (16 bytes).  Blocks that lie inside one M/=/X op (~95 %) are 32 consecutive
+// SEQ nibbles mapped through the 16-entry code table; the others (op boundaries, indels, the terminator) are queued
+// in shared memory and packed column by column by densely filled warps.
+constexpr int kPackThreads = 256;
+__device__ __forceinline__ uint64_t map_codes16(uint64_t v) {  // 16 BAM nibbles (first at the top) -> 16 codes, byte order of memory
     const uint64_t lut = (4ULL << 0) | (0ULL << 4) | (1ULL << 8) | (6ULL << 12) | (2ULL << 16) | (4ULL << 20) |
                          (4ULL << 24) | (4ULL << 28) | (3ULL << 32) | (4ULL << 36) | (4ULL << 40) | (4ULL << 44) |
                          (4ULL << 48) | (4ULL << 52) | (4ULL << 56) | (5ULL << 60);
-    auto pack_slow = [&](uint32_t o0) {
-        uint64_t word = 0;
-        OpCur cur;
-        if (o0 < n) op_seek(R, r, shift + o0, cur);
+    uint64_t codes = 0;
 #pragma unroll
-        for (uint32_t x = 0; x < 16; x++) {
-            uint32_t o = o0 + x, nib = 15;
-            if (o < n) {
-                uint32_t c = shift + o;
-                while (c >= cur.c_end) {
-                    cur.i++;
-                    op_load(R, cur);
-                }
-                bool match;
-                col_eval(R, ref, pos, seq4, cur, c, match, nib);
+    for (int x = 0; x < 16; x++) codes = codes << 4 | ((lut >> (4 * ((v >> (60 - 4 * x)) & 15))) & 15);
+    const uint32_t hi = (uint32_t)(codes >> 32), lo = (uint32_t)codes;
+    return (uint64_t)__byte_perm(hi, 0, 0x0123) | (uint64_t)__byte_perm(lo, 0, 0x0123) << 32;
+}
+__device__ __forceinline__ void pack_block_slow(const ReadsDev &R, const uint8_t *__restrict__ ref, uint32_t g) {
+    const uint32_t r = R.ck_read[g];
+    const uint32_t n = R.n[r], shift = R.shift[r], pos = R.pos[r];
+    const uint32_t o0 = (g - R.ck_off[r]) * 32;
+    const uint8_t *seq4 = R.blob + R.seq_off[r];
+    uint64_t word[2] = {0, 0};
+    OpCur cur;
+    if (o0 < n) op_seek(R, r, shift + o0, cur);
+    for (uint32_t x = 0; x < 32; x++) {
+        uint32_t o = o0 + x, nib = 15;
+        if (o < n) {
+            uint32_t c = shift + o;
+            while (c >= cur.c_end) {
+                cur.i++;
+                op_load(R, cur);
             }
-            // column o -> byte o/2, high nibble when o is even
-            word |= (uint64_t)nib << (8 * (x >> 1) + ((x & 1) ? 0 : 4));
+            bool match;
+            col_eval(R, ref, pos, seq4, cur, c, match, nib);
         }
-        *(uint64_t *)(out + (o0 >> 1)) = word;
-    };
-    auto drain = [&](bool all) {
-        while (n_slow >= 32 || (all && n_slow > 0)) {
-            const uint32_t m = min(32u, n_slow);
-            __syncwarp();
-            if (lane < m) pack_slow(slow[n_slow - m + lane]);
-            n_slow -= m;
-            __syncwarp();
-        }
-    };
-    for (uint32_t base = 0; base <= n; base += 512) {
-        const uint32_t o0 = base + lane * 16;
-        bool is_slow = o0 <= n;
-        if (o0 < n) {
-            OpCur cur;
-            op_seek(R, r, shift + o0, cur);
-            if ((o0 & 31) == 0) {
+        // column o -> byte o/2, high nibble when o is even
+        word[x >> 4] |= (uint64_t)nib << (8 * ((x & 15) >> 1) + ((x & 1) ? 0 : 4));
+    }
+    uint64_t *out = (uint64_t *)(R.nib + R.nib_off[r] + (o0 >> 1));
+    out[0] = word[0];
+    out[1] = word[1];
+}
+__global__ void __launch_bounds__(kPackThreads) k_pack_columns(ReadsDev R, const uint8_t *__restrict__ ref,
+                                                               uint32_t n_blocks) {
+    __shared__ uint32_t q[kPackThreads], qn;
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
+    const uint32_t g = blockIdx.x * kPackThreads + threadIdx.x;
+    if (g < n_blocks) {
+        const uint32_t r = R.ck_read[g];
+        const uint32_t n = R.n[r];
+        const uint32_t o0 = (g - R.ck_off[r]) * 32;
+        if (n && o0 <= n) {
+            bool done = false;
+            if (o0 < n) {
+                const uint32_t shift = R.shift[r], pos = R.pos[r];
+                OpCur cur;
+                op_seek(R, r, shift + o0, cur);
                 uint32_t tp, dl;
                 col_tpos(R, r, pos, cur, shift + o0, tp, dl);
-                R.ck_tpos[ck0 + (o0 >> 5)] = tp;
-                R.ck_delta[ck0 + (o0 >> 5)] = (uint16_t)dl;
+                R.ck_tpos[g] = tp;
+                R.ck_delta[g] = (uint16_t)dl;
+                if (o0 + 32 <= n && cur.op != 1 && cur.op != 2 && shift + o0 + 32 <= cur.c_end) {
+                    const uint32_t qi = cur.q + (shift + o0 - cur.c_beg);
+                    const uint8_t *sp = R.blob + R.seq_off[r] + (qi >> 1);
+                    // 17 bytes from an arbitrary address: five aligned words, funnel-shifted
+                    const uint32_t mis = (uint32_t)((uintptr_t)sp & 3);
+                    const uint32_t *wp = (const uint32_t *)(sp - mis);
+                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+                    const uint32_t sh = mis * 8;
+                    // big-endian numeric words: first SEQ byte in the most significant position
+                    const uint32_t b0 = __byte_perm(__funnelshift_r(w0, w1, sh), 0, 0x0123);
+                    const uint32_t b1 = __byte_perm(__funnelshift_r(w1, w2, sh), 0, 0x0123);
+                    const uint32_t b2 = __byte_perm(__funnelshift_r(w2, w3, sh), 0, 0x0123);
+                    const uint32_t b3 = __byte_perm(__funnelshift_r(w3, w4, sh), 0, 0x0123);
+                    uint64_t hi = (uint64_t)b0 << 32 | b1, lo = (uint64_t)b2 << 32 | b3;
+                    if (qi & 1) {  // odd query index: the stream starts at the low nibble of the first byte
+                        const uint32_t b16 = (__funnelshift_r(w4, 0, sh)) & 255u;  // 17th byte
+                        hi = hi << 4 | lo >> 60;
+                        lo = lo << 4 | (b16 >> 4);
+                    }
+                    uint64_t *out = (uint64_t *)(R.nib + R.nib_off[r] + (o0 >> 1));
+                    out[0] = map_codes16(hi);
+                    out[1] = map_codes16(lo);
+                    done = true;
+                }
             }
-            if (o0 + 16 <= n && cur.op != 1 && cur.op != 2 && shift + o0 + 16 <= cur.c_end) {
-                // 16 consecutive SEQ nibbles mapped through the code table
-                const uint32_t qi = cur.q + (shift + o0 - cur.c_beg);
-                const uint8_t *sp = seq4 + (qi >> 1);
-                uint64_t v = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) v = v << 8 | sp[j];
-                if (qi & 1) v = v << 4 | (sp[8] >> 4);
-                uint64_t codes = 0;  // column x at bits 60 - 4x
-#pragma unroll
-                for (int x = 0; x < 16; x++) codes = codes << 4 | ((lut >> (4 * ((v >> (60 - 4 * x)) & 15))) & 15);
-                // memory order: byte j holds columns 2j (high nibble), 2j+1 -> byte-reverse the numeric word
-                const uint32_t hi = (uint32_t)(codes >> 32), lo = (uint32_t)codes;
-                *(uint64_t *)(out + (o0 >> 1)) =
-                    (uint64_t)__byte_perm(hi, 0, 0x0123) | (uint64_t)__byte_perm(lo, 0, 0x0123) << 32;
-                is_slow = false;
-            }
+            if (!done) q[atomicAdd(&qn, 1u)] = g;
         }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, is_slow);
-        if (is_slow) slow[n_slow + __popc(bal & ((1u << lane) - 1))] = o0;
-        n_slow += __popc(bal);
-        drain(false);
     }
-    drain(true);
+    __syncthreads();
+    const uint32_t nq = qn;
+    for (uint32_t i = threadIdx.x; i < nq; i += kPackThreads) pack_block_slow(R, ref, q[i]);
 }
-void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
+void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, uint32_t n_blocks, cudaStream_t s) {
     if (!r.n_reads) return;
     NP2_K(k_expand_trim_pack)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
+    if (n_blocks) NP2_K(k_pack_columns)<<<cdiv(n_blocks, kPackThreads), kPackThreads, 0, s>>>(r, d_ref, n_blocks);
 }
 
 /* =============================================================== K2: pileup */

@@ -44,12 +44,13 @@ struct ReadsDev {
     const uint8_t *blob = nullptr;
     // outputs
     uint32_t *t_s = nullptr, *t_e = nullptr, *n = nullptr;  // trimmed start / inclusive end / column count (0 = no anchor)
+    uint32_t *shift = nullptr;                               // first kept column (trim start)
     uint8_t *nib = nullptr;
     uint32_t *ck_tpos = nullptr;
     uint16_t *ck_delta = nullptr;
     uint32_t *ck_read = nullptr;
 };
-void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s);
+void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, uint32_t n_blocks, cudaStream_t s);
 
 /* ------------------------------------------------------------------ K2 pileup */
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);
