@@ -174,7 +174,8 @@ def run_ours(args):
         t1 = time.perf_counter()
         j = np2.Job(ctx, contig_np, bam_np, tables, opts)
         j.upload().run(-1)
-        first, last, base = j.bases()  # the FASTA record: header span + bases
+        first, last, base = j.bases(copy=False)  # the FASTA record (header span + bases) in host memory
+        assert len(base) == len(c["hap1"]) and base[-1] == c["hap1"][-1]
         t2 = time.perf_counter()
         tr = j.traffic()
         j.destroy()

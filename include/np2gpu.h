@@ -97,6 +97,14 @@ int np2_seq_kscore(np2_ctx *ctx, const np2_table *t, const uint8_t *seqs, const 
  * scratch buffer of buf_bytes — the measured random-read peak K5 is compared with. */
 int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms);
 
+/* ---- page-locked host buffers ----
+ * Record buffers handed to np2_polish_contig / np2_job_create may live in any host memory.  When they are
+ * page-locked (from np2_host_alloc, cudaHostAlloc, cudaHostRegister, torch pin_memory ...) the device gathers the
+ * SEQ fields straight out of them over PCIe and QUAL / names / tags never cross the bus; pageable buffers are
+ * compacted by host threads into a pinned ring first.  Same results either way. */
+int np2_host_alloc(uint64_t bytes, void **out);
+void np2_host_free(void *p);
+
 /* ---- per-contig polish ----
  * tseq/tlen : contig sequence (raw FASTA bytes, case preserved)
  * bam       : this contig's BAM alignment records, concatenated in file order, each with its block_size prefix
@@ -110,6 +118,9 @@ int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const ui
 int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
                    np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out);
 int np2_job_upload(np2_job *job);
+/* tseq and bam must stay valid (and unchanged) until np2_job_upload / np2_polish_contig returns.
+ * 1 = SEQ gathered by the device from page-locked records, 2 = compacted on the host, 0 = contig below min_ctg_len */
+int np2_job_ingest_path(const np2_job *job);
 /* dump_iter >= 0: keep that iteration's intermediates on the host for the np2_job_get_* stage getters */
 int np2_job_run(np2_job *job, int32_t dump_iter);
 void np2_job_destroy(np2_job *job);
@@ -134,6 +145,13 @@ uint64_t np2_job_get_dropped(np2_job *job, const uint32_t **ids);
 uint32_t np2_job_get_timings(np2_job *job, const char **names, const float **ms, const uint32_t **launches);
 void np2_job_get_traffic(np2_job *job, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *n_kernel_launches,
                          uint64_t *n_alignment_columns, uint64_t *n_probes);
+
+/* Test seam (host only, no device needed): parses + filters a record buffer (main.rs:1758-1771, 386-440) split into
+ * `threads` speculative byte ranges (0 = automatic) and returns a digest of everything the parse produces:
+ * out[0] records, out[1] kept reads, out[2] column-consuming CIGAR ops, out[3] alignment columns,
+ * out[4] ranges re-walked sequentially because the guessed record boundary was wrong, out[5] FNV-1a of all arrays. */
+int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts *opts, uint32_t threads,
+                    uint64_t out[6]);
 
 /* FASTA record exactly as display_consensusbase_vec prints it (main.rs:607-645); returns bytes needed. */
 uint64_t np2_format_fasta(const char *tid, const uint32_t *pos, const uint8_t *base, uint64_t n, int uppercase,

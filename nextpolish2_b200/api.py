@@ -45,6 +45,7 @@ EXPORTS = [
     "np2_seq_kscore", "np2_bench_gather32", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
     "np2_job_get_consensus", "np2_job_get_span", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
+    "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
 ]
 
 
@@ -79,6 +80,10 @@ def load_library():
     L.np2_polish_contig.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_job_create.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_job_upload.argtypes = [vp]
+    L.np2_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.np2_host_free.argtypes = [vp]
+    L.np2_job_ingest_path.argtypes = [vp]
+    L.np2_debug_parse.argtypes = [vp, u64, u32, vp, u32, vp]
     L.np2_job_run.argtypes = [vp, C.c_int32]
     L.np2_job_destroy.argtypes = [vp]
     for name, n in [("np2_job_get_consensus", 2), ("np2_job_get_reads", 6), ("np2_job_get_msa", 5),
@@ -129,6 +134,38 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class PinnedBuffer:
+    """Page-locked host bytes from np2_host_alloc: records placed here are gathered by the device itself (K0)."""
+
+    def __init__(self, data):
+        data = np.ascontiguousarray(data, np.uint8)
+        self.p = C.c_void_p()
+        _check(load_library().np2_host_alloc(max(len(data), 1), C.byref(self.p)))
+        self.array = np.frombuffer((C.c_char * max(len(data), 1)).from_address(self.p.value), dtype=np.uint8)[:len(data)]
+        self.array[:] = data
+
+    def free(self):
+        if self.p:
+            self.array = None
+            load_library().np2_host_free(self.p)
+            self.p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def debug_parse(bam, tlen, opts=None, threads=0):
+    """Host-only test seam: record parse + filter over `threads` speculative byte ranges -> counts and a digest."""
+    bam = np.ascontiguousarray(bam, np.uint8)
+    opts = opts or Opts()
+    out = (C.c_uint64 * 6)()
+    _check(load_library().np2_debug_parse(bam.ctypes.data, len(bam), tlen, C.byref(opts), threads, out))
+    return dict(zip(["records", "reads", "ops", "columns", "fallback", "digest"], [int(x) for x in out]))
 
 
 def bench_gather32(ctx, buf_bytes, n_loads, repeat=5):
@@ -222,6 +259,11 @@ class Job:
         _check(load_library().np2_job_upload(self.h))
         return self
 
+    @property
+    def ingest_path(self):
+        """1 = SEQ gathered by the device from page-locked records, 2 = compacted on the host, 0 = passthrough."""
+        return load_library().np2_job_ingest_path(self.h)
+
     def run(self, dump_iter=-1):
         _check(load_library().np2_job_run(self.h, dump_iter))
         return self
@@ -235,13 +277,16 @@ class Job:
         n, p = self._get("np2_job_get_consensus", 2)
         return _arr(p[0], n, np.uint32), _arr(p[1], n, np.uint8)
 
-    def bases(self):
-        """(first_pos, last_pos, bases): all the FASTA record needs, without materialising per-base positions."""
+    def bases(self, copy=True):
+        """(first_pos, last_pos, bases): all the FASTA record needs, without materialising per-base positions.
+        copy=False returns a view of the library's page-locked result buffer (valid until destroy())."""
         base = C.c_void_p()
         n = load_library().np2_job_get_consensus(self.h, None, C.byref(base))
         f, l = C.c_uint32(), C.c_uint32()
         load_library().np2_job_get_span(self.h, C.byref(f), C.byref(l))
-        return f.value, l.value, _arr(base, n, np.uint8)
+        if copy or n == 0:
+            return f.value, l.value, _arr(base, n, np.uint8)
+        return f.value, l.value, np.frombuffer((C.c_char * n).from_address(base.value), dtype=np.uint8)
 
     def reads(self):
         n, p = self._get("np2_job_get_reads", 6)

@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/np2gpu.h"
@@ -163,9 +164,15 @@ struct StageTimer {
 struct JobScratch {
     Ingest ing;
     std::vector<uint8_t> tseq, h_seeds, h_rech_pool;
-    PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage;
+    PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage, p_seq_stage;
     PBuf<uint32_t> p_cpos;
+    std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
+    cudaEvent_t seq_ev[2] = {nullptr, nullptr};
     StageTimer timer;
+    ~JobScratch() {
+        for (auto e : seq_ev)
+            if (e) cudaEventDestroy(e);
+    }
 };
 // bump allocator over a pinned staging buffer: many small device arrays come back with one synchronisation and
 // without the implicit host-side staging of pageable destinations
@@ -231,11 +238,14 @@ struct np2_job {
     JobScratch *sc = nullptr;
     np2_opts opt;
     std::vector<np2_table *> tables;  // sorted by k
-    std::vector<uint8_t> &tseq;
+    std::vector<uint8_t> &tseq;  // host copy only for contigs below min_ctg_len (echoed back unchanged)
+    uint32_t L = 0;
     const uint8_t *bam = nullptr;
     uint64_t bam_len = 0;
     Ingest &ing;
-    bool uploaded = false, blob_sent = false;
+    bool uploaded = false;
+    uint64_t seq_blob_bytes = 0;
+    int seq_path = 0;  // 1 = gathered by the device from page-locked records, 2 = compacted by host threads
     explicit np2_job(np2_ctx *c)
         : ctx(c), sc(c->take_scratch()), tseq(sc->tseq), ing(sc->ing), res_base(sc->res_base), p_cpos(sc->p_cpos),
           p_cbase(sc->p_cbase), p_cflags(sc->p_cflags), timer(sc->timer), h_seeds(sc->h_seeds),
@@ -294,6 +304,8 @@ struct np2_job {
     std::vector<uint8_t> dm_can_seq;
     std::vector<uint32_t> dm_dropped;
 
+    void send_contig(const uint8_t *tseq_host);
+    void send_seq();
     void upload();
     void run(int32_t dump_iter);
     void ingest_finish();
@@ -302,18 +314,99 @@ struct np2_job {
 
 /* ================================================================= pipeline */
 
-void np2_job::upload() {
+// The contig goes up straight from the caller's buffer (asynchronously when it is page-locked).
+void np2_job::send_contig(const uint8_t *tseq_host) {
     cudaStream_t s = ctx->stream;
-    const uint32_t L = (uint32_t)tseq.size();
-    const uint32_t n = (uint32_t)ing.pos.size();
     d_ref.alloc(L, s);
-    d_ref.upload(tseq.data(), L);
+    d_ref.upload(tseq_host, L);
     d_code.alloc(L, s);
     d_refpk.alloc(L / 8 + 8, s);
-    if (!blob_sent) {
-        d_blob.alloc(bam_len ? bam_len : 1, s);
-        if (bam_len) d_blob.upload(bam, bam_len);
+    h2d += L;
+}
+
+// Only the 4-bit SEQ fields of the kept records go to the device (a third of the record bytes for HiFi BAMs with
+// QUAL): compact blob, one 16-byte aligned slot per read that keeps the source's misalignment.
+//  * page-locked caller buffer (cudaHostAlloc / cudaHostRegister): K0 gathers over PCIe from the mapped records
+//  * pageable buffer: host threads compact into a pooled pinned ring, one DMA per round
+void np2_job::send_seq() {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = (uint32_t)ing.pos.size();
+    const uint8_t *src = bam;
+    seq_path = 2;
+    if (bam_len) {
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, bam);
+        if (e != cudaSuccess) cudaGetLastError();  // older runtimes flag plain malloc memory as an error
+        else if (at.type == cudaMemoryTypeHost && at.devicePointer) {
+            src = static_cast<const uint8_t *>(at.devicePointer);
+            seq_path = 1;
+        }
     }
+    std::vector<uint64_t> &co = sc->cseq_off;
+    co.resize(n);
+    uint64_t D = 0;
+    for (uint32_t r = 0; r < n; r++) {
+        const uint64_t mis = (uintptr_t)(src + ing.seq_off[r]) & 15;
+        co[r] = D + mis;
+        D += ((mis + ing.seq_bytes[r] + 15) & ~15ull) + 32;  // slack: the pack kernel reads whole words past the end
+    }
+    seq_blob_bytes = D;
+    d_blob.alloc(D + 64, s);
+    d_seq_off.alloc(std::max<size_t>(n, 1), s);
+    if (n) d_seq_off.upload(co.data(), n);
+    h2d += (uint64_t)n * 8;
+    if (!n) return;
+    if (seq_path == 1) {
+        DBuf<uint64_t> d_src_off;
+        DBuf<uint32_t> d_nbytes;
+        d_src_off.alloc(n, s);
+        d_nbytes.alloc(n, s);
+        d_src_off.upload(ing.seq_off.data(), n);
+        d_nbytes.upload(ing.seq_bytes.data(), n);
+        gather_seq(src, d_src_off.p, d_seq_off.p, d_nbytes.p, d_blob.p, n, s);
+        h2d += (uint64_t)n * 12;
+        for (uint32_t r = 0; r < n; r++) h2d += ing.seq_bytes[r];
+        return;  // scratch is freed in stream order, after the kernel
+    }
+    // pageable source: rounds of <= kRound bytes through two halves of a pinned ring
+    const uint64_t kRound = 64ull << 20;
+    uint64_t max_slot = 0;
+    for (uint32_t r = 0; r < n; r++) max_slot = std::max<uint64_t>(max_slot, (uint64_t)ing.seq_bytes[r] + 64);
+    const uint64_t half = std::max(kRound, max_slot);
+    sc->p_seq_stage.resize(2 * half);
+    for (auto &ev : sc->seq_ev)
+        if (!ev) NP2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    uint32_t r0 = 0;
+    for (uint32_t round = 0; r0 < n; round++) {
+        const uint64_t D0 = co[r0] & ~15ull;
+        uint32_t r1 = r0 + 1;
+        auto slot_end = [&](uint32_t r) { return (r + 1 < n) ? (co[r + 1] & ~15ull) : D; };
+        while (r1 < n && slot_end(r1) - D0 <= half) r1++;
+        const uint64_t D1 = slot_end(r1 - 1);
+        uint8_t *buf = sc->p_seq_stage.p + (round & 1) * half;
+        if (round >= 2) NP2_CUDA(cudaEventSynchronize(sc->seq_ev[round & 1]));
+        auto work = [&](unsigned ti) {
+            const uint32_t b = r0 + (uint64_t)(r1 - r0) * ti / T, e = r0 + (uint64_t)(r1 - r0) * (ti + 1) / T;
+            for (uint32_t r = b; r < e; r++) memcpy(buf + (co[r] - D0), bam + ing.seq_off[r], ing.seq_bytes[r]);
+        };
+        if (r1 - r0 < 256) {
+            for (unsigned ti = 0; ti < T; ti++) work(ti);
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned ti = 0; ti < T; ti++) th.emplace_back(work, ti);
+            for (auto &t : th) t.join();
+        }
+        NP2_CUDA(cudaMemcpyAsync(d_blob.p + D0, buf, D1 - D0, cudaMemcpyHostToDevice, s));
+        NP2_CUDA(cudaEventRecord(sc->seq_ev[round & 1], s));
+        h2d += D1 - D0;
+        r0 = r1;
+    }
+}
+
+void np2_job::upload() {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = (uint32_t)ing.pos.size();
     auto up32 = [&](DBuf<uint32_t> &d, const std::vector<uint32_t> &h) {
         d.alloc(std::max<size_t>(h.size(), 1), s);
         if (!h.empty()) d.upload(h.data(), h.size());
@@ -323,15 +416,25 @@ void np2_job::upload() {
     up32(d_op_off, ing.op_off);
     up32(d_ncols, ing.ncols);
     up32(d_ck_off, ing.ck_off);
-    up32(d_op_col, ing.op_col);
-    up32(d_op_q, ing.op_q);
-    up32(d_op_t, ing.op_t);
-    up32(d_op_cig, ing.op_cig);
-    d_seq_off.alloc(std::max<size_t>(n, 1), s);
-    if (n) d_seq_off.upload(ing.seq_off.data(), n);
+    {  // the op arrays go up chunk by chunk from the page-locked segment arrays they were parsed into
+        const size_t no = std::max<size_t>(ing.n_ops, 1);
+        d_op_col.alloc(no, s);
+        d_op_q.alloc(no, s);
+        d_op_t.alloc(no, s);
+        d_op_cig.alloc(no, s);
+        size_t w = 0;
+        for (const Ingest::OpChunk &c : ing.op_chunks) {
+            NP2_CUDA(cudaMemcpyAsync(d_op_col.p + w, c.col, c.n * 4, cudaMemcpyHostToDevice, s));
+            NP2_CUDA(cudaMemcpyAsync(d_op_q.p + w, c.q, c.n * 4, cudaMemcpyHostToDevice, s));
+            NP2_CUDA(cudaMemcpyAsync(d_op_t.p + w, c.t, c.n * 4, cudaMemcpyHostToDevice, s));
+            NP2_CUDA(cudaMemcpyAsync(d_op_cig.p + w, c.cig, c.n * 4, cudaMemcpyHostToDevice, s));
+            w += c.n;
+        }
+        h2d += (uint64_t)ing.n_ops * 16;
+    }
     d_nib_off.alloc(n + 1, s);
     d_nib_off.upload(ing.nib_off.data(), n + 1);
-    h2d += L + bam_len + (uint64_t)n * 8 * 2;
+    h2d += (uint64_t)n * 8;
     const uint32_t nck = ing.ck_off.back();
     d_nib.alloc(ing.nib_off.back() + 16, s);
     d_ts.alloc(std::max(n, 1u), s);
@@ -369,7 +472,6 @@ void np2_job::upload() {
 // after K1: which candidate reads become alignseqs (main.rs:1800-1813), clip filter (main.rs:531-574)
 void np2_job::ingest_finish() {
     const uint32_t n = R.n_reads;
-    const uint32_t L = (uint32_t)tseq.size();
     h_blank.assign(std::max(n, 1u), 1);
     read_order.assign(n, 0);
     as_read.clear();
@@ -438,7 +540,6 @@ void np2_job::ingest_finish() {
 // state already on the device instead of being recomputed.  Returns the next iteration that needs a fresh build.
 uint32_t np2_job::iteration(uint32_t iter0) {
     cudaStream_t s = ctx->stream;
-    const uint32_t L = (uint32_t)tseq.size();
     const uint32_t n_reads = R.n_reads;
     const uint32_t n_blocks = ing.ck_off.back();
     int h;
@@ -1084,6 +1185,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     const uint32_t *h_rs = st1.fetch(d_rstart.p, nreg), *h_re = st1.fetch(d_rend.p, nreg);
     const uint32_t *h_ra = st1.fetch(d_ra.p, nreg), *h_rb = st1.fetch(d_rb.p, nreg);
     NP2_CUDA(cudaStreamSynchronize(s));
+    timer.hend("host:seed_sync1");
     const int gerr = *h_gerr;
     const uint64_t rech_bytes = *h_rech_bytes;
     if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
@@ -1120,6 +1222,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         d_ent_poff.download(ent_poff.data(), n_ent);
     }
     NP2_CUDA(cudaStreamSynchronize(s));
+    timer.hend("host:seed_sync2");
     d2h += (uint64_t)N + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
     // patched view, regions in ascending position (q = nreg - 1 - r)
     Patched &pc = res_patch;
@@ -1157,7 +1260,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             }
         }
     }
-    timer.hend("host:seed_download");
+    timer.hend("host:seed_view");
     bool changed = false;
     for (size_t ti = 0; ti < tables.size(); ti++) {
         Reupdate ru;
@@ -1216,6 +1319,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     scan(d_q_delta.p, d_q_shift.p, (int)nreg + 1);
     assemble_final(ad, d_out.p, s);
     timer.end(h);
+    timer.hend("host:assemble_prep");
     d_out.download(res_base.p, out_n);
     NP2_CUDA(cudaStreamSynchronize(s));
     d2h += out_n;
@@ -1231,7 +1335,6 @@ uint32_t np2_job::iteration(uint32_t iter0) {
 void np2_job::run(int32_t dump_it) {
     dump_iter = dump_it;
     cudaStream_t s = ctx->stream;
-    const uint32_t L = (uint32_t)tseq.size();
     res_base.n = 0;
     res_pos.clear();
     res_pos_valid = false;
@@ -1369,6 +1472,11 @@ int np2_ctx_create(int device, np2_ctx **out) {
                                                cudaGetErrorString(e) + ")");
         if (device < 0 || device >= n) throw np2::Error(NP2_ERR_ARG, "bad device index");
         NP2_CUDA(cudaSetDevice(device));
+        np2::host_alloc_hook = [](size_t n) -> void * {
+            void *p = nullptr;
+            return cudaHostAlloc(&p, n, cudaHostAllocPortable) == cudaSuccess ? p : nullptr;
+        };
+        np2::host_free_hook = [](void *p) { cudaFreeHost(p); };
         np2_ctx *c = new np2_ctx();
         c->device = device;
         NP2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1575,28 +1683,39 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
         for (uint32_t i = 0; i < n_tables; i++) j->tables.push_back(tables[i]);
         std::stable_sort(j->tables.begin(), j->tables.end(),
                          [](np2_table *a, np2_table *b) { return a->dev.k < b->dev.k; });  // option.rs:238
-        j->tseq.assign(tseq, tseq + tlen);
+        j->L = tlen;
         j->bam = bam;
         j->bam_len = bam_len;
         if (tlen >= opts->min_ctg_len) {
             if (tlen < 16) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig shorter than 16 bp");
             if (tlen >= (1u << 30)) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig >= 2^30 bp (main.rs:270)");
-            // start moving the records to the device before parsing them: the DMA overlaps the host walk
             NP2_CUDA(cudaSetDevice(ctx->device));
-            j->d_blob.alloc(bam_len ? bam_len : 1, ctx->stream);
-            if (bam_len) j->d_blob.upload(bam, bam_len);
-            j->blob_sent = true;
+            j->send_contig(tseq);  // in flight while the host walks the records
             parse_records(bam, bam_len, tlen, *opts, j->ing);
+            j->send_seq();
+        } else {
+            j->tseq.assign(tseq, tseq + tlen);
         }
         ctx->refs++;
         *out = j.release();
     });
 }
 
+int np2_host_alloc(uint64_t bytes, void **out) {
+    return guard([&] {
+        if (!out) throw np2::Error(NP2_ERR_ARG, "null argument");
+        NP2_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    });
+}
+void np2_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+int np2_job_ingest_path(const np2_job *job) { return job->seq_path; }
+
 int np2_job_upload(np2_job *job) {
     return guard([&] {
         NP2_CUDA(cudaSetDevice(job->ctx->device));
-        if (job->tseq.size() >= job->opt.min_ctg_len) job->upload();
+        if (job->L >= job->opt.min_ctg_len) job->upload();
     });
 }
 
@@ -1716,6 +1835,42 @@ void np2_job_get_traffic(np2_job *j, uint64_t *h2d_bytes, uint64_t *d2h_bytes, u
     if (n_kernel_launches) *n_kernel_launches = j->n_launch;
     if (n_alignment_columns) *n_alignment_columns = j->ing.total_cols;
     if (n_probes) *n_probes = j->n_probes;
+}
+
+int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts *opts, uint32_t threads,
+                    uint64_t out[6]) {
+    return guard([&] {
+        Ingest ing;
+        parse_records(bam, bam_len, tlen, *opts, ing, threads);
+        uint64_t h = 0xcbf29ce484222325ull;
+        auto mix = [&](const void *p, size_t n) {
+            const uint8_t *b = static_cast<const uint8_t *>(p);
+            for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 0x100000001b3ull;
+        };
+        auto mixv = [&](const auto &v) { mix(v.data(), v.size() * sizeof(v[0])); };
+        mixv(ing.all_tid);
+        mixv(ing.all_pos);
+        mixv(ing.rec_idx);
+        mixv(ing.pos);
+        mixv(ing.ncols);
+        mixv(ing.rlen);
+        mixv(ing.rspan);
+        mixv(ing.is_clip);
+        mixv(ing.seq_off);
+        mixv(ing.seq_bytes);
+        mixv(ing.op_off);
+        mixv(ing.nib_off);
+        mixv(ing.ck_off);
+        for (int a = 0; a < 4; a++)
+            for (const Ingest::OpChunk &c : ing.op_chunks)
+                mix(a == 0 ? c.col : a == 1 ? c.q : a == 2 ? c.t : c.cig, c.n * 4);
+        out[0] = ing.all_tid.size();
+        out[1] = ing.pos.size();
+        out[2] = ing.n_ops;
+        out[3] = ing.total_cols;
+        out[4] = ing.n_fallback;
+        out[5] = h;
+    });
 }
 
 uint64_t np2_format_fasta(const char *tid, const uint32_t *pos, const uint8_t *base, uint64_t n, int uppercase,

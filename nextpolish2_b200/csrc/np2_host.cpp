@@ -18,18 +18,22 @@ namespace np2 {
 
 /* ================================================================= ingest */
 
-namespace {
-typedef Ingest::RecOut RecOut;
-struct ParseErr {
-    int64_t rec = INT64_MAX;
-    std::string msg;
-};
-}  // namespace
+static void *default_alloc(size_t n) { return malloc(n); }
+static void default_free(void *p) { free(p); }
+void *(*host_alloc_hook)(size_t) = default_alloc;
+void (*host_free_hook)(void *) = default_free;
+template <class T>
+void HVec<T>::grow(size_t need) {
+    size_t nc = std::max<size_t>(std::max(need, cap * 2), 65536);
+    T *np_ = static_cast<T *>(host_alloc_hook(nc * sizeof(T)));
+    if (!np_) herr(NP2_ERR_INTERNAL, "host allocation failed");
+    if (n) memcpy(np_, p, n * sizeof(T));
+    if (p) host_free_hook(p);
+    p = np_;
+    cap = nc;
+}
+template struct HVec<uint32_t>;
 
-// Record-level filter (main.rs:1758-1771) and fill_with_cigar bookkeeping (main.rs:386-440) without materialising
-// the gapped strings.  Pass 1 walks the block_size chain (sequential by nature); pass 2 processes the records'
-// CIGARs on all host threads; pass 3 concatenates.  The first failing record in file order decides the error,
-// like the reference's sequential loop would.
 void Ingest::clear() {
     all_tid.clear();
     all_pos.clear();
@@ -40,173 +44,193 @@ void Ingest::clear() {
     rspan.clear();
     is_clip.clear();
     seq_off.clear();
+    seq_bytes.clear();
     op_off.clear();
-    op_col.clear();
-    op_q.clear();
-    op_t.clear();
-    op_cig.clear();
     nib_off.clear();
     ck_off.clear();
+    op_chunks.clear();
     total_cols = 0;
-    rec_off.clear();
-    ro.clear();
+    n_ops = 0;
+    n_fallback = 0;
 }
 
-void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out) {
-    out.clear();
-    std::vector<uint64_t> &rec_off = out.rec_off;
-    {
-        uint64_t off = 0;
-        while (off + 4 <= bam_len) {
-            int32_t bs;
-            memcpy(&bs, bam + off, 4);
-            if (bs < 32 || off + 4 + (uint64_t)bs > bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
-            rec_off.push_back(off + 4);
-            off += 4 + (uint64_t)bs;
+namespace {
+typedef Ingest::RecOut RecOut;
+typedef Ingest::Segment Segment;
+
+inline int32_t rd32(const uint8_t *p) {
+    int32_t v;
+    memcpy(&v, p, 4);
+    return v;
+}
+// Could a record (block_size prefix included) start at byte p?  Only used to pick speculative starting points; the
+// join below accepts a segment only when the verified walk before it lands exactly on its start.
+inline bool plausible(const uint8_t *bam, uint64_t bam_len, uint64_t p) {
+    if (p + 36 > bam_len) return false;
+    const int32_t bs = rd32(bam + p);
+    if (bs < 32 || p + 4 + (uint64_t)bs > bam_len) return false;
+    const uint8_t *r = bam + p + 4;
+    const int32_t ref_id = rd32(r), pos = rd32(r + 4), l_seq = rd32(r + 16);
+    const uint32_t l_name = r[8];
+    uint16_t n_cig;
+    memcpy(&n_cig, r + 12, 2);
+    if (ref_id < -1 || pos < -1 || l_seq < 0 || l_name == 0) return false;
+    if (32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 > (uint64_t)bs) return false;
+    return r[32 + l_name - 1] == 0;  // read_name is NUL terminated
+}
+uint64_t find_start(const uint8_t *bam, uint64_t bam_len, uint64_t lo, uint64_t hi) {
+    for (uint64_t p = lo; p < hi; p++) {
+        uint64_t x = p;
+        int k = 0;
+        for (; k < 4; k++) {
+            if (x == bam_len) break;  // the chain reaches the end of the buffer
+            if (!plausible(bam, bam_len, x)) {
+                k = -1;
+                break;
+            }
+            x += 4 + (uint64_t)rd32(bam + x);
         }
-        if (off != bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+        if (k != -1) return p;
     }
-    const size_t nrec = rec_off.size();
-    out.all_tid.resize(nrec);
-    out.all_pos.resize(nrec);
-    std::vector<RecOut> &ro = out.ro;
-    ro.assign(nrec, RecOut());
-    unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (nrec < 2048) T = 1;
-    auto &t_col = out.t_col, &t_q = out.t_q, &t_t = out.t_t, &t_cig = out.t_cig;
-    if (t_col.size() < T) {
-        t_col.resize(T);
-        t_q.resize(T);
-        t_t.resize(T);
-        t_cig.resize(T);
-    }
-    std::vector<ParseErr> t_err(T);
-    auto work = [&](unsigned ti) {
-        const size_t b = nrec * ti / T, e = nrec * (ti + 1) / T;
-        // thread-local vectors: the shared arrays of vector headers would false-share on every push_back
-        std::vector<uint32_t> vcol, vq, vt, vcig;
-        vcol.swap(t_col[ti]);  // take last job's capacity
-        vq.swap(t_q[ti]);
-        vt.swap(t_t[ti]);
-        vcig.swap(t_cig[ti]);
-        vcol.clear();
-        vq.clear();
-        vt.clear();
-        vcig.clear();
-        const size_t guess = (e - b) * 64;
-        vcol.reserve(guess);
-        vq.reserve(guess);
-        vt.reserve(guess);
-        vcig.reserve(guess);
-        struct Publish {
-            std::vector<uint32_t> &a, &b, &c, &d, &A, &B, &C, &D;
-            ~Publish() {
-                A.swap(a);
-                B.swap(b);
-                C.swap(c);
-                D.swap(d);
-            }
-        } publish{vcol, vq, vt, vcig, t_col[ti], t_q[ti], t_t[ti], t_cig[ti]};
-        ParseErr my_err;
-        struct PublishErr {
-            ParseErr &src, &dst;
-            ~PublishErr() { dst = src; }
-        } publish_err{my_err, t_err[ti]};
-        auto fail = [&](size_t rec, const char *m) {
-            if ((int64_t)rec < my_err.rec) {
-                my_err.rec = (int64_t)rec;
-                my_err.msg = m;
-            }
-        };
-        for (size_t rec = b; rec < e; rec++) {
-            const uint8_t *r = bam + rec_off[rec];
-            int32_t bs, ref_id, pos, l_seq;
-            uint16_t n_cig, flag;
-            memcpy(&bs, r - 4, 4);
-            memcpy(&ref_id, r, 4);
-            memcpy(&pos, r + 4, 4);
-            const uint32_t l_name = r[8], mapq = r[9];
-            memcpy(&n_cig, r + 12, 2);
-            memcpy(&flag, r + 14, 2);
-            memcpy(&l_seq, r + 16, 4);
-            out.all_tid[rec] = ref_id;
-            out.all_pos[rec] = pos;
-            if (l_seq < 0 || 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 > (uint64_t)bs) {
-                fail(rec, "BAM/SAM parsing failed!");
-                return;  // a sequential reader stops here
-            }
-            const uint8_t *cg = r + 32 + l_name;
-            // seq_len_from_cigar(true), bam_endpos
-            uint64_t rlen = 0, rspan = 0;
-            for (uint32_t i = 0; i < n_cig; i++) {
-                uint32_t c;
-                memcpy(&c, cg + 4 * i, 4);
-                const uint32_t l = c >> 4, op = c & 15;
-                if (op == 0 || op == 1 || op == 4 || op == 5 || op == 7 || op == 8) rlen += l;
-                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rspan += l;
-            }
-            const int64_t span = ((flag & 4) || n_cig == 0 || rspan == 0) ? 1 : (int64_t)rspan;
-            const int64_t need = std::max<int64_t>((int64_t)opt.min_map_len, (int64_t)((float)rlen * opt.min_map_fra));
-            if ((flag & 0x404) || (int16_t)mapq <= (int16_t)opt.min_map_qual || rlen <= opt.min_read_len ||
-                ((flag & 0x100) && !opt.use_secondary) || ((flag & 0x800) && !opt.use_supplementary) || span < need)
-                continue;
-            if (pos < 0 || (uint64_t)pos > tlen) {
-                fail(rec, "alignment starts outside the contig");
-                return;
-            }
-            uint32_t qs = 0, ts = 0, col = 0, aln_q_s = 0, aln_q_e = 0, n_ops = 0;
-            bool first = true;
-            const char *bad = nullptr;
-            for (uint32_t i = 0; i < n_cig && !bad; i++) {
-                uint32_t c;
-                memcpy(&c, cg + 4 * i, 4);
-                const uint32_t l = c >> 4, op = c & 15;
-                switch (op) {
-                    case 4:
-                        qs += l;
-                        if (first) aln_q_s = qs;
-                        else aln_q_e = qs - l;
-                        break;
-                    case 0: case 7: case 8: case 1: case 2:
-                        if (op != 2 && (uint64_t)qs + l > (uint64_t)l_seq) {
-                            bad = "CIGAR consumes more query bases than SEQ holds";
-                            break;
-                        }
-                        if (op != 1 && (uint64_t)pos + ts + l > tlen) {
-                            bad = "alignment runs past the end of the contig";
-                            break;
-                        }
-                        if (l) {
-                            vcol.push_back(col);
-                            vq.push_back(qs);
-                            vt.push_back(ts);
-                            vcig.push_back(c);
-                            n_ops++;
-                        }
-                        col += l;
-                        if (op != 2) qs += l;
-                        if (op != 1) ts += l;
-                        break;
-                    case 5:
-                        break;
-                    default:
-                        bad = "Unknown cigar";
+    return UINT64_MAX;
+}
+
+// One record: filter (main.rs:1758-1771) + fill_with_cigar bookkeeping (main.rs:386-440) without the strings.
+// Returns an error message when the reference would panic on it.
+const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const np2_opts &opt, Segment &sg) {
+    const uint8_t *r = bam + payload;
+    const int32_t bs = rd32(r - 4), ref_id = rd32(r), pos = rd32(r + 4), l_seq = rd32(r + 16);
+    const uint32_t l_name = r[8], mapq = r[9];
+    uint16_t n_cig, flag;
+    memcpy(&n_cig, r + 12, 2);
+    memcpy(&flag, r + 14, 2);
+    sg.tid.push_back(ref_id);
+    sg.pos.push_back(pos);
+    sg.ro.emplace_back();
+    if (l_seq < 0 || 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 > (uint64_t)bs)
+        return "BAM/SAM parsing failed!";
+    const uint8_t *cg = r + 32 + l_name;
+    // One pass over the CIGAR: seq_len_from_cigar(true) and bam_endpos for the filter, and the
+    // column-consuming ops for the kernels.  The ops are rolled back when the filter rejects the record; what the
+    // reference would panic on only counts for records that pass it.
+    const size_t ops0 = sg.col.n;
+    uint64_t rlen = 0, rspan = 0;
+    uint32_t qs = 0, ts = 0, col = 0, aln_q_s = 0, aln_q_e = 0, n_ops = 0;
+    bool first = true;
+    const char *bad = nullptr;
+    for (uint32_t i = 0; i < n_cig; i++) {
+        const uint32_t c = (uint32_t)rd32(cg + 4 * i);
+        const uint32_t l = c >> 4, op = c & 15;
+        if (op == 0 || op == 1 || op == 4 || op == 5 || op == 7 || op == 8) rlen += l;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rspan += l;
+        if (bad) continue;
+        switch (op) {
+            case 4:
+                qs += l;
+                if (first) aln_q_s = qs;
+                else aln_q_e = qs - l;
+                break;
+            case 0: case 7: case 8: case 1: case 2:
+                if (op != 2 && (uint64_t)qs + l > (uint64_t)l_seq) {
+                    bad = "CIGAR consumes more query bases than SEQ holds";
+                    break;
                 }
-                first = false;
-            }
-            if (bad) {
-                fail(rec, bad);
-                return;
-            }
-            if (aln_q_e == 0) aln_q_e = qs;
-            RecOut &o = ro[rec];
-            o.kept = 1;
-            o.is_clip = (uint32_t)(aln_q_e - aln_q_s + opt.max_clip_len) < (uint32_t)rlen ? 1 : 0;  // main.rs:1796
-            o.ncols = col;
-            o.rlen = (uint32_t)rlen;
-            o.rspan = (uint32_t)rspan;
-            o.n_ops = n_ops;
-            o.seq_off = rec_off[rec] + 32 + l_name + 4ull * n_cig;
+                if (op != 1 && (uint64_t)(uint32_t)pos + ts + l > tlen) {
+                    bad = "alignment runs past the end of the contig";
+                    break;
+                }
+                if (l) {
+                    sg.col.push_back(col);
+                    sg.q.push_back(qs);
+                    sg.t.push_back(ts);
+                    sg.cig.push_back(c);
+                    n_ops++;
+                }
+                col += l;
+                if (op != 2) qs += l;
+                if (op != 1) ts += l;
+                break;
+            case 5:
+                break;
+            default:
+                bad = "Unknown cigar";
+        }
+        first = false;
+    }
+    const int64_t span = ((flag & 4) || n_cig == 0 || rspan == 0) ? 1 : (int64_t)rspan;
+    const int64_t need = std::max<int64_t>((int64_t)opt.min_map_len, (int64_t)((float)rlen * opt.min_map_fra));
+    const bool rejected = (flag & 0x404) || (int16_t)mapq <= (int16_t)opt.min_map_qual || rlen <= opt.min_read_len ||
+                          ((flag & 0x100) && !opt.use_secondary) || ((flag & 0x800) && !opt.use_supplementary) ||
+                          span < need;
+    if (rejected || bad || pos < 0 || (uint64_t)pos > tlen) {
+        sg.col.n = sg.q.n = sg.t.n = sg.cig.n = ops0;
+        if (rejected) return nullptr;
+        if (pos < 0 || (uint64_t)pos > tlen) return "alignment starts outside the contig";
+        return bad;
+    }
+    if (aln_q_e == 0) aln_q_e = qs;
+    RecOut &o = sg.ro.back();
+    o.kept = 1;
+    o.is_clip = (uint32_t)(aln_q_e - aln_q_s + opt.max_clip_len) < (uint32_t)rlen ? 1 : 0;  // main.rs:1796
+    o.ncols = col;
+    o.rlen = (uint32_t)rlen;
+    o.rspan = (uint32_t)rspan;
+    o.n_ops = n_ops;
+    o.seq_off = payload + 32 + l_name + 4ull * n_cig;
+    o.seq_bytes = ((uint32_t)l_seq + 1) / 2;
+    return nullptr;
+}
+
+// walk the block_size chain from byte `from` while the record starts before `limit`, parsing as it goes
+void walk(const uint8_t *bam, uint64_t bam_len, uint64_t from, uint64_t limit, uint32_t tlen, const np2_opts &opt,
+          Segment &sg) {
+    uint64_t p = from;
+    sg.start = from;
+    while (p < limit && p + 4 <= bam_len) {
+        const int32_t bs = rd32(bam + p);
+        if (bs < 32 || p + 4 + (uint64_t)bs > bam_len) {
+            sg.err_rec = (int64_t)sg.ro.size();
+            sg.err_msg = "BAM/SAM parsing failed!";
+            break;
+        }
+        const char *m = parse_one(bam, p + 4, tlen, opt, sg);
+        if (m) {
+            sg.err_rec = (int64_t)sg.ro.size() - 1;
+            sg.err_msg = m;
+            break;
+        }
+        p += 4 + (uint64_t)bs;
+    }
+    sg.end = p;
+}
+}  // namespace
+
+// The block_size chain is a linked list through a buffer of hundreds of MB: followed from the front it is one
+// cache + TLB miss per record, strictly serial.  Instead every host thread takes a byte range, guesses the first
+// record boundary inside it (a run of four plausible headers), and walks + parses from there.  A range is accepted
+// only if the verified walk before it ends exactly on its guessed start; otherwise that range is re-walked
+// sequentially.  So the result never depends on the guess, only the speed does.
+void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out,
+                   unsigned threads) {
+    out.clear();
+    unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (bam_len < (8u << 20)) T = 1;
+    if (threads) T = std::min(threads, 64u);
+    auto &segs = out.segs;
+    while (segs.size() < T) segs.emplace_back(new Segment());
+    auto bound = [&](unsigned ti) { return ti >= T ? bam_len : bam_len / T * ti; };
+    auto work = [&](unsigned ti) {
+        Segment &sg = *segs[ti];
+        sg.reset();
+        const uint64_t lo = bound(ti), hi = bound(ti + 1);
+        const uint64_t from = ti == 0 ? 0 : find_start(bam, bam_len, lo, hi);
+        if (from == UINT64_MAX) return;
+        sg.found = true;
+        try {
+            walk(bam, bam_len, from, hi, tlen, opt, sg);
+        } catch (const std::exception &) {  // allocation failure inside a worker thread
+            sg.err_rec = (int64_t)sg.ro.size();
+            sg.err_msg = "host allocation failed while parsing the records";
         }
     };
     if (T == 1) {
@@ -216,13 +240,34 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
         for (unsigned ti = 0; ti < T; ti++) th.emplace_back(work, ti);
         for (auto &t : th) t.join();
     }
-    const ParseErr *first_err = nullptr;
-    for (auto &e : t_err)
-        if (e.rec != INT64_MAX && (!first_err || e.rec < first_err->rec)) first_err = &e;
-    if (first_err) herr(NP2_ERR_FORMAT, first_err->msg);
-    // pass 3: compact the kept records, concatenate the per-thread op lists (already in record order)
-    size_t nk = 0, nops = 0;
-    for (auto &o : ro) nk += o.kept, nops += o.n_ops;
+    // join: accept, or re-walk what the speculation missed
+    std::vector<Segment *> order;
+    uint64_t cur = 0;
+    for (unsigned ti = 0; ti < T; ti++) {
+        Segment *sg = segs[ti].get();
+        const uint64_t hi = bound(ti + 1);
+        if (!(sg->found && sg->start == cur)) {
+            if (cur >= hi) continue;  // a record spans the whole range
+            const size_t idx = T + out.n_fallback++;
+            if (segs.size() <= idx) segs.emplace_back(new Segment());
+            sg = segs[idx].get();
+            sg->reset();
+            sg->found = true;
+            walk(bam, bam_len, cur, hi, tlen, opt, *sg);
+        }
+        order.push_back(sg);
+        if (sg->err_msg) herr(NP2_ERR_FORMAT, sg->err_msg);
+        cur = sg->end;
+    }
+    if (cur != bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+    // concatenate the per-record scalars (small); the op arrays stay where they are
+    size_t nrec = 0, nk = 0;
+    for (Segment *sg : order) {
+        nrec += sg->ro.size();
+        for (auto &o : sg->ro) nk += o.kept;
+    }
+    out.all_tid.reserve(nrec);
+    out.all_pos.reserve(nrec);
     out.rec_idx.reserve(nk);
     out.pos.reserve(nk);
     out.ncols.reserve(nk);
@@ -230,42 +275,37 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
     out.rspan.reserve(nk);
     out.is_clip.reserve(nk);
     out.seq_off.reserve(nk);
+    out.seq_bytes.reserve(nk);
     out.op_off.reserve(nk + 1);
     out.nib_off.reserve(nk + 1);
     out.ck_off.reserve(nk + 1);
     out.op_off.push_back(0);
     out.nib_off.push_back(0);
     out.ck_off.push_back(0);
-    for (size_t rec = 0; rec < nrec; rec++) {
-        const RecOut &o = ro[rec];
-        if (!o.kept) continue;
-        out.rec_idx.push_back((int32_t)rec);
-        out.pos.push_back((uint32_t)out.all_pos[rec]);
-        out.ncols.push_back(o.ncols);
-        out.rlen.push_back(o.rlen);
-        out.rspan.push_back(o.rspan);
-        out.is_clip.push_back(o.is_clip);
-        out.seq_off.push_back(o.seq_off);
-        out.op_off.push_back(out.op_off.back() + o.n_ops);
-        out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)o.ncols / 16 + 1) * 8 + 15) & ~15ull));
-        out.ck_off.push_back(out.ck_off.back() + (o.ncols + 31) / 32);
-        out.total_cols += o.ncols;
-    }
-    out.op_col.resize(nops);
-    out.op_q.resize(nops);
-    out.op_t.resize(nops);
-    out.op_cig.resize(nops);
-    size_t w = 0;
-    for (unsigned ti = 0; ti < T; ti++) {
-        const size_t n = t_col[ti].size();
-        if (n) {
-            memcpy(out.op_col.data() + w, t_col[ti].data(), n * 4);
-            memcpy(out.op_q.data() + w, t_q[ti].data(), n * 4);
-            memcpy(out.op_t.data() + w, t_t[ti].data(), n * 4);
-            memcpy(out.op_cig.data() + w, t_cig[ti].data(), n * 4);
+    size_t rec = 0;
+    for (Segment *sg : order) {
+        out.all_tid.insert(out.all_tid.end(), sg->tid.begin(), sg->tid.end());
+        out.all_pos.insert(out.all_pos.end(), sg->pos.begin(), sg->pos.end());
+        for (size_t i = 0; i < sg->ro.size(); i++, rec++) {
+            const RecOut &o = sg->ro[i];
+            if (!o.kept) continue;
+            out.rec_idx.push_back((int32_t)rec);
+            out.pos.push_back((uint32_t)sg->pos[i]);
+            out.ncols.push_back(o.ncols);
+            out.rlen.push_back(o.rlen);
+            out.rspan.push_back(o.rspan);
+            out.is_clip.push_back(o.is_clip);
+            out.seq_off.push_back(o.seq_off);
+            out.seq_bytes.push_back(o.seq_bytes);
+            out.op_off.push_back(out.op_off.back() + o.n_ops);
+            out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)o.ncols / 16 + 1) * 8 + 15) & ~15ull));
+            out.ck_off.push_back(out.ck_off.back() + (o.ncols + 31) / 32);
+            out.total_cols += o.ncols;
         }
-        w += n;
+        if (sg->col.n) out.op_chunks.push_back({sg->col.p, sg->q.p, sg->t.p, sg->cig.p, sg->col.n});
+        out.n_ops += sg->col.n;
     }
+    if (out.n_ops >= (1ull << 32)) herr(NP2_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one contig");
 }
 
 /* ================================================================= phasing: graph + Louvain */

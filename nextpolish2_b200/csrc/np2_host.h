@@ -4,6 +4,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -12,31 +13,87 @@
 namespace np2 {
 
 /* ---------------------------------------------------------------- ingest */
+// Host arrays that are DMA sources live in memory from these hooks (malloc/free by default; the library points them
+// at page-locked allocations so that uploads are asynchronous and run at PCIe speed).
+extern void *(*host_alloc_hook)(size_t);
+extern void (*host_free_hook)(void *);
+template <class T>
+struct HVec {  // minimal growable array of trivially copyable T on the hook allocator; capacity survives clear()
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    HVec() {}
+    HVec(const HVec &) = delete;
+    HVec &operator=(const HVec &) = delete;
+    HVec(HVec &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr, o.n = o.cap = 0; }
+    ~HVec() {
+        if (p) host_free_hook(p);
+    }
+    void grow(size_t need);
+    void push_back(T v) {
+        if (n == cap) grow(n + 1);
+        p[n++] = v;
+    }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+};
+
 struct Ingest {
     // candidate reads = records that pass the record-level filter (main.rs:1758-1771)
     std::vector<int32_t> all_tid, all_pos;  // every record, for the sortedness assertion (main.rs:1753-1756)
     std::vector<int32_t> rec_idx;
     std::vector<uint32_t> pos, ncols, rlen, rspan;
     std::vector<uint8_t> is_clip;
-    std::vector<uint64_t> seq_off;      // byte offset of SEQ in the blob
+    std::vector<uint64_t> seq_off;      // byte offset of SEQ in the caller's record buffer
+    std::vector<uint32_t> seq_bytes;    // (l_seq + 1) / 2
     std::vector<uint32_t> op_off;       // n + 1
-    std::vector<uint32_t> op_col, op_q, op_t, op_cig;  // column-consuming ops only (M,=,X,I,D)
     std::vector<uint64_t> nib_off;      // n + 1, bytes, 16-B aligned
     std::vector<uint32_t> ck_off;       // n + 1, 32-column blocks
     uint64_t total_cols = 0;
-    // scratch kept between jobs (capacity reuse: fresh host pages are expensive to fault in)
+    uint64_t n_ops = 0;
+    uint32_t n_fallback = 0;            // segments that had to be re-walked sequentially (speculation miss)
+    // Column-consuming CIGAR ops (M,=,X,I,D) stay in the per-segment arrays they were parsed into; uploaded back to
+    // back in file order they form the device arrays op_off[] indexes.
+    struct OpChunk {
+        const uint32_t *col, *q, *t, *cig;
+        size_t n;
+    };
+    std::vector<OpChunk> op_chunks;
+
     struct RecOut {
         uint8_t kept = 0, is_clip = 0;
-        uint32_t ncols = 0, rlen = 0, rspan = 0, n_ops = 0;
+        uint32_t ncols = 0, rlen = 0, rspan = 0, n_ops = 0, seq_bytes = 0;
         uint64_t seq_off = 0;
     };
-    std::vector<uint64_t> rec_off;
-    std::vector<RecOut> ro;
-    std::vector<std::vector<uint32_t>> t_col, t_q, t_t, t_cig;
+    // one byte range of the record buffer, walked and parsed by one host thread
+    struct Segment {
+        uint64_t start = 0, end = 0;
+        bool found = false;
+        std::vector<int32_t> tid, pos;
+        std::vector<RecOut> ro;
+        HVec<uint32_t> col, q, t, cig;
+        int64_t err_rec = -1;  // local index of the first record that fails (the walk stops there)
+        const char *err_msg = nullptr;
+        void reset() {
+            start = end = 0;
+            found = false;
+            tid.clear();
+            pos.clear();
+            ro.clear();
+            col.clear();
+            q.clear();
+            t.clear();
+            cig.clear();
+            err_rec = -1;
+            err_msg = nullptr;
+        }
+    };
+    std::vector<std::unique_ptr<Segment>> segs;  // pooled between jobs (capacity reuse: fresh pages are expensive)
     void clear();
 };
-// throws np2::Error(NP2_ERR_FORMAT) where the reference panics
-void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out);
+// throws np2::Error(NP2_ERR_FORMAT) where the reference panics (the first failing record in file order decides)
+// threads = 0: one range per host thread (a single range below 8 MB); otherwise exactly that many ranges
+void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out,
+                   unsigned threads = 0);
 
 /* ---------------------------------------------------------------- regions */
 struct Regions {

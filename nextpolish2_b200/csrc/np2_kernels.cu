@@ -270,6 +270,35 @@ void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, uint32_t *d_re
     NP2_K(k_ref_pack)<<<cdiv(nw, kThreads), kThreads, 0, s>>>(d_code, L, nw, d_refpk);
 }
 
+/* =============================================================== K0: SEQ gather from the caller's pinned records */
+// The BAM records of a contig are ~2/3 QUAL bytes, read names and tags the path never looks at.  When the caller's
+// record buffer is page-locked, the device pulls just the 4-bit SEQ fields over PCIe itself (mapped host memory, UVA):
+// one CTA per read, 16-byte vectors, source and destination share the same misalignment so every access is aligned.
+// A vector that straddles the SEQ ends only touches bytes of the same 16-byte line, i.e. of a mapped page.
+__global__ void __launch_bounds__(256) k_gather_seq(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                                                    const uint64_t *__restrict__ dst_off,
+                                                    const uint32_t *__restrict__ nbytes, uint8_t *__restrict__ dst) {
+    const uint32_t r = blockIdx.x;
+    const uint8_t *a = src + src_off[r];
+    const uint32_t mis = (uint32_t)((uintptr_t)a & 15);
+    const uint4 *sp = reinterpret_cast<const uint4 *>(a - mis);
+    uint4 *dp = reinterpret_cast<uint4 *>(dst + dst_off[r] - mis);
+    const uint32_t nv = (mis + nbytes[r] + 15) >> 4;
+    for (uint32_t i = threadIdx.x; i < nv; i += 4 * 256) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i + u * 256 < nv) v[u] = __ldcs(sp + i + u * 256);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i + u * 256 < nv) dp[i + u * 256] = v[u];
+    }
+}
+void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
+                uint8_t *d_dst, uint32_t n_reads, cudaStream_t s) {
+    if (n_reads) NP2_K(k_gather_seq)<<<n_reads, 256, 0, s>>>(src_mapped, d_src_off, d_dst_off, d_nbytes, d_dst);
+}
+
 /* =============================================================== K1: expand + trim + pack */
 
 struct OpCur {

@@ -50,6 +50,9 @@ struct ReadsDev {
     uint16_t *ck_delta = nullptr;
     uint32_t *ck_read = nullptr;
 };
+// K0: pull the SEQ fields out of a page-locked (mapped) record buffer; dst_off[r] is 16-B aligned + (source address & 15)
+void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
+                uint8_t *d_dst, uint32_t n_reads, cudaStream_t s);
 void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, uint32_t n_blocks, cudaStream_t s);
 
 /* ------------------------------------------------------------------ K2 pileup */

@@ -65,6 +65,7 @@ CASES = [
     ("dip600k", common.KS, {"use_supplementary": 1, "min_map_qual": -1, "max_clip_len": 1000}),
     ("hap300k", common.KS, {"min_kmer_count": 40}),
     ("deep80k", (21, 51), {"max_indel_len": 1}),
+    ("tandem200k", (21, 31, 51), {}),  # configs[3] in small: tandem repeats, three tables (k51 = bit-plane hash)
 ]
 
 
@@ -84,6 +85,43 @@ def test_polish_fasta_identical(ctx, name, ks, optkw):
     assert hashlib.sha256(fo).hexdigest() == hashlib.sha256(fg).hexdigest()
     # sanity property of the domain: the polish does something (consensus differs from the draft assembly)
     assert bytes(gbase) != bytes(ds["contig"])
+
+
+@pytest.mark.parametrize("name,shift", [("clip120k", 0), ("dip600k", 5), ("exotic", 3)])
+def test_pinned_records_device_gather(ctx, name, shift):
+    """Page-locked record buffers take the K0 path (the device gathers SEQ over PCIe, QUAL never crosses the bus);
+    pageable ones are compacted on the host.  Same reads, same consensus, at any buffer misalignment."""
+    import exotic
+    import nextpolish2_b200 as np2
+    from nextpolish2_b200 import synth
+    if name == "exotic":
+        contig, bam = exotic.make()
+        up = np.char.upper(contig.view("S1")).view(np.uint8)
+        tabs = {k: synth.make_table(5, k, [up]) for k in (21, 31)}
+    else:
+        ds = common.dataset(name)
+        contig, bam, tabs = ds["contig"], ds["bam"], ds["tables"]
+    oo, go = common.same_opts()
+    oj = O.Job(contig, bam, [O.Table.from_arrays(k, *tabs[k]) for k in (21, 31)], oo, dump_iter=0)
+    gt = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in (21, 31)]
+    pb = np2.PinnedBuffer(np.concatenate([np.zeros(shift, np.uint8), bam]))
+    pc = np2.PinnedBuffer(contig)
+    try:
+        gj = np2.Job(ctx, pc.array, pb.array[shift:], gt, go)
+        assert gj.ingest_path == 1
+        gj.upload().run(0)
+        common.assert_same_dict("reads", oj.reads(), gj.reads(), ["rec_idx", "t_s", "t_e", "blank", "nib_off", "nib"])
+        opos, obase = oj.consensus()
+        gpos, gbase = gj.consensus()
+        common.assert_same("final.base", obase, gbase)
+        common.assert_same("final.pos", opos, gpos)
+        gj.destroy()
+        pj = np2.Job(ctx, contig, bam, gt, go)
+        assert pj.ingest_path == 2
+        pj.destroy()
+    finally:
+        pb.free()
+        pc.free()
 
 
 def test_passthrough_and_errors(ctx):

@@ -1,0 +1,77 @@
+"""Host-side record parse (main.rs:1758-1771 filter + fill_with_cigar bookkeeping 386-440): the block_size chain is
+walked speculatively from several byte offsets at once; whatever the guesses are, the result must be the one a
+sequential reader produces.  Host only (np2_debug_parse needs no device)."""
+import numpy as np
+import pytest
+
+import common
+from nextpolish2_b200 import api, synth
+
+
+def _parse(bam, tlen, threads, **kw):
+    return api.debug_parse(bam, tlen, api.Opts(min_ctg_len=0, **kw), threads)
+
+
+@pytest.mark.parametrize("name", ["tiny20k", "clip120k", "dip600k"])
+def test_ranges_do_not_change_the_parse(name):
+    ds = common.dataset(name)
+    L = len(ds["contig"])
+    serial = _parse(ds["bam"], L, 1)
+    assert serial["fallback"] == 0 and serial["reads"] > 0 and serial["ops"] >= serial["reads"]
+    for t in (2, 3, 7, 16, 64):
+        got = _parse(ds["bam"], L, t)
+        assert {k: got[k] for k in ("records", "reads", "ops", "columns", "digest")} == \
+               {k: serial[k] for k in ("records", "reads", "ops", "columns", "digest")}, (t, got, serial)
+    # the filter options reach the parse
+    assert _parse(ds["bam"], L, 4, min_read_len=10**6)["reads"] == 0
+
+
+def _decoy_record(ref, pos, n):
+    """A real record whose QUAL bytes spell a chain of five well-formed little records (a wrong but plausible
+    place to start walking)."""
+    rec = synth.bam_record(0, pos, [("M", n)], ref[pos:pos + n].tobytes().decode()).copy()
+    decoy = np.concatenate([synth.bam_record(0, 7, [("M", 40)], "ACGT" * 10, name="decoy") for _ in range(5)])
+    assert len(decoy) < n - 64
+    rec[len(rec) - n + 16:len(rec) - n + 16 + len(decoy)] = decoy  # inside QUAL (the last n bytes of the record)
+    return rec
+
+
+def test_decoy_chains_inside_qual_are_rejected():
+    ds = common.dataset("tiny20k")
+    ref = ds["contig"]
+    L = len(ref)
+    recs = [_decoy_record(ref, p, 2400) for p in range(0, L - 2400, 150)]
+    bam = np.concatenate(recs)
+    serial = _parse(bam, L, 1)
+    assert serial["records"] == len(recs) and serial["reads"] == len(recs)
+    missed = 0
+    for t in (2, 5, 8, 16, 33):
+        got = _parse(bam, L, t)
+        missed += got["fallback"]
+        assert got["digest"] == serial["digest"] and got["records"] == serial["records"], (t, got)
+    assert missed > 0, "no byte range ever started on a decoy: the test does not exercise the fallback"
+
+
+def test_first_error_in_file_order_wins():
+    ds = common.dataset("tiny20k")
+    ref = ds["contig"]
+    L = len(ref)
+    good = [synth.bam_record(0, p, [("M", 2400)], ref[p:p + 2400].tobytes().decode()) for p in range(0, L - 2400, 400)]
+    bad_cigar = synth.bam_record(0, 300, [("M", 1200), ("N", 5), ("M", 1200)], "ACGT" * 600)
+    for t in (1, 4, 9):
+        with pytest.raises(api.Np2Error) as e:
+            _parse(np.concatenate(good[:10] + [bad_cigar] + good[10:]), L, t)
+        assert "Unknown cigar" in str(e.value)
+        trunc = np.concatenate(good + [good[0][:100]])
+        with pytest.raises(api.Np2Error) as e:
+            _parse(trunc, L, t)
+        assert "BAM/SAM parsing failed" in str(e.value)
+        # both: the unknown CIGAR comes first in the file, a sequential reader never reaches the truncation
+        with pytest.raises(api.Np2Error) as e:
+            _parse(np.concatenate(good[:3] + [bad_cigar] + good[3:] + [good[0][:100]]), L, t)
+        assert "Unknown cigar" in str(e.value)
+    # a rejected record (MAPQ 0) may hold anything in its CIGAR (the reference filters before fill_with_cigar)
+    lowq = synth.bam_record(0, 300, [("M", 1200), ("N", 5), ("M", 1200)], "ACGT" * 600, mapq=0)
+    assert _parse(np.concatenate(good[:5] + [lowq] + good[5:]), L, 3)["reads"] == len(good)
+    assert _parse(np.empty(0, np.uint8), L, 0) == {"records": 0, "reads": 0, "ops": 0, "columns": 0, "fallback": 0,
+                                                   "digest": _parse(np.empty(0, np.uint8), L, 1)["digest"]}
