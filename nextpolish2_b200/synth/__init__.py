@@ -16,9 +16,9 @@ _lib = None
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "np2_synth.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _LIB_PATH, src, "-lz", "-lpthread"])
+    srcs = [os.path.join(_HERE, f) for f in ("np2_synth.cpp", "np2_align.cpp")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _LIB_PATH] + srcs + ["-lz", "-lpthread"])
 
 
 def lib():
@@ -40,8 +40,54 @@ def lib():
         L.np2s_write_short_reads.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
                                              C.c_uint32, C.c_double]
         L.np2s_write_bam.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.np2s_align.restype = C.c_void_p
+        L.np2s_align.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64, C.c_int]
+        L.np2s_aln_size.restype = C.c_uint64
+        L.np2s_aln_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.np2s_aln_copy.argtypes = [C.c_void_p, C.c_void_p]
+        L.np2s_aln_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+def read_fasta(path):
+    """[(name, bytes)] from a FASTA/FASTQ file, .gz or not (first word of the header, like kseq)."""
+    import gzip
+    op = gzip.open if path.endswith(".gz") else open
+    out, name, parts = [], None, []
+    with op(path, "rb") as f:
+        data = f.read()
+    lines = data.split(b"\n")
+    if data[:1] == b">":
+        for line in lines:
+            if line[:1] == b">":
+                if name is not None:
+                    out.append((name, b"".join(parts)))
+                name, parts = line[1:].split()[0].decode(), []
+            elif line:
+                parts.append(line.strip())
+        if name is not None:
+            out.append((name, b"".join(parts)))
+    else:
+        for i in range(0, len(lines) - 3, 4):
+            out.append((lines[i][1:].split()[0].decode(), lines[i + 1].strip()))
+    return out
+
+
+def align_reads(contig, reads, ref_id=0, threads=8):
+    """Mini-aligner (np2_align.cpp): reads = [(name, bytes)] -> (BAM records blob sorted by position, #aligned)."""
+    T = np.ascontiguousarray(contig, dtype=np.uint8)
+    seqs = np.frombuffer(b"".join(r[1] for r in reads), np.uint8)
+    off = np.zeros(len(reads) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r[1]) for r in reads])
+    names = b"".join(r[0].encode() + b"\0" for r in reads)
+    h = lib().np2s_align(T.ctypes.data, len(T), ref_id, seqs.ctypes.data, off.ctypes.data, names, len(reads), threads)
+    n = C.c_uint64()
+    size = lib().np2s_aln_size(h, C.byref(n))
+    bam = np.empty(size, np.uint8)
+    lib().np2s_aln_copy(h, bam.ctypes.data)
+    lib().np2s_aln_free(h)
+    return bam, n.value
 
 
 def genome(seed, length, gc=0.41, tandem_frac=0.0):
