@@ -24,8 +24,14 @@
  * negative NP2_ERR_* code; np2_last_error() returns the message of the calling thread's
  * last failure.  The library never aborts: conditions on which the reference panics
  * (unsorted BAM, unknown CIGAR op, bad yak magic ...) are reported as errors and the CLI
- * maps them to the reference's exit behaviour.  One context per GPU; calls on one
- * context must be serialised by the caller, contexts are independent.
+ * maps them to the reference's exit behaviour.
+ *
+ * Threading: one context = one GPU + one stream; calls on one context must be serialised
+ * by the caller, contexts are independent.  Tables are read-only once loaded and may be
+ * used by jobs of ANY context on the same GPU, so a caller that wants two contigs in
+ * flight per GPU (PCIe upload + record parsing of one overlapping the kernels of the
+ * other) creates two contexts, drives each from its own thread and shares one set of
+ * tables (this is what the np2 CLI and bench.py's e2e arm do).
  */
 #ifndef NP2GPU_H
 #define NP2GPU_H
@@ -39,7 +45,7 @@ extern "C" {
 #define NP2_ERR_ARG (-2)         /* bad argument */
 #define NP2_ERR_IO (-3)          /* file missing / unreadable */
 #define NP2_ERR_FORMAT (-4)      /* reference would panic while parsing (bad magic, BAM parse, unknown CIGAR, unsorted input) */
-#define NP2_ERR_UNSUPPORTED (-5) /* valid for the reference but outside this library's scope (-S, k>=32 as smallest table ...) */
+#define NP2_ERR_UNSUPPORTED (-5) /* valid for the reference but outside this library's scope (k>=32 as smallest table ...) */
 #define NP2_ERR_INTERNAL (-6)
 
 /* CLI options that reach the hot path (src/utils/option.rs:15-41, defaults 267-292). */
@@ -51,7 +57,7 @@ typedef struct np2_opts {
     uint64_t min_ctg_len;       /* -L 1000000 */
     int32_t  max_indel_len;     /* -n 20 */
     uint32_t use_supplementary; /* -s */
-    uint32_t use_secondary;     /* -S (NP2_ERR_UNSUPPORTED when set) */
+    uint32_t use_secondary;     /* -S: records must have been through np2_secmap_fill */
     uint32_t use_all_reads;     /* -r */
     uint32_t min_map_len;       /* integer part of -a 500.5 */
     float    min_map_fra;       /* fractional part of -a 500.5 */
@@ -96,6 +102,24 @@ int np2_seq_kscore(np2_ctx *ctx, const np2_table *t, const uint8_t *seqs, const 
 /* measurement aid (bench.py): mean time of n_loads independent uniformly random 32-byte sector reads over a
  * scratch buffer of buf_bytes — the measured random-read peak K5 is compared with. */
 int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms);
+
+/* ---- -S / --use_secondary: SEQ of secondary alignments (src/utils/secondary.rs:8-158, main.rs:1775-1788) ----
+ * Secondary records carry no SEQ.  Like the reference, the caller makes two passes over EVERY contig's records before
+ * polishing: np2_secmap_scan_ids (names of secondary records; retrieve_secondary_ids secondary.rs:8-66), then
+ * np2_secmap_scan_seqs (SEQ of the primary record of each such name, in the read's original orientation;
+ * retrieve_secondary_seq_from_bam secondary.rs:85-150; two primaries with one name -> NP2_ERR_FORMAT like the
+ * reference's assert).  np2_secmap_fill then rewrites one contig's record blob so that every secondary record holds
+ * its SEQ (reverse-complemented when the record is on the reverse strand, A<->T C<->G only, main.rs:1776-1783) with
+ * 0xFF QUAL; the result is what np2_polish_contig takes when opts.use_secondary is set.  A secondary record whose
+ * name has no primary keeps an empty SEQ: if it passes the filter the polish fails (the reference panics there).
+ * np2_secmap_fill: out may be NULL / cap 0 to size the buffer; *need = bytes required.  Host only, no device. */
+typedef struct np2_secmap np2_secmap;
+int np2_secmap_create(np2_secmap **out);
+void np2_secmap_destroy(np2_secmap *m);
+int np2_secmap_scan_ids(np2_secmap *m, const uint8_t *bam, uint64_t bam_len);
+int np2_secmap_scan_seqs(np2_secmap *m, const uint8_t *bam, uint64_t bam_len);
+int np2_secmap_fill(const np2_secmap *m, const uint8_t *bam, uint64_t bam_len, uint8_t *out, uint64_t cap, uint64_t *need);
+uint64_t np2_secmap_size(const np2_secmap *m, uint64_t *n_seqs); /* #secondary names; *n_seqs = #recovered SEQs */
 
 /* ---- page-locked host buffers ----
  * Record buffers handed to np2_polish_contig / np2_job_create may live in any host memory.  When they are

@@ -46,6 +46,7 @@ EXPORTS = [
     "np2_job_get_consensus", "np2_job_get_span", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
+    "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
 ]
 
 
@@ -99,6 +100,13 @@ def load_library():
     L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
     L.np2_format_fasta.restype = u64
     L.np2_format_fasta.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int, vp, u64]
+    L.np2_secmap_create.argtypes = [C.POINTER(vp)]
+    L.np2_secmap_destroy.argtypes = [vp]
+    L.np2_secmap_scan_ids.argtypes = [vp, vp, u64]
+    L.np2_secmap_scan_seqs.argtypes = [vp, vp, u64]
+    L.np2_secmap_fill.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64)]
+    L.np2_secmap_size.restype = u64
+    L.np2_secmap_size.argtypes = [vp, C.POINTER(u64)]
     _LIB = L
     return L
 
@@ -361,6 +369,52 @@ def polish_contig(ctx, contig, bam, tables, opts=None):
         return j.consensus()
     finally:
         j.destroy()
+
+
+class SecondarySeqs:
+    """-S / --use_secondary: the reference's sec_seqs map (src/utils/secondary.rs:85-150) over record blobs.
+
+    scan_ids(blob) for every contig, then scan_seqs(blob) for every contig, then fill(blob) per contig gives the
+    record blob np2_polish_contig takes with Opts(use_secondary=1).  Host only."""
+
+    def __init__(self):
+        self.h = C.c_void_p()
+        _check(load_library().np2_secmap_create(C.byref(self.h)))
+
+    def scan_ids(self, bam):
+        bam = np.ascontiguousarray(bam, np.uint8)
+        _check(load_library().np2_secmap_scan_ids(self.h, bam.ctypes.data, len(bam)))
+        return self
+
+    def scan_seqs(self, bam):
+        bam = np.ascontiguousarray(bam, np.uint8)
+        _check(load_library().np2_secmap_scan_seqs(self.h, bam.ctypes.data, len(bam)))
+        return self
+
+    def fill(self, bam):
+        bam = np.ascontiguousarray(bam, np.uint8)
+        need = C.c_uint64()
+        _check(load_library().np2_secmap_fill(self.h, bam.ctypes.data, len(bam), None, 0, C.byref(need)))
+        out = np.empty(need.value, np.uint8)
+        _check(load_library().np2_secmap_fill(self.h, bam.ctypes.data, len(bam), out.ctypes.data, len(out), C.byref(need)))
+        return out
+
+    @property
+    def counts(self):
+        n = C.c_uint64()
+        ids = load_library().np2_secmap_size(self.h, C.byref(n))
+        return ids, n.value
+
+    def close(self):
+        if self.h:
+            load_library().np2_secmap_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def format_fasta(tid, pos, base, uppercase=False, out_pos=False):

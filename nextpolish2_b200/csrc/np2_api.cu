@@ -163,7 +163,8 @@ struct StageTimer {
 // faults of fresh vectors cost milliseconds each, far more than the kernels they feed.
 struct JobScratch {
     Ingest ing;
-    std::vector<uint8_t> tseq, h_seeds, h_rech_pool;
+    std::vector<uint8_t> tseq, h_seeds, h_rech_pool, h_win;
+    Patched patch;
     PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage, p_seq_stage;
     PBuf<uint32_t> p_cpos;
     std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
@@ -248,7 +249,7 @@ struct np2_job {
     int seq_path = 0;  // 1 = gathered by the device from page-locked records, 2 = compacted by host threads
     explicit np2_job(np2_ctx *c)
         : ctx(c), sc(c->take_scratch()), tseq(sc->tseq), ing(sc->ing), res_base(sc->res_base), p_cpos(sc->p_cpos),
-          p_cbase(sc->p_cbase), p_cflags(sc->p_cflags), timer(sc->timer), h_seeds(sc->h_seeds),
+          p_cbase(sc->p_cbase), p_cflags(sc->p_cflags), timer(sc->timer), h_seeds(sc->h_seeds), h_win(sc->h_win), res_patch(sc->patch),
           h_rech_pool(sc->h_rech_pool) {}
     ~np2_job() { ctx->scratch_pool.push_back(sc); }
 
@@ -273,10 +274,10 @@ struct np2_job {
     DBuf<uint32_t> jd_cpos;                  // DP consensus of the last iteration stays on the device
     DBuf<uint8_t> jd_cbase, jd_cflags;
     uint32_t res_N = 0;
-    std::vector<uint8_t> &h_seeds, &h_rech_pool;
+    std::vector<uint8_t> &h_seeds, &h_rech_pool, &h_win;
     uint32_t res_first = 0, res_last = 0;
     bool res_pos_valid = false;
-    Patched res_patch;                       // kept so that positions can be produced lazily
+    Patched &res_patch;                      // kept so that positions can be produced lazily (pooled with the scratch)
     PBuf<uint32_t> &p_cpos;
     PBuf<uint8_t> &p_cbase, &p_cflags;
     DBuf<uint32_t> d_order;
@@ -874,7 +875,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             if ((int32_t)iter == dump_iter) dump_stage1();
             if (iter + 1 < opt.iter_count) continue;
             fetch_edge_pos();
-            res_patch = Patched();
+            res_patch.reset(0);
             res_base.resize(std::max(N, 1u));
             res_base.n = N;
             d_cbase.download(res_base.p, N);
@@ -1167,8 +1168,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     timer.end(h);
     timer.hbegin();
     // round 1: everything whose size is known (one synchronisation, pinned destinations)
-    p_cbase.resize(std::max(N, 1u));
-    d_cbase.download(p_cbase.p, N);
+    p_cbase.resize(std::max(N, 1u));  // filled sparsely below: only the windows around RECH regions cross PCIe
     Stager st1(sc->p_stage, s, (size_t)nreg * 64 + 4096);
     const int *h_gerr = st1.fetch(d_err.p, 1);
     const uint64_t *h_rech_bytes = st1.fetch(d_rech_boff.p + nreg, 1);
@@ -1205,7 +1205,37 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     d_ent_order.alloc(std::max(n_ent, 1u), s);
     d_ent_len.alloc(std::max(n_ent, 1u), s);
     d_ent_poff.alloc(std::max(n_ent, 1u), s);
-    h = timer.begin("seed_gather", 2);
+    // The re-check reads the DP bases only next to RECH regions (k-1 flank bases, the stretch between chained
+    // regions): one window [a - W, b + W) per RECH region is gathered on the device instead of downloading all N.
+    const uint32_t kWin = 128;
+    std::vector<uint32_t> win_lo, win_r;
+    std::vector<uint64_t> win_off(1, 0);
+    for (uint32_t r = nreg; r-- > 0;)  // ascending position
+        if (lab[r] & LABLE_RECH) {
+            const uint32_t lo = rg.a[r] > kWin ? rg.a[r] - kWin : 0, hi = (uint32_t)std::min<uint64_t>((uint64_t)rg.b[r] + kWin, N);
+            win_lo.push_back(lo);
+            win_r.push_back(r);
+            win_off.push_back(win_off.back() + (hi - lo));
+        }
+    const uint32_t n_win = (uint32_t)win_lo.size();
+    bool full_cbase = win_off.back() > N / 2;
+    DBuf<uint32_t> d_win_lo;
+    DBuf<uint64_t> d_win_off;
+    DBuf<uint8_t> d_win;
+    h = timer.begin("seed_gather", 3);
+    if (full_cbase) {
+        d_cbase.download(p_cbase.p, N);
+    } else if (n_win) {
+        d_win_lo.alloc(n_win, s);
+        d_win_off.alloc(n_win + 1, s);
+        d_win.alloc(win_off.back() + 1, s);
+        d_win_lo.upload(win_lo.data(), n_win);
+        d_win_off.upload(win_off.data(), n_win + 1);
+        gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, n_win, d_win.p, s);
+        h_win.resize(win_off.back() + 16);
+        d_win.download(h_win.data(), win_off.back());
+        h2d += (uint64_t)n_win * 12;
+    }
     assemble_seed_gather(ad, d_seeds.p, s);
     if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
     timer.end(h);
@@ -1223,20 +1253,55 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     }
     NP2_CUDA(cudaStreamSynchronize(s));
     timer.hend("host:seed_sync2");
-    d2h += (uint64_t)N + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
+    d2h += (full_cbase ? (uint64_t)N : win_off.back()) + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
+    if (!full_cbase && n_win) {
+        for (uint32_t w = 0; w < n_win; w++)
+            memcpy(p_cbase.p + win_lo[w], h_win.data() + win_off[w], win_off[w + 1] - win_off[w]);
+        // Exactness check: every DP base the re-check can touch must lie inside a window.  Left/right flanks take at
+        // most kmax-1 DP bases walking over neighbouring regions (their alleles only shorten the walk); chained
+        // regions (closer than kmax in position) read the whole stretch between them.
+        const uint32_t need = tables.back()->dev.k - 1;
+        bool ok = true;
+        for (uint32_t w = 0; w < n_win && ok; w++) {
+            const uint32_t r = win_r[w];
+            const uint64_t wlo = win_lo[w], whi = wlo + (win_off[w + 1] - win_off[w]);
+            uint32_t got = 0, rr = r;  // left walk (r grows towards lower positions)
+            uint64_t i = rg.a[r];
+            for (;;) {
+                const uint64_t lo = rr + 1 < nreg ? rg.b[rr + 1] : 0;
+                const uint64_t take = std::min<uint64_t>(need - got, i - lo);
+                if (i - take < wlo) ok = false;
+                got += (uint32_t)take;
+                if (got >= need || rr + 1 >= nreg) break;
+                rr++;
+                i = rg.a[rr];
+            }
+            got = 0, rr = r, i = rg.b[r];
+            for (;;) {
+                const uint64_t hi = rr > 0 ? rg.a[rr - 1] : N;
+                const uint64_t take = std::min<uint64_t>(need - got, hi - i);
+                if (i + take > whi) ok = false;
+                got += (uint32_t)take;
+                if (got >= need || rr == 0) break;
+                rr--;
+                i = rg.b[rr];
+            }
+            if (w + 1 < n_win) {
+                const uint32_t r2 = win_r[w + 1];
+                if (rg.start[r2] < rg.end[r] + need + 1 && rg.a[r2] > whi && win_lo[w + 1] > whi) ok = false;
+            }
+        }
+        if (!ok) {  // pathological layout (very long insertions next to a RECH region): take everything
+            d_cbase.download(p_cbase.p, N);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            d2h += N;
+        }
+    }
     // patched view, regions in ascending position (q = nreg - 1 - r)
     Patched &pc = res_patch;
-    pc = Patched();
+    pc.reset(nreg);
     pc.cbase = p_cbase.p;
-    pc.cpos = nullptr;
     pc.N = N;
-    pc.start.resize(nreg);
-    pc.end.resize(nreg);
-    pc.a.resize(nreg);
-    pc.b.resize(nreg);
-    pc.lable.resize(nreg);
-    pc.seed.resize(nreg);
-    pc.cand.resize(nreg);
     {
         uint64_t rb = 0;
         for (uint32_t r = 0; r < nreg; r++) {
@@ -1338,7 +1403,7 @@ void np2_job::run(int32_t dump_it) {
     res_base.n = 0;
     res_pos.clear();
     res_pos_valid = false;
-    res_patch = Patched();
+    res_patch.reset(0);
     timer.s = s;
     timer.reset();
     const unsigned long long launches0 = launch_counter();
@@ -1675,12 +1740,15 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
                    np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out) {
     return guard([&] {
         if (!ctx || !tseq || !opts || !out) throw np2::Error(NP2_ERR_ARG, "null argument");
-        if (opts->use_secondary) throw np2::Error(NP2_ERR_UNSUPPORTED, "-S / use_secondary is out of scope");
         if (n_tables == 0) throw np2::Error(NP2_ERR_ARG, "Missing yak file!");
         if (opts->iter_count == 0) throw np2::Error(NP2_ERR_ARG, "iter_count must be >= 1");
         std::unique_ptr<np2_job> j(new np2_job(ctx));
         j->opt = *opts;
-        for (uint32_t i = 0; i < n_tables; i++) j->tables.push_back(tables[i]);
+        for (uint32_t i = 0; i < n_tables; i++) {
+            if (!tables[i] || tables[i]->ctx->device != ctx->device)
+                throw np2::Error(NP2_ERR_ARG, "table is null or lives on another GPU than the context");
+            j->tables.push_back(tables[i]);
+        }
         std::stable_sort(j->tables.begin(), j->tables.end(),
                          [](np2_table *a, np2_table *b) { return a->dev.k < b->dev.k; });  // option.rs:238
         j->L = tlen;
@@ -1700,6 +1768,41 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
         *out = j.release();
     });
 }
+
+/* ---- -S / --use_secondary (np2_secondary.cpp) */
+struct np2_secmap {
+    np2::SecMap *m;
+};
+int np2_secmap_create(np2_secmap **out) {
+    return guard([&] {
+        if (!out) throw np2::Error(NP2_ERR_ARG, "null argument");
+        *out = new np2_secmap{np2::secmap_new()};
+    });
+}
+void np2_secmap_destroy(np2_secmap *m) {
+    if (!m) return;
+    np2::secmap_delete(m->m);
+    delete m;
+}
+int np2_secmap_scan_ids(np2_secmap *m, const uint8_t *bam, uint64_t bam_len) {
+    return guard([&] {
+        if (!m || (!bam && bam_len)) throw np2::Error(NP2_ERR_ARG, "null argument");
+        np2::secmap_scan_ids(*m->m, bam, bam_len);
+    });
+}
+int np2_secmap_scan_seqs(np2_secmap *m, const uint8_t *bam, uint64_t bam_len) {
+    return guard([&] {
+        if (!m || (!bam && bam_len)) throw np2::Error(NP2_ERR_ARG, "null argument");
+        np2::secmap_scan_seqs(*m->m, bam, bam_len);
+    });
+}
+int np2_secmap_fill(const np2_secmap *m, const uint8_t *bam, uint64_t bam_len, uint8_t *out, uint64_t cap, uint64_t *need) {
+    return guard([&] {
+        if (!m || (!bam && bam_len) || !need) throw np2::Error(NP2_ERR_ARG, "null argument");
+        *need = np2::secmap_fill(*m->m, bam, bam_len, out, cap);
+    });
+}
+uint64_t np2_secmap_size(const np2_secmap *m, uint64_t *n_seqs) { return m ? np2::secmap_counts(*m->m, n_seqs) : 0; }
 
 int np2_host_alloc(uint64_t bytes, void **out) {
     return guard([&] {

@@ -285,7 +285,7 @@ void usage() {
             "  -L, --min_ctg_len <INT>     don't correct reference sequences with length <= INT [default: 1000000]\n"
             "  -n, --max_indel_len <INT>   ignore indel errors with length > INT [default: 20]\n"
             "  -s, --use_supplementary     use supplementary alignments\n"
-            "  -S, --use_secondary         use secondary alignments (not supported by this build)\n"
+            "  -S, --use_secondary         use secondary alignments\n"
             "  -a, --min_map_len <FLOAT>   filter alignments with alignment length <= min(INT, FLOAT * read_length) [default: 500.5]\n"
             "  -q, --min_map_qual <INT>    filter alignments with mapping quality <= INT [default: 1]\n"
             "  -c, --max_clip_len <INT>    filter alignments with unaligned length >= INT [default: 100]\n"
@@ -413,12 +413,75 @@ int main(int argc, char **argv) {
         }
         std::mutex bam_mu, err_mu;
         std::string first_err;
+        // -S: two passes over every reference's records, like retrieve_secondary_seq_from_bam (secondary.rs:85-150)
+        np2_secmap *secmap = nullptr;
+        if (cli.o.use_secondary) {
+            if (np2_secmap_create(&secmap) != NP2_OK) die(np2_last_error());
+            std::vector<uint8_t> blob;
+            for (int pass = 0; pass < 2; pass++)
+                for (size_t r = 0; r < bf.ref_names.size(); r++) {
+                    fetch_records(bf, (int)r, blob);
+                    const int rc = pass == 0 ? np2_secmap_scan_ids(secmap, blob.data(), blob.size())
+                                             : np2_secmap_scan_seqs(secmap, blob.data(), blob.size());
+                    if (rc != NP2_OK) die(np2_last_error());
+                }
+        }
+        // Per GPU: the tables are staged once, then two host threads (one context + stream each, tables shared) take
+        // that GPU's contigs in input order, so BGZF decoding / record parsing / upload of one contig overlap the
+        // kernels of the other.
+        auto fail = [&](const std::string &m) {
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (first_err.empty()) first_err = m;
+        };
+        auto polish_one = [&](np2_ctx *ctx, std::vector<np2_table *> &tabs, size_t i, std::vector<uint8_t> &blob) -> bool {
+            {
+                std::lock_guard<std::mutex> lk(bam_mu);
+                int tid = -1;
+                for (size_t r = 0; r < bf.ref_names.size(); r++)
+                    if (bf.ref_names[r] == contigs[i].name) tid = (int)r;
+                if (tid < 0) return fail("Faield random access BAM/SAM!"), false;
+                fetch_records(bf, tid, blob);
+            }
+            if (secmap) {  // secondary records get their SEQ (main.rs:1775-1783)
+                uint64_t need = 0;
+                if (np2_secmap_fill(secmap, blob.data(), blob.size(), nullptr, 0, &need) != NP2_OK)
+                    return fail(np2_last_error()), false;
+                std::vector<uint8_t> filled(need);
+                if (np2_secmap_fill(secmap, blob.data(), blob.size(), filled.data(), need, &need) != NP2_OK)
+                    return fail(np2_last_error()), false;
+                blob.swap(filled);
+            }
+            np2_job *job = nullptr;
+            if (np2_polish_contig(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(), blob.data(),
+                                  blob.size(), tabs.data(), (uint32_t)tabs.size(), &cli.o, &job) != NP2_OK)
+                return fail(np2_last_error()), false;
+            const uint32_t *pos;
+            const uint8_t *base;
+            uint64_t nb = np2_job_get_consensus(job, cli.o.out_pos ? &pos : nullptr, &base);
+            if (cli.o.out_pos) {
+                uint64_t need = np2_format_fasta(contigs[i].name.c_str(), pos, base, nb, cli.o.uppercase, 1, nullptr, 0);
+                results[i].resize(need);
+                np2_format_fasta(contigs[i].name.c_str(), pos, base, nb, cli.o.uppercase, 1, results[i].data(), need);
+            } else {
+                uint32_t span[2];
+                np2_job_get_span(job, &span[0], &span[1]);
+                // header needs the first / last position only: format with a two-entry position view
+                std::string hdr = ">" + contigs[i].name + " start:" + std::to_string(span[0]) +
+                                  " end:" + std::to_string(span[1]) + "\n";
+                results[i].assign(hdr.begin(), hdr.end());
+                size_t o = results[i].size();
+                results[i].resize(o + nb + 1);
+                if (cli.o.uppercase)
+                    for (uint64_t x = 0; x < nb; x++) results[i][o + x] = (uint8_t)toupper(base[x]);
+                else memcpy(results[i].data() + o, base, nb);
+                results[i][o + nb] = '\n';
+            }
+            np2_job_destroy(job);
+            done[i] = 1;
+            return true;
+        };
         auto worker = [&](int g) {
             np2_ctx *ctx = nullptr;
-            auto fail = [&](const std::string &m) {
-                std::lock_guard<std::mutex> lk(err_mu);
-                if (first_err.empty()) first_err = m;
-            };
             if (np2_ctx_create(g, &ctx) != NP2_OK) return fail(np2_last_error());
             std::vector<np2_table *> tabs;
             for (auto &y : cli.yaks) {
@@ -427,51 +490,32 @@ int main(int argc, char **argv) {
                 tabs.push_back(t);
             }
             std::sort(share[g].begin(), share[g].end());
-            std::vector<uint8_t> blob;
-            for (size_t i : share[g]) {
-                {
-                    std::lock_guard<std::mutex> lk(bam_mu);
-                    int tid = -1;
-                    for (size_t r = 0; r < bf.ref_names.size(); r++)
-                        if (bf.ref_names[r] == contigs[i].name) tid = (int)r;
-                    if (tid < 0) return fail("Faield random access BAM/SAM!");
-                    fetch_records(bf, tid, blob);
+            std::atomic<size_t> next{0};
+            auto lane = [&](np2_ctx *c) {
+                std::vector<uint8_t> blob;
+                for (;;) {
+                    const size_t x = next.fetch_add(1);
+                    if (x >= share[g].size()) break;
+                    {
+                        std::lock_guard<std::mutex> lk(err_mu);
+                        if (!first_err.empty()) break;
+                    }
+                    if (!polish_one(c, tabs, share[g][x], blob)) break;
                 }
-                np2_job *job = nullptr;
-                if (np2_polish_contig(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(),
-                                      blob.data(), blob.size(), tabs.data(), (uint32_t)tabs.size(), &cli.o,
-                                      &job) != NP2_OK)
-                    return fail(np2_last_error());
-                const uint32_t *pos;
-                const uint8_t *base;
-                uint64_t nb = np2_job_get_consensus(job, cli.o.out_pos ? &pos : nullptr, &base);
-                if (cli.o.out_pos) {
-                    uint64_t need = np2_format_fasta(contigs[i].name.c_str(), pos, base, nb, cli.o.uppercase, 1, nullptr, 0);
-                    results[i].resize(need);
-                    np2_format_fasta(contigs[i].name.c_str(), pos, base, nb, cli.o.uppercase, 1, results[i].data(), need);
-                } else {
-                    uint32_t span[2];
-                    np2_job_get_span(job, &span[0], &span[1]);
-                    // header needs the first / last position only: format with a two-entry position view
-                    std::string hdr = ">" + contigs[i].name + " start:" + std::to_string(span[0]) +
-                                      " end:" + std::to_string(span[1]) + "\n";
-                    results[i].assign(hdr.begin(), hdr.end());
-                    size_t o = results[i].size();
-                    results[i].resize(o + nb + 1);
-                    if (cli.o.uppercase)
-                        for (uint64_t x = 0; x < nb; x++) results[i][o + x] = (uint8_t)toupper(base[x]);
-                    else memcpy(results[i].data() + o, base, nb);
-                    results[i][o + nb] = '\n';
-                }
-                np2_job_destroy(job);
-                done[i] = 1;
-            }
+            };
+            np2_ctx *ctx2 = nullptr;
+            std::thread second;
+            if (share[g].size() > 1 && np2_ctx_create(g, &ctx2) == NP2_OK) second = std::thread(lane, ctx2);
+            lane(ctx);
+            if (second.joinable()) second.join();
+            if (ctx2) np2_ctx_destroy(ctx2);
             for (auto t : tabs) np2_yak_free(t);
             np2_ctx_destroy(ctx);
         };
         std::vector<std::thread> th;
         for (int g = 0; g < n_gpu; g++) th.emplace_back(worker, g);
         for (auto &t : th) t.join();
+        np2_secmap_destroy(secmap);
         if (!first_err.empty()) die(first_err);
     }
     for (size_t i = 0; i < n; i++) fwrite(results[i].data(), 1, results[i].size(), out);

@@ -6,6 +6,7 @@
 
 #include <memory>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/np2gpu.h"
@@ -128,6 +129,21 @@ struct Patched {
     std::vector<uint8_t> lable;
     std::vector<Allele> seed;                 // current sudoseed per region
     std::vector<std::vector<Allele>> cand;    // surviving candidates of RECH regions (retain_sort_seqs order)
+    // empties the view for n regions but keeps every allocation (fresh multi-MB vectors cost page faults per contig)
+    void reset(size_t n) {
+        cbase = nullptr;
+        cpos = nullptr;
+        N = 0;
+        start.resize(n);
+        end.resize(n);
+        a.resize(n);
+        b.resize(n);
+        lable.resize(n);
+        seed.resize(n);
+        const size_t keep = std::min(n, cand.size());
+        for (size_t i = 0; i < keep; i++) cand[i].clear();
+        cand.resize(n);
+    }
 };
 // reupdate_consensus_with_lqseqs (main.rs:1060-1420), split around the device scoring call
 struct Reupdate {
@@ -145,5 +161,14 @@ void reupdate_apply(Patched &pc, const Reupdate &ru, const uint16_t *kscores, ui
 // ConsensusBase.pos of the final consensus (the bases are assembled on the device): DP positions outside the
 // regions, region.start for every base of a patched region (main.rs:1039-1045)
 void positions(const Patched &pc, std::vector<uint32_t> &pos);
+
+// -S / --use_secondary (np2_secondary.cpp; secondary.rs:8-158)
+struct SecMap;
+void secmap_scan_ids(SecMap &m, const uint8_t *bam, uint64_t len);
+void secmap_scan_seqs(SecMap &m, const uint8_t *bam, uint64_t len);
+uint64_t secmap_fill(const SecMap &m, const uint8_t *bam, uint64_t len, uint8_t *out, uint64_t cap);
+SecMap *secmap_new();
+void secmap_delete(SecMap *m);
+uint64_t secmap_counts(const SecMap &m, uint64_t *n_seqs);
 
 }  // namespace np2

@@ -17,7 +17,7 @@
 namespace np2 {
 
 unsigned long long &launch_counter() {
-    static unsigned long long c = 0;
+    static thread_local unsigned long long c = 0;  // a job runs on its caller's thread
     return c;
 }
 
@@ -1001,22 +1001,39 @@ __global__ void k_emit_runs(MsaDev m, const uint32_t *__restrict__ run_start, ui
         if ((threadIdx.x & 31) == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
     }
 }
-__global__ void k_emit_singles(MsaDev m, const uint32_t *__restrict__ emit_off, uint32_t *__restrict__ out_pos,
-                               uint8_t *__restrict__ out_base, uint8_t *__restrict__ out_flags, DpOut o) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kEmitPerThread = 4;
+__global__ void __launch_bounds__(kThreads) k_emit_singles(MsaDev m, const uint32_t *__restrict__ emit_off,
+                                                           uint32_t *__restrict__ out_pos, uint8_t *__restrict__ out_base,
+                                                           uint8_t *__restrict__ out_flags, DpOut o) {
+    // every single-entry position adds 10*count - 4*coverage to the path score (main.rs:1659): reduced per block,
+    // one atomic per 1024 positions (one per warp serialised on the single accumulator)
+    __shared__ long long wsum[kThreads / 32];
     long long sum = 0;
-    if (p < m.L && !m.multi[p]) {
-        const int64_t cov = m.cover[p], cnt = m.dense_cnt[p];
-        sum = 10 * cnt - 4 * cov;
-        if (m.code[p] != 4) {
-            uint32_t w = emit_off[p];
-            out_pos[w] = p;
-            out_base[w] = code_char(m.code[p]);
-            out_flags[w] = (uint8_t)((cnt * 100 / cov < 95 ? 1 : 0) | (cov < 2 ? 2 : 0));
+    const uint32_t base = blockIdx.x * (kThreads * kEmitPerThread) + threadIdx.x;
+#pragma unroll
+    for (int x = 0; x < kEmitPerThread; x++) {
+        const uint32_t p = base + x * kThreads;
+        if (p < m.L && !m.multi[p]) {
+            const uint32_t cov = m.cover[p], cnt = m.dense_cnt[p];
+            sum += 10ll * cnt - 4ll * cov;
+            const uint8_t c = m.code[p];
+            if (c != 4) {
+                const uint32_t w = emit_off[p];
+                out_pos[w] = p;
+                out_base[w] = code_char(c);
+                // qv = cnt*100/cov < 95  <=>  cnt*100 < 95*cov (floor division, cov >= 1: the ref read covers p)
+                out_flags[w] = (uint8_t)(((uint64_t)cnt * 100 < (uint64_t)cov * 95 ? 1 : 0) | (cov < 2 ? 2 : 0));
+            }
         }
     }
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-    if ((threadIdx.x & 31) == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        sum = threadIdx.x < kThreads / 32 ? wsum[threadIdx.x] : 0;
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (threadIdx.x == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
+    }
 }
 void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, uint32_t *d_n_emit,
                      cudaStream_t s) {
@@ -1026,7 +1043,7 @@ void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpO
 }
 void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, const uint32_t *d_n_emit,
                 const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s) {
-    NP2_K(k_emit_singles)<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags, o);
+    NP2_K(k_emit_singles)<<<cdiv(m.L, kThreads * kEmitPerThread), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags, o);
     if (n_runs)
         NP2_K(k_emit_runs<true>)<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, const_cast<uint32_t *>(d_n_emit),
                                                           d_emit_off, d_pos, d_base, d_flags);

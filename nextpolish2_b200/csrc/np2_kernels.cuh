@@ -158,6 +158,8 @@ struct AssembleDev {
 };
 void assemble_sizes(AssembleDev a, cudaStream_t s);
 void assemble_seed_gather(AssembleDev a, uint8_t *d_out, cudaStream_t s);
+void gather_ranges(const uint8_t *d_src, const uint32_t *d_lo, const uint64_t *d_off, uint32_t n, uint8_t *d_out,
+                   cudaStream_t s);
 void rech_sizes(GenoDev g, uint32_t *d_bytes, cudaStream_t s);
 void rech_gather(GenoDev g, const uint32_t *d_ent_off, const uint64_t *d_byte_off, uint32_t *d_order, uint32_t *d_len,
                  uint64_t *d_pool_off, uint8_t *d_out, cudaStream_t s);

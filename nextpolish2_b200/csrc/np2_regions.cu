@@ -166,6 +166,23 @@ __global__ void __launch_bounds__(128) k_assemble(AssembleDev a, uint8_t *__rest
     }
 }
 
+// out[off[i] .. off[i+1]) = src[lo[i] ..): one warp per range (the DP-base windows around RECH regions)
+__global__ void __launch_bounds__(128) k_gather_ranges(const uint8_t *__restrict__ src, const uint32_t *__restrict__ lo,
+                                                       const uint64_t *__restrict__ off, uint32_t n,
+                                                       uint8_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const uint64_t o = off[i];
+    const uint32_t len = (uint32_t)(off[i + 1] - o);
+    const uint8_t *sp = src + lo[i];
+    for (uint32_t x = lane; x < len; x += 32) out[o + x] = sp[x];
+}
+void gather_ranges(const uint8_t *d_src, const uint32_t *d_lo, const uint64_t *d_off, uint32_t n, uint8_t *d_out,
+                   cudaStream_t s) {
+    if (n) NP2_K(k_gather_ranges)<<<cdiv((uint64_t)n * 32, 128), 128, 0, s>>>(d_src, d_lo, d_off, n, d_out);
+}
+
 void assemble_sizes(AssembleDev a, cudaStream_t s) {
     if (a.nreg) NP2_K(k_patch_sizes)<<<cdiv(a.nreg, 128), 128, 0, s>>>(a);
 }

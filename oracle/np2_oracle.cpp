@@ -1526,7 +1526,8 @@ std::vector<ConsensusBase> np2o_job::get_cns_from_align_tags(std::vector<Msa> &m
 // worker closure main.rs:1726-1838
 void np2o_job::run() {
     const size_t tlen = tseq.size();
-    if (opt.use_secondary) fail("-S / use_secondary is out of scope (SURVEY §2 row 12)");
+    // -S: secondary records are expected to carry their SEQ already (the caller recovered it from the primary
+    // record, secondary.rs:85-150 + main.rs:1775-1783); the filter below then keeps them (main.rs:1764).
     if (tables.empty()) fail("Missing yak file!");
     if (opt.iter_count == 0) fail("iter_count must be >= 1");
     if (tlen < opt.min_ctg_len) {  // main.rs:1727-1730

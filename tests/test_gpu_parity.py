@@ -150,8 +150,6 @@ def test_passthrough_and_errors(ctx):
     mixed = np.concatenate([j1, r0])
     common.assert_same("unsorted-but-unpushed", O.Job(ds["contig"], mixed, common.oracle_tables(ds), O.Opts(min_ctg_len=0)).consensus()[1],
                        np2.polish_contig(ctx, ds["contig"], mixed, gt, np2.Opts(min_ctg_len=0))[1])
-    with pytest.raises(np2.Np2Error):
-        np2.polish_contig(ctx, ds["contig"], ds["bam"], gt, np2.Opts(min_ctg_len=0, use_secondary=1))
 
 
 def test_no_reads(ctx):
