@@ -25,6 +25,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WORKLOAD = "synthetic 10 Mbp haploid contig, 30x HiFi (N(15k,2k), 0.2% err), asm err 2e-5/bp, k21+k31"
+WORKLOAD_DIPLOID = ("synthetic %.0f Mbp diploid contig (%.1f%% het), 30x HiFi from both haplotypes, asm err 2e-5/bp, k21+k31 "
+                    "(one contig of configs[2]; exercises phasing)")
 KS = (21, 31)
 
 
@@ -32,12 +34,12 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_workload(seed, length, threads):
+def make_workload(seed, length, threads, het=0.0):
     from nextpolish2_b200 import synth
     t0 = time.time()
     A = synth.genome(seed, length)
-    c = synth.make_contig(seed + 1, A, depth=30.0, asm_err=2e-5, het=0.0, read_err=0.002, threads=threads)
-    tabs = {k: synth.make_table(seed + 2, k, [c["hap1"]]) for k in KS}
+    c = synth.make_contig(seed + 1, A, depth=30.0, asm_err=2e-5, het=het, read_err=0.002, threads=threads)
+    tabs = {k: synth.make_table(seed + 2, k, [c["hap1"]] + ([c["hap2"]] if het > 0 else [])) for k in KS}
     log("[bench] workload seed %d: %d bp, %d reads, %.1f MB of BAM records, tables %s  (%.1fs)" % (
         seed, length, c["n_reads"], len(c["bam"]) / 1e6, {k: len(v[0]) for k, v in tabs.items()}, time.time() - t0))
     return A, c, tabs
@@ -129,7 +131,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     threads = max(1, (os.cpu_count() or 8) // max(world, 1))
-    A, c, tabs = make_workload(20260002 + 1000 * rank, args.length, min(threads, 16))
+    A, c, tabs = make_workload(20260002 + 1000 * rank, args.length, min(threads, 16), args.het)
+    workload = WORKLOAD if args.het == 0 else WORKLOAD_DIPLOID % (args.length / 1e6, args.het * 100)
     ctx = np2.Context(local)
     tables = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in KS]
     opts = np2.Opts()  # reference defaults; the 10 Mbp contig is above -L 1000000
@@ -174,7 +177,7 @@ def run_ours(args):
         j = np2.Job(cx, contig_np, bam_np, tables, opts)
         j.upload().run(-1)
         first, last, base = j.bases(copy=False)  # the FASTA record (header span + bases) in host memory
-        assert len(base) == len(c["hap1"]) and base[-1] == c["hap1"][-1]
+        assert len(base) == len(gbase) and base[-1] == gbase[-1] and base[len(base) // 2] == gbase[len(base) // 2]
         tr = j.traffic()
         j.destroy()
         return tr
@@ -239,8 +242,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_time / args.steps * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "contig_bp": args.length, "contigs_per_gpu": 1, "depth": 30,
-                       "tables": "k21+k31 synthesised from the truth haplotype", "partition": "one contig per GPU, no collective",
+            "config": {"workload": workload, "contig_bp": args.length, "contigs_per_gpu": 1, "depth": 30,
+                       "tables": "k21+k31 synthesised from the truth haplotype(s)", "partition": "one contig per GPU, no collective",
                        "l2": "inputs (%.0f MB of BAM records per GPU) are larger than the 126 MB L2" % (len(c["bam"]) / 1e6)},
             "e2e": {"value": round(mbp_total / e2e_time, 3), "unit": "Mbp/s", "h2d_bytes_per_step": tr["h2d_bytes"],
                     "d2h_bytes_per_step": tr["d2h_bytes"], "contigs_in_flight": args.e2e_inflight,
@@ -255,7 +258,7 @@ def run_ours(args):
         if not args.no_yak_bench:
             line["yak_lookup"] = yak_bench(ctx, np2, torch, peak)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_sample(args, steps=1)
+            line["cpu_baseline"] = cpu_sample(args, steps=args.cpu_steps)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -297,7 +300,7 @@ def yak_bench(ctx, np2, torch, peak):
     return res
 
 
-def cpu_sample(args, steps=1):
+def cpu_sample(args, steps=1, warmup=0):
     """The reference's CPU algorithm (oracle port, in-memory tables) on a bounded sample of the same workload:
     `cores` contigs of 1 Mbp each, one worker thread per contig (the reference's unit of parallelism)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -309,12 +312,12 @@ def cpu_sample(args, steps=1):
     data = []
     for i in range(cores):
         A = G[i * clen:(i + 1) * clen].copy()
-        data.append((A, synth.make_contig(20260100 + i, A, depth=30.0, asm_err=2e-5, het=0.0, read_err=0.002, threads=4)))
-    haps = [d[1]["hap1"] for d in data]
+        data.append((A, synth.make_contig(20260100 + i, A, depth=30.0, asm_err=2e-5, het=args.het, read_err=0.002, threads=4)))
+    haps = [d[1]["hap1"] for d in data] + ([d[1]["hap2"] for d in data] if args.het > 0 else [])
     tabs = [O.Table.from_arrays(k, *synth.make_table(20260003, k, haps)) for k in KS]
     opts = O.Opts(min_ctg_len=0)
     vals = []
-    for _ in range(steps):
+    for it in range(warmup + steps):
         res = [None] * cores
 
         def work(i):
@@ -324,25 +327,24 @@ def cpu_sample(args, steps=1):
         [t.start() for t in th]
         [t.join() for t in th]
         dt = time.perf_counter() - t0
-        assert all(bytes(res[i].consensus()[1]) == bytes(haps[i]) for i in range(cores))
-        vals.append(cores * clen / 1e6 / dt)
+        assert args.het > 0 or all(bytes(res[i].consensus()[1]) == bytes(haps[i]) for i in range(cores))
+        if it >= warmup:
+            vals.append(cores * clen / 1e6 / dt)
     return {"value": round(float(np.mean(vals)), 4), "unit": "Mbp/s", "cores": cores, "kind": "port",
             "sample": "%d contigs x %d bp of the same synthetic workload (30x), one oracle thread per contig, "
                       "tables in memory (kinder to the CPU than the reference's per-pass .yak file streaming); "
                       "restatement of the reference algorithm, not the Rust binary (no cargo in this image)" % (cores, clen),
-            "seconds": round(cores * clen / 1e6 / float(np.mean(vals)), 2)}
+            "seconds": round(len(vals) * cores * clen / 1e6 / float(np.mean(vals)), 2)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    for _ in range(args.warmup and 0):
-        pass
-    b = cpu_sample(args, steps=max(1, args.steps))
+    b = cpu_sample(args, steps=max(1, args.steps), warmup=min(args.warmup, 2))
     line = {"impl": "reference", "metric": "polished Mbp/s", "value": b["value"], "unit": "Mbp/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(b["seconds"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(b["seconds"] * 1e3 / max(1, args.steps), 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": b["sample"]},
             "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -358,7 +360,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--length", type=int, default=10_000_000, help="contig length per GPU (configs[1] = 10 Mbp)")
     ap.add_argument("--cpu-contig", type=int, default=1_000_000)
+    ap.add_argument("--cpu-steps", type=int, default=10, help="passes over the CPU sample for cpu_baseline (~1 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--het", type=float, default=0.0, help="heterozygosity of the synthetic contig (configs[2]: 0.01)")
     ap.add_argument("--no-yak-bench", action="store_true")
     ap.add_argument("--e2e-inflight", type=int, default=2, help="contigs in flight per GPU in the end-to-end arm")
     args = ap.parse_args()

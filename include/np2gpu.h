@@ -177,6 +177,15 @@ void np2_job_get_traffic(np2_job *job, uint64_t *h2d_bytes, uint64_t *d2h_bytes,
 int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts *opts, uint32_t threads,
                     uint64_t out[6]);
 
+/* Test seam (host only): the host half of phase_reads_by_lqseqs (main.rs:994-1015) + louvain.rs:59-356 on reduced
+ * agreement edges.  keys[e] = a << 32 | b (read orders, a < b, sorted ascending; a = 0 is the ref read),
+ * vals[e] = sum over shared HETE regions of (+1 if the two reads agree, (1 << 32) - 1 if they differ).
+ * dropped: read orders to blank, ascending (up to cap are written); *n_dropped = how many there are;
+ * *path (optional) = 1 when the flat-array implementation served the call, 2 when it handed over to the general
+ * one (a community with negative internal weight, louvain.rs:136-165). */
+int np2_debug_phase(const uint64_t *keys, const int64_t *vals, uint64_t n_edges, uint32_t model, uint32_t use_all_reads,
+                    uint32_t *dropped, uint64_t cap, uint64_t *n_dropped, uint32_t *path);
+
 /* FASTA record exactly as display_consensusbase_vec prints it (main.rs:607-645); returns bytes needed. */
 uint64_t np2_format_fasta(const char *tid, const uint32_t *pos, const uint8_t *base, uint64_t n, int uppercase,
                           int out_pos, uint8_t *out, uint64_t cap);

@@ -47,6 +47,7 @@ EXPORTS = [
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
+    "np2_debug_phase",
 ]
 
 
@@ -100,6 +101,7 @@ def load_library():
     L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
     L.np2_format_fasta.restype = u64
     L.np2_format_fasta.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int, vp, u64]
+    L.np2_debug_phase.argtypes = [vp, vp, u64, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u32)]
     L.np2_secmap_create.argtypes = [C.POINTER(vp)]
     L.np2_secmap_destroy.argtypes = [vp]
     L.np2_secmap_scan_ids.argtypes = [vp, vp, u64]
@@ -165,6 +167,18 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def debug_phase(keys, vals, model=0, use_all_reads=False, with_path=False):
+    """Host-only test seam: reduced agreement edges -> read orders that phasing drops (np2_debug_phase)."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    vals = np.ascontiguousarray(vals, np.int64)
+    n, path = C.c_uint64(), C.c_uint32()
+    out = np.empty(max(len(keys) * 2 + 1, 1), np.uint32)
+    _check(load_library().np2_debug_phase(keys.ctypes.data, vals.ctypes.data, len(keys), model, int(use_all_reads),
+                                          out.ctypes.data, len(out), C.byref(n), C.byref(path)))
+    res = out[:n.value].copy()
+    return (res, path.value) if with_path else res
 
 
 def debug_parse(bam, tlen, opts=None, threads=0):

@@ -12,8 +12,10 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/np2gpu.h"
@@ -39,6 +41,17 @@ int guard(F f) {
     }
 }
 
+// Every context allocates from its OWN stream-ordered pool.  With the device's default pool shared by two contexts, a
+// block freed on one stream and handed to the other makes the second stream wait for the first (the pool's
+// cross-stream reuse dependencies), which serialises two contigs that are meant to be in flight together.
+std::mutex g_pool_mu;
+std::unordered_map<cudaStream_t, cudaMemPool_t> g_stream_pool;
+cudaMemPool_t pool_of(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_stream_pool.find(st);
+    return it == g_stream_pool.end() ? nullptr : it->second;
+}
+
 template <class T>
 struct DBuf {  // stream-ordered device buffer
     T *p = nullptr;
@@ -52,7 +65,9 @@ struct DBuf {  // stream-ordered device buffer
         s = st;
         n = count;
         if (count) {
-            cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), st);
+            cudaMemPool_t pool = pool_of(st);
+            cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), pool, st)
+                                 : cudaMallocAsync((void **)&p, count * sizeof(T), st);
             if (e != cudaSuccess) {
                 p = nullptr;
                 throw np2::Error(NP2_ERR_CUDA, std::string("cudaMallocAsync of ") + std::to_string(count) + " x " +
@@ -195,6 +210,7 @@ struct Stager {
 struct np2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
     int refs = 1;  // tables and jobs keep their context alive (np2_ctx_destroy only drops the caller's reference)
     std::vector<JobScratch *> scratch_pool;
     JobScratch *take_scratch() {
@@ -209,7 +225,12 @@ static void ctx_release(np2_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (JobScratch *sc : ctx->scratch_pool) delete sc;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_stream_pool.erase(ctx->stream);
+    }
     cudaStreamDestroy(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -1076,19 +1097,22 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             d_ev2.alloc(n_edges, s);
             d_uv.alloc(n_edges, s);
             d_nu.alloc(1, s);
-            h = timer.begin("pair_edges", 6);
-            geno_edges_emit(g, d_ek.p, d_ev.p, s);
+            uint32_t id_bits = 1;  // read orders are < as_read.size()
+            while ((1ull << id_bits) < as_read.size()) id_bits++;
+            h = timer.begin("pair_edges", 7);
+            geno_edges_emit(g, d_ek.p, d_ev.p, id_bits, s);
             {
                 size_t tb = 0;
-                cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 64, s);
+                cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 2 * id_bits, s);
                 if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-                cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 64, s);
+                cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 2 * id_bits, s);
                 tb = 0;
                 cub::DeviceReduce::ReduceByKey(nullptr, tb, d_ek2.p, d_uk.p, d_ev2.p, d_uv.p, d_nu.p, cub::Sum(),
                                                (int)n_edges, s);
                 if (tb > d_tmp.n) d_tmp.alloc(tb, s);
                 cub::DeviceReduce::ReduceByKey(d_tmp.p, tb, d_ek2.p, d_uk.p, d_ev2.p, d_uv.p, d_nu.p, cub::Sum(),
                                                (int)n_edges, s);
+                geno_edges_unpack(d_uk.p, d_nu.p, n_edges, id_bits, s);
             }
             timer.end(h);
             uint32_t nu = 0;
@@ -1545,11 +1569,20 @@ int np2_ctx_create(int device, np2_ctx **out) {
         np2_ctx *c = new np2_ctx();
         c->device = device;
         NP2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        // keep freed blocks in the pool: per-iteration scratch is re-used instead of going back to the driver
-        cudaMemPool_t pool;
-        NP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        // a private pool that keeps freed blocks: per-iteration scratch is re-used instead of going back to the driver
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        NP2_CUDA(cudaMemPoolCreate(&c->pool, &props));
         uint64_t thr = UINT64_MAX;
-        NP2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        NP2_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            g_stream_pool[c->stream] = c->pool;
+        }
         *out = c;
     });
 }
@@ -1938,6 +1971,18 @@ void np2_job_get_traffic(np2_job *j, uint64_t *h2d_bytes, uint64_t *d2h_bytes, u
     if (n_kernel_launches) *n_kernel_launches = j->n_launch;
     if (n_alignment_columns) *n_alignment_columns = j->ing.total_cols;
     if (n_probes) *n_probes = j->n_probes;
+}
+
+int np2_debug_phase(const uint64_t *keys, const int64_t *vals, uint64_t n_edges, uint32_t model, uint32_t use_all_reads,
+                    uint32_t *dropped, uint64_t cap, uint64_t *n_dropped, uint32_t *path) {
+    return guard([&] {
+        if ((!keys || !vals) && n_edges) throw np2::Error(NP2_ERR_ARG, "null argument");
+        std::vector<uint32_t> d = phase_reads(keys, reinterpret_cast<const long long *>(vals), n_edges, model == 0,
+                                              use_all_reads != 0);
+        if (path) *path = (uint32_t)np2::phase_last_path();
+        if (n_dropped) *n_dropped = d.size();
+        if (dropped) memcpy(dropped, d.data(), std::min<uint64_t>(cap, d.size()) * 4);
+    });
 }
 
 int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts *opts, uint32_t threads,

@@ -79,27 +79,39 @@ __device__ __forceinline__ ScanOut scan_read_region(const ReadsDev &R, uint32_t 
         if (ck[mid] < start) lo = mid;
         else hi = mid;
     }
-    uint32_t tpos = ck[lo];
     const uint64_t mask = (1ULL << (2 * k)) - 1;
     const uint32_t sh = 2 * (k - 1);
     uint64_t k0 = 0, k1 = 0;
     uint32_t l = 0, len = 0;
-    for (uint32_t o = lo * 32; o < n; o++) {
+    // t_pos of a column = checkpoint + non-insertion columns after the block's first one.  Pre-decrementing for a
+    // non-insertion first column makes "every non-insertion column advances t_pos" hold from the first column on.
+    uint32_t o = lo * 32;
+    uint32_t tpos = ck[lo] - ((nib[o >> 1] >> 4) & 8 ? 0u : 1u);
+    // skip phase, 8 columns (one aligned word) at a time: a word whose last column is still before `start` holds
+    // nothing the loop below would look at
+    const uint32_t *nw = reinterpret_cast<const uint32_t *>(nib);
+    while (o + 8 <= n) {
+        const uint32_t adv = __popc(~nw[o >> 3] & 0x88888888u);
+        if (tpos + adv >= start) break;  // (a wrapped tpos = -1 only exists before the first word, whose adv >= 1)
+        tpos += adv;
+        o += 8;
+    }
+    for (; o < n; o++) {
         const uint32_t b = nib[o >> 1];
         const uint32_t v = (o & 1) ? (b & 15) : (b >> 4);
-        if (o != lo * 32 && !(v & 8)) tpos++;
+        if (!(v & 8)) tpos++;
         const uint32_t q = v & 7;
         if (tpos >= start && q != 4) {
             if (tpos <= end) {
                 if (WRITE) out[len] = code_char(q);
                 len++;
             }
-            if (l < k) {
+            if (!WRITE && l < k) {
                 k0 = (k0 << 2 | (uint64_t)q) & mask;
                 k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
                 l++;
             }
-            if (tpos > end && l >= k) break;
+            if (tpos > end && (WRITE || l >= k)) break;
         }
         if (tpos > limit) break;
     }
@@ -123,12 +135,12 @@ __device__ __forceinline__ ScanOut scan_ref_region(const uint8_t *__restrict__ c
                 if (WRITE) out[len] = code_char(q);
                 len++;
             }
-            if (l < k) {
+            if (!WRITE && l < k) {
                 k0 = (k0 << 2 | (uint64_t)q) & mask;
                 k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
                 l++;
             }
-            if (p > end && l >= k) break;
+            if (p > end && (WRITE || l >= k)) break;
         }
         if (p > limit) break;
     }
@@ -208,7 +220,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_select(GenoDev g, 
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, len > 0);  // empty candidates are not pushed (main.rs:1509)
         const uint32_t slot = ncand + __popc(bal & ((1u << lane) - 1));
         if (len > 0 && slot < kMaxCand) {
-            g.c_src[base + slot] = pair;
+            g.c_src[base + slot] = i;  // the read; k_cand_write re-decodes it over the region
             g.c_len[base + slot] = len;
             g.c_order[base + slot] = g.rd_order[i];
             g.c_kmer[base + slot] = g.p_kmer[pair];
@@ -250,13 +262,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_cand_write(GenoDev g, Rea
             if (src == 0xFFFFFFFFu) {
                 scan_ref_region<true>(code, L, start, end, g.end[0] + k, k, g.pool + off);
             } else {
-                uint32_t lo = 0, hi = R.n_reads;  // read owning the pair
-                while (hi - lo > 1) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (g.rd_poff[mid] <= src) lo = mid;
-                    else hi = mid;
-                }
-                scan_read_region<true>(R, lo, start, end, g.end[g.rd_j[lo]] + k, k, g.pool + off);
+                scan_read_region<true>(R, src, start, end, g.end[g.rd_j[src]] + k, k, g.pool + off);
             }
         }
     }
@@ -459,8 +465,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_hete(GenoDev g) {
 
 // all pairs (i < j) of supported candidates of a heterozygous region: key = (min order, max order), value +1 when
 // the strings agree, -1 (and one "differs" count in the high half) when they do not (main.rs:953-992)
+// The key is packed as x << id_bits | y so that the radix sort only has to look at 2 * id_bits bits.
 __global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_emit(GenoDev g, uint64_t *__restrict__ ekey,
-                                                                  long long *__restrict__ eval) {
+                                                                  long long *__restrict__ eval, uint32_t id_bits) {
     __shared__ uint8_t s_valid[kWarpsPerCta][kMaxCand];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -487,7 +494,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_emit(GenoDev g, uin
             const uint32_t ob = g.c_order[base + pb];
             const bool same = g.c_rep[base + pb] == ra;
             const uint32_t x = min(oa, ob), y = max(oa, ob);
-            ekey[w0 + row0 + (b - a - 1)] = (uint64_t)x << 32 | y;
+            ekey[w0 + row0 + (b - a - 1)] = (uint64_t)x << id_bits | y;
             eval[w0 + row0 + (b - a - 1)] = same ? 1LL : (-1LL + (1LL << 32));
         }
     }
@@ -588,8 +595,18 @@ void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStre
 void geno_region_hete(GenoDev g, cudaStream_t s) {
     NP2_K(k_region_hete)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g);
 }
-void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, cudaStream_t s) {
-    NP2_K(k_edges_emit)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_key, d_val);
+void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, uint32_t id_bits, cudaStream_t s) {
+    NP2_K(k_edges_emit)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_key, d_val, id_bits);
+}
+// packed keys of the reduced edges back to (min order << 32 | max order), the form phase_reads takes
+__global__ void k_edges_unpack(uint64_t *__restrict__ key, const uint32_t *__restrict__ n, uint32_t id_bits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n) return;
+    const uint64_t k = key[i];
+    key[i] = (k >> id_bits) << 32 | (k & ((1ULL << id_bits) - 1));
+}
+void geno_edges_unpack(uint64_t *d_key, const uint32_t *d_n, uint64_t n_max, uint32_t id_bits, cudaStream_t s) {
+    if (n_max) NP2_K(k_edges_unpack)<<<cdiv(n_max, 256), 256, 0, s>>>(d_key, d_n, id_bits);
 }
 void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s) {
     NP2_K(k_region_seed)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, d_err);

@@ -491,8 +491,10 @@ struct Community {
 
 }  // namespace
 
-std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
-                                  bool use_all_reads) {
+// General path: handles every quirk of louvain.rs (communities that fall apart again, re-keyed vertices).  The flat
+// implementation in np2_phase.cpp serves the common case and comes here when it meets a negative community.
+std::vector<uint32_t> phase_reads_general(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
+                                          bool use_all_reads) {
     std::map<uint32_t, float> ref_w;
     bool have_ref = false;
     std::set<uint32_t> invalid;

@@ -107,6 +107,10 @@ struct Regions {
 // Order 0 is the ref read (its pairs only feed ref_data / invalid_ids).  Returns the alignseq indices to blank.
 std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
                                   bool use_all_reads);
+std::vector<uint32_t> phase_reads_general(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
+                                  bool use_all_reads);
+// which implementation served the calling thread's last phase_reads: 1 = flat arrays, 2 = general path
+int phase_last_path();
 
 /* ---------------------------------------------------------------- consensus patching */
 const uint8_t LABLE_TEMP = 0x01, LABLE_SUCC = 0x80, LABLE_HETE = 0x40, LABLE_RECH = 0x20;  // main.rs:655-658

@@ -277,26 +277,33 @@ void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, uint32_t *d_re
 // A vector that straddles the SEQ ends only touches bytes of the same 16-byte line, i.e. of a mapped page.
 __global__ void __launch_bounds__(256) k_gather_seq(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
                                                     const uint64_t *__restrict__ dst_off,
-                                                    const uint32_t *__restrict__ nbytes, uint8_t *__restrict__ dst) {
-    const uint32_t r = blockIdx.x;
-    const uint8_t *a = src + src_off[r];
-    const uint32_t mis = (uint32_t)((uintptr_t)a & 15);
-    const uint4 *sp = reinterpret_cast<const uint4 *>(a - mis);
-    uint4 *dp = reinterpret_cast<uint4 *>(dst + dst_off[r] - mis);
-    const uint32_t nv = (mis + nbytes[r] + 15) >> 4;
-    for (uint32_t i = threadIdx.x; i < nv; i += 4 * 256) {
-        uint4 v[4];
+                                                    const uint32_t *__restrict__ nbytes, uint8_t *__restrict__ dst,
+                                                    uint32_t n_reads) {
+    for (uint32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const uint8_t *a = src + src_off[r];
+        const uint32_t mis = (uint32_t)((uintptr_t)a & 15);
+        const uint4 *sp = reinterpret_cast<const uint4 *>(a - mis);
+        uint4 *dp = reinterpret_cast<uint4 *>(dst + dst_off[r] - mis);
+        const uint32_t nv = (mis + nbytes[r] + 15) >> 4;
+        for (uint32_t i = threadIdx.x; i < nv; i += 4 * 256) {
+            uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (i + u * 256 < nv) v[u] = __ldcs(sp + i + u * 256);
+            for (int u = 0; u < 4; u++)
+                if (i + u * 256 < nv) v[u] = __ldcs(sp + i + u * 256);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (i + u * 256 < nv) dp[i + u * 256] = v[u];
+            for (int u = 0; u < 4; u++)
+                if (i + u * 256 < nv) dp[i + u * 256] = v[u];
+        }
     }
 }
+// A small persistent grid (two CTAs per SM): the loads wait on PCIe, not on the SMs, and ~2.4 MB in flight saturate
+// the link; a CTA per read would fill every SM with waiting threads and lock out the kernels of the other contig
+// that is in flight on this GPU.
 void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
                 uint8_t *d_dst, uint32_t n_reads, cudaStream_t s) {
-    if (n_reads) NP2_K(k_gather_seq)<<<n_reads, 256, 0, s>>>(src_mapped, d_src_off, d_dst_off, d_nbytes, d_dst);
+    if (n_reads)
+        NP2_K(k_gather_seq)<<<std::min<uint32_t>(n_reads, 2 * 148), 256, 0, s>>>(src_mapped, d_src_off, d_dst_off, d_nbytes,
+                                                                               d_dst, n_reads);
 }
 
 /* =============================================================== K1: expand + trim + pack */

@@ -128,7 +128,8 @@ void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, co
 void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s);
 void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s);
 void geno_region_hete(GenoDev g, cudaStream_t s);
-void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, cudaStream_t s);
+void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, uint32_t id_bits, cudaStream_t s);
+void geno_edges_unpack(uint64_t *d_key, const uint32_t *d_n, uint64_t n_max, uint32_t id_bits, cudaStream_t s);
 void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s);
 
 /* ------------------------------------------------------------------ regions + assembly (np2_regions.cu) */

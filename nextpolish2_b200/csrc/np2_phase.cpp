@@ -1,0 +1,355 @@
+// np2_phase.cpp — the host half of phase_reads_by_lqseqs (main.rs:994-1015) + louvain.rs:59-356, flat arrays.
+//
+// Input: the read x read agreement edges reduced on the device (one record per read pair).  Everything here is
+// CSR / id-indexed arrays: no node-based containers on the common path.  Why that is exact:
+//   * all weights are small integers or halves of them (sums of +-1, "/ 2.0" of such sums), so every f32 sum is
+//     exact and independent of the order of accumulation; only the ORDER OF DECISIONS matters, and that is kept:
+//     vertices are visited in ascending id (louvain.rs:77), ties go to the smaller community id (99-101), a move
+//     needs a positive weight and a different community (103);
+//   * a level's communities are the groups of equal `cid`; the reference's `communities` map holds exactly those
+//     sets (plus empty ones it skips), so they are rebuilt from `cid` after the moves instead of being maintained.
+// The one thing not handled here is a community whose internal weight is negative (louvain.rs:136-165: it falls
+// apart again and its vertices are re-keyed, with quirks): when one shows up the call is served from scratch by the
+// general map/set implementation (phase_reads_general in np2_host.cpp), which reproduces those quirks.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/np2gpu.h"
+#include "np2_error.h"
+#include "np2_host.h"
+
+namespace np2 {
+
+namespace {
+
+thread_local int g_phase_path = 0;
+
+struct Lvl {
+    uint32_t n = 0;                   // every array below is indexed by vertex / community id < n
+    std::vector<uint32_t> verts;      // all vertices of the level, ascending (keys of `communities`)
+    std::vector<uint32_t> ids;        // those that appear in `data` (louvain.rs:77 iterates these), ascending
+    std::vector<uint32_t> aoff, ato;  // adjacency (CSR), neighbours ascending
+    std::vector<float> aw;
+    std::vector<uint32_t> cid;        // vertex -> community
+    std::vector<float> nweight;       // Node.weight
+    std::vector<uint32_t> moff, mdat; // Node.nodes: original vertices of each vertex (CSR)
+};
+
+// louvain.rs:72-117.  The outcome of visiting a vertex depends only on its neighbours' communities, so a vertex is
+// re-examined only when one of them changed since its last visit (a skipped visit would have moved nothing).
+bool move_vertices(Lvl &lv) {
+    bool moved_any = false;
+    std::vector<std::pair<uint32_t, float>> acc;
+    std::vector<uint8_t> dirty(lv.n, 1);
+    for (;;) {
+        bool stop = true;
+        for (uint32_t v : lv.ids) {
+            if (!dirty[v]) continue;
+            dirty[v] = 0;
+            const uint32_t cur = lv.cid[v];
+            acc.clear();
+            for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) {
+                const uint32_t c = lv.cid[lv.ato[e]];
+                bool found = false;
+                for (auto &a : acc)
+                    if (a.first == c) {
+                        a.second += lv.aw[e];
+                        found = true;
+                        break;
+                    }
+                if (!found) acc.emplace_back(c, lv.aw[e]);
+            }
+            if (acc.empty()) continue;
+            uint32_t bid = acc[0].first;
+            float bw = acc[0].second;
+            for (auto &a : acc)
+                if (a.second > bw || (a.second == bw && a.first < bid)) {  // max weight, ties -> smaller id
+                    bid = a.first;
+                    bw = a.second;
+                }
+            if (bw > 0.0f && bid != cur) {
+                lv.cid[v] = bid;
+                for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) dirty[lv.ato[e]] = 1;
+                stop = false;
+                moved_any = true;
+            }
+        }
+        if (stop) break;
+    }
+    return moved_any;
+}
+
+// vertices grouped by community: comms ascending, members of each ascending
+struct Groups {
+    std::vector<uint32_t> comms, off, dat;  // off is indexed by position in comms
+};
+void group_by_cid(const Lvl &lv, Groups &g, std::vector<uint32_t> &slot) {
+    slot.assign(lv.n, 0);
+    for (uint32_t v : lv.verts) slot[lv.cid[v]]++;
+    g.comms.clear();
+    g.off.assign(1, 0);
+    for (uint32_t c = 0; c < lv.n; c++)
+        if (slot[c]) {
+            g.comms.push_back(c);
+            g.off.push_back(g.off.back() + slot[c]);
+            slot[c] = (uint32_t)g.comms.size() - 1;  // community -> its position
+        }
+    g.dat.resize(lv.verts.size());
+    std::vector<uint32_t> cur(g.off.begin(), g.off.end() - 1);
+    for (uint32_t v : lv.verts) g.dat[cur[slot[lv.cid[v]]]++] = v;
+}
+// Node.weight of a community: its vertices' weights + every internal edge once (seen from both ends, halved)
+float internal_weight(const Lvl &lv, const Groups &g, size_t gi) {
+    const uint32_t c = g.comms[gi];
+    float w = 0.f;
+    for (uint32_t x = g.off[gi]; x < g.off[gi + 1]; x++) {
+        const uint32_t v = g.dat[x];
+        w += lv.nweight[v];
+        for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++)
+            if (lv.cid[lv.ato[e]] == c) w += lv.aw[e] / 2.0f;
+    }
+    return w;
+}
+// sum of the edges between every pair of communities (c1 < c2), emitted in ascending (c1, c2)
+struct PairSum {
+    uint32_t c1, c2;
+    float w;
+};
+void between_communities(const Lvl &lv, const Groups &g, std::vector<PairSum> &out) {
+    out.clear();
+    std::vector<uint32_t> stamp(lv.n, 0), touched;
+    std::vector<float> acc(lv.n, 0.f);
+    for (size_t gi = 0; gi < g.comms.size(); gi++) {
+        const uint32_t c = g.comms[gi];
+        touched.clear();
+        for (uint32_t x = g.off[gi]; x < g.off[gi + 1]; x++) {
+            const uint32_t v = g.dat[x];
+            for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) {
+                const uint32_t o = lv.cid[lv.ato[e]];
+                if (!(o > c)) continue;
+                if (stamp[o] != c + 1) {
+                    stamp[o] = c + 1;
+                    acc[o] = 0.f;
+                    touched.push_back(o);
+                }
+                acc[o] += lv.aw[e];
+            }
+        }
+        std::sort(touched.begin(), touched.end());
+        for (uint32_t o : touched) out.push_back({c, o, acc[o]});
+    }
+}
+
+// louvain.rs:119-195 when no community has to be declustered; false when one has
+bool aggregate(const Lvl &lv, Lvl &nx) {
+    Groups g;
+    std::vector<uint32_t> slot;
+    group_by_cid(lv, g, slot);
+    nx = Lvl();
+    nx.n = lv.n;
+    nx.cid.assign(lv.n, 0);
+    nx.nweight.assign(lv.n, 0.f);
+    nx.moff.assign(lv.n + 1, 0);
+    nx.verts = g.comms;
+    for (size_t gi = 0; gi < g.comms.size(); gi++) {
+        const float w = internal_weight(lv, g, gi);
+        if (w < 0.f) return false;
+        const uint32_t c = g.comms[gi];
+        nx.cid[c] = c;
+        nx.nweight[c] = w;
+        uint32_t m = 0;
+        for (uint32_t x = g.off[gi]; x < g.off[gi + 1]; x++) m += lv.moff[g.dat[x] + 1] - lv.moff[g.dat[x]];
+        nx.moff[c + 1] = m;
+    }
+    for (uint32_t c = 0; c < lv.n; c++) nx.moff[c + 1] += nx.moff[c];
+    nx.mdat.resize(nx.moff[lv.n]);
+    for (size_t gi = 0; gi < g.comms.size(); gi++) {
+        const uint32_t c = g.comms[gi];
+        uint32_t w = nx.moff[c];
+        for (uint32_t x = g.off[gi]; x < g.off[gi + 1]; x++) {
+            const uint32_t v = g.dat[x];
+            for (uint32_t y = lv.moff[v]; y < lv.moff[v + 1]; y++) nx.mdat[w++] = lv.mdat[y];
+        }
+        std::sort(nx.mdat.begin() + nx.moff[c], nx.mdat.begin() + w);  // members of distinct vertices are disjoint
+    }
+    std::vector<PairSum> ps;
+    between_communities(lv, g, ps);
+    nx.aoff.assign(lv.n + 1, 0);
+    for (auto &p : ps)
+        if (p.w != 0.f) {
+            nx.aoff[p.c1 + 1]++;
+            nx.aoff[p.c2 + 1]++;
+        }
+    for (uint32_t c = 0; c < lv.n; c++) nx.aoff[c + 1] += nx.aoff[c];
+    nx.ato.resize(nx.aoff[lv.n]);
+    nx.aw.resize(nx.aoff[lv.n]);
+    std::vector<uint32_t> cur(nx.aoff.begin(), nx.aoff.end() - 1);
+    for (auto &p : ps)  // ascending (c1, c2): every list receives its smaller neighbours first, each part ascending
+        if (p.w != 0.f) {
+            nx.ato[cur[p.c1]] = p.c2;
+            nx.aw[cur[p.c1]++] = p.w;
+            nx.ato[cur[p.c2]] = p.c1;
+            nx.aw[cur[p.c2]++] = p.w;
+        }
+    for (uint32_t c : nx.verts)
+        if (nx.aoff[c + 1] > nx.aoff[c]) nx.ids.push_back(c);  // louvain.rs:183-186
+    return true;
+}
+
+struct Community {
+    uint32_t id;
+    float weight;
+    uint32_t gi;
+};
+
+}  // namespace
+
+int phase_last_path() { return g_phase_path; }
+
+std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
+                                  bool use_all_reads) {
+    g_phase_path = 1;
+    uint32_t max_id = 0;
+    for (uint64_t e = 0; e < n_edges; e++) max_id = std::max(max_id, (uint32_t)keys[e]);  // b > a
+    const uint32_t n = max_id + 1;
+    // ref pairs (main.rs:972-980): keys are sorted, they come first
+    std::vector<float> ref_w(n, 0.f);
+    std::vector<uint8_t> in_ref(n, 0), bad_v(n, 0), has(n, 0);
+    bool have_ref = false;
+    uint64_t e0 = 0;
+    for (; e0 < n_edges && (keys[e0] >> 32) == 0; e0++) {
+        const uint32_t b = (uint32_t)keys[e0];
+        const long long v = vals[e0];
+        const long long ndif = (v + (1LL << 31)) >> 32;
+        if (asref) {
+            ref_w[b] = (float)(v - (ndif << 32));
+            in_ref[b] = 1;
+            have_ref = true;
+        }
+        if (ndif > 0 && !use_all_reads) bad_v[b] = 1;
+    }
+    // level 0: the reads (main.rs:994-1010: `dif <= -3` override, invalid reads leave, their partners stay)
+    Lvl lv;
+    lv.n = n;
+    lv.aoff.assign(n + 1, 0);
+    for (uint64_t e = e0; e < n_edges; e++) {
+        const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+        if (!use_all_reads && (bad_v[a] || bad_v[b])) {
+            if (!bad_v[a]) has[a] = 1;
+            if (!bad_v[b]) has[b] = 1;
+            continue;
+        }
+        has[a] = has[b] = 1;
+        lv.aoff[a + 1]++;
+        lv.aoff[b + 1]++;
+    }
+    for (uint32_t v = 0; v < n; v++) lv.aoff[v + 1] += lv.aoff[v];
+    lv.ato.resize(lv.aoff[n]);
+    lv.aw.resize(lv.aoff[n]);
+    {
+        std::vector<uint32_t> cur(lv.aoff.begin(), lv.aoff.end() - 1);
+        for (uint64_t e = e0; e < n_edges; e++) {  // sorted keys: every list comes out ascending
+            const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+            if (!use_all_reads && (bad_v[a] || bad_v[b])) continue;
+            const long long v = vals[e];
+            const long long ndif = (v + (1LL << 31)) >> 32;  // number of disagreeing sites
+            const long long sum = v - (ndif << 32);          // sum of +-1 over shared heterozygous regions
+            const float w = ndif >= 3 ? -(float)ndif : (float)sum;  // main.rs:996-1002
+            lv.ato[cur[a]] = b;
+            lv.aw[cur[a]++] = w;
+            lv.ato[cur[b]] = a;
+            lv.aw[cur[b]++] = w;
+        }
+    }
+    lv.cid.resize(n);
+    lv.nweight.assign(n, 0.f);
+    lv.moff.assign(n + 1, 0);
+    for (uint32_t v = 0; v < n; v++) {
+        lv.cid[v] = v;
+        lv.moff[v + 1] = lv.moff[v] + (has[v] ? 1 : 0);
+        if (has[v]) {
+            lv.verts.push_back(v);
+            lv.mdat.push_back(v);
+        }
+    }
+    lv.ids = lv.verts;
+    // ---- Louvain (louvain.rs:59-257)
+    while (move_vertices(lv)) {
+        Lvl nx;
+        if (!aggregate(lv, nx)) {
+            g_phase_path = 2;
+            return phase_reads_general(keys, vals, n_edges, asref, use_all_reads);
+        }
+        lv = std::move(nx);
+    }
+    // get_communities (louvain.rs:197-245)
+    Groups g;
+    std::vector<uint32_t> slot;
+    group_by_cid(lv, g, slot);
+    std::vector<Community> comms;
+    for (size_t gi = 0; gi < g.comms.size(); gi++) comms.push_back({g.comms[gi], internal_weight(lv, g, gi), (uint32_t)gi});
+    std::vector<PairSum> ps;
+    between_communities(lv, g, ps);
+    std::vector<std::vector<uint32_t>> conflict(g.comms.size());  // by position in g.comms
+    for (auto &p : ps) {
+        if (p.w == 0.f) continue;
+        if (!(p.w < 0.f)) throw Error(NP2_ERR_FORMAT, "the weight of two conflicting community is not less than 0");
+        conflict[slot[p.c1]].push_back(slot[p.c2]);
+        conflict[slot[p.c2]].push_back(slot[p.c1]);
+    }
+    // ---- phase_communities (louvain.rs:290-356)
+    if (have_ref) {
+        std::vector<std::pair<std::pair<int32_t, float>, size_t>> key;
+        for (size_t i = 0; i < comms.size(); i++) {
+            int32_t cnt = 0;
+            float w = 0.f;
+            const uint32_t gi = comms[i].gi;
+            for (uint32_t x = g.off[gi]; x < g.off[gi + 1]; x++) {
+                const uint32_t v = g.dat[x];
+                for (uint32_t y = lv.moff[v]; y < lv.moff[v + 1]; y++) {
+                    const uint32_t m = lv.mdat[y];
+                    if (!in_ref[m]) continue;
+                    if (ref_w[m] > 0.f) cnt++;
+                    else if (ref_w[m] < 0.f) cnt--;
+                    w += ref_w[m];
+                }
+            }
+            key.push_back({{cnt, w}, i});
+        }
+        std::stable_sort(key.begin(), key.end(),
+                         [](const std::pair<std::pair<int32_t, float>, size_t> &x,
+                            const std::pair<std::pair<int32_t, float>, size_t> &y) { return x.first > y.first; });
+        std::vector<Community> sorted;
+        for (auto &k : key) sorted.push_back(comms[k.second]);
+        comms.swap(sorted);
+    } else {
+        std::stable_sort(comms.begin(), comms.end(),
+                         [](const Community &x, const Community &y) { return x.weight > y.weight; });
+    }
+    // keep the first, drop whatever conflicts with a kept one (louvain.rs:327-353)
+    std::vector<uint8_t> bad(g.comms.size(), 0);
+    std::vector<uint32_t> rank(g.comms.size(), 0);
+    for (size_t p = 0; p < comms.size(); p++) rank[comms[p].gi] = (uint32_t)p;
+    for (size_t p = 0; p < comms.size(); p++) {
+        if (bad[comms[p].gi]) continue;
+        for (uint32_t q : conflict[comms[p].gi])
+            if (rank[q] > p) bad[q] = 1;
+    }
+    std::vector<uint32_t> out;
+    for (uint32_t v = 0; v < n; v++)
+        if (bad_v[v]) out.push_back(v);
+    for (size_t gi = 0; gi < g.comms.size(); gi++) {
+        if (!bad[gi]) continue;
+        for (uint32_t x = g.off[gi]; x < g.off[gi + 1]; x++) {
+            const uint32_t v = g.dat[x];
+            out.insert(out.end(), lv.mdat.begin() + lv.moff[v], lv.mdat.begin() + lv.moff[v + 1]);
+        }
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    return out;
+}
+
+}  // namespace np2

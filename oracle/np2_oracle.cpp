@@ -1813,6 +1813,57 @@ uint64_t np2o_get_dropped(np2o_job *j, const uint32_t **ids) {
     *ids = j->d_dropped.data();
     return j->d_dropped.size();
 }
+/* Test seam: the tail of phase_reads_by_lqseqs (main.rs:994-1015) + Louvain + phase_communities on pair weights that
+ * were already summed per read pair.  keys[e] = a << 32 | b (a < b), vals[e] = #agree + #differ * ((1 << 32) - 1).
+ * Feeding the sums through insert_data / assign_data gives the same maps as the per-region +-1 updates. */
+int64_t np2o_debug_phase(const uint64_t *keys, const int64_t *vals, uint64_t n, uint32_t model, uint32_t use_all_reads,
+                         uint32_t *out, uint64_t cap) {
+    try {
+        const bool asref = model == 0, use_all = use_all_reads != 0;
+        Graph data, dif, ref_data;
+        std::set<uint32_t> invalid_ids;
+        for (uint64_t e = 0; e < n; e++) {
+            const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+            const int64_t ndif = (vals[e] + (1LL << 31)) >> 32;
+            const int64_t sum = vals[e] - (ndif << 32);
+            if (a == 0) {
+                if (asref) insert_data(ref_data, a, b, (float)sum);
+                if (ndif > 0 && !use_all) invalid_ids.insert(b);
+                continue;
+            }
+            if (ndif > 0) {
+                insert_data(dif, a, b, -(float)ndif);
+                insert_data(dif, b, a, -(float)ndif);
+            }
+            insert_data(data, a, b, (float)sum);
+            insert_data(data, b, a, (float)sum);
+        }
+        for (auto &n1 : dif)
+            for (auto &n2 : n1.second)
+                if (n2.second <= -3.f) assign_data(data, n1.first, n2.first, n2.second);
+        if (!use_all) {
+            for (auto it = data.begin(); it != data.end();) {
+                if (invalid_ids.count(it->first)) it = data.erase(it);
+                else ++it;
+            }
+            for (auto &n1 : data)
+                for (auto it = n1.second.begin(); it != n1.second.end();) {
+                    if (invalid_ids.count(it->first)) it = n1.second.erase(it);
+                    else ++it;
+                }
+        }
+        const std::map<uint32_t, float> *rw = ref_data.empty() ? nullptr : &ref_data.begin()->second;
+        std::vector<uint32_t> res = phase_communities(std::move(data), rw);
+        res.insert(res.end(), invalid_ids.begin(), invalid_ids.end());
+        std::sort(res.begin(), res.end());
+        res.erase(std::unique(res.begin(), res.end()), res.end());
+        for (uint64_t i = 0; i < res.size() && i < cap; i++) out[i] = res[i];
+        return (int64_t)res.size();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 uint64_t np2o_get_consensus(np2o_job *j, const uint32_t **pos, const uint8_t **base) {
     *pos = j->d_cns_pos.data();
     *base = j->d_cns_base.data();

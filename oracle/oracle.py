@@ -75,6 +75,8 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_uint64
             f.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * n
+        L.np2o_debug_phase.restype = C.c_int64
+        L.np2o_debug_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
         L.np2o_format_fasta.restype = C.c_uint64
         L.np2o_format_fasta.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         _lib = L
@@ -211,6 +213,17 @@ class Job:
         if getattr(self, "h", None) and _lib is not None:
             _lib.np2o_job_destroy(self.h)
             self.h = None
+
+
+def debug_phase(keys, vals, model=0, use_all_reads=False):
+    """Phasing (main.rs:994-1015 + louvain.rs) on pre-summed pair weights -> sorted read orders to drop."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    vals = np.ascontiguousarray(vals, np.int64)
+    out = np.empty(max(len(keys) * 2 + 1, 1), np.uint32)
+    n = lib().np2o_debug_phase(keys.ctypes.data, vals.ctypes.data, len(keys), model, int(use_all_reads), out.ctypes.data, len(out))
+    if n < 0:
+        raise OracleError(lib().np2o_last_error().decode())
+    return out[:n].copy()
 
 
 def format_fasta(tid, pos, base, uppercase=False, out_pos=False):
