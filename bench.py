@@ -94,9 +94,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-# (profiles/r01_pipeline_full.txt was taken at 4 Mbp; scaled x2.5 to the 10 Mbp launch), bytes
-NCU_TRAFFIC = {"expand_trim_pack": None, "pileup_emit": None, "pileup_scan": None}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
+# THIS workload (profiles/r01h_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.
+NCU_TRAFFIC = {"pack_columns": None, "pileup_count": None, "pileup_emit": None}
 
 
 def peaks():
@@ -106,16 +106,22 @@ def peaks():
     return 6650.0, "fallback"
 
 
-# Algorithmic bytes per alignment column / per unit for each stage (DESIGN.md "Kernels").
+# Algorithmic bytes of the single-kernel stages (DESIGN.md "Kernels"): what the kernel must move through HBM once.
 def stage_bytes(stage, st):
-    cols, L, recs = st["alignment_columns"], st["L"], st.get("records", 0)
+    cols, L = st["alignment_columns"], st["L"]
     return {
-        # 4-bit SEQ in (0.5) + ref byte (1.0, cached across overlapping reads but counted once per column) + nibble out (0.5)
-        "expand_trim_pack": cols * 2.0 + L * 2,
-        # count pass: packed columns (0.5) + checkpoints (10 B / 32 columns) + ref codes (1 B / column)
-        "pileup_scan": cols * (0.5 + 10 / 32 + 1.0) + L * 8,
-        "pileup_emit": cols * (0.5 + 10 / 32 + 1.0) + recs * 12,
+        # 4-bit SEQ in (0.5 B/column), packed nibble out (0.5), one 10-byte checkpoint per 32 columns out
+        "pack_columns": cols * (0.5 + 0.5 + 10 / 32),
+        # packed columns in (0.5) + checkpoints in (10/32); the packed reference (0.5 B/bp) is shared by the ~30 reads
+        # over a position and counted once
+        "pileup_count": cols * (0.5 + 10 / 32) + L * 0.5,
+        "pileup_emit": cols * (0.5 + 10 / 32) + L * 0.5 + st.get("records", 0) * 12,
     }.get(stage)
+
+
+# bytes the whole pipeline must move per polished bp, D = depth, q = yak probes per bp
+def pipeline_bytes_per_bp(depth, q):
+    return 1.5 * depth + 111 + 42 * q
 
 
 def run_ours(args):
@@ -160,6 +166,7 @@ def run_ours(args):
         step_ms.append(tm["total"][0])
         for k, v in tm.items():
             stage_acc.setdefault(k, []).append(v[0])
+        stage_launches = {k: v[1] for k, v in tm.items()}
         launches += job.traffic()["kernel_launches"]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -173,13 +180,28 @@ def run_ours(args):
     # ---- end to end: host buffers in, consensus out, every step.  `--e2e-inflight` contigs are in flight at once
     # (one host thread + one context + one stream each, tables shared: the CLI's double buffering), so the PCIe
     # upload and host-side record parsing of one contig overlap the kernels of another.
-    def e2e_step(cx):
+    e2e_parts = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
+
+    def e2e_step(cx, acc=None):
+        t0 = time.perf_counter()
         j = np2.Job(cx, contig_np, bam_np, tables, opts)
-        j.upload().run(-1)
+        t1 = time.perf_counter()
+        j.upload()
+        t2 = time.perf_counter()
+        j.run(-1)
+        t3 = time.perf_counter()
         first, last, base = j.bases(copy=False)  # the FASTA record (header span + bases) in host memory
         assert len(base) == len(gbase) and base[-1] == gbase[-1] and base[len(base) // 2] == gbase[len(base) // 2]
         tr = j.traffic()
+        tm_up = {k: v[0] for k, v in j.timings().items() if k.startswith("upload:")} if acc is not None else {}
         j.destroy()
+        t4 = time.perf_counter()
+        if acc is not None:
+            for k, v in zip(("create_parse", "upload", "run", "result"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                acc[k] += v * 1e3
+            for k, v in tm_up.items():
+                acc[k] = acc.get(k, 0.0) + v
+            acc["n"] += 1
         return tr
 
     def e2e_run(n_inflight):
@@ -193,7 +215,7 @@ def run_ours(args):
         def work(w):
             try:
                 for _ in range(share[w]):
-                    tr_box[0] = e2e_step(ctxs[w])
+                    tr_box[0] = e2e_step(ctxs[w], e2e_parts if n_inflight == 1 else None)
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         torch.cuda.synchronize()
@@ -226,17 +248,26 @@ def run_ours(args):
         peak, peak_kind = peaks()
         stages = {k: float(np.mean(v)) for k, v in stage_acc.items()}
         st = {"alignment_columns": traffic["alignment_columns"], "L": args.length, "records": 0}
-        kern = {k: v for k, v in stages.items() if k != "total" and stage_bytes(k, st)}
+        kern = {k: v for k, v in stages.items() if stage_bytes(k, st)}
         dom = max(kern, key=kern.get) if kern else None
         roofline = None
         if dom:
-            # stage ms is accumulated over the step; pileup stages run once per iteration (iter_count = 2)
-            n_launch = 2 if dom.startswith("pileup") else 1
+            # single-kernel stages; the stage time is summed over the launches of the step
+            n_launch = max(1, int(round(stage_launches.get(dom, 1))))
             per_launch_ms = stages[dom] / n_launch
             achieved = stage_bytes(dom, st) / (per_launch_ms * 1e-3) / 1e9
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_kind,
-                        "launch_ms": round(per_launch_ms, 4), "share_of_step": round(stages[dom] / stages["total"], 4)}
+                        "launch_ms": round(per_launch_ms, 4), "launches_per_step": n_launch,
+                        "share_of_step": round(stages[dom] / stages["total"], 4),
+                        "algorithmic_bytes_per_launch": int(stage_bytes(dom, st)),
+                        "note": "largest of the streaming kernels with a defined byte count (pack_columns, pileup_count, "
+                                "pileup_emit); the step is ~50 short kernels + host phases, none above 10% of it"}
+        q = traffic["probes"] / float(args.length)
+        pipe_bytes = pipeline_bytes_per_bp(30, q) * args.length
+        pipeline = {"bytes_per_bp": round(pipeline_bytes_per_bp(30, q), 1), "probes_per_bp": round(q, 3),
+                    "achieved_GBps": round(pipe_bytes / (stages["total"] * 1e-3) / 1e9, 1),
+                    "frac_of_hbm_peak": round(pipe_bytes / (stages["total"] * 1e-3) / 1e9 / peak, 4)}
         line = {
             "metric": "polished Mbp/s", "value": round(mbp_total / dev_time, 3), "unit": "Mbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_time / args.steps * 1e3, 3),
@@ -247,10 +278,12 @@ def run_ours(args):
                        "l2": "inputs (%.0f MB of BAM records per GPU) are larger than the 126 MB L2" % (len(c["bam"]) / 1e6)},
             "e2e": {"value": round(mbp_total / e2e_time, 3), "unit": "Mbp/s", "h2d_bytes_per_step": tr["h2d_bytes"],
                     "d2h_bytes_per_step": tr["d2h_bytes"], "contigs_in_flight": args.e2e_inflight,
-                    "one_at_a_time": round(mbp_total / e2e_serial_time, 3)},
+                    "one_at_a_time": round(mbp_total / e2e_serial_time, 3),
+                    "one_at_a_time_ms": {k: round(v / max(1, e2e_parts["n"]), 3) for k, v in e2e_parts.items() if k != "n"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "pipeline_roofline": pipeline,
             "stages_ms": {k: round(v, 4) for k, v in stages.items()},
             "identical_to_truth_haplotype": bool(ident),
             "wall_ms_per_step": round(wall / args.steps * 1e3, 3),

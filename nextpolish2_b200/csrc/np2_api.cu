@@ -164,9 +164,12 @@ struct StageTimer {
         ms[id(name)] += std::chrono::duration<float, std::milli>(t - h0).count();
         h0 = t;
     }
-    void reset() {
-        std::fill(ms.begin(), ms.end(), 0.f);
-        std::fill(launches.begin(), launches.end(), 0u);
+    void reset(bool upload_too = false) {  // "upload:*" stages belong to np2_job_create/upload and survive a run
+        for (size_t i = 0; i < names.size(); i++)
+            if (upload_too || names[i].compare(0, 7, "upload:") != 0) {
+                ms[i] = 0.f;
+                launches[i] = 0u;
+            }
     }
     ~StageTimer() {
         for (auto e : pool) cudaEventDestroy(e);
@@ -184,10 +187,16 @@ struct JobScratch {
     PBuf<uint32_t> p_cpos;
     std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
     cudaEvent_t seq_ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    PBuf<uint8_t> p_up_stage, p_seq_args;
     StageTimer timer;
     ~JobScratch() {
         for (auto e : seq_ev)
             if (e) cudaEventDestroy(e);
+        if (ev_alloc) cudaEventDestroy(ev_alloc);
+        if (ev_copied) cudaEventDestroy(ev_copied);
+        if (ev_t0) cudaEventDestroy(ev_t0);
+        if (ev_t1) cudaEventDestroy(ev_t1);
     }
 };
 // bump allocator over a pinned staging buffer: many small device arrays come back with one synchronisation and
@@ -210,6 +219,7 @@ struct Stager {
 struct np2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the per-read arrays, concurrent with the K0 gather
     cudaMemPool_t pool = nullptr;
     int refs = 1;  // tables and jobs keep their context alive (np2_ctx_destroy only drops the caller's reference)
     std::vector<JobScratch *> scratch_pool;
@@ -230,6 +240,7 @@ static void ctx_release(np2_ctx *ctx) {
         g_stream_pool.erase(ctx->stream);
     }
     cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
@@ -277,7 +288,8 @@ struct np2_job {
     // device inputs
     DBuf<uint8_t> d_ref, d_code, d_blob, d_nib, d_blank;
     DBuf<uint32_t> d_refpk;
-    DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off, d_op_col, d_op_q, d_op_t, d_op_cig;
+    DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off;
+    DBuf<Op> d_ops;
     DBuf<uint64_t> d_seq_off, d_nib_off;
     DBuf<uint32_t> d_ts, d_te, d_n, d_shift, d_ck_tpos, d_ck_read;
     DBuf<uint16_t> d_ck_delta;
@@ -328,6 +340,7 @@ struct np2_job {
 
     void send_contig(const uint8_t *tseq_host);
     void send_seq();
+    void enqueue_arrays();
     void upload();
     void run(int32_t dump_iter);
     void ingest_finish();
@@ -339,8 +352,12 @@ struct np2_job {
 // The contig goes up straight from the caller's buffer (asynchronously when it is page-locked).
 void np2_job::send_contig(const uint8_t *tseq_host) {
     cudaStream_t s = ctx->stream;
+    timer.s = s;
+    timer.reset(true);
+    int h = timer.begin("upload:contig", 0);
     d_ref.alloc(L, s);
     d_ref.upload(tseq_host, L);
+    timer.end(h);
     d_code.alloc(L, s);
     d_refpk.alloc(L / 8 + 8, s);
     h2d += L;
@@ -375,7 +392,14 @@ void np2_job::send_seq() {
     seq_blob_bytes = D;
     d_blob.alloc(D + 64, s);
     d_seq_off.alloc(std::max<size_t>(n, 1), s);
-    if (n) d_seq_off.upload(co.data(), n);
+    // offsets go through a pinned staging buffer: a pageable cudaMemcpyAsync would block this thread
+    sc->p_seq_args.resize((size_t)n * 20 + 64);
+    uint8_t *st = sc->p_seq_args.p;
+    if (n) {
+        np2::copy_streaming(st, co.data(), (size_t)n * 8);
+        np2::store_fence();
+        NP2_CUDA(cudaMemcpyAsync(d_seq_off.p, st, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    }
     h2d += (uint64_t)n * 8;
     if (!n) return;
     if (seq_path == 1) {
@@ -383,9 +407,14 @@ void np2_job::send_seq() {
         DBuf<uint32_t> d_nbytes;
         d_src_off.alloc(n, s);
         d_nbytes.alloc(n, s);
-        d_src_off.upload(ing.seq_off.data(), n);
-        d_nbytes.upload(ing.seq_bytes.data(), n);
+        np2::copy_streaming(st + (size_t)n * 8, ing.seq_off.data(), (size_t)n * 8);
+        np2::copy_streaming(st + (size_t)n * 16, ing.seq_bytes.data(), (size_t)n * 4);
+        np2::store_fence();
+        NP2_CUDA(cudaMemcpyAsync(d_src_off.p, st + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        NP2_CUDA(cudaMemcpyAsync(d_nbytes.p, st + (size_t)n * 16, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        int h = timer.begin("upload:seq_gather", 1);
         gather_seq(src, d_src_off.p, d_seq_off.p, d_nbytes.p, d_blob.p, n, s);
+        timer.end(h);
         h2d += (uint64_t)n * 12;
         for (uint32_t r = 0; r < n; r++) h2d += ing.seq_bytes[r];
         return;  // scratch is freed in stream order, after the kernel
@@ -410,7 +439,8 @@ void np2_job::send_seq() {
         if (round >= 2) NP2_CUDA(cudaEventSynchronize(sc->seq_ev[round & 1]));
         auto work = [&](unsigned ti) {
             const uint32_t b = r0 + (uint64_t)(r1 - r0) * ti / T, e = r0 + (uint64_t)(r1 - r0) * (ti + 1) / T;
-            for (uint32_t r = b; r < e; r++) memcpy(buf + (co[r] - D0), bam + ing.seq_off[r], ing.seq_bytes[r]);
+            for (uint32_t r = b; r < e; r++) np2::copy_streaming(buf + (co[r] - D0), bam + ing.seq_off[r], ing.seq_bytes[r]);
+            np2::store_fence();  // the DMA reads this ring next: keep it out of the cores' caches
         };
         if (r1 - r0 < 256) {
             for (unsigned ti = 0; ti < T; ti++) work(ti);
@@ -426,37 +456,21 @@ void np2_job::send_seq() {
     }
 }
 
-void np2_job::upload() {
-    cudaStream_t s = ctx->stream;
+// Everything but the SEQ bytes: per-read scalars and the CIGAR op arrays.  Enqueued by np2_job_create right after
+// the parse, on the context's COPY stream, so that these DMA transfers run while the main stream's K0 kernel pulls
+// the SEQ bytes over the same link and the host never blocks on a pageable copy (the small arrays are staged through
+// one pinned buffer).  Device buffers are allocated on the main stream; the two streams meet through two events.
+void np2_job::enqueue_arrays() {
+    cudaStream_t s = ctx->stream, c2 = ctx->copy_stream;
     const uint32_t n = (uint32_t)ing.pos.size();
-    auto up32 = [&](DBuf<uint32_t> &d, const std::vector<uint32_t> &h) {
-        d.alloc(std::max<size_t>(h.size(), 1), s);
-        if (!h.empty()) d.upload(h.data(), h.size());
-        h2d += h.size() * 4;
-    };
-    up32(d_pos, ing.pos);
-    up32(d_op_off, ing.op_off);
-    up32(d_ncols, ing.ncols);
-    up32(d_ck_off, ing.ck_off);
-    {  // the op arrays go up chunk by chunk from the page-locked segment arrays they were parsed into
-        const size_t no = std::max<size_t>(ing.n_ops, 1);
-        d_op_col.alloc(no, s);
-        d_op_q.alloc(no, s);
-        d_op_t.alloc(no, s);
-        d_op_cig.alloc(no, s);
-        size_t w = 0;
-        for (const Ingest::OpChunk &c : ing.op_chunks) {
-            NP2_CUDA(cudaMemcpyAsync(d_op_col.p + w, c.col, c.n * 4, cudaMemcpyHostToDevice, s));
-            NP2_CUDA(cudaMemcpyAsync(d_op_q.p + w, c.q, c.n * 4, cudaMemcpyHostToDevice, s));
-            NP2_CUDA(cudaMemcpyAsync(d_op_t.p + w, c.t, c.n * 4, cudaMemcpyHostToDevice, s));
-            NP2_CUDA(cudaMemcpyAsync(d_op_cig.p + w, c.cig, c.n * 4, cudaMemcpyHostToDevice, s));
-            w += c.n;
-        }
-        h2d += (uint64_t)ing.n_ops * 16;
-    }
+    timer.hbegin();
+    const size_t no = std::max<size_t>(ing.n_ops, 1);
+    d_pos.alloc(std::max(n, 1u), s);
+    d_op_off.alloc(n + 1, s);
+    d_ncols.alloc(std::max(n, 1u), s);
+    d_ck_off.alloc(n + 1, s);
     d_nib_off.alloc(n + 1, s);
-    d_nib_off.upload(ing.nib_off.data(), n + 1);
-    h2d += (uint64_t)n * 8;
+    d_ops.alloc(no, s);
     const uint32_t nck = ing.ck_off.back();
     d_nib.alloc(ing.nib_off.back() + 16, s);
     d_ts.alloc(std::max(n, 1u), s);
@@ -467,18 +481,51 @@ void np2_job::upload() {
     d_ck_delta.alloc(std::max(nck, 1u), s);
     d_ck_read.alloc(std::max(nck, 1u), s);
     d_blank.alloc(std::max(n, 1u), s);
+    if (!sc->ev_alloc) {
+        NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_alloc, cudaEventDisableTiming));
+        NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_copied, cudaEventDisableTiming));
+    }
+    NP2_CUDA(cudaEventRecord(sc->ev_alloc, s));
+    NP2_CUDA(cudaStreamWaitEvent(c2, sc->ev_alloc, 0));
+    // small arrays -> one pinned staging buffer -> device
+    const size_t small = (size_t)n * 8 + (size_t)(n + 1) * 20 + 256;
+    sc->p_up_stage.resize(small);
+    uint8_t *st = sc->p_up_stage.p;
+    auto stage = [&](void *dev, const void *host, size_t bytes) {
+        if (!bytes) return;
+        np2::copy_streaming(st, host, bytes);
+        NP2_CUDA(cudaMemcpyAsync(dev, st, bytes, cudaMemcpyHostToDevice, c2));
+        st += (bytes + 15) & ~(size_t)15;
+        h2d += bytes;
+    };
+    stage(d_pos.p, ing.pos.data(), (size_t)n * 4);
+    stage(d_ncols.p, ing.ncols.data(), (size_t)n * 4);
+    stage(d_op_off.p, ing.op_off.data(), (size_t)(n + 1) * 4);
+    stage(d_ck_off.p, ing.ck_off.data(), (size_t)(n + 1) * 4);
+    stage(d_nib_off.p, ing.nib_off.data(), (size_t)(n + 1) * 8);
+    if (!sc->ev_t0) {
+        NP2_CUDA(cudaEventCreate(&sc->ev_t0));
+        NP2_CUDA(cudaEventCreate(&sc->ev_t1));
+    }
+    np2::store_fence();
+    NP2_CUDA(cudaEventRecord(sc->ev_t0, c2));
+    {  // the op records go up chunk by chunk from the page-locked segment arrays they were parsed into
+        size_t w = 0;
+        for (const Ingest::OpChunk &c : ing.op_chunks) {
+            NP2_CUDA(cudaMemcpyAsync(d_ops.p + w, c.ops, c.n * sizeof(Op), cudaMemcpyHostToDevice, c2));
+            w += c.n;
+        }
+        h2d += (uint64_t)ing.n_ops * 16;
+    }
+    NP2_CUDA(cudaEventRecord(sc->ev_t1, c2));
+    NP2_CUDA(cudaEventRecord(sc->ev_copied, c2));
     R.n_reads = n;
     R.pos = d_pos.p;
     R.op_off = d_op_off.p;
-    R.seq_off = d_seq_off.p;
     R.ncols = d_ncols.p;
     R.nib_off = d_nib_off.p;
     R.ck_off = d_ck_off.p;
-    R.op_col = d_op_col.p;
-    R.op_q = d_op_q.p;
-    R.op_t = d_op_t.p;
-    R.op_cig = d_op_cig.p;
-    R.blob = d_blob.p;
+    R.ops = reinterpret_cast<const uint4 *>(d_ops.p);
     R.t_s = d_ts.p;
     R.t_e = d_te.p;
     R.n = d_n.p;
@@ -487,7 +534,21 @@ void np2_job::upload() {
     R.ck_tpos = d_ck_tpos.p;
     R.ck_delta = d_ck_delta.p;
     R.ck_read = d_ck_read.p;
-    NP2_CUDA(cudaStreamSynchronize(s));
+    timer.hend("upload:host_enqueue_arrays");
+}
+
+void np2_job::upload() {
+    cudaStream_t s = ctx->stream;
+    R.seq_off = d_seq_off.p;
+    R.blob = d_blob.p;
+    timer.hbegin();
+    NP2_CUDA(cudaStreamSynchronize(s));  // the main stream has waited for the copy stream (np2_job_create)
+    timer.hend("upload:host_wait");
+    timer.collect();
+    if (sc->ev_t0 && L >= opt.min_ctg_len) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, sc->ev_t0, sc->ev_t1) == cudaSuccess) timer.ms[timer.id("upload:ops_on_copy_stream")] += t;
+    }
     uploaded = true;
 }
 
@@ -576,7 +637,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     DBuf<uint8_t> d_tmp;
     size_t tmp_bytes = 0;
 
-    h = timer.begin("pileup_scan", 4);
+    h = timer.begin("pileup_scan", 2);
     d_cover.zero();
     {
         int32_t one = 1;  // the ref read spans [0, L-1]
@@ -590,7 +651,11 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_cover.p, d_cover.p, L + 1, s);
     }
     d_cta_cnt.zero();
+    timer.end(h);
+    h = timer.begin("pileup_count", 1);  // single kernel
     pileup_count(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, d_cta_cnt.p, s);
+    timer.end(h);
+    h = timer.begin("pileup_scan", 1);
     {
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cta_cnt.p, d_cta_off.p, n_cta + 1, s);
@@ -1462,12 +1527,17 @@ void np2_job::run(int32_t dump_it) {
     if (!uploaded) upload();
     const uint32_t n = R.n_reads;
     const int h_total = timer.begin("total", 0);
-    int h = timer.begin("expand_trim_pack", 2);
     DBuf<int> d_bad;
     d_bad.alloc(1, s);
     d_bad.zero();
+    int h = timer.begin("ref_codes", 2);
     ref_codes(d_ref.p, L, d_code.p, d_refpk.p, d_bad.p, s);
-    expand_trim_pack(R, d_ref.p, L, ing.ck_off.back(), s);
+    timer.end(h);
+    h = timer.begin("trim_scan", 1);
+    trim_scan(R, d_ref.p, L, s);
+    timer.end(h);
+    h = timer.begin("pack_columns", 1);  // a single kernel: the roofline line of bench.py is computed on it
+    pack_columns(R, d_ref.p, ing.ck_off.back(), s);
     timer.end(h);
     int bad_ref = 0;
     d_bad.download(&bad_ref, 1);
@@ -1569,6 +1639,7 @@ int np2_ctx_create(int device, np2_ctx **out) {
         np2_ctx *c = new np2_ctx();
         c->device = device;
         NP2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        NP2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         // a private pool that keeps freed blocks: per-iteration scratch is re-used instead of going back to the driver
         cudaMemPoolProps props;
         memset(&props, 0, sizeof props);
@@ -1793,7 +1864,10 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
             NP2_CUDA(cudaSetDevice(ctx->device));
             j->send_contig(tseq);  // in flight while the host walks the records
             parse_records(bam, bam_len, tlen, *opts, j->ing);
-            j->send_seq();
+            j->enqueue_arrays();   // copy stream
+            if (getenv("NP2_DEBUG_ORDER")) NP2_CUDA(cudaStreamWaitEvent(ctx->stream, j->sc->ev_copied, 0));
+            j->send_seq();         // main stream (K0 gather), overlapping the copies
+            NP2_CUDA(cudaStreamWaitEvent(ctx->stream, j->sc->ev_copied, 0));
         } else {
             j->tseq.assign(tseq, tseq + tlen);
         }
@@ -2011,7 +2085,10 @@ int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const n
         mixv(ing.ck_off);
         for (int a = 0; a < 4; a++)
             for (const Ingest::OpChunk &c : ing.op_chunks)
-                mix(a == 0 ? c.col : a == 1 ? c.q : a == 2 ? c.t : c.cig, c.n * 4);
+                for (size_t i = 0; i < c.n; i++) {
+                    const uint32_t v = a == 0 ? c.ops[i].col : a == 1 ? c.ops[i].q : a == 2 ? c.ops[i].t : c.ops[i].cig;
+                    mix(&v, 4);
+                }
         out[0] = ing.all_tid.size();
         out[1] = ing.pos.size();
         out[2] = ing.n_ops;

@@ -32,7 +32,30 @@ void HVec<T>::grow(size_t need) {
     p = np_;
     cap = nc;
 }
-template struct HVec<uint32_t>;
+template struct HVec<Op>;
+
+void copy_streaming(void *dst, const void *src, size_t n) {
+#if defined(__x86_64__) || defined(_M_X64)
+    uint8_t *d = static_cast<uint8_t *>(dst);
+    const uint8_t *s = static_cast<const uint8_t *>(src);
+    size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (head > n) head = n;
+    memcpy(d, s, head);
+    d += head, s += head, n -= head;
+    for (; n >= 64; n -= 64, d += 64, s += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)s), b = _mm_loadu_si128((const __m128i *)(s + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i *)(s + 32)), e = _mm_loadu_si128((const __m128i *)(s + 48));
+        _mm_stream_si128((__m128i *)d, a);
+        _mm_stream_si128((__m128i *)(d + 16), b);
+        _mm_stream_si128((__m128i *)(d + 32), c);
+        _mm_stream_si128((__m128i *)(d + 48), e);
+    }
+    for (; n >= 16; n -= 16, d += 16, s += 16) _mm_stream_si128((__m128i *)d, _mm_loadu_si128((const __m128i *)s));
+    memcpy(d, s, n);
+#else
+    memcpy(dst, src, n);
+#endif
+}
 
 void Ingest::clear() {
     all_tid.clear();
@@ -113,7 +136,7 @@ const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const
     // One pass over the CIGAR: seq_len_from_cigar(true) and bam_endpos for the filter, and the
     // column-consuming ops for the kernels.  The ops are rolled back when the filter rejects the record; what the
     // reference would panic on only counts for records that pass it.
-    const size_t ops0 = sg.col.n;
+    const size_t ops0 = sg.ops.n;
     uint64_t rlen = 0, rspan = 0;
     uint32_t qs = 0, ts = 0, col = 0, aln_q_s = 0, aln_q_e = 0, n_ops = 0;
     bool first = true;
@@ -140,10 +163,7 @@ const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const
                     break;
                 }
                 if (l) {
-                    sg.col.push_back(col);
-                    sg.q.push_back(qs);
-                    sg.t.push_back(ts);
-                    sg.cig.push_back(c);
+                    sg.ops.push_back(Op{col, qs, ts, c});
                     n_ops++;
                 }
                 col += l;
@@ -163,7 +183,7 @@ const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const
                           ((flag & 0x100) && !opt.use_secondary) || ((flag & 0x800) && !opt.use_supplementary) ||
                           span < need;
     if (rejected || bad || pos < 0 || (uint64_t)pos > tlen) {
-        sg.col.n = sg.q.n = sg.t.n = sg.cig.n = ops0;
+        sg.ops.n = ops0;
         if (rejected) return nullptr;
         if (pos < 0 || (uint64_t)pos > tlen) return "alignment starts outside the contig";
         return bad;
@@ -232,6 +252,7 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
             sg.err_rec = (int64_t)sg.ro.size();
             sg.err_msg = "host allocation failed while parsing the records";
         }
+        store_fence();  // the op arrays were written with streaming stores
     };
     if (T == 1) {
         work(0);
@@ -254,6 +275,7 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
             sg->reset();
             sg->found = true;
             walk(bam, bam_len, cur, hi, tlen, opt, *sg);
+            store_fence();
         }
         order.push_back(sg);
         if (sg->err_msg) herr(NP2_ERR_FORMAT, sg->err_msg);
@@ -302,8 +324,8 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
             out.ck_off.push_back(out.ck_off.back() + (o.ncols + 31) / 32);
             out.total_cols += o.ncols;
         }
-        if (sg->col.n) out.op_chunks.push_back({sg->col.p, sg->q.p, sg->t.p, sg->cig.p, sg->col.n});
-        out.n_ops += sg->col.n;
+        if (sg->ops.n) out.op_chunks.push_back({sg->ops.p, sg->ops.n});
+        out.n_ops += sg->ops.n;
     }
     if (out.n_ops >= (1ull << 32)) herr(NP2_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one contig");
 }

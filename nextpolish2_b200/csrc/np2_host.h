@@ -3,6 +3,9 @@
 // regions with more than one supported allele.  Everything works on flat arrays produced/consumed by the kernels.
 #pragma once
 #include <stdint.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 
 #include <memory>
 #include <string>
@@ -18,6 +21,22 @@ namespace np2 {
 // at page-locked allocations so that uploads are asynchronous and run at PCIe speed).
 extern void *(*host_alloc_hook)(size_t);
 extern void (*host_free_hook)(void *);
+// One column-consuming CIGAR op as the kernels read it (one 16-byte load): first alignment column, first query base,
+// reference offset from the record's pos, and the raw BAM op word (len << 4 | op).
+struct alignas(16) Op {
+    uint32_t col, q, t, cig;
+};
+#if defined(__x86_64__) || defined(_M_X64)
+inline void stream_store(Op *p, const Op &v) {
+    _mm_stream_si128(reinterpret_cast<__m128i *>(p), _mm_set_epi32((int)v.cig, (int)v.t, (int)v.q, (int)v.col));
+}
+inline void store_fence() { _mm_sfence(); }
+#else
+inline void stream_store(Op *p, const Op &v) { *p = v; }
+inline void store_fence() {}
+#endif
+// memcpy whose destination bypasses the cache (16-byte streaming stores once dst is aligned)
+void copy_streaming(void *dst, const void *src, size_t n);
 template <class T>
 struct HVec {  // minimal growable array of trivially copyable T on the hook allocator; capacity survives clear()
     T *p = nullptr;
@@ -30,9 +49,13 @@ struct HVec {  // minimal growable array of trivially copyable T on the hook all
         if (p) host_free_hook(p);
     }
     void grow(size_t need);
+    // Streaming (non-temporal) store: these arrays are written once by the parse threads and then read by the GPU's
+    // copy engine only.  Written through the cache, the DMA has to snoop freshly dirtied lines out of the cores'
+    // caches and drops from ~30 to ~8 GB/s on the test box (profiles/microbench/h2d_small_copies.cu); call
+    // np2::store_fence() before handing the buffer to CUDA.
     void push_back(T v) {
         if (n == cap) grow(n + 1);
-        p[n++] = v;
+        stream_store(&p[n++], v);
     }
     void clear() { n = 0; }
     size_t size() const { return n; }
@@ -55,7 +78,7 @@ struct Ingest {
     // Column-consuming CIGAR ops (M,=,X,I,D) stay in the per-segment arrays they were parsed into; uploaded back to
     // back in file order they form the device arrays op_off[] indexes.
     struct OpChunk {
-        const uint32_t *col, *q, *t, *cig;
+        const Op *ops;
         size_t n;
     };
     std::vector<OpChunk> op_chunks;
@@ -71,7 +94,7 @@ struct Ingest {
         bool found = false;
         std::vector<int32_t> tid, pos;
         std::vector<RecOut> ro;
-        HVec<uint32_t> col, q, t, cig;
+        HVec<Op> ops;  // page-locked; uploaded from where it was parsed
         int64_t err_rec = -1;  // local index of the first record that fails (the walk stops there)
         const char *err_msg = nullptr;
         void reset() {
@@ -80,10 +103,7 @@ struct Ingest {
             tid.clear();
             pos.clear();
             ro.clear();
-            col.clear();
-            q.clear();
-            t.clear();
-            cig.clear();
+            ops.clear();
             err_rec = -1;
             err_msg = nullptr;
         }

@@ -2,7 +2,7 @@
 //
 //   K5  table_insert / table_probe / seq_kscore   yak k-mer table in HBM (kmer.rs:113-170, 255-314)
 //   K0  ref_codes                                  SEQ_NUM codes of the contig (kmer.rs:11-22)
-//   K1  expand_trim_pack                           fill_with_cigar + trim(8) + AlignSeq::new (main.rs:386-513, 279-312)
+//   K1  trim_scan + pack_columns                        fill_with_cigar + trim(8) + AlignSeq::new (main.rs:386-513, 279-312)
 //   K2  cover_diff / pileup_count / pileup_emit    update_msas + Msa::push/sort/coverage (main.rs:576-589, 193-241)
 //       mark_heads / groups_* / pos_finalize
 //   K3  dp_runs / emit_*                           get_cns_from_align_tags + backtrack (main.rs:1645-1687, 1572-1634)
@@ -314,12 +314,12 @@ struct OpCur {
     uint32_t q, t, op;
 };
 __device__ __forceinline__ void op_load(const ReadsDev &R, OpCur &c) {
-    uint32_t cig = R.op_cig[c.i];
-    c.op = cig & 15;
-    c.c_beg = R.op_col[c.i];
-    c.c_end = c.c_beg + (cig >> 4);
-    c.q = R.op_q[c.i];
-    c.t = R.op_t[c.i];
+    const uint4 o = __ldg(R.ops + c.i);
+    c.op = o.w & 15;
+    c.c_beg = o.x;
+    c.c_end = o.x + (o.w >> 4);
+    c.q = o.y;
+    c.t = o.z;
 }
 // position the cursor on the op containing column col (col < total columns)
 __device__ __forceinline__ void op_seek(const ReadsDev &R, uint32_t r, uint32_t col, OpCur &c) {
@@ -327,7 +327,7 @@ __device__ __forceinline__ void op_seek(const ReadsDev &R, uint32_t r, uint32_t 
     c.i_end = hi;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (R.op_col[mid] <= col) lo = mid;
+        if (R.ops[mid].x <= col) lo = mid;
         else hi = mid;
     }
     c.i = lo;
@@ -389,8 +389,8 @@ __device__ __forceinline__ void col_tpos(const ReadsDev &R, uint32_t r, uint32_t
         tpos = pos + c.t - 1;
         delta = off + 1;
         uint32_t i = c.i;
-        while (i > R.op_off[r] && (R.op_cig[i - 1] & 15) == 1) {
-            delta += R.op_cig[i - 1] >> 4;
+        while (i > R.op_off[r] && (R.ops[i - 1].w & 15) == 1) {
+            delta += R.ops[i - 1].w >> 4;
             i--;
         }
     } else {
@@ -400,7 +400,7 @@ __device__ __forceinline__ void col_tpos(const ReadsDev &R, uint32_t r, uint32_t
 }
 
 // One warp per read.
-__global__ void __launch_bounds__(128) k_expand_trim_pack(ReadsDev R, const uint8_t *__restrict__ ref, uint32_t L) {
+__global__ void __launch_bounds__(128) k_trim_scan(ReadsDev R, const uint8_t *__restrict__ ref, uint32_t L) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= R.n_reads) return;
@@ -562,10 +562,12 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_columns(ReadsDev R, const
     const uint32_t nq = qn;
     for (uint32_t i = threadIdx.x; i < nq; i += kPackThreads) pack_block_slow(R, ref, q[i]);
 }
-void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, uint32_t n_blocks, cudaStream_t s) {
-    if (!r.n_reads) return;
-    NP2_K(k_expand_trim_pack)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
-    if (n_blocks) NP2_K(k_pack_columns)<<<cdiv(n_blocks, kPackThreads), kPackThreads, 0, s>>>(r, d_ref, n_blocks);
+void trim_scan(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
+    if (r.n_reads) NP2_K(k_trim_scan)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
+}
+void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cudaStream_t s) {
+    if (r.n_reads && n_blocks)
+        NP2_K(k_pack_columns)<<<cdiv(n_blocks, kPackThreads), kPackThreads, 0, s>>>(r, d_ref, n_blocks);
 }
 
 /* =============================================================== K2: pileup */

@@ -40,7 +40,7 @@ struct ReadsDev {
     const uint32_t *ncols = nullptr;    // alignment columns before trimming
     const uint64_t *nib_off = nullptr;  // byte offset into nib (16-B aligned), n_reads + 1
     const uint32_t *ck_off = nullptr;   // first 32-column block of the read, n_reads + 1
-    const uint32_t *op_col = nullptr, *op_q = nullptr, *op_t = nullptr, *op_cig = nullptr;
+    const uint4 *ops = nullptr;  // per op: x = first column, y = first query base, z = ref offset, w = len << 4 | op
     const uint8_t *blob = nullptr;
     // outputs
     uint32_t *t_s = nullptr, *t_e = nullptr, *n = nullptr;  // trimmed start / inclusive end / column count (0 = no anchor)
@@ -53,7 +53,8 @@ struct ReadsDev {
 // K0: pull the SEQ fields out of a page-locked (mapped) record buffer; dst_off[r] is 16-B aligned + (source address & 15)
 void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
                 uint8_t *d_dst, uint32_t n_reads, cudaStream_t s);
-void expand_trim_pack(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, uint32_t n_blocks, cudaStream_t s);
+void trim_scan(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s);
+void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cudaStream_t s);
 
 /* ------------------------------------------------------------------ K2 pileup */
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);
