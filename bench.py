@@ -140,6 +140,9 @@ def run_ours(args):
     A, c, tabs = make_workload(20260002 + 1000 * rank, args.length, min(threads, 16), args.het)
     workload = WORKLOAD if args.het == 0 else WORKLOAD_DIPLOID % (args.length / 1e6, args.het * 100)
     ctx = np2.Context(local)
+    # the box's cores are shared by the ranks and by the contigs each rank keeps in flight
+    from nextpolish2_b200.api import set_host_threads
+    set_host_threads(max(2, min(16, (os.cpu_count() or 8) // max(world, 1) // max(1, min(args.e2e_inflight, 2)) * 2)))
     tables = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in KS]
     opts = np2.Opts()  # reference defaults; the 10 Mbp contig is above -L 1000000
     bam_pinned = torch.from_numpy(c["bam"]).pin_memory()
@@ -397,7 +400,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--het", type=float, default=0.0, help="heterozygosity of the synthetic contig (configs[2]: 0.01)")
     ap.add_argument("--no-yak-bench", action="store_true")
-    ap.add_argument("--e2e-inflight", type=int, default=2, help="contigs in flight per GPU in the end-to-end arm")
+    ap.add_argument("--e2e-inflight", type=int, default=3, help="contigs in flight per GPU in the end-to-end arm")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

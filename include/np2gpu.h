@@ -75,6 +75,10 @@ typedef struct np2_job np2_job;
 const char *np2_last_error(void);
 void np2_opts_default(np2_opts *o); /* option.rs:267-292 */
 
+/* host threads one call may use for record parsing and SEQ compaction (0 = NP2_HOST_THREADS from the environment, else
+ * min(16, hardware threads)); process-wide.  A caller running several contexts or ranks on one box divides the cores. */
+void np2_set_host_threads(uint32_t n);
+
 int np2_ctx_create(int device, np2_ctx **out);
 void np2_ctx_destroy(np2_ctx *ctx);
 

@@ -47,7 +47,7 @@ EXPORTS = [
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
-    "np2_debug_phase",
+    "np2_debug_phase", "np2_set_host_threads",
 ]
 
 
@@ -101,6 +101,8 @@ def load_library():
     L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
     L.np2_format_fasta.restype = u64
     L.np2_format_fasta.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int, vp, u64]
+    L.np2_set_host_threads.argtypes = [u32]
+    L.np2_set_host_threads.restype = None
     L.np2_debug_phase.argtypes = [vp, vp, u64, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u32)]
     L.np2_secmap_create.argtypes = [C.POINTER(vp)]
     L.np2_secmap_destroy.argtypes = [vp]
@@ -383,6 +385,11 @@ def polish_contig(ctx, contig, bam, tables, opts=None):
         return j.consensus()
     finally:
         j.destroy()
+
+
+def set_host_threads(n):
+    """Host threads one call may use for record parsing / SEQ compaction (np2_set_host_threads)."""
+    load_library().np2_set_host_threads(int(n))
 
 
 class SecondarySeqs:

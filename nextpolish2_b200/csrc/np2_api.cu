@@ -427,7 +427,7 @@ void np2_job::send_seq() {
     sc->p_seq_stage.resize(2 * half);
     for (auto &ev : sc->seq_ev)
         if (!ev) NP2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned T = np2::host_threads();
     uint32_t r0 = 0;
     for (uint32_t round = 0; r0 < n; round++) {
         const uint64_t D0 = co[r0] & ~15ull;
@@ -1910,6 +1910,8 @@ int np2_secmap_fill(const np2_secmap *m, const uint8_t *bam, uint64_t bam_len, u
     });
 }
 uint64_t np2_secmap_size(const np2_secmap *m, uint64_t *n_seqs) { return m ? np2::secmap_counts(*m->m, n_seqs) : 0; }
+
+void np2_set_host_threads(uint32_t n) { np2::set_host_threads(n); }
 
 int np2_host_alloc(uint64_t bytes, void **out) {
     return guard([&] {

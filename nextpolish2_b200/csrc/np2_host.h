@@ -35,6 +35,11 @@ inline void store_fence() { _mm_sfence(); }
 inline void stream_store(Op *p, const Op &v) { *p = v; }
 inline void store_fence() {}
 #endif
+// Host threads one call may use for record parsing / SEQ compaction: np2_set_host_threads(), else the environment
+// variable NP2_HOST_THREADS, else min(16, hardware threads).  Callers that run several contexts or ranks on one box
+// divide the cores between them.
+unsigned host_threads();
+void set_host_threads(unsigned n);
 // memcpy whose destination bypasses the cache (16-byte streaming stores once dst is aligned)
 void copy_streaming(void *dst, const void *src, size_t n);
 template <class T>
