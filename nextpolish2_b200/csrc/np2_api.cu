@@ -183,7 +183,7 @@ struct JobScratch {
     Ingest ing;
     std::vector<uint8_t> tseq, h_seeds, h_rech_pool, h_win;
     Patched patch;
-    PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage, p_seq_stage;
+    PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage, p_stage2, p_seq_stage;
     PBuf<uint32_t> p_cpos;
     std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
     cudaEvent_t seq_ev[2] = {nullptr, nullptr};
@@ -305,6 +305,9 @@ struct np2_job {
     PBuf<uint8_t> &res_base;
     std::vector<uint32_t> res_pos;
     DBuf<uint32_t> jd_cpos;                  // DP consensus of the last iteration stays on the device
+    DBuf<uint32_t> jd_reg_start, jd_reg_a, jd_reg_b, jd_reg_len;  // final regions (r order) for lazy positions
+    uint32_t res_nreg = 0;
+    bool res_sparse = false;                 // res_patch only holds the regions the re-check looked at
     DBuf<uint8_t> jd_cbase, jd_cflags;
     uint32_t res_N = 0;
     std::vector<uint8_t> &h_seeds, &h_rech_pool, &h_win;
@@ -1246,171 +1249,356 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         if (tb > d_tmp.n) d_tmp.alloc(tb, s);
         cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, in, out, n, s);
     };
-    h = timer.begin("seed_gather", 4);
-    assemble_sizes(ad, s);
-    NP2_CUDA(cudaMemsetAsync(d_q_seedlen.p + nreg, 0, 4, s));
-    scan(d_q_seedlen.p, d_q_seedoff.p, (int)nreg + 1);
-    rech_sizes(g, d_rech_bytes.p, s);
-    NP2_CUDA(cudaMemsetAsync(d_rech_bytes.p + nreg, 0, 4, s));
-    scan(d_rech_bytes.p, d_rech_boff.p, (int)nreg + 1);
-    scan(d_r_nsurv.p, d_ent_off.p, (int)nreg);  // last entry handled below
-    timer.end(h);
-    timer.hbegin();
-    // round 1: everything whose size is known (one synchronisation, pinned destinations)
-    p_cbase.resize(std::max(N, 1u));  // filled sparsely below: only the windows around RECH regions cross PCIe
-    Stager st1(sc->p_stage, s, (size_t)nreg * 64 + 4096);
-    const int *h_gerr = st1.fetch(d_err.p, 1);
-    const uint64_t *h_rech_bytes = st1.fetch(d_rech_boff.p + nreg, 1);
-    const uint8_t *lab = st1.fetch(d_r_lable.p, nreg);
-    uint32_t *seed_len = st1.fetch(d_r_seed_len.p, nreg);
-    uint64_t *seed_off = st1.fetch(d_r_seed_off.p, nreg);
-    const uint32_t *nsurv = st1.fetch(d_r_nsurv.p, nreg);
-    const uint32_t *ent_off = st1.fetch(d_ent_off.p, nreg);
-    const uint64_t *q_seedoff = st1.fetch(d_q_seedoff.p, nreg + 1);
-    rg.start.resize(nreg);
-    rg.end.resize(nreg);
-    rg.a.resize(nreg);
-    rg.b.resize(nreg);
-    const uint32_t *h_rs = st1.fetch(d_rstart.p, nreg), *h_re = st1.fetch(d_rend.p, nreg);
-    const uint32_t *h_ra = st1.fetch(d_ra.p, nreg), *h_rb = st1.fetch(d_rb.p, nreg);
-    NP2_CUDA(cudaStreamSynchronize(s));
-    timer.hend("host:seed_sync1");
-    const int gerr = *h_gerr;
-    const uint64_t rech_bytes = *h_rech_bytes;
-    if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
-    if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
-    if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
-    memcpy(rg.start.data(), h_rs, (size_t)nreg * 4);
-    memcpy(rg.end.data(), h_re, (size_t)nreg * 4);
-    memcpy(rg.a.data(), h_ra, (size_t)nreg * 4);
-    memcpy(rg.b.data(), h_rb, (size_t)nreg * 4);
-    const uint32_t n_ent = nreg ? ent_off[nreg - 1] + nsurv[nreg - 1] : 0;
-    const uint64_t seeds_bytes = q_seedoff[nreg];
-    DBuf<uint8_t> d_seeds, d_rech_pool;
-    DBuf<uint32_t> d_ent_order, d_ent_len;
-    DBuf<uint64_t> d_ent_poff;
-    d_seeds.alloc(seeds_bytes + 1, s);
-    d_rech_pool.alloc(rech_bytes + 1, s);
-    d_ent_order.alloc(std::max(n_ent, 1u), s);
-    d_ent_len.alloc(std::max(n_ent, 1u), s);
-    d_ent_poff.alloc(std::max(n_ent, 1u), s);
-    // The re-check reads the DP bases only next to RECH regions (k-1 flank bases, the stretch between chained
-    // regions): one window [a - W, b + W) per RECH region is gathered on the device instead of downloading all N.
-    const uint32_t kWin = 128;
-    std::vector<uint32_t> win_lo, win_r;
-    std::vector<uint64_t> win_off(1, 0);
-    for (uint32_t r = nreg; r-- > 0;)  // ascending position
-        if (lab[r] & LABLE_RECH) {
-            const uint32_t lo = rg.a[r] > kWin ? rg.a[r] - kWin : 0, hi = (uint32_t)std::min<uint64_t>((uint64_t)rg.b[r] + kWin, N);
-            win_lo.push_back(lo);
-            win_r.push_back(r);
-            win_off.push_back(win_off.back() + (hi - lo));
+    Patched &pc = res_patch;
+    uint32_t *seed_len = nullptr;   // full path: staged copies of the per-region seed (r order)
+    uint64_t *seed_off = nullptr;
+    auto phase1_sizes = [&]() {
+        h = timer.begin("seed_gather", 4);
+        assemble_sizes(ad, s);
+        NP2_CUDA(cudaMemsetAsync(d_q_seedlen.p + nreg, 0, 4, s));
+        scan(d_q_seedlen.p, d_q_seedoff.p, (int)nreg + 1);
+        rech_sizes(g, d_rech_bytes.p, s);
+        NP2_CUDA(cudaMemsetAsync(d_rech_bytes.p + nreg, 0, 4, s));
+        scan(d_rech_bytes.p, d_rech_boff.p, (int)nreg + 1);
+        scan(d_r_nsurv.p, d_ent_off.p, (int)nreg);  // last entry handled below
+        timer.end(h);
+    };
+    /* Sparse host view (the normal case): the host only looks at the RECH regions and at what lies within
+     * kRecheckWindow DP bases of them, plus the first and the last region (FASTA header span).  Everything is selected,
+     * compacted and gathered on the device; per-region work on the host is O(selected), not O(nreg).  Returns false
+     * (nothing committed) when the windows would cover most of the contig or the layout check fails. */
+    std::vector<uint32_t> sv_sub;         // selected regions, ascending r
+    std::vector<uint64_t> sv_init_off;    // per selected region (q' order): the seed it started with
+    std::vector<uint32_t> sv_init_len;
+    long long sv_shift0 = 0;
+    bool sparse_view = false;
+    auto build_sparse_view = [&]() -> bool {
+        DBuf<uint8_t> d_near;
+        DBuf<uint32_t> d_sub, d_nsub, d_win_lo, d_win_len;
+        DBuf<uint64_t> d_win_off;
+        d_near.alloc(nreg, s);
+        d_sub.alloc(nreg, s);
+        d_nsub.alloc(1, s);
+        d_win_lo.alloc(nreg, s);
+        d_win_len.alloc(nreg + 1, s);
+        d_win_off.alloc(nreg + 1, s);
+        SubMeta sm;
+        DBuf<uint32_t> m_start, m_end, m_a, m_b, m_seed_len, m_nsurv, m_ent_off;
+        DBuf<uint64_t> m_seed_off, m_qseedoff;
+        DBuf<uint8_t> m_lable;
+        for (DBuf<uint32_t> *d : {&m_start, &m_end, &m_a, &m_b, &m_seed_len, &m_nsurv, &m_ent_off}) d->alloc(nreg, s);
+        m_seed_off.alloc(nreg, s);
+        m_qseedoff.alloc(nreg, s);
+        m_lable.alloc(nreg, s);
+        sm.start = m_start.p, sm.end = m_end.p, sm.a = m_a.p, sm.b = m_b.p, sm.seed_len = m_seed_len.p;
+        sm.nsurv = m_nsurv.p, sm.ent_off = m_ent_off.p, sm.seed_off = m_seed_off.p, sm.q_seedoff = m_qseedoff.p;
+        sm.lable = m_lable.p;
+        int hh = timer.begin("seed_gather", 6);
+        d_near.zero();
+        near_mark(nreg, N, d_r_lable.p, d_ra.p, d_rb.p, d_near.p, s);
+        ad.near = d_near.p;
+        timer.end(hh);
+        phase1_sizes();
+        hh = timer.begin("seed_gather", 4);
+        NP2_CUDA(cudaMemsetAsync(d_q_delta.p + nreg, 0, 8, s));
+        scan(d_q_delta.p, d_q_shift.p, (int)nreg + 1);
+        window_sizes(nreg, N, d_r_lable.p, d_ra.p, d_rb.p, d_win_lo.p, d_win_len.p, s);
+        NP2_CUDA(cudaMemsetAsync(d_win_len.p + nreg, 0, 4, s));
+        scan(d_win_len.p, d_win_off.p, (int)nreg + 1);
+        {
+            size_t tb = 0;
+            cub::CountingInputIterator<uint32_t> it(0);
+            cub::DeviceSelect::Flagged(nullptr, tb, it, d_near.p, d_sub.p, d_nsub.p, (int)nreg, s);
+            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+            cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_near.p, d_sub.p, d_nsub.p, (int)nreg, s);
         }
-    const uint32_t n_win = (uint32_t)win_lo.size();
-    bool full_cbase = win_off.back() > N / 2;
-    DBuf<uint32_t> d_win_lo;
-    DBuf<uint64_t> d_win_off;
-    DBuf<uint8_t> d_win;
-    h = timer.begin("seed_gather", 3);
-    if (full_cbase) {
-        d_cbase.download(p_cbase.p, N);
-    } else if (n_win) {
-        d_win_lo.alloc(n_win, s);
-        d_win_off.alloc(n_win + 1, s);
-        d_win.alloc(win_off.back() + 1, s);
-        d_win_lo.upload(win_lo.data(), n_win);
-        d_win_off.upload(win_off.data(), n_win + 1);
-        gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, n_win, d_win.p, s);
-        h_win.resize(win_off.back() + 16);
-        d_win.download(h_win.data(), win_off.back());
-        h2d += (uint64_t)n_win * 12;
-    }
-    assemble_seed_gather(ad, d_seeds.p, s);
-    if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
-    timer.end(h);
-    // round 2: the seed strings and the survivors of the RECH regions
-    h_seeds.resize(seeds_bytes + 16);
-    h_rech_pool.resize(rech_bytes + 16);
-    d_seeds.download(h_seeds.data(), seeds_bytes);
-    if (rech_bytes) d_rech_pool.download(h_rech_pool.data(), rech_bytes);
-    std::vector<uint32_t> ent_order(n_ent), ent_len(n_ent);
-    std::vector<uint64_t> ent_poff(n_ent);
-    if (n_ent) {
-        d_ent_order.download(ent_order.data(), n_ent);
-        d_ent_len.download(ent_len.data(), n_ent);
-        d_ent_poff.download(ent_poff.data(), n_ent);
-    }
-    NP2_CUDA(cudaStreamSynchronize(s));
-    timer.hend("host:seed_sync2");
-    d2h += (full_cbase ? (uint64_t)N : win_off.back()) + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
-    if (!full_cbase && n_win) {
-        for (uint32_t w = 0; w < n_win; w++)
-            memcpy(p_cbase.p + win_lo[w], h_win.data() + win_off[w], win_off[w + 1] - win_off[w]);
-        // Exactness check: every DP base the re-check can touch must lie inside a window.  Left/right flanks take at
-        // most kmax-1 DP bases walking over neighbouring regions (their alleles only shorten the walk); chained
-        // regions (closer than kmax in position) read the whole stretch between them.
+        sub_meta_gather(d_sub.p, d_nsub.p, nreg, d_rstart.p, d_rend.p, d_ra.p, d_rb.p, d_r_lable.p, d_r_seed_len.p,
+                        d_r_seed_off.p, d_r_nsurv.p, d_ent_off.p, d_q_seedoff.p, sm, s);
+        timer.end(hh);
+        timer.hbegin();
+        Stager st1(sc->p_stage, s, 4096);
+        const int *h_gerr = st1.fetch(d_err.p, 1);
+        const uint32_t *h_nsub = st1.fetch(d_nsub.p, 1);
+        const uint64_t *h_seeds_bytes = st1.fetch(d_q_seedoff.p + nreg, 1);
+        const uint64_t *h_rech_bytes = st1.fetch(d_rech_boff.p + nreg, 1);
+        const uint64_t *h_win_bytes = st1.fetch(d_win_off.p + nreg, 1);
+        const long long *h_shift0 = st1.fetch(d_q_shift.p + nreg, 1);
+        const uint32_t *h_last_ent = st1.fetch(d_ent_off.p + (nreg - 1), 1);
+        const uint32_t *h_last_ns = st1.fetch(d_r_nsurv.p + (nreg - 1), 1);
+        NP2_CUDA(cudaStreamSynchronize(s));
+        timer.hend("host:seed_sync1");
+        const int gerr = *h_gerr;
+        if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
+        if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
+        if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
+        const uint32_t nsub = *h_nsub, n_ent = *h_last_ent + *h_last_ns;
+        const uint64_t seeds_bytes = *h_seeds_bytes, rech_bytes = *h_rech_bytes, win_bytes = *h_win_bytes;
+        sv_shift0 = *h_shift0;
+        if (win_bytes > N / 2) return false;
+        DBuf<uint8_t> d_seeds, d_rech_pool, d_win;
+        DBuf<uint32_t> d_ent_order, d_ent_len;
+        DBuf<uint64_t> d_ent_poff;
+        d_seeds.alloc(seeds_bytes + 1, s);
+        d_rech_pool.alloc(rech_bytes + 1, s);
+        d_win.alloc(win_bytes + 1, s);
+        d_ent_order.alloc(std::max(n_ent, 1u), s);
+        d_ent_len.alloc(std::max(n_ent, 1u), s);
+        d_ent_poff.alloc(std::max(n_ent, 1u), s);
+        hh = timer.begin("seed_gather", 3);
+        assemble_seed_gather(ad, d_seeds.p, s);
+        if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
+        if (win_bytes) gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, nreg, d_win.p, s);
+        timer.end(hh);
+        Stager st2(sc->p_stage2, s, (size_t)nsub * 56 + (size_t)n_ent * 16 + 4096);
+        const uint32_t *h_sub = st2.fetch(d_sub.p, nsub);
+        const uint32_t *ms = st2.fetch(m_start.p, nsub), *me = st2.fetch(m_end.p, nsub), *ma = st2.fetch(m_a.p, nsub);
+        const uint32_t *mb = st2.fetch(m_b.p, nsub), *msl = st2.fetch(m_seed_len.p, nsub);
+        const uint32_t *mns = st2.fetch(m_nsurv.p, nsub), *meo = st2.fetch(m_ent_off.p, nsub);
+        const uint64_t *mso = st2.fetch(m_seed_off.p, nsub), *mqo = st2.fetch(m_qseedoff.p, nsub);
+        const uint8_t *ml = st2.fetch(m_lable.p, nsub);
+        const uint32_t *ent_order = st2.fetch(d_ent_order.p, n_ent), *ent_len = st2.fetch(d_ent_len.p, n_ent);
+        const uint64_t *ent_poff = st2.fetch(d_ent_poff.p, n_ent);
+        h_seeds.resize(seeds_bytes + 16);
+        h_rech_pool.resize(rech_bytes + 16);
+        h_win.resize(win_bytes + 16);
+        d_seeds.download(h_seeds.data(), seeds_bytes);
+        if (rech_bytes) d_rech_pool.download(h_rech_pool.data(), rech_bytes);
+        if (win_bytes) d_win.download(h_win.data(), win_bytes);
+        NP2_CUDA(cudaStreamSynchronize(s));
+        timer.hend("host:seed_sync2");
+        d2h += seeds_bytes + rech_bytes + win_bytes + (uint64_t)nsub * 53 + (uint64_t)n_ent * 16 + 64;
+        // the view over the selected regions, ascending position (q' = nsub - 1 - i)
+        pc.reset(nsub);
+        pc.cbase = p_cbase.p;
+        pc.N = N;
+        sv_sub.assign(h_sub, h_sub + nsub);
+        sv_init_off.resize(nsub);
+        sv_init_len.resize(nsub);
+        uint64_t rb = 0;
+        for (uint32_t i = 0; i < nsub; i++) {
+            const uint32_t q = nsub - 1 - i;
+            pc.start[q] = ms[i];
+            pc.end[q] = me[i];
+            pc.a[q] = ma[i];
+            pc.b[q] = mb[i];
+            pc.lable[q] = ml[i];
+            pc.seed[q].s = h_seeds.data() + mqo[i];
+            pc.seed[q].len = msl[i];
+            pc.seed[q].dev_off = mso[i];
+            sv_init_off[q] = mso[i];
+            sv_init_len[q] = msl[i];
+            for (uint32_t x = 0; x < mns[i]; x++) {  // rech pool is laid out in r order, survivors in rank order
+                Allele al;
+                al.s = h_rech_pool.data() + rb;
+                al.len = ent_len[meo[i] + x];
+                al.order = ent_order[meo[i] + x];
+                al.dev_off = ent_poff[meo[i] + x];
+                rb += al.len;
+                pc.cand[q].push_back(al);
+            }
+        }
+        // windows into their true places + the layout check (DESIGN.md "Re-check windows")
         const uint32_t need = tables.back()->dev.k - 1;
+        uint64_t woff = 0, prev_whi = 0;
+        int64_t prev_rech = -1;
         bool ok = true;
-        for (uint32_t w = 0; w < n_win && ok; w++) {
-            const uint32_t r = win_r[w];
-            const uint64_t wlo = win_lo[w], whi = wlo + (win_off[w + 1] - win_off[w]);
-            uint32_t got = 0, rr = r;  // left walk (r grows towards lower positions)
-            uint64_t i = rg.a[r];
+        for (uint32_t q = 0; q < nsub && ok; q++) {
+            if (!(pc.lable[q] & LABLE_RECH)) continue;
+            const uint64_t wlo = pc.a[q] > kRecheckWindow ? pc.a[q] - kRecheckWindow : 0;
+            const uint64_t whi = std::min<uint64_t>((uint64_t)pc.b[q] + kRecheckWindow, N);
+            memcpy(p_cbase.p + wlo, h_win.data() + woff, whi - wlo);
+            woff += whi - wlo;
+            uint32_t got = 0, rr = q;  // left flank
+            uint64_t i = pc.a[q];
             for (;;) {
-                const uint64_t lo = rr + 1 < nreg ? rg.b[rr + 1] : 0;
+                const uint64_t lo = rr > 0 ? pc.b[rr - 1] : 0;
                 const uint64_t take = std::min<uint64_t>(need - got, i - lo);
                 if (i - take < wlo) ok = false;
                 got += (uint32_t)take;
-                if (got >= need || rr + 1 >= nreg) break;
-                rr++;
-                i = rg.a[rr];
+                if (got >= need || rr == 0) break;
+                rr--;
+                i = pc.a[rr];
             }
-            got = 0, rr = r, i = rg.b[r];
+            got = 0, rr = q, i = pc.b[q];  // right flank
             for (;;) {
-                const uint64_t hi = rr > 0 ? rg.a[rr - 1] : N;
+                const uint64_t hi = rr + 1 < nsub ? pc.a[rr + 1] : N;
                 const uint64_t take = std::min<uint64_t>(need - got, hi - i);
                 if (i + take > whi) ok = false;
                 got += (uint32_t)take;
-                if (got >= need || rr == 0) break;
-                rr--;
-                i = rg.b[rr];
+                if (got >= need || rr + 1 >= nsub) break;
+                rr++;
+                i = pc.b[rr];
             }
-            if (w + 1 < n_win) {
-                const uint32_t r2 = win_r[w + 1];
-                if (rg.start[r2] < rg.end[r] + need + 1 && rg.a[r2] > whi && win_lo[w + 1] > whi) ok = false;
-            }
+            if (prev_rech >= 0 && pc.start[q] < pc.end[prev_rech] + need + 1 && pc.a[q] > prev_whi && wlo > prev_whi) ok = false;
+            prev_rech = q;
+            prev_whi = whi;
         }
-        if (!ok) {  // pathological layout (very long insertions next to a RECH region): take everything
-            d_cbase.download(p_cbase.p, N);
-            NP2_CUDA(cudaStreamSynchronize(s));
-            d2h += N;
-        }
+        if (woff != win_bytes) ok = false;
+        return ok;
+    };
+    if (!dump) {
+        p_cbase.resize(std::max(N, 1u));
+        sparse_view = build_sparse_view();
+        ad.near = nullptr;
     }
-    // patched view, regions in ascending position (q = nreg - 1 - r)
-    Patched &pc = res_patch;
-    pc.reset(nreg);
-    pc.cbase = p_cbase.p;
-    pc.N = N;
-    {
-        uint64_t rb = 0;
-        for (uint32_t r = 0; r < nreg; r++) {
-            const uint32_t q = nreg - 1 - r;
-            pc.start[q] = rg.start[r];
-            pc.end[q] = rg.end[r];
-            pc.a[q] = rg.a[r];
-            pc.b[q] = rg.b[r];
-            pc.lable[q] = lab[r];
-            pc.seed[q].s = h_seeds.data() + q_seedoff[q];
-            pc.seed[q].len = seed_len[r];
-            pc.seed[q].dev_off = seed_off[r];
-            for (uint32_t x = 0; x < nsurv[r]; x++) {  // rech pool is laid out in r order, survivors in rank order
-                Allele al;
-                al.s = h_rech_pool.data() + rb;
-                al.len = ent_len[ent_off[r] + x];
-                al.order = ent_order[ent_off[r] + x];
-                al.dev_off = ent_poff[ent_off[r] + x];
-                rb += al.len;
-                pc.cand[q].push_back(al);
+    if (!sparse_view) {
+        phase1_sizes();
+        timer.hbegin();
+        // round 1: everything whose size is known (one synchronisation, pinned destinations)
+        p_cbase.resize(std::max(N, 1u));  // filled sparsely below: only the windows around RECH regions cross PCIe
+        Stager st1(sc->p_stage, s, (size_t)nreg * 64 + 4096);
+        const int *h_gerr = st1.fetch(d_err.p, 1);
+        const uint64_t *h_rech_bytes = st1.fetch(d_rech_boff.p + nreg, 1);
+        const uint8_t *lab = st1.fetch(d_r_lable.p, nreg);
+        seed_len = st1.fetch(d_r_seed_len.p, nreg);
+        seed_off = st1.fetch(d_r_seed_off.p, nreg);
+        const uint32_t *nsurv = st1.fetch(d_r_nsurv.p, nreg);
+        const uint32_t *ent_off = st1.fetch(d_ent_off.p, nreg);
+        const uint64_t *q_seedoff = st1.fetch(d_q_seedoff.p, nreg + 1);
+        rg.start.resize(nreg);
+        rg.end.resize(nreg);
+        rg.a.resize(nreg);
+        rg.b.resize(nreg);
+        const uint32_t *h_rs = st1.fetch(d_rstart.p, nreg), *h_re = st1.fetch(d_rend.p, nreg);
+        const uint32_t *h_ra = st1.fetch(d_ra.p, nreg), *h_rb = st1.fetch(d_rb.p, nreg);
+        NP2_CUDA(cudaStreamSynchronize(s));
+        timer.hend("host:seed_sync1");
+        const int gerr = *h_gerr;
+        const uint64_t rech_bytes = *h_rech_bytes;
+        if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
+        if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
+        if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
+        memcpy(rg.start.data(), h_rs, (size_t)nreg * 4);
+        memcpy(rg.end.data(), h_re, (size_t)nreg * 4);
+        memcpy(rg.a.data(), h_ra, (size_t)nreg * 4);
+        memcpy(rg.b.data(), h_rb, (size_t)nreg * 4);
+        const uint32_t n_ent = nreg ? ent_off[nreg - 1] + nsurv[nreg - 1] : 0;
+        const uint64_t seeds_bytes = q_seedoff[nreg];
+        DBuf<uint8_t> d_seeds, d_rech_pool;
+        DBuf<uint32_t> d_ent_order, d_ent_len;
+        DBuf<uint64_t> d_ent_poff;
+        d_seeds.alloc(seeds_bytes + 1, s);
+        d_rech_pool.alloc(rech_bytes + 1, s);
+        d_ent_order.alloc(std::max(n_ent, 1u), s);
+        d_ent_len.alloc(std::max(n_ent, 1u), s);
+        d_ent_poff.alloc(std::max(n_ent, 1u), s);
+        // The re-check reads the DP bases only next to RECH regions (k-1 flank bases, the stretch between chained
+        // regions): one window [a - W, b + W) per RECH region is gathered on the device instead of downloading all N.
+        const uint32_t kWin = 128;
+        std::vector<uint32_t> win_lo, win_r;
+        std::vector<uint64_t> win_off(1, 0);
+        for (uint32_t r = nreg; r-- > 0;)  // ascending position
+            if (lab[r] & LABLE_RECH) {
+                const uint32_t lo = rg.a[r] > kWin ? rg.a[r] - kWin : 0, hi = (uint32_t)std::min<uint64_t>((uint64_t)rg.b[r] + kWin, N);
+                win_lo.push_back(lo);
+                win_r.push_back(r);
+                win_off.push_back(win_off.back() + (hi - lo));
+            }
+        const uint32_t n_win = (uint32_t)win_lo.size();
+        bool full_cbase = win_off.back() > N / 2;
+        DBuf<uint32_t> d_win_lo;
+        DBuf<uint64_t> d_win_off;
+        DBuf<uint8_t> d_win;
+        h = timer.begin("seed_gather", 3);
+        if (full_cbase) {
+            d_cbase.download(p_cbase.p, N);
+        } else if (n_win) {
+            d_win_lo.alloc(n_win, s);
+            d_win_off.alloc(n_win + 1, s);
+            d_win.alloc(win_off.back() + 1, s);
+            d_win_lo.upload(win_lo.data(), n_win);
+            d_win_off.upload(win_off.data(), n_win + 1);
+            gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, n_win, d_win.p, s);
+            h_win.resize(win_off.back() + 16);
+            d_win.download(h_win.data(), win_off.back());
+            h2d += (uint64_t)n_win * 12;
+        }
+        assemble_seed_gather(ad, d_seeds.p, s);
+        if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
+        timer.end(h);
+        // round 2: the seed strings and the survivors of the RECH regions
+        h_seeds.resize(seeds_bytes + 16);
+        h_rech_pool.resize(rech_bytes + 16);
+        d_seeds.download(h_seeds.data(), seeds_bytes);
+        if (rech_bytes) d_rech_pool.download(h_rech_pool.data(), rech_bytes);
+        std::vector<uint32_t> ent_order(n_ent), ent_len(n_ent);
+        std::vector<uint64_t> ent_poff(n_ent);
+        if (n_ent) {
+            d_ent_order.download(ent_order.data(), n_ent);
+            d_ent_len.download(ent_len.data(), n_ent);
+            d_ent_poff.download(ent_poff.data(), n_ent);
+        }
+        NP2_CUDA(cudaStreamSynchronize(s));
+        timer.hend("host:seed_sync2");
+        d2h += (full_cbase ? (uint64_t)N : win_off.back()) + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
+        if (!full_cbase && n_win) {
+            for (uint32_t w = 0; w < n_win; w++)
+                memcpy(p_cbase.p + win_lo[w], h_win.data() + win_off[w], win_off[w + 1] - win_off[w]);
+            // Exactness check: every DP base the re-check can touch must lie inside a window.  Left/right flanks take at
+            // most kmax-1 DP bases walking over neighbouring regions (their alleles only shorten the walk); chained
+            // regions (closer than kmax in position) read the whole stretch between them.
+            const uint32_t need = tables.back()->dev.k - 1;
+            bool ok = true;
+            for (uint32_t w = 0; w < n_win && ok; w++) {
+                const uint32_t r = win_r[w];
+                const uint64_t wlo = win_lo[w], whi = wlo + (win_off[w + 1] - win_off[w]);
+                uint32_t got = 0, rr = r;  // left walk (r grows towards lower positions)
+                uint64_t i = rg.a[r];
+                for (;;) {
+                    const uint64_t lo = rr + 1 < nreg ? rg.b[rr + 1] : 0;
+                    const uint64_t take = std::min<uint64_t>(need - got, i - lo);
+                    if (i - take < wlo) ok = false;
+                    got += (uint32_t)take;
+                    if (got >= need || rr + 1 >= nreg) break;
+                    rr++;
+                    i = rg.a[rr];
+                }
+                got = 0, rr = r, i = rg.b[r];
+                for (;;) {
+                    const uint64_t hi = rr > 0 ? rg.a[rr - 1] : N;
+                    const uint64_t take = std::min<uint64_t>(need - got, hi - i);
+                    if (i + take > whi) ok = false;
+                    got += (uint32_t)take;
+                    if (got >= need || rr == 0) break;
+                    rr--;
+                    i = rg.b[rr];
+                }
+                if (w + 1 < n_win) {
+                    const uint32_t r2 = win_r[w + 1];
+                    if (rg.start[r2] < rg.end[r] + need + 1 && rg.a[r2] > whi && win_lo[w + 1] > whi) ok = false;
+                }
+            }
+            if (!ok) {  // pathological layout (very long insertions next to a RECH region): take everything
+                d_cbase.download(p_cbase.p, N);
+                NP2_CUDA(cudaStreamSynchronize(s));
+                d2h += N;
+            }
+        }
+        // patched view, regions in ascending position (q = nreg - 1 - r)
+        pc.reset(nreg);
+        pc.cbase = p_cbase.p;
+        pc.N = N;
+        {
+            uint64_t rb = 0;
+            for (uint32_t r = 0; r < nreg; r++) {
+                const uint32_t q = nreg - 1 - r;
+                pc.start[q] = rg.start[r];
+                pc.end[q] = rg.end[r];
+                pc.a[q] = rg.a[r];
+                pc.b[q] = rg.b[r];
+                pc.lable[q] = lab[r];
+                pc.seed[q].s = h_seeds.data() + q_seedoff[q];
+                pc.seed[q].len = seed_len[r];
+                pc.seed[q].dev_off = seed_off[r];
+                for (uint32_t x = 0; x < nsurv[r]; x++) {  // rech pool is laid out in r order, survivors in rank order
+                    Allele al;
+                    al.s = h_rech_pool.data() + rb;
+                    al.len = ent_len[ent_off[r] + x];
+                    al.order = ent_order[ent_off[r] + x];
+                    al.dev_off = ent_poff[ent_off[r] + x];
+                    rb += al.len;
+                    pc.cand[q].push_back(al);
+                }
             }
         }
     }
@@ -1450,18 +1638,47 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         for (uint32_t r = 0; r < nreg; r++) dm_reg_lable[r] = pc.lable[nreg - 1 - r];
     }
     /* ---- final consensus assembled on the device from the (possibly re-chosen) seeds */
-    if (changed) {
-        for (uint32_t r = 0; r < nreg; r++) {
-            const Allele &al = pc.seed[nreg - 1 - r];
-            seed_off[r] = al.dev_off;
-            seed_len[r] = al.len;
-        }
-        d_r_seed_off.upload(seed_off, nreg);
-        d_r_seed_len.upload(seed_len, nreg);
-        h2d += (uint64_t)nreg * 12;
-    }
     long long total_shift = 0;
-    for (uint32_t q = 0; q < nreg; q++) total_shift += (long long)pc.seed[q].len - (long long)(pc.b[q] - pc.a[q]);
+    DBuf<uint32_t> d_ch_r, d_ch_len;
+    DBuf<uint64_t> d_ch_off;
+    if (sparse_view) {  // only the seeds the re-check changed go back to the device
+        std::vector<uint32_t> ch_r, ch_len;
+        std::vector<uint64_t> ch_off;
+        total_shift = sv_shift0;
+        const uint32_t nsub = (uint32_t)sv_sub.size();
+        for (uint32_t q = 0; q < nsub; q++) {
+            const Allele &al = pc.seed[q];
+            if (al.dev_off == sv_init_off[q] && al.len == sv_init_len[q]) continue;
+            ch_r.push_back(sv_sub[nsub - 1 - q]);
+            ch_off.push_back(al.dev_off);
+            ch_len.push_back(al.len);
+            total_shift += (long long)al.len - (long long)sv_init_len[q];
+        }
+        if (!ch_r.empty()) {
+            const uint32_t nc = (uint32_t)ch_r.size();
+            d_ch_r.alloc(nc, s);
+            d_ch_len.alloc(nc, s);
+            d_ch_off.alloc(nc, s);
+            d_ch_r.upload(ch_r.data(), nc);
+            d_ch_len.upload(ch_len.data(), nc);
+            d_ch_off.upload(ch_off.data(), nc);
+            seed_scatter(nc, d_ch_r.p, d_ch_off.p, d_ch_len.p, d_r_seed_off.p, d_r_seed_len.p, s);
+            NP2_CUDA(cudaStreamSynchronize(s));  // the host vectors above are pageable: finish before they go
+            h2d += (uint64_t)nc * 16;
+        }
+    } else {
+        if (changed) {
+            for (uint32_t r = 0; r < nreg; r++) {
+                const Allele &al = pc.seed[nreg - 1 - r];
+                seed_off[r] = al.dev_off;
+                seed_len[r] = al.len;
+            }
+            d_r_seed_off.upload(seed_off, nreg);
+            d_r_seed_len.upload(seed_len, nreg);
+            h2d += (uint64_t)nreg * 12;
+        }
+        for (uint32_t q = 0; q < nreg; q++) total_shift += (long long)pc.seed[q].len - (long long)(pc.b[q] - pc.a[q]);
+    }
     const uint64_t out_n = (uint64_t)((long long)N + total_shift);
     DBuf<uint8_t> d_out;
     d_out.alloc(out_n + 1, s);
@@ -1478,9 +1695,22 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     NP2_CUDA(cudaStreamSynchronize(s));
     d2h += out_n;
     // FASTA header span (main.rs:627-632)
+    const size_t nview = pc.a.size();  // the sparse view always holds the first and the last region
     res_first = (pc.a[0] == 0) ? pc.start[0] : edge_pos[0];
-    res_last = (pc.b[nreg - 1] == N) ? pc.start[nreg - 1] : edge_pos[1];
+    res_last = (pc.b[nview - 1] == N) ? pc.start[nview - 1] : edge_pos[1];
     res_pos_valid = false;
+    res_sparse = sparse_view;
+    if (sparse_view) {  // positions are produced on request from the device copies (np2_job_get_consensus)
+        res_nreg = nreg;
+        jd_reg_start.alloc(nreg, s);
+        jd_reg_a.alloc(nreg, s);
+        jd_reg_b.alloc(nreg, s);
+        jd_reg_len.alloc(nreg, s);
+        NP2_CUDA(cudaMemcpyAsync(jd_reg_start.p, d_rstart.p, (size_t)nreg * 4, cudaMemcpyDeviceToDevice, s));
+        NP2_CUDA(cudaMemcpyAsync(jd_reg_a.p, d_ra.p, (size_t)nreg * 4, cudaMemcpyDeviceToDevice, s));
+        NP2_CUDA(cudaMemcpyAsync(jd_reg_b.p, d_rb.p, (size_t)nreg * 4, cudaMemcpyDeviceToDevice, s));
+        NP2_CUDA(cudaMemcpyAsync(jd_reg_len.p, d_r_seed_len.p, (size_t)nreg * 4, cudaMemcpyDeviceToDevice, s));
+    }
     timer.hend("host:assemble");
     return iter + 1;
   }
@@ -1493,6 +1723,7 @@ void np2_job::run(int32_t dump_it) {
     res_pos.clear();
     res_pos_valid = false;
     res_patch.reset(0);
+    res_sparse = false;
     timer.s = s;
     timer.reset();
     const unsigned long long launches0 = launch_counter();
@@ -1968,6 +2199,25 @@ uint64_t np2_job_get_consensus(np2_job *j, const uint32_t **pos, const uint8_t *
             j->p_cpos.resize(std::max(j->res_N, 1u));
             cudaMemcpyAsync(j->p_cpos.p, j->jd_cpos.p, (size_t)j->res_N * 4, cudaMemcpyDeviceToHost, j->ctx->stream);
             cudaStreamSynchronize(j->ctx->stream);
+            if (j->res_sparse) {  // rebuild the full region list from the device copies
+                const uint32_t nr = j->res_nreg;
+                std::vector<uint32_t> st(nr), ra(nr), rb(nr), sl(nr);
+                cudaMemcpyAsync(st.data(), j->jd_reg_start.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, j->ctx->stream);
+                cudaMemcpyAsync(ra.data(), j->jd_reg_a.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, j->ctx->stream);
+                cudaMemcpyAsync(rb.data(), j->jd_reg_b.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, j->ctx->stream);
+                cudaMemcpyAsync(sl.data(), j->jd_reg_len.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, j->ctx->stream);
+                cudaStreamSynchronize(j->ctx->stream);
+                Patched &pc = j->res_patch;
+                pc.reset(nr);
+                for (uint32_t r = 0; r < nr; r++) {
+                    const uint32_t q = nr - 1 - r;
+                    pc.start[q] = st[r];
+                    pc.a[q] = ra[r];
+                    pc.b[q] = rb[r];
+                    pc.seed[q].len = sl[r];
+                }
+                j->res_sparse = false;
+            }
             j->res_patch.cpos = j->p_cpos.p;
             j->res_patch.N = j->res_N;
             positions(j->res_patch, j->res_pos);

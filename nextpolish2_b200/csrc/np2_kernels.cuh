@@ -157,7 +157,26 @@ struct AssembleDev {
     long long *q_delta = nullptr, *q_shift = nullptr;  // q_shift: nreg + 1
     uint32_t *q_seedlen = nullptr;
     uint64_t *q_seedoff = nullptr;                      // nreg + 1
+    const uint8_t *near = nullptr;  // optional (r order): only these regions' seed strings are gathered for the host
 };
+// ---- sparse host view: the host only looks at RECH regions and what lies within kRecheckWindow DP bases of them
+constexpr uint32_t kRecheckWindow = 128;
+struct SubMeta {  // compact copies for the selected regions, in the order of `sub` (ascending r = descending position)
+    uint32_t *start = nullptr, *end = nullptr, *a = nullptr, *b = nullptr, *seed_len = nullptr, *nsurv = nullptr,
+             *ent_off = nullptr;
+    uint64_t *seed_off = nullptr, *q_seedoff = nullptr;
+    uint8_t *lable = nullptr;
+};
+void near_mark(uint32_t nreg, uint32_t N, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b, uint8_t *d_near,
+               cudaStream_t s);
+void window_sizes(uint32_t nreg, uint32_t N, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b,
+                  uint32_t *d_win_lo_q, uint32_t *d_win_len_q, cudaStream_t s);
+void sub_meta_gather(const uint32_t *d_sub, const uint32_t *d_nsub, uint32_t nreg, const uint32_t *d_start,
+                     const uint32_t *d_end, const uint32_t *d_a, const uint32_t *d_b, const uint8_t *d_lable,
+                     const uint32_t *d_seed_len, const uint64_t *d_seed_off, const uint32_t *d_nsurv,
+                     const uint32_t *d_ent_off, const uint64_t *d_q_seedoff, SubMeta out, cudaStream_t s);
+void seed_scatter(uint32_t n, const uint32_t *d_r, const uint64_t *d_off, const uint32_t *d_len, uint64_t *d_seed_off,
+                  uint32_t *d_seed_len, cudaStream_t s);
 void assemble_sizes(AssembleDev a, cudaStream_t s);
 void assemble_seed_gather(AssembleDev a, uint8_t *d_out, cudaStream_t s);
 void gather_ranges(const uint8_t *d_src, const uint32_t *d_lo, const uint64_t *d_off, uint32_t n, uint8_t *d_out,

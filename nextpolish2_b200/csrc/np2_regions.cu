@@ -111,7 +111,7 @@ __global__ void k_patch_sizes(AssembleDev a) {
     if (q >= a.nreg) return;
     const uint32_t r = a.nreg - 1 - q;
     a.q_delta[q] = (long long)a.r_seed_len[r] - (long long)(a.r_b[r] - a.r_a[r]);
-    a.q_seedlen[q] = a.r_seed_len[r];
+    a.q_seedlen[q] = (!a.near || a.near[r]) ? a.r_seed_len[r] : 0;
 }
 // compact copy of every region's seed string (for the host's flank extraction), q order
 __global__ void k_seed_gather(AssembleDev a, uint8_t *__restrict__ out) {
@@ -119,6 +119,7 @@ __global__ void k_seed_gather(AssembleDev a, uint8_t *__restrict__ out) {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= a.nreg) return;
     const uint32_t r = a.nreg - 1 - q;
+    if (a.near && !a.near[r]) return;
     const uint8_t *src = a.pool + a.r_seed_off[r];
     uint8_t *dst = out + a.q_seedoff[q];
     for (uint32_t x = lane; x < a.r_seed_len[r]; x += 32) dst[x] = src[x];
@@ -181,6 +182,85 @@ __global__ void __launch_bounds__(128) k_gather_ranges(const uint8_t *__restrict
 void gather_ranges(const uint8_t *d_src, const uint32_t *d_lo, const uint64_t *d_off, uint32_t n, uint8_t *d_out,
                    cudaStream_t s) {
     if (n) NP2_K(k_gather_ranges)<<<cdiv((uint64_t)n * 32, 128), 128, 0, s>>>(d_src, d_lo, d_off, n, d_out);
+}
+
+/* ---- sparse host view (np2_api.cu, final phase): regions are stored in descending position (r order) */
+// near[r] = 1 for every RECH region and every region whose DP index range [a, b) reaches into the window
+// [a_R - W, b_R + W) of a RECH region R; the first and the last region are always selected (FASTA header span).
+__global__ void k_near_mark(uint32_t nreg, uint32_t N, const uint8_t *__restrict__ lable, const uint32_t *__restrict__ ra,
+                            const uint32_t *__restrict__ rb, uint8_t *__restrict__ near) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreg) return;
+    if (r == 0 || r == nreg - 1) near[r] = 1;
+    if (!(lable[r] & 0x20)) return;  // LABLE_RECH
+    near[r] = 1;
+    const uint32_t lo = ra[r] > kRecheckWindow ? ra[r] - kRecheckWindow : 0;
+    const uint64_t hi = min((uint64_t)rb[r] + kRecheckWindow, (uint64_t)N);
+    for (uint32_t x = r + 1; x < nreg && rb[x] > lo; x++) near[x] = 1;  // towards lower positions
+    for (uint32_t x = r; x-- > 0 && ra[x] < hi;) near[x] = 1;           // towards higher positions
+}
+// window of DP bases around each RECH region, in ascending position (q = nreg - 1 - r)
+__global__ void k_window_sizes(uint32_t nreg, uint32_t N, const uint8_t *__restrict__ lable,
+                               const uint32_t *__restrict__ ra, const uint32_t *__restrict__ rb,
+                               uint32_t *__restrict__ win_lo, uint32_t *__restrict__ win_len) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nreg) return;
+    const uint32_t r = nreg - 1 - q;
+    uint32_t lo = 0, len = 0;
+    if (lable[r] & 0x20) {
+        lo = ra[r] > kRecheckWindow ? ra[r] - kRecheckWindow : 0;
+        len = (uint32_t)min((uint64_t)rb[r] + kRecheckWindow, (uint64_t)N) - lo;
+    }
+    win_lo[q] = lo;
+    win_len[q] = len;
+}
+__global__ void k_sub_meta(const uint32_t *__restrict__ sub, const uint32_t *__restrict__ nsub, uint32_t nreg,
+                           const uint32_t *__restrict__ start, const uint32_t *__restrict__ end,
+                           const uint32_t *__restrict__ ra, const uint32_t *__restrict__ rb,
+                           const uint8_t *__restrict__ lable, const uint32_t *__restrict__ seed_len,
+                           const uint64_t *__restrict__ seed_off, const uint32_t *__restrict__ nsurv,
+                           const uint32_t *__restrict__ ent_off, const uint64_t *__restrict__ q_seedoff, SubMeta o) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nsub) return;
+    const uint32_t r = sub[i];
+    o.start[i] = start[r];
+    o.end[i] = end[r];
+    o.a[i] = ra[r];
+    o.b[i] = rb[r];
+    o.lable[i] = lable[r];
+    o.seed_len[i] = seed_len[r];
+    o.seed_off[i] = seed_off[r];
+    o.nsurv[i] = nsurv[r];
+    o.ent_off[i] = ent_off[r];
+    o.q_seedoff[i] = q_seedoff[nreg - 1 - r];
+}
+__global__ void k_seed_scatter(uint32_t n, const uint32_t *__restrict__ r, const uint64_t *__restrict__ off,
+                               const uint32_t *__restrict__ len, uint64_t *__restrict__ seed_off,
+                               uint32_t *__restrict__ seed_len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    seed_off[r[i]] = off[i];
+    seed_len[r[i]] = len[i];
+}
+void near_mark(uint32_t nreg, uint32_t N, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b, uint8_t *d_near,
+               cudaStream_t s) {
+    if (nreg) NP2_K(k_near_mark)<<<cdiv(nreg, 128), 128, 0, s>>>(nreg, N, d_lable, d_a, d_b, d_near);
+}
+void window_sizes(uint32_t nreg, uint32_t N, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b,
+                  uint32_t *d_win_lo_q, uint32_t *d_win_len_q, cudaStream_t s) {
+    if (nreg) NP2_K(k_window_sizes)<<<cdiv(nreg, 128), 128, 0, s>>>(nreg, N, d_lable, d_a, d_b, d_win_lo_q, d_win_len_q);
+}
+void sub_meta_gather(const uint32_t *d_sub, const uint32_t *d_nsub, uint32_t nreg, const uint32_t *d_start,
+                     const uint32_t *d_end, const uint32_t *d_a, const uint32_t *d_b, const uint8_t *d_lable,
+                     const uint32_t *d_seed_len, const uint64_t *d_seed_off, const uint32_t *d_nsurv,
+                     const uint32_t *d_ent_off, const uint64_t *d_q_seedoff, SubMeta out, cudaStream_t s) {
+    if (nreg)
+        NP2_K(k_sub_meta)<<<cdiv(nreg, 128), 128, 0, s>>>(d_sub, d_nsub, nreg, d_start, d_end, d_a, d_b, d_lable, d_seed_len,
+                                                           d_seed_off, d_nsurv, d_ent_off, d_q_seedoff, out);
+}
+void seed_scatter(uint32_t n, const uint32_t *d_r, const uint64_t *d_off, const uint32_t *d_len, uint64_t *d_seed_off,
+                  uint32_t *d_seed_len, cudaStream_t s) {
+    if (n) NP2_K(k_seed_scatter)<<<cdiv(n, 128), 128, 0, s>>>(n, d_r, d_off, d_len, d_seed_off, d_seed_len);
 }
 
 void assemble_sizes(AssembleDev a, cudaStream_t s) {
