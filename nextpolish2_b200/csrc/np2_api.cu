@@ -188,7 +188,7 @@ struct JobScratch {
     std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
     cudaEvent_t seq_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-    PBuf<uint8_t> p_up_stage, p_seq_args;
+    PBuf<uint8_t> p_up_stage, p_seq_args, p_phase;
     StageTimer timer;
     ~JobScratch() {
         for (auto e : seq_ev)
@@ -1151,8 +1151,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         NP2_CUDA(cudaMemcpyAsync(&n_edges, d_r_edge_off.p + nreg, 8, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaStreamSynchronize(s));
         if (dump) dump_candidates(true);
-        std::vector<uint64_t> ukeys;
-        std::vector<long long> uvals;
+        std::vector<uint32_t> drop;
         if (n_edges) {
             if (n_edges >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^31 read-pair observations");
             DBuf<uint64_t> d_ek, d_ek2, d_uk;
@@ -1186,24 +1185,77 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             uint32_t nu = 0;
             d_nu.download(&nu, 1);
             NP2_CUDA(cudaStreamSynchronize(s));
-            ukeys.resize(nu);
-            uvals.resize(nu);
             if (nu) {
-                d_uk.download(ukeys.data(), nu);
-                d_uv.download(uvals.data(), nu);
+                // level 0 of the phasing graph on the device: per-read flags + CSR adjacency (np2_geno.cu k_phase_*)
+                const uint32_t n_ids = (uint32_t)as_read.size(), n2 = 2 * nu;
+                const bool asref = opt.model == 0, use_all = opt.use_all_reads != 0;
+                DBuf<uint8_t> d_flags;  // has | bad_v | in_ref
+                DBuf<float> d_refw, d_dw, d_dw2;
+                DBuf<uint64_t> d_dk, d_dk2;
+                DBuf<uint32_t> d_aoff, d_ato;
+                d_flags.alloc((size_t)n_ids * 3, s);
+                d_refw.alloc(n_ids, s);
+                d_dk.alloc(n2, s);
+                d_dk2.alloc(n2, s);
+                d_dw.alloc(n2, s);
+                d_dw2.alloc(n2, s);
+                d_aoff.alloc(n_ids + 1, s);
+                d_ato.alloc(n2, s);
+                PhaseDev pd;
+                pd.has = d_flags.p;
+                pd.bad_v = d_flags.p + n_ids;
+                pd.in_ref = d_flags.p + 2 * (size_t)n_ids;
+                pd.ref_w = d_refw.p;
+                h = timer.begin("phase_graph", 5);
+                d_flags.zero();
+                d_refw.zero();
+                d_aoff.zero();
+                phase_ref(d_uk.p, d_uv.p, nu, pd, asref, use_all, s);
+                phase_expand(d_uk.p, d_uv.p, nu, pd, use_all, id_bits, d_dk.p, d_dw.p, s);
+                {
+                    size_t tb = 0;
+                    cub::DeviceRadixSort::SortPairs(nullptr, tb, d_dk.p, d_dk2.p, d_dw.p, d_dw2.p, (int)n2, 0, 2 * id_bits + 1, s);
+                    if (tb > d_tmp.n) d_tmp.alloc(tb, s);
+                    cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_dk.p, d_dk2.p, d_dw.p, d_dw2.p, (int)n2, 0, 2 * id_bits + 1, s);
+                }
+                phase_csr(d_dk2.p, n2, id_bits, n_ids, d_aoff.p, d_ato.p, s);
+                timer.end(h);
+                // one pinned block: aoff | ato | aw | ref_w | flags
+                const size_t o_ato = ((size_t)(n_ids + 1) * 4 + 15) & ~(size_t)15, o_aw = o_ato + (((size_t)n2 * 4 + 15) & ~(size_t)15);
+                const size_t o_rw = o_aw + (((size_t)n2 * 4 + 15) & ~(size_t)15), o_fl = o_rw + (((size_t)n_ids * 4 + 15) & ~(size_t)15);
+                sc->p_phase.resize(o_fl + (size_t)n_ids * 3 + 16);
+                uint8_t *pb = sc->p_phase.p;
+                d_aoff.download(reinterpret_cast<uint32_t *>(pb), n_ids + 1);
+                d_ato.download(reinterpret_cast<uint32_t *>(pb + o_ato), n2);
+                d_dw2.download(reinterpret_cast<float *>(pb + o_aw), n2);
+                d_refw.download(reinterpret_cast<float *>(pb + o_rw), n_ids);
+                d_flags.download(pb + o_fl, (size_t)n_ids * 3);
                 NP2_CUDA(cudaStreamSynchronize(s));
+                d2h += (uint64_t)n2 * 8 + (uint64_t)n_ids * 11;
+                timer.hbegin();
+                drop = phase_reads_csr(n_ids, reinterpret_cast<const uint32_t *>(pb), reinterpret_cast<const uint32_t *>(pb + o_ato),
+                                       reinterpret_cast<const float *>(pb + o_aw), pb + o_fl, pb + o_fl + n_ids,
+                                       pb + o_fl + 2 * (size_t)n_ids, reinterpret_cast<const float *>(pb + o_rw), asref, [&]() {
+                                           // a community has to be declustered: the general path wants the pair records
+                                           std::vector<uint64_t> ukeys(nu);
+                                           std::vector<long long> uvals(nu);
+                                           d_uk.download(ukeys.data(), nu);
+                                           d_uv.download(uvals.data(), nu);
+                                           NP2_CUDA(cudaStreamSynchronize(s));
+                                           d2h += (uint64_t)nu * 16;
+                                           return phase_reads_general(ukeys.data(), uvals.data(), nu, asref, use_all);
+                                       });
+                timer.hend("host:phase_reads");
+                static const char *kPhase[4] = {"host:phase_reads.build", "host:phase_reads.move", "host:phase_reads.aggregate",
+                                                "host:phase_reads.communities"};
+                for (int x = 0; x < 4; x++) timer.ms[timer.id(kPhase[x])] += np2::phase_last_ms()[x];
             }
-            d2h += (uint64_t)nu * 16;
         }
-        timer.hbegin();
-        std::vector<uint32_t> drop = phase_reads(ukeys.data(), uvals.data(), ukeys.size(), opt.model == 0,
-                                                 opt.use_all_reads != 0);
         for (uint32_t a : drop) {
             if (a == 0 || a >= as_read.size()) throw np2::Error(NP2_ERR_INTERNAL, "phasing returned a bad read index");
             h_blank[as_read[a]] = 1;
             dm_dropped.push_back(a);
         }
-        timer.hend("host:phase_reads");
         if (drop.empty()) continue;  // same reads => the next iteration is this one again
         d_blank.upload(h_blank.data(), n_reads);
         NP2_CUDA(cudaStreamSynchronize(s));

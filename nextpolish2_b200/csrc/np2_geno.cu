@@ -608,6 +608,77 @@ __global__ void k_edges_unpack(uint64_t *__restrict__ key, const uint32_t *__res
 void geno_edges_unpack(uint64_t *d_key, const uint32_t *d_n, uint64_t n_max, uint32_t id_bits, cudaStream_t s) {
     if (n_max) NP2_K(k_edges_unpack)<<<cdiv(n_max, 256), 256, 0, s>>>(d_key, d_n, id_bits);
 }
+/* ---------------------------------------------------------------- level 0 of the phasing graph (np2_phase.cpp)
+ * From the reduced pair records (key = a << 32 | b ascending, a = 0 is the ref read) to what the host Louvain starts
+ * from: per-read flags, and the adjacency in CSR form with the `dif <= -3` override applied and the reads that
+ * disagree with the ref read removed (main.rs:972-1010). */
+__global__ void k_phase_ref(const uint64_t *__restrict__ key, const long long *__restrict__ val, uint32_t nu, PhaseDev p,
+                            int asref, int use_all) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nu) return;
+    const uint64_t k = key[e];
+    if (k >> 32) return;
+    const uint32_t b = (uint32_t)k;
+    const long long v = val[e];
+    const long long ndif = (v + (1LL << 31)) >> 32;
+    if (asref) {
+        p.ref_w[b] = (float)(v - (ndif << 32));
+        p.in_ref[b] = 1;
+    }
+    if (ndif > 0 && !use_all) p.bad_v[b] = 1;
+}
+__global__ void k_phase_expand(const uint64_t *__restrict__ key, const long long *__restrict__ val, uint32_t nu, PhaseDev p,
+                               int use_all, uint32_t id_bits, uint64_t *__restrict__ dkey, float *__restrict__ dw) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nu) return;
+    const uint64_t k = key[e];
+    const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
+    uint64_t k0 = ~0ULL, k1 = ~0ULL;  // sentinel: sorts behind every edge
+    float w = 0.f;
+    if (a != 0) {
+        const bool ba = !use_all && p.bad_v[a], bb = !use_all && p.bad_v[b];
+        if (!ba) p.has[a] = 1;
+        if (!bb) p.has[b] = 1;
+        if (!ba && !bb) {
+            const long long v = val[e];
+            const long long ndif = (v + (1LL << 31)) >> 32;
+            w = ndif >= 3 ? -(float)ndif : (float)(v - (ndif << 32));
+            k0 = (uint64_t)a << id_bits | b;
+            k1 = (uint64_t)b << id_bits | a;
+        }
+    }
+    dkey[2 * (size_t)e] = k0;
+    dkey[2 * (size_t)e + 1] = k1;
+    dw[2 * (size_t)e] = w;
+    dw[2 * (size_t)e + 1] = w;
+}
+// sorted directed edges -> CSR: aoff[v] = first edge whose source is >= v (aoff has n + 1 entries, zeroed before)
+__global__ void k_phase_csr(const uint64_t *__restrict__ dkey, uint32_t n2, uint32_t id_bits, uint32_t n,
+                            uint32_t *__restrict__ aoff, uint32_t *__restrict__ ato) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    auto src_of = [&](uint64_t k) { return (k >> (2 * id_bits)) ? n : (uint32_t)(k >> id_bits); };
+    const uint64_t k = dkey[i];
+    const uint32_t s = src_of(k);
+    if (s < n) ato[i] = (uint32_t)(k & ((1ULL << id_bits) - 1));
+    const uint32_t sp = i ? src_of(dkey[i - 1]) : 0;
+    for (uint32_t v = i ? sp + 1 : 0; v <= s && v <= n; v++) aoff[v] = i;
+    if (i == n2 - 1 && s < n)
+        for (uint32_t v = s + 1; v <= n; v++) aoff[v] = n2;
+}
+void phase_ref(const uint64_t *d_key, const long long *d_val, uint32_t nu, PhaseDev p, bool asref, bool use_all,
+               cudaStream_t s) {
+    if (nu) NP2_K(k_phase_ref)<<<cdiv(nu, 256), 256, 0, s>>>(d_key, d_val, nu, p, asref, use_all);
+}
+void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t nu, PhaseDev p, bool use_all, uint32_t id_bits,
+                  uint64_t *d_dkey, float *d_dw, cudaStream_t s) {
+    if (nu) NP2_K(k_phase_expand)<<<cdiv(nu, 256), 256, 0, s>>>(d_key, d_val, nu, p, use_all, id_bits, d_dkey, d_dw);
+}
+void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n, uint32_t *d_aoff, uint32_t *d_ato,
+               cudaStream_t s) {
+    if (n2) NP2_K(k_phase_csr)<<<cdiv(n2, 256), 256, 0, s>>>(d_dkey, n2, id_bits, n, d_aoff, d_ato);
+}
+
 void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s) {
     NP2_K(k_region_seed)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, d_err);
 }

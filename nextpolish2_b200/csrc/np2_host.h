@@ -7,6 +7,7 @@
 #include <emmintrin.h>
 #endif
 
+#include <functional>
 #include <memory>
 #include <string>
 #include <algorithm>
@@ -134,8 +135,15 @@ std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, u
                                   bool use_all_reads);
 std::vector<uint32_t> phase_reads_general(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
                                   bool use_all_reads);
+// the same from a level-0 graph already in CSR form (built on the device); `general` is called when the flat path
+// has to hand over (it must produce the answer from the original edges)
+std::vector<uint32_t> phase_reads_csr(uint32_t n, const uint32_t *aoff, const uint32_t *ato, const float *aw,
+                                      const uint8_t *has, const uint8_t *bad_v, const uint8_t *in_ref, const float *ref_w,
+                                      bool asref, const std::function<std::vector<uint32_t>()> &general);
 // which implementation served the calling thread's last phase_reads: 1 = flat arrays, 2 = general path
 int phase_last_path();
+// host milliseconds of the last flat-array call: adjacency build, vertex moves, aggregation, communities
+const float *phase_last_ms();
 
 /* ---------------------------------------------------------------- consensus patching */
 const uint8_t LABLE_TEMP = 0x01, LABLE_SUCC = 0x80, LABLE_HETE = 0x40, LABLE_RECH = 0x20;  // main.rs:655-658

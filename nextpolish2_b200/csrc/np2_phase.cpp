@@ -12,8 +12,10 @@
 // apart again and its vertices are re-keyed, with quirks): when one shows up the call is served from scratch by the
 // general map/set implementation (phase_reads_general in np2_host.cpp), which reproduces those quirks.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "../../include/np2gpu.h"
@@ -25,16 +27,25 @@ namespace np2 {
 namespace {
 
 thread_local int g_phase_path = 0;
+thread_local float g_phase_ms[4] = {0, 0, 0, 0};  // build, move, aggregate, communities
 
 struct Lvl {
     uint32_t n = 0;                   // every array below is indexed by vertex / community id < n
     std::vector<uint32_t> verts;      // all vertices of the level, ascending (keys of `communities`)
     std::vector<uint32_t> ids;        // those that appear in `data` (louvain.rs:77 iterates these), ascending
-    std::vector<uint32_t> aoff, ato;  // adjacency (CSR), neighbours ascending
-    std::vector<float> aw;
+    // adjacency (CSR), neighbours ascending: views, so that level 0 can sit in the buffer it was downloaded into
+    const uint32_t *aoff = nullptr, *ato = nullptr;
+    const float *aw = nullptr;
+    std::vector<uint32_t> aoff_own, ato_own;
+    std::vector<float> aw_own;
     std::vector<uint32_t> cid;        // vertex -> community
     std::vector<float> nweight;       // Node.weight
     std::vector<uint32_t> moff, mdat; // Node.nodes: original vertices of each vertex (CSR)
+    void bind_own() {
+        aoff = aoff_own.data();
+        ato = ato_own.data();
+        aw = aw_own.data();
+    }
 };
 
 // louvain.rs:72-117.  The outcome of visiting a vertex depends only on its neighbours' communities, so a vertex is
@@ -176,23 +187,24 @@ bool aggregate(const Lvl &lv, Lvl &nx) {
     }
     std::vector<PairSum> ps;
     between_communities(lv, g, ps);
-    nx.aoff.assign(lv.n + 1, 0);
+    nx.aoff_own.assign(lv.n + 1, 0);
     for (auto &p : ps)
         if (p.w != 0.f) {
-            nx.aoff[p.c1 + 1]++;
-            nx.aoff[p.c2 + 1]++;
+            nx.aoff_own[p.c1 + 1]++;
+            nx.aoff_own[p.c2 + 1]++;
         }
-    for (uint32_t c = 0; c < lv.n; c++) nx.aoff[c + 1] += nx.aoff[c];
-    nx.ato.resize(nx.aoff[lv.n]);
-    nx.aw.resize(nx.aoff[lv.n]);
-    std::vector<uint32_t> cur(nx.aoff.begin(), nx.aoff.end() - 1);
+    for (uint32_t c = 0; c < lv.n; c++) nx.aoff_own[c + 1] += nx.aoff_own[c];
+    nx.ato_own.resize(nx.aoff_own[lv.n]);
+    nx.aw_own.resize(nx.aoff_own[lv.n]);
+    std::vector<uint32_t> cur(nx.aoff_own.begin(), nx.aoff_own.end() - 1);
     for (auto &p : ps)  // ascending (c1, c2): every list receives its smaller neighbours first, each part ascending
         if (p.w != 0.f) {
-            nx.ato[cur[p.c1]] = p.c2;
-            nx.aw[cur[p.c1]++] = p.w;
-            nx.ato[cur[p.c2]] = p.c1;
-            nx.aw[cur[p.c2]++] = p.w;
+            nx.ato_own[cur[p.c1]] = p.c2;
+            nx.aw_own[cur[p.c1]++] = p.w;
+            nx.ato_own[cur[p.c2]] = p.c1;
+            nx.aw_own[cur[p.c2]++] = p.w;
         }
+    nx.bind_own();
     for (uint32_t c : nx.verts)
         if (nx.aoff[c + 1] > nx.aoff[c]) nx.ids.push_back(c);  // louvain.rs:183-186
     return true;
@@ -207,82 +219,33 @@ struct Community {
 }  // namespace
 
 int phase_last_path() { return g_phase_path; }
+const float *phase_last_ms() { return g_phase_ms; }
 
-std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
-                                  bool use_all_reads) {
-    g_phase_path = 1;
-    uint32_t max_id = 0;
-    for (uint64_t e = 0; e < n_edges; e++) max_id = std::max(max_id, (uint32_t)keys[e]);  // b > a
-    const uint32_t n = max_id + 1;
-    // ref pairs (main.rs:972-980): keys are sorted, they come first
-    std::vector<float> ref_w(n, 0.f);
-    std::vector<uint8_t> in_ref(n, 0), bad_v(n, 0), has(n, 0);
-    bool have_ref = false;
-    uint64_t e0 = 0;
-    for (; e0 < n_edges && (keys[e0] >> 32) == 0; e0++) {
-        const uint32_t b = (uint32_t)keys[e0];
-        const long long v = vals[e0];
-        const long long ndif = (v + (1LL << 31)) >> 32;
-        if (asref) {
-            ref_w[b] = (float)(v - (ndif << 32));
-            in_ref[b] = 1;
-            have_ref = true;
-        }
-        if (ndif > 0 && !use_all_reads) bad_v[b] = 1;
-    }
-    // level 0: the reads (main.rs:994-1010: `dif <= -3` override, invalid reads leave, their partners stay)
-    Lvl lv;
-    lv.n = n;
-    lv.aoff.assign(n + 1, 0);
-    for (uint64_t e = e0; e < n_edges; e++) {
-        const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
-        if (!use_all_reads && (bad_v[a] || bad_v[b])) {
-            if (!bad_v[a]) has[a] = 1;
-            if (!bad_v[b]) has[b] = 1;
-            continue;
-        }
-        has[a] = has[b] = 1;
-        lv.aoff[a + 1]++;
-        lv.aoff[b + 1]++;
-    }
-    for (uint32_t v = 0; v < n; v++) lv.aoff[v + 1] += lv.aoff[v];
-    lv.ato.resize(lv.aoff[n]);
-    lv.aw.resize(lv.aoff[n]);
-    {
-        std::vector<uint32_t> cur(lv.aoff.begin(), lv.aoff.end() - 1);
-        for (uint64_t e = e0; e < n_edges; e++) {  // sorted keys: every list comes out ascending
-            const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
-            if (!use_all_reads && (bad_v[a] || bad_v[b])) continue;
-            const long long v = vals[e];
-            const long long ndif = (v + (1LL << 31)) >> 32;  // number of disagreeing sites
-            const long long sum = v - (ndif << 32);          // sum of +-1 over shared heterozygous regions
-            const float w = ndif >= 3 ? -(float)ndif : (float)sum;  // main.rs:996-1002
-            lv.ato[cur[a]] = b;
-            lv.aw[cur[a]++] = w;
-            lv.ato[cur[b]] = a;
-            lv.aw[cur[b]++] = w;
-        }
-    }
-    lv.cid.resize(n);
-    lv.nweight.assign(n, 0.f);
-    lv.moff.assign(n + 1, 0);
-    for (uint32_t v = 0; v < n; v++) {
-        lv.cid[v] = v;
-        lv.moff[v + 1] = lv.moff[v] + (has[v] ? 1 : 0);
-        if (has[v]) {
-            lv.verts.push_back(v);
-            lv.mdat.push_back(v);
-        }
-    }
-    lv.ids = lv.verts;
+namespace {
+// Louvain + phase_communities on a prepared level 0.  `general` serves the call from scratch when a community has to
+// be declustered.
+std::vector<uint32_t> phase_core(Lvl &lv, uint32_t n, const uint8_t *bad_v, const uint8_t *in_ref, const float *ref_w,
+                                 bool have_ref, const std::function<std::vector<uint32_t>()> &general,
+                                 std::chrono::steady_clock::time_point T0) {
+    auto lap = [&](int slot) {
+        auto t = std::chrono::steady_clock::now();
+        g_phase_ms[slot] += std::chrono::duration<float, std::milli>(t - T0).count();
+        T0 = t;
+    };
+    lap(0);
     // ---- Louvain (louvain.rs:59-257)
-    while (move_vertices(lv)) {
+    for (;;) {
+        const bool moved = move_vertices(lv);
+        lap(1);
+        if (!moved) break;
         Lvl nx;
         if (!aggregate(lv, nx)) {
             g_phase_path = 2;
-            return phase_reads_general(keys, vals, n_edges, asref, use_all_reads);
+            return general();
         }
         lv = std::move(nx);
+        if (lv.aoff == nullptr || lv.aoff_own.data() != lv.aoff) lv.bind_own();  // views follow the moved vectors
+        lap(2);
     }
     // get_communities (louvain.rs:197-245)
     Groups g;
@@ -349,7 +312,106 @@ std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, u
     }
     std::sort(out.begin(), out.end());
     out.erase(std::unique(out.begin(), out.end()), out.end());
+    lap(3);
     return out;
+}
+// level-0 vertices: every read that still has a pair (its members are itself)
+void level0_vertices(Lvl &lv, uint32_t n, const uint8_t *has) {
+    lv.n = n;
+    lv.cid.resize(n);
+    lv.nweight.assign(n, 0.f);
+    lv.moff.assign(n + 1, 0);
+    for (uint32_t v = 0; v < n; v++) {
+        lv.cid[v] = v;
+        lv.moff[v + 1] = lv.moff[v] + (has[v] ? 1 : 0);
+        if (has[v]) {
+            lv.verts.push_back(v);
+            lv.mdat.push_back(v);
+        }
+    }
+    lv.ids = lv.verts;
+}
+}  // namespace
+
+// Level 0 as built on the device (np2_geno.cu k_phase_*): adjacency in CSR form with the `dif <= -3` override applied,
+// invalid reads already removed, per-read flags.  The arrays are used in place.
+std::vector<uint32_t> phase_reads_csr(uint32_t n, const uint32_t *aoff, const uint32_t *ato, const float *aw,
+                                      const uint8_t *has, const uint8_t *bad_v, const uint8_t *in_ref, const float *ref_w,
+                                      bool asref, const std::function<std::vector<uint32_t>()> &general) {
+    g_phase_path = 1;
+    for (float &x : g_phase_ms) x = 0.f;
+    auto T0 = std::chrono::steady_clock::now();
+    bool have_ref = false;
+    if (asref)
+        for (uint32_t v = 0; v < n && !have_ref; v++) have_ref = in_ref[v] != 0;
+    Lvl lv;
+    lv.aoff = aoff;
+    lv.ato = ato;
+    lv.aw = aw;
+    level0_vertices(lv, n, has);
+    return phase_core(lv, n, bad_v, in_ref, ref_w, have_ref, general, T0);
+}
+
+std::vector<uint32_t> phase_reads(const uint64_t *keys, const long long *vals, uint64_t n_edges, bool asref,
+                                  bool use_all_reads) {
+    g_phase_path = 1;
+    for (float &x : g_phase_ms) x = 0.f;
+    auto T0 = std::chrono::steady_clock::now();
+    uint32_t max_id = 0;
+    for (uint64_t e = 0; e < n_edges; e++) max_id = std::max(max_id, (uint32_t)keys[e]);  // b > a
+    const uint32_t n = max_id + 1;
+    // ref pairs (main.rs:972-980): keys are sorted, they come first
+    std::vector<float> ref_w(n, 0.f);
+    std::vector<uint8_t> in_ref(n, 0), bad_v(n, 0), has(n, 0);
+    bool have_ref = false;
+    uint64_t e0 = 0;
+    for (; e0 < n_edges && (keys[e0] >> 32) == 0; e0++) {
+        const uint32_t b = (uint32_t)keys[e0];
+        const long long v = vals[e0];
+        const long long ndif = (v + (1LL << 31)) >> 32;
+        if (asref) {
+            ref_w[b] = (float)(v - (ndif << 32));
+            in_ref[b] = 1;
+            have_ref = true;
+        }
+        if (ndif > 0 && !use_all_reads) bad_v[b] = 1;
+    }
+    // level 0: the reads (main.rs:994-1010: `dif <= -3` override, invalid reads leave, their partners stay)
+    Lvl lv;
+    lv.aoff_own.assign(n + 1, 0);
+    for (uint64_t e = e0; e < n_edges; e++) {
+        const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+        if (!use_all_reads && (bad_v[a] || bad_v[b])) {
+            if (!bad_v[a]) has[a] = 1;
+            if (!bad_v[b]) has[b] = 1;
+            continue;
+        }
+        has[a] = has[b] = 1;
+        lv.aoff_own[a + 1]++;
+        lv.aoff_own[b + 1]++;
+    }
+    for (uint32_t v = 0; v < n; v++) lv.aoff_own[v + 1] += lv.aoff_own[v];
+    lv.ato_own.resize(lv.aoff_own[n]);
+    lv.aw_own.resize(lv.aoff_own[n]);
+    {
+        std::vector<uint32_t> cur(lv.aoff_own.begin(), lv.aoff_own.end() - 1);
+        for (uint64_t e = e0; e < n_edges; e++) {  // sorted keys: every list comes out ascending
+            const uint32_t a = (uint32_t)(keys[e] >> 32), b = (uint32_t)keys[e];
+            if (!use_all_reads && (bad_v[a] || bad_v[b])) continue;
+            const long long v = vals[e];
+            const long long ndif = (v + (1LL << 31)) >> 32;  // number of disagreeing sites
+            const long long sum = v - (ndif << 32);          // sum of +-1 over shared heterozygous regions
+            const float w = ndif >= 3 ? -(float)ndif : (float)sum;  // main.rs:996-1002
+            lv.ato_own[cur[a]] = b;
+            lv.aw_own[cur[a]++] = w;
+            lv.ato_own[cur[b]] = a;
+            lv.aw_own[cur[b]++] = w;
+        }
+    }
+    lv.bind_own();
+    level0_vertices(lv, n, has.data());
+    return phase_core(lv, n, bad_v.data(), in_ref.data(), ref_w.data(), have_ref,
+                      [&]() { return phase_reads_general(keys, vals, n_edges, asref, use_all_reads); }, T0);
 }
 
 }  // namespace np2
