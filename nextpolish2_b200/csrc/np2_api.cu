@@ -299,6 +299,8 @@ struct np2_job {
     std::vector<uint32_t> h_ts, h_te, h_n;
     std::vector<uint8_t> h_blank;          // per candidate read
     std::vector<int32_t> as_read;          // alignseq index -> candidate read (-1 = ref)
+    std::vector<uint64_t> pair_off;        // pair-accumulator slot ranges per alignseq (np2_geno.cu k_edges_accum)
+    DBuf<uint64_t> d_pair_off;
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
     // result: bases always; positions are materialised on request (np2_job_get_consensus with pos != NULL)
@@ -589,6 +591,19 @@ void np2_job::ingest_finish() {
         as_te.push_back(h_te[i]);
         as_lab.push_back(ing.is_clip[i]);
         h_blank[i] = 0;
+    }
+    // index windows for the pair accumulator: alignseqs are in position order, so a later read y can only share a
+    // region with x when it starts before x ends; the ref read (order 0) pairs with everyone
+    {
+        const size_t na = as_read.size();
+        std::vector<uint32_t> as_pos(na, 0);
+        for (size_t a = 1; a < na; a++) as_pos[a] = ing.pos[as_read[a]];
+        pair_off.assign(na + 1, 0);
+        pair_off[1] = na ? na - 1 : 0;
+        for (size_t a = 1; a < na; a++) {
+            const size_t ub = std::upper_bound(as_pos.begin() + a + 1, as_pos.end(), as_te[a]) - as_pos.begin();
+            pair_off[a + 1] = pair_off[a] + (ub - (a + 1));
+        }
     }
     // merged [t_s + 50, t_e - 50] of unlabelled reads; labelled reads inside a range are blanked
     std::vector<std::pair<uint32_t, uint32_t>> ranges;
@@ -1153,38 +1168,44 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         if (dump) dump_candidates(true);
         std::vector<uint32_t> drop;
         if (n_edges) {
-            if (n_edges >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^31 read-pair observations");
-            DBuf<uint64_t> d_ek, d_ek2, d_uk;
-            DBuf<long long> d_ev, d_ev2, d_uv;
-            DBuf<uint32_t> d_nu;
-            d_ek.alloc(n_edges, s);
-            d_ek2.alloc(n_edges, s);
-            d_uk.alloc(n_edges, s);
-            d_ev.alloc(n_edges, s);
-            d_ev2.alloc(n_edges, s);
-            d_uv.alloc(n_edges, s);
-            d_nu.alloc(1, s);
+            // dense pair accumulator (np2_geno.cu k_edges_accum): one slot per (x, y) inside x's index window
+            const uint32_t n_ids0 = (uint32_t)as_read.size();
+            const uint64_t n_slots = pair_off.back();
+            if (n_slots >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^31 overlapping read pairs");
             uint32_t id_bits = 1;  // read orders are < as_read.size()
             while ((1ull << id_bits) < as_read.size()) id_bits++;
-            h = timer.begin("pair_edges", 7);
-            geno_edges_emit(g, d_ek.p, d_ev.p, id_bits, s);
+            DBuf<unsigned long long> d_acc;
+            DBuf<uint32_t> d_sel, d_nu;
+            DBuf<uint64_t> d_uk;
+            DBuf<long long> d_uv;
+            DBuf<int> d_perr;
+            d_acc.alloc(std::max<uint64_t>(n_slots, 1), s);
+            d_sel.alloc(std::max<uint64_t>(n_slots, 1), s);
+            d_nu.alloc(1, s);
+            d_perr.alloc(1, s);
+            h = timer.begin("pair_edges", 2);
+            d_acc.zero();
+            d_perr.zero();
+            d_nu.zero();
+            geno_edges_accum(g, d_pair_off.p, d_acc.p, d_perr.p, s);
             {
                 size_t tb = 0;
-                cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 2 * id_bits, s);
+                geno_edges_select(d_acc.p, (uint32_t)n_slots, d_sel.p, d_nu.p, nullptr, tb, s);
                 if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-                cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_ek.p, d_ek2.p, d_ev.p, d_ev2.p, (int)n_edges, 0, 2 * id_bits, s);
-                tb = 0;
-                cub::DeviceReduce::ReduceByKey(nullptr, tb, d_ek2.p, d_uk.p, d_ev2.p, d_uv.p, d_nu.p, cub::Sum(),
-                                               (int)n_edges, s);
-                if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-                cub::DeviceReduce::ReduceByKey(d_tmp.p, tb, d_ek2.p, d_uk.p, d_ev2.p, d_uv.p, d_nu.p, cub::Sum(),
-                                               (int)n_edges, s);
-                geno_edges_unpack(d_uk.p, d_nu.p, n_edges, id_bits, s);
+                geno_edges_select(d_acc.p, (uint32_t)n_slots, d_sel.p, d_nu.p, d_tmp.p, tb, s);
             }
             timer.end(h);
             uint32_t nu = 0;
+            int perr = 0;
             d_nu.download(&nu, 1);
+            d_perr.download(&perr, 1);
             NP2_CUDA(cudaStreamSynchronize(s));
+            if (perr) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
+            d_uk.alloc(std::max(nu, 1u), s);
+            d_uv.alloc(std::max(nu, 1u), s);
+            h = timer.begin("pair_edges", 1);
+            geno_edges_finish(d_sel.p, nu, d_pair_off.p, n_ids0, d_acc.p, d_uk.p, d_uv.p, s);
+            timer.end(h);
             if (nu) {
                 // level 0 of the phasing graph on the device: per-read flags + CSR adjacency (np2_geno.cu k_phase_*)
                 const uint32_t n_ids = (uint32_t)as_read.size(), n2 = 2 * nu;
@@ -1841,6 +1862,8 @@ void np2_job::run(int32_t dump_it) {
     d_blank.upload(h_blank.data(), std::max(n, 1u));
     d_order.alloc(std::max(n, 1u), s);
     if (n) d_order.upload(read_order.data(), n);
+    d_pair_off.alloc(pair_off.size(), s);
+    d_pair_off.upload(pair_off.data(), pair_off.size());
     max_span = 0;
     for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
 

@@ -8,6 +8,9 @@
 //   k_region_hete      fill_order_stat + mark_hete_lqseqs (main.rs:813-849, 916-946) + edge counts
 //   k_edges_emit       the pair loop of phase_reads_by_lqseqs (main.rs:953-992)
 //   k_region_seed      fill_order_stat + fill_seed_lqseqs + retain_sort_seqs (main.rs:862-914, 714-726)
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
 #include "np2_kernels.cuh"
 
 namespace np2 {
@@ -463,17 +466,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_hete(GenoDev g) {
     for (uint32_t c = lane; c < n; c += 32) g.c_rep[r * kMaxCand + c] = sm.rep[c];
 }
 
-// all pairs (i < j) of supported candidates of a heterozygous region: key = (min order, max order), value +1 when
-// the strings agree, -1 (and one "differs" count in the high half) when they do not (main.rs:953-992)
-// The key is packed as x << id_bits | y so that the radix sort only has to look at 2 * id_bits bits.
-__global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_emit(GenoDev g, uint64_t *__restrict__ ekey,
-                                                                  long long *__restrict__ eval, uint32_t id_bits) {
+// all pairs (i < j) of supported candidates of a heterozygous region (main.rs:953-992): +1 when the strings agree,
+// 2^32 - 1 (a "differs" count in the high half, -1 in the low half) when they do not.
+// Reads are ordered by position, so the partners y > x of read x lie in the index window (x, x + W_x] (W_x = reads that
+// start before x ends, computed once on the host): the pair (x, y) owns slot pair_off[x] + (y - x - 1) of a dense
+// accumulator.  No pair list, no sort: every observation is one 64-bit atomic add, and the non-zero slots read in slot
+// order are the reduced pair records in (x, y) order.
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_accum(GenoDev g, const uint64_t *__restrict__ pair_off,
+                                                                   unsigned long long *__restrict__ acc, int *err) {
     __shared__ uint8_t s_valid[kWarpsPerCta][kMaxCand];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= g.nreg) return;
-    const uint32_t ne = g.r_nedge[r];
-    if (!ne) return;
+    if (!g.r_nedge[r]) return;
     uint8_t *valid = s_valid[threadIdx.x >> 5];
     const uint32_t n = g.r_ncand[r], base = r * kMaxCand;
     uint32_t m = 0;
@@ -483,10 +488,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_emit(GenoDev g, uin
     }
     m = __shfl_sync(0xFFFFFFFFu, m, 0);
     __syncwarp();
-    const uint64_t w0 = g.r_edge_off[r];
     for (uint32_t a = 0; a + 1 < m; a++) {
-        // edges of row a start after rows 0..a-1: sum_{x<a} (m-1-x)
-        const uint32_t row0 = a * (m - 1) - a * (a - 1) / 2;
         const uint32_t pa = valid[a];
         const uint32_t oa = g.c_order[base + pa], ra = g.c_rep[base + pa];
         for (uint32_t b = a + 1 + lane; b < m; b += 32) {
@@ -494,10 +496,34 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_emit(GenoDev g, uin
             const uint32_t ob = g.c_order[base + pb];
             const bool same = g.c_rep[base + pb] == ra;
             const uint32_t x = min(oa, ob), y = max(oa, ob);
-            ekey[w0 + row0 + (b - a - 1)] = (uint64_t)x << id_bits | y;
-            eval[w0 + row0 + (b - a - 1)] = same ? 1LL : (-1LL + (1LL << 32));
+            const uint64_t slot = pair_off[x] + (y - x - 1);
+            if (slot >= pair_off[x + 1]) {
+                atomicExch(err, 4);
+                continue;
+            }
+            atomicAdd(acc + slot, same ? 1ULL : 0xFFFFFFFFULL);
         }
     }
+}
+struct SlotNonZero {
+    const unsigned long long *acc;
+    __device__ __forceinline__ bool operator()(const uint32_t &i) const { return acc[i] != 0; }
+};
+// selected slots -> pair records (key = x << 32 | y, value) in (x, y) order
+__global__ void k_edges_finish(const uint32_t *__restrict__ sel, uint32_t nu, const uint64_t *__restrict__ pair_off,
+                               uint32_t n_ids, const unsigned long long *__restrict__ acc, uint64_t *__restrict__ key,
+                               long long *__restrict__ val) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    const uint32_t slot = sel[i];
+    uint32_t lo = 0, hi = n_ids;  // largest x with pair_off[x] <= slot
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pair_off[mid] <= slot) lo = mid;
+        else hi = mid;
+    }
+    key[i] = (uint64_t)lo << 32 | (lo + 1 + (uint32_t)(slot - pair_off[lo]));
+    val[i] = (long long)acc[slot];
 }
 
 // fill_seed_lqseqs (main.rs:862-914) with retain_sort_seqs (714-726)
@@ -595,18 +621,18 @@ void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStre
 void geno_region_hete(GenoDev g, cudaStream_t s) {
     NP2_K(k_region_hete)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g);
 }
-void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, uint32_t id_bits, cudaStream_t s) {
-    NP2_K(k_edges_emit)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_key, d_val, id_bits);
+void geno_edges_accum(GenoDev g, const uint64_t *d_pair_off, unsigned long long *d_acc, int *d_err, cudaStream_t s) {
+    NP2_K(k_edges_accum)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_pair_off, d_acc, d_err);
 }
-// packed keys of the reduced edges back to (min order << 32 | max order), the form phase_reads takes
-__global__ void k_edges_unpack(uint64_t *__restrict__ key, const uint32_t *__restrict__ n, uint32_t id_bits) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n) return;
-    const uint64_t k = key[i];
-    key[i] = (k >> id_bits) << 32 | (k & ((1ULL << id_bits) - 1));
+// non-zero slots in slot order; *d_nu = how many
+void geno_edges_select(const unsigned long long *d_acc, uint32_t n_slots, uint32_t *d_sel, uint32_t *d_nu, void *d_tmp,
+                       size_t &tmp_bytes, cudaStream_t s) {
+    cub::CountingInputIterator<uint32_t> it(0);
+    cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_sel, d_nu, (int)n_slots, SlotNonZero{d_acc}, s);
 }
-void geno_edges_unpack(uint64_t *d_key, const uint32_t *d_n, uint64_t n_max, uint32_t id_bits, cudaStream_t s) {
-    if (n_max) NP2_K(k_edges_unpack)<<<cdiv(n_max, 256), 256, 0, s>>>(d_key, d_n, id_bits);
+void geno_edges_finish(const uint32_t *d_sel, uint32_t nu, const uint64_t *d_pair_off, uint32_t n_ids,
+                       const unsigned long long *d_acc, uint64_t *d_key, long long *d_val, cudaStream_t s) {
+    if (nu) NP2_K(k_edges_finish)<<<cdiv(nu, 256), 256, 0, s>>>(d_sel, nu, d_pair_off, n_ids, d_acc, d_key, d_val);
 }
 /* ---------------------------------------------------------------- level 0 of the phasing graph (np2_phase.cpp)
  * From the reduced pair records (key = a << 32 | b ascending, a = 0 is the ref read) to what the host Louvain starts

@@ -129,7 +129,11 @@ void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, co
 void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s);
 void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s);
 void geno_region_hete(GenoDev g, cudaStream_t s);
-void geno_edges_emit(GenoDev g, uint64_t *d_key, long long *d_val, uint32_t id_bits, cudaStream_t s);
+void geno_edges_accum(GenoDev g, const uint64_t *d_pair_off, unsigned long long *d_acc, int *d_err, cudaStream_t s);
+void geno_edges_select(const unsigned long long *d_acc, uint32_t n_slots, uint32_t *d_sel, uint32_t *d_nu, void *d_tmp,
+                       size_t &tmp_bytes, cudaStream_t s);
+void geno_edges_finish(const uint32_t *d_sel, uint32_t nu, const uint64_t *d_pair_off, uint32_t n_ids,
+                       const unsigned long long *d_acc, uint64_t *d_key, long long *d_val, cudaStream_t s);
 struct PhaseDev {  // per read order (< n)
     uint8_t *has = nullptr, *bad_v = nullptr, *in_ref = nullptr;
     float *ref_w = nullptr;
@@ -140,7 +144,6 @@ void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t nu, Ph
                   uint64_t *d_dkey, float *d_dw, cudaStream_t s);
 void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n, uint32_t *d_aoff, uint32_t *d_ato,
                cudaStream_t s);
-void geno_edges_unpack(uint64_t *d_key, const uint32_t *d_n, uint64_t n_max, uint32_t id_bits, cudaStream_t s);
 void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s);
 
 /* ------------------------------------------------------------------ regions + assembly (np2_regions.cu) */
