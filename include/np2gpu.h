@@ -103,6 +103,21 @@ int np2_yak_lookup_device(np2_ctx *ctx, const np2_table *t, const uint64_t *d_ha
 int np2_seq_kscore(np2_ctx *ctx, const np2_table *t, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n,
                    uint32_t min_count, uint16_t *kscore);
 
+/* ---- yak count on the device: the producer of the tables (yak/count.c:28-165, htab.c:51-78, main.c:24-83) ----
+ * np2_count_add takes reads as concatenated bases + n_seqs + 1 offsets (host memory), any number of times.  The counter
+ * then holds, for every canonical k-mer hash (yak_hash64 for k < 32, yak_hash_long for 32 <= k < 64), its number of
+ * occurrences clamped at 1023 — what `yak count` leaves in its hash tables.  np2_count_finish keeps the hashes with
+ * count >= min_count (1 = plain `yak count`; 2 = `yak count -b N in.fq in.fq`, whose second pass + yak_ch_shrink(2)
+ * drop the singletons the Bloom filter let through), optionally writes them in yak's dump format (readable by the
+ * reference and by yak itself; the order of keys inside a sub-table is not yak's hash-table order) and / or stages
+ * them as a table.  Either of dump_path / out_table may be NULL. */
+typedef struct np2_counter np2_counter;
+int np2_count_create(np2_ctx *ctx, uint32_t k, np2_counter **out);
+int np2_count_add(np2_counter *c, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n_seqs);
+uint64_t np2_count_distinct(const np2_counter *c, uint64_t *n_kmers); /* distinct hashes so far; *n_kmers = k-mers seen */
+int np2_count_finish(np2_counter *c, uint32_t min_count, const char *dump_path, np2_table **out_table);
+void np2_count_destroy(np2_counter *c);
+
 /* measurement aid (bench.py): mean time of n_loads independent uniformly random 32-byte sector reads over a
  * scratch buffer of buf_bytes — the measured random-read peak K5 is compared with. */
 int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms);

@@ -48,6 +48,7 @@ EXPORTS = [
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
     "np2_debug_phase", "np2_set_host_threads",
+    "np2_count_create", "np2_count_add", "np2_count_distinct", "np2_count_finish", "np2_count_destroy",
 ]
 
 
@@ -101,6 +102,12 @@ def load_library():
     L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
     L.np2_format_fasta.restype = u64
     L.np2_format_fasta.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int, vp, u64]
+    L.np2_count_create.argtypes = [vp, u32, C.POINTER(vp)]
+    L.np2_count_add.argtypes = [vp, vp, vp, u64]
+    L.np2_count_distinct.restype = u64
+    L.np2_count_distinct.argtypes = [vp, C.POINTER(u64)]
+    L.np2_count_finish.argtypes = [vp, u32, C.c_char_p, C.POINTER(vp)]
+    L.np2_count_destroy.argtypes = [vp]
     L.np2_set_host_threads.argtypes = [u32]
     L.np2_set_host_threads.restype = None
     L.np2_debug_phase.argtypes = [vp, vp, u64, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u32)]
@@ -385,6 +392,47 @@ def polish_contig(ctx, contig, bam, tables, opts=None):
         return j.consensus()
     finally:
         j.destroy()
+
+
+class Counter:
+    """`yak count` on the device (np2_count_*): add reads, then dump a .yak file and / or stage a Table."""
+
+    def __init__(self, ctx, k):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _check(load_library().np2_count_create(ctx.h, k, C.byref(self.h)))
+
+    def add(self, seqs):
+        """seqs: list of bytes / uint8 arrays"""
+        arrs = [np.frombuffer(x, np.uint8) if isinstance(x, (bytes, bytearray)) else np.ascontiguousarray(x, np.uint8) for x in seqs]
+        off = np.zeros(len(arrs) + 1, np.uint64)
+        off[1:] = np.cumsum([len(a) for a in arrs])
+        cat = np.concatenate(arrs) if arrs else np.empty(0, np.uint8)
+        _check(load_library().np2_count_add(self.h, cat.ctypes.data, off.ctypes.data, len(arrs)))
+        return self
+
+    @property
+    def distinct(self):
+        n = C.c_uint64()
+        d = load_library().np2_count_distinct(self.h, C.byref(n))
+        return d, n.value
+
+    def finish(self, min_count=1, dump_path=None, table=False):
+        t = C.c_void_p()
+        _check(load_library().np2_count_finish(self.h, min_count, dump_path.encode() if dump_path else None,
+                                               C.byref(t) if table else None))
+        return Table(self.ctx, t) if table else None
+
+    def close(self):
+        if self.h:
+            load_library().np2_count_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def set_host_threads(n):

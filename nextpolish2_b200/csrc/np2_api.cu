@@ -2051,6 +2051,122 @@ int np2_yak_from_arrays(np2_ctx *ctx, uint32_t k, const uint64_t *hashes, const 
     });
 }
 
+/* ---- yak count on the device (np2_count.cu) */
+struct np2_counter {
+    np2_ctx *ctx = nullptr;
+    uint32_t k = 0;
+    np2::KmerCounts acc;
+    uint64_t n_kmers = 0;
+};
+int np2_count_create(np2_ctx *ctx, uint32_t k, np2_counter **out) {
+    return guard([&] {
+        if (!ctx || !out) throw np2::Error(NP2_ERR_ARG, "null argument");
+        if (k == 0 || k > 63) throw np2::Error(NP2_ERR_ARG, "-k must be smaller than 64");  // yak/main.c:57-60
+        np2_counter *c = new np2_counter();
+        c->ctx = ctx;
+        c->k = k;
+        ctx->refs++;
+        *out = c;
+    });
+}
+void np2_count_destroy(np2_counter *c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    np2::count_free(c->acc, c->ctx->stream);
+    cudaStreamSynchronize(c->ctx->stream);
+    np2_ctx *ctx = c->ctx;
+    delete c;
+    ctx_release(ctx);
+}
+int np2_count_add(np2_counter *c, const uint8_t *seqs, const uint64_t *seq_off, uint64_t n_seqs) {
+    return guard([&] {
+        if (!c || (!seqs && n_seqs) || !seq_off) throw np2::Error(NP2_ERR_ARG, "null argument");
+        NP2_CUDA(cudaSetDevice(c->ctx->device));
+        cudaStream_t s = c->ctx->stream;
+        // batches of <= 1 Gbase: reads joined by 'N' (any non-ACGT byte restarts yak's k-mer window, count.c:41)
+        const uint64_t kBatch = 1ull << 30;
+        PBuf<uint8_t> stage;
+        DBuf<uint8_t> d_seq;
+        uint64_t i = 0;
+        while (i < n_seqs) {
+            uint64_t j = i, bytes = 0;
+            while (j < n_seqs && (j == i || bytes + (seq_off[j + 1] - seq_off[j]) + 1 <= kBatch)) {
+                bytes += seq_off[j + 1] - seq_off[j] + 1;
+                j++;
+            }
+            if (bytes >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "a single sequence of 2^31 bases or more");
+            stage.resize(bytes);
+            uint64_t w = 0;
+            for (uint64_t r = i; r < j; r++) {
+                const uint64_t l = seq_off[r + 1] - seq_off[r];
+                memcpy(stage.p + w, seqs + seq_off[r], l);
+                stage.p[w + l] = 'N';
+                w += l + 1;
+            }
+            d_seq.alloc(bytes, s);
+            d_seq.upload(stage.p, bytes);
+            np2::count_add(c->acc, d_seq.p, bytes, c->k, &c->n_kmers, s);
+            i = j;
+        }
+    });
+}
+uint64_t np2_count_distinct(const np2_counter *c, uint64_t *n_kmers) {
+    if (n_kmers) *n_kmers = c->n_kmers;
+    return c->acc.n;
+}
+int np2_count_finish(np2_counter *c, uint32_t min_count, const char *dump_path, np2_table **out_table) {
+    return guard([&] {
+        if (!c) throw np2::Error(NP2_ERR_ARG, "null argument");
+        NP2_CUDA(cudaSetDevice(c->ctx->device));
+        cudaStream_t s = c->ctx->stream;
+        uint64_t *d_keys = nullptr, n = 0;
+        uint16_t *d_cnt = nullptr;
+        uint32_t sub[1024];
+        np2::count_filter(c->acc, std::max(min_count, 1u), &d_keys, &d_cnt, &n, sub, s);
+        struct Free {
+            uint64_t *k;
+            uint16_t *c;
+            cudaStream_t s;
+            ~Free() {
+                cudaFreeAsync(k, s);
+                cudaFreeAsync(c, s);
+            }
+        } fr{d_keys, d_cnt, s};
+        if (dump_path) {  // yak_ch_dump (yak/htab.c:190-211)
+            std::vector<uint64_t> fk(n);
+            np2::count_file_keys(d_keys, d_cnt, n, fk.data(), s);
+            FILE *fp = fopen(dump_path, "wb");
+            if (!fp) throw np2::Error(NP2_ERR_IO, std::string("cannot write ") + dump_path);
+            std::unique_ptr<FILE, int (*)(FILE *)> fc(fp, fclose);
+            const uint32_t hdr[3] = {c->k, 10, 10};
+            bool ok = fwrite("YAK\2", 1, 4, fp) == 4 && fwrite(hdr, 4, 3, fp) == 3;
+            uint64_t o = 0;
+            for (int b = 0; b < 1024 && ok; b++) {
+                uint32_t cap = 4;  // khashl keeps its load below 0.75
+                while ((uint64_t)cap * 3 / 4 < sub[b]) cap <<= 1;
+                const uint32_t t[2] = {cap, sub[b]};
+                ok = fwrite(t, 4, 2, fp) == 2 && fwrite(fk.data() + o, 8, sub[b], fp) == sub[b];
+                o += sub[b];
+            }
+            if (!ok) throw np2::Error(NP2_ERR_IO, std::string("short write to ") + dump_path);
+        }
+        if (out_table) {
+            std::unique_ptr<np2_table> t(new np2_table());
+            table_alloc(c->ctx, t.get(), c->k, n, *std::max_element(sub, sub + 1024));
+            DBuf<int> d_err;
+            d_err.alloc(1, s);
+            d_err.zero();
+            table_insert(t->dev, d_keys, d_cnt, n, d_err.p, s);
+            int err = 0;
+            d_err.download(&err, 1);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            if (err) throw np2::Error(NP2_ERR_INTERNAL, "table insertion overflow");
+            *out_table = t.release();
+        }
+        NP2_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 void np2_yak_free(np2_table *t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);

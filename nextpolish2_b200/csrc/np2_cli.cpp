@@ -2,12 +2,14 @@
 //
 // Same surface as the reference CLI (src/utils/option.rs:45-225): positional <sorted.bam> <genome.fa[.gz]>
 // <k1.yak> [k2.yak ...], options -o -u --out_pos -k -t -i -m -l -L -n -s -S -a -q -c -r --min_base_cov, same
-// defaults (option.rs:267-292).  Extensions: -g/--gpus N (GPUs to use, default all visible).
+// defaults (option.rs:267-292).  Extensions: -g/--gpus N (GPUs to use, default all visible); the sub-command
+// `nextPolish2 count` (yak count on the GPU: FASTA/FASTQ[.gz] in, .yak dump out; yak/main.c:24-83).
 //
 // This file is the caller side of the hot path: hand-written BGZF/BAM/BAI and FASTA(.gz) readers
 // (zlib only) that hand each contig's raw alignment records to np2_polish_contig, and the orchestration
-// the reference does with three thread stages (main.rs:1698-1853): contigs are LPT-partitioned over the GPUs, one host
-// thread per GPU, records are printed in INPUT order (= the reference with -t 1).
+// the reference does with three thread stages (main.rs:1698-1853): contigs are LPT-partitioned over the GPUs, up to
+// three host threads (contexts) per GPU share one set of tables, records are printed in INPUT order (= the reference
+// with -t 1).
 #include <zlib.h>
 
 #include <algorithm>
@@ -72,6 +74,112 @@ std::vector<Contig> read_fasta(const std::string &path) {
     if (in_header) end_header();
     gzclose(f);
     return out;
+}
+
+/* ---------------------------------------------------------------- `count`: yak count on the GPU (yak/main.c:24-83) */
+// FASTA / FASTQ (optionally gzipped) streamed in batches of bases: cb(bases, offsets) per batch
+template <class F>
+void stream_sequences(const std::string &path, size_t batch_bases, F cb) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) die("\"" + path + "\" does not exist!");
+    gzbuffer(f, 1 << 20);
+    std::vector<uint8_t> seq;
+    std::vector<uint64_t> off(1, 0);
+    std::string line;
+    auto getline = [&]() -> bool {  // without the line terminator
+        line.clear();
+        for (;;) {
+            char tmp[1 << 16];
+            if (!gzgets(f, tmp, sizeof tmp)) return !line.empty();
+            size_t l = strlen(tmp);
+            const bool eol = l && tmp[l - 1] == '\n';
+            while (l && (tmp[l - 1] == '\n' || tmp[l - 1] == '\r')) l--;
+            line.append(tmp, l);
+            if (eol) return true;
+        }
+    };
+    auto flush = [&](bool force) {
+        if (off.size() > 1 && (force || seq.size() >= batch_bases)) {
+            cb(seq, off);
+            seq.clear();
+            off.assign(1, 0);
+        }
+    };
+    bool have = getline();
+    while (have) {
+        if (line.empty()) {
+            have = getline();
+            continue;
+        }
+        if (line[0] == '>') {  // FASTA: sequence lines until the next header
+            while ((have = getline()) && (line.empty() || (line[0] != '>' && line[0] != '@')))
+                seq.insert(seq.end(), line.begin(), line.end());
+            off.push_back(seq.size());
+        } else if (line[0] == '@') {  // FASTQ: sequence lines until '+', then as many quality characters
+            size_t n = 0;
+            while ((have = getline()) && !(line.size() && line[0] == '+')) {
+                seq.insert(seq.end(), line.begin(), line.end());
+                n += line.size();
+            }
+            off.push_back(seq.size());
+            size_t q = 0;
+            while (q < n && (have = getline())) q += line.size();
+            have = getline();
+        } else die("sequence parsing failed: " + path);
+        flush(false);
+    }
+    flush(true);
+    gzclose(f);
+}
+int main_count(int argc, char **argv) {
+    int k = 31, bloom = 0, pre = 10, gpu = 0;
+    std::string out;
+    std::vector<std::string> in;
+    for (int i = 2; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&]() -> std::string {
+            if (i + 1 >= argc) die("option " + a + " needs a value");
+            return argv[++i];
+        };
+        if (a == "-k") k = atoi(val().c_str());
+        else if (a == "-b") bloom = atoi(val().c_str());
+        else if (a == "-p") pre = atoi(val().c_str());
+        else if (a == "-o") out = val();
+        else if (a == "-g") gpu = atoi(val().c_str());
+        else if (a == "-t" || a == "-K" || a == "-H") val();  // accepted for compatibility with `yak count`
+        else in.push_back(a);
+    }
+    if (in.empty() || out.empty()) {
+        fprintf(stderr,
+                "Usage: nextPolish2 count [options] -o <out.yak> <in.fa|fq[.gz]> [in.fa]\n"
+                "  -k INT   k-mer size [31]\n"
+                "  -b INT   as in `yak count`: when > 0 the (second, else the first) file is counted and only k-mers\n"
+                "           seen at least twice are kept (what yak's Bloom-filter pass + second pass + shrink leave)\n"
+                "  -o FILE  dump the counts in yak's format\n"
+                "  -g INT   GPU to use [0]\n");
+        return 1;
+    }
+    if (pre != 10) die("ERROR: -p must be 10 (NextPolish2 compares hash >> 10, kmer.rs:52-54)");
+    if (k >= 64) die("ERROR: -k must be smaller than 64");
+    np2_ctx *ctx = nullptr;
+    if (np2_ctx_create(gpu, &ctx) != NP2_OK) die(np2_last_error());
+    np2_counter *c = nullptr;
+    if (np2_count_create(ctx, (uint32_t)k, &c) != NP2_OK) die(np2_last_error());
+    // yak main.c:65-71: without -b the first file is counted; with -b the table is rebuilt from the second one
+    const std::string &src = (bloom > 0 && in.size() >= 2) ? in[1] : in[0];
+    uint64_t n_seq = 0;
+    stream_sequences(src, 256u << 20, [&](const std::vector<uint8_t> &seq, const std::vector<uint64_t> &off) {
+        if (np2_count_add(c, seq.data(), off.data(), off.size() - 1) != NP2_OK) die(np2_last_error());
+        n_seq += off.size() - 1;
+    });
+    uint64_t n_kmers = 0;
+    const uint64_t distinct = np2_count_distinct(c, &n_kmers);
+    if (np2_count_finish(c, bloom > 0 ? 2 : 1, out.c_str(), nullptr) != NP2_OK) die(np2_last_error());
+    fprintf(stderr, "[M::count] %llu sequences, %llu k-mers, %llu distinct; dumped to '%s'\n", (unsigned long long)n_seq,
+            (unsigned long long)n_kmers, (unsigned long long)distinct, out.c_str());
+    np2_count_destroy(c);
+    np2_ctx_destroy(ctx);
+    return 0;
 }
 
 /* ---------------------------------------------------------------- BGZF / BAM / BAI */
@@ -352,6 +460,7 @@ Cli parse_args(int argc, char **argv) {
 }  // namespace
 
 int main(int argc, char **argv) {
+    if (argc >= 2 && std::string(argv[1]) == "count") return main_count(argc, argv);
     Cli cli = parse_args(argc, argv);
     FILE *out = stdout;
     if (cli.out != "stdout") {  // option.rs:308-328: refuse to overwrite

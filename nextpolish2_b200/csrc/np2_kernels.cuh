@@ -199,4 +199,19 @@ void rech_gather(GenoDev g, const uint32_t *d_ent_off, const uint64_t *d_byte_of
                  uint64_t *d_pool_off, uint8_t *d_out, cudaStream_t s);
 void assemble_final(AssembleDev a, uint8_t *d_out, cudaStream_t s);
 
+/* ------------------------------------------------------------------ yak count on the device (np2_count.cu) */
+struct KmerCounts {  // distinct hashes, ascending, with their counts (clamped at 1023); device memory
+    uint64_t *keys = nullptr;
+    uint32_t *cnts = nullptr;
+    uint64_t n = 0;
+};
+// adds the canonical k-mers of d_seq (len bytes; reads separated by any non-ACGT byte) to acc
+void count_add(KmerCounts &acc, const uint8_t *d_seq, uint64_t len, uint32_t k, uint64_t *n_kmers, cudaStream_t s);
+void count_free(KmerCounts &acc, cudaStream_t s);
+// hashes with count >= min_count: compact device copies (caller frees with cudaFreeAsync) + size of every sub-table
+void count_filter(const KmerCounts &acc, uint32_t min_count, uint64_t **d_keys, uint16_t **d_cnt, uint64_t *n,
+                  uint32_t sub_size[1024], cudaStream_t s);
+// the same keys as yak writes them ((hash >> 10) << 10 | count), grouped by sub-table, into host memory
+void count_file_keys(const uint64_t *d_keys, const uint16_t *d_cnt, uint64_t n, uint64_t *h_out, cudaStream_t s);
+
 }  // namespace np2

@@ -52,7 +52,11 @@ struct Lvl {
 // re-examined only when one of them changed since its last visit (a skipped visit would have moved nothing).
 bool move_vertices(Lvl &lv) {
     bool moved_any = false;
+    // per-visit accumulator: weight towards each neighbouring community, found through a stamped slot table (the
+    // choice below only depends on the sums, not on the order the communities were met in)
     std::vector<std::pair<uint32_t, float>> acc;
+    std::vector<uint32_t> slot(lv.n, 0), stamp(lv.n, 0);
+    uint32_t visit = 0;
     std::vector<uint8_t> dirty(lv.n, 1);
     for (;;) {
         bool stop = true;
@@ -61,16 +65,19 @@ bool move_vertices(Lvl &lv) {
             dirty[v] = 0;
             const uint32_t cur = lv.cid[v];
             acc.clear();
+            if (++visit == 0) {  // stamp wrap-around
+                std::fill(stamp.begin(), stamp.end(), 0u);
+                visit = 1;
+            }
             for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) {
                 const uint32_t c = lv.cid[lv.ato[e]];
-                bool found = false;
-                for (auto &a : acc)
-                    if (a.first == c) {
-                        a.second += lv.aw[e];
-                        found = true;
-                        break;
-                    }
-                if (!found) acc.emplace_back(c, lv.aw[e]);
+                if (stamp[c] != visit) {
+                    stamp[c] = visit;
+                    slot[c] = (uint32_t)acc.size();
+                    acc.emplace_back(c, lv.aw[e]);
+                } else {
+                    acc[slot[c]].second += lv.aw[e];
+                }
             }
             if (acc.empty()) continue;
             uint32_t bid = acc[0].first;
