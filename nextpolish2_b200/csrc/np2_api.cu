@@ -600,8 +600,11 @@ void np2_job::ingest_finish() {
         for (size_t a = 1; a < na; a++) as_pos[a] = ing.pos[as_read[a]];
         pair_off.assign(na + 1, 0);
         pair_off[1] = na ? na - 1 : 0;
+        size_t ub = 2;  // first alignseq after a that starts behind a's end; moves little from one read to the next
         for (size_t a = 1; a < na; a++) {
-            const size_t ub = std::upper_bound(as_pos.begin() + a + 1, as_pos.end(), as_te[a]) - as_pos.begin();
+            ub = std::max(ub, a + 1);
+            while (ub < na && as_pos[ub] <= as_te[a]) ub++;
+            while (ub > a + 1 && as_pos[ub - 1] > as_te[a]) ub--;
             pair_off[a + 1] = pair_off[a] + (ub - (a + 1));
         }
     }
