@@ -96,7 +96,7 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
 # THIS workload (profiles/r01h_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.
-NCU_TRAFFIC = {"pack_columns": 379848704, "pileup_count": 244173312, "pileup_emit": 277608192}
+NCU_TRAFFIC = {"pack_columns": 379848704, "pileup_emit": 277608192}
 
 
 def peaks():
@@ -114,7 +114,6 @@ def stage_bytes(stage, st):
         "pack_columns": cols * (0.5 + 0.5 + 10 / 32),
         # packed columns in (0.5) + checkpoints in (10/32); the packed reference (0.5 B/bp) is shared by the ~30 reads
         # over a position and counted once
-        "pileup_count": cols * (0.5 + 10 / 32) + L * 0.5,
         "pileup_emit": cols * (0.5 + 10 / 32) + L * 0.5 + st.get("records", 0) * 12,
     }.get(stage)
 
@@ -264,7 +263,7 @@ def run_ours(args):
                         "launch_ms": round(per_launch_ms, 4), "launches_per_step": n_launch,
                         "share_of_step": round(stages[dom] / stages["total"], 4),
                         "algorithmic_bytes_per_launch": int(stage_bytes(dom, st)),
-                        "note": "largest of the streaming kernels with a defined byte count (pack_columns, pileup_count, "
+                        "note": "largest of the streaming kernels with a defined byte count (pack_columns, "
                                 "pileup_emit); the step is ~50 short kernels + host phases, none above 10% of it"}
         q = traffic["probes"] / float(args.length)
         pipe_bytes = pipeline_bytes_per_bp(30, q) * args.length

@@ -292,14 +292,15 @@ struct np2_job {
     DBuf<Op> d_ops;
     DBuf<uint64_t> d_seq_off, d_nib_off;
     DBuf<uint32_t> d_ts, d_te, d_n, d_shift, d_ck_tpos, d_ck_read;
-    DBuf<uint16_t> d_ck_delta;
+    DBuf<uint16_t> d_ck_delta, d_blk_op;
     ReadsDev R;
 
     // host state
     std::vector<uint32_t> h_ts, h_te, h_n;
     std::vector<uint8_t> h_blank;          // per candidate read
     std::vector<int32_t> as_read;          // alignseq index -> candidate read (-1 = ref)
-    std::vector<uint64_t> pair_off;        // pair-accumulator slot ranges per alignseq (np2_geno.cu k_edges_accum)
+    uint32_t rec_cap_hint = 0;             // 3-mer records of the last pileup (sizes the next one-pass emit)
+    std::vector<uint32_t> h_as_pos, h_as_te;  // record pos / last column of every alignseq (pair-accumulator windows)
     DBuf<uint64_t> d_pair_off;
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
@@ -485,6 +486,7 @@ void np2_job::enqueue_arrays() {
     d_ck_tpos.alloc(std::max(nck, 1u), s);
     d_ck_delta.alloc(std::max(nck, 1u), s);
     d_ck_read.alloc(std::max(nck, 1u), s);
+    d_blk_op.alloc(std::max(nck, 1u), s);
     d_blank.alloc(std::max(n, 1u), s);
     if (!sc->ev_alloc) {
         NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_alloc, cudaEventDisableTiming));
@@ -539,6 +541,7 @@ void np2_job::enqueue_arrays() {
     R.ck_tpos = d_ck_tpos.p;
     R.ck_delta = d_ck_delta.p;
     R.ck_read = d_ck_read.p;
+    R.blk_op = d_blk_op.p;
     timer.hend("upload:host_enqueue_arrays");
 }
 
@@ -592,22 +595,11 @@ void np2_job::ingest_finish() {
         as_lab.push_back(ing.is_clip[i]);
         h_blank[i] = 0;
     }
-    // index windows for the pair accumulator: alignseqs are in position order, so a later read y can only share a
-    // region with x when it starts before x ends; the ref read (order 0) pairs with everyone
-    {
-        const size_t na = as_read.size();
-        std::vector<uint32_t> as_pos(na, 0);
-        for (size_t a = 1; a < na; a++) as_pos[a] = ing.pos[as_read[a]];
-        pair_off.assign(na + 1, 0);
-        pair_off[1] = na ? na - 1 : 0;
-        size_t ub = 2;  // first alignseq after a that starts behind a's end; moves little from one read to the next
-        for (size_t a = 1; a < na; a++) {
-            ub = std::max(ub, a + 1);
-            while (ub < na && as_pos[ub] <= as_te[a]) ub++;
-            while (ub > a + 1 && as_pos[ub - 1] > as_te[a]) ub--;
-            pair_off[a + 1] = pair_off[a] + (ub - (a + 1));
-        }
-    }
+    // inputs of the pair-accumulator windows (np2_geno.cu k_pair_windows): alignseqs are in position order, so a later
+    // read y can only share a region with x when it starts before x ends
+    h_as_pos.assign(as_read.size(), 0);
+    for (size_t a = 1; a < as_read.size(); a++) h_as_pos[a] = ing.pos[as_read[a]];
+    h_as_te = as_te;
     // merged [t_s + 50, t_e - 50] of unlabelled reads; labelled reads inside a range are blanked
     std::vector<std::pair<uint32_t, uint32_t>> ranges;
     uint32_t s = 0, e = 0;
@@ -651,12 +643,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     /* ---------------- K2: pileup */
     DBuf<int32_t> d_cover;
     d_cover.alloc(L + 1, s);
-    DBuf<uint32_t> d_cta_cnt, d_cta_off;
-    const uint32_t n_cta = std::max(1u, pileup_ctas(n_blocks));
-    d_cta_cnt.alloc(n_cta + 1, s);
-    d_cta_off.alloc(n_cta + 1, s);
     DBuf<uint8_t> d_tmp;
-    size_t tmp_bytes = 0;
 
     h = timer.begin("pileup_scan", 2);
     d_cover.zero();
@@ -671,37 +658,37 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         d_tmp.alloc(tb, s);
         cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_cover.p, d_cover.p, L + 1, s);
     }
-    d_cta_cnt.zero();
     timer.end(h);
-    h = timer.begin("pileup_count", 1);  // single kernel
-    pileup_count(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, d_cta_cnt.p, s);
-    timer.end(h);
-    h = timer.begin("pileup_scan", 1);
-    {
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cta_cnt.p, d_cta_off.p, n_cta + 1, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_cta_cnt.p, d_cta_off.p, n_cta + 1, s);
-    }
-    timer.end(h);
-    uint32_t n_rec = 0;
-    NP2_CUDA(cudaMemcpyAsync(&n_rec, d_cta_off.p + n_cta, 4, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
-    n_rec += 2;
-    timer.hbegin();
-
+    // Non-reference 3-mer records (~3-5 % of the columns) are emitted in ONE pass into a buffer sized from the last
+    // count (first time: 1/8 of the columns); the kernel keeps counting when it overflows and is then re-run exactly.
     DBuf<uint64_t> d_key, d_key2;
     DBuf<uint32_t> d_rd, d_rd2, d_head, d_gidx;
-    d_key.alloc(n_rec, s);
+    DBuf<unsigned int> d_nrec;
+    d_nrec.alloc(1, s);
+    uint32_t n_rec = 0;
+    uint64_t cap = rec_cap_hint ? (uint64_t)rec_cap_hint + rec_cap_hint / 8 + 1024 : ing.total_cols / 8 + 4096;
+    for (int attempt = 0;; attempt++) {
+        cap = std::min<uint64_t>(cap, 0xFFFFFFF0ull);
+        d_key.alloc(cap, s);
+        d_rd.alloc(cap, s);
+        const unsigned int two = 2;
+        NP2_CUDA(cudaMemcpyAsync(d_nrec.p, &two, 4, cudaMemcpyHostToDevice, s));
+        h = timer.begin("pileup_emit", 1);
+        pileup_emit(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, d_nrec.p, (uint32_t)cap, d_key.p, d_rd.p, s);
+        timer.end(h);
+        NP2_CUDA(cudaMemcpyAsync(&n_rec, d_nrec.p, 4, cudaMemcpyDeviceToHost, s));
+        NP2_CUDA(cudaStreamSynchronize(s));
+        if (n_rec <= cap) break;
+        if (attempt) throw np2::Error(NP2_ERR_INTERNAL, "3-mer record count changed between two passes");
+        cap = n_rec;
+    }
+    rec_cap_hint = n_rec;
+    timer.hbegin();
     d_key2.alloc(n_rec, s);
-    d_rd.alloc(n_rec, s);
     d_rd2.alloc(n_rec, s);
     d_head.alloc(n_rec + 1, s);
     d_gidx.alloc(n_rec + 1, s);
     timer.hend("host:alloc_records");
-    h = timer.begin("pileup_emit", 1);
-    pileup_emit(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, d_cta_off.p, d_key.p, d_rd.p, s);
-    timer.end(h);
     int pbits = 1;
     while ((1ull << pbits) < (uint64_t)L) pbits++;
     h = timer.begin("pileup_sort", 8);
@@ -1173,7 +1160,9 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         if (n_edges) {
             // dense pair accumulator (np2_geno.cu k_edges_accum): one slot per (x, y) inside x's index window
             const uint32_t n_ids0 = (uint32_t)as_read.size();
-            const uint64_t n_slots = pair_off.back();
+            uint64_t n_slots = 0;
+            NP2_CUDA(cudaMemcpyAsync(&n_slots, d_pair_off.p + n_ids0, 8, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaStreamSynchronize(s));
             if (n_slots >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^31 overlapping read pairs");
             uint32_t id_bits = 1;  // read orders are < as_read.size()
             while ((1ull << id_bits) < as_read.size()) id_bits++;
@@ -1865,8 +1854,23 @@ void np2_job::run(int32_t dump_it) {
     d_blank.upload(h_blank.data(), std::max(n, 1u));
     d_order.alloc(std::max(n, 1u), s);
     if (n) d_order.upload(read_order.data(), n);
-    d_pair_off.alloc(pair_off.size(), s);
-    d_pair_off.upload(pair_off.data(), pair_off.size());
+    if (opt.iter_count > 1) {  // slot ranges of the pair accumulator: windows + exclusive scan, all on the device
+        const uint32_t na = (uint32_t)as_read.size();
+        DBuf<uint32_t> d_as_pos, d_as_te, d_W;
+        d_as_pos.alloc(na, s);
+        d_as_te.alloc(na, s);
+        d_W.alloc(na + 1, s);
+        d_pair_off.alloc(na + 1, s);
+        d_as_pos.upload(h_as_pos.data(), na);
+        d_as_te.upload(h_as_te.data(), na);
+        geno_pair_windows(d_as_pos.p, d_as_te.p, na, d_W.p, s);
+        DBuf<uint8_t> d_tmpw;
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_W.p, d_pair_off.p, (int)na + 1, s);
+        d_tmpw.alloc(tb, s);
+        cub::DeviceScan::ExclusiveSum(d_tmpw.p, tb, d_W.p, d_pair_off.p, (int)na + 1, s);
+        NP2_CUDA(cudaStreamSynchronize(s));  // the uploads above come from pageable vectors
+    }
     max_span = 0;
     for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
 

@@ -505,6 +505,31 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_accum(GenoDev g, co
         }
     }
 }
+// W[x] = number of alignseqs y > x that start (record pos) at or before x's last column; x = 0 (ref) pairs with all
+__global__ void k_pair_windows(const uint32_t *__restrict__ as_pos, const uint32_t *__restrict__ as_te, uint32_t na,
+                               uint32_t *__restrict__ W) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a > na) return;
+    if (a == na) {
+        W[a] = 0;
+        return;
+    }
+    if (a == 0) {
+        W[0] = na - 1;
+        return;
+    }
+    const uint32_t te = as_te[a];
+    uint32_t lo = a + 1, hi = na;  // first y in (a, na) with as_pos[y] > te
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (as_pos[mid] <= te) lo = mid + 1;
+        else hi = mid;
+    }
+    W[a] = lo - (a + 1);
+}
+void geno_pair_windows(const uint32_t *d_as_pos, const uint32_t *d_as_te, uint32_t na, uint32_t *d_W, cudaStream_t s) {
+    NP2_K(k_pair_windows)<<<cdiv(na + 1, 256), 256, 0, s>>>(d_as_pos, d_as_te, na, d_W);
+}
 struct SlotNonZero {
     const unsigned long long *acc;
     __device__ __forceinline__ bool operator()(const uint32_t &i) const { return acc[i] != 0; }

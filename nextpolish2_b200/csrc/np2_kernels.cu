@@ -3,7 +3,7 @@
 //   K5  table_insert / table_probe / seq_kscore   yak k-mer table in HBM (kmer.rs:113-170, 255-314)
 //   K0  ref_codes                                  SEQ_NUM codes of the contig (kmer.rs:11-22)
 //   K1  trim_scan + pack_columns                        fill_with_cigar + trim(8) + AlignSeq::new (main.rs:386-513, 279-312)
-//   K2  cover_diff / pileup_count / pileup_emit    update_msas + Msa::push/sort/coverage (main.rs:576-589, 193-241)
+//   K2  cover_diff / pileup_emit                   update_msas + Msa::push/sort/coverage (main.rs:576-589, 193-241)
 //       mark_heads / groups_* / pos_finalize
 //   K3  dp_runs / emit_*                           get_cns_from_align_tags + backtrack (main.rs:1645-1687, 1572-1634)
 //   (K4/K6 and the genotype kernels live in np2_geno.cu)
@@ -333,6 +333,17 @@ __device__ __forceinline__ void op_seek(const ReadsDev &R, uint32_t r, uint32_t 
     c.i = lo;
     op_load(R, c);
 }
+// the op holding the first column of block g (written by k_trim_scan); reads with >= 65535 ops search instead
+__device__ __forceinline__ void op_at_block(const ReadsDev &R, uint32_t r, uint32_t g, uint32_t col, OpCur &c) {
+    const uint32_t v = R.blk_op[g];
+    if (v == 0xFFFFu) {
+        op_seek(R, r, col, c);
+        return;
+    }
+    c.i = R.op_off[r] + v;
+    c.i_end = R.op_off[r + 1];
+    op_load(R, c);
+}
 // column -> (match?, nibble).  M/=/X compare raw bytes like trim() (main.rs:454); the nibble is
 // SEQ_NUM[q] | 8 for an insertion column (main.rs:292-294).
 __device__ __forceinline__ void col_eval(const ReadsDev &R, const uint8_t *__restrict__ ref, uint32_t pos,
@@ -467,6 +478,18 @@ __global__ void __launch_bounds__(128) k_trim_scan(ReadsDev R, const uint8_t *__
         R.shift[r] = shift;
         if ((n & 31) == 0) *(uint64_t *)(R.nib + R.nib_off[r] + (n >> 1)) = 0xFFFFFFFFFFFFFFFFULL;
     }
+    // which op holds the first column of every 32-column block of the trimmed read: one lane per op writes the
+    // (few, consecutive) blocks that start inside it, so that the pack threads need no search of their own
+    const uint32_t op0 = R.op_off[r], op1 = R.op_off[r + 1], nblk = (n + 31) >> 5;
+    for (uint32_t i = op0 + lane; i < op1; i += 32) {
+        const uint4 o = __ldg(R.ops + i);
+        const uint32_t c_end = o.x + (o.w >> 4);
+        if (c_end <= shift) continue;
+        const uint32_t b_lo = o.x > shift ? (o.x - shift + 31) >> 5 : 0;
+        const uint32_t b_hi = min(nblk, ((c_end - 1 - shift) >> 5) + 1);  // exclusive
+        const uint16_t v = (uint16_t)min(i - op0, 0xFFFFu);
+        for (uint32_t b = b_lo; b < b_hi; b++) R.blk_op[ck0 + b] = v;
+    }
 }
 
 // ---- pack columns [shift, shift + n) into nibbles + terminator (main.rs:287-310) and write the checkpoints.
@@ -474,41 +497,117 @@ __global__ void __launch_bounds__(128) k_trim_scan(ReadsDev R, const uint8_t *__
 // SEQ nibbles mapped through the 16-entry code table; the others (op boundaries, indels, the terminator) are queued
 // in shared memory and packed column by column by densely filled warps.
 constexpr int kPackThreads = 256;
-__device__ __forceinline__ uint64_t map_codes16(uint64_t v) {  // 16 BAM nibbles (first at the top) -> 16 codes, byte order of memory
-    const uint64_t lut = (4ULL << 0) | (0ULL << 4) | (1ULL << 8) | (6ULL << 12) | (2ULL << 16) | (4ULL << 20) |
-                         (4ULL << 24) | (4ULL << 28) | (3ULL << 32) | (4ULL << 36) | (4ULL << 40) | (4ULL << 44) |
-                         (4ULL << 48) | (4ULL << 52) | (4ULL << 56) | (5ULL << 60);
-    uint64_t codes = 0;
-#pragma unroll
-    for (int x = 0; x < 16; x++) codes = codes << 4 | ((lut >> (4 * ((v >> (60 - 4 * x)) & 15))) & 15);
-    const uint32_t hi = (uint32_t)(codes >> 32), lo = (uint32_t)codes;
-    return (uint64_t)__byte_perm(hi, 0, 0x0123) | (uint64_t)__byte_perm(lo, 0, 0x0123) << 32;
+// 16 BAM nibbles (first column in the top nibble) -> 16 SEQ_NUM codes in the byte order of memory (column 0 in the high
+// nibble of byte 0).  Four nibbles at a time through PRMT: the 16-bit group IS the selector; two 8-entry byte tables
+// (codes of "=ACMGRSV" and of "TWYHKDBN") are looked up with the low three bits, and a third PRMT over 0x80 bytes turns
+// bit 3 of every nibble into a byte mask (sign replication) that picks between them.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {  // PTX generic form: selector bit 3 of
+    uint32_t d;                                                                  // a nibble replicates the byte's msb
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
-__device__ __forceinline__ void pack_block_slow(const ReadsDev &R, const uint8_t *__restrict__ ref, uint32_t g) {
+__device__ __forceinline__ uint32_t map_codes4(uint32_t sel) {
+    const uint32_t s7 = sel & 0x7777u;
+    const uint32_t lo = prmt(0x06010004u, 0x04040402u, s7);  // = A C M | G R S V -> 4 0 1 6 | 2 4 4 4
+    const uint32_t hi = prmt(0x04040403u, 0x05040404u, s7);  // T W Y H | K D B N -> 3 4 4 4 | 4 4 4 5
+    const uint32_t m = prmt(0x80808080u, 0x80808080u, sel);  // 0xFF where the nibble is >= 8, else 0x80
+    const uint32_t r = (lo & ~m) | (hi & m);                        // one code per byte, last column in byte 0
+    const uint32_t p = (r | r >> 4) & 0x00FF00FFu;                  // pairs: byte 0 = cols 2,3; byte 2 = cols 0,1
+    return __byte_perm(p, 0, 0x4402);                               // 16 bits, cols 0,1 in the low (first) byte
+}
+__device__ __forceinline__ uint64_t map_codes16(uint64_t v) {
+    return (uint64_t)map_codes4((uint32_t)(v >> 48)) | (uint64_t)map_codes4((uint32_t)(v >> 32)) << 16 |
+           (uint64_t)map_codes4((uint32_t)(v >> 16)) << 32 | (uint64_t)map_codes4((uint32_t)v) << 48;
+}
+// 32 SEQ nibbles starting at query index qi, numeric order (first nibble at the top of hi).  Reads 20 bytes from an
+// arbitrary address as five aligned words (every read slot has 32 bytes of slack behind it).
+__device__ __forceinline__ void load_seq32(const uint8_t *__restrict__ seq4, uint32_t qi, uint64_t &hi, uint64_t &lo) {
+    const uint8_t *sp = seq4 + (qi >> 1);
+    const uint32_t mis = (uint32_t)((uintptr_t)sp & 3);
+    const uint32_t *wp = (const uint32_t *)(sp - mis);
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+    const uint32_t sh = mis * 8;
+    // big-endian numeric words: first SEQ byte in the most significant position
+    const uint32_t b0 = __byte_perm(__funnelshift_r(w0, w1, sh), 0, 0x0123);
+    const uint32_t b1 = __byte_perm(__funnelshift_r(w1, w2, sh), 0, 0x0123);
+    const uint32_t b2 = __byte_perm(__funnelshift_r(w2, w3, sh), 0, 0x0123);
+    const uint32_t b3 = __byte_perm(__funnelshift_r(w3, w4, sh), 0, 0x0123);
+    hi = (uint64_t)b0 << 32 | b1;
+    lo = (uint64_t)b2 << 32 | b3;
+    if (qi & 1) {  // odd query index: the stream starts at the low nibble of the first byte
+        const uint32_t b16 = (__funnelshift_r(w4, 0, sh)) & 255u;  // 17th byte
+        hi = hi << 4 | lo >> 60;
+        lo = lo << 4 | (b16 >> 4);
+    }
+}
+// 128-bit helpers on (hi, lo) = columns 0-15 / 16-31, column 0 in the top nibble of hi
+__device__ __forceinline__ void shr_nib(uint64_t &hi, uint64_t &lo, uint32_t s) {  // towards later columns, s < 32
+    if (s >= 16) {
+        lo = hi >> (4 * (s - 16));
+        hi = 0;
+    } else if (s) {
+        lo = lo >> (4 * s) | hi << (64 - 4 * s);
+        hi >>= 4 * s;
+    }
+}
+__device__ __forceinline__ void first_nib(uint32_t len, uint64_t &hi, uint64_t &lo) {  // 0xF in the first len columns
+    hi = len >= 16 ? ~0ULL : (len ? ~0ULL << (64 - 4 * len) : 0);
+    lo = len >= 32 ? ~0ULL : (len > 16 ? ~0ULL << (64 - 4 * (len - 16)) : 0);
+}
+// A block that is not one plain run of M/=/X columns (an op boundary, an indel, the end of the read): assembled
+// segment by segment with the same word operations as the fast path instead of column by column.
+__device__ __forceinline__ void pack_block_slow(const ReadsDev &R, uint32_t g) {
     const uint32_t r = R.ck_read[g];
-    const uint32_t n = R.n[r], shift = R.shift[r], pos = R.pos[r];
+    const uint32_t n = R.n[r], shift = R.shift[r];
     const uint32_t o0 = (g - R.ck_off[r]) * 32;
     const uint8_t *seq4 = R.blob + R.seq_off[r];
-    uint64_t word[2] = {0, 0};
-    OpCur cur;
-    if (o0 < n) op_seek(R, r, shift + o0, cur);
-    for (uint32_t x = 0; x < 32; x++) {
-        uint32_t o = o0 + x, nib = 15;
-        if (o < n) {
-            uint32_t c = shift + o;
-            while (c >= cur.c_end) {
-                cur.i++;
-                op_load(R, cur);
+    const uint32_t ncol = min(32u, n > o0 ? n - o0 : 0u);  // columns of the read inside this block
+    uint64_t src_hi = 0, src_lo = 0;                        // BAM nibbles of the M/=/X/I columns
+    uint64_t ins_hi = 0, ins_lo = 0, del_hi = 0, del_lo = 0;  // 0xF where the column is an insertion / a deletion
+    if (ncol) {
+        OpCur cur;
+        op_at_block(R, r, g, shift + o0, cur);
+        uint32_t c = 0;  // column inside the block
+        for (;;) {
+            const uint32_t col = shift + o0 + c;
+            const uint32_t len = min(cur.c_end - col, ncol - c);
+            uint64_t mh, ml;
+            first_nib(len, mh, ml);
+            shr_nib(mh, ml, c);
+            if (cur.op == 2) {
+                del_hi |= mh;
+                del_lo |= ml;
+            } else {
+                uint64_t h, l;
+                load_seq32(seq4, cur.q + (col - cur.c_beg), h, l);
+                shr_nib(h, l, c);
+                src_hi |= h & mh;
+                src_lo |= l & ml;
+                if (cur.op == 1) {
+                    ins_hi |= mh;
+                    ins_lo |= ml;
+                }
             }
-            bool match;
-            col_eval(R, ref, pos, seq4, cur, c, match, nib);
+            c += len;
+            if (c >= ncol) break;
+            cur.i++;
+            op_load(R, cur);
         }
-        // column o -> byte o/2, high nibble when o is even
-        word[x >> 4] |= (uint64_t)nib << (8 * ((x & 15) >> 1) + ((x & 1) ? 0 : 4));
     }
+    uint64_t th, tl;  // terminator / padding: 0xF in every column at or behind n
+    first_nib(ncol, th, tl);
+    th = ~th;
+    tl = ~tl;
+    const uint64_t k4 = 0x4444444444444444ULL, k8 = 0x8888888888888888ULL;
+    // numeric nibble order -> memory order: reverse the bytes of each half
+    auto to_mem = [](uint64_t x) {
+        return (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123) | (uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32;
+    };
+    const uint64_t w0 = (map_codes16(src_hi) & ~to_mem(del_hi | th)) | to_mem((ins_hi & k8) | (del_hi & k4) | th);
+    const uint64_t w1 = (map_codes16(src_lo) & ~to_mem(del_lo | tl)) | to_mem((ins_lo & k8) | (del_lo & k4) | tl);
     uint64_t *out = (uint64_t *)(R.nib + R.nib_off[r] + (o0 >> 1));
-    out[0] = word[0];
-    out[1] = word[1];
+    out[0] = w0;
+    out[1] = w1;
 }
 __global__ void __launch_bounds__(kPackThreads) k_pack_columns(ReadsDev R, const uint8_t *__restrict__ ref,
                                                                uint32_t n_blocks) {
@@ -525,30 +624,14 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_columns(ReadsDev R, const
             if (o0 < n) {
                 const uint32_t shift = R.shift[r], pos = R.pos[r];
                 OpCur cur;
-                op_seek(R, r, shift + o0, cur);
+                op_at_block(R, r, g, shift + o0, cur);
                 uint32_t tp, dl;
                 col_tpos(R, r, pos, cur, shift + o0, tp, dl);
                 R.ck_tpos[g] = tp;
                 R.ck_delta[g] = (uint16_t)dl;
                 if (o0 + 32 <= n && cur.op != 1 && cur.op != 2 && shift + o0 + 32 <= cur.c_end) {
-                    const uint32_t qi = cur.q + (shift + o0 - cur.c_beg);
-                    const uint8_t *sp = R.blob + R.seq_off[r] + (qi >> 1);
-                    // 17 bytes from an arbitrary address: five aligned words, funnel-shifted
-                    const uint32_t mis = (uint32_t)((uintptr_t)sp & 3);
-                    const uint32_t *wp = (const uint32_t *)(sp - mis);
-                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-                    const uint32_t sh = mis * 8;
-                    // big-endian numeric words: first SEQ byte in the most significant position
-                    const uint32_t b0 = __byte_perm(__funnelshift_r(w0, w1, sh), 0, 0x0123);
-                    const uint32_t b1 = __byte_perm(__funnelshift_r(w1, w2, sh), 0, 0x0123);
-                    const uint32_t b2 = __byte_perm(__funnelshift_r(w2, w3, sh), 0, 0x0123);
-                    const uint32_t b3 = __byte_perm(__funnelshift_r(w3, w4, sh), 0, 0x0123);
-                    uint64_t hi = (uint64_t)b0 << 32 | b1, lo = (uint64_t)b2 << 32 | b3;
-                    if (qi & 1) {  // odd query index: the stream starts at the low nibble of the first byte
-                        const uint32_t b16 = (__funnelshift_r(w4, 0, sh)) & 255u;  // 17th byte
-                        hi = hi << 4 | lo >> 60;
-                        lo = lo << 4 | (b16 >> 4);
-                    }
+                    uint64_t hi, lo;
+                    load_seq32(R.blob + R.seq_off[r], cur.q + (shift + o0 - cur.c_beg), hi, lo);
                     uint64_t *out = (uint64_t *)(R.nib + R.nib_off[r] + (o0 >> 1));
                     out[0] = map_codes16(hi);
                     out[1] = map_codes16(lo);
@@ -560,7 +643,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_columns(ReadsDev R, const
     }
     __syncthreads();
     const uint32_t nq = qn;
-    for (uint32_t i = threadIdx.x; i < nq; i += kPackThreads) pack_block_slow(R, ref, q[i]);
+    for (uint32_t i = threadIdx.x; i < nq; i += kPackThreads) pack_block_slow(R, q[i]);
 }
 void trim_scan(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
     if (r.n_reads) NP2_K(k_trim_scan)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
@@ -714,45 +797,36 @@ __device__ __forceinline__ uint32_t pile_queue(const ReadsDev &R, uint32_t n_blo
     __syncthreads();
     return *qn;
 }
-__global__ void __launch_bounds__(kPileThreads) k_pileup_count(ReadsDev R, uint32_t n_blocks,
-                                                               const uint8_t *__restrict__ blank,
-                                                               const uint8_t *__restrict__ code,
-                                                               const uint32_t *__restrict__ refpk,
-                                                               uint32_t *__restrict__ cta_count) {
-    typedef cub::BlockReduce<uint32_t, kPileThreads> BR;
-    __shared__ typename BR::TempStorage tmp;
-    __shared__ uint32_t q[kPileCta], qn;
-    const uint32_t nq = pile_queue(R, n_blocks, blank, code, refpk, q, &qn);
-    uint32_t c = 0;
-    for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads)
-        scan_block32(R, q[i], code, [&](uint32_t, uint32_t, uint32_t) { c++; });
-    uint32_t tot = BR(tmp).Sum(c);
-    if (threadIdx.x == 0) cta_count[blockIdx.x] = tot;
-}
 __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32_t n_blocks,
                                                               const uint8_t *__restrict__ blank,
                                                               const uint8_t *__restrict__ code,
                                                               const uint32_t *__restrict__ refpk,
-                                                              const uint32_t *__restrict__ cta_off,
+                                                              unsigned int *__restrict__ n_rec, uint32_t cap,
                                                               uint64_t *__restrict__ key, uint32_t *__restrict__ rd) {
     typedef cub::BlockScan<uint32_t, kPileThreads> BS;
     __shared__ typename BS::TempStorage tmp;
-    __shared__ uint32_t q[kPileCta], qn;
+    __shared__ uint32_t q[kPileCta], qn, cta_base;
     const uint32_t nq = pile_queue(R, n_blocks, blank, code, refpk, q, &qn);
     uint32_t c = 0;
     for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads)
         scan_block32(R, q[i], code, [&](uint32_t, uint32_t, uint32_t) { c++; });
-    uint32_t off;
-    BS(tmp).ExclusiveSum(c, off);
-    // +2: records 0 and 1 are the reference read's two head 3-mers (main.rs:1732-1739, 579-584).  Record order inside
-    // the buffer is arbitrary: the first read of a 3-mer is taken as a minimum over its records (k_groups_fill).
-    uint32_t w = cta_off[blockIdx.x] + off + 2;
+    uint32_t off, tot;
+    BS(tmp).ExclusiveSum(c, off, tot);
+    // Record order inside the buffer is arbitrary (the first read of a 3-mer is taken as a minimum over its records,
+    // k_groups_fill), so every CTA simply reserves its range with one atomic: no counting pass, no scan of CTA totals.
+    // *n_rec starts at 2: records 0 and 1 are the reference read's two head 3-mers (main.rs:1732-1739, 579-584).
+    // It keeps counting past `cap` (nothing is written there): the host then re-runs with the exact size.
+    if (threadIdx.x == 0) cta_base = tot ? atomicAdd(n_rec, tot) : 0;
+    __syncthreads();
+    uint32_t w = cta_base + off;
     for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads) {
         const uint32_t g = q[i];
         const uint32_t order = R.ck_read[g] + 1;
         scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) {
-            key[w] = (uint64_t)p << 32 | (uint64_t)bases << 16 | dl1;
-            rd[w] = order;
+            if (w < cap) {
+                key[w] = (uint64_t)p << 32 | (uint64_t)bases << 16 | dl1;
+                rd[w] = order;
+            }
             w++;
         });
     }
@@ -763,16 +837,11 @@ __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32
         rd[1] = 0;
     }
 }
-void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                  const uint32_t *d_refpk, uint32_t L, uint32_t *d_cta_count, cudaStream_t s) {
-    NP2_K(k_pileup_count)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk,
-                                                                                  d_cta_count);
-}
 void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                 const uint32_t *d_refpk, uint32_t L, const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read,
+                 const uint32_t *d_refpk, uint32_t L, unsigned int *d_n_rec, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
                  cudaStream_t s) {
     NP2_K(k_pileup_emit)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk,
-                                                                                 d_cta_off, d_key, d_read);
+                                                                                 d_n_rec, cap, d_key, d_read);
 }
 
 __global__ void k_mark_heads(const uint64_t *__restrict__ key, uint32_t n, uint32_t *__restrict__ head) {

@@ -49,6 +49,7 @@ struct ReadsDev {
     uint32_t *ck_tpos = nullptr;
     uint16_t *ck_delta = nullptr;
     uint32_t *ck_read = nullptr;
+    uint16_t *blk_op = nullptr;  // per 32-column block: op (relative to op_off[read]) holding its first column; 0xFFFF = search
 };
 // K0: pull the SEQ fields out of a page-locked (mapped) record buffer; dst_off[r] is 16-B aligned + (source address & 15)
 void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
@@ -59,10 +60,10 @@ void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cu
 /* ------------------------------------------------------------------ K2 pileup */
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);
 // pass 1: per-CTA count of non-reference 3-mers; pass 2: write (key, read) records at the scanned offsets
-void pileup_count(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                  const uint32_t *d_refpk, uint32_t L, uint32_t *d_cta_count, cudaStream_t s);
+// single pass: every CTA reserves its output range with one atomic on *d_n_rec (must start at 2); records beyond
+// `cap` are counted but not written (the caller re-runs with the exact capacity)
 void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                 const uint32_t *d_refpk, uint32_t L, const uint32_t *d_cta_off, uint64_t *d_key, uint32_t *d_read,
+                 const uint32_t *d_refpk, uint32_t L, unsigned int *d_n_rec, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
                  cudaStream_t s);
 uint32_t pileup_ctas(uint32_t n_blocks);
 
@@ -129,6 +130,8 @@ void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, co
 void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s);
 void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s);
 void geno_region_hete(GenoDev g, cudaStream_t s);
+// pair-accumulator windows (d_W has na + 1 entries, the last one 0) from the alignseqs' record positions and ends
+void geno_pair_windows(const uint32_t *d_as_pos, const uint32_t *d_as_te, uint32_t na, uint32_t *d_W, cudaStream_t s);
 void geno_edges_accum(GenoDev g, const uint64_t *d_pair_off, unsigned long long *d_acc, int *d_err, cudaStream_t s);
 void geno_edges_select(const unsigned long long *d_acc, uint32_t n_slots, uint32_t *d_sel, uint32_t *d_nu, void *d_tmp,
                        size_t &tmp_bytes, cudaStream_t s);
