@@ -110,8 +110,9 @@ def peaks():
 def stage_bytes(stage, st):
     cols, L = st["alignment_columns"], st["L"]
     return {
-        # 4-bit SEQ in (0.5 B/column), packed nibble out (0.5), one 10-byte checkpoint per 32 columns out
-        "pack_columns": cols * (0.5 + 0.5 + 10 / 32),
+        # 4-bit SEQ in (0.5 B/column), packed nibble out (0.5), one 10-byte checkpoint out and one 2-byte op index in
+        # per 32 columns
+        "pack_columns": cols * (0.5 + 0.5 + 10 / 32 + 2 / 32),
         # packed columns in (0.5) + checkpoints in (10/32); the packed reference (0.5 B/bp) is shared by the ~30 reads
         # over a position and counted once
         "pileup_emit": cols * (0.5 + 10 / 32) + L * 0.5 + st.get("records", 0) * 12,
