@@ -6,14 +6,19 @@
 // `nextPolish2 count` (yak count on the GPU: FASTA/FASTQ[.gz] in, .yak dump out; yak/main.c:24-83).
 //
 // This file is the caller side of the hot path: hand-written BGZF/BAM/BAI and FASTA(.gz) readers
-// (zlib only) that hand each contig's raw alignment records to np2_polish_contig, and the orchestration
+// (zlib only; the BAM is memory-mapped and a contig's BGZF members are inflated in parallel, in place) that hand each contig's raw alignment records to np2_polish_contig, and the orchestration
 // the reference does with three thread stages (main.rs:1698-1853): contigs are LPT-partitioned over the GPUs, up to
 // three host threads (contexts) per GPU share one set of tables, records are printed in INPUT order (= the reference
 // with -t 1).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -183,91 +188,113 @@ int main_count(int argc, char **argv) {
 }
 
 /* ---------------------------------------------------------------- BGZF / BAM / BAI */
+// The file is memory-mapped.  A contig's records are the bytes between two virtual offsets the index gives (first
+// chunk begin, last chunk end of the reference): the BGZF members in between are located by a serial walk over their
+// headers (a few thousand per contig) and inflated IN PARALLEL straight into their final place in the record buffer,
+// so no byte is copied twice and no lock is held while a contig is decoded.
 struct BamFile {
-    FILE *fp = nullptr;
+    const uint8_t *map = nullptr;
+    size_t size = 0;
     std::vector<std::string> ref_names;
     std::vector<uint32_t> ref_lens;
     std::vector<uint64_t> ref_voff;  // virtual offset of the first record of each reference (UINT64_MAX = none / unknown)
+    std::vector<uint64_t> ref_vend;  // virtual offset just behind its last record
     uint64_t first_rec_voff = 0;
     bool have_index = false;
     int threads = 1;
 };
-
-struct RawBlock {
-    uint64_t coff;
-    std::vector<uint8_t> cdata;  // deflate payload
-    uint32_t isize;
+struct Member {   // one BGZF member (gzip member with the BC extra field)
+    uint64_t coff;   // file offset of the member
+    uint64_t data;   // file offset of the deflate payload
+    uint32_t clen;   // payload bytes
+    uint32_t isize;  // inflated bytes
+    uint32_t total;  // member bytes
 };
-// reads the next BGZF member; returns false at EOF
-bool read_block(FILE *fp, RawBlock &b) {
-    uint8_t h[18];
-    b.coff = (uint64_t)ftello(fp);
-    size_t n = fread(h, 1, 18, fp);
-    if (n == 0) return false;
-    if (n != 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) die("BAM/SAM parsing failed!");
+// parses the member header at file offset o; false at EOF
+bool member_at(const BamFile &bf, uint64_t o, Member &m) {
+    if (o >= bf.size) return false;
+    const uint8_t *h = bf.map + o;
+    if (o + 18 > bf.size || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) die("BAM/SAM parsing failed!");
     const uint32_t xlen = h[10] | h[11] << 8;
+    if (o + 12 + xlen > bf.size) die("BAM/SAM parsing failed!");
     uint32_t bsize = 0;
-    std::vector<uint8_t> extra(xlen);
-    memcpy(extra.data(), h + 12, std::min<uint32_t>(6, xlen));
-    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fp) != xlen - 6) die("BAM/SAM parsing failed!");
-    for (uint32_t o = 0; o + 4 <= xlen;) {
-        const uint32_t slen = extra[o + 2] | extra[o + 3] << 8;
-        if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2) bsize = (extra[o + 4] | extra[o + 5] << 8) + 1;
-        o += 4 + slen;
+    for (uint32_t x = 0; x + 4 <= xlen;) {
+        const uint8_t *e = h + 12 + x;
+        const uint32_t slen = e[2] | e[3] << 8;
+        if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = (e[4] | e[5] << 8) + 1;
+        x += 4 + slen;
     }
-    if (!bsize || bsize < 12 + xlen + 8) die("BAM/SAM parsing failed!");
-    const uint32_t clen = bsize - 12 - xlen - 8;
-    b.cdata.resize(clen);
-    uint8_t tail[8];
-    if (fread(b.cdata.data(), 1, clen, fp) != clen || fread(tail, 1, 8, fp) != 8) die("BAM/SAM parsing failed!");
-    memcpy(&b.isize, tail + 4, 4);
+    if (!bsize || bsize < 12 + xlen + 8 || o + bsize > bf.size) die("BAM/SAM parsing failed!");
+    m.coff = o;
+    m.data = o + 12 + xlen;
+    m.clen = bsize - 12 - xlen - 8;
+    m.total = bsize;
+    memcpy(&m.isize, h + bsize - 4, 4);
     return true;
 }
-void inflate_block(const RawBlock &b, uint8_t *out) {
-    if (!b.isize) return;
+void inflate_member(const BamFile &bf, const Member &m, uint8_t *out) {
+    if (!m.isize) return;
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, -15) != Z_OK) die("BAM/SAM parsing failed!");
-    zs.next_in = (Bytef *)b.cdata.data();
-    zs.avail_in = (uInt)b.cdata.size();
+    zs.next_in = (Bytef *)(bf.map + m.data);
+    zs.avail_in = m.clen;
     zs.next_out = out;
-    zs.avail_out = b.isize;
+    zs.avail_out = m.isize;
     const int rc = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
-    if (rc != Z_STREAM_END || zs.total_out != b.isize) die("BAM/SAM parsing failed!");
+    if (rc != Z_STREAM_END || zs.total_out != m.isize) die("BAM/SAM parsing failed!");
 }
-// inflates a batch of blocks in parallel into one contiguous buffer
-void inflate_batch(const std::vector<RawBlock> &blocks, std::vector<uint8_t> &out, std::vector<uint64_t> &uoff,
-                   int threads) {
-    uoff.assign(blocks.size() + 1, 0);
-    for (size_t i = 0; i < blocks.size(); i++) uoff[i + 1] = uoff[i] + blocks[i].isize;
-    out.resize(uoff.back());
-    std::atomic<size_t> next{0};
-    auto work = [&]() {
-        for (size_t i; (i = next.fetch_add(1)) < blocks.size();) inflate_block(blocks[i], out.data() + uoff[i]);
-    };
-    const int T = std::max(1, std::min<int>(threads, (int)blocks.size()));
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; t++) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
-}
+// growable byte buffer that is never zero-filled (a std::vector::resize would touch every page first)
+struct Blob {
+    uint8_t *p = nullptr;
+    size_t n = 0, cap = 0;
+    Blob() {}
+    Blob(const Blob &) = delete;
+    Blob &operator=(const Blob &) = delete;
+    ~Blob() { free(p); }
+    void resize(size_t want) {
+        if (want > cap) {
+            free(p);
+            cap = want + want / 8 + 4096;
+            p = static_cast<uint8_t *>(malloc(cap));
+            if (!p) die("out of memory");
+        }
+        n = want;
+    }
+    void swap(Blob &o) {
+        std::swap(p, o.p);
+        std::swap(n, o.n);
+        std::swap(cap, o.cap);
+    }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return n; }
+};
 
 void open_bam(const std::string &path, BamFile &bf) {
-    bf.fp = fopen(path.c_str(), "rb");
-    if (!bf.fp) die("\"" + path + "\" does not exist!");
-    // header: sequential blocks until the reference dictionary is complete
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) die("\"" + path + "\" does not exist!");
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) die("BAM/SAM parsing failed!");
+    bf.size = (size_t)st.st_size;
+    void *mp = mmap(nullptr, bf.size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (mp == MAP_FAILED) die("BAM/SAM parsing failed!");
+    bf.map = static_cast<const uint8_t *>(mp);
+    // header: sequential members until the reference dictionary is complete
     std::vector<uint8_t> u;
     std::vector<uint64_t> blk_coff, blk_uoff;
+    uint64_t next = 0;
     auto need = [&](size_t n) {
         while (u.size() < n) {
-            RawBlock b;
-            if (!read_block(bf.fp, b)) die("BAM/SAM parsing failed!");
-            blk_coff.push_back(b.coff);
+            Member m;
+            if (!member_at(bf, next, m)) die("BAM/SAM parsing failed!");
+            blk_coff.push_back(m.coff);
             blk_uoff.push_back(u.size());
-            size_t o = u.size();
-            u.resize(o + b.isize);
-            inflate_block(b, u.data() + o);
+            const size_t o = u.size();
+            u.resize(o + m.isize);
+            inflate_member(bf, m, u.data() + o);
+            next = m.coff + m.total;
         }
     };
     need(12);
@@ -291,10 +318,11 @@ void open_bam(const std::string &path, BamFile &bf) {
     // virtual offset of the first alignment record
     size_t bi = blk_uoff.size() - 1;
     while (blk_uoff[bi] > o) bi--;
-    if (o == u.size()) bf.first_rec_voff = (uint64_t)ftello(bf.fp) << 16;
+    if (o == u.size()) bf.first_rec_voff = next << 16;
     else bf.first_rec_voff = blk_coff[bi] << 16 | (o - blk_uoff[bi]);
     bf.ref_voff.assign(n_ref, UINT64_MAX);
-    // BAI: smallest chunk start of each reference
+    bf.ref_vend.assign(n_ref, 0);
+    // BAI: smallest chunk begin and largest chunk end of each reference
     for (const std::string &ip : {path + ".bai", path.substr(0, path.size() > 4 ? path.size() - 4 : 0) + ".bai"}) {
         FILE *fi = fopen(ip.c_str(), "rb");
         if (!fi) continue;
@@ -304,7 +332,7 @@ void open_bam(const std::string &path, BamFile &bf) {
         for (int32_t r = 0; r < nr && r < n_ref; r++) {
             int32_t n_bin;
             if (fread(&n_bin, 4, 1, fi) != 1) die("bad BAI");
-            uint64_t best = UINT64_MAX;
+            uint64_t best = UINT64_MAX, last = 0;
             for (int32_t b = 0; b < n_bin; b++) {
                 uint32_t bin;
                 int32_t n_chunk;
@@ -312,13 +340,17 @@ void open_bam(const std::string &path, BamFile &bf) {
                 for (int32_t c = 0; c < n_chunk; c++) {
                     uint64_t be[2];
                     if (fread(be, 8, 2, fi) != 2) die("bad BAI");
-                    if (bin != 37450) best = std::min(best, be[0]);
+                    if (bin != 37450) {
+                        best = std::min(best, be[0]);
+                        last = std::max(last, be[1]);
+                    }
                 }
             }
             int32_t n_intv;
             if (fread(&n_intv, 4, 1, fi) != 1) die("bad BAI");
             fseeko(fi, (off_t)n_intv * 8, SEEK_CUR);
             bf.ref_voff[r] = best;
+            bf.ref_vend[r] = last;
         }
         fclose(fi);
         bf.have_index = true;
@@ -327,48 +359,64 @@ void open_bam(const std::string &path, BamFile &bf) {
     if (!bf.have_index) die("Faield random access BAM/SAM!");  // IndexedReader needs the index (main.rs:1745-1747)
 }
 
-// IndexedReader::fetch((tid, 0, len)) + read loop (main.rs:1745-1751): every record of that reference, file order
-void fetch_records(BamFile &bf, int tid, std::vector<uint8_t> &blob) {
-    blob.clear();
+// IndexedReader::fetch((tid, 0, len)) + read loop (main.rs:1745-1751): every record of that reference, file order.
+// Thread-safe (the map is read-only); `threads` inflate workers.
+void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads) {
+    blob.resize(0);
     if (tid < 0 || bf.ref_voff[tid] == UINT64_MAX) return;
-    const uint64_t voff = bf.ref_voff[tid];
-    fseeko(bf.fp, (off_t)(voff >> 16), SEEK_SET);
-    size_t skip = voff & 0xFFFF;
-    std::vector<uint8_t> carry, u;
-    std::vector<uint64_t> uoff;
-    std::vector<RawBlock> batch;
-    bool done = false, eof = false;
-    while (!done && !eof) {
-        batch.clear();
-        const size_t want = (size_t)std::max(64, bf.threads * 16);
-        for (size_t i = 0; i < want; i++) {
-            RawBlock b;
-            if (!read_block(bf.fp, b)) {
-                eof = true;
-                break;
-            }
-            batch.push_back(std::move(b));
+    const uint64_t v0 = bf.ref_voff[tid], v1 = bf.ref_vend[tid];
+    if (v1 <= v0) return;
+    const uint64_t c0 = v0 >> 16, c1 = v1 >> 16;
+    const uint32_t u0 = (uint32_t)(v0 & 0xFFFF), u1 = (uint32_t)(v1 & 0xFFFF);
+    // members [c0, c1]; the one at c1 only contributes its first u1 bytes (none when u1 == 0)
+    std::vector<Member> ms;
+    std::vector<uint64_t> uoff(1, 0);
+    for (uint64_t o = c0; o <= c1;) {
+        Member m;
+        if (!member_at(bf, o, m)) {
+            if (o == c1 && u1 == 0) break;  // the end offset may point at EOF
+            die("BAM/SAM parsing failed!");
         }
-        inflate_batch(batch, u, uoff, bf.threads);
-        size_t o = std::min(skip, u.size());
-        skip -= o;
-        // stitch the partial record left over from the previous batch
-        carry.insert(carry.end(), u.begin() + o, u.end());
-        size_t p = 0;
-        while (p + 8 <= carry.size()) {
-            int32_t bs, ref_id;
-            memcpy(&bs, carry.data() + p, 4);
-            if (bs < 32) die("BAM/SAM parsing failed!");
-            if (p + 4 + (size_t)bs > carry.size()) break;
-            memcpy(&ref_id, carry.data() + p + 4, 4);
-            if (ref_id != tid) {
-                done = true;
-                break;
+        if (o == c1 && u1 == 0) break;
+        ms.push_back(m);
+        uoff.push_back(uoff.back() + m.isize);
+        o += m.total;
+    }
+    if (ms.empty()) return;
+    const uint64_t total = uoff.back();
+    const uint64_t cut_tail = (ms.back().coff == c1) ? ms.back().isize - std::min<uint32_t>(u1, ms.back().isize) : 0;
+    if ((uint64_t)u0 + cut_tail > total) die("BAM/SAM parsing failed!");
+    const uint64_t n = total - u0 - cut_tail;
+    blob.resize(n);
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        std::vector<uint8_t> tmp;
+        for (size_t i; (i = next.fetch_add(1)) < ms.size();) {
+            const uint64_t b = uoff[i], e = uoff[i + 1];          // position of the member in the untrimmed stream
+            const uint64_t lo = std::max<uint64_t>(b, u0), hi = std::min<uint64_t>(e, total - cut_tail);
+            if (lo >= hi) continue;
+            if (lo == b && hi == e) {
+                inflate_member(bf, ms[i], blob.p + (b - u0));       // whole member: straight into place
+            } else {                                               // first / last member: through a scratch buffer
+                tmp.resize(ms[i].isize);
+                inflate_member(bf, ms[i], tmp.data());
+                memcpy(blob.p + (lo - u0), tmp.data() + (lo - b), hi - lo);
             }
-            p += 4 + (size_t)bs;
         }
-        blob.insert(blob.end(), carry.begin(), carry.begin() + p);
-        carry.erase(carry.begin(), carry.begin() + p);
+    };
+    const int T = std::max(1, std::min<int>(threads, (int)ms.size()));
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    // the index is trusted for the range, the records are not: every one must belong to this reference
+    for (uint64_t p = 0; p < n;) {
+        int32_t bs, ref_id;
+        if (p + 8 > n) die("BAM/SAM parsing failed!");
+        memcpy(&bs, blob.p + p, 4);
+        memcpy(&ref_id, blob.p + p + 4, 4);
+        if (bs < 32 || p + 4 + (uint64_t)bs > n || ref_id != tid) die("BAM/SAM parsing failed!");
+        p += 4 + (uint64_t)bs;
     }
 }
 
@@ -459,8 +507,35 @@ Cli parse_args(int argc, char **argv) {
 
 }  // namespace
 
+// `nextPolish2 records <in.bam> <reference name> [threads]`: the raw alignment records of one reference on stdout
+// (what IndexedReader::fetch + read hand the worker closure) - a host-only seam for the BGZF / BAI reader tests
+int main_records(int argc, char **argv) {
+    if (argc < 4) {
+        fprintf(stderr, "Usage: nextPolish2 records <in.bam> <reference name> [threads]\n");
+        return 1;
+    }
+    BamFile bf;
+    bf.threads = argc > 4 ? std::max(1, atoi(argv[4])) : 4;
+    open_bam(argv[2], bf);
+    int tid = -1;
+    for (size_t r = 0; r < bf.ref_names.size(); r++)
+        if (bf.ref_names[r] == argv[3]) tid = (int)r;
+    if (tid < 0) die("Faield random access BAM/SAM!");
+    Blob blob;
+    fetch_records(bf, tid, blob, bf.threads);
+    fwrite(blob.data(), 1, blob.size(), stdout);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc >= 2 && std::string(argv[1]) == "count") return main_count(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "records") return main_records(argc, argv);
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
+    std::atomic<uint64_t> us_fetch{0}, us_polish{0}, us_tables{0}, us_lib_total{0}, us_lib_wait{0}, us_destroy{0}, us_call{0};
+    const bool timing = getenv("NP2_CLI_TIMING") != nullptr;
     Cli cli = parse_args(argc, argv);
     FILE *out = stdout;
     if (cli.out != "stdout") {  // option.rs:308-328: refuse to overwrite
@@ -527,10 +602,10 @@ int main(int argc, char **argv) {
         np2_secmap *secmap = nullptr;
         if (cli.o.use_secondary) {
             if (np2_secmap_create(&secmap) != NP2_OK) die(np2_last_error());
-            std::vector<uint8_t> blob;
+            Blob blob;
             for (int pass = 0; pass < 2; pass++)
                 for (size_t r = 0; r < bf.ref_names.size(); r++) {
-                    fetch_records(bf, (int)r, blob);
+                    fetch_records(bf, (int)r, blob, bf.threads);
                     const int rc = pass == 0 ? np2_secmap_scan_ids(secmap, blob.data(), blob.size())
                                              : np2_secmap_scan_seqs(secmap, blob.data(), blob.size());
                     if (rc != NP2_OK) die(np2_last_error());
@@ -543,28 +618,34 @@ int main(int argc, char **argv) {
             std::lock_guard<std::mutex> lk(err_mu);
             if (first_err.empty()) first_err = m;
         };
-        auto polish_one = [&](np2_ctx *ctx, std::vector<np2_table *> &tabs, size_t i, std::vector<uint8_t> &blob) -> bool {
+        auto polish_one = [&](np2_ctx *ctx, std::vector<np2_table *> &tabs, size_t i, Blob &blob) -> bool {
             {
                 std::lock_guard<std::mutex> lk(bam_mu);
+                const auto t0 = std::chrono::steady_clock::now();
                 int tid = -1;
                 for (size_t r = 0; r < bf.ref_names.size(); r++)
                     if (bf.ref_names[r] == contigs[i].name) tid = (int)r;
                 if (tid < 0) return fail("Faield random access BAM/SAM!"), false;
-                fetch_records(bf, tid, blob);
+                fetch_records(bf, tid, blob, bf.threads);
+                us_fetch += (uint64_t)(since(t0) * 1e6);
             }
+            const auto t_polish = std::chrono::steady_clock::now();
             if (secmap) {  // secondary records get their SEQ (main.rs:1775-1783)
                 uint64_t need = 0;
                 if (np2_secmap_fill(secmap, blob.data(), blob.size(), nullptr, 0, &need) != NP2_OK)
                     return fail(np2_last_error()), false;
-                std::vector<uint8_t> filled(need);
-                if (np2_secmap_fill(secmap, blob.data(), blob.size(), filled.data(), need, &need) != NP2_OK)
+                Blob filled;
+                filled.resize(need);
+                if (np2_secmap_fill(secmap, blob.data(), blob.size(), filled.p, need, &need) != NP2_OK)
                     return fail(np2_last_error()), false;
                 blob.swap(filled);
             }
             np2_job *job = nullptr;
+            const auto t_call = std::chrono::steady_clock::now();
             if (np2_polish_contig(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(), blob.data(),
                                   blob.size(), tabs.data(), (uint32_t)tabs.size(), &cli.o, &job) != NP2_OK)
                 return fail(np2_last_error()), false;
+            us_call += (uint64_t)(since(t_call) * 1e6);
             const uint32_t *pos;
             const uint8_t *base;
             uint64_t nb = np2_job_get_consensus(job, cli.o.out_pos ? &pos : nullptr, &base);
@@ -586,23 +667,39 @@ int main(int argc, char **argv) {
                 else memcpy(results[i].data() + o, base, nb);
                 results[i][o + nb] = '\n';
             }
+            if (timing) {  // the library's own clocks: device-side step and the upload stages
+                const char *names;
+                const float *ms;
+                const uint32_t *ln;
+                const uint32_t ns = np2_job_get_timings(job, &names, &ms, &ln);
+                for (uint32_t x = 0; x < ns; x++) {
+                    if (!strcmp(names, "total")) us_lib_total += (uint64_t)(ms[x] * 1e3);
+                    if (!strcmp(names, "upload:host_wait")) us_lib_wait += (uint64_t)(ms[x] * 1e3);
+                    names += strlen(names) + 1;
+                }
+            }
+            const auto t_destroy = std::chrono::steady_clock::now();
             np2_job_destroy(job);
+            us_destroy += (uint64_t)(since(t_destroy) * 1e6);
             done[i] = 1;
+            us_polish += (uint64_t)(since(t_polish) * 1e6);
             return true;
         };
         auto worker = [&](int g) {
             np2_ctx *ctx = nullptr;
             if (np2_ctx_create(g, &ctx) != NP2_OK) return fail(np2_last_error());
             std::vector<np2_table *> tabs;
+            const auto t_tab = std::chrono::steady_clock::now();
             for (auto &y : cli.yaks) {
                 np2_table *t = nullptr;
                 if (np2_yak_load(ctx, y.c_str(), &t) != NP2_OK) return fail(np2_last_error());
                 tabs.push_back(t);
             }
+            us_tables += (uint64_t)(since(t_tab) * 1e6);
             std::sort(share[g].begin(), share[g].end());
             std::atomic<size_t> next{0};
             auto lane = [&](np2_ctx *c) {
-                std::vector<uint8_t> blob;
+                Blob blob;
                 for (;;) {
                     const size_t x = next.fetch_add(1);
                     if (x >= share[g].size()) break;
@@ -634,7 +731,20 @@ int main(int argc, char **argv) {
         np2_secmap_destroy(secmap);
         if (!first_err.empty()) die(first_err);
     }
+    const auto t_write = std::chrono::steady_clock::now();
     for (size_t i = 0; i < n; i++) fwrite(results[i].data(), 1, results[i].size(), out);
     if (out != stdout) fclose(out);
+    if (timing) {
+        uint64_t bp = 0;
+        for (size_t i : todo) bp += contigs[i].seq.size();
+        const double wall = since(t_start);
+        fprintf(stderr,
+                "[np2 timing] wall %.3f s, %.1f Mbp polished -> %.1f Mbp/s end to end; summed over worker threads: table "
+                "staging %.3f s, BGZF inflate + record fetch %.3f s (serialised), parse + upload + GPU + result %.3f s; "
+                "FASTA write %.3f s; inside it: np2_polish_contig %.3f s (of which the library's run step %.3f s, waiting "
+                "for the upload %.3f s), job destroy %.3f s\n",
+                wall, bp / 1e6, bp / 1e6 / wall, us_tables / 1e6, us_fetch / 1e6, us_polish / 1e6, since(t_write),
+                us_call / 1e6, us_lib_total / 1e6, us_lib_wait / 1e6, us_destroy / 1e6);
+    }
     return 0;
 }

@@ -255,6 +255,9 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
     auto work = [&](unsigned ti) {
         Segment &sg = *segs[ti];
         sg.reset();
+        // one page-locked allocation per segment instead of a chain of doublings (each one a cudaHostAlloc + copy +
+        // cudaFreeHost): HiFi records carry about one column-consuming op per 400 bytes
+        sg.ops.reserve((bound(ti + 1) - bound(ti)) / 256 + 65536);
         const uint64_t lo = bound(ti), hi = bound(ti + 1);
         const uint64_t from = ti == 0 ? 0 : find_start(bam, bam_len, lo, hi);
         if (from == UINT64_MAX) return;

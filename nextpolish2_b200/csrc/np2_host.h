@@ -64,6 +64,9 @@ struct HVec {  // minimal growable array of trivially copyable T on the hook all
         stream_store(&p[n++], v);
     }
     void clear() { n = 0; }
+    void reserve(size_t want) {  // only when empty: growing would have to copy
+        if (n == 0 && want > cap) grow(want);
+    }
     size_t size() const { return n; }
 };
 

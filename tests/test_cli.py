@@ -103,3 +103,19 @@ def test_cli_end_to_end_matches_oracle(files):
         j = O.Job(s, b, ots, O.Opts(min_ctg_len=30_000))
         want_pos += O.format_fasta(n, *j.consensus(), out_pos=True)
     assert r2.returncode == 0 and r2.stdout == want_pos
+
+
+@pytest.mark.parametrize("level", [0, 1, 6])
+def test_bam_reader_returns_every_record_of_a_reference(files, tmp_path, level):
+    """BGZF members located through the BAI (first chunk begin .. last chunk end) and inflated in parallel, in place:
+    the bytes handed to the polish are exactly the reference's records, for stored and deflated BGZF, any thread count,
+    including references whose records start / end in the middle of a member."""
+    bam = str(tmp_path / ("l%d.bam" % level))
+    synth.write_bam(bam, files["names"], [len(c) for c in files["contigs"]], files["blobs"], level=level)
+    for name, blob in zip(files["names"], files["blobs"]):
+        for threads in (1, 5):
+            r = subprocess.run([CLI, "records", bam, name, str(threads)], capture_output=True, timeout=120)
+            assert r.returncode == 0, r.stderr
+            assert r.stdout == bytes(blob)
+    r = subprocess.run([CLI, "records", bam, "nope"], capture_output=True)
+    assert r.returncode != 0
