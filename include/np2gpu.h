@@ -79,6 +79,7 @@ void np2_opts_default(np2_opts *o); /* option.rs:267-292 */
  * min(16, hardware threads)); process-wide.  A caller running several contexts or ranks on one box divides the cores. */
 void np2_set_host_threads(uint32_t n);
 
+int np2_device_count(void); /* visible CUDA devices (0 when there is none / no driver) */
 int np2_ctx_create(int device, np2_ctx **out);
 void np2_ctx_destroy(np2_ctx *ctx);
 

@@ -48,7 +48,7 @@ EXPORTS = [
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
     "np2_debug_phase", "np2_set_host_threads",
-    "np2_count_create", "np2_count_add", "np2_count_distinct", "np2_count_finish", "np2_count_destroy",
+    "np2_device_count", "np2_count_create", "np2_count_add", "np2_count_distinct", "np2_count_finish", "np2_count_destroy",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library():
     L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
     L.np2_format_fasta.restype = u64
     L.np2_format_fasta.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int, vp, u64]
+    L.np2_device_count.restype = C.c_int
     L.np2_count_create.argtypes = [vp, u32, C.POINTER(vp)]
     L.np2_count_add.argtypes = [vp, vp, vp, u64]
     L.np2_count_distinct.restype = u64

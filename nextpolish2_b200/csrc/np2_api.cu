@@ -221,6 +221,7 @@ struct np2_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of the per-read arrays, concurrent with the K0 gather
     cudaMemPool_t pool = nullptr;
+    uint64_t pool_warm = 0;  // bytes the pool has been grown to in one step (np2_job_create)
     int refs = 1;  // tables and jobs keep their context alive (np2_ctx_destroy only drops the caller's reference)
     std::vector<JobScratch *> scratch_pool;
     JobScratch *take_scratch() {
@@ -1935,6 +1936,15 @@ void np2_opts_default(np2_opts *o) {
     o->max_clip_len = 100;
 }
 
+int np2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int np2_ctx_create(int device, np2_ctx **out) {
     return guard([&] {
         int n = 0;
@@ -2291,6 +2301,20 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
             if (tlen < 16) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig shorter than 16 bp");
             if (tlen >= (1u << 30)) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig >= 2^30 bp (main.rs:270)");
             NP2_CUDA(cudaSetDevice(ctx->device));
+            {   // Grow the context's memory pool in ONE step to what a contig of this size needs (record bytes ~ 1.5 x
+                // alignment columns; ~6 B per column + ~100 B per position of device state): a cold pool otherwise grows
+                // by a hundred small mappings, which costs more than the whole polish.
+                const uint64_t want = bam_len * 4 + (uint64_t)tlen * 100 + (64ull << 20);
+                if (want > ctx->pool_warm) {
+                    void *p = nullptr;
+                    if (cudaMallocFromPoolAsync(&p, want, ctx->pool, ctx->stream) == cudaSuccess) {
+                        cudaFreeAsync(p, ctx->stream);
+                        ctx->pool_warm = want;
+                    } else {
+                        cudaGetLastError();  // not enough room for the estimate: let the pool grow on demand
+                    }
+                }
+            }
             j->send_contig(tseq);  // in flight while the host walks the records
             parse_records(bam, bam_len, tlen, *opts, j->ing);
             j->enqueue_arrays();   // copy stream

@@ -47,33 +47,52 @@ std::vector<Contig> read_fasta(const std::string &path) {
     if (!f) die("\"" + path + "\" does not exist!");
     gzbuffer(f, 1 << 20);
     std::vector<Contig> out;
-    std::vector<char> buf(1 << 20);
-    std::string line;
+    std::vector<char> buf(4 << 20);
+    std::string header;
     bool in_header = false, bol = true;
     auto end_header = [&]() {
         size_t e = 0;
-        while (e < line.size() && !isspace((unsigned char)line[e])) e++;
-        out.push_back(Contig{line.substr(1, e - 1), std::string()});
-        line.clear();
+        while (e < header.size() && !isspace((unsigned char)header[e])) e++;
+        out.push_back(Contig{header.substr(0, e), std::string()});
+        header.clear();
     };
     for (;;) {
-        int n = gzread(f, buf.data(), (unsigned)buf.size());
+        const int n = gzread(f, buf.data(), (unsigned)buf.size());
         if (n <= 0) break;
-        for (int i = 0; i < n; i++) {
-            const char c = buf[i];
-            if (in_header) {
-                if (c == '\n') {
+        int i = 0;
+        while (i < n) {
+            if (in_header) {  // up to the end of the line
+                const char *e = (const char *)memchr(buf.data() + i, '\n', n - i);
+                const int stop = e ? (int)(e - buf.data()) : n;
+                header.append(buf.data() + i, stop - i);
+                i = stop;
+                if (e) {
+                    while (!header.empty() && header.back() == '\r') header.pop_back();
                     end_header();
                     in_header = false;
-                } else if (c != '\r') line.push_back(c);
-            } else if (c == '>' && bol) {
+                    bol = true;
+                    i++;
+                }
+            } else if (bol && buf[i] == '>') {
                 in_header = true;
-                line.assign(1, '>');
-            } else if (c != '\n' && c != '\r') {
-                if (out.empty()) die("FASTA parsing failed!");
-                out.back().seq.push_back(c);
+                bol = false;
+                i++;
+            } else {  // a stretch of sequence: everything up to the next line break goes in with one append
+                const char *e = (const char *)memchr(buf.data() + i, '\n', n - i);
+                int stop = e ? (int)(e - buf.data()) : n;
+                int len = stop - i;
+                while (len > 0 && buf[i + len - 1] == '\r') len--;
+                if (len > 0) {
+                    if (out.empty()) die("FASTA parsing failed!");
+                    out.back().seq.append(buf.data() + i, len);
+                }
+                i = stop;
+                bol = false;
+                if (e) {
+                    bol = true;
+                    i++;
+                }
             }
-            bol = c == '\n';
         }
     }
     if (in_header) end_header();
@@ -245,19 +264,39 @@ void inflate_member(const BamFile &bf, const Member &m, uint8_t *out) {
     inflateEnd(&zs);
     if (rc != Z_STREAM_END || zs.total_out != m.isize) die("BAM/SAM parsing failed!");
 }
-// growable byte buffer that is never zero-filled (a std::vector::resize would touch every page first)
+// growable byte buffer that is never zero-filled (a std::vector::resize would touch every page first).  The polish
+// lanes use page-locked memory (np2_host_alloc): the device then pulls the SEQ fields straight out of the inflated
+// records and the library's host-side compaction pass is skipped.
 struct Blob {
     uint8_t *p = nullptr;
     size_t n = 0, cap = 0;
-    Blob() {}
+    bool pinned = false;
+    explicit Blob(bool page_locked = false) : pinned(page_locked) {}
     Blob(const Blob &) = delete;
     Blob &operator=(const Blob &) = delete;
-    ~Blob() { free(p); }
+    ~Blob() { release(); }
+    void release() {
+        if (p) {
+            if (pinned) np2_host_free(p);
+            else free(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
     void resize(size_t want) {
         if (want > cap) {
-            free(p);
-            cap = want + want / 8 + 4096;
-            p = static_cast<uint8_t *>(malloc(cap));
+            release();
+            cap = want + want / 4 + 4096;
+            if (pinned) {
+                void *q = nullptr;
+                if (np2_host_alloc(cap, &q) != NP2_OK) {  // fall back to pageable memory
+                    pinned = false;
+                    q = malloc(cap);
+                }
+                p = static_cast<uint8_t *>(q);
+            } else {
+                p = static_cast<uint8_t *>(malloc(cap));
+            }
             if (!p) die("out of memory");
         }
         n = want;
@@ -266,6 +305,7 @@ struct Blob {
         std::swap(p, o.p);
         std::swap(n, o.n);
         std::swap(cap, o.cap);
+        std::swap(pinned, o.pinned);
     }
     const uint8_t *data() const { return p; }
     size_t size() const { return n; }
@@ -547,6 +587,8 @@ int main(int argc, char **argv) {
         if (!out) die("Failed to freopen: \"" + cli.out + "\"");
     }
     std::vector<Contig> contigs = read_fasta(cli.fa);
+    const double s_fasta = since(t_start);
+    double s_setup = 0, s_workers = 0;
     const size_t n = contigs.size();
     for (auto &c : contigs)
         if (c.seq.size() >= 0xFFFFFFFFull) die(c.name + " is too long!");  // main.rs:1707-1711
@@ -573,15 +615,8 @@ int main(int argc, char **argv) {
         open_bam(cli.bam, bf);
         int n_gpu = cli.gpus;
         if (n_gpu <= 0) {
-            // probe: contexts are created until one fails
-            n_gpu = 0;
-            for (int d = 0; d < 16; d++) {
-                np2_ctx *c = nullptr;
-                if (np2_ctx_create(d, &c) != NP2_OK) break;
-                np2_ctx_destroy(c);
-                n_gpu++;
-            }
-            if (n_gpu == 0) die(std::string("no usable GPU: ") + np2_last_error());
+            n_gpu = np2_device_count();
+            if (n_gpu == 0) die("no usable GPU (libnp2gpu has no CPU fallback)");
         }
         n_gpu = (int)std::min<size_t>(n_gpu, todo.size());
         // LPT partition by contig length (weight ~ length x depth)
@@ -634,7 +669,7 @@ int main(int argc, char **argv) {
                 uint64_t need = 0;
                 if (np2_secmap_fill(secmap, blob.data(), blob.size(), nullptr, 0, &need) != NP2_OK)
                     return fail(np2_last_error()), false;
-                Blob filled;
+                Blob filled(false);
                 filled.resize(need);
                 if (np2_secmap_fill(secmap, blob.data(), blob.size(), filled.p, need, &need) != NP2_OK)
                     return fail(np2_last_error()), false;
@@ -699,7 +734,9 @@ int main(int argc, char **argv) {
             std::sort(share[g].begin(), share[g].end());
             std::atomic<size_t> next{0};
             auto lane = [&](np2_ctx *c) {
-                Blob blob;
+                // pageable on purpose: page-locking ~0.5 GB per lane costs more than the library's compaction pass
+                // saves on anything but very large inputs (measured, profiles/r01_cli_e2e.txt)
+                Blob blob(false);
                 for (;;) {
                     const size_t x = next.fetch_add(1);
                     if (x >= share[g].size()) break;
@@ -725,9 +762,11 @@ int main(int argc, char **argv) {
             for (auto t : tabs) np2_yak_free(t);
             np2_ctx_destroy(ctx);
         };
+        s_setup = since(t_start);
         std::vector<std::thread> th;
         for (int g = 0; g < n_gpu; g++) th.emplace_back(worker, g);
         for (auto &t : th) t.join();
+        s_workers = since(t_start);
         np2_secmap_destroy(secmap);
         if (!first_err.empty()) die(first_err);
     }
@@ -739,11 +778,12 @@ int main(int argc, char **argv) {
         for (size_t i : todo) bp += contigs[i].seq.size();
         const double wall = since(t_start);
         fprintf(stderr,
-                "[np2 timing] wall %.3f s, %.1f Mbp polished -> %.1f Mbp/s end to end; summed over worker threads: table "
+                "[np2 timing] wall %.3f s (FASTA read until %.3f, BAM open + GPU probe until %.3f, workers until %.3f), "
+                "%.1f Mbp polished -> %.1f Mbp/s end to end; summed over worker threads: table "
                 "staging %.3f s, BGZF inflate + record fetch %.3f s (serialised), parse + upload + GPU + result %.3f s; "
                 "FASTA write %.3f s; inside it: np2_polish_contig %.3f s (of which the library's run step %.3f s, waiting "
                 "for the upload %.3f s), job destroy %.3f s\n",
-                wall, bp / 1e6, bp / 1e6 / wall, us_tables / 1e6, us_fetch / 1e6, us_polish / 1e6, since(t_write),
+                wall, s_fasta, s_setup, s_workers, bp / 1e6, bp / 1e6 / wall, us_tables / 1e6, us_fetch / 1e6, us_polish / 1e6, since(t_write),
                 us_call / 1e6, us_lib_total / 1e6, us_lib_wait / 1e6, us_destroy / 1e6);
     }
     return 0;
