@@ -142,10 +142,11 @@ def run_ours(args):
     ctx = np2.Context(local)
     # the box's cores are shared by the ranks and by the contigs each rank keeps in flight
     from nextpolish2_b200.api import set_host_threads
-    set_host_threads(max(2, min(16, (os.cpu_count() or 8) // max(world, 1) // max(1, min(args.e2e_inflight, 2)) * 2)))
+    set_host_threads(args.host_threads or
+                     max(2, min(16, (os.cpu_count() or 8) // max(world, 1) // max(1, min(args.e2e_inflight, 2)) * 2)))
     tables = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in KS]
     opts = np2.Opts()  # reference defaults; the 10 Mbp contig is above -L 1000000
-    bam_pinned = torch.from_numpy(c["bam"]).pin_memory()
+    bam_pinned = torch.from_numpy(c["bam"]) if args.pageable else torch.from_numpy(c["bam"]).pin_memory()
     contig_pinned = torch.from_numpy(A.copy()).pin_memory()
     bam_np, contig_np = bam_pinned.numpy(), contig_pinned.numpy()
 
@@ -184,6 +185,7 @@ def run_ours(args):
     # (one host thread + one context + one stream each, tables shared: the CLI's double buffering), so the PCIe
     # upload and host-side record parsing of one contig overlap the kernels of another.
     e2e_parts = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
+    e2e_parts_inflight = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
 
     def e2e_step(cx, acc=None):
         t0 = time.perf_counter()
@@ -218,7 +220,7 @@ def run_ours(args):
         def work(w):
             try:
                 for _ in range(share[w]):
-                    tr_box[0] = e2e_step(ctxs[w], e2e_parts if n_inflight == 1 else None)
+                    tr_box[0] = e2e_step(ctxs[w], e2e_parts if n_inflight == 1 else e2e_parts_inflight)
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         torch.cuda.synchronize()
@@ -282,7 +284,10 @@ def run_ours(args):
             "e2e": {"value": round(mbp_total / e2e_time, 3), "unit": "Mbp/s", "h2d_bytes_per_step": tr["h2d_bytes"],
                     "d2h_bytes_per_step": tr["d2h_bytes"], "contigs_in_flight": args.e2e_inflight,
                     "one_at_a_time": round(mbp_total / e2e_serial_time, 3),
-                    "one_at_a_time_ms": {k: round(v / max(1, e2e_parts["n"]), 3) for k, v in e2e_parts.items() if k != "n"}},
+                    "one_at_a_time_ms": {k: round(v / max(1, e2e_parts["n"]), 3) for k, v in e2e_parts.items() if k != "n"},
+                    "in_flight_ms_per_contig_per_thread": {k: round(v / max(1, e2e_parts_inflight["n"]), 3)
+                                                           for k, v in e2e_parts_inflight.items()
+                                                           if k in ("create_parse", "upload", "run", "result")}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -400,6 +405,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--het", type=float, default=0.0, help="heterozygosity of the synthetic contig (configs[2]: 0.01)")
     ap.add_argument("--no-yak-bench", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="record buffer in pageable memory (host compaction path)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads per library call (0 = cores / ranks / ~in flight)")
     ap.add_argument("--e2e-inflight", type=int, default=3, help="contigs in flight per GPU in the end-to-end arm")
     args = ap.parse_args()
     if args.impl == "reference":

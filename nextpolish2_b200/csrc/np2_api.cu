@@ -52,11 +52,76 @@ cudaMemPool_t pool_of(cudaStream_t st) {
     return it == g_stream_pool.end() ? nullptr : it->second;
 }
 
+// Per-run scratch arena.  A run makes ~150 small stream-ordered allocations (and as many frees); each is a driver call,
+// and with several contigs in flight the threads queue up on the driver's lock.  Inside np2_job::run every allocation
+// below kArenaMax is a pointer bump in a block that lives with the context's scratch (so in steady state a run
+// allocates nothing); large buffers still come from the context's pool.
+struct Arena {
+    struct Block {
+        uint8_t *p;
+        size_t cap;
+    };
+    std::vector<Block> blocks;
+    size_t cur = 0, off = 0, used_total = 0;
+    void *bump(size_t bytes, cudaStream_t st) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        while (cur < blocks.size() && off + bytes > blocks[cur].cap) {
+            cur++;
+            off = 0;
+        }
+        if (cur == blocks.size()) {
+            Block b;
+            b.cap = std::max<size_t>(bytes, 64u << 20);
+            cudaMemPool_t pool = pool_of(st);
+            cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&b.p, b.cap, pool, st) : cudaMallocAsync((void **)&b.p, b.cap, st);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            blocks.push_back(b);
+            off = 0;
+        }
+        void *r = blocks[cur].p + off;
+        off += bytes;
+        used_total += bytes;
+        return r;
+    }
+    // start of a run: everything handed out before is dead (same stream, so reuse is ordered); a run that spilled
+    // into several blocks gets one block of the right size next time
+    void reset(cudaStream_t st) {
+        if (blocks.size() > 1) {
+            for (auto &b : blocks) cudaFreeAsync(b.p, st);
+            blocks.clear();
+            Block b;
+            b.cap = used_total + used_total / 4 + (16u << 20);
+            cudaMemPool_t pool = pool_of(st);
+            cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&b.p, b.cap, pool, st) : cudaMallocAsync((void **)&b.p, b.cap, st);
+            if (e == cudaSuccess) blocks.push_back(b);
+            else cudaGetLastError();
+        }
+        cur = 0;
+        off = 0;
+        used_total = 0;
+    }
+    void destroy(cudaStream_t st) {
+        for (auto &b : blocks) cudaFreeAsync(b.p, st);
+        blocks.clear();
+    }
+};
+constexpr size_t kArenaMax = 4u << 20;
+thread_local Arena *g_arena = nullptr;
+struct ArenaScope {
+    Arena *prev;
+    explicit ArenaScope(Arena *a) : prev(g_arena) { g_arena = a; }
+    ~ArenaScope() { g_arena = prev; }
+};
+
 template <class T>
 struct DBuf {  // stream-ordered device buffer
     T *p = nullptr;
     size_t n = 0;
     cudaStream_t s = nullptr;
+    bool from_arena = false;
     DBuf() {}
     DBuf(const DBuf &) = delete;
     DBuf &operator=(const DBuf &) = delete;
@@ -64,6 +129,13 @@ struct DBuf {  // stream-ordered device buffer
         release();
         s = st;
         n = count;
+        if (count && g_arena && count * sizeof(T) <= kArenaMax) {
+            p = static_cast<T *>(g_arena->bump(count * sizeof(T), st));
+            if (p) {
+                from_arena = true;
+                return;
+            }
+        }
         if (count) {
             cudaMemPool_t pool = pool_of(st);
             cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), pool, st)
@@ -81,9 +153,10 @@ struct DBuf {  // stream-ordered device buffer
     void upload(const T *h, size_t count) { NP2_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
     void download(T *h, size_t count) const { NP2_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && !from_arena) cudaFreeAsync(p, s);
         p = nullptr;
         n = 0;
+        from_arena = false;
     }
     ~DBuf() { release(); }
 };
@@ -187,7 +260,8 @@ struct JobScratch {
     PBuf<uint32_t> p_cpos;
     std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
     cudaEvent_t seq_ev[2] = {nullptr, nullptr};
-    cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr;
+    Arena arena;  // per-run device scratch (small allocations)
     PBuf<uint8_t> p_up_stage, p_seq_args, p_phase;
     StageTimer timer;
     ~JobScratch() {
@@ -197,6 +271,7 @@ struct JobScratch {
         if (ev_copied) cudaEventDestroy(ev_copied);
         if (ev_t0) cudaEventDestroy(ev_t0);
         if (ev_t1) cudaEventDestroy(ev_t1);
+        if (ev_k0) cudaEventDestroy(ev_k0);
     }
 };
 // bump allocator over a pinned staging buffer: many small device arrays come back with one synchronisation and
@@ -235,7 +310,11 @@ static void ctx_release(np2_ctx *ctx) {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (JobScratch *sc : ctx->scratch_pool) delete sc;
+    for (JobScratch *sc : ctx->scratch_pool) {
+        sc->arena.destroy(ctx->stream);
+        delete sc;
+    }
+    cudaStreamSynchronize(ctx->stream);
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         g_stream_pool.erase(ctx->stream);
@@ -419,9 +498,20 @@ void np2_job::send_seq() {
         np2::store_fence();
         NP2_CUDA(cudaMemcpyAsync(d_src_off.p, st + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, s));
         NP2_CUDA(cudaMemcpyAsync(d_nbytes.p, st + (size_t)n * 16, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        // K0 runs on the context's high-priority copy stream: its CTAs only wait on PCIe, but they must be RESIDENT
+        // to keep enough loads in flight; when another contig's kernels fill the SMs, a normal-priority K0 gets its
+        // CTAs scheduled late and the link idles.  The main stream joins again before the offsets are freed.
+        cudaStream_t c2 = ctx->copy_stream;
+        if (!sc->ev_k0) NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_k0, cudaEventDisableTiming));
+        NP2_CUDA(cudaEventRecord(sc->ev_k0, s));  // allocations + offset uploads above
+        NP2_CUDA(cudaStreamWaitEvent(c2, sc->ev_k0, 0));
+        timer.s = c2;
         int h = timer.begin("upload:seq_gather", 1);
-        gather_seq(src, d_src_off.p, d_seq_off.p, d_nbytes.p, d_blob.p, n, s);
+        gather_seq(src, d_src_off.p, d_seq_off.p, d_nbytes.p, d_blob.p, n, c2);
         timer.end(h);
+        timer.s = s;
+        NP2_CUDA(cudaEventRecord(sc->ev_k0, c2));
+        NP2_CUDA(cudaStreamWaitEvent(s, sc->ev_k0, 0));
         h2d += (uint64_t)n * 12;
         for (uint32_t r = 0; r < n; r++) h2d += ing.seq_bytes[r];
         return;  // scratch is freed in stream order, after the kernel
@@ -1823,6 +1913,8 @@ void np2_job::run(int32_t dump_it) {
     }
     if (!uploaded) upload();
     const uint32_t n = R.n_reads;
+    sc->arena.reset(s);
+    ArenaScope arena_scope(&sc->arena);
     const int h_total = timer.begin("total", 0);
     DBuf<int> d_bad;
     d_bad.alloc(1, s);
@@ -1962,7 +2054,11 @@ int np2_ctx_create(int device, np2_ctx **out) {
         np2_ctx *c = new np2_ctx();
         c->device = device;
         NP2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        NP2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        {
+            int lo = 0, hi = 0;  // numerically lower = higher priority
+            NP2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            NP2_CUDA(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi));
+        }
         // a private pool that keeps freed blocks: per-iteration scratch is re-used instead of going back to the driver
         cudaMemPoolProps props;
         memset(&props, 0, sizeof props);

@@ -301,9 +301,10 @@ __global__ void __launch_bounds__(256) k_gather_seq(const uint8_t *__restrict__ 
 // that is in flight on this GPU.
 void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
                 uint8_t *d_dst, uint32_t n_reads, cudaStream_t s) {
+    static const uint32_t ctas = getenv("NP2_K0_CTAS") ? (uint32_t)atoi(getenv("NP2_K0_CTAS")) : 2 * 148;
     if (n_reads)
-        NP2_K(k_gather_seq)<<<std::min<uint32_t>(n_reads, 2 * 148), 256, 0, s>>>(src_mapped, d_src_off, d_dst_off, d_nbytes,
-                                                                               d_dst, n_reads);
+        NP2_K(k_gather_seq)<<<std::min<uint32_t>(n_reads, std::max(1u, ctas)), 256, 0, s>>>(src_mapped, d_src_off, d_dst_off,
+                                                                                       d_nbytes, d_dst, n_reads);
 }
 
 /* =============================================================== K1: expand + trim + pack */
