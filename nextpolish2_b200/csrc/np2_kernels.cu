@@ -9,6 +9,7 @@
 //   (K4/K6 and the genotype kernels live in np2_geno.cu)
 //
 // All of this is integer / byte work bound by HBM traffic and latency; there is no tensor-core term.
+#include <cuda/ptx>
 #include <cub/block/block_reduce.cuh>
 #include <cub/block/block_scan.cuh>
 
@@ -296,12 +297,87 @@ __global__ void __launch_bounds__(256) k_gather_seq(const uint8_t *__restrict__ 
         }
     }
 }
+// ---- the same gather with the TMA engines (cp.async.bulk, 1-D): one thread per CTA drives a two-stage pipeline
+// host memory -> shared memory -> device memory; no register, LSU or warp-slot cost per byte, so the SMs stay free
+// for the kernels of the other contigs in flight.  Source, destination and size are multiples of 16 bytes by
+// construction (the destination slot keeps the source's misalignment).
+constexpr uint32_t kTmaStage = 16u << 10;  // 2 stages x 16 KB per CTA: a small shared-memory footprint keeps the L1 of
+                                           // the kernels running next to it
+__global__ void __launch_bounds__(32) k_gather_seq_tma(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                                                       const uint64_t *__restrict__ dst_off,
+                                                       const uint32_t *__restrict__ nbytes, uint8_t *__restrict__ dst,
+                                                       uint32_t n_reads) {
+    extern __shared__ __align__(128) uint8_t smem[];  // 2 stages
+    __shared__ __align__(8) uint64_t bar[2];
+    if (threadIdx.x != 0) return;
+    namespace ptx = cuda::ptx;
+    ptx::mbarrier_init(&bar[0], 1);
+    ptx::mbarrier_init(&bar[1], 1);
+    ptx::fence_proxy_async(ptx::space_shared);  // barrier initialisation visible to the async proxy
+    uint32_t phase[2] = {0, 0};
+    uint32_t issued = 0;       // chunks whose load has been issued
+    uint8_t *pend_dst = nullptr;  // the chunk loaded into stage (issued - 1) & 1, waiting to be stored
+    uint32_t pend_bytes = 0;
+    auto flush = [&]() {  // wait for the pending load, store it
+        if (!pend_bytes) return;
+        const uint32_t st = (issued - 1) & 1;
+        while (!ptx::mbarrier_try_wait_parity(&bar[st], phase[st])) {
+        }
+        phase[st] ^= 1;
+        ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, pend_dst, smem + st * kTmaStage, pend_bytes);
+        ptx::cp_async_bulk_commit_group();
+        pend_bytes = 0;
+    };
+    for (uint32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const uint8_t *a = src + src_off[r];
+        const uint32_t mis = (uint32_t)((uintptr_t)a & 15);
+        const uint8_t *sp = a - mis;
+        uint8_t *dp = dst + dst_off[r] - mis;
+        const uint32_t total = ((mis + nbytes[r] + 15) >> 4) << 4;
+        for (uint32_t o = 0; o < total; o += kTmaStage) {
+            const uint32_t bytes = min(kTmaStage, total - o);
+            const uint32_t st = issued & 1;
+            // the store that last read this stage was committed in the previous round: it must have finished READING
+            // shared memory (not writing global memory) before the stage is loaded again
+            ptx::cp_async_bulk_wait_group_read(ptx::n32_t<0>());
+            ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, &bar[st], bytes);
+            ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, smem + st * kTmaStage, sp + o, bytes, &bar[st]);
+            uint8_t *this_dst = dp + o;
+            issued++;
+            // while this load is in flight, retire the previous one
+            if (pend_bytes) {
+                const uint32_t pst = (issued - 2) & 1;
+                while (!ptx::mbarrier_try_wait_parity(&bar[pst], phase[pst])) {
+                }
+                phase[pst] ^= 1;
+                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, pend_dst, smem + pst * kTmaStage, pend_bytes);
+                ptx::cp_async_bulk_commit_group();
+            }
+            pend_dst = this_dst;
+            pend_bytes = bytes;
+        }
+    }
+    flush();
+    ptx::cp_async_bulk_wait_group(ptx::n32_t<0>());
+}
 // A small persistent grid (two CTAs per SM): the loads wait on PCIe, not on the SMs, and ~2.4 MB in flight saturate
 // the link; a CTA per read would fill every SM with waiting threads and lock out the kernels of the other contig
 // that is in flight on this GPU.
 void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
                 uint8_t *d_dst, uint32_t n_reads, cudaStream_t s) {
     static const uint32_t ctas = getenv("NP2_K0_CTAS") ? (uint32_t)atoi(getenv("NP2_K0_CTAS")) : 2 * 148;
+    static const bool use_tma = !(getenv("NP2_K0_TMA") && atoi(getenv("NP2_K0_TMA")) == 0);
+    if (n_reads && use_tma) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_gather_seq_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kTmaStage));
+            attr_set = true;
+        }
+        static const uint32_t tma_ctas = getenv("NP2_K0_CTAS") ? ctas : 148;  // one single-thread CTA per SM
+        NP2_K(k_gather_seq_tma)<<<std::min<uint32_t>(n_reads, std::max(1u, tma_ctas)), 32, 2 * kTmaStage, s>>>(
+            src_mapped, d_src_off, d_dst_off, d_nbytes, d_dst, n_reads);
+        return;
+    }
     if (n_reads)
         NP2_K(k_gather_seq)<<<std::min<uint32_t>(n_reads, std::max(1u, ctas)), 256, 0, s>>>(src_mapped, d_src_off, d_dst_off,
                                                                                        d_nbytes, d_dst, n_reads);
