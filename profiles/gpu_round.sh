@@ -14,7 +14,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${tag}_bench_
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-yak-bench --e2e-inflight 1 > gpurun_out/${tag}_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_pack_columns|k_trim_scan|k_pileup_emit|k_pileup_count|k_emit_singles|k_cand_write|k_pair_scan|k_dp_runs|k_region_seed|k_region_hete|k_region_select|k_gather_seq' \
-    -c 12 -o gpurun_out/${tag}_full python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-yak-bench --e2e-inflight 1 \
+    -k regex:'k_pack_columns|k_trim_scan|k_pileup_emit|k_emit_singles|k_emit_runs|k_cand_write|k_pair_scan|k_dp_runs|k_region_seed|k_region_hete|k_region_select|k_gather_seq_tma|k_pos_finalize' \
+    -c 14 -o gpurun_out/${tag}_full python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-yak-bench --e2e-inflight 1 \
     > gpurun_out/${tag}_ncu_full.log 2>&1
 ls -la gpurun_out | tail -10

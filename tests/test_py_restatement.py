@@ -1,0 +1,80 @@
+"""The C++ oracle against an independent pure-Python restatement of the same reference code (tests/py_restatement.py):
+reads after trim / clip filter, the per-position 3-mer lists in Msa order with counts and back pointers, the DP
+consensus with its qv / coverage flags and the LQ regions must all be identical.  CPU only."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import common
+import exotic
+import oracle as O
+import py_restatement as P
+from nextpolish2_b200 import synth
+
+
+def compare(contig, bam, **optkw):
+    tseq = bytes(contig).decode()
+    oj = O.Job(contig, bam, [O.Table.from_arrays(21, np.array([1], np.uint64), np.array([9], np.uint16))],
+               O.Opts(min_ctg_len=0, iter_count=1, **optkw), dump_iter=0)
+    als, rec_idx = P.ingest(tseq, bam, **{k: v for k, v in optkw.items() if k in ("max_clip_len", "min_map_qual", "use_supplementary")})
+    r = oj.reads()
+    assert list(r["rec_idx"]) == rec_idx
+    assert [a.aln_t_s for a in als] == list(r["t_s"]) and [a.aln_t_e for a in als] == list(r["t_e"])
+    assert [0 if a.align_bases else 1 for a in als] == list(r["blank"])
+    nib = b"".join(bytes(a.align_bases) for a in als[1:])  # the ref read (alignseq 0) is implicit in the dump
+    got = bytes(r["nib"])
+    assert got == nib or got == b"".join(bytes(a.align_bases) for a in als)
+    msas = P.build_msas(len(tseq), als)
+    best = P.dp(msas)
+    m = oj.msa()
+    assert list(m["off"]) == list(np.cumsum([0] + [len(x) for x in msas]))
+    assert list(m["bases"]) == [k.bases for x in msas for k in x]
+    assert list(m["delta"]) == [k.delta for x in msas for k in x]
+    assert list(m["count"]) == [k.count for x in msas for k in x]
+    assert list(m["besti"]) == [k.besti for x in msas for k in x]
+    cns, regions = P.backtrack(msas, best)
+    d = oj.dp_consensus()
+    assert list(d["pos"]) == [c[0] for c in cns]
+    assert bytes(d["base"]).decode() == "".join(c[1] for c in cns)
+    assert list(d["flags"]) == [c[2] for c in cns]
+    reg = oj.regions()
+    assert list(zip(reg["start"], reg["end"])) == regions
+    return len(als), len(regions)
+
+
+def test_synthetic_haploid_and_diploid():
+    n, nreg = compare(common.dataset("tiny20k")["contig"], common.dataset("tiny20k")["bam"])
+    assert n > 30 and nreg > 0
+    A = synth.genome(41, 12_000)
+    c = synth.make_contig(42, A, depth=25, asm_err=1e-3, het=0.004, mean_len=4000, sd_len=600, min_len=1500,
+                          frac_clip=0.05, frac_lowq=0.03, frac_supp=0.03, eqx=True, read_err=0.006, threads=2)
+    n, nreg = compare(A, c["bam"])
+    assert nreg > 5
+    compare(A, c["bam"], use_supplementary=1, min_map_qual=-1, max_clip_len=1000)
+
+
+def test_exotic_alignments():
+    """IUPAC / N bases, lower case, clips, indels at the ends, long indels, reads without an anchor (tests/exotic.py)"""
+    ref, blob = exotic.make()
+    compare(ref, blob)
+    compare(ref, blob, max_clip_len=1000)
+
+
+def test_real_reads_window():
+    """the first 12 kb of the bundled contig with the real HiFi reads aligned inside it (configs[0] data)"""
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_40k")
+    contig = np.frombuffer(gzip.open(os.path.join(d, "contig.bin.gz")).read(), np.uint8)
+    bam = np.frombuffer(gzip.open(os.path.join(d, "records.bin.gz")).read(), np.uint8)
+    # keep the records that end inside a 14 kb window so that the pure-Python loops stay within seconds
+    W, keep, off = 14_000, [], 0
+    recs = P.records(bam)
+    for tid, pos, mapq, flag, cig, seq in recs:
+        bs = int(np.frombuffer(bam[off:off + 4], "<i4")[0])
+        if pos + sum(l for op, l in cig if op in (0, 2, 3, 7, 8)) <= W:
+            keep.append(bam[off:off + 4 + bs])
+        off += 4 + bs
+    assert len(keep) >= 10
+    n, nreg = compare(contig[:W], np.concatenate(keep))
+    assert nreg > 10
