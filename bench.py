@@ -95,8 +95,8 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
-# THIS workload (profiles/r01h_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.
-NCU_TRAFFIC = {"pack_columns": 379848704, "pileup_emit": 277608192}
+# THIS workload (profiles/r01fin_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.
+NCU_TRAFFIC = {"pack_columns": 389402368, "pileup_emit": 277744896}
 
 
 def peaks():

@@ -353,3 +353,60 @@ def backtrack(msas, best):  # generate_cns_from_best_score_lq main.rs:1555-1643
         _, base2, base3 = kmer_bases(k.bases, k.delta, base2[2])
     cns.reverse()
     return cns, regions
+
+
+def yak_hash64(key, mask):  # kmer.rs:223-233 (= yak/yak-priv.h:10-21)
+    key = (~key + (key << 21)) & mask
+    key = key ^ key >> 24
+    key = ((key + (key << 3)) + (key << 8)) & mask
+    key = key ^ key >> 14
+    key = ((key + (key << 2)) + (key << 4)) & mask
+    key = key ^ key >> 28
+    key = (key + (key << 31)) & mask
+    return key
+
+
+INVALID_KMER = (1 << 64) - 1
+
+
+def candidates(alignseqs, regions, ksize, max_can=60):  # generate_lqseqs_from_tags_kmer main.rs:1422-1521
+    """regions: [(start, end)] in the reference's (descending) order -> per region [(order, seq, kmer hash)]"""
+    out = [[] for _ in regions]
+    shift, mask, m64 = 2 * (ksize - 1), (1 << (2 * ksize)) - 1, (1 << 64) - 1
+    s = len(regions) - 1
+    for idx, a in enumerate(alignseqs):
+        if not a.align_bases:
+            continue
+        while s > 0 and regions[s][0] < a.aln_t_s:
+            s -= 1
+        if regions[s][0] < a.aln_t_s or regions[s][1] > a.aln_t_e:
+            continue
+        j = s
+        while j > 0 and regions[j][1] <= a.aln_t_e:
+            j -= 1
+        if regions[j][1] > a.aln_t_e:
+            j += 1
+        bases = []
+        for b in a.tags():
+            bases.append(b)
+            if b[2] > regions[j][1] + ksize:
+                break
+        for r in range(j, s + 1):
+            if len(out[r]) >= max_can:
+                continue
+            start, end = regions[r]
+            l, k0, k1, seq = 0, 0, 0, []
+            for q, _d, t_pos in bases[start - a.aln_t_s:]:
+                if t_pos >= start and q != 4:
+                    if t_pos <= end:
+                        seq.append(chr(SEQ_NUM[q]))
+                    if l < ksize:
+                        k0 = ((k0 << 2) | q) & mask
+                        k1 = ((k1 >> 2) | ((3 ^ q) << shift)) & m64
+                        l += 1
+                    if t_pos > end and l >= ksize:
+                        break
+            kmer = min(k0, k1) if l >= ksize else INVALID_KMER
+            if seq:
+                out[r].append((idx, "".join(seq), yak_hash64(kmer, mask) if kmer != INVALID_KMER else INVALID_KMER))
+    return out

@@ -1,6 +1,7 @@
 """The C++ oracle against an independent pure-Python restatement of the same reference code (tests/py_restatement.py):
 reads after trim / clip filter, the per-position 3-mer lists in Msa order with counts and back pointers, the DP
-consensus with its qv / coverage flags and the LQ regions must all be identical.  CPU only."""
+consensus with its qv / coverage flags, the LQ regions and the candidate alleles of every region (read order, string,
+first-k k-mer hash, the 60 cap, the monotone region cursor) must all be identical.  CPU only."""
 import gzip
 import os
 
@@ -41,6 +42,15 @@ def compare(contig, bam, **optkw):
     assert list(d["flags"]) == [c[2] for c in cns]
     reg = oj.regions()
     assert list(zip(reg["start"], reg["end"])) == regions
+    if regions:  # candidates in read order with the 60 cap: order, string, hash of the first-k k-mer (k = 21)
+        cand = P.candidates(als, regions, 21)
+        c = oj.candidates()
+        assert list(c["roff"]) == list(np.cumsum([0] + [len(x) for x in cand]))
+        flat = [x for r in cand for x in r]
+        assert list(c["order"]) == [x[0] for x in flat]
+        assert bytes(c["seq"]).decode() == "".join(x[1] for x in flat)
+        assert list(c["seq_off"]) == list(np.cumsum([0] + [len(x[1]) for x in flat]))
+        assert [int(v) for v in c["kmer"]] == [x[2] for x in flat]
     return len(als), len(regions)
 
 
