@@ -1,5 +1,6 @@
 // np2_api.cu — C ABI (include/np2gpu.h) and the per-contig pipeline that strings the kernels and host
-// phases together.  One np2_ctx = one GPU + one stream; all device work of a job is enqueued on that stream.
+// phases together.  One np2_ctx = one GPU + a compute stream (all kernels of a job), a high-priority copy stream
+// (uploads, the K0 gather) and a private stream-ordered memory pool; per-run scratch comes from an arena.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>

@@ -6,7 +6,8 @@
 //   k_cand_write       candidate strings into a compact pool
 //   k_cand_kscore_*    retrieve_kmer_count (main.rs:740-778)
 //   k_region_hete      fill_order_stat + mark_hete_lqseqs (main.rs:813-849, 916-946) + edge counts
-//   k_edges_emit       the pair loop of phase_reads_by_lqseqs (main.rs:953-992)
+//   k_edges_accum      the pair loop of phase_reads_by_lqseqs (main.rs:953-992) into a dense pair accumulator
+//   k_phase_*          level 0 of the Louvain graph: ref pairs, `dif <= -3`, invalid reads, CSR (main.rs:972-1010)
 //   k_region_seed      fill_order_stat + fill_seed_lqseqs + retain_sort_seqs (main.rs:862-914, 714-726)
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_hete(GenoDev g) {
         g.r_lable[r] = lable;
         g.r_nedge[r] = nedge;
     }
-    // rep is needed again by k_edges_emit
+    // rep is needed again by k_edges_accum
     for (uint32_t c = lane; c < n; c += 32) g.c_rep[r * kMaxCand + c] = sm.rep[c];
 }
 
