@@ -543,9 +543,7 @@ void np2_job::send_seq() {
         if (r1 - r0 < 256) {
             for (unsigned ti = 0; ti < T; ti++) work(ti);
         } else {
-            std::vector<std::thread> th;
-            for (unsigned ti = 0; ti < T; ti++) th.emplace_back(work, ti);
-            for (auto &t : th) t.join();
+            np2::parallel_for(T, work);
         }
         NP2_CUDA(cudaMemcpyAsync(d_blob.p + D0, buf, D1 - D0, cudaMemcpyHostToDevice, s));
         NP2_CUDA(cudaEventRecord(sc->seq_ev[round & 1], s));

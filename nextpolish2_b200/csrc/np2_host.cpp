@@ -5,6 +5,10 @@
 #include "np2_error.h"
 
 #include <algorithm>
+#include <mutex>
+#include <memory>
+#include <functional>
+#include <condition_variable>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +49,90 @@ unsigned host_threads() {
         if (!n) n = std::min(16u, std::thread::hardware_concurrency());
     }
     return std::max(1u, std::min(n, 64u));
+}
+
+namespace {
+struct Pool {
+    struct Batch {
+        const std::function<void(unsigned)> *f;
+        std::atomic<unsigned> next{0}, done{0};
+        unsigned n = 0;
+    };
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::shared_ptr<Batch>> open;  // batches that still have unclaimed indices
+    std::vector<std::thread> workers;
+    bool stop = false;
+    void ensure(unsigned want) {
+        while (workers.size() < want) workers.emplace_back([this] { loop(); });
+    }
+    static bool run_one(Batch &b) {
+        const unsigned i = b.next.fetch_add(1);
+        if (i >= b.n) return false;
+        (*b.f)(i);
+        b.done.fetch_add(1);
+        return true;
+    }
+    void loop() {
+        for (;;) {
+            std::shared_ptr<Batch> b;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || !open.empty(); });
+                if (stop) return;
+                b = open.back();
+                if (b->next.load() >= b->n) {
+                    open.pop_back();
+                    continue;
+                }
+            }
+            while (run_one(*b)) {
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                cv_done.notify_all();
+            }
+        }
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+    }
+};
+Pool &pool() {
+    static Pool *p = new Pool();  // never destroyed: worker threads may outlive static destruction order otherwise
+    return *p;
+}
+}  // namespace
+
+void parallel_for(unsigned n, const std::function<void(unsigned)> &f) {
+    if (n <= 1) {
+        if (n) f(0);
+        return;
+    }
+    Pool &p = pool();
+    auto b = std::make_shared<Pool::Batch>();
+    b->f = &f;
+    b->n = n;
+    {
+        std::lock_guard<std::mutex> lk(p.mu);
+        p.ensure(std::min(n - 1, 63u));
+        p.open.push_back(b);
+    }
+    p.cv_work.notify_all();
+    while (Pool::run_one(*b)) {
+    }
+    std::unique_lock<std::mutex> lk(p.mu);
+    p.cv_done.wait(lk, [&] { return b->done.load() >= n; });
+    for (size_t i = 0; i < p.open.size(); i++)
+        if (p.open[i] == b) {
+            p.open.erase(p.open.begin() + i);
+            break;
+        }
 }
 
 void copy_streaming(void *dst, const void *src, size_t n) {
@@ -270,13 +358,7 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
         }
         store_fence();  // the op arrays were written with streaming stores
     };
-    if (T == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (unsigned ti = 0; ti < T; ti++) th.emplace_back(work, ti);
-        for (auto &t : th) t.join();
-    }
+    parallel_for(T, work);
     // join: accept, or re-walk what the speculation missed
     std::vector<Segment *> order;
     uint64_t cur = 0;
