@@ -686,7 +686,7 @@ __device__ __forceinline__ void pack_block_slow(const ReadsDev &R, uint32_t g) {
     out[0] = w0;
     out[1] = w1;
 }
-__global__ void __launch_bounds__(kPackThreads) k_pack_columns(ReadsDev R, const uint8_t *__restrict__ ref,
+__global__ void __launch_bounds__(kPackThreads, 8) k_pack_columns(ReadsDev R, const uint8_t *__restrict__ ref,
                                                                uint32_t n_blocks) {
     __shared__ uint32_t q[kPackThreads], qn;
     if (threadIdx.x == 0) qn = 0;
