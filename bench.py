@@ -95,8 +95,8 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
-# THIS workload (profiles/r01fin_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.
-NCU_TRAFFIC = {"pack_columns": 389402368, "pileup_emit": 277744896}
+# THIS workload (profiles/r01end_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.
+NCU_TRAFFIC = {"pack_columns": 402109696, "pileup_emit": 279334400}
 
 
 def peaks():
@@ -268,6 +268,17 @@ def run_ours(args):
                         "algorithmic_bytes_per_launch": int(stage_bytes(dom, st)),
                         "note": "largest of the streaming kernels with a defined byte count (pack_columns, "
                                 "pileup_emit); the step is ~50 short kernels + host phases, none above 10% of it"}
+        others = []
+        for kname in kern:
+            if kname == dom:
+                continue
+            nl = max(1, int(round(stage_launches.get(kname, 1))))
+            ms1 = stages[kname] / nl
+            ach = stage_bytes(kname, st) / (ms1 * 1e-3) / 1e9
+            others.append({"kernel": "k_" + kname, "achieved": round(ach, 1), "frac": round(ach / peak, 4),
+                           "launch_ms": round(ms1, 4), "traffic": NCU_TRAFFIC.get(kname)})
+        if roofline is not None:
+            roofline["other_streaming_kernels"] = others
         q = traffic["probes"] / float(args.length)
         pipe_bytes = pipeline_bytes_per_bp(30, q) * args.length
         pipeline = {"bytes_per_bp": round(pipeline_bytes_per_bp(30, q), 1), "probes_per_bp": round(q, 3),
