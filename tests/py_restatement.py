@@ -1,4 +1,5 @@
-"""A SECOND, independent restatement of the reference's core (ingest -> AlignSeq -> Msa -> DP -> backtrack -> LQ regions),
+"""A SECOND, independent restatement of the reference's core (ingest -> AlignSeq -> Msa -> DP -> backtrack -> LQ regions
+-> candidates -> k-mer scores -> heterozygous regions),
 written in plain Python straight from src/main.rs with the reference's own data structures (strings, lists of 3-mers).
 
 The Rust binary cannot be built in this image, so nothing pins the C++ oracle (oracle/np2_oracle.cpp) against the
@@ -8,7 +9,9 @@ different languages and with different data structures, must agree bit for bit a
 
 Follows: record filter main.rs:1758-1771; fill_with_cigar 386-440; trim 447-513; AlignSeq::new 279-312;
 get_align_tag 314-338; post-trim filter 1796-1813; filter_alignseqs_by_clip 531-574; update_msas 576-589; Kmer 84-184;
-Msa 193-241; get_cns_from_align_tags 1645-1687; generate_cns_from_best_score_lq 1555-1643.
+Msa 193-241; get_cns_from_align_tags 1645-1687; generate_cns_from_best_score_lq 1555-1643;
+generate_lqseqs_from_tags_kmer 1422-1521; retrieve_kmer_count 740-778 + kmer.rs:102-125, 255-287; is_valid_snp 780-801;
+get_min_count 803-811; fill_order_stat 813-849; mark_hete_lqseqs 916-946.
 """
 import struct
 
@@ -410,3 +413,94 @@ def candidates(alignseqs, regions, ksize, max_can=60):  # generate_lqseqs_from_t
             if seq:
                 out[r].append((idx, "".join(seq), yak_hash64(kmer, mask) if kmer != INVALID_KMER else INVALID_KMER))
     return out
+
+
+def iter2kmer(seq, ksize):  # kmer.rs:255-287 (k < 32): canonical 2-bit k-mers, the window restarts at a non-ACGT base
+    shift, mask, m64 = 2 * (ksize - 1), (1 << (2 * ksize)) - 1, (1 << 64) - 1
+    k0 = k1 = l = 0
+    for ch in seq:
+        c = SEQ_NUM[ord(ch)]
+        if c < 4:
+            k0 = ((k0 << 2) | c) & mask
+            k1 = ((k1 >> 2) | ((3 ^ c) << shift)) & m64
+            l += 1
+        else:
+            l = 0
+        if l >= ksize:
+            yield min(k0, k1)
+
+
+def kscores(cand, table, ksize, min_kmer_count=5):  # retrieve_kmer_count main.rs:740-778
+    """cand: per region [(order, seq, kmer hash)]; table: {hash >> 10: count} -> per region [kscore]"""
+    mask = (1 << (2 * ksize)) - 1
+
+    def get(h):  # KmerInfo::get after retrieve_kmers: the stored count if it reaches min_count, else 0
+        c = table.get(h >> 10, 0)
+        return c if c >= min_kmer_count else 0
+    out = []
+    for region in cand:
+        ks = []
+        for _order, seq, kmer in region:
+            if len(seq) > ksize:
+                vals = [get(yak_hash64(x, mask)) for x in iter2kmer(seq, ksize)]
+                ks.append(min(vals) if vals else 0)
+            elif kmer != INVALID_KMER:
+                ks.append(get(kmer))
+            else:
+                ks.append(0)
+        out.append(ks)
+    return out
+
+
+def is_valid_snp(s1, s2):  # main.rs:780-801
+    i = j = 0
+    while i < len(s1) and j < len(s2):
+        if s1[i] != s2[j]:
+            return True
+        while i + 1 < len(s1) and s1[i] == s1[i + 1]:
+            i += 1
+        while j + 1 < len(s2) and s2[j] == s2[j + 1]:
+            j += 1
+        i += 1
+        j += 1
+    return False
+
+
+def get_min_count(c):  # main.rs:803-811
+    return 3 if c >= 9 else 2 if c >= 6 else 1
+
+
+def fill_order_stat(region, ks):  # main.rs:813-849 -> stats per candidate, (max1_c, max1_p, max2_c, max2_p)
+    n = len(region)
+    stats = [0] * n
+    max1_c = max1_p = max2_c = max2_p = 0
+    for p1 in range(n):
+        if ks[p1] <= 0 or stats[p1] > 0:
+            continue
+        seq = region[p1][1]
+        same = [p for p in range(p1, n) if region[p][1] == seq]
+        c = len(same)
+        for p in same:
+            stats[p] = c
+        if c > max1_c or (c == max1_c and region[p1][0] == 0):
+            max2_c, max2_p = max1_c, max1_p
+            max1_c, max1_p = c, p1
+        elif max1_p == max2_p or c > max2_c:
+            max2_c, max2_p = c, p1
+    return stats, (max1_c, max1_p, max2_c, max2_p)
+
+
+def mark_hete(cand, ks):  # mark_hete_lqseqs main.rs:916-946 -> per region HETE flag; ks is updated in place
+    flags = []
+    for region, k in zip(cand, ks):
+        stats, (max1_c, max1_p, max2_c, max2_p) = fill_order_stat(region, k)
+        min_c = get_min_count(len(region))
+        hete = (max2_c >= min_c
+                and (len(region[max1_p][1]) == len(region[max2_p][1]) or (len(region) >= 6 and max2_c >= max1_c // 2))
+                and is_valid_snp(region[max1_p][1], region[max2_p][1]))
+        if hete:
+            for p in range(len(region)):
+                if k[p] > 0 and stats[p] < min_c:
+                    k[p] = 0
+        flags.append(hete)
+    return flags

@@ -15,10 +15,12 @@ import py_restatement as P
 from nextpolish2_b200 import synth
 
 
-def compare(contig, bam, **optkw):
+def compare(contig, bam, table=None, **optkw):
     tseq = bytes(contig).decode()
-    oj = O.Job(contig, bam, [O.Table.from_arrays(21, np.array([1], np.uint64), np.array([9], np.uint16))],
-               O.Opts(min_ctg_len=0, iter_count=1, **optkw), dump_iter=0)
+    if table is None:
+        table = (np.array([1], np.uint64), np.array([9], np.uint16))
+    # iter_count = 2 and the dump of iteration 0: the non-final iteration runs retrieve_kmer_count + mark_hete_lqseqs
+    oj = O.Job(contig, bam, [O.Table.from_arrays(21, *table)], O.Opts(min_ctg_len=0, iter_count=2, **optkw), dump_iter=0)
     als, rec_idx = P.ingest(tseq, bam, **{k: v for k, v in optkw.items() if k in ("max_clip_len", "min_map_qual", "use_supplementary")})
     r = oj.reads()
     assert list(r["rec_idx"]) == rec_idx
@@ -51,18 +53,28 @@ def compare(contig, bam, **optkw):
         assert bytes(c["seq"]).decode() == "".join(x[1] for x in flat)
         assert list(c["seq_off"]) == list(np.cumsum([0] + [len(x[1]) for x in flat]))
         assert [int(v) for v in c["kmer"]] == [x[2] for x in flat]
-    return len(als), len(regions)
+        # k-mer scores (retrieve_kmer_count) and heterozygous regions (fill_order_stat + mark_hete_lqseqs, which also
+        # zeroes the scores of the minor alleles)
+        tab = {int(h) >> 10: int(n) for h, n in zip(*table)}
+        ks = P.kscores(cand, tab, 21)
+        assert [int(v) for v in c["kscore"]] == [x for r in ks for x in r]  # (the oracle dumps them before mark_hete)
+        hete = P.mark_hete(cand, ks)
+        assert [bool(l & 0x40) for l in reg["lable"]] == hete
+        return len(als), len(regions), sum(hete)
+    return len(als), len(regions), 0
 
 
 def test_synthetic_haploid_and_diploid():
-    n, nreg = compare(common.dataset("tiny20k")["contig"], common.dataset("tiny20k")["bam"])
+    ds = common.dataset("tiny20k")
+    n, nreg, _ = compare(ds["contig"], ds["bam"], table=ds["tables"][21])
     assert n > 30 and nreg > 0
     A = synth.genome(41, 12_000)
     c = synth.make_contig(42, A, depth=25, asm_err=1e-3, het=0.004, mean_len=4000, sd_len=600, min_len=1500,
                           frac_clip=0.05, frac_lowq=0.03, frac_supp=0.03, eqx=True, read_err=0.006, threads=2)
-    n, nreg = compare(A, c["bam"])
-    assert nreg > 5
-    compare(A, c["bam"], use_supplementary=1, min_map_qual=-1, max_clip_len=1000)
+    tab = synth.make_table(43, 21, [c["hap1"], c["hap2"]])
+    n, nreg, nhete = compare(A, c["bam"], table=tab)
+    assert nreg > 5 and nhete > 3  # real heterozygous sites are recognised by both
+    compare(A, c["bam"], table=tab, use_supplementary=1, min_map_qual=-1, max_clip_len=1000)
 
 
 def test_exotic_alignments():
@@ -86,5 +98,9 @@ def test_real_reads_window():
             keep.append(bam[off:off + 4 + bs])
         off += 4 + bs
     assert len(keep) >= 10
-    n, nreg = compare(contig[:W], np.concatenate(keep))
-    assert nreg > 10
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_c1 import read_yak
+    _, h, cnt = read_yak(os.path.join(d, "k21.yak"))
+    n, nreg, nhete = compare(contig[:W], np.concatenate(keep), table=(h, cnt))
+    assert nreg > 10 and nhete > 0
