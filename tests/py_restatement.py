@@ -1,5 +1,6 @@
-"""A SECOND, independent restatement of the reference's core (ingest -> AlignSeq -> Msa -> DP -> backtrack -> LQ regions
--> candidates -> k-mer scores -> heterozygous regions),
+"""A SECOND, independent restatement of the reference's whole per-contig path (ingest -> AlignSeq -> Msa -> DP ->
+backtrack -> LQ regions -> candidates -> k-mer scores -> heterozygous regions -> read phasing with Louvain -> seed
+choice -> consensus patching -> k-mer re-check -> iteration loop; `polish()` at the end runs all of it),
 written in plain Python straight from src/main.rs with the reference's own data structures (strings, lists of 3-mers).
 
 The Rust binary cannot be built in this image, so nothing pins the C++ oracle (oracle/np2_oracle.cpp) against the
@@ -11,7 +12,9 @@ Follows: record filter main.rs:1758-1771; fill_with_cigar 386-440; trim 447-513;
 get_align_tag 314-338; post-trim filter 1796-1813; filter_alignseqs_by_clip 531-574; update_msas 576-589; Kmer 84-184;
 Msa 193-241; get_cns_from_align_tags 1645-1687; generate_cns_from_best_score_lq 1555-1643;
 generate_lqseqs_from_tags_kmer 1422-1521; retrieve_kmer_count 740-778 + kmer.rs:102-125, 255-287; is_valid_snp 780-801;
-get_min_count 803-811; fill_order_stat 813-849; mark_hete_lqseqs 916-946.
+get_min_count 803-811; fill_order_stat 813-849; mark_hete_lqseqs 916-946; fill_seed_lqseqs 862-914;
+phase_reads_by_lqseqs 948-1015; update_consensus_with_lqseqs 1017-1058; reupdate_consensus_with_lqseqs 1060-1420;
+the iteration loop 1821-1838; utils/louvain.rs.
 """
 import struct
 
@@ -504,3 +507,510 @@ def mark_hete(cand, ks):  # mark_hete_lqseqs main.rs:916-946 -> per region HETE 
                     k[p] = 0
         flags.append(hete)
     return flags
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The rest of the per-contig path: seed choice, read phasing (Louvain), consensus patching, the k-mer re-check and
+# the iteration loop.  Follows main.rs:851-914 (fill_seed_lqseqs), 707-719 (retain_sort_seqs), 948-1015
+# (phase_reads_by_lqseqs), 1017-1058 (update_consensus_with_lqseqs), 1060-1420 (reupdate_consensus_with_lqseqs),
+# 1524-1553 (the tail of generate_lqseqs_from_tags_kmer), 1821-1838 (the iteration loop) and utils/louvain.rs.
+# Where the reference iterates an FxHashMap and the order can reach the result (louvain.rs:123, 145-165, 199) the
+# keys are visited in ascending order: the same documented choice as oracle/np2_oracle.cpp.
+LABLE_TEMP, LABLE_SUCC, LABLE_HETE, LABLE_RECH = 0x01, 0x80, 0x40, 0x20
+
+
+class LqSeq:
+    __slots__ = ("order", "kscore", "kmer", "seq")
+
+    def __init__(self, order, kscore, kmer, seq):
+        self.order, self.kscore, self.kmer, self.seq = order, kscore, kmer, seq
+
+
+class LqSeqs:
+    def __init__(self, start, end, seqs):
+        self.lable, self.start, self.end, self.sudoseed, self.seqs = 0, start, end, "", seqs
+
+
+def order_stats(lq):  # fill_order_stat main.rs:813-849 on LqSeqs, with the order -> count map it fills
+    n = len(lq.seqs)
+    stats, order_stat = [0] * n, {}
+    max1_c = max1_p = max2_c = max2_p = 0
+    for p1, s in enumerate(lq.seqs):
+        if s.kscore <= 0 or stats[p1] > 0:
+            continue
+        c = sum(1 for x in lq.seqs[p1:] if x.seq == s.seq)
+        order_stat[s.order] = c
+        for p2 in range(p1, n):
+            if lq.seqs[p2].seq == s.seq:
+                stats[p2] = c
+        if c > max1_c or (c == max1_c and s.order == 0):
+            max2_c, max2_p = max1_c, max1_p
+            max1_c, max1_p = c, p1
+        elif max1_p == max2_p or c > max2_c:
+            max2_c, max2_p = c, p1
+    return stats, (max1_c, max1_p, max2_c, max2_p), order_stat
+
+
+def no_dupseq(lq):  # main.rs:851-860
+    for p1 in range(1, len(lq.seqs)):
+        for s2 in lq.seqs[p1 + 1:]:
+            if lq.seqs[p1].seq == s2.seq:
+                return False
+    return True
+
+
+def retain_sort_seqs(lq, stat, min_c):  # main.rs:707-719
+    lq.seqs.sort(key=lambda v: -stat.get(v.order, 0))  # stable
+    c = 0
+    for v in lq.seqs:
+        if stat.get(v.order, 0) < min_c:
+            break
+        c += 1
+    del lq.seqs[c:]
+
+
+def fill_seed_lqseqs(lqseqs, max_indel_len):  # main.rs:862-914
+    for lq in lqseqs:
+        _, (max1_c, max1_p, _, _), order_stat = order_stats(lq)
+        lq.sudoseed = lq.seqs[max1_p].seq
+        lq.lable |= LABLE_SUCC | LABLE_RECH
+        min_c = get_min_count(len(lq.seqs))
+        assert lq.seqs[0].order == 0, "the first lqseq is not ref."
+        if 0 in order_stat:
+            if 1 < order_stat[0] < min_c:
+                order_stat[0] = min_c
+        elif sum(1 for x in lq.seqs if x.seq == lq.seqs[0].seq) > 1:
+            order_stat[0] = min_c
+        if max1_p != 0 and max1_c < min_c and (max1_c > 1 or no_dupseq(lq)):
+            assert lq.seqs[max1_p].order in order_stat  # .unwrap()
+            order_stat[lq.seqs[max1_p].order] = min_c
+            order_stat[0] = min_c
+        elif max1_c < min_c:
+            order_stat[0] = min_c
+        retain_sort_seqs(lq, order_stat, min_c)
+        skip_long = abs(len(lq.sudoseed) - len(lq.seqs[0].seq)) > max_indel_len
+        if len(lq.seqs) <= 1 or skip_long:
+            if lq.seqs or skip_long:
+                lq.sudoseed = lq.seqs[0].seq
+            lq.lable ^= LABLE_RECH
+            lq.seqs = []
+
+
+def mark_hete_lqseqs(lqseqs):  # main.rs:916-946
+    for lq in lqseqs:
+        stats, (max1_c, max1_p, max2_c, max2_p), _ = order_stats(lq)
+        min_c = get_min_count(len(lq.seqs))
+        if (max2_c >= min_c
+                and (len(lq.seqs[max1_p].seq) == len(lq.seqs[max2_p].seq) or (len(lq.seqs) >= 6 and max2_c >= max1_c // 2))
+                and is_valid_snp(lq.seqs[max1_p].seq, lq.seqs[max2_p].seq)):
+            lq.lable |= LABLE_HETE
+            for p, s in enumerate(lq.seqs):
+                if s.kscore > 0 and stats[p] < min_c:
+                    s.kscore = 0
+
+
+# ---- utils/louvain.rs
+def insert_data(data, k1, k2, v):  # louvain.rs:272-279
+    d = data.setdefault(k1, {})
+    d[k2] = d.get(k2, 0.0) + v
+
+
+def assign_data(data, k1, k2, v):  # louvain.rs:281-288
+    data.setdefault(k1, {})[k2] = v
+
+
+class LvNode:
+    def __init__(self, id_, weight, nodes):
+        self.id, self.weight, self.nodes = id_, weight, set(nodes)
+
+
+class Louvain:
+    def __init__(self, data):  # louvain.rs:60-70
+        self.data = data
+        self.communities = {v: {v} for v in data}
+        self.node = {v: LvNode(v, 0.0, [v]) for v in data}
+
+    def first_stage(self):  # louvain.rs:72-117
+        mod_inc = False
+        visit = sorted(self.data)
+        while True:
+            can_stop = True
+            for v in visit:
+                v_nid = self.node[v].id
+                node_ids = {}
+                for w in self.data[v]:
+                    w_nid = self.node[w].id
+                    if w_nid in node_ids:
+                        continue
+                    com = self.communities[w_nid]
+                    node_ids[w_nid] = sum(x for k, x in self.data[v].items() if k in com)
+                if node_ids:
+                    # max_by(weight, then the smaller id is the greater): the last maximum wins among exact equals,
+                    # and there are none because the ids differ
+                    best = max(node_ids.items(), key=lambda kv: (kv[1], -kv[0]))
+                    if best[1] > 0.0 and best[0] != v_nid:
+                        self.node[v].id = best[0]
+                        self.communities[best[0]].add(v)
+                        self.communities[v_nid].discard(v)
+                        can_stop = False
+                        mod_inc = True
+            if can_stop:
+                return mod_inc
+
+    def second_stage(self):  # louvain.rs:119-195
+        node, communities, decluster = {}, {}, []
+        for cid in sorted(self.communities):
+            nodes = self.communities[cid]
+            if not nodes:
+                continue
+            nn = LvNode(cid, 0.0, [])
+            for nid in nodes:
+                vertex = self.node[nid]
+                nn.nodes |= vertex.nodes
+                nn.weight += vertex.weight
+                for k, v in self.data.get(nid, {}).items():
+                    if k in nodes:
+                        nn.weight += v / 2.0
+            if nn.weight < 0.0:
+                decluster.append(cid)
+            else:
+                communities[cid] = {cid}
+                node[cid] = nn
+        for cid in decluster:
+            nodes = self.communities.pop(cid)
+            for nid in sorted(nodes):
+                new_nid = nid
+                while new_nid in communities or new_nid in node:
+                    new_nid += 1
+                communities[new_nid] = {new_nid}
+                node[new_nid] = LvNode(new_nid, self.node[nid].weight, self.node[nid].nodes)
+                self.communities[new_nid] = {nid}
+        data = {}
+        live = [(k, v) for k, v in sorted(self.communities.items()) if v]
+        for nid1, nodes1 in live:
+            for nid2, nodes2 in live:
+                if nid2 <= nid1:
+                    continue
+                w = 0.0
+                for vid in nodes1:
+                    for k, v in self.data.get(vid, {}).items():
+                        if k in nodes2:
+                            w += v
+                if w != 0.0:
+                    insert_data(data, nid1, nid2, w)
+                    insert_data(data, nid2, nid1, w)
+        nxt = Louvain.__new__(Louvain)
+        nxt.data, nxt.communities, nxt.node = data, communities, node
+        return nxt
+
+    def get_communities(self):  # louvain.rs:197-245
+        out = []
+        for cid in sorted(self.communities):
+            nodes = self.communities[cid]
+            if not nodes:
+                continue
+            weight, new_nodes = 0.0, set()
+            for vid in nodes:
+                v = self.node[vid]
+                new_nodes |= v.nodes
+                weight += v.weight
+                for k, x in self.data.get(vid, {}).items():
+                    if k in nodes:
+                        weight += x / 2.0
+            out.append(LvNode(cid, weight, new_nodes))
+        data = {}
+        for c1 in out:
+            for c2 in out:
+                if c2.id <= c1.id:
+                    continue
+                w = 0.0
+                for n1 in self.communities[c1.id]:
+                    for n2 in self.communities[c2.id]:
+                        w += self.data.get(n1, {}).get(n2, 0.0)
+                if w != 0.0:
+                    assert w < 0.0, "the weight of two conflicting community is not less than 0"
+                    insert_data(data, c1.id, c2.id, w)
+                    insert_data(data, c2.id, c1.id, w)
+        return data, out
+
+    def execute(self):  # louvain.rs:247-256
+        lv = self
+        while lv.first_stage():
+            lv = lv.second_stage()
+        return lv.get_communities()
+
+
+def phase_communities(data, ref_weight):  # louvain.rs:290-356
+    cdata, communities = Louvain(data).execute()
+    if ref_weight is not None:
+        def stat(nodes):
+            count, weight = 0, 0.0
+            for n in nodes:
+                v = ref_weight.get(n)
+                if v is not None:
+                    count += 1 if v > 0 else -1 if v < 0 else 0
+                    weight += v
+            return (count, weight)
+        keyed = [(stat(c.nodes), c) for c in communities]
+        keyed.sort(key=lambda kc: (-kc[0][0], -kc[0][1]))  # Reverse((count, weight)), stable
+        communities = [c for _, c in keyed]
+    else:
+        communities.sort(key=lambda c: -c.weight)
+    invalid = set()
+    for p, c in enumerate(communities):
+        if c.id in invalid:
+            continue
+        vs = cdata.get(c.id)
+        if vs is not None:
+            for chk in communities[p + 1:]:
+                if chk.id not in invalid and chk.id in vs:
+                    invalid.add(chk.id)
+    out = []
+    for c in communities:
+        if c.id in invalid:
+            out.extend(c.nodes)
+    return out
+
+
+def phase_reads_by_lqseqs(lqseqs, asref, use_all_reads):  # main.rs:948-1015
+    data, dif, ref_data, invalid_ids = {}, {}, {}, set()
+    for lq in lqseqs:
+        if not lq.lable & LABLE_HETE:
+            continue
+        for i, s1 in enumerate(lq.seqs):
+            if s1.kscore == 0:
+                continue
+            for s2 in lq.seqs[i + 1:]:
+                if s2.kscore == 0:
+                    continue
+                w = 1.0 if s1.seq == s2.seq else -1.0
+                if s1.order == 0:
+                    if asref:
+                        insert_data(ref_data, s1.order, s2.order, w)
+                    if w < 0 and not use_all_reads:
+                        invalid_ids.add(s2.order)
+                    continue
+                assert s2.order != 0, "seq2 order is equal to 0"
+                if w == -1.0:
+                    insert_data(dif, s1.order, s2.order, -1.0)
+                    insert_data(dif, s2.order, s1.order, -1.0)
+                insert_data(data, s1.order, s2.order, w)
+                insert_data(data, s2.order, s1.order, w)
+    for n1, vs in dif.items():
+        for n2, w in vs.items():
+            if w <= -3.0:
+                assign_data(data, n1, n2, w)
+    if not use_all_reads:
+        data = {k: {k2: w for k2, w in vs.items() if k2 not in invalid_ids} for k, vs in data.items()
+                if k not in invalid_ids}
+    out = phase_communities(data, ref_data[0] if ref_data else None)
+    return out + sorted(invalid_ids)
+
+
+def update_consensus_with_lqseqs(lqseqs, consensus, lable):  # main.rs:1017-1058; consensus = [(pos, base)]
+    def next_idx(i):  # get_lqseqs_next_idx_by_lable: usize arithmetic, "below 0" is any index >= len
+        i -= 1
+        while 0 <= i < len(lqseqs) and not lqseqs[i].lable & lable:
+            i -= 1
+        return i
+    out, i, li = [], 0, next_idx(len(lqseqs))
+    while i < len(consensus):
+        p = consensus[i][0]
+        if 0 <= li < len(lqseqs) and p == lqseqs[li].start:
+            out.extend((p, b) for b in lqseqs[li].sudoseed)
+            while i < len(consensus) and consensus[i][0] <= lqseqs[li].end:
+                i += 1
+            li = next_idx(li)
+        else:
+            out.append(consensus[i])
+            i += 1
+    return out
+
+
+def reupdate_consensus_with_lqseqs(lqseqs, consensus, get, ksize, iter_count):  # main.rs:1060-1420
+    """get(hash) = KmerInfo::get after retrieve_kmers(min_kmer_count) for this table; ksize < 32"""
+    mask = (1 << (2 * ksize)) - 1
+    idx = [0]
+
+    def pos(i):
+        assert 0 <= i < len(consensus), "index out of range (the reference panics)"
+        return consensus[i][0]
+
+    def region(s, e):  # iter_consensus_region: the bases strictly between s and e
+        i = idx[0]
+        while pos(i) <= s:
+            i += 1
+        while pos(i) > s:
+            i -= 1
+        i += 1
+        si = i
+        while pos(i) >= e:
+            i -= 1
+        while pos(i) < e:
+            i += 1
+        i -= 1
+        idx[0] = i
+        return si, i + 1
+
+    def extend(p, l, toleft):  # iter_consensus_extend: l bases left of / right of position p
+        i = idx[0]
+        if toleft:
+            while pos(i) >= p:
+                i -= 1
+            while pos(i) < p:
+                i += 1
+            idx[0] = i
+            return (i - l if i > l else 0), i
+        while pos(i) <= p:
+            i += 1
+        while pos(i) > p:
+            i -= 1
+        idx[0] = i
+        return i + 1, (i + l + 1 if i + l < len(consensus) else len(consensus))
+
+    def bases(si, ei):
+        return "".join(b for _, b in consensus[si:ei])
+
+    def chain(combo, sj, left, right):  # iter_chain_lqseqs
+        s = bases(*left)
+        for i, (_, seq) in enumerate(combo):
+            s += seq
+            if i < len(combo) - 1:
+                a, b = lqseqs[rech[sj + i]].end, lqseqs[rech[sj + i + 1]].start
+                if a + 1 != b:
+                    s += bases(*region(a, b))
+            else:
+                s += bases(*right)
+        return s
+
+    def score(s):
+        vals = [get(yak_hash64(x, mask)) for x in iter2kmer(s, ksize)]
+        return min(vals) if vals else 0
+
+    import itertools
+    rech = [i for i in range(len(lqseqs) - 1, -1, -1) if lqseqs[i].lable & LABLE_RECH]
+    # (the first pass of the reference only collects the k-mers to look up; `get` already answers for any k-mer, but
+    # the cursor walk of that pass is repeated because it moves idx, main.rs:1193-1261)
+    for collect in (True, False):
+        idx[0] = 0
+        sj = 0
+        while sj < len(rech):
+            ej = sj + 1
+            while ej < len(rech) and lqseqs[rech[ej]].start < lqseqs[rech[ej - 1]].end + ksize:
+                ej += 1
+                if ej > sj + 5:
+                    break
+            left = extend(lqseqs[rech[sj]].start, ksize - 1, True)
+            right = extend(lqseqs[rech[ej - 1]].end, ksize - 1, False)
+            if ej == sj + 1:
+                if not collect:
+                    for s in lqseqs[rech[sj]].seqs:
+                        s.kscore = score(bases(*left) + s.seq + bases(*right))
+            else:
+                buf = []
+                for combo in itertools.product(*[list(enumerate(x.seq for x in lqseqs[rech[x_]].seqs)) for x_ in range(sj, ej)]):
+                    ks = score(chain(combo, sj, left, right))
+                    if ks > 0 and not collect:
+                        for i, (p, _) in enumerate(combo):
+                            buf.append((rech[sj + i], p, ks))
+                if not collect:
+                    for x_ in range(sj, ej):
+                        for s in lqseqs[rech[x_]].seqs:
+                            s.kscore = 0
+                    for i, p, ks in buf:
+                        lqseqs[i].seqs[p].kscore = ks
+            sj = ej
+    for lq in lqseqs:
+        if not lq.lable & LABLE_RECH:
+            continue
+        c = valid = 0
+        for p, s in enumerate(lq.seqs):
+            if s.kscore != 0:
+                if c == 0 or s.order == 0:
+                    c = p + 1
+                valid += 1
+        if valid > 1:
+            lq.lable |= LABLE_TEMP
+        if c != 0:
+            lq.sudoseed = lq.seqs[c - 1].seq
+        elif iter_count == 1:
+            i = 0
+            for p, s in enumerate(lq.seqs):
+                if s.order == 0:
+                    i = p
+                    break
+            lq.sudoseed = lq.seqs[i].seq
+    consensus = update_consensus_with_lqseqs(lqseqs, consensus, LABLE_RECH)
+    for lq in lqseqs:
+        if lq.lable & LABLE_RECH:
+            lq.lable ^= LABLE_TEMP if lq.lable & LABLE_TEMP else LABLE_RECH
+    return consensus
+
+
+def polish(tseq, bam, tables, iter_count=2, asref=True, use_all_reads=False, max_indel_len=20, min_kmer_count=5,
+           **ingest_kw):
+    """One contig through the whole path (main.rs:1727-1838).  tables = [(ksize, {hash >> 10: count})] with ksize < 32.
+    -> (consensus [(pos, base)], [sorted read indices blanked by each non-final iteration])"""
+    tables = sorted(tables, key=lambda t: t[0])  # option.rs:238
+    k0, tab0 = tables[0]
+
+    def getter(tab):
+        def get(h):
+            c = tab.get(h >> 10, 0)
+            return c if c >= min_kmer_count else 0
+        return get
+    als, _ = ingest(tseq, bam, **ingest_kw)
+    dropped, i = [], 0
+    while True:
+        msas = build_msas(len(tseq), als)
+        cns, regions = backtrack(msas, dp(msas))
+        consensus = [(p, b) for p, b, _ in cns]
+        final = i + 1 == iter_count
+        if regions:
+            cand = candidates(als, regions, k0)
+            ks = kscores(cand, tab0, k0, min_kmer_count)
+            lqseqs = [LqSeqs(s, e, [LqSeq(o, k, h, q) for (o, q, h), k in zip(c, kk)])
+                      for (s, e), c, kk in zip(regions, cand, ks)]
+            if final:
+                fill_seed_lqseqs(lqseqs, max_indel_len)
+                consensus = update_consensus_with_lqseqs(lqseqs, consensus, LABLE_SUCC)
+                for p, (k, tab) in enumerate(tables):
+                    consensus = reupdate_consensus_with_lqseqs(lqseqs, consensus, getter(tab), k, p + 1)
+            else:
+                mark_hete_lqseqs(lqseqs)
+                bad = phase_reads_by_lqseqs(lqseqs, asref, use_all_reads)
+                for r in bad:
+                    als[r].align_bases = []
+                dropped.append(sorted(set(bad)))
+        elif not final:
+            dropped.append([])
+        if final:
+            return consensus, dropped
+        i += 1
+
+
+def phase_from_pairs(pairs, asref=True, use_all_reads=False):
+    """phase_reads_by_lqseqs (main.rs:948-1015) fed with (a, b, #agree, #differ) per read pair (a < b; a == 0 is the
+    ref read) instead of LqSeqs: the per-site +1 / -1 updates are replayed one by one."""
+    data, dif, ref_data, invalid_ids = {}, {}, {}, set()
+    for a, b, agree, differ in pairs:
+        for w in [1.0] * agree + [-1.0] * differ:
+            if a == 0:
+                if asref:
+                    insert_data(ref_data, a, b, w)
+                if w < 0 and not use_all_reads:
+                    invalid_ids.add(b)
+                continue
+            if w == -1.0:
+                insert_data(dif, a, b, -1.0)
+                insert_data(dif, b, a, -1.0)
+            insert_data(data, a, b, w)
+            insert_data(data, b, a, w)
+    for n1, vs in dif.items():
+        for n2, w in vs.items():
+            if w <= -3.0:
+                assign_data(data, n1, n2, w)
+    if not use_all_reads:
+        data = {k: {k2: w for k2, w in vs.items() if k2 not in invalid_ids} for k, vs in data.items()
+                if k not in invalid_ids}
+    return sorted(set(phase_communities(data, ref_data[0] if ref_data else None)) | invalid_ids)

@@ -1,7 +1,9 @@
 """The C++ oracle against an independent pure-Python restatement of the same reference code (tests/py_restatement.py):
 reads after trim / clip filter, the per-position 3-mer lists in Msa order with counts and back pointers, the DP
 consensus with its qv / coverage flags, the LQ regions and the candidate alleles of every region (read order, string,
-first-k k-mer hash, the 60 cap, the monotone region cursor) must all be identical.  CPU only."""
+first-k k-mer hash, the 60 cap, the monotone region cursor) must all be identical; so must the reads blanked by
+the phasing step, the Louvain result on synthetic read graphs and the final consensus (positions and bases) of the
+whole path with one or two k-mer tables.  CPU only."""
 import gzip
 import os
 
@@ -104,3 +106,63 @@ def test_real_reads_window():
     _, h, cnt = read_yak(os.path.join(d, "k21.yak"))
     n, nreg, nhete = compare(contig[:W], np.concatenate(keep), table=(h, cnt))
     assert nreg > 10 and nhete > 0
+
+
+def compare_full(contig, bam, tables, **optkw):
+    """the whole path: reads blanked by the phasing of iteration 0 and the final consensus (positions + bases)"""
+    tseq = bytes(contig).decode()
+    ots = [O.Table.from_arrays(k, h, c) for k, (h, c) in tables.items()]
+    oj = O.Job(contig, bam, ots, O.Opts(min_ctg_len=0, **optkw), dump_iter=0)
+    want_pos, want_base = oj.consensus()
+    ptabs = [(k, {int(h) >> 10: int(n) for h, n in zip(*t)}) for k, t in tables.items()]
+    kw = {k: v for k, v in optkw.items() if k in ("iter_count", "max_indel_len", "min_kmer_count")}
+    cns, dropped = P.polish(tseq, bam, ptabs, asref=optkw.get("model", 0) == 0,
+                            use_all_reads=bool(optkw.get("use_all_reads", 0)), **kw)
+    if optkw.get("iter_count", 2) > 1:
+        assert sorted(set(int(x) for x in oj.dropped())) == dropped[0]
+    assert [p for p, _ in cns] == list(want_pos)
+    assert "".join(b for _, b in cns) == bytes(want_base).decode()
+    changed = "".join(b for _, b in cns) != tseq
+    return len(dropped[0]) if dropped else 0, changed
+
+
+def test_full_path_diploid():
+    """seed choice, Louvain phasing, consensus patching and the k-mer re-check with two tables (k = 21, 31)"""
+    A = synth.genome(51, 12_000)
+    c = synth.make_contig(52, A, depth=25, asm_err=1e-3, het=0.004, mean_len=4000, sd_len=600, min_len=1500,
+                          read_err=0.006, threads=2)
+    tabs = {k: synth.make_table(53, k, [c["hap1"], c["hap2"]]) for k in (21, 31)}
+    ndrop, changed = compare_full(A, c["bam"], tabs)
+    assert ndrop > 3 and changed  # reads of the other haplotype are blanked, assembly errors are corrected
+    for kw in ({"model": 1}, {"use_all_reads": 1}, {"iter_count": 1}, {"iter_count": 3}, {"max_indel_len": 0}):
+        compare_full(A, c["bam"], tabs, **kw)
+    compare_full(A, c["bam"], {21: tabs[21]})
+
+
+def test_full_path_haploid_and_exotic():
+    ds = common.dataset("tiny20k")
+    compare_full(ds["contig"], ds["bam"], {21: ds["tables"][21], 31: ds["tables"][31]})
+    ref, blob = exotic.make()
+    compare_full(ref, blob, {21: (np.array([1], np.uint64), np.array([9], np.uint16))})
+
+
+@pytest.mark.parametrize("model,use_all", [(0, False), (1, False), (0, True)])
+def test_louvain_phasing_on_read_graphs(model, use_all):
+    """louvain.rs through both restatements on synthetic two-haplotype read graphs (tests/test_phase_host.py), the
+    community that falls apart again included; the Python side replays the per-site +1 / -1 updates one at a time"""
+    import test_phase_host as T
+    D = (1 << 32) - 1
+    graphs = [T.make_graph(seed=1, n_reads=60), T.make_graph(seed=21, n_reads=250, span=20, noise=0.08),
+              T.make_graph(seed=22, n_reads=200, span=15, noise=0.3, gap_every=40),
+              T.make_graph(seed=23, n_reads=150, span=20, ref=False), T.gadget()]
+    k2, v2 = T.make_graph(seed=24, n_reads=80, span=10)
+    gk, gv = T.gadget(base=100)
+    graphs.append((np.concatenate([k2, gk]), np.concatenate([v2, gv])))
+    for keys, vals in graphs:
+        pairs = []
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            differ = (v + (1 << 31)) >> 32
+            pairs.append((k >> 32, k & D, v - differ * D, differ))
+            assert pairs[-1][2] >= 0
+        want = O.debug_phase(keys, vals, model, use_all)
+        assert P.phase_from_pairs(pairs, model == 0, use_all) == [int(x) for x in want]
