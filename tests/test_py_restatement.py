@@ -106,6 +106,8 @@ def test_real_reads_window():
     _, h, cnt = read_yak(os.path.join(d, "k21.yak"))
     n, nreg, nhete = compare(contig[:W], np.concatenate(keep), table=(h, cnt))
     assert nreg > 10 and nhete > 0
+    _, h31, cnt31 = read_yak(os.path.join(d, "k31.yak"))
+    compare_full(contig[:W], np.concatenate(keep), {21: (h, cnt), 31: (h31, cnt31)})
 
 
 def compare_full(contig, bam, tables, **optkw):
