@@ -418,7 +418,41 @@ def candidates(alignseqs, regions, ksize, max_can=60):  # generate_lqseqs_from_t
     return out
 
 
-def iter2kmer(seq, ksize):  # kmer.rs:255-287 (k < 32): canonical 2-bit k-mers, the window restarts at a non-ACGT base
+def yak_hash64_64(key):  # kmer.rs:235-244
+    m = (1 << 64) - 1
+    key = (~key + (key << 21)) & m
+    key = key ^ key >> 24
+    key = ((key + (key << 3)) + (key << 8)) & m
+    key = key ^ key >> 14
+    key = ((key + (key << 2)) + (key << 4)) & m
+    key = key ^ key >> 28
+    key = (key + (key << 31)) & m
+    return key
+
+
+def to_hash(kmer, ksize):  # KmerInfo::to_hash kmer.rs:102-110: long k-mers come out of iter2kmer already hashed
+    return yak_hash64(kmer, (1 << (2 * ksize)) - 1) if ksize < 32 else kmer
+
+
+def iter2kmer(seq, ksize):  # kmer.rs:255-310: canonical k-mers, the window restarts at a non-ACGT base
+    if ksize >= 32:  # two bit planes per strand, kmer.rs:288-309; yak_hash_long 246-249
+        shift, mask = ksize - 1, (1 << ksize) - 1
+        x, l = [0, 0, 0, 0], 0
+        for ch in seq:
+            c = SEQ_NUM[ord(ch)]
+            if c < 4:
+                x[0] = (x[0] << 1 | (c & 1)) & mask
+                x[1] = (x[1] << 1 | (c >> 1)) & mask
+                x[2] = x[2] >> 1 | (1 - (c & 1)) << shift
+                x[3] = x[3] >> 1 | (1 - (c >> 1)) << shift
+                l += 1
+            else:
+                l = 0
+                x = [0, 0, 0, 0]
+            if l >= ksize:
+                j = 0 if x[1] < x[3] else 1
+                yield (yak_hash64_64(x[j << 1]) + yak_hash64_64(x[j << 1 | 1])) & ((1 << 64) - 1)
+        return
     shift, mask, m64 = 2 * (ksize - 1), (1 << (2 * ksize)) - 1, (1 << 64) - 1
     k0 = k1 = l = 0
     for ch in seq:
@@ -828,8 +862,7 @@ def update_consensus_with_lqseqs(lqseqs, consensus, lable):  # main.rs:1017-1058
 
 
 def reupdate_consensus_with_lqseqs(lqseqs, consensus, get, ksize, iter_count):  # main.rs:1060-1420
-    """get(hash) = KmerInfo::get after retrieve_kmers(min_kmer_count) for this table; ksize < 32"""
-    mask = (1 << (2 * ksize)) - 1
+    """get(hash) = KmerInfo::get after retrieve_kmers(min_kmer_count) for this table"""
     idx = [0]
 
     def pos(i):
@@ -884,7 +917,7 @@ def reupdate_consensus_with_lqseqs(lqseqs, consensus, get, ksize, iter_count):  
         return s
 
     def score(s):
-        vals = [get(yak_hash64(x, mask)) for x in iter2kmer(s, ksize)]
+        vals = [get(to_hash(x, ksize)) for x in iter2kmer(s, ksize)]
         return min(vals) if vals else 0
 
     import itertools
@@ -949,7 +982,7 @@ def reupdate_consensus_with_lqseqs(lqseqs, consensus, get, ksize, iter_count):  
 
 def polish(tseq, bam, tables, iter_count=2, asref=True, use_all_reads=False, max_indel_len=20, min_kmer_count=5,
            **ingest_kw):
-    """One contig through the whole path (main.rs:1727-1838).  tables = [(ksize, {hash >> 10: count})] with ksize < 32.
+    """One contig through the whole path (main.rs:1727-1838).  tables = [(ksize, {hash >> 10: count})]; the smallest ksize < 32 (main.rs:1432-1434).
     -> (consensus [(pos, base)], [sorted read indices blanked by each non-final iteration])"""
     tables = sorted(tables, key=lambda t: t[0])  # option.rs:238
     k0, tab0 = tables[0]

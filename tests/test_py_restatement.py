@@ -133,7 +133,9 @@ def test_full_path_diploid():
     A = synth.genome(51, 12_000)
     c = synth.make_contig(52, A, depth=25, asm_err=1e-3, het=0.004, mean_len=4000, sd_len=600, min_len=1500,
                           read_err=0.006, threads=2)
-    tabs = {k: synth.make_table(53, k, [c["hap1"], c["hap2"]]) for k in (21, 31)}
+    tabs = {k: synth.make_table(53, k, [c["hap1"], c["hap2"]]) for k in (21, 31, 51)}
+    compare_full(A, c["bam"], tabs)  # the third re-check uses the bit-plane k-mers of k >= 32 (kmer.rs:288-309)
+    del tabs[51]
     ndrop, changed = compare_full(A, c["bam"], tabs)
     assert ndrop > 3 and changed  # reads of the other haplotype are blanked, assembly errors are corrected
     for kw in ({"model": 1}, {"use_all_reads": 1}, {"iter_count": 1}, {"iter_count": 3}, {"max_indel_len": 0}):
@@ -144,6 +146,7 @@ def test_full_path_diploid():
 def test_full_path_haploid_and_exotic():
     ds = common.dataset("tiny20k")
     compare_full(ds["contig"], ds["bam"], {21: ds["tables"][21], 31: ds["tables"][31]})
+    compare_full(ds["contig"], ds["bam"], {51: ds["tables"][51], 21: ds["tables"][21]})  # bit-plane k-mers, k >= 32
     ref, blob = exotic.make()
     compare_full(ref, blob, {21: (np.array([1], np.uint64), np.array([9], np.uint16))})
 
