@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(128) k_trim_scan(ReadsDev R, const uint8_t *__
 // SEQ nibbles mapped through the 16-entry code table; the others (op boundaries, indels, the terminator) are queued
 // in shared memory and packed column by column by densely filled warps.
 constexpr int kPackThreads = 256;
+constexpr int kPackBatchDefault = 2;  // blocks per thread of k_pack_columns_batched (1 = k_pack_columns)
 // 16 BAM nibbles (first column in the top nibble) -> 16 SEQ_NUM codes in the byte order of memory (column 0 in the high
 // nibble of byte 0).  Four nibbles at a time through PRMT: the 16-bit group IS the selector; two 8-entry byte tables
 // (codes of "=ACMGRSV" and of "TWYHKDBN") are looked up with the low three bits, and a third PRMT over 0x80 bytes turns
@@ -722,12 +723,92 @@ __global__ void __launch_bounds__(kPackThreads, 8) k_pack_columns(ReadsDev R, co
     const uint32_t nq = qn;
     for (uint32_t i = threadIdx.x; i < nq; i += kPackThreads) pack_block_slow(R, q[i]);
 }
+// Two (B) blocks per thread with the loads of each level of the chain block -> read -> op -> SEQ words issued for all
+// of them before the first use: one block per thread leaves too few bytes in flight per SM (56% of the samples of
+// k_pack_columns were long-scoreboard stalls on that chain, profiles/r01end).  Plain blocks (32 M/=/X columns of one
+// op) are finished here; everything else goes through the queue to the general per-block code.
+__device__ __forceinline__ void pack_block_queued(const ReadsDev &R, uint32_t g) {
+    const uint32_t r = R.ck_read[g];
+    const uint32_t n = R.n[r];
+    const uint32_t o0 = (g - R.ck_off[r]) * 32;
+    if (o0 < n) {
+        const uint32_t shift = R.shift[r], pos = R.pos[r];
+        OpCur cur;
+        op_at_block(R, r, g, shift + o0, cur);
+        uint32_t tp, dl;
+        col_tpos(R, r, pos, cur, shift + o0, tp, dl);
+        R.ck_tpos[g] = tp;
+        R.ck_delta[g] = (uint16_t)dl;
+    }
+    pack_block_slow(R, g);
+}
+template <int B>
+__global__ void __launch_bounds__(kPackThreads, 4) k_pack_columns_batched(ReadsDev R, uint32_t n_blocks) {
+    __shared__ uint32_t q[kPackThreads * B], qn;
+    if (threadIdx.x == 0) qn = 0;
+    __syncthreads();
+    uint32_t g[B], r[B], v[B];
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        g[u] = (blockIdx.x * B + u) * kPackThreads + threadIdx.x;
+        const uint32_t gc = min(g[u], n_blocks - 1);  // n_blocks > 0 (host wrapper)
+        r[u] = R.ck_read[gc];
+        v[u] = R.blk_op[gc];
+    }
+    uint32_t n[B], o0[B], shift[B], pos[B], opi[B];
+    uint64_t soff[B], noff[B];
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        n[u] = R.n[r[u]];
+        o0[u] = (min(g[u], n_blocks - 1) - R.ck_off[r[u]]) * 32;
+        shift[u] = R.shift[r[u]];
+        pos[u] = R.pos[r[u]];
+        opi[u] = R.op_off[r[u]] + v[u];
+        soff[u] = R.seq_off[r[u]];
+        noff[u] = R.nib_off[r[u]];
+    }
+    bool full[B];
+    uint4 o[B];
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        full[u] = g[u] < n_blocks && v[u] != 0xFFFFu && o0[u] + 32 <= n[u];  // 32 columns of the read, op known
+        o[u] = make_uint4(0, 0, 0, 2);
+        if (full[u]) o[u] = __ldg(R.ops + opi[u]);
+    }
+    bool plain[B];
+    uint64_t hi[B], lo[B];
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        const uint32_t op = o[u].w & 15, c_end = o[u].x + (o[u].w >> 4), col = shift[u] + o0[u];
+        plain[u] = full[u] && op != 1 && op != 2 && col + 32 <= c_end;
+        hi[u] = lo[u] = 0;
+        if (plain[u]) load_seq32(R.blob + soff[u], o[u].y + (col - o[u].x), hi[u], lo[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+        if (plain[u]) {
+            R.ck_tpos[g[u]] = pos[u] + o[u].z + (shift[u] + o0[u] - o[u].x);  // col_tpos of an M/=/X column
+            R.ck_delta[g[u]] = 0;
+            uint64_t *out = (uint64_t *)(R.nib + noff[u] + (o0[u] >> 1));
+            out[0] = map_codes16(hi[u]);
+            out[1] = map_codes16(lo[u]);
+        } else if (g[u] < n_blocks && n[u] && o0[u] <= n[u]) {
+            q[atomicAdd(&qn, 1u)] = g[u];
+        }
+    }
+    __syncthreads();
+    const uint32_t nq = qn;
+    for (uint32_t i = threadIdx.x; i < nq; i += kPackThreads) pack_block_queued(R, q[i]);
+}
 void trim_scan(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
     if (r.n_reads) NP2_K(k_trim_scan)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
 }
 void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cudaStream_t s) {
-    if (r.n_reads && n_blocks)
-        NP2_K(k_pack_columns)<<<cdiv(n_blocks, kPackThreads), kPackThreads, 0, s>>>(r, d_ref, n_blocks);
+    if (!r.n_reads || !n_blocks) return;
+    const char *e = getenv("NP2_PACK_BATCH");
+    const int batch = e ? atoi(e) : kPackBatchDefault;
+    if (batch <= 1) NP2_K(k_pack_columns)<<<cdiv(n_blocks, kPackThreads), kPackThreads, 0, s>>>(r, d_ref, n_blocks);
+    else NP2_K(k_pack_columns_batched<2>)<<<cdiv(n_blocks, 2 * kPackThreads), kPackThreads, 0, s>>>(r, n_blocks);
 }
 
 /* =============================================================== K2: pileup */
@@ -856,6 +937,8 @@ __device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, cons
 constexpr int kPileThreads = 256;
 constexpr int kPilePerThread = 4;  // 32-column blocks examined per thread in the fast pass
 constexpr int kPileCta = kPileThreads * kPilePerThread;
+constexpr int kPileBatchDefault = 2;  // blocks whose loads are in flight together in the fast pass (0 = one at a time;
+                                      // 4 needs 64 registers and loses more to occupancy than it gains: profiles/r01ab_ab.log)
 uint32_t pileup_ctas(uint32_t n_blocks) { return cdiv(n_blocks, kPileCta); }
 
 // Both passes: (1) every thread checks kPilePerThread blocks against the reference with word compares and queues the
@@ -874,16 +957,94 @@ __device__ __forceinline__ uint32_t pile_queue(const ReadsDev &R, uint32_t n_blo
     __syncthreads();
     return *qn;
 }
+// The same test for B blocks of one thread at a time, written without early exits: block_all_reference is a chain of
+// four dependent loads (block -> read -> nibbles -> reference) and a thread that walks it block after block spends its
+// time in long-scoreboard stalls (40% of the kernel's samples, profiles/r01end).  Here the loads of every level are
+// issued for all B blocks before the first use, and the two bytes of code[] are replaced by one more word of refpk
+// (the two columns in front of the block = the low byte of the 8 reference nibbles that end at tpos - 1).
+// A block the test cannot decide (first / last block of a read, tpos < 8) is queued: the column walk is the general path.
+template <int B>
+__device__ __forceinline__ uint32_t pile_queue_batched(const ReadsDev &R, uint32_t n_blocks,
+                                                       const uint8_t *__restrict__ blank,
+                                                       const uint32_t *__restrict__ refpk, uint32_t pk_last, uint32_t *q,
+                                                       uint32_t *qn) {
+    static_assert(kPilePerThread % B == 0, "batch must divide the blocks per thread");
+    if (threadIdx.x == 0) *qn = 0;
+    __syncthreads();
+    if (n_blocks) {
+#pragma unroll
+        for (int u0 = 0; u0 < kPilePerThread; u0 += B) {
+            uint32_t g[B], r[B], tpos[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                g[u] = blockIdx.x * kPileCta + (u0 + u) * kPileThreads + threadIdx.x;
+                const uint32_t gc = min(g[u], n_blocks - 1);
+                r[u] = R.ck_read[gc];
+                tpos[u] = R.ck_tpos[gc];  // not written for blocks without columns: only used clamped until proven valid
+            }
+            uint32_t n[B], o0[B], bl[B], pk[B][6];
+            uint64_t noff[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                bl[u] = blank[r[u]];
+                n[u] = R.n[r[u]];
+                o0[u] = (min(g[u], n_blocks - 1) - R.ck_off[r[u]]) * 32;
+                noff[u] = R.nib_off[r[u]];
+                const uint32_t k = min(tpos[u] >> 3, pk_last);
+                pk[u][0] = refpk[k ? k - 1 : 0];
+#pragma unroll
+                for (int j = 0; j < 5; j++) pk[u][j + 1] = refpk[k + j];
+            }
+            uint4 w4[B];
+            uint32_t pb[B];
+            bool cand[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                cand[u] = g[u] < n_blocks && !bl[u] && o0[u] > 0 && o0[u] + 32 <= n[u];  // a whole block inside a read
+                w4[u] = make_uint4(0, 0, 0, 0);
+                pb[u] = 0;
+                if (cand[u]) {
+                    const uint8_t *nib = R.nib + noff[u] + (o0[u] >> 1);
+                    w4[u] = *reinterpret_cast<const uint4 *>(nib);
+                    pb[u] = nib[-1];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const bool none = g[u] >= n_blocks || bl[u] || o0[u] >= n[u];  // nothing to emit
+                bool all_ref = false;
+                if (cand[u]) {
+                    const uint32_t sh = (tpos[u] & 7) * 4;
+                    const uint32_t w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+                    uint32_t diff = ((w[0] | w[1] | w[2] | w[3]) & 0xCCCCCCCCu) | (pb[u] & 0xCCu);
+                    diff |= (tpos[u] >> 3) == 0;
+                    diff |= pb[u] ^ (__funnelshift_l(pk[u][1], pk[u][0], sh) & 0xFFu);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        diff |= __byte_perm(w[j], 0, 0x0123) ^ __funnelshift_l(pk[u][j + 2], pk[u][j + 1], sh);
+                    all_ref = diff == 0;
+                }
+                if (!none && !all_ref) q[atomicAdd(qn, 1u)] = g[u];
+            }
+        }
+    }
+    __syncthreads();
+    return *qn;
+}
+// B = 0: the one-block-at-a-time fast pass (kept for A/B runs, NP2_PILE_BATCH=0)
+template <int B>
 __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32_t n_blocks,
                                                               const uint8_t *__restrict__ blank,
                                                               const uint8_t *__restrict__ code,
-                                                              const uint32_t *__restrict__ refpk,
+                                                              const uint32_t *__restrict__ refpk, uint32_t pk_last,
                                                               unsigned int *__restrict__ n_rec, uint32_t cap,
                                                               uint64_t *__restrict__ key, uint32_t *__restrict__ rd) {
     typedef cub::BlockScan<uint32_t, kPileThreads> BS;
     __shared__ typename BS::TempStorage tmp;
     __shared__ uint32_t q[kPileCta], qn, cta_base;
-    const uint32_t nq = pile_queue(R, n_blocks, blank, code, refpk, q, &qn);
+    uint32_t nq;
+    if constexpr (B == 0) nq = pile_queue(R, n_blocks, blank, code, refpk, q, &qn);
+    else nq = pile_queue_batched<B>(R, n_blocks, blank, refpk, pk_last, q, &qn);
     uint32_t c = 0;
     for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads)
         scan_block32(R, q[i], code, [&](uint32_t, uint32_t, uint32_t) { c++; });
@@ -917,8 +1078,19 @@ __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32
 void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
                  const uint32_t *d_refpk, uint32_t L, unsigned int *d_n_rec, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
                  cudaStream_t s) {
-    NP2_K(k_pileup_emit)<<<max(1u, pileup_ctas(n_blocks)), kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk,
-                                                                                 d_n_rec, cap, d_key, d_read);
+    // refpk holds L / 8 + 8 words (ref_codes): a clamped word index k <= L / 8 + 3 keeps k + 4 inside
+    const uint32_t pk_last = L / 8 + 3, grid = max(1u, pileup_ctas(n_blocks));
+    const char *e = getenv("NP2_PILE_BATCH");
+    const int batch = e ? atoi(e) : kPileBatchDefault;
+    if (batch == 0)
+        NP2_K(k_pileup_emit<0>)<<<grid, kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk, pk_last, d_n_rec, cap,
+                                                             d_key, d_read);
+    else if (batch == 2)
+        NP2_K(k_pileup_emit<2>)<<<grid, kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk, pk_last, d_n_rec, cap,
+                                                             d_key, d_read);
+    else
+        NP2_K(k_pileup_emit<4>)<<<grid, kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk, pk_last, d_n_rec, cap,
+                                                             d_key, d_read);
 }
 
 __global__ void k_mark_heads(const uint64_t *__restrict__ key, uint32_t n, uint32_t *__restrict__ head) {
