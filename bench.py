@@ -94,8 +94,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# the kernel behind each single-kernel stage as ncu lists it (defaults: NP2_PACK_BATCH=2, NP2_PILE_BATCH=2)
+KERNEL_OF = {"pack_columns": "k_pack_columns_batched<2>", "pileup_emit": "k_pileup_emit<2>"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
-# THIS workload (profiles/r01end_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.
+# THIS workload (profiles/r01end_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.  (Captured on the
+# one-block-per-thread forms of the two kernels; the batched forms move the same arrays.)
 NCU_TRAFFIC = {"pack_columns": 402109696, "pileup_emit": 279334400}
 
 
@@ -261,7 +264,7 @@ def run_ours(args):
             n_launch = max(1, int(round(stage_launches.get(dom, 1))))
             per_launch_ms = stages[dom] / n_launch
             achieved = stage_bytes(dom, st) / (per_launch_ms * 1e-3) / 1e9
-            roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            roofline = {"kernel": KERNEL_OF.get(dom, "k_" + dom), "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_kind,
                         "launch_ms": round(per_launch_ms, 4), "launches_per_step": n_launch,
                         "share_of_step": round(stages[dom] / stages["total"], 4),
@@ -275,7 +278,7 @@ def run_ours(args):
             nl = max(1, int(round(stage_launches.get(kname, 1))))
             ms1 = stages[kname] / nl
             ach = stage_bytes(kname, st) / (ms1 * 1e-3) / 1e9
-            others.append({"kernel": "k_" + kname, "achieved": round(ach, 1), "frac": round(ach / peak, 4),
+            others.append({"kernel": KERNEL_OF.get(kname, "k_" + kname), "achieved": round(ach, 1), "frac": round(ach / peak, 4),
                            "launch_ms": round(ms1, 4), "traffic": NCU_TRAFFIC.get(kname)})
         if roofline is not None:
             roofline["other_streaming_kernels"] = others
