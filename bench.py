@@ -96,10 +96,9 @@ class ClockSampler:
 
 # the kernel behind each single-kernel stage as ncu lists it (defaults: NP2_PACK_BATCH=2, NP2_PILE_BATCH=2)
 KERNEL_OF = {"pack_columns": "k_pack_columns_batched<2>", "pileup_emit": "k_pileup_emit<2>"}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed `ncu --set full` capture of
-# THIS workload (profiles/r01end_kernels_full.txt, 10 Mbp / 30x launch), bytes.  None = not captured.  (Captured on the
-# one-block-per-thread forms of the two kernels; the batched forms move the same arrays.)
-NCU_TRAFFIC = {"pack_columns": 402109696, "pileup_emit": 279334400}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed ncu capture of THIS workload
+# (profiles/r01ab_ncu_variants.txt, 10 Mbp / 30x launch; averages over the launches), bytes.  None = not captured.
+NCU_TRAFFIC = {"pack_columns": 384700000, "pileup_emit": 273600000}
 
 
 def peaks():
