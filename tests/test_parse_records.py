@@ -75,3 +75,38 @@ def test_first_error_in_file_order_wins():
     assert _parse(np.concatenate(good[:5] + [lowq] + good[5:]), L, 3)["reads"] == len(good)
     assert _parse(np.empty(0, np.uint8), L, 0) == {"records": 0, "reads": 0, "ops": 0, "columns": 0, "fallback": 0,
                                                    "digest": _parse(np.empty(0, np.uint8), L, 1)["digest"]}
+
+
+def _expected_counts(bam, min_read_len=1000, min_map_len=500, min_map_fra=0.5, min_map_qual=1):
+    """records / candidate reads / column-consuming ops / alignment columns from the pure-Python record reader and the
+    record-level filter of main.rs:1758-1771 (tests/py_restatement.py); zero-length ops make no column and no op"""
+    import py_restatement as P
+    recs = P.records(bam)
+    reads = ops = cols = 0
+    for _tid, _pos, mapq, flag, cig, _seq in recs:
+        rlen = sum(l for op, l in cig if op in (0, 1, 4, 7, 8, 5))
+        span = sum(l for op, l in cig if op in (0, 2, 3, 7, 8))
+        if flag & 4 or not cig or span == 0:
+            span = 1
+        frac = int(float(np.float32(rlen) * np.float32(min_map_fra)))
+        if (flag & 0x404 or mapq <= min_map_qual or rlen <= min_read_len or flag & 0x900
+                or span < max(min_map_len, frac)):
+            continue
+        reads += 1
+        ops += sum(1 for op, l in cig if op in (0, 1, 2, 7, 8) and l > 0)
+        cols += sum(l for op, l in cig if op in (0, 1, 2, 7, 8))
+    return {"records": len(recs), "reads": reads, "ops": ops, "columns": cols}
+
+
+def test_counts_match_an_independent_record_reader():
+    import exotic
+    ref, blob = exotic.make()  # flags, MAPQ 0/1, clips, N bases, zero-length ops, long indels
+    sets = [(blob, len(ref))] + [(common.dataset(n)["bam"], len(common.dataset(n)["contig"])) for n in ("tiny20k", "clip120k")]
+    for bam, L in sets:
+        want = _expected_counts(bam)
+        for t in (1, 3):
+            got = _parse(bam, L, t)
+            assert {k: got[k] for k in want} == want
+    want = _expected_counts(blob, min_map_qual=-1, min_read_len=0)
+    got = _parse(blob, len(ref), 2, min_map_qual=-1, min_read_len=0)
+    assert {k: got[k] for k in want} == want and want["reads"] > _expected_counts(blob)["reads"]
