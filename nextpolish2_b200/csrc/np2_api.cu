@@ -2413,8 +2413,7 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
             j->send_contig(tseq);  // in flight while the host walks the records
             parse_records(bam, bam_len, tlen, *opts, j->ing);
             j->enqueue_arrays();   // copy stream
-            if (getenv("NP2_DEBUG_ORDER")) NP2_CUDA(cudaStreamWaitEvent(ctx->stream, j->sc->ev_copied, 0));
-            j->send_seq();         // main stream (K0 gather), overlapping the copies
+            j->send_seq();         // K0 gather on the (high-priority) copy stream
             NP2_CUDA(cudaStreamWaitEvent(ctx->stream, j->sc->ev_copied, 0));
         } else {
             j->tseq.assign(tseq, tseq + tlen);
