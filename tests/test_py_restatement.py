@@ -120,8 +120,8 @@ def compare_full(contig, bam, tables, **optkw):
     kw = {k: v for k, v in optkw.items() if k in ("iter_count", "max_indel_len", "min_kmer_count")}
     cns, dropped = P.polish(tseq, bam, ptabs, asref=optkw.get("model", 0) == 0,
                             use_all_reads=bool(optkw.get("use_all_reads", 0)), **kw)
-    if optkw.get("iter_count", 2) > 1:
-        assert sorted(set(int(x) for x in oj.dropped())) == dropped[0]
+    # the oracle's list accumulates over the non-final iterations (a blanked read cannot be dropped again)
+    assert sorted(int(x) for x in oj.dropped()) == sorted(x for d in dropped for x in d)
     assert [p for p, _ in cns] == list(want_pos)
     assert "".join(b for _, b in cns) == bytes(want_base).decode()
     changed = "".join(b for _, b in cns) != tseq
