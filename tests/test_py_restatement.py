@@ -164,3 +164,21 @@ def test_louvain_phasing_on_read_graphs(model, use_all):
             assert pairs[-1][2] >= 0
         want = O.debug_phase(keys, vals, model, use_all)
         assert P.phase_from_pairs(pairs, model == 0, use_all) == [int(x) for x in want]
+
+
+def test_real_reads_whole_bundled_contig():
+    """configs[0] in full: the whole bundled contig (100 kb), every read, the unmodified yak tables (git-ignored fixture
+    built by tests/golden/make_c1.py --full at build() time)"""
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "_c1")
+    if not os.path.exists(os.path.join(d, "records.bin")):
+        pytest.skip("fixture _c1 not built (tests/golden/make_c1.py needs /root/reference)")
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_c1 import read_yak
+    contig = np.fromfile(os.path.join(d, "contig.bin"), np.uint8)
+    bam = np.fromfile(os.path.join(d, "records.bin"), np.uint8)
+    tabs = {k: read_yak(os.path.join(d, "k%d.yak" % k))[1:] for k in (21, 31)}
+    n, nreg, nhete = compare(contig, bam, table=tabs[21])
+    assert n > 300 and nreg > 2000 and nhete > 300
+    ndrop, changed = compare_full(contig, bam, tabs)
+    assert ndrop > 150 and changed  # (-m, -r and -i 3 agree as well; left out of the suite for time)
