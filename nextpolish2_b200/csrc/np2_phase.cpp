@@ -12,6 +12,7 @@
 // apart again and its vertices are re-keyed, with quirks): when one shows up the call is served from scratch by the
 // general map/set implementation (phase_reads_general in np2_host.cpp), which reproduces those quirks.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -50,23 +51,24 @@ struct Lvl {
 
 // louvain.rs:72-117.  The outcome of visiting a vertex depends only on its neighbours' communities, so a vertex is
 // re-examined only when one of them changed since its last visit (a skipped visit would have moved nothing).
-bool move_vertices(Lvl &lv) {
+// Works on ids[i0, i1); slot / stamp / dirty are indexed by vertex id and shared between concurrent calls, which touch
+// disjoint id ranges (see move_vertices).
+bool move_range(Lvl &lv, size_t i0, size_t i1, uint32_t *slot, uint32_t *stamp, uint8_t *dirty) {
     bool moved_any = false;
     // per-visit accumulator: weight towards each neighbouring community, found through a stamped slot table (the
     // choice below only depends on the sums, not on the order the communities were met in)
     std::vector<std::pair<uint32_t, float>> acc;
-    std::vector<uint32_t> slot(lv.n, 0), stamp(lv.n, 0);
     uint32_t visit = 0;
-    std::vector<uint8_t> dirty(lv.n, 1);
     for (;;) {
         bool stop = true;
-        for (uint32_t v : lv.ids) {
+        for (size_t i = i0; i < i1; i++) {
+            const uint32_t v = lv.ids[i];
             if (!dirty[v]) continue;
             dirty[v] = 0;
             const uint32_t cur = lv.cid[v];
             acc.clear();
-            if (++visit == 0) {  // stamp wrap-around
-                std::fill(stamp.begin(), stamp.end(), 0u);
+            if (++visit == 0) {  // stamp wrap-around (communities of this range are vertices of this range)
+                for (size_t x = i0; x < i1; x++) stamp[lv.ids[x]] = 0;
                 visit = 1;
             }
             for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) {
@@ -97,6 +99,48 @@ bool move_vertices(Lvl &lv) {
         if (stop) break;
     }
     return moved_any;
+}
+// The sweeps over all vertices (ascending id, repeated until nothing moves) split exactly into the same sweeps over
+// every set of vertices that no edge leaves: a visit only reads and writes communities of the vertex's own neighbours,
+// and a set in which a sweep moved nothing has no dirty vertex left, so later sweeps of the whole graph pass over
+// it.  Reads are numbered along the contig and only overlapping reads share an edge, so such sets are found as id
+// intervals (a cut wherever no earlier vertex has a neighbour at or beyond the next one: phase-block boundaries) and
+// are moved concurrently on the host pool.
+bool move_vertices(Lvl &lv) {
+    std::vector<uint32_t> slot(lv.n, 0), stamp(lv.n, 0);
+    std::vector<uint8_t> dirty(lv.n, 1);
+    const size_t ni = lv.ids.size();
+    const unsigned threads = host_threads();
+    const uint64_t n_edges = ni ? lv.aoff[lv.ids[ni - 1] + 1] - lv.aoff[lv.ids[0]] : 0;
+    if (threads < 2 || n_edges < 100000) return move_range(lv, 0, ni, slot.data(), stamp.data(), dirty.data());
+    // independent intervals, then chunks of whole intervals with about the same number of edges
+    const uint64_t per_chunk = n_edges / (4 * threads) + 1;
+    std::vector<size_t> chunk_begin(1, 0);
+    uint64_t reach = 0, in_chunk = 0;  // reach: 1 + the largest neighbour id seen so far
+    for (size_t i = 0; i < ni; i++) {
+        const uint32_t v = lv.ids[i];
+        if (i && reach <= v && in_chunk >= per_chunk) {
+            chunk_begin.push_back(i);
+            in_chunk = 0;
+        }
+        const uint32_t deg = lv.aoff[v + 1] - lv.aoff[v];
+        if (deg) reach = std::max<uint64_t>(reach, (uint64_t)lv.ato[lv.aoff[v + 1] - 1] + 1);  // neighbours ascending
+        reach = std::max<uint64_t>(reach, (uint64_t)v + 1);
+        in_chunk += deg;
+    }
+    chunk_begin.push_back(ni);
+    const size_t n_chunks = chunk_begin.size() - 1;
+    if (n_chunks < 2) return move_range(lv, 0, ni, slot.data(), stamp.data(), dirty.data());
+    std::atomic<size_t> next(0);
+    std::atomic<int> moved(0);
+    parallel_for((unsigned)std::min<size_t>(threads, n_chunks), [&](unsigned) {
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= n_chunks) break;
+            if (move_range(lv, chunk_begin[c], chunk_begin[c + 1], slot.data(), stamp.data(), dirty.data())) moved.store(1);
+        }
+    });
+    return moved.load() != 0;
 }
 
 // vertices grouped by community: comms ascending, members of each ascending
