@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — polished Mbp/s of the B200 polish path on BASELINE.json's configs[1]
-(synthetic 10 Mbp haploid contig, 30x HiFi, k21+k31), one contig per GPU (contigs are independent: weak scaling,
-no collective on the data path).
+"""bench.py — polished Mbp/s of the B200 polish path (BASELINE.json: "polished Mbp/sec at 1/2/4/8 B200 vs reference
+CPU; identical FASTA output").
 
-    python bench.py --gpus N --steps K --warmup W             # our arm
-    python bench.py --impl reference --steps K --warmup W     # the reference's CPU algorithm (oracle port)
+    python bench.py --gpus N --steps K --warmup W              # our arm (headline: configs[1], one contig per GPU)
+    python bench.py --config 2|3 [--full]                      # another config as the headline workload
+    python bench.py --impl reference --steps K --warmup W      # the reference's CPU algorithm (oracle port)
 
-One JSON line on stdout (rank 0).  `value` = polished Mbp/s with the inputs already resident in HBM when the
-timed region starts; `e2e` = the same metric through np2_polish_contig with HOST buffers (H2D + D2H inside the
-timed region).  `roofline` describes the dominant kernel of the step, `yak_lookup` the named K5 kernel at a
-table size far above L2, `cpu_baseline` the oracle port on a bounded sample of the same workload.
+One JSON line on stdout (rank 0).  A "step" is one pass of the polish path over the workload's contigs.
+  value     polished Mbp/s with the inputs already resident in HBM when the timed region starts (np2_job_run)
+  e2e       the same metric through np2_job_create/upload/run with HOST buffers (H2D + D2H inside the timed region)
+  verify    SHA-256 of the FASTA the GPU produced vs the FASTA of the CPU oracle on the same inputs
+  configs   (N = 1) the other BASELINE.json configs at a bounded size, each with its own value / e2e / verify:
+            "2" = 10 Mbp diploid contigs (1 % het, phasing), "3" = tandem-repeat contig, 40x, k21+k31+k51
+  strong_scaling   24 diploid contigs with configs[4]'s length distribution (scaled), LPT-partitioned over the N ranks,
+            tables staged once and broadcast over NVLink, FASTA digest in input order (must be the same at every N)
+  roofline  the largest single-kernel stage of the step against the measured HBM peak; yak_lookup = K5 at scale;
+  cpu_baseline     the oracle port on a bounded sample of the same workload.
+Full-size runs (`--config 2 --full`, `--config 3 --full`) are kept under profiles/.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -24,25 +32,48 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = "synthetic 10 Mbp haploid contig, 30x HiFi (N(15k,2k), 0.2% err), asm err 2e-5/bp, k21+k31"
-WORKLOAD_DIPLOID = ("synthetic %.0f Mbp diploid contig (%.1f%% het), 30x HiFi from both haplotypes, asm err 2e-5/bp, k21+k31 "
-                    "(one contig of configs[2]; exercises phasing)")
-KS = (21, 31)
+# BASELINE.json configs (sizes: SURVEY.md 8d).  "bounded" = what the default run uses when the config is an extra.
+CONFIGS = {
+    1: {"label": "configs[1]", "contigs": 1, "length": 10_000_000, "het": 0.0, "tandem": 0.0, "depth": 30.0, "ks": (21, 31),
+        "text": "synthetic 10 Mbp haploid contig, 30x HiFi (N(15k,2k), 0.2% err), asm err 2e-5/bp, k21+k31"},
+    2: {"label": "configs[2]", "contigs": 10, "length": 10_000_000, "het": 0.01, "tandem": 0.0, "depth": 30.0, "ks": (21, 31),
+        "bounded": {"contigs": 2},
+        "text": "synthetic diploid (1% het: 0.8% SNV + 0.2% indel), %d x %.0f Mbp contigs, 30x HiFi from both haplotypes, "
+                "asm err 2e-5/bp, k21+k31 (exercises phasing)"},
+    3: {"label": "configs[3]", "contigs": 1, "length": 250_000_000, "het": 0.0, "tandem": 0.05, "depth": 40.0, "ks": (21, 31, 51),
+        "bounded": {"length": 20_000_000},
+        "text": "synthetic chr1-scale contig, %d x %.0f Mbp, 5%% tandem-repeat blocks (unit 2-60 bp), 40x HiFi, "
+                "k21+k31+k51 (k51 = bit-plane hash)"},
+}
+SEED0 = 20260000  # SURVEY 8d: seed = 20260000 + config number
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_workload(seed, length, threads, het=0.0):
+def config_text(cfg):
+    return cfg["text"] % (cfg["contigs"], cfg["length"] / 1e6) if "%" in cfg["text"] else cfg["text"]
+
+
+def make_workload(cfg, seed, threads):
+    """[(name, contig, hap1, hap2, bam)], {k: (hashes, counts)} of one config (deterministic)."""
     from nextpolish2_b200 import synth
     t0 = time.time()
-    A = synth.genome(seed, length)
-    c = synth.make_contig(seed + 1, A, depth=30.0, asm_err=2e-5, het=het, read_err=0.002, threads=threads)
-    tabs = {k: synth.make_table(seed + 2, k, [c["hap1"]] + ([c["hap2"]] if het > 0 else [])) for k in KS}
-    log("[bench] workload seed %d: %d bp, %d reads, %.1f MB of BAM records, tables %s  (%.1fs)" % (
-        seed, length, c["n_reads"], len(c["bam"]) / 1e6, {k: len(v[0]) for k, v in tabs.items()}, time.time() - t0))
-    return A, c, tabs
+    contigs = []
+    for i in range(cfg["contigs"]):
+        A = synth.genome(seed + 10 * i, cfg["length"], tandem_frac=cfg["tandem"])
+        c = synth.make_contig(seed + 10 * i + 1, A, depth=cfg["depth"], asm_err=2e-5, het=cfg["het"], read_err=0.002,
+                              threads=threads)
+        contigs.append({"name": "ctg%03d" % i, "contig": A, "hap1": c["hap1"], "hap2": c["hap2"], "bam": c["bam"],
+                        "n_reads": c["n_reads"]})
+    t1 = time.time()
+    haps = [c["hap1"] for c in contigs] + [c["hap2"] for c in contigs if len(c["hap2"])]
+    tabs = {k: synth.make_table_mt(seed + 2, k, haps, threads=threads) for k in cfg["ks"]}
+    log("[bench] %s seed %d: %d x %d bp, %d reads, %.1f MB of BAM records (%.1fs), tables %s (%.1fs)" % (
+        cfg["label"], seed, cfg["contigs"], cfg["length"], sum(c["n_reads"] for c in contigs),
+        sum(len(c["bam"]) for c in contigs) / 1e6, t1 - t0, {k: len(v[0]) for k, v in tabs.items()}, time.time() - t1))
+    return contigs, tabs
 
 
 class ClockSampler:
@@ -94,13 +125,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# the kernel behind each single-kernel stage as ncu lists it (defaults: NP2_PACK_BATCH=2, NP2_PILE_BATCH=2)
-KERNEL_OF = {"pack_columns": "k_pack_columns_batched<2>", "pileup_emit": "k_pileup_emit<2>"}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed ncu capture of THIS workload
-# (profiles/r01ab_ncu_variants.txt, 10 Mbp / 30x launch; averages over the launches), bytes.  None = not captured.
-NCU_TRAFFIC = {"pack_columns": 384700000, "pileup_emit": 273600000}
-
-
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -108,17 +132,25 @@ def peaks():
     return 6650.0, "fallback"
 
 
-# Algorithmic bytes of the single-kernel stages (DESIGN.md "Kernels"): what the kernel must move through HBM once.
-def stage_bytes(stage, st):
-    cols, L = st["alignment_columns"], st["L"]
-    return {
-        # 4-bit SEQ in (0.5 B/column), packed nibble out (0.5), one 10-byte checkpoint out and one 2-byte op index in
-        # per 32 columns
-        "pack_columns": cols * (0.5 + 0.5 + 10 / 32 + 2 / 32),
-        # packed columns in (0.5) + checkpoints in (10/32); the packed reference (0.5 B/bp) is shared by the ~30 reads
-        # over a position and counted once
-        "pileup_emit": cols * (0.5 + 10 / 32) + L * 0.5 + st.get("records", 0) * 12,
-    }.get(stage)
+# ---------------------------------------------------------------------------------------------------------------------
+# Algorithmic bytes of the single-kernel stages: what the kernel must move through HBM once.
+# name -> (kernel as ncu lists it, bytes(st)); st = {"cols", "L", "records", "groups", "N"}
+STAGE_MODELS = {
+    # 4-bit SEQ in (0.5 B/column), packed nibble out (0.5), one 10-byte checkpoint out + one 2-byte op index in per 32 columns
+    "pack_columns": ("k_pack_columns_batched<2>", lambda st: st["cols"] * (0.5 + 0.5 + 10 / 32 + 2 / 32)),
+    # packed columns in (0.5) + checkpoints in (10/32); packed reference (0.5 B/bp) counted once; 12 B per record out
+    "pileup_emit": ("k_pileup_emit<2>", lambda st: st["cols"] * (0.5 + 10 / 32) + st["L"] * 0.5 + st["records"] * 12),
+    # 12-byte records in and out once per partition pass (2 passes) + group arrays out
+    "pileup_sort": ("pileup ordering (stripe partition + in-stripe sort)", lambda st: st["records"] * 12 * 4 + st["groups"] * 16),
+    # per position: cover 4 + sp_off 4 in, dense count 4 + flags 2 out; per group 16 in + 8 out
+    "pileup_finalize": ("k_pos_finalize", lambda st: st["L"] * 14 + st["groups"] * 24),
+    # per position of a run: sp_off 4 + cover 4 + multi 1 in, dense score/besti 12 out; per group 16 in, 12 out
+    "dp_runs": ("k_dp_runs", lambda st: st["L"] * 9 * 0.2 + st["groups"] * 28),
+    # per position: multi 1 + cover 4 + dense count 4 + code 1 + offset 4 in; 6 B per consensus base out
+    "consensus_emit": ("k_emit_singles + k_emit_runs", lambda st: st["L"] * 14 + st["N"] * 6),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of configs[1] (profiles/), bytes
+NCU_TRAFFIC = {"pack_columns": 384700000, "pileup_emit": 273600000}
 
 
 # bytes the whole pipeline must move per polished bp, D = depth, q = yak probes per bp
@@ -126,103 +158,143 @@ def pipeline_bytes_per_bp(depth, q):
     return 1.5 * depth + 111 + 42 * q
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import nextpolish2_b200 as np2
-    rank = int(os.environ.get("RANK", 0))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    if world > 1:
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    threads = max(1, (os.cpu_count() or 8) // max(world, 1))
-    A, c, tabs = make_workload(20260002 + 1000 * rank, args.length, min(threads, 16), args.het)
-    workload = WORKLOAD if args.het == 0 else WORKLOAD_DIPLOID % (args.length / 1e6, args.het * 100)
-    ctx = np2.Context(local)
-    # the box's cores are shared by the ranks and by the contigs each rank keeps in flight
-    from nextpolish2_b200.api import set_host_threads
-    set_host_threads(args.host_threads or
-                     max(2, min(16, (os.cpu_count() or 8) // max(world, 1) // max(1, min(args.e2e_inflight, 2)) * 2)))
-    tables = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in KS]
-    opts = np2.Opts()  # reference defaults; the 10 Mbp contig is above -L 1000000
-    bam_pinned = torch.from_numpy(c["bam"]) if args.pageable else torch.from_numpy(c["bam"]).pin_memory()
-    contig_pinned = torch.from_numpy(A.copy()).pin_memory()
-    bam_np, contig_np = bam_pinned.numpy(), contig_pinned.numpy()
+def fasta_record(name, first, last, base):
+    """display_consensusbase_vec (main.rs:627-643): header with the first/last consensus position, one line of bases."""
+    return (">%s start:%d end:%d\n" % (name, first, last)).encode() + bytes(base) + b"\n"
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    # ---- device-resident arm: inputs uploaded once, the timed step is np2_job_run
-    job = np2.Job(ctx, contig_np, bam_np, tables, opts).upload()
-    for _ in range(args.warmup):
-        job.run(-1)
+def oracle_fasta(contigs, tabs, ks, opts_kw, threads, stream_scan=False):
+    """FASTA records of the CPU oracle for every contig (one oracle thread per contig, `threads` at a time)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    otabs = [O.Table.from_arrays(k, *tabs[k]) for k in ks]
+    for t in otabs:
+        t.set_stream_scan(stream_scan)
+    out, dropped, secs = [None] * len(contigs), [0] * len(contigs), [0.0] * len(contigs)
+    nxt, lock = [0], threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= len(contigs):
+                return
+            c = contigs[i]
+            j = O.Job(c["contig"], c["bam"], otabs, O.Opts(**opts_kw), dump_iter=-1)
+            pos, base = j.consensus()
+            out[i] = fasta_record(c["name"], int(pos[0]), int(pos[-1]), base) if len(base) else b""
+            dropped[i] = len(j.dropped())
+            secs[i] = j.seconds
+    th = [threading.Thread(target=work) for _ in range(max(1, min(threads, len(contigs))))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return out, dropped, secs
+
+
+class Measured:
+    pass
+
+
+def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, warmup, barrier, inflight):
+    """Device-resident arm + end-to-end arm over `contigs`; returns a Measured with times (seconds for `steps` steps)."""
+    m = Measured()
+    pinned = []
+    for c in contigs:
+        bam_t = torch.from_numpy(c["bam"]) if args.pageable else torch.from_numpy(c["bam"]).pin_memory()
+        ctg_t = torch.from_numpy(c["contig"].copy()).pin_memory()
+        pinned.append((ctg_t, bam_t, ctg_t.numpy(), bam_t.numpy()))
+    m.pinned = pinned
+    total_bp = sum(len(c["contig"]) for c in contigs)
+
+    # ---- device-resident arm: inputs uploaded once, the timed step is np2_job_run over every contig
+    jobs = [np2.Job(ctx, p[2], p[3], tables, opts).upload() for p in pinned]
+    for _ in range(warmup):
+        for j in jobs:
+            j.run(-1)
     barrier()
-    sampler = ClockSampler(local)
-    step_ms, stage_acc, launches = [], {}, 0
+    step_ms, stage_acc, launches, stage_launches = [], {}, 0, {}
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        job.run(-1)
-        tm = job.timings()
-        step_ms.append(tm["total"][0])
-        for k, v in tm.items():
-            stage_acc.setdefault(k, []).append(v[0])
-        stage_launches = {k: v[1] for k, v in tm.items()}
-        launches += job.traffic()["kernel_launches"]
+    for _ in range(steps):
+        tot, acc = 0.0, {}
+        for j in jobs:
+            j.run(-1)
+            tm = j.timings()
+            tot += tm["total"][0]
+            for k, v in tm.items():
+                acc[k] = acc.get(k, 0.0) + v[0]
+                stage_launches[k] = v[1]
+            launches += j.traffic()["kernel_launches"]
+        step_ms.append(tot)
+        for k, v in acc.items():
+            stage_acc.setdefault(k, []).append(v)
     torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
+    m.wall = time.perf_counter() - t0
     barrier()
-    traffic = job.traffic()
-    _, _, gbase = job.bases()
-    dev_time = sum(step_ms) / 1e3  # CUDA events on the library's stream around each whole step (includes host phases)
-    ident = bytes(gbase) == bytes(c["hap1"])
-    job.destroy()
+    m.traffic = {k: sum(j.traffic()[k] for j in jobs) for k in jobs[0].traffic()}
+    m.stats = {}
+    for k in jobs[0].stats() if hasattr(jobs[0], "stats") else {}:
+        m.stats[k] = sum(j.stats()[k] for j in jobs)
+    m.records, m.dropped = [], []
+    for c, j in zip(contigs, jobs):
+        first, last, base = j.bases()
+        m.records.append(fasta_record(c["name"], first, last, base))
+        m.dropped.append(len(j.dropped()))
+    m.dev_time = sum(step_ms) / 1e3  # CUDA events on the library's stream around each whole run (includes host phases)
+    m.stages = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    m.stage_launches = stage_launches
+    m.launches = launches
+    for j in jobs:
+        j.destroy()
 
-    # ---- end to end: host buffers in, consensus out, every step.  `--e2e-inflight` contigs are in flight at once
-    # (one host thread + one context + one stream each, tables shared: the CLI's double buffering), so the PCIe
-    # upload and host-side record parsing of one contig overlap the kernels of another.
-    e2e_parts = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
-    e2e_parts_inflight = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
+    # ---- end to end: host buffers in, FASTA record out, every step.  `inflight` contigs are in flight at once
+    # (one host thread + one context + one stream each, tables shared: the CLI's scheme), so the PCIe upload and
+    # host-side record parsing of one contig overlap the kernels of another.
+    parts1 = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
+    partsN = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
+    expect = [len(r) for r in m.records]
 
-    def e2e_step(cx, acc=None):
+    def e2e_one(cx, ci, acc=None):
+        c, p = contigs[ci], pinned[ci]
         t0 = time.perf_counter()
-        j = np2.Job(cx, contig_np, bam_np, tables, opts)
+        j = np2.Job(cx, p[2], p[3], tables, opts)
         t1 = time.perf_counter()
         j.upload()
         t2 = time.perf_counter()
         j.run(-1)
         t3 = time.perf_counter()
         first, last, base = j.bases(copy=False)  # the FASTA record (header span + bases) in host memory
-        assert len(base) == len(gbase) and base[-1] == gbase[-1] and base[len(base) // 2] == gbase[len(base) // 2]
+        rec_len = len(">%s start:%d end:%d\n" % (c["name"], first, last)) + len(base) + 1
+        assert rec_len == expect[ci], "end-to-end FASTA record differs from the device-resident run"
         tr = j.traffic()
-        tm_up = {k: v[0] for k, v in j.timings().items() if k.startswith("upload:")} if acc is not None else {}
         j.destroy()
         t4 = time.perf_counter()
         if acc is not None:
             for k, v in zip(("create_parse", "upload", "run", "result"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                 acc[k] += v * 1e3
-            for k, v in tm_up.items():
-                acc[k] = acc.get(k, 0.0) + v
             acc["n"] += 1
         return tr
 
     def e2e_run(n_inflight):
         ctxs = [ctx] + [np2.Context(local) for _ in range(n_inflight - 1)]
         for cx in ctxs:  # warm every context's pools
-            for _ in range(max(1, args.warmup // n_inflight)):
-                e2e_step(cx)
-        tr_box, errs = [None], []
-        share = [args.steps // n_inflight + (1 if w < args.steps % n_inflight else 0) for w in range(n_inflight)]
+            for _ in range(max(1, warmup // n_inflight)):
+                e2e_one(cx, 0)
+        work_items = [ci for _ in range(steps) for ci in range(len(contigs))]
+        nxt, lock, errs, tr_sum = [0], threading.Lock(), [], {"h2d_bytes": 0, "d2h_bytes": 0}
 
         def work(w):
             try:
-                for _ in range(share[w]):
-                    tr_box[0] = e2e_step(ctxs[w], e2e_parts if n_inflight == 1 else e2e_parts_inflight)
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= len(work_items):
+                        return
+                    tr = e2e_one(ctxs[w], work_items[i], parts1 if n_inflight == 1 else partsN)
+                    with lock:
+                        tr_sum["h2d_bytes"] += tr["h2d_bytes"]
+                        tr_sum["d2h_bytes"] += tr["d2h_bytes"]
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         torch.cuda.synchronize()
@@ -236,79 +308,205 @@ def run_ours(args):
             cx.close()
         if errs:
             raise errs[0]
-        return t2 - t1, tr_box[0]
+        return t2 - t1, {k: v // steps for k, v in tr_sum.items()}
 
-    e2e_serial_time, tr = e2e_run(1)
-    e2e_time = e2e_serial_time
-    if args.e2e_inflight > 1:
-        e2e_time, tr = e2e_run(args.e2e_inflight)
+    barrier()
+    m.e2e_serial_time, m.e2e_traffic = e2e_run(1)
+    m.e2e_time = m.e2e_serial_time
+    if inflight > 1:
+        barrier()
+        m.e2e_time, m.e2e_traffic = e2e_run(inflight)
+    m.parts1, m.partsN = parts1, partsN
+    m.total_bp = total_bp
+    return m
+
+
+def verify(contigs, tabs, cfg, records, dropped_gpu, opts_kw, threads):
+    t0 = time.time()
+    orec, odrop, osec = oracle_fasta(contigs, tabs, cfg["ks"], opts_kw, threads)
+    g = hashlib.sha256(b"".join(records)).hexdigest()
+    o = hashlib.sha256(b"".join(orec)).hexdigest()
+    truth = [bytes(r.split(b"\n", 2)[1]) == bytes(c["hap1"]) for r, c in zip(records, contigs)]
+    return {"fasta_sha256_gpu": g, "fasta_sha256_oracle": o, "identical": g == o, "contigs_checked": len(contigs),
+            "fasta_bytes": sum(len(r) for r in records), "reads_dropped_by_phasing_gpu": int(sum(dropped_gpu)),
+            "reads_dropped_by_phasing_oracle": int(sum(odrop)), "identical_to_truth_haplotype": bool(all(truth)),
+            "oracle_cpu_seconds": round(float(sum(osec)), 1), "oracle_wall_seconds": round(time.time() - t0, 1)}
+
+
+def summarise(m, cfg, steps, world, peak):
+    """value / e2e / pipeline roofline of one measured config (rank-local times; the caller reduces over ranks)."""
+    q = m.traffic["probes"] / float(m.total_bp)
+    bpb = pipeline_bytes_per_bp(cfg["depth"], q)
+    step_ms = m.dev_time / steps * 1e3
+    return {
+        "workload": config_text(cfg), "contigs": cfg["contigs"], "contig_bp": cfg["length"],
+        "value": round(world * m.total_bp * steps / 1e6 / m.dev_time, 3), "unit": "Mbp/s",
+        "ms_per_step": round(step_ms, 3), "ms_per_10Mbp": round(step_ms * 1e7 / m.total_bp, 3),
+        "e2e": {"value": round(world * m.total_bp * steps / 1e6 / m.e2e_time, 3), "unit": "Mbp/s",
+                "h2d_bytes_per_step": m.e2e_traffic["h2d_bytes"], "d2h_bytes_per_step": m.e2e_traffic["d2h_bytes"]},
+        "pipeline_roofline": {"bytes_per_bp": round(bpb, 1), "probes_per_bp": round(q, 3),
+                              "achieved_GBps": round(bpb * m.total_bp / (step_ms * 1e-3) / 1e9, 1),
+                              "frac_of_hbm_peak": round(bpb * m.total_bp / (step_ms * 1e-3) / 1e9 / peak, 4)},
+        "stages_ms": {k: round(v, 4) for k, v in m.stages.items()},
+        "gpu_launches": int(m.launches),
+    }
+
+
+def roofline_of(m, cfg, peak, peak_kind):
+    st = {"cols": m.traffic["alignment_columns"], "L": m.total_bp, "records": m.stats.get("records", 0),
+          "groups": m.stats.get("groups", 0), "N": m.total_bp}
+    kern = {k: v for k, v in m.stages.items() if k in STAGE_MODELS and v > 0}
+    if not kern:
+        return None
+    rows = []
+    for k, ms in kern.items():
+        nl = max(1, int(round(m.stage_launches.get(k, 1))))
+        n_jobs = max(1, cfg["contigs"])
+        per_launch_ms = ms / n_jobs  # stage time summed over the contigs of the step; one stage instance per contig
+        ach = STAGE_MODELS[k][1](st) / n_jobs / (per_launch_ms * 1e-3) / 1e9
+        rows.append({"stage": k, "kernel": STAGE_MODELS[k][0], "achieved": round(ach, 1), "frac": round(ach / peak, 4),
+                     "launch_ms": round(per_launch_ms, 4), "kernels_in_stage": nl,
+                     "share_of_step": round(ms / m.stages["total"], 4),
+                     "algorithmic_bytes_per_launch": int(STAGE_MODELS[k][1](st) / n_jobs), "traffic": NCU_TRAFFIC.get(k)})
+    rows.sort(key=lambda r: -r["launch_ms"])
+    dom = rows[0]
+    return {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_kind, "launch_ms": dom["launch_ms"],
+            "share_of_step": dom["share_of_step"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+            "stage": dom["stage"], "note": "the slowest stage of the step that has a byte model (DESIGN.md 4); the others follow",
+            "other_stages": rows[1:]}
+
+
+def cfg_for(n, full):
+    cfg = dict(CONFIGS[n])
+    if not full:
+        cfg.update(cfg.get("bounded", {}))
+    cfg.pop("bounded", None)
+    return cfg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nextpolish2_b200 as np2
+    from nextpolish2_b200.api import set_host_threads
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    cores = max(1, (os.cpu_count() or 8) // max(world, 1))
+    threads = min(cores, 16)
+    cfg = cfg_for(args.config, args.full or args.config == 1)
+    if args.length:
+        cfg["length"] = args.length
+    if args.contigs:
+        cfg["contigs"] = args.contigs
+    if args.het is not None:
+        cfg["het"] = args.het
+    ctx = np2.Context(local)
+    # the box's cores are shared by the ranks and by the contigs each rank keeps in flight
+    set_host_threads(args.host_threads or max(2, min(16, cores // max(1, min(args.e2e_inflight, 2)) * 2)))
+    opts_kw = {}
+    opts = np2.Opts(**opts_kw)  # reference defaults; every contig is above -L 1000000
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    contigs, tabs = make_workload(cfg, SEED0 + args.config + 1000 * rank, threads)
+    tables = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in cfg["ks"]]
+    sampler = ClockSampler(local)
+    m = measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, args.steps, args.warmup, barrier, args.e2e_inflight)
     clocks = sampler.stop()  # sampled over both timed regions (device-resident steps and end-to-end steps)
 
-    t_dev = torch.tensor([dev_time, e2e_time, wall, e2e_serial_time], dtype=torch.float64, device="cuda")
+    t_dev = torch.tensor([m.dev_time, m.e2e_time, m.wall, m.e2e_serial_time], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_time, e2e_time, wall, e2e_serial_time = [float(x) for x in t_dev.tolist()]
-    mbp_total = world * args.length * args.steps / 1e6
+    m.dev_time, m.e2e_time, m.wall, m.e2e_serial_time = [float(x) for x in t_dev.tolist()]
+
+    ver = None
+    if not args.no_verify:
+        ver = verify(contigs, tabs, cfg, m.records, m.dropped, opts_kw, cores)
+        if world > 1:  # every rank checked its own contigs
+            allv = [None] * world
+            dist.all_gather_object(allv, ver)
+            ver = dict(allv[0])
+            ver["identical"] = all(v["identical"] for v in allv)
+            ver["contigs_checked"] = sum(v["contigs_checked"] for v in allv)
+            ver["per_rank_sha256_gpu"] = [v["fasta_sha256_gpu"][:16] for v in allv]
 
     line = None
+    peak, peak_kind = peaks()
     if rank == 0:
-        peak, peak_kind = peaks()
-        stages = {k: float(np.mean(v)) for k, v in stage_acc.items()}
-        st = {"alignment_columns": traffic["alignment_columns"], "L": args.length, "records": 0}
-        kern = {k: v for k, v in stages.items() if stage_bytes(k, st)}
-        dom = max(kern, key=kern.get) if kern else None
-        roofline = None
-        if dom:
-            # single-kernel stages; the stage time is summed over the launches of the step
-            n_launch = max(1, int(round(stage_launches.get(dom, 1))))
-            per_launch_ms = stages[dom] / n_launch
-            achieved = stage_bytes(dom, st) / (per_launch_ms * 1e-3) / 1e9
-            roofline = {"kernel": KERNEL_OF.get(dom, "k_" + dom), "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_kind,
-                        "launch_ms": round(per_launch_ms, 4), "launches_per_step": n_launch,
-                        "share_of_step": round(stages[dom] / stages["total"], 4),
-                        "algorithmic_bytes_per_launch": int(stage_bytes(dom, st)),
-                        "note": "largest of the streaming kernels with a defined byte count (pack_columns, "
-                                "pileup_emit); the step is ~50 short kernels + host phases, none above 10% of it"}
-        others = []
-        for kname in kern:
-            if kname == dom:
-                continue
-            nl = max(1, int(round(stage_launches.get(kname, 1))))
-            ms1 = stages[kname] / nl
-            ach = stage_bytes(kname, st) / (ms1 * 1e-3) / 1e9
-            others.append({"kernel": KERNEL_OF.get(kname, "k_" + kname), "achieved": round(ach, 1), "frac": round(ach / peak, 4),
-                           "launch_ms": round(ms1, 4), "traffic": NCU_TRAFFIC.get(kname)})
-        if roofline is not None:
-            roofline["other_streaming_kernels"] = others
-        q = traffic["probes"] / float(args.length)
-        pipe_bytes = pipeline_bytes_per_bp(30, q) * args.length
-        pipeline = {"bytes_per_bp": round(pipeline_bytes_per_bp(30, q), 1), "probes_per_bp": round(q, 3),
-                    "achieved_GBps": round(pipe_bytes / (stages["total"] * 1e-3) / 1e9, 1),
-                    "frac_of_hbm_peak": round(pipe_bytes / (stages["total"] * 1e-3) / 1e9 / peak, 4)}
+        s = summarise(m, cfg, args.steps, world, peak)
+        mbp_total = world * m.total_bp * args.steps / 1e6
         line = {
-            "metric": "polished Mbp/s", "value": round(mbp_total / dev_time, 3), "unit": "Mbp/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_time / args.steps * 1e3, 3),
+            "metric": "polished Mbp/s", "value": s["value"], "unit": "Mbp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer",
             "data": "synthetic",
-            "config": {"workload": workload, "contig_bp": args.length, "contigs_per_gpu": 1, "depth": 30,
-                       "tables": "k21+k31 synthesised from the truth haplotype(s)", "partition": "one contig per GPU, no collective",
-                       "l2": "inputs (%.0f MB of BAM records per GPU) are larger than the 126 MB L2" % (len(c["bam"]) / 1e6)},
-            "e2e": {"value": round(mbp_total / e2e_time, 3), "unit": "Mbp/s", "h2d_bytes_per_step": tr["h2d_bytes"],
-                    "d2h_bytes_per_step": tr["d2h_bytes"], "contigs_in_flight": args.e2e_inflight,
-                    "one_at_a_time": round(mbp_total / e2e_serial_time, 3),
-                    "one_at_a_time_ms": {k: round(v / max(1, e2e_parts["n"]), 3) for k, v in e2e_parts.items() if k != "n"},
-                    "in_flight_ms_per_contig_per_thread": {k: round(v / max(1, e2e_parts_inflight["n"]), 3)
-                                                           for k, v in e2e_parts_inflight.items()
-                                                           if k in ("create_parse", "upload", "run", "result")}},
-            "gpu_launches": int(launches),
+            "config": {"workload": config_text(cfg), "baseline_config": cfg["label"], "contig_bp": cfg["length"],
+                       "contigs_per_gpu": cfg["contigs"], "depth": cfg["depth"],
+                       "tables": "+".join("k%d" % k for k in cfg["ks"]) + " synthesised from the truth haplotype(s)",
+                       "partition": "one workload replica per GPU, no collective on the data path",
+                       "l2": "inputs (%.0f MB of BAM records per GPU) are larger than the 126 MB L2" % (
+                           sum(len(c["bam"]) for c in contigs) / 1e6)},
+            "e2e": dict(s["e2e"], contigs_in_flight=args.e2e_inflight,
+                        one_at_a_time=round(mbp_total / m.e2e_serial_time, 3),
+                        one_at_a_time_ms={k: round(v / max(1, m.parts1["n"]), 3) for k, v in m.parts1.items() if k != "n"},
+                        in_flight_ms_per_contig_per_thread={k: round(v / max(1, m.partsN["n"]), 3)
+                                                            for k, v in m.partsN.items() if k != "n"}),
+            "gpu_launches": s["gpu_launches"],
             "clocks": clocks,
-            "roofline": roofline,
-            "pipeline_roofline": pipeline,
-            "stages_ms": {k: round(v, 4) for k, v in stages.items()},
-            "identical_to_truth_haplotype": bool(ident),
-            "wall_ms_per_step": round(wall / args.steps * 1e3, 3),
+            "roofline": roofline_of(m, cfg, peak, peak_kind),
+            "pipeline_roofline": s["pipeline_roofline"],
+            "stages_ms": s["stages_ms"],
+            "verify": ver,
+            "identical_to_oracle": None if ver is None else ver["identical"],
+            "wall_ms_per_step": round(m.wall / args.steps * 1e3, 3),
         }
+    del m
+    for t in tables:
+        t.free()
+    del contigs, tabs
+
+    # ---- the other configs, bounded (N = 1): same measurement, fewer steps
+    if world == 1 and not args.no_extras:
+        extras = {}
+        for n in (2, 3):
+            if n == args.config:
+                continue
+            ecfg = cfg_for(n, False)
+            try:
+                ec, et = make_workload(ecfg, SEED0 + n, threads)
+                etab = [np2.Table.from_arrays(ctx, k, *et[k]) for k in ecfg["ks"]]
+                em = measure(np2, torch, ctx, local, ec, etab, ecfg, args, opts, max(2, args.steps // 4), 3, barrier,
+                             args.e2e_inflight)
+                es = summarise(em, ecfg, max(2, args.steps // 4), 1, peak)
+                es.pop("stages_ms")
+                es["stages_ms_top"] = dict(sorted(em.stages.items(), key=lambda kv: -kv[1])[:8])
+                es["stages_ms_top"] = {k: round(v, 3) for k, v in es["stages_ms_top"].items()}
+                es["verify"] = None if args.no_verify else verify(ec, et, ecfg, em.records, em.dropped, opts_kw, cores)
+                extras[str(n)] = es
+                for t in etab:
+                    t.free()
+                del em, ec, et
+            except Exception as e:  # noqa: BLE001
+                extras[str(n)] = {"error": repr(e)[:300]}
+        line["configs"] = extras
+
+    if not args.no_strong:
+        ss = strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barrier)
+        if rank == 0:
+            line["strong_scaling"] = ss
+
+    if rank == 0:
         if not args.no_yak_bench:
             line["yak_lookup"] = yak_bench(ctx, np2, torch, peak)
         if world == 1 and not args.no_cpu_baseline:
@@ -318,6 +516,139 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def strong_contig_lengths(total_bp, n=24):
+    """configs[4]: 24 contigs of 50-250 Mbp summing to 3 Gbp, scaled to total_bp."""
+    raw = np.linspace(250.0, 50.0, n)
+    return [int(x / raw.sum() * total_bp) // 1000 * 1000 for x in raw]
+
+
+def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barrier):
+    """configs[4] scaled: a FIXED set of 24 diploid contigs, LPT-partitioned over the ranks (contigs are independent:
+    no collective on the data path); the tables are staged by rank 0 and broadcast over NVLink; every rank polishes its
+    share end to end (host buffers -> FASTA records, several contigs in flight); rank 0 gathers the records in input
+    order.  The digest must be the same at every N; rank 0 checks its own contigs against the oracle."""
+    from nextpolish2_b200 import synth
+    from nextpolish2_b200.shard import lpt_partition, broadcast_tables
+    lens = strong_contig_lengths(int(args.strong_mbp * 1e6))
+    seed, ks, threads = SEED0 + 4, (21, 31), min(cores, 16)
+    opts_kw = {"min_ctg_len": 100000}  # the contigs are scaled down ~60x from configs[4]; so is -L
+    opts = np2.Opts(**opts_kw)
+    t0 = time.time()
+    tabs, tables = None, []
+    if rank == 0:  # haplotypes of every contig (no reads) -> tables
+        haps = []
+        for i, ln in enumerate(lens):
+            A = synth.genome(seed + 10 * i, ln)
+            c = synth.make_contig(seed + 10 * i + 1, A, depth=0.0, asm_err=2e-5, het=0.01, read_err=0.002, threads=1)
+            haps += [c["hap1"], c["hap2"]]
+        tabs = {k: synth.make_table_mt(seed + 2, k, haps, threads=threads) for k in ks}
+        tables = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in ks]
+        del haps
+    t_tab = time.time() - t0
+    torch.cuda.synchronize()
+    t0 = time.time()
+    tables = broadcast_tables(ctx, tables, rank, world)
+    torch.cuda.synchronize()
+    t_bcast = time.time() - t0
+    mine = lpt_partition([float(x) for x in lens], world)[rank]
+    t0 = time.time()
+    contigs = []
+    for i in mine:
+        A = synth.genome(seed + 10 * i, lens[i])
+        c = synth.make_contig(seed + 10 * i + 1, A, depth=30.0, asm_err=2e-5, het=0.01, read_err=0.002, threads=threads)
+        contigs.append({"idx": i, "name": "ctg%03d" % i, "contig": A, "hap1": c["hap1"], "hap2": c["hap2"], "bam": c["bam"]})
+    pinned = [(torch.from_numpy(c["contig"].copy()).pin_memory(), torch.from_numpy(c["bam"]).pin_memory()) for c in contigs]
+    t_synth = time.time() - t0
+    inflight = max(1, min(args.e2e_inflight, len(contigs)))
+    ctxs = [ctx] + [np2.Context(local) for _ in range(inflight - 1)]
+
+    def polish(cx, ci):
+        c, p = contigs[ci], pinned[ci]
+        j = np2.Job(cx, p[0].numpy(), p[1].numpy(), tables, opts)
+        j.upload().run(-1)
+        first, last, base = j.bases(copy=False)
+        rec = fasta_record(c["name"], first, last, base)
+        nd = len(j.dropped())
+        j.destroy()
+        return rec, nd
+
+    def one_pass():
+        out, nxt, lock, errs = {}, [0], threading.Lock(), []
+
+        def work(w):
+            try:
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= len(contigs):
+                        return
+                    out[contigs[i]["idx"]] = polish(ctxs[w], i)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(w,)) for w in range(inflight)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if errs:
+            raise errs[0]
+        return out
+    if contigs:
+        for cx in ctxs:
+            polish(cx, 0)  # warm pools
+    passes = max(1, args.strong_passes)
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(passes):
+        local_out = one_pass()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t1
+    barrier()
+    for cx in ctxs[1:]:
+        cx.close()
+    t_dev = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dt_max = float(t_dev.item())
+    digests = {i: (hashlib.sha256(r).hexdigest(), len(r), nd) for i, (r, nd) in local_out.items()}
+    gathered = [digests]
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(digests, gathered, dst=0)
+    res = None
+    if rank == 0:
+        merged = {}
+        for d in gathered:
+            merged.update(d)
+        assert sorted(merged) == list(range(len(lens))), "a contig is missing from the gathered FASTA"
+        h = hashlib.sha256()
+        for i in range(len(lens)):  # input order (= the reference with -t 1)
+            h.update(merged[i][0].encode())
+        orec, odrop, osec = oracle_fasta(contigs, tabs, ks, opts_kw, cores) if not args.no_verify else ([], [], [])
+        ok = all(hashlib.sha256(o).hexdigest() == merged[c["idx"]][0] for o, c in zip(orec, contigs))
+        total = float(sum(lens))
+        res = {"workload": "configs[4] scaled: 24 diploid contigs (1%% het, 30x), lengths %.2f-%.2f Mbp (configs[4]'s 250-50 Mbp "
+                           "distribution), %.0f Mbp in total, -L 100000, k21+k31" % (max(lens) / 1e6, min(lens) / 1e6, total / 1e6),
+               "n_gpus": world, "scaling": "strong", "partition": "LPT by contig length over the ranks, no data-path collective",
+               "value": round(total * passes / 1e6 / dt_max, 3), "unit": "Mbp/s (end to end, host buffers in, FASTA records out)",
+               "seconds_per_pass": round(dt_max / passes, 4), "passes": passes, "contigs_in_flight_per_gpu": inflight,
+               "contigs_per_rank": [len(p) for p in lpt_partition([float(x) for x in lens], world)],
+               "fasta_sha256_in_input_order": h.hexdigest(), "fasta_bytes": int(sum(v[1] for v in merged.values())),
+               "reads_dropped_by_phasing": int(sum(v[2] for v in merged.values())),
+               "oracle_checked_contigs": [c["idx"] for c in contigs] if not args.no_verify else [],
+               "identical_to_oracle": (bool(ok) if not args.no_verify else None),
+               "table_stage_s": round(t_tab, 2), "table_broadcast_s": round(t_bcast, 3),
+               "table_bytes": int(sum(t.device_bytes for t in tables)),
+               "table_broadcast_GBps": (round(sum(t.device_bytes for t in tables) / t_bcast / 1e9, 1) if world > 1 else None),
+               "synth_s": round(t_synth, 1)}
+    if rank != 0:  # adopted replicas
+        for t in tables:
+            t.free()
+    else:
+        for t in tables:
+            t.free()
+    return res
 
 
 def yak_bench(ctx, np2, torch, peak):
@@ -354,21 +685,26 @@ def yak_bench(ctx, np2, torch, peak):
     return res
 
 
-def cpu_sample(args, steps=1, warmup=0):
-    """The reference's CPU algorithm (oracle port, in-memory tables) on a bounded sample of the same workload:
-    `cores` contigs of 1 Mbp each, one worker thread per contig (the reference's unit of parallelism)."""
+def cpu_sample(args, steps=1, warmup=0, faithful=False):
+    """The reference's CPU algorithm (oracle port) on a bounded sample of configs[1]: `cores` contigs of 1 Mbp each, one
+    worker thread per contig (the reference's unit of parallelism, main.rs:1698-1853).  faithful: every k-mer retrieval
+    pass scans ALL keys of the table against the query set (kmer.rs:132-170: the reference streams the whole .yak file
+    per pass, per contig, per thread) instead of probing an in-memory hash table."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     from nextpolish2_b200 import synth
+    cfg = CONFIGS[1]
     cores = min(os.cpu_count() or 1, 32)
     clen = args.cpu_contig
-    G = synth.genome(20260002, clen * cores)
+    G = synth.genome(SEED0 + 2, clen * cores)
     data = []
     for i in range(cores):
         A = G[i * clen:(i + 1) * clen].copy()
-        data.append((A, synth.make_contig(20260100 + i, A, depth=30.0, asm_err=2e-5, het=args.het, read_err=0.002, threads=4)))
-    haps = [d[1]["hap1"] for d in data] + ([d[1]["hap2"] for d in data] if args.het > 0 else [])
-    tabs = [O.Table.from_arrays(k, *synth.make_table(20260003, k, haps)) for k in KS]
+        data.append((A, synth.make_contig(SEED0 + 100 + i, A, depth=cfg["depth"], asm_err=2e-5, het=0.0, read_err=0.002, threads=4)))
+    haps = [d[1]["hap1"] for d in data]
+    tabs = [O.Table.from_arrays(k, *synth.make_table_mt(SEED0 + 3, k, haps, threads=min(cores, 16))) for k in cfg["ks"]]
+    for t in tabs:
+        t.set_stream_scan(faithful)
     opts = O.Opts(min_ctg_len=0)
     vals = []
     for it in range(warmup + steps):
@@ -381,13 +717,15 @@ def cpu_sample(args, steps=1, warmup=0):
         [t.start() for t in th]
         [t.join() for t in th]
         dt = time.perf_counter() - t0
-        assert args.het > 0 or all(bytes(res[i].consensus()[1]) == bytes(haps[i]) for i in range(cores))
+        assert all(bytes(res[i].consensus()[1]) == bytes(haps[i]) for i in range(cores))
         if it >= warmup:
             vals.append(cores * clen / 1e6 / dt)
+    how = ("every retrieval pass scans all table keys against the query set, as the reference streams the whole .yak file "
+           "per pass (kmer.rs:132-170); keys held in memory, so still kinder than the reference's file reads"
+           if faithful else "tables probed in memory (kinder to the CPU than the reference's per-pass .yak file streaming)")
     return {"value": round(float(np.mean(vals)), 4), "unit": "Mbp/s", "cores": cores, "kind": "port",
-            "sample": "%d contigs x %d bp of the same synthetic workload (30x), one oracle thread per contig, "
-                      "tables in memory (kinder to the CPU than the reference's per-pass .yak file streaming); "
-                      "restatement of the reference algorithm, not the Rust binary (no cargo in this image)" % (cores, clen),
+            "sample": "%d contigs x %d bp of configs[1]'s synthetic workload (30x), one oracle thread per contig, %s; "
+                      "restatement of the reference algorithm, not the Rust binary (no cargo in this image)" % (cores, clen, how),
             "seconds": round(len(vals) * cores * clen / 1e6 / float(np.mean(vals)), 2)}
 
 
@@ -400,24 +738,36 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(b["seconds"] * 1e3 / max(1, args.steps), 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": b["sample"]},
+            "config": {"workload": CONFIGS[1]["text"], "baseline_config": "configs[1]", "sample": b["sample"]},
             "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": b["value"], "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_ref_faithful:
+        f = cpu_sample(args, steps=max(1, min(args.steps, 3)), warmup=0, faithful=True)
+        line["ref_faithful"] = {k: f[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--length", type=int, default=10_000_000, help="contig length per GPU (configs[1] = 10 Mbp)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3], help="BASELINE.json configs[N] as the headline workload")
+    ap.add_argument("--full", action="store_true", help="configs 2/3 at their stated size (10 x 10 Mbp; 250 Mbp)")
+    ap.add_argument("--length", type=int, default=0, help="override the contig length")
+    ap.add_argument("--contigs", type=int, default=0, help="override the number of contigs per GPU")
+    ap.add_argument("--het", type=float, default=None, help="override the heterozygosity")
     ap.add_argument("--cpu-contig", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=10, help="passes over the CPU sample for cpu_baseline (~1 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--het", type=float, default=0.0, help="heterozygosity of the synthetic contig (configs[2]: 0.01)")
     ap.add_argument("--no-yak-bench", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle FASTA comparison")
+    ap.add_argument("--no-extras", action="store_true", help="skip the bounded configs[2] / configs[3] arms")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling arm (configs[4] scaled)")
+    ap.add_argument("--no-ref-faithful", action="store_true")
+    ap.add_argument("--strong-mbp", type=float, default=36.0, help="total size of the 24 contigs of the strong-scaling arm")
+    ap.add_argument("--strong-passes", type=int, default=2)
     ap.add_argument("--pageable", action="store_true", help="record buffer in pageable memory (host compaction path)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per library call (0 = cores / ranks / ~in flight)")
     ap.add_argument("--e2e-inflight", type=int, default=3, help="contigs in flight per GPU in the end-to-end arm")

@@ -92,6 +92,16 @@ void np2_yak_free(np2_table *t);
 uint32_t np2_yak_k(const np2_table *t);
 uint64_t np2_yak_size(const np2_table *t);
 uint64_t np2_yak_device_bytes(const np2_table *t);
+/* Replicating a staged table to the other GPUs of the box over NVLink instead of staging it N times over PCIe
+ * (SURVEY.md 8e).  Every GPU holds a full replica (the reference clones its KmerInfo per worker thread, main.rs:1724).
+ *  - np2_yak_clone: same process, another GPU: one peer copy of the device image (cudaMemcpyPeerAsync).
+ *  - np2_yak_image + np2_yak_adopt: one process per GPU: the owner exposes the device image (a flat byte array), the
+ *    caller moves it with its own collective (ncclBroadcast / torch.distributed.broadcast into a device buffer) and
+ *    every other rank adopts the received bytes (copied; the buffer may be freed afterwards). */
+int np2_yak_clone(np2_ctx *dst_ctx, const np2_table *src, np2_table **out);
+int np2_yak_image(const np2_table *t, const void **d_image, uint64_t *bytes, uint32_t *buckets_per_subtable);
+int np2_yak_adopt(np2_ctx *ctx, uint32_t k, uint64_t n_keys, uint32_t buckets_per_subtable, const void *d_image,
+                  uint64_t bytes, np2_table **out);
 /* counts[i] = stored count of hashes[i] if present and >= min_count, else 0.  Host buffers. */
 int np2_yak_lookup(np2_ctx *ctx, const np2_table *t, const uint64_t *hashes, uint64_t n, uint32_t min_count,
                    uint16_t *counts);
@@ -189,6 +199,12 @@ uint64_t np2_job_get_dropped(np2_job *job, const uint32_t **ids);
 uint32_t np2_job_get_timings(np2_job *job, const char **names, const float **ms, const uint32_t **launches);
 void np2_job_get_traffic(np2_job *job, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *n_kernel_launches,
                          uint64_t *n_alignment_columns, uint64_t *n_probes);
+
+/* sizes of the last np2_job_run (last iteration that was built): out[0] non-reference 3-mer records, out[1] distinct
+ * non-reference 3-mers (Msa entries besides the reference's), out[2] runs of multi-entry positions, out[3] DP consensus
+ * bases, out[4] LQ regions, out[5] (read, region) pairs, out[6] read pairs with a non-zero agreement weight,
+ * out[7] iterations built from scratch. */
+void np2_job_get_stats(np2_job *job, uint64_t out[8]);
 
 /* Test seam (host only, no device needed): parses + filters a record buffer (main.rs:1758-1771, 386-440) split into
  * `threads` speculative byte ranges (0 = automatic) and returns a digest of everything the parse produces:

@@ -41,10 +41,10 @@ class Opts(C.Structure):
 
 EXPORTS = [
     "np2_last_error", "np2_opts_default", "np2_ctx_create", "np2_ctx_destroy", "np2_yak_load", "np2_yak_from_arrays",
-    "np2_yak_free", "np2_yak_k", "np2_yak_size", "np2_yak_device_bytes", "np2_yak_lookup", "np2_yak_lookup_device",
+    "np2_yak_free", "np2_yak_clone", "np2_yak_image", "np2_yak_adopt", "np2_yak_k", "np2_yak_size", "np2_yak_device_bytes", "np2_yak_lookup", "np2_yak_lookup_device",
     "np2_seq_kscore", "np2_bench_gather32", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
     "np2_job_get_consensus", "np2_job_get_span", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
-    "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_format_fasta",
+    "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_job_get_stats", "np2_format_fasta",
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
     "np2_debug_phase", "np2_set_host_threads",
@@ -70,6 +70,9 @@ def load_library():
     L.np2_yak_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.np2_yak_from_arrays.argtypes = [vp, u32, vp, vp, u64, C.POINTER(vp)]
     L.np2_yak_free.argtypes = [vp]
+    L.np2_yak_clone.argtypes = [vp, vp, C.POINTER(vp)]
+    L.np2_yak_image.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
+    L.np2_yak_adopt.argtypes = [vp, u32, u64, u32, vp, u64, C.POINTER(vp)]
     L.np2_yak_k.restype = u32
     L.np2_yak_k.argtypes = [vp]
     L.np2_yak_size.restype = u64
@@ -100,6 +103,8 @@ def load_library():
     L.np2_job_get_timings.restype = u32
     L.np2_job_get_timings.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.np2_job_get_traffic.argtypes = [vp] + [C.POINTER(u64)] * 5
+    L.np2_job_get_stats.argtypes = [vp, vp]
+    L.np2_job_get_stats.restype = None
     L.np2_format_fasta.restype = u64
     L.np2_format_fasta.argtypes = [C.c_char_p, vp, vp, u64, C.c_int, C.c_int, vp, u64]
     L.np2_device_count.restype = C.c_int
@@ -226,6 +231,25 @@ class Table:
         counts = np.ascontiguousarray(counts, np.uint16)
         h = C.c_void_p()
         _check(load_library().np2_yak_from_arrays(ctx.h, k, hashes.ctypes.data, counts.ctypes.data, len(hashes), C.byref(h)))
+        return cls(ctx, h)
+
+    def clone(self, ctx):
+        """A replica on another GPU of this process: one peer copy of the device image (np2_yak_clone)."""
+        h = C.c_void_p()
+        _check(load_library().np2_yak_clone(ctx.h, self.h, C.byref(h)))
+        return Table(ctx, h)
+
+    def image(self):
+        """(device pointer, bytes, buckets per sub-table) of the staged table: what a broadcast moves."""
+        p, n, nb = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        _check(load_library().np2_yak_image(self.h, C.byref(p), C.byref(n), C.byref(nb)))
+        return p.value, n.value, nb.value
+
+    @classmethod
+    def adopt(cls, ctx, k, n_keys, buckets_per_subtable, d_image_ptr, nbytes):
+        """A table from a received device image (np2_yak_adopt copies it)."""
+        h = C.c_void_p()
+        _check(load_library().np2_yak_adopt(ctx.h, k, n_keys, buckets_per_subtable, d_image_ptr, nbytes, C.byref(h)))
         return cls(ctx, h)
 
     @property
@@ -372,6 +396,12 @@ class Job:
         v = [C.c_uint64() for _ in range(5)]
         load_library().np2_job_get_traffic(self.h, *[C.byref(x) for x in v])
         return dict(zip(["h2d_bytes", "d2h_bytes", "kernel_launches", "alignment_columns", "probes"], [x.value for x in v]))
+
+    def stats(self):
+        v = (C.c_uint64 * 8)()
+        load_library().np2_job_get_stats(self.h, v)
+        return dict(zip(["records", "groups", "runs", "dp_bases", "regions", "read_region_pairs", "pair_edges",
+                         "iterations_built"], [int(x) for x in v]))
 
     def destroy(self):
         if self.h:

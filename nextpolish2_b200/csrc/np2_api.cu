@@ -404,6 +404,7 @@ struct np2_job {
     uint32_t max_span = 0;
     StageTimer &timer;
     uint64_t h2d = 0, d2h = 0, n_launch = 0, n_probes = 0;
+    uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // np2_job_get_stats
     std::string timing_names;
 
     // dumps
@@ -773,6 +774,8 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         cap = n_rec;
     }
     rec_cap_hint = n_rec;
+    stats[0] = n_rec;
+    stats[7]++;
     timer.hbegin();
     d_key2.alloc(n_rec, s);
     d_rd2.alloc(n_rec, s);
@@ -803,6 +806,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     NP2_CUDA(cudaMemcpyAsync(&G, d_gidx.p + n_rec, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
 
+    stats[1] = G;
     MsaDev m;
     m.L = L;
     m.G = G;
@@ -872,6 +876,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     uint32_t n_runs = 0;
     NP2_CUDA(cudaMemcpyAsync(&n_runs, d_nruns.p, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
+    stats[2] = n_runs;
     DpOut dpo;
     dpo.best_last = d_best_last.p;
     dpo.score_total = d_total.p;
@@ -899,6 +904,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     d_events.alloc(std::max(N, 1u), s);
     d_nev.alloc(1, s);
     res_N = N;
+    stats[3] = N;
     h = timer.begin("consensus_emit", 0);
     emit_write(m, d_run_start.p, n_runs, dpo, d_n_emit.p, d_emit_off.p, d_cpos.p, d_cbase.p, d_cflags.p, s);
     {
@@ -1053,6 +1059,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         NP2_CUDA(cudaMemcpyAsync(&edge_pos[1], d_cpos.p + (N - 1), 4, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaStreamSynchronize(s));
     };
+    stats[4] = nreg;
     uint32_t iter = iter0;
     if (nreg == 0) {  // main.rs:1638-1640: no LQ region; nothing can be dropped, the DP consensus is the answer
         for (;; iter++) {
@@ -1111,6 +1118,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     NP2_CUDA(cudaMemcpyAsync(&n_pairs, d_rd_poff.p + n_reads, 4, cudaMemcpyDeviceToHost, s));
     NP2_CUDA(cudaStreamSynchronize(s));
     g.n_pairs = n_pairs;
+    stats[5] = n_pairs;
 
     const uint64_t nslot = (uint64_t)nreg * kMaxCand;
     DBuf<uint32_t> d_p_len, d_c_src, d_c_len, d_c_order, d_r_ncand, d_r_bytes, d_r_nedge, d_r_seed_len, d_r_nsurv;
@@ -1283,6 +1291,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             d_perr.download(&perr, 1);
             NP2_CUDA(cudaStreamSynchronize(s));
             if (perr) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
+            stats[6] = nu;
             d_uk.alloc(std::max(nu, 1u), s);
             d_uv.alloc(std::max(nu, 1u), s);
             h = timer.begin("pair_edges", 1);
@@ -1884,6 +1893,7 @@ void np2_job::run(int32_t dump_it) {
     const unsigned long long launches0 = launch_counter();
     n_launch = 0;
     n_probes = 0;
+    memset(stats, 0, sizeof stats);
     dm_dropped.clear();
     dm_msa_off.clear();
     dm_msa_bases.clear();
@@ -2160,6 +2170,64 @@ int np2_yak_from_arrays(np2_ctx *ctx, uint32_t k, const uint64_t *hashes, const 
         NP2_CUDA(cudaStreamSynchronize(ctx->stream));
         if (err) throw np2::Error(NP2_ERR_INTERNAL, "table insertion overflow");
         *out = t.release();
+    });
+}
+
+/* ---- table replicas for the other GPUs of the box */
+static np2_table *table_shell(np2_ctx *ctx, uint32_t k, uint64_t n, uint32_t nb) {
+    std::unique_ptr<np2_table> t(new np2_table());
+    t->ctx = ctx;
+    t->dev.k = k;
+    t->dev.n = n;
+    t->dev.nb = nb;
+    t->bytes = 1024ull * nb * kBucketSlots * 8;
+    NP2_CUDA(cudaMalloc((void **)&t->dev.slots, t->bytes));
+    ctx->refs++;
+    return t.release();
+}
+int np2_yak_clone(np2_ctx *dst_ctx, const np2_table *src, np2_table **out) {
+    return guard([&] {
+        if (!dst_ctx || !src || !out) throw np2::Error(NP2_ERR_ARG, "null argument");
+        NP2_CUDA(cudaSetDevice(src->ctx->device));
+        NP2_CUDA(cudaStreamSynchronize(src->ctx->stream));  // the source image is complete
+        NP2_CUDA(cudaSetDevice(dst_ctx->device));
+        np2_table *t = table_shell(dst_ctx, src->dev.k, src->dev.n, src->dev.nb);
+        cudaError_t e = cudaMemcpyPeerAsync(t->dev.slots, dst_ctx->device, src->dev.slots, src->ctx->device, t->bytes,
+                                            dst_ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(dst_ctx->stream);
+        if (e != cudaSuccess) {
+            np2_yak_free(t);
+            throw np2::Error(NP2_ERR_CUDA, std::string("peer copy of the table image: ") + cudaGetErrorString(e));
+        }
+        *out = t;
+    });
+}
+int np2_yak_image(const np2_table *t, const void **d_image, uint64_t *bytes, uint32_t *buckets_per_subtable) {
+    return guard([&] {
+        if (!t || !d_image || !bytes || !buckets_per_subtable) throw np2::Error(NP2_ERR_ARG, "null argument");
+        NP2_CUDA(cudaSetDevice(t->ctx->device));
+        NP2_CUDA(cudaStreamSynchronize(t->ctx->stream));
+        *d_image = t->dev.slots;
+        *bytes = t->bytes;
+        *buckets_per_subtable = t->dev.nb;
+    });
+}
+int np2_yak_adopt(np2_ctx *ctx, uint32_t k, uint64_t n_keys, uint32_t buckets_per_subtable, const void *d_image,
+                  uint64_t bytes, np2_table **out) {
+    return guard([&] {
+        if (!ctx || !d_image || !out) throw np2::Error(NP2_ERR_ARG, "null argument");
+        if (k == 0 || k > 63 || buckets_per_subtable == 0) throw np2::Error(NP2_ERR_ARG, "bad table geometry");
+        if (bytes != 1024ull * buckets_per_subtable * kBucketSlots * 8)
+            throw np2::Error(NP2_ERR_ARG, "image size does not match buckets_per_subtable");
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        np2_table *t = table_shell(ctx, k, n_keys, buckets_per_subtable);
+        cudaError_t e = cudaMemcpyAsync(t->dev.slots, d_image, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            np2_yak_free(t);
+            throw np2::Error(NP2_ERR_CUDA, std::string("copy of the table image: ") + cudaGetErrorString(e));
+        }
+        *out = t;
     });
 }
 
@@ -2614,6 +2682,8 @@ void np2_job_get_traffic(np2_job *j, uint64_t *h2d_bytes, uint64_t *d2h_bytes, u
     if (n_alignment_columns) *n_alignment_columns = j->ing.total_cols;
     if (n_probes) *n_probes = j->n_probes;
 }
+
+void np2_job_get_stats(np2_job *j, uint64_t out[8]) { memcpy(out, j->stats, sizeof j->stats); }
 
 int np2_debug_phase(const uint64_t *keys, const int64_t *vals, uint64_t n_edges, uint32_t model, uint32_t use_all_reads,
                     uint32_t *dropped, uint64_t cap, uint64_t *n_dropped, uint32_t *path) {

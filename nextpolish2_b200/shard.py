@@ -37,3 +37,44 @@ def polish_sharded(n_items, weights, polish_fn, rank=0, world=1, group=None):
     for d in gathered:
         merged.update(d)
     return [merged[i] for i in range(n_items)]
+
+
+class _DeviceBytes:
+    """A device pointer as a __cuda_array_interface__ object, so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def table_meta(table):
+    """What the receiving ranks need besides the image bytes."""
+    ptr, nbytes, nb = table.image()
+    return {"k": table.k, "n_keys": len(table), "buckets_per_subtable": nb, "bytes": nbytes}
+
+
+def broadcast_tables(ctx, tables, rank=0, world=1, src=0, group=None):
+    """One rank stages the yak tables (from .yak files or arrays); every other rank of the box receives the device
+    images over NVLink (ncclBroadcast through torch.distributed) and adopts them, instead of each rank reading and
+    staging its own copy over PCIe.  `tables` is the list of staged Tables on `src` and ignored elsewhere.
+    Returns this rank's tables (the originals on `src`)."""
+    if world == 1:
+        return list(tables)
+    import torch
+    import torch.distributed as dist
+    from .api import Table
+    metas = [[table_meta(t) for t in tables] if rank == src else None]
+    dist.broadcast_object_list(metas, src=src, group=group)
+    out = []
+    for i, m in enumerate(metas[0]):
+        if rank == src:
+            ptr, nbytes, _ = tables[i].image()
+            buf = torch.as_tensor(_DeviceBytes(ptr, nbytes), device="cuda")  # the staged image itself, no copy
+            dist.broadcast(buf, src=src, group=group)
+            out.append(tables[i])
+        else:
+            buf = torch.empty(m["bytes"], dtype=torch.uint8, device="cuda")
+            dist.broadcast(buf, src=src, group=group)
+            torch.cuda.synchronize()
+            out.append(Table.adopt(ctx, m["k"], m["n_keys"], m["buckets_per_subtable"], buf.data_ptr(), m["bytes"]))
+            del buf
+    return out

@@ -36,6 +36,9 @@ def lib():
         L.np2s_table.restype = C.c_uint64
         L.np2s_table.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_uint32,
                                  C.c_void_p, C.c_void_p, C.c_uint64]
+        L.np2s_table_mt.restype = C.c_uint64
+        L.np2s_table_mt.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_uint32,
+                                    C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
         L.np2s_write_yak.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
         L.np2s_write_short_reads.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
                                              C.c_uint32, C.c_double]
@@ -127,6 +130,18 @@ def make_table(seed, k, seqs, mean_count=40.0, keep_min=2):
     n2 = lib().np2s_table(seed, k, ptrs, lens, len(seqs), mean_count, keep_min, h.ctypes.data, c.ctypes.data, n)
     assert n2 == n
     return h, c
+
+
+def make_table_mt(seed, k, seqs, mean_count=40.0, keep_min=2, threads=8):
+    """make_table built by `threads` workers in one call; counts are a function of (seed, k, hash, multiplicity), so the
+    table is independent of the thread count (but not identical to make_table's sequential draw)."""
+    seqs, ptrs, lens = _seq_ptrs(seqs)
+    cap = int(sum(len(x) for x in seqs))
+    h = np.empty(cap, np.uint64)
+    c = np.empty(cap, np.uint16)
+    n = lib().np2s_table_mt(seed, k, ptrs, lens, len(seqs), mean_count, keep_min, h.ctypes.data, c.ctypes.data, cap, threads)
+    assert n <= cap
+    return h[:n].copy(), c[:n].copy()
 
 
 def write_yak(path, k, hashes, counts):

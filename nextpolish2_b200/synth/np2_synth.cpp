@@ -11,6 +11,7 @@
  * produce table keys and is restated from yak/yak-priv.h:10-38).
  */
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -571,6 +572,88 @@ uint64_t np2s_table(uint64_t seed, uint32_t k, const uint8_t *const *seqs, const
             n++;
         }
         i = j;
+    }
+    return n;
+}
+
+/* The same table, built by `threads` workers: sequences are hashed in slices, hashes are partitioned by their top
+ * bits, every partition is sorted and reduced on its own.  Counts are a pure function of (seed, k, hash, multiplicity),
+ * so the result does not depend on the thread count (it differs from np2s_table's sequential draw).  Output is in
+ * ascending hash order.  Returns the number of k-mers kept (call with out == NULL first). */
+uint64_t np2s_table_mt(uint64_t seed, uint32_t k, const uint8_t *const *seqs, const uint64_t *lens, uint32_t n_seqs,
+                       double mean_count, uint32_t keep_min, uint64_t *out_hash, uint16_t *out_count, uint64_t cap,
+                       uint32_t threads) {
+    const uint32_t T = std::max(1u, threads), P = 256;  // P partitions on the top 8 bits of the 2k-bit (or 64-bit) hash
+    const int top_shift = (k < 32 ? 2 * (int)k : 64) - 8;
+    struct Slice {
+        uint32_t s;
+        uint64_t b, e;
+    };
+    std::vector<Slice> slices;
+    const uint64_t kSlice = 1u << 20;
+    for (uint32_t i = 0; i < n_seqs; i++)
+        for (uint64_t b = 0; b < lens[i]; b += kSlice) {
+            const uint64_t e = std::min<uint64_t>(lens[i], b + kSlice + k - 1);  // k-mers starting inside [b, b + kSlice)
+            slices.push_back({i, b, e});
+        }
+    std::vector<std::vector<std::vector<uint64_t>>> part(T, std::vector<std::vector<uint64_t>>(P));
+    std::atomic<size_t> next(0);
+    {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < T; t++)
+            th.emplace_back([&, t] {
+                std::vector<uint64_t> h;
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= slices.size()) break;
+                    h.clear();
+                    seq_hashes(seqs[slices[i].s] + slices[i].b, slices[i].e - slices[i].b, (int)k, h);
+                    for (uint64_t v : h) part[t][(v >> top_shift) & (P - 1)].push_back(v);
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    std::vector<std::vector<uint64_t>> keep_h(P);
+    std::vector<std::vector<uint16_t>> keep_c(P);
+    next = 0;
+    {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < T; t++)
+            th.emplace_back([&] {
+                std::vector<uint64_t> h;
+                for (;;) {
+                    const size_t p = next.fetch_add(1);
+                    if (p >= P) break;
+                    h.clear();
+                    for (uint32_t u = 0; u < T; u++) {
+                        h.insert(h.end(), part[u][p].begin(), part[u][p].end());
+                        std::vector<uint64_t>().swap(part[u][p]);
+                    }
+                    std::sort(h.begin(), h.end());
+                    for (size_t i = 0; i < h.size();) {
+                        size_t j = i;
+                        while (j < h.size() && h[j] == h[i]) j++;
+                        Rng rng(seed ^ (0xABCDEFULL * k) ^ (h[i] * 0x9E3779B97F4A7C15ULL));
+                        uint32_t c = rng.poisson(mean_count * (double)(j - i));
+                        if (c > 1023) c = 1023;
+                        if (c >= keep_min && c >= 1) {
+                            keep_h[p].push_back(h[i]);
+                            keep_c[p].push_back((uint16_t)c);
+                        }
+                        i = j;
+                    }
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    uint64_t n = 0;
+    for (uint32_t p = 0; p < P; p++) {
+        if (out_hash)
+            for (size_t i = 0; i < keep_h[p].size() && n + i < cap; i++) {
+                out_hash[n + i] = keep_h[p][i];
+                out_count[n + i] = keep_c[p][i];
+            }
+        n += keep_h[p].size();
     }
     return n;
 }

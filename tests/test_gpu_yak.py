@@ -95,3 +95,31 @@ def test_large_table_roundtrip(ctx):
     assert int(gt.lookup(other, 0).sum()) == 0
     flt = gt.lookup(h, 512)
     assert np.array_equal(flt, np.where(c >= 512, c, 0))
+
+
+def test_table_image_adopt_clone(ctx):
+    """Replication seam: a table adopted from the device image of another one, and a peer clone, answer
+    exactly like the original (what bench.py's NVLink broadcast and the CLI's -g N rely on)."""
+    import torch
+    import nextpolish2_b200 as np2
+    from nextpolish2_b200.shard import table_meta, _DeviceBytes
+    ds = common.dataset("hap300k")
+    h, c = ds["tables"][31]
+    src = np2.Table.from_arrays(ctx, 31, h, c)
+    meta = table_meta(src)
+    ptr, nbytes, nb = src.image()
+    assert meta == {"k": 31, "n_keys": len(h), "buckets_per_subtable": nb, "bytes": nbytes} and nbytes == src.device_bytes
+    view = torch.as_tensor(_DeviceBytes(ptr, nbytes), device="cuda")  # zero-copy view, as the broadcast uses it
+    buf = view.clone()                                                  # stands in for the received buffer
+    torch.cuda.synchronize()
+    rep = np2.Table.adopt(ctx, 31, len(h), nb, buf.data_ptr(), nbytes)
+    del buf
+    cl = src.clone(ctx)
+    rng = np.random.default_rng(3)
+    q = np.concatenate([h[::7], rng.integers(0, 2**63, 100_000, dtype=np.uint64)])
+    want = src.lookup(q, 5)
+    common.assert_same("adopted image", want, rep.lookup(q, 5))
+    common.assert_same("peer clone", want, cl.lookup(q, 5))
+    assert len(rep) == len(h) and rep.k == 31 and cl.device_bytes == nbytes
+    with pytest.raises(np2.api.Np2Error):
+        np2.Table.adopt(ctx, 31, len(h), nb + 1, ptr, nbytes)
