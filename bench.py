@@ -38,7 +38,7 @@ CONFIGS = {
         "text": "synthetic 10 Mbp haploid contig, 30x HiFi (N(15k,2k), 0.2% err), asm err 2e-5/bp, k21+k31"},
     2: {"label": "configs[2]", "contigs": 10, "length": 10_000_000, "het": 0.01, "tandem": 0.0, "depth": 30.0, "ks": (21, 31),
         "bounded": {"contigs": 2},
-        "text": "synthetic diploid (1% het: 0.8% SNV + 0.2% indel), %d x %.0f Mbp contigs, 30x HiFi from both haplotypes, "
+        "text": "synthetic diploid (1%% het: 0.8%% SNV + 0.2%% indel), %d x %.0f Mbp contigs, 30x HiFi from both haplotypes, "
                 "asm err 2e-5/bp, k21+k31 (exercises phasing)"},
     3: {"label": "configs[3]", "contigs": 1, "length": 250_000_000, "het": 0.0, "tandem": 0.05, "depth": 40.0, "ks": (21, 31, 51),
         "bounded": {"length": 20_000_000},
@@ -53,7 +53,7 @@ def log(*a):
 
 
 def config_text(cfg):
-    return cfg["text"] % (cfg["contigs"], cfg["length"] / 1e6) if "%" in cfg["text"] else cfg["text"]
+    return cfg["text"] % (cfg["contigs"], cfg["length"] / 1e6) if "%d x" in cfg["text"] else cfg["text"]
 
 
 def make_workload(cfg, seed, threads):
