@@ -200,11 +200,13 @@ uint32_t np2_job_get_timings(np2_job *job, const char **names, const float **ms,
 void np2_job_get_traffic(np2_job *job, uint64_t *h2d_bytes, uint64_t *d2h_bytes, uint64_t *n_kernel_launches,
                          uint64_t *n_alignment_columns, uint64_t *n_probes);
 
-/* sizes of the last np2_job_run (last iteration that was built): out[0] non-reference 3-mer records, out[1] distinct
+/* sizes of the last np2_job_run (last pass that was built): out[0] non-reference 3-mer records, out[1] distinct
  * non-reference 3-mers (Msa entries besides the reference's), out[2] runs of multi-entry positions, out[3] DP consensus
  * bases, out[4] LQ regions, out[5] (read, region) pairs, out[6] read pairs with a non-zero agreement weight,
- * out[7] iterations built from scratch. */
-void np2_job_get_stats(np2_job *job, uint64_t out[8]);
+ * out[7] passes built from scratch; since the job was created: out[8] passes that ran with speculative capacities
+ * (sizes kept on the device, no read-back until the host needs data), out[9] passes that had to be repeated with
+ * exact sizes; out[10] host synchronisations of the last run; out[11] reserved. */
+void np2_job_get_stats(np2_job *job, uint64_t out[12]);
 
 /* Test seam (host only, no device needed): parses + filters a record buffer (main.rs:1758-1771, 386-440) split into
  * `threads` speculative byte ranges (0 = automatic) and returns a digest of everything the parse produces:

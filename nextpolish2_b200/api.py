@@ -398,10 +398,10 @@ class Job:
         return dict(zip(["h2d_bytes", "d2h_bytes", "kernel_launches", "alignment_columns", "probes"], [x.value for x in v]))
 
     def stats(self):
-        v = (C.c_uint64 * 8)()
+        v = (C.c_uint64 * 12)()
         load_library().np2_job_get_stats(self.h, v)
         return dict(zip(["records", "groups", "runs", "dp_bases", "regions", "read_region_pairs", "pair_edges",
-                         "iterations_built"], [int(x) for x in v]))
+                         "iterations_built", "speculative_passes", "repeated_passes", "host_syncs"], [int(x) for x in v]))
 
     def destroy(self):
         if self.h:

@@ -253,8 +253,21 @@ struct StageTimer {
 
 // Host-side buffers a job needs, pooled per context: pinned allocations (cudaMallocHost) and first-touch page
 // faults of fresh vectors cost milliseconds each, far more than the kernels they feed.
+constexpr int kHintSlots = 4;
+// sizes of the last pass of one kind (slot = iteration the pass started at): the capacities of the next one
+struct Hints {
+    bool valid = false;
+    uint32_t L = 0;
+    uint64_t cols = 0;
+    CountsHost h = CountsHost();
+};
+struct Respeculate {};  // a speculative pass met a count above its capacity: repeat it in exact mode
 struct JobScratch {
     Ingest ing;
+    Hints hints[kHintSlots];
+    ScanPool scan_pool;
+    uint32_t *d_counts = nullptr;  // CountsDev block (256 bytes)
+    PBuf<uint8_t> p_counts;        // its pinned mirror (+ two words for the FASTA header positions)
     std::vector<uint8_t> tseq, h_seeds, h_rech_pool, h_win;
     Patched patch;
     PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage, p_stage2, p_seq_stage;
@@ -313,6 +326,8 @@ static void ctx_release(np2_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (JobScratch *sc : ctx->scratch_pool) {
         sc->arena.destroy(ctx->stream);
+        sc->scan_pool.destroy(ctx->stream);
+        if (sc->d_counts) cudaFree(sc->d_counts);
         delete sc;
     }
     cudaStreamSynchronize(ctx->stream);
@@ -405,6 +420,12 @@ struct np2_job {
     StageTimer &timer;
     uint64_t h2d = 0, d2h = 0, n_launch = 0, n_probes = 0;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // np2_job_get_stats
+    uint64_t n_spec_ok = 0, n_respec = 0, n_sync = 0;  // speculative passes, passes repeated in exact mode, host syncs of the run
+    bool spec = false;        // the pass under way sizes everything from capacities and does not read counts back
+    CountsHost caps = CountsHost();
+    CountsHost *hc = nullptr;  // pinned mirror of the device counts
+    CountsDev cd;
+    uint64_t pair_slots = 0;  // slots of the dense pair accumulator (depends on the reads only)
     std::string timing_names;
 
     // dumps
@@ -433,6 +454,10 @@ struct np2_job {
     void run(int32_t dump_iter);
     void ingest_finish();
     uint32_t iteration(uint32_t iter0);
+    uint32_t iteration_pass(uint32_t iter0, Hints &hint);
+    void fetch_counts();
+    uint32_t cnt_get(int idx);
+    void segment_end();
 };
 
 /* ================================================================= pipeline */
@@ -722,113 +747,148 @@ void np2_job::ingest_finish() {
     }
 }
 
-// Runs iteration iter0 of the reference's loop (main.rs:1819-1836).  When a non-final iteration blanks no read, the
-// next iteration would rebuild exactly the same Msa, consensus, regions and candidates, so it is served from the
-// state already on the device instead of being recomputed.  Returns the next iteration that needs a fresh build.
+// One pass = the device work of iteration iter0 of the reference's loop (main.rs:1819-1836) plus the host phase that
+// follows it.  When a non-final iteration blanks no read, the next iteration would rebuild exactly the same Msa,
+// consensus, regions and candidates, so it is served from the state already on the device instead of being
+// recomputed.  Returns the next iteration that needs a fresh build.
+//
+// Sizes live on the device (CountsDev).  In SPECULATIVE mode the capacities of every buffer and grid come from the last
+// pass of the same kind (scaled to this contig), nothing is read back until the host needs data, and a count that
+// exceeds its capacity aborts the rest of the pass on the device: the pass is then repeated in EXACT mode, where every
+// count is read back before the buffers that depend on it are sized (one synchronisation per count, as a first run
+// has to do anyway).
 uint32_t np2_job::iteration(uint32_t iter0) {
+    const uint64_t probes0 = n_probes, built0 = stats[7];
+    const size_t dropped0 = dm_dropped.size();
+    Hints &hint = sc->hints[std::min<uint32_t>(iter0, kHintSlots - 1)];
+    static const bool enabled = [] {
+        const char *e = getenv("NP2_SPECULATE");
+        return !e || atoi(e) != 0;
+    }();
+    if (enabled && dump_iter < 0 && hint.valid) {
+        // scale the remembered counts to this contig; 25 % + 1024 of slack
+        const double sc_l = hint.L ? (double)L / hint.L : 1.0, sc_c = hint.cols ? (double)ing.total_cols / hint.cols : 1.0;
+        const double scale = std::max(sc_l, sc_c) * 1.25;
+        for (int i = 0; i < C_COUNT; i++) caps.c[i] = (uint32_t)std::min<double>(hint.h.c[i] * scale + 1024.0, 4.0e9);
+        for (int i = 0; i < Q_COUNT; i++) caps.q[i] = (unsigned long long)(hint.h.q[i] * scale) + 65536;
+        try {
+            spec = true;
+            const uint32_t r = iteration_pass(iter0, hint);
+            n_spec_ok++;
+            return r;
+        } catch (const Respeculate &) {
+            n_probes = probes0;
+            stats[7] = built0;
+            dm_dropped.resize(dropped0);
+            n_respec++;
+        }
+    }
+    spec = false;
+    return iteration_pass(iter0, hint);
+}
+
+void np2_job::fetch_counts() {
+    cudaStream_t s = ctx->stream;
+    NP2_CUDA(cudaMemcpyAsync(hc, cd.c, sizeof(CountsHost), cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    n_sync++;
+}
+// capacity of a count in speculative mode, its exact value (one synchronisation) in exact mode
+uint32_t np2_job::cnt_get(int idx) {
+    if (spec) return caps.c[idx];
+    fetch_counts();
+    return hc->c[idx];
+}
+// end of the speculative stretch: everything enqueued so far has its counts in *hc; from here on the pass is exact
+void np2_job::segment_end() {
+    fetch_counts();
+    if (spec && hc->c[C_ABORT]) throw Respeculate();
+    spec = false;
+}
+
+uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     cudaStream_t s = ctx->stream;
     const uint32_t n_reads = R.n_reads;
     const uint32_t n_blocks = ing.ck_off.back();
+    ScanPool &sp = sc->scan_pool;
     int h;
+    sp.begin(s);
+    counts_init(cd, s);
 
     /* ---------------- K2: pileup */
     DBuf<int32_t> d_cover;
     d_cover.alloc(L + 1, s);
     DBuf<uint8_t> d_tmp;
 
-    h = timer.begin("pileup_scan", 2);
+    h = timer.begin("pileup_scan", 3);
     d_cover.zero();
-    {
-        int32_t one = 1;  // the ref read spans [0, L-1]
-        NP2_CUDA(cudaMemcpyAsync(d_cover.p, &one, 4, cudaMemcpyHostToDevice, s));
-    }
     cover_diff(R, d_blank.p, d_cover.p, s);
-    {
-        size_t tb = 0;
-        cub::DeviceScan::InclusiveSum(nullptr, tb, d_cover.p, d_cover.p, L + 1, s);
-        d_tmp.alloc(tb, s);
-        cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_cover.p, d_cover.p, L + 1, s);
-    }
+    cover_scan(d_cover.p, L + 1, sp, s);
     timer.end(h);
     // Non-reference 3-mer records (~3-5 % of the columns) are emitted in ONE pass into a buffer sized from the last
-    // count (first time: 1/8 of the columns); the kernel keeps counting when it overflows and is then re-run exactly.
+    // count (first time: 1/8 of the columns); the kernel keeps counting when it overflows (exact mode: re-run with the
+    // exact size; speculative mode: the pass is abandoned).
     DBuf<uint64_t> d_key, d_key2;
-    DBuf<uint32_t> d_rd, d_rd2, d_head, d_gidx;
-    DBuf<unsigned int> d_nrec;
-    d_nrec.alloc(1, s);
-    uint32_t n_rec = 0;
-    uint64_t cap = rec_cap_hint ? (uint64_t)rec_cap_hint + rec_cap_hint / 8 + 1024 : ing.total_cols / 8 + 4096;
+    DBuf<uint32_t> d_rd, d_rd2;
+    uint64_t cap_rec = spec ? caps.c[C_NREC]
+                            : (rec_cap_hint ? (uint64_t)rec_cap_hint + rec_cap_hint / 8 + 1024 : ing.total_cols / 8 + 4096);
     for (int attempt = 0;; attempt++) {
-        cap = std::min<uint64_t>(cap, 0xFFFFFFF0ull);
-        d_key.alloc(cap, s);
-        d_rd.alloc(cap, s);
-        const unsigned int two = 2;
-        NP2_CUDA(cudaMemcpyAsync(d_nrec.p, &two, 4, cudaMemcpyHostToDevice, s));
+        cap_rec = std::min<uint64_t>(cap_rec, 0xFFFFFFF0ull);
+        d_key.alloc(cap_rec, s);
+        d_rd.alloc(cap_rec, s);
         h = timer.begin("pileup_emit", 1);
-        pileup_emit(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, d_nrec.p, (uint32_t)cap, d_key.p, d_rd.p, s);
+        pileup_emit(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, cd, (uint32_t)cap_rec, d_key.p, d_rd.p, s);
         timer.end(h);
-        NP2_CUDA(cudaMemcpyAsync(&n_rec, d_nrec.p, 4, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaStreamSynchronize(s));
-        if (n_rec <= cap) break;
+        if (spec) break;
+        const uint32_t n_rec = cnt_get(C_NREC);
+        if (n_rec <= cap_rec) {
+            cap_rec = n_rec;
+            break;
+        }
         if (attempt) throw np2::Error(NP2_ERR_INTERNAL, "3-mer record count changed between two passes");
-        cap = n_rec;
+        cap_rec = n_rec;
+        counts_init(cd, s);
     }
-    rec_cap_hint = n_rec;
-    stats[0] = n_rec;
-    stats[7]++;
     timer.hbegin();
-    d_key2.alloc(n_rec, s);
-    d_rd2.alloc(n_rec, s);
-    d_head.alloc(n_rec + 1, s);
-    d_gidx.alloc(n_rec + 1, s);
+    d_key2.alloc(cap_rec, s);
+    d_rd2.alloc(cap_rec, s);
     timer.hend("host:alloc_records");
     int pbits = 1;
     while ((1ull << pbits) < (uint64_t)L) pbits++;
-    h = timer.begin("pileup_sort", 8);
+    h = timer.begin("pileup_sort", 9);
+    pileup_pad(d_key.p, (uint32_t)cap_rec, cd, s);  // the tail of a capacity-sized buffer sorts behind every record
     {
         size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)n_rec, 0, 32 + pbits, s);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)cap_rec, 0, 32 + pbits, s);
         if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)n_rec, 0, 32 + pbits, s);
+        cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)cap_rec, 0, 32 + pbits, s);
     }
     timer.end(h);
-    h = timer.begin("pileup_group", 3);
-    mark_heads(d_key2.p, n_rec, d_head.p, s);
-    NP2_CUDA(cudaMemsetAsync(d_head.p + n_rec, 0, 4, s));
-    {
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_head.p, d_gidx.p, n_rec + 1, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_head.p, d_gidx.p, n_rec + 1, s);
-    }
-    timer.end(h);
-    uint32_t G = 0;
-    NP2_CUDA(cudaMemcpyAsync(&G, d_gidx.p + n_rec, 4, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
 
-    stats[1] = G;
+    // groups: in exact mode their number is only known after the scan that also fills them, so the arrays are sized by
+    // the number of records there
+    const uint32_t cap_g_alloc = spec ? caps.c[C_G] : (uint32_t)cap_rec;
     MsaDev m;
     m.L = L;
-    m.G = G;
+    m.cnt = cd.c;
     DBuf<uint32_t> d_sp_off, d_gcount, d_gfirst, d_gbesti, d_gstart, d_gpos, d_dense_cnt, d_dense_besti, d_n_emit,
         d_emit_off;
     DBuf<uint16_t> d_gbases, d_gdelta;
     DBuf<int64_t> d_gscore, d_dense_score;
-    DBuf<uint8_t> d_multi, d_flag;
+    DBuf<uint8_t> d_multi;
     d_sp_off.alloc(L + 1, s);
-    d_gcount.alloc(G, s);
-    d_gfirst.alloc(G, s);
-    d_gbesti.alloc(G, s);
-    d_gstart.alloc(G, s);
-    d_gpos.alloc(G, s);
-    d_gbases.alloc(G, s);
-    d_gdelta.alloc(G, s);
-    d_gscore.alloc(G, s);
+    d_gcount.alloc(cap_g_alloc, s);
+    d_gfirst.alloc(cap_g_alloc, s);
+    d_gbesti.alloc(cap_g_alloc, s);
+    d_gstart.alloc(cap_g_alloc, s);
+    d_gpos.alloc(cap_g_alloc, s);
+    d_gbases.alloc(cap_g_alloc, s);
+    d_gdelta.alloc(cap_g_alloc, s);
+    d_gscore.alloc(cap_g_alloc, s);
     d_dense_cnt.alloc(L, s);
     d_dense_besti.alloc(L, s);
     d_dense_score.alloc(L, s);
     d_multi.alloc(L, s);
-    d_flag.alloc(L, s);
     d_n_emit.alloc(L + 1, s);
     d_emit_off.alloc(L + 1, s);
     m.sp_off = d_sp_off.p;
@@ -845,157 +905,103 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     m.multi = d_multi.p;
     m.code = d_code.p;
 
+    h = timer.begin("pileup_group", 1);
+    groups_build(d_key2.p, d_rd2.p, (uint32_t)cap_rec, cap_g_alloc, d_gstart.p, d_gpos.p, m, cd, sp, s);
+    timer.end(h);
+    const uint32_t G = cnt_get(C_G);
     h = timer.begin("pileup_finalize", 4);
     d_sp_off.zero();
     d_dense_besti.zero();
-    groups_fill(d_key2.p, d_rd2.p, d_head.p, d_gidx.p, n_rec, G, d_gstart.p, d_gpos.p, m, s);
-    groups_finish(d_gstart.p, d_gpos.p, n_rec, m, s);
-    NP2_CUDA(cudaMemsetAsync(d_n_emit.p + L, 0, 4, s));
+    groups_finish(d_gstart.p, d_gpos.p, G, m, s);
     pos_finalize(m, d_n_emit.p, s);
     timer.end(h);
 
     /* ---------------- K3: DP over runs, backtrack, consensus */
-    DBuf<uint32_t> d_run_start, d_nruns, d_best_last;
-    DBuf<unsigned long long> d_total;
-    d_run_start.alloc(L, s);
-    d_nruns.alloc(1, s);
-    d_best_last.alloc(1, s);
-    d_total.alloc(1, s);
-    d_best_last.zero();
-    d_total.zero();
-    h = timer.begin("dp_runs_select", 2);
-    run_flags(d_multi.p, L, d_flag.p, s);
-    {
-        size_t tb = 0;
-        cub::CountingInputIterator<uint32_t> it(0);
-        cub::DeviceSelect::Flagged(nullptr, tb, it, d_flag.p, d_run_start.p, d_nruns.p, (int)L, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_flag.p, d_run_start.p, d_nruns.p, (int)L, s);
-    }
+    DBuf<uint32_t> d_run_start;
+    const uint32_t cap_runs_alloc = spec ? caps.c[C_NRUNS] : L / 2 + 2;  // runs are separated by single-entry positions
+    d_run_start.alloc(cap_runs_alloc, s);
+    h = timer.begin("dp_runs_select", 1);
+    runs_select(d_multi.p, L, d_run_start.p, cap_runs_alloc, cd, sp, s);
     timer.end(h);
-    uint32_t n_runs = 0;
-    NP2_CUDA(cudaMemcpyAsync(&n_runs, d_nruns.p, 4, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
-    stats[2] = n_runs;
-    DpOut dpo;
-    dpo.best_last = d_best_last.p;
-    dpo.score_total = d_total.p;
+    const uint32_t n_runs = cnt_get(C_NRUNS);
     h = timer.begin("dp_runs", 1);
-    dp_runs(m, d_run_start.p, n_runs, dpo, s);
+    dp_runs(m, d_run_start.p, n_runs, cd, s);
     timer.end(h);
-    h = timer.begin("consensus_emit", 5);
-    emit_count_runs(m, d_run_start.p, n_runs, dpo, d_n_emit.p, s);
-    {
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_n_emit.p, d_emit_off.p, L + 1, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_n_emit.p, d_emit_off.p, L + 1, s);
-    }
+    h = timer.begin("consensus_emit", 2);
+    emit_count_runs(m, d_run_start.p, n_runs, cd, d_n_emit.p, s);
+    emit_offsets(d_n_emit.p, d_emit_off.p, L, spec ? caps.c[C_N] : 0xFFFFFFFFu, cd, sp, s);
     timer.end(h);
-    uint32_t N = 0;
-    NP2_CUDA(cudaMemcpyAsync(&N, d_emit_off.p + L, 4, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
+    const uint32_t N = cnt_get(C_N);
     DBuf<uint32_t> &d_cpos = jd_cpos;
     DBuf<uint8_t> &d_cbase = jd_cbase, &d_cflags = jd_cflags;
-    DBuf<uint32_t> d_events, d_nev;
+    DBuf<uint32_t> d_events;
     d_cpos.alloc(std::max(N, 1u), s);
     d_cbase.alloc(std::max(N, 1u), s);
     d_cflags.alloc(std::max(N, 1u), s);
     d_events.alloc(std::max(N, 1u), s);
-    d_nev.alloc(1, s);
-    res_N = N;
-    stats[3] = N;
-    h = timer.begin("consensus_emit", 0);
-    emit_write(m, d_run_start.p, n_runs, dpo, d_n_emit.p, d_emit_off.p, d_cpos.p, d_cbase.p, d_cflags.p, s);
-    {
-        size_t tb = 0;
-        cub::CountingInputIterator<uint32_t> it(0);
-        cub::DeviceSelect::Flagged(nullptr, tb, it, d_cflags.p, d_events.p, d_nev.p, (int)N, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_cflags.p, d_events.p, d_nev.p, (int)N, s);
-    }
+    h = timer.begin("consensus_emit", 3);
+    emit_write(m, d_run_start.p, n_runs, cd, d_n_emit.p, d_emit_off.p, d_cpos.p, d_cbase.p, d_cflags.p, s);
+    events_select(d_cflags.p, N, d_events.p, std::max(N, 1u), cd, sp, s);
     timer.end(h);
-    uint32_t n_ev = 0;
-    long long total = 0;
-    NP2_CUDA(cudaMemcpyAsync(&n_ev, d_nev.p, 4, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
-    if (total < 0)
-        throw np2::Error(NP2_ERR_UNSUPPORTED,
-                         "best path has a negative total score (main.rs:1680 picks the default 3-mer): not supported");
+    const uint32_t n_ev = cnt_get(C_NEV);
+    auto check_total = [&]() {
+        if ((long long)hc->q[Q_TOTAL] < 0)
+            throw np2::Error(NP2_ERR_UNSUPPORTED,
+                             "best path has a negative total score (main.rs:1680 picks the default 3-mer): not supported");
+    };
+    if (!spec) check_total();
 
     /* ---------------- LQ regions on the device (np2_regions.cu) */
     RegionDev rd;
-    rd.N = N;
-    rd.n_ev = n_ev;
+    rd.cnt = cd.c;
     rd.events = d_events.p;
     rd.cflags = d_cflags.p;
     rd.cbase = d_cbase.p;
     rd.cpos = d_cpos.p;
-    DBuf<uint32_t> d_ev_close, d_c_t, d_c_start, d_c_end, d_c_a, d_c_b, d_c_head, d_c_hrank, d_ncand;
+    DBuf<uint32_t> d_ev_close, d_c_t, d_c_start, d_c_end, d_c_a, d_c_b, d_c_head, d_c_hrank;
     DBuf<uint8_t> d_ev_boundary, d_ev_closes;
     DBuf<uint32_t> d_rstart, d_rend, d_ra, d_rb;
     d_ev_close.alloc(std::max(n_ev, 1u), s);
     d_ev_boundary.alloc(std::max(n_ev, 1u), s);
     d_ev_closes.alloc(std::max(n_ev, 1u), s);
     d_c_t.alloc(std::max(n_ev, 1u), s);
-    d_ncand.alloc(1, s);
     rd.ev_close = d_ev_close.p;
     rd.ev_boundary = d_ev_boundary.p;
     rd.ev_closes = d_ev_closes.p;
     rd.c_t = d_c_t.p;
-    uint32_t n_cand = 0, nreg = 0;
-    if (n_ev) {
-        h = timer.begin("regions", 2);
-        regions_event_close(rd, s);
-        {
-            size_t tb = 0;
-            cub::CountingInputIterator<uint32_t> it(0);
-            cub::DeviceSelect::Flagged(nullptr, tb, it, d_ev_closes.p, d_c_t.p, d_ncand.p, (int)n_ev, s);
-            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-            cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_ev_closes.p, d_c_t.p, d_ncand.p, (int)n_ev, s);
-        }
-        timer.end(h);
-        NP2_CUDA(cudaMemcpyAsync(&n_cand, d_ncand.p, 4, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaStreamSynchronize(s));
-    }
-    if (n_cand) {
-        d_c_start.alloc(n_cand, s);
-        d_c_end.alloc(n_cand, s);
-        d_c_a.alloc(n_cand, s);
-        d_c_b.alloc(n_cand, s);
-        d_c_head.alloc(n_cand + 1, s);
-        d_c_hrank.alloc(n_cand + 1, s);
-        rd.c_start = d_c_start.p;
-        rd.c_end = d_c_end.p;
-        rd.c_a = d_c_a.p;
-        rd.c_b = d_c_b.p;
-        rd.c_head = d_c_head.p;
-        rd.c_hrank = d_c_hrank.p;
-        h = timer.begin("regions", 3);
-        regions_make(rd, n_cand, s);
-        NP2_CUDA(cudaMemsetAsync(d_c_head.p + n_cand, 0, 4, s));
-        {
-            size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, d_c_head.p, d_c_hrank.p, (int)n_cand + 1, s);
-            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-            cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_c_head.p, d_c_hrank.p, (int)n_cand + 1, s);
-        }
-        timer.end(h);
-        NP2_CUDA(cudaMemcpyAsync(&nreg, d_c_hrank.p + n_cand, 4, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaStreamSynchronize(s));
-        d_rstart.alloc(nreg, s);
-        d_rend.alloc(nreg, s);
-        d_ra.alloc(nreg, s);
-        d_rb.alloc(nreg, s);
-        rd.r_start = d_rstart.p;
-        rd.r_end = d_rend.p;
-        rd.r_a = d_ra.p;
-        rd.r_b = d_rb.p;
-        h = timer.begin("regions", 1);
-        regions_out(rd, n_cand, nreg, s);
-        timer.end(h);
-    }
+    h = timer.begin("regions", 2);
+    regions_event_close(rd, n_ev, s);
+    regions_cand_select(rd, n_ev, std::max(n_ev, 1u), cd, sp, s);
+    timer.end(h);
+    const uint32_t n_cand = cnt_get(C_NCAND);
+    d_c_start.alloc(std::max(n_cand, 1u), s);
+    d_c_end.alloc(std::max(n_cand, 1u), s);
+    d_c_a.alloc(std::max(n_cand, 1u), s);
+    d_c_b.alloc(std::max(n_cand, 1u), s);
+    d_c_head.alloc(n_cand + 1, s);
+    d_c_hrank.alloc(n_cand + 1, s);
+    rd.c_start = d_c_start.p;
+    rd.c_end = d_c_end.p;
+    rd.c_a = d_c_a.p;
+    rd.c_b = d_c_b.p;
+    rd.c_head = d_c_head.p;
+    rd.c_hrank = d_c_hrank.p;
+    h = timer.begin("regions", 3);
+    regions_make(rd, n_cand, s);
+    regions_rank(rd, n_cand, spec ? caps.c[C_NREG] : 0xFFFFFFFFu, cd, sp, s);
+    timer.end(h);
+    uint32_t nreg = cnt_get(C_NREG);
+    d_rstart.alloc(std::max(nreg, 1u), s);
+    d_rend.alloc(std::max(nreg, 1u), s);
+    d_ra.alloc(std::max(nreg, 1u), s);
+    d_rb.alloc(std::max(nreg, 1u), s);
+    rd.r_start = d_rstart.p;
+    rd.r_end = d_rend.p;
+    rd.r_a = d_ra.p;
+    rd.r_b = d_rb.p;
+    h = timer.begin("regions", 1);
+    regions_out(rd, n_cand, s);
+    timer.end(h);
     Regions rg;  // host copy only when needed (dump, final iteration)
     auto fetch_regions = [&]() {
         rg.start.resize(nreg);
@@ -1012,7 +1018,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         }
     };
 
-    auto dump_stage1 = [&]() {
+    auto dump_stage1 = [&]() {  // exact mode only
         // Msa in the reference's order: reference 3-mer first (p >= 2), then the sorted sparse ones
         std::vector<uint32_t> sp_off(L + 1), gc(G), gb(G), dc(L), db(L);
         std::vector<uint16_t> gba(G), gde(G);
@@ -1053,24 +1059,51 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         dm_reg_end = rg.end;
     };
     uint32_t edge_pos[2] = {0, 0};  // ConsensusBase.pos of the first / last DP base (FASTA header)
-    auto fetch_edge_pos = [&]() {
-        if (!N) return;
-        NP2_CUDA(cudaMemcpyAsync(&edge_pos[0], d_cpos.p, 4, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaMemcpyAsync(&edge_pos[1], d_cpos.p + (N - 1), 4, cudaMemcpyDeviceToHost, s));
+    auto fetch_edge_pos = [&](uint32_t n_true) {
+        if (!n_true) return;
+        uint32_t *pe = reinterpret_cast<uint32_t *>(hc + 1);  // two pinned words behind the counts
+        NP2_CUDA(cudaMemcpyAsync(pe, d_cpos.p, 4, cudaMemcpyDeviceToHost, s));
+        NP2_CUDA(cudaMemcpyAsync(pe + 1, d_cpos.p + (n_true - 1), 4, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaStreamSynchronize(s));
+        n_sync++;
+        edge_pos[0] = pe[0];
+        edge_pos[1] = pe[1];
     };
-    stats[4] = nreg;
+    auto note_sizes = [&]() {  // after a fetch: what bench.py and the next pass's capacities want to know
+        stats[0] = hc->c[C_NREC];
+        stats[1] = hc->c[C_G];
+        stats[2] = hc->c[C_NRUNS];
+        stats[3] = hc->c[C_N];
+        stats[4] = hc->c[C_NREG];
+        stats[5] = hc->c[C_NPAIRS];
+        rec_cap_hint = hc->c[C_NREC];
+        res_N = hc->c[C_N];
+    };
+    auto remember = [&]() {
+        hint.valid = true;
+        hint.L = L;
+        hint.cols = ing.total_cols;
+        for (int i = 0; i < C_COUNT; i++) hint.h.c[i] = std::max(hint.h.c[i], hc->c[i]);
+        for (int i = 0; i < Q_COUNT; i++) hint.h.q[i] = std::max(hint.h.q[i], hc->q[i]);
+        hint.h.c[C_ABORT] = 0;
+        hint.h.q[Q_TOTAL] = hint.h.q[Q_SHIFT] = 0;
+    };
+    stats[7]++;
     uint32_t iter = iter0;
-    if (nreg == 0) {  // main.rs:1638-1640: no LQ region; nothing can be dropped, the DP consensus is the answer
+    if (!spec && nreg == 0) {  // main.rs:1638-1640: no LQ region; nothing can be dropped, the DP consensus is the answer
+        note_sizes();
+        hint.h = CountsHost();
+        remember();
         for (;; iter++) {
             if ((int32_t)iter == dump_iter) dump_stage1();
             if (iter + 1 < opt.iter_count) continue;
-            fetch_edge_pos();
+            fetch_edge_pos(N);
             res_patch.reset(0);
             res_base.resize(std::max(N, 1u));
             res_base.n = N;
             d_cbase.download(res_base.p, N);
             NP2_CUDA(cudaStreamSynchronize(s));
+            n_sync++;
             d2h += N;
             res_first = edge_pos[0];
             res_last = edge_pos[1];
@@ -1084,7 +1117,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     const uint32_t k0 = t0->dev.k;
     if (k0 >= 32) throw np2::Error(NP2_ERR_UNSUPPORTED, "the smallest yak table must have k < 32 (main.rs:1432-1434)");
     GenoDev g;
-    g.nreg = nreg;
+    g.cnt = cd.c;
     DBuf<uint32_t> d_rd_s, d_rd_j, d_rd_np, d_rd_poff;
     d_rd_s.alloc(n_reads + 1, s);
     d_rd_j.alloc(n_reads + 1, s);
@@ -1099,28 +1132,13 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     g.rd_order = d_order.p;
     h = timer.begin("read_ranges", 4);
     geno_read_cursor(g, R, d_blank.p, s);
-    if (n_reads) {  // the cursor only ever moves down: prefix-min in read order (main.rs:1446-1448)
-        size_t tb = 0;
-        cub::DeviceScan::InclusiveScan(nullptr, tb, d_rd_s.p, d_rd_s.p, cub::Min(), (int)n_reads, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceScan::InclusiveScan(d_tmp.p, tb, d_rd_s.p, d_rd_s.p, cub::Min(), (int)n_reads, s);
-    }
+    geno_cursor_min(d_rd_s.p, n_reads, cd.c + C_ABORT, sp, s);  // the cursor only ever moves down (main.rs:1446-1448)
     geno_read_ranges(g, R, d_blank.p, k0, s);
-    NP2_CUDA(cudaMemsetAsync(d_rd_np.p + n_reads, 0, 4, s));
-    {
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_rd_np.p, d_rd_poff.p, (int)n_reads + 1, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_rd_np.p, d_rd_poff.p, (int)n_reads + 1, s);
-    }
+    geno_pair_offsets(g, n_reads, spec ? caps.c[C_NPAIRS] : 0xFFFFFFFFu, cd, sp, s);
     timer.end(h);
-    uint32_t n_pairs = 0;
-    NP2_CUDA(cudaMemcpyAsync(&n_pairs, d_rd_poff.p + n_reads, 4, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
-    g.n_pairs = n_pairs;
-    stats[5] = n_pairs;
+    const uint32_t n_pairs = cnt_get(C_NPAIRS);
 
-    const uint64_t nslot = (uint64_t)nreg * kMaxCand;
+    const uint64_t nslot = (uint64_t)std::max(nreg, 1u) * kMaxCand;
     DBuf<uint32_t> d_p_len, d_c_src, d_c_len, d_c_order, d_r_ncand, d_r_bytes, d_r_nedge, d_r_seed_len, d_r_nsurv;
     DBuf<uint64_t> d_p_kmer, d_c_kmer, d_c_off, d_r_pool_off, d_r_edge_off, d_r_seed_off;
     DBuf<uint16_t> d_c_ks;
@@ -1137,18 +1155,16 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     d_r_ncand.alloc(nreg + 1, s);
     d_r_bytes.alloc(nreg + 1, s);
     d_r_nedge.alloc(nreg + 1, s);
-    d_r_seed_len.alloc(nreg, s);
-    d_r_nsurv.alloc(nreg, s);
+    d_r_seed_len.alloc(nreg + 1, s);
+    d_r_nsurv.alloc(nreg + 1, s);
     d_r_pool_off.alloc(nreg + 1, s);
     d_r_edge_off.alloc(nreg + 1, s);
-    d_r_seed_off.alloc(nreg, s);
-    d_r_lable.alloc(nreg, s);
+    d_r_seed_off.alloc(nreg + 1, s);
+    d_r_lable.alloc(nreg + 1, s);
     d_r_surv.alloc(nslot, s);
-    DBuf<uint32_t> d_long_list, d_long_count;
+    DBuf<uint32_t> d_long_list;
     d_long_list.alloc(nslot, s);
-    d_long_count.alloc(1, s);
     g.long_list = d_long_list.p;
-    g.long_count = d_long_count.p;
     g.p_len = d_p_len.p;
     g.p_kmer = d_p_kmer.p;
     g.c_src = d_c_src.p;
@@ -1170,32 +1186,27 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     g.r_surv = d_r_surv.p;
 
     h = timer.begin("cand_scan", 1);
-    geno_pair_scan(g, R, k0, s);
+    geno_pair_scan(g, R, k0, n_pairs, s);
     timer.end(h);
     h = timer.begin("region_select", 2);
-    geno_region_select(g, R, d_blank.p, d_code.p, L, k0, max_span, s);
-    NP2_CUDA(cudaMemsetAsync(d_r_bytes.p + nreg, 0, 4, s));
-    {  // 64-bit offsets out of 32-bit per-region byte counts
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_r_bytes.p, d_r_pool_off.p, (int)nreg + 1, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_r_bytes.p, d_r_pool_off.p, (int)nreg + 1, s);
-    }
+    geno_region_select(g, R, d_blank.p, d_code.p, L, k0, max_span, nreg, s);
+    geno_pool_offsets(g, nreg, spec ? caps.q[Q_POOL] : ~0ULL, cd, sp, s);
     timer.end(h);
-    uint64_t pool_bytes = 0;
-    NP2_CUDA(cudaMemcpyAsync(&pool_bytes, d_r_pool_off.p + nreg, 8, cudaMemcpyDeviceToHost, s));
-    NP2_CUDA(cudaStreamSynchronize(s));
+    uint64_t pool_bytes = caps.q[Q_POOL];
+    if (!spec) {
+        fetch_counts();
+        pool_bytes = hc->q[Q_POOL];
+    }
     d_gpool.alloc(pool_bytes + 16, s);
     g.pool = d_gpool.p;
     h = timer.begin("cand_write", 1);
-    geno_cand_write(g, R, d_code.p, L, k0, s);
+    geno_cand_write(g, R, d_code.p, L, k0, nreg, s);
     timer.end(h);
     h = timer.begin("yak_probe", 2);
-    geno_cand_kscore(g, t0->dev, opt.min_kmer_count, s);
+    geno_cand_kscore(g, t0->dev, opt.min_kmer_count, nreg, cd, s);
     timer.end(h);
-    n_probes += n_pairs;
 
-    auto dump_candidates = [&](bool with_lable) {
+    auto dump_candidates = [&](bool with_lable) {  // exact mode only
         std::vector<uint32_t> ncand(nreg), clen(nslot), cord(nslot);
         std::vector<uint64_t> ckm(nslot), coff(nslot);
         std::vector<uint16_t> cks(nslot);
@@ -1229,139 +1240,146 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     };
     // mark_hete_lqseqs zeroes kscores in place: keep the retrieve_kmer_count values for a re-used iteration
     DBuf<uint16_t> d_c_ks_orig;
-    d_c_ks_orig.alloc(nslot, s);
-    NP2_CUDA(cudaMemcpyAsync(d_c_ks_orig.p, d_c_ks.p, nslot * 2, cudaMemcpyDeviceToDevice, s));
+    const bool may_reuse = iter0 + 2 <= opt.iter_count;  // a non-final iteration may be followed by a re-used one
+    if (may_reuse) {
+        d_c_ks_orig.alloc(nslot, s);
+        NP2_CUDA(cudaMemcpyAsync(d_c_ks_orig.p, d_c_ks.p, nslot * 2, cudaMemcpyDeviceToDevice, s));
+    }
+    const uint32_t n_ids0 = (uint32_t)as_read.size();
   for (;; iter++) {
     const bool final_iter = iter + 1 == opt.iter_count;
     const bool dump = (int32_t)iter == dump_iter;
-    if (iter > iter0) NP2_CUDA(cudaMemcpyAsync(d_c_ks.p, d_c_ks_orig.p, nslot * 2, cudaMemcpyDeviceToDevice, s));
+    if (iter > iter0 && may_reuse) NP2_CUDA(cudaMemcpyAsync(d_c_ks.p, d_c_ks_orig.p, nslot * 2, cudaMemcpyDeviceToDevice, s));
     if (dump) dump_stage1();
     if (dump) dump_candidates(false);
 
     if (!final_iter) {
         /* ---------------- heterozygous regions, agreement edges (device); Louvain (host) — main.rs:1544-1552 */
         h = timer.begin("region_hete", 2);
-        geno_region_hete(g, s);
-        NP2_CUDA(cudaMemsetAsync(d_r_nedge.p + nreg, 0, 4, s));
-        {
-            size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, d_r_nedge.p, d_r_edge_off.p, (int)nreg + 1, s);
-            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-            cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_r_nedge.p, d_r_edge_off.p, (int)nreg + 1, s);
-        }
+        geno_region_hete(g, nreg, s);
+        geno_edge_offsets(g, nreg, cd, sp, s);
         timer.end(h);
-        uint64_t n_edges = 0;
-        NP2_CUDA(cudaMemcpyAsync(&n_edges, d_r_edge_off.p + nreg, 8, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaStreamSynchronize(s));
+        // dense pair accumulator (np2_geno.cu k_edges_accum): one slot per (x, y) inside x's index window; the
+        // number of slots only depends on the reads (np2_job::run)
+        if (pair_slots >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^31 overlapping read pairs");
+        const uint32_t n_slots = (uint32_t)pair_slots;
+        uint32_t id_bits = 1;  // read orders are < as_read.size()
+        while ((1ull << id_bits) < as_read.size()) id_bits++;
+        uint64_t n_edges = 1;
+        if (!spec) {
+            fetch_counts();
+            n_edges = hc->q[Q_EDGES];
+        }
         if (dump) dump_candidates(true);
         std::vector<uint32_t> drop;
+        DBuf<unsigned long long> d_acc;
+        DBuf<uint32_t> d_sel;
+        DBuf<uint64_t> d_uk;
+        DBuf<long long> d_uv;
+        DBuf<uint8_t> d_flags;  // has | bad_v | in_ref
+        DBuf<float> d_refw, d_dw, d_dw2;
+        DBuf<uint64_t> d_dk, d_dk2;
+        DBuf<uint32_t> d_aoff, d_ato;
+        uint32_t nu = 0;
         if (n_edges) {
-            // dense pair accumulator (np2_geno.cu k_edges_accum): one slot per (x, y) inside x's index window
-            const uint32_t n_ids0 = (uint32_t)as_read.size();
-            uint64_t n_slots = 0;
-            NP2_CUDA(cudaMemcpyAsync(&n_slots, d_pair_off.p + n_ids0, 8, cudaMemcpyDeviceToHost, s));
-            NP2_CUDA(cudaStreamSynchronize(s));
-            if (n_slots >= (1ull << 31)) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 2^31 overlapping read pairs");
-            uint32_t id_bits = 1;  // read orders are < as_read.size()
-            while ((1ull << id_bits) < as_read.size()) id_bits++;
-            DBuf<unsigned long long> d_acc;
-            DBuf<uint32_t> d_sel, d_nu;
-            DBuf<uint64_t> d_uk;
-            DBuf<long long> d_uv;
-            DBuf<int> d_perr;
             d_acc.alloc(std::max<uint64_t>(n_slots, 1), s);
-            d_sel.alloc(std::max<uint64_t>(n_slots, 1), s);
-            d_nu.alloc(1, s);
-            d_perr.alloc(1, s);
-            h = timer.begin("pair_edges", 2);
+            const uint32_t cap_nu_sel = spec ? std::min(caps.c[C_NU], std::max(n_slots, 1u)) : std::max(n_slots, 1u);
+            d_sel.alloc(cap_nu_sel, s);
+            h = timer.begin("pair_edges", 3);
             d_acc.zero();
-            d_perr.zero();
-            d_nu.zero();
-            geno_edges_accum(g, d_pair_off.p, d_acc.p, d_perr.p, s);
-            {
-                size_t tb = 0;
-                geno_edges_select(d_acc.p, (uint32_t)n_slots, d_sel.p, d_nu.p, nullptr, tb, s);
-                if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-                geno_edges_select(d_acc.p, (uint32_t)n_slots, d_sel.p, d_nu.p, d_tmp.p, tb, s);
-            }
+            geno_edges_accum(g, d_pair_off.p, d_acc.p, nreg, cd, s);
+            geno_edges_select(d_acc.p, n_slots, d_sel.p, cap_nu_sel, cd, sp, s);
             timer.end(h);
-            uint32_t nu = 0;
-            int perr = 0;
-            d_nu.download(&nu, 1);
-            d_perr.download(&perr, 1);
-            NP2_CUDA(cudaStreamSynchronize(s));
-            if (perr) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
-            stats[6] = nu;
-            d_uk.alloc(std::max(nu, 1u), s);
-            d_uv.alloc(std::max(nu, 1u), s);
-            h = timer.begin("pair_edges", 1);
-            geno_edges_finish(d_sel.p, nu, d_pair_off.p, n_ids0, d_acc.p, d_uk.p, d_uv.p, s);
-            timer.end(h);
+            nu = spec ? cap_nu_sel : cnt_get(C_NU);  // exact: the number of pair records; speculative: its capacity
+            if (!spec && hc->c[C_PERR]) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
             if (nu) {
+                d_uk.alloc(nu, s);
+                d_uv.alloc(nu, s);
+                h = timer.begin("pair_edges", 1);
+                geno_edges_finish(d_sel.p, nu, d_pair_off.p, n_ids0, d_acc.p, d_uk.p, d_uv.p, cd, s);
+                timer.end(h);
                 // level 0 of the phasing graph on the device: per-read flags + CSR adjacency (np2_geno.cu k_phase_*)
-                const uint32_t n_ids = (uint32_t)as_read.size(), n2 = 2 * nu;
+                const uint32_t n2 = 2 * nu;
                 const bool asref = opt.model == 0, use_all = opt.use_all_reads != 0;
-                DBuf<uint8_t> d_flags;  // has | bad_v | in_ref
-                DBuf<float> d_refw, d_dw, d_dw2;
-                DBuf<uint64_t> d_dk, d_dk2;
-                DBuf<uint32_t> d_aoff, d_ato;
-                d_flags.alloc((size_t)n_ids * 3, s);
-                d_refw.alloc(n_ids, s);
+                d_flags.alloc((size_t)n_ids0 * 3, s);
+                d_refw.alloc(n_ids0, s);
                 d_dk.alloc(n2, s);
                 d_dk2.alloc(n2, s);
                 d_dw.alloc(n2, s);
                 d_dw2.alloc(n2, s);
-                d_aoff.alloc(n_ids + 1, s);
+                d_aoff.alloc(n_ids0 + 1, s);
                 d_ato.alloc(n2, s);
                 PhaseDev pd;
                 pd.has = d_flags.p;
-                pd.bad_v = d_flags.p + n_ids;
-                pd.in_ref = d_flags.p + 2 * (size_t)n_ids;
+                pd.bad_v = d_flags.p + n_ids0;
+                pd.in_ref = d_flags.p + 2 * (size_t)n_ids0;
                 pd.ref_w = d_refw.p;
                 h = timer.begin("phase_graph", 5);
                 d_flags.zero();
                 d_refw.zero();
                 d_aoff.zero();
-                phase_ref(d_uk.p, d_uv.p, nu, pd, asref, use_all, s);
-                phase_expand(d_uk.p, d_uv.p, nu, pd, use_all, id_bits, d_dk.p, d_dw.p, s);
+                phase_ref(d_uk.p, d_uv.p, nu, cd, pd, asref, use_all, s);
+                phase_expand(d_uk.p, d_uv.p, nu, cd, pd, use_all, id_bits, d_dk.p, d_dw.p, s);
                 {
                     size_t tb = 0;
                     cub::DeviceRadixSort::SortPairs(nullptr, tb, d_dk.p, d_dk2.p, d_dw.p, d_dw2.p, (int)n2, 0, 2 * id_bits + 1, s);
                     if (tb > d_tmp.n) d_tmp.alloc(tb, s);
                     cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_dk.p, d_dk2.p, d_dw.p, d_dw2.p, (int)n2, 0, 2 * id_bits + 1, s);
                 }
-                phase_csr(d_dk2.p, n2, id_bits, n_ids, d_aoff.p, d_ato.p, s);
+                phase_csr(d_dk2.p, n2, id_bits, n_ids0, d_aoff.p, d_ato.p, cd.c + C_ABORT, s);
                 timer.end(h);
-                // one pinned block: aoff | ato | aw | ref_w | flags
-                const size_t o_ato = ((size_t)(n_ids + 1) * 4 + 15) & ~(size_t)15, o_aw = o_ato + (((size_t)n2 * 4 + 15) & ~(size_t)15);
-                const size_t o_rw = o_aw + (((size_t)n2 * 4 + 15) & ~(size_t)15), o_fl = o_rw + (((size_t)n_ids * 4 + 15) & ~(size_t)15);
-                sc->p_phase.resize(o_fl + (size_t)n_ids * 3 + 16);
-                uint8_t *pb = sc->p_phase.p;
-                d_aoff.download(reinterpret_cast<uint32_t *>(pb), n_ids + 1);
-                d_ato.download(reinterpret_cast<uint32_t *>(pb + o_ato), n2);
-                d_dw2.download(reinterpret_cast<float *>(pb + o_aw), n2);
-                d_refw.download(reinterpret_cast<float *>(pb + o_rw), n_ids);
-                d_flags.download(pb + o_fl, (size_t)n_ids * 3);
-                NP2_CUDA(cudaStreamSynchronize(s));
-                d2h += (uint64_t)n2 * 8 + (uint64_t)n_ids * 11;
-                timer.hbegin();
-                drop = phase_reads_csr(n_ids, reinterpret_cast<const uint32_t *>(pb), reinterpret_cast<const uint32_t *>(pb + o_ato),
-                                       reinterpret_cast<const float *>(pb + o_aw), pb + o_fl, pb + o_fl + n_ids,
-                                       pb + o_fl + 2 * (size_t)n_ids, reinterpret_cast<const float *>(pb + o_rw), asref, [&]() {
-                                           // a community has to be declustered: the general path wants the pair records
-                                           std::vector<uint64_t> ukeys(nu);
-                                           std::vector<long long> uvals(nu);
-                                           d_uk.download(ukeys.data(), nu);
-                                           d_uv.download(uvals.data(), nu);
-                                           NP2_CUDA(cudaStreamSynchronize(s));
-                                           d2h += (uint64_t)nu * 16;
-                                           return phase_reads_general(ukeys.data(), uvals.data(), nu, asref, use_all);
-                                       });
-                timer.hend("host:phase_reads");
-                static const char *kPhase[4] = {"host:phase_reads.build", "host:phase_reads.move", "host:phase_reads.aggregate",
-                                                "host:phase_reads.communities"};
-                for (int x = 0; x < 4; x++) timer.ms[timer.id(kPhase[x])] += np2::phase_last_ms()[x];
             }
+        }
+        const bool was_spec = spec;
+        if (spec) {  // the one synchronisation of the speculative stretch
+            timer.hbegin();
+            segment_end();
+            timer.hend("host:segment_sync");
+            check_total();
+            if (hc->c[C_NREG] == 0) throw Respeculate();  // the no-region path is only taken in exact mode
+            if (hc->c[C_PERR]) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
+            nreg = hc->c[C_NREG];
+        }
+        note_sizes();
+        stats[6] = hc->c[C_NU];
+        remember();
+        const uint32_t nu_true = hc->c[C_NU];
+        if (n_edges && nu && nu_true) {
+            const bool asref = opt.model == 0, use_all = opt.use_all_reads != 0;
+            // Directed edges that survive are in front of the sentinels: aoff[n_ids0] of them.  In exact mode that is at
+            // most 2 * nu; after a speculative stretch the arrays are capacity-sized, so fetch the bound first.
+            uint32_t n_dir = 2 * nu_true;
+            (void)was_spec;
+            // one pinned block: aoff | ato | aw | ref_w | flags
+            const size_t o_ato = ((size_t)(n_ids0 + 1) * 4 + 15) & ~(size_t)15, o_aw = o_ato + (((size_t)n_dir * 4 + 15) & ~(size_t)15);
+            const size_t o_rw = o_aw + (((size_t)n_dir * 4 + 15) & ~(size_t)15), o_fl = o_rw + (((size_t)n_ids0 * 4 + 15) & ~(size_t)15);
+            sc->p_phase.resize(o_fl + (size_t)n_ids0 * 3 + 16);
+            uint8_t *pb = sc->p_phase.p;
+            d_aoff.download(reinterpret_cast<uint32_t *>(pb), n_ids0 + 1);
+            d_ato.download(reinterpret_cast<uint32_t *>(pb + o_ato), n_dir);
+            d_dw2.download(reinterpret_cast<float *>(pb + o_aw), n_dir);
+            d_refw.download(reinterpret_cast<float *>(pb + o_rw), n_ids0);
+            d_flags.download(pb + o_fl, (size_t)n_ids0 * 3);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            n_sync++;
+            d2h += (uint64_t)n_dir * 8 + (uint64_t)n_ids0 * 11;
+            timer.hbegin();
+            drop = phase_reads_csr(n_ids0, reinterpret_cast<const uint32_t *>(pb), reinterpret_cast<const uint32_t *>(pb + o_ato),
+                                   reinterpret_cast<const float *>(pb + o_aw), pb + o_fl, pb + o_fl + n_ids0,
+                                   pb + o_fl + 2 * (size_t)n_ids0, reinterpret_cast<const float *>(pb + o_rw), asref, [&]() {
+                                       // a community has to be declustered: the general path wants the pair records
+                                       std::vector<uint64_t> ukeys(nu_true);
+                                       std::vector<long long> uvals(nu_true);
+                                       d_uk.download(ukeys.data(), nu_true);
+                                       d_uv.download(uvals.data(), nu_true);
+                                       NP2_CUDA(cudaStreamSynchronize(s));
+                                       d2h += (uint64_t)nu_true * 16;
+                                       return phase_reads_general(ukeys.data(), uvals.data(), nu_true, asref, use_all);
+                                   });
+            timer.hend("host:phase_reads");
+            static const char *kPhase[4] = {"host:phase_reads.build", "host:phase_reads.move", "host:phase_reads.aggregate",
+                                            "host:phase_reads.communities"};
+            for (int x = 0; x < 4; x++) timer.ms[timer.id(kPhase[x])] += np2::phase_last_ms()[x];
         }
         for (uint32_t a : drop) {
             if (a == 0 || a >= as_read.size()) throw np2::Error(NP2_ERR_INTERNAL, "phasing returned a bad read index");
@@ -1371,22 +1389,18 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         if (drop.empty()) continue;  // same reads => the next iteration is this one again
         d_blank.upload(h_blank.data(), n_reads);
         NP2_CUDA(cudaStreamSynchronize(s));
+        n_sync++;
         return iter + 1;
     }
-    fetch_edge_pos();
 
     /* ---------------- final: seed alleles (device), then re-check with every table (main.rs:1527-1543) */
-    DBuf<int> d_err;
-    d_err.alloc(1, s);
-    d_err.zero();
     h = timer.begin("region_seed", 1);
-    geno_region_seed(g, opt.max_indel_len, d_err.p, s);
+    geno_region_seed(g, opt.max_indel_len, nreg, cd, s);
     timer.end(h);
     /* ---- what the host needs for the re-check: regions, every region's seed string, the survivors of the regions
      *      that stay RECH, and the DP bases (flanks).  Everything else stays on the device. */
     AssembleDev ad;
-    ad.nreg = nreg;
-    ad.N = N;
+    ad.cnt = cd.c;
     ad.cbase = d_cbase.p;
     ad.pool = d_gpool.p;
     ad.r_a = d_ra.p;
@@ -1407,25 +1421,23 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     ad.q_shift = d_q_shift.p;
     ad.q_seedlen = d_q_seedlen.p;
     ad.q_seedoff = d_q_seedoff.p;
-    auto scan = [&](auto *in, auto *out, int n) {
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, in, out, n, s);
-    };
     Patched &pc = res_patch;
     uint32_t *seed_len = nullptr;   // full path: staged copies of the per-region seed (r order)
     uint64_t *seed_off = nullptr;
     auto phase1_sizes = [&]() {
-        h = timer.begin("seed_gather", 4);
-        assemble_sizes(ad, s);
-        NP2_CUDA(cudaMemsetAsync(d_q_seedlen.p + nreg, 0, 4, s));
-        scan(d_q_seedlen.p, d_q_seedoff.p, (int)nreg + 1);
-        rech_sizes(g, d_rech_bytes.p, s);
-        NP2_CUDA(cudaMemsetAsync(d_rech_bytes.p + nreg, 0, 4, s));
-        scan(d_rech_bytes.p, d_rech_boff.p, (int)nreg + 1);
-        scan(d_r_nsurv.p, d_ent_off.p, (int)nreg);  // last entry handled below
+        h = timer.begin("seed_gather", 5);
+        assemble_sizes(ad, nreg, s);
+        region_scan_u64(d_q_seedlen.p, d_q_seedoff.p, nreg, Q_SEEDS, cd, sp, s);
+        rech_sizes(g, d_rech_bytes.p, nreg, s);
+        region_scan_u64(d_rech_bytes.p, d_rech_boff.p, nreg, Q_RECH, cd, sp, s);
+        region_scan_u32(d_r_nsurv.p, d_ent_off.p, nreg, C_NENT, cd, sp, s);
         timer.end(h);
+    };
+    auto raise_gerr = [&]() {
+        const uint32_t gerr = hc->c[C_GERR];
+        if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
+        if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
+        if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
     };
     /* Sparse host view (the normal case): the host only looks at the RECH regions and at what lies within
      * kRecheckWindow DP bases of them, plus the first and the last region (FASTA header span).  Everything is selected,
@@ -1436,69 +1448,59 @@ uint32_t np2_job::iteration(uint32_t iter0) {
     std::vector<uint32_t> sv_init_len;
     long long sv_shift0 = 0;
     bool sparse_view = false;
+    uint32_t N_true = N;
     auto build_sparse_view = [&]() -> bool {
         DBuf<uint8_t> d_near;
-        DBuf<uint32_t> d_sub, d_nsub, d_win_lo, d_win_len;
+        DBuf<uint32_t> d_sub, d_win_lo, d_win_len;
         DBuf<uint64_t> d_win_off;
-        d_near.alloc(nreg, s);
-        d_sub.alloc(nreg, s);
-        d_nsub.alloc(1, s);
-        d_win_lo.alloc(nreg, s);
+        d_near.alloc(nreg + 1, s);
+        d_sub.alloc(nreg + 1, s);
+        d_win_lo.alloc(nreg + 1, s);
         d_win_len.alloc(nreg + 1, s);
         d_win_off.alloc(nreg + 1, s);
         SubMeta sm;
         DBuf<uint32_t> m_start, m_end, m_a, m_b, m_seed_len, m_nsurv, m_ent_off;
         DBuf<uint64_t> m_seed_off, m_qseedoff;
         DBuf<uint8_t> m_lable;
-        for (DBuf<uint32_t> *d : {&m_start, &m_end, &m_a, &m_b, &m_seed_len, &m_nsurv, &m_ent_off}) d->alloc(nreg, s);
-        m_seed_off.alloc(nreg, s);
-        m_qseedoff.alloc(nreg, s);
-        m_lable.alloc(nreg, s);
+        for (DBuf<uint32_t> *d : {&m_start, &m_end, &m_a, &m_b, &m_seed_len, &m_nsurv, &m_ent_off}) d->alloc(nreg + 1, s);
+        m_seed_off.alloc(nreg + 1, s);
+        m_qseedoff.alloc(nreg + 1, s);
+        m_lable.alloc(nreg + 1, s);
         sm.start = m_start.p, sm.end = m_end.p, sm.a = m_a.p, sm.b = m_b.p, sm.seed_len = m_seed_len.p;
         sm.nsurv = m_nsurv.p, sm.ent_off = m_ent_off.p, sm.seed_off = m_seed_off.p, sm.q_seedoff = m_qseedoff.p;
         sm.lable = m_lable.p;
-        int hh = timer.begin("seed_gather", 6);
+        int hh = timer.begin("seed_gather", 2);
         d_near.zero();
-        near_mark(nreg, N, d_r_lable.p, d_ra.p, d_rb.p, d_near.p, s);
+        near_mark(cd.c, nreg, d_r_lable.p, d_ra.p, d_rb.p, d_near.p, s);
         ad.near = d_near.p;
         timer.end(hh);
         phase1_sizes();
-        hh = timer.begin("seed_gather", 4);
-        NP2_CUDA(cudaMemsetAsync(d_q_delta.p + nreg, 0, 8, s));
-        scan(d_q_delta.p, d_q_shift.p, (int)nreg + 1);
-        window_sizes(nreg, N, d_r_lable.p, d_ra.p, d_rb.p, d_win_lo.p, d_win_len.p, s);
-        NP2_CUDA(cudaMemsetAsync(d_win_len.p + nreg, 0, 4, s));
-        scan(d_win_len.p, d_win_off.p, (int)nreg + 1);
-        {
-            size_t tb = 0;
-            cub::CountingInputIterator<uint32_t> it(0);
-            cub::DeviceSelect::Flagged(nullptr, tb, it, d_near.p, d_sub.p, d_nsub.p, (int)nreg, s);
-            if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-            cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_near.p, d_sub.p, d_nsub.p, (int)nreg, s);
-        }
-        sub_meta_gather(d_sub.p, d_nsub.p, nreg, d_rstart.p, d_rend.p, d_ra.p, d_rb.p, d_r_lable.p, d_r_seed_len.p,
+        hh = timer.begin("seed_gather", 5);
+        region_scan_i64(d_q_delta.p, d_q_shift.p, nreg, Q_SHIFT, cd, sp, s);
+        window_sizes(cd.c, nreg, d_r_lable.p, d_ra.p, d_rb.p, d_win_lo.p, d_win_len.p, s);
+        region_scan_u64(d_win_len.p, d_win_off.p, nreg, Q_WIN, cd, sp, s);
+        near_select(d_near.p, nreg, d_sub.p, cd, sp, s);
+        sub_meta_gather(d_sub.p, cd.c, nreg, d_rstart.p, d_rend.p, d_ra.p, d_rb.p, d_r_lable.p, d_r_seed_len.p,
                         d_r_seed_off.p, d_r_nsurv.p, d_ent_off.p, d_q_seedoff.p, sm, s);
         timer.end(hh);
         timer.hbegin();
-        Stager st1(sc->p_stage, s, 4096);
-        const int *h_gerr = st1.fetch(d_err.p, 1);
-        const uint32_t *h_nsub = st1.fetch(d_nsub.p, 1);
-        const uint64_t *h_seeds_bytes = st1.fetch(d_q_seedoff.p + nreg, 1);
-        const uint64_t *h_rech_bytes = st1.fetch(d_rech_boff.p + nreg, 1);
-        const uint64_t *h_win_bytes = st1.fetch(d_win_off.p + nreg, 1);
-        const long long *h_shift0 = st1.fetch(d_q_shift.p + nreg, 1);
-        const uint32_t *h_last_ent = st1.fetch(d_ent_off.p + (nreg - 1), 1);
-        const uint32_t *h_last_ns = st1.fetch(d_r_nsurv.p + (nreg - 1), 1);
-        NP2_CUDA(cudaStreamSynchronize(s));
+        if (spec) {
+            segment_end();
+            check_total();
+            if (hc->c[C_NREG] == 0) throw Respeculate();
+        } else {
+            fetch_counts();
+        }
         timer.hend("host:seed_sync1");
-        const int gerr = *h_gerr;
-        if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
-        if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
-        if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
-        const uint32_t nsub = *h_nsub, n_ent = *h_last_ent + *h_last_ns;
-        const uint64_t seeds_bytes = *h_seeds_bytes, rech_bytes = *h_rech_bytes, win_bytes = *h_win_bytes;
-        sv_shift0 = *h_shift0;
-        if (win_bytes > N / 2) return false;
+        note_sizes();
+        remember();
+        nreg = hc->c[C_NREG];
+        N_true = hc->c[C_N];
+        raise_gerr();
+        const uint32_t nsub = hc->c[C_NSUB], n_ent = hc->c[C_NENT];
+        const uint64_t seeds_bytes = hc->q[Q_SEEDS], rech_bytes = hc->q[Q_RECH], win_bytes = hc->q[Q_WIN];
+        sv_shift0 = (long long)hc->q[Q_SHIFT];
+        if (win_bytes > N_true / 2) return false;
         DBuf<uint8_t> d_seeds, d_rech_pool, d_win;
         DBuf<uint32_t> d_ent_order, d_ent_len;
         DBuf<uint64_t> d_ent_poff;
@@ -1509,9 +1511,9 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         d_ent_len.alloc(std::max(n_ent, 1u), s);
         d_ent_poff.alloc(std::max(n_ent, 1u), s);
         hh = timer.begin("seed_gather", 3);
-        assemble_seed_gather(ad, d_seeds.p, s);
-        if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
-        if (win_bytes) gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, nreg, d_win.p, s);
+        assemble_seed_gather(ad, d_seeds.p, nreg, s);
+        if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, nreg, s);
+        if (win_bytes) gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, cd.c + C_NREG, nreg, d_win.p, s);
         timer.end(hh);
         Stager st2(sc->p_stage2, s, (size_t)nsub * 56 + (size_t)n_ent * 16 + 4096);
         const uint32_t *h_sub = st2.fetch(d_sub.p, nsub);
@@ -1528,13 +1530,23 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         d_seeds.download(h_seeds.data(), seeds_bytes);
         if (rech_bytes) d_rech_pool.download(h_rech_pool.data(), rech_bytes);
         if (win_bytes) d_win.download(h_win.data(), win_bytes);
+        if (N_true) {  // ConsensusBase.pos of the first / last DP base (FASTA header), in the same round trip
+            uint32_t *pe = reinterpret_cast<uint32_t *>(hc + 1);
+            NP2_CUDA(cudaMemcpyAsync(pe, d_cpos.p, 4, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaMemcpyAsync(pe + 1, d_cpos.p + (N_true - 1), 4, cudaMemcpyDeviceToHost, s));
+        }
         NP2_CUDA(cudaStreamSynchronize(s));
+        n_sync++;
+        if (N_true) {
+            edge_pos[0] = reinterpret_cast<uint32_t *>(hc + 1)[0];
+            edge_pos[1] = reinterpret_cast<uint32_t *>(hc + 1)[1];
+        }
         timer.hend("host:seed_sync2");
         d2h += seeds_bytes + rech_bytes + win_bytes + (uint64_t)nsub * 53 + (uint64_t)n_ent * 16 + 64;
         // the view over the selected regions, ascending position (q' = nsub - 1 - i)
         pc.reset(nsub);
         pc.cbase = p_cbase.p;
-        pc.N = N;
+        pc.N = N_true;
         sv_sub.assign(h_sub, h_sub + nsub);
         sv_init_off.resize(nsub);
         sv_init_len.resize(nsub);
@@ -1569,7 +1581,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         for (uint32_t q = 0; q < nsub && ok; q++) {
             if (!(pc.lable[q] & LABLE_RECH)) continue;
             const uint64_t wlo = pc.a[q] > kRecheckWindow ? pc.a[q] - kRecheckWindow : 0;
-            const uint64_t whi = std::min<uint64_t>((uint64_t)pc.b[q] + kRecheckWindow, N);
+            const uint64_t whi = std::min<uint64_t>((uint64_t)pc.b[q] + kRecheckWindow, N_true);
             memcpy(p_cbase.p + wlo, h_win.data() + woff, whi - wlo);
             woff += whi - wlo;
             uint32_t got = 0, rr = q;  // left flank
@@ -1585,7 +1597,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             }
             got = 0, rr = q, i = pc.b[q];  // right flank
             for (;;) {
-                const uint64_t hi = rr + 1 < nsub ? pc.a[rr + 1] : N;
+                const uint64_t hi = rr + 1 < nsub ? pc.a[rr + 1] : N_true;
                 const uint64_t take = std::min<uint64_t>(need - got, hi - i);
                 if (i + take > whi) ok = false;
                 got += (uint32_t)take;
@@ -1601,18 +1613,29 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         return ok;
     };
     if (!dump) {
-        p_cbase.resize(std::max(N, 1u));
+        p_cbase.resize(std::max<uint64_t>(N, 1u));
         sparse_view = build_sparse_view();
         ad.near = nullptr;
     }
     if (!sparse_view) {
         phase1_sizes();
         timer.hbegin();
+        if (spec) {
+            segment_end();
+            check_total();
+            if (hc->c[C_NREG] == 0) throw Respeculate();
+        } else {
+            fetch_counts();
+        }
+        note_sizes();
+        remember();
+        nreg = hc->c[C_NREG];
+        N_true = hc->c[C_N];
+        raise_gerr();
+        fetch_edge_pos(N_true);
         // round 1: everything whose size is known (one synchronisation, pinned destinations)
-        p_cbase.resize(std::max(N, 1u));  // filled sparsely below: only the windows around RECH regions cross PCIe
+        p_cbase.resize(std::max(N_true, 1u));  // filled sparsely below: only the windows around RECH regions cross PCIe
         Stager st1(sc->p_stage, s, (size_t)nreg * 64 + 4096);
-        const int *h_gerr = st1.fetch(d_err.p, 1);
-        const uint64_t *h_rech_bytes = st1.fetch(d_rech_boff.p + nreg, 1);
         const uint8_t *lab = st1.fetch(d_r_lable.p, nreg);
         seed_len = st1.fetch(d_r_seed_len.p, nreg);
         seed_off = st1.fetch(d_r_seed_off.p, nreg);
@@ -1626,17 +1649,14 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         const uint32_t *h_rs = st1.fetch(d_rstart.p, nreg), *h_re = st1.fetch(d_rend.p, nreg);
         const uint32_t *h_ra = st1.fetch(d_ra.p, nreg), *h_rb = st1.fetch(d_rb.p, nreg);
         NP2_CUDA(cudaStreamSynchronize(s));
+        n_sync++;
         timer.hend("host:seed_sync1");
-        const int gerr = *h_gerr;
-        const uint64_t rech_bytes = *h_rech_bytes;
-        if (gerr == 1) throw np2::Error(NP2_ERR_FORMAT, "LQ region without any candidate (reference would panic)");
-        if (gerr == 2) throw np2::Error(NP2_ERR_FORMAT, "the first lqseq is not ref.");
-        if (gerr == 3) throw np2::Error(NP2_ERR_FORMAT, "no candidate survives retain_sort_seqs (reference would panic)");
+        const uint64_t rech_bytes = hc->q[Q_RECH];
         memcpy(rg.start.data(), h_rs, (size_t)nreg * 4);
         memcpy(rg.end.data(), h_re, (size_t)nreg * 4);
         memcpy(rg.a.data(), h_ra, (size_t)nreg * 4);
         memcpy(rg.b.data(), h_rb, (size_t)nreg * 4);
-        const uint32_t n_ent = nreg ? ent_off[nreg - 1] + nsurv[nreg - 1] : 0;
+        const uint32_t n_ent = hc->c[C_NENT];
         const uint64_t seeds_bytes = q_seedoff[nreg];
         DBuf<uint8_t> d_seeds, d_rech_pool;
         DBuf<uint32_t> d_ent_order, d_ent_len;
@@ -1653,32 +1673,32 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         std::vector<uint64_t> win_off(1, 0);
         for (uint32_t r = nreg; r-- > 0;)  // ascending position
             if (lab[r] & LABLE_RECH) {
-                const uint32_t lo = rg.a[r] > kWin ? rg.a[r] - kWin : 0, hi = (uint32_t)std::min<uint64_t>((uint64_t)rg.b[r] + kWin, N);
+                const uint32_t lo = rg.a[r] > kWin ? rg.a[r] - kWin : 0, hi = (uint32_t)std::min<uint64_t>((uint64_t)rg.b[r] + kWin, N_true);
                 win_lo.push_back(lo);
                 win_r.push_back(r);
                 win_off.push_back(win_off.back() + (hi - lo));
             }
         const uint32_t n_win = (uint32_t)win_lo.size();
-        bool full_cbase = win_off.back() > N / 2;
+        bool full_cbase = win_off.back() > N_true / 2;
         DBuf<uint32_t> d_win_lo;
         DBuf<uint64_t> d_win_off;
         DBuf<uint8_t> d_win;
         h = timer.begin("seed_gather", 3);
         if (full_cbase) {
-            d_cbase.download(p_cbase.p, N);
+            d_cbase.download(p_cbase.p, N_true);
         } else if (n_win) {
             d_win_lo.alloc(n_win, s);
             d_win_off.alloc(n_win + 1, s);
             d_win.alloc(win_off.back() + 1, s);
             d_win_lo.upload(win_lo.data(), n_win);
             d_win_off.upload(win_off.data(), n_win + 1);
-            gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, n_win, d_win.p, s);
+            gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, nullptr, n_win, d_win.p, s);
             h_win.resize(win_off.back() + 16);
             d_win.download(h_win.data(), win_off.back());
             h2d += (uint64_t)n_win * 12;
         }
-        assemble_seed_gather(ad, d_seeds.p, s);
-        if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, s);
+        assemble_seed_gather(ad, d_seeds.p, nreg, s);
+        if (n_ent) rech_gather(g, d_ent_off.p, d_rech_boff.p, d_ent_order.p, d_ent_len.p, d_ent_poff.p, d_rech_pool.p, nreg, s);
         timer.end(h);
         // round 2: the seed strings and the survivors of the RECH regions
         h_seeds.resize(seeds_bytes + 16);
@@ -1693,8 +1713,9 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             d_ent_poff.download(ent_poff.data(), n_ent);
         }
         NP2_CUDA(cudaStreamSynchronize(s));
+        n_sync++;
         timer.hend("host:seed_sync2");
-        d2h += (full_cbase ? (uint64_t)N : win_off.back()) + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
+        d2h += (full_cbase ? (uint64_t)N_true : win_off.back()) + seeds_bytes + rech_bytes + (uint64_t)nreg * 49 + (uint64_t)n_ent * 16;
         if (!full_cbase && n_win) {
             for (uint32_t w = 0; w < n_win; w++)
                 memcpy(p_cbase.p + win_lo[w], h_win.data() + win_off[w], win_off[w + 1] - win_off[w]);
@@ -1719,7 +1740,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
                 }
                 got = 0, rr = r, i = rg.b[r];
                 for (;;) {
-                    const uint64_t hi = rr > 0 ? rg.a[rr - 1] : N;
+                    const uint64_t hi = rr > 0 ? rg.a[rr - 1] : N_true;
                     const uint64_t take = std::min<uint64_t>(need - got, hi - i);
                     if (i + take > whi) ok = false;
                     got += (uint32_t)take;
@@ -1733,15 +1754,16 @@ uint32_t np2_job::iteration(uint32_t iter0) {
                 }
             }
             if (!ok) {  // pathological layout (very long insertions next to a RECH region): take everything
-                d_cbase.download(p_cbase.p, N);
+                d_cbase.download(p_cbase.p, N_true);
                 NP2_CUDA(cudaStreamSynchronize(s));
-                d2h += N;
+                n_sync++;
+                d2h += N_true;
             }
         }
         // patched view, regions in ascending position (q = nreg - 1 - r)
         pc.reset(nreg);
         pc.cbase = p_cbase.p;
-        pc.N = N;
+        pc.N = N_true;
         {
             uint64_t rb = 0;
             for (uint32_t r = 0; r < nreg; r++) {
@@ -1788,6 +1810,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             timer.end(h);
             d_rk.download(ks.data(), ns);
             NP2_CUDA(cudaStreamSynchronize(s));
+            n_sync++;
             h2d += ru.pool.size() + (ns + 1) * 8;
             d2h += ns * 2;
             n_probes += ru.pool.size();
@@ -1828,6 +1851,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
             d_ch_off.upload(ch_off.data(), nc);
             seed_scatter(nc, d_ch_r.p, d_ch_off.p, d_ch_len.p, d_r_seed_off.p, d_r_seed_len.p, s);
             NP2_CUDA(cudaStreamSynchronize(s));  // the host vectors above are pageable: finish before they go
+            n_sync++;
             h2d += (uint64_t)nc * 16;
         }
     } else {
@@ -1843,25 +1867,25 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         }
         for (uint32_t q = 0; q < nreg; q++) total_shift += (long long)pc.seed[q].len - (long long)(pc.b[q] - pc.a[q]);
     }
-    const uint64_t out_n = (uint64_t)((long long)N + total_shift);
+    const uint64_t out_n = (uint64_t)((long long)N_true + total_shift);
     DBuf<uint8_t> d_out;
     d_out.alloc(out_n + 1, s);
     res_base.resize(std::max<uint64_t>(out_n, 1));
     res_base.n = out_n;
     h = timer.begin("assemble", 3);
-    assemble_sizes(ad, s);
-    NP2_CUDA(cudaMemsetAsync(d_q_delta.p + nreg, 0, 8, s));
-    scan(d_q_delta.p, d_q_shift.p, (int)nreg + 1);
-    assemble_final(ad, d_out.p, s);
+    assemble_sizes(ad, nreg, s);
+    region_scan_i64(d_q_delta.p, d_q_shift.p, nreg, -1, cd, sp, s);
+    assemble_final(ad, d_out.p, nreg, s);
     timer.end(h);
     timer.hend("host:assemble_prep");
     d_out.download(res_base.p, out_n);
     NP2_CUDA(cudaStreamSynchronize(s));
+    n_sync++;
     d2h += out_n;
     // FASTA header span (main.rs:627-632)
     const size_t nview = pc.a.size();  // the sparse view always holds the first and the last region
     res_first = (pc.a[0] == 0) ? pc.start[0] : edge_pos[0];
-    res_last = (pc.b[nview - 1] == N) ? pc.start[nview - 1] : edge_pos[1];
+    res_last = (pc.b[nview - 1] == N_true) ? pc.start[nview - 1] : edge_pos[1];
     res_pos_valid = false;
     res_sparse = sparse_view;
     if (sparse_view) {  // positions are produced on request from the device copies (np2_job_get_consensus)
@@ -1893,6 +1917,7 @@ void np2_job::run(int32_t dump_it) {
     const unsigned long long launches0 = launch_counter();
     n_launch = 0;
     n_probes = 0;
+    n_sync = 0;
     memset(stats, 0, sizeof stats);
     dm_dropped.clear();
     dm_msa_off.clear();
@@ -1924,6 +1949,14 @@ void np2_job::run(int32_t dump_it) {
     const uint32_t n = R.n_reads;
     sc->arena.reset(s);
     ArenaScope arena_scope(&sc->arena);
+    if (!sc->d_counts) NP2_CUDA(cudaMalloc((void **)&sc->d_counts, sizeof(CountsHost)));
+    sc->p_counts.resize(sizeof(CountsHost) + 16);
+    hc = reinterpret_cast<CountsHost *>(sc->p_counts.p);
+    cd.c = sc->d_counts;
+    cd.q = reinterpret_cast<unsigned long long *>(sc->d_counts + C_COUNT);
+    // tickets + tile descriptors of one pass: ~10 position-sized scans, a few record- and region-sized ones
+    sc->scan_pool.reserve(12 * ((size_t)L / kScanTile + 2) + 4 * ((size_t)ing.total_cols / 8 / kScanTile + 2) + 8192, s);
+    sc->scan_pool.begin(s);
     const int h_total = timer.begin("total", 0);
     DBuf<int> d_bad;
     d_bad.alloc(1, s);
@@ -1948,6 +1981,7 @@ void np2_job::run(int32_t dump_it) {
         d_n.download(h_n.data(), n);
     }
     NP2_CUDA(cudaStreamSynchronize(s));
+    n_sync++;
     d2h += (uint64_t)n * 12;
     if (bad_ref) throw np2::Error(NP2_ERR_FORMAT, "contig holds a byte the reference cannot index (>= 128 or '-')");
     timer.hbegin();
@@ -1966,12 +2000,11 @@ void np2_job::run(int32_t dump_it) {
         d_as_pos.upload(h_as_pos.data(), na);
         d_as_te.upload(h_as_te.data(), na);
         geno_pair_windows(d_as_pos.p, d_as_te.p, na, d_W.p, s);
-        DBuf<uint8_t> d_tmpw;
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, d_W.p, d_pair_off.p, (int)na + 1, s);
-        d_tmpw.alloc(tb, s);
-        cub::DeviceScan::ExclusiveSum(d_tmpw.p, tb, d_W.p, d_pair_off.p, (int)na + 1, s);
+        geno_pair_window_offsets(d_W.p, d_pair_off.p, na, sc->scan_pool, s);
+        NP2_CUDA(cudaMemcpyAsync(&hc->q[0], d_pair_off.p + na, 8, cudaMemcpyDeviceToHost, s));
         NP2_CUDA(cudaStreamSynchronize(s));  // the uploads above come from pageable vectors
+        n_sync++;
+        pair_slots = hc->q[0];
     }
     max_span = 0;
     for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
@@ -2015,6 +2048,7 @@ void np2_job::run(int32_t dump_it) {
     n_launch = launch_counter() - launches0;
     NP2_CUDA(cudaStreamSynchronize(s));
     timer.collect();
+    hc = nullptr;
 }
 
 /* ================================================================= C ABI */
@@ -2683,7 +2717,13 @@ void np2_job_get_traffic(np2_job *j, uint64_t *h2d_bytes, uint64_t *d2h_bytes, u
     if (n_probes) *n_probes = j->n_probes;
 }
 
-void np2_job_get_stats(np2_job *j, uint64_t out[8]) { memcpy(out, j->stats, sizeof j->stats); }
+void np2_job_get_stats(np2_job *j, uint64_t out[12]) {
+    memcpy(out, j->stats, sizeof j->stats);
+    out[8] = j->n_spec_ok;
+    out[9] = j->n_respec;
+    out[10] = j->n_sync;
+    out[11] = 0;
+}
 
 int np2_debug_phase(const uint64_t *keys, const int64_t *vals, uint64_t n_edges, uint32_t model, uint32_t use_all_reads,
                     uint32_t *dropped, uint64_t cap, uint64_t *n_dropped, uint32_t *path) {

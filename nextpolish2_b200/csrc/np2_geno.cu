@@ -9,9 +9,6 @@
 //   k_edges_accum      the pair loop of phase_reads_by_lqseqs (main.rs:953-992) into a dense pair accumulator
 //   k_phase_*          level 0 of the Louvain graph: ref pairs, `dif <= -3`, invalid reads, CSR (main.rs:972-1010)
 //   k_region_seed      fill_order_stat + fill_seed_lqseqs + retain_sort_seqs (main.rs:862-914, 714-726)
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-
 #include "np2_kernels.cuh"
 
 namespace np2 {
@@ -27,11 +24,12 @@ constexpr int kWarpsPerCta = 4;
 // is >= t_s (regions are stored in descending position), 0 if there is none.  Blank reads do not move the cursor.
 __global__ void k_read_cursor(GenoDev g, ReadsDev R, const uint8_t *__restrict__ blank) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R.n_reads) return;
-    uint32_t v = g.nreg - 1;
-    if (!blank[i]) {
+    const uint32_t nreg = g.cnt[C_NREG];
+    if (i >= R.n_reads || g.cnt[C_ABORT]) return;
+    uint32_t v = nreg ? nreg - 1 : 0;
+    if (!blank[i] && nreg) {
         const uint32_t ts = R.t_s[i];
-        uint32_t lo = 0, hi = g.nreg;  // count of regions with start >= ts
+        uint32_t lo = 0, hi = nreg;  // count of regions with start >= ts
         while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
             if (g.start[mid] >= ts) lo = mid + 1;
@@ -44,12 +42,13 @@ __global__ void k_read_cursor(GenoDev g, ReadsDev R, const uint8_t *__restrict__
 // after the prefix-min over reads: j, pair count and decode limit of every read (main.rs:1449-1471)
 __global__ void k_read_ranges(GenoDev g, ReadsDev R, const uint8_t *__restrict__ blank, uint32_t k) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R.n_reads) return;
+    const uint32_t nreg = g.cnt[C_NREG];
+    if (i >= R.n_reads || g.cnt[C_ABORT]) return;
     uint32_t np = 0, j = 0;
-    if (!blank[i]) {
+    if (!blank[i] && nreg) {
         const uint32_t s = g.rd_s[i], ts = R.t_s[i], te = R.t_e[i];
         if (!(g.start[s] < ts || g.end[s] > te)) {
-            uint32_t lo = 0, hi = g.nreg;  // count of regions with end > te
+            uint32_t lo = 0, hi = nreg;  // count of regions with end > te
             while (lo < hi) {
                 uint32_t mid = (lo + hi) >> 1;
                 if (g.end[mid] > te) lo = mid + 1;
@@ -156,7 +155,7 @@ __device__ __forceinline__ ScanOut scan_ref_region(const uint8_t *__restrict__ c
 
 __global__ void k_pair_scan(GenoDev g, ReadsDev R, uint32_t k) {
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= g.n_pairs) return;
+    if (g.cnt[C_ABORT] || pi >= g.cnt[C_NPAIRS]) return;
     uint32_t lo = 0, hi = R.n_reads;  // read owning pair pi: largest i with rd_poff[i] <= pi
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
@@ -179,7 +178,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_select(GenoDev g, 
                                                                      uint32_t k, uint32_t max_span) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= g.nreg) return;
+    if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
     const uint32_t start = g.start[r], end = g.end[r];
     const uint32_t base = r * kMaxCand;
     uint32_t ncand = 0, bytes = 0;
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_cand_write(GenoDev g, Rea
                                                                   uint32_t k) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= g.nreg) return;
+    if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
     const uint32_t n = g.r_ncand[r], base = r * kMaxCand;
     const uint32_t start = g.start[r], end = g.end[r];
     uint64_t run = g.r_pool_off[r];
@@ -302,13 +301,13 @@ __device__ __forceinline__ uint32_t g_probe(const TableDev &t, uint64_t h, uint3
 }
 // candidates no longer than k: the single pre-computed first-k k-mer (main.rs:770-774); INVALID_KMER keeps 0.
 // The (rare) longer ones are queued for the warp-per-candidate kernel below.
-__global__ void k_cand_kscore_short(GenoDev g, TableDev t, uint32_t min_count) {
+__global__ void k_cand_kscore_short(GenoDev g, TableDev t, uint32_t min_count, uint32_t *long_count) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= g.nreg * kMaxCand) return;
+    if (g.cnt[C_ABORT] || s >= g.cnt[C_NREG] * kMaxCand) return;
     const uint32_t r = s / kMaxCand, c = s - r * kMaxCand;
     if (c >= g.r_ncand[r]) return;
     if (g.c_len[s] > t.k) {
-        g.long_list[atomicAdd(g.long_count, 1u)] = s;
+        g.long_list[atomicAdd(long_count, 1u)] = s;
         return;
     }
     const uint64_t h = g.c_kmer[s];
@@ -317,7 +316,8 @@ __global__ void k_cand_kscore_short(GenoDev g, TableDev t, uint32_t min_count) {
 // candidates longer than k: min over all their k-mers (main.rs:760-769); warps stride over the queue, k < 32 here
 __global__ void __launch_bounds__(32 * kWarpsPerCta) k_cand_kscore_long(GenoDev g, TableDev t, uint32_t min_count) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n_long = *g.long_count;
+    if (g.cnt[C_ABORT]) return;
+    const uint32_t n_long = g.cnt[C_NLONG];
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_long; w += nw) {
         const uint32_t s = g.long_list[w];
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_hete(GenoDev g) {
     __shared__ RegionSmem smem[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= g.nreg) return;
+    if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
     RegionSmem &sm = smem[threadIdx.x >> 5];
     const uint32_t n = g.r_ncand[r];
     region_load(g, r, n, lane, sm);
@@ -474,11 +474,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_hete(GenoDev g) {
 // accumulator.  No pair list, no sort: every observation is one 64-bit atomic add, and the non-zero slots read in slot
 // order are the reduced pair records in (x, y) order.
 __global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_accum(GenoDev g, const uint64_t *__restrict__ pair_off,
-                                                                   unsigned long long *__restrict__ acc, int *err) {
+                                                                   unsigned long long *__restrict__ acc, uint32_t *err) {
     __shared__ uint8_t s_valid[kWarpsPerCta][kMaxCand];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= g.nreg) return;
+    if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
     if (!g.r_nedge[r]) return;
     uint8_t *valid = s_valid[threadIdx.x >> 5];
     const uint32_t n = g.r_ncand[r], base = r * kMaxCand;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_edges_accum(GenoDev g, co
             const uint32_t x = min(oa, ob), y = max(oa, ob);
             const uint64_t slot = pair_off[x] + (y - x - 1);
             if (slot >= pair_off[x + 1]) {
-                atomicExch(err, 4);
+                atomicExch(err, 4u);
                 continue;
             }
             atomicAdd(acc + slot, same ? 1ULL : 0xFFFFFFFFULL);
@@ -531,16 +531,23 @@ __global__ void k_pair_windows(const uint32_t *__restrict__ as_pos, const uint32
 void geno_pair_windows(const uint32_t *d_as_pos, const uint32_t *d_as_te, uint32_t na, uint32_t *d_W, cudaStream_t s) {
     NP2_K(k_pair_windows)<<<cdiv(na + 1, 256), 256, 0, s>>>(d_as_pos, d_as_te, na, d_W);
 }
-struct SlotNonZero {
-    const unsigned long long *acc;
-    __device__ __forceinline__ bool operator()(const uint32_t &i) const { return acc[i] != 0; }
-};
+void geno_pair_window_offsets(const uint32_t *d_W, uint64_t *d_pair_off, uint32_t na, ScanPool &pool, cudaStream_t s) {
+    ScanOffsets<uint32_t, uint64_t> f;
+    f.in = d_W;
+    f.out = d_pair_off;
+    f.c_slot = nullptr;
+    f.q_slot = nullptr;
+    f.cap = ~0ULL;
+    f.abort = nullptr;
+    scan_launch(f, nullptr, 0, na, pool, s);
+}
 // selected slots -> pair records (key = x << 32 | y, value) in (x, y) order
-__global__ void k_edges_finish(const uint32_t *__restrict__ sel, uint32_t nu, const uint64_t *__restrict__ pair_off,
-                               uint32_t n_ids, const unsigned long long *__restrict__ acc, uint64_t *__restrict__ key,
+__global__ void k_edges_finish(const uint32_t *__restrict__ sel, const uint32_t *__restrict__ cnt,
+                               const uint64_t *__restrict__ pair_off, uint32_t n_ids,
+                               const unsigned long long *__restrict__ acc, uint64_t *__restrict__ key,
                                long long *__restrict__ val) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nu) return;
+    if (cnt[C_ABORT] || i >= cnt[C_NU]) return;
     const uint32_t slot = sel[i];
     uint32_t lo = 0, hi = n_ids;  // largest x with pair_off[x] <= slot
     while (hi - lo > 1) {
@@ -553,17 +560,17 @@ __global__ void k_edges_finish(const uint32_t *__restrict__ sel, uint32_t nu, co
 }
 
 // fill_seed_lqseqs (main.rs:862-914) with retain_sort_seqs (714-726)
-__global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, int32_t max_indel_len, int *err) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, int32_t max_indel_len, uint32_t *err) {
     __shared__ RegionSmem smem[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= g.nreg) return;
+    if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
     RegionSmem &sm = smem[threadIdx.x >> 5];
     const uint32_t n = g.r_ncand[r];
     region_load(g, r, n, lane, sm);
     if (lane != 0) return;
     if (n == 0 || sm.order[0] != 0) {  // reference would panic: no candidate / "the first lqseq is not ref."
-        atomicExch(err, n == 0 ? 1 : 2);
+        atomicExch(err, n == 0 ? 1u : 2u);
         return;
     }
     region_order_stat(n, sm);
@@ -601,7 +608,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, in
         sm.surv[q] = (uint8_t)p;
     }
     if (ns == 0) {
-        atomicExch(err, 3);
+        atomicExch(err, 3u);
         return;
     }
     uint8_t lable = 0x80 | 0x20;
@@ -621,53 +628,96 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, in
 
 /* ---------------------------------------------------------------- launch wrappers */
 
+namespace {
+inline uint32_t region_grid(uint32_t cap_reg) { return cdiv((uint64_t)cap_reg * 32, 32 * kWarpsPerCta); }
+}  // namespace
 void geno_read_cursor(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, cudaStream_t s) {
     if (R.n_reads) NP2_K(k_read_cursor)<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank);
+}
+void geno_cursor_min(uint32_t *d_rd_s, uint32_t n_reads, const uint32_t *d_abort, ScanPool &pool, cudaStream_t s) {
+    if (n_reads) scan_launch(ScanInclusiveMinU32{d_rd_s}, nullptr, 0, n_reads, pool, s, d_abort);
 }
 void geno_read_ranges(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, uint32_t k, cudaStream_t s) {
     if (R.n_reads) NP2_K(k_read_ranges)<<<cdiv(R.n_reads, 256), 256, 0, s>>>(g, R, d_blank, k);
 }
-void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, cudaStream_t s) {
-    if (g.n_pairs) NP2_K(k_pair_scan)<<<cdiv(g.n_pairs, 128), 128, 0, s>>>(g, R, k);
+void geno_pair_offsets(GenoDev g, uint32_t n_reads, uint32_t cap_pairs, CountsDev cd, ScanPool &pool, cudaStream_t s) {
+    ScanOffsets<uint32_t, uint32_t> f;
+    f.in = g.rd_np;
+    f.out = g.rd_poff;
+    f.c_slot = cd.c + C_NPAIRS;
+    f.q_slot = nullptr;
+    f.cap = cap_pairs;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, nullptr, 0, n_reads, pool, s, cd.c + C_ABORT);
+}
+void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, uint32_t cap_pairs, cudaStream_t s) {
+    if (cap_pairs) NP2_K(k_pair_scan)<<<cdiv(cap_pairs, 128), 128, 0, s>>>(g, R, k);
 }
 void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                        uint32_t k, uint32_t max_span, cudaStream_t s) {
-    NP2_K(k_region_select)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_blank, d_code, L,
-                                                                                               k, max_span);
+                        uint32_t k, uint32_t max_span, uint32_t cap_reg, cudaStream_t s) {
+    if (cap_reg) NP2_K(k_region_select)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, R, d_blank, d_code, L, k, max_span);
 }
-void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s) {
-    NP2_K(k_cand_write)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, d_code, L, k);
+void geno_pool_offsets(GenoDev g, uint32_t cap_reg, unsigned long long cap_pool, CountsDev cd, ScanPool &pool,
+                       cudaStream_t s) {
+    ScanOffsets<uint32_t, uint64_t> f;  // 64-bit offsets out of 32-bit per-region byte counts
+    f.in = g.r_bytes;
+    f.out = g.r_pool_off;
+    f.c_slot = nullptr;
+    f.q_slot = cd.q + Q_POOL;
+    f.cap = cap_pool;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, cd.c + C_NREG, 0, cap_reg, pool, s, cd.c + C_ABORT);
 }
-void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s) {
-    const uint64_t slots = (uint64_t)g.nreg * kMaxCand;
-    cudaMemsetAsync(g.long_count, 0, 4, s);
-    NP2_K(k_cand_kscore_short)<<<cdiv(slots, 256), 256, 0, s>>>(g, t, min_count);
+void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, uint32_t cap_reg,
+                     cudaStream_t s) {
+    if (cap_reg) NP2_K(k_cand_write)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, R, d_code, L, k);
+}
+void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, uint32_t cap_reg, CountsDev cd, cudaStream_t s) {
+    if (!cap_reg) return;
+    const uint64_t slots = (uint64_t)cap_reg * kMaxCand;
+    NP2_K(k_cand_kscore_short)<<<cdiv(slots, 256), 256, 0, s>>>(g, t, min_count, cd.c + C_NLONG);
     NP2_K(k_cand_kscore_long)<<<148 * 4, 32 * kWarpsPerCta, 0, s>>>(g, t, min_count);
 }
-void geno_region_hete(GenoDev g, cudaStream_t s) {
-    NP2_K(k_region_hete)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g);
+void geno_region_hete(GenoDev g, uint32_t cap_reg, cudaStream_t s) {
+    if (cap_reg) NP2_K(k_region_hete)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g);
 }
-void geno_edges_accum(GenoDev g, const uint64_t *d_pair_off, unsigned long long *d_acc, int *d_err, cudaStream_t s) {
-    NP2_K(k_edges_accum)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, d_pair_off, d_acc, d_err);
+void geno_edge_offsets(GenoDev g, uint32_t cap_reg, CountsDev cd, ScanPool &pool, cudaStream_t s) {
+    ScanOffsets<uint32_t, uint64_t> f;
+    f.in = g.r_nedge;
+    f.out = g.r_edge_off;
+    f.c_slot = nullptr;
+    f.q_slot = cd.q + Q_EDGES;
+    f.cap = ~0ULL;
+    f.abort = nullptr;
+    scan_launch(f, cd.c + C_NREG, 0, cap_reg, pool, s, cd.c + C_ABORT);
 }
-// non-zero slots in slot order; *d_nu = how many
-void geno_edges_select(const unsigned long long *d_acc, uint32_t n_slots, uint32_t *d_sel, uint32_t *d_nu, void *d_tmp,
-                       size_t &tmp_bytes, cudaStream_t s) {
-    cub::CountingInputIterator<uint32_t> it(0);
-    cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_sel, d_nu, (int)n_slots, SlotNonZero{d_acc}, s);
+void geno_edges_accum(GenoDev g, const uint64_t *d_pair_off, unsigned long long *d_acc, uint32_t cap_reg, CountsDev cd,
+                      cudaStream_t s) {
+    if (cap_reg) NP2_K(k_edges_accum)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, d_pair_off, d_acc, cd.c + C_PERR);
 }
-void geno_edges_finish(const uint32_t *d_sel, uint32_t nu, const uint64_t *d_pair_off, uint32_t n_ids,
-                       const unsigned long long *d_acc, uint64_t *d_key, long long *d_val, cudaStream_t s) {
-    if (nu) NP2_K(k_edges_finish)<<<cdiv(nu, 256), 256, 0, s>>>(d_sel, nu, d_pair_off, n_ids, d_acc, d_key, d_val);
+// non-zero slots in slot order
+void geno_edges_select(const unsigned long long *d_acc, uint32_t n_slots, uint32_t *d_sel, uint32_t cap_nu, CountsDev cd,
+                       ScanPool &pool, cudaStream_t s) {
+    ScanSelect<PredNonZeroU64> f;
+    f.pred = PredNonZeroU64{d_acc};
+    f.out = d_sel;
+    f.count = cd.c + C_NU;
+    f.cap = cap_nu;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, nullptr, 0, n_slots, pool, s, cd.c + C_ABORT);
+}
+void geno_edges_finish(const uint32_t *d_sel, uint32_t cap_nu, const uint64_t *d_pair_off, uint32_t n_ids,
+                       const unsigned long long *d_acc, uint64_t *d_key, long long *d_val, CountsDev cd, cudaStream_t s) {
+    if (cap_nu) NP2_K(k_edges_finish)<<<cdiv(cap_nu, 256), 256, 0, s>>>(d_sel, cd.c, d_pair_off, n_ids, d_acc, d_key, d_val);
 }
 /* ---------------------------------------------------------------- level 0 of the phasing graph (np2_phase.cpp)
  * From the reduced pair records (key = a << 32 | b ascending, a = 0 is the ref read) to what the host Louvain starts
  * from: per-read flags, and the adjacency in CSR form with the `dif <= -3` override applied and the reads that
  * disagree with the ref read removed (main.rs:972-1010). */
-__global__ void k_phase_ref(const uint64_t *__restrict__ key, const long long *__restrict__ val, uint32_t nu, PhaseDev p,
-                            int asref, int use_all) {
+__global__ void k_phase_ref(const uint64_t *__restrict__ key, const long long *__restrict__ val,
+                            const uint32_t *__restrict__ cnt, PhaseDev p, int asref, int use_all) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nu) return;
+    if (cnt[C_ABORT] || e >= cnt[C_NU]) return;
     const uint64_t k = key[e];
     if (k >> 32) return;
     const uint32_t b = (uint32_t)k;
@@ -679,15 +729,17 @@ __global__ void k_phase_ref(const uint64_t *__restrict__ key, const long long *_
     }
     if (ndif > 0 && !use_all) p.bad_v[b] = 1;
 }
-__global__ void k_phase_expand(const uint64_t *__restrict__ key, const long long *__restrict__ val, uint32_t nu, PhaseDev p,
-                               int use_all, uint32_t id_bits, uint64_t *__restrict__ dkey, float *__restrict__ dw) {
+__global__ void k_phase_expand(const uint64_t *__restrict__ key, const long long *__restrict__ val,
+                               const uint32_t *__restrict__ cnt, uint32_t cap_nu, PhaseDev p, int use_all, uint32_t id_bits,
+                               uint64_t *__restrict__ dkey, float *__restrict__ dw) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nu) return;
-    const uint64_t k = key[e];
+    if (cnt[C_ABORT] || e >= cap_nu) return;
+    const bool real = e < cnt[C_NU];  // the tail up to the capacity is filled with sentinels
+    const uint64_t k = real ? key[e] : 0;
     const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
     uint64_t k0 = ~0ULL, k1 = ~0ULL;  // sentinel: sorts behind every edge
     float w = 0.f;
-    if (a != 0) {
+    if (real && a != 0) {
         const bool ba = !use_all && p.bad_v[a], bb = !use_all && p.bad_v[b];
         if (!ba) p.has[a] = 1;
         if (!bb) p.has[b] = 1;
@@ -706,9 +758,9 @@ __global__ void k_phase_expand(const uint64_t *__restrict__ key, const long long
 }
 // sorted directed edges -> CSR: aoff[v] = first edge whose source is >= v (aoff has n + 1 entries, zeroed before)
 __global__ void k_phase_csr(const uint64_t *__restrict__ dkey, uint32_t n2, uint32_t id_bits, uint32_t n,
-                            uint32_t *__restrict__ aoff, uint32_t *__restrict__ ato) {
+                            uint32_t *__restrict__ aoff, uint32_t *__restrict__ ato, const uint32_t *__restrict__ d_abort) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n2) return;
+    if (*d_abort || i >= n2) return;
     auto src_of = [&](uint64_t k) { return (k >> (2 * id_bits)) ? n : (uint32_t)(k >> id_bits); };
     const uint64_t k = dkey[i];
     const uint32_t s = src_of(k);
@@ -718,21 +770,21 @@ __global__ void k_phase_csr(const uint64_t *__restrict__ dkey, uint32_t n2, uint
     if (i == n2 - 1 && s < n)
         for (uint32_t v = s + 1; v <= n; v++) aoff[v] = n2;
 }
-void phase_ref(const uint64_t *d_key, const long long *d_val, uint32_t nu, PhaseDev p, bool asref, bool use_all,
-               cudaStream_t s) {
-    if (nu) NP2_K(k_phase_ref)<<<cdiv(nu, 256), 256, 0, s>>>(d_key, d_val, nu, p, asref, use_all);
+void phase_ref(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool asref,
+               bool use_all, cudaStream_t s) {
+    if (cap_nu) NP2_K(k_phase_ref)<<<cdiv(cap_nu, 256), 256, 0, s>>>(d_key, d_val, cd.c, p, asref, use_all);
 }
-void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t nu, PhaseDev p, bool use_all, uint32_t id_bits,
-                  uint64_t *d_dkey, float *d_dw, cudaStream_t s) {
-    if (nu) NP2_K(k_phase_expand)<<<cdiv(nu, 256), 256, 0, s>>>(d_key, d_val, nu, p, use_all, id_bits, d_dkey, d_dw);
+void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool use_all,
+                  uint32_t id_bits, uint64_t *d_dkey, float *d_dw, cudaStream_t s) {
+    if (cap_nu) NP2_K(k_phase_expand)<<<cdiv(cap_nu, 256), 256, 0, s>>>(d_key, d_val, cd.c, cap_nu, p, use_all, id_bits, d_dkey, d_dw);
 }
 void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n, uint32_t *d_aoff, uint32_t *d_ato,
-               cudaStream_t s) {
-    if (n2) NP2_K(k_phase_csr)<<<cdiv(n2, 256), 256, 0, s>>>(d_dkey, n2, id_bits, n, d_aoff, d_ato);
+               const uint32_t *d_abort, cudaStream_t s) {
+    if (n2) NP2_K(k_phase_csr)<<<cdiv(n2, 256), 256, 0, s>>>(d_dkey, n2, id_bits, n, d_aoff, d_ato, d_abort);
 }
 
-void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s) {
-    NP2_K(k_region_seed)<<<cdiv((uint64_t)g.nreg * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, d_err);
+void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, cudaStream_t s) {
+    if (cap_reg) NP2_K(k_region_seed)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, cd.c + C_GERR);
 }
 
 }  // namespace np2

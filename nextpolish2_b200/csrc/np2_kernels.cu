@@ -815,14 +815,23 @@ void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cu
 
 __global__ void k_cover_diff(ReadsDev R, const uint8_t *__restrict__ blank, int32_t *diff) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == R.n_reads) atomicAdd(&diff[0], 1);  // the ref read spans [0, L - 1] (main.rs:1732-1739)
     if (r >= R.n_reads || blank[r] || R.n[r] == 0) return;
     atomicAdd(&diff[R.t_s[r]], 1);
     atomicAdd(&diff[R.t_e[r] + 1], -1);
 }
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s) {
-    if (!r.n_reads) return;
-    NP2_K(k_cover_diff)<<<cdiv(r.n_reads, kThreads), kThreads, 0, s>>>(r, d_blank, d_diff);
+    NP2_K(k_cover_diff)<<<cdiv(r.n_reads + 1, kThreads), kThreads, 0, s>>>(r, d_blank, d_diff);
 }
+void cover_scan(int32_t *d_cover, uint32_t n, ScanPool &pool, cudaStream_t s) {
+    scan_launch(ScanInclusiveI32{{}, d_cover}, nullptr, 0, n, pool, s);
+}
+__global__ void k_counts_init(CountsDev cd) {
+    const uint32_t i = threadIdx.x;
+    if (i < C_COUNT) cd.c[i] = i == C_NREC ? 2u : 0u;
+    if (i < Q_COUNT) cd.q[i] = 0;
+}
+void counts_init(CountsDev cd, cudaStream_t s) { NP2_K(k_counts_init)<<<1, 32, 0, s>>>(cd); }
 
 __device__ __forceinline__ uint32_t nib_at(const uint8_t *__restrict__ nib, uint32_t o) {
     uint32_t b = nib[o >> 1];
@@ -1076,10 +1085,11 @@ __global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32
     }
 }
 void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                 const uint32_t *d_refpk, uint32_t L, unsigned int *d_n_rec, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
+                 const uint32_t *d_refpk, uint32_t L, CountsDev cd, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
                  cudaStream_t s) {
     // refpk holds L / 8 + 8 words (ref_codes): a clamped word index k <= L / 8 + 3 keeps k + 4 inside
     const uint32_t pk_last = L / 8 + 3, grid = max(1u, pileup_ctas(n_blocks));
+    unsigned int *d_n_rec = cd.c + C_NREC;
     const char *e = getenv("NP2_PILE_BATCH");
     const int batch = e ? atoi(e) : kPileBatchDefault;
     if (batch == 0)
@@ -1092,54 +1102,84 @@ void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, c
         NP2_K(k_pileup_emit<4>)<<<grid, kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk, pk_last, d_n_rec, cap,
                                                              d_key, d_read);
 }
+__global__ void k_pileup_pad(uint64_t *__restrict__ key, uint32_t cap, CountsDev cd) {
+    const uint32_t n = cd.c[C_NREC];
+    if (n > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(cd.c + C_ABORT, 1u);
+        return;
+    }
+    for (uint64_t i = (uint64_t)n + blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+        key[i] = ~0ULL;
+}
+void pileup_pad(uint64_t *d_key, uint32_t cap, CountsDev cd, cudaStream_t s) {
+    NP2_K(k_pileup_pad)<<<148 * 2, kThreads, 0, s>>>(d_key, cap, cd);
+}
 
-__global__ void k_mark_heads(const uint64_t *__restrict__ key, uint32_t n, uint32_t *__restrict__ head) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+// Sorted records -> groups in ONE scan: an element is 1 when its key differs from the one before (a head); the
+// exclusive prefix of a head is its group index, and the head's thread fills the group (position, 3-mer, first read =
+// minimum read over the records of the group, which lie right behind it).
+struct ScanGroups : ScanSumBase {
+    const uint64_t *key;
+    const uint32_t *rd;
+    const uint32_t *cnt;  // C_NREC
+    uint32_t *gstart, *gpos;
+    MsaDev m;
+    uint32_t cap_g;
+    uint32_t *count, *abort;
+    __device__ unsigned long long load(uint32_t i) const { return (i == 0 || key[i] != key[i - 1]) ? 1ULL : 0ULL; }
+    __device__ void store(uint32_t i, unsigned long long ex, unsigned long long in) const {
+        if (in == ex || ex >= cap_g) return;
+        const uint32_t g = (uint32_t)ex, n = cnt[C_NREC];
+        const uint64_t k = key[i];
+        gstart[g] = i;
+        gpos[g] = (uint32_t)(k >> 32);
+        m.g_bases[g] = (uint16_t)(k >> 16);
+        m.g_delta[g] = (uint16_t)k;
+        uint32_t first = rd[i];
+        for (uint32_t j = i + 1; j < n && key[j] == k; j++) first = min(first, rd[j]);
+        m.g_first[g] = first;
+    }
+    __device__ void total(unsigned long long t, uint32_t) const {
+        *count = (uint32_t)t;
+        if (t > cap_g) atomicExch(abort, 1u);
+    }
+};
+void groups_build(const uint64_t *d_key, const uint32_t *d_read, uint32_t cap_rec, uint32_t cap_g, uint32_t *d_gstart,
+                  uint32_t *d_gpos, MsaDev m, CountsDev cd, ScanPool &pool, cudaStream_t s) {
+    ScanGroups f;
+    f.key = d_key;
+    f.rd = d_read;
+    f.cnt = cd.c;
+    f.gstart = d_gstart;
+    f.gpos = d_gpos;
+    f.m = m;
+    f.cap_g = cap_g;
+    f.count = cd.c + C_G;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, cd.c + C_NREC, 0, cap_rec, pool, s, cd.c + C_ABORT);
 }
-void mark_heads(const uint64_t *d_key, uint32_t n, uint32_t *d_head, cudaStream_t s) {
-    NP2_K(k_mark_heads)<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, n, d_head);
-}
-__global__ void k_groups_fill(const uint64_t *__restrict__ key, const uint32_t *__restrict__ rd,
-                              const uint32_t *__restrict__ head, const uint32_t *__restrict__ gidx, uint32_t n,
-                              uint32_t *__restrict__ gstart, uint32_t *__restrict__ gpos, MsaDev m) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !head[i]) return;
-    uint32_t g = gidx[i];
-    uint64_t k = key[i];
-    gstart[g] = i;
-    gpos[g] = (uint32_t)(k >> 32);
-    m.g_bases[g] = (uint16_t)(k >> 16);
-    m.g_delta[g] = (uint16_t)k;
-    uint32_t first = rd[i];  // first read that carried this 3-mer = minimum over its records
-    for (uint32_t j = i + 1; j < n && key[j] == k; j++) first = min(first, rd[j]);
-    m.g_first[g] = first;
-}
-void groups_fill(const uint64_t *d_key, const uint32_t *d_read, const uint32_t *d_head, const uint32_t *d_gidx,
-                 uint32_t n, uint32_t G, uint32_t *d_gstart, uint32_t *d_gpos, MsaDev m, cudaStream_t s) {
-    NP2_K(k_groups_fill)<<<cdiv(n, kThreads), kThreads, 0, s>>>(d_key, d_read, d_head, d_gidx, n, d_gstart, d_gpos, m);
-}
-__global__ void k_groups_finish(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ gpos, uint32_t n,
-                                MsaDev m) {
+__global__ void k_groups_finish(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ gpos, MsaDev m) {
+    if (m.cnt[C_ABORT]) return;
+    const uint32_t G = m.cnt[C_G], n = m.cnt[C_NREC];
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= m.G) return;
-    m.g_count[g] = (g + 1 < m.G ? gstart[g + 1] : n) - gstart[g];
+    if (g >= G) return;
+    m.g_count[g] = (g + 1 < G ? gstart[g + 1] : n) - gstart[g];
     uint32_t p = gpos[g];
     uint32_t from = g ? gpos[g - 1] + 1 : 0;
     for (uint32_t q = from; q <= p; q++) m.sp_off[q] = g;
-    if (g + 1 == m.G)
-        for (uint32_t q = p + 1; q <= m.L; q++) m.sp_off[q] = m.G;
+    if (g + 1 == G)
+        for (uint32_t q = p + 1; q <= m.L; q++) m.sp_off[q] = G;
 }
-void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t n, MsaDev m, cudaStream_t s) {
-    if (!m.G) return;
-    NP2_K(k_groups_finish)<<<cdiv(m.G, kThreads), kThreads, 0, s>>>(d_gstart, d_gpos, n, m);
+void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t cap_g, MsaDev m, cudaStream_t s) {
+    if (!cap_g) return;
+    NP2_K(k_groups_finish)<<<cdiv(cap_g, kThreads), kThreads, 0, s>>>(d_gstart, d_gpos, m);
 }
 
 // Per position: order the sparse 3-mers like Msa::sort after first-seen pushes (main.rs:193-229): by b3.delta,
 // then by the first read that carried them; derive the reference 3-mer's count and the articulation flag.
 __global__ void k_pos_finalize(MsaDev m, uint32_t *__restrict__ n_emit) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= m.L) return;
+    if (p >= m.L || m.cnt[C_ABORT]) return;
     const uint32_t lo = m.sp_off[p], hi = m.sp_off[p + 1];
     uint32_t sum0 = 0;
     for (uint32_t i = lo; i < hi; i++) {
@@ -1175,14 +1215,25 @@ void pos_finalize(MsaDev m, uint32_t *d_n_emit, cudaStream_t s) {
 
 /* =============================================================== K3: DP over runs + consensus */
 
-__global__ void k_run_flags(const uint8_t *__restrict__ multi, uint32_t L, uint8_t *__restrict__ flag) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < L) flag[p] = multi[p] && (p == 0 || !multi[p - 1]);
-}
-void run_flags(const uint8_t *d_multi, uint32_t L, uint8_t *d_flag, cudaStream_t s) {
-    NP2_K(k_run_flags)<<<cdiv(L, kThreads), kThreads, 0, s>>>(d_multi, L, d_flag);
+struct PredRunStart {
+    const uint8_t *multi;
+    __device__ bool operator()(uint32_t p) const { return multi[p] && (p == 0 || !multi[p - 1]); }
+};
+void runs_select(const uint8_t *d_multi, uint32_t L, uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, ScanPool &pool,
+                 cudaStream_t s) {
+    ScanSelect<PredRunStart> f;
+    f.pred = PredRunStart{d_multi};
+    f.out = d_run_start;
+    f.count = cd.c + C_NRUNS;
+    f.cap = cap_runs;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, nullptr, 0, L, pool, s, cd.c + C_ABORT);
 }
 
+struct DpOut {
+    uint32_t *best_last = nullptr;   // entry index chosen at p = L - 1 when L - 1 is inside a run
+    unsigned long long *score_total = nullptr;
+};
 struct Entry {
     uint16_t bases, delta;
     uint32_t count;
@@ -1210,9 +1261,9 @@ constexpr int64_t kDead = INT64_MIN >> 1;  // main.rs:1661
 
 // One thread per run of multi-entry positions [s, e); e is the next articulation position (single entry,
 // every path passes through it), so scores can be kept relative to the articulation before s.
-__global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, uint32_t n_runs, DpOut o) {
+__global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, DpOut o) {
     uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ri >= n_runs) return;
+    if (m.cnt[C_ABORT] || ri >= m.cnt[C_NRUNS]) return;
     const uint32_t s = run_start[ri], L = m.L;
     int64_t best = 0;
     uint32_t best_idx = 0;
@@ -1267,20 +1318,28 @@ __global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, uint
     }
     *o.best_last = best_idx;  // the run reached the contig end
 }
-void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, cudaStream_t s) {
-    if (!n_runs) return;
-    NP2_K(k_dp_runs)<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o);
+static DpOut dp_out(CountsDev cd) {
+    DpOut o;
+    o.best_last = cd.c + C_BESTLAST;
+    o.score_total = cd.q + Q_TOTAL;
+    return o;
+}
+void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, cudaStream_t s) {
+    if (!cap_runs) return;
+    NP2_K(k_dp_runs)<<<cdiv(cap_runs, 64), 64, 0, s>>>(m, d_run_start, dp_out(cd));
 }
 
 // Backtrack of one run (main.rs:1572-1634 without the LQ state machine).  WRITE = false: count emitted
 // bases per position; WRITE = true: write them at the scanned offsets (ascending order == reversed vec).
 template <bool WRITE>
-__global__ void k_emit_runs(MsaDev m, const uint32_t *__restrict__ run_start, uint32_t n_runs, DpOut o,
+__global__ void k_emit_runs(MsaDev m, const uint32_t *__restrict__ run_start, DpOut o,
                             uint32_t *__restrict__ n_emit, const uint32_t *__restrict__ emit_off,
                             uint32_t *__restrict__ out_pos, uint8_t *__restrict__ out_base,
                             uint8_t *__restrict__ out_flags) {
     uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
     long long sum = 0;
+    if (m.cnt[C_ABORT]) return;
+    const uint32_t n_runs = m.cnt[C_NRUNS];
     if (ri < n_runs) {
         const uint32_t s = run_start[ri], L = m.L;
         uint32_t e = s;
@@ -1337,6 +1396,7 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(MsaDev m, const uint3
     __shared__ long long wsum[kThreads / 32];
     long long sum = 0;
     const uint32_t base = blockIdx.x * (kThreads * kEmitPerThread) + threadIdx.x;
+    if (m.cnt[C_ABORT]) return;
 #pragma unroll
     for (int x = 0; x < kEmitPerThread; x++) {
         const uint32_t p = base + x * kThreads;
@@ -1362,18 +1422,40 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(MsaDev m, const uint3
         if (threadIdx.x == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
     }
 }
-void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, uint32_t *d_n_emit,
+void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, uint32_t *d_n_emit,
                      cudaStream_t s) {
-    if (!n_runs) return;
-    NP2_K(k_emit_runs<false>)<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, d_n_emit, nullptr, nullptr, nullptr,
-                                                       nullptr);
+    if (!cap_runs) return;
+    NP2_K(k_emit_runs<false>)<<<cdiv(cap_runs, 64), 64, 0, s>>>(m, d_run_start, dp_out(cd), d_n_emit, nullptr, nullptr, nullptr,
+                                                        nullptr);
 }
-void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, const uint32_t *d_n_emit,
+void emit_offsets(const uint32_t *d_n_emit, uint32_t *d_emit_off, uint32_t L, uint32_t cap_n, CountsDev cd, ScanPool &pool,
+                  cudaStream_t s) {
+    ScanOffsets<uint32_t, uint32_t> f;
+    f.in = d_n_emit;
+    f.out = d_emit_off;
+    f.c_slot = cd.c + C_N;
+    f.q_slot = nullptr;
+    f.cap = cap_n;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, nullptr, 0, L, pool, s, cd.c + C_ABORT);
+}
+void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, const uint32_t *d_n_emit,
                 const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s) {
-    NP2_K(k_emit_singles)<<<cdiv(m.L, kThreads * kEmitPerThread), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags, o);
-    if (n_runs)
-        NP2_K(k_emit_runs<true>)<<<cdiv(n_runs, 64), 64, 0, s>>>(m, d_run_start, n_runs, o, const_cast<uint32_t *>(d_n_emit),
-                                                          d_emit_off, d_pos, d_base, d_flags);
+    NP2_K(k_emit_singles)<<<cdiv(m.L, kThreads * kEmitPerThread), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags,
+                                                                              dp_out(cd));
+    if (cap_runs)
+        NP2_K(k_emit_runs<true>)<<<cdiv(cap_runs, 64), 64, 0, s>>>(m, d_run_start, dp_out(cd), const_cast<uint32_t *>(d_n_emit),
+                                                           d_emit_off, d_pos, d_base, d_flags);
+}
+void events_select(const uint8_t *d_cflags, uint32_t cap_n, uint32_t *d_events, uint32_t cap_ev, CountsDev cd,
+                   ScanPool &pool, cudaStream_t s) {
+    ScanSelect<PredFlagU8> f;
+    f.pred = PredFlagU8{d_cflags};
+    f.out = d_events;
+    f.count = cd.c + C_NEV;
+    f.cap = cap_ev;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, cd.c + C_N, 0, cap_n, pool, s, cd.c + C_ABORT);
 }
 
 }  // namespace np2

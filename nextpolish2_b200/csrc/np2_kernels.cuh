@@ -1,8 +1,56 @@
 // np2_kernels.cuh — launch wrappers of the sm_100a kernels (definitions in np2_kernels.cu).
 #pragma once
 #include "np2_common.cuh"
+#include "np2_scan.cuh"
 
 namespace np2 {
+
+/* ------------------------------------------------------------------ device-resident counts
+ * Every size that one kernel produces and the next ones consume (records, groups, runs, consensus bases, events,
+ * regions, pairs ...) lives in ONE small device block; kernels read their bounds from it and are launched over a
+ * host-side CAPACITY.  The host therefore does not have to synchronise to size the next launch: capacities come from
+ * the previous run (or are read back one by one on a first, "exact" run), the block is fetched once where the host
+ * needs data anyway, and a producer that finds more than its capacity sets C_ABORT, on which every later kernel
+ * returns at once (the host then repeats the pass in exact mode). */
+enum Cnt : int {
+    C_ABORT = 0,  // a count exceeded its capacity: everything after is skipped
+    C_NREC,       // non-reference 3-mer records (starts at 2: the ref read's two head 3-mers)
+    C_G,          // distinct non-reference 3-mers
+    C_NRUNS,      // runs of multi-entry positions
+    C_N,          // DP consensus bases
+    C_NEV,        // consensus bases with qv < 95 or coverage < 2
+    C_NCAND,      // closing events = candidate regions
+    C_NREG,       // LQ regions
+    C_NPAIRS,     // (read, region) pairs
+    C_NLONG,      // candidates longer than k
+    C_NU,         // read pairs with a non-zero agreement weight
+    C_NSUB,       // regions the host looks at in the final phase
+    C_BESTLAST,   // entry chosen at p = L - 1 when the last position is inside a run
+    C_GERR,       // genotype-rule error (reference would panic)
+    C_PERR,       // read pair outside its index window
+    C_NENT,       // survivors of the RECH regions
+    C_COUNT = 32
+};
+enum Cnt64 : int {
+    Q_TOTAL = 0,  // score of the best path (main.rs:1680)
+    Q_POOL,       // bytes of candidate strings
+    Q_EDGES,      // candidate pairs of the heterozygous regions
+    Q_SEEDS,      // bytes of seed strings the host wants
+    Q_RECH,       // bytes of survivor strings
+    Q_WIN,        // bytes of DP-base windows
+    Q_SHIFT,      // total length change of all patches (signed)
+    Q_COUNT = 16
+};
+struct CountsHost {
+    uint32_t c[C_COUNT];
+    unsigned long long q[Q_COUNT];
+};
+// device view: c = 32 x u32, q = 16 x u64 right behind
+struct CountsDev {
+    uint32_t *c = nullptr;
+    unsigned long long *q = nullptr;
+};
+void counts_init(CountsDev cd, cudaStream_t s);  // zero, C_NREC = 2
 
 /* ------------------------------------------------------------------ yak table (K5) */
 constexpr int kBucketSlots = 4;  // 4 x u64 = one 32-byte DRAM sector per probe
@@ -59,17 +107,19 @@ void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cu
 
 /* ------------------------------------------------------------------ K2 pileup */
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);
-// pass 1: per-CTA count of non-reference 3-mers; pass 2: write (key, read) records at the scanned offsets
-// single pass: every CTA reserves its output range with one atomic on *d_n_rec (must start at 2); records beyond
-// `cap` are counted but not written (the caller re-runs with the exact capacity)
+void cover_scan(int32_t *d_cover, uint32_t n, ScanPool &pool, cudaStream_t s);  // in-place inclusive sum
+// single pass: every CTA reserves its output range with one atomic on cd.c[C_NREC] (starts at 2); records beyond
+// `cap` are counted but not written (the count then exceeds the capacity: see pileup_sort)
 void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                 const uint32_t *d_refpk, uint32_t L, unsigned int *d_n_rec, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
+                 const uint32_t *d_refpk, uint32_t L, CountsDev cd, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
                  cudaStream_t s);
 uint32_t pileup_ctas(uint32_t n_blocks);
+// keys [n_rec, cap) = ~0 (they sort behind every record); sets C_ABORT when n_rec > cap
+void pileup_pad(uint64_t *d_key, uint32_t cap, CountsDev cd, cudaStream_t s);
 
 struct MsaDev {
     uint32_t L = 0;
-    uint32_t G = 0;             // sparse groups
+    const uint32_t *cnt = nullptr;  // C_G = sparse groups
     uint32_t *sp_off = nullptr;  // L + 1
     uint16_t *g_bases = nullptr, *g_delta = nullptr;
     uint32_t *g_count = nullptr, *g_first = nullptr, *g_besti = nullptr;
@@ -81,28 +131,32 @@ struct MsaDev {
     uint8_t *multi = nullptr;        // L: more than one entry (or p < 2)
     const uint8_t *code = nullptr;   // ref codes
 };
-void mark_heads(const uint64_t *d_key, uint32_t n, uint32_t *d_head, cudaStream_t s);
-void groups_fill(const uint64_t *d_key, const uint32_t *d_read, const uint32_t *d_head, const uint32_t *d_gidx,
-                 uint32_t n, uint32_t G, uint32_t *d_gstart, uint32_t *d_gpos, MsaDev m, cudaStream_t s);
-void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t n, MsaDev m, cudaStream_t s);
+// sorted records -> groups: heads, their ranks and the per-group fields in one scan (C_G = number of groups)
+void groups_build(const uint64_t *d_key, const uint32_t *d_read, uint32_t cap_rec, uint32_t cap_g, uint32_t *d_gstart,
+                  uint32_t *d_gpos, MsaDev m, CountsDev cd, ScanPool &pool, cudaStream_t s);
+void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t cap_g, MsaDev m, cudaStream_t s);
 void pos_finalize(MsaDev m, uint32_t *d_n_emit, cudaStream_t s);
 
 /* ------------------------------------------------------------------ K3 DP + consensus */
-void run_flags(const uint8_t *d_multi, uint32_t L, uint8_t *d_flag, cudaStream_t s);
-struct DpOut {
-    uint32_t *best_last = nullptr;   // entry index chosen at p = L - 1 when L - 1 is inside a run
-    unsigned long long *score_total = nullptr;
-};
-void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, cudaStream_t s);
-void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, uint32_t *d_n_emit,
+// first positions of the runs of multi-entry positions (C_NRUNS)
+void runs_select(const uint8_t *d_multi, uint32_t L, uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, ScanPool &pool,
+                 cudaStream_t s);
+void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, cudaStream_t s);
+void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, uint32_t *d_n_emit,
                      cudaStream_t s);
-void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t n_runs, DpOut o, const uint32_t *d_n_emit,
+// emit_off = exclusive sum of n_emit (L + 1 entries), C_N = number of consensus bases
+void emit_offsets(const uint32_t *d_n_emit, uint32_t *d_emit_off, uint32_t L, uint32_t cap_n, CountsDev cd, ScanPool &pool,
+                  cudaStream_t s);
+void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, const uint32_t *d_n_emit,
                 const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s);
+// consensus indices with flags != 0, ascending (C_NEV)
+void events_select(const uint8_t *d_cflags, uint32_t cap_n, uint32_t *d_events, uint32_t cap_ev, CountsDev cd,
+                   ScanPool &pool, cudaStream_t s);
 
 /* ------------------------------------------------------------------ per-region pipeline (np2_geno.cu) */
 constexpr int kMaxCand = 60;  // LQSEQ_MAX_CAN_COUNT main.rs:30
 struct GenoDev {
-    uint32_t nreg = 0, n_pairs = 0;
+    const uint32_t *cnt = nullptr;  // C_NREG regions, C_NPAIRS (read, region) pairs
     const uint32_t *start = nullptr, *end = nullptr;  // regions, descending position (reference order)
     // per candidate read
     uint32_t *rd_s = nullptr, *rd_j = nullptr, *rd_np = nullptr, *rd_poff = nullptr;
@@ -116,42 +170,52 @@ struct GenoDev {
     uint16_t *c_kscore = nullptr;
     uint8_t *c_rep = nullptr;
     uint8_t *pool = nullptr;
-    uint32_t *long_list = nullptr, *long_count = nullptr;  // candidates longer than k (scored over all their k-mers)
+    uint32_t *long_list = nullptr;  // candidates longer than k (scored over all their k-mers); count = C_NLONG
     // per region
     uint32_t *r_ncand = nullptr, *r_bytes = nullptr, *r_nedge = nullptr, *r_seed_len = nullptr, *r_nsurv = nullptr;
     uint64_t *r_pool_off = nullptr, *r_edge_off = nullptr, *r_seed_off = nullptr;
     uint8_t *r_lable = nullptr, *r_surv = nullptr;
 };
 void geno_read_cursor(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, cudaStream_t s);
+void geno_cursor_min(uint32_t *d_rd_s, uint32_t n_reads, const uint32_t *d_abort, ScanPool &pool, cudaStream_t s);
 void geno_read_ranges(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, uint32_t k, cudaStream_t s);
-void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, cudaStream_t s);
+void geno_pair_offsets(GenoDev g, uint32_t n_reads, uint32_t cap_pairs, CountsDev cd, ScanPool &pool, cudaStream_t s);
+void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, uint32_t cap_pairs, cudaStream_t s);
 void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                        uint32_t k, uint32_t max_span, cudaStream_t s);
-void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, cudaStream_t s);
-void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, cudaStream_t s);
-void geno_region_hete(GenoDev g, cudaStream_t s);
+                        uint32_t k, uint32_t max_span, uint32_t cap_reg, cudaStream_t s);
+void geno_pool_offsets(GenoDev g, uint32_t cap_reg, unsigned long long cap_pool, CountsDev cd, ScanPool &pool,
+                       cudaStream_t s);
+void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, uint32_t cap_reg,
+                     cudaStream_t s);
+void geno_cand_kscore(GenoDev g, const TableDev &t, uint32_t min_count, uint32_t cap_reg, CountsDev cd, cudaStream_t s);
+void geno_region_hete(GenoDev g, uint32_t cap_reg, cudaStream_t s);
+void geno_edge_offsets(GenoDev g, uint32_t cap_reg, CountsDev cd, ScanPool &pool, cudaStream_t s);
 // pair-accumulator windows (d_W has na + 1 entries, the last one 0) from the alignseqs' record positions and ends
 void geno_pair_windows(const uint32_t *d_as_pos, const uint32_t *d_as_te, uint32_t na, uint32_t *d_W, cudaStream_t s);
-void geno_edges_accum(GenoDev g, const uint64_t *d_pair_off, unsigned long long *d_acc, int *d_err, cudaStream_t s);
-void geno_edges_select(const unsigned long long *d_acc, uint32_t n_slots, uint32_t *d_sel, uint32_t *d_nu, void *d_tmp,
-                       size_t &tmp_bytes, cudaStream_t s);
-void geno_edges_finish(const uint32_t *d_sel, uint32_t nu, const uint64_t *d_pair_off, uint32_t n_ids,
-                       const unsigned long long *d_acc, uint64_t *d_key, long long *d_val, cudaStream_t s);
+void geno_pair_window_offsets(const uint32_t *d_W, uint64_t *d_pair_off, uint32_t na, ScanPool &pool, cudaStream_t s);
+void geno_edges_accum(GenoDev g, const uint64_t *d_pair_off, unsigned long long *d_acc, uint32_t cap_reg, CountsDev cd,
+                      cudaStream_t s);
+// non-zero slots in slot order (C_NU = how many)
+void geno_edges_select(const unsigned long long *d_acc, uint32_t n_slots, uint32_t *d_sel, uint32_t cap_nu, CountsDev cd,
+                       ScanPool &pool, cudaStream_t s);
+void geno_edges_finish(const uint32_t *d_sel, uint32_t cap_nu, const uint64_t *d_pair_off, uint32_t n_ids,
+                       const unsigned long long *d_acc, uint64_t *d_key, long long *d_val, CountsDev cd, cudaStream_t s);
 struct PhaseDev {  // per read order (< n)
     uint8_t *has = nullptr, *bad_v = nullptr, *in_ref = nullptr;
     float *ref_w = nullptr;
 };
-void phase_ref(const uint64_t *d_key, const long long *d_val, uint32_t nu, PhaseDev p, bool asref, bool use_all,
-               cudaStream_t s);
-void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t nu, PhaseDev p, bool use_all, uint32_t id_bits,
-                  uint64_t *d_dkey, float *d_dw, cudaStream_t s);
+void phase_ref(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool asref,
+               bool use_all, cudaStream_t s);
+// directed edges (2 per pair record; non-edges and the tail up to 2 * cap_nu get a sentinel that sorts behind)
+void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool use_all,
+                  uint32_t id_bits, uint64_t *d_dkey, float *d_dw, cudaStream_t s);
 void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n, uint32_t *d_aoff, uint32_t *d_ato,
-               cudaStream_t s);
-void geno_region_seed(GenoDev g, int32_t max_indel_len, int *d_err, cudaStream_t s);
+               const uint32_t *d_abort, cudaStream_t s);
+void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, cudaStream_t s);
 
 /* ------------------------------------------------------------------ regions + assembly (np2_regions.cu) */
 struct RegionDev {
-    uint32_t N = 0, n_ev = 0;
+    const uint32_t *cnt = nullptr;     // C_N, C_NEV, C_NCAND, C_NREG
     const uint32_t *events = nullptr;  // consensus indices with flags != 0, ascending
     const uint8_t *cflags = nullptr, *cbase = nullptr;
     const uint32_t *cpos = nullptr;
@@ -161,12 +225,14 @@ struct RegionDev {
     uint32_t *c_head = nullptr, *c_hrank = nullptr;
     uint32_t *r_start = nullptr, *r_end = nullptr, *r_a = nullptr, *r_b = nullptr;
 };
-void regions_event_close(RegionDev d, cudaStream_t s);
-void regions_make(RegionDev d, uint32_t n_cand, cudaStream_t s);
-void regions_out(RegionDev d, uint32_t n_cand, uint32_t n_heads, cudaStream_t s);
+void regions_event_close(RegionDev d, uint32_t cap_ev, cudaStream_t s);
+void regions_cand_select(RegionDev d, uint32_t cap_ev, uint32_t cap_cand, CountsDev cd, ScanPool &pool, cudaStream_t s);
+void regions_make(RegionDev d, uint32_t cap_cand, cudaStream_t s);
+void regions_rank(RegionDev d, uint32_t cap_cand, uint32_t cap_reg, CountsDev cd, ScanPool &pool, cudaStream_t s);
+void regions_out(RegionDev d, uint32_t cap_cand, cudaStream_t s);
 
 struct AssembleDev {
-    uint32_t nreg = 0, N = 0;
+    const uint32_t *cnt = nullptr;  // C_NREG, C_N
     const uint8_t *cbase = nullptr, *pool = nullptr;
     const uint32_t *r_a = nullptr, *r_b = nullptr, *r_seed_len = nullptr;
     const uint64_t *r_seed_off = nullptr;
@@ -183,24 +249,33 @@ struct SubMeta {  // compact copies for the selected regions, in the order of `s
     uint64_t *seed_off = nullptr, *q_seedoff = nullptr;
     uint8_t *lable = nullptr;
 };
-void near_mark(uint32_t nreg, uint32_t N, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b, uint8_t *d_near,
-               cudaStream_t s);
-void window_sizes(uint32_t nreg, uint32_t N, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b,
+void near_mark(const uint32_t *d_cnt, uint32_t cap_reg, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b,
+               uint8_t *d_near, cudaStream_t s);
+void window_sizes(const uint32_t *d_cnt, uint32_t cap_reg, const uint8_t *d_lable, const uint32_t *d_a, const uint32_t *d_b,
                   uint32_t *d_win_lo_q, uint32_t *d_win_len_q, cudaStream_t s);
-void sub_meta_gather(const uint32_t *d_sub, const uint32_t *d_nsub, uint32_t nreg, const uint32_t *d_start,
+void near_select(const uint8_t *d_near, uint32_t cap_reg, uint32_t *d_sub, CountsDev cd, ScanPool &pool, cudaStream_t s);  // C_NSUB
+void sub_meta_gather(const uint32_t *d_sub, const uint32_t *d_cnt, uint32_t cap_reg, const uint32_t *d_start,
                      const uint32_t *d_end, const uint32_t *d_a, const uint32_t *d_b, const uint8_t *d_lable,
                      const uint32_t *d_seed_len, const uint64_t *d_seed_off, const uint32_t *d_nsurv,
                      const uint32_t *d_ent_off, const uint64_t *d_q_seedoff, SubMeta out, cudaStream_t s);
 void seed_scatter(uint32_t n, const uint32_t *d_r, const uint64_t *d_off, const uint32_t *d_len, uint64_t *d_seed_off,
                   uint32_t *d_seed_len, cudaStream_t s);
-void assemble_sizes(AssembleDev a, cudaStream_t s);
-void assemble_seed_gather(AssembleDev a, uint8_t *d_out, cudaStream_t s);
-void gather_ranges(const uint8_t *d_src, const uint32_t *d_lo, const uint64_t *d_off, uint32_t n, uint8_t *d_out,
-                   cudaStream_t s);
-void rech_sizes(GenoDev g, uint32_t *d_bytes, cudaStream_t s);
+void assemble_sizes(AssembleDev a, uint32_t cap_reg, cudaStream_t s);
+// region-level offset scans over C_NREG elements (out has nreg + 1 entries); the total also goes to cd.q[q_slot] when
+// q_slot >= 0 and to cd.c[c_slot] when c_slot >= 0
+void region_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint32_t cap_reg, int c_slot, CountsDev cd, ScanPool &pool,
+                     cudaStream_t s);
+void region_scan_u64(const uint32_t *d_in, uint64_t *d_out, uint32_t cap_reg, int q_slot, CountsDev cd, ScanPool &pool,
+                     cudaStream_t s);
+void region_scan_i64(const long long *d_in, long long *d_out, uint32_t cap_reg, int q_slot, CountsDev cd, ScanPool &pool,
+                     cudaStream_t s);
+void assemble_seed_gather(AssembleDev a, uint8_t *d_out, uint32_t cap_reg, cudaStream_t s);
+void gather_ranges(const uint8_t *d_src, const uint32_t *d_lo, const uint64_t *d_off, const uint32_t *d_n, uint32_t cap,
+                   uint8_t *d_out, cudaStream_t s);
+void rech_sizes(GenoDev g, uint32_t *d_bytes, uint32_t cap_reg, cudaStream_t s);
 void rech_gather(GenoDev g, const uint32_t *d_ent_off, const uint64_t *d_byte_off, uint32_t *d_order, uint32_t *d_len,
-                 uint64_t *d_pool_off, uint8_t *d_out, cudaStream_t s);
-void assemble_final(AssembleDev a, uint8_t *d_out, cudaStream_t s);
+                 uint64_t *d_pool_off, uint8_t *d_out, uint32_t cap_reg, cudaStream_t s);
+void assemble_final(AssembleDev a, uint8_t *d_out, uint32_t cap_reg, cudaStream_t s);
 
 /* ------------------------------------------------------------------ yak count on the device (np2_count.cu) */
 struct KmerCounts {  // distinct hashes, ascending, with their counts (clamped at 1023); device memory

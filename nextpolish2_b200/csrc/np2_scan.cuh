@@ -77,11 +77,12 @@ __device__ __forceinline__ uint32_t scan_pad(uint32_t i) { return i + (i >> 5); 
 // n = *d_n + n_plus (clamped to cap) when d_n != nullptr, else cap.
 template <class Tr>
 __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__restrict__ d_n, uint32_t n_plus, uint32_t cap,
-                                                       unsigned long long *ws) {
+                                                       unsigned long long *ws, const uint32_t *__restrict__ d_abort) {
     __shared__ unsigned long long s_ex[kScanTile + kScanTile / 32], s_in[kScanTile + kScanTile / 32];
     __shared__ unsigned long long s_warp[kScanThreads / 32], s_prefix;
     __shared__ uint32_t s_tile;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (d_abort && *d_abort) return;  // set by an earlier kernel: the same for every tile of this launch
     if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int *>(ws), 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -171,10 +172,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__
 inline uint32_t scan_tiles(uint32_t cap) { return cap ? (cap + kScanTile - 1) / kScanTile : 1u; }
 
 template <class Tr>
-inline void scan_launch(const Tr &tr, const uint32_t *d_n, uint32_t n_plus, uint32_t cap, ScanPool &pool, cudaStream_t s) {
+inline void scan_launch(const Tr &tr, const uint32_t *d_n, uint32_t n_plus, uint32_t cap, ScanPool &pool, cudaStream_t s,
+                        const uint32_t *d_abort = nullptr) {
     const uint32_t tiles = scan_tiles(cap);
     unsigned long long *ws = pool.take((size_t)tiles + 1, s);
-    NP2_K(k_scan<Tr>)<<<tiles, kScanThreads, 0, s>>>(tr, d_n, n_plus, cap, ws);
+    NP2_K(k_scan<Tr>)<<<tiles, kScanThreads, 0, s>>>(tr, d_n, n_plus, cap, ws, d_abort);
 }
 
 /* ---------------------------------------------------------------- the functors the pipeline uses */
@@ -185,22 +187,36 @@ struct ScanSumBase {
 };
 __device__ __forceinline__ long long scan_signed(unsigned long long v) { return (long long)(v << 2) >> 2; }
 
-// out[i] = sum of in[0..i) for i < n, out[n] = total (the "n + 1 entries" offset array); In = uint32_t, Out = u32 / u64
+// out[i] = sum of in[0..i) for i < n, out[n] = total (the "n + 1 entries" offset array).  The total also goes to
+// *c_slot / *q_slot (the device-resident counts) and raises *abort when it exceeds `cap`.
 template <class In, class Out>
-struct ScanExclusive : ScanSumBase {
+struct ScanOffsets : ScanSumBase {
     const In *in;
     Out *out;
+    uint32_t *c_slot;
+    unsigned long long *q_slot;
+    unsigned long long cap;
+    uint32_t *abort;
     __device__ unsigned long long load(uint32_t i) const { return (unsigned long long)in[i]; }
     __device__ void store(uint32_t i, unsigned long long ex, unsigned long long) const { out[i] = (Out)ex; }
-    __device__ void total(unsigned long long t, uint32_t n) const { out[n] = (Out)t; }
+    __device__ void total(unsigned long long t, uint32_t n) const {
+        out[n] = (Out)t;
+        if (c_slot) *c_slot = (uint32_t)(t > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : t);
+        if (q_slot) *q_slot = t;
+        if (abort && t > cap) atomicExch(abort, 1u);
+    }
 };
 // signed 64-bit version (patch length deltas)
-struct ScanExclusiveI64 : ScanSumBase {
+struct ScanOffsetsI64 : ScanSumBase {
     const long long *in;
     long long *out;
+    unsigned long long *q_slot;
     __device__ unsigned long long load(uint32_t i) const { return (unsigned long long)in[i] & kScanMask; }
     __device__ void store(uint32_t i, unsigned long long ex, unsigned long long) const { out[i] = scan_signed(ex); }
-    __device__ void total(unsigned long long t, uint32_t n) const { out[n] = scan_signed(t); }
+    __device__ void total(unsigned long long t, uint32_t n) const {
+        out[n] = scan_signed(t);
+        if (q_slot) *q_slot = (unsigned long long)scan_signed(t);
+    }
 };
 // in-place inclusive sum of signed 32-bit values (coverage from the difference array)
 struct ScanInclusiveI32 : ScanSumBase {
@@ -218,16 +234,22 @@ struct ScanInclusiveMinU32 {
     __device__ void store(uint32_t i, unsigned long long, unsigned long long in) const { a[i] = (uint32_t)in; }
     __device__ void total(unsigned long long, uint32_t) const {}
 };
-// compaction: out[rank] = i for every i with pred(i), *count = how many.  Pred: __device__ bool operator()(uint32_t) const
+// compaction: out[rank] = i for every i with pred(i), *count = how many (may exceed `cap`: then nothing is written past
+// the capacity and *abort is raised).  Pred: __device__ bool operator()(uint32_t) const
 template <class Pred>
 struct ScanSelect : ScanSumBase {
     Pred pred;
     uint32_t *out, *count;
+    uint32_t cap;
+    uint32_t *abort;
     __device__ unsigned long long load(uint32_t i) const { return pred(i) ? 1ULL : 0ULL; }
     __device__ void store(uint32_t i, unsigned long long ex, unsigned long long in) const {
-        if (in != ex) out[ex] = i;
+        if (in != ex && ex < cap) out[ex] = i;
     }
-    __device__ void total(unsigned long long t, uint32_t) const { *count = (uint32_t)t; }
+    __device__ void total(unsigned long long t, uint32_t) const {
+        *count = (uint32_t)t;
+        if (abort && t > cap) atomicExch(abort, 1u);
+    }
 };
 struct PredFlagU8 {
     const uint8_t *flag;
