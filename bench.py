@@ -347,7 +347,9 @@ def summarise(m, cfg, steps, world, peak):
         "pipeline_roofline": {"bytes_per_bp": round(bpb, 1), "probes_per_bp": round(q, 3),
                               "achieved_GBps": round(bpb * m.total_bp / (step_ms * 1e-3) / 1e9, 1),
                               "frac_of_hbm_peak": round(bpb * m.total_bp / (step_ms * 1e-3) / 1e9 / peak, 4)},
-        "stages_ms": {k: round(v, 4) for k, v in m.stages.items()},
+        "stages_ms": {k: round(v, 4) for k, v in m.stages.items() if not k.startswith("upload:")},
+        "upload_stages_ms": {k: round(v, 4) for k, v in m.stages.items() if k.startswith("upload:")},
+        "sizes": dict(m.stats, alignment_columns=int(m.traffic["alignment_columns"])),
         "gpu_launches": int(m.launches),
     }
 
@@ -467,6 +469,7 @@ def run_ours(args):
             "roofline": roofline_of(m, cfg, peak, peak_kind),
             "pipeline_roofline": s["pipeline_roofline"],
             "stages_ms": s["stages_ms"],
+            "sizes": s["sizes"],
             "verify": ver,
             "identical_to_oracle": None if ver is None else ver["identical"],
             "wall_ms_per_step": round(m.wall / args.steps * 1e3, 3),
@@ -490,7 +493,9 @@ def run_ours(args):
                              args.e2e_inflight)
                 es = summarise(em, ecfg, max(2, args.steps // 4), 1, peak)
                 es.pop("stages_ms")
-                es["stages_ms_top"] = dict(sorted(em.stages.items(), key=lambda kv: -kv[1])[:8])
+                es.pop("upload_stages_ms")
+                es["stages_ms_top"] = dict(sorted([kv for kv in em.stages.items() if not kv[0].startswith("upload:")],
+                                                  key=lambda kv: -kv[1])[:10])
                 es["stages_ms_top"] = {k: round(v, 3) for k, v in es["stages_ms_top"].items()}
                 es["verify"] = None if args.no_verify else verify(ec, et, ecfg, em.records, em.dropped, opts_kw, cores)
                 extras[str(n)] = es

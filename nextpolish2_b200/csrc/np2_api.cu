@@ -825,66 +825,18 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     cover_diff(R, d_blank.p, d_cover.p, s);
     cover_scan(d_cover.p, L + 1, sp, s);
     timer.end(h);
-    // Non-reference 3-mer records (~3-5 % of the columns) are emitted in ONE pass into a buffer sized from the last
-    // count (first time: 1/8 of the columns); the kernel keeps counting when it overflows (exact mode: re-run with the
-    // exact size; speculative mode: the pass is abandoned).
-    DBuf<uint64_t> d_key, d_key2;
-    DBuf<uint32_t> d_rd, d_rd2;
-    uint64_t cap_rec = spec ? caps.c[C_NREC]
-                            : (rec_cap_hint ? (uint64_t)rec_cap_hint + rec_cap_hint / 8 + 1024 : ing.total_cols / 8 + 4096);
-    for (int attempt = 0;; attempt++) {
-        cap_rec = std::min<uint64_t>(cap_rec, 0xFFFFFFF0ull);
-        d_key.alloc(cap_rec, s);
-        d_rd.alloc(cap_rec, s);
-        h = timer.begin("pileup_emit", 1);
-        pileup_emit(R, n_blocks, d_blank.p, d_code.p, d_refpk.p, L, cd, (uint32_t)cap_rec, d_key.p, d_rd.p, s);
-        timer.end(h);
-        if (spec) break;
-        const uint32_t n_rec = cnt_get(C_NREC);
-        if (n_rec <= cap_rec) {
-            cap_rec = n_rec;
-            break;
-        }
-        if (attempt) throw np2::Error(NP2_ERR_INTERNAL, "3-mer record count changed between two passes");
-        cap_rec = n_rec;
-        counts_init(cd, s);
-    }
-    timer.hbegin();
-    d_key2.alloc(cap_rec, s);
-    d_rd2.alloc(cap_rec, s);
-    timer.hend("host:alloc_records");
-    int pbits = 1;
-    while ((1ull << pbits) < (uint64_t)L) pbits++;
-    h = timer.begin("pileup_sort", 9);
-    pileup_pad(d_key.p, (uint32_t)cap_rec, cd, s);  // the tail of a capacity-sized buffer sorts behind every record
-    {
-        size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)cap_rec, 0, 32 + pbits, s);
-        if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-        cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_key.p, d_key2.p, d_rd.p, d_rd2.p, (int)cap_rec, 0, 32 + pbits, s);
-    }
-    timer.end(h);
-
-    // groups: in exact mode their number is only known after the scan that also fills them, so the arrays are sized by
-    // the number of records there
-    const uint32_t cap_g_alloc = spec ? caps.c[C_G] : (uint32_t)cap_rec;
+    // K2 proper: one CTA per stripe of positions finds, buckets and merges the non-reference 3-mers in shared memory and
+    // writes the finished Msa entries (np2_kernels.cu k_pileup_stripe).  Exact mode sizes the entry arrays from a
+    // counting run of the same kernel.
     MsaDev m;
     m.L = L;
     m.cnt = cd.c;
-    DBuf<uint32_t> d_sp_off, d_gcount, d_gfirst, d_gbesti, d_gstart, d_gpos, d_dense_cnt, d_dense_besti, d_n_emit,
-        d_emit_off;
-    DBuf<uint16_t> d_gbases, d_gdelta;
+    DBuf<uint32_t> d_sp_off, d_gcount, d_gfirst, d_gbesti, d_dense_cnt, d_dense_besti, d_n_emit, d_emit_off;
+    DBuf<uint16_t> d_gbases, d_gdelta, d_sp_cnt;
     DBuf<int64_t> d_gscore, d_dense_score;
     DBuf<uint8_t> d_multi;
     d_sp_off.alloc(L + 1, s);
-    d_gcount.alloc(cap_g_alloc, s);
-    d_gfirst.alloc(cap_g_alloc, s);
-    d_gbesti.alloc(cap_g_alloc, s);
-    d_gstart.alloc(cap_g_alloc, s);
-    d_gpos.alloc(cap_g_alloc, s);
-    d_gbases.alloc(cap_g_alloc, s);
-    d_gdelta.alloc(cap_g_alloc, s);
-    d_gscore.alloc(cap_g_alloc, s);
+    d_sp_cnt.alloc(L + 1, s);
     d_dense_cnt.alloc(L, s);
     d_dense_besti.alloc(L, s);
     d_dense_score.alloc(L, s);
@@ -892,28 +844,36 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     d_n_emit.alloc(L + 1, s);
     d_emit_off.alloc(L + 1, s);
     m.sp_off = d_sp_off.p;
-    m.g_bases = d_gbases.p;
-    m.g_delta = d_gdelta.p;
-    m.g_count = d_gcount.p;
-    m.g_first = d_gfirst.p;
-    m.g_besti = d_gbesti.p;
-    m.g_score = d_gscore.p;
+    m.sp_cnt = d_sp_cnt.p;
     m.cover = d_cover.p;
     m.dense_cnt = d_dense_cnt.p;
     m.dense_besti = d_dense_besti.p;
     m.dense_score = d_dense_score.p;
     m.multi = d_multi.p;
     m.code = d_code.p;
-
-    h = timer.begin("pileup_group", 1);
-    groups_build(d_key2.p, d_rd2.p, (uint32_t)cap_rec, cap_g_alloc, d_gstart.p, d_gpos.p, m, cd, sp, s);
-    timer.end(h);
-    const uint32_t G = cnt_get(C_G);
-    h = timer.begin("pileup_finalize", 4);
-    d_sp_off.zero();
-    d_dense_besti.zero();
-    groups_finish(d_gstart.p, d_gpos.p, G, m, s);
-    pos_finalize(m, d_n_emit.p, s);
+    uint32_t G = spec ? caps.c[C_G] : 0;
+    if (!spec) {
+        h = timer.begin("pileup_count", 1);
+        pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, m, max_span, 0, cd, d_n_emit.p, true, s);
+        timer.end(h);
+        G = cnt_get(C_G);
+        counts_reset_pileup(cd, s);
+    }
+    d_gcount.alloc(std::max(G, 1u), s);
+    d_gfirst.alloc(std::max(G, 1u), s);
+    d_gbesti.alloc(std::max(G, 1u), s);
+    d_gbases.alloc(std::max(G, 1u), s);
+    d_gdelta.alloc(std::max(G, 1u), s);
+    d_gscore.alloc(std::max(G, 1u), s);
+    m.g_bases = d_gbases.p;
+    m.g_delta = d_gdelta.p;
+    m.g_count = d_gcount.p;
+    m.g_first = d_gfirst.p;
+    m.g_besti = d_gbesti.p;
+    m.g_score = d_gscore.p;
+    h = timer.begin("pileup_stripe", 1);
+    if (dump_iter >= 0) d_dense_besti.zero();  // the stage getter reports besti of every position
+    pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, m, max_span, G, cd, d_n_emit.p, false, s);
     timer.end(h);
 
     /* ---------------- K3: DP over runs, backtrack, consensus */
@@ -1021,9 +981,10 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     auto dump_stage1 = [&]() {  // exact mode only
         // Msa in the reference's order: reference 3-mer first (p >= 2), then the sorted sparse ones
         std::vector<uint32_t> sp_off(L + 1), gc(G), gb(G), dc(L), db(L);
-        std::vector<uint16_t> gba(G), gde(G);
+        std::vector<uint16_t> gba(G), gde(G), sp_cnt(L + 1);
         std::vector<uint8_t> code(L);
-        d_sp_off.download(sp_off.data(), L + 1);
+        d_sp_off.download(sp_off.data(), L);
+        d_sp_cnt.download(sp_cnt.data(), L);
         d_gcount.download(gc.data(), G);
         d_gbesti.download(gb.data(), G);
         d_gbases.download(gba.data(), G);
@@ -1046,7 +1007,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
                 dm_msa_count.push_back(dc[p]);
                 dm_msa_besti.push_back(db[p]);
             }
-            for (uint32_t g = sp_off[p]; g < sp_off[p + 1]; g++) {
+            for (uint32_t g = sp_off[p]; g < sp_off[p] + sp_cnt[p]; g++) {
                 dm_msa_bases.push_back(gba[g]);
                 dm_msa_delta.push_back(gde[g]);
                 dm_msa_count.push_back(gc[g]);
@@ -1076,7 +1037,6 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         stats[3] = hc->c[C_N];
         stats[4] = hc->c[C_NREG];
         stats[5] = hc->c[C_NPAIRS];
-        rec_cap_hint = hc->c[C_NREC];
         res_N = hc->c[C_N];
     };
     auto remember = [&]() {

@@ -3,8 +3,7 @@
 //   K5  table_insert / table_probe / seq_kscore   yak k-mer table in HBM (kmer.rs:113-170, 255-314)
 //   K0  ref_codes                                  SEQ_NUM codes of the contig (kmer.rs:11-22)
 //   K1  trim_scan + pack_columns                        fill_with_cigar + trim(8) + AlignSeq::new (main.rs:386-513, 279-312)
-//   K2  cover_diff / pileup_emit                   update_msas + Msa::push/sort/coverage (main.rs:576-589, 193-241)
-//       mark_heads / groups_* / pos_finalize
+//   K2  cover_diff / pileup_stripe                 update_msas + Msa::push/sort/coverage (main.rs:576-589, 193-241)
 //   K3  dp_runs / emit_*                           get_cns_from_align_tags + backtrack (main.rs:1645-1687, 1572-1634)
 //   (K4/K6 and the genotype kernels live in np2_geno.cu)
 //
@@ -828,7 +827,7 @@ void cover_scan(int32_t *d_cover, uint32_t n, ScanPool &pool, cudaStream_t s) {
 }
 __global__ void k_counts_init(CountsDev cd) {
     const uint32_t i = threadIdx.x;
-    if (i < C_COUNT) cd.c[i] = i == C_NREC ? 2u : 0u;
+    if (i < C_COUNT) cd.c[i] = 0u;
     if (i < Q_COUNT) cd.q[i] = 0;
 }
 void counts_init(CountsDev cd, cudaStream_t s) { NP2_K(k_counts_init)<<<1, 32, 0, s>>>(cd); }
@@ -877,7 +876,7 @@ __device__ __forceinline__ bool block_all_reference(const ReadsDev &R, uint32_t 
 }
 
 // Walks the 32 columns of global block g and calls f(p, bases, delta1) for every 3-mer that is NOT the
-// reference 3-mer of its position (those are counted as cover[p] - #others, see pos_finalize).
+// reference 3-mer of its position (those are counted as cover[p] - #others, see k_pileup_stripe).
 template <class F>
 __device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, const uint8_t *__restrict__ code, F f) {
     const uint32_t r = R.ck_read[g];
@@ -943,277 +942,328 @@ __device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, cons
     }
 }
 
-constexpr int kPileThreads = 256;
-constexpr int kPilePerThread = 4;  // 32-column blocks examined per thread in the fast pass
-constexpr int kPileCta = kPileThreads * kPilePerThread;
-constexpr int kPileBatchDefault = 2;  // blocks whose loads are in flight together in the fast pass (0 = one at a time;
-                                      // 4 needs 64 registers and loses more to occupancy than it gains: profiles/r01ab_ab.log)
-uint32_t pileup_ctas(uint32_t n_blocks) { return cdiv(n_blocks, kPileCta); }
-
-// Both passes: (1) every thread checks kPilePerThread blocks against the reference with word compares and queues the
-// few that hold something else in shared memory; (2) the queued blocks are walked column by column by densely packed
-// threads (without the queue, one odd block per warp would drag 31 idle lanes through the slow loop).
-__device__ __forceinline__ uint32_t pile_queue(const ReadsDev &R, uint32_t n_blocks, const uint8_t *__restrict__ blank,
-                                               const uint8_t *__restrict__ code, const uint32_t *__restrict__ refpk,
-                                               uint32_t *q, uint32_t *qn) {
-    if (threadIdx.x == 0) *qn = 0;
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kPilePerThread; u++) {
-        const uint32_t g = blockIdx.x * kPileCta + u * kPileThreads + threadIdx.x;
-        if (g < n_blocks && !block_all_reference(R, g, blank, code, refpk)) q[atomicAdd(qn, 1u)] = g;
-    }
-    __syncthreads();
-    return *qn;
-}
-// The same test for B blocks of one thread at a time, written without early exits: block_all_reference is a chain of
-// four dependent loads (block -> read -> nibbles -> reference) and a thread that walks it block after block spends its
-// time in long-scoreboard stalls (40% of the kernel's samples, profiles/r01end).  Here the loads of every level are
-// issued for all B blocks before the first use, and the two bytes of code[] are replaced by one more word of refpk
-// (the two columns in front of the block = the low byte of the 8 reference nibbles that end at tpos - 1).
-// A block the test cannot decide (first / last block of a read, tpos < 8) is queued: the column walk is the general path.
-template <int B>
-__device__ __forceinline__ uint32_t pile_queue_batched(const ReadsDev &R, uint32_t n_blocks,
-                                                       const uint8_t *__restrict__ blank,
-                                                       const uint32_t *__restrict__ refpk, uint32_t pk_last, uint32_t *q,
-                                                       uint32_t *qn) {
-    static_assert(kPilePerThread % B == 0, "batch must divide the blocks per thread");
-    if (threadIdx.x == 0) *qn = 0;
-    __syncthreads();
-    if (n_blocks) {
-#pragma unroll
-        for (int u0 = 0; u0 < kPilePerThread; u0 += B) {
-            uint32_t g[B], r[B], tpos[B];
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                g[u] = blockIdx.x * kPileCta + (u0 + u) * kPileThreads + threadIdx.x;
-                const uint32_t gc = min(g[u], n_blocks - 1);
-                r[u] = R.ck_read[gc];
-                tpos[u] = R.ck_tpos[gc];  // not written for blocks without columns: only used clamped until proven valid
-            }
-            uint32_t n[B], o0[B], bl[B], pk[B][6];
-            uint64_t noff[B];
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                bl[u] = blank[r[u]];
-                n[u] = R.n[r[u]];
-                o0[u] = (min(g[u], n_blocks - 1) - R.ck_off[r[u]]) * 32;
-                noff[u] = R.nib_off[r[u]];
-                const uint32_t k = min(tpos[u] >> 3, pk_last);
-                pk[u][0] = refpk[k ? k - 1 : 0];
-#pragma unroll
-                for (int j = 0; j < 5; j++) pk[u][j + 1] = refpk[k + j];
-            }
-            uint4 w4[B];
-            uint32_t pb[B];
-            bool cand[B];
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                cand[u] = g[u] < n_blocks && !bl[u] && o0[u] > 0 && o0[u] + 32 <= n[u];  // a whole block inside a read
-                w4[u] = make_uint4(0, 0, 0, 0);
-                pb[u] = 0;
-                if (cand[u]) {
-                    const uint8_t *nib = R.nib + noff[u] + (o0[u] >> 1);
-                    w4[u] = *reinterpret_cast<const uint4 *>(nib);
-                    pb[u] = nib[-1];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < B; u++) {
-                const bool none = g[u] >= n_blocks || bl[u] || o0[u] >= n[u];  // nothing to emit
-                bool all_ref = false;
-                if (cand[u]) {
-                    const uint32_t sh = (tpos[u] & 7) * 4;
-                    const uint32_t w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
-                    uint32_t diff = ((w[0] | w[1] | w[2] | w[3]) & 0xCCCCCCCCu) | (pb[u] & 0xCCu);
-                    diff |= (tpos[u] >> 3) == 0;
-                    diff |= pb[u] ^ (__funnelshift_l(pk[u][1], pk[u][0], sh) & 0xFFu);
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        diff |= __byte_perm(w[j], 0, 0x0123) ^ __funnelshift_l(pk[u][j + 2], pk[u][j + 1], sh);
-                    all_ref = diff == 0;
-                }
-                if (!none && !all_ref) q[atomicAdd(qn, 1u)] = g[u];
-            }
-        }
-    }
-    __syncthreads();
-    return *qn;
-}
-// B = 0: the one-block-at-a-time fast pass (kept for A/B runs, NP2_PILE_BATCH=0)
-template <int B>
-__global__ void __launch_bounds__(kPileThreads) k_pileup_emit(ReadsDev R, uint32_t n_blocks,
-                                                              const uint8_t *__restrict__ blank,
-                                                              const uint8_t *__restrict__ code,
-                                                              const uint32_t *__restrict__ refpk, uint32_t pk_last,
-                                                              unsigned int *__restrict__ n_rec, uint32_t cap,
-                                                              uint64_t *__restrict__ key, uint32_t *__restrict__ rd) {
-    typedef cub::BlockScan<uint32_t, kPileThreads> BS;
-    __shared__ typename BS::TempStorage tmp;
-    __shared__ uint32_t q[kPileCta], qn, cta_base;
-    uint32_t nq;
-    if constexpr (B == 0) nq = pile_queue(R, n_blocks, blank, code, refpk, q, &qn);
-    else nq = pile_queue_batched<B>(R, n_blocks, blank, refpk, pk_last, q, &qn);
-    uint32_t c = 0;
-    for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads)
-        scan_block32(R, q[i], code, [&](uint32_t, uint32_t, uint32_t) { c++; });
-    uint32_t off, tot;
-    BS(tmp).ExclusiveSum(c, off, tot);
-    // Record order inside the buffer is arbitrary (the first read of a 3-mer is taken as a minimum over its records,
-    // k_groups_fill), so every CTA simply reserves its range with one atomic: no counting pass, no scan of CTA totals.
-    // *n_rec starts at 2: records 0 and 1 are the reference read's two head 3-mers (main.rs:1732-1739, 579-584).
-    // It keeps counting past `cap` (nothing is written there): the host then re-runs with the exact size.
-    if (threadIdx.x == 0) cta_base = tot ? atomicAdd(n_rec, tot) : 0;
-    __syncthreads();
-    uint32_t w = cta_base + off;
-    for (uint32_t i = threadIdx.x; i < nq; i += kPileThreads) {
-        const uint32_t g = q[i];
-        const uint32_t order = R.ck_read[g] + 1;
-        scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) {
-            if (w < cap) {
-                key[w] = (uint64_t)p << 32 | (uint64_t)bases << 16 | dl1;
-                rd[w] = order;
-            }
-            w++;
-        });
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        key[0] = (uint64_t)0 << 32 | (uint64_t)(0x4000u | 15u << 8 | 15u << 4 | code[0]) << 16 | 0;
-        rd[0] = 0;
-        key[1] = (uint64_t)1 << 32 | (uint64_t)(15u << 8 | (uint32_t)code[0] << 4 | code[1]) << 16 | 1;
-        rd[1] = 0;
-    }
-}
-void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                 const uint32_t *d_refpk, uint32_t L, CountsDev cd, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
-                 cudaStream_t s) {
-    // refpk holds L / 8 + 8 words (ref_codes): a clamped word index k <= L / 8 + 3 keeps k + 4 inside
-    const uint32_t pk_last = L / 8 + 3, grid = max(1u, pileup_ctas(n_blocks));
-    unsigned int *d_n_rec = cd.c + C_NREC;
-    const char *e = getenv("NP2_PILE_BATCH");
-    const int batch = e ? atoi(e) : kPileBatchDefault;
-    if (batch == 0)
-        NP2_K(k_pileup_emit<0>)<<<grid, kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk, pk_last, d_n_rec, cap,
-                                                             d_key, d_read);
-    else if (batch == 2)
-        NP2_K(k_pileup_emit<2>)<<<grid, kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk, pk_last, d_n_rec, cap,
-                                                             d_key, d_read);
-    else
-        NP2_K(k_pileup_emit<4>)<<<grid, kPileThreads, 0, s>>>(r, n_blocks, d_blank, d_code, d_refpk, pk_last, d_n_rec, cap,
-                                                             d_key, d_read);
-}
-__global__ void k_pileup_pad(uint64_t *__restrict__ key, uint32_t cap, CountsDev cd) {
-    const uint32_t n = cd.c[C_NREC];
-    if (n > cap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(cd.c + C_ABORT, 1u);
-        return;
-    }
-    for (uint64_t i = (uint64_t)n + blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
-        key[i] = ~0ULL;
-}
-void pileup_pad(uint64_t *d_key, uint32_t cap, CountsDev cd, cudaStream_t s) {
-    NP2_K(k_pileup_pad)<<<148 * 2, kThreads, 0, s>>>(d_key, cap, cd);
-}
-
-// Sorted records -> groups in ONE scan: an element is 1 when its key differs from the one before (a head); the
-// exclusive prefix of a head is its group index, and the head's thread fills the group (position, 3-mer, first read =
-// minimum read over the records of the group, which lie right behind it).
-struct ScanGroups : ScanSumBase {
-    const uint64_t *key;
-    const uint32_t *rd;
-    const uint32_t *cnt;  // C_NREC
-    uint32_t *gstart, *gpos;
-    MsaDev m;
-    uint32_t cap_g;
-    uint32_t *count, *abort;
-    __device__ unsigned long long load(uint32_t i) const { return (i == 0 || key[i] != key[i - 1]) ? 1ULL : 0ULL; }
-    __device__ void store(uint32_t i, unsigned long long ex, unsigned long long in) const {
-        if (in == ex || ex >= cap_g) return;
-        const uint32_t g = (uint32_t)ex, n = cnt[C_NREC];
-        const uint64_t k = key[i];
-        gstart[g] = i;
-        gpos[g] = (uint32_t)(k >> 32);
-        m.g_bases[g] = (uint16_t)(k >> 16);
-        m.g_delta[g] = (uint16_t)k;
-        uint32_t first = rd[i];
-        for (uint32_t j = i + 1; j < n && key[j] == k; j++) first = min(first, rd[j]);
-        m.g_first[g] = first;
-    }
-    __device__ void total(unsigned long long t, uint32_t) const {
-        *count = (uint32_t)t;
-        if (t > cap_g) atomicExch(abort, 1u);
-    }
+/* ---------------------------------------------------------------------------------------------------------------
+ * K2 proper: update_msas + Msa::push / sort / coverage (main.rs:576-589, 193-241) for one STRIPE of kStripeW contig
+ * positions per CTA, entirely in shared memory.
+ *
+ * Reads are coordinate-sorted, so the reads that can cover a stripe sit in a window of the read array; for each of
+ * them the checkpoints give the 32-column blocks that can hold a column of the stripe.  Those (read, block) items are
+ * tested against the reference with four word compares (block_all_reference); the few odd ones are walked column by
+ * column (scan_block32) and their non-reference 3-mers land in a shared-memory record list.  The list is bucketed by
+ * position (counting sort), identical 3-mers of a position are merged into Msa entries (count, first read), the
+ * entries of every position are put into Msa::sort order (b3.delta, then first read — unique per entry, so the result
+ * does not depend on the order the records were found in), and per position the kernel writes what the DP needs:
+ * where its entries are, how many, the count of the implicit reference 3-mer (cover - sum of the others with
+ * b3.delta == 0), whether it has more than one entry, and how many consensus bases a single-entry position emits.
+ * Nothing but the finished entries ever goes to HBM: no record buffer, no global sort, no separate group / finalize
+ * passes.  Entries of a stripe get their place in the global arrays by ONE atomic reservation (their order across
+ * stripes is irrelevant: every position knows its own offset and count).
+ *
+ * A stripe whose records do not fit the list (kStripeRmax) is split in halves by position, recursively; the walk is
+ * repeated for each half.  WRITE = false only counts entries (exact mode sizes the arrays from that). */
+constexpr int kStripeW = 512;
+constexpr int kStripeThreads = 256;
+constexpr int kStripeRmax = 2048;
+constexpr int kStripeReads = 64;    // candidate reads examined per batch
+constexpr int kStripeWork = 2048;   // (read, block) items per batch
+struct StripeSmem {
+    uint32_t bd[kStripeRmax], rd[kStripeRmax], first[kStripeRmax];
+    uint16_t kp[kStripeRmax], perm[kStripeRmax], cnt[kStripeRmax], slot[kStripeRmax];
+    uint32_t off[kStripeW + 2], goff[kStripeW + 2];
+    uint32_t odd[kStripeWork];
+    uint32_t rg0[kStripeReads], rn[kStripeReads + 1];
+    uint32_t stk_a[12], stk_b[12];
+    uint32_t nrec, nodd, base, ok;
+    int sp;
 };
-void groups_build(const uint64_t *d_key, const uint32_t *d_read, uint32_t cap_rec, uint32_t cap_g, uint32_t *d_gstart,
-                  uint32_t *d_gpos, MsaDev m, CountsDev cd, ScanPool &pool, cudaStream_t s) {
-    ScanGroups f;
-    f.key = d_key;
-    f.rd = d_read;
-    f.cnt = cd.c;
-    f.gstart = d_gstart;
-    f.gpos = d_gpos;
-    f.m = m;
-    f.cap_g = cap_g;
-    f.count = cd.c + C_G;
-    f.abort = cd.c + C_ABORT;
-    scan_launch(f, cd.c + C_NREC, 0, cap_rec, pool, s, cd.c + C_ABORT);
-}
-__global__ void k_groups_finish(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ gpos, MsaDev m) {
-    if (m.cnt[C_ABORT]) return;
-    const uint32_t G = m.cnt[C_G], n = m.cnt[C_NREC];
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
-    m.g_count[g] = (g + 1 < G ? gstart[g + 1] : n) - gstart[g];
-    uint32_t p = gpos[g];
-    uint32_t from = g ? gpos[g - 1] + 1 : 0;
-    for (uint32_t q = from; q <= p; q++) m.sp_off[q] = g;
-    if (g + 1 == G)
-        for (uint32_t q = p + 1; q <= m.L; q++) m.sp_off[q] = G;
-}
-void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t cap_g, MsaDev m, cudaStream_t s) {
-    if (!cap_g) return;
-    NP2_K(k_groups_finish)<<<cdiv(cap_g, kThreads), kThreads, 0, s>>>(d_gstart, d_gpos, m);
-}
+uint32_t pileup_stripes(uint32_t L) { return cdiv(L, kStripeW); }
 
-// Per position: order the sparse 3-mers like Msa::sort after first-seen pushes (main.rs:193-229): by b3.delta,
-// then by the first read that carried them; derive the reference 3-mer's count and the articulation flag.
-__global__ void k_pos_finalize(MsaDev m, uint32_t *__restrict__ n_emit) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= m.L || m.cnt[C_ABORT]) return;
-    const uint32_t lo = m.sp_off[p], hi = m.sp_off[p + 1];
-    uint32_t sum0 = 0;
-    for (uint32_t i = lo; i < hi; i++) {
-        uint16_t bs = m.g_bases[i], dl = m.g_delta[i];
-        uint32_t cn = m.g_count[i], fr = m.g_first[i];
-        uint32_t kd = kmer_b3delta(bs, dl);
-        if (kd == 0) sum0 += cn;
-        uint32_t j = i;
-        while (j > lo) {
-            uint32_t kd2 = kmer_b3delta(m.g_bases[j - 1], m.g_delta[j - 1]);
-            if (kd2 < kd || (kd2 == kd && m.g_first[j - 1] <= fr)) break;
-            m.g_bases[j] = m.g_bases[j - 1];
-            m.g_delta[j] = m.g_delta[j - 1];
-            m.g_count[j] = m.g_count[j - 1];
-            m.g_first[j] = m.g_first[j - 1];
-            j--;
+template <bool WRITE>
+__global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, const uint8_t *__restrict__ blank,
+                                                                  const uint8_t *__restrict__ code,
+                                                                  const uint32_t *__restrict__ refpk, MsaDev m,
+                                                                  uint32_t max_span, uint32_t cap_g, CountsDev cd,
+                                                                  uint32_t *__restrict__ n_emit) {
+    extern __shared__ __align__(16) unsigned char stripe_smem_raw[];
+    StripeSmem &S = *reinterpret_cast<StripeSmem *>(stripe_smem_raw);
+    typedef cub::BlockScan<uint32_t, kStripeThreads> BS;
+    __shared__ typename BS::TempStorage bs_tmp;
+    const uint32_t tid = threadIdx.x, L = m.L;
+    if (cd.c[C_ABORT]) return;
+    if (tid == 0) {
+        S.sp = 1;
+        S.stk_a[0] = blockIdx.x * kStripeW;
+        S.stk_b[0] = min(blockIdx.x * kStripeW + kStripeW, L);
+    }
+    for (;;) {
+        __syncthreads();
+        if (S.sp == 0) break;
+        const uint32_t a = S.stk_a[S.sp - 1], b = S.stk_b[S.sp - 1];
+        __syncthreads();
+        if (tid == 0) {
+            S.sp--;
+            S.nrec = 0;
         }
-        if (j != i) {
-            m.g_bases[j] = bs;
-            m.g_delta[j] = dl;
-            m.g_count[j] = cn;
-            m.g_first[j] = fr;
+        __syncthreads();
+        auto append = [&](uint32_t p, uint32_t bases, uint32_t dl1, uint32_t order) {
+            if (p < a || p >= b) return;
+            const uint32_t i = atomicAdd(&S.nrec, 1u);
+            if (i < kStripeRmax) {
+                S.kp[i] = (uint16_t)(p - a);
+                S.bd[i] = bases << 16 | dl1;
+                S.rd[i] = order;
+            }
+        };
+        // the reference read's two head 3-mers (main.rs:1732-1739, 579-584)
+        if (tid == 0) {
+            append(0, 0x4000u | 15u << 8 | 15u << 4 | code[0], 0, 0);
+            append(1, 15u << 8 | (uint32_t)code[0] << 4 | code[1], 1, 0);
+        }
+        // candidate reads: pos in [a - max_span, b - 1]
+        const uint32_t lo_pos = a > max_span ? a - max_span : 0;
+        uint32_t r_lo, r_hi;
+        {
+            uint32_t lo = 0, hi = R.n_reads;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (R.pos[mid] < lo_pos) lo = mid + 1;
+                else hi = mid;
+            }
+            r_lo = lo;
+            hi = R.n_reads;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (R.pos[mid] < b) lo = mid + 1;
+                else hi = mid;
+            }
+            r_hi = lo;
+        }
+        for (uint32_t rb = r_lo; rb < r_hi; rb += kStripeReads) {
+            // blocks of read rb + tid that can hold a column of [a, b): from the last block that starts before a to the
+            // last block that starts before b
+            if (tid < kStripeReads) {
+                const uint32_t r = rb + tid;
+                uint32_t g0 = 0, nb = 0;
+                if (r < r_hi && !blank[r]) {
+                    const uint32_t n = R.n[r];
+                    if (n && R.t_e[r] >= a && R.t_s[r] < b) {
+                        const uint32_t nblk = (n + 31) >> 5, c0 = R.ck_off[r];
+                        const uint32_t *ck = R.ck_tpos + c0;
+                        uint32_t lo = 0, hi = nblk;  // blocks with first t_pos < a
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (ck[mid] < a) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        const uint32_t b0 = lo ? lo - 1 : 0;
+                        hi = nblk;  // blocks with first t_pos < b
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (ck[mid] < b) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        g0 = c0 + b0;
+                        nb = lo > b0 ? lo - b0 : 0;
+                    }
+                }
+                S.rg0[tid] = g0;
+                S.rn[tid] = nb;
+            }
+            __syncthreads();
+            if (tid == 0) {  // exclusive offsets of the batch (64 adds)
+                uint32_t acc = 0;
+                for (int i = 0; i < kStripeReads; i++) {
+                    const uint32_t v = S.rn[i];
+                    S.rn[i] = acc;
+                    acc += v;
+                }
+                S.rn[kStripeReads] = acc;
+            }
+            __syncthreads();
+            const uint32_t total = S.rn[kStripeReads];
+            for (uint32_t w0 = 0; w0 < total; w0 += kStripeWork) {
+                const uint32_t wn = min(total - w0, (uint32_t)kStripeWork);
+                if (tid == 0) S.nodd = 0;
+                __syncthreads();
+                for (uint32_t t = tid; t < wn; t += kStripeThreads) {
+                    const uint32_t x = w0 + t;
+                    uint32_t lo = 0, hi = kStripeReads;  // read owning item x: largest i with rn[i] <= x
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (S.rn[mid] <= x) lo = mid;
+                        else hi = mid;
+                    }
+                    const uint32_t g = S.rg0[lo] + (x - S.rn[lo]);
+                    if (!block_all_reference(R, g, blank, code, refpk)) S.odd[atomicAdd(&S.nodd, 1u)] = g;
+                }
+                __syncthreads();
+                const uint32_t nodd = S.nodd;
+                for (uint32_t t = tid; t < nodd; t += kStripeThreads) {
+                    const uint32_t g = S.odd[t];
+                    const uint32_t order = R.ck_read[g] + 1;
+                    scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) { append(p, bases, dl1, order); });
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        const uint32_t nrec = S.nrec;
+        if (nrec > kStripeRmax) {  // split by position and walk again
+            if (tid == 0) {
+                if (b - a <= 1) {
+                    atomicExch(cd.c + C_PERR, 5u);  // one position with more records than the list holds
+                } else {
+                    const uint32_t mid = a + (b - a) / 2;
+                    S.stk_a[S.sp] = mid;
+                    S.stk_b[S.sp] = b;
+                    S.stk_a[S.sp + 1] = a;
+                    S.stk_b[S.sp + 1] = mid;
+                    S.sp += 2;
+                }
+            }
+            continue;
+        }
+        const uint32_t W = b - a;
+        // ---- counting sort by position
+        for (uint32_t i = tid; i < kStripeW + 2; i += kStripeThreads) S.off[i] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < nrec; i += kStripeThreads) atomicAdd(&S.off[S.kp[i]], 1u);
+        __syncthreads();
+        {
+            const uint32_t v0 = S.off[2 * tid], v1 = S.off[2 * tid + 1];
+            uint32_t ex;
+            BS(bs_tmp).ExclusiveSum(v0 + v1, ex);
+            S.off[2 * tid] = ex;
+            S.off[2 * tid + 1] = ex + v0;
+            S.goff[2 * tid] = ex;  // cursors
+            S.goff[2 * tid + 1] = ex + v0;
+            if (tid == kStripeThreads - 1) S.off[kStripeW] = ex + v0 + v1;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < nrec; i += kStripeThreads) S.perm[atomicAdd(&S.goff[S.kp[i]], 1u)] = (uint16_t)i;
+        __syncthreads();
+        for (uint32_t i = tid; i < kStripeW + 2; i += kStripeThreads) S.goff[i] = 0;
+        __syncthreads();
+        // ---- entries: the first record of every distinct 3-mer of a position counts its copies
+        for (uint32_t j = tid; j < nrec; j += kStripeThreads) {
+            const uint32_t i = S.perm[j], k = S.kp[i], bdv = S.bd[i];
+            const uint32_t lo = S.off[k], hi = S.off[k + 1];
+            bool head = true;
+            for (uint32_t x = lo; x < j; x++)
+                if (S.bd[S.perm[x]] == bdv) {
+                    head = false;
+                    break;
+                }
+            uint32_t slot = 0xFFFFu;
+            if (head) {
+                uint32_t c = 1, f = S.rd[i];
+                for (uint32_t x = j + 1; x < hi; x++) {
+                    const uint32_t i2 = S.perm[x];
+                    if (S.bd[i2] == bdv) {
+                        c++;
+                        f = min(f, S.rd[i2]);
+                    }
+                }
+                slot = atomicAdd(&S.goff[k], 1u);
+                if (c > 0xFFFFu) atomicExch(cd.c + C_PERR, 6u);
+                S.cnt[j] = (uint16_t)min(c, 0xFFFFu);
+                S.first[j] = f;
+            }
+            S.slot[j] = (uint16_t)slot;
+        }
+        __syncthreads();
+        uint32_t ng_total;
+        {
+            const uint32_t v0 = S.goff[2 * tid], v1 = S.goff[2 * tid + 1];
+            uint32_t ex;
+            BS(bs_tmp).ExclusiveSum(v0 + v1, ex, ng_total);
+            __syncthreads();
+            S.goff[2 * tid] = ex;
+            S.goff[2 * tid + 1] = ex + v0;
+            if (tid == kStripeThreads - 1) S.goff[kStripeW] = ex + v0 + v1;
+        }
+        if (tid == 0) {
+            const uint32_t base = atomicAdd(cd.c + C_G, ng_total);
+            atomicAdd(cd.c + C_NREC, nrec);
+            S.base = base;
+            S.ok = 1;
+            if (WRITE && (uint64_t)base + ng_total > cap_g) {
+                atomicExch(cd.c + C_ABORT, 1u);
+                S.ok = 0;
+            }
+        }
+        __syncthreads();
+        if (!WRITE || !S.ok) continue;
+        const uint32_t base = S.base;
+        for (uint32_t j = tid; j < nrec; j += kStripeThreads) {
+            const uint32_t slot = S.slot[j];
+            if (slot == 0xFFFFu) continue;
+            const uint32_t i = S.perm[j];
+            const uint32_t g = base + S.goff[S.kp[i]] + slot;
+            m.g_bases[g] = (uint16_t)(S.bd[i] >> 16);
+            m.g_delta[g] = (uint16_t)S.bd[i];
+            m.g_count[g] = S.cnt[j];
+            m.g_first[g] = S.first[j];
+        }
+        __syncthreads();
+        // ---- per position: Msa::sort order (main.rs:193-229), reference 3-mer count, articulation flag
+        for (uint32_t k = tid; k < W; k += kStripeThreads) {
+            const uint32_t p = a + k;
+            const uint32_t lo = base + S.goff[k], hi = base + S.goff[k + 1];
+            uint32_t sum0 = 0;
+            for (uint32_t i = lo; i < hi; i++) {
+                uint16_t bs = m.g_bases[i], dl = m.g_delta[i];
+                uint32_t cn = m.g_count[i], fr = m.g_first[i];
+                uint32_t kd = kmer_b3delta(bs, dl);
+                if (kd == 0) sum0 += cn;
+                uint32_t j = i;
+                while (j > lo) {
+                    uint32_t kd2 = kmer_b3delta(m.g_bases[j - 1], m.g_delta[j - 1]);
+                    if (kd2 < kd || (kd2 == kd && m.g_first[j - 1] <= fr)) break;
+                    m.g_bases[j] = m.g_bases[j - 1];
+                    m.g_delta[j] = m.g_delta[j - 1];
+                    m.g_count[j] = m.g_count[j - 1];
+                    m.g_first[j] = m.g_first[j - 1];
+                    j--;
+                }
+                if (j != i) {
+                    m.g_bases[j] = bs;
+                    m.g_delta[j] = dl;
+                    m.g_count[j] = cn;
+                    m.g_first[j] = fr;
+                }
+            }
+            m.sp_off[p] = lo;
+            m.sp_cnt[p] = (uint16_t)min(hi - lo, 0xFFFFu);
+            if (hi - lo > 0xFFFFu) atomicExch(cd.c + C_PERR, 6u);
+            m.dense_cnt[p] = p >= 2 ? (uint32_t)m.cover[p] - sum0 : 0;
+            const bool multi = p < 2 || hi > lo;
+            m.multi[p] = multi;
+            n_emit[p] = multi ? 0 : (m.code[p] != 4);
         }
     }
-    m.dense_cnt[p] = p >= 2 ? (uint32_t)m.cover[p] - sum0 : 0;
-    const bool multi = p < 2 || hi > lo;
-    m.multi[p] = multi;
-    n_emit[p] = multi ? 0 : (m.code[p] != 4);
 }
-void pos_finalize(MsaDev m, uint32_t *d_n_emit, cudaStream_t s) {
-    NP2_K(k_pos_finalize)<<<cdiv(m.L, kThreads), kThreads, 0, s>>>(m, d_n_emit);
+// count = true: only C_G / C_NREC are produced (exact mode sizes the entry arrays from them)
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk, MsaDev m,
+                   uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit, bool count_only, cudaStream_t s) {
+    static bool attr_done = false;
+    const int smem = (int)sizeof(StripeSmem);
+    if (!attr_done) {
+        NP2_CUDA(cudaFuncSetAttribute(k_pileup_stripe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NP2_CUDA(cudaFuncSetAttribute(k_pileup_stripe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    const uint32_t grid = pileup_stripes(m.L);
+    if (count_only)
+        NP2_K(k_pileup_stripe<false>)<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, m, max_span, cap_g, cd, d_n_emit);
+    else
+        NP2_K(k_pileup_stripe<true>)<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, m, max_span, cap_g, cd, d_n_emit);
 }
-
-/* =============================================================== K3: DP over runs + consensus */
+__global__ void k_counts_reset_pileup(CountsDev cd) {
+    cd.c[C_G] = 0;
+    cd.c[C_NREC] = 0;
+}
+void counts_reset_pileup(CountsDev cd, cudaStream_t s) { NP2_K(k_counts_reset_pileup)<<<1, 1, 0, s>>>(cd); }
 
 struct PredRunStart {
     const uint8_t *multi;
@@ -1240,7 +1290,7 @@ struct Entry {
     uint32_t g;  // sparse index or 0xFFFFFFFF for the reference 3-mer
 };
 __device__ __forceinline__ uint32_t n_ent(const MsaDev &m, uint32_t p) {
-    return (p >= 2 ? 1u : 0u) + m.sp_off[p + 1] - m.sp_off[p];
+    return (p >= 2 ? 1u : 0u) + m.sp_cnt[p];
 }
 __device__ __forceinline__ Entry get_entry(const MsaDev &m, uint32_t p, uint32_t idx) {
     Entry e;

@@ -14,7 +14,7 @@ namespace np2 {
  * returns at once (the host then repeats the pass in exact mode). */
 enum Cnt : int {
     C_ABORT = 0,  // a count exceeded its capacity: everything after is skipped
-    C_NREC,       // non-reference 3-mer records (starts at 2: the ref read's two head 3-mers)
+    C_NREC,       // non-reference 3-mer records
     C_G,          // distinct non-reference 3-mers
     C_NRUNS,      // runs of multi-entry positions
     C_N,          // DP consensus bases
@@ -50,7 +50,7 @@ struct CountsDev {
     uint32_t *c = nullptr;
     unsigned long long *q = nullptr;
 };
-void counts_init(CountsDev cd, cudaStream_t s);  // zero, C_NREC = 2
+void counts_init(CountsDev cd, cudaStream_t s);  // all zero
 
 /* ------------------------------------------------------------------ yak table (K5) */
 constexpr int kBucketSlots = 4;  // 4 x u64 = one 32-byte DRAM sector per probe
@@ -108,19 +108,15 @@ void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cu
 /* ------------------------------------------------------------------ K2 pileup */
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);
 void cover_scan(int32_t *d_cover, uint32_t n, ScanPool &pool, cudaStream_t s);  // in-place inclusive sum
-// single pass: every CTA reserves its output range with one atomic on cd.c[C_NREC] (starts at 2); records beyond
-// `cap` are counted but not written (the count then exceeds the capacity: see pileup_sort)
-void pileup_emit(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_blank, const uint8_t *d_code,
-                 const uint32_t *d_refpk, uint32_t L, CountsDev cd, uint32_t cap, uint64_t *d_key, uint32_t *d_read,
-                 cudaStream_t s);
-uint32_t pileup_ctas(uint32_t n_blocks);
-// keys [n_rec, cap) = ~0 (they sort behind every record); sets C_ABORT when n_rec > cap
-void pileup_pad(uint64_t *d_key, uint32_t cap, CountsDev cd, cudaStream_t s);
-
+// One CTA per stripe of contig positions: non-reference 3-mers found, bucketed, merged into Msa entries and ordered in
+// shared memory; per position: entry offset / count, reference 3-mer count, articulation flag, bases a single-entry
+// position emits.  C_NREC = records seen, C_G = entries written (reserved by one atomic per stripe).
+uint32_t pileup_stripes(uint32_t L);
 struct MsaDev {
     uint32_t L = 0;
     const uint32_t *cnt = nullptr;  // C_G = sparse groups
-    uint32_t *sp_off = nullptr;  // L + 1
+    uint32_t *sp_off = nullptr;  // L: first sparse entry of the position
+    uint16_t *sp_cnt = nullptr;  // L: how many
     uint16_t *g_bases = nullptr, *g_delta = nullptr;
     uint32_t *g_count = nullptr, *g_first = nullptr, *g_besti = nullptr;
     int64_t *g_score = nullptr;
@@ -131,11 +127,9 @@ struct MsaDev {
     uint8_t *multi = nullptr;        // L: more than one entry (or p < 2)
     const uint8_t *code = nullptr;   // ref codes
 };
-// sorted records -> groups: heads, their ranks and the per-group fields in one scan (C_G = number of groups)
-void groups_build(const uint64_t *d_key, const uint32_t *d_read, uint32_t cap_rec, uint32_t cap_g, uint32_t *d_gstart,
-                  uint32_t *d_gpos, MsaDev m, CountsDev cd, ScanPool &pool, cudaStream_t s);
-void groups_finish(const uint32_t *d_gstart, const uint32_t *d_gpos, uint32_t cap_g, MsaDev m, cudaStream_t s);
-void pos_finalize(MsaDev m, uint32_t *d_n_emit, cudaStream_t s);
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk, MsaDev m,
+                   uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit, bool count_only, cudaStream_t s);
+void counts_reset_pileup(CountsDev cd, cudaStream_t s);
 
 /* ------------------------------------------------------------------ K3 DP + consensus */
 // first positions of the runs of multi-entry positions (C_NRUNS)

@@ -66,7 +66,6 @@ __device__ __forceinline__ unsigned long long scan_ld(const unsigned long long *
 __device__ __forceinline__ void scan_st(unsigned long long *p, unsigned long long v) {
     *reinterpret_cast<volatile unsigned long long *>(p) = v;
 }
-__device__ __forceinline__ uint32_t scan_pad(uint32_t i) { return i + (i >> 5); }
 
 // Tr: struct with
 //   __device__ unsigned long long load(uint32_t i) const        value of element i (< n), already reduced to 62 bits
@@ -78,7 +77,6 @@ __device__ __forceinline__ uint32_t scan_pad(uint32_t i) { return i + (i >> 5); 
 template <class Tr>
 __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__restrict__ d_n, uint32_t n_plus, uint32_t cap,
                                                        unsigned long long *ws, const uint32_t *__restrict__ d_abort) {
-    __shared__ unsigned long long s_ex[kScanTile + kScanTile / 32], s_in[kScanTile + kScanTile / 32];
     __shared__ unsigned long long s_warp[kScanThreads / 32], s_prefix;
     __shared__ uint32_t s_tile;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,18 +91,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__
     }
     const uint64_t base64 = (uint64_t)tile * kScanTile;
     if (base64 >= n && tile > 0) return;
-    const uint32_t base = (uint32_t)base64;
     unsigned long long *desc = ws + 1;
-#pragma unroll
-    for (int j = 0; j < kScanItems; j++) {
-        const uint32_t x = j * kScanThreads + tid, i = base + x;
-        s_in[scan_pad(x)] = (i < n && i >= base) ? tr.load(i) : Tr::identity();
-    }
-    __syncthreads();
+    // every thread owns kScanItems consecutive elements (a warp covers one contiguous kilobyte of 4-byte elements)
+    const uint64_t i0 = base64 + (uint64_t)tid * kScanItems;
     unsigned long long loc[kScanItems], sum = Tr::identity();
 #pragma unroll
     for (int j = 0; j < kScanItems; j++) {
-        loc[j] = s_in[scan_pad(tid * kScanItems + j)];
+        loc[j] = i0 + j < n ? tr.load((uint32_t)(i0 + j)) : Tr::identity();
         sum = Tr::op(sum, loc[j]);
     }
     unsigned long long incl = sum;  // inclusive scan of the thread sums inside the warp
@@ -151,19 +144,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__
         if (lane == 0) s_prefix = ex;
     }
     __syncthreads();
-    unsigned long long run = Tr::op(s_prefix, thread_ex);
+    unsigned long long run = Tr::op(s_prefix, thread_ex) & kScanMask;
 #pragma unroll
     for (int j = 0; j < kScanItems; j++) {
-        const uint32_t x = scan_pad(tid * kScanItems + j);
-        s_ex[x] = run & kScanMask;
-        run = Tr::op(run, loc[j]);
-        s_in[x] = run & kScanMask;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kScanItems; j++) {
-        const uint32_t x = j * kScanThreads + tid, i = base + x;
-        if (i < n && i >= base) tr.store(i, s_ex[scan_pad(x)], s_in[scan_pad(x)]);
+        const unsigned long long ex = run;
+        run = Tr::op(run, loc[j]) & kScanMask;
+        if (i0 + j < n) tr.store((uint32_t)(i0 + j), ex, run);
     }
     const uint32_t last_tile = n ? (n - 1) / kScanTile : 0;
     if (tile == last_tile && tid == 0) tr.total(Tr::op(s_prefix, agg) & kScanMask, n);
