@@ -274,7 +274,8 @@ struct JobScratch {
     PBuf<uint32_t> p_cpos;
     std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
     cudaEvent_t seq_ev[2] = {nullptr, nullptr};
-    cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr;
+    cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_trim = nullptr;
+    PBuf<uint8_t> p_trim;
     Arena arena;  // per-run device scratch (small allocations)
     PBuf<uint8_t> p_up_stage, p_seq_args, p_phase;
     StageTimer timer;
@@ -286,6 +287,7 @@ struct JobScratch {
         if (ev_t0) cudaEventDestroy(ev_t0);
         if (ev_t1) cudaEventDestroy(ev_t1);
         if (ev_k0) cudaEventDestroy(ev_k0);
+        if (ev_trim) cudaEventDestroy(ev_trim);
     }
 };
 // bump allocator over a pinned staging buffer: many small device arrays come back with one synchronisation and
@@ -383,6 +385,7 @@ struct np2_job {
 
     // device inputs
     DBuf<uint8_t> d_ref, d_code, d_blob, d_nib, d_blank;
+    DBuf<int> d_bad;  // the contig holds a byte the reference cannot index
     DBuf<uint32_t> d_refpk;
     DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off;
     DBuf<Op> d_ops;
@@ -398,6 +401,7 @@ struct np2_job {
     uint32_t rec_cap_hint = 0;             // 3-mer records of the last pileup (sizes the next one-pass emit)
     std::vector<uint32_t> h_as_pos, h_as_te;  // record pos / last column of every alignseq (pair-accumulator windows)
     DBuf<uint64_t> d_pair_off;
+    DBuf<uint32_t> d_first_ge;             // read window of every pileup stripe (np2_kernels.cu stripe_reads)
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
     // result: bases always; positions are materialised on request (np2_job_get_consensus with pos != NULL)
@@ -473,6 +477,11 @@ void np2_job::send_contig(const uint8_t *tseq_host) {
     timer.end(h);
     d_code.alloc(L, s);
     d_refpk.alloc(L / 8 + 8, s);
+    d_bad.alloc(1, s);
+    d_bad.zero();
+    h = timer.begin("upload:ref_codes", 2);  // SEQ_NUM codes of the contig: input preparation, once per job
+    ref_codes(d_ref.p, L, d_code.p, d_refpk.p, d_bad.p, s);
+    timer.end(h);
     h2d += L;
 }
 
@@ -854,7 +863,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     uint32_t G = spec ? caps.c[C_G] : 0;
     if (!spec) {
         h = timer.begin("pileup_count", 1);
-        pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, m, max_span, 0, cd, d_n_emit.p, true, s);
+        pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, d_first_ge.p, m, max_span, 0, cd, d_n_emit.p, true, s);
         timer.end(h);
         G = cnt_get(C_G);
         counts_reset_pileup(cd, s);
@@ -873,7 +882,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     m.g_score = d_gscore.p;
     h = timer.begin("pileup_stripe", 1);
     if (dump_iter >= 0) d_dense_besti.zero();  // the stage getter reports besti of every position
-    pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, m, max_span, G, cd, d_n_emit.p, false, s);
+    pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, d_first_ge.p, m, max_span, G, cd, d_n_emit.p, false, s);
     timer.end(h);
 
     /* ---------------- K3: DP over runs, backtrack, consensus */
@@ -887,20 +896,22 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     h = timer.begin("dp_runs", 1);
     dp_runs(m, d_run_start.p, n_runs, cd, s);
     timer.end(h);
-    h = timer.begin("consensus_emit", 2);
-    emit_count_runs(m, d_run_start.p, n_runs, cd, d_n_emit.p, s);
-    emit_offsets(d_n_emit.p, d_emit_off.p, L, spec ? caps.c[C_N] : 0xFFFFFFFFu, cd, sp, s);
-    timer.end(h);
-    const uint32_t N = cnt_get(C_N);
+    // consensus bases: at most one per position plus the insertions the best path takes (<= the sparse entries)
+    const uint32_t cap_n = spec ? caps.c[C_N] : (uint32_t)std::min<uint64_t>((uint64_t)L + G + 16, 0xFFFFFFF0ull);
     DBuf<uint32_t> &d_cpos = jd_cpos;
     DBuf<uint8_t> &d_cbase = jd_cbase, &d_cflags = jd_cflags;
     DBuf<uint32_t> d_events;
-    d_cpos.alloc(std::max(N, 1u), s);
-    d_cbase.alloc(std::max(N, 1u), s);
-    d_cflags.alloc(std::max(N, 1u), s);
-    d_events.alloc(std::max(N, 1u), s);
-    h = timer.begin("consensus_emit", 3);
+    d_cpos.alloc(cap_n, s);
+    d_cbase.alloc(cap_n, s);
+    d_cflags.alloc(cap_n, s);
+    h = timer.begin("consensus_emit", 4);
+    emit_count_runs(m, d_run_start.p, n_runs, cd, d_n_emit.p, s);
+    emit_offsets(m, d_n_emit.p, d_emit_off.p, d_cpos.p, d_cbase.p, d_cflags.p, cap_n, cd, sp, s);
     emit_write(m, d_run_start.p, n_runs, cd, d_n_emit.p, d_emit_off.p, d_cpos.p, d_cbase.p, d_cflags.p, s);
+    timer.end(h);
+    const uint32_t N = cnt_get(C_N);
+    d_events.alloc(std::max(N, 1u), s);
+    h = timer.begin("consensus_emit", 1);
     events_select(d_cflags.p, N, d_events.p, std::max(N, 1u), cd, sp, s);
     timer.end(h);
     const uint32_t n_ev = cnt_get(C_NEV);
@@ -909,7 +920,16 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             throw np2::Error(NP2_ERR_UNSUPPORTED,
                              "best path has a negative total score (main.rs:1680 picks the default 3-mer): not supported");
     };
-    if (!spec) check_total();
+    auto check_perr = [&]() {
+        const uint32_t e = hc->c[C_PERR];
+        if (e == 4) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
+        if (e == 5) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 1024 non-reference 3-mers at one position (coverage too deep)");
+        if (e == 6) throw np2::Error(NP2_ERR_UNSUPPORTED, "more than 65535 copies or kinds of a 3-mer at one position");
+    };
+    if (!spec) {
+        check_total();
+        check_perr();
+    }
 
     /* ---------------- LQ regions on the device (np2_regions.cu) */
     RegionDev rd;
@@ -1225,7 +1245,10 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         const uint32_t n_slots = (uint32_t)pair_slots;
         uint32_t id_bits = 1;  // read orders are < as_read.size()
         while ((1ull << id_bits) < as_read.size()) id_bits++;
-        uint64_t n_edges = 1;
+        // speculative mode: the pair kernels are only enqueued when the last pass of this kind had heterozygous
+        // regions; a pass that finds some although the last one had none is repeated
+        uint64_t n_edges = hint.h.q[Q_EDGES];
+        const bool edges_enqueued = n_edges != 0;
         if (!spec) {
             fetch_counts();
             n_edges = hc->q[Q_EDGES];
@@ -1251,7 +1274,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             geno_edges_select(d_acc.p, n_slots, d_sel.p, cap_nu_sel, cd, sp, s);
             timer.end(h);
             nu = spec ? cap_nu_sel : cnt_get(C_NU);  // exact: the number of pair records; speculative: its capacity
-            if (!spec && hc->c[C_PERR]) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
+            if (!spec) check_perr();
             if (nu) {
                 d_uk.alloc(nu, s);
                 d_uv.alloc(nu, s);
@@ -1297,7 +1320,8 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             timer.hend("host:segment_sync");
             check_total();
             if (hc->c[C_NREG] == 0) throw Respeculate();  // the no-region path is only taken in exact mode
-            if (hc->c[C_PERR]) throw np2::Error(NP2_ERR_INTERNAL, "read pair outside its index window");
+            if (hc->q[Q_EDGES] != 0 && !edges_enqueued) throw Respeculate();
+            check_perr();
             nreg = hc->c[C_NREG];
         }
         note_sizes();
@@ -1447,6 +1471,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         if (spec) {
             segment_end();
             check_total();
+            check_perr();
             if (hc->c[C_NREG] == 0) throw Respeculate();
         } else {
             fetch_counts();
@@ -1583,6 +1608,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         if (spec) {
             segment_end();
             check_total();
+            check_perr();
             if (hc->c[C_NREG] == 0) throw Respeculate();
         } else {
             fetch_counts();
@@ -1918,33 +1944,37 @@ void np2_job::run(int32_t dump_it) {
     sc->scan_pool.reserve(12 * ((size_t)L / kScanTile + 2) + 4 * ((size_t)ing.total_cols / 8 / kScanTile + 2) + 8192, s);
     sc->scan_pool.begin(s);
     const int h_total = timer.begin("total", 0);
-    DBuf<int> d_bad;
-    d_bad.alloc(1, s);
-    d_bad.zero();
-    int h = timer.begin("ref_codes", 2);
-    ref_codes(d_ref.p, L, d_code.p, d_refpk.p, d_bad.p, s);
-    timer.end(h);
-    h = timer.begin("trim_scan", 1);
+    int h = timer.begin("trim_scan", 1);
     trim_scan(R, d_ref.p, L, s);
     timer.end(h);
-    h = timer.begin("pack_columns", 1);  // a single kernel: the roofline line of bench.py is computed on it
+    // The per-read results of the trim go to the host on the copy stream while the main stream packs the columns; the
+    // host decides which reads are kept (ingest_finish) during that kernel.
+    if (!sc->ev_trim) NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_trim, cudaEventDisableTiming));
+    NP2_CUDA(cudaEventRecord(sc->ev_trim, s));
+    h = timer.begin("pack_columns", 1);  // a single kernel
     pack_columns(R, d_ref.p, ing.ck_off.back(), s);
     timer.end(h);
-    int bad_ref = 0;
-    d_bad.download(&bad_ref, 1);
-    h_ts.resize(n);
-    h_te.resize(n);
-    h_n.resize(n);
-    if (n) {
-        d_ts.download(h_ts.data(), n);
-        d_te.download(h_te.data(), n);
-        d_n.download(h_n.data(), n);
+    {
+        cudaStream_t c2 = ctx->copy_stream;
+        NP2_CUDA(cudaStreamWaitEvent(c2, sc->ev_trim, 0));
+        sc->p_trim.resize((size_t)std::max(n, 1u) * 12 + 16);
+        uint32_t *pt = reinterpret_cast<uint32_t *>(sc->p_trim.p);
+        if (n) {
+            NP2_CUDA(cudaMemcpyAsync(pt, d_ts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c2));
+            NP2_CUDA(cudaMemcpyAsync(pt + n, d_te.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c2));
+            NP2_CUDA(cudaMemcpyAsync(pt + 2 * (size_t)n, d_n.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c2));
+        }
+        NP2_CUDA(cudaMemcpyAsync(pt + 3 * (size_t)n, d_bad.p, 4, cudaMemcpyDeviceToHost, c2));
+        timer.hbegin();
+        NP2_CUDA(cudaStreamSynchronize(c2));
+        timer.hend("host:trim_sync");
+        n_sync++;
+        h_ts.assign(pt, pt + n);
+        h_te.assign(pt + n, pt + 2 * (size_t)n);
+        h_n.assign(pt + 2 * (size_t)n, pt + 3 * (size_t)n);
+        d2h += (uint64_t)n * 12;
+        if (pt[3 * (size_t)n]) throw np2::Error(NP2_ERR_FORMAT, "contig holds a byte the reference cannot index (>= 128 or '-')");
     }
-    NP2_CUDA(cudaStreamSynchronize(s));
-    n_sync++;
-    d2h += (uint64_t)n * 12;
-    if (bad_ref) throw np2::Error(NP2_ERR_FORMAT, "contig holds a byte the reference cannot index (>= 128 or '-')");
-    timer.hbegin();
     ingest_finish();
     timer.hend("host:ingest_finish");
     d_blank.upload(h_blank.data(), std::max(n, 1u));
@@ -1968,6 +1998,8 @@ void np2_job::run(int32_t dump_it) {
     }
     max_span = 0;
     for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
+    d_first_ge.alloc(pileup_stripes(L) + 1, s);
+    stripe_reads(R, L, d_first_ge.p, s);
 
     if (dump_iter >= 0) {  // reads as the oracle reports them (after the clip filter)
         std::vector<uint8_t> nib(ing.nib_off.back() + 16);

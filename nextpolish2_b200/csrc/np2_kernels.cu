@@ -942,6 +942,28 @@ __device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, cons
     }
 }
 
+// block_all_reference for a block whose read is already known: 32 plain columns o0 .. o0 + 31 of a read of n columns
+// (nib = its packed columns, tpos = t_pos of column o0) that equal the reference and follow two plain matching columns
+__device__ __forceinline__ bool block_all_reference_at(const uint8_t *__restrict__ nib, uint32_t n, uint32_t o0,
+                                                       uint32_t tpos, const uint8_t *__restrict__ code,
+                                                       const uint32_t *__restrict__ refpk) {
+    if (o0 >= n) return true;
+    if (o0 == 0 || o0 + 32 > n || tpos < 2) return false;
+    const uint4 w4 = *reinterpret_cast<const uint4 *>(nib + (o0 >> 1));
+    if (((w4.x | w4.y | w4.z | w4.w) & 0xCCCCCCCCu) != 0) return false;
+    const uint32_t pb = nib[(o0 >> 1) - 1];
+    if ((pb & 0xCCu) != 0 || (pb >> 4) != code[tpos - 2] || (pb & 15u) != code[tpos - 1]) return false;
+    const uint32_t k = tpos >> 3, sh = (tpos & 7) * 4;
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    uint32_t diff = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t rj = __byte_perm(w[j], 0, 0x0123);  // column 8j in the most significant nibble
+        diff |= rj ^ __funnelshift_l(refpk[k + j + 1], refpk[k + j], sh);
+    }
+    return diff == 0;
+}
+
 /* ---------------------------------------------------------------------------------------------------------------
  * K2 proper: update_msas + Msa::push / sort / coverage (main.rs:576-589, 193-241) for one STRIPE of kStripeW contig
  * positions per CTA, entirely in shared memory.
@@ -961,31 +983,44 @@ __device__ __forceinline__ void scan_block32(const ReadsDev &R, uint32_t g, cons
  *
  * A stripe whose records do not fit the list (kStripeRmax) is split in halves by position, recursively; the walk is
  * repeated for each half.  WRITE = false only counts entries (exact mode sizes the arrays from that). */
-constexpr int kStripeW = 512;
 constexpr int kStripeThreads = 256;
-constexpr int kStripeRmax = 2048;
+constexpr int kStripeRmax = 1024;   // records of one position range held in shared memory
 constexpr int kStripeReads = 64;    // candidate reads examined per batch
-constexpr int kStripeWork = 2048;   // (read, block) items per batch
+constexpr int kStripeWork = 1024;   // (read, block) items per batch
+template <int kStripeW>
 struct StripeSmem {
     uint32_t bd[kStripeRmax], rd[kStripeRmax], first[kStripeRmax];
     uint16_t kp[kStripeRmax], perm[kStripeRmax], cnt[kStripeRmax], slot[kStripeRmax];
     uint32_t off[kStripeW + 2], goff[kStripeW + 2];
     uint32_t odd[kStripeWork];
-    uint32_t rg0[kStripeReads], rn[kStripeReads + 1];
+    unsigned long long r_nib[kStripeReads];                              // per candidate read of the batch: nibble offset,
+    uint32_t r_c0[kStripeReads], r_n[kStripeReads], r_b0[kStripeReads];  // first block id, columns, first block of interest
+    uint32_t rn[kStripeReads + 1];                                       // and the prefix of its block count
     uint32_t stk_a[12], stk_b[12];
     uint32_t nrec, nodd, base, ok;
+    unsigned long long score;  // 10 * count - 4 * coverage over the single-entry positions of the range (main.rs:1659)
     int sp;
 };
-uint32_t pileup_stripes(uint32_t L) { return cdiv(L, kStripeW); }
+// positions per stripe: 1024 (NP2_STRIPE_W=512 for A/B runs)
+static int stripe_w() {
+    static const int w = [] {
+        const char *e = getenv("NP2_STRIPE_W");
+        return e && atoi(e) == 512 ? 512 : 1024;
+    }();
+    return w;
+}
+uint32_t pileup_stripes(uint32_t L) { return cdiv(L, stripe_w()); }
 
-template <bool WRITE>
+template <int kStripeW, bool WRITE>
 __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, const uint8_t *__restrict__ blank,
                                                                   const uint8_t *__restrict__ code,
-                                                                  const uint32_t *__restrict__ refpk, MsaDev m,
+                                                                  const uint32_t *__restrict__ refpk,
+                                                                  const uint32_t *__restrict__ first_ge, MsaDev m,
                                                                   uint32_t max_span, uint32_t cap_g, CountsDev cd,
                                                                   uint32_t *__restrict__ n_emit) {
     extern __shared__ __align__(16) unsigned char stripe_smem_raw[];
-    StripeSmem &S = *reinterpret_cast<StripeSmem *>(stripe_smem_raw);
+    StripeSmem<kStripeW> &S = *reinterpret_cast<StripeSmem<kStripeW> *>(stripe_smem_raw);
+    constexpr int kPer = kStripeW / kStripeThreads;  // positions per thread in the block scans
     typedef cub::BlockScan<uint32_t, kStripeThreads> BS;
     __shared__ typename BS::TempStorage bs_tmp;
     const uint32_t tid = threadIdx.x, L = m.L;
@@ -1003,6 +1038,7 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         if (tid == 0) {
             S.sp--;
             S.nrec = 0;
+            S.score = 0;
         }
         __syncthreads();
         auto append = [&](uint32_t p, uint32_t bases, uint32_t dl1, uint32_t order) {
@@ -1019,65 +1055,65 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
             append(0, 0x4000u | 15u << 8 | 15u << 4 | code[0], 0, 0);
             append(1, 15u << 8 | (uint32_t)code[0] << 4 | code[1], 1, 0);
         }
-        // candidate reads: pos in [a - max_span, b - 1]
+        // candidate reads: pos in [a - max_span, b - 1], from the per-stripe index (first read at or behind a stripe start)
         const uint32_t lo_pos = a > max_span ? a - max_span : 0;
-        uint32_t r_lo, r_hi;
-        {
-            uint32_t lo = 0, hi = R.n_reads;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (R.pos[mid] < lo_pos) lo = mid + 1;
-                else hi = mid;
-            }
-            r_lo = lo;
-            hi = R.n_reads;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (R.pos[mid] < b) lo = mid + 1;
-                else hi = mid;
-            }
-            r_hi = lo;
-        }
+        const uint32_t r_lo = first_ge[lo_pos / kStripeW], r_hi = first_ge[min((b + kStripeW - 1) / kStripeW, gridDim.x)];
         for (uint32_t rb = r_lo; rb < r_hi; rb += kStripeReads) {
             // blocks of read rb + tid that can hold a column of [a, b): from the last block that starts before a to the
-            // last block that starts before b
+            // last block that starts before b.  HiFi alignments have few indels, so the block is guessed from the
+            // distance to the read's start and corrected by walking the checkpoints.
             if (tid < kStripeReads) {
                 const uint32_t r = rb + tid;
-                uint32_t g0 = 0, nb = 0;
+                uint32_t c0 = 0, n = 0, b0 = 0, nb = 0;
+                unsigned long long noff = 0;
                 if (r < r_hi && !blank[r]) {
-                    const uint32_t n = R.n[r];
-                    if (n && R.t_e[r] >= a && R.t_s[r] < b) {
-                        const uint32_t nblk = (n + 31) >> 5, c0 = R.ck_off[r];
+                    n = R.n[r];
+                    const uint32_t ts = R.t_s[r], te = R.t_e[r];
+                    c0 = R.ck_off[r];
+                    noff = R.nib_off[r];
+                    if (n && te >= a && ts < b) {
+                        const uint32_t nblk = (n + 31) >> 5;
                         const uint32_t *ck = R.ck_tpos + c0;
-                        uint32_t lo = 0, hi = nblk;  // blocks with first t_pos < a
-                        while (lo < hi) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (ck[mid] < a) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        const uint32_t b0 = lo ? lo - 1 : 0;
-                        hi = nblk;  // blocks with first t_pos < b
-                        while (lo < hi) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (ck[mid] < b) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        g0 = c0 + b0;
-                        nb = lo > b0 ? lo - b0 : 0;
+                        // cnt_lt(x) = number of blocks whose first t_pos is < x, from a guess; a long indel makes the
+                        // guess useless, then it is a binary search
+                        auto cnt_lt = [&](uint32_t x, uint32_t guess) {
+                            uint32_t e = min(guess, nblk), steps = 0;
+                            while (e > 0 && ck[e - 1] >= x && steps < 4) e--, steps++;
+                            while (e < nblk && ck[e] < x && steps < 4) e++, steps++;
+                            if (steps >= 4) {
+                                uint32_t lo = 0, hi = nblk;
+                                while (lo < hi) {
+                                    const uint32_t mid = (lo + hi) >> 1;
+                                    if (ck[mid] < x) lo = mid + 1;
+                                    else hi = mid;
+                                }
+                                e = lo;
+                            }
+                            return e;
+                        };
+                        const uint32_t na = cnt_lt(a, a > ts ? ((a - ts) >> 5) + 1 : 0);
+                        b0 = na ? na - 1 : 0;
+                        const uint32_t e = cnt_lt(b, na + ((b - a) >> 5));
+                        nb = e > b0 ? e - b0 : 0;
                     }
                 }
-                S.rg0[tid] = g0;
+                S.r_nib[tid] = noff;
+                S.r_c0[tid] = c0;
+                S.r_n[tid] = n;
+                S.r_b0[tid] = b0;
                 S.rn[tid] = nb;
             }
             __syncthreads();
-            if (tid == 0) {  // exclusive offsets of the batch (64 adds)
-                uint32_t acc = 0;
-                for (int i = 0; i < kStripeReads; i++) {
-                    const uint32_t v = S.rn[i];
-                    S.rn[i] = acc;
-                    acc += v;
+            if (tid < 32) {  // exclusive offsets of the batch
+                const uint32_t v0 = S.rn[2 * tid], v1 = S.rn[2 * tid + 1];
+                uint32_t incl = v0 + v1;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (tid >= (uint32_t)d) incl += t;
                 }
-                S.rn[kStripeReads] = acc;
+                S.rn[2 * tid] = incl - v0 - v1;
+                S.rn[2 * tid + 1] = incl - v1;
+                if (tid == 31) S.rn[kStripeReads] = incl;
             }
             __syncthreads();
             const uint32_t total = S.rn[kStripeReads];
@@ -1085,16 +1121,31 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
                 const uint32_t wn = min(total - w0, (uint32_t)kStripeWork);
                 if (tid == 0) S.nodd = 0;
                 __syncthreads();
-                for (uint32_t t = tid; t < wn; t += kStripeThreads) {
-                    const uint32_t x = w0 + t;
-                    uint32_t lo = 0, hi = kStripeReads;  // read owning item x: largest i with rn[i] <= x
-                    while (hi - lo > 1) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (S.rn[mid] <= x) lo = mid;
-                        else hi = mid;
+                // two items per thread and round: the loads of both are issued before either is tested
+                for (uint32_t t = tid; t < wn; t += 2 * kStripeThreads) {
+                    uint32_t g[2], o0[2], nn[2], tp[2];
+                    const uint8_t *nb_[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const uint32_t x = min(w0 + t + u * kStripeThreads, w0 + wn - 1);
+                        uint32_t lo = 0, hi = kStripeReads;  // read owning item x: largest i with rn[i] <= x
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (S.rn[mid] <= x) lo = mid;
+                            else hi = mid;
+                        }
+                        const uint32_t blk = S.r_b0[lo] + (x - S.rn[lo]);
+                        g[u] = S.r_c0[lo] + blk;
+                        o0[u] = blk * 32;
+                        nn[u] = S.r_n[lo];
+                        nb_[u] = R.nib + S.r_nib[lo];
                     }
-                    const uint32_t g = S.rg0[lo] + (x - S.rn[lo]);
-                    if (!block_all_reference(R, g, blank, code, refpk)) S.odd[atomicAdd(&S.nodd, 1u)] = g;
+                    tp[0] = R.ck_tpos[g[0]];
+                    tp[1] = R.ck_tpos[g[1]];
+                    const bool ref0 = block_all_reference_at(nb_[0], nn[0], o0[0], tp[0], code, refpk);
+                    const bool ref1 = block_all_reference_at(nb_[1], nn[1], o0[1], tp[1], code, refpk);
+                    if (!ref0) S.odd[atomicAdd(&S.nodd, 1u)] = g[0];
+                    if (!ref1 && t + kStripeThreads < wn) S.odd[atomicAdd(&S.nodd, 1u)] = g[1];
                 }
                 __syncthreads();
                 const uint32_t nodd = S.nodd;
@@ -1130,14 +1181,17 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         for (uint32_t i = tid; i < nrec; i += kStripeThreads) atomicAdd(&S.off[S.kp[i]], 1u);
         __syncthreads();
         {
-            const uint32_t v0 = S.off[2 * tid], v1 = S.off[2 * tid + 1];
-            uint32_t ex;
-            BS(bs_tmp).ExclusiveSum(v0 + v1, ex);
-            S.off[2 * tid] = ex;
-            S.off[2 * tid + 1] = ex + v0;
-            S.goff[2 * tid] = ex;  // cursors
-            S.goff[2 * tid + 1] = ex + v0;
-            if (tid == kStripeThreads - 1) S.off[kStripeW] = ex + v0 + v1;
+            uint32_t v[kPer], sum = 0, ex;
+#pragma unroll
+            for (int u = 0; u < kPer; u++) sum += v[u] = S.off[kPer * tid + u];
+            BS(bs_tmp).ExclusiveSum(sum, ex);
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                S.off[kPer * tid + u] = ex;
+                S.goff[kPer * tid + u] = ex;  // cursors
+                ex += v[u];
+            }
+            if (tid == kStripeThreads - 1) S.off[kStripeW] = ex;
         }
         __syncthreads();
         for (uint32_t i = tid; i < nrec; i += kStripeThreads) S.perm[atomicAdd(&S.goff[S.kp[i]], 1u)] = (uint16_t)i;
@@ -1174,13 +1228,17 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         __syncthreads();
         uint32_t ng_total;
         {
-            const uint32_t v0 = S.goff[2 * tid], v1 = S.goff[2 * tid + 1];
-            uint32_t ex;
-            BS(bs_tmp).ExclusiveSum(v0 + v1, ex, ng_total);
+            uint32_t v[kPer], sum = 0, ex;
+#pragma unroll
+            for (int u = 0; u < kPer; u++) sum += v[u] = S.goff[kPer * tid + u];
+            BS(bs_tmp).ExclusiveSum(sum, ex, ng_total);
             __syncthreads();
-            S.goff[2 * tid] = ex;
-            S.goff[2 * tid + 1] = ex + v0;
-            if (tid == kStripeThreads - 1) S.goff[kStripeW] = ex + v0 + v1;
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                S.goff[kPer * tid + u] = ex;
+                ex += v[u];
+            }
+            if (tid == kStripeThreads - 1) S.goff[kStripeW] = ex;
         }
         if (tid == 0) {
             const uint32_t base = atomicAdd(cd.c + C_G, ng_total);
@@ -1207,6 +1265,7 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         }
         __syncthreads();
         // ---- per position: Msa::sort order (main.rs:193-229), reference 3-mer count, articulation flag
+        long long score = 0;
         for (uint32_t k = tid; k < W; k += kStripeThreads) {
             const uint32_t p = a + k;
             const uint32_t lo = base + S.goff[k], hi = base + S.goff[k + 1];
@@ -1236,28 +1295,64 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
             m.sp_off[p] = lo;
             m.sp_cnt[p] = (uint16_t)min(hi - lo, 0xFFFFu);
             if (hi - lo > 0xFFFFu) atomicExch(cd.c + C_PERR, 6u);
-            m.dense_cnt[p] = p >= 2 ? (uint32_t)m.cover[p] - sum0 : 0;
+            const uint32_t cov = (uint32_t)m.cover[p];
+            m.dense_cnt[p] = p >= 2 ? cov - sum0 : 0;
             const bool multi = p < 2 || hi > lo;
             m.multi[p] = multi;
             n_emit[p] = multi ? 0 : (m.code[p] != 4);
+            if (!multi) score += 6ll * cov;  // its only entry is the reference 3-mer: count == coverage
         }
+        for (int d = 16; d > 0; d >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, d);
+        if ((tid & 31) == 0 && score) atomicAdd(&S.score, (unsigned long long)score);
+        __syncthreads();
+        if (tid == 0 && S.score) atomicAdd(cd.q + Q_TOTAL, S.score);
     }
 }
-// count = true: only C_G / C_NREC are produced (exact mode sizes the entry arrays from them)
-void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk, MsaDev m,
-                   uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit, bool count_only, cudaStream_t s) {
+// first_ge[i] = first read whose record position is >= i * W (i = 0 .. stripes): the read window of a stripe
+__global__ void k_stripe_reads(const uint32_t *__restrict__ pos, uint32_t n_reads, uint32_t n_entries, uint32_t W,
+                               uint32_t *__restrict__ first_ge) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    const uint64_t want = (uint64_t)i * W;
+    uint32_t lo = 0, hi = n_reads;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pos[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    first_ge[i] = lo;
+}
+void stripe_reads(const ReadsDev &r, uint32_t L, uint32_t *d_first_ge, cudaStream_t s) {
+    const uint32_t n = pileup_stripes(L) + 1;
+    NP2_K(k_stripe_reads)<<<cdiv(n, kThreads), kThreads, 0, s>>>(r.pos, r.n_reads, n, (uint32_t)stripe_w(), d_first_ge);
+}
+template <int W>
+static void pileup_stripe_w(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk,
+                            const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd,
+                            uint32_t *d_n_emit, bool count_only, cudaStream_t s) {
     static bool attr_done = false;
-    const int smem = (int)sizeof(StripeSmem);
+    const int smem = (int)sizeof(StripeSmem<W>);
     if (!attr_done) {
-        NP2_CUDA(cudaFuncSetAttribute(k_pileup_stripe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        NP2_CUDA(cudaFuncSetAttribute(k_pileup_stripe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NP2_CUDA(cudaFuncSetAttribute(k_pileup_stripe<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NP2_CUDA(cudaFuncSetAttribute(k_pileup_stripe<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    const uint32_t grid = pileup_stripes(m.L);
+    const uint32_t grid = cdiv(m.L, W);
     if (count_only)
-        NP2_K(k_pileup_stripe<false>)<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, m, max_span, cap_g, cd, d_n_emit);
+        NP2_K((k_pileup_stripe<W, false>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span,
+                                                                           cap_g, cd, d_n_emit);
     else
-        NP2_K(k_pileup_stripe<true>)<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, m, max_span, cap_g, cd, d_n_emit);
+        NP2_K((k_pileup_stripe<W, true>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span,
+                                                                          cap_g, cd, d_n_emit);
+}
+// count_only: only C_G / C_NREC are produced (exact mode sizes the entry arrays from them)
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk,
+                   const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit,
+                   bool count_only, cudaStream_t s) {
+    if (stripe_w() == 512)
+        pileup_stripe_w<512>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
+    else
+        pileup_stripe_w<1024>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
 }
 __global__ void k_counts_reset_pileup(CountsDev cd) {
     cd.c[C_G] = 0;
@@ -1437,62 +1532,52 @@ __global__ void k_emit_runs(MsaDev m, const uint32_t *__restrict__ run_start, Dp
         if ((threadIdx.x & 31) == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
     }
 }
-constexpr int kEmitPerThread = 4;
-__global__ void __launch_bounds__(kThreads) k_emit_singles(MsaDev m, const uint32_t *__restrict__ emit_off,
-                                                           uint32_t *__restrict__ out_pos, uint8_t *__restrict__ out_base,
-                                                           uint8_t *__restrict__ out_flags, DpOut o) {
-    // every single-entry position adds 10*count - 4*coverage to the path score (main.rs:1659): reduced per block,
-    // one atomic per 1024 positions (one per warp serialised on the single accumulator)
-    __shared__ long long wsum[kThreads / 32];
-    long long sum = 0;
-    const uint32_t base = blockIdx.x * (kThreads * kEmitPerThread) + threadIdx.x;
-    if (m.cnt[C_ABORT]) return;
-#pragma unroll
-    for (int x = 0; x < kEmitPerThread; x++) {
-        const uint32_t p = base + x * kThreads;
-        if (p < m.L && !m.multi[p]) {
-            const uint32_t cov = m.cover[p], cnt = m.dense_cnt[p];
-            sum += 10ll * cnt - 4ll * cov;
-            const uint8_t c = m.code[p];
-            if (c != 4) {
-                const uint32_t w = emit_off[p];
-                out_pos[w] = p;
-                out_base[w] = code_char(c);
-                // qv = cnt*100/cov < 95  <=>  cnt*100 < 95*cov (floor division, cov >= 1: the ref read covers p)
-                out_flags[w] = (uint8_t)(((uint64_t)cnt * 100 < (uint64_t)cov * 95 ? 1 : 0) | (cov < 2 ? 2 : 0));
-            }
+// emit_off = exclusive sum of n_emit; a single-entry position emits its own consensus base right here (its only entry is
+// the reference 3-mer with count == coverage: qv = 100, so the only flag it can carry is coverage < 2, main.rs:1576-1588)
+struct ScanEmit : ScanSumBase {
+    MsaDev m;
+    const uint32_t *n_emit;
+    uint32_t *emit_off, *out_pos;
+    uint8_t *out_base, *out_flags;
+    uint32_t cap_n;
+    uint32_t *count, *abort;
+    __device__ unsigned long long load(uint32_t p) const { return n_emit[p]; }
+    __device__ void store(uint32_t p, unsigned long long ex, unsigned long long in) const {
+        emit_off[p] = (uint32_t)ex;
+        if (in != ex && ex < cap_n && !m.multi[p]) {
+            out_pos[ex] = p;
+            out_base[ex] = code_char(m.code[p]);
+            out_flags[ex] = m.cover[p] < 2 ? 2 : 0;
         }
     }
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        sum = threadIdx.x < kThreads / 32 ? wsum[threadIdx.x] : 0;
-        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-        if (threadIdx.x == 0 && sum != 0) atomicAdd(o.score_total, (unsigned long long)sum);
+    __device__ void total(unsigned long long t, uint32_t n) const {
+        emit_off[n] = (uint32_t)t;
+        *count = (uint32_t)(t > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : t);
+        if (t > cap_n) atomicExch(abort, 1u);
     }
-}
+};
 void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, uint32_t *d_n_emit,
                      cudaStream_t s) {
     if (!cap_runs) return;
     NP2_K(k_emit_runs<false>)<<<cdiv(cap_runs, 64), 64, 0, s>>>(m, d_run_start, dp_out(cd), d_n_emit, nullptr, nullptr, nullptr,
                                                         nullptr);
 }
-void emit_offsets(const uint32_t *d_n_emit, uint32_t *d_emit_off, uint32_t L, uint32_t cap_n, CountsDev cd, ScanPool &pool,
-                  cudaStream_t s) {
-    ScanOffsets<uint32_t, uint32_t> f;
-    f.in = d_n_emit;
-    f.out = d_emit_off;
-    f.c_slot = cd.c + C_N;
-    f.q_slot = nullptr;
-    f.cap = cap_n;
+void emit_offsets(MsaDev m, const uint32_t *d_n_emit, uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags,
+                  uint32_t cap_n, CountsDev cd, ScanPool &pool, cudaStream_t s) {
+    ScanEmit f;
+    f.m = m;
+    f.n_emit = d_n_emit;
+    f.emit_off = d_emit_off;
+    f.out_pos = d_pos;
+    f.out_base = d_base;
+    f.out_flags = d_flags;
+    f.cap_n = cap_n;
+    f.count = cd.c + C_N;
     f.abort = cd.c + C_ABORT;
-    scan_launch(f, nullptr, 0, L, pool, s, cd.c + C_ABORT);
+    scan_launch(f, nullptr, 0, m.L, pool, s, cd.c + C_ABORT);
 }
 void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, const uint32_t *d_n_emit,
                 const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s) {
-    NP2_K(k_emit_singles)<<<cdiv(m.L, kThreads * kEmitPerThread), kThreads, 0, s>>>(m, d_emit_off, d_pos, d_base, d_flags,
-                                                                              dp_out(cd));
     if (cap_runs)
         NP2_K(k_emit_runs<true>)<<<cdiv(cap_runs, 64), 64, 0, s>>>(m, d_run_start, dp_out(cd), const_cast<uint32_t *>(d_n_emit),
                                                            d_emit_off, d_pos, d_base, d_flags);

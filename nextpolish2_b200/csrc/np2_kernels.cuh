@@ -127,8 +127,11 @@ struct MsaDev {
     uint8_t *multi = nullptr;        // L: more than one entry (or p < 2)
     const uint8_t *code = nullptr;   // ref codes
 };
-void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk, MsaDev m,
-                   uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit, bool count_only, cudaStream_t s);
+// d_first_ge: pileup_stripes(L) + 1 entries, the first read at or behind every stripe start (stripe_reads, once per job)
+void stripe_reads(const ReadsDev &r, uint32_t L, uint32_t *d_first_ge, cudaStream_t s);
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk,
+                   const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit,
+                   bool count_only, cudaStream_t s);
 void counts_reset_pileup(CountsDev cd, cudaStream_t s);
 
 /* ------------------------------------------------------------------ K3 DP + consensus */
@@ -138,9 +141,10 @@ void runs_select(const uint8_t *d_multi, uint32_t L, uint32_t *d_run_start, uint
 void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, cudaStream_t s);
 void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, uint32_t *d_n_emit,
                      cudaStream_t s);
-// emit_off = exclusive sum of n_emit (L + 1 entries), C_N = number of consensus bases
-void emit_offsets(const uint32_t *d_n_emit, uint32_t *d_emit_off, uint32_t L, uint32_t cap_n, CountsDev cd, ScanPool &pool,
-                  cudaStream_t s);
+// emit_off = exclusive sum of n_emit (L + 1 entries), C_N = number of consensus bases; the bases of the single-entry
+// positions are written by the same scan (d_pos / d_base / d_flags hold cap_n elements)
+void emit_offsets(MsaDev m, const uint32_t *d_n_emit, uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags,
+                  uint32_t cap_n, CountsDev cd, ScanPool &pool, cudaStream_t s);
 void emit_write(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, const uint32_t *d_n_emit,
                 const uint32_t *d_emit_off, uint32_t *d_pos, uint8_t *d_base, uint8_t *d_flags, cudaStream_t s);
 // consensus indices with flags != 0, ascending (C_NEV)
