@@ -411,7 +411,7 @@ def run_ours(args):
         cfg["het"] = args.het
     ctx = np2.Context(local)
     # the box's cores are shared by the ranks and by the contigs each rank keeps in flight
-    set_host_threads(args.host_threads or max(2, min(16, cores // max(1, min(args.e2e_inflight, 2)) * 2)))
+    set_host_threads(args.host_threads or max(2, min(16, cores // max(1, args.e2e_inflight))))
     opts_kw = {}
     opts = np2.Opts(**opts_kw)  # reference defaults; every contig is above -L 1000000
 

@@ -1379,7 +1379,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
 
     /* ---------------- final: seed alleles (device), then re-check with every table (main.rs:1527-1543) */
     h = timer.begin("region_seed", 1);
-    geno_region_seed(g, opt.max_indel_len, nreg, cd, s);
+    geno_region_seed(g, opt.max_indel_len, nreg, cd, iter > iter0, s);
     timer.end(h);
     /* ---- what the host needs for the re-check: regions, every region's seed string, the survivors of the regions
      *      that stay RECH, and the DP bases (flanks).  Everything else stays on the device. */

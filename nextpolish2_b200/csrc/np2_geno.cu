@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_cand_kscore_long(GenoDev 
 
 /* ---------------------------------------------------------------- genotype rules (one warp per region) */
 
+constexpr int kRegionPool = 1536;  // bytes of candidate strings staged per region (a longer slice is read from HBM)
 struct RegionSmem {
     uint32_t len[kMaxCand];
     uint32_t order[kMaxCand];
@@ -353,25 +354,40 @@ struct RegionSmem {
     uint8_t ostat[kMaxCand];    // order_stat value of the candidate's own order (0 = absent)
     uint8_t surv[kMaxCand];
     uint32_t max1_c, max1_p, max2_c, max2_p;
+    const uint8_t *str0;        // candidate c's string = str0 + off[c]
+    uint8_t pool[kRegionPool];
 };
 
-__device__ __forceinline__ void region_load(const GenoDev &g, uint32_t r, uint32_t n, uint32_t lane, RegionSmem &sm) {
+// Loads the candidates of region r; the region's slice of the string pool (contiguous, k_cand_write) is staged in
+// shared memory so that the all-pairs string comparisons below do not go to HBM byte by byte.
+// have_rep: c_rep already holds "first candidate with the same string" (k_region_hete ran on these candidates).
+__device__ __forceinline__ void region_load(const GenoDev &g, uint32_t r, uint32_t n, uint32_t lane, RegionSmem &sm,
+                                            bool have_rep) {
     const uint32_t base = r * kMaxCand;
     for (uint32_t c = lane; c < n; c += 32) {
         sm.len[c] = g.c_len[base + c];
         sm.order[c] = g.c_order[base + c];
         sm.off[c] = g.c_off[base + c];
         sm.kscore[c] = g.c_kscore[base + c];
+        if (have_rep) sm.rep[c] = g.c_rep[base + c];
     }
+    const uint64_t p0 = g.r_pool_off[r];
+    const uint32_t bytes = g.r_bytes[r];
+    const bool staged = bytes <= kRegionPool;
+    if (staged)
+        for (uint32_t x = lane; x < bytes; x += 32) sm.pool[x] = g.pool[p0 + x];
+    if (lane == 0) sm.str0 = staged ? sm.pool - p0 : g.pool;
     __syncwarp();
+    if (have_rep) return;
     // rep[c] = first index holding the same string (exact byte comparison)
+    const uint8_t *str0 = sm.str0;
     for (uint32_t c = lane; c < n; c += 32) {
         uint32_t rp = c;
-        const uint8_t *a = g.pool + sm.off[c];
+        const uint8_t *a = str0 + sm.off[c];
         const uint32_t la = sm.len[c];
         for (uint32_t d = 0; d < c; d++) {
             if (sm.len[d] != la) continue;
-            const uint8_t *b = g.pool + sm.off[d];
+            const uint8_t *b = str0 + sm.off[d];
             bool eq = true;
             for (uint32_t x = 0; x < la; x++)
                 if (a[x] != b[x]) {
@@ -387,34 +403,51 @@ __device__ __forceinline__ void region_load(const GenoDev &g, uint32_t r, uint32
     }
     __syncwarp();
 }
-// fill_order_stat (main.rs:813-849), run by lane 0
-__device__ __forceinline__ void region_order_stat(uint32_t n, RegionSmem &sm) {
-    uint32_t max1_c = 0, max1_p = 0, max2_c = 0, max2_p = 0;
-    for (uint32_t c = 0; c < n; c++) {
-        sm.per_pos[c] = 0;
-        sm.ostat[c] = 0;
-    }
-    for (uint32_t p1 = 0; p1 < n; p1++) {
-        if (sm.kscore[p1] == 0 || sm.per_pos[p1] > 0) continue;
-        uint32_t c = 0;
-        for (uint32_t x = p1; x < n; x++) c += sm.rep[x] == sm.rep[p1];
-        sm.ostat[p1] = (uint8_t)c;
-        for (uint32_t x = p1; x < n; x++)
-            if (sm.rep[x] == sm.rep[p1]) sm.per_pos[x] = (uint8_t)c;
-        if (c > max1_c || (c == max1_c && sm.order[p1] == 0)) {
-            max2_c = max1_c;
-            max2_p = max1_p;
-            max1_c = c;
-            max1_p = p1;
-        } else if (max1_p == max2_p || c > max2_c) {
-            max2_c = c;
-            max2_p = p1;
+// fill_order_stat (main.rs:813-849).  The reference walks the candidates in order; a candidate with kscore > 0 that no
+// earlier one of the same string has claimed becomes the LEADER of its string: its count is the number of candidates
+// from itself on that hold the string (kscore or not), and every one of those gets that count as per_pos.  All lanes
+// work that out for two candidates each; lane 0 then applies the reference's max1 / max2 update to the leaders in
+// ascending order (a handful per region).
+__device__ __forceinline__ void region_order_stat(uint32_t n, uint32_t lane, RegionSmem &sm) {
+    uint32_t lead_mask[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t c = lane + 32 * h;
+        uint32_t lead = 0xFFu, cnt = 0;
+        if (c < n) {
+            const uint32_t rc = sm.rep[c];
+            for (uint32_t x = 0; x < n; x++) {
+                if (sm.rep[x] != rc) continue;
+                if (lead == 0xFFu && sm.kscore[x] > 0) lead = x;
+                if (lead != 0xFFu) cnt++;
+            }
+            sm.per_pos[c] = (lead != 0xFFu && lead <= c) ? (uint8_t)cnt : 0;
+            sm.ostat[c] = lead == c ? (uint8_t)cnt : 0;
         }
+        lead_mask[h] = __ballot_sync(0xFFFFFFFFu, c < n && lead == c);
     }
-    sm.max1_c = max1_c;
-    sm.max1_p = max1_p;
-    sm.max2_c = max2_c;
-    sm.max2_p = max2_p;
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t max1_c = 0, max1_p = 0, max2_c = 0, max2_p = 0;
+        for (int h = 0; h < 2; h++)
+            for (uint32_t mk = lead_mask[h]; mk; mk &= mk - 1) {
+                const uint32_t p1 = (uint32_t)__ffs(mk) - 1 + 32 * h, c = sm.ostat[p1];
+                if (c > max1_c || (c == max1_c && sm.order[p1] == 0)) {
+                    max2_c = max1_c;
+                    max2_p = max1_p;
+                    max1_c = c;
+                    max1_p = p1;
+                } else if (max1_p == max2_p || c > max2_c) {
+                    max2_c = c;
+                    max2_p = p1;
+                }
+            }
+        sm.max1_c = max1_c;
+        sm.max1_p = max1_p;
+        sm.max2_c = max2_c;
+        sm.max2_p = max2_p;
+    }
+    __syncwarp();
 }
 __device__ __forceinline__ uint32_t min_count_for(uint32_t c) { return c >= 9 ? 3 : (c >= 6 ? 2 : 1); }  // main.rs:803
 // is_valid_snp (main.rs:780-801)
@@ -438,16 +471,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_hete(GenoDev g) {
     if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
     RegionSmem &sm = smem[threadIdx.x >> 5];
     const uint32_t n = g.r_ncand[r];
-    region_load(g, r, n, lane, sm);
+    region_load(g, r, n, lane, sm, false);
+    if (n) region_order_stat(n, lane, sm);
     if (lane == 0) {
         uint8_t lable = 0;
         uint32_t nedge = 0;
         if (n) {
-            region_order_stat(n, sm);
             const uint32_t min_c = min_count_for(n);
             const uint32_t a = sm.max1_p, b = sm.max2_p;
             if (sm.max2_c >= min_c && (sm.len[a] == sm.len[b] || (n >= 6 && sm.max2_c >= sm.max1_c / 2)) &&
-                hp_differ(g.pool + sm.off[a], sm.len[a], g.pool + sm.off[b], sm.len[b])) {
+                hp_differ(sm.str0 + sm.off[a], sm.len[a], sm.str0 + sm.off[b], sm.len[b])) {
                 lable = 0x40;
                 uint32_t m = 0;
                 for (uint32_t p = 0; p < n; p++) {
@@ -560,20 +593,21 @@ __global__ void k_edges_finish(const uint32_t *__restrict__ sel, const uint32_t 
 }
 
 // fill_seed_lqseqs (main.rs:862-914) with retain_sort_seqs (714-726)
-__global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, int32_t max_indel_len, uint32_t *err) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_seed(GenoDev g, int32_t max_indel_len, uint32_t *err,
+                                                                   int have_rep) {
     __shared__ RegionSmem smem[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
     RegionSmem &sm = smem[threadIdx.x >> 5];
     const uint32_t n = g.r_ncand[r];
-    region_load(g, r, n, lane, sm);
-    if (lane != 0) return;
+    region_load(g, r, n, lane, sm, have_rep != 0);
     if (n == 0 || sm.order[0] != 0) {  // reference would panic: no candidate / "the first lqseq is not ref."
-        atomicExch(err, n == 0 ? 1u : 2u);
+        if (lane == 0) atomicExch(err, n == 0 ? 1u : 2u);
         return;
     }
-    region_order_stat(n, sm);
+    region_order_stat(n, lane, sm);
+    if (lane != 0) return;
     uint32_t seed = sm.max1_p;
     const uint32_t min_c = min_count_for(n), max1_c = sm.max1_c, max1_p = sm.max1_p;
     if (sm.ostat[0]) {  // keep the reference allele when it has support (main.rs:876-890)
@@ -783,8 +817,9 @@ void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n
     if (n2) NP2_K(k_phase_csr)<<<cdiv(n2, 256), 256, 0, s>>>(d_dkey, n2, id_bits, n, d_aoff, d_ato, d_abort);
 }
 
-void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, cudaStream_t s) {
-    if (cap_reg) NP2_K(k_region_seed)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, cd.c + C_GERR);
+void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, bool have_rep, cudaStream_t s) {
+    if (cap_reg)
+        NP2_K(k_region_seed)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, cd.c + C_GERR, have_rep ? 1 : 0);
 }
 
 }  // namespace np2

@@ -209,7 +209,8 @@ void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu
                   uint32_t id_bits, uint64_t *d_dkey, float *d_dw, cudaStream_t s);
 void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n, uint32_t *d_aoff, uint32_t *d_ato,
                const uint32_t *d_abort, cudaStream_t s);
-void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, cudaStream_t s);
+// have_rep: k_region_hete already ran on the same candidates of this pass (c_rep is valid)
+void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, bool have_rep, cudaStream_t s);
 
 /* ------------------------------------------------------------------ regions + assembly (np2_regions.cu) */
 struct RegionDev {

@@ -18,7 +18,7 @@
 namespace np2 {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr unsigned long long kScanMask = (1ULL << 62) - 1;
 
@@ -92,21 +92,30 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__
     const uint64_t base64 = (uint64_t)tile * kScanTile;
     if (base64 >= n && tile > 0) return;
     unsigned long long *desc = ws + 1;
-    // every thread owns kScanItems consecutive elements (a warp covers one contiguous kilobyte of 4-byte elements)
-    const uint64_t i0 = base64 + (uint64_t)tid * kScanItems;
-    unsigned long long loc[kScanItems], sum = Tr::identity();
+    // Warp-striped: a warp owns kScanItems * 32 consecutive elements, element j * 32 + lane of them sits in loc[j] of
+    // lane `lane`, so every load and store instruction of a warp touches 32 consecutive elements.
+    const uint64_t w0 = base64 + (uint64_t)warp * (kScanItems * 32) + lane;
+    unsigned long long loc[kScanItems];
 #pragma unroll
     for (int j = 0; j < kScanItems; j++) {
-        loc[j] = i0 + j < n ? tr.load((uint32_t)(i0 + j)) : Tr::identity();
-        sum = Tr::op(sum, loc[j]);
+        const uint64_t i = w0 + (uint64_t)j * 32;
+        loc[j] = i < n ? tr.load((uint32_t)i) : Tr::identity();
     }
-    unsigned long long incl = sum;  // inclusive scan of the thread sums inside the warp
+    // inclusive scan in element order inside the warp: a shuffle scan per row, rows chained through lane 31
+    unsigned long long carry = Tr::identity();
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= d) incl = Tr::op(t, incl);
+    for (int j = 0; j < kScanItems; j++) {
+        unsigned long long v = loc[j];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= d) v = Tr::op(t, v);
+        }
+        v = Tr::op(carry, v);
+        loc[j] = v;
+        carry = __shfl_sync(0xFFFFFFFFu, v, 31);
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) s_warp[warp] = carry;
     __syncthreads();
     unsigned long long warp_ex = Tr::identity(), agg = Tr::identity();
 #pragma unroll
@@ -114,9 +123,6 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__
         if (w < (int)warp) warp_ex = Tr::op(warp_ex, s_warp[w]);
         agg = Tr::op(agg, s_warp[w]);
     }
-    unsigned long long lane_ex = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-    if (lane == 0) lane_ex = Tr::identity();
-    const unsigned long long thread_ex = Tr::op(warp_ex, lane_ex);
     if (warp == 0) {
         unsigned long long ex = Tr::identity();
         if (tile == 0) {
@@ -127,7 +133,13 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__
             for (;;) {
                 const int idx = look - (int)lane;
                 unsigned long long dsc = idx >= 0 ? scan_ld(desc + idx) : (2ULL << 62 | (Tr::identity() & kScanMask));
-                while (__any_sync(0xFFFFFFFFu, (dsc >> 62) == 0)) {
+                // wait for the descriptors in front of the nearest inclusive prefix (all of them if there is none yet)
+                for (;;) {
+                    const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (dsc >> 62) == 2);
+                    const uint32_t inv = __ballot_sync(0xFFFFFFFFu, (dsc >> 62) == 0);
+                    const uint32_t need = inc ? ((inc & (0u - inc)) - 1u) : 0xFFFFFFFFu;  // lanes below the first inclusive one
+                    if (!(inv & need)) break;
+                    __nanosleep(40);
                     if ((dsc >> 62) == 0) dsc = scan_ld(desc + idx);
                 }
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, (dsc >> 62) == 2);
@@ -144,12 +156,15 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(Tr tr, const uint32_t *__
         if (lane == 0) s_prefix = ex;
     }
     __syncthreads();
-    unsigned long long run = Tr::op(s_prefix, thread_ex) & kScanMask;
+    const unsigned long long pre = Tr::op(s_prefix, warp_ex) & kScanMask;
+    unsigned long long row_carry = Tr::identity();  // inclusive value of the last element of the previous row
 #pragma unroll
     for (int j = 0; j < kScanItems; j++) {
-        const unsigned long long ex = run;
-        run = Tr::op(run, loc[j]) & kScanMask;
-        if (i0 + j < n) tr.store((uint32_t)(i0 + j), ex, run);
+        unsigned long long prev = __shfl_up_sync(0xFFFFFFFFu, loc[j], 1);
+        if (lane == 0) prev = row_carry;
+        row_carry = __shfl_sync(0xFFFFFFFFu, loc[j], 31);
+        const uint64_t i = w0 + (uint64_t)j * 32;
+        if (i < n) tr.store((uint32_t)i, Tr::op(pre, prev) & kScanMask, Tr::op(pre, loc[j]) & kScanMask);
     }
     const uint32_t last_tile = n ? (n - 1) / kScanTile : 0;
     if (tile == last_tile && tid == 0) tr.total(Tr::op(s_prefix, agg) & kScanMask, n);
