@@ -402,6 +402,7 @@ struct np2_job {
     std::vector<uint32_t> h_as_pos, h_as_te;  // record pos / last column of every alignseq (pair-accumulator windows)
     DBuf<uint64_t> d_pair_off;
     DBuf<uint32_t> d_first_ge;             // read window of every pileup stripe (np2_kernels.cu stripe_reads)
+    DBuf<uint32_t> d_blk_odd;              // one bit per 32-column block: not all reference (np2_kernels.cu block_flags)
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
     // result: bases always; positions are materialised on request (np2_job_get_consensus with pos != NULL)
@@ -863,7 +864,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     uint32_t G = spec ? caps.c[C_G] : 0;
     if (!spec) {
         h = timer.begin("pileup_count", 1);
-        pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, d_first_ge.p, m, max_span, 0, cd, d_n_emit.p, true, s);
+        pileup_stripe(R, d_blank.p, d_code.p, d_blk_odd.p, d_first_ge.p, m, max_span, 0, cd, d_n_emit.p, true, s);
         timer.end(h);
         G = cnt_get(C_G);
         counts_reset_pileup(cd, s);
@@ -882,7 +883,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     m.g_score = d_gscore.p;
     h = timer.begin("pileup_stripe", 1);
     if (dump_iter >= 0) d_dense_besti.zero();  // the stage getter reports besti of every position
-    pileup_stripe(R, d_blank.p, d_code.p, d_refpk.p, d_first_ge.p, m, max_span, G, cd, d_n_emit.p, false, s);
+    pileup_stripe(R, d_blank.p, d_code.p, d_blk_odd.p, d_first_ge.p, m, max_span, G, cd, d_n_emit.p, false, s);
     timer.end(h);
 
     /* ---------------- K3: DP over runs, backtrack, consensus */
@@ -2000,6 +2001,10 @@ void np2_job::run(int32_t dump_it) {
     for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
     d_first_ge.alloc(pileup_stripes(L) + 1, s);
     stripe_reads(R, L, d_first_ge.p, s);
+    d_blk_odd.alloc(((size_t)ing.ck_off.back() + 255) / 256 * 8 + 8, s);
+    h = timer.begin("block_flags", 1);
+    block_flags(R, ing.ck_off.back(), d_code.p, d_refpk.p, d_blk_odd.p, s);
+    timer.end(h);
 
     if (dump_iter >= 0) {  // reads as the oracle reports them (after the clip filter)
         std::vector<uint8_t> nib(ing.nib_off.back() + 16);

@@ -993,9 +993,7 @@ struct StripeSmem {
     uint16_t kp[kStripeRmax], perm[kStripeRmax], cnt[kStripeRmax], slot[kStripeRmax];
     uint32_t off[kStripeW + 2], goff[kStripeW + 2];
     uint32_t odd[kStripeWork];
-    unsigned long long r_nib[kStripeReads];                              // per candidate read of the batch: nibble offset,
-    uint32_t r_c0[kStripeReads], r_n[kStripeReads], r_b0[kStripeReads];  // first block id, columns, first block of interest
-    uint32_t rn[kStripeReads + 1];                                       // and the prefix of its block count
+    uint32_t rn[kStripeReads + 1];  // per candidate read of the batch: prefix of its odd-block count
     uint32_t stk_a[12], stk_b[12];
     uint32_t nrec, nodd, base, ok;
     unsigned long long score;  // 10 * count - 4 * coverage over the single-entry positions of the range (main.rs:1659)
@@ -1014,7 +1012,7 @@ uint32_t pileup_stripes(uint32_t L) { return cdiv(L, stripe_w()); }
 template <int kStripeW, bool WRITE>
 __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, const uint8_t *__restrict__ blank,
                                                                   const uint8_t *__restrict__ code,
-                                                                  const uint32_t *__restrict__ refpk,
+                                                                  const uint32_t *__restrict__ blk_odd,
                                                                   const uint32_t *__restrict__ first_ge, MsaDev m,
                                                                   uint32_t max_span, uint32_t cap_g, CountsDev cd,
                                                                   uint32_t *__restrict__ n_emit) {
@@ -1059,49 +1057,50 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         const uint32_t lo_pos = a > max_span ? a - max_span : 0;
         const uint32_t r_lo = first_ge[lo_pos / kStripeW], r_hi = first_ge[min((b + kStripeW - 1) / kStripeW, gridDim.x)];
         for (uint32_t rb = r_lo; rb < r_hi; rb += kStripeReads) {
-            // blocks of read rb + tid that can hold a column of [a, b): from the last block that starts before a to the
-            // last block that starts before b.  HiFi alignments have few indels, so the block is guessed from the
-            // distance to the read's start and corrected by walking the checkpoints.
+            // Blocks of read rb + tid that can hold a column of [a, b): from the last block that starts before a to the
+            // last block that starts before b.  HiFi alignments have few indels, so the range is guessed from the
+            // distance to the read's start with two blocks of margin (a block outside the stripe costs a walk that emits
+            // nothing) and VERIFIED with two checkpoints; a long indel makes the guess useless, then it is a binary
+            // search.  Which of those blocks hold anything but reference 3-mers is a property of the read alone and was
+            // worked out once (k_block_flags): only their bits are looked at here.
+            uint32_t g_lo = 0, g_hi = 0, n_odd = 0;
             if (tid < kStripeReads) {
                 const uint32_t r = rb + tid;
-                uint32_t c0 = 0, n = 0, b0 = 0, nb = 0;
-                unsigned long long noff = 0;
                 if (r < r_hi && !blank[r]) {
-                    n = R.n[r];
-                    const uint32_t ts = R.t_s[r], te = R.t_e[r];
-                    c0 = R.ck_off[r];
-                    noff = R.nib_off[r];
+                    const uint32_t n = R.n[r], ts = R.t_s[r], te = R.t_e[r], c0 = R.ck_off[r];
                     if (n && te >= a && ts < b) {
                         const uint32_t nblk = (n + 31) >> 5;
                         const uint32_t *ck = R.ck_tpos + c0;
-                        // cnt_lt(x) = number of blocks whose first t_pos is < x, from a guess; a long indel makes the
-                        // guess useless, then it is a binary search
-                        auto cnt_lt = [&](uint32_t x, uint32_t guess) {
-                            uint32_t e = min(guess, nblk), steps = 0;
-                            while (e > 0 && ck[e - 1] >= x && steps < 4) e--, steps++;
-                            while (e < nblk && ck[e] < x && steps < 4) e++, steps++;
-                            if (steps >= 4) {
-                                uint32_t lo = 0, hi = nblk;
-                                while (lo < hi) {
-                                    const uint32_t mid = (lo + hi) >> 1;
-                                    if (ck[mid] < x) lo = mid + 1;
-                                    else hi = mid;
-                                }
-                                e = lo;
+                        const uint32_t ga = a > ts ? (a - ts) >> 5 : 0;
+                        uint32_t b0 = ga > 2 ? min(ga - 2, nblk - 1) : 0, e = min(nblk, ga + ((b - a) >> 5) + 4);
+                        const uint32_t ck_b0 = ck[b0], ck_e = e < nblk ? ck[e] : 0xFFFFFFFFu;
+                        if ((b0 > 0 && ck_b0 >= a) || ck_e < b) {  // exact range
+                            uint32_t lo = 0, hi = nblk;  // blocks whose first t_pos is < a
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (ck[mid] < a) lo = mid + 1;
+                                else hi = mid;
                             }
-                            return e;
-                        };
-                        const uint32_t na = cnt_lt(a, a > ts ? ((a - ts) >> 5) + 1 : 0);
-                        b0 = na ? na - 1 : 0;
-                        const uint32_t e = cnt_lt(b, na + ((b - a) >> 5));
-                        nb = e > b0 ? e - b0 : 0;
+                            b0 = lo ? lo - 1 : 0;
+                            hi = nblk;  // blocks whose first t_pos is < b
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (ck[mid] < b) lo = mid + 1;
+                                else hi = mid;
+                            }
+                            e = max(lo, b0);
+                        }
+                        g_lo = c0 + b0;
+                        g_hi = c0 + e;
+                        for (uint32_t w = g_lo >> 5; g_hi > g_lo && w <= (g_hi - 1) >> 5; w++) {
+                            uint32_t bits = blk_odd[w];
+                            if (w == g_lo >> 5) bits &= 0xFFFFFFFFu << (g_lo & 31);
+                            if (w == (g_hi - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((g_hi - 1) & 31));
+                            n_odd += __popc(bits);
+                        }
                     }
                 }
-                S.r_nib[tid] = noff;
-                S.r_c0[tid] = c0;
-                S.r_n[tid] = n;
-                S.r_b0[tid] = b0;
-                S.rn[tid] = nb;
+                S.rn[tid] = n_odd;
             }
             __syncthreads();
             if (tid < 32) {  // exclusive offsets of the batch
@@ -1116,46 +1115,28 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
                 if (tid == 31) S.rn[kStripeReads] = incl;
             }
             __syncthreads();
-            const uint32_t total = S.rn[kStripeReads];
-            for (uint32_t w0 = 0; w0 < total; w0 += kStripeWork) {
-                const uint32_t wn = min(total - w0, (uint32_t)kStripeWork);
-                if (tid == 0) S.nodd = 0;
+            const uint32_t nodd = S.rn[kStripeReads];
+            if (nodd > kStripeWork) {  // too many odd blocks for the queue: treat like a record overflow (split the range)
                 __syncthreads();
-                // two items per thread and round: the loads of both are issued before either is tested
-                for (uint32_t t = tid; t < wn; t += 2 * kStripeThreads) {
-                    uint32_t g[2], o0[2], nn[2], tp[2];
-                    const uint8_t *nb_[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const uint32_t x = min(w0 + t + u * kStripeThreads, w0 + wn - 1);
-                        uint32_t lo = 0, hi = kStripeReads;  // read owning item x: largest i with rn[i] <= x
-                        while (hi - lo > 1) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (S.rn[mid] <= x) lo = mid;
-                            else hi = mid;
-                        }
-                        const uint32_t blk = S.r_b0[lo] + (x - S.rn[lo]);
-                        g[u] = S.r_c0[lo] + blk;
-                        o0[u] = blk * 32;
-                        nn[u] = S.r_n[lo];
-                        nb_[u] = R.nib + S.r_nib[lo];
-                    }
-                    tp[0] = R.ck_tpos[g[0]];
-                    tp[1] = R.ck_tpos[g[1]];
-                    const bool ref0 = block_all_reference_at(nb_[0], nn[0], o0[0], tp[0], code, refpk);
-                    const bool ref1 = block_all_reference_at(nb_[1], nn[1], o0[1], tp[1], code, refpk);
-                    if (!ref0) S.odd[atomicAdd(&S.nodd, 1u)] = g[0];
-                    if (!ref1 && t + kStripeThreads < wn) S.odd[atomicAdd(&S.nodd, 1u)] = g[1];
-                }
-                __syncthreads();
-                const uint32_t nodd = S.nodd;
-                for (uint32_t t = tid; t < nodd; t += kStripeThreads) {
-                    const uint32_t g = S.odd[t];
-                    const uint32_t order = R.ck_read[g] + 1;
-                    scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) { append(p, bases, dl1, order); });
-                }
-                __syncthreads();
+                if (tid == 0) S.nrec = kStripeRmax + 1;
+                break;
             }
+            if (n_odd) {
+                uint32_t w_out = S.rn[tid];
+                for (uint32_t w = g_lo >> 5; w <= (g_hi - 1) >> 5; w++) {
+                    uint32_t bits = blk_odd[w];
+                    if (w == g_lo >> 5) bits &= 0xFFFFFFFFu << (g_lo & 31);
+                    if (w == (g_hi - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((g_hi - 1) & 31));
+                    for (; bits; bits &= bits - 1) S.odd[w_out++] = (w << 5) + (uint32_t)__ffs(bits) - 1;
+                }
+            }
+            __syncthreads();
+            for (uint32_t t = tid; t < nodd; t += kStripeThreads) {
+                const uint32_t g = S.odd[t];
+                const uint32_t order = R.ck_read[g] + 1;
+                scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) { append(p, bases, dl1, order); });
+            }
+            __syncthreads();
         }
         __syncthreads();
         const uint32_t nrec = S.nrec;
@@ -1308,6 +1289,24 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         if (tid == 0 && S.score) atomicAdd(cd.q + Q_TOTAL, S.score);
     }
 }
+// bit g of blk_odd = 32-column block g holds something else than reference 3-mers (or cannot be decided by the word
+// test: first / last block of a read).  A property of the read and the contig only: computed once per job.
+__global__ void __launch_bounds__(kThreads) k_block_flags(ReadsDev R, uint32_t n_blocks, const uint8_t *__restrict__ code,
+                                                          const uint32_t *__restrict__ refpk, uint32_t *__restrict__ blk_odd) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool odd = false;
+    if (g < n_blocks) {
+        const uint32_t r = R.ck_read[g];
+        const uint32_t n = R.n[r], o0 = (g - R.ck_off[r]) * 32;
+        if (o0 < n) odd = !block_all_reference_at(R.nib + R.nib_off[r], n, o0, R.ck_tpos[g], code, refpk);
+    }
+    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, odd);
+    if ((threadIdx.x & 31) == 0) blk_odd[g >> 5] = bits;
+}
+void block_flags(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_code, const uint32_t *d_refpk, uint32_t *d_blk_odd,
+                 cudaStream_t s) {
+    if (n_blocks) NP2_K(k_block_flags)<<<cdiv(n_blocks, kThreads), kThreads, 0, s>>>(r, n_blocks, d_code, d_refpk, d_blk_odd);
+}
 // first_ge[i] = first read whose record position is >= i * W (i = 0 .. stripes): the read window of a stripe
 __global__ void k_stripe_reads(const uint32_t *__restrict__ pos, uint32_t n_reads, uint32_t n_entries, uint32_t W,
                                uint32_t *__restrict__ first_ge) {
@@ -1327,7 +1326,7 @@ void stripe_reads(const ReadsDev &r, uint32_t L, uint32_t *d_first_ge, cudaStrea
     NP2_K(k_stripe_reads)<<<cdiv(n, kThreads), kThreads, 0, s>>>(r.pos, r.n_reads, n, (uint32_t)stripe_w(), d_first_ge);
 }
 template <int W>
-static void pileup_stripe_w(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk,
+static void pileup_stripe_w(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_blk_odd,
                             const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd,
                             uint32_t *d_n_emit, bool count_only, cudaStream_t s) {
     static bool attr_done = false;
@@ -1339,20 +1338,20 @@ static void pileup_stripe_w(const ReadsDev &r, const uint8_t *d_blank, const uin
     }
     const uint32_t grid = cdiv(m.L, W);
     if (count_only)
-        NP2_K((k_pileup_stripe<W, false>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span,
+        NP2_K((k_pileup_stripe<W, false>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span,
                                                                            cap_g, cd, d_n_emit);
     else
-        NP2_K((k_pileup_stripe<W, true>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span,
+        NP2_K((k_pileup_stripe<W, true>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span,
                                                                           cap_g, cd, d_n_emit);
 }
 // count_only: only C_G / C_NREC are produced (exact mode sizes the entry arrays from them)
-void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk,
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_blk_odd,
                    const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit,
                    bool count_only, cudaStream_t s) {
     if (stripe_w() == 512)
-        pileup_stripe_w<512>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
+        pileup_stripe_w<512>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
     else
-        pileup_stripe_w<1024>(r, d_blank, d_code, d_refpk, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
+        pileup_stripe_w<1024>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
 }
 __global__ void k_counts_reset_pileup(CountsDev cd) {
     cd.c[C_G] = 0;

@@ -128,8 +128,12 @@ struct MsaDev {
     const uint8_t *code = nullptr;   // ref codes
 };
 // d_first_ge: pileup_stripes(L) + 1 entries, the first read at or behind every stripe start (stripe_reads, once per job)
+// d_blk_odd: one bit per 32-column block, set when the block holds more than reference 3-mers (block_flags, once per job;
+//            (n_blocks + 255) / 256 * 8 words)
 void stripe_reads(const ReadsDev &r, uint32_t L, uint32_t *d_first_ge, cudaStream_t s);
-void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_refpk,
+void block_flags(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_code, const uint32_t *d_refpk, uint32_t *d_blk_odd,
+                 cudaStream_t s);
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_blk_odd,
                    const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit,
                    bool count_only, cudaStream_t s);
 void counts_reset_pileup(CountsDev cd, cudaStream_t s);
