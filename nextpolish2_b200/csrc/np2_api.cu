@@ -1170,7 +1170,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     geno_pair_scan(g, R, k0, n_pairs, s);
     timer.end(h);
     h = timer.begin("region_select", 2);
-    geno_region_select(g, R, d_blank.p, d_code.p, L, k0, max_span, nreg, s);
+    geno_region_select(g, R, d_blank.p, d_code.p, L, k0, max_span, d_first_ge.p, pileup_stripe_width(), nreg, s);
     geno_pool_offsets(g, nreg, spec ? caps.q[Q_POOL] : ~0ULL, cd, sp, s);
     timer.end(h);
     uint64_t pool_bytes = caps.q[Q_POOL];

@@ -76,11 +76,20 @@ __device__ __forceinline__ ScanOut scan_read_region(const ReadsDev &R, uint32_t 
     const uint32_t n = R.n[r];
     const uint8_t *nib = R.nib + R.nib_off[r];
     const uint32_t *ck = R.ck_tpos + R.ck_off[r];
-    uint32_t lo = 0, hi = (n + 31) >> 5;  // last 32-column block whose first t_pos is < start (or block 0)
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (ck[mid] < start) lo = mid;
-        else hi = mid;
+    // last 32-column block whose first t_pos is < start (or block 0): guessed from the distance to the read's start
+    // (few indels in a HiFi alignment), corrected by a few steps along the checkpoints, else a binary search
+    const uint32_t nblk = (n + 31) >> 5, ts = R.t_s[r];
+    uint32_t lo = start > ts ? min((start - ts) >> 5, nblk - 1) : 0, steps = 0;
+    while (lo > 0 && ck[lo] >= start && steps < 4) lo--, steps++;
+    while (lo + 1 < nblk && ck[lo + 1] < start && steps < 4) lo++, steps++;
+    if (steps >= 4) {
+        uint32_t hi = nblk;
+        lo = 0;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (ck[mid] < start) lo = mid;
+            else hi = mid;
+        }
     }
     const uint64_t mask = (1ULL << (2 * k)) - 1;
     const uint32_t sh = 2 * (k - 1);
@@ -153,19 +162,20 @@ __device__ __forceinline__ ScanOut scan_ref_region(const uint8_t *__restrict__ c
     return so;
 }
 
-__global__ void k_pair_scan(GenoDev g, ReadsDev R, uint32_t k) {
-    uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g.cnt[C_ABORT] || pi >= g.cnt[C_NPAIRS]) return;
-    uint32_t lo = 0, hi = R.n_reads;  // read owning pair pi: largest i with rd_poff[i] <= pi
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (g.rd_poff[mid] <= pi) lo = mid;
-        else hi = mid;
+// one warp per read, a lane per region the read covers: the lanes of a warp walk the same read
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_pair_scan(GenoDev g, ReadsDev R, uint32_t k) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g.cnt[C_ABORT] || i >= R.n_reads) return;
+    const uint32_t np = g.rd_np[i];
+    if (!np) return;
+    const uint32_t j = g.rd_j[i], poff = g.rd_poff[i], limit = g.end[j] + k;
+    for (uint32_t x = lane; x < np; x += 32) {
+        const uint32_t reg = j + x;
+        ScanOut so = scan_read_region<false>(R, i, g.start[reg], g.end[reg], limit, k, nullptr);
+        g.p_len[poff + x] = so.len;
+        g.p_kmer[poff + x] = so.kmer;
     }
-    const uint32_t i = lo, j = g.rd_j[i], reg = j + (pi - g.rd_poff[i]);
-    ScanOut so = scan_read_region<false>(R, i, g.start[reg], g.end[reg], g.end[j] + k, k, nullptr);
-    g.p_len[pi] = so.len;
-    g.p_kmer[pi] = so.kmer;
 }
 
 /* ---------------------------------------------------------------- per-region candidate selection */
@@ -175,7 +185,8 @@ __global__ void k_pair_scan(GenoDev g, ReadsDev R, uint32_t k) {
 __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_select(GenoDev g, ReadsDev R,
                                                                      const uint8_t *__restrict__ blank,
                                                                      const uint8_t *__restrict__ code, uint32_t L,
-                                                                     uint32_t k, uint32_t max_span) {
+                                                                     uint32_t k, uint32_t max_span,
+                                                                     const uint32_t *__restrict__ first_ge, uint32_t W) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g.cnt[C_ABORT] || r >= g.cnt[C_NREG]) return;
@@ -195,21 +206,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_region_select(GenoDev g, 
     }
     ncand = __shfl_sync(0xFFFFFFFFu, ncand, 0);
     bytes = __shfl_sync(0xFFFFFFFFu, bytes, 0);
+    // a superset of the reads with pos in [start - max_span, start], from the per-stripe read index (the test below is
+    // exact: a read covers region r iff j <= r <= s)
     const uint32_t lo_pos = start > max_span ? start - max_span : 0;
-    uint32_t lo = 0, hi = R.n_reads;  // first read with pos >= lo_pos
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (R.pos[mid] < lo_pos) lo = mid + 1;
-        else hi = mid;
-    }
-    const uint32_t first = lo;
-    hi = R.n_reads;  // first read with pos > start
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (R.pos[mid] <= start) lo = mid + 1;
-        else hi = mid;
-    }
-    const uint32_t last = lo;
+    const uint32_t first = first_ge[lo_pos / W], last = first_ge[start / W + 1];
     for (uint32_t i0 = first; i0 < last && ncand < kMaxCand; i0 += 32) {
         const uint32_t i = i0 + lane;
         uint32_t len = 0, pair = 0;
@@ -685,11 +685,15 @@ void geno_pair_offsets(GenoDev g, uint32_t n_reads, uint32_t cap_pairs, CountsDe
     scan_launch(f, nullptr, 0, n_reads, pool, s, cd.c + C_ABORT);
 }
 void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, uint32_t cap_pairs, cudaStream_t s) {
-    if (cap_pairs) NP2_K(k_pair_scan)<<<cdiv(cap_pairs, 128), 128, 0, s>>>(g, R, k);
+    if (cap_pairs && R.n_reads)
+        NP2_K(k_pair_scan)<<<cdiv((uint64_t)R.n_reads * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(g, R, k);
 }
 void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                        uint32_t k, uint32_t max_span, uint32_t cap_reg, cudaStream_t s) {
-    if (cap_reg) NP2_K(k_region_select)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, R, d_blank, d_code, L, k, max_span);
+                        uint32_t k, uint32_t max_span, const uint32_t *d_first_ge, uint32_t stripe_width, uint32_t cap_reg,
+                        cudaStream_t s) {
+    if (cap_reg)
+        NP2_K(k_region_select)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, R, d_blank, d_code, L, k, max_span, d_first_ge,
+                                                                                  stripe_width);
 }
 void geno_pool_offsets(GenoDev g, uint32_t cap_reg, unsigned long long cap_pool, CountsDev cd, ScanPool &pool,
                        cudaStream_t s) {

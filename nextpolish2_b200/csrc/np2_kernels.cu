@@ -1008,6 +1008,7 @@ static int stripe_w() {
     return w;
 }
 uint32_t pileup_stripes(uint32_t L) { return cdiv(L, stripe_w()); }
+uint32_t pileup_stripe_width() { return (uint32_t)stripe_w(); }
 
 template <int kStripeW, bool WRITE>
 __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, const uint8_t *__restrict__ blank,

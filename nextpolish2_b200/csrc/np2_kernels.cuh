@@ -112,6 +112,7 @@ void cover_scan(int32_t *d_cover, uint32_t n, ScanPool &pool, cudaStream_t s);  
 // shared memory; per position: entry offset / count, reference 3-mer count, articulation flag, bases a single-entry
 // position emits.  C_NREC = records seen, C_G = entries written (reserved by one atomic per stripe).
 uint32_t pileup_stripes(uint32_t L);
+uint32_t pileup_stripe_width();
 struct MsaDev {
     uint32_t L = 0;
     const uint32_t *cnt = nullptr;  // C_G = sparse groups
@@ -183,8 +184,10 @@ void geno_cursor_min(uint32_t *d_rd_s, uint32_t n_reads, const uint32_t *d_abort
 void geno_read_ranges(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, uint32_t k, cudaStream_t s);
 void geno_pair_offsets(GenoDev g, uint32_t n_reads, uint32_t cap_pairs, CountsDev cd, ScanPool &pool, cudaStream_t s);
 void geno_pair_scan(GenoDev g, const ReadsDev &R, uint32_t k, uint32_t cap_pairs, cudaStream_t s);
+// d_first_ge / stripe_width: the per-stripe read index of the pileup (stripe_reads)
 void geno_region_select(GenoDev g, const ReadsDev &R, const uint8_t *d_blank, const uint8_t *d_code, uint32_t L,
-                        uint32_t k, uint32_t max_span, uint32_t cap_reg, cudaStream_t s);
+                        uint32_t k, uint32_t max_span, const uint32_t *d_first_ge, uint32_t stripe_width, uint32_t cap_reg,
+                        cudaStream_t s);
 void geno_pool_offsets(GenoDev g, uint32_t cap_reg, unsigned long long cap_pool, CountsDev cd, ScanPool &pool,
                        cudaStream_t s);
 void geno_cand_write(GenoDev g, const ReadsDev &R, const uint8_t *d_code, uint32_t L, uint32_t k, uint32_t cap_reg,

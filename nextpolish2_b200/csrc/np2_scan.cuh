@@ -9,8 +9,8 @@
 //
 // Algorithm: reduce-then-scan over a FIXED partition.  The elements are cut into one contiguous chunk per CTA
 // (at most kScanMaxCtas of them); pass 1 reduces every chunk (loads only), a one-CTA pass scans the chunk totals, and
-// pass 2 re-reads every chunk, scans it in registers (warp-striped rows, so every load / store instruction of a warp
-// touches 32 consecutive elements) and calls the functor's store.  The input is read twice, but nothing ever waits for
+// pass 2 re-reads every chunk, scans it in registers (every thread owns 16 consecutive elements: 15 serial operations, one
+// shuffle scan per warp) and calls the functor's store.  The input is read twice, but nothing ever waits for
 // another CTA: a chained single-pass scan with look-back measured 2-3x slower here, because with ~500 tiles in flight
 // every tile walks back through hundreds of descriptors that only hold aggregates (profiles/r02h_launches.csv).
 // Small inputs (one chunk) take a single launch.  Values are kept in 62 bits (functors sign-extend if they scan signed
@@ -156,30 +156,23 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(Tr tr, const uint32
     const uint64_t end = begin + chunk < n ? begin + chunk : n;
     unsigned long long tile_pre = partial ? partial[blockIdx.x] : Tr::identity();
     for (uint64_t t0 = begin; t0 < end; t0 += kScanTile) {
-        // Warp-striped: a warp owns kScanItems * 32 consecutive elements, element j * 32 + lane of them sits in loc[j]
-        const uint64_t w0 = t0 + (uint64_t)warp * (kScanItems * 32) + lane;
-        unsigned long long loc[kScanItems];
+        // blocked: a thread owns kScanItems consecutive elements, scanned serially in registers; one shuffle scan of the
+        // thread totals per warp and one pass over the warp totals give its offset inside the tile
+        const uint64_t i0 = t0 + (uint64_t)tid * kScanItems;
+        unsigned long long loc[kScanItems], sum = Tr::identity();
 #pragma unroll
         for (int j = 0; j < kScanItems; j++) {
-            const uint64_t i = w0 + (uint64_t)j * 32;
-            loc[j] = i < end ? tr.load((uint32_t)i) : Tr::identity();
+            loc[j] = i0 + j < end ? tr.load((uint32_t)(i0 + j)) : Tr::identity();
+            sum = Tr::op(sum, loc[j]);
         }
-        // inclusive scan in element order inside the warp: a shuffle scan per row, rows chained through lane 31
-        unsigned long long carry = Tr::identity();
+        unsigned long long incl = sum;
 #pragma unroll
-        for (int j = 0; j < kScanItems; j++) {
-            unsigned long long v = loc[j];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, v, d);
-                if (lane >= d) v = Tr::op(t, v);
-            }
-            v = Tr::op(carry, v);
-            loc[j] = v;
-            carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl = Tr::op(t, incl);
         }
         __syncthreads();  // s_warp of the previous tile has been read
-        if (lane == 31) s_warp[warp] = carry;
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         unsigned long long warp_ex = Tr::identity(), agg = Tr::identity();
 #pragma unroll
@@ -187,15 +180,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(Tr tr, const uint32
             if (w < (int)warp) warp_ex = Tr::op(warp_ex, s_warp[w]);
             agg = Tr::op(agg, s_warp[w]);
         }
-        const unsigned long long pre = Tr::op(tile_pre, warp_ex) & kScanMask;
-        unsigned long long row_carry = Tr::identity();  // inclusive value of the last element of the previous row
+        unsigned long long lane_ex = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane == 0) lane_ex = Tr::identity();
+        unsigned long long run = Tr::op(Tr::op(tile_pre, warp_ex), lane_ex) & kScanMask;
 #pragma unroll
         for (int j = 0; j < kScanItems; j++) {
-            unsigned long long prev = __shfl_up_sync(0xFFFFFFFFu, loc[j], 1);
-            if (lane == 0) prev = row_carry;
-            row_carry = __shfl_sync(0xFFFFFFFFu, loc[j], 31);
-            const uint64_t i = w0 + (uint64_t)j * 32;
-            if (i < end) tr.store((uint32_t)i, Tr::op(pre, prev) & kScanMask, Tr::op(pre, loc[j]) & kScanMask);
+            const unsigned long long ex = run;
+            run = Tr::op(run, loc[j]) & kScanMask;
+            if (i0 + j < end) tr.store((uint32_t)(i0 + j), ex, run);
         }
         tile_pre = Tr::op(tile_pre, agg) & kScanMask;
     }
