@@ -1541,7 +1541,7 @@ struct ScanEmit : ScanSumBase {
     uint8_t *out_base, *out_flags;
     uint32_t cap_n;
     uint32_t *count, *abort;
-    __device__ unsigned long long load(uint32_t p) const { return n_emit[p]; }
+    __device__ uint32_t load(uint32_t p) const { return n_emit[p]; }
     __device__ void store(uint32_t p, unsigned long long ex, unsigned long long in) const {
         emit_off[p] = (uint32_t)ex;
         if (in != ex && ex < cap_n && !m.multi[p]) {

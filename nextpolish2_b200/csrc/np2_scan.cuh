@@ -59,11 +59,14 @@ struct ScanPool {
 };
 
 // Tr: struct with
-//   __device__ unsigned long long load(uint32_t i) const        value of element i (< n), already reduced to 62 bits;
-//                                                               no side effects (it is called twice per element)
-//   __device__ static unsigned long long op(a, b)               associative and commutative, closed on 62-bit values
-//   __device__ static unsigned long long identity()
-//   __device__ void store(uint32_t i, excl, incl) const         prefix before / including element i
+//   __device__ uint32_t load(uint32_t i) const                  value of element i (< n); no side effects (it is called
+//                                                               twice per element)
+//   __device__ static uint32_t op32(a, b), identity32()         the operation on 32-bit values: used INSIDE a tile of 4096
+//                                                               elements, whose partial results must fit 32 bits
+//   __device__ static unsigned long long widen(uint32_t)        a tile-local partial result as a 62-bit value
+//   __device__ static unsigned long long op(a, b), identity()   the operation on 62-bit values (chunk and tile prefixes);
+//                                                               associative and commutative
+//   __device__ void store(uint32_t i, excl, incl) const         prefix before / including element i (62-bit values)
 //   __device__ void total(unsigned long long t, uint32_t n) const   once, after the last element (also when n == 0)
 // n = *d_n + n_plus (clamped to cap) when d_n != nullptr, else cap.
 __device__ __forceinline__ uint32_t scan_count(const uint32_t *d_n, uint32_t n_plus, uint32_t cap) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(Tr tr, const uint3
     const uint64_t chunk = scan_chunk(n, gridDim.x), begin = blockIdx.x * chunk;
     const uint64_t end = begin + chunk < n ? begin + chunk : n;
     unsigned long long acc = Tr::identity();
-    for (uint64_t i = begin + threadIdx.x; i < end; i += kScanThreads) acc = Tr::op(acc, tr.load((uint32_t)i));
+    for (uint64_t i = begin + threadIdx.x; i < end; i += kScanThreads) acc = Tr::op(acc, Tr::widen(tr.load((uint32_t)i)));
     acc = scan_block_reduce<Tr>(acc, s_warp);
     if (threadIdx.x == 0) partial[blockIdx.x] = acc & kScanMask;
 }
@@ -154,42 +157,55 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(Tr tr, const uint32
     const uint32_t n = scan_count(d_n, n_plus, cap);
     const uint64_t chunk = scan_chunk(n, gridDim.x), begin = blockIdx.x * chunk;
     const uint64_t end = begin + chunk < n ? begin + chunk : n;
+    __shared__ uint32_t s_w32[kScanThreads / 32];
     unsigned long long tile_pre = partial ? partial[blockIdx.x] : Tr::identity();
     for (uint64_t t0 = begin; t0 < end; t0 += kScanTile) {
-        // blocked: a thread owns kScanItems consecutive elements, scanned serially in registers; one shuffle scan of the
-        // thread totals per warp and one pass over the warp totals give its offset inside the tile
-        const uint64_t i0 = t0 + (uint64_t)tid * kScanItems;
-        unsigned long long loc[kScanItems], sum = Tr::identity();
+        // Warp-striped: a warp owns kScanItems * 32 consecutive elements, element j * 32 + lane of them sits in loc[j] of
+        // lane `lane`, so every load and store instruction of a warp touches 32 consecutive elements.  Inside the tile
+        // the arithmetic is 32-bit; the 62-bit prefix of the tile is applied when the results are handed to the functor.
+        const uint64_t w0 = t0 + (uint64_t)warp * (kScanItems * 32) + lane;
+        uint32_t loc[kScanItems];
 #pragma unroll
         for (int j = 0; j < kScanItems; j++) {
-            loc[j] = i0 + j < end ? tr.load((uint32_t)(i0 + j)) : Tr::identity();
-            sum = Tr::op(sum, loc[j]);
+            const uint64_t i = w0 + (uint64_t)j * 32;
+            loc[j] = i < end ? tr.load((uint32_t)i) : Tr::identity32();
         }
-        unsigned long long incl = sum;
+        // inclusive scan of every row (independent shuffle chains), then the rows are chained through their last lane
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl = Tr::op(t, incl);
-        }
-        __syncthreads();  // s_warp of the previous tile has been read
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        unsigned long long warp_ex = Tr::identity(), agg = Tr::identity();
 #pragma unroll
-        for (int w = 0; w < kScanThreads / 32; w++) {
-            if (w < (int)warp) warp_ex = Tr::op(warp_ex, s_warp[w]);
-            agg = Tr::op(agg, s_warp[w]);
+            for (int j = 0; j < kScanItems; j++) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, loc[j], d);
+                if (lane >= d) loc[j] = Tr::op32(t, loc[j]);
+            }
         }
-        unsigned long long lane_ex = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-        if (lane == 0) lane_ex = Tr::identity();
-        unsigned long long run = Tr::op(Tr::op(tile_pre, warp_ex), lane_ex) & kScanMask;
+        uint32_t carry = Tr::identity32();
 #pragma unroll
         for (int j = 0; j < kScanItems; j++) {
-            const unsigned long long ex = run;
-            run = Tr::op(run, loc[j]) & kScanMask;
-            if (i0 + j < end) tr.store((uint32_t)(i0 + j), ex, run);
+            loc[j] = Tr::op32(carry, loc[j]);
+            carry = __shfl_sync(0xFFFFFFFFu, loc[j], 31);
         }
-        tile_pre = Tr::op(tile_pre, agg) & kScanMask;
+        __syncthreads();  // s_w32 of the previous tile has been read
+        if (lane == 31) s_w32[warp] = carry;
+        __syncthreads();
+        uint32_t warp_ex = Tr::identity32(), agg = Tr::identity32();
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; w++) {
+            if (w < (int)warp) warp_ex = Tr::op32(warp_ex, s_w32[w]);
+            agg = Tr::op32(agg, s_w32[w]);
+        }
+        uint32_t row_carry = Tr::identity32();  // inclusive value of the last element of the previous row
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) {
+            uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, loc[j], 1);
+            if (lane == 0) prev = row_carry;
+            row_carry = __shfl_sync(0xFFFFFFFFu, loc[j], 31);
+            const uint64_t i = w0 + (uint64_t)j * 32;
+            if (i < end)
+                tr.store((uint32_t)i, Tr::op(tile_pre, Tr::widen(Tr::op32(warp_ex, prev))) & kScanMask,
+                         Tr::op(tile_pre, Tr::widen(Tr::op32(warp_ex, loc[j]))) & kScanMask);
+        }
+        tile_pre = Tr::op(tile_pre, Tr::widen(agg)) & kScanMask;
     }
     if (!partial && tid == 0) tr.total(tile_pre, n);
 }
@@ -215,9 +231,15 @@ inline void scan_launch(const Tr &tr, const uint32_t *d_n, uint32_t n_plus, uint
 
 /* ---------------------------------------------------------------- the functors the pipeline uses */
 
-struct ScanSumBase {
+struct ScanSumBase {  // sums of unsigned values
     __device__ static unsigned long long op(unsigned long long a, unsigned long long b) { return (a + b) & kScanMask; }
     __device__ static unsigned long long identity() { return 0; }
+    __device__ static uint32_t op32(uint32_t a, uint32_t b) { return a + b; }
+    __device__ static uint32_t identity32() { return 0; }
+    __device__ static unsigned long long widen(uint32_t v) { return v; }
+};
+struct ScanSignedSumBase : ScanSumBase {  // sums of signed values: tile-local partial sums fit an int32
+    __device__ static unsigned long long widen(uint32_t v) { return (unsigned long long)(long long)(int32_t)v & kScanMask; }
 };
 __device__ __forceinline__ long long scan_signed(unsigned long long v) { return (long long)(v << 2) >> 2; }
 
@@ -231,7 +253,7 @@ struct ScanOffsets : ScanSumBase {
     unsigned long long *q_slot;
     unsigned long long cap;
     uint32_t *abort;
-    __device__ unsigned long long load(uint32_t i) const { return (unsigned long long)in[i]; }
+    __device__ uint32_t load(uint32_t i) const { return (uint32_t)in[i]; }
     __device__ void store(uint32_t i, unsigned long long ex, unsigned long long) const { out[i] = (Out)ex; }
     __device__ void total(unsigned long long t, uint32_t n) const {
         out[n] = (Out)t;
@@ -241,11 +263,11 @@ struct ScanOffsets : ScanSumBase {
     }
 };
 // signed 64-bit version (patch length deltas)
-struct ScanOffsetsI64 : ScanSumBase {
+struct ScanOffsetsI64 : ScanSignedSumBase {
     const long long *in;
     long long *out;
     unsigned long long *q_slot;
-    __device__ unsigned long long load(uint32_t i) const { return (unsigned long long)in[i] & kScanMask; }
+    __device__ uint32_t load(uint32_t i) const { return (uint32_t)in[i]; }
     __device__ void store(uint32_t i, unsigned long long ex, unsigned long long) const { out[i] = scan_signed(ex); }
     __device__ void total(unsigned long long t, uint32_t n) const {
         out[n] = scan_signed(t);
@@ -253,9 +275,9 @@ struct ScanOffsetsI64 : ScanSumBase {
     }
 };
 // in-place inclusive sum of signed 32-bit values (coverage from the difference array)
-struct ScanInclusiveI32 : ScanSumBase {
+struct ScanInclusiveI32 : ScanSignedSumBase {
     int32_t *a;
-    __device__ unsigned long long load(uint32_t i) const { return (unsigned long long)(long long)a[i] & kScanMask; }
+    __device__ uint32_t load(uint32_t i) const { return (uint32_t)a[i]; }
     __device__ void store(uint32_t i, unsigned long long, unsigned long long in) const { a[i] = (int32_t)scan_signed(in); }
     __device__ void total(unsigned long long, uint32_t) const {}
 };
@@ -264,7 +286,10 @@ struct ScanInclusiveMinU32 {
     uint32_t *a;
     __device__ static unsigned long long op(unsigned long long x, unsigned long long y) { return x < y ? x : y; }
     __device__ static unsigned long long identity() { return kScanMask; }
-    __device__ unsigned long long load(uint32_t i) const { return a[i]; }
+    __device__ static uint32_t op32(uint32_t x, uint32_t y) { return x < y ? x : y; }
+    __device__ static uint32_t identity32() { return 0xFFFFFFFFu; }
+    __device__ static unsigned long long widen(uint32_t v) { return v; }
+    __device__ uint32_t load(uint32_t i) const { return a[i]; }
     __device__ void store(uint32_t i, unsigned long long, unsigned long long in) const { a[i] = (uint32_t)in; }
     __device__ void total(unsigned long long, uint32_t) const {}
 };
@@ -276,7 +301,7 @@ struct ScanSelect : ScanSumBase {
     uint32_t *out, *count;
     uint32_t cap;
     uint32_t *abort;
-    __device__ unsigned long long load(uint32_t i) const { return pred(i) ? 1ULL : 0ULL; }
+    __device__ uint32_t load(uint32_t i) const { return pred(i) ? 1u : 0u; }
     __device__ void store(uint32_t i, unsigned long long ex, unsigned long long in) const {
         if (in != ex && ex < cap) out[ex] = i;
     }

@@ -17,6 +17,7 @@
 #include "np2_oracle.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -729,6 +730,14 @@ void mark_hete_lqseqs(std::vector<LqSeqs> &lqseqs) {
 
 /* ------------------------------------------------------------- louvain.rs */
 
+// Where the reference's result can depend on FxHashMap iteration order (SURVEY hard part 3), counted so that the
+// exposure can be MEASURED on real inputs (np2o_order_exposure):
+//  [0] calls of phase_communities, [1] communities declustered in second_stage (louvain.rs:136-165: their new ids depend
+//  on the order communities and nodes are visited in), [2] pairs of communities with EQUAL sort keys that conflict with
+//  each other while both are still valid (louvain.rs:316-339: which of the two is dropped depends on their order
+//  before the stable sort), [3] reads in the communities of [2].
+static std::atomic<uint64_t> g_order_exposure[4];
+
 typedef std::map<uint32_t, std::map<uint32_t, float>> Graph;  // louvain.rs:31 (ascending-id iteration, see header)
 
 void insert_data(Graph &data, uint32_t k1, uint32_t k2, float v) {  // louvain.rs:273-279
@@ -832,7 +841,10 @@ struct Louvain {  // louvain.rs:30-257
                     for (auto &e : it->second)
                         if (nodes.count(e.first)) nn.weight += e.second / 2.0f;
             }
-            if (nn.weight < 0.f) decluster_ids.push_back(id);
+            if (nn.weight < 0.f) {
+                decluster_ids.push_back(id);
+                g_order_exposure[1]++;
+            }
             else {
                 new_comm[id] = {id};
                 new_node[id] = nn;
@@ -921,6 +933,7 @@ struct Louvain {  // louvain.rs:30-257
 
 // louvain.rs:290-356
 std::vector<uint32_t> phase_communities(Graph data, const std::map<uint32_t, float> *ref_weight) {
+    g_order_exposure[0]++;
     Louvain lv(std::move(data));
     for (;;) {  // louvain.rs:247-256
         bool mod_inc = lv.first_stage();
@@ -930,6 +943,7 @@ std::vector<uint32_t> phase_communities(Graph data, const std::map<uint32_t, flo
     Graph cdata;
     std::vector<Node> communities;
     lv.get_communities(cdata, communities);
+    std::map<uint32_t, std::pair<int64_t, float>> sort_key;  // community id -> key it was sorted by (exposure count)
 
     if (ref_weight) {
         struct Key {
@@ -949,6 +963,7 @@ std::vector<uint32_t> phase_communities(Graph data, const std::map<uint32_t, flo
                 }
             }
             keyed.push_back({{count, weight}, i});
+            sort_key[communities[i].id] = {count, weight};
         }
         std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<Key, size_t> &a, const std::pair<Key, size_t> &b) {
             // Reverse((count, weight)): descending
@@ -959,6 +974,7 @@ std::vector<uint32_t> phase_communities(Graph data, const std::map<uint32_t, flo
         for (auto &k : keyed) sorted.push_back(std::move(communities[k.second]));
         communities.swap(sorted);
     } else {
+        for (auto &c : communities) sort_key[c.id] = {0, c.weight};
         std::stable_sort(communities.begin(), communities.end(),
                          [](const Node &a, const Node &b) { return b.weight < a.weight; });
     }
@@ -970,7 +986,13 @@ std::vector<uint32_t> phase_communities(Graph data, const std::map<uint32_t, flo
         if (it != cdata.end()) {
             for (size_t q = p + 1; q < communities.size(); q++) {
                 if (invalid_ids.count(communities[q].id)) continue;
-                if (it->second.count(communities[q].id)) invalid_ids.insert(communities[q].id);
+                if (it->second.count(communities[q].id)) {
+                    invalid_ids.insert(communities[q].id);
+                    if (sort_key[communities[p].id] == sort_key[communities[q].id]) {  // order decided who is dropped
+                        g_order_exposure[2]++;
+                        g_order_exposure[3] += communities[p].nodes.size() + communities[q].nodes.size();
+                    }
+                }
             }
         }
     }
@@ -1870,6 +1892,12 @@ uint64_t np2o_get_consensus(np2o_job *j, const uint32_t **pos, const uint8_t **b
     return j->d_cns_pos.size();
 }
 double np2o_get_seconds(np2o_job *j) { return j->seconds; }
+void np2o_order_exposure(uint64_t out[4], int reset) {
+    for (int i = 0; i < 4; i++) {
+        out[i] = g_order_exposure[i].load();
+        if (reset) g_order_exposure[i] = 0;
+    }
+}
 
 // main.rs:607-645
 uint64_t np2o_format_fasta(const char *tid, const uint32_t *pos, const uint8_t *base, uint64_t n, int uppercase,

@@ -99,6 +99,11 @@ int64_t np2o_debug_phase(const uint64_t *keys, const int64_t *vals, uint64_t n, 
 uint64_t np2o_get_consensus(np2o_job *, const uint32_t **pos, const uint8_t **base);
 /* seconds spent in np2o_job_run */
 double np2o_get_seconds(np2o_job *);
+/* How often a result could have depended on FxHashMap iteration order (process-wide counters since the last reset):
+ * out[0] phasing calls, out[1] communities declustered (louvain.rs:136-165), out[2] conflicting community pairs with
+ * equal sort keys (louvain.rs:316-339), out[3] reads in those communities.  0 / 0 means the ascending-id order used
+ * here cannot have changed anything. */
+void np2o_order_exposure(uint64_t out[4], int reset);
 
 /* FASTA record exactly as display_consensusbase_vec (main.rs:607-645) prints it; returns bytes written (or needed if cap too small) */
 uint64_t np2o_format_fasta(const char *tid, const uint32_t *pos, const uint8_t *base, uint64_t n,

@@ -75,6 +75,7 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_uint64
             f.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * n
+        L.np2o_order_exposure.argtypes = [C.c_void_p, C.c_int]
         L.np2o_debug_phase.restype = C.c_int64
         L.np2o_debug_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
         L.np2o_format_fasta.restype = C.c_uint64
@@ -213,6 +214,14 @@ class Job:
         if getattr(self, "h", None) and _lib is not None:
             _lib.np2o_job_destroy(self.h)
             self.h = None
+
+
+def order_exposure(reset=False):
+    """Counters of the places where the reference's result depends on FxHashMap iteration order (np2_oracle.h)."""
+    v = (C.c_uint64 * 4)()
+    lib().np2o_order_exposure(v, int(reset))
+    return {"phasing_calls": int(v[0]), "declustered_communities": int(v[1]), "tied_conflicting_pairs": int(v[2]),
+            "reads_in_tied_pairs": int(v[3])}
 
 
 def debug_phase(keys, vals, model=0, use_all_reads=False):
