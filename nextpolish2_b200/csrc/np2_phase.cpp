@@ -15,6 +15,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <vector>
@@ -106,13 +107,36 @@ bool move_range(Lvl &lv, size_t i0, size_t i1, uint32_t *slot, uint32_t *stamp, 
 // it.  Reads are numbered along the contig and only overlapping reads share an edge, so such sets are found as id
 // intervals (a cut wherever no earlier vertex has a neighbour at or beyond the next one: phase-block boundaries) and
 // are moved concurrently on the host pool.
+// adjacency entries below which a level is handled by one thread (NP2_PHASE_PAR_MIN lowers it so that small test graphs
+// reach the concurrent paths)
+uint64_t par_min_edges() {
+    static const uint64_t v = [] {
+        const char *e = getenv("NP2_PHASE_PAR_MIN");
+        return e ? (uint64_t)strtoull(e, nullptr, 10) : 100000ull;
+    }();
+    return v;
+}
+// NP2_PHASE_CHECK=1: verify the invariants the concurrent paths rest on (neighbour lists ascending, no self loops)
+void check_level(const Lvl &lv) {
+    static const bool on = [] {
+        const char *e = getenv("NP2_PHASE_CHECK");
+        return e && atoi(e) != 0;
+    }();
+    if (!on) return;
+    for (uint32_t v : lv.ids)
+        for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) {
+            if (lv.ato[e] == v) throw Error(NP2_ERR_INTERNAL, "phase graph: self loop");
+            if (e > lv.aoff[v] && lv.ato[e - 1] >= lv.ato[e]) throw Error(NP2_ERR_INTERNAL, "phase graph: neighbour list not ascending");
+        }
+}
 bool move_vertices(Lvl &lv) {
     std::vector<uint32_t> slot(lv.n, 0), stamp(lv.n, 0);
     std::vector<uint8_t> dirty(lv.n, 1);
     const size_t ni = lv.ids.size();
     const unsigned threads = host_threads();
     const uint64_t n_edges = ni ? lv.aoff[lv.ids[ni - 1] + 1] - lv.aoff[lv.ids[0]] : 0;
-    if (threads < 2 || n_edges < 100000) return move_range(lv, 0, ni, slot.data(), stamp.data(), dirty.data());
+    check_level(lv);
+    if (threads < 2 || n_edges < par_min_edges()) return move_range(lv, 0, ni, slot.data(), stamp.data(), dirty.data());
     // independent intervals, then chunks of whole intervals with about the same number of edges
     const uint64_t per_chunk = n_edges / (4 * threads) + 1;
     std::vector<size_t> chunk_begin(1, 0);
@@ -179,11 +203,10 @@ struct PairSum {
     uint32_t c1, c2;
     float w;
 };
-void between_communities(const Lvl &lv, const Groups &g, std::vector<PairSum> &out) {
-    out.clear();
+void between_range(const Lvl &lv, const Groups &g, size_t g0, size_t g1, std::vector<PairSum> &out) {
     std::vector<uint32_t> stamp(lv.n, 0), touched;
     std::vector<float> acc(lv.n, 0.f);
-    for (size_t gi = 0; gi < g.comms.size(); gi++) {
+    for (size_t gi = g0; gi < g1; gi++) {
         const uint32_t c = g.comms[gi];
         touched.clear();
         for (uint32_t x = g.off[gi]; x < g.off[gi + 1]; x++) {
@@ -203,6 +226,67 @@ void between_communities(const Lvl &lv, const Groups &g, std::vector<PairSum> &o
         for (uint32_t o : touched) out.push_back({c, o, acc[o]});
     }
 }
+// chunks of whole communities with about the same number of member vertices (the sums of a community only read)
+std::vector<size_t> community_chunks(const Lvl &lv, const Groups &g, unsigned &threads) {
+    threads = host_threads();
+    const uint64_t n_edges = lv.verts.empty() ? 0 : lv.aoff[lv.verts.back() + 1] - lv.aoff[lv.verts.front()];
+    std::vector<size_t> cb(1, 0);
+    if (threads < 2 || n_edges < par_min_edges() || g.comms.size() < 2) {
+        cb.push_back(g.comms.size());
+        threads = 1;
+        return cb;
+    }
+    const uint64_t per = g.dat.size() / (4 * threads) + 1;
+    uint64_t in_chunk = 0;
+    for (size_t gi = 0; gi < g.comms.size(); gi++) {
+        if (gi && in_chunk >= per) {
+            cb.push_back(gi);
+            in_chunk = 0;
+        }
+        in_chunk += g.off[gi + 1] - g.off[gi];
+    }
+    cb.push_back(g.comms.size());
+    return cb;
+}
+void between_communities(const Lvl &lv, const Groups &g, std::vector<PairSum> &out) {
+    out.clear();
+    unsigned threads;
+    const std::vector<size_t> cb = community_chunks(lv, g, threads);
+    const size_t nc = cb.size() - 1;
+    if (nc < 2) {
+        between_range(lv, g, 0, g.comms.size(), out);
+        return;
+    }
+    std::vector<std::vector<PairSum>> part(nc);
+    std::atomic<size_t> next(0);
+    parallel_for((unsigned)std::min<size_t>(threads, nc), [&](unsigned) {
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= nc) break;
+            between_range(lv, g, cb[c], cb[c + 1], part[c]);
+        }
+    });
+    for (auto &p : part) out.insert(out.end(), p.begin(), p.end());  // chunks in community order: ascending (c1, c2)
+}
+// Node.weight of every community, by position in g.comms
+void internal_weights(const Lvl &lv, const Groups &g, std::vector<float> &w) {
+    w.assign(g.comms.size(), 0.f);
+    unsigned threads;
+    const std::vector<size_t> cb = community_chunks(lv, g, threads);
+    const size_t nc = cb.size() - 1;
+    if (nc < 2) {
+        for (size_t gi = 0; gi < g.comms.size(); gi++) w[gi] = internal_weight(lv, g, gi);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    parallel_for((unsigned)std::min<size_t>(threads, nc), [&](unsigned) {
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= nc) break;
+            for (size_t gi = cb[c]; gi < cb[c + 1]; gi++) w[gi] = internal_weight(lv, g, gi);
+        }
+    });
+}
 
 // louvain.rs:119-195 when no community has to be declustered; false when one has
 bool aggregate(const Lvl &lv, Lvl &nx) {
@@ -215,8 +299,10 @@ bool aggregate(const Lvl &lv, Lvl &nx) {
     nx.nweight.assign(lv.n, 0.f);
     nx.moff.assign(lv.n + 1, 0);
     nx.verts = g.comms;
+    std::vector<float> iw;
+    internal_weights(lv, g, iw);
     for (size_t gi = 0; gi < g.comms.size(); gi++) {
-        const float w = internal_weight(lv, g, gi);
+        const float w = iw[gi];
         if (w < 0.f) return false;
         const uint32_t c = g.comms[gi];
         nx.cid[c] = c;
@@ -303,7 +389,9 @@ std::vector<uint32_t> phase_core(Lvl &lv, uint32_t n, const uint8_t *bad_v, cons
     std::vector<uint32_t> slot;
     group_by_cid(lv, g, slot);
     std::vector<Community> comms;
-    for (size_t gi = 0; gi < g.comms.size(); gi++) comms.push_back({g.comms[gi], internal_weight(lv, g, gi), (uint32_t)gi});
+    std::vector<float> iw;
+    internal_weights(lv, g, iw);
+    for (size_t gi = 0; gi < g.comms.size(); gi++) comms.push_back({g.comms[gi], iw[gi], (uint32_t)gi});
     std::vector<PairSum> ps;
     between_communities(lv, g, ps);
     std::vector<std::vector<uint32_t>> conflict(g.comms.size());  // by position in g.comms

@@ -84,3 +84,52 @@ def test_phase_decluster_goes_through_general_path():
         assert path == 2
         assert np.array_equal(np.sort(got), O.debug_phase(keys, vals, model, use_all))
     assert api.debug_phase(k2, v2, with_path=True)[1] == 1  # the common case stays on the flat-array path
+
+
+_CHILD = r"""
+import json, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle"); sys.path.insert(0, %(root)r + "/tests")
+import numpy as np
+import oracle as O
+import nextpolish2_b200.api as api
+from test_phase_host import make_graph
+out = []
+for case in %(cases)r:
+    keys, vals = make_graph(**case)
+    for model, use_all in ((0, False), (1, False), (0, True)):
+        got, path = api.debug_phase(keys, vals, model, use_all, with_path=True)
+        want = O.debug_phase(keys, vals, model, use_all)
+        out.append([bool(np.array_equal(np.sort(got), want)), int(path), np.sort(got).tolist()])
+print(json.dumps(out))
+"""
+
+PAR_CASES = [dict(seed=21, n_reads=8000, span=30, gap_every=150), dict(seed=22, n_reads=3000, span=40, gap_every=400, noise=0.1),
+             dict(seed=23, n_reads=2500, span=25), dict(seed=24, n_reads=1500, span=20, gap_every=60, noise=0.3, ref=False)]
+
+
+@pytest.mark.timeout(600)
+def test_phase_concurrent_paths_match_serial_and_oracle():
+    """the concurrent vertex-move path (closed id intervals on the host pool) and the concurrent aggregation
+    only start above 100k adjacency entries.  A child process lowers the threshold (NP2_PHASE_PAR_MIN=1), uses 8 host
+    threads and switches the invariant checks on (NP2_PHASE_CHECK=1: neighbour lists ascending, no self loops); its
+    results must equal the oracle's AND the serial results of this process, graph by graph."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    serial = []
+    for case in PAR_CASES:
+        keys, vals = make_graph(**case)
+        for model, use_all in ((0, False), (1, False), (0, True)):
+            serial.append(np.sort(api.debug_phase(keys, vals, model, use_all)).tolist())
+    env = dict(os.environ, NP2_PHASE_PAR_MIN="1", NP2_HOST_THREADS="8", NP2_PHASE_CHECK="1")
+    r = subprocess.run([sys.executable, "-c", _CHILD % {"root": root, "cases": PAR_CASES}], env=env, capture_output=True,
+                       text=True, timeout=550)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(res) == len(serial)
+    for (ok, path, got), want in zip(res, serial):
+        assert ok, "concurrent phasing differs from the oracle"
+        assert path == 1
+        assert got == want, "concurrent phasing differs from the serial run"
