@@ -657,7 +657,11 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
 
 
 def yak_bench(ctx, np2, torch, peak):
-    """K5 at scale: 2^26 keys (~0.9 GB table >> L2), 2^26 device-resident queries, half present / half absent."""
+    """K5 at scale: 2^26 keys (~0.9 GB table >> L2), 2^26 device-resident queries, half present / half absent.
+    One probe needs one 32-byte bucket.  What DRAM really delivers per L2 miss depends on the device's L2 fetch
+    granularity (cudaLimitMaxL2FetchGranularity): the lookup is measured at 32 / 64 / 128 bytes, next to a plain random
+    gather of whole 32 / 64 / 128-byte blocks (the peak of each access size), and the best setting is reported."""
+    from nextpolish2_b200.api import bench_gather, l2_fetch_granularity
     n = 1 << 26
     g = torch.Generator(device="cuda")
     g.manual_seed(1)
@@ -671,20 +675,35 @@ def yak_bench(ctx, np2, torch, peak):
     q = q[torch.randperm(q.numel(), device="cuda", generator=g)].contiguous()
     out = torch.empty(q.numel(), dtype=torch.int16, device="cuda")
     torch.cuda.synchronize()
-    tab.lookup_device(q.data_ptr(), q.numel(), out.data_ptr(), 5, repeat=3)
-    ms = tab.lookup_device(q.data_ptr(), q.numel(), out.data_ptr(), 5, repeat=10)
+    probes = q.numel()
+    default_gran = l2_fetch_granularity(ctx, 0)
+    sweep = {}
+    for gran in (32, 64, 128):
+        l2_fetch_granularity(ctx, gran)
+        tab.lookup_device(q.data_ptr(), probes, out.data_ptr(), 5, repeat=3)
+        ms = tab.lookup_device(q.data_ptr(), probes, out.data_ptr(), 5, repeat=10)
+        g32 = bench_gather(ctx, tab.device_bytes, probes, 32, repeat=10)
+        sweep[str(gran)] = {"lookup_ms": round(ms, 4), "gprobes_per_s": round(probes / ms / 1e6, 3),
+                            "gather32_GBps": round(probes * 32 / g32 / 1e6, 1)}
+    l2_fetch_granularity(ctx, default_gran)
+    blocks = {}
+    for bb in (32, 64, 128):  # whole aligned blocks of bb bytes at the default granularity: the DRAM-side peak per size
+        gm = bench_gather(ctx, tab.device_bytes, probes, bb, repeat=10)
+        blocks[str(bb)] = {"Gblocks_per_s": round(probes / gm / 1e6, 3), "GBps": round(probes * bb / gm / 1e6, 1)}
+    best = min(sweep, key=lambda k: sweep[k]["lookup_ms"])
+    ms = sweep[best]["lookup_ms"]
+    gather_gbs = max(v["gather32_GBps"] for v in sweep.values())
     # size-independent check: present keys answer their count (>= 5 filter), absent answer 0
     exp = torch.where(cnt[perm] >= 5, cnt[perm], torch.zeros_like(cnt[perm]))
     ok = bool((tab.lookup(keys[perm].cpu().numpy().view(np.uint64), 5) == exp.cpu().numpy().view(np.uint16)).all())
-    probes = q.numel()
-    from nextpolish2_b200.api import bench_gather32
-    g_ms = bench_gather32(ctx, tab.device_bytes, probes, repeat=10)
-    gather_gbs = probes * 32 / g_ms / 1e6
-    res = {"probes": probes, "table_keys": nk, "table_bytes": tab.device_bytes, "ms": round(ms, 4),
+    res = {"probes": probes, "table_keys": nk, "table_bytes": tab.device_bytes, "ms": ms,
            "gprobes_per_s": round(probes / ms / 1e6, 3),
            "sector_GBps": round(probes * 32 / ms / 1e6, 1), "algorithmic_GBps": round(probes * 42 / ms / 1e6, 1),
            "frac_of_stream_peak": round(probes * 42 / ms / 1e6 / peak, 4),
-           "random_gather_peak_GBps": round(gather_gbs, 1), "frac_of_random_gather_peak": round(probes * 32 / ms / 1e6 / gather_gbs, 4),
+           "random_gather_peak_GBps": gather_gbs, "frac_of_random_gather_peak": round(probes * 32 / ms / 1e6 / gather_gbs, 4),
+           "l2_fetch_granularity": {"default": default_gran, "best": int(best), "sweep": sweep},
+           "random_block_gather": blocks,
+           "bucket_load": "one 256-bit ld.global.nc.L2::evict_first per probe (LDG.E.256)",
            "correct": ok}
     tab.free()
     return res

@@ -132,6 +132,12 @@ void np2_count_destroy(np2_counter *c);
 /* measurement aid (bench.py): mean time of n_loads independent uniformly random 32-byte sector reads over a
  * scratch buffer of buf_bytes — the measured random-read peak K5 is compared with. */
 int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms);
+/* the same with block_bytes = 32, 64 or 128: every load reads ALL sectors of a random aligned block of that size (what
+ * DRAM delivers when the L2 fetches more than the one sector a probe needs) */
+int np2_bench_gather(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t block_bytes, uint32_t repeat, float *ms);
+/* cudaLimitMaxL2FetchGranularity of the context's device (a hint: 32, 64 or 128 bytes fetched from DRAM per L2 miss).
+ * bytes = 0 only queries.  Device-wide, so a caller that changes it for a lookup-heavy phase restores *previous. */
+int np2_l2_fetch_granularity(np2_ctx *ctx, uint32_t bytes, uint32_t *previous);
 
 /* ---- -S / --use_secondary: SEQ of secondary alignments (src/utils/secondary.rs:8-158, main.rs:1775-1788) ----
  * Secondary records carry no SEQ.  Like the reference, the caller makes two passes over EVERY contig's records before

@@ -42,7 +42,7 @@ class Opts(C.Structure):
 EXPORTS = [
     "np2_last_error", "np2_opts_default", "np2_ctx_create", "np2_ctx_destroy", "np2_yak_load", "np2_yak_from_arrays",
     "np2_yak_free", "np2_yak_clone", "np2_yak_image", "np2_yak_adopt", "np2_yak_k", "np2_yak_size", "np2_yak_device_bytes", "np2_yak_lookup", "np2_yak_lookup_device",
-    "np2_seq_kscore", "np2_bench_gather32", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
+    "np2_seq_kscore", "np2_bench_gather32", "np2_bench_gather", "np2_l2_fetch_granularity", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
     "np2_job_get_consensus", "np2_job_get_span", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_job_get_stats", "np2_format_fasta",
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
@@ -83,6 +83,8 @@ def load_library():
     L.np2_yak_lookup_device.argtypes = [vp, vp, vp, u64, u32, vp, u32, C.POINTER(C.c_float)]
     L.np2_seq_kscore.argtypes = [vp, vp, vp, vp, u64, u32, vp]
     L.np2_bench_gather32.argtypes = [vp, u64, u64, u32, C.POINTER(C.c_float)]
+    L.np2_bench_gather.argtypes = [vp, u64, u64, u32, u32, C.POINTER(C.c_float)]
+    L.np2_l2_fetch_granularity.argtypes = [vp, u32, C.POINTER(u32)]
     L.np2_polish_contig.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_job_create.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_job_upload.argtypes = [vp]
@@ -203,6 +205,20 @@ def debug_parse(bam, tlen, opts=None, threads=0):
     out = (C.c_uint64 * 6)()
     _check(load_library().np2_debug_parse(bam.ctypes.data, len(bam), tlen, C.byref(opts), threads, out))
     return dict(zip(["records", "reads", "ops", "columns", "fallback", "digest"], [int(x) for x in out]))
+
+
+def bench_gather(ctx, buf_bytes, n_loads, block_bytes=32, repeat=5):
+    """Mean ms of n_loads random aligned block reads of block_bytes (32 / 64 / 128) over a buf_bytes scratch buffer."""
+    ms = C.c_float()
+    _check(load_library().np2_bench_gather(ctx.h, buf_bytes, n_loads, block_bytes, repeat, C.byref(ms)))
+    return ms.value
+
+
+def l2_fetch_granularity(ctx, nbytes=0):
+    """Sets (nbytes = 32 / 64 / 128) or queries (0) the device's L2 fetch granularity hint; returns the previous value."""
+    prev = C.c_uint32()
+    _check(load_library().np2_l2_fetch_granularity(ctx.h, nbytes, C.byref(prev)))
+    return prev.value
 
 
 def bench_gather32(ctx, buf_bytes, n_loads, repeat=5):

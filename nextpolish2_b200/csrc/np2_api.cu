@@ -2428,21 +2428,23 @@ int np2_yak_lookup_device(np2_ctx *ctx, const np2_table *t, const uint64_t *d_ha
     });
 }
 
-int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms) {
+int np2_bench_gather(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t block_bytes, uint32_t repeat, float *ms) {
     return guard([&] {
         NP2_CUDA(cudaSetDevice(ctx->device));
+        if (block_bytes != 32 && block_bytes != 64 && block_bytes != 128) throw np2::Error(NP2_ERR_ARG, "block_bytes must be 32, 64 or 128");
         if (repeat == 0) repeat = 1;
         DBuf<uint64_t> buf, sink;
-        const uint64_t n_sectors = buf_bytes / 32;
+        const uint64_t n_sectors = buf_bytes / 128 * 4;
         buf.alloc(n_sectors * 4, ctx->stream);
         sink.alloc(1, ctx->stream);
         NP2_CUDA(cudaMemsetAsync(buf.p, 0x5A, n_sectors * 32, ctx->stream));
-        gather32(buf.p, n_sectors, n_loads, 1, sink.p, ctx->stream);  // warm-up
+        gather32(buf.p, n_sectors, n_loads, 1, sink.p, ctx->stream, (int)block_bytes);  // warm-up
         cudaEvent_t a, b;
         NP2_CUDA(cudaEventCreate(&a));
         NP2_CUDA(cudaEventCreate(&b));
         NP2_CUDA(cudaEventRecord(a, ctx->stream));
-        for (uint32_t r = 0; r < repeat; r++) gather32(buf.p, n_sectors, n_loads, 7 + r * n_loads, sink.p, ctx->stream);
+        for (uint32_t r = 0; r < repeat; r++)
+            gather32(buf.p, n_sectors, n_loads, 7 + r * n_loads, sink.p, ctx->stream, (int)block_bytes);
         NP2_CUDA(cudaEventRecord(b, ctx->stream));
         NP2_CUDA(cudaStreamSynchronize(ctx->stream));
         float t = 0;
@@ -2451,6 +2453,18 @@ int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint3
         cudaEventDestroy(b);
         NP2_CUDA(cudaGetLastError());
         *ms = t / repeat;
+    });
+}
+int np2_bench_gather32(np2_ctx *ctx, uint64_t buf_bytes, uint64_t n_loads, uint32_t repeat, float *ms) {
+    return np2_bench_gather(ctx, buf_bytes, n_loads, 32, repeat, ms);
+}
+int np2_l2_fetch_granularity(np2_ctx *ctx, uint32_t bytes, uint32_t *previous) {
+    return guard([&] {
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        size_t cur = 0;
+        NP2_CUDA(cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity));
+        if (previous) *previous = (uint32_t)cur;
+        if (bytes) NP2_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, bytes));
     });
 }
 

@@ -81,6 +81,15 @@ __host__ __device__ __forceinline__ uint64_t yak_hash64_64(uint64_t key) {
     return key;
 }
 
+// One bucket of the yak table (4 x u64 = one 32-byte sector) in ONE 256-bit load (LDG.E.256, sm_100+), read-only path,
+// evict-first in L2: a probe never comes back to its bucket, so the line should not push the streaming data of the
+// surrounding kernels out of L2.
+__device__ __forceinline__ void ld_bucket(const uint64_t *p, uint64_t v[4]) {
+    asm volatile("ld.global.nc.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
+                 : "l"(p));
+}
+
 // One aligned base (reference AlignBase main.rs:33-52), packed for registers.
 struct ABase {
     uint32_t t_pos;

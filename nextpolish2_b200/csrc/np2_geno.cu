@@ -282,9 +282,8 @@ __device__ __forceinline__ uint32_t g_probe(const TableDev &t, uint64_t h, uint3
     const uint64_t tag = h >> 10;
     uint32_t b = g_bucket_of(tag, t.nb);
     for (uint32_t step = 0; step < t.nb; step++) {
-        const ulonglong2 *bp = (const ulonglong2 *)(t.slots + ((uint64_t)sub * t.nb + b) * kBucketSlots);
-        const ulonglong2 lo = __ldg(bp), hi = __ldg(bp + 1);
-        const uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
+        uint64_t v[4];
+        ld_bucket(t.slots + ((uint64_t)sub * t.nb + b) * kBucketSlots, v);
         bool empty = false;
 #pragma unroll
         for (int j = 0; j < 4; j++) {

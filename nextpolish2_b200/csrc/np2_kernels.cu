@@ -74,12 +74,22 @@ __global__ void k_table_insert_filekeys(uint64_t *slots, uint32_t nb, const uint
 
 // One probe = one 32-byte sector: 8 B query in, 32 B bucket, 2 B out.  Each thread keeps kProbeIlp
 // independent probes in flight so that DRAM latency is covered by memory-level parallelism.
+// WIDE: the bucket comes in one 256-bit evict-first load (ld_bucket); !WIDE: two 128-bit __ldg (kept for A/B runs,
+// NP2_PROBE_WIDE=0).
 constexpr int kProbeIlp = 4;
+template <bool WIDE>
+__device__ __forceinline__ void load_bucket(const uint64_t *bp, uint64_t v[4]) {
+    if (WIDE) {
+        ld_bucket(bp, v);
+    } else {
+        const ulonglong2 lo = __ldg((const ulonglong2 *)bp), hi = __ldg((const ulonglong2 *)bp + 1);
+        v[0] = lo.x, v[1] = lo.y, v[2] = hi.x, v[3] = hi.y;
+    }
+}
+template <bool WIDE>
 __device__ __forceinline__ uint16_t probe_finish(const uint64_t *__restrict__ slots, uint32_t nb, uint32_t sub,
-                                                 uint32_t b, uint64_t tag, ulonglong2 lo, ulonglong2 hi,
-                                                 uint32_t min_count) {
+                                                 uint32_t b, uint64_t tag, uint64_t v[4], uint32_t min_count) {
     for (uint32_t step = 0;; step++) {
-        uint64_t v[4] = {lo.x, lo.y, hi.x, hi.y};
         bool empty = false;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -91,12 +101,11 @@ __device__ __forceinline__ uint16_t probe_finish(const uint64_t *__restrict__ sl
         }
         if (empty || step + 1 >= nb) return 0;
         b = b + 1 == nb ? 0 : b + 1;
-        const ulonglong2 *bp = (const ulonglong2 *)(slots + ((uint64_t)sub * nb + b) * kBucketSlots);
-        lo = __ldg(bp);
-        hi = __ldg(bp + 1);
+        load_bucket<WIDE>(slots + ((uint64_t)sub * nb + b) * kBucketSlots, v);
     }
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kThreads) k_table_probe(const uint64_t *__restrict__ slots, uint32_t nb,
                                                           const uint64_t *__restrict__ hashes, uint64_t n,
                                                           uint32_t min_count, uint16_t *__restrict__ out) {
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) k_table_probe(const uint64_t *__rest
     for (; i0 < n; i0 += stride * kProbeIlp) {
         uint64_t tag[kProbeIlp];
         uint32_t sub[kProbeIlp], b[kProbeIlp];
-        ulonglong2 lo[kProbeIlp], hi[kProbeIlp];
+        uint64_t v[kProbeIlp][4];
 #pragma unroll
         for (int u = 0; u < kProbeIlp; u++) {
             uint64_t i = i0 + u * stride;
@@ -115,15 +124,12 @@ __global__ void __launch_bounds__(kThreads) k_table_probe(const uint64_t *__rest
             b[u] = bucket_of(tag[u], nb);
         }
 #pragma unroll
-        for (int u = 0; u < kProbeIlp; u++) {
-            const ulonglong2 *bp = (const ulonglong2 *)(slots + ((uint64_t)sub[u] * nb + b[u]) * kBucketSlots);
-            lo[u] = __ldg(bp);
-            hi[u] = __ldg(bp + 1);
-        }
+        for (int u = 0; u < kProbeIlp; u++)
+            load_bucket<WIDE>(slots + ((uint64_t)sub[u] * nb + b[u]) * kBucketSlots, v[u]);
 #pragma unroll
         for (int u = 0; u < kProbeIlp; u++) {
             uint64_t i = i0 + u * stride;
-            if (i < n) out[i] = probe_finish(slots, nb, sub[u], b[u], tag[u], lo[u], hi[u], min_count);
+            if (i < n) out[i] = probe_finish<WIDE>(slots, nb, sub[u], b[u], tag[u], v[u], min_count);
         }
     }
 }
@@ -133,8 +139,9 @@ __device__ __forceinline__ uint16_t probe_one(const uint64_t *__restrict__ slots
     uint32_t sub = (uint32_t)(h & 1023);
     uint64_t tag = h >> 10;
     uint32_t b = bucket_of(tag, nb);
-    const ulonglong2 *bp = (const ulonglong2 *)(slots + ((uint64_t)sub * nb + b) * kBucketSlots);
-    return probe_finish(slots, nb, sub, b, tag, __ldg(bp), __ldg(bp + 1), min_count);
+    uint64_t v[4];
+    load_bucket<true>(slots + ((uint64_t)sub * nb + b) * kBucketSlots, v);
+    return probe_finish<true>(slots, nb, sub, b, tag, v, min_count);
 }
 
 // kscore of a byte string: one warp per string, one lane per k-mer end position (iter2kmer kmer.rs:255-314,
@@ -201,7 +208,12 @@ void table_probe(const TableDev &t, const uint64_t *d_hashes, uint64_t n, uint32
     if (!n) return;
     // persistent-style grid: a multiple of the 148 SMs x 8 resident CTAs of 256 threads
     uint32_t grid = min(cdiv(n, (uint64_t)kThreads * kProbeIlp), 148u * 8u);
-    NP2_K(k_table_probe)<<<grid, kThreads, 0, s>>>(t.slots, t.nb, d_hashes, n, min_count, d_out);
+    static const bool wide = [] {
+        const char *e = getenv("NP2_PROBE_WIDE");
+        return !e || atoi(e) != 0;
+    }();
+    if (wide) NP2_K(k_table_probe<true>)<<<grid, kThreads, 0, s>>>(t.slots, t.nb, d_hashes, n, min_count, d_out);
+    else NP2_K(k_table_probe<false>)<<<grid, kThreads, 0, s>>>(t.slots, t.nb, d_hashes, n, min_count, d_out);
 }
 void seq_kscore(const TableDev &t, const uint8_t *d_seqs, const uint64_t *d_off, const uint32_t *d_sel, uint64_t n,
                 uint32_t min_count, uint16_t *d_out, cudaStream_t s) {
@@ -213,32 +225,39 @@ void seq_kscore(const TableDev &t, const uint8_t *d_seqs, const uint64_t *d_off,
 /* --------------------------------------------------------------- measurement: random 32-B sector gather
  * The denominator for K5's roofline: independent uniformly random 32-byte sector reads over a buffer far larger
  * than L2, same ILP and grid shape as k_table_probe but no hashing, no compare, no dependent second probe. */
+// BYTES = 32: one 256-bit load per random sector; 64 / 128: the 2 / 4 sectors of an aligned 64- / 128-byte block, for the
+// comparison that shows what granularity DRAM really serves (profiles/)
+template <int BYTES>
 __global__ void __launch_bounds__(kThreads) k_gather32(const uint64_t *__restrict__ buf, uint64_t n_sectors,
                                                        uint64_t n_loads, uint64_t seed, uint64_t *__restrict__ sink) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    constexpr int kS = BYTES / 32;
     uint64_t acc = 0;
     for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < n_loads; i0 += stride * kProbeIlp) {
-        ulonglong2 lo[kProbeIlp], hi[kProbeIlp];
+        uint64_t v[kProbeIlp][kS][4];
 #pragma unroll
         for (int u = 0; u < kProbeIlp; u++) {
             uint64_t x = (i0 + u * stride + seed) * 0x9E3779B97F4A7C15ULL;
             x ^= x >> 29;
             x *= 0xBF58476D1CE4E5B9ULL;
             x ^= x >> 32;
-            const uint64_t sct = (uint64_t)(((unsigned __int128)x * n_sectors) >> 64);
-            const ulonglong2 *bp = (const ulonglong2 *)(buf + sct * 4);
-            lo[u] = __ldg(bp);
-            hi[u] = __ldg(bp + 1);
+            const uint64_t sct = (uint64_t)(((unsigned __int128)x * (n_sectors / kS)) >> 64) * kS;
+#pragma unroll
+            for (int q = 0; q < kS; q++) ld_bucket(buf + (sct + q) * 4, v[u][q]);
         }
 #pragma unroll
-        for (int u = 0; u < kProbeIlp; u++) acc ^= lo[u].x ^ lo[u].y ^ hi[u].x ^ hi[u].y;
+        for (int u = 0; u < kProbeIlp; u++)
+#pragma unroll
+            for (int q = 0; q < kS; q++) acc ^= v[u][q][0] ^ v[u][q][1] ^ v[u][q][2] ^ v[u][q][3];
     }
     if (acc == 0x123456789ABCDEFULL) *sink = acc;  // keeps the loads alive
 }
 void gather32(const uint64_t *d_buf, uint64_t n_sectors, uint64_t n_loads, uint64_t seed, uint64_t *d_sink,
-              cudaStream_t s) {
+              cudaStream_t s, int bytes) {
     uint32_t grid = min(cdiv(n_loads, (uint64_t)kThreads * kProbeIlp), 148u * 8u);
-    NP2_K(k_gather32)<<<grid, kThreads, 0, s>>>(d_buf, n_sectors, n_loads, seed, d_sink);
+    if (bytes == 128) NP2_K(k_gather32<128>)<<<grid, kThreads, 0, s>>>(d_buf, n_sectors, n_loads, seed, d_sink);
+    else if (bytes == 64) NP2_K(k_gather32<64>)<<<grid, kThreads, 0, s>>>(d_buf, n_sectors, n_loads, seed, d_sink);
+    else NP2_K(k_gather32<32>)<<<grid, kThreads, 0, s>>>(d_buf, n_sectors, n_loads, seed, d_sink);
 }
 
 /* =============================================================== K0: reference codes */

@@ -72,8 +72,9 @@ void table_probe(const TableDev &t, const uint64_t *d_hashes, uint64_t n, uint32
 void seq_kscore(const TableDev &t, const uint8_t *d_seqs, const uint64_t *d_off, const uint32_t *d_sel, uint64_t n,
                 uint32_t min_count, uint16_t *d_out, cudaStream_t s);
 
+// bytes = 32 (one random sector per load), 64 or 128 (all sectors of a random aligned block of that size)
 void gather32(const uint64_t *d_buf, uint64_t n_sectors, uint64_t n_loads, uint64_t seed, uint64_t *d_sink,
-              cudaStream_t s);
+              cudaStream_t s, int bytes = 32);
 
 /* ------------------------------------------------------------------ K0/K1 ingest */
 void ref_codes(const uint8_t *d_ref, uint32_t L, uint8_t *d_code, uint32_t *d_refpk /* L/8 + 8 words */, int *d_bad,
