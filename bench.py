@@ -267,12 +267,18 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
         rec_len = len(">%s start:%d end:%d\n" % (c["name"], first, last)) + len(base) + 1
         assert rec_len == expect[ci], "end-to-end FASTA record differs from the device-resident run"
         tr = j.traffic()
+        tm = j.timings() if acc is not None else {}
+        st = j.stats() if acc is not None else {}
         j.destroy()
         t4 = time.perf_counter()
         if acc is not None:
             for k, v in zip(("create_parse", "upload", "run", "result"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                 acc[k] += v * 1e3
             acc["n"] += 1
+            sa = acc.setdefault("stages", {})
+            for k, v in tm.items():
+                sa[k] = sa.get(k, 0.0) + v[0]
+            acc["repeated_passes"] = acc.get("repeated_passes", 0) + st.get("repeated_passes", 0)
         return tr
 
     def e2e_run(n_inflight):
@@ -461,9 +467,13 @@ def run_ours(args):
                            sum(len(c["bam"]) for c in contigs) / 1e6)},
             "e2e": dict(s["e2e"], contigs_in_flight=args.e2e_inflight,
                         one_at_a_time=round(mbp_total / m.e2e_serial_time, 3),
-                        one_at_a_time_ms={k: round(v / max(1, m.parts1["n"]), 3) for k, v in m.parts1.items() if k != "n"},
+                        one_at_a_time_ms={k: round(v / max(1, m.parts1["n"]), 3) for k, v in m.parts1.items()
+                                          if k in ("create_parse", "upload", "run", "result")},
                         in_flight_ms_per_contig_per_thread={k: round(v / max(1, m.partsN["n"]), 3)
-                                                            for k, v in m.partsN.items() if k != "n"}),
+                                                            for k, v in m.partsN.items() if k in ("create_parse", "upload", "run", "result")},
+                        in_flight_stage_ms_per_contig={k: round(v / max(1, m.partsN["n"]), 3)
+                                                       for k, v in sorted(m.partsN.get("stages", {}).items(), key=lambda kv: -kv[1])[:14]},
+                        repeated_passes=m.partsN.get("repeated_passes", 0) + m.parts1.get("repeated_passes", 0)),
             "gpu_launches": s["gpu_launches"],
             "clocks": clocks,
             "roofline": roofline_of(m, cfg, peak, peak_kind),

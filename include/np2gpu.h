@@ -199,6 +199,10 @@ uint64_t np2_job_get_regions(np2_job *job, const uint32_t **start, const uint32_
 uint64_t np2_job_get_candidates(np2_job *job, const uint64_t **roff, const uint32_t **order, const uint16_t **kscore,
                                 const uint64_t **kmer, const uint64_t **seq_off, const uint8_t **seq);
 uint64_t np2_job_get_dropped(np2_job *job, const uint32_t **ids);
+/* pair weights of the dumped (non-final) iteration, the output of the pair loop of phase_reads_by_lqseqs
+ * (main.rs:953-992) before anything is derived from it: keys = a << 32 | b (read orders, a < b, a = 0 is the ref read),
+ * ascending; vals = #heterozygous regions where the two reads agree + #where they differ * (2^32 - 1) */
+uint64_t np2_job_get_pair_weights(np2_job *job, const uint64_t **keys, const int64_t **vals);
 
 /* measurement: per-stage device time of the last np2_job_run (CUDA events on the library's stream), kernel
  * launch count, bytes moved.  names: NUL-separated stage names; returns the number of stages. */

@@ -44,7 +44,7 @@ EXPORTS = [
     "np2_yak_free", "np2_yak_clone", "np2_yak_image", "np2_yak_adopt", "np2_yak_k", "np2_yak_size", "np2_yak_device_bytes", "np2_yak_lookup", "np2_yak_lookup_device",
     "np2_seq_kscore", "np2_bench_gather32", "np2_bench_gather", "np2_l2_fetch_granularity", "np2_polish_contig", "np2_job_create", "np2_job_upload", "np2_job_run", "np2_job_destroy",
     "np2_job_get_consensus", "np2_job_get_span", "np2_job_get_reads", "np2_job_get_msa", "np2_job_get_dp_consensus", "np2_job_get_regions",
-    "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_timings", "np2_job_get_traffic", "np2_job_get_stats", "np2_format_fasta",
+    "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_pair_weights", "np2_job_get_timings", "np2_job_get_traffic", "np2_job_get_stats", "np2_format_fasta",
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
     "np2_debug_phase", "np2_set_host_threads",
@@ -96,7 +96,7 @@ def load_library():
     L.np2_job_destroy.argtypes = [vp]
     for name, n in [("np2_job_get_consensus", 2), ("np2_job_get_reads", 6), ("np2_job_get_msa", 5),
                     ("np2_job_get_dp_consensus", 3), ("np2_job_get_regions", 3), ("np2_job_get_candidates", 6),
-                    ("np2_job_get_dropped", 1)]:
+                    ("np2_job_get_dropped", 1), ("np2_job_get_pair_weights", 2)]:
         f = getattr(L, name)
         f.restype = u64
         f.argtypes = [vp] + [C.POINTER(vp)] * n
@@ -392,6 +392,11 @@ class Job:
     def dropped(self):
         n, p = self._get("np2_job_get_dropped", 1)
         return _arr(p[0], n, np.uint32)
+
+    def pair_weights(self):
+        """(keys a << 32 | b ascending, vals #agree + #differ * (2^32 - 1)) of the dumped iteration (main.rs:953-992)."""
+        n, p = self._get("np2_job_get_pair_weights", 2)
+        return _arr(p[0], n, np.uint64), _arr(p[1], n, np.int64)
 
     def timings(self):
         names, ms, ln = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -451,6 +451,8 @@ struct np2_job {
     std::vector<uint16_t> dm_can_kscore;
     std::vector<uint8_t> dm_can_seq;
     std::vector<uint32_t> dm_dropped;
+    std::vector<uint64_t> dm_pair_key;
+    std::vector<int64_t> dm_pair_val;
 
     void send_contig(const uint8_t *tseq_host);
     void send_seq();
@@ -1282,6 +1284,13 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
                 h = timer.begin("pair_edges", 1);
                 geno_edges_finish(d_sel.p, nu, d_pair_off.p, n_ids0, d_acc.p, d_uk.p, d_uv.p, cd, s);
                 timer.end(h);
+                if (dump) {  // stage seam: the reduced pair records as they leave K6 (exact mode: nu is exact)
+                    dm_pair_key.resize(nu);
+                    dm_pair_val.resize(nu);
+                    d_uk.download(dm_pair_key.data(), nu);
+                    NP2_CUDA(cudaMemcpyAsync(dm_pair_val.data(), d_uv.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, s));
+                    NP2_CUDA(cudaStreamSynchronize(s));
+                }
                 // level 0 of the phasing graph on the device: per-read flags + CSR adjacency (np2_geno.cu k_phase_*)
                 const uint32_t n2 = 2 * nu;
                 const bool asref = opt.model == 0, use_all = opt.use_all_reads != 0;
@@ -1907,6 +1916,8 @@ void np2_job::run(int32_t dump_it) {
     n_sync = 0;
     memset(stats, 0, sizeof stats);
     dm_dropped.clear();
+    dm_pair_key.clear();
+    dm_pair_val.clear();
     dm_msa_off.clear();
     dm_msa_bases.clear();
     dm_msa_delta.clear();
@@ -2706,6 +2717,11 @@ uint64_t np2_job_get_candidates(np2_job *j, const uint64_t **roff, const uint32_
 uint64_t np2_job_get_dropped(np2_job *j, const uint32_t **ids) {
     *ids = j->dm_dropped.data();
     return j->dm_dropped.size();
+}
+uint64_t np2_job_get_pair_weights(np2_job *j, const uint64_t **keys, const int64_t **vals) {
+    *keys = j->dm_pair_key.data();
+    *vals = j->dm_pair_val.data();
+    return j->dm_pair_key.size();
 }
 
 uint32_t np2_job_get_timings(np2_job *j, const char **names, const float **ms, const uint32_t **launches) {

@@ -1003,7 +1003,11 @@ std::vector<uint32_t> phase_communities(Graph data, const std::map<uint32_t, flo
 }
 
 // main.rs:948-1015
-std::vector<uint32_t> phase_reads_by_lqseqs(const std::vector<LqSeqs> &lqseqs, bool asref, bool use_all_reads) {
+// pair_weights (optional, stage dump): per read pair (a < b, a = 0 is the ref read) the number of heterozygous regions
+// in which the two reads agree / differ, as #agree + #differ * (2^32 - 1) -- the pair loop of main.rs:953-992 before
+// anything is derived from it
+std::vector<uint32_t> phase_reads_by_lqseqs(const std::vector<LqSeqs> &lqseqs, bool asref, bool use_all_reads,
+                                            std::map<uint64_t, int64_t> *pair_weights = nullptr) {
     Graph data, dif, ref_data;
     std::set<uint32_t> invalid_ids;
     for (auto &lqseq : lqseqs) {
@@ -1015,6 +1019,10 @@ std::vector<uint32_t> phase_reads_by_lqseqs(const std::vector<LqSeqs> &lqseqs, b
                 const LqSeq &seq2 = lqseq.seqs[j];
                 if (seq2.kscore == 0) continue;
                 float w = seq1.seq == seq2.seq ? 1.f : -1.f;
+                if (pair_weights) {
+                    const uint32_t a = std::min(seq1.order, seq2.order), b = std::max(seq1.order, seq2.order);
+                    (*pair_weights)[(uint64_t)a << 32 | b] += w > 0.f ? 1 : ((int64_t)1 << 32) - 1;
+                }
                 if (seq1.order == 0) {
                     if (asref) insert_data(ref_data, seq1.order, seq2.order, w);
                     if (w < 0.f && !use_all_reads) invalid_ids.insert(seq2.order);
@@ -1305,6 +1313,8 @@ struct np2o_job {
     std::vector<uint16_t> d_can_kscore;
     std::vector<uint8_t> d_can_seq;
     std::vector<uint32_t> d_dropped;
+    std::vector<uint64_t> d_pair_key;
+    std::vector<int64_t> d_pair_val;
     std::vector<uint32_t> d_cns_pos;
     std::vector<uint8_t> d_cns_base;
 
@@ -1533,7 +1543,13 @@ std::vector<ConsensusBase> np2o_job::get_cns_from_align_tags(std::vector<Msa> &m
         mark_hete_lqseqs(lqseqs);
         if (dump)
             for (auto &r : lqseqs) d_reg_lable.push_back(r.lable);
-        std::vector<uint32_t> invalid_ids = phase_reads_by_lqseqs(lqseqs, opt.model == 0, opt.use_all_reads != 0);
+        std::map<uint64_t, int64_t> pw;
+        std::vector<uint32_t> invalid_ids = phase_reads_by_lqseqs(lqseqs, opt.model == 0, opt.use_all_reads != 0, dump ? &pw : nullptr);
+        if (dump)
+            for (auto &kv : pw) {
+                d_pair_key.push_back(kv.first);
+                d_pair_val.push_back(kv.second);
+            }
         std::sort(invalid_ids.begin(), invalid_ids.end());
         invalid_ids.erase(std::unique(invalid_ids.begin(), invalid_ids.end()), invalid_ids.end());
         for (uint32_t id : invalid_ids) {
@@ -1834,6 +1850,11 @@ uint64_t np2o_get_candidates(np2o_job *j, const uint64_t **roff, const uint32_t 
 uint64_t np2o_get_dropped(np2o_job *j, const uint32_t **ids) {
     *ids = j->d_dropped.data();
     return j->d_dropped.size();
+}
+uint64_t np2o_get_pair_weights(np2o_job *j, const uint64_t **keys, const int64_t **vals) {
+    *keys = j->d_pair_key.data();
+    *vals = j->d_pair_val.data();
+    return j->d_pair_key.size();
 }
 /* Test seam: the tail of phase_reads_by_lqseqs (main.rs:994-1015) + Louvain + phase_communities on pair weights that
  * were already summed per read pair.  keys[e] = a << 32 | b (a < b), vals[e] = #agree + #differ * ((1 << 32) - 1).

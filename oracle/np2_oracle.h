@@ -92,6 +92,9 @@ uint64_t np2o_get_candidates(np2o_job *, const uint64_t **roff, const uint32_t *
                              const uint64_t **kmer, const uint64_t **seq_off, const uint8_t **seq);
 /* reads blanked by phasing after each non-final iteration (concatenated), sorted ascending per iteration */
 uint64_t np2o_get_dropped(np2o_job *, const uint32_t **ids);
+/* pair weights of iteration dump_iter (main.rs:953-992): keys = a << 32 | b (read orders, a < b, a = 0 is the ref read),
+ * ascending; vals = #heterozygous regions where the two agree + #where they differ * (2^32 - 1) */
+uint64_t np2o_get_pair_weights(np2o_job *, const uint64_t **keys, const int64_t **vals);
 /* test seam: phasing on pre-summed pair weights (see np2_oracle.cpp); returns the number of dropped reads or -1 */
 int64_t np2o_debug_phase(const uint64_t *keys, const int64_t *vals, uint64_t n, uint32_t model, uint32_t use_all_reads,
                          uint32_t *out, uint64_t cap);

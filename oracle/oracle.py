@@ -71,7 +71,8 @@ def lib():
         L.np2o_get_seconds.restype = C.c_double
         L.np2o_get_seconds.argtypes = [C.c_void_p]
         for name, n in [("np2o_get_reads", 6), ("np2o_get_msa", 5), ("np2o_get_dp_consensus", 3), ("np2o_get_regions", 3),
-                        ("np2o_get_candidates", 6), ("np2o_get_dropped", 1), ("np2o_get_consensus", 2)]:
+                        ("np2o_get_candidates", 6), ("np2o_get_dropped", 1), ("np2o_get_consensus", 2),
+                        ("np2o_get_pair_weights", 2)]:
             f = getattr(L, name)
             f.restype = C.c_uint64
             f.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * n
@@ -205,6 +206,11 @@ class Job:
     def dropped(self):
         n, p = self._get("np2o_get_dropped", range(1))
         return _arr(p[0], n, np.uint32)
+
+    def pair_weights(self):
+        """(keys a << 32 | b ascending, vals #agree + #differ * (2^32 - 1)) of the dumped iteration (main.rs:953-992)."""
+        n, p = self._get("np2o_get_pair_weights", range(2))
+        return _arr(p[0], n, np.uint64), _arr(p[1], n, np.int64)
 
     def consensus(self):
         n, p = self._get("np2o_get_consensus", range(2))

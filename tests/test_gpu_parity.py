@@ -192,3 +192,22 @@ def test_exotic_alignments(ctx, optkw):
         gpos, gbase = gj.consensus()
         common.assert_same("final.base", obase, gbase)
         common.assert_same("final.pos", opos, gpos)
+
+
+@pytest.mark.parametrize("name", ["dip600k", "clip120k"])
+def test_stage_pair_weights(ctx, name):
+    """Stage seam VERDICT r01 asked for: the output of the pair loop of phase_reads_by_lqseqs (main.rs:953-992), one
+    record per read pair with #agree + #differ * (2^32 - 1), exactly as it leaves K6 (k_edges_accum / k_edges_finish),
+    against the oracle's per-region accumulation."""
+    ds = common.dataset(name)
+    oo, go = common.same_opts()
+    oj = O.Job(ds["contig"], ds["bam"], common.oracle_tables(ds), oo, dump_iter=0)
+    import nextpolish2_b200 as np2
+    gj = np2.Job(ctx, ds["contig"], ds["bam"], common.gpu_tables(ctx, ds), go).upload().run(0)
+    ok, ov = oj.pair_weights()
+    gk, gv = gj.pair_weights()
+    assert len(ok) > 1000
+    common.assert_same("pair keys", ok, gk)
+    common.assert_same("pair weights", ov, gv)
+    assert (ok >> np.uint64(32) < (ok & np.uint64(0xFFFFFFFF))).all() and (np.diff(ok.astype(np.int64)) > 0).all()
+    gj.destroy()
