@@ -209,7 +209,41 @@ struct StageTimer {
         NP2_CUDA(cudaEventCreate(&e));
         return e;
     }
+    // NP2_TRACE=1: wall-clock marks of every stage begin / host phase end of a run, printed to stderr when it ends
+    // (shows where the HOST thread spends its time, e.g. blocked in the driver while other contexts are busy)
+    std::vector<std::pair<std::string, double>> trace;
+    std::chrono::steady_clock::time_point trace_t0;
+    static bool tracing() {
+        static const bool on = [] {
+            const char *e = getenv("NP2_TRACE");
+            return e && atoi(e) != 0;
+        }();
+        return on;
+    }
+    void mark(const char *what) {
+        if (tracing())
+            trace.emplace_back(what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - trace_t0).count());
+    }
+    void trace_begin() {
+        trace.clear();
+        trace_t0 = std::chrono::steady_clock::now();
+    }
+    void trace_dump(const void *tag) {
+        if (!tracing() || trace.empty()) return;
+        std::string out = "[np2 trace " + std::to_string((uintptr_t)tag % 100000) + "]";
+        double prev = 0;
+        char buf[160];
+        for (auto &t : trace) {
+            if (t.second - prev >= 0.05) {
+                snprintf(buf, sizeof buf, " %s@%.2f(+%.2f)", t.first.c_str(), t.second, t.second - prev);
+                out += buf;
+            }
+            prev = t.second;
+        }
+        fprintf(stderr, "%s\n", out.c_str());
+    }
     int begin(const char *name, uint32_t n_launch) {
+        mark(name);
         Rec r;
         r.stage = id(name);
         r.a = ev();
@@ -234,6 +268,7 @@ struct StageTimer {
     std::chrono::steady_clock::time_point h0;
     void hbegin() { h0 = std::chrono::steady_clock::now(); }
     void hend(const char *name) {
+        mark(name);
         auto t = std::chrono::steady_clock::now();
         ms[id(name)] += std::chrono::duration<float, std::milli>(t - h0).count();
         h0 = t;
@@ -1955,6 +1990,7 @@ void np2_job::run(int32_t dump_it) {
     // tickets + tile descriptors of one pass: ~10 position-sized scans, a few record- and region-sized ones
     sc->scan_pool.reserve(12 * ((size_t)L / kScanTile + 2) + 4 * ((size_t)ing.total_cols / 8 / kScanTile + 2) + 8192, s);
     sc->scan_pool.begin(s);
+    timer.trace_begin();
     const int h_total = timer.begin("total", 0);
     int h = timer.begin("trim_scan", 1);
     trim_scan(R, d_ref.p, L, s);
@@ -2055,6 +2091,8 @@ void np2_job::run(int32_t dump_it) {
     timer.end(h_total);
     n_launch = launch_counter() - launches0;
     NP2_CUDA(cudaStreamSynchronize(s));
+    timer.mark("end");
+    timer.trace_dump(this);
     timer.collect();
     hc = nullptr;
 }

@@ -1014,6 +1014,14 @@ struct StripeSmem {
     uint32_t odd[kStripeWork];
     uint32_t rn[kStripeReads + 1];  // per candidate read of the batch: prefix of its odd-block count
     uint32_t stk_a[12], stk_b[12];
+    // the stripe's window of the per-position inputs (coverage, reference codes), brought in by TMA bulk copies while
+    // the reads are walked, and its per-position outputs, staged here and written back by TMA bulk stores
+    alignas(16) int32_t w_cover[kStripeW];
+    alignas(16) uint8_t w_code[kStripeW];
+    alignas(16) uint32_t o_sp_off[kStripeW], o_dense[kStripeW], o_emit[kStripeW];
+    alignas(16) uint16_t o_sp_cnt[kStripeW];
+    alignas(16) uint8_t o_multi[kStripeW];
+    alignas(8) uint64_t bar;
     uint32_t nrec, nodd, base, ok;
     unsigned long long score;  // 10 * count - 4 * coverage over the single-entry positions of the range (main.rs:1659)
     int sp;
@@ -1041,13 +1049,17 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
     constexpr int kPer = kStripeW / kStripeThreads;  // positions per thread in the block scans
     typedef cub::BlockScan<uint32_t, kStripeThreads> BS;
     __shared__ typename BS::TempStorage bs_tmp;
+    namespace ptx = cuda::ptx;
     const uint32_t tid = threadIdx.x, L = m.L;
     if (cd.c[C_ABORT]) return;
     if (tid == 0) {
         S.sp = 1;
         S.stk_a[0] = blockIdx.x * kStripeW;
         S.stk_b[0] = min(blockIdx.x * kStripeW + kStripeW, L);
+        ptx::mbarrier_init(&S.bar, 1);
+        ptx::fence_proxy_async(ptx::space_shared);  // barrier initialisation visible to the async proxy
     }
+    uint32_t bar_phase = 0;
     for (;;) {
         __syncthreads();
         if (S.sp == 0) break;
@@ -1059,6 +1071,15 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
             S.score = 0;
         }
         __syncthreads();
+        // TMA: coverage and reference codes of [a, b) into shared memory, in flight while the reads are walked.  Whole
+        // 16-byte units only (stripes start at multiples of 1024; a split range falls back to plain loads).
+        const uint32_t Wr = b - a;
+        const bool tma_in = WRITE && (a & 15) == 0 && (Wr & 15) == 0;
+        if (tma_in && tid == 0) {
+            ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, &S.bar, Wr * 5);
+            ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, S.w_cover, m.cover + a, Wr * 4, &S.bar);
+            ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, S.w_code, m.code + a, Wr, &S.bar);
+        }
         auto append = [&](uint32_t p, uint32_t bases, uint32_t dl1, uint32_t order) {
             if (p < a || p >= b) return;
             const uint32_t i = atomicAdd(&S.nrec, 1u);
@@ -1161,6 +1182,11 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         __syncthreads();
         const uint32_t nrec = S.nrec;
         if (nrec > kStripeRmax) {  // split by position and walk again
+            if (tma_in) {  // the window is not used: let the copies land before the buffers are reused
+                while (!ptx::mbarrier_try_wait_parity(&S.bar, bar_phase)) {
+                }
+                bar_phase ^= 1;
+            }
             if (tid == 0) {
                 if (b - a <= 1) {
                     atomicExch(cd.c + C_PERR, 5u);  // one position with more records than the list holds
@@ -1266,6 +1292,12 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
         }
         __syncthreads();
         // ---- per position: Msa::sort order (main.rs:193-229), reference 3-mer count, articulation flag
+        if (tma_in) {
+            while (!ptx::mbarrier_try_wait_parity(&S.bar, bar_phase)) {
+            }
+            bar_phase ^= 1;
+        }
+        const bool tma_out = tma_in;  // same alignment condition: outputs leave through bulk stores
         long long score = 0;
         for (uint32_t k = tid; k < W; k += kStripeThreads) {
             const uint32_t p = a + k;
@@ -1293,21 +1325,45 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
                     m.g_first[j] = fr;
                 }
             }
-            m.sp_off[p] = lo;
-            m.sp_cnt[p] = (uint16_t)min(hi - lo, 0xFFFFu);
             if (hi - lo > 0xFFFFu) atomicExch(cd.c + C_PERR, 6u);
-            const uint32_t cov = (uint32_t)m.cover[p];
-            m.dense_cnt[p] = p >= 2 ? cov - sum0 : 0;
+            const uint32_t cov = tma_in ? (uint32_t)S.w_cover[k] : (uint32_t)m.cover[p];
+            const uint32_t cde = tma_in ? S.w_code[k] : m.code[p];
             const bool multi = p < 2 || hi > lo;
-            m.multi[p] = multi;
-            n_emit[p] = multi ? 0 : (m.code[p] != 4);
+            const uint32_t dense = p >= 2 ? cov - sum0 : 0, ne = multi ? 0 : (cde != 4);
+            if (tma_out) {
+                S.o_sp_off[k] = lo;
+                S.o_sp_cnt[k] = (uint16_t)min(hi - lo, 0xFFFFu);
+                S.o_dense[k] = dense;
+                S.o_multi[k] = multi;
+                S.o_emit[k] = ne;
+            } else {
+                m.sp_off[p] = lo;
+                m.sp_cnt[p] = (uint16_t)min(hi - lo, 0xFFFFu);
+                m.dense_cnt[p] = dense;
+                m.multi[p] = multi;
+                n_emit[p] = ne;
+            }
             if (!multi) score += 6ll * cov;  // its only entry is the reference 3-mer: count == coverage
+        }
+        if (tma_out) {  // shared -> global through the async proxy: five bulk stores per stripe instead of 15 B x W LSU stores
+            ptx::fence_proxy_async(ptx::space_shared);
+            __syncthreads();
+            if (tid == 0) {
+                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.sp_off + a, S.o_sp_off, W * 4);
+                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.dense_cnt + a, S.o_dense, W * 4);
+                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, n_emit + a, S.o_emit, W * 4);
+                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.sp_cnt + a, S.o_sp_cnt, W * 2);
+                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.multi + a, S.o_multi, W);
+                ptx::cp_async_bulk_commit_group();
+                ptx::cp_async_bulk_wait_group_read(ptx::n32_t<0>());  // the staging buffers may be overwritten again
+            }
         }
         for (int d = 16; d > 0; d >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, d);
         if ((tid & 31) == 0 && score) atomicAdd(&S.score, (unsigned long long)score);
         __syncthreads();
         if (tid == 0 && S.score) atomicAdd(cd.q + Q_TOTAL, S.score);
     }
+    if (tid == 0) ptx::cp_async_bulk_wait_group(ptx::n32_t<0>());  // bulk stores complete before the CTA retires
 }
 // bit g of blk_odd = 32-column block g holds something else than reference 3-mers (or cannot be decided by the word
 // test: first / last block of a read).  A property of the read and the contig only: computed once per job.

@@ -1,0 +1,54 @@
+"""Small end-to-end runs for compute-sanitizer (memcheck / racecheck / synccheck): a haploid and a diploid contig through
+np2_job_create/upload/run twice each (the first run sizes everything exactly, the second one runs with speculative
+capacities), compared with the oracle.  Kept small: the sanitizer slows kernels down 10-100x.
+
+    compute-sanitizer --tool memcheck  python tests/sanitize_run.py > profiles/r02_sanitizer_memcheck.log
+    compute-sanitizer --tool racecheck python tests/sanitize_run.py > profiles/r02_sanitizer_racecheck.log
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+import oracle as O  # noqa: E402
+import nextpolish2_b200 as np2  # noqa: E402
+from nextpolish2_b200 import synth  # noqa: E402
+
+
+def one(ctx, seed, L, het, depth, tandem=0.0):
+    A = synth.genome(seed, L, tandem_frac=tandem)
+    c = synth.make_contig(seed + 1, A, depth=depth, asm_err=3e-4, het=het, mean_len=6000, sd_len=1000, min_len=2000, threads=2)
+    haps = [c["hap1"]] + ([c["hap2"]] if het > 0 else [])
+    tabs = {k: synth.make_table(seed + 2, k, haps) for k in (21, 31)}
+    gt = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in (21, 31)]
+    oj = O.Job(A, c["bam"], [O.Table.from_arrays(k, *tabs[k]) for k in (21, 31)], O.Opts(min_ctg_len=0), dump_iter=-1)
+    opos, obase = oj.consensus()
+    job = np2.Job(ctx, A, c["bam"], gt, np2.Opts(min_ctg_len=0)).upload()
+    for rnd in range(2):
+        job.run(-1)
+        gpos, gbase = job.consensus()
+        assert np.array_equal(gbase, obase) and np.array_equal(gpos, opos), "GPU consensus differs from the oracle"
+        assert np.array_equal(np.sort(job.dropped()), np.sort(oj.dropped()))
+    st = job.stats()
+    job.destroy()
+    print("ok L=%d het=%g: %d regions, %d reads dropped, speculative passes %d, repeated %d" % (
+        L, het, st["regions"], len(oj.dropped()), st["speculative_passes"], st["repeated_passes"]), flush=True)
+
+
+def main():
+    ctx = np2.Context(0)
+    one(ctx, 11, 20_000, 0.0, 20)
+    one(ctx, 21, 40_000, 0.004, 30)
+    one(ctx, 31, 30_000, 0.002, 25, tandem=0.08)
+    h = np.unique(np.random.default_rng(1).integers(0, 2**62, 200_000, dtype=np.uint64))
+    t = np2.Table.from_arrays(ctx, 31, h, (h % 1000 + 1).astype(np.uint16))
+    assert (t.lookup(h, 0) == (h % 1000 + 1)).all()
+    print("ok table lookup", flush=True)
+
+
+if __name__ == "__main__":
+    main()
