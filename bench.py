@@ -283,9 +283,10 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
 
     def e2e_run(n_inflight):
         ctxs = [ctx] + [np2.Context(local) for _ in range(n_inflight - 1)]
-        for cx in ctxs:  # warm every context's pools
-            for _ in range(max(1, warmup // n_inflight)):
-                e2e_one(cx, 0)
+        for cx in ctxs:  # warm every context: pools, page-locked buffers, and the sizes the speculative passes start from
+            for _ in range(max(2, warmup // n_inflight)):
+                for ci in range(len(contigs)):
+                    e2e_one(cx, ci)
         work_items = [ci for _ in range(steps) for ci in range(len(contigs))]
         nxt, lock, errs, tr_sum = [0], threading.Lock(), [], {"h2d_bytes": 0, "d2h_bytes": 0}
 

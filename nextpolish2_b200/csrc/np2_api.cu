@@ -109,6 +109,24 @@ struct Arena {
         blocks.clear();
     }
 };
+// NP2_TRACE: driver calls that block for more than half a millisecond are reported with their size
+thread_local std::vector<std::pair<std::string, double>> *g_trace = nullptr;
+thread_local std::chrono::steady_clock::time_point g_trace_t0;
+struct SlowCall {
+    const char *what;
+    size_t bytes;
+    std::chrono::steady_clock::time_point t;
+    SlowCall(const char *w, size_t b) : what(w), bytes(b), t(std::chrono::steady_clock::now()) {}
+    ~SlowCall() {
+        if (!g_trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(now - t).count();
+        if (ms < 0.5) return;
+        char buf[96];
+        snprintf(buf, sizeof buf, "SLOW:%s(%zuB,%.2fms)", what, bytes, ms);
+        g_trace->emplace_back(buf, std::chrono::duration<double, std::milli>(now - g_trace_t0).count());
+    }
+};
 constexpr size_t kArenaMax = 4u << 20;
 thread_local Arena *g_arena = nullptr;
 struct ArenaScope {
@@ -138,6 +156,7 @@ struct DBuf {  // stream-ordered device buffer
             }
         }
         if (count) {
+            SlowCall sc_("pool_alloc", count * sizeof(T));
             cudaMemPool_t pool = pool_of(st);
             cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), pool, st)
                                  : cudaMallocAsync((void **)&p, count * sizeof(T), st);
@@ -151,8 +170,14 @@ struct DBuf {  // stream-ordered device buffer
     void zero() {
         if (n) NP2_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
     }
-    void upload(const T *h, size_t count) { NP2_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)); }
-    void download(T *h, size_t count) const { NP2_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+    void upload(const T *h, size_t count) {
+        SlowCall sc_("h2d", count * sizeof(T));
+        NP2_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T *h, size_t count) const {
+        SlowCall sc_("d2h", count * sizeof(T));
+        NP2_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
     void release() {
         if (p && !from_arena) cudaFreeAsync(p, s);
         p = nullptr;
@@ -168,12 +193,20 @@ struct PBuf {  // pinned host buffer
     size_t n = 0, cap = 0;
     void resize(size_t count) {
         if (count > cap) {
+            SlowCall sc_("pinned_alloc", count * sizeof(T));
             if (p) cudaFreeHost(p);
             p = nullptr;
             cap = std::max(count, cap * 2);
             NP2_CUDA(cudaMallocHost((void **)&p, cap * sizeof(T)));
         }
         n = count;
+    }
+    // capacity without changing n: page-locked (re)allocations stall every context of the device for milliseconds,
+    // so buffers whose final size is known roughly are made large enough once
+    void reserve(size_t count) {
+        const size_t keep = n;
+        if (count > cap) resize(count);
+        n = keep;
     }
     ~PBuf() {
         if (p) cudaFreeHost(p);
@@ -227,6 +260,8 @@ struct StageTimer {
     void trace_begin() {
         trace.clear();
         trace_t0 = std::chrono::steady_clock::now();
+        g_trace = tracing() ? &trace : nullptr;
+        g_trace_t0 = trace_t0;
     }
     void trace_dump(const void *tag) {
         if (!tracing() || trace.empty()) return;
@@ -234,7 +269,7 @@ struct StageTimer {
         double prev = 0;
         char buf[160];
         for (auto &t : trace) {
-            if (t.second - prev >= 0.05) {
+            if (t.second - prev >= 0.05 || t.first.compare(0, 5, "SLOW:") == 0) {
                 snprintf(buf, sizeof buf, " %s@%.2f(+%.2f)", t.first.c_str(), t.second, t.second - prev);
                 out += buf;
             }
@@ -303,6 +338,8 @@ struct JobScratch {
     ScanPool scan_pool;
     uint32_t *d_counts = nullptr;  // CountsDev block (256 bytes)
     PBuf<uint8_t> p_counts;        // its pinned mirror (+ two words for the FASTA header positions)
+    PBuf<uint8_t> p_h2d;           // staging area of the small uploads of a run (Uploader)
+    size_t h2d_used = 0;
     std::vector<uint8_t> tseq, h_seeds, h_rech_pool, h_win;
     Patched patch;
     PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage, p_stage2, p_seq_stage;
@@ -340,6 +377,27 @@ struct Stager {
         if (n) NP2_CUDA(cudaMemcpyAsync(dst, dev, n * sizeof(T), cudaMemcpyDeviceToHost, s));
         used += n * sizeof(T);
         return dst;
+    }
+};
+// Host -> device copies of small host arrays through a page-locked staging area: a cudaMemcpyAsync from pageable memory
+// blocks the calling thread inside the driver (for tens of milliseconds when other contexts are busy), a copy from
+// page-locked memory is just enqueued.  The area is handed out by a bump pointer and recycled when a run starts.
+struct Uploader {
+    PBuf<uint8_t> &buf;
+    size_t &used;
+    cudaStream_t s;
+    template <class T>
+    void put(T *dev, const T *host, size_t count) {
+        const size_t bytes = count * sizeof(T);
+        if (!bytes) return;
+        const size_t at = (used + 15) & ~(size_t)15;
+        if (at + bytes > buf.cap) {  // does not fit: plain (blocking) copy
+            NP2_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s));
+            return;
+        }
+        memcpy(buf.p + at, host, bytes);
+        NP2_CUDA(cudaMemcpyAsync(dev, buf.p + at, bytes, cudaMemcpyHostToDevice, s));
+        used = at + bytes;
     }
 };
 struct np2_ctx {
@@ -1416,9 +1474,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             dm_dropped.push_back(a);
         }
         if (drop.empty()) continue;  // same reads => the next iteration is this one again
-        d_blank.upload(h_blank.data(), n_reads);
-        NP2_CUDA(cudaStreamSynchronize(s));
-        n_sync++;
+        Uploader{sc->p_h2d, sc->h2d_used, s}.put(d_blank.p, h_blank.data(), n_reads);
         return iter + 1;
     }
 
@@ -1721,8 +1777,8 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             d_win_lo.alloc(n_win, s);
             d_win_off.alloc(n_win + 1, s);
             d_win.alloc(win_off.back() + 1, s);
-            d_win_lo.upload(win_lo.data(), n_win);
-            d_win_off.upload(win_off.data(), n_win + 1);
+            Uploader{sc->p_h2d, sc->h2d_used, s}.put(d_win_lo.p, win_lo.data(), n_win);
+            Uploader{sc->p_h2d, sc->h2d_used, s}.put(d_win_off.p, win_off.data(), (size_t)n_win + 1);
             gather_ranges(d_cbase.p, d_win_lo.p, d_win_off.p, nullptr, n_win, d_win.p, s);
             h_win.resize(win_off.back() + 16);
             d_win.download(h_win.data(), win_off.back());
@@ -1834,8 +1890,8 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             d_rp.alloc(ru.pool.size() + 1, s);
             d_ro.alloc(ns + 1, s);
             d_rk.alloc(ns, s);
-            d_rp.upload(ru.pool.data(), ru.pool.size());
-            d_ro.upload(ru.off.data(), ns + 1);
+            Uploader{sc->p_h2d, sc->h2d_used, s}.put(d_rp.p, ru.pool.data(), ru.pool.size());
+            Uploader{sc->p_h2d, sc->h2d_used, s}.put(d_ro.p, ru.off.data(), ns + 1);
             h = timer.begin("yak_seq_kscore", 1);
             seq_kscore(tables[ti]->dev, d_rp.p, d_ro.p, nullptr, ns, opt.min_kmer_count, d_rk.p, s);
             timer.end(h);
@@ -1877,12 +1933,11 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             d_ch_r.alloc(nc, s);
             d_ch_len.alloc(nc, s);
             d_ch_off.alloc(nc, s);
-            d_ch_r.upload(ch_r.data(), nc);
-            d_ch_len.upload(ch_len.data(), nc);
-            d_ch_off.upload(ch_off.data(), nc);
+            Uploader upl{sc->p_h2d, sc->h2d_used, s};
+            upl.put(d_ch_r.p, ch_r.data(), nc);
+            upl.put(d_ch_len.p, ch_len.data(), nc);
+            upl.put(d_ch_off.p, ch_off.data(), nc);
             seed_scatter(nc, d_ch_r.p, d_ch_off.p, d_ch_len.p, d_r_seed_off.p, d_r_seed_len.p, s);
-            NP2_CUDA(cudaStreamSynchronize(s));  // the host vectors above are pageable: finish before they go
-            n_sync++;
             h2d += (uint64_t)nc * 16;
         }
     } else {
@@ -1990,6 +2045,12 @@ void np2_job::run(int32_t dump_it) {
     // tickets + tile descriptors of one pass: ~10 position-sized scans, a few record- and region-sized ones
     sc->scan_pool.reserve(12 * ((size_t)L / kScanTile + 2) + 4 * ((size_t)ing.total_cols / 8 / kScanTile + 2) + 8192, s);
     sc->scan_pool.begin(s);
+    // page-locked buffers at their final size right away (see PBuf::reserve)
+    sc->p_h2d.reserve((size_t)n * 24 + (4u << 20));
+    sc->h2d_used = 0;
+    p_cbase.reserve((size_t)L + L / 4 + 65536);
+    res_base.reserve((size_t)L + L / 4 + 65536);
+    Uploader up{sc->p_h2d, sc->h2d_used, s};
     timer.trace_begin();
     const int h_total = timer.begin("total", 0);
     int h = timer.begin("trim_scan", 1);
@@ -2025,9 +2086,9 @@ void np2_job::run(int32_t dump_it) {
     }
     ingest_finish();
     timer.hend("host:ingest_finish");
-    d_blank.upload(h_blank.data(), std::max(n, 1u));
+    up.put(d_blank.p, h_blank.data(), std::max(n, 1u));
     d_order.alloc(std::max(n, 1u), s);
-    if (n) d_order.upload(read_order.data(), n);
+    if (n) up.put(d_order.p, read_order.data(), n);
     if (opt.iter_count > 1) {  // slot ranges of the pair accumulator: windows + exclusive scan, all on the device
         const uint32_t na = (uint32_t)as_read.size();
         DBuf<uint32_t> d_as_pos, d_as_te, d_W;
@@ -2035,12 +2096,12 @@ void np2_job::run(int32_t dump_it) {
         d_as_te.alloc(na, s);
         d_W.alloc(na + 1, s);
         d_pair_off.alloc(na + 1, s);
-        d_as_pos.upload(h_as_pos.data(), na);
-        d_as_te.upload(h_as_te.data(), na);
+        up.put(d_as_pos.p, h_as_pos.data(), na);
+        up.put(d_as_te.p, h_as_te.data(), na);
         geno_pair_windows(d_as_pos.p, d_as_te.p, na, d_W.p, s);
         geno_pair_window_offsets(d_W.p, d_pair_off.p, na, sc->scan_pool, s);
         NP2_CUDA(cudaMemcpyAsync(&hc->q[0], d_pair_off.p + na, 8, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaStreamSynchronize(s));  // the uploads above come from pageable vectors
+        NP2_CUDA(cudaStreamSynchronize(s));
         n_sync++;
         pair_slots = hc->q[0];
     }
@@ -2092,6 +2153,7 @@ void np2_job::run(int32_t dump_it) {
     n_launch = launch_counter() - launches0;
     NP2_CUDA(cudaStreamSynchronize(s));
     timer.mark("end");
+    g_trace = nullptr;
     timer.trace_dump(this);
     timer.collect();
     hc = nullptr;

@@ -1015,12 +1015,10 @@ struct StripeSmem {
     uint32_t rn[kStripeReads + 1];  // per candidate read of the batch: prefix of its odd-block count
     uint32_t stk_a[12], stk_b[12];
     // the stripe's window of the per-position inputs (coverage, reference codes), brought in by TMA bulk copies while
-    // the reads are walked, and its per-position outputs, staged here and written back by TMA bulk stores
+    // the reads are walked.  (Staging the per-position outputs too and writing them back with bulk stores was measured:
+    // the extra 15 KB of shared memory cost more occupancy than the stores cost LSU time, 0.35 vs 0.30 ms.)
     alignas(16) int32_t w_cover[kStripeW];
     alignas(16) uint8_t w_code[kStripeW];
-    alignas(16) uint32_t o_sp_off[kStripeW], o_dense[kStripeW], o_emit[kStripeW];
-    alignas(16) uint16_t o_sp_cnt[kStripeW];
-    alignas(16) uint8_t o_multi[kStripeW];
     alignas(8) uint64_t bar;
     uint32_t nrec, nodd, base, ok;
     unsigned long long score;  // 10 * count - 4 * coverage over the single-entry positions of the range (main.rs:1659)
@@ -1297,7 +1295,6 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
             }
             bar_phase ^= 1;
         }
-        const bool tma_out = tma_in;  // same alignment condition: outputs leave through bulk stores
         long long score = 0;
         for (uint32_t k = tid; k < W; k += kStripeThreads) {
             const uint32_t p = a + k;
@@ -1330,40 +1327,18 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
             const uint32_t cde = tma_in ? S.w_code[k] : m.code[p];
             const bool multi = p < 2 || hi > lo;
             const uint32_t dense = p >= 2 ? cov - sum0 : 0, ne = multi ? 0 : (cde != 4);
-            if (tma_out) {
-                S.o_sp_off[k] = lo;
-                S.o_sp_cnt[k] = (uint16_t)min(hi - lo, 0xFFFFu);
-                S.o_dense[k] = dense;
-                S.o_multi[k] = multi;
-                S.o_emit[k] = ne;
-            } else {
-                m.sp_off[p] = lo;
-                m.sp_cnt[p] = (uint16_t)min(hi - lo, 0xFFFFu);
-                m.dense_cnt[p] = dense;
-                m.multi[p] = multi;
-                n_emit[p] = ne;
-            }
+            m.sp_off[p] = lo;
+            m.sp_cnt[p] = (uint16_t)min(hi - lo, 0xFFFFu);
+            m.dense_cnt[p] = dense;
+            m.multi[p] = multi;
+            n_emit[p] = ne;
             if (!multi) score += 6ll * cov;  // its only entry is the reference 3-mer: count == coverage
-        }
-        if (tma_out) {  // shared -> global through the async proxy: five bulk stores per stripe instead of 15 B x W LSU stores
-            ptx::fence_proxy_async(ptx::space_shared);
-            __syncthreads();
-            if (tid == 0) {
-                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.sp_off + a, S.o_sp_off, W * 4);
-                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.dense_cnt + a, S.o_dense, W * 4);
-                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, n_emit + a, S.o_emit, W * 4);
-                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.sp_cnt + a, S.o_sp_cnt, W * 2);
-                ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, m.multi + a, S.o_multi, W);
-                ptx::cp_async_bulk_commit_group();
-                ptx::cp_async_bulk_wait_group_read(ptx::n32_t<0>());  // the staging buffers may be overwritten again
-            }
         }
         for (int d = 16; d > 0; d >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, d);
         if ((tid & 31) == 0 && score) atomicAdd(&S.score, (unsigned long long)score);
         __syncthreads();
         if (tid == 0 && S.score) atomicAdd(cd.q + Q_TOTAL, S.score);
     }
-    if (tid == 0) ptx::cp_async_bulk_wait_group(ptx::n32_t<0>());  // bulk stores complete before the CTA retires
 }
 // bit g of blk_odd = 32-column block g holds something else than reference 3-mers (or cannot be decided by the word
 // test: first / last block of a read).  A property of the read and the contig only: computed once per job.
