@@ -24,6 +24,7 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kScanMaxCtas = 592;  // 4 per SM
+constexpr int kScanSingleCtaTiles = 8;  // up to 32768 elements are scanned by one CTA in one launch (three launches cost more)
 constexpr unsigned long long kScanMask = (1ULL << 62) - 1;
 
 // 64-bit scratch words for the chunk totals of the scans of one pipeline pass; slices are handed out in enqueue order
@@ -218,7 +219,8 @@ inline uint32_t scan_ctas(uint32_t cap) {
 template <class Tr>
 inline void scan_launch(const Tr &tr, const uint32_t *d_n, uint32_t n_plus, uint32_t cap, ScanPool &pool, cudaStream_t s,
                         const uint32_t *d_abort = nullptr) {
-    const uint32_t ctas = scan_ctas(cap);
+    uint32_t ctas = scan_ctas(cap);
+    if (ctas <= kScanSingleCtaTiles) ctas = 1;  // a few tiles: one CTA walks them in a single launch
     if (ctas == 1) {
         NP2_K(k_scan_apply<Tr>)<<<1, kScanThreads, 0, s>>>(tr, d_n, n_plus, cap, nullptr, d_abort);
         return;
