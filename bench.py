@@ -395,6 +395,19 @@ def cfg_for(n, full):
 
 
 def run_ours(args):
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run_ours(args):
     import torch
     import torch.distributed as dist
     import nextpolish2_b200 as np2
@@ -530,8 +543,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    return line if rank == 0 else None
 
 
 def strong_contig_lengths(total_bp, n=24):

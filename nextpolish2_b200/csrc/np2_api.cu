@@ -989,8 +989,10 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     runs_select(d_multi.p, L, d_run_start.p, cap_runs_alloc, cd, sp, s);
     timer.end(h);
     const uint32_t n_runs = cnt_get(C_NRUNS);
-    h = timer.begin("dp_runs", 1);
-    dp_runs(m, d_run_start.p, n_runs, cd, s);
+    DBuf<uint32_t> d_long_runs;
+    d_long_runs.alloc(std::max(n_runs, 1u), s);
+    h = timer.begin("dp_runs", 2);
+    dp_runs(m, d_run_start.p, n_runs, cd, d_long_runs.p, s);
     timer.end(h);
     // consensus bases: at most one per position plus the insertions the best path takes (<= the sparse entries)
     const uint32_t cap_n = spec ? caps.c[C_N] : (uint32_t)std::min<uint64_t>((uint64_t)L + G + 16, 0xFFFFFFF0ull);

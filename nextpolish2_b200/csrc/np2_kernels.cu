@@ -1456,56 +1456,77 @@ __device__ __forceinline__ Entry get_entry(const MsaDev &m, uint32_t p, uint32_t
 }
 constexpr int64_t kDead = INT64_MIN >> 1;  // main.rs:1661
 
+// Score of entry idx of position p inside the run that starts at s (main.rs:1653-1679): best predecessor among the
+// entries of b2's position whose (b2, b3) equal this entry's (b1, b2).
+__device__ __forceinline__ int64_t dp_entry(const MsaDev &m, uint32_t s, uint32_t p, uint32_t idx, int64_t cov, bool single,
+                                            uint32_t &kd_out) {
+    const Entry x = get_entry(m, p, idx);
+    ABase b1, b2, b3;
+    kmer_bases(x.bases, x.delta, p, b1, b2, b3);
+    kd_out = kmer_b3delta(x.bases, x.delta);
+    const int64_t inc = 10 * (int64_t)x.count - 4 * cov;
+    uint32_t besti = 0;
+    int64_t score;
+    if (b2.q == 15) {
+        score = inc;
+    } else {
+        score = kDead;
+        const uint32_t pp = b2.t_pos;
+        const uint32_t base23 = ((uint32_t)b1.q << 4 | b2.q) & 255u;
+        const uint32_t delta23 = b1.t_pos == b2.t_pos ? 1u : 0u;
+        const bool boundary = pp < s;  // the articulation before the run: one entry, local score 0
+        const uint32_t npe = boundary ? 1u : (pp == p ? idx : n_ent(m, pp));
+        for (uint32_t pi = 0; pi < npe; pi++) {
+            const Entry v = get_entry(m, pp, pi);
+            if ((v.bases & 255u) != base23 || ((v.bases >> 12) & 1u) != delta23) continue;
+            ABase v1, v2, v3;
+            kmer_bases(v.bases, v.delta, pp, v1, v2, v3);
+            if (!(v2.eq(b1) && v3.eq(b2))) continue;
+            if (pp >= 3 && v1.q == 15) continue;  // main.rs:1666-1668
+            const int64_t vs = boundary ? 0 : (v.g == 0xFFFFFFFFu ? m.dense_score[pp] : m.g_score[v.g]);
+            const int64_t sc = vs + inc;
+            if (sc > score || (sc == score && v1.q != 4)) {  // main.rs:1670
+                score = sc;
+                besti = pi;
+            }
+        }
+    }
+    if (x.g == 0xFFFFFFFFu) {
+        m.dense_besti[p] = besti;
+        if (!single) m.dense_score[p] = score;
+    } else {
+        m.g_besti[x.g] = besti;
+        m.g_score[x.g] = score;
+    }
+    return score;
+}
+constexpr uint32_t kDpLongWork = 4096;  // entry x predecessor tests after which a run is handed to a whole warp
+                                        // (NP2_DP_LONG_WORK overrides it: 0 sends every run there, for the tests)
+
 // One thread per run of multi-entry positions [s, e); e is the next articulation position (single entry,
 // every path passes through it), so scores can be kept relative to the articulation before s.
-__global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, DpOut o) {
+// A run whose work (entries x predecessors) passes kDpLongWork — a tandem-repeat block with tens of 3-mers per position
+// — is put on a queue and done again from its start by a whole warp (k_dp_runs_long).
+__global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, DpOut o, uint32_t *__restrict__ long_runs,
+                          uint32_t *__restrict__ n_long, uint32_t long_work) {
     uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
     if (m.cnt[C_ABORT] || ri >= m.cnt[C_NRUNS]) return;
     const uint32_t s = run_start[ri], L = m.L;
     int64_t best = 0;
-    uint32_t best_idx = 0;
+    uint32_t best_idx = 0, work = 0, ne_prev = 1;
     for (uint32_t p = s; p < L; p++) {
         const bool single = !m.multi[p];
         const uint32_t ne = n_ent(m, p);
         const int64_t cov = m.cover[p];
+        work += ne * ne_prev;
+        if (work > long_work) {
+            long_runs[atomicAdd(n_long, 1u)] = s;
+            return;
+        }
+        ne_prev = ne;
         for (uint32_t idx = 0; idx < ne; idx++) {
-            const Entry x = get_entry(m, p, idx);
-            ABase b1, b2, b3;
-            kmer_bases(x.bases, x.delta, p, b1, b2, b3);
-            const int64_t inc = 10 * (int64_t)x.count - 4 * cov;
-            uint32_t besti = 0;
-            int64_t score;
-            if (b2.q == 15) {
-                score = inc;
-            } else {
-                score = kDead;
-                const uint32_t pp = b2.t_pos;
-                const uint32_t base23 = ((uint32_t)b1.q << 4 | b2.q) & 255u;
-                const uint32_t delta23 = b1.t_pos == b2.t_pos ? 1u : 0u;
-                const bool boundary = pp < s;  // the articulation before the run: one entry, local score 0
-                const uint32_t npe = boundary ? 1u : (pp == p ? idx : n_ent(m, pp));
-                for (uint32_t pi = 0; pi < npe; pi++) {
-                    const Entry v = get_entry(m, pp, pi);
-                    if ((v.bases & 255u) != base23 || ((v.bases >> 12) & 1u) != delta23) continue;
-                    ABase v1, v2, v3;
-                    kmer_bases(v.bases, v.delta, pp, v1, v2, v3);
-                    if (!(v2.eq(b1) && v3.eq(b2))) continue;
-                    if (pp >= 3 && v1.q == 15) continue;  // main.rs:1666-1668
-                    const int64_t vs = boundary ? 0 : (v.g == 0xFFFFFFFFu ? m.dense_score[pp] : m.g_score[v.g]);
-                    const int64_t sc = vs + inc;
-                    if (sc > score || (sc == score && v1.q != 4)) {  // main.rs:1670
-                        score = sc;
-                        besti = pi;
-                    }
-                }
-            }
-            if (x.g == 0xFFFFFFFFu) {
-                m.dense_besti[p] = besti;
-                if (!single) m.dense_score[p] = score;
-            } else {
-                m.g_besti[x.g] = besti;
-                m.g_score[x.g] = score;
-            }
+            uint32_t kd;
+            const int64_t score = dp_entry(m, s, p, idx, cov, single, kd);
             if (p == L - 1 && (idx == 0 || score >= best)) {  // main.rs:1680, offset-invariant form
                 best = score;
                 best_idx = idx;
@@ -1515,15 +1536,68 @@ __global__ void k_dp_runs(MsaDev m, const uint32_t *__restrict__ run_start, DpOu
     }
     *o.best_last = best_idx;  // the run reached the contig end
 }
+// One warp per long run.  Positions stay sequential (every position needs the scores of the one before); the entries of a
+// position are spread over the lanes.  An entry whose predecessor sits at the SAME position (b3 is an insertion column)
+// needs that predecessor's score first: its b3.delta is one less, and the entries of a position are ordered by b3.delta
+// (Msa::sort), so the lanes take them in waves of equal b3.delta.
+__global__ void __launch_bounds__(128) k_dp_runs_long(MsaDev m, DpOut o, const uint32_t *__restrict__ long_runs,
+                                                      const uint32_t *__restrict__ n_long) {
+    const uint32_t lane = threadIdx.x & 31, L = m.L;
+    if (m.cnt[C_ABORT]) return;
+    const uint32_t nl = *n_long, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nl; w += nw) {
+        const uint32_t s = long_runs[w];
+        int64_t best = 0;
+        uint32_t best_idx = 0;
+        bool any = false, ended = false;
+        for (uint32_t p = s; p < L && !ended; p++) {
+            const bool single = !m.multi[p];
+            const uint32_t ne = n_ent(m, p);
+            const int64_t cov = m.cover[p];
+            for (uint32_t done = 0; done < ne;) {
+                const uint32_t idx = done + lane;
+                uint32_t kd = 0xFFFFFFFFu;
+                if (idx < ne) {
+                    const Entry x = get_entry(m, p, idx);
+                    kd = kmer_b3delta(x.bases, x.delta);
+                }
+                const uint32_t kd0 = __shfl_sync(0xFFFFFFFFu, kd, 0);
+                const uint32_t same = __ballot_sync(0xFFFFFFFFu, idx < ne && kd == kd0);
+                const uint32_t cnt = same == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs(~same) - 1;  // leading lanes of the wave
+                int64_t score = INT64_MIN;
+                if (lane < cnt) {
+                    uint32_t kd_;
+                    score = dp_entry(m, s, p, idx, cov, single, kd_);
+                }
+                __syncwarp();
+                if (p == L - 1) {  // main.rs:1680: the last entry among those with the highest score
+                    int64_t mx = score;
+                    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+                    const uint32_t at = __ballot_sync(0xFFFFFFFFu, lane < cnt && score == mx);
+                    if (!any || mx >= best) {
+                        best = mx;
+                        best_idx = done + (31 - __clz(at));
+                        any = true;
+                    }
+                }
+                done += cnt;
+            }
+            if (single) ended = true;
+        }
+        if (!ended && lane == 0) *o.best_last = best_idx;  // the run reached the contig end
+    }
+}
 static DpOut dp_out(CountsDev cd) {
     DpOut o;
     o.best_last = cd.c + C_BESTLAST;
     o.score_total = cd.q + Q_TOTAL;
     return o;
 }
-void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, cudaStream_t s) {
+void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, uint32_t *d_long_runs, cudaStream_t s) {
     if (!cap_runs) return;
-    NP2_K(k_dp_runs)<<<cdiv(cap_runs, 64), 64, 0, s>>>(m, d_run_start, dp_out(cd));
+    static const uint32_t long_work = getenv("NP2_DP_LONG_WORK") ? (uint32_t)atoi(getenv("NP2_DP_LONG_WORK")) : kDpLongWork;
+    NP2_K(k_dp_runs)<<<cdiv(cap_runs, 64), 64, 0, s>>>(m, d_run_start, dp_out(cd), d_long_runs, cd.c + C_NLONGRUN, long_work);
+    NP2_K(k_dp_runs_long)<<<148 * 4, 128, 0, s>>>(m, dp_out(cd), d_long_runs, cd.c + C_NLONGRUN);
 }
 
 // Backtrack of one run (main.rs:1572-1634 without the LQ state machine).  WRITE = false: count emitted

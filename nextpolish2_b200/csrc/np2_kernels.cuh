@@ -29,6 +29,7 @@ enum Cnt : int {
     C_GERR,       // genotype-rule error (reference would panic)
     C_PERR,       // read pair outside its index window
     C_NENT,       // survivors of the RECH regions
+    C_NLONGRUN,   // runs whose DP is done by a whole warp (k_dp_runs_long)
     C_COUNT = 32
 };
 enum Cnt64 : int {
@@ -144,7 +145,8 @@ void counts_reset_pileup(CountsDev cd, cudaStream_t s);
 // first positions of the runs of multi-entry positions (C_NRUNS)
 void runs_select(const uint8_t *d_multi, uint32_t L, uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, ScanPool &pool,
                  cudaStream_t s);
-void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, cudaStream_t s);
+// d_long_runs: cap_runs entries, the runs handed over to the warp-cooperative kernel
+void dp_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, uint32_t *d_long_runs, cudaStream_t s);
 void emit_count_runs(MsaDev m, const uint32_t *d_run_start, uint32_t cap_runs, CountsDev cd, uint32_t *d_n_emit,
                      cudaStream_t s);
 // emit_off = exclusive sum of n_emit (L + 1 entries), C_N = number of consensus bases; the bases of the single-entry

@@ -56,43 +56,81 @@ struct Lvl {
 // disjoint id ranges (see move_vertices).
 bool move_range(Lvl &lv, size_t i0, size_t i1, uint32_t *slot, uint32_t *stamp, uint8_t *dirty) {
     bool moved_any = false;
-    // per-visit accumulator: weight towards each neighbouring community, found through a stamped slot table (the
-    // choice below only depends on the sums, not on the order the communities were met in)
+    // per-visit accumulator: weight towards each neighbouring community (the choice below only depends on the sums, not
+    // on the order the communities were met in).  A read's neighbours sit in a handful of communities, so the first
+    // kSmall of them live in a small array that is searched linearly (registers / L1); only a vertex that touches
+    // more falls back to the stamped slot table.
+    constexpr int kSmall = 8;
+    uint32_t sc[kSmall];
+    float sw[kSmall];
     std::vector<std::pair<uint32_t, float>> acc;
     uint32_t visit = 0;
+    const uint32_t *aoff = lv.aoff, *ato = lv.ato;
+    const float *aw = lv.aw;
+    uint32_t *cid = lv.cid.data();
     for (;;) {
         bool stop = true;
         for (size_t i = i0; i < i1; i++) {
             const uint32_t v = lv.ids[i];
             if (!dirty[v]) continue;
             dirty[v] = 0;
-            const uint32_t cur = lv.cid[v];
-            acc.clear();
-            if (++visit == 0) {  // stamp wrap-around (communities of this range are vertices of this range)
-                for (size_t x = i0; x < i1; x++) stamp[lv.ids[x]] = 0;
-                visit = 1;
-            }
-            for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) {
-                const uint32_t c = lv.cid[lv.ato[e]];
-                if (stamp[c] != visit) {
-                    stamp[c] = visit;
-                    slot[c] = (uint32_t)acc.size();
-                    acc.emplace_back(c, lv.aw[e]);
+            const uint32_t cur = cid[v];
+            const uint32_t e0 = aoff[v], e1 = aoff[v + 1];
+            if (e0 == e1) continue;
+            int ns = 0;
+            bool spilled = false;
+            uint32_t e = e0;
+            for (; e < e1; e++) {
+                const uint32_t c = cid[ato[e]];
+                int k = 0;
+                while (k < ns && sc[k] != c) k++;
+                if (k < ns) {
+                    sw[k] += aw[e];
+                } else if (ns < kSmall) {
+                    sc[ns] = c;
+                    sw[ns++] = aw[e];
                 } else {
-                    acc[slot[c]].second += lv.aw[e];
+                    spilled = true;
+                    break;
                 }
             }
-            if (acc.empty()) continue;
-            uint32_t bid = acc[0].first;
-            float bw = acc[0].second;
-            for (auto &a : acc)
-                if (a.second > bw || (a.second == bw && a.first < bid)) {  // max weight, ties -> smaller id
-                    bid = a.first;
-                    bw = a.second;
+            uint32_t bid;
+            float bw;
+            if (!spilled) {
+                bid = sc[0];
+                bw = sw[0];
+                for (int k = 1; k < ns; k++)
+                    if (sw[k] > bw || (sw[k] == bw && sc[k] < bid)) {  // max weight, ties -> smaller id
+                        bid = sc[k];
+                        bw = sw[k];
+                    }
+            } else {  // many neighbouring communities: start over with the slot table
+                acc.clear();
+                if (++visit == 0) {  // stamp wrap-around (communities of this range are vertices of this range)
+                    for (size_t x = i0; x < i1; x++) stamp[lv.ids[x]] = 0;
+                    visit = 1;
                 }
+                for (e = e0; e < e1; e++) {
+                    const uint32_t c = cid[ato[e]];
+                    if (stamp[c] != visit) {
+                        stamp[c] = visit;
+                        slot[c] = (uint32_t)acc.size();
+                        acc.emplace_back(c, aw[e]);
+                    } else {
+                        acc[slot[c]].second += aw[e];
+                    }
+                }
+                bid = acc[0].first;
+                bw = acc[0].second;
+                for (auto &a : acc)
+                    if (a.second > bw || (a.second == bw && a.first < bid)) {
+                        bid = a.first;
+                        bw = a.second;
+                    }
+            }
             if (bw > 0.0f && bid != cur) {
-                lv.cid[v] = bid;
-                for (uint32_t e = lv.aoff[v]; e < lv.aoff[v + 1]; e++) dirty[lv.ato[e]] = 1;
+                cid[v] = bid;
+                for (e = e0; e < e1; e++) dirty[ato[e]] = 1;
                 stop = false;
                 moved_any = true;
             }

@@ -211,3 +211,37 @@ def test_stage_pair_weights(ctx, name):
     common.assert_same("pair weights", ov, gv)
     assert (ok >> np.uint64(32) < (ok & np.uint64(0xFFFFFFFF))).all() and (np.diff(ok.astype(np.int64)) > 0).all()
     gj.destroy()
+
+
+_LONG_DP_CHILD = r"""
+import sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle"); sys.path.insert(0, %(root)r + "/tests")
+import numpy as np
+import common, oracle as O, nextpolish2_b200 as np2
+ctx = np2.Context(0)
+for name in ("tandem200k", "dip600k", "deep80k"):
+    ds = common.dataset(name)
+    oo, go = common.same_opts()
+    oj = O.Job(ds["contig"], ds["bam"], common.oracle_tables(ds), oo, dump_iter=0)
+    gj = np2.Job(ctx, ds["contig"], ds["bam"], common.gpu_tables(ctx, ds), go).upload().run(0)
+    common.assert_same_dict("msa", oj.msa(), gj.msa())          # besti of every Msa entry
+    common.assert_same_dict("dp", oj.dp_consensus(), gj.dp_consensus())
+    op, ob = oj.consensus(); gp, gb = gj.consensus()
+    assert np.array_equal(ob, gb) and np.array_equal(op, gp)
+    gj.destroy()
+print("LONG-DP-OK")
+"""
+
+
+@pytest.mark.timeout(600)
+def test_warp_cooperative_dp_matches_oracle():
+    """K3 for long runs: with NP2_DP_LONG_WORK=0 EVERY run of multi-entry positions goes through the
+    warp-cooperative kernel (entries of a position over the lanes, waves of equal b3.delta); besti of every Msa entry, the
+    DP consensus and the final consensus must equal the oracle's on the tandem-repeat, diploid and deep sets."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NP2_DP_LONG_WORK="0")
+    r = subprocess.run([sys.executable, "-c", _LONG_DP_CHILD % {"root": root}], env=env, capture_output=True, text=True, timeout=550)
+    assert r.returncode == 0 and "LONG-DP-OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
