@@ -138,19 +138,19 @@ def peaks():
 STAGE_MODELS = {
     # 4-bit SEQ in (0.5 B/column), packed nibble out (0.5), one 10-byte checkpoint out + one 2-byte op index in per 32 columns
     "pack_columns": ("k_pack_columns_batched<2>", lambda st: st["cols"] * (0.5 + 0.5 + 10 / 32 + 2 / 32)),
-    # packed columns in (0.5) + checkpoints in (10/32); packed reference (0.5 B/bp) counted once; 12 B per record out
-    "pileup_emit": ("k_pileup_emit<2>", lambda st: st["cols"] * (0.5 + 10 / 32) + st["L"] * 0.5 + st["records"] * 12),
-    # 12-byte records in and out once per partition pass (2 passes) + group arrays out
-    "pileup_sort": ("pileup ordering (stripe partition + in-stripe sort)", lambda st: st["records"] * 12 * 4 + st["groups"] * 16),
-    # per position: cover 4 + sp_off 4 in, dense count 4 + flags 2 out; per group 16 in + 8 out
-    "pileup_finalize": ("k_pos_finalize", lambda st: st["L"] * 14 + st["groups"] * 24),
-    # per position of a run: sp_off 4 + cover 4 + multi 1 in, dense score/besti 12 out; per group 16 in, 12 out
-    "dp_runs": ("k_dp_runs", lambda st: st["L"] * 9 * 0.2 + st["groups"] * 28),
-    # per position: multi 1 + cover 4 + dense count 4 + code 1 + offset 4 in; 6 B per consensus base out
-    "consensus_emit": ("k_emit_singles + k_emit_runs", lambda st: st["L"] * 14 + st["N"] * 6),
+    # once per job: packed columns in (0.5 B/column), checkpoint t_pos + read id in (8 B / 32 columns), one bit out per block,
+    # packed reference (0.5 B/bp) counted once
+    "block_flags": ("k_block_flags", lambda st: st["cols"] * (0.5 + 8 / 32 + 1 / 256) + st["L"] * 0.5),
+    # K2: per position coverage 4 + code 1 in, entry offset 4 + count 2 + reference count 4 + flag 1 + emit count 4 out;
+    # one bit per 32-column block in; per not-all-reference block (<= one per record) 16 B of columns + 10 B checkpoint in;
+    # 16 B per Msa entry out
+    "pileup_stripe": ("k_pileup_stripe<1024, true>",
+                      lambda st: st["L"] * 20 + st["cols"] / 256 + st["records"] * 26 + st["groups"] * 16),
+    # per multi-entry position: offset 4 + count 2 + coverage 4 + flag 1 in, reference score / besti 12 out; per entry 16 in, 12 out
+    "dp_runs": ("k_dp_runs (+ k_dp_runs_long)", lambda st: st["groups"] * (11 + 12) + st["groups"] * 28),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of configs[1] (profiles/), bytes
-NCU_TRAFFIC = {"pack_columns": 384700000, "pileup_emit": 273600000}
+NCU_TRAFFIC = {"pack_columns": 384700000}
 
 
 # bytes the whole pipeline must move per polished bp, D = depth, q = yak probes per bp
