@@ -254,10 +254,16 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
     partsN = {"create_parse": 0.0, "upload": 0.0, "run": 0.0, "result": 0.0, "n": 0}
     expect = [len(r) for r in m.records]
 
-    def e2e_one(cx, ci, acc=None):
-        c, p = contigs[ci], pinned[ci]
+    def e2e_begin(cx, ci):
+        """np2_job_create: record parse on the host, then everything the upload needs is ENQUEUED (K0's gather of the SEQ
+        fields over PCIe, the per-read arrays on the copy stream) and the call returns."""
         t0 = time.perf_counter()
-        j = np2.Job(cx, p[2], p[3], tables, opts)
+        j = np2.Job(cx, pinned[ci][2], pinned[ci][3], tables, opts)
+        return j, ci, time.perf_counter() - t0
+
+    def e2e_finish(started, acc=None):
+        j, ci, t_create = started
+        c = contigs[ci]
         t1 = time.perf_counter()
         j.upload()
         t2 = time.perf_counter()
@@ -272,7 +278,7 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
         j.destroy()
         t4 = time.perf_counter()
         if acc is not None:
-            for k, v in zip(("create_parse", "upload", "run", "result"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            for k, v in zip(("create_parse", "upload", "run", "result"), (t_create, t2 - t1, t3 - t2, t4 - t3)):
                 acc[k] += v * 1e3
             acc["n"] += 1
             sa = acc.setdefault("stages", {})
@@ -281,8 +287,15 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
             acc["repeated_passes"] = acc.get("repeated_passes", 0) + st.get("repeated_passes", 0)
         return tr
 
+    def e2e_one(cx, ci, acc=None):
+        return e2e_finish(e2e_begin(cx, ci), acc)
+
     def e2e_run(n_inflight):
-        ctxs = [ctx] + [np2.Context(local) for _ in range(n_inflight - 1)]
+        # every worker thread owns `depth` contexts: while it runs contig i on one, contig i + 1 is already parsed and its
+        # upload is under way on the other (np2_job_create only enqueues), so the link does not idle while the worker
+        # is inside np2_job_run and no extra host thread competes for the cores
+        depth = 2 if (args.e2e_prefetch and n_inflight > 1) else 1
+        ctxs = [ctx] + [np2.Context(local) for _ in range(n_inflight * depth - 1)]
         for cx in ctxs:  # warm every context: pools, page-locked buffers, and the sizes the speculative passes start from
             for _ in range(max(2, warmup // n_inflight)):
                 for ci in range(len(contigs)):
@@ -290,18 +303,33 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
         work_items = [ci for _ in range(steps) for ci in range(len(contigs))]
         nxt, lock, errs, tr_sum = [0], threading.Lock(), [], {"h2d_bytes": 0, "d2h_bytes": 0}
 
+        def take():
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            return i if i < len(work_items) else None
+
         def work(w):
+            acc = parts1 if n_inflight == 1 else partsN
             try:
-                while True:
-                    with lock:
-                        i = nxt[0]
-                        nxt[0] += 1
-                    if i >= len(work_items):
-                        return
-                    tr = e2e_one(ctxs[w], work_items[i], parts1 if n_inflight == 1 else partsN)
+                mine, turn = ctxs[w * depth:(w + 1) * depth], 0
+                i = take()
+                cur = e2e_begin(mine[0], work_items[i]) if i is not None else None
+                while cur is not None:
+                    nx = None
+                    if depth > 1:
+                        i = take()
+                        if i is not None:
+                            turn ^= 1
+                            nx = e2e_begin(mine[turn], work_items[i])
+                    tr = e2e_finish(cur, acc)
                     with lock:
                         tr_sum["h2d_bytes"] += tr["h2d_bytes"]
                         tr_sum["d2h_bytes"] += tr["d2h_bytes"]
+                    if depth == 1:
+                        i = take()
+                        nx = e2e_begin(mine[0], work_items[i]) if i is not None else None
+                    cur = nx
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         torch.cuda.synchronize()
@@ -479,7 +507,8 @@ def _run_ours(args):
                        "partition": "one workload replica per GPU, no collective on the data path",
                        "l2": "inputs (%.0f MB of BAM records per GPU) are larger than the 126 MB L2" % (
                            sum(len(c["bam"]) for c in contigs) / 1e6)},
-            "e2e": dict(s["e2e"], contigs_in_flight=args.e2e_inflight,
+            "e2e": dict(s["e2e"], contigs_in_flight=args.e2e_inflight * (2 if args.e2e_prefetch and args.e2e_inflight > 1 else 1),
+                        worker_threads=args.e2e_inflight, prefetch=bool(args.e2e_prefetch),
                         one_at_a_time=round(mbp_total / m.e2e_serial_time, 3),
                         one_at_a_time_ms={k: round(v / max(1, m.parts1["n"]), 3) for k, v in m.parts1.items()
                                           if k in ("create_parse", "upload", "run", "result")},
@@ -590,30 +619,64 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
     pinned = [(torch.from_numpy(c["contig"].copy()).pin_memory(), torch.from_numpy(c["bam"]).pin_memory()) for c in contigs]
     t_synth = time.time() - t0
     inflight = max(1, min(args.e2e_inflight, len(contigs)))
-    ctxs = [ctx] + [np2.Context(local) for _ in range(inflight - 1)]
+    depth = 2 if (args.e2e_prefetch and len(contigs) > inflight) else 1  # see measure(): next contig parsed + uploading
+    ctxs = [ctx] + [np2.Context(local) for _ in range(inflight * depth - 1)]
+
+    def begin(cx, ci):
+        p = pinned[ci]
+        return np2.Job(cx, p[0].numpy(), p[1].numpy(), tables, opts), ci
+
+    parts = {"upload_wait": 0.0, "run": 0.0, "result": 0.0, "n": 0, "repeated_passes": 0, "host_syncs": 0}
+
+    def finish(started):
+        j, ci = started
+        t0 = time.perf_counter()
+        j.upload()
+        t1 = time.perf_counter()
+        j.run(-1)
+        t2 = time.perf_counter()
+        first, last, base = j.bases(copy=False)
+        rec = fasta_record(contigs[ci]["name"], first, last, base)
+        nd = len(j.dropped())
+        st = j.stats()
+        j.destroy()
+        t3 = time.perf_counter()
+        for k, v in (("upload_wait", t1 - t0), ("run", t2 - t1), ("result", t3 - t2)):
+            parts[k] += v * 1e3
+        parts["n"] += 1
+        parts["repeated_passes"] += st.get("repeated_passes", 0)
+        parts["host_syncs"] += st.get("host_syncs", 0)
+        return rec, nd
 
     def polish(cx, ci):
-        c, p = contigs[ci], pinned[ci]
-        j = np2.Job(cx, p[0].numpy(), p[1].numpy(), tables, opts)
-        j.upload().run(-1)
-        first, last, base = j.bases(copy=False)
-        rec = fasta_record(c["name"], first, last, base)
-        nd = len(j.dropped())
-        j.destroy()
-        return rec, nd
+        return finish(begin(cx, ci))
 
     def one_pass():
         out, nxt, lock, errs = {}, [0], threading.Lock(), []
 
+        def take():
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            return i if i < len(contigs) else None
+
         def work(w):
             try:
-                while True:
-                    with lock:
-                        i = nxt[0]
-                        nxt[0] += 1
-                    if i >= len(contigs):
-                        return
-                    out[contigs[i]["idx"]] = polish(ctxs[w], i)
+                mine, turn = ctxs[w * depth:(w + 1) * depth], 0
+                i = take()
+                cur = begin(mine[0], i) if i is not None else None
+                while cur is not None:
+                    nx = None
+                    if depth > 1:
+                        i = take()
+                        if i is not None:
+                            turn ^= 1
+                            nx = begin(mine[turn], i)
+                    out[contigs[cur[1]]["idx"]] = finish(cur)
+                    if depth == 1:
+                        i = take()
+                        nx = begin(mine[0], i) if i is not None else None
+                    cur = nx
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         th = [threading.Thread(target=work, args=(w,)) for w in range(inflight)]
@@ -625,6 +688,8 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
     if contigs:
         for cx in ctxs:
             polish(cx, 0)  # warm pools
+    for k in parts:
+        parts[k] = 0
     passes = max(1, args.strong_passes)
     barrier()
     t1 = time.perf_counter()
@@ -662,6 +727,7 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
                "value": round(total * passes / 1e6 / dt_max, 3), "unit": "Mbp/s (end to end, host buffers in, FASTA records out)",
                "seconds_per_pass": round(dt_max / passes, 4), "passes": passes, "contigs_in_flight_per_gpu": inflight,
                "contigs_per_rank": [len(p) for p in lpt_partition([float(x) for x in lens], world)],
+               "rank0_ms_per_contig_per_thread": {k: round(v / max(1, parts["n"]), 3) for k, v in parts.items() if k != "n"},
                "fasta_sha256_in_input_order": h.hexdigest(), "fasta_bytes": int(sum(v[1] for v in merged.values())),
                "reads_dropped_by_phasing": int(sum(v[2] for v in merged.values())),
                "oracle_checked_contigs": [c["idx"] for c in contigs] if not args.no_verify else [],
@@ -817,7 +883,8 @@ def main():
     ap.add_argument("--strong-passes", type=int, default=2)
     ap.add_argument("--pageable", action="store_true", help="record buffer in pageable memory (host compaction path)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per library call (0 = cores / ranks / ~in flight)")
-    ap.add_argument("--e2e-inflight", type=int, default=3, help="contigs in flight per GPU in the end-to-end arm")
+    ap.add_argument("--e2e-inflight", type=int, default=3, help="worker threads per GPU in the end-to-end arm")
+    ap.add_argument("--e2e-prefetch", type=int, default=1, help="1: every worker parses and starts the upload of its next contig before it runs the current one")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
