@@ -198,6 +198,7 @@ class Measured:
 
 def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, warmup, barrier, inflight):
     """Device-resident arm + end-to-end arm over `contigs`; returns a Measured with times (seconds for `steps` steps)."""
+    from nextpolish2_b200.api import set_stage_timing
     m = Measured()
     pinned = []
     for c in contigs:
@@ -295,6 +296,8 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
         # upload is under way on the other (np2_job_create only enqueues), so the link does not idle while the worker
         # is inside np2_job_run and no extra host thread competes for the cores
         depth = 2 if (args.e2e_prefetch and n_inflight > 1) else 1
+        # stage timers (two event records per stage) only while one contig is processed at a time
+        set_stage_timing(n_inflight == 1 or args.e2e_stage_timers)
         ctxs = [ctx] + [np2.Context(local) for _ in range(n_inflight * depth - 1)]
         for cx in ctxs:  # warm every context: pools, page-locked buffers, and the sizes the speculative passes start from
             for _ in range(max(2, warmup // n_inflight)):
@@ -341,6 +344,7 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
         t2 = time.perf_counter()
         for cx in ctxs[1:]:
             cx.close()
+        set_stage_timing(True)
         if errs:
             raise errs[0]
         return t2 - t1, {k: v // steps for k, v in tr_sum.items()}
@@ -685,6 +689,8 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
         if errs:
             raise errs[0]
         return out
+    from nextpolish2_b200.api import set_stage_timing
+    set_stage_timing(False)
     if contigs:
         for cx in ctxs:
             polish(cx, 0)  # warm pools
@@ -700,6 +706,7 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
     barrier()
     for cx in ctxs[1:]:
         cx.close()
+    set_stage_timing(True)
     t_dev = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -884,6 +891,7 @@ def main():
     ap.add_argument("--pageable", action="store_true", help="record buffer in pageable memory (host compaction path)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per library call (0 = cores / ranks / ~in flight)")
     ap.add_argument("--e2e-inflight", type=int, default=3, help="worker threads per GPU in the end-to-end arm")
+    ap.add_argument("--e2e-stage-timers", action="store_true", help="keep the per-stage event timers on with contigs in flight")
     ap.add_argument("--e2e-prefetch", type=int, default=1, help="1: every worker parses and starts the upload of its next contig before it runs the current one")
     args = ap.parse_args()
     if args.impl == "reference":

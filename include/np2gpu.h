@@ -78,6 +78,9 @@ void np2_opts_default(np2_opts *o); /* option.rs:267-292 */
 /* host threads one call may use for record parsing and SEQ compaction (0 = NP2_HOST_THREADS from the environment, else
  * min(16, hardware threads)); process-wide.  A caller running several contexts or ranks on one box divides the cores. */
 void np2_set_host_threads(uint32_t n);
+/* per-stage CUDA-event timers behind np2_job_get_timings (default on, NP2_STAGE_TIMING=0 in the environment turns them
+ * off): off keeps only "total" and the host phases, and saves two submissions per stage; process-wide. */
+void np2_set_stage_timing(int on);
 
 int np2_device_count(void); /* visible CUDA devices (0 when there is none / no driver) */
 int np2_ctx_create(int device, np2_ctx **out);
@@ -221,7 +224,10 @@ void np2_job_get_stats(np2_job *job, uint64_t out[12]);
 /* Test seam (host only, no device needed): parses + filters a record buffer (main.rs:1758-1771, 386-440) split into
  * `threads` speculative byte ranges (0 = automatic) and returns a digest of everything the parse produces:
  * out[0] records, out[1] kept reads, out[2] column-consuming CIGAR ops, out[3] alignment columns,
- * out[4] ranges re-walked sequentially because the guessed record boundary was wrong, out[5] FNV-1a of all arrays. */
+ * out[4] ranges re-walked sequentially because the guessed record boundary was wrong, out[5] FNV-1a of all arrays.
+ * threads: low 16 bits = byte ranges (0 = default); bit 16 = parse as np2_job_create does (the CIGAR is only summed, the
+ * op records are expanded on the device) and digest the per-record arrays only; bit 17 = build the op records on the
+ * host (as without flags) but digest the per-record arrays only, so that the two digests can be compared. */
 int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts *opts, uint32_t threads,
                     uint64_t out[6]);
 

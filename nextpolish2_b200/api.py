@@ -47,7 +47,7 @@ EXPORTS = [
     "np2_job_get_candidates", "np2_job_get_dropped", "np2_job_get_pair_weights", "np2_job_get_timings", "np2_job_get_traffic", "np2_job_get_stats", "np2_format_fasta",
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
-    "np2_debug_phase", "np2_set_host_threads",
+    "np2_debug_phase", "np2_set_host_threads", "np2_set_stage_timing",
     "np2_device_count", "np2_count_create", "np2_count_add", "np2_count_distinct", "np2_count_finish", "np2_count_destroy",
 ]
 
@@ -118,6 +118,8 @@ def load_library():
     L.np2_count_destroy.argtypes = [vp]
     L.np2_set_host_threads.argtypes = [u32]
     L.np2_set_host_threads.restype = None
+    L.np2_set_stage_timing.argtypes = [C.c_int]
+    L.np2_set_stage_timing.restype = None
     L.np2_debug_phase.argtypes = [vp, vp, u64, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u32)]
     L.np2_secmap_create.argtypes = [C.POINTER(vp)]
     L.np2_secmap_destroy.argtypes = [vp]
@@ -490,6 +492,11 @@ class Counter:
 def set_host_threads(n):
     """Host threads one call may use for record parsing / SEQ compaction (np2_set_host_threads)."""
     load_library().np2_set_host_threads(int(n))
+
+
+def set_stage_timing(on):
+    """Per-stage CUDA-event timers of Job.timings() on / off (np2_set_stage_timing); "total" and host phases stay."""
+    load_library().np2_set_stage_timing(1 if on else 0)
 
 
 class SecondarySeqs:

@@ -8,6 +8,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -110,6 +111,12 @@ struct Arena {
     }
 };
 // NP2_TRACE: driver calls that block for more than half a millisecond are reported with their size
+// per-stage CUDA events (np2_job_get_timings): two event records per stage are two more submissions per stage; with
+// several contigs in flight and the link busy every submission costs (np2_set_stage_timing(0) keeps only "total")
+std::atomic<int> g_stage_events{[] {
+    const char *e = getenv("NP2_STAGE_TIMING");
+    return !e || atoi(e) != 0 ? 1 : 0;
+}()};
 thread_local std::vector<std::pair<std::string, double>> *g_trace = nullptr;
 thread_local std::chrono::steady_clock::time_point g_trace_t0;
 struct SlowCall {
@@ -279,6 +286,10 @@ struct StageTimer {
     }
     int begin(const char *name, uint32_t n_launch) {
         mark(name);
+        if (!g_stage_events.load(std::memory_order_relaxed) && strcmp(name, "total") != 0) {
+            launches[id(name)] += n_launch;
+            return -1;
+        }
         Rec r;
         r.stage = id(name);
         r.a = ev();
@@ -288,7 +299,9 @@ struct StageTimer {
         recs.push_back(r);
         return (int)recs.size() - 1;
     }
-    void end(int h) { NP2_CUDA(cudaEventRecord(recs[h].b, s)); }
+    void end(int h) {
+        if (h >= 0) NP2_CUDA(cudaEventRecord(recs[h].b, s));
+    }
     void collect() {  // after a stream sync
         for (auto &r : recs) {
             float t = 0;
@@ -344,7 +357,8 @@ struct JobScratch {
     Patched patch;
     PBuf<uint8_t> res_base, p_cbase, p_cflags, p_stage, p_stage2, p_seq_stage;
     PBuf<uint32_t> p_cpos;
-    std::vector<uint64_t> cseq_off;  // SEQ offsets in the compact device blob
+    std::vector<uint64_t> cseq_off, cseq_start, cspan_off;  // span / SEQ offsets in the compact device blob, span sources
+    std::vector<uint32_t> cspan_bytes;
     cudaEvent_t seq_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_trim = nullptr;
     PBuf<uint8_t> p_trim;
@@ -480,7 +494,7 @@ struct np2_job {
     DBuf<uint8_t> d_ref, d_code, d_blob, d_nib, d_blank;
     DBuf<int> d_bad;  // the contig holds a byte the reference cannot index
     DBuf<uint32_t> d_refpk;
-    DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off;
+    DBuf<uint32_t> d_pos, d_op_off, d_ncols, d_ck_off, d_ncig;
     DBuf<Op> d_ops;
     DBuf<uint64_t> d_seq_off, d_nib_off;
     DBuf<uint32_t> d_ts, d_te, d_n, d_shift, d_ck_tpos, d_ck_read;
@@ -562,6 +576,38 @@ struct np2_job {
 
 /* ================================================================= pipeline */
 
+// One K0 at a time per device.  A K0 keeps ~0.5 MB of reads outstanding on the link; every other transfer — the
+// command fetches of every kernel launch of the contigs that are being polished meanwhile, their count read-backs —
+// queues behind those reads, and with two or three K0s of different contexts running at once a kernel launch goes
+// from ~8 to ~40 us (profiles/r02w_diag_probe.json).  The link is the shared resource anyway, so the K0s of a device
+// are chained through events: each waits for the one enqueued before it, on the device, without blocking a host thread.
+struct K0Chain {
+    std::mutex mu;
+    static constexpr int kRing = 64;
+    cudaEvent_t ev[kRing] = {};
+    uint64_t n = 0;
+};
+K0Chain g_k0_chain[16];
+static const bool g_k0_serial = [] {
+    const char *e = getenv("NP2_K0_SERIAL");
+    return !e || atoi(e) != 0;
+}();
+void k0_chain_enter(int device, cudaStream_t c2) {  // before the K0 launch; returns with the chain's mutex HELD
+    K0Chain &ch = g_k0_chain[device & 15];
+    ch.mu.lock();
+    if (ch.n) NP2_CUDA(cudaStreamWaitEvent(c2, ch.ev[(ch.n - 1) % K0Chain::kRing], 0));
+}
+void k0_chain_leave(int device, cudaStream_t c2) {  // after the K0 launch
+    K0Chain &ch = g_k0_chain[device & 15];
+    cudaEvent_t &e = ch.ev[ch.n % K0Chain::kRing];
+    cudaError_t err = cudaSuccess;
+    if (!e) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventRecord(e, c2);
+    ch.n++;
+    ch.mu.unlock();
+    if (err != cudaSuccess) throw np2::Error(NP2_ERR_CUDA, cudaGetErrorString(err));
+}
+
 // The contig goes up straight from the caller's buffer (asynchronously when it is page-locked).
 void np2_job::send_contig(const uint8_t *tseq_host) {
     cudaStream_t s = ctx->stream;
@@ -599,37 +645,50 @@ void np2_job::send_seq() {
             seq_path = 1;
         }
     }
-    std::vector<uint64_t> &co = sc->cseq_off;
+    // One span per read: its raw CIGAR words and, right behind them in the record, its SEQ bytes.  co[] = where the
+    // span lands in the blob, sq[] = where its SEQ part starts (what the kernels index), span_off / span_bytes = the source.
+    std::vector<uint64_t> &co = sc->cseq_off, &sq = sc->cseq_start, &span_off = sc->cspan_off;
+    std::vector<uint32_t> &span_bytes = sc->cspan_bytes;
     co.resize(n);
+    sq.resize(n);
+    span_off.resize(n);
+    span_bytes.resize(n);
     uint64_t D = 0;
     for (uint32_t r = 0; r < n; r++) {
-        const uint64_t mis = (uintptr_t)(src + ing.seq_off[r]) & 15;
+        const uint64_t cig = ing.host_ops ? 0 : 4ull * ing.n_cig[r];
+        span_off[r] = ing.seq_off[r] - cig;
+        span_bytes[r] = (uint32_t)(ing.seq_bytes[r] + cig);
+        const uint64_t mis = (uintptr_t)(src + span_off[r]) & 15;
         co[r] = D + mis;
-        D += ((mis + ing.seq_bytes[r] + 15) & ~15ull) + 32;  // slack: the pack kernel reads whole words past the end
+        sq[r] = co[r] + cig;
+        D += ((mis + span_bytes[r] + 15) & ~15ull) + 32;  // slack: the pack kernel reads whole words past the end
     }
     seq_blob_bytes = D;
     d_blob.alloc(D + 64, s);
     d_seq_off.alloc(std::max<size_t>(n, 1), s);
     // offsets go through a pinned staging buffer: a pageable cudaMemcpyAsync would block this thread
-    sc->p_seq_args.resize((size_t)n * 20 + 64);
+    sc->p_seq_args.resize((size_t)n * 28 + 64);
     uint8_t *st = sc->p_seq_args.p;
     if (n) {
-        np2::copy_streaming(st, co.data(), (size_t)n * 8);
+        np2::copy_streaming(st, sq.data(), (size_t)n * 8);
         np2::store_fence();
         NP2_CUDA(cudaMemcpyAsync(d_seq_off.p, st, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     }
     h2d += (uint64_t)n * 8;
     if (!n) return;
     if (seq_path == 1) {
-        DBuf<uint64_t> d_src_off;
+        DBuf<uint64_t> d_src_off, d_dst_off;
         DBuf<uint32_t> d_nbytes;
         d_src_off.alloc(n, s);
+        d_dst_off.alloc(n, s);
         d_nbytes.alloc(n, s);
-        np2::copy_streaming(st + (size_t)n * 8, ing.seq_off.data(), (size_t)n * 8);
-        np2::copy_streaming(st + (size_t)n * 16, ing.seq_bytes.data(), (size_t)n * 4);
+        np2::copy_streaming(st + (size_t)n * 8, span_off.data(), (size_t)n * 8);
+        np2::copy_streaming(st + (size_t)n * 16, co.data(), (size_t)n * 8);
+        np2::copy_streaming(st + (size_t)n * 24, span_bytes.data(), (size_t)n * 4);
         np2::store_fence();
         NP2_CUDA(cudaMemcpyAsync(d_src_off.p, st + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-        NP2_CUDA(cudaMemcpyAsync(d_nbytes.p, st + (size_t)n * 16, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        NP2_CUDA(cudaMemcpyAsync(d_dst_off.p, st + (size_t)n * 16, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        NP2_CUDA(cudaMemcpyAsync(d_nbytes.p, st + (size_t)n * 24, (size_t)n * 4, cudaMemcpyHostToDevice, s));
         // K0 runs on the context's high-priority copy stream: its CTAs only wait on PCIe, but they must be RESIDENT
         // to keep enough loads in flight; when another contig's kernels fill the SMs, a normal-priority K0 gets its
         // CTAs scheduled late and the link idles.  The main stream joins again before the offsets are freed.
@@ -639,19 +698,30 @@ void np2_job::send_seq() {
         NP2_CUDA(cudaStreamWaitEvent(c2, sc->ev_k0, 0));
         timer.s = c2;
         int h = timer.begin("upload:seq_gather", 1);
-        gather_seq(src, d_src_off.p, d_seq_off.p, d_nbytes.p, d_blob.p, n, c2);
+        if (g_k0_serial) {
+            k0_chain_enter(ctx->device, c2);
+            try {
+                gather_seq(src, d_src_off.p, d_dst_off.p, d_nbytes.p, d_blob.p, n, c2);
+            } catch (...) {
+                g_k0_chain[ctx->device & 15].mu.unlock();
+                throw;
+            }
+            k0_chain_leave(ctx->device, c2);
+        } else {
+            gather_seq(src, d_src_off.p, d_dst_off.p, d_nbytes.p, d_blob.p, n, c2);
+        }
         timer.end(h);
         timer.s = s;
         NP2_CUDA(cudaEventRecord(sc->ev_k0, c2));
         NP2_CUDA(cudaStreamWaitEvent(s, sc->ev_k0, 0));
-        h2d += (uint64_t)n * 12;
-        for (uint32_t r = 0; r < n; r++) h2d += ing.seq_bytes[r];
+        h2d += (uint64_t)n * 20;
+        for (uint32_t r = 0; r < n; r++) h2d += span_bytes[r];
         return;  // scratch is freed in stream order, after the kernel
     }
     // pageable source: rounds of <= kRound bytes through two halves of a pinned ring
     const uint64_t kRound = 64ull << 20;
     uint64_t max_slot = 0;
-    for (uint32_t r = 0; r < n; r++) max_slot = std::max<uint64_t>(max_slot, (uint64_t)ing.seq_bytes[r] + 64);
+    for (uint32_t r = 0; r < n; r++) max_slot = std::max<uint64_t>(max_slot, (uint64_t)span_bytes[r] + 64);
     const uint64_t half = std::max(kRound, max_slot);
     sc->p_seq_stage.resize(2 * half);
     for (auto &ev : sc->seq_ev)
@@ -668,7 +738,7 @@ void np2_job::send_seq() {
         if (round >= 2) NP2_CUDA(cudaEventSynchronize(sc->seq_ev[round & 1]));
         auto work = [&](unsigned ti) {
             const uint32_t b = r0 + (uint64_t)(r1 - r0) * ti / T, e = r0 + (uint64_t)(r1 - r0) * (ti + 1) / T;
-            for (uint32_t r = b; r < e; r++) np2::copy_streaming(buf + (co[r] - D0), bam + ing.seq_off[r], ing.seq_bytes[r]);
+            for (uint32_t r = b; r < e; r++) np2::copy_streaming(buf + (co[r] - D0), bam + span_off[r], span_bytes[r]);
             np2::store_fence();  // the DMA reads this ring next: keep it out of the cores' caches
         };
         if (r1 - r0 < 256) {
@@ -709,6 +779,7 @@ void np2_job::enqueue_arrays() {
     d_ck_read.alloc(std::max(nck, 1u), s);
     d_blk_op.alloc(std::max(nck, 1u), s);
     d_blank.alloc(std::max(n, 1u), s);
+    d_ncig.alloc(std::max(n, 1u), s);
     if (!sc->ev_alloc) {
         NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_alloc, cudaEventDisableTiming));
         NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_copied, cudaEventDisableTiming));
@@ -716,7 +787,7 @@ void np2_job::enqueue_arrays() {
     NP2_CUDA(cudaEventRecord(sc->ev_alloc, s));
     NP2_CUDA(cudaStreamWaitEvent(c2, sc->ev_alloc, 0));
     // small arrays -> one pinned staging buffer -> device
-    const size_t small = (size_t)n * 8 + (size_t)(n + 1) * 20 + 256;
+    const size_t small = (size_t)n * 12 + (size_t)(n + 1) * 20 + 256;
     sc->p_up_stage.resize(small);
     uint8_t *st = sc->p_up_stage.p;
     auto stage = [&](void *dev, const void *host, size_t bytes) {
@@ -731,6 +802,7 @@ void np2_job::enqueue_arrays() {
     stage(d_op_off.p, ing.op_off.data(), (size_t)(n + 1) * 4);
     stage(d_ck_off.p, ing.ck_off.data(), (size_t)(n + 1) * 4);
     stage(d_nib_off.p, ing.nib_off.data(), (size_t)(n + 1) * 8);
+    stage(d_ncig.p, ing.n_cig.data(), (size_t)n * 4);
     if (!sc->ev_t0) {
         NP2_CUDA(cudaEventCreate(&sc->ev_t0));
         NP2_CUDA(cudaEventCreate(&sc->ev_t1));
@@ -743,7 +815,7 @@ void np2_job::enqueue_arrays() {
             NP2_CUDA(cudaMemcpyAsync(d_ops.p + w, c.ops, c.n * sizeof(Op), cudaMemcpyHostToDevice, c2));
             w += c.n;
         }
-        h2d += (uint64_t)ing.n_ops * 16;
+        if (!ing.op_chunks.empty()) h2d += (uint64_t)ing.n_ops * 16;
     }
     NP2_CUDA(cudaEventRecord(sc->ev_t1, c2));
     NP2_CUDA(cudaEventRecord(sc->ev_copied, c2));
@@ -2641,6 +2713,10 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
             j->enqueue_arrays();   // copy stream
             j->send_seq();         // K0 gather on the (high-priority) copy stream
             NP2_CUDA(cudaStreamWaitEvent(ctx->stream, j->sc->ev_copied, 0));
+            // spans and per-read arrays are on the device (in stream order): CIGAR words -> op records
+            if (!j->ing.host_ops)
+                cigar_ops(j->d_blob.p, j->d_seq_off.p, j->d_ncig.p, j->d_op_off.p, reinterpret_cast<uint4 *>(j->d_ops.p),
+                          (uint32_t)j->ing.pos.size(), ctx->stream);
         } else {
             j->tseq.assign(tseq, tseq + tlen);
         }
@@ -2685,6 +2761,7 @@ int np2_secmap_fill(const np2_secmap *m, const uint8_t *bam, uint64_t bam_len, u
 uint64_t np2_secmap_size(const np2_secmap *m, uint64_t *n_seqs) { return m ? np2::secmap_counts(*m->m, n_seqs) : 0; }
 
 void np2_set_host_threads(uint32_t n) { np2::set_host_threads(n); }
+void np2_set_stage_timing(int on) { g_stage_events.store(on ? 1 : 0); }
 
 int np2_host_alloc(uint64_t bytes, void **out) {
     return guard([&] {
@@ -2870,7 +2947,10 @@ int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const n
                     uint64_t out[6]) {
     return guard([&] {
         Ingest ing;
-        parse_records(bam, bam_len, tlen, *opts, ing, threads);
+        // threads bit 16: the job path's parse (CIGAR summed, no op records); bit 17: op records built but left out of
+        // the digest (so that the two can be compared)
+        const bool fast = threads & 0x10000u, scalars_only = threads & 0x30000u;
+        parse_records(bam, bam_len, tlen, *opts, ing, threads & 0xFFFFu, !fast);
         uint64_t h = 0xcbf29ce484222325ull;
         auto mix = [&](const void *p, size_t n) {
             const uint8_t *b = static_cast<const uint8_t *>(p);
@@ -2890,7 +2970,8 @@ int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const n
         mixv(ing.op_off);
         mixv(ing.nib_off);
         mixv(ing.ck_off);
-        for (int a = 0; a < 4; a++)
+        mixv(ing.n_cig);
+        for (int a = 0; a < 4 && !scalars_only; a++)
             for (const Ingest::OpChunk &c : ing.op_chunks)
                 for (size_t i = 0; i < c.n; i++) {
                     const uint32_t v = a == 0 ? c.ops[i].col : a == 1 ? c.ops[i].q : a == 2 ? c.ops[i].t : c.ops[i].cig;

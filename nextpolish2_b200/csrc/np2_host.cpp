@@ -169,6 +169,7 @@ void Ingest::clear() {
     is_clip.clear();
     seq_off.clear();
     seq_bytes.clear();
+    n_cig.clear();
     op_off.clear();
     nib_off.clear();
     ck_off.clear();
@@ -219,9 +220,60 @@ uint64_t find_start(const uint8_t *bam, uint64_t bam_len, uint64_t lo, uint64_t 
     return UINT64_MAX;
 }
 
+// The CIGAR of one record summed without building anything (the op records are expanded on the device): everything the
+// filter and the buffer sizes need.  Returns false when the record has anything the general loop of parse_one would
+// flag or treat specially (an op the reference does not know, more query bases than SEQ holds, an alignment that runs
+// past the contig, a soft clip that is not the first op but is followed by aligned columns ...): the caller then runs
+// that loop, so the fast path never has to reproduce an error message or a corner case.
+struct CigarSums {
+    uint64_t rlen = 0, rspan = 0, ncols = 0, qs = 0, ts = 0;
+    uint32_t n_ops = 0, aln_q_s = 0, aln_q_e = 0;
+};
+inline bool cigar_sums(const uint8_t *cg, uint32_t n_cig, int32_t l_seq, int32_t pos, uint32_t tlen, CigarSums &o) {
+    // membership masks over the op code (bit op set = the op takes part)
+    constexpr uint32_t kRlen = 0x1B3;   // M I S H = X   (seq_len_from_cigar(true))
+    constexpr uint32_t kRspan = 0x18D;  // M D N = X     (bam_endpos)
+    constexpr uint32_t kCol = 0x187;    // M I D = X     (alignment columns)
+    constexpr uint32_t kQs = 0x193;     // M I S = X     (query bases consumed)
+    constexpr uint32_t kTs = 0x185;     // M D = X       (contig bases consumed)
+    constexpr uint32_t kKnown = 0x1B7;  // M I D S H = X
+    constexpr uint32_t kMI = 0x183;     // M I = X       (ops whose query range is checked against l_seq)
+    uint64_t rlen = 0, rspan = 0, ncols = 0, qs = 0, ts = 0, q_hi = 0;
+    uint32_t n_ops = 0, unknown = 0, aln_q_s = 0, aln_q_e = 0;
+    for (uint32_t i = 0; i < n_cig; i++) {
+        const uint32_t c = (uint32_t)rd32(cg + 4 * i);
+        const uint32_t l = c >> 4, op = c & 15;
+        const uint32_t bit = 1u << op;  // op < 16
+        unknown |= bit & ~kKnown;
+        if (op == 4) {  // main.rs via parse_one: the first op sets aln_q_s, any later soft clip sets aln_q_e
+            if (i == 0) aln_q_s = l;
+            else aln_q_e = (uint32_t)qs;
+        }
+        rlen += (bit & kRlen) ? l : 0;
+        rspan += (bit & kRspan) ? l : 0;
+        ncols += (bit & kCol) ? l : 0;
+        n_ops += ((bit & kCol) && l) ? 1u : 0u;
+        qs += (bit & kQs) ? l : 0;
+        ts += (bit & kTs) ? l : 0;
+        q_hi = (bit & kMI) ? qs : q_hi;
+    }
+    if (unknown || q_hi > (uint64_t)(uint32_t)l_seq || pos < 0 || (uint64_t)(uint32_t)pos + ts > tlen || ncols >= (1ull << 32) ||
+        qs >= (1ull << 32))
+        return false;
+    o.rlen = rlen;
+    o.rspan = rspan;
+    o.ncols = ncols;
+    o.qs = qs;
+    o.ts = ts;
+    o.n_ops = n_ops;
+    o.aln_q_s = aln_q_s;
+    o.aln_q_e = aln_q_e;
+    return true;
+}
+
 // One record: filter (main.rs:1758-1771) + fill_with_cigar bookkeeping (main.rs:386-440) without the strings.
 // Returns an error message when the reference would panic on it.
-const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const np2_opts &opt, Segment &sg) {
+const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const np2_opts &opt, Segment &sg, bool host_ops) {
     const uint8_t *r = bam + payload;
     const int32_t bs = rd32(r - 4), ref_id = rd32(r), pos = rd32(r + 4), l_seq = rd32(r + 16);
     const uint32_t l_name = r[8], mapq = r[9];
@@ -234,6 +286,27 @@ const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const
     if (l_seq < 0 || 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 > (uint64_t)bs)
         return "BAM/SAM parsing failed!";
     const uint8_t *cg = r + 32 + l_name;
+    CigarSums cs;
+    if (!host_ops && cigar_sums(cg, n_cig, l_seq, pos, tlen, cs)) {
+        const int64_t span = ((flag & 4) || n_cig == 0 || cs.rspan == 0) ? 1 : (int64_t)cs.rspan;
+        const int64_t need = std::max<int64_t>((int64_t)opt.min_map_len, (int64_t)((float)cs.rlen * opt.min_map_fra));
+        const bool rejected = (flag & 0x404) || (int16_t)mapq <= (int16_t)opt.min_map_qual || cs.rlen <= opt.min_read_len ||
+                              ((flag & 0x100) && !opt.use_secondary) || ((flag & 0x800) && !opt.use_supplementary) ||
+                              span < need;
+        if (rejected) return nullptr;
+        const uint32_t aln_q_e = cs.aln_q_e ? cs.aln_q_e : (uint32_t)cs.qs;
+        RecOut &o = sg.ro.back();
+        o.kept = 1;
+        o.is_clip = (uint32_t)(aln_q_e - cs.aln_q_s + opt.max_clip_len) < (uint32_t)cs.rlen ? 1 : 0;  // main.rs:1796
+        o.ncols = (uint32_t)cs.ncols;
+        o.rlen = (uint32_t)cs.rlen;
+        o.rspan = (uint32_t)cs.rspan;
+        o.n_ops = cs.n_ops;
+        o.n_cig = n_cig;
+        o.seq_off = payload + 32 + l_name + 4ull * n_cig;
+        o.seq_bytes = ((uint32_t)l_seq + 1) / 2;
+        return nullptr;
+    }
     // One pass over the CIGAR: seq_len_from_cigar(true) and bam_endpos for the filter, and the
     // column-consuming ops for the kernels.  The ops are rolled back when the filter rejects the record; what the
     // reference would panic on only counts for records that pass it.
@@ -264,7 +337,7 @@ const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const
                     break;
                 }
                 if (l) {
-                    sg.ops.push_back(Op{col, qs, ts, c});
+                    if (host_ops) sg.ops.push_back(Op{col, qs, ts, c});
                     n_ops++;
                 }
                 col += l;
@@ -297,6 +370,7 @@ const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const
     o.rlen = (uint32_t)rlen;
     o.rspan = (uint32_t)rspan;
     o.n_ops = n_ops;
+    o.n_cig = n_cig;
     o.seq_off = payload + 32 + l_name + 4ull * n_cig;
     o.seq_bytes = ((uint32_t)l_seq + 1) / 2;
     return nullptr;
@@ -304,7 +378,7 @@ const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const
 
 // walk the block_size chain from byte `from` while the record starts before `limit`, parsing as it goes
 void walk(const uint8_t *bam, uint64_t bam_len, uint64_t from, uint64_t limit, uint32_t tlen, const np2_opts &opt,
-          Segment &sg) {
+          Segment &sg, bool host_ops) {
     uint64_t p = from;
     sg.start = from;
     while (p < limit && p + 4 <= bam_len) {
@@ -314,7 +388,7 @@ void walk(const uint8_t *bam, uint64_t bam_len, uint64_t from, uint64_t limit, u
             sg.err_msg = "BAM/SAM parsing failed!";
             break;
         }
-        const char *m = parse_one(bam, p + 4, tlen, opt, sg);
+        const char *m = parse_one(bam, p + 4, tlen, opt, sg, host_ops);
         if (m) {
             sg.err_rec = (int64_t)sg.ro.size() - 1;
             sg.err_msg = m;
@@ -332,8 +406,9 @@ void walk(const uint8_t *bam, uint64_t bam_len, uint64_t from, uint64_t limit, u
 // only if the verified walk before it ends exactly on its guessed start; otherwise that range is re-walked
 // sequentially.  So the result never depends on the guess, only the speed does.
 void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out,
-                   unsigned threads) {
+                   unsigned threads, bool host_ops) {
     out.clear();
+    out.host_ops = host_ops;
     unsigned T = host_threads();
     if (bam_len < (8u << 20)) T = 1;
     if (threads) T = std::min(threads, 64u);
@@ -345,13 +420,13 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
         sg.reset();
         // one page-locked allocation per segment instead of a chain of doublings (each one a cudaHostAlloc + copy +
         // cudaFreeHost): HiFi records carry about one column-consuming op per 400 bytes
-        sg.ops.reserve((bound(ti + 1) - bound(ti)) / 256 + 65536);
+        if (host_ops) sg.ops.reserve((bound(ti + 1) - bound(ti)) / 256 + 65536);
         const uint64_t lo = bound(ti), hi = bound(ti + 1);
         const uint64_t from = ti == 0 ? 0 : find_start(bam, bam_len, lo, hi);
         if (from == UINT64_MAX) return;
         sg.found = true;
         try {
-            walk(bam, bam_len, from, hi, tlen, opt, sg);
+            walk(bam, bam_len, from, hi, tlen, opt, sg, host_ops);
         } catch (const std::exception &) {  // allocation failure inside a worker thread
             sg.err_rec = (int64_t)sg.ro.size();
             sg.err_msg = "host allocation failed while parsing the records";
@@ -372,7 +447,7 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
             sg = segs[idx].get();
             sg->reset();
             sg->found = true;
-            walk(bam, bam_len, cur, hi, tlen, opt, *sg);
+            walk(bam, bam_len, cur, hi, tlen, opt, *sg, host_ops);
             store_fence();
         }
         order.push_back(sg);
@@ -396,6 +471,7 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
     out.is_clip.reserve(nk);
     out.seq_off.reserve(nk);
     out.seq_bytes.reserve(nk);
+    out.n_cig.reserve(nk);
     out.op_off.reserve(nk + 1);
     out.nib_off.reserve(nk + 1);
     out.ck_off.reserve(nk + 1);
@@ -417,14 +493,17 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
             out.is_clip.push_back(o.is_clip);
             out.seq_off.push_back(o.seq_off);
             out.seq_bytes.push_back(o.seq_bytes);
+            out.n_cig.push_back(o.n_cig);
             out.op_off.push_back(out.op_off.back() + o.n_ops);
             out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)o.ncols / 16 + 1) * 8 + 15) & ~15ull));
             out.ck_off.push_back(out.ck_off.back() + (o.ncols + 31) / 32);
             out.total_cols += o.ncols;
         }
         if (sg->ops.n) out.op_chunks.push_back({sg->ops.p, sg->ops.n});
-        out.n_ops += sg->ops.n;
     }
+    for (Segment *sg : order)
+        for (auto &o : sg->ro)
+            if (o.kept) out.n_ops += o.n_ops;
     if (out.n_ops >= (1ull << 32)) herr(NP2_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one contig");
 }
 

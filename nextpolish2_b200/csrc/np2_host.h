@@ -81,14 +81,18 @@ struct Ingest {
     std::vector<uint8_t> is_clip;
     std::vector<uint64_t> seq_off;      // byte offset of SEQ in the caller's record buffer
     std::vector<uint32_t> seq_bytes;    // (l_seq + 1) / 2
+    std::vector<uint32_t> n_cig;        // raw CIGAR words of the record: they sit right in front of SEQ
     std::vector<uint32_t> op_off;       // n + 1
     std::vector<uint64_t> nib_off;      // n + 1, bytes, 16-B aligned
     std::vector<uint32_t> ck_off;       // n + 1, 32-column blocks
     uint64_t total_cols = 0;
     uint64_t n_ops = 0;
     uint32_t n_fallback = 0;            // segments that had to be re-walked sequentially (speculation miss)
-    // Column-consuming CIGAR ops (M,=,X,I,D) stay in the per-segment arrays they were parsed into; uploaded back to
-    // back in file order they form the device arrays op_off[] indexes.
+    // The 16-byte op records the kernels read are expanded ON THE DEVICE from the raw CIGAR words, which travel with
+    // SEQ in one span per read (np2_kernels.cu k_cigar_ops); the host only sums the CIGAR (filter, sizes).  With
+    // host_ops (np2_debug_parse) the host builds the same records itself: column-consuming CIGAR ops (M,=,X,I,D) in
+    // the per-segment arrays they were parsed into; back to back in file order they are the array op_off[] indexes.
+    bool host_ops = false;
     struct OpChunk {
         const Op *ops;
         size_t n;
@@ -97,7 +101,7 @@ struct Ingest {
 
     struct RecOut {
         uint8_t kept = 0, is_clip = 0;
-        uint32_t ncols = 0, rlen = 0, rspan = 0, n_ops = 0, seq_bytes = 0;
+        uint32_t ncols = 0, rlen = 0, rspan = 0, n_ops = 0, seq_bytes = 0, n_cig = 0;
         uint64_t seq_off = 0;
     };
     // one byte range of the record buffer, walked and parsed by one host thread
@@ -125,8 +129,9 @@ struct Ingest {
 };
 // throws np2::Error(NP2_ERR_FORMAT) where the reference panics (the first failing record in file order decides)
 // threads = 0: one range per host thread (a single range below 8 MB); otherwise exactly that many ranges
+// host_ops: also build the op records on the host (debug seam); the job path leaves that to the device
 void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out,
-                   unsigned threads = 0);
+                   unsigned threads = 0, bool host_ops = false);
 
 /* ---------------------------------------------------------------- regions */
 struct Regions {

@@ -820,6 +820,55 @@ __global__ void __launch_bounds__(kPackThreads, 4) k_pack_columns_batched(ReadsD
     const uint32_t nq = qn;
     for (uint32_t i = threadIdx.x; i < nq; i += kPackThreads) pack_block_queued(R, q[i]);
 }
+// ---- CIGAR -> op records (fill_with_cigar's bookkeeping, main.rs:386-440).  The raw CIGAR words of a read arrive in
+// front of its SEQ bytes (one span per read over the link: 4 bytes per op instead of a host-built 16-byte record); a
+// warp turns them into the records the other kernels read with one load: {first column, first query base, contig
+// offset, raw word} of every op that owns alignment columns (M, I, D, =, X with a non-zero length).  Column, query
+// and contig positions are exclusive prefix sums over the ops (S advances the query only, H nothing); the host has
+// already rejected records with any other op, so no check is repeated here.
+__global__ void __launch_bounds__(128) k_cigar_ops(const uint8_t *__restrict__ blob, const uint64_t *__restrict__ seq_off,
+                                                   const uint32_t *__restrict__ n_cig, const uint32_t *__restrict__ op_off,
+                                                   uint4 *__restrict__ ops, uint32_t n_reads) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= n_reads) return;
+    const uint32_t nc = n_cig[r];
+    const uint8_t *cg = blob + seq_off[r] - 4ull * nc;  // BAM records are not aligned: neither are their CIGAR words
+    const uint32_t mis = (uint32_t)((uintptr_t)cg & 3), sh = mis * 8;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(cg - mis);
+    uint32_t col = 0, q = 0, t = 0, w = op_off[r];
+    for (uint32_t base = 0; base < nc; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t c = 0xF;  // an op code nothing counts
+        if (i < nc) c = __funnelshift_r(wp[i], mis ? wp[i + 1] : 0u, sh);
+        const uint32_t l = c >> 4, bit = 1u << (c & 15);
+        uint32_t dc = (bit & 0x187u) ? l : 0u;  // M I D = X
+        uint32_t dq = (bit & 0x193u) ? l : 0u;  // M I S = X
+        uint32_t dt = (bit & 0x185u) ? l : 0u;  // M D = X
+        const bool emit = dc != 0;
+        const uint32_t l0 = dc, q0 = dq, t0 = dt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, dc, d), b = __shfl_up_sync(0xFFFFFFFFu, dq, d),
+                           e = __shfl_up_sync(0xFFFFFFFFu, dt, d);
+            if (lane >= (uint32_t)d) {
+                dc += a;
+                dq += b;
+                dt += e;
+            }
+        }
+        const uint32_t em = __ballot_sync(0xFFFFFFFFu, emit);
+        if (emit) ops[w + __popc(em & ((1u << lane) - 1))] = make_uint4(col + dc - l0, q + dq - q0, t + dt - t0, c);
+        col += __shfl_sync(0xFFFFFFFFu, dc, 31);
+        q += __shfl_sync(0xFFFFFFFFu, dq, 31);
+        t += __shfl_sync(0xFFFFFFFFu, dt, 31);
+        w += __popc(em);
+    }
+}
+void cigar_ops(const uint8_t *d_blob, const uint64_t *d_seq_off, const uint32_t *d_n_cig, const uint32_t *d_op_off,
+               uint4 *d_ops, uint32_t n_reads, cudaStream_t s) {
+    if (n_reads)
+        NP2_K(k_cigar_ops)<<<cdiv((uint64_t)n_reads * 32, 128), 128, 0, s>>>(d_blob, d_seq_off, d_n_cig, d_op_off, d_ops, n_reads);
+}
 void trim_scan(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
     if (r.n_reads) NP2_K(k_trim_scan)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
 }

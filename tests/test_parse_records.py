@@ -110,3 +110,64 @@ def test_counts_match_an_independent_record_reader():
     want = _expected_counts(blob, min_map_qual=-1, min_read_len=0)
     got = _parse(blob, len(ref), 2, min_map_qual=-1, min_read_len=0)
     assert {k: got[k] for k in want} == want and want["reads"] > _expected_counts(blob)["reads"]
+
+
+FAST, SCALARS = 0x10000, 0x20000  # np2_debug_parse flags: the job path's parse / host-built ops left out of the digest
+
+
+def _same_scalars(bam, L, **kw):
+    keys = ("records", "reads", "ops", "columns", "digest")
+    for t in (1, 3):
+        a, b = _parse(bam, L, t | FAST, **kw), _parse(bam, L, t | SCALARS, **kw)
+        assert {k: a[k] for k in keys} == {k: b[k] for k in keys}, (t, a, b)
+    return a
+
+
+def test_summed_cigar_parse_equals_the_op_building_parse():
+    """np2_job_create only sums every CIGAR (the op records are expanded on the device); filter decisions, sizes and
+    offsets must be the ones of the loop that builds the records, on real-looking data and on odd CIGARs."""
+    import exotic
+    ref, blob = exotic.make()
+    _same_scalars(blob, len(ref))
+    _same_scalars(blob, len(ref), min_map_qual=-1, min_read_len=0)
+    for n in ("tiny20k", "clip120k", "dip600k"):
+        ds = common.dataset(n)
+        assert _same_scalars(ds["bam"], len(ds["contig"]))["reads"] > 0
+    # random CIGARs over every op the reference knows, soft / hard clips anywhere, zero lengths
+    rng = np.random.default_rng(5)
+    L = 50_000
+    recs = []
+    for i in range(400):
+        ops, q = [], 0
+        for _ in range(int(rng.integers(1, 12))):
+            o = "MIDSH=X"[int(rng.integers(0, 7))]
+            l = int(rng.integers(0, 400))
+            ops.append((o, l))
+            if o in "MIS=X":
+                q += l
+        extra = int(rng.integers(0, 3))  # SEQ may be longer than the CIGAR consumes
+        recs.append(synth.bam_record(0, int(rng.integers(0, 40_000)), ops, "ACGT"[i % 4] * (q + extra), mapq=int(rng.integers(0, 61))))
+    bam = np.concatenate(recs)
+    got = _same_scalars(bam, L, min_read_len=0, min_map_len=0, min_map_qual=-1)
+    assert got["records"] == 400 and got["reads"] > 100
+
+
+def test_summed_cigar_parse_reports_the_same_errors():
+    ds = common.dataset("tiny20k")
+    ref = ds["contig"]
+    L = len(ref)
+    good = [synth.bam_record(0, p, [("M", 2400)], ref[p:p + 2400].tobytes().decode()) for p in range(0, L - 2400, 400)]
+    cases = {
+        "Unknown cigar": synth.bam_record(0, 300, [("M", 1200), ("N", 5), ("M", 1200)], "ACGT" * 600),
+        "more query bases": synth.bam_record(0, 300, [("M", 1200), ("I", 10), ("M", 1200)], "ACGT" * 600),
+        "past the end": synth.bam_record(0, L - 1000, [("M", 1200), ("D", 3), ("M", 1200)], "ACGT" * 600),
+        "outside the contig": synth.bam_record(0, L + 5, [("M", 2400)], "ACGT" * 600),
+    }
+    for msg, bad in cases.items():
+        for flags in (FAST, 0):
+            with pytest.raises(api.Np2Error) as e:
+                _parse(np.concatenate(good[:4] + [bad] + good[4:]), L, 2 | flags)
+            assert msg in str(e.value), (msg, flags, str(e.value))
+    # a trailing soft clip may run past SEQ without complaint (only aligned ops are checked), in both parses
+    tail = synth.bam_record(0, 300, [("M", 2400), ("S", 50)], "ACGT" * 600)
+    _same_scalars(np.concatenate(good[:4] + [tail] + good[4:]), L)
