@@ -516,6 +516,8 @@ def _run_ours(args):
                         one_at_a_time=round(mbp_total / m.e2e_serial_time, 3),
                         one_at_a_time_ms={k: round(v / max(1, m.parts1["n"]), 3) for k, v in m.parts1.items()
                                           if k in ("create_parse", "upload", "run", "result")},
+                        one_at_a_time_upload_stages_ms={k: round(v / max(1, m.parts1["n"]), 3)
+                                                        for k, v in m.parts1.get("stages", {}).items() if k.startswith("upload:")},
                         in_flight_ms_per_contig_per_thread={k: round(v / max(1, m.partsN["n"]), 3)
                                                             for k, v in m.partsN.items() if k in ("create_parse", "upload", "run", "result")},
                         in_flight_stage_ms_per_contig={k: round(v / max(1, m.partsN["n"]), 3)

@@ -2709,9 +2709,13 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
                 }
             }
             j->send_contig(tseq);  // in flight while the host walks the records
+            j->timer.hbegin();
             parse_records(bam, bam_len, tlen, *opts, j->ing);
+            j->timer.hend("upload:host_parse");
             j->enqueue_arrays();   // copy stream
+            j->timer.hbegin();
             j->send_seq();         // K0 gather on the (high-priority) copy stream
+            j->timer.hend("upload:host_send_seq");
             NP2_CUDA(cudaStreamWaitEvent(ctx->stream, j->sc->ev_copied, 0));
             // spans and per-read arrays are on the device (in stream order): CIGAR words -> op records
             if (!j->ing.host_ops)

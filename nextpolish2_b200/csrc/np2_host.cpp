@@ -1,6 +1,9 @@
 // np2_host.cpp — host phases of the polish path (see np2_host.h).  Citations are to the reference
 // (Nextomics/NextPolish2 @ 283dc5a).  Nothing here calls into oracle/.
 #include "np2_host.h"
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 #include "np2_error.h"
 
@@ -229,18 +232,98 @@ struct CigarSums {
     uint64_t rlen = 0, rspan = 0, ncols = 0, qs = 0, ts = 0;
     uint32_t n_ops = 0, aln_q_s = 0, aln_q_e = 0;
 };
+// membership masks over the op code (bit op set = the op takes part)
+constexpr uint32_t kRlen = 0x1B3;   // M I S H = X   (seq_len_from_cigar(true))
+constexpr uint32_t kRspan = 0x18D;  // M D N = X     (bam_endpos)
+constexpr uint32_t kCol = 0x187;    // M I D = X     (alignment columns)
+constexpr uint32_t kQs = 0x193;     // M I S = X     (query bases consumed)
+constexpr uint32_t kTs = 0x185;     // M D = X       (contig bases consumed)
+constexpr uint32_t kKnown = 0x1B7;  // M I D S H = X
+constexpr uint32_t kMI = 0x183;     // M I = X       (ops whose query range is checked against l_seq)
+#if defined(__x86_64__) && defined(__GNUC__)
+// Eight ops per step.  Only groups of plain ops (M I D = X, each shorter than 2^24) are summed here; the caller walks
+// every other group — the first one, any with a clip or an unknown op — with the scalar loop, which also keeps the
+// order-dependent values (aln_q_s / aln_q_e, the query position after the last aligned op).  Returns how many ops
+// (a multiple of 8, counted from `from`) were consumed before a group it does not take.
+struct CigarAcc {
+    uint64_t ncols, qs, ts;
+    uint32_t n_ops;
+};
+__attribute__((target("avx2"))) inline void cigar_flush_avx2(__m256i &a_col, __m256i &a_q, __m256i &a_t, __m256i &a_n, CigarAcc &acc) {
+    alignas(32) uint32_t v[4][8];
+    _mm256_store_si256((__m256i *)v[0], a_col);
+    _mm256_store_si256((__m256i *)v[1], a_q);
+    _mm256_store_si256((__m256i *)v[2], a_t);
+    _mm256_store_si256((__m256i *)v[3], a_n);
+    for (int k = 0; k < 8; k++) {
+        acc.ncols += v[0][k];
+        acc.qs += v[1][k];
+        acc.ts += v[2][k];
+        acc.n_ops += v[3][k];
+    }
+    a_col = a_q = a_t = a_n = _mm256_setzero_si256();
+}
+__attribute__((target("avx2"))) inline uint32_t cigar_groups_avx2(const uint8_t *cg, uint32_t from, uint32_t n_cig, CigarAcc &acc) {
+    const __m256i one = _mm256_set1_epi32(1), zero = _mm256_setzero_si256(), ones = _mm256_set1_epi32(-1);
+    const __m256i m_plain = _mm256_set1_epi32((int)kCol), m_q = _mm256_set1_epi32((int)(kQs & kCol)), m_t = _mm256_set1_epi32((int)kTs);
+    __m256i a_col = zero, a_q = zero, a_t = zero, a_n = zero;
+    uint32_t i = from, steps = 0;
+    for (; i + 8 <= n_cig; i += 8) {
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(cg + 4 * (size_t)i));
+        const __m256i l = _mm256_srli_epi32(c, 4), bit = _mm256_sllv_epi32(one, _mm256_and_si256(c, _mm256_set1_epi32(15)));
+        const __m256i plain = _mm256_cmpeq_epi32(_mm256_and_si256(bit, m_plain), bit);  // all ones where M I D = X
+        const __m256i small = _mm256_cmpeq_epi32(_mm256_srli_epi32(l, 24), zero);
+        if (_mm256_movemask_epi8(_mm256_and_si256(plain, small)) != -1) break;
+        const __m256i isq = _mm256_cmpeq_epi32(_mm256_and_si256(bit, m_q), bit), ist = _mm256_cmpeq_epi32(_mm256_and_si256(bit, m_t), bit);
+        a_col = _mm256_add_epi32(a_col, l);
+        a_q = _mm256_add_epi32(a_q, _mm256_and_si256(l, isq));
+        a_t = _mm256_add_epi32(a_t, _mm256_and_si256(l, ist));
+        a_n = _mm256_sub_epi32(a_n, _mm256_xor_si256(_mm256_cmpeq_epi32(l, zero), ones));  // += (l != 0)
+        if (++steps == 120) {  // 120 x 2^24 < 2^31 per lane
+            cigar_flush_avx2(a_col, a_q, a_t, a_n, acc);
+            steps = 0;
+        }
+    }
+    cigar_flush_avx2(a_col, a_q, a_t, a_n, acc);
+    return i - from;
+}
+inline bool have_avx2() {
+    static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+}
+#else
+struct CigarAcc {
+    uint64_t ncols, qs, ts;
+    uint32_t n_ops;
+};
+inline uint32_t cigar_groups_avx2(const uint8_t *, uint32_t, uint32_t, CigarAcc &) { return 0; }
+inline bool have_avx2() { return false; }
+#endif
 inline bool cigar_sums(const uint8_t *cg, uint32_t n_cig, int32_t l_seq, int32_t pos, uint32_t tlen, CigarSums &o) {
-    // membership masks over the op code (bit op set = the op takes part)
-    constexpr uint32_t kRlen = 0x1B3;   // M I S H = X   (seq_len_from_cigar(true))
-    constexpr uint32_t kRspan = 0x18D;  // M D N = X     (bam_endpos)
-    constexpr uint32_t kCol = 0x187;    // M I D = X     (alignment columns)
-    constexpr uint32_t kQs = 0x193;     // M I S = X     (query bases consumed)
-    constexpr uint32_t kTs = 0x185;     // M D = X       (contig bases consumed)
-    constexpr uint32_t kKnown = 0x1B7;  // M I D S H = X
-    constexpr uint32_t kMI = 0x183;     // M I = X       (ops whose query range is checked against l_seq)
     uint64_t rlen = 0, rspan = 0, ncols = 0, qs = 0, ts = 0, q_hi = 0;
     uint32_t n_ops = 0, unknown = 0, aln_q_s = 0, aln_q_e = 0;
+    const bool vec = have_avx2();
     for (uint32_t i = 0; i < n_cig; i++) {
+        if (vec && i && (i & 7) == 0 && i + 8 <= n_cig) {
+            // runs of plain groups: M I = X add to rlen what they add to the query position, M D = X to rspan what
+            // they add to the contig position
+            CigarAcc acc{0, 0, 0, 0};
+            const uint32_t took = cigar_groups_avx2(cg, i, n_cig, acc);
+            if (took) {
+                ncols += acc.ncols;
+                qs += acc.qs;
+                ts += acc.ts;
+                rlen += acc.qs;
+                rspan += acc.ts;
+                n_ops += acc.n_ops;
+                // q_hi = query position after the last M I = X op: deletions at the end of the run do not move it
+                uint32_t j = i + took;
+                while (j > i && ((uint32_t)rd32(cg + 4 * (size_t)(j - 1)) & 15) == 2) j--;
+                if (j > i) q_hi = qs;
+                i += took - 1;
+                continue;
+            }
+        }
         const uint32_t c = (uint32_t)rd32(cg + 4 * i);
         const uint32_t l = c >> 4, op = c & 15;
         const uint32_t bit = 1u << op;  // op < 16
@@ -387,6 +470,15 @@ void walk(const uint8_t *bam, uint64_t bam_len, uint64_t from, uint64_t limit, u
             sg.err_rec = (int64_t)sg.ro.size();
             sg.err_msg = "BAM/SAM parsing failed!";
             break;
+        }
+        // The next record's address is known as soon as this block_size is: start its cache (and TLB) misses now — header,
+        // name and the first CIGAR words, eight lines — so that they overlap the parse of this record instead of
+        // stalling the next iteration (the walk is otherwise one chain of dependent misses through a buffer of
+        // hundreds of MB: ~0.5 us per record, most of it waiting).
+        {
+            const uint64_t nx = p + 4 + (uint64_t)bs;
+            if (nx + 512 <= bam_len)
+                for (int k = 0; k < 8; k++) __builtin_prefetch(bam + nx + 64 * k, 0, 1);
         }
         const char *m = parse_one(bam, p + 4, tlen, opt, sg, host_ops);
         if (m) {
