@@ -296,6 +296,13 @@ def measure(np2, torch, ctx, local, contigs, tables, cfg, args, opts, steps, war
         # upload is under way on the other (np2_job_create only enqueues), so the link does not idle while the worker
         # is inside np2_job_run and no extra host thread competes for the cores
         depth = 2 if (args.e2e_prefetch and n_inflight > 1) else 1
+        # every context grows its own device pool to what its largest contig needs (np2_job_create: ~4 x the record bytes
+        # + 100 B per bp): bound the contexts by the memory that is free now
+        want = max(len(c["bam"]) * 4 + len(c["contig"]) * 100 + (64 << 20) for c in contigs)
+        fit = max(1, int(torch.cuda.mem_get_info()[0] * 0.8 // want))
+        if n_inflight * depth > fit:
+            depth = 2 if (depth == 2 and fit >= 2) else 1
+            n_inflight = max(1, fit // depth)
         # stage timers (two event records per stage) only while one contig is processed at a time
         set_stage_timing(n_inflight == 1 or args.e2e_stage_timers)
         ctxs = [ctx] + [np2.Context(local) for _ in range(n_inflight * depth - 1)]
