@@ -510,6 +510,7 @@ struct np2_job {
     DBuf<uint64_t> d_pair_off;
     DBuf<uint32_t> d_first_ge;             // read window of every pileup stripe (np2_kernels.cu stripe_reads)
     DBuf<uint32_t> d_blk_odd;              // one bit per 32-column block: not all reference (np2_kernels.cu block_flags)
+    DBuf<uint32_t> d_odd_off, d_odd_list;  // per pileup stripe: the flagged blocks that can touch it (np2_kernels.cu k_stripe_odd)
     std::vector<uint32_t> read_order;      // candidate read -> alignseq index (0 = not kept)
 
     // result: bases always; positions are materialised on request (np2_job_get_consensus with pos != NULL)
@@ -1031,7 +1032,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     uint32_t G = spec ? caps.c[C_G] : 0;
     if (!spec) {
         h = timer.begin("pileup_count", 1);
-        pileup_stripe(R, d_blank.p, d_code.p, d_blk_odd.p, d_first_ge.p, m, max_span, 0, cd, d_n_emit.p, true, s);
+        pileup_stripe(R, d_blank.p, d_code.p, d_odd_off.p, d_odd_list.p, m, 0, cd, d_n_emit.p, true, s);
         timer.end(h);
         G = cnt_get(C_G);
         counts_reset_pileup(cd, s);
@@ -1050,7 +1051,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     m.g_score = d_gscore.p;
     h = timer.begin("pileup_stripe", 1);
     if (dump_iter >= 0) d_dense_besti.zero();  // the stage getter reports besti of every position
-    pileup_stripe(R, d_blank.p, d_code.p, d_blk_odd.p, d_first_ge.p, m, max_span, G, cd, d_n_emit.p, false, s);
+    pileup_stripe(R, d_blank.p, d_code.p, d_odd_off.p, d_odd_list.p, m, G, cd, d_n_emit.p, false, s);
     timer.end(h);
 
     /* ---------------- K3: DP over runs, backtrack, consensus */
@@ -2163,9 +2164,9 @@ void np2_job::run(int32_t dump_it) {
     up.put(d_blank.p, h_blank.data(), std::max(n, 1u));
     d_order.alloc(std::max(n, 1u), s);
     if (n) up.put(d_order.p, read_order.data(), n);
+    DBuf<uint32_t> d_as_pos, d_as_te, d_W;
+    const uint32_t na = (uint32_t)as_read.size();
     if (opt.iter_count > 1) {  // slot ranges of the pair accumulator: windows + exclusive scan, all on the device
-        const uint32_t na = (uint32_t)as_read.size();
-        DBuf<uint32_t> d_as_pos, d_as_te, d_W;
         d_as_pos.alloc(na, s);
         d_as_te.alloc(na, s);
         d_W.alloc(na + 1, s);
@@ -2175,17 +2176,32 @@ void np2_job::run(int32_t dump_it) {
         geno_pair_windows(d_as_pos.p, d_as_te.p, na, d_W.p, s);
         geno_pair_window_offsets(d_W.p, d_pair_off.p, na, sc->scan_pool, s);
         NP2_CUDA(cudaMemcpyAsync(&hc->q[0], d_pair_off.p + na, 8, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaStreamSynchronize(s));
-        n_sync++;
-        pair_slots = hc->q[0];
     }
     max_span = 0;
     for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
-    d_first_ge.alloc(pileup_stripes(L) + 1, s);
+    const uint32_t n_stripes = pileup_stripes(L);
+    d_first_ge.alloc(n_stripes + 1, s);
     stripe_reads(R, L, d_first_ge.p, s);
     d_blk_odd.alloc(((size_t)ing.ck_off.back() + 255) / 256 * 8 + 8, s);
-    h = timer.begin("block_flags", 1);
+    h = timer.begin("block_flags", 4);
     block_flags(R, ing.ck_off.back(), d_code.p, d_refpk.p, d_blk_odd.p, s);
+    // per stripe: which of its blocks K2 has to walk (a property of the reads and the contig, like the flags)
+    DBuf<uint32_t> d_odd_cnt;
+    d_odd_cnt.alloc(n_stripes, s);
+    d_odd_off.alloc(n_stripes + 1, s);
+    stripe_odd_count(R, d_blk_odd.p, d_first_ge.p, L, max_span, d_odd_cnt.p, s);
+    stripe_odd_offsets(d_odd_cnt.p, d_odd_off.p, L, nullptr, sc->scan_pool, s);
+    timer.end(h);
+    NP2_CUDA(cudaMemcpyAsync(&hc->c[0], d_odd_off.p + n_stripes, 4, cudaMemcpyDeviceToHost, s));
+    timer.hbegin();
+    NP2_CUDA(cudaStreamSynchronize(s));
+    timer.hend("host:stripe_list_sync");
+    n_sync++;
+    if (opt.iter_count > 1) pair_slots = hc->q[0];
+    const uint32_t n_odd_list = hc->c[0];
+    d_odd_list.alloc(std::max(n_odd_list, 1u), s);
+    h = timer.begin("block_flags", 1);
+    stripe_odd_fill(R, d_blk_odd.p, d_first_ge.p, L, max_span, d_odd_off.p, d_odd_list.p, n_odd_list, s);
     timer.end(h);
 
     if (dump_iter >= 0) {  // reads as the oracle reports them (after the clip filter)

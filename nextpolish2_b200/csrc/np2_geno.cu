@@ -108,24 +108,41 @@ __device__ __forceinline__ ScanOut scan_read_region(const ReadsDev &R, uint32_t 
         tpos += adv;
         o += 8;
     }
-    for (; o < n; o++) {
-        const uint32_t b = nib[o >> 1];
-        const uint32_t v = (o & 1) ? (b & 15) : (b >> 4);
-        if (!(v & 8)) tpos++;
-        const uint32_t q = v & 7;
-        if (tpos >= start && q != 4) {
-            if (tpos <= end) {
-                if (WRITE) out[len] = code_char(q);
-                len++;
+    // column loop, eight columns (one aligned word, o is a multiple of 8 here) per round from registers: the next
+    // word is requested before this one is decoded, so no column waits for its own load
+    uint32_t w = o < n ? nw[o >> 3] : 0;
+    for (bool stop = false; o < n && !stop; o += 8) {
+        const uint32_t wn = o + 8 < n ? nw[(o >> 3) + 1] : 0;
+        const uint32_t cols = min(8u, n - o);
+        // column c of the word in bits 4c .. 4c+3 (memory order has the first column in the HIGH nibble of each byte)
+        const uint32_t r = (w & 0x0F0F0F0Fu) << 4 | (w >> 4 & 0x0F0F0F0Fu);
+#pragma unroll
+        for (uint32_t c = 0; c < 8; c++) {
+            if (c >= cols) break;
+            const uint32_t v = r >> (4 * c) & 15;
+            if (!(v & 8)) tpos++;
+            const uint32_t q = v & 7;
+            if (tpos >= start && q != 4) {
+                if (tpos <= end) {
+                    if (WRITE) out[len] = code_char(q);
+                    len++;
+                }
+                if (!WRITE && l < k) {
+                    k0 = (k0 << 2 | (uint64_t)q) & mask;
+                    k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
+                    l++;
+                }
+                if (tpos > end && (WRITE || l >= k)) {
+                    stop = true;
+                    break;
+                }
             }
-            if (!WRITE && l < k) {
-                k0 = (k0 << 2 | (uint64_t)q) & mask;
-                k1 = (k1 >> 2) | (uint64_t)(3 ^ q) << sh;
-                l++;
+            if (tpos > limit) {
+                stop = true;
+                break;
             }
-            if (tpos > end && (WRITE || l >= k)) break;
         }
-        if (tpos > limit) break;
+        w = wn;
     }
     ScanOut so;
     so.len = len;

@@ -1041,7 +1041,10 @@ __device__ __forceinline__ bool block_all_reference_at(const uint8_t *__restrict
  * Reads are coordinate-sorted, so the reads that can cover a stripe sit in a window of the read array; for each of
  * them the checkpoints give the 32-column blocks that can hold a column of the stripe.  Those (read, block) items are
  * tested against the reference with four word compares (block_all_reference); the few odd ones are walked column by
- * column (scan_block32) and their non-reference 3-mers land in a shared-memory record list.  The list is bucketed by
+ * column (scan_block32) and their non-reference 3-mers land in a shared-memory record list.  Which blocks those are
+ * does not depend on the iteration: k_block_flags + k_stripe_odd list them per stripe once per job, this kernel only
+ * reads its list (and skips the reads the iteration has blanked) — finding them here, 64 threads per batch of reads
+ * with the other 192 at a barrier, was 45 % of the kernel's time (profiles/r02u_source_hotspots.txt).  The list is bucketed by
  * position (counting sort), identical 3-mers of a position are merged into Msa entries (count, first read), the
  * entries of every position are put into Msa::sort order (b3.delta, then first read — unique per entry, so the result
  * does not depend on the order the records were found in), and per position the kernel writes what the DP needs:
@@ -1055,15 +1058,11 @@ __device__ __forceinline__ bool block_all_reference_at(const uint8_t *__restrict
  * repeated for each half.  WRITE = false only counts entries (exact mode sizes the arrays from that). */
 constexpr int kStripeThreads = 256;
 constexpr int kStripeRmax = 1024;   // records of one position range held in shared memory
-constexpr int kStripeReads = 64;    // candidate reads examined per batch
-constexpr int kStripeWork = 1024;   // (read, block) items per batch
 template <int kStripeW>
 struct StripeSmem {
     uint32_t bd[kStripeRmax], rd[kStripeRmax], first[kStripeRmax];
     uint16_t kp[kStripeRmax], perm[kStripeRmax], cnt[kStripeRmax], slot[kStripeRmax];
     uint32_t off[kStripeW + 2], goff[kStripeW + 2];
-    uint32_t odd[kStripeWork];
-    uint32_t rn[kStripeReads + 1];  // per candidate read of the batch: prefix of its odd-block count
     uint32_t stk_a[12], stk_b[12];
     // the stripe's window of the per-position inputs (coverage, reference codes), brought in by TMA bulk copies while
     // the reads are walked.  (Staging the per-position outputs too and writing them back with bulk stores was measured:
@@ -1089,9 +1088,9 @@ uint32_t pileup_stripe_width() { return (uint32_t)stripe_w(); }
 template <int kStripeW, bool WRITE>
 __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, const uint8_t *__restrict__ blank,
                                                                   const uint8_t *__restrict__ code,
-                                                                  const uint32_t *__restrict__ blk_odd,
-                                                                  const uint32_t *__restrict__ first_ge, MsaDev m,
-                                                                  uint32_t max_span, uint32_t cap_g, CountsDev cd,
+                                                                  const uint32_t *__restrict__ odd_off,
+                                                                  const uint32_t *__restrict__ odd_list, MsaDev m,
+                                                                  uint32_t cap_g, CountsDev cd,
                                                                   uint32_t *__restrict__ n_emit) {
     extern __shared__ __align__(16) unsigned char stripe_smem_raw[];
     StripeSmem<kStripeW> &S = *reinterpret_cast<StripeSmem<kStripeW> *>(stripe_smem_raw);
@@ -1143,90 +1142,17 @@ __global__ void __launch_bounds__(kStripeThreads) k_pileup_stripe(ReadsDev R, co
             append(0, 0x4000u | 15u << 8 | 15u << 4 | code[0], 0, 0);
             append(1, 15u << 8 | (uint32_t)code[0] << 4 | code[1], 1, 0);
         }
-        // candidate reads: pos in [a - max_span, b - 1], from the per-stripe index (first read at or behind a stripe start)
-        const uint32_t lo_pos = a > max_span ? a - max_span : 0;
-        const uint32_t r_lo = first_ge[lo_pos / kStripeW], r_hi = first_ge[min((b + kStripeW - 1) / kStripeW, gridDim.x)];
-        for (uint32_t rb = r_lo; rb < r_hi; rb += kStripeReads) {
-            // Blocks of read rb + tid that can hold a column of [a, b): from the last block that starts before a to the
-            // last block that starts before b.  HiFi alignments have few indels, so the range is guessed from the
-            // distance to the read's start with two blocks of margin (a block outside the stripe costs a walk that emits
-            // nothing) and VERIFIED with two checkpoints; a long indel makes the guess useless, then it is a binary
-            // search.  Which of those blocks hold anything but reference 3-mers is a property of the read alone and was
-            // worked out once (k_block_flags): only their bits are looked at here.
-            uint32_t g_lo = 0, g_hi = 0, n_odd = 0;
-            if (tid < kStripeReads) {
-                const uint32_t r = rb + tid;
-                if (r < r_hi && !blank[r]) {
-                    const uint32_t n = R.n[r], ts = R.t_s[r], te = R.t_e[r], c0 = R.ck_off[r];
-                    if (n && te >= a && ts < b) {
-                        const uint32_t nblk = (n + 31) >> 5;
-                        const uint32_t *ck = R.ck_tpos + c0;
-                        const uint32_t ga = a > ts ? (a - ts) >> 5 : 0;
-                        uint32_t b0 = ga > 2 ? min(ga - 2, nblk - 1) : 0, e = min(nblk, ga + ((b - a) >> 5) + 4);
-                        const uint32_t ck_b0 = ck[b0], ck_e = e < nblk ? ck[e] : 0xFFFFFFFFu;
-                        if ((b0 > 0 && ck_b0 >= a) || ck_e < b) {  // exact range
-                            uint32_t lo = 0, hi = nblk;  // blocks whose first t_pos is < a
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                if (ck[mid] < a) lo = mid + 1;
-                                else hi = mid;
-                            }
-                            b0 = lo ? lo - 1 : 0;
-                            hi = nblk;  // blocks whose first t_pos is < b
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                if (ck[mid] < b) lo = mid + 1;
-                                else hi = mid;
-                            }
-                            e = max(lo, b0);
-                        }
-                        g_lo = c0 + b0;
-                        g_hi = c0 + e;
-                        for (uint32_t w = g_lo >> 5; g_hi > g_lo && w <= (g_hi - 1) >> 5; w++) {
-                            uint32_t bits = blk_odd[w];
-                            if (w == g_lo >> 5) bits &= 0xFFFFFFFFu << (g_lo & 31);
-                            if (w == (g_hi - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((g_hi - 1) & 31));
-                            n_odd += __popc(bits);
-                        }
-                    }
-                }
-                S.rn[tid] = n_odd;
+        // The blocks that can hold a column of this stripe and are not all reference were listed once per job
+        // (k_stripe_odd_*): walk them, skipping the reads that are blank in this iteration.  (A split range walks the
+        // whole stripe's list again; append() keeps what falls into [a, b).)
+        {
+            const uint32_t l0 = odd_off[blockIdx.x], l1 = odd_off[blockIdx.x + 1];
+            for (uint32_t t = l0 + tid; t < l1; t += kStripeThreads) {
+                const uint32_t g = odd_list[t];
+                const uint32_t r = R.ck_read[g];
+                if (blank[r]) continue;
+                scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) { append(p, bases, dl1, r + 1); });
             }
-            __syncthreads();
-            if (tid < 32) {  // exclusive offsets of the batch
-                const uint32_t v0 = S.rn[2 * tid], v1 = S.rn[2 * tid + 1];
-                uint32_t incl = v0 + v1;
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (tid >= (uint32_t)d) incl += t;
-                }
-                S.rn[2 * tid] = incl - v0 - v1;
-                S.rn[2 * tid + 1] = incl - v1;
-                if (tid == 31) S.rn[kStripeReads] = incl;
-            }
-            __syncthreads();
-            const uint32_t nodd = S.rn[kStripeReads];
-            if (nodd > kStripeWork) {  // too many odd blocks for the queue: treat like a record overflow (split the range)
-                __syncthreads();
-                if (tid == 0) S.nrec = kStripeRmax + 1;
-                break;
-            }
-            if (n_odd) {
-                uint32_t w_out = S.rn[tid];
-                for (uint32_t w = g_lo >> 5; w <= (g_hi - 1) >> 5; w++) {
-                    uint32_t bits = blk_odd[w];
-                    if (w == g_lo >> 5) bits &= 0xFFFFFFFFu << (g_lo & 31);
-                    if (w == (g_hi - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((g_hi - 1) & 31));
-                    for (; bits; bits &= bits - 1) S.odd[w_out++] = (w << 5) + (uint32_t)__ffs(bits) - 1;
-                }
-            }
-            __syncthreads();
-            for (uint32_t t = tid; t < nodd; t += kStripeThreads) {
-                const uint32_t g = S.odd[t];
-                const uint32_t order = R.ck_read[g] + 1;
-                scan_block32(R, g, code, [&](uint32_t p, uint32_t bases, uint32_t dl1) { append(p, bases, dl1, order); });
-            }
-            __syncthreads();
         }
         __syncthreads();
         const uint32_t nrec = S.nrec;
@@ -1427,10 +1353,137 @@ void stripe_reads(const ReadsDev &r, uint32_t L, uint32_t *d_first_ge, cudaStrea
     const uint32_t n = pileup_stripes(L) + 1;
     NP2_K(k_stripe_reads)<<<cdiv(n, kThreads), kThreads, 0, s>>>(r.pos, r.n_reads, n, (uint32_t)stripe_w(), d_first_ge);
 }
+// ---- per-stripe lists of the not-all-reference blocks, once per job.  For every stripe: the reads whose record
+// position lies in [stripe start - max_span, stripe end) (per-stripe read index), for each of them the 32-column blocks
+// that can hold a column of the stripe — from the last block that starts before the stripe to the last block that
+// starts before its end.  HiFi alignments have few indels, so the range is guessed from the distance to the read's
+// start with two blocks of margin (a block outside the stripe costs a walk that emits nothing) and VERIFIED with two
+// checkpoints; a long indel makes the guess useless, then it is a binary search.  Of those blocks the ones whose
+// k_block_flags bit is set go on the stripe's list.  Pass 0 counts, pass 1 (after the offsets scan) writes.  Neither
+// the trim nor the flags depend on which reads an iteration blanks: K2 filters those while it walks.
+__device__ __forceinline__ void stripe_block_range(const ReadsDev &R, uint32_t r, uint32_t a, uint32_t b, uint32_t &g_lo,
+                                                   uint32_t &g_hi) {
+    g_lo = g_hi = 0;
+    const uint32_t n = R.n[r], ts = R.t_s[r], te = R.t_e[r], c0 = R.ck_off[r];
+    if (!n || te < a || ts >= b) return;
+    const uint32_t nblk = (n + 31) >> 5;
+    const uint32_t *ck = R.ck_tpos + c0;
+    const uint32_t ga = a > ts ? (a - ts) >> 5 : 0;
+    uint32_t b0 = ga > 2 ? min(ga - 2, nblk - 1) : 0, e = min(nblk, ga + ((b - a) >> 5) + 4);
+    const uint32_t ck_b0 = ck[b0], ck_e = e < nblk ? ck[e] : 0xFFFFFFFFu;
+    if ((b0 > 0 && ck_b0 >= a) || ck_e < b) {  // exact range
+        uint32_t lo = 0, hi = nblk;  // blocks whose first t_pos is < a
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (ck[mid] < a) lo = mid + 1;
+            else hi = mid;
+        }
+        b0 = lo ? lo - 1 : 0;
+        hi = nblk;  // blocks whose first t_pos is < b
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (ck[mid] < b) lo = mid + 1;
+            else hi = mid;
+        }
+        e = max(lo, b0);
+    }
+    g_lo = c0 + b0;
+    g_hi = c0 + e;
+}
+constexpr int kOddThreads = 64;
+template <bool WRITE>
+__global__ void __launch_bounds__(kOddThreads) k_stripe_odd(ReadsDev R, const uint32_t *__restrict__ blk_odd,
+                                                            const uint32_t *__restrict__ first_ge, uint32_t L, uint32_t W,
+                                                            uint32_t max_span, uint32_t *__restrict__ odd_cnt,
+                                                            const uint32_t *__restrict__ odd_off,
+                                                            uint32_t *__restrict__ odd_list, uint32_t cap) {
+    __shared__ uint32_t s_warp[kOddThreads / 32], s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t a = blockIdx.x * W, b = min(a + W, L);
+    const uint32_t lo_pos = a > max_span ? a - max_span : 0;
+    const uint32_t r_lo = first_ge[lo_pos / W], r_hi = first_ge[min((b + W - 1) / W, gridDim.x)];
+    uint32_t total = 0;  // WRITE: entries of this stripe written by the batches before
+    if (WRITE && tid == 0) s_base = odd_off[blockIdx.x];
+    for (uint32_t rb = r_lo; rb < r_hi; rb += kOddThreads) {
+        const uint32_t r = rb + tid;
+        uint32_t g_lo = 0, g_hi = 0, n_odd = 0;
+        if (r < r_hi) {
+            stripe_block_range(R, r, a, b, g_lo, g_hi);
+            for (uint32_t w = g_lo >> 5; g_hi > g_lo && w <= (g_hi - 1) >> 5; w++) {
+                uint32_t bits = blk_odd[w];
+                if (w == g_lo >> 5) bits &= 0xFFFFFFFFu << (g_lo & 31);
+                if (w == (g_hi - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((g_hi - 1) & 31));
+                n_odd += __popc(bits);
+            }
+        }
+        if (!WRITE) {
+            total += n_odd;
+            continue;
+        }
+        // exclusive offsets inside the batch
+        uint32_t incl = n_odd;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        __syncthreads();  // s_warp of the batch before has been read (and s_base is visible)
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t ex = incl - n_odd, all = 0;
+#pragma unroll
+        for (int w = 0; w < kOddThreads / 32; w++) {
+            if (w < (int)warp) ex += s_warp[w];
+            all += s_warp[w];
+        }
+        uint32_t w_out = s_base + total + ex;
+        for (uint32_t w = g_lo >> 5; n_odd && w <= (g_hi - 1) >> 5; w++) {
+            uint32_t bits = blk_odd[w];
+            if (w == g_lo >> 5) bits &= 0xFFFFFFFFu << (g_lo & 31);
+            if (w == (g_hi - 1) >> 5) bits &= 0xFFFFFFFFu >> (31 - ((g_hi - 1) & 31));
+            for (; bits; bits &= bits - 1, w_out++)
+                if (w_out < cap) odd_list[w_out] = (w << 5) + (uint32_t)__ffs(bits) - 1;
+        }
+        total += all;
+    }
+    if (!WRITE) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
+        if (lane == 0) s_warp[warp] = total;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < kOddThreads / 32; w++) t += s_warp[w];
+            odd_cnt[blockIdx.x] = t;
+        }
+    }
+}
+void stripe_odd_count(const ReadsDev &r, const uint32_t *d_blk_odd, const uint32_t *d_first_ge, uint32_t L, uint32_t max_span,
+                      uint32_t *d_odd_cnt, cudaStream_t s) {
+    NP2_K(k_stripe_odd<false>)<<<pileup_stripes(L), kOddThreads, 0, s>>>(r, d_blk_odd, d_first_ge, L, (uint32_t)stripe_w(), max_span,
+                                                                       d_odd_cnt, nullptr, nullptr, 0);
+}
+// d_odd_off[stripes + 1] = exclusive sum of the counts; the total also goes to *d_total
+void stripe_odd_offsets(const uint32_t *d_odd_cnt, uint32_t *d_odd_off, uint32_t L, uint32_t *d_total, ScanPool &pool,
+                        cudaStream_t s) {
+    ScanOffsets<uint32_t, uint32_t> f;
+    f.in = d_odd_cnt;
+    f.out = d_odd_off;
+    f.c_slot = d_total;
+    f.q_slot = nullptr;
+    f.cap = ~0ULL;
+    f.abort = nullptr;
+    scan_launch(f, nullptr, 0, pileup_stripes(L), pool, s);
+}
+void stripe_odd_fill(const ReadsDev &r, const uint32_t *d_blk_odd, const uint32_t *d_first_ge, uint32_t L, uint32_t max_span,
+                     const uint32_t *d_odd_off, uint32_t *d_odd_list, uint32_t cap, cudaStream_t s) {
+    NP2_K(k_stripe_odd<true>)<<<pileup_stripes(L), kOddThreads, 0, s>>>(r, d_blk_odd, d_first_ge, L, (uint32_t)stripe_w(), max_span,
+                                                                      nullptr, d_odd_off, d_odd_list, cap);
+}
 template <int W>
-static void pileup_stripe_w(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_blk_odd,
-                            const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd,
-                            uint32_t *d_n_emit, bool count_only, cudaStream_t s) {
+static void pileup_stripe_w(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_odd_off,
+                            const uint32_t *d_odd_list, MsaDev m, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit,
+                            bool count_only, cudaStream_t s) {
     static bool attr_done = false;
     const int smem = (int)sizeof(StripeSmem<W>);
     if (!attr_done) {
@@ -1440,20 +1493,20 @@ static void pileup_stripe_w(const ReadsDev &r, const uint8_t *d_blank, const uin
     }
     const uint32_t grid = cdiv(m.L, W);
     if (count_only)
-        NP2_K((k_pileup_stripe<W, false>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span,
-                                                                           cap_g, cd, d_n_emit);
+        NP2_K((k_pileup_stripe<W, false>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_odd_off, d_odd_list, m, cap_g, cd,
+                                                                           d_n_emit);
     else
-        NP2_K((k_pileup_stripe<W, true>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span,
-                                                                          cap_g, cd, d_n_emit);
+        NP2_K((k_pileup_stripe<W, true>))<<<grid, kStripeThreads, smem, s>>>(r, d_blank, d_code, d_odd_off, d_odd_list, m, cap_g, cd,
+                                                                          d_n_emit);
 }
 // count_only: only C_G / C_NREC are produced (exact mode sizes the entry arrays from them)
-void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_blk_odd,
-                   const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit,
-                   bool count_only, cudaStream_t s) {
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_odd_off,
+                   const uint32_t *d_odd_list, MsaDev m, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit, bool count_only,
+                   cudaStream_t s) {
     if (stripe_w() == 512)
-        pileup_stripe_w<512>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
+        pileup_stripe_w<512>(r, d_blank, d_code, d_odd_off, d_odd_list, m, cap_g, cd, d_n_emit, count_only, s);
     else
-        pileup_stripe_w<1024>(r, d_blank, d_code, d_blk_odd, d_first_ge, m, max_span, cap_g, cd, d_n_emit, count_only, s);
+        pileup_stripe_w<1024>(r, d_blank, d_code, d_odd_off, d_odd_list, m, cap_g, cd, d_n_emit, count_only, s);
 }
 __global__ void k_counts_reset_pileup(CountsDev cd) {
     cd.c[C_G] = 0;

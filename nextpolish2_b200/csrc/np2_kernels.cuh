@@ -139,9 +139,17 @@ struct MsaDev {
 void stripe_reads(const ReadsDev &r, uint32_t L, uint32_t *d_first_ge, cudaStream_t s);
 void block_flags(const ReadsDev &r, uint32_t n_blocks, const uint8_t *d_code, const uint32_t *d_refpk, uint32_t *d_blk_odd,
                  cudaStream_t s);
-void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_blk_odd,
-                   const uint32_t *d_first_ge, MsaDev m, uint32_t max_span, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit,
-                   bool count_only, cudaStream_t s);
+// per-stripe lists of the not-all-reference blocks (once per job): count, offsets (d_odd_off[stripes + 1], total also in
+// d_odd_off[stripes]), fill
+void stripe_odd_count(const ReadsDev &r, const uint32_t *d_blk_odd, const uint32_t *d_first_ge, uint32_t L, uint32_t max_span,
+                      uint32_t *d_odd_cnt, cudaStream_t s);
+void stripe_odd_offsets(const uint32_t *d_odd_cnt, uint32_t *d_odd_off, uint32_t L, uint32_t *d_total, ScanPool &pool,
+                        cudaStream_t s);
+void stripe_odd_fill(const ReadsDev &r, const uint32_t *d_blk_odd, const uint32_t *d_first_ge, uint32_t L, uint32_t max_span,
+                     const uint32_t *d_odd_off, uint32_t *d_odd_list, uint32_t cap, cudaStream_t s);
+void pileup_stripe(const ReadsDev &r, const uint8_t *d_blank, const uint8_t *d_code, const uint32_t *d_odd_off,
+                   const uint32_t *d_odd_list, MsaDev m, uint32_t cap_g, CountsDev cd, uint32_t *d_n_emit, bool count_only,
+                   cudaStream_t s);
 void counts_reset_pileup(CountsDev cd, cudaStream_t s);
 
 /* ------------------------------------------------------------------ K3 DP + consensus */

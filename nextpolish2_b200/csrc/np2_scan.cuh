@@ -8,8 +8,8 @@
 // (load / op / store / total), so "flag, scan the flags, scatter" or "count, scan, emit" is one scan.
 //
 // Algorithm: reduce-then-scan over a FIXED partition.  The elements are cut into one contiguous chunk per CTA
-// (at most kScanMaxCtas of them); pass 1 reduces every chunk (loads only), a one-CTA pass scans the chunk totals, and
-// pass 2 re-reads every chunk, scans it in registers (every thread owns 16 consecutive elements: 15 serial operations, one
+// (at most kScanMaxCtas of them); pass 1 reduces every chunk (loads only) and its last CTA to finish scans the chunk
+// totals; pass 2 re-reads every chunk, scans it in registers (every thread owns 16 consecutive elements: 15 serial operations, one
 // shuffle scan per warp) and calls the functor's store.  The input is read twice, but nothing ever waits for
 // another CTA: a chained single-pass scan with look-back measured 2-3x slower here, because with ~500 tiles in flight
 // every tile walks back through hundreds of descriptors that only hold aggregates (profiles/r02h_launches.csv).
@@ -29,15 +29,29 @@ constexpr unsigned long long kScanMask = (1ULL << 62) - 1;
 
 // 64-bit scratch words for the chunk totals of the scans of one pipeline pass; slices are handed out in enqueue order
 // and never reused inside a pass
+constexpr int kScanTickets = 64;
 struct ScanPool {
     unsigned long long *d = nullptr;
     size_t cap = 0, used = 0;
+    // "which CTA of the reduce pass finishes last" counters: zero when a scan starts, set back to zero by the CTA that
+    // draws the last ticket.  The scans of a pool run on one stream, one after the other; they still rotate through a
+    // few counters so that no scan depends on the one before it having cleaned up.
+    uint32_t *tickets = nullptr;
+    uint32_t n_scans = 0;
     void reserve(size_t words, cudaStream_t s) {
+        if (!tickets) {
+            NP2_CUDA(cudaMallocAsync((void **)&tickets, kScanTickets * 4, s));
+            NP2_CUDA(cudaMemsetAsync(tickets, 0, kScanTickets * 4, s));
+        }
         if (words <= cap) return;
         if (d) cudaFreeAsync(d, s);
         cap = words + words / 2;
         NP2_CUDA(cudaMallocAsync((void **)&d, cap * 8, s));
         used = 0;
+    }
+    uint32_t *ticket(cudaStream_t s) {
+        if (!tickets) reserve(1, s);
+        return tickets + (n_scans++ % kScanTickets);
     }
     void begin(cudaStream_t) { used = 0; }  // start of a pass: everything handed out before is dead (same stream)
     unsigned long long *take(size_t words, cudaStream_t s) {
@@ -54,7 +68,9 @@ struct ScanPool {
     }
     void destroy(cudaStream_t s) {
         if (d) cudaFreeAsync(d, s);
+        if (tickets) cudaFreeAsync(tickets, s);
         d = nullptr;
+        tickets = nullptr;
         cap = used = 0;
     }
 };
@@ -92,34 +108,17 @@ __device__ __forceinline__ unsigned long long scan_block_reduce(unsigned long lo
     return r;
 }
 
+// one CTA's worth of work: exclusive scan of the chunk totals in place, the grand total goes to the functor
 template <class Tr>
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(Tr tr, const uint32_t *__restrict__ d_n, uint32_t n_plus,
-                                                              uint32_t cap, unsigned long long *__restrict__ partial,
-                                                              const uint32_t *__restrict__ d_abort) {
-    __shared__ unsigned long long s_warp[kScanThreads / 32];
-    if (d_abort && *d_abort) return;
-    const uint32_t n = scan_count(d_n, n_plus, cap);
-    const uint64_t chunk = scan_chunk(n, gridDim.x), begin = blockIdx.x * chunk;
-    const uint64_t end = begin + chunk < n ? begin + chunk : n;
-    unsigned long long acc = Tr::identity();
-    for (uint64_t i = begin + threadIdx.x; i < end; i += kScanThreads) acc = Tr::op(acc, Tr::widen(tr.load((uint32_t)i)));
-    acc = scan_block_reduce<Tr>(acc, s_warp);
-    if (threadIdx.x == 0) partial[blockIdx.x] = acc & kScanMask;
-}
-// one CTA: exclusive scan of the chunk totals in place, the grand total goes to the functor
-template <class Tr>
-__global__ void __launch_bounds__(kScanThreads) k_scan_mid(Tr tr, const uint32_t *__restrict__ d_n, uint32_t n_plus, uint32_t cap,
-                                                           unsigned long long *__restrict__ partial, uint32_t ctas,
-                                                           const uint32_t *__restrict__ d_abort) {
-    __shared__ unsigned long long s_warp[kScanThreads / 32];
-    if (d_abort && *d_abort) return;
+__device__ __forceinline__ void scan_partials(const Tr &tr, const uint32_t *__restrict__ d_n, uint32_t n_plus, uint32_t cap,
+                                              unsigned long long *partial, uint32_t ctas, unsigned long long *s_warp) {
     constexpr int kPer = (kScanMaxCtas + kScanThreads - 1) / kScanThreads;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long v[kPer], sum = Tr::identity();
 #pragma unroll
     for (int u = 0; u < kPer; u++) {
         const uint32_t c = tid * kPer + u;
-        v[u] = c < ctas ? partial[c] : Tr::identity();
+        v[u] = c < ctas ? __ldcg(partial + c) : Tr::identity();  // written by other CTAs: not through this SM's L1
         sum = Tr::op(sum, v[u]);
     }
     unsigned long long incl = sum;
@@ -128,6 +127,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_mid(Tr tr, const uint32_t
         const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if (lane >= d) incl = Tr::op(t, incl);
     }
+    __syncthreads();  // s_warp may still be read by the block reduction before
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     unsigned long long ex = Tr::identity(), all = Tr::identity();
@@ -146,6 +146,33 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_mid(Tr tr, const uint32_t
         ex = Tr::op(ex, v[u]);
     }
     if (tid == 0) tr.total(all & kScanMask, scan_count(d_n, n_plus, cap));
+}
+// pass 1: every CTA reduces its chunk; the CTA that finishes LAST (a ticket counter) also scans the chunk totals, so
+// the one-CTA pass in between costs no launch of its own
+template <class Tr>
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(Tr tr, const uint32_t *__restrict__ d_n, uint32_t n_plus,
+                                                              uint32_t cap, unsigned long long *partial,
+                                                              uint32_t *ticket, const uint32_t *__restrict__ d_abort) {
+    __shared__ unsigned long long s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_last;
+    if (d_abort && *d_abort) return;
+    const uint32_t n = scan_count(d_n, n_plus, cap);
+    const uint64_t chunk = scan_chunk(n, gridDim.x), begin = blockIdx.x * chunk;
+    const uint64_t end = begin + chunk < n ? begin + chunk : n;
+    unsigned long long acc = Tr::identity();
+    for (uint64_t i = begin + threadIdx.x; i < end; i += kScanThreads) acc = Tr::op(acc, Tr::widen(tr.load((uint32_t)i)));
+    acc = scan_block_reduce<Tr>(acc, s_warp);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = acc & kScanMask;
+        __threadfence();  // the total is visible before the ticket is drawn
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_last = t == gridDim.x - 1;
+        if (s_last) *ticket = 0;  // for the next scan that uses this counter (same stream: after this kernel)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    scan_partials(tr, d_n, n_plus, cap, partial, gridDim.x, s_warp);
 }
 // pass 2 (or the only pass when there is one chunk: partial == nullptr, the total is reported here)
 template <class Tr>
@@ -226,8 +253,7 @@ inline void scan_launch(const Tr &tr, const uint32_t *d_n, uint32_t n_plus, uint
         return;
     }
     unsigned long long *partial = pool.take(ctas, s);
-    NP2_K(k_scan_reduce<Tr>)<<<ctas, kScanThreads, 0, s>>>(tr, d_n, n_plus, cap, partial, d_abort);
-    NP2_K(k_scan_mid<Tr>)<<<1, kScanThreads, 0, s>>>(tr, d_n, n_plus, cap, partial, ctas, d_abort);
+    NP2_K(k_scan_reduce<Tr>)<<<ctas, kScanThreads, 0, s>>>(tr, d_n, n_plus, cap, partial, pool.ticket(s), d_abort);
     NP2_K(k_scan_apply<Tr>)<<<ctas, kScanThreads, 0, s>>>(tr, d_n, n_plus, cap, partial, d_abort);
 }
 
