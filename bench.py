@@ -433,6 +433,27 @@ def cfg_for(n, full):
     return cfg
 
 
+def bind_to_gpu_cpus(local, world):
+    """One rank per GPU on a multi-socket box: keep this rank's threads (and, by first touch, its page-locked record
+    buffers) on the CPUs NVML reports as local to its GPU, so that K0's reads of host memory and the record parse do not
+    cross the socket interconnect.  A no-op when NVML reports no proper subset of the CPUs this process may use."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        mine = os.sched_getaffinity(0)
+        cpus &= mine
+        if cpus and cpus != mine and len(cpus) >= max(2, len(mine) // max(1, world)):
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "of": len(mine)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:80]}
+    return None
+
+
 def run_ours(args):
     # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner ...) goes to stderr
     real_stdout = os.dup(1)
@@ -459,8 +480,11 @@ def _run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_cpus(local, world) if world > 1 and not args.no_bind else None
     cores = max(1, (os.cpu_count() or 8) // max(world, 1))
     threads = min(cores, 16)
+    if args.e2e_inflight <= 0:
+        args.e2e_inflight = max(1, min(3, cores // 2))
     cfg = cfg_for(args.config, args.full or args.config == 1)
     if args.length:
         cfg["length"] = args.length
@@ -531,6 +555,7 @@ def _run_ours(args):
                                                        for k, v in sorted(m.partsN.get("stages", {}).items(), key=lambda kv: -kv[1])[:14]},
                         repeated_passes=m.partsN.get("repeated_passes", 0) + m.parts1.get("repeated_passes", 0)),
             "gpu_launches": s["gpu_launches"],
+            "cpu_binding": numa,
             "clocks": clocks,
             "roofline": roofline_of(m, cfg, peak, peak_kind),
             "pipeline_roofline": s["pipeline_roofline"],
@@ -899,7 +924,10 @@ def main():
     ap.add_argument("--strong-passes", type=int, default=2)
     ap.add_argument("--pageable", action="store_true", help="record buffer in pageable memory (host compaction path)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per library call (0 = cores / ranks / ~in flight)")
-    ap.add_argument("--e2e-inflight", type=int, default=3, help="worker threads per GPU in the end-to-end arm")
+    ap.add_argument("--e2e-inflight", type=int, default=0,
+                    help="worker threads per GPU in the end-to-end arm (0 = min(3, host cores per rank / 2): 3 on a 16-core box "
+                         "with one GPU, 2 with 8 ranks on 32 cores, where a third worker only oversubscribes the cores)")
+    ap.add_argument("--no-bind", action="store_true", help="N > 1: do not bind the rank to the CPUs local to its GPU")
     ap.add_argument("--e2e-stage-timers", action="store_true", help="keep the per-stage event timers on with contigs in flight")
     ap.add_argument("--e2e-prefetch", type=int, default=1, help="1: every worker parses and starts the upload of its next contig before it runs the current one")
     args = ap.parse_args()
