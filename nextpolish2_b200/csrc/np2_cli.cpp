@@ -32,8 +32,10 @@
 
 namespace {
 
+std::string g_partial_out;  // -o file being written: removed when the run dies, so that no truncated FASTA is left behind
 [[noreturn]] void die(const std::string &m) {
     fprintf(stderr, "%s\n", m.c_str());
+    if (!g_partial_out.empty()) remove(g_partial_out.c_str());
     exit(101);  // the reference aborts with a panic message
 }
 
@@ -177,12 +179,20 @@ int main_count(int argc, char **argv) {
         fprintf(stderr,
                 "Usage: nextPolish2 count [options] -o <out.yak> <in.fa|fq[.gz]> [in.fa]\n"
                 "  -k INT   k-mer size [31]\n"
-                "  -b INT   as in `yak count`: when > 0 the (second, else the first) file is counted and only k-mers\n"
-                "           seen at least twice are kept (what yak's Bloom-filter pass + second pass + shrink leave)\n"
+                "  -b INT   as in `yak count`: when > 0 only k-mers seen at least twice are kept (what yak's Bloom-filter\n"
+                "           pass + second pass + shrink leave, without the Bloom filter's false positives); a second\n"
+                "           input must be the same file as the first\n"
                 "  -o FILE  dump the counts in yak's format\n"
                 "  -g INT   GPU to use [0]\n");
         return 1;
     }
+    // yak with -b and two DIFFERENT files keeps the k-mers of file 2 that passed the Bloom pass over file 1 (main.c:65-71):
+    // that is not what "count the second file, keep counts >= 2" computes, so it is refused rather than mis-answered.
+    // The usual invocation (the same reads twice, as test/hh.sh does) is the supported one.  yak's Bloom false positives
+    // (singletons that survive) are not reproduced either way: this dump holds exactly the k-mers seen twice or more.
+    if (bloom > 0 && in.size() >= 2 && in[0] != in[1])
+        die("ERROR: count -b with two different input files is not supported (give the same file twice, as yak's own "
+            "two-pass recipe does)");
     if (pre != 10) die("ERROR: -p must be 10 (NextPolish2 compares hash >> 10, kmer.rs:52-54)");
     if (k >= 64) die("ERROR: -k must be smaller than 64");
     np2_ctx *ctx = nullptr;
@@ -240,6 +250,7 @@ bool member_at(const BamFile &bf, uint64_t o, Member &m) {
     for (uint32_t x = 0; x + 4 <= xlen;) {
         const uint8_t *e = h + 12 + x;
         const uint32_t slen = e[2] | e[3] << 8;
+        if (x + 4 + slen > xlen) die("BAM/SAM parsing failed!");  // the subfield runs past the extra field
         if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = (e[4] | e[5] << 8) + 1;
         x += 4 + slen;
     }
@@ -249,6 +260,7 @@ bool member_at(const BamFile &bf, uint64_t o, Member &m) {
     m.clen = bsize - 12 - xlen - 8;
     m.total = bsize;
     memcpy(&m.isize, h + bsize - 4, 4);
+    if (m.isize > 65536) die("BAM/SAM parsing failed!");  // a BGZF member inflates to at most 64 KiB
     return true;
 }
 void inflate_member(const BamFile &bf, const Member &m, uint8_t *out) {
@@ -341,15 +353,18 @@ void open_bam(const std::string &path, BamFile &bf) {
     if (memcmp(u.data(), "BAM\1", 4) != 0) die("BAM/SAM parsing failed!");
     int32_t l_text, n_ref;
     memcpy(&l_text, u.data() + 4, 4);
+    if (l_text < 0) die("BAM/SAM parsing failed!");
     need(12 + (size_t)l_text);
     memcpy(&n_ref, u.data() + 8 + l_text, 4);
+    if (n_ref < 0) die("BAM/SAM parsing failed!");
     size_t o = 12 + (size_t)l_text;
     for (int32_t i = 0; i < n_ref; i++) {
         need(o + 4);
         int32_t l_name;
         memcpy(&l_name, u.data() + o, 4);
+        if (l_name <= 0 || l_name > (1 << 20)) die("BAM/SAM parsing failed!");
         need(o + 4 + l_name + 4);
-        bf.ref_names.emplace_back((const char *)u.data() + o + 4);
+        bf.ref_names.emplace_back((const char *)u.data() + o + 4, strnlen((const char *)u.data() + o + 4, (size_t)l_name));
         uint32_t l_ref;
         memcpy(&l_ref, u.data() + o + 4 + l_name, 4);
         bf.ref_lens.push_back(l_ref);
@@ -585,6 +600,7 @@ int main(int argc, char **argv) {
         }
         out = fopen(cli.out.c_str(), "wb");
         if (!out) die("Failed to freopen: \"" + cli.out + "\"");
+        g_partial_out = cli.out;
     }
     std::vector<Contig> contigs = read_fasta(cli.fa);
     const double s_fasta = since(t_start);
@@ -594,6 +610,19 @@ int main(int argc, char **argv) {
         if (c.seq.size() >= 0xFFFFFFFFull) die(c.name + " is too long!");  // main.rs:1707-1711
     std::vector<std::vector<uint8_t>> results(n);
     std::vector<uint8_t> done(n, 0);
+    // Records leave in input order as soon as every contig before them is done (the reference's writer thread streams
+    // them as they finish, main.rs:1845-1851): the finished prefix is written and freed, not held until the end.
+    std::mutex write_mu;
+    size_t next_write = 0;
+    auto flush_ready = [&]() {
+        std::lock_guard<std::mutex> lk(write_mu);
+        while (next_write < n && done[next_write]) {
+            std::vector<uint8_t> &r = results[next_write];
+            if (fwrite(r.data(), 1, r.size(), out) != r.size()) die("Failed to write the output!");
+            std::vector<uint8_t>().swap(r);
+            next_write++;
+        }
+    };
     std::vector<size_t> todo;
     for (size_t i = 0; i < n; i++) {
         if (contigs[i].seq.size() < cli.o.min_ctg_len) {  // main.rs:1727-1730, no GPU involved
@@ -716,7 +745,11 @@ int main(int argc, char **argv) {
             const auto t_destroy = std::chrono::steady_clock::now();
             np2_job_destroy(job);
             us_destroy += (uint64_t)(since(t_destroy) * 1e6);
-            done[i] = 1;
+            {
+                std::lock_guard<std::mutex> lk(write_mu);  // done[] is read under this lock
+                done[i] = 1;
+            }
+            flush_ready();
             us_polish += (uint64_t)(since(t_polish) * 1e6);
             return true;
         };
@@ -771,8 +804,10 @@ int main(int argc, char **argv) {
         if (!first_err.empty()) die(first_err);
     }
     const auto t_write = std::chrono::steady_clock::now();
-    for (size_t i = 0; i < n; i++) fwrite(results[i].data(), 1, results[i].size(), out);
+    flush_ready();  // whatever is left (contigs below -L behind the last polished one, or a run without any)
+    if (next_write != n) die("internal error: a contig was not written");
     if (out != stdout) fclose(out);
+    g_partial_out.clear();
     if (timing) {
         uint64_t bp = 0;
         for (size_t i : todo) bp += contigs[i].seq.size();
