@@ -137,10 +137,8 @@ def peaks():
 # name -> (kernel as ncu lists it, bytes(st)); st = {"cols", "L", "records", "groups", "N"}
 STAGE_MODELS = {
     # 4-bit SEQ in (0.5 B/column), packed nibble out (0.5), one 10-byte checkpoint out + one 2-byte op index in per 32 columns
+    # (+ one "not all reference" bit out per block and the packed reference, 0.5 B/bp, once: below 2 % of the rest)
     "pack_columns": ("k_pack_columns_batched<2>", lambda st: st["cols"] * (0.5 + 0.5 + 10 / 32 + 2 / 32)),
-    # once per job: packed columns in (0.5 B/column), checkpoint t_pos + read id in (8 B / 32 columns), one bit out per block,
-    # packed reference (0.5 B/bp) counted once
-    "block_flags": ("k_block_flags", lambda st: st["cols"] * (0.5 + 8 / 32 + 1 / 256) + st["L"] * 0.5),
     # K2: per position coverage 4 + code 1 in, entry offset 4 + count 2 + reference count 4 + flag 1 + emit count 4 out;
     # one bit per 32-column block in; per not-all-reference block (<= one per record) 16 B of columns + 10 B checkpoint in;
     # 16 B per Msa entry out

@@ -2135,8 +2135,9 @@ void np2_job::run(int32_t dump_it) {
     // host decides which reads are kept (ingest_finish) during that kernel.
     if (!sc->ev_trim) NP2_CUDA(cudaEventCreateWithFlags(&sc->ev_trim, cudaEventDisableTiming));
     NP2_CUDA(cudaEventRecord(sc->ev_trim, s));
-    h = timer.begin("pack_columns", 1);  // a single kernel
-    pack_columns(R, d_ref.p, ing.ck_off.back(), s);
+    h = timer.begin("pack_columns", 1);  // a single kernel; the plain blocks' "not all reference" bits fall out of it
+    d_blk_odd.alloc(((size_t)ing.ck_off.back() + 255) / 256 * 8 + 8, s);
+    const bool flags_done = pack_columns(R, d_ref.p, ing.ck_off.back(), d_refpk.p, d_blk_odd.p, s);
     timer.end(h);
     {
         cudaStream_t c2 = ctx->copy_stream;
@@ -2182,9 +2183,8 @@ void np2_job::run(int32_t dump_it) {
     const uint32_t n_stripes = pileup_stripes(L);
     d_first_ge.alloc(n_stripes + 1, s);
     stripe_reads(R, L, d_first_ge.p, s);
-    d_blk_odd.alloc(((size_t)ing.ck_off.back() + 255) / 256 * 8 + 8, s);
     h = timer.begin("block_flags", 4);
-    block_flags(R, ing.ck_off.back(), d_code.p, d_refpk.p, d_blk_odd.p, s);
+    if (!flags_done) block_flags(R, ing.ck_off.back(), d_code.p, d_refpk.p, d_blk_odd.p, s);
     // per stripe: which of its blocks K2 has to walk (a property of the reads and the contig, like the flags)
     DBuf<uint32_t> d_odd_cnt;
     d_odd_cnt.alloc(n_stripes, s);

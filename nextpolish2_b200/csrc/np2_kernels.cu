@@ -762,8 +762,41 @@ __device__ __forceinline__ void pack_block_queued(const ReadsDev &R, uint32_t g)
     }
     pack_block_slow(R, g);
 }
+// SEQ_NUM code of one BAM nibble ("=ACMGRSVTWYHKDBN" -> 4 0 1 6 2 4 4 4 3 4 4 4 4 4 4 5), as map_codes4 maps four
+__device__ __forceinline__ uint32_t code_of_nibble(uint32_t v) { return (uint32_t)(0x5444444344426104ULL >> (4 * v)) & 15u; }
+// The "holds something else than reference 3-mers" bit of a PLAIN block (32 M/=/X columns of one op), from what the pack
+// thread has in registers: its 32 codes (memory-order words w0, w1) against the packed reference at tpos, and the two
+// columns in front of the block, which are the two query bases before q0 when the op started at least two columns
+// earlier (otherwise the block is simply called odd: K2 then walks it and finds nothing, which is exact, only slower).
+// Same verdict as block_all_reference_at on the packed columns wherever it answers "all reference".
+__device__ __forceinline__ bool plain_block_odd(uint64_t w0, uint64_t w1, uint32_t tpos, uint32_t o0, bool prev_in_op,
+                                                const uint8_t *__restrict__ seq4, uint32_t q0,
+                                                const uint32_t *__restrict__ refpk) {
+    if (o0 == 0 || tpos < 2 || !prev_in_op) return true;
+    if (((w0 | w1) & 0xCCCCCCCCCCCCCCCCULL) != 0) return true;
+    const uint32_t k = tpos >> 3, sh = (tpos & 7) * 4;
+    const uint32_t r0 = refpk[k], r1 = refpk[k + 1], r2 = refpk[k + 2], r3 = refpk[k + 3], r4 = refpk[k + 4];
+    const uint32_t rp = k ? refpk[k - 1] : 0;
+    const uint32_t w[4] = {(uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32)};
+    uint32_t diff = 0;
+    diff |= __byte_perm(w[0], 0, 0x0123) ^ __funnelshift_l(r1, r0, sh);
+    diff |= __byte_perm(w[1], 0, 0x0123) ^ __funnelshift_l(r2, r1, sh);
+    diff |= __byte_perm(w[2], 0, 0x0123) ^ __funnelshift_l(r3, r2, sh);
+    diff |= __byte_perm(w[3], 0, 0x0123) ^ __funnelshift_l(r4, r3, sh);
+    if (diff) return true;
+    // reference codes at tpos - 2, tpos - 1 (position i sits in nibble 7 - (i & 7) of word i >> 3)
+    const uint32_t i2 = tpos - 2, i1 = tpos - 1;
+    const uint32_t c2 = ((i2 >> 3) == k ? r0 : rp) >> (28 - 4 * (i2 & 7)) & 15u;
+    const uint32_t c1 = ((i1 >> 3) == k ? r0 : rp) >> (28 - 4 * (i1 & 7)) & 15u;
+    const uint32_t b2 = seq4[(q0 - 2) >> 1], b1 = seq4[(q0 - 1) >> 1];
+    const uint32_t s2 = code_of_nibble(((q0 - 2) & 1) ? (b2 & 15u) : (b2 >> 4));
+    const uint32_t s1 = code_of_nibble(((q0 - 1) & 1) ? (b1 & 15u) : (b1 >> 4));
+    return s2 >= 4 || s1 >= 4 || s2 != c2 || s1 != c1;
+}
 template <int B>
-__global__ void __launch_bounds__(kPackThreads, 4) k_pack_columns_batched(ReadsDev R, uint32_t n_blocks) {
+__global__ void __launch_bounds__(kPackThreads, 4) k_pack_columns_batched(ReadsDev R, uint32_t n_blocks,
+                                                                          const uint32_t *__restrict__ refpk,
+                                                                          uint32_t *__restrict__ blk_odd) {
     __shared__ uint32_t q[kPackThreads * B], qn;
     if (threadIdx.x == 0) qn = 0;
     __syncthreads();
@@ -806,15 +839,24 @@ __global__ void __launch_bounds__(kPackThreads, 4) k_pack_columns_batched(ReadsD
     }
 #pragma unroll
     for (int u = 0; u < B; u++) {
+        bool odd = false;
         if (plain[u]) {
-            R.ck_tpos[g[u]] = pos[u] + o[u].z + (shift[u] + o0[u] - o[u].x);  // col_tpos of an M/=/X column
+            const uint32_t col = shift[u] + o0[u];
+            const uint32_t tp = pos[u] + o[u].z + (col - o[u].x);  // col_tpos of an M/=/X column
+            R.ck_tpos[g[u]] = tp;
             R.ck_delta[g[u]] = 0;
             uint64_t *out = (uint64_t *)(R.nib + noff[u] + (o0[u] >> 1));
-            out[0] = map_codes16(hi[u]);
-            out[1] = map_codes16(lo[u]);
+            const uint64_t w0 = map_codes16(hi[u]), w1 = map_codes16(lo[u]);
+            out[0] = w0;
+            out[1] = w1;
+            odd = plain_block_odd(w0, w1, tp, o0[u], col >= o[u].x + 2, R.blob + soff[u], o[u].y + (col - o[u].x), refpk);
         } else if (g[u] < n_blocks && n[u] && o0[u] <= n[u]) {
             q[atomicAdd(&qn, 1u)] = g[u];
+            odd = o0[u] < n[u];  // an op boundary, an indel or the end of the read inside the block: K2 walks it
         }
+        // bit g of blk_odd (what k_block_flags computes from the packed columns): the 32 blocks of a warp are one word
+        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, odd);
+        if ((threadIdx.x & 31) == 0 && (g[u] >> 5) < ((n_blocks + 31) >> 5)) blk_odd[g[u] >> 5] = bits;
     }
     __syncthreads();
     const uint32_t nq = qn;
@@ -872,12 +914,21 @@ void cigar_ops(const uint8_t *d_blob, const uint64_t *d_seq_off, const uint32_t 
 void trim_scan(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s) {
     if (r.n_reads) NP2_K(k_trim_scan)<<<cdiv((uint64_t)r.n_reads * 32, 128), 128, 0, s>>>(r, d_ref, L);
 }
-void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cudaStream_t s) {
-    if (!r.n_reads || !n_blocks) return;
-    const char *e = getenv("NP2_PACK_BATCH");
-    const int batch = e ? atoi(e) : kPackBatchDefault;
-    if (batch <= 1) NP2_K(k_pack_columns)<<<cdiv(n_blocks, kPackThreads), kPackThreads, 0, s>>>(r, d_ref, n_blocks);
-    else NP2_K(k_pack_columns_batched<2>)<<<cdiv(n_blocks, 2 * kPackThreads), kPackThreads, 0, s>>>(r, n_blocks);
+// returns true when the per-block "not all reference" bits (d_blk_odd) were produced along the way; the
+// one-block-per-thread form (NP2_PACK_BATCH=1, A/B runs) leaves them to block_flags
+bool pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, const uint32_t *d_refpk, uint32_t *d_blk_odd,
+                  cudaStream_t s) {
+    if (!r.n_reads || !n_blocks) return false;
+    static const int batch = [] {
+        const char *e = getenv("NP2_PACK_BATCH");
+        return e ? atoi(e) : kPackBatchDefault;
+    }();
+    if (batch <= 1) {
+        NP2_K(k_pack_columns)<<<cdiv(n_blocks, kPackThreads), kPackThreads, 0, s>>>(r, d_ref, n_blocks);
+        return false;
+    }
+    NP2_K(k_pack_columns_batched<2>)<<<cdiv(n_blocks, 2 * kPackThreads), kPackThreads, 0, s>>>(r, n_blocks, d_refpk, d_blk_odd);
+    return true;
 }
 
 /* =============================================================== K2: pileup */

@@ -108,7 +108,8 @@ void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint
 void cigar_ops(const uint8_t *d_blob, const uint64_t *d_seq_off, const uint32_t *d_n_cig, const uint32_t *d_op_off,
                uint4 *d_ops, uint32_t n_reads, cudaStream_t s);
 void trim_scan(const ReadsDev &r, const uint8_t *d_ref, uint32_t L, cudaStream_t s);
-void pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, cudaStream_t s);
+bool pack_columns(const ReadsDev &r, const uint8_t *d_ref, uint32_t n_blocks, const uint32_t *d_refpk, uint32_t *d_blk_odd,
+                  cudaStream_t s);
 
 /* ------------------------------------------------------------------ K2 pileup */
 void cover_diff(const ReadsDev &r, const uint8_t *d_blank, int32_t *d_diff, cudaStream_t s);

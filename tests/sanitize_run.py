@@ -19,7 +19,7 @@ import nextpolish2_b200 as np2  # noqa: E402
 from nextpolish2_b200 import synth  # noqa: E402
 
 
-def one(ctx, seed, L, het, depth, tandem=0.0):
+def one(ctx, seed, L, het, depth, tandem=0.0, pinned=False):
     A = synth.genome(seed, L, tandem_frac=tandem)
     c = synth.make_contig(seed + 1, A, depth=depth, asm_err=3e-4, het=het, mean_len=6000, sd_len=1000, min_len=2000, threads=2)
     haps = [c["hap1"]] + ([c["hap2"]] if het > 0 else [])
@@ -27,7 +27,14 @@ def one(ctx, seed, L, het, depth, tandem=0.0):
     gt = [np2.Table.from_arrays(ctx, k, *tabs[k]) for k in (21, 31)]
     oj = O.Job(A, c["bam"], [O.Table.from_arrays(k, *tabs[k]) for k in (21, 31)], O.Opts(min_ctg_len=0), dump_iter=-1)
     opos, obase = oj.consensus()
-    job = np2.Job(ctx, A, c["bam"], gt, np2.Opts(min_ctg_len=0)).upload()
+    pb = None
+    bam = c["bam"]
+    if pinned:  # page-locked records: K0 (the TMA gather of the CIGAR + SEQ spans) instead of the host compaction
+        from nextpolish2_b200.api import PinnedBuffer
+        pb = PinnedBuffer(bam)
+        bam = pb.array
+    job = np2.Job(ctx, A, bam, gt, np2.Opts(min_ctg_len=0)).upload()
+    assert job.ingest_path == (1 if pinned else 2)
     for rnd in range(2):
         job.run(-1)
         gpos, gbase = job.consensus()
@@ -35,8 +42,11 @@ def one(ctx, seed, L, het, depth, tandem=0.0):
         assert np.array_equal(np.sort(job.dropped()), np.sort(oj.dropped()))
     st = job.stats()
     job.destroy()
-    print("ok L=%d het=%g: %d regions, %d reads dropped, speculative passes %d, repeated %d" % (
-        L, het, st["regions"], len(oj.dropped()), st["speculative_passes"], st["repeated_passes"]), flush=True)
+    if pb is not None:
+        pb.free()
+    print("ok L=%d het=%g%s: %d regions, %d reads dropped, speculative passes %d, repeated %d" % (
+        L, het, " (page-locked records)" if pinned else "", st["regions"], len(oj.dropped()), st["speculative_passes"],
+        st["repeated_passes"]), flush=True)
 
 
 def main():
@@ -44,6 +54,7 @@ def main():
     one(ctx, 11, 20_000, 0.0, 20)
     one(ctx, 21, 40_000, 0.004, 30)
     one(ctx, 31, 30_000, 0.002, 25, tandem=0.08)
+    one(ctx, 41, 40_000, 0.004, 30, pinned=True)
     h = np.unique(np.random.default_rng(1).integers(0, 2**62, 200_000, dtype=np.uint64))
     t = np2.Table.from_arrays(ctx, 31, h, (h % 1000 + 1).astype(np.uint16))
     assert (t.lookup(h, 0) == (h % 1000 + 1)).all()
