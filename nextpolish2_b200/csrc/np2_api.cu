@@ -1,11 +1,6 @@
 // np2_api.cu — C ABI (include/np2gpu.h) and the per-contig pipeline that strings the kernels and host
 // phases together.  One np2_ctx = one GPU + a compute stream (all kernels of a job), a high-priority copy stream
 // (uploads, the K0 gather) and a private stream-ordered memory pool; per-run scratch comes from an arena.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_reduce.cuh>
-#include <cub/device/device_scan.cuh>
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
 #include <atomic>
@@ -508,6 +503,7 @@ struct np2_job {
     uint32_t rec_cap_hint = 0;             // 3-mer records of the last pileup (sizes the next one-pass emit)
     std::vector<uint32_t> h_as_pos, h_as_te;  // record pos / last column of every alignseq (pair-accumulator windows)
     DBuf<uint64_t> d_pair_off;
+    DBuf<uint32_t> d_as_pos;               // record position of every alignseq (device copy of h_as_pos)
     DBuf<uint32_t> d_first_ge;             // read window of every pileup stripe (np2_kernels.cu stripe_reads)
     DBuf<uint32_t> d_blk_odd;              // one bit per 32-column block: not all reference (np2_kernels.cu block_flags)
     DBuf<uint32_t> d_odd_off, d_odd_list;  // per pileup stripe: the flagged blocks that can touch it (np2_kernels.cu k_stripe_odd)
@@ -1427,69 +1423,71 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         if (dump) dump_candidates(true);
         std::vector<uint32_t> drop;
         DBuf<unsigned long long> d_acc;
-        DBuf<uint32_t> d_sel;
-        DBuf<uint64_t> d_uk;
-        DBuf<long long> d_uv;
         DBuf<uint8_t> d_flags;  // has | bad_v | in_ref
-        DBuf<float> d_refw, d_dw, d_dw2;
-        DBuf<uint64_t> d_dk, d_dk2;
+        DBuf<float> d_refw, d_aw;
         DBuf<uint32_t> d_aoff, d_ato;
-        uint32_t nu = 0;
+        uint32_t nu = 0, n_dir_cap = 0;
         if (n_edges) {
             d_acc.alloc(std::max<uint64_t>(n_slots, 1), s);
-            const uint32_t cap_nu_sel = spec ? std::min(caps.c[C_NU], std::max(n_slots, 1u)) : std::max(n_slots, 1u);
-            d_sel.alloc(cap_nu_sel, s);
-            h = timer.begin("pair_edges", 3);
+            h = timer.begin("pair_edges", 2);
             d_acc.zero();
             geno_edges_accum(g, d_pair_off.p, d_acc.p, nreg, cd, s);
-            geno_edges_select(d_acc.p, n_slots, d_sel.p, cap_nu_sel, cd, sp, s);
             timer.end(h);
-            nu = spec ? cap_nu_sel : cnt_get(C_NU);  // exact: the number of pair records; speculative: its capacity
+            // level 0 of the phasing graph on the device, straight from the accumulator (np2_geno.cu k_phase_adj): per-read
+            // flags + CSR adjacency with every neighbour list in ascending order
+            const bool asref = opt.model == 0, use_all = opt.use_all_reads != 0;
+            DBuf<uint32_t> d_deg;
+            d_flags.alloc((size_t)n_ids0 * 3, s);
+            d_refw.alloc(n_ids0, s);
+            d_deg.alloc(n_ids0 + 1, s);
+            d_aoff.alloc(n_ids0 + 1, s);
+            PhaseDev pd;
+            pd.has = d_flags.p;
+            pd.bad_v = d_flags.p + n_ids0;
+            pd.in_ref = d_flags.p + 2 * (size_t)n_ids0;
+            pd.ref_w = d_refw.p;
+            h = timer.begin("phase_graph", 6);
+            d_flags.zero();
+            d_refw.zero();
+            phase_ref_acc(d_acc.p, d_pair_off.p, n_ids0, cd, pd, asref, use_all, s);
+            phase_adj_count(d_acc.p, d_pair_off.p, d_as_pos.p, n_ids0, max_span, cd, pd, use_all, d_deg.p, s);
+            const uint32_t cap_dir = spec ? caps.c[C_NDIR] : 0xFFFFFFFFu;
+            phase_adj_offsets(d_deg.p, d_aoff.p, n_ids0, cap_dir, cd, sp, s);
+            timer.end(h);
+            n_dir_cap = spec ? cap_dir : cnt_get(C_NDIR);
             if (!spec) check_perr();
-            if (nu) {
-                d_uk.alloc(nu, s);
-                d_uv.alloc(nu, s);
-                h = timer.begin("pair_edges", 1);
-                geno_edges_finish(d_sel.p, nu, d_pair_off.p, n_ids0, d_acc.p, d_uk.p, d_uv.p, cd, s);
-                timer.end(h);
-                if (dump) {  // stage seam: the reduced pair records as they leave K6 (exact mode: nu is exact)
-                    dm_pair_key.resize(nu);
-                    dm_pair_val.resize(nu);
-                    d_uk.download(dm_pair_key.data(), nu);
-                    NP2_CUDA(cudaMemcpyAsync(dm_pair_val.data(), d_uv.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, s));
-                    NP2_CUDA(cudaStreamSynchronize(s));
-                }
-                // level 0 of the phasing graph on the device: per-read flags + CSR adjacency (np2_geno.cu k_phase_*)
-                const uint32_t n2 = 2 * nu;
-                const bool asref = opt.model == 0, use_all = opt.use_all_reads != 0;
-                d_flags.alloc((size_t)n_ids0 * 3, s);
-                d_refw.alloc(n_ids0, s);
-                d_dk.alloc(n2, s);
-                d_dk2.alloc(n2, s);
-                d_dw.alloc(n2, s);
-                d_dw2.alloc(n2, s);
-                d_aoff.alloc(n_ids0 + 1, s);
-                d_ato.alloc(n2, s);
-                PhaseDev pd;
-                pd.has = d_flags.p;
-                pd.bad_v = d_flags.p + n_ids0;
-                pd.in_ref = d_flags.p + 2 * (size_t)n_ids0;
-                pd.ref_w = d_refw.p;
-                h = timer.begin("phase_graph", 5);
-                d_flags.zero();
-                d_refw.zero();
-                d_aoff.zero();
-                phase_ref(d_uk.p, d_uv.p, nu, cd, pd, asref, use_all, s);
-                phase_expand(d_uk.p, d_uv.p, nu, cd, pd, use_all, id_bits, d_dk.p, d_dw.p, s);
-                {
-                    size_t tb = 0;
-                    cub::DeviceRadixSort::SortPairs(nullptr, tb, d_dk.p, d_dk2.p, d_dw.p, d_dw2.p, (int)n2, 0, 2 * id_bits + 1, s);
-                    if (tb > d_tmp.n) d_tmp.alloc(tb, s);
-                    cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_dk.p, d_dk2.p, d_dw.p, d_dw2.p, (int)n2, 0, 2 * id_bits + 1, s);
-                }
-                phase_csr(d_dk2.p, n2, id_bits, n_ids0, d_aoff.p, d_ato.p, cd.c + C_ABORT, s);
-                timer.end(h);
-            }
+            nu = 1;  // "the pair kernels were enqueued"
+            d_ato.alloc(std::max(n_dir_cap, 1u), s);
+            d_aw.alloc(std::max(n_dir_cap, 1u), s);
+            h = timer.begin("phase_graph", 1);
+            phase_adj_fill(d_acc.p, d_pair_off.p, d_as_pos.p, n_ids0, max_span, cd, pd, use_all, d_aoff.p, d_ato.p, d_aw.p,
+                           n_dir_cap, s);
+            timer.end(h);
+        }
+        // the reduced pair records in (x, y) order (key = x << 32 | y): only the stage seam and the general phasing path
+        // want them
+        auto pair_records = [&](std::vector<uint64_t> &keys, std::vector<long long> &vals, uint32_t nu_exact) {
+            keys.resize(nu_exact);
+            vals.resize(nu_exact);
+            if (!nu_exact) return;
+            DBuf<uint32_t> d_sel;
+            DBuf<uint64_t> d_uk;
+            DBuf<long long> d_uv;
+            d_sel.alloc(nu_exact, s);
+            d_uk.alloc(nu_exact, s);
+            d_uv.alloc(nu_exact, s);
+            geno_edges_select(d_acc.p, n_slots, d_sel.p, nu_exact, cd, sp, s);  // rewrites C_NU with the same value
+            geno_edges_finish(d_sel.p, nu_exact, d_pair_off.p, n_ids0, d_acc.p, d_uk.p, d_uv.p, cd, s);
+            d_uk.download(keys.data(), nu_exact);
+            NP2_CUDA(cudaMemcpyAsync(vals.data(), d_uv.p, (size_t)nu_exact * 8, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaStreamSynchronize(s));
+            d2h += (uint64_t)nu_exact * 16;
+        };
+        if (dump && n_edges) {  // stage seam: the pair weights as they leave K6 (exact mode)
+            fetch_counts();
+            std::vector<long long> v;
+            pair_records(dm_pair_key, v, hc->c[C_NU]);
+            dm_pair_val.assign(v.begin(), v.end());
         }
         const bool was_spec = spec;
         if (spec) {  // the one synchronisation of the speculative stretch
@@ -1508,9 +1506,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         const uint32_t nu_true = hc->c[C_NU];
         if (n_edges && nu && nu_true) {
             const bool asref = opt.model == 0, use_all = opt.use_all_reads != 0;
-            // Directed edges that survive are in front of the sentinels: aoff[n_ids0] of them.  In exact mode that is at
-            // most 2 * nu; after a speculative stretch the arrays are capacity-sized, so fetch the bound first.
-            uint32_t n_dir = 2 * nu_true;
+            const uint32_t n_dir = hc->c[C_NDIR];  // exact: the counts were fetched above
             (void)was_spec;
             // one pinned block: aoff | ato | aw | ref_w | flags
             const size_t o_ato = ((size_t)(n_ids0 + 1) * 4 + 15) & ~(size_t)15, o_aw = o_ato + (((size_t)n_dir * 4 + 15) & ~(size_t)15);
@@ -1519,7 +1515,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             uint8_t *pb = sc->p_phase.p;
             d_aoff.download(reinterpret_cast<uint32_t *>(pb), n_ids0 + 1);
             d_ato.download(reinterpret_cast<uint32_t *>(pb + o_ato), n_dir);
-            d_dw2.download(reinterpret_cast<float *>(pb + o_aw), n_dir);
+            d_aw.download(reinterpret_cast<float *>(pb + o_aw), n_dir);
             d_refw.download(reinterpret_cast<float *>(pb + o_rw), n_ids0);
             d_flags.download(pb + o_fl, (size_t)n_ids0 * 3);
             NP2_CUDA(cudaStreamSynchronize(s));
@@ -1530,12 +1526,9 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
                                    reinterpret_cast<const float *>(pb + o_aw), pb + o_fl, pb + o_fl + n_ids0,
                                    pb + o_fl + 2 * (size_t)n_ids0, reinterpret_cast<const float *>(pb + o_rw), asref, [&]() {
                                        // a community has to be declustered: the general path wants the pair records
-                                       std::vector<uint64_t> ukeys(nu_true);
-                                       std::vector<long long> uvals(nu_true);
-                                       d_uk.download(ukeys.data(), nu_true);
-                                       d_uv.download(uvals.data(), nu_true);
-                                       NP2_CUDA(cudaStreamSynchronize(s));
-                                       d2h += (uint64_t)nu_true * 16;
+                                       std::vector<uint64_t> ukeys;
+                                       std::vector<long long> uvals;
+                                       pair_records(ukeys, uvals, nu_true);
                                        return phase_reads_general(ukeys.data(), uvals.data(), nu_true, asref, use_all);
                                    });
             timer.hend("host:phase_reads");
@@ -2165,7 +2158,7 @@ void np2_job::run(int32_t dump_it) {
     up.put(d_blank.p, h_blank.data(), std::max(n, 1u));
     d_order.alloc(std::max(n, 1u), s);
     if (n) up.put(d_order.p, read_order.data(), n);
-    DBuf<uint32_t> d_as_pos, d_as_te, d_W;
+    DBuf<uint32_t> d_as_te, d_W;
     const uint32_t na = (uint32_t)as_read.size();
     if (opt.iter_count > 1) {  // slot ranges of the pair accumulator: windows + exclusive scan, all on the device
         d_as_pos.alloc(na, s);

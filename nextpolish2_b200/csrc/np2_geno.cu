@@ -765,17 +765,23 @@ void geno_edges_finish(const uint32_t *d_sel, uint32_t cap_nu, const uint64_t *d
     if (cap_nu) NP2_K(k_edges_finish)<<<cdiv(cap_nu, 256), 256, 0, s>>>(d_sel, cd.c, d_pair_off, n_ids, d_acc, d_key, d_val);
 }
 /* ---------------------------------------------------------------- level 0 of the phasing graph (np2_phase.cpp)
- * From the reduced pair records (key = a << 32 | b ascending, a = 0 is the ref read) to what the host Louvain starts
- * from: per-read flags, and the adjacency in CSR form with the `dif <= -3` override applied and the reads that
- * disagree with the ref read removed (main.rs:972-1010). */
-__global__ void k_phase_ref(const uint64_t *__restrict__ key, const long long *__restrict__ val,
-                            const uint32_t *__restrict__ cnt, PhaseDev p, int asref, int use_all) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cnt[C_ABORT] || e >= cnt[C_NU]) return;
-    const uint64_t k = key[e];
-    if (k >> 32) return;
-    const uint32_t b = (uint32_t)k;
-    const long long v = val[e];
+ * From the pair accumulator (slot (a, b), a = 0 is the ref read) to what the host Louvain starts from: per-read flags,
+ * and the adjacency in CSR form with the `dif <= -3` override applied and the reads that disagree with the ref read
+ * removed (main.rs:972-1010). */
+/* Everything is read from the dense accumulator, whose slot order IS the (x, y) order.  A read v has its later partners in its own window (slots pair_off[v] .. pair_off[v + 1]) and its
+ * earlier partners u wherever u's window reaches v; those u start at most max_span before v (reads are in position
+ * order), so they are found by one binary search and a short scan.  Both halves come out in ascending partner order,
+ * which is the order the host Louvain needs, so no sort is involved. */
+__device__ __forceinline__ float pair_weight(long long v) {  // main.rs:972-992: `dif <= -3` override
+    const long long ndif = (v + (1LL << 31)) >> 32;
+    return ndif >= 3 ? -(float)ndif : (float)(v - (ndif << 32));
+}
+__global__ void k_phase_ref_acc(const unsigned long long *__restrict__ acc, const uint64_t *__restrict__ pair_off, uint32_t n,
+                                const uint32_t *__restrict__ cnt, PhaseDev p, int asref, int use_all) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (cnt[C_ABORT] || b >= n) return;
+    const long long v = (long long)acc[pair_off[0] + b - 1];  // the ref read's window holds every read
+    if (!v) return;
     const long long ndif = (v + (1LL << 31)) >> 32;
     if (asref) {
         p.ref_w[b] = (float)(v - (ndif << 32));
@@ -783,60 +789,120 @@ __global__ void k_phase_ref(const uint64_t *__restrict__ key, const long long *_
     }
     if (ndif > 0 && !use_all) p.bad_v[b] = 1;
 }
-__global__ void k_phase_expand(const uint64_t *__restrict__ key, const long long *__restrict__ val,
-                               const uint32_t *__restrict__ cnt, uint32_t cap_nu, PhaseDev p, int use_all, uint32_t id_bits,
-                               uint64_t *__restrict__ dkey, float *__restrict__ dw) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cnt[C_ABORT] || e >= cap_nu) return;
-    const bool real = e < cnt[C_NU];  // the tail up to the capacity is filled with sentinels
-    const uint64_t k = real ? key[e] : 0;
-    const uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k;
-    uint64_t k0 = ~0ULL, k1 = ~0ULL;  // sentinel: sorts behind every edge
-    float w = 0.f;
-    if (real && a != 0) {
-        const bool ba = !use_all && p.bad_v[a], bb = !use_all && p.bad_v[b];
-        if (!ba) p.has[a] = 1;
-        if (!bb) p.has[b] = 1;
-        if (!ba && !bb) {
-            const long long v = val[e];
-            const long long ndif = (v + (1LL << 31)) >> 32;
-            w = ndif >= 3 ? -(float)ndif : (float)(v - (ndif << 32));
-            k0 = (uint64_t)a << id_bits | b;
-            k1 = (uint64_t)b << id_bits | a;
+template <bool FILL>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_phase_adj(const unsigned long long *__restrict__ acc,
+                                                                 const uint64_t *__restrict__ pair_off,
+                                                                 const uint32_t *__restrict__ as_pos, uint32_t n,
+                                                                 uint32_t max_span, uint32_t *__restrict__ cnt, PhaseDev p,
+                                                                 int use_all, uint32_t *__restrict__ deg,
+                                                                 const uint32_t *__restrict__ aoff,
+                                                                 uint32_t *__restrict__ ato, float *__restrict__ aw,
+                                                                 uint32_t cap_dir) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cnt[C_ABORT] || v >= n) return;
+    const uint64_t s0 = pair_off[v], s1 = pair_off[v + 1];
+    if (v == 0) {  // the ref read is no vertex; its non-zero slots only count as pair records
+        if (!FILL) {
+            uint32_t nz = 0;
+            for (uint64_t sl = s0 + lane; sl < s1; sl += 32) nz += acc[sl] != 0;
+            for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, d);
+            if (lane == 0) {
+                if (nz) atomicAdd(cnt + C_NU, nz);
+                deg[0] = 0;
+                deg[n] = 0;
+            }
+        }
+        return;
+    }
+    const bool bad_self = !use_all && p.bad_v[v];
+    uint32_t w_out = FILL ? aoff[v] : 0, n_edge = 0, nz_fwd = 0;
+    bool any = false;
+    // earlier partners: u in [lo, v) with as_pos[u] + max_span >= as_pos[v] (u >= 1)
+    const uint32_t pv = as_pos[v], want = pv > max_span ? pv - max_span : 0;
+    uint32_t lo = 1, hi = v;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (as_pos[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    for (uint32_t u0 = lo; u0 < v; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        unsigned long long val = 0;
+        if (u < v) {
+            const uint64_t sl = pair_off[u] + (v - u - 1);
+            if (sl < pair_off[u + 1]) val = acc[sl];
+        }
+        const bool edge = val != 0 && !bad_self && !(!use_all && p.bad_v[u]);
+        any |= val != 0;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, edge);
+        if (FILL && edge) {
+            const uint32_t at = w_out + __popc(bal & ((1u << lane) - 1));
+            if (at < cap_dir) {
+                ato[at] = u;
+                aw[at] = pair_weight((long long)val);
+            }
+        }
+        w_out += __popc(bal);
+        n_edge += __popc(bal);
+    }
+    // later partners: v's own window, y = v + 1 + (slot - s0)
+    for (uint64_t b0 = s0; b0 < s1; b0 += 32) {
+        const uint64_t sl = b0 + lane;
+        const unsigned long long val = sl < s1 ? acc[sl] : 0;
+        const uint32_t y = v + 1 + (uint32_t)(sl - s0);
+        const bool edge = val != 0 && !bad_self && !(!use_all && p.bad_v[y < n ? y : v]);
+        any |= val != 0;
+        nz_fwd += val != 0;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, edge);
+        if (FILL && edge) {
+            const uint32_t at = w_out + __popc(bal & ((1u << lane) - 1));
+            if (at < cap_dir) {
+                ato[at] = y;
+                aw[at] = pair_weight((long long)val);
+            }
+        }
+        w_out += __popc(bal);
+        n_edge += __popc(bal);
+    }
+    if (!FILL) {
+        any = __any_sync(0xFFFFFFFFu, any);
+        for (int d = 16; d > 0; d >>= 1) nz_fwd += __shfl_xor_sync(0xFFFFFFFFu, nz_fwd, d);
+        if (lane == 0) {
+            deg[v] = n_edge;
+            if (any && !bad_self) p.has[v] = 1;
+            if (nz_fwd) atomicAdd(cnt + C_NU, nz_fwd);
         }
     }
-    dkey[2 * (size_t)e] = k0;
-    dkey[2 * (size_t)e + 1] = k1;
-    dw[2 * (size_t)e] = w;
-    dw[2 * (size_t)e + 1] = w;
 }
-// sorted directed edges -> CSR: aoff[v] = first edge whose source is >= v (aoff has n + 1 entries, zeroed before)
-__global__ void k_phase_csr(const uint64_t *__restrict__ dkey, uint32_t n2, uint32_t id_bits, uint32_t n,
-                            uint32_t *__restrict__ aoff, uint32_t *__restrict__ ato, const uint32_t *__restrict__ d_abort) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (*d_abort || i >= n2) return;
-    auto src_of = [&](uint64_t k) { return (k >> (2 * id_bits)) ? n : (uint32_t)(k >> id_bits); };
-    const uint64_t k = dkey[i];
-    const uint32_t s = src_of(k);
-    if (s < n) ato[i] = (uint32_t)(k & ((1ULL << id_bits) - 1));
-    const uint32_t sp = i ? src_of(dkey[i - 1]) : 0;
-    for (uint32_t v = i ? sp + 1 : 0; v <= s && v <= n; v++) aoff[v] = i;
-    if (i == n2 - 1 && s < n)
-        for (uint32_t v = s + 1; v <= n; v++) aoff[v] = n2;
+void phase_ref_acc(const unsigned long long *d_acc, const uint64_t *d_pair_off, uint32_t n, CountsDev cd, PhaseDev p,
+                   bool asref, bool use_all, cudaStream_t s) {
+    if (n > 1) NP2_K(k_phase_ref_acc)<<<cdiv(n - 1, 256), 256, 0, s>>>(d_acc, d_pair_off, n, cd.c, p, asref, use_all);
 }
-void phase_ref(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool asref,
-               bool use_all, cudaStream_t s) {
-    if (cap_nu) NP2_K(k_phase_ref)<<<cdiv(cap_nu, 256), 256, 0, s>>>(d_key, d_val, cd.c, p, asref, use_all);
+void phase_adj_count(const unsigned long long *d_acc, const uint64_t *d_pair_off, const uint32_t *d_as_pos, uint32_t n,
+                     uint32_t max_span, CountsDev cd, PhaseDev p, bool use_all, uint32_t *d_deg, cudaStream_t s) {
+    if (n)
+        NP2_K(k_phase_adj<false>)<<<cdiv((uint64_t)n * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(
+            d_acc, d_pair_off, d_as_pos, n, max_span, cd.c, p, use_all, d_deg, nullptr, nullptr, nullptr, 0);
 }
-void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool use_all,
-                  uint32_t id_bits, uint64_t *d_dkey, float *d_dw, cudaStream_t s) {
-    if (cap_nu) NP2_K(k_phase_expand)<<<cdiv(cap_nu, 256), 256, 0, s>>>(d_key, d_val, cd.c, cap_nu, p, use_all, id_bits, d_dkey, d_dw);
+void phase_adj_offsets(const uint32_t *d_deg, uint32_t *d_aoff, uint32_t n, uint32_t cap_dir, CountsDev cd, ScanPool &pool,
+                       cudaStream_t s) {
+    ScanOffsets<uint32_t, uint32_t> f;
+    f.in = d_deg;
+    f.out = d_aoff;
+    f.c_slot = cd.c + C_NDIR;
+    f.q_slot = nullptr;
+    f.cap = cap_dir;
+    f.abort = cd.c + C_ABORT;
+    scan_launch(f, nullptr, 0, n, pool, s, cd.c + C_ABORT);
 }
-void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n, uint32_t *d_aoff, uint32_t *d_ato,
-               const uint32_t *d_abort, cudaStream_t s) {
-    if (n2) NP2_K(k_phase_csr)<<<cdiv(n2, 256), 256, 0, s>>>(d_dkey, n2, id_bits, n, d_aoff, d_ato, d_abort);
+void phase_adj_fill(const unsigned long long *d_acc, const uint64_t *d_pair_off, const uint32_t *d_as_pos, uint32_t n,
+                    uint32_t max_span, CountsDev cd, PhaseDev p, bool use_all, const uint32_t *d_aoff, uint32_t *d_ato,
+                    float *d_aw, uint32_t cap_dir, cudaStream_t s) {
+    if (n)
+        NP2_K(k_phase_adj<true>)<<<cdiv((uint64_t)n * 32, 32 * kWarpsPerCta), 32 * kWarpsPerCta, 0, s>>>(
+            d_acc, d_pair_off, d_as_pos, n, max_span, cd.c, p, use_all, nullptr, d_aoff, d_ato, d_aw, cap_dir);
 }
-
 void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, bool have_rep, cudaStream_t s) {
     if (cap_reg)
         NP2_K(k_region_seed)<<<region_grid(cap_reg), 32 * kWarpsPerCta, 0, s>>>(g, max_indel_len, cd.c + C_GERR, have_rep ? 1 : 0);

@@ -30,6 +30,7 @@ enum Cnt : int {
     C_PERR,       // read pair outside its index window
     C_NENT,       // survivors of the RECH regions
     C_NLONGRUN,   // runs whose DP is done by a whole warp (k_dp_runs_long)
+    C_NDIR,       // directed edges of the level-0 phasing graph (entries of its CSR adjacency)
     C_COUNT = 32
 };
 enum Cnt64 : int {
@@ -224,13 +225,21 @@ struct PhaseDev {  // per read order (< n)
     uint8_t *has = nullptr, *bad_v = nullptr, *in_ref = nullptr;
     float *ref_w = nullptr;
 };
-void phase_ref(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool asref,
-               bool use_all, cudaStream_t s);
-// directed edges (2 per pair record; non-edges and the tail up to 2 * cap_nu get a sentinel that sorts behind)
-void phase_expand(const uint64_t *d_key, const long long *d_val, uint32_t cap_nu, CountsDev cd, PhaseDev p, bool use_all,
-                  uint32_t id_bits, uint64_t *d_dkey, float *d_dw, cudaStream_t s);
-void phase_csr(const uint64_t *d_dkey, uint32_t n2, uint32_t id_bits, uint32_t n, uint32_t *d_aoff, uint32_t *d_ato,
-               const uint32_t *d_abort, cudaStream_t s);
+// Level 0 of the phasing graph straight from the dense pair accumulator (no pair list, no sort): ref flags from the
+// slots (0, b); then, a warp per read v, its neighbours in ascending order — the earlier reads u whose window reaches v
+// (slot pair_off[u] + v - u - 1), then v's own window.  phase_adj_count writes the degrees (d_deg[n + 1]), has[] and
+// C_NU (non-zero slots); the caller scans the degrees into d_aoff (total -> C_NDIR) and phase_adj_fill writes
+// d_ato / d_aw.  d_as_pos: record position of every alignseq (ascending from index 1), max_span: longest reference span.
+void phase_ref_acc(const unsigned long long *d_acc, const uint64_t *d_pair_off, uint32_t n, CountsDev cd, PhaseDev p,
+                   bool asref, bool use_all, cudaStream_t s);
+void phase_adj_count(const unsigned long long *d_acc, const uint64_t *d_pair_off, const uint32_t *d_as_pos, uint32_t n,
+                     uint32_t max_span, CountsDev cd, PhaseDev p, bool use_all, uint32_t *d_deg, cudaStream_t s);
+void phase_adj_offsets(const uint32_t *d_deg, uint32_t *d_aoff, uint32_t n, uint32_t cap_dir, CountsDev cd, ScanPool &pool,
+                       cudaStream_t s);
+void phase_adj_fill(const unsigned long long *d_acc, const uint64_t *d_pair_off, const uint32_t *d_as_pos, uint32_t n,
+                    uint32_t max_span, CountsDev cd, PhaseDev p, bool use_all, const uint32_t *d_aoff, uint32_t *d_ato,
+                    float *d_aw, uint32_t cap_dir, cudaStream_t s);
+
 // have_rep: k_region_hete already ran on the same candidates of this pass (c_rep is valid)
 void geno_region_seed(GenoDev g, int32_t max_indel_len, uint32_t cap_reg, CountsDev cd, bool have_rep, cudaStream_t s);
 
