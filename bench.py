@@ -514,6 +514,12 @@ def _run_ours(args):
     m.dev_time, m.e2e_time, m.wall, m.e2e_serial_time = [float(x) for x in t_dev.tolist()]
 
     ver = None
+    if args.no_verify and not cfg["het"]:
+        # size-independent property instead of the oracle run: polishing a haploid contig's reads gives back the haplotype
+        # the reads were drawn from, byte for byte (tests/test_oracle_polish.py holds the oracle to the same property)
+        ver = {"oracle": "skipped (--no-verify)", "contigs_checked": len(contigs),
+               "identical_to_truth_haplotype": bool(all(bytes(r.split(b"\n", 2)[1]) == bytes(c["hap1"])
+                                                        for r, c in zip(m.records, contigs)))}
     if not args.no_verify:
         ver = verify(contigs, tabs, cfg, m.records, m.dropped, opts_kw, cores)
         if world > 1:  # every rank checked its own contigs
@@ -560,7 +566,7 @@ def _run_ours(args):
             "stages_ms": s["stages_ms"],
             "sizes": s["sizes"],
             "verify": ver,
-            "identical_to_oracle": None if ver is None else ver["identical"],
+            "identical_to_oracle": None if ver is None else ver.get("identical"),
             "wall_ms_per_step": round(m.wall / args.steps * 1e3, 3),
         }
     del m

@@ -641,6 +641,7 @@ int main(int argc, char **argv) {
         BamFile bf;
         bf.threads = cli.threads > 0 ? cli.threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         np2_set_host_threads((uint32_t)bf.threads);
+        np2_set_stage_timing(timing ? 1 : 0);  // the per-stage event timers only serve NP2_CLI_TIMING
         open_bam(cli.bam, bf);
         int n_gpu = cli.gpus;
         if (n_gpu <= 0) {
