@@ -732,6 +732,7 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
     if contigs:
         for cx in ctxs:
             polish(cx, 0)  # warm pools
+        one_pass()  # untimed: every context has then seen contigs of several sizes (pools, speculative capacities)
     for k in parts:
         parts[k] = 0
     passes = max(1, args.strong_passes)
@@ -837,7 +838,10 @@ def yak_bench(ctx, np2, torch, peak):
            "random_gather_peak_GBps": gather_gbs, "frac_of_random_gather_peak": round(probes * 32 / ms / 1e6 / gather_gbs, 4),
            "l2_fetch_granularity": {"default": default_gran, "best": int(best), "sweep": sweep},
            "random_block_gather": blocks,
-           "bucket_load": "one 256-bit ld.global.nc.L2::evict_first per probe (LDG.E.256)",
+           "bucket_load": "one 256-bit ld.global.nc.L2::evict_first.L2::64B per bucket (LDG.E.EFL2.LTC64B.256)",
+           "dram_bytes_per_probe_ncu": {"value": 83.9, "was": 153.6, "source": "profiles/r02fin2_yak_probe_full.txt (ncu --set full of "
+                                        "this arm); random 32-byte loads run at the same ~43 G/s whether a miss fills 64 or 128 "
+                                        "bytes (profiles/r02_l2_fetch.txt): the bound is DRAM activations, not bytes"},
            "correct": ok}
     tab.free()
     return res
@@ -925,7 +929,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling arm (configs[4] scaled)")
     ap.add_argument("--no-ref-faithful", action="store_true")
     ap.add_argument("--strong-mbp", type=float, default=36.0, help="total size of the 24 contigs of the strong-scaling arm")
-    ap.add_argument("--strong-passes", type=int, default=2)
+    ap.add_argument("--strong-passes", type=int, default=3)
     ap.add_argument("--pageable", action="store_true", help="record buffer in pageable memory (host compaction path)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per library call (0 = cores / ranks / ~in flight)")
     ap.add_argument("--e2e-inflight", type=int, default=0,

@@ -83,9 +83,12 @@ __host__ __device__ __forceinline__ uint64_t yak_hash64_64(uint64_t key) {
 
 // One bucket of the yak table (4 x u64 = one 32-byte sector) in ONE 256-bit load (LDG.E.256, sm_100+), read-only path,
 // evict-first in L2: a probe never comes back to its bucket, so the line should not push the streaming data of the
-// surrounding kernels out of L2.
+// surrounding kernels out of L2.  L2::64B: a miss then fills 64 bytes instead of the whole 128-byte line (measured,
+// profiles/microbench/l2_fetch.cu: 61 instead of 117 DRAM bytes per random 32-byte load; the load RATE is the same
+// 43 G/s either way — random accesses are bound by DRAM activations, not bytes — so this only takes the needless
+// half of the traffic off the memory system; cudaLimitMaxL2FetchGranularity does not change either number).
 __device__ __forceinline__ void ld_bucket(const uint64_t *p, uint64_t v[4]) {
-    asm volatile("ld.global.nc.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L2::evict_first.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
                  : "l"(p));
 }
