@@ -335,6 +335,7 @@ constexpr int kHintSlots = 4;
 // sizes of the last pass of one kind (slot = iteration the pass started at): the capacities of the next one
 struct Hints {
     bool valid = false;
+    bool in_pass = false;  // the pass under way has already written its counts here (later fetches of the pass merge)
     uint32_t L = 0;
     uint64_t cols = 0;
     CountsHost h = CountsHost();
@@ -939,6 +940,7 @@ uint32_t np2_job::iteration(uint32_t iter0) {
         const char *e = getenv("NP2_SPECULATE");
         return !e || atoi(e) != 0;
     }();
+    hint.in_pass = false;
     if (enabled && dump_iter < 0 && hint.valid) {
         // scale the remembered counts to this contig; 25 % + 1024 of slack
         const double sc_l = hint.L ? (double)L / hint.L : 1.0, sc_c = hint.cols ? (double)ing.total_cols / hint.cols : 1.0;
@@ -1079,7 +1081,9 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     const uint32_t N = cnt_get(C_N);
     d_events.alloc(std::max(N, 1u), s);
     h = timer.begin("consensus_emit", 1);
-    events_select(d_cflags.p, N, d_events.p, std::max(N, 1u), cd, sp, s);
+    // speculative mode: the event arrays below are sized from the remembered count, so THAT is the capacity the select
+    // has to defend (more events than it => abort => the pass is repeated in exact mode), not the size of d_events
+    events_select(d_cflags.p, N, d_events.p, spec ? std::min(std::max(N, 1u), caps.c[C_NEV]) : std::max(N, 1u), cd, sp, s);
     timer.end(h);
     const uint32_t n_ev = cnt_get(C_NEV);
     auto check_total = [&]() {
@@ -1118,7 +1122,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
     rd.c_t = d_c_t.p;
     h = timer.begin("regions", 2);
     regions_event_close(rd, n_ev, s);
-    regions_cand_select(rd, n_ev, std::max(n_ev, 1u), cd, sp, s);
+    regions_cand_select(rd, n_ev, spec ? std::min(std::max(n_ev, 1u), caps.c[C_NCAND]) : std::max(n_ev, 1u), cd, sp, s);
     timer.end(h);
     const uint32_t n_cand = cnt_get(C_NCAND);
     d_c_start.alloc(std::max(n_cand, 1u), s);
@@ -1227,6 +1231,13 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         res_N = hc->c[C_N];
     };
     auto remember = [&]() {
+        // the counts of THIS pass (its fetches only ever add information), not the largest ever seen: a context that
+        // polishes contigs of shrinking size would otherwise keep the capacities of its largest one, scaled only by the
+        // length ratio to the previous contig, and do several times the work on the small ones
+        if (!hint.in_pass) {
+            hint.h = CountsHost();
+            hint.in_pass = true;
+        }
         hint.valid = true;
         hint.L = L;
         hint.cols = ing.total_cols;

@@ -245,3 +245,37 @@ def test_warp_cooperative_dp_matches_oracle():
     env = dict(os.environ, NP2_DP_LONG_WORK="0")
     r = subprocess.run([sys.executable, "-c", _LONG_DP_CHILD % {"root": root}], env=env, capture_output=True, text=True, timeout=550)
     assert r.returncode == 0 and "LONG-DP-OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+def test_speculative_capacities_across_unlike_contigs(ctx):
+    """A context sizes the buffers of a pass from the LAST pass of the same kind, scaled by the contig length.  Contigs
+    that are nothing like their predecessor (haploid -> diploid with ten times the events per base, long -> short,
+    three iterations -> one) make those capacities wrong in both directions: every one of them has to be caught on the
+    device (the pass is then repeated with exact sizes), never to end in a wrong consensus.  One context, resident
+    hints, every result against the oracle."""
+    import nextpolish2_b200 as np2
+    seq = [("tiny20k", {}), ("dip600k", {"iter_count": 1}), ("tiny20k", {"iter_count": 1}), ("dip600k", {}),
+           ("clip120k", {"iter_count": 2}), ("deep80k", {}), ("hap300k", {}), ("dip600k", {"iter_count": 2}), ("tiny20k", {})]
+    own = np2.Context(0)  # fresh hints: the order above is the whole history
+    repeated = 0
+    oracle_cache = {}
+    for name, optkw in seq:
+        ds = common.dataset(name)
+        oo, go = common.same_opts(**optkw)
+        key = (name, tuple(sorted(optkw.items())))
+        if key not in oracle_cache:
+            oj = O.Job(ds["contig"], ds["bam"], common.oracle_tables(ds), oo, dump_iter=-1)
+            oracle_cache[key] = oj.consensus() + (np.sort(oj.dropped()),)
+        opos, obase, odrop = oracle_cache[key]
+        tabs = common.gpu_tables(own, ds)
+        job = np2.Job(own, ds["contig"], ds["bam"], tabs, go).upload().run(-1)
+        gpos, gbase = job.consensus()
+        common.assert_same("%s %r consensus.base" % (name, optkw), obase, gbase)
+        common.assert_same("%s %r consensus.pos" % (name, optkw), opos, gpos)
+        common.assert_same("%s %r dropped" % (name, optkw), odrop, np.sort(job.dropped()))
+        repeated += job.stats()["repeated_passes"]
+        job.destroy()
+        for t in tabs:
+            t.free()
+    own.close()
+    assert repeated > 0, "no pass was ever repeated: the sequence does not exercise a capacity overflow"
