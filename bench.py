@@ -660,7 +660,10 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
         contigs.append({"idx": i, "name": "ctg%03d" % i, "contig": A, "hap1": c["hap1"], "hap2": c["hap2"], "bam": c["bam"]})
     pinned = [(torch.from_numpy(c["contig"].copy()).pin_memory(), torch.from_numpy(c["bam"]).pin_memory()) for c in contigs]
     t_synth = time.time() - t0
-    inflight = max(1, min(args.e2e_inflight, len(contigs)))
+    # small contigs are latency bound (a run is ~9 round trips and ~250 short kernels whatever the size): more workers
+    # than the 3 that saturate the link with 10 Mbp contigs keep the GPU busier, as far as the rank's cores allow
+    small = contigs and sum(len(c["contig"]) for c in contigs) / len(contigs) < 5e6
+    inflight = max(1, min(max(args.e2e_inflight, min(6, cores // 2)) if small else args.e2e_inflight, len(contigs)))
     depth = 2 if (args.e2e_prefetch and len(contigs) > inflight) else 1  # see measure(): next contig parsed + uploading
     ctxs = [ctx] + [np2.Context(local) for _ in range(inflight * depth - 1)]
 
@@ -678,7 +681,7 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
         j.run(-1)
         t2 = time.perf_counter()
         first, last, base = j.bases(copy=False)
-        rec = fasta_record(contigs[ci]["name"], first, last, base)
+        rec = fasta_record(contigs[ci]["name"], first, last, base)  # header + a copy of the bases, in host memory
         nd = len(j.dropped())
         st = j.stats()
         j.destroy()
