@@ -163,8 +163,8 @@ uint64_t np2_secmap_size(const np2_secmap *m, uint64_t *n_seqs); /* #secondary n
 /* ---- page-locked host buffers ----
  * Record buffers handed to np2_polish_contig / np2_job_create may live in any host memory.  When they are
  * page-locked (from np2_host_alloc, cudaHostAlloc, cudaHostRegister, torch pin_memory ...) the device gathers the
- * SEQ fields straight out of them over PCIe and QUAL / names / tags never cross the bus; pageable buffers are
- * compacted by host threads into a pinned ring first.  Same results either way. */
+ * CIGAR words + SEQ field of every kept record straight out of them over PCIe and QUAL / names / tags never cross the
+ * bus; pageable buffers are compacted by host threads into a pinned ring first.  Same results either way. */
 int np2_host_alloc(uint64_t bytes, void **out);
 void np2_host_free(void *p);
 
@@ -176,8 +176,10 @@ void np2_host_free(void *p);
 int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
                       np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out);
 
-/* staged form: create parses + filters the records on the host (main.rs:1758-1771), upload puts the inputs
- * into HBM, run executes the device pipeline + host phases from resident inputs. */
+/* staged form: create parses + filters the records on the host (main.rs:1758-1771) and ENQUEUES the upload of the
+ * inputs (it returns while the transfer runs); upload waits until they are in HBM; run executes the device pipeline +
+ * host phases from resident inputs.  A caller that keeps two contexts per worker thread can therefore create the job of
+ * its next contig before it runs the current one: the link and the GPU are then busy at the same time. */
 int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
                    np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out);
 int np2_job_upload(np2_job *job);
