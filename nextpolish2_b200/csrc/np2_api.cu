@@ -2143,6 +2143,23 @@ void np2_job::run(int32_t dump_it) {
     d_blk_odd.alloc(((size_t)ing.ck_off.back() + 255) / 256 * 8 + 8, s);
     const bool flags_done = pack_columns(R, d_ref.p, ing.ck_off.back(), d_refpk.p, d_blk_odd.p, s);
     timer.end(h);
+    // The per-stripe block lists only need the trim and the packed columns: enqueued here, they run while the host waits
+    // for the trim results and decides which reads are kept.
+    max_span = 0;
+    for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
+    const uint32_t n_stripes = pileup_stripes(L);
+    d_first_ge.alloc(n_stripes + 1, s);
+    stripe_reads(R, L, d_first_ge.p, s);
+    h = timer.begin("block_flags", 4);
+    if (!flags_done) block_flags(R, ing.ck_off.back(), d_code.p, d_refpk.p, d_blk_odd.p, s);
+    // per stripe: which of its blocks K2 has to walk (a property of the reads and the contig, like the flags)
+    DBuf<uint32_t> d_odd_cnt;
+    d_odd_cnt.alloc(n_stripes, s);
+    d_odd_off.alloc(n_stripes + 1, s);
+    stripe_odd_count(R, d_blk_odd.p, d_first_ge.p, L, max_span, d_odd_cnt.p, s);
+    stripe_odd_offsets(d_odd_cnt.p, d_odd_off.p, L, nullptr, sc->scan_pool, s);
+    timer.end(h);
+    NP2_CUDA(cudaMemcpyAsync(&hc->c[0], d_odd_off.p + n_stripes, 4, cudaMemcpyDeviceToHost, s));
     {
         cudaStream_t c2 = ctx->copy_stream;
         NP2_CUDA(cudaStreamWaitEvent(c2, sc->ev_trim, 0));
@@ -2182,21 +2199,6 @@ void np2_job::run(int32_t dump_it) {
         geno_pair_window_offsets(d_W.p, d_pair_off.p, na, sc->scan_pool, s);
         NP2_CUDA(cudaMemcpyAsync(&hc->q[0], d_pair_off.p + na, 8, cudaMemcpyDeviceToHost, s));
     }
-    max_span = 0;
-    for (uint32_t v : ing.rspan) max_span = std::max(max_span, v);
-    const uint32_t n_stripes = pileup_stripes(L);
-    d_first_ge.alloc(n_stripes + 1, s);
-    stripe_reads(R, L, d_first_ge.p, s);
-    h = timer.begin("block_flags", 4);
-    if (!flags_done) block_flags(R, ing.ck_off.back(), d_code.p, d_refpk.p, d_blk_odd.p, s);
-    // per stripe: which of its blocks K2 has to walk (a property of the reads and the contig, like the flags)
-    DBuf<uint32_t> d_odd_cnt;
-    d_odd_cnt.alloc(n_stripes, s);
-    d_odd_off.alloc(n_stripes + 1, s);
-    stripe_odd_count(R, d_blk_odd.p, d_first_ge.p, L, max_span, d_odd_cnt.p, s);
-    stripe_odd_offsets(d_odd_cnt.p, d_odd_off.p, L, nullptr, sc->scan_pool, s);
-    timer.end(h);
-    NP2_CUDA(cudaMemcpyAsync(&hc->c[0], d_odd_off.p + n_stripes, 4, cudaMemcpyDeviceToHost, s));
     timer.hbegin();
     NP2_CUDA(cudaStreamSynchronize(s));
     timer.hend("host:stripe_list_sync");
