@@ -168,6 +168,20 @@ uint64_t np2_secmap_size(const np2_secmap *m, uint64_t *n_seqs); /* #secondary n
 int np2_host_alloc(uint64_t bytes, void **out);
 void np2_host_free(void *p);
 
+/* ---- BGZF inflate on the device: the decode layer under the reference's bam::IndexedReader::fetch + records()
+ * (src/main.rs:1745-1757; rust-htslib -> htslib bgzf_read_block -> zlib inflate of every <= 64 KiB member) ----
+ * comp/comp_len: host buffer holding the compressed members (e.g. the memory-mapped BAM file; pageable or page-locked).
+ * Member i's raw DEFLATE payload is comp[payload_off[i] .. + payload_len[i]) (the bytes between the BGZF header and the
+ * CRC32/ISIZE trailer) and inflates to isize[i] bytes (the trailer's ISIZE, <= 65536).  The members are inflated back to
+ * back in the order given, one warp per member, and bytes [skip, skip + out_len) of that concatenation are written to
+ * `out` (host; page-locked memory from np2_host_alloc makes the copy a DMA) — a contig's records usually start and end
+ * inside a member.  Only the bytes between the first and the last payload cross the link, compressed.  CRC32 is not
+ * checked (neither does the inflate call of the host path); a member that is no valid DEFLATE stream of exactly its
+ * ISIZE gives NP2_ERR_FORMAT.  *kernel_ms (optional): device time of the inflate kernel from CUDA events. */
+int np2_bgzf_inflate(np2_ctx *ctx, const uint8_t *comp, uint64_t comp_len, const uint64_t *payload_off,
+                     const uint32_t *payload_len, const uint32_t *isize, uint32_t n_members, uint64_t skip, uint64_t out_len,
+                     uint8_t *out, float *kernel_ms);
+
 /* ---- per-contig polish ----
  * tseq/tlen : contig sequence (raw FASTA bytes, case preserved)
  * bam       : this contig's BAM alignment records, concatenated in file order, each with its block_size prefix

@@ -5,6 +5,6 @@ libnp2gpu.so (hand-written CUDA kernels + C++ host phases).  There is no CPU fal
 loudly when the library is missing and every call fails when no CUDA device is present.
 """
 from .api import (Context, Table, Job, Opts, Np2Error, PinnedBuffer, SecondarySeqs, Counter, polish_contig, format_fasta, lib_path,
-                  load_library)  # noqa: F401
+                  load_library, bgzf_members, bgzf_inflate)  # noqa: F401
 
-__all__ = ["Context", "Table", "Job", "Opts", "Np2Error", "PinnedBuffer", "SecondarySeqs", "Counter", "polish_contig", "format_fasta", "lib_path", "load_library"]
+__all__ = ["Context", "Table", "Job", "Opts", "Np2Error", "PinnedBuffer", "SecondarySeqs", "Counter", "polish_contig", "format_fasta", "lib_path", "load_library", "bgzf_members", "bgzf_inflate"]

@@ -7,7 +7,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnp2gpu.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-diag-suppress", "177", "-Xcompiler", "-Wno-deprecated-declarations", "-shared"]
-SOURCES = ["np2_kernels.cu", "np2_geno.cu", "np2_regions.cu", "np2_count.cu", "np2_api.cu", "np2_host.cpp", "np2_secondary.cpp", "np2_phase.cpp"]
+SOURCES = ["np2_kernels.cu", "np2_geno.cu", "np2_regions.cu", "np2_count.cu", "np2_inflate.cu", "np2_api.cu", "np2_host.cpp", "np2_secondary.cpp", "np2_phase.cpp"]
 
 
 def _stale(target, deps):

@@ -48,6 +48,7 @@ EXPORTS = [
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
     "np2_debug_phase", "np2_set_host_threads", "np2_set_stage_timing",
+    "np2_bgzf_inflate",
     "np2_device_count", "np2_count_create", "np2_count_add", "np2_count_distinct", "np2_count_finish", "np2_count_destroy",
 ]
 
@@ -89,6 +90,7 @@ def load_library():
     L.np2_job_create.argtypes = [vp, vp, u32, vp, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_job_upload.argtypes = [vp]
     L.np2_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.np2_bgzf_inflate.argtypes = [vp, vp, u64, vp, vp, vp, u32, u64, u64, vp, C.POINTER(C.c_float)]
     L.np2_host_free.argtypes = [vp]
     L.np2_job_ingest_path.argtypes = [vp]
     L.np2_debug_parse.argtypes = [vp, u64, u32, vp, u32, vp]
@@ -186,6 +188,52 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def bgzf_members(buf):
+    """Walks the BGZF member headers of a byte buffer (SAM spec 4.1): -> (payload_off u64[], payload_len u32[],
+    isize u32[]) of the raw DEFLATE payloads, in file order.  Host only."""
+    b = np.ascontiguousarray(buf, np.uint8)
+    off, ln, isz = [], [], []
+    o, n = 0, len(b)
+    while o < n:
+        if o + 18 > n or b[o] != 31 or b[o + 1] != 139 or b[o + 2] != 8 or not (b[o + 3] & 4):
+            raise ValueError("not a BGZF member at byte %d" % o)
+        xlen = int(b[o + 10]) | int(b[o + 11]) << 8
+        x, end, bsize = o + 12, o + 12 + xlen, None
+        while x + 4 <= end:
+            slen = int(b[x + 2]) | int(b[x + 3]) << 8
+            if b[x] == 66 and b[x + 1] == 67 and slen == 2:
+                bsize = int(b[x + 4]) | int(b[x + 5]) << 8
+            x += 4 + slen
+        if bsize is None or o + bsize + 1 > n or bsize + 1 < 12 + xlen + 8:
+            raise ValueError("bad BGZF member at byte %d" % o)
+        total = bsize + 1
+        off.append(o + 12 + xlen)
+        ln.append(total - 12 - xlen - 8)
+        isz.append(int(b[o + total - 4]) | int(b[o + total - 3]) << 8 | int(b[o + total - 2]) << 16 | int(b[o + total - 1]) << 24)
+        o += total
+    return np.array(off, np.uint64), np.array(ln, np.uint32), np.array(isz, np.uint32)
+
+
+def bgzf_inflate(ctx, comp, payload_off, payload_len, isize, skip=0, out_len=None, out=None):
+    """np2_bgzf_inflate: the members inflated on the device, bytes [skip, skip + out_len) of their concatenation.
+    comp: np.uint8 array or PinnedBuffer; out: optional PinnedBuffer / np.uint8 array to receive the bytes.
+    -> (np.uint8 array, kernel milliseconds)"""
+    carr = comp.array if isinstance(comp, PinnedBuffer) else np.ascontiguousarray(comp, np.uint8)
+    po = np.ascontiguousarray(payload_off, np.uint64)
+    pl = np.ascontiguousarray(payload_len, np.uint32)
+    iz = np.ascontiguousarray(isize, np.uint32)
+    total = int(iz.astype(np.uint64).sum())
+    if out_len is None:
+        out_len = total - skip
+    if out is None:
+        out = np.empty(max(out_len, 1), np.uint8)
+    oarr = out.array if isinstance(out, PinnedBuffer) else out
+    ms = C.c_float(0)
+    _check(load_library().np2_bgzf_inflate(ctx.h, carr.ctypes.data, len(carr), po.ctypes.data, pl.ctypes.data, iz.ctypes.data,
+                                           len(po), skip, out_len, oarr.ctypes.data, C.byref(ms)))
+    return oarr[:out_len], ms.value
 
 
 def debug_phase(keys, vals, model=0, use_all_reads=False, with_path=False):

@@ -17,6 +17,7 @@
 
 #include "../../include/np2gpu.h"
 #include "np2_host.h"
+#include "np2_inflate.cuh"
 #include "np2_kernels.cuh"
 
 using namespace np2;
@@ -418,6 +419,7 @@ struct np2_ctx {
     uint64_t pool_warm = 0;  // bytes the pool has been grown to in one step (np2_job_create)
     int refs = 1;  // tables and jobs keep their context alive (np2_ctx_destroy only drops the caller's reference)
     std::vector<JobScratch *> scratch_pool;
+    PBuf<uint8_t> p_infl_in, p_infl_args;  // np2_bgzf_inflate: staged compressed bytes, member table
     JobScratch *take_scratch() {
         if (scratch_pool.empty()) return new JobScratch();
         JobScratch *sc = scratch_pool.back();
@@ -1404,6 +1406,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
         NP2_CUDA(cudaMemcpyAsync(d_c_ks_orig.p, d_c_ks.p, nslot * 2, cudaMemcpyDeviceToDevice, s));
     }
     const uint32_t n_ids0 = (uint32_t)as_read.size();
+    bool unchecked_edges = false;  // a non-final iteration of this stretch went on without reading its counts back
   for (;; iter++) {
     const bool final_iter = iter + 1 == opt.iter_count;
     const bool dump = (int32_t)iter == dump_iter;
@@ -1501,6 +1504,14 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             dm_pair_val.assign(v.begin(), v.end());
         }
         const bool was_spec = spec;
+        if (spec && !edges_enqueued && !dump) {
+            // No pair kernel was enqueued (the last pass of this kind had no heterozygous region).  If this one has some,
+            // the pass is repeated in exact mode anyway; if it has none, no read can be dropped and the next iteration
+            // is this one again: nothing to wait for here.  The stretch goes on into the next iteration, and the
+            // heterozygous-region count is looked at where the stretch does end.
+            unchecked_edges = true;
+            continue;
+        }
         if (spec) {  // the one synchronisation of the speculative stretch
             timer.hbegin();
             segment_end();
@@ -1653,6 +1664,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             check_total();
             check_perr();
             if (hc->c[C_NREG] == 0) throw Respeculate();
+            if (unchecked_edges && hc->q[Q_EDGES] != 0) throw Respeculate();
         } else {
             fetch_counts();
         }
@@ -1790,6 +1802,7 @@ uint32_t np2_job::iteration_pass(uint32_t iter0, Hints &hint) {
             check_total();
             check_perr();
             if (hc->c[C_NREG] == 0) throw Respeculate();
+            if (unchecked_edges && hc->q[Q_EDGES] != 0) throw Respeculate();
         } else {
             fetch_counts();
         }
@@ -2788,6 +2801,125 @@ uint64_t np2_secmap_size(const np2_secmap *m, uint64_t *n_seqs) { return m ? np2
 
 void np2_set_host_threads(uint32_t n) { np2::set_host_threads(n); }
 void np2_set_stage_timing(int on) { g_stage_events.store(on ? 1 : 0); }
+
+/* BGZF members -> records, on the device (np2_inflate.cu).  The compressed span travels once (through a page-locked
+ * ring when the caller's buffer is pageable, e.g. a memory-mapped file: host threads copy a chunk while the DMA moves the
+ * previous one), one warp inflates each member into its final place, the wanted byte range comes back. */
+int np2_bgzf_inflate(np2_ctx *ctx, const uint8_t *comp, uint64_t comp_len, const uint64_t *payload_off,
+                     const uint32_t *payload_len, const uint32_t *isize, uint32_t n_members, uint64_t skip, uint64_t out_len,
+                     uint8_t *out, float *kernel_ms) {
+    return guard([&] {
+        if (!ctx || (n_members && (!comp || !payload_off || !payload_len || !isize)) || (out_len && !out))
+            throw np2::Error(NP2_ERR_ARG, "null argument");
+        if (kernel_ms) *kernel_ms = 0;
+        uint64_t lo = ~0ull, hi = 0, total = 0;
+        for (uint32_t i = 0; i < n_members; i++) {
+            if (payload_off[i] > comp_len || payload_len[i] > comp_len - payload_off[i])
+                throw np2::Error(NP2_ERR_ARG, "BGZF member outside the compressed buffer");
+            if (isize[i] > np2::infl::kMaxMember) throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed! (BGZF member larger than 64 KiB)");
+            lo = std::min(lo, payload_off[i]);
+            hi = std::max(hi, payload_off[i] + payload_len[i]);
+            total += isize[i];
+        }
+        if (skip > total || out_len > total - skip) throw np2::Error(NP2_ERR_ARG, "requested range outside the inflated members");
+        if (!n_members || !out_len) return;
+        NP2_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->stream;
+        const uint64_t span = hi - lo;
+        constexpr uint64_t kFront = 16;  // the decoder reads whole aligned words: slack on both sides of the span
+        DBuf<uint8_t> d_comp, d_out, d_args;
+        d_comp.alloc(span + kFront + 32, s);
+        d_out.alloc(total + 64, s);
+        // member table: off | out_off | clen | isize | bad[2], one pinned block
+        const size_t o_out = (size_t)n_members * 8, o_clen = o_out + (size_t)n_members * 8, o_isz = o_clen + (size_t)n_members * 4;
+        const size_t o_bad = o_isz + (size_t)n_members * 4, args_bytes = o_bad + 16;
+        ctx->p_infl_args.resize(args_bytes + 16);
+        uint8_t *pa = ctx->p_infl_args.p;
+        {
+            uint64_t *a_off = reinterpret_cast<uint64_t *>(pa), *a_out = reinterpret_cast<uint64_t *>(pa + o_out);
+            uint32_t *a_clen = reinterpret_cast<uint32_t *>(pa + o_clen), *a_isz = reinterpret_cast<uint32_t *>(pa + o_isz);
+            uint32_t *a_bad = reinterpret_cast<uint32_t *>(pa + o_bad);
+            uint64_t w = 0;
+            for (uint32_t i = 0; i < n_members; i++) {
+                a_off[i] = kFront + payload_off[i] - lo;
+                a_out[i] = w;
+                a_clen[i] = payload_len[i];
+                a_isz[i] = isize[i];
+                w += isize[i];
+            }
+            a_bad[0] = 0;
+            a_bad[1] = 0xFFFFFFFFu;
+        }
+        d_args.alloc(args_bytes, s);
+        NP2_CUDA(cudaMemcpyAsync(d_args.p, pa, args_bytes, cudaMemcpyHostToDevice, s));
+        NP2_CUDA(cudaMemsetAsync(d_comp.p, 0, kFront, s));
+        NP2_CUDA(cudaMemsetAsync(d_comp.p + kFront + span, 0, 32, s));
+        bool pinned = false;
+        {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, comp) != cudaSuccess) cudaGetLastError();
+            else pinned = at.type == cudaMemoryTypeHost;
+        }
+        if (pinned) {
+            NP2_CUDA(cudaMemcpyAsync(d_comp.p + kFront, comp + lo, span, cudaMemcpyHostToDevice, s));
+        } else {
+            const uint64_t kChunk = 8ull << 20;
+            const uint64_t n_chunks = (span + kChunk - 1) / kChunk;
+            ctx->p_infl_in.resize(std::min<uint64_t>(span, 2 * kChunk));  // two halves: copy into one while the other is on the link
+            cudaEvent_t ev[2] = {nullptr, nullptr};
+            NP2_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+            NP2_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+            const unsigned T = std::max(1u, np2::host_threads());
+            try {
+                for (uint64_t c = 0; c < n_chunks; c++) {
+                    const uint64_t b = c * kChunk, e = std::min(span, b + kChunk);
+                    uint8_t *half = ctx->p_infl_in.p + (c & 1) * kChunk;
+                    if (c >= 2) NP2_CUDA(cudaEventSynchronize(ev[c & 1]));
+                    np2::parallel_for(T, [&](unsigned ti) {
+                        const uint64_t tb = b + (e - b) * ti / T, te = b + (e - b) * (ti + 1) / T;
+                        np2::copy_streaming(half + (tb - b), comp + lo + tb, te - tb);
+                        np2::store_fence();
+                    });
+                    NP2_CUDA(cudaMemcpyAsync(d_comp.p + kFront + b, half, e - b, cudaMemcpyHostToDevice, s));
+                    NP2_CUDA(cudaEventRecord(ev[c & 1], s));
+                }
+            } catch (...) {
+                cudaStreamSynchronize(s);
+                cudaEventDestroy(ev[0]);
+                cudaEventDestroy(ev[1]);
+                throw;
+            }
+            NP2_CUDA(cudaStreamSynchronize(s));  // the ring is reused by the next call
+            cudaEventDestroy(ev[0]);
+            cudaEventDestroy(ev[1]);
+        }
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (kernel_ms) {
+            NP2_CUDA(cudaEventCreate(&t0));
+            NP2_CUDA(cudaEventCreate(&t1));
+            NP2_CUDA(cudaEventRecord(t0, s));
+        }
+        uint32_t *d_bad = reinterpret_cast<uint32_t *>(d_args.p + o_bad);
+        bgzf_inflate(d_comp.p, reinterpret_cast<const uint64_t *>(d_args.p), reinterpret_cast<const uint32_t *>(d_args.p + o_clen),
+                     reinterpret_cast<const uint64_t *>(d_args.p + o_out), reinterpret_cast<const uint32_t *>(d_args.p + o_isz),
+                     n_members, d_out.p, d_bad, s);
+        if (kernel_ms) NP2_CUDA(cudaEventRecord(t1, s));
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) throw np2::Error(NP2_ERR_CUDA, std::string("k_bgzf_inflate: ") + cudaGetErrorString(le));
+        NP2_CUDA(cudaMemcpyAsync(out, d_out.p + skip, out_len, cudaMemcpyDeviceToHost, s));
+        uint32_t *h_bad = reinterpret_cast<uint32_t *>(pa + args_bytes);  // behind the uploaded part of the block
+        NP2_CUDA(cudaMemcpyAsync(h_bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
+        NP2_CUDA(cudaStreamSynchronize(s));
+        if (kernel_ms) {
+            cudaEventElapsedTime(kernel_ms, t0, t1);
+            cudaEventDestroy(t0);
+            cudaEventDestroy(t1);
+        }
+        if (h_bad[0])
+            throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed! (BGZF member " + std::to_string(h_bad[1]) + " of " +
+                                                 std::to_string(n_members) + " does not inflate to its ISIZE)");
+    });
+}
 
 int np2_host_alloc(uint64_t bytes, void **out) {
     return guard([&] {

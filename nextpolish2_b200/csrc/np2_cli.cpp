@@ -6,7 +6,9 @@
 // `nextPolish2 count` (yak count on the GPU: FASTA/FASTQ[.gz] in, .yak dump out; yak/main.c:24-83).
 //
 // This file is the caller side of the hot path: hand-written BGZF/BAM/BAI and FASTA(.gz) readers
-// (zlib only; the BAM is memory-mapped and a contig's BGZF members are inflated in parallel, in place) that hand each contig's raw alignment records to np2_polish_contig, and the orchestration
+// (the BAM is memory-mapped; a contig's BGZF members are inflated on the device by np2_bgzf_inflate, one
+// warp per member, or with --host-inflate by zlib on the host threads, in parallel and in place) that hand each contig's
+// raw alignment records to np2_polish_contig, and the orchestration
 // the reference does with three thread stages (main.rs:1698-1853): contigs are LPT-partitioned over the GPUs, up to
 // three host threads (contexts) per GPU share one set of tables, records are printed in INPUT order (= the reference
 // with -t 1).
@@ -415,8 +417,11 @@ void open_bam(const std::string &path, BamFile &bf) {
 }
 
 // IndexedReader::fetch((tid, 0, len)) + read loop (main.rs:1745-1751): every record of that reference, file order.
-// Thread-safe (the map is read-only); `threads` inflate workers.
-void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads) {
+// Thread-safe (the map is read-only).  With a context the members are inflated ON THE DEVICE (np2_bgzf_inflate: the
+// compressed span goes up, one warp inflates each member, the records come back into the blob — page-locked in the polish
+// lanes, so both copies are DMA transfers); without one, `threads` host workers call zlib (--host-inflate, and the
+// passes that run before any context exists).
+void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads, np2_ctx *gpu = nullptr) {
     blob.resize(0);
     if (tid < 0 || bf.ref_voff[tid] == UINT64_MAX) return;
     const uint64_t v0 = bf.ref_voff[tid], v1 = bf.ref_vend[tid];
@@ -443,7 +448,19 @@ void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads) {
     if ((uint64_t)u0 + cut_tail > total) die("BAM/SAM parsing failed!");
     const uint64_t n = total - u0 - cut_tail;
     blob.resize(n);
-    std::atomic<size_t> next{0};
+    if (gpu) {
+        std::vector<uint64_t> off(ms.size());
+        std::vector<uint32_t> clen(ms.size()), isz(ms.size());
+        for (size_t i = 0; i < ms.size(); i++) {
+            off[i] = ms[i].data;
+            clen[i] = ms[i].clen;
+            isz[i] = ms[i].isize;
+        }
+        if (np2_bgzf_inflate(gpu, bf.map, bf.size, off.data(), clen.data(), isz.data(), (uint32_t)ms.size(), u0, n, blob.p,
+                             nullptr) != NP2_OK)
+            die(np2_last_error());
+    }
+    std::atomic<size_t> next{gpu ? ms.size() : 0};
     auto work = [&]() {
         std::vector<uint8_t> tmp;
         for (size_t i; (i = next.fetch_add(1)) < ms.size();) {
@@ -459,7 +476,7 @@ void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads) {
             }
         }
     };
-    const int T = std::max(1, std::min<int>(threads, (int)ms.size()));
+    const int T = gpu ? 1 : std::max(1, std::min<int>(threads, (int)ms.size()));
     std::vector<std::thread> th;
     for (int t = 1; t < T; t++) th.emplace_back(work);
     work();
@@ -481,6 +498,7 @@ struct Cli {
     std::vector<std::string> yaks;
     np2_opts o;
     int threads = 0, gpus = 0;  // threads 0 = not given: BGZF inflate and record parsing use up to 16 hardware threads
+    bool host_inflate = false;  // --host-inflate: zlib on the host threads instead of the device inflate kernel
 };
 void usage() {
     fprintf(stderr,
@@ -502,7 +520,8 @@ void usage() {
             "  -c, --max_clip_len <INT>    filter alignments with unaligned length >= INT [default: 100]\n"
             "  -r, --use_all_reads         use all unfiltered reads\n"
             "      --min_base_cov <INT>    accepted for compatibility (unused by the reference as well)\n"
-            "  -g, --gpus <INT>            GPUs to use [default: all visible]\n");
+            "  -g, --gpus <INT>            GPUs to use [default: all visible]\n"
+            "      --host-inflate          inflate the BGZF members with zlib on the host threads instead of on the GPU\n");
 }
 Cli parse_args(int argc, char **argv) {
     Cli c;
@@ -544,6 +563,7 @@ Cli parse_args(int argc, char **argv) {
         else if (a == "-r" || a == "--use_all_reads") c.o.use_all_reads = 1;
         else if (a == "--min_base_cov") val(i);
         else if (a == "-g" || a == "--gpus") c.gpus = atoi(val(i).c_str());
+        else if (a == "--host-inflate") c.host_inflate = true;
         else if (!a.empty() && a[0] == '-' && a.size() > 1) {
             fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str());
             usage();
@@ -562,23 +582,30 @@ Cli parse_args(int argc, char **argv) {
 
 }  // namespace
 
-// `nextPolish2 records <in.bam> <reference name> [threads]`: the raw alignment records of one reference on stdout
-// (what IndexedReader::fetch + read hand the worker closure) - a host-only seam for the BGZF / BAI reader tests
+// `nextPolish2 records <in.bam> <reference name> [threads | gpu]`: the raw alignment records of one reference on stdout
+// (what IndexedReader::fetch + read hand the worker closure) - a seam for the BGZF / BAI reader tests: host-only with a
+// thread count, through the device inflate kernel with `gpu`
 int main_records(int argc, char **argv) {
     if (argc < 4) {
-        fprintf(stderr, "Usage: nextPolish2 records <in.bam> <reference name> [threads]\n");
+        fprintf(stderr, "Usage: nextPolish2 records <in.bam> <reference name> [threads | gpu]\n");
         return 1;
     }
     BamFile bf;
-    bf.threads = argc > 4 ? std::max(1, atoi(argv[4])) : 4;
+    const bool on_gpu = argc > 4 && std::string(argv[4]) == "gpu";
+    bf.threads = argc > 4 && !on_gpu ? std::max(1, atoi(argv[4])) : 4;
     open_bam(argv[2], bf);
     int tid = -1;
     for (size_t r = 0; r < bf.ref_names.size(); r++)
         if (bf.ref_names[r] == argv[3]) tid = (int)r;
     if (tid < 0) die("Faield random access BAM/SAM!");
-    Blob blob;
-    fetch_records(bf, tid, blob, bf.threads);
-    fwrite(blob.data(), 1, blob.size(), stdout);
+    np2_ctx *ctx = nullptr;
+    if (on_gpu && np2_ctx_create(0, &ctx) != NP2_OK) die(np2_last_error());
+    {
+        Blob blob(on_gpu);
+        fetch_records(bf, tid, blob, bf.threads, ctx);
+        fwrite(blob.data(), 1, blob.size(), stdout);
+    }
+    np2_ctx_destroy(ctx);
     return 0;
 }
 
@@ -590,7 +617,7 @@ int main(int argc, char **argv) {
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     };
     std::atomic<uint64_t> us_fetch{0}, us_polish{0}, us_tables{0}, us_lib_total{0}, us_lib_wait{0}, us_destroy{0}, us_call{0};
-    const bool timing = getenv("NP2_CLI_TIMING") != nullptr;
+    const int timing = getenv("NP2_CLI_TIMING") ? std::max(1, atoi(getenv("NP2_CLI_TIMING"))) : 0;  // 2: a line per contig
     Cli cli = parse_args(argc, argv);
     FILE *out = stdout;
     if (cli.out != "stdout") {  // option.rs:308-328: refuse to overwrite
@@ -641,7 +668,7 @@ int main(int argc, char **argv) {
         BamFile bf;
         bf.threads = cli.threads > 0 ? cli.threads : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         np2_set_host_threads((uint32_t)bf.threads);
-        np2_set_stage_timing(timing ? 1 : 0);  // the per-stage event timers only serve NP2_CLI_TIMING
+        np2_set_stage_timing(timing == 1 ? 1 : 0);  // the per-stage event timers only serve NP2_CLI_TIMING
         open_bam(cli.bam, bf);
         int n_gpu = cli.gpus;
         if (n_gpu <= 0) {
@@ -684,15 +711,20 @@ int main(int argc, char **argv) {
             if (first_err.empty()) first_err = m;
         };
         auto polish_one = [&](np2_ctx *ctx, std::vector<np2_table *> &tabs, size_t i, Blob &blob) -> bool {
+            double ms_fetch = 0;
             {
-                std::lock_guard<std::mutex> lk(bam_mu);
+                // the host inflate uses every thread, so the lanes take turns; the device inflate of a lane runs on the
+                // lane's own context next to the kernels of the others
+                std::unique_lock<std::mutex> lk(bam_mu, std::defer_lock);
+                if (cli.host_inflate) lk.lock();
                 const auto t0 = std::chrono::steady_clock::now();
                 int tid = -1;
                 for (size_t r = 0; r < bf.ref_names.size(); r++)
                     if (bf.ref_names[r] == contigs[i].name) tid = (int)r;
                 if (tid < 0) return fail("Faield random access BAM/SAM!"), false;
-                fetch_records(bf, tid, blob, bf.threads);
-                us_fetch += (uint64_t)(since(t0) * 1e6);
+                fetch_records(bf, tid, blob, bf.threads, cli.host_inflate ? nullptr : ctx);
+                ms_fetch = since(t0) * 1e3;
+                us_fetch += (uint64_t)(ms_fetch * 1e3);
             }
             const auto t_polish = std::chrono::steady_clock::now();
             if (secmap) {  // secondary records get their SEQ (main.rs:1775-1783)
@@ -707,9 +739,21 @@ int main(int argc, char **argv) {
             }
             np2_job *job = nullptr;
             const auto t_call = std::chrono::steady_clock::now();
-            if (np2_polish_contig(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(), blob.data(),
-                                  blob.size(), tabs.data(), (uint32_t)tabs.size(), &cli.o, &job) != NP2_OK)
-                return fail(np2_last_error()), false;
+            // = np2_polish_contig, in its three steps so that NP2_CLI_TIMING=2 can clock them
+            double ms_create = 0, ms_upload = 0, ms_run = 0;
+            {
+                int rc = np2_job_create(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(), blob.data(),
+                                        blob.size(), tabs.data(), (uint32_t)tabs.size(), &cli.o, &job);
+                ms_create = since(t_call) * 1e3;
+                if (rc == NP2_OK) rc = np2_job_upload(job);
+                ms_upload = since(t_call) * 1e3 - ms_create;
+                if (rc == NP2_OK) rc = np2_job_run(job, -1);
+                ms_run = since(t_call) * 1e3 - ms_create - ms_upload;
+                if (rc != NP2_OK) {
+                    np2_job_destroy(job);
+                    return fail(np2_last_error()), false;
+                }
+            }
             us_call += (uint64_t)(since(t_call) * 1e6);
             const uint32_t *pos;
             const uint8_t *base;
@@ -752,6 +796,10 @@ int main(int argc, char **argv) {
             }
             flush_ready();
             us_polish += (uint64_t)(since(t_polish) * 1e6);
+            if (timing > 1)
+                fprintf(stderr, "[np2 contig] %s ctx %p: done at %.3f s; fetch %.1f ms, create %.1f, upload %.1f, run %.1f, rest %.1f ms\n",
+                        contigs[i].name.c_str(), (void *)ctx, since(t_start), ms_fetch, ms_create, ms_upload, ms_run,
+                        since(t_polish) * 1e3 - ms_create - ms_upload - ms_run);
             return true;
         };
         auto worker = [&](int g) {
@@ -768,9 +816,10 @@ int main(int argc, char **argv) {
             std::sort(share[g].begin(), share[g].end());
             std::atomic<size_t> next{0};
             auto lane = [&](np2_ctx *c) {
-                // pageable on purpose: page-locking ~0.5 GB per lane costs more than the library's compaction pass
-                // saves on anything but very large inputs (measured, profiles/r01_cli_e2e.txt)
-                Blob blob(false);
+                // device inflate: page-locked, so the records come back by DMA and the device gathers the SEQ fields out of
+                // them itself.  Host inflate: pageable on purpose — page-locking ~0.5 GB per lane costs more than the
+                // library's compaction pass saves on anything but very large inputs (measured, profiles/r01_cli_e2e.txt)
+                Blob blob(!cli.host_inflate);
                 for (;;) {
                     const size_t x = next.fetch_add(1);
                     if (x >= share[g].size()) break;
@@ -816,7 +865,7 @@ int main(int argc, char **argv) {
         fprintf(stderr,
                 "[np2 timing] wall %.3f s (FASTA read until %.3f, BAM open + GPU probe until %.3f, workers until %.3f), "
                 "%.1f Mbp polished -> %.1f Mbp/s end to end; summed over worker threads: table "
-                "staging %.3f s, BGZF inflate + record fetch %.3f s (serialised), parse + upload + GPU + result %.3f s; "
+                "staging %.3f s, BGZF inflate + record fetch %.3f s, parse + upload + GPU + result %.3f s; "
                 "FASTA write %.3f s; inside it: np2_polish_contig %.3f s (of which the library's run step %.3f s, waiting "
                 "for the upload %.3f s), job destroy %.3f s\n",
                 wall, s_fasta, s_setup, s_workers, bp / 1e6, bp / 1e6 / wall, us_tables / 1e6, us_fetch / 1e6, us_polish / 1e6, since(t_write),

@@ -322,4 +322,11 @@ void count_filter(const KmerCounts &acc, uint32_t min_count, uint64_t **d_keys, 
 // the same keys as yak writes them ((hash >> 10) << 10 | count), grouped by sub-table, into host memory
 void count_file_keys(const uint64_t *d_keys, const uint16_t *d_cnt, uint64_t n, uint64_t *h_out, cudaStream_t s);
 
+/* ------------------------------------------------------------------ BGZF inflate on the device (np2_inflate.cu) */
+// member i: raw DEFLATE payload d_comp[d_off[i] .. + d_clen[i]) -> d_out[d_out_off[i] .. + d_isize[i]); one warp each.
+// d_comp needs 3 readable bytes in front of the first payload and 8 behind the last.  d_bad: two words, {0, 0xFFFFFFFF}
+// before the launch -> {members that are no valid DEFLATE stream of their ISIZE, index of the first one}
+void bgzf_inflate(const uint8_t *d_comp, const uint64_t *d_off, const uint32_t *d_clen, const uint64_t *d_out_off,
+                  const uint32_t *d_isize, uint32_t n_members, uint8_t *d_out, uint32_t *d_bad, cudaStream_t s);
+
 }  // namespace np2

@@ -712,7 +712,7 @@ int np2s_write_short_reads(const char *path, uint64_t seed, const uint8_t *const
 
 /* ---- BGZF / BAM / BAI writers ---- */
 
-static void bgzf_block(FILE *fp, const uint8_t *data, size_t n, int level) {
+static void bgzf_block(std::vector<uint8_t> &dst, const uint8_t *data, size_t n, int level) {
     uint8_t out[70000];
     z_stream zs;
     memset(&zs, 0, sizeof zs);
@@ -733,7 +733,7 @@ static void bgzf_block(FILE *fp, const uint8_t *data, size_t n, int level) {
     uint32_t isz = (uint32_t)n;
     memcpy(out + 18 + clen, &crc, 4);
     memcpy(out + 18 + clen + 4, &isz, 4);
-    fwrite(out, 1, 18 + clen + 8, fp);
+    dst.assign(out, out + 18 + clen + 8);
 }
 
 /*
@@ -763,13 +763,15 @@ int np2s_write_bam(const char *path, uint32_t n_ref, const char *names, const ui
         hdr.push_back(0);
         put32(hdr, ref_len[i]);
     }
-    uint64_t coff = 0;  // compressed offset of the block being filled
+    // Blocks are cut first (their boundaries only depend on the record sizes), compressed in parallel afterwards; until
+    // then a virtual offset is (index of the block << 16 | offset inside it) and `coff` counts blocks.
+    uint64_t coff = 0;  // index of the block being filled
     std::vector<uint8_t> blk;
+    std::vector<std::vector<uint8_t>> raw_blocks;
     auto flush = [&]() {
         if (blk.empty()) return;
-        long before = ftell(fp);
-        bgzf_block(fp, blk.data(), blk.size(), level);
-        coff += (uint64_t)(ftell(fp) - before);
+        raw_blocks.emplace_back(blk);
+        coff++;
         blk.clear();
     };
     for (size_t o = 0; o < hdr.size();) {
@@ -824,6 +826,35 @@ int np2s_write_bam(const char *path, uint32_t n_ref, const char *names, const ui
         }
     }
     flush();
+    std::vector<uint64_t> block_coff(raw_blocks.size() + 1, 0);
+    {
+        std::vector<std::vector<uint8_t>> packed(raw_blocks.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t i; (i = next.fetch_add(1)) < raw_blocks.size();) {
+                bgzf_block(packed[i], raw_blocks[i].data(), raw_blocks[i].size(), level);
+                std::vector<uint8_t>().swap(raw_blocks[i]);
+            }
+        };
+        const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        for (size_t i = 0; i < packed.size(); i++) {
+            fwrite(packed[i].data(), 1, packed[i].size(), fp);
+            block_coff[i + 1] = block_coff[i] + packed[i].size();
+        }
+    }
+    auto real_voff = [&](uint64_t v) { return block_coff[v >> 16] << 16 | (v & 0xFFFF); };
+    for (RefIdx &ri : ridx) {
+        for (auto &c : ri.chunks) {
+            c.second.first = real_voff(c.second.first);
+            c.second.second = real_voff(c.second.second);
+        }
+        for (uint64_t &l : ri.lin)
+            if (l) l = real_voff(l);
+    }
     static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     fwrite(eof, 1, 28, fp);
     fclose(fp);

@@ -96,6 +96,10 @@ def test_cli_end_to_end_matches_oracle(files):
     r = _run(["-L", "30000", "-t", "4", files["bam"], files["fa"]] + files["yaks"][::-1])  # yak order must not matter
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == want
+    # the same through zlib on the host threads instead of the device inflate kernel
+    r = _run(["-L", "30000", "-t", "4", "--host-inflate", files["bam"], files["fa"]] + files["yaks"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == want
     assert want.count(b">") == 3 and bytes(files["contigs"][1]) in want  # ctgB (25 kb) passed through unchanged
     r2 = _run(["-L", "30000", "-g", "1", "--out_pos", files["bam"], files["fa"]] + files["yaks"])
     want_pos = b""
@@ -119,3 +123,15 @@ def test_bam_reader_returns_every_record_of_a_reference(files, tmp_path, level):
             assert r.stdout == bytes(blob)
     r = subprocess.run([CLI, "records", bam, "nope"], capture_output=True)
     assert r.returncode != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [0, 1, 6])
+def test_bam_reader_with_device_inflate(files, tmp_path, level):
+    """the same seam with the members inflated by np2_bgzf_inflate (one warp per member) instead of zlib"""
+    bam = str(tmp_path / ("g%d.bam" % level))
+    synth.write_bam(bam, files["names"], [len(c) for c in files["contigs"]], files["blobs"], level=level)
+    for name, blob in zip(files["names"], files["blobs"]):
+        r = subprocess.run([CLI, "records", bam, name, "gpu"], capture_output=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == bytes(blob)

@@ -1,0 +1,124 @@
+"""np2_bgzf_inflate (device: one warp per BGZF member) against zlib, through the C ABI."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import bgzf as OB  # oracle/bgzf.py: member walk + zlib
+import nextpolish2_b200 as np2
+from nextpolish2_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def table(buf):
+    ms = OB.members(buf)
+    return (np.array([m[0] for m in ms], np.uint64), np.array([m[1] for m in ms], np.uint32),
+            np.array([m[2] for m in ms], np.uint32))
+
+
+@pytest.fixture(scope="module")
+def bam_files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("bgzf")
+    A = synth.genome(21, 400_000)
+    c = synth.make_contig(22, A, depth=25, asm_err=1e-4, het=0.001, threads=4)
+    out = {}
+    for level in (0, 1, 6):
+        path = str(d / ("t%d.bam" % level))
+        synth.write_bam(path, ["ctg"], [len(A)], [c["bam"]], level=level)
+        out[level] = np.fromfile(path, np.uint8)
+    return out, bytes(c["bam"])
+
+
+@pytest.mark.parametrize("level", [0, 1, 6])
+def test_whole_file_matches_zlib(ctx, bam_files, level):
+    files, records = bam_files
+    buf = files[level]
+    po, pl, iz = np2.bgzf_members(buf)
+    opo, opl, oiz = table(buf)
+    assert np.array_equal(po, opo) and np.array_equal(pl, opl) and np.array_equal(iz, oiz)
+    want = OB.inflate_all(buf)
+    got, ms = np2.bgzf_inflate(ctx, buf, po, pl, iz)
+    assert bytes(got) == want
+    assert ms > 0
+    at = want.find(records[:4096])
+    assert at > 0 and want[at:at + len(records)] == records  # the records sit behind the BAM header, as written
+
+
+def test_subrange_pinned_buffers_and_member_subset(ctx, bam_files):
+    files, _ = bam_files
+    buf = files[1]
+    po, pl, iz = np2.bgzf_members(buf)
+    want = OB.inflate_all(buf)
+    pin_in = np2.PinnedBuffer(buf)
+    # the members 3 .. n-2 only, and a byte range that starts and ends inside a member (what a contig's records do)
+    lo, hi = 3, len(po) - 2
+    base = int(iz[:lo].astype(np.uint64).sum())
+    total = int(iz[lo:hi].astype(np.uint64).sum())
+    skip, n = 12345, total - 12345 - 6789
+    pin_out = np2.PinnedBuffer(np.zeros(n, np.uint8))
+    got, _ = np2.bgzf_inflate(ctx, pin_in, po[lo:hi], pl[lo:hi], iz[lo:hi], skip=skip, out_len=n, out=pin_out)
+    assert bytes(got) == want[base + skip:base + skip + n]
+    got2, _ = np2.bgzf_inflate(ctx, buf, po[lo:hi], pl[lo:hi], iz[lo:hi], skip=skip, out_len=n)  # pageable in and out
+    assert bytes(got2) == bytes(got)
+    pin_in.free()
+    pin_out.free()
+
+
+def test_every_block_type(ctx):
+    """Members made with every zlib strategy / level: stored, fixed and dynamic blocks, several blocks per member,
+    overlapping matches, empty members (the BGZF EOF marker)."""
+    rng = random.Random(7)
+    parts, datas = [], []
+
+    def some(n):
+        k = rng.randrange(5)
+        if k == 0:
+            return bytes(rng.getrandbits(8) for _ in range(n))
+        if k == 1:
+            return b"\xff" * n
+        if k == 2:
+            return (b"abc" * n)[:n]
+        if k == 3:
+            return bytes(rng.choice(b"\x11\x12\x14\x18\x21\x22\x24\x28\x41\x42\x44\x48\x81\x82\x84\x88") for _ in range(n))
+        w = [bytes(rng.getrandbits(8) for _ in range(rng.randint(1, 30))) for _ in range(12)]
+        b = b""
+        while len(b) < n:
+            b += rng.choice(w)
+        return b[:n]
+    for i in range(300):
+        n = rng.choice([0, 1, 2, 17, 300, 4000, 30000, 65280, 65536])
+        data = some(n)
+        kw = dict(level=rng.choice([0, 1, 6, 9]), mem_level=rng.choice([1, 8, 9]),
+                  strategy=rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE]))
+        try:
+            m = OB.make_member(data, **kw)
+        except ValueError:  # incompressible: does not fit BSIZE
+            data = data[:60000]
+            m = OB.make_member(data, **kw)
+        parts.append(m)
+        datas.append(data)
+    buf = np.frombuffer(b"".join(parts), np.uint8)
+    po, pl, iz = np2.bgzf_members(buf)
+    assert len(po) == 300
+    got, _ = np2.bgzf_inflate(ctx, buf, po, pl, iz)
+    assert bytes(got) == b"".join(datas)
+
+
+def test_bad_member_is_an_error(ctx, bam_files):
+    files, _ = bam_files
+    buf = files[6].copy()
+    po, pl, iz = np2.bgzf_members(buf)
+    i = len(po) // 2
+    wrong = iz.copy()
+    wrong[i] -= 1  # ISIZE does not match the stream
+    with pytest.raises(np2.Np2Error) as e:
+        np2.bgzf_inflate(ctx, buf, po, pl, wrong)
+    assert e.value.code == -4 and "BAM/SAM parsing failed!" in str(e.value) and ("member %d " % i) in str(e.value)
+    buf[int(po[i]):int(po[i]) + 40] ^= 0x5A  # garbage block header / code lengths
+    with pytest.raises(np2.Np2Error):
+        np2.bgzf_inflate(ctx, buf, po, pl, iz)
+    # the context is still usable
+    got, _ = np2.bgzf_inflate(ctx, files[6], po, pl, iz)
+    assert bytes(got) == OB.inflate_all(files[6])
