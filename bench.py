@@ -572,6 +572,11 @@ def _run_ours(args):
     del m
     for t in tables:
         t.free()
+    if rank == 0 and world == 1 and not args.no_bgzf_bench:  # the ingest step in front of the path, on the same records
+        try:
+            line["bgzf_inflate"] = bgzf_bench(ctx, np2, contigs[0]["bam"], int(len(contigs[0]["contig"])), cores)
+        except Exception as e:  # noqa: BLE001
+            line["bgzf_inflate"] = {"error": repr(e)[:300]}
     del contigs, tabs
 
     # ---- the other configs, bounded (N = 1): same measurement, fewer steps
@@ -794,6 +799,63 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
     return res
 
 
+def bgzf_bench(ctx, np2, bam_records, ref_len, cores):
+    """The ingest step in front of the hot path: the headline contig's records written as a BAM
+    (BGZF level 1 and 6, the synthetic-input tool's writer), every member inflated on the device by np2_bgzf_inflate
+    (a group of lanes per member) from a page-locked copy of the file into a page-locked record buffer.  Reported: the
+    kernel's time from CUDA events, the whole call with the compressed span going up and the records coming back, the
+    same members through zlib on the host threads (ThreadPool; zlib releases the GIL), and the byte-for-byte comparison
+    with zlib's output (oracle/bgzf.py)."""
+    import tempfile
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    from nextpolish2_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bgzf as OB  # the checker: member walk + zlib
+    res = {}
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    for level in (1, 6):
+        path = os.path.join(d, "np2_bench_%d.l%d.bam" % (os.getpid(), level))
+        synth.write_bam(path, ["ctg000"], [ref_len], [bam_records], level=level)
+        buf = np.fromfile(path, np.uint8)
+        for f in (path, path + ".bai"):
+            if os.path.exists(f):
+                os.remove(f)
+        po, pl, iz = np2.bgzf_members(buf)
+        total = int(iz.astype(np.uint64).sum())
+        raw = bytes(buf)
+
+        def host(i):
+            return zlib.decompress(raw[int(po[i]):int(po[i]) + int(pl[i])], -15)
+        with ThreadPoolExecutor(cores) as ex:
+            t0 = time.perf_counter()
+            parts = list(ex.map(host, range(len(po)), chunksize=64))
+            t_host = time.perf_counter() - t0
+        want = b"".join(parts)
+        del parts
+        pin_in, pin_out = np2.PinnedBuffer(buf), np2.PinnedBuffer(np.zeros(total, np.uint8))
+        ks, ws = [], []
+        for rep in range(6):
+            t0 = time.perf_counter()
+            got, kms = np2.bgzf_inflate(ctx, pin_in, po, pl, iz, out=pin_out)
+            ws.append((time.perf_counter() - t0) * 1e3)
+            ks.append(kms)
+        same = bytes(got) == want
+        kms, wms = float(np.median(ks[1:])), float(np.median(ws[1:]))
+        res["level%d" % level] = {
+            "members": int(len(po)), "compressed_MB": round(len(buf) / 1e6, 1), "records_MB": round(total / 1e6, 1),
+            "kernel_ms": round(kms, 3), "kernel_GBps_out": round(total / kms / 1e6, 1), "kernel_GBps_in": round(len(buf) / kms / 1e6, 1),
+            "call_ms_pinned_in_pinned_out": round(wms, 2), "h2d_bytes": int(len(buf)), "d2h_bytes": total,
+            "host_zlib_ms": round(t_host * 1e3, 1), "host_threads": cores, "identical_to_zlib": bool(same)}
+        pin_in.free()
+        pin_out.free()
+        del want, raw, buf
+    res["kernel"] = "k_bgzf_inflate<16, 4> (np2_inflate.cu): 16 lanes per BGZF member, Huffman tables in shared memory"
+    res["note"] = ("not part of `value` / `e2e` (those start from uncompressed records, as the reference's worker closure does); "
+                   "the command line's file -> FASTA numbers are in profiles/r02ay_cli_e2e.txt")
+    return res
+
+
 def yak_bench(ctx, np2, torch, peak):
     """K5 at scale: 2^26 keys (~0.9 GB table >> L2), 2^26 device-resident queries, half present / half absent.
     One probe needs one 32-byte bucket.  What DRAM really delivers per L2 miss depends on the device's L2 fetch
@@ -927,6 +989,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10, help="passes over the CPU sample for cpu_baseline (~1 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-yak-bench", action="store_true")
+    ap.add_argument("--no-bgzf-bench", action="store_true", help="skip the device BGZF inflate arm")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle FASTA comparison")
     ap.add_argument("--no-extras", action="store_true", help="skip the bounded configs[2] / configs[3] arms")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling arm (configs[4] scaled)")

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <future>
 #include <thread>
 #include <vector>
 
@@ -38,7 +39,9 @@ std::string g_partial_out;  // -o file being written: removed when the run dies,
 [[noreturn]] void die(const std::string &m) {
     fprintf(stderr, "%s\n", m.c_str());
     if (!g_partial_out.empty()) remove(g_partial_out.c_str());
-    exit(101);  // the reference aborts with a panic message
+    fflush(stdout);
+    fflush(stderr);
+    _exit(101);  // the reference aborts with a panic message; no atexit handlers: other threads may be inside CUDA calls
 }
 
 /* ---------------------------------------------------------------- FASTA (kseq semantics) */
@@ -710,7 +713,8 @@ int main(int argc, char **argv) {
             std::lock_guard<std::mutex> lk(err_mu);
             if (first_err.empty()) first_err = m;
         };
-        auto polish_one = [&](np2_ctx *ctx, std::vector<np2_table *> &tabs, size_t i, Blob &blob) -> bool {
+        auto polish_one = [&](np2_ctx *ctx, std::vector<np2_table *> &tabs, std::shared_future<bool> &tabs_ready, size_t i,
+                              Blob &blob) -> bool {
             double ms_fetch = 0;
             {
                 // the host inflate uses every thread, so the lanes take turns; the device inflate of a lane runs on the
@@ -737,6 +741,7 @@ int main(int argc, char **argv) {
                     return fail(np2_last_error()), false;
                 blob.swap(filled);
             }
+            if (!tabs_ready.get()) return false;  // the staging thread has reported the error
             np2_job *job = nullptr;
             const auto t_call = std::chrono::steady_clock::now();
             // = np2_polish_contig, in its three steps so that NP2_CLI_TIMING=2 can clock them
@@ -805,21 +810,44 @@ int main(int argc, char **argv) {
         auto worker = [&](int g) {
             np2_ctx *ctx = nullptr;
             if (np2_ctx_create(g, &ctx) != NP2_OK) return fail(np2_last_error());
+            // The tables are staged first, on a context of their own (they serve the jobs of every context of this GPU).
+            // Staging them next to the lanes' first fetches was tried and gained nothing: page-locking the record
+            // buffers, growing the pools and loading the tables all queue on the same driver locks
+            // (profiles/r02aw_cli_e2e.txt).
             std::vector<np2_table *> tabs;
-            const auto t_tab = std::chrono::steady_clock::now();
-            for (auto &y : cli.yaks) {
-                np2_table *t = nullptr;
-                if (np2_yak_load(ctx, y.c_str(), &t) != NP2_OK) return fail(np2_last_error());
-                tabs.push_back(t);
+            np2_ctx *tab_ctx = nullptr;
+            if (np2_ctx_create(g, &tab_ctx) != NP2_OK) return fail(np2_last_error());
+            std::promise<bool> tab_promise;
+            std::shared_future<bool> tabs_ready = tab_promise.get_future().share();
+            {
+                const auto t_tab = std::chrono::steady_clock::now();
+                bool ok = true;
+                for (auto &y : cli.yaks) {
+                    np2_table *t = nullptr;
+                    if (np2_yak_load(tab_ctx, y.c_str(), &t) != NP2_OK) {
+                        fail(np2_last_error());
+                        ok = false;
+                        break;
+                    }
+                    tabs.push_back(t);
+                }
+                us_tables += (uint64_t)(since(t_tab) * 1e6);
+                tab_promise.set_value(ok);
+                if (!ok) return;
             }
-            us_tables += (uint64_t)(since(t_tab) * 1e6);
             std::sort(share[g].begin(), share[g].end());
             std::atomic<size_t> next{0};
-            auto lane = [&](np2_ctx *c) {
-                // device inflate: page-locked, so the records come back by DMA and the device gathers the SEQ fields out of
-                // them itself.  Host inflate: pageable on purpose — page-locking ~0.5 GB per lane costs more than the
-                // library's compaction pass saves on anything but very large inputs (measured, profiles/r01_cli_e2e.txt)
-                Blob blob(!cli.host_inflate);
+            // Record buffers, one per lane.  Device inflate: page-locked, so the records come back by DMA and the device
+            // gathers the SEQ fields out of them itself.  Host inflate: pageable on purpose — page-locking ~0.5 GB per lane
+            // costs more than the library's compaction pass saves on anything but very large inputs (measured,
+            // profiles/r01_cli_e2e.txt).  They, the contexts and the tables are NOT released when a lane or a GPU is done:
+            // freeing page-locked memory or a pool synchronises the device and stalls the lanes still at work (100 ms
+            // and more, profiles/r02av_cli_e2e.txt), and the process ends right after the last record is written.
+            const size_t want_lanes = getenv("NP2_CLI_LANES") ? (size_t)std::max(1, atoi(getenv("NP2_CLI_LANES"))) : 3;
+            const size_t n_lanes = std::max<size_t>(1, std::min<size_t>(want_lanes, share[g].size()));
+            std::vector<Blob *> blobs;
+            for (size_t x = 0; x < n_lanes; x++) blobs.push_back(new Blob(!cli.host_inflate));
+            auto lane = [&](np2_ctx *c, Blob *blob) {
                 for (;;) {
                     const size_t x = next.fetch_add(1);
                     if (x >= share[g].size()) break;
@@ -827,23 +855,20 @@ int main(int argc, char **argv) {
                         std::lock_guard<std::mutex> lk(err_mu);
                         if (!first_err.empty()) break;
                     }
-                    if (!polish_one(c, tabs, share[g][x], blob)) break;
+                    if (!polish_one(c, tabs, tabs_ready, share[g][x], *blob)) break;
                 }
             };
             // up to three contigs in flight per GPU (measured: 1.0 / 1.24 / 1.49 Gbp/s for 1 / 2 / 3 on 10 Mbp contigs)
             std::vector<np2_ctx *> extra;
             std::vector<std::thread> more;
-            for (size_t x = 1; x < std::min<size_t>(3, share[g].size()); x++) {
+            for (size_t x = 1; x < n_lanes; x++) {
                 np2_ctx *c2 = nullptr;
                 if (np2_ctx_create(g, &c2) != NP2_OK) break;
                 extra.push_back(c2);
-                more.emplace_back(lane, c2);
+                more.emplace_back(lane, c2, blobs[x]);
             }
-            lane(ctx);
+            lane(ctx, blobs[0]);
             for (auto &t : more) t.join();
-            for (np2_ctx *c2 : extra) np2_ctx_destroy(c2);
-            for (auto t : tabs) np2_yak_free(t);
-            np2_ctx_destroy(ctx);
         };
         s_setup = since(t_start);
         std::vector<std::thread> th;
@@ -871,5 +896,11 @@ int main(int argc, char **argv) {
                 wall, s_fasta, s_setup, s_workers, bp / 1e6, bp / 1e6 / wall, us_tables / 1e6, us_fetch / 1e6, us_polish / 1e6, since(t_write),
                 us_call / 1e6, us_lib_total / 1e6, us_lib_wait / 1e6, us_destroy / 1e6);
     }
+    // Every record is written and the file is closed.  Leave without the static destructors and the CUDA runtime's own
+    // teardown of contexts, pools and page-locked buffers (more than a second for three lanes; the kernel reclaims the
+    // same resources when the process is gone).
+    fflush(stdout);
+    fflush(stderr);
+    if (!todo.empty()) _exit(0);
     return 0;
 }

@@ -8,6 +8,7 @@
 // it behind the other resident warps (one member each): throughput comes from the ~6000 members in flight, not from
 // any single one.  Output goes straight to its final place in the contig's record buffer (members are laid out back to
 // back by the caller's prefix sum of ISIZE), compressed input is read through the read-only path.
+#include <algorithm>
 #include <cstdlib>
 
 #include "np2_common.cuh"
@@ -21,13 +22,14 @@ constexpr uint32_t kInflThreads = 256;
 
 // G lanes per member (8, 16 or 32): the leader lane of a group decodes, the group copies.  With G < 32 a warp carries
 // 32 / G independent decode chains at the register cost of one, which is what hides the chains' latency.
-template <uint32_t G>
-__global__ void __launch_bounds__(kInflThreads, 4) k_bgzf_inflate(const uint8_t *__restrict__ comp,
+template <uint32_t G, int MINB>
+__global__ void __launch_bounds__(kInflThreads, MINB) k_bgzf_inflate(const uint8_t *__restrict__ comp,
                                                                const uint64_t *__restrict__ m_off,
                                                                const uint32_t *__restrict__ m_clen,
                                                                const uint64_t *__restrict__ m_out,
                                                                const uint32_t *__restrict__ m_isize, uint32_t n,
-                                                               uint8_t *__restrict__ out, uint32_t *__restrict__ bad) {
+                                                               uint8_t *__restrict__ out, uint32_t *__restrict__ bad,
+                                                               uint32_t inline_max) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     infl::Tabs *tabs = reinterpret_cast<infl::Tabs *>(smem_raw);
     constexpr uint32_t kPerCta = kInflThreads / G;
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(kInflThreads, 4) k_bgzf_inflate(const uint8_t 
     uint8_t *o = out + m_out[m];
     const uint32_t isize = m_isize[m];
     infl::State st;
-    if (gl == 0) infl::init(st, payload, m_clen[m], o, isize);
+    if (gl == 0) infl::init(st, payload, m_clen[m], o, isize, inline_max);
     uint32_t pos = 0;
     bool ok = false;
     for (;;) {
@@ -83,29 +85,40 @@ __global__ void __launch_bounds__(kInflThreads, 4) k_bgzf_inflate(const uint8_t 
     }
 }
 
-template <uint32_t G>
+template <uint32_t G, int MINB>
 void launch_inflate(const uint8_t *d_comp, const uint64_t *d_off, const uint32_t *d_clen, const uint64_t *d_out_off,
-                    const uint32_t *d_isize, uint32_t n_members, uint8_t *d_out, uint32_t *d_bad, cudaStream_t s) {
+                    const uint32_t *d_isize, uint32_t n_members, uint8_t *d_out, uint32_t *d_bad, uint32_t inline_max,
+                    cudaStream_t s) {
     constexpr uint32_t kPerCta = kInflThreads / G;
     constexpr int kSmem = (int)(kPerCta * sizeof(infl::Tabs));
     static bool attr_set = false;
     if (!attr_set) {
-        NP2_CUDA(cudaFuncSetAttribute(k_bgzf_inflate<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        NP2_CUDA(cudaFuncSetAttribute(k_bgzf_inflate<G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
-    NP2_K(k_bgzf_inflate<G>)<<<(n_members + kPerCta - 1) / kPerCta, kInflThreads, kSmem, s>>>(
-        d_comp, d_off, d_clen, d_out_off, d_isize, n_members, d_out, d_bad);
+    NP2_K((k_bgzf_inflate<G, MINB>))<<<(n_members + kPerCta - 1) / kPerCta, kInflThreads, kSmem, s>>>(
+        d_comp, d_off, d_clen, d_out_off, d_isize, n_members, d_out, d_bad, inline_max);
+}
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 }  // namespace
 
 // d_bad: two words, {0, 0xFFFFFFFF} before the launch -> {members that failed, index of the first one}
+// Tuning knobs (read at every call; profiles/bgzf_inflate_bench.py sweeps them): NP2_INFLATE_LANES = lanes per member
+// (8 / 16 / 32), NP2_INFLATE_INLINE = longest match the decoding lane copies itself (0..8), NP2_INFLATE_MINB = resident
+// CTAs per SM the kernel is compiled for (3: 80 registers, 4: 64 registers with a few spills).
 void bgzf_inflate(const uint8_t *d_comp, const uint64_t *d_off, const uint32_t *d_clen, const uint64_t *d_out_off,
                   const uint32_t *d_isize, uint32_t n_members, uint8_t *d_out, uint32_t *d_bad, cudaStream_t s) {
     if (!n_members) return;
-    static const int lanes = getenv("NP2_INFLATE_LANES") ? atoi(getenv("NP2_INFLATE_LANES")) : 8;
-    if (lanes == 32) launch_inflate<32>(d_comp, d_off, d_clen, d_out_off, d_isize, n_members, d_out, d_bad, s);
-    else if (lanes == 16) launch_inflate<16>(d_comp, d_off, d_clen, d_out_off, d_isize, n_members, d_out, d_bad, s);
-    else launch_inflate<8>(d_comp, d_off, d_clen, d_out_off, d_isize, n_members, d_out, d_bad, s);
+    const int lanes = env_int("NP2_INFLATE_LANES", 16), minb = env_int("NP2_INFLATE_MINB", 4);
+    const uint32_t inl = (uint32_t)std::max(0, env_int("NP2_INFLATE_INLINE", (int)infl::kInlineMatch));
+#define NP2_INFL(G, MB) launch_inflate<G, MB>(d_comp, d_off, d_clen, d_out_off, d_isize, n_members, d_out, d_bad, inl, s)
+    if (lanes == 32) minb == 3 ? NP2_INFL(32, 3) : NP2_INFL(32, 4);
+    else if (lanes == 8) minb == 3 ? NP2_INFL(8, 3) : NP2_INFL(8, 4);
+    else minb == 3 ? NP2_INFL(16, 3) : NP2_INFL(16, 4);
+#undef NP2_INFL
 }
 
 }  // namespace np2

@@ -29,7 +29,7 @@ namespace np2 {
 namespace infl {
 
 constexpr uint32_t kLitBits = 9, kDistBits = 7;
-constexpr uint32_t kInlineMatch = 8;     // matches up to this length are copied by the decoding lane itself
+constexpr uint32_t kInlineMatch = 8;     // matches up to this length are copied by the decoding lane itself (8: see infl_step)
 constexpr uint32_t kMaxMember = 65536;  // a BGZF member inflates to at most 64 KiB
 
 struct Tabs {
@@ -60,6 +60,7 @@ struct State {
     uint8_t *out;
     uint32_t pos, cap;
     // block state
+    uint32_t inline_max; // matches up to this length (<= kInlineMatch) are copied by infl_step itself
     uint32_t in_block;   // 0 = a block header comes next, 1 = inside a Huffman block
     uint32_t last;       // BFINAL of the current block
 };
@@ -83,8 +84,10 @@ NP2_HD void seat(State &s, uint64_t byte_off) {  // (re)start the bit reader at 
     s.wi = 1;
     s.ahead = load_word(s.w + (1 < s.wmax ? 1 : s.wmax));
 }
-NP2_HD void init(State &s, const uint8_t *payload, uint32_t clen, uint8_t *out, uint32_t cap) {
+NP2_HD void init(State &s, const uint8_t *payload, uint32_t clen, uint8_t *out, uint32_t cap,
+                 uint32_t inline_max = kInlineMatch) {
     s.payload = payload;
+    s.inline_max = inline_max < kInlineMatch ? inline_max : kInlineMatch;
     s.limit_bits = (uint64_t)clen * 8;
     s.out = out;
     s.pos = 0;
@@ -328,24 +331,18 @@ NP2_HD uint32_t infl_step(State &s, Tabs &t, uint32_t &a, uint32_t &b) {
                 dist = 1 + ((2 + (d & 1)) << e) + take(s, e);
             }
             if (dist > s.pos || s.pos + len > s.cap) return EV_ERROR;
-            if (len <= kInlineMatch) {
+            if (len <= s.inline_max) {
                 // Short matches are most of what a fast deflate level makes of DNA (any 3 bytes of 4-bit SEQ have
-                // occurred in the last 32 KiB): copied right here.  All loads are issued before the first store, so
-                // their (L2) latencies overlap; only an overlapping pair has to go byte by byte.
+                // occurred in the last 32 KiB): copied right here.  Whenever the source lies a full 8 bytes back and the
+                // member still has 8 bytes of room, all 8 are copied without looking at the length — the surplus lands
+                // on bytes the following symbols write anyway (a valid member fills exactly its ISIZE), the loads are
+                // issued together (their L2 latencies overlap) and nothing is predicated.
                 uint8_t *d = s.out + s.pos;
                 const uint8_t *src = d - dist;
-                if (dist >= len) {
-                    uint8_t v[kInlineMatch];
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-                    for (uint32_t i = 0; i < kInlineMatch; i++)
-                        if (i < len) v[i] = src[i];
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-                    for (uint32_t i = 0; i < kInlineMatch; i++)
-                        if (i < len) d[i] = v[i];
+                if (dist >= kInlineMatch && s.pos + kInlineMatch <= s.cap) {
+                    const uint8_t v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4], v5 = src[5], v6 = src[6],
+                                  v7 = src[7];
+                    d[0] = v0, d[1] = v1, d[2] = v2, d[3] = v3, d[4] = v4, d[5] = v5, d[6] = v6, d[7] = v7;
                 } else {
                     for (uint32_t i = 0; i < len; i++) d[i] = src[i];
                 }

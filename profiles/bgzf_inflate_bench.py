@@ -1,5 +1,6 @@
 """BGZF inflate of one contig's records: np2_bgzf_inflate (device, one warp per member) against zlib on the host cores.
-usage: python profiles/bgzf_inflate_bench.py [contig_bp] [levels, e.g. 1,6]   (run on the GPU box)"""
+usage: python profiles/bgzf_inflate_bench.py [contig_bp] [levels, e.g. 1,6] [sweep]   (run on the GPU box)
+sweep: also time the kernel for every combination of the tuning knobs of np2_inflate.cu."""
 import os
 import sys
 import time
@@ -48,6 +49,17 @@ for level in levels:
             ks.append(kms)
         assert bytes(got) == want, "device inflate differs from zlib"
         res[name] = (min(ks[1:]), min(ws[1:]))
+    if len(sys.argv) > 3 and sys.argv[3] == "sweep":
+        for lanes in (8, 16, 32):
+            for inl in (0, 4, 8):
+                for minb in (3, 4):
+                    os.environ.update(NP2_INFLATE_LANES=str(lanes), NP2_INFLATE_INLINE=str(inl), NP2_INFLATE_MINB=str(minb))
+                    ks = [np2.bgzf_inflate(ctx, pin_in, po, pl, iz, out=pin_out)[1] for _ in range(4)]
+                    assert bytes(pin_out.array[:total]) == want
+                    print("  level %d sweep: lanes %2d inline<=%d min CTAs/SM %d: kernel %.2f ms" % (level, lanes, inl, minb, min(ks[1:])),
+                          flush=True)
+        for k in ("NP2_INFLATE_LANES", "NP2_INFLATE_INLINE", "NP2_INFLATE_MINB"):
+            os.environ.pop(k, None)
     print("level %d: %d members, %.1f MB -> %.1f MB | zlib on %d host threads %.1f ms (%.2f GB/s out) | device kernel %.2f ms "
           "(%.1f GB/s out, %.1f GB/s in) | call incl. H2D of the compressed span + D2H of the records: pinned source %.1f ms, "
           "pageable source %.1f ms | identical to zlib" % (

@@ -57,18 +57,26 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
         t0 = time.time()
         synth.write_bam(bam, names, [L] * n_ctg, blobs, level=level)
         print("BAM level %d: %.1f MB written in %.1f s" % (level, os.path.getsize(bam) / 1e6, time.time() - t0), flush=True)
-        for mode in ([], ["--host-inflate"]):
+        modes = [("device inflate, 3 lanes", [], {}), ("device inflate, 4 lanes", [], {"NP2_CLI_LANES": "4"}),
+                 ("device inflate, 5 lanes", [], {"NP2_CLI_LANES": "5"}), ("host inflate (zlib), 3 lanes", ["--host-inflate"], {})]
+        for label, mode, env in modes:
             for rep in range(2):
                 out = os.path.join(d, "out.fa")
                 if os.path.exists(out):
                     os.remove(out)
                 t0 = time.time()
                 r = subprocess.run([cli, "-t", "16", "-o", out] + mode + [bam, fa] + yaks, capture_output=True, text=True,
-                                   env=dict(os.environ, NP2_CLI_TIMING=timing_level))
+                                   env=dict(os.environ, NP2_CLI_TIMING=timing_level, **env))
                 dt = time.time() - t0
                 got = open(out, "rb").read() if r.returncode == 0 else b""
                 ok = r.returncode == 0 and all(bytes(h) in got for h in haps)
-                print("level %d %s run %d: %.2f s wall (%.1f Mbp/s), rc %d, every contig == its truth haplotype: %s\n   %s" % (
-                    level, "host inflate (zlib)" if mode else "device inflate", rep, dt, n_ctg * L / 1e6 / dt, r.returncode, ok,
-                    "\n   ".join(l for l in r.stderr.strip().splitlines() if l.startswith("[np2"))), flush=True)
+                lines = [l for l in r.stderr.strip().splitlines() if l.startswith("[np2")]
+                done = sorted(float(l.split("done at ")[1].split(" s")[0]) for l in lines if l.startswith("[np2 contig]"))
+                skip = 2 * int(env.get("NP2_CLI_LANES", 3))  # every lane's first contig pays the first-use costs
+                steady = ""
+                if len(done) > skip + 4:
+                    per = (done[-1] - done[skip - 1]) / (len(done) - skip)
+                    steady = "; steady state after the first %d contigs: %.1f ms per contig = %.0f Mbp/s" % (skip, per * 1e3, L / 1e6 / per)
+                print("level %d %s run %d: %.2f s wall (%.1f Mbp/s)%s, rc %d, every contig == its truth haplotype: %s\n   %s" % (
+                    level, label, rep, dt, n_ctg * L / 1e6 / dt, steady, r.returncode, ok, "\n   ".join(lines)), flush=True)
         os.remove(bam)
