@@ -196,9 +196,21 @@ int np2_polish_contig(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const ui
  * its next contig before it runs the current one: the link and the GPU are then busy at the same time. */
 int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
                    np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out);
+/* The same from the contig's BGZF members (arguments as np2_bgzf_inflate; [skip, skip + rec_len) of the inflated
+ * members = the contig's records): the members are inflated on the device and the records never come to the host.  The
+ * record boundaries are found on the device (guessed per 64 KiB chunk, walked, joined on the host exactly like the host
+ * parser joins its byte ranges) and only what the filter reads of a record — its fixed fields and CIGAR words, ~2 % of
+ * the bytes — comes down; the SEQ + CIGAR spans are gathered device to device.  Same result as np2_bgzf_inflate +
+ * np2_job_create, one third of the link traffic and no page-locked record buffer.  Replaces fetch + records() + the
+ * filter of the worker closure (main.rs:1745-1771).  Not for -S (np2_secmap_fill rewrites the records on the host). */
+int np2_job_create_bgzf(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *comp, uint64_t comp_len,
+                        const uint64_t *payload_off, const uint32_t *payload_len, const uint32_t *isize, uint32_t n_members,
+                        uint64_t skip, uint64_t rec_len, np2_table *const *tables, uint32_t n_tables, const np2_opts *opts,
+                        np2_job **out);
 int np2_job_upload(np2_job *job);
 /* tseq and bam must stay valid (and unchanged) until np2_job_upload / np2_polish_contig returns.
- * 1 = SEQ gathered by the device from page-locked records, 2 = compacted on the host, 0 = contig below min_ctg_len */
+ * 1 = SEQ gathered by the device from page-locked records, 2 = compacted on the host, 3 = gathered device to device from
+ * records inflated there (np2_job_create_bgzf), 0 = contig below min_ctg_len */
 int np2_job_ingest_path(const np2_job *job);
 /* dump_iter >= 0: keep that iteration's intermediates on the host for the np2_job_get_* stage getters */
 int np2_job_run(np2_job *job, int32_t dump_iter);
@@ -243,7 +255,9 @@ void np2_job_get_stats(np2_job *job, uint64_t out[12]);
  * out[4] ranges re-walked sequentially because the guessed record boundary was wrong, out[5] FNV-1a of all arrays.
  * threads: low 16 bits = byte ranges (0 = default); bit 16 = parse as np2_job_create does (the CIGAR is only summed, the
  * op records are expanded on the device) and digest the per-record arrays only; bit 17 = build the op records on the
- * host (as without flags) but digest the per-record arrays only, so that the two digests can be compared. */
+ * host (as without flags) but digest the per-record arrays only, so that the two digests can be compared; bit 18 = the
+ * parse np2_job_create_bgzf runs (only the heads of the records, gathered here by a plain walk, and their offsets are
+ * read), per-record arrays only: same digest as bit 16. */
 int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts *opts, uint32_t threads,
                     uint64_t out[6]);
 

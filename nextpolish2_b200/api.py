@@ -48,7 +48,7 @@ EXPORTS = [
     "np2_host_alloc", "np2_host_free", "np2_job_ingest_path", "np2_debug_parse",
     "np2_secmap_create", "np2_secmap_destroy", "np2_secmap_scan_ids", "np2_secmap_scan_seqs", "np2_secmap_fill", "np2_secmap_size",
     "np2_debug_phase", "np2_set_host_threads", "np2_set_stage_timing",
-    "np2_bgzf_inflate",
+    "np2_bgzf_inflate", "np2_job_create_bgzf",
     "np2_device_count", "np2_count_create", "np2_count_add", "np2_count_distinct", "np2_count_finish", "np2_count_destroy",
 ]
 
@@ -91,6 +91,7 @@ def load_library():
     L.np2_job_upload.argtypes = [vp]
     L.np2_host_alloc.argtypes = [u64, C.POINTER(vp)]
     L.np2_bgzf_inflate.argtypes = [vp, vp, u64, vp, vp, vp, u32, u64, u64, vp, C.POINTER(C.c_float)]
+    L.np2_job_create_bgzf.argtypes = [vp, vp, u32, vp, u64, vp, vp, vp, u32, u64, u64, vp, u32, vp, C.POINTER(vp)]
     L.np2_host_free.argtypes = [vp]
     L.np2_job_ingest_path.argtypes = [vp]
     L.np2_debug_parse.argtypes = [vp, u64, u32, vp, u32, vp]
@@ -376,6 +377,26 @@ class Job:
         self.h = C.c_void_p()
         _check(load_library().np2_job_create(ctx.h, self.contig.ctypes.data, len(self.contig), self.bam.ctypes.data,
                                              len(self.bam), tp, len(self.tables), C.byref(self.opts), C.byref(self.h)))
+
+    @classmethod
+    def from_bgzf(cls, ctx, contig, comp, payload_off, payload_len, isize, skip, rec_len, tables, opts=None):
+        """np2_job_create_bgzf: the contig's BGZF members in (comp = the compressed file bytes), the records never
+        leave the device."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.contig = np.ascontiguousarray(contig, np.uint8)
+        self.bam = comp.array if isinstance(comp, PinnedBuffer) else np.ascontiguousarray(comp, np.uint8)
+        self.tables = list(tables)
+        self.opts = opts or Opts()
+        po = np.ascontiguousarray(payload_off, np.uint64)
+        pl = np.ascontiguousarray(payload_len, np.uint32)
+        iz = np.ascontiguousarray(isize, np.uint32)
+        tp = (C.c_void_p * len(self.tables))(*[t.h for t in self.tables])
+        self.h = C.c_void_p()
+        _check(load_library().np2_job_create_bgzf(ctx.h, self.contig.ctypes.data, len(self.contig), self.bam.ctypes.data,
+                                                  len(self.bam), po.ctypes.data, pl.ctypes.data, iz.ctypes.data, len(po), skip,
+                                                  rec_len, tp, len(self.tables), C.byref(self.opts), C.byref(self.h)))
+        return self
 
     def upload(self):
         _check(load_library().np2_job_upload(self.h))

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -478,10 +479,13 @@ struct np2_job {
     uint32_t L = 0;
     const uint8_t *bam = nullptr;
     uint64_t bam_len = 0;
+    DBuf<uint8_t> d_records;         // np2_job_create_bgzf: the inflated members (bam points into them)
+    bool records_on_device = false;
     Ingest &ing;
     bool uploaded = false;
     uint64_t seq_blob_bytes = 0;
-    int seq_path = 0;  // 1 = gathered by the device from page-locked records, 2 = compacted by host threads
+    int seq_path = 0;  // 1 = gathered by the device from page-locked records, 2 = compacted by host threads,
+                       // 3 = gathered device to device from records inflated there (np2_job_create_bgzf)
     explicit np2_job(np2_ctx *c)
         : ctx(c), sc(c->take_scratch()), tseq(sc->tseq), ing(sc->ing), res_base(sc->res_base), p_cpos(sc->p_cpos),
           p_cbase(sc->p_cbase), p_cflags(sc->p_cflags), timer(sc->timer), h_seeds(sc->h_seeds), h_win(sc->h_win), res_patch(sc->patch),
@@ -643,6 +647,8 @@ void np2_job::send_seq() {
         else if (at.type == cudaMemoryTypeHost && at.devicePointer) {
             src = static_cast<const uint8_t *>(at.devicePointer);
             seq_path = 1;
+        } else if (at.type == cudaMemoryTypeDevice) {  // records inflated on this device (np2_job_create_bgzf)
+            seq_path = 3;
         }
     }
     // One span per read: its raw CIGAR words and, right behind them in the record, its SEQ bytes.  co[] = where the
@@ -676,7 +682,7 @@ void np2_job::send_seq() {
     }
     h2d += (uint64_t)n * 8;
     if (!n) return;
-    if (seq_path == 1) {
+    if (seq_path == 1 || seq_path == 3) {
         DBuf<uint64_t> d_src_off, d_dst_off;
         DBuf<uint32_t> d_nbytes;
         d_src_off.alloc(n, s);
@@ -698,7 +704,7 @@ void np2_job::send_seq() {
         NP2_CUDA(cudaStreamWaitEvent(c2, sc->ev_k0, 0));
         timer.s = c2;
         int h = timer.begin("upload:seq_gather", 1);
-        if (g_k0_serial) {
+        if (g_k0_serial && seq_path == 1) {  // one K0 at a time on the LINK; a device-to-device gather does not use it
             k0_chain_enter(ctx->device, c2);
             try {
                 gather_seq(src, d_src_off.p, d_dst_off.p, d_nbytes.p, d_blob.p, n, c2);
@@ -715,7 +721,8 @@ void np2_job::send_seq() {
         NP2_CUDA(cudaEventRecord(sc->ev_k0, c2));
         NP2_CUDA(cudaStreamWaitEvent(s, sc->ev_k0, 0));
         h2d += (uint64_t)n * 20;
-        for (uint32_t r = 0; r < n; r++) h2d += span_bytes[r];
+        if (seq_path == 1)
+            for (uint32_t r = 0; r < n; r++) h2d += span_bytes[r];
         return;  // scratch is freed in stream order, after the kernel
     }
     // pageable source: rounds of <= kRound bytes through two halves of a pinned ring
@@ -845,6 +852,7 @@ void np2_job::upload() {
     timer.hbegin();
     NP2_CUDA(cudaStreamSynchronize(s));  // the main stream has waited for the copy stream (np2_job_create)
     timer.hend("upload:host_wait");
+    d_records.release();  // np2_job_create_bgzf: the spans have been gathered out of the inflated records
     timer.collect();
     if (sc->ev_t0 && L >= opt.min_ctg_len) {
         float t = 0;
@@ -2707,8 +2715,16 @@ int np2_seq_kscore(np2_ctx *ctx, const np2_table *t, const uint8_t *seqs, const 
     });
 }
 
-int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
-                   np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out) {
+static void bgzf_to_device(np2_ctx *ctx, const uint8_t *comp, uint64_t comp_len, const uint64_t *payload_off,
+                           const uint32_t *payload_len, const uint32_t *isize, uint32_t n_members, DBuf<uint8_t> &d_out,
+                           uint64_t &total, float *kernel_ms);
+
+// The body of np2_job_create / np2_job_create_bgzf.  `records` fills j.ing and leaves in j.bam / j.bam_len the buffer the
+// SEQ + CIGAR spans are gathered from (host memory, or the device's own copy of the inflated records); size_hint = the
+// record bytes the pool is sized for (known before the records are, in the BGZF case from the ISIZE fields).
+static int job_create_impl(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, uint64_t size_hint,
+                           const std::function<void(np2_job &)> &records, np2_table *const *tables, uint32_t n_tables,
+                           const np2_opts *opts, np2_job **out) {
     return guard([&] {
         if (!ctx || !tseq || !opts || !out) throw np2::Error(NP2_ERR_ARG, "null argument");
         if (n_tables == 0) throw np2::Error(NP2_ERR_ARG, "Missing yak file!");
@@ -2723,8 +2739,6 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
         std::stable_sort(j->tables.begin(), j->tables.end(),
                          [](np2_table *a, np2_table *b) { return a->dev.k < b->dev.k; });  // option.rs:238
         j->L = tlen;
-        j->bam = bam;
-        j->bam_len = bam_len;
         if (tlen >= opts->min_ctg_len) {
             if (tlen < 16) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig shorter than 16 bp");
             if (tlen >= (1u << 30)) throw np2::Error(NP2_ERR_UNSUPPORTED, "contig >= 2^30 bp (main.rs:270)");
@@ -2732,7 +2746,7 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
             {   // Grow the context's memory pool in ONE step to what a contig of this size needs (record bytes ~ 1.5 x
                 // alignment columns; ~6 B per column + ~100 B per position of device state): a cold pool otherwise grows
                 // by a hundred small mappings, which costs more than the whole polish.
-                const uint64_t want = bam_len * 4 + (uint64_t)tlen * 100 + (64ull << 20);
+                const uint64_t want = size_hint * 4 + (uint64_t)tlen * 100 + (64ull << 20);
                 if (want > ctx->pool_warm) {
                     void *p = nullptr;
                     if (cudaMallocFromPoolAsync(&p, want, ctx->pool, ctx->stream) == cudaSuccess) {
@@ -2745,7 +2759,7 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
             }
             j->send_contig(tseq);  // in flight while the host walks the records
             j->timer.hbegin();
-            parse_records(bam, bam_len, tlen, *opts, j->ing);
+            records(*j);
             j->timer.hend("upload:host_parse");
             j->enqueue_arrays();   // copy stream
             j->timer.hbegin();
@@ -2762,6 +2776,109 @@ int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8
         ctx->refs++;
         *out = j.release();
     });
+}
+
+int np2_job_create(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *bam, uint64_t bam_len,
+                   np2_table *const *tables, uint32_t n_tables, const np2_opts *opts, np2_job **out) {
+    return job_create_impl(
+        ctx, tseq, tlen, bam_len,
+        [&](np2_job &j) {
+            j.bam = bam;
+            j.bam_len = bam_len;
+            parse_records(bam, bam_len, tlen, *opts, j.ing);
+        },
+        tables, n_tables, opts, out);
+}
+
+/* A contig straight from its BGZF members: they are inflated on the device and the records STAY there.  What the host
+ * parse reads of a record — block_size, the 32 fixed bytes, the read name's length, the CIGAR words — is found and
+ * gathered on the device (np2_inflate.cu: guessed record boundaries per 64 KiB chunk, walked per chunk, joined here) and
+ * comes down as one compact buffer (~2 % of the record bytes); the SEQ + CIGAR spans are then gathered device to device.
+ * The join accepts a chunk only when the chain that starts at the region's first byte ends exactly on the chunk's guessed
+ * start; any miss, and any record the walk cannot take, sends the whole region through the host path instead (records
+ * downloaded once, parse_records), so the result never depends on the guess. */
+int np2_job_create_bgzf(np2_ctx *ctx, const uint8_t *tseq, uint32_t tlen, const uint8_t *comp, uint64_t comp_len,
+                        const uint64_t *payload_off, const uint32_t *payload_len, const uint32_t *isize, uint32_t n_members,
+                        uint64_t skip, uint64_t rec_len, np2_table *const *tables, uint32_t n_tables, const np2_opts *opts,
+                        np2_job **out) {
+    uint64_t hint = 0;
+    for (uint32_t i = 0; isize && i < n_members; i++) hint += isize[i];
+    return job_create_impl(
+        ctx, tseq, tlen, hint,
+        [&](np2_job &j) {
+            cudaStream_t s = ctx->stream;
+            uint64_t total = 0;
+            bgzf_to_device(ctx, comp, comp_len, payload_off, payload_len, isize, n_members, j.d_records, total, nullptr);
+            for (uint32_t i = 0; i < n_members; i++) j.h2d += payload_len[i];
+            if (skip > total || rec_len > total - skip) throw np2::Error(NP2_ERR_ARG, "requested range outside the inflated members");
+            const uint8_t *d_rec = j.d_records.p + skip;
+            j.bam = rec_len ? d_rec : nullptr;
+            j.bam_len = rec_len;
+            j.records_on_device = true;
+            if (!rec_len) {
+                parse_heads(nullptr, nullptr, nullptr, 0, 0, tlen, *opts, j.ing);
+                return;
+            }
+            auto host_path = [&]() {  // the speculation missed: the records come down once and are walked on the host
+                std::vector<uint8_t> host(rec_len);
+                NP2_CUDA(cudaMemcpyAsync(host.data(), d_rec, rec_len, cudaMemcpyDeviceToHost, s));
+                NP2_CUDA(cudaStreamSynchronize(s));
+                parse_records(host.data(), rec_len, tlen, *opts, j.ing);
+                j.ing.n_fallback += 1u << 16;
+            };
+            const uint32_t nc = rec_chunk_count(rec_len);
+            const uint64_t CH = rec_chunk_bytes();
+            DBuf<uint64_t> d_start, d_end, d_hb, d_base;
+            DBuf<uint32_t> d_cnt;
+            d_start.alloc(nc, s);
+            d_end.alloc(nc, s);
+            d_hb.alloc(nc, s);
+            d_cnt.alloc(nc, s);
+            rec_chunk_starts(d_rec, rec_len, d_start.p, s);
+            rec_chunk_count_walk(d_rec, rec_len, d_start.p, d_end.p, d_cnt.p, d_hb.p, s);
+            std::vector<uint64_t> start(nc), end(nc), hb(nc), base(2 * (size_t)nc, ~0ull);
+            std::vector<uint32_t> cnt(nc);
+            d_start.download(start.data(), nc);
+            d_end.download(end.data(), nc);
+            d_hb.download(hb.data(), nc);
+            d_cnt.download(cnt.data(), nc);
+            NP2_CUDA(cudaStreamSynchronize(s));
+            // join: follow the chain of chunks from byte 0
+            uint64_t n_rec = 0, n_head = 0;
+            bool ok = start[0] == 0;
+            for (uint64_t c = 0; ok;) {
+                base[c] = n_rec;
+                base[nc + c] = n_head;
+                n_rec += cnt[c];
+                n_head += hb[c];
+                const uint64_t e = end[c];
+                if (e == ~0ull) ok = false;  // a record the walk could not take
+                else if (e == rec_len) break;
+                else if (e > rec_len || start[e / CH] != e) ok = false;
+                else c = e / CH;
+            }
+            if (!ok || n_rec >= (1ull << 31)) return host_path();
+            DBuf<uint64_t> d_rec_off, d_head_off;
+            DBuf<uint8_t> d_heads;
+            d_base.alloc(2 * (size_t)nc, s);
+            d_rec_off.alloc(std::max<uint64_t>(n_rec, 1), s);
+            d_head_off.alloc(std::max<uint64_t>(n_rec, 1), s);
+            d_heads.alloc(n_head + 64, s);
+            NP2_CUDA(cudaMemcpyAsync(d_base.p, base.data(), 2 * (size_t)nc * 8, cudaMemcpyHostToDevice, s));
+            rec_chunk_write_walk(d_rec, rec_len, d_start.p, d_base.p, d_base.p + nc, d_rec_off.p, d_head_off.p, d_heads.p, s);
+            // heads | head offsets | record offsets -> one page-locked block of the context
+            const size_t o_ho = (n_head + 64 + 15) & ~(size_t)15, o_ro = o_ho + n_rec * 8;
+            ctx->p_infl_in.resize(o_ro + n_rec * 8 + 16);
+            uint8_t *hp = ctx->p_infl_in.p;
+            NP2_CUDA(cudaMemcpyAsync(hp, d_heads.p, n_head, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaMemcpyAsync(hp + o_ho, d_head_off.p, n_rec * 8, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaMemcpyAsync(hp + o_ro, d_rec_off.p, n_rec * 8, cudaMemcpyDeviceToHost, s));
+            NP2_CUDA(cudaStreamSynchronize(s));
+            j.d2h += n_head + n_rec * 16;
+            parse_heads(hp, reinterpret_cast<const uint64_t *>(hp + o_ho), reinterpret_cast<const uint64_t *>(hp + o_ro), n_rec,
+                        rec_len, tlen, *opts, j.ing);
+        },
+        tables, n_tables, opts, out);
 }
 
 /* ---- -S / --use_secondary (np2_secondary.cpp) */
@@ -2804,120 +2921,132 @@ void np2_set_stage_timing(int on) { g_stage_events.store(on ? 1 : 0); }
 
 /* BGZF members -> records, on the device (np2_inflate.cu).  The compressed span travels once (through a page-locked
  * ring when the caller's buffer is pageable, e.g. a memory-mapped file: host threads copy a chunk while the DMA moves the
- * previous one), one warp inflates each member into its final place, the wanted byte range comes back. */
+ * previous one), a group of lanes inflates each member into its final place.  bgzf_to_device leaves the members' bytes,
+ * back to back, in d_out (the stream is synchronised: the failure flag has been read). */
+static void bgzf_to_device(np2_ctx *ctx, const uint8_t *comp, uint64_t comp_len, const uint64_t *payload_off,
+                           const uint32_t *payload_len, const uint32_t *isize, uint32_t n_members, DBuf<uint8_t> &d_out,
+                           uint64_t &total, float *kernel_ms) {
+    if (!ctx || (n_members && (!comp || !payload_off || !payload_len || !isize))) throw np2::Error(NP2_ERR_ARG, "null argument");
+    if (kernel_ms) *kernel_ms = 0;
+    uint64_t lo = ~0ull, hi = 0;
+    total = 0;
+    for (uint32_t i = 0; i < n_members; i++) {
+        if (payload_off[i] > comp_len || payload_len[i] > comp_len - payload_off[i])
+            throw np2::Error(NP2_ERR_ARG, "BGZF member outside the compressed buffer");
+        if (isize[i] > np2::infl::kMaxMember) throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed! (BGZF member larger than 64 KiB)");
+        lo = std::min(lo, payload_off[i]);
+        hi = std::max(hi, payload_off[i] + payload_len[i]);
+        total += isize[i];
+    }
+    if (!n_members) return;
+    NP2_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t span = hi - lo;
+    constexpr uint64_t kFront = 16;  // the decoder reads whole aligned words: slack on both sides of the span
+    DBuf<uint8_t> d_comp, d_args;
+    d_comp.alloc(span + kFront + 32, s);
+    d_out.alloc(total + 64, s);
+    // member table: off | out_off | clen | isize | bad[2], one pinned block
+    const size_t o_out = (size_t)n_members * 8, o_clen = o_out + (size_t)n_members * 8, o_isz = o_clen + (size_t)n_members * 4;
+    const size_t o_bad = o_isz + (size_t)n_members * 4, args_bytes = o_bad + 16;
+    ctx->p_infl_args.resize(args_bytes + 16);
+    uint8_t *pa = ctx->p_infl_args.p;
+    {
+        uint64_t *a_off = reinterpret_cast<uint64_t *>(pa), *a_out = reinterpret_cast<uint64_t *>(pa + o_out);
+        uint32_t *a_clen = reinterpret_cast<uint32_t *>(pa + o_clen), *a_isz = reinterpret_cast<uint32_t *>(pa + o_isz);
+        uint32_t *a_bad = reinterpret_cast<uint32_t *>(pa + o_bad);
+        uint64_t w = 0;
+        for (uint32_t i = 0; i < n_members; i++) {
+            a_off[i] = kFront + payload_off[i] - lo;
+            a_out[i] = w;
+            a_clen[i] = payload_len[i];
+            a_isz[i] = isize[i];
+            w += isize[i];
+        }
+        a_bad[0] = 0;
+        a_bad[1] = 0xFFFFFFFFu;
+    }
+    d_args.alloc(args_bytes, s);
+    NP2_CUDA(cudaMemcpyAsync(d_args.p, pa, args_bytes, cudaMemcpyHostToDevice, s));
+    NP2_CUDA(cudaMemsetAsync(d_comp.p, 0, kFront, s));
+    NP2_CUDA(cudaMemsetAsync(d_comp.p + kFront + span, 0, 32, s));
+    bool pinned = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, comp) != cudaSuccess) cudaGetLastError();
+        else pinned = at.type == cudaMemoryTypeHost;
+    }
+    if (pinned) {
+        NP2_CUDA(cudaMemcpyAsync(d_comp.p + kFront, comp + lo, span, cudaMemcpyHostToDevice, s));
+    } else {
+        const uint64_t kChunk = 8ull << 20;
+        const uint64_t n_chunks = (span + kChunk - 1) / kChunk;
+        ctx->p_infl_in.resize(std::min<uint64_t>(span, 2 * kChunk));  // two halves: copy into one while the other is on the link
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        NP2_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        NP2_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+        const unsigned T = std::max(1u, np2::host_threads());
+        try {
+            for (uint64_t c = 0; c < n_chunks; c++) {
+                const uint64_t b = c * kChunk, e = std::min(span, b + kChunk);
+                uint8_t *half = ctx->p_infl_in.p + (c & 1) * kChunk;
+                if (c >= 2) NP2_CUDA(cudaEventSynchronize(ev[c & 1]));
+                np2::parallel_for(T, [&](unsigned ti) {
+                    const uint64_t tb = b + (e - b) * ti / T, te = b + (e - b) * (ti + 1) / T;
+                    np2::copy_streaming(half + (tb - b), comp + lo + tb, te - tb);
+                    np2::store_fence();
+                });
+                NP2_CUDA(cudaMemcpyAsync(d_comp.p + kFront + b, half, e - b, cudaMemcpyHostToDevice, s));
+                NP2_CUDA(cudaEventRecord(ev[c & 1], s));
+            }
+        } catch (...) {
+            cudaStreamSynchronize(s);
+            cudaEventDestroy(ev[0]);
+            cudaEventDestroy(ev[1]);
+            throw;
+        }
+        NP2_CUDA(cudaStreamSynchronize(s));  // the ring is reused by the next call
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+    }
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (kernel_ms) {
+        NP2_CUDA(cudaEventCreate(&t0));
+        NP2_CUDA(cudaEventCreate(&t1));
+        NP2_CUDA(cudaEventRecord(t0, s));
+    }
+    uint32_t *d_bad = reinterpret_cast<uint32_t *>(d_args.p + o_bad);
+    bgzf_inflate(d_comp.p, reinterpret_cast<const uint64_t *>(d_args.p), reinterpret_cast<const uint32_t *>(d_args.p + o_clen),
+                 reinterpret_cast<const uint64_t *>(d_args.p + o_out), reinterpret_cast<const uint32_t *>(d_args.p + o_isz),
+                 n_members, d_out.p, d_bad, s);
+    if (kernel_ms) NP2_CUDA(cudaEventRecord(t1, s));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) throw np2::Error(NP2_ERR_CUDA, std::string("k_bgzf_inflate: ") + cudaGetErrorString(le));
+    uint32_t *h_bad = reinterpret_cast<uint32_t *>(pa + args_bytes);  // behind the uploaded part of the block
+    NP2_CUDA(cudaMemcpyAsync(h_bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
+    NP2_CUDA(cudaStreamSynchronize(s));
+    if (kernel_ms) {
+        cudaEventElapsedTime(kernel_ms, t0, t1);
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+    }
+    if (h_bad[0])
+        throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed! (BGZF member " + std::to_string(h_bad[1]) + " of " +
+                                             std::to_string(n_members) + " does not inflate to its ISIZE)");
+}
+
 int np2_bgzf_inflate(np2_ctx *ctx, const uint8_t *comp, uint64_t comp_len, const uint64_t *payload_off,
                      const uint32_t *payload_len, const uint32_t *isize, uint32_t n_members, uint64_t skip, uint64_t out_len,
                      uint8_t *out, float *kernel_ms) {
     return guard([&] {
-        if (!ctx || (n_members && (!comp || !payload_off || !payload_len || !isize)) || (out_len && !out))
-            throw np2::Error(NP2_ERR_ARG, "null argument");
-        if (kernel_ms) *kernel_ms = 0;
-        uint64_t lo = ~0ull, hi = 0, total = 0;
-        for (uint32_t i = 0; i < n_members; i++) {
-            if (payload_off[i] > comp_len || payload_len[i] > comp_len - payload_off[i])
-                throw np2::Error(NP2_ERR_ARG, "BGZF member outside the compressed buffer");
-            if (isize[i] > np2::infl::kMaxMember) throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed! (BGZF member larger than 64 KiB)");
-            lo = std::min(lo, payload_off[i]);
-            hi = std::max(hi, payload_off[i] + payload_len[i]);
-            total += isize[i];
-        }
+        if (out_len && !out) throw np2::Error(NP2_ERR_ARG, "null argument");
+        DBuf<uint8_t> d_out;
+        uint64_t total = 0;
+        bgzf_to_device(ctx, comp, comp_len, payload_off, payload_len, isize, n_members, d_out, total, kernel_ms);
         if (skip > total || out_len > total - skip) throw np2::Error(NP2_ERR_ARG, "requested range outside the inflated members");
-        if (!n_members || !out_len) return;
-        NP2_CUDA(cudaSetDevice(ctx->device));
-        cudaStream_t s = ctx->stream;
-        const uint64_t span = hi - lo;
-        constexpr uint64_t kFront = 16;  // the decoder reads whole aligned words: slack on both sides of the span
-        DBuf<uint8_t> d_comp, d_out, d_args;
-        d_comp.alloc(span + kFront + 32, s);
-        d_out.alloc(total + 64, s);
-        // member table: off | out_off | clen | isize | bad[2], one pinned block
-        const size_t o_out = (size_t)n_members * 8, o_clen = o_out + (size_t)n_members * 8, o_isz = o_clen + (size_t)n_members * 4;
-        const size_t o_bad = o_isz + (size_t)n_members * 4, args_bytes = o_bad + 16;
-        ctx->p_infl_args.resize(args_bytes + 16);
-        uint8_t *pa = ctx->p_infl_args.p;
-        {
-            uint64_t *a_off = reinterpret_cast<uint64_t *>(pa), *a_out = reinterpret_cast<uint64_t *>(pa + o_out);
-            uint32_t *a_clen = reinterpret_cast<uint32_t *>(pa + o_clen), *a_isz = reinterpret_cast<uint32_t *>(pa + o_isz);
-            uint32_t *a_bad = reinterpret_cast<uint32_t *>(pa + o_bad);
-            uint64_t w = 0;
-            for (uint32_t i = 0; i < n_members; i++) {
-                a_off[i] = kFront + payload_off[i] - lo;
-                a_out[i] = w;
-                a_clen[i] = payload_len[i];
-                a_isz[i] = isize[i];
-                w += isize[i];
-            }
-            a_bad[0] = 0;
-            a_bad[1] = 0xFFFFFFFFu;
-        }
-        d_args.alloc(args_bytes, s);
-        NP2_CUDA(cudaMemcpyAsync(d_args.p, pa, args_bytes, cudaMemcpyHostToDevice, s));
-        NP2_CUDA(cudaMemsetAsync(d_comp.p, 0, kFront, s));
-        NP2_CUDA(cudaMemsetAsync(d_comp.p + kFront + span, 0, 32, s));
-        bool pinned = false;
-        {
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, comp) != cudaSuccess) cudaGetLastError();
-            else pinned = at.type == cudaMemoryTypeHost;
-        }
-        if (pinned) {
-            NP2_CUDA(cudaMemcpyAsync(d_comp.p + kFront, comp + lo, span, cudaMemcpyHostToDevice, s));
-        } else {
-            const uint64_t kChunk = 8ull << 20;
-            const uint64_t n_chunks = (span + kChunk - 1) / kChunk;
-            ctx->p_infl_in.resize(std::min<uint64_t>(span, 2 * kChunk));  // two halves: copy into one while the other is on the link
-            cudaEvent_t ev[2] = {nullptr, nullptr};
-            NP2_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-            NP2_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-            const unsigned T = std::max(1u, np2::host_threads());
-            try {
-                for (uint64_t c = 0; c < n_chunks; c++) {
-                    const uint64_t b = c * kChunk, e = std::min(span, b + kChunk);
-                    uint8_t *half = ctx->p_infl_in.p + (c & 1) * kChunk;
-                    if (c >= 2) NP2_CUDA(cudaEventSynchronize(ev[c & 1]));
-                    np2::parallel_for(T, [&](unsigned ti) {
-                        const uint64_t tb = b + (e - b) * ti / T, te = b + (e - b) * (ti + 1) / T;
-                        np2::copy_streaming(half + (tb - b), comp + lo + tb, te - tb);
-                        np2::store_fence();
-                    });
-                    NP2_CUDA(cudaMemcpyAsync(d_comp.p + kFront + b, half, e - b, cudaMemcpyHostToDevice, s));
-                    NP2_CUDA(cudaEventRecord(ev[c & 1], s));
-                }
-            } catch (...) {
-                cudaStreamSynchronize(s);
-                cudaEventDestroy(ev[0]);
-                cudaEventDestroy(ev[1]);
-                throw;
-            }
-            NP2_CUDA(cudaStreamSynchronize(s));  // the ring is reused by the next call
-            cudaEventDestroy(ev[0]);
-            cudaEventDestroy(ev[1]);
-        }
-        cudaEvent_t t0 = nullptr, t1 = nullptr;
-        if (kernel_ms) {
-            NP2_CUDA(cudaEventCreate(&t0));
-            NP2_CUDA(cudaEventCreate(&t1));
-            NP2_CUDA(cudaEventRecord(t0, s));
-        }
-        uint32_t *d_bad = reinterpret_cast<uint32_t *>(d_args.p + o_bad);
-        bgzf_inflate(d_comp.p, reinterpret_cast<const uint64_t *>(d_args.p), reinterpret_cast<const uint32_t *>(d_args.p + o_clen),
-                     reinterpret_cast<const uint64_t *>(d_args.p + o_out), reinterpret_cast<const uint32_t *>(d_args.p + o_isz),
-                     n_members, d_out.p, d_bad, s);
-        if (kernel_ms) NP2_CUDA(cudaEventRecord(t1, s));
-        cudaError_t le = cudaGetLastError();
-        if (le != cudaSuccess) throw np2::Error(NP2_ERR_CUDA, std::string("k_bgzf_inflate: ") + cudaGetErrorString(le));
-        NP2_CUDA(cudaMemcpyAsync(out, d_out.p + skip, out_len, cudaMemcpyDeviceToHost, s));
-        uint32_t *h_bad = reinterpret_cast<uint32_t *>(pa + args_bytes);  // behind the uploaded part of the block
-        NP2_CUDA(cudaMemcpyAsync(h_bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
-        NP2_CUDA(cudaStreamSynchronize(s));
-        if (kernel_ms) {
-            cudaEventElapsedTime(kernel_ms, t0, t1);
-            cudaEventDestroy(t0);
-            cudaEventDestroy(t1);
-        }
-        if (h_bad[0])
-            throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed! (BGZF member " + std::to_string(h_bad[1]) + " of " +
-                                                 std::to_string(n_members) + " does not inflate to its ISIZE)");
+        if (!out_len) return;
+        NP2_CUDA(cudaMemcpyAsync(out, d_out.p + skip, out_len, cudaMemcpyDeviceToHost, ctx->stream));
+        NP2_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
 
@@ -3107,8 +3236,31 @@ int np2_debug_parse(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const n
         Ingest ing;
         // threads bit 16: the job path's parse (CIGAR summed, no op records); bit 17: op records built but left out of
         // the digest (so that the two can be compared)
-        const bool fast = threads & 0x10000u, scalars_only = threads & 0x30000u;
-        parse_records(bam, bam_len, tlen, *opts, ing, threads & 0xFFFFu, !fast);
+        // bit 18: the parse np2_job_create_bgzf runs — only the heads of the records (gathered here by a plain walk) and
+        // their offsets are looked at; digest of the per-record arrays only
+        const bool fast = threads & 0x10000u, heads_only = threads & 0x40000u, scalars_only = threads & 0x70000u;
+        if (heads_only) {
+            std::vector<uint8_t> heads;
+            std::vector<uint64_t> head_off, rec_off;
+            for (uint64_t p = 0; p < bam_len;) {
+                if (p + 36 > bam_len) throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+                int32_t bs;
+                memcpy(&bs, bam + p, 4);
+                uint16_t n_cig;
+                memcpy(&n_cig, bam + p + 16, 2);
+                const uint64_t head = 36ull + bam[p + 12] + 4ull * n_cig;
+                if (bs < 32 || p + 4 + (uint64_t)bs > bam_len || head > 4ull + (uint64_t)bs)
+                    throw np2::Error(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+                rec_off.push_back(p);
+                head_off.push_back(heads.size());
+                heads.insert(heads.end(), bam + p, bam + p + head);
+                p += 4 + (uint64_t)bs;
+            }
+            heads.resize(heads.size() + 64);
+            parse_heads(heads.data(), head_off.data(), rec_off.data(), rec_off.size(), bam_len, tlen, *opts, ing, threads & 0xFFFFu);
+        } else {
+            parse_records(bam, bam_len, tlen, *opts, ing, threads & 0xFFFFu, !fast);
+        }
         uint64_t h = 0xcbf29ce484222325ull;
         auto mix = [&](const void *p, size_t n) {
             const uint8_t *b = static_cast<const uint8_t *>(p);

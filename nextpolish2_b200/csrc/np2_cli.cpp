@@ -424,16 +424,18 @@ void open_bam(const std::string &path, BamFile &bf) {
 // compressed span goes up, one warp inflates each member, the records come back into the blob — page-locked in the polish
 // lanes, so both copies are DMA transfers); without one, `threads` host workers call zlib (--host-inflate, and the
 // passes that run before any context exists).
-void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads, np2_ctx *gpu = nullptr) {
-    blob.resize(0);
-    if (tid < 0 || bf.ref_voff[tid] == UINT64_MAX) return;
+// the BGZF members that hold the records of reference `tid`, and which bytes of their inflated concatenation the records
+// are: [u0, u0 + n).  false = the reference has no records.
+bool locate_members(const BamFile &bf, int tid, std::vector<Member> &ms, uint64_t &u0_out, uint64_t &n_out) {
+    ms.clear();
+    u0_out = n_out = 0;
+    if (tid < 0 || bf.ref_voff[tid] == UINT64_MAX) return false;
     const uint64_t v0 = bf.ref_voff[tid], v1 = bf.ref_vend[tid];
-    if (v1 <= v0) return;
+    if (v1 <= v0) return false;
     const uint64_t c0 = v0 >> 16, c1 = v1 >> 16;
     const uint32_t u0 = (uint32_t)(v0 & 0xFFFF), u1 = (uint32_t)(v1 & 0xFFFF);
     // members [c0, c1]; the one at c1 only contributes its first u1 bytes (none when u1 == 0)
-    std::vector<Member> ms;
-    std::vector<uint64_t> uoff(1, 0);
+    uint64_t total = 0;
     for (uint64_t o = c0; o <= c1;) {
         Member m;
         if (!member_at(bf, o, m)) {
@@ -442,23 +444,39 @@ void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads, np2_ctx 
         }
         if (o == c1 && u1 == 0) break;
         ms.push_back(m);
-        uoff.push_back(uoff.back() + m.isize);
+        total += m.isize;
         o += m.total;
     }
-    if (ms.empty()) return;
-    const uint64_t total = uoff.back();
+    if (ms.empty()) return false;
     const uint64_t cut_tail = (ms.back().coff == c1) ? ms.back().isize - std::min<uint32_t>(u1, ms.back().isize) : 0;
     if ((uint64_t)u0 + cut_tail > total) die("BAM/SAM parsing failed!");
-    const uint64_t n = total - u0 - cut_tail;
+    u0_out = u0;
+    n_out = total - u0 - cut_tail;
+    return true;
+}
+void member_table(const std::vector<Member> &ms, std::vector<uint64_t> &off, std::vector<uint32_t> &clen, std::vector<uint32_t> &isz) {
+    off.resize(ms.size());
+    clen.resize(ms.size());
+    isz.resize(ms.size());
+    for (size_t i = 0; i < ms.size(); i++) {
+        off[i] = ms[i].data;
+        clen[i] = ms[i].clen;
+        isz[i] = ms[i].isize;
+    }
+}
+void fetch_records(const BamFile &bf, int tid, Blob &blob, int threads, np2_ctx *gpu = nullptr) {
+    blob.resize(0);
+    std::vector<Member> ms;
+    uint64_t u0 = 0, n = 0;
+    if (!locate_members(bf, tid, ms, u0, n)) return;
+    std::vector<uint64_t> uoff(1, 0);
+    for (const Member &m : ms) uoff.push_back(uoff.back() + m.isize);
+    const uint64_t total = uoff.back(), cut_tail = total - u0 - n;
     blob.resize(n);
     if (gpu) {
-        std::vector<uint64_t> off(ms.size());
-        std::vector<uint32_t> clen(ms.size()), isz(ms.size());
-        for (size_t i = 0; i < ms.size(); i++) {
-            off[i] = ms[i].data;
-            clen[i] = ms[i].clen;
-            isz[i] = ms[i].isize;
-        }
+        std::vector<uint64_t> off;
+        std::vector<uint32_t> clen, isz;
+        member_table(ms, off, clen, isz);
         if (np2_bgzf_inflate(gpu, bf.map, bf.size, off.data(), clen.data(), isz.data(), (uint32_t)ms.size(), u0, n, blob.p,
                              nullptr) != NP2_OK)
             die(np2_last_error());
@@ -713,19 +731,24 @@ int main(int argc, char **argv) {
             std::lock_guard<std::mutex> lk(err_mu);
             if (first_err.empty()) first_err = m;
         };
+        const bool records_on_device = !cli.host_inflate && !(getenv("NP2_CLI_RECORDS_ON_HOST") && atoi(getenv("NP2_CLI_RECORDS_ON_HOST")));
         auto polish_one = [&](np2_ctx *ctx, std::vector<np2_table *> &tabs, std::shared_future<bool> &tabs_ready, size_t i,
                               Blob &blob) -> bool {
             double ms_fetch = 0;
-            {
+            int tid = -1;
+            for (size_t r = 0; r < bf.ref_names.size(); r++)
+                if (bf.ref_names[r] == contigs[i].name) tid = (int)r;
+            if (tid < 0) return fail("Faield random access BAM/SAM!"), false;
+            // Default: the contig's BGZF members go to the device, are inflated there and the records stay there
+            // (np2_job_create_bgzf).  -S rewrites the records on the host and --host-inflate asks for zlib: both need the
+            // records in host memory (NP2_CLI_RECORDS_ON_HOST=1 does the same with the device inflate, for comparisons).
+            const bool on_device = records_on_device && !secmap;
+            if (!on_device) {
                 // the host inflate uses every thread, so the lanes take turns; the device inflate of a lane runs on the
                 // lane's own context next to the kernels of the others
                 std::unique_lock<std::mutex> lk(bam_mu, std::defer_lock);
                 if (cli.host_inflate) lk.lock();
                 const auto t0 = std::chrono::steady_clock::now();
-                int tid = -1;
-                for (size_t r = 0; r < bf.ref_names.size(); r++)
-                    if (bf.ref_names[r] == contigs[i].name) tid = (int)r;
-                if (tid < 0) return fail("Faield random access BAM/SAM!"), false;
                 fetch_records(bf, tid, blob, bf.threads, cli.host_inflate ? nullptr : ctx);
                 ms_fetch = since(t0) * 1e3;
                 us_fetch += (uint64_t)(ms_fetch * 1e3);
@@ -747,8 +770,21 @@ int main(int argc, char **argv) {
             // = np2_polish_contig, in its three steps so that NP2_CLI_TIMING=2 can clock them
             double ms_create = 0, ms_upload = 0, ms_run = 0;
             {
-                int rc = np2_job_create(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(), blob.data(),
+                int rc;
+                if (on_device) {
+                    std::vector<Member> ms;
+                    uint64_t u0 = 0, nrec = 0;
+                    std::vector<uint64_t> off;
+                    std::vector<uint32_t> clen, isz;
+                    locate_members(bf, tid, ms, u0, nrec);
+                    member_table(ms, off, clen, isz);
+                    rc = np2_job_create_bgzf(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(), bf.map,
+                                             bf.size, off.data(), clen.data(), isz.data(), (uint32_t)ms.size(), u0, nrec,
+                                             tabs.data(), (uint32_t)tabs.size(), &cli.o, &job);
+                } else {
+                    rc = np2_job_create(ctx, (const uint8_t *)contigs[i].seq.data(), (uint32_t)contigs[i].seq.size(), blob.data(),
                                         blob.size(), tabs.data(), (uint32_t)tabs.size(), &cli.o, &job);
+                }
                 ms_create = since(t_call) * 1e3;
                 if (rc == NP2_OK) rc = np2_job_upload(job);
                 ms_upload = since(t_call) * 1e3 - ms_create;
@@ -846,7 +882,7 @@ int main(int argc, char **argv) {
             const size_t want_lanes = getenv("NP2_CLI_LANES") ? (size_t)std::max(1, atoi(getenv("NP2_CLI_LANES"))) : 3;
             const size_t n_lanes = std::max<size_t>(1, std::min<size_t>(want_lanes, share[g].size()));
             std::vector<Blob *> blobs;
-            for (size_t x = 0; x < n_lanes; x++) blobs.push_back(new Blob(!cli.host_inflate));
+            for (size_t x = 0; x < n_lanes; x++) blobs.push_back(new Blob(!cli.host_inflate && !records_on_device));
             auto lane = [&](np2_ctx *c, Blob *blob) {
                 for (;;) {
                     const size_t x = next.fetch_add(1);

@@ -356,8 +356,14 @@ inline bool cigar_sums(const uint8_t *cg, uint32_t n_cig, int32_t l_seq, int32_t
 
 // One record: filter (main.rs:1758-1771) + fill_with_cigar bookkeeping (main.rs:386-440) without the strings.
 // Returns an error message when the reference would panic on it.
+// r: the record's bytes behind its block_size (which sits at r - 4); payload: where r lies in the caller's record
+// buffer (what seq_off is counted from) — the same place for a parse of the records themselves, another one when only
+// the heads of the records are at hand (parse_heads).
+const char *parse_rec(const uint8_t *r, uint64_t payload, uint32_t tlen, const np2_opts &opt, Segment &sg, bool host_ops);
 const char *parse_one(const uint8_t *bam, uint64_t payload, uint32_t tlen, const np2_opts &opt, Segment &sg, bool host_ops) {
-    const uint8_t *r = bam + payload;
+    return parse_rec(bam + payload, payload, tlen, opt, sg, host_ops);
+}
+const char *parse_rec(const uint8_t *r, uint64_t payload, uint32_t tlen, const np2_opts &opt, Segment &sg, bool host_ops) {
     const int32_t bs = rd32(r - 4), ref_id = rd32(r), pos = rd32(r + 4), l_seq = rd32(r + 16);
     const uint32_t l_name = r[8], mapq = r[9];
     uint16_t n_cig, flag;
@@ -490,6 +496,59 @@ void walk(const uint8_t *bam, uint64_t bam_len, uint64_t from, uint64_t limit, u
     }
     sg.end = p;
 }
+
+// concatenate the per-record scalars of the accepted segments (small); the op arrays stay where they are
+void finish_ingest(const std::vector<Segment *> &order, Ingest &out) {
+    size_t nrec = 0, nk = 0;
+    for (Segment *sg : order) {
+        nrec += sg->ro.size();
+        for (auto &o : sg->ro) nk += o.kept;
+    }
+    out.all_tid.reserve(nrec);
+    out.all_pos.reserve(nrec);
+    out.rec_idx.reserve(nk);
+    out.pos.reserve(nk);
+    out.ncols.reserve(nk);
+    out.rlen.reserve(nk);
+    out.rspan.reserve(nk);
+    out.is_clip.reserve(nk);
+    out.seq_off.reserve(nk);
+    out.seq_bytes.reserve(nk);
+    out.n_cig.reserve(nk);
+    out.op_off.reserve(nk + 1);
+    out.nib_off.reserve(nk + 1);
+    out.ck_off.reserve(nk + 1);
+    out.op_off.push_back(0);
+    out.nib_off.push_back(0);
+    out.ck_off.push_back(0);
+    size_t rec = 0;
+    for (Segment *sg : order) {
+        out.all_tid.insert(out.all_tid.end(), sg->tid.begin(), sg->tid.end());
+        out.all_pos.insert(out.all_pos.end(), sg->pos.begin(), sg->pos.end());
+        for (size_t i = 0; i < sg->ro.size(); i++, rec++) {
+            const RecOut &o = sg->ro[i];
+            if (!o.kept) continue;
+            out.rec_idx.push_back((int32_t)rec);
+            out.pos.push_back((uint32_t)sg->pos[i]);
+            out.ncols.push_back(o.ncols);
+            out.rlen.push_back(o.rlen);
+            out.rspan.push_back(o.rspan);
+            out.is_clip.push_back(o.is_clip);
+            out.seq_off.push_back(o.seq_off);
+            out.seq_bytes.push_back(o.seq_bytes);
+            out.n_cig.push_back(o.n_cig);
+            out.op_off.push_back(out.op_off.back() + o.n_ops);
+            out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)o.ncols / 16 + 1) * 8 + 15) & ~15ull));
+            out.ck_off.push_back(out.ck_off.back() + (o.ncols + 31) / 32);
+            out.total_cols += o.ncols;
+        }
+        if (sg->ops.n) out.op_chunks.push_back({sg->ops.p, sg->ops.n});
+    }
+    for (Segment *sg : order)
+        for (auto &o : sg->ro)
+            if (o.kept) out.n_ops += o.n_ops;
+    if (out.n_ops >= (1ull << 32)) herr(NP2_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one contig");
+}
 }  // namespace
 
 // The block_size chain is a linked list through a buffer of hundreds of MB: followed from the front it is one
@@ -547,56 +606,56 @@ void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np
         cur = sg->end;
     }
     if (cur != bam_len) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
-    // concatenate the per-record scalars (small); the op arrays stay where they are
-    size_t nrec = 0, nk = 0;
-    for (Segment *sg : order) {
-        nrec += sg->ro.size();
-        for (auto &o : sg->ro) nk += o.kept;
-    }
-    out.all_tid.reserve(nrec);
-    out.all_pos.reserve(nrec);
-    out.rec_idx.reserve(nk);
-    out.pos.reserve(nk);
-    out.ncols.reserve(nk);
-    out.rlen.reserve(nk);
-    out.rspan.reserve(nk);
-    out.is_clip.reserve(nk);
-    out.seq_off.reserve(nk);
-    out.seq_bytes.reserve(nk);
-    out.n_cig.reserve(nk);
-    out.op_off.reserve(nk + 1);
-    out.nib_off.reserve(nk + 1);
-    out.ck_off.reserve(nk + 1);
-    out.op_off.push_back(0);
-    out.nib_off.push_back(0);
-    out.ck_off.push_back(0);
-    size_t rec = 0;
-    for (Segment *sg : order) {
-        out.all_tid.insert(out.all_tid.end(), sg->tid.begin(), sg->tid.end());
-        out.all_pos.insert(out.all_pos.end(), sg->pos.begin(), sg->pos.end());
-        for (size_t i = 0; i < sg->ro.size(); i++, rec++) {
-            const RecOut &o = sg->ro[i];
-            if (!o.kept) continue;
-            out.rec_idx.push_back((int32_t)rec);
-            out.pos.push_back((uint32_t)sg->pos[i]);
-            out.ncols.push_back(o.ncols);
-            out.rlen.push_back(o.rlen);
-            out.rspan.push_back(o.rspan);
-            out.is_clip.push_back(o.is_clip);
-            out.seq_off.push_back(o.seq_off);
-            out.seq_bytes.push_back(o.seq_bytes);
-            out.n_cig.push_back(o.n_cig);
-            out.op_off.push_back(out.op_off.back() + o.n_ops);
-            out.nib_off.push_back(out.nib_off.back() + ((((uint64_t)o.ncols / 16 + 1) * 8 + 15) & ~15ull));
-            out.ck_off.push_back(out.ck_off.back() + (o.ncols + 31) / 32);
-            out.total_cols += o.ncols;
+    finish_ingest(order, out);
+}
+
+// Records whose boundaries are already known and of which only the HEADS are in host memory (the records themselves
+// were inflated on the device and stay there: np2_job_create_bgzf).  heads + head_off[i] = record i's block_size, 32
+// fixed bytes, read name and CIGAR words; rec_off[i] = where the record starts in the device's record region of
+// region_len bytes (what seq_off is counted from).  The chain is checked here: every record must begin where the one
+// before it ends and the last one must end with the region.
+void parse_heads(const uint8_t *heads, const uint64_t *head_off, const uint64_t *rec_off, uint64_t n_rec, uint64_t region_len,
+                 uint32_t tlen, const np2_opts &opt, Ingest &out, unsigned threads) {
+    out.clear();
+    out.host_ops = false;
+    unsigned T = host_threads();
+    if (n_rec < 4096) T = 1;
+    if (threads) T = std::min(threads, 64u);
+    T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(T, n_rec ? n_rec : 1));
+    auto &segs = out.segs;
+    while (segs.size() < T) segs.emplace_back(new Segment());
+    auto work = [&](unsigned ti) {
+        Segment &sg = *segs[ti];
+        sg.reset();
+        sg.found = true;
+        const uint64_t b = n_rec * ti / T, e = n_rec * (ti + 1) / T;
+        for (uint64_t i = b; i < e; i++) {
+            const uint8_t *h = heads + head_off[i];
+            const int32_t bs = rd32(h);
+            const uint64_t next = i + 1 < n_rec ? rec_off[i + 1] : region_len;
+            if (bs < 32 || rec_off[i] + 4 + (uint64_t)bs != next) {
+                sg.err_rec = (int64_t)sg.ro.size();
+                sg.err_msg = "BAM/SAM parsing failed!";
+                break;
+            }
+            if (i + 8 < e) __builtin_prefetch(heads + head_off[i + 8], 0, 1);
+            const char *m = parse_rec(h + 4, rec_off[i] + 4, tlen, opt, sg, false);
+            if (m) {
+                sg.err_rec = (int64_t)sg.ro.size() - 1;
+                sg.err_msg = m;
+                break;
+            }
         }
-        if (sg->ops.n) out.op_chunks.push_back({sg->ops.p, sg->ops.n});
+    };
+    parallel_for(T, work);
+    if (n_rec ? rec_off[0] != 0 : region_len != 0) herr(NP2_ERR_FORMAT, "BAM/SAM parsing failed!");
+    std::vector<Segment *> order;
+    for (unsigned ti = 0; ti < T; ti++) {
+        Segment *sg = segs[ti].get();
+        order.push_back(sg);
+        if (sg->err_msg) herr(NP2_ERR_FORMAT, sg->err_msg);
     }
-    for (Segment *sg : order)
-        for (auto &o : sg->ro)
-            if (o.kept) out.n_ops += o.n_ops;
-    if (out.n_ops >= (1ull << 32)) herr(NP2_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one contig");
+    finish_ingest(order, out);
 }
 
 /* ================================================================= phasing: graph + Louvain */

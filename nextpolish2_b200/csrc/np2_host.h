@@ -133,6 +133,12 @@ struct Ingest {
 void parse_records(const uint8_t *bam, uint64_t bam_len, uint32_t tlen, const np2_opts &opt, Ingest &out,
                    unsigned threads = 0, bool host_ops = false);
 
+// The same from the HEADS of records whose boundaries are known (np2_job_create_bgzf: the records were inflated on the
+// device and stay there).  heads + head_off[i] = record i's block_size, 32 fixed bytes, read name and CIGAR words;
+// rec_off[i] = the record's offset in the device's record region of region_len bytes (seq_off counts from there).
+void parse_heads(const uint8_t *heads, const uint64_t *head_off, const uint64_t *rec_off, uint64_t n_rec, uint64_t region_len,
+                 uint32_t tlen, const np2_opts &opt, Ingest &out, unsigned threads = 0);
+
 /* ---------------------------------------------------------------- regions */
 struct Regions {
     std::vector<uint32_t> start, end;  // reference order: descending position

@@ -33,8 +33,16 @@ constexpr uint32_t kInlineMatch = 8;     // matches up to this length are copied
 constexpr uint32_t kMaxMember = 65536;  // a BGZF member inflates to at most 64 KiB
 
 struct Tabs {
-    uint16_t lit_fast[1u << kLitBits];    // sym << 4 | len, 0 = code longer than kLitBits (or unused)
-    uint16_t dist_fast[1u << kDistBits];
+    // first-level tables, 0 = code longer than the table's bits (or unused); entries carry what the symbol MEANS, so the
+    // hot loop does no arithmetic on symbol numbers:
+    //   lit_fast : literal b      -> b << 4 | codelen                                   (< 0x1000)
+    //              end of block   -> 0x1000 | codelen
+    //              length code    -> 0x8000 | extra bits << 12 | (base length - 3) << 4 | codelen
+    //              286, 287       -> 0x2000 | codelen (invalid)
+    //   dist_fast: distance code  -> base distance << 8 | extra bits << 4 | codelen;  30, 31 -> base 0 (invalid)
+    // (the code-length code of a dynamic header is decoded through lit_fast as plain sym << 4 | codelen)
+    uint16_t lit_fast[1u << kLitBits];
+    uint32_t dist_fast[1u << kDistBits];
     uint16_t lit_sym[288];                // symbols ordered by (code length, symbol)
     uint16_t dist_sym[32];
     uint16_t lit_cnt[16];                 // codes per length
@@ -120,10 +128,35 @@ NP2_HD uint32_t rev_bits(uint32_t v, uint32_t n) {  // reverse the low n bits (n
     return r;
 }
 
+enum Kind : uint32_t { K_RAW = 0, K_LIT = 1, K_DIST = 2 };
+NP2_HD uint32_t lit_entry(uint32_t sym, uint32_t l) {  // RFC 1951 3.2.5, lengths
+    if (sym < 256) return sym << 4 | l;
+    if (sym == 256) return 0x1000u | l;
+    if (sym > 285) return 0x2000u | l;
+    const uint32_t i = sym - 257;
+    uint32_t extra = 0, base = 3 + i;
+    if (i == 28) {
+        base = 258;
+    } else if (i >= 8) {
+        extra = (i - 4) >> 2;
+        base = 3 + ((4 + (i & 3)) << extra);
+    }
+    return 0x8000u | extra << 12 | (base - 3) << 4 | l;
+}
+NP2_HD uint32_t dist_entry(uint32_t d, uint32_t l) {  // RFC 1951 3.2.5, distances
+    if (d > 29) return l;
+    uint32_t extra = 0, base = d + 1;
+    if (d >= 4) {
+        extra = (d >> 1) - 1;
+        base = 1 + ((2 + (d & 1)) << extra);
+    }
+    return base << 8 | extra << 4 | l;
+}
 // Canonical Huffman code from n code lengths (RFC 1951 3.2.2).  false = a set of lengths zlib refuses as well: over-
 // subscribed, or incomplete — except no code at all, or (not for the code-length code) one single 1-bit code.
-NP2_HDN bool build(const uint8_t *lens, uint32_t n, uint16_t *cnt, uint16_t *sym, uint16_t *fast, uint32_t fast_bits,
-                   bool code_length_code) {
+// kind: what the first-level entries hold (Tabs); K_RAW and K_LIT fill fast16, K_DIST fast32.
+NP2_HDN bool build(const uint8_t *lens, uint32_t n, uint16_t *cnt, uint16_t *sym, uint16_t *fast16, uint32_t *fast32,
+                   uint32_t fast_bits, uint32_t kind) {
     for (uint32_t l = 0; l < 16; l++) cnt[l] = 0;
     for (uint32_t i = 0; i < n; i++) cnt[lens[i]]++;
     cnt[0] = 0;
@@ -141,16 +174,22 @@ NP2_HDN bool build(const uint8_t *lens, uint32_t n, uint16_t *cnt, uint16_t *sym
     }
     uint32_t max_len = 15;
     while (max_len && !cnt[max_len]) max_len--;
-    if (left > 0 && max_len != 0 && (code_length_code || max_len != 1)) return false;
-    for (uint32_t i = 0; i < (1u << fast_bits); i++) fast[i] = 0;
+    if (left > 0 && max_len != 0 && (kind == K_RAW || max_len != 1)) return false;
+    for (uint32_t i = 0; i < (1u << fast_bits); i++) {
+        if (kind == K_DIST) fast32[i] = 0;
+        else fast16[i] = 0;
+    }
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t l = lens[i];
         if (!l) continue;
         sym[offs[l]++] = (uint16_t)i;
         const uint32_t c = next_code[l]++;
         if (l <= fast_bits) {
-            const uint16_t e = (uint16_t)(i << 4 | l);
-            for (uint32_t j = rev_bits(c, l); j < (1u << fast_bits); j += 1u << l) fast[j] = e;
+            const uint32_t e = kind == K_RAW ? (i << 4 | l) : (kind == K_LIT ? lit_entry(i, l) : dist_entry(i, l));
+            for (uint32_t j = rev_bits(c, l); j < (1u << fast_bits); j += 1u << l) {
+                if (kind == K_DIST) fast32[j] = e;
+                else fast16[j] = (uint16_t)e;
+            }
         }
     }
     return true;
@@ -171,10 +210,11 @@ NP2_HDN uint32_t decode_long(uint64_t bits, const uint16_t *cnt, const uint16_t 
     }
     return 0xFFFF0u;  // no such code
 }
-// One symbol of a code; needs >= 15 valid bits.  Returns the symbol or 0xFFFF (no such code).
-NP2_HD uint32_t decode_sym(State &s, const uint16_t *fast, uint32_t fast_bits, const uint16_t *cnt, const uint16_t *sym) {
-    uint32_t e = fast[(uint32_t)s.buf & ((1u << fast_bits) - 1)];
-    if (!e) e = decode_long(s.buf, cnt, sym);
+// One symbol of the code-length code (raw entries in the first kDistBits-wide slots of lit_fast; its codes are at most
+// 7 bits long, so the first level always answers).  Returns the symbol or 0xFFFF (no such code).
+NP2_HD uint32_t decode_raw(State &s, const uint16_t *fast, uint32_t fast_bits) {
+    const uint32_t e = fast[(uint32_t)s.buf & ((1u << fast_bits) - 1)];
+    if (!e) return 0xFFFFu;
     s.buf >>= (e & 15);
     s.cnt -= (e & 15);
     return e >> 4;
@@ -194,12 +234,12 @@ NP2_HD bool dynamic_tables(State &s, Tabs &t) {
         refill(s);
         cl[ord] = (uint8_t)take(s, 3);
     }
-    // the code-length code is decoded through the distance table's slots (they are rebuilt right after)
-    if (!build(cl, 19, t.dist_cnt, t.dist_sym, t.dist_fast, kDistBits, true)) return false;
+    // the code-length code is decoded through the literal table's slots (they are rebuilt right after)
+    if (!build(cl, 19, t.dist_cnt, t.dist_sym, t.lit_fast, nullptr, kDistBits, K_RAW)) return false;
     uint32_t n = 0, prev = 0;
     while (n < hlit + hdist) {
         refill(s);
-        const uint32_t c = decode_sym(s, t.dist_fast, kDistBits, t.dist_cnt, t.dist_sym);
+        const uint32_t c = decode_raw(s, t.lit_fast, kDistBits);
         if (c < 16) {
             t.lens[n++] = (uint8_t)c;
             prev = c;
@@ -222,16 +262,16 @@ NP2_HD bool dynamic_tables(State &s, Tabs &t) {
         prev = v;
     }
     if (t.lens[256] == 0) return false;  // no end-of-block code
-    if (!build(t.lens, hlit, t.lit_cnt, t.lit_sym, t.lit_fast, kLitBits, false)) return false;
-    return build(t.lens + hlit, hdist, t.dist_cnt, t.dist_sym, t.dist_fast, kDistBits, false);
+    if (!build(t.lens, hlit, t.lit_cnt, t.lit_sym, t.lit_fast, nullptr, kLitBits, K_LIT)) return false;
+    return build(t.lens + hlit, hdist, t.dist_cnt, t.dist_sym, nullptr, t.dist_fast, kDistBits, K_DIST);
 }
 NP2_HDN bool fixed_tables(Tabs &t) {  // RFC 1951 3.2.6
     for (uint32_t i = 0; i < 288; i++) t.lens[i] = (uint8_t)(i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8)));
-    if (!build(t.lens, 288, t.lit_cnt, t.lit_sym, t.lit_fast, kLitBits, false)) return false;
+    if (!build(t.lens, 288, t.lit_cnt, t.lit_sym, t.lit_fast, nullptr, kLitBits, K_LIT)) return false;
     for (uint32_t i = 0; i < 30; i++) t.lens[i] = 5;
     // zlib's fixed distance table has all 32 five-bit codes (a complete set); 30 and 31 are rejected when they are used
     t.lens[30] = t.lens[31] = 5;
-    return build(t.lens, 32, t.dist_cnt, t.dist_sym, t.dist_fast, kDistBits, false);
+    return build(t.lens, 32, t.dist_cnt, t.dist_sym, nullptr, t.dist_fast, kDistBits, K_DIST);
 }
 
 // Runs until bytes have to be copied or the member ends.
@@ -295,41 +335,34 @@ NP2_HD uint32_t infl_step(State &s, Tabs &t, uint32_t &a, uint32_t &b) {
                 }
                 refill(s);  // only adds bits above the ones e was looked up with
             }
-            if (!e) e = decode_long(s.buf, t.lit_cnt, t.lit_sym);
+            if (!e) {  // a code longer than the first level: its symbol, turned into the same kind of entry
+                const uint32_t x = decode_long(s.buf, t.lit_cnt, t.lit_sym);
+                e = x == 0xFFFF0u ? 0x2000u : lit_entry(x >> 4, x & 15);
+            }
             s.buf >>= (e & 15);
             s.cnt -= (e & 15);
-            uint32_t sym = e >> 4;
-            if (sym < 256) {
+            if (e < 0x1000u) {  // literal
                 if (s.pos >= s.cap) return EV_ERROR;
-                s.out[s.pos++] = (uint8_t)sym;
+                s.out[s.pos++] = (uint8_t)(e >> 4);
                 continue;
             }
-            if (sym == 256) {
-                s.in_block = 0;
+            if (!(e & 0x8000u)) {
+                if (e >= 0x2000u) return EV_ERROR;  // 286, 287 and "no such code"
+                s.in_block = 0;                     // end of block
                 if (consumed_bits(s) > s.limit_bits) return EV_ERROR;
                 break;
             }
-            if (sym > 285) return EV_ERROR;  // 286, 287 and "no such code"
-            sym -= 257;
-            uint32_t len;
-            if (sym < 8) {
-                len = 3 + sym;
-            } else if (sym == 28) {
-                len = 258;
-            } else {
-                const uint32_t e = (sym - 4) >> 2;
-                len = 3 + ((4 + (sym & 3)) << e) + take(s, e);
-            }
+            const uint32_t len = 3 + ((e >> 4) & 0xFFu) + take(s, (e >> 12) & 7u);
             refill(s);
-            const uint32_t d = decode_sym(s, t.dist_fast, kDistBits, t.dist_cnt, t.dist_sym);
-            if (d > 29) return EV_ERROR;
-            uint32_t dist;
-            if (d < 4) {
-                dist = d + 1;
-            } else {
-                const uint32_t e = (d >> 1) - 1;
-                dist = 1 + ((2 + (d & 1)) << e) + take(s, e);
+            uint32_t de = t.dist_fast[(uint32_t)s.buf & ((1u << kDistBits) - 1)];
+            if (!de) {
+                const uint32_t x = decode_long(s.buf, t.dist_cnt, t.dist_sym);
+                de = x == 0xFFFF0u ? 0u : dist_entry(x >> 4, x & 15);
             }
+            s.buf >>= (de & 15);
+            s.cnt -= (de & 15);
+            if (!(de >> 8)) return EV_ERROR;  // 30, 31 and "no such code"
+            const uint32_t dist = (de >> 8) + take(s, (de >> 4) & 15u);
             if (dist > s.pos || s.pos + len > s.cap) return EV_ERROR;
             if (len <= s.inline_max) {
                 // Short matches are most of what a fast deflate level makes of DNA (any 3 bytes of 4-bit SEQ have

@@ -328,5 +328,17 @@ void count_file_keys(const uint64_t *d_keys, const uint16_t *d_cnt, uint64_t n, 
 // before the launch -> {members that are no valid DEFLATE stream of their ISIZE, index of the first one}
 void bgzf_inflate(const uint8_t *d_comp, const uint64_t *d_off, const uint32_t *d_clen, const uint64_t *d_out_off,
                   const uint32_t *d_isize, uint32_t n_members, uint8_t *d_out, uint32_t *d_bad, cudaStream_t s);
+// Record boundaries of an inflated contig without bringing the records to the host (np2_inflate.cu): per 64 KiB chunk
+// the guessed first record start (~0 = none), then per chunk the walk's end / record count / head bytes; after the host
+// has joined the chunks (rec_base / head_base = exclusive prefix sums over the accepted chunks, ~0 for the others) the
+// offsets of all records and their heads (block_size + 32 fixed bytes + read name + CIGAR words) in one compact buffer.
+uint32_t rec_chunk_count(uint64_t n);
+uint32_t rec_chunk_bytes();
+void rec_chunk_starts(const uint8_t *d_rec, uint64_t n, uint64_t *d_start, cudaStream_t s);
+void rec_chunk_count_walk(const uint8_t *d_rec, uint64_t n, const uint64_t *d_start, uint64_t *d_end, uint32_t *d_cnt,
+                          uint64_t *d_hbytes, cudaStream_t s);
+void rec_chunk_write_walk(const uint8_t *d_rec, uint64_t n, const uint64_t *d_start, const uint64_t *d_rec_base,
+                          const uint64_t *d_head_base, uint64_t *d_rec_off, uint64_t *d_head_off, uint8_t *d_heads,
+                          cudaStream_t s);
 
 }  // namespace np2

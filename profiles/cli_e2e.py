@@ -57,8 +57,9 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
         t0 = time.time()
         synth.write_bam(bam, names, [L] * n_ctg, blobs, level=level)
         print("BAM level %d: %.1f MB written in %.1f s" % (level, os.path.getsize(bam) / 1e6, time.time() - t0), flush=True)
-        modes = [("device inflate, 3 lanes", [], {}), ("device inflate, 4 lanes", [], {"NP2_CLI_LANES": "4"}),
-                 ("device inflate, 5 lanes", [], {"NP2_CLI_LANES": "5"}), ("host inflate (zlib), 3 lanes", ["--host-inflate"], {})]
+        modes = [("device inflate, records stay on the device (default)", [], {}),
+                 ("device inflate, records come back to the host", [], {"NP2_CLI_RECORDS_ON_HOST": "1"}),
+                 ("host inflate (zlib)", ["--host-inflate"], {})]
         for label, mode, env in modes:
             for rep in range(2):
                 out = os.path.join(d, "out.fa")

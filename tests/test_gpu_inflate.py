@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import bgzf as OB  # oracle/bgzf.py: member walk + zlib
+import oracle as O
 import nextpolish2_b200 as np2
 from nextpolish2_b200 import synth
 
@@ -122,3 +123,56 @@ def test_bad_member_is_an_error(ctx, bam_files):
     # the context is still usable
     got, _ = np2.bgzf_inflate(ctx, files[6], po, pl, iz)
     assert bytes(got) == OB.inflate_all(files[6])
+
+
+@pytest.mark.parametrize("name", ["hap300k", "dip600k", "clip120k"])
+def test_job_from_bgzf_members_equals_job_from_records(ctx, tmp_path, name):
+    """np2_job_create_bgzf: members inflated on the device, record boundaries found there, only the record heads on
+    the host — same consensus, same dropped reads, same ingest as the job made from the records themselves."""
+    import common
+    ds = common.dataset(name)
+    A, rec = ds["contig"], np.ascontiguousarray(ds["bam"], np.uint8)
+    path = str(tmp_path / "c.bam")
+    synth.write_bam(path, ["ctg"], [len(A)], [rec], level=1)
+    buf = np.fromfile(path, np.uint8)
+    po, pl, iz = np2.bgzf_members(buf)
+    skip = OB.inflate_all(buf).find(bytes(rec[:4096]))
+    assert skip > 0
+    tabs = common.gpu_tables(ctx, ds)
+    opts = np2.Opts(min_ctg_len=0)
+    a = np2.Job(ctx, A, rec, tabs, opts).upload().run()
+    b = np2.Job.from_bgzf(ctx, A, buf, po, pl, iz, skip, len(rec), tabs, opts)
+    assert b.ingest_path == 3
+    b.upload().run()
+    pa, ba = a.consensus()
+    pb, bb = b.consensus()
+    assert np.array_equal(ba, bb) and np.array_equal(pa, pb)
+    assert np.array_equal(a.dropped(), b.dropped())
+    oj = O.Job(A, rec, common.oracle_tables(ds), O.Opts(min_ctg_len=0))
+    opos, obase = oj.consensus()
+    assert np.array_equal(bb, obase) and np.array_equal(pb, opos)
+    a.destroy()
+    b.destroy()
+    for t in tabs:
+        t.free()
+
+
+def test_job_from_bgzf_reports_bad_records(ctx, tmp_path):
+    """a region that does not start at a record boundary: 'BAM/SAM parsing failed!' like the host path"""
+    import common
+    ds = common.dataset("tiny20k")
+    A, rec = ds["contig"], np.ascontiguousarray(ds["bam"], np.uint8)
+    path = str(tmp_path / "c.bam")
+    synth.write_bam(path, ["ctg"], [len(A)], [rec], level=6)
+    buf = np.fromfile(path, np.uint8)
+    po, pl, iz = np2.bgzf_members(buf)
+    skip = OB.inflate_all(buf).find(bytes(rec[:4096]))
+    tabs = common.gpu_tables(ctx, ds)
+    with pytest.raises(np2.Np2Error) as e:
+        np2.Job.from_bgzf(ctx, A, buf, po, pl, iz, skip + 7, len(rec) - 7, tabs, np2.Opts(min_ctg_len=0))
+    assert e.value.code == -4
+    ok = np2.Job.from_bgzf(ctx, A, buf, po, pl, iz, skip, len(rec), tabs, np2.Opts(min_ctg_len=0)).upload().run()
+    assert bytes(ok.consensus()[1]) == bytes(ds["haps"][0])
+    ok.destroy()
+    for t in tabs:
+        t.free()

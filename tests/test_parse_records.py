@@ -113,6 +113,7 @@ def test_counts_match_an_independent_record_reader():
 
 
 FAST, SCALARS = 0x10000, 0x20000  # np2_debug_parse flags: the job path's parse / host-built ops left out of the digest
+HEADS = 0x40000                   # the parse of np2_job_create_bgzf: record heads + offsets only
 
 
 def _same_scalars(bam, L, **kw):
@@ -120,6 +121,8 @@ def _same_scalars(bam, L, **kw):
     for t in (1, 3):
         a, b = _parse(bam, L, t | FAST, **kw), _parse(bam, L, t | SCALARS, **kw)
         assert {k: a[k] for k in keys} == {k: b[k] for k in keys}, (t, a, b)
+        c = _parse(bam, L, t | HEADS, **kw)  # same records seen through their heads only
+        assert {k: a[k] for k in keys} == {k: c[k] for k in keys}, (t, a, c)
     return a
 
 
@@ -190,7 +193,7 @@ def test_summed_cigar_parse_reports_the_same_errors():
         "outside the contig": synth.bam_record(0, L + 5, [("M", 2400)], "ACGT" * 600),
     }
     for msg, bad in cases.items():
-        for flags in (FAST, 0):
+        for flags in (FAST, 0, HEADS):
             with pytest.raises(api.Np2Error) as e:
                 _parse(np.concatenate(good[:4] + [bad] + good[4:]), L, 2 | flags)
             assert msg in str(e.value), (msg, flags, str(e.value))
