@@ -852,7 +852,7 @@ def bgzf_bench(ctx, np2, bam_records, ref_len, cores):
         del want, raw, buf
     res["kernel"] = "k_bgzf_inflate<16, 4> (np2_inflate.cu): 16 lanes per BGZF member, Huffman tables in shared memory"
     res["note"] = ("not part of `value` / `e2e` (those start from uncompressed records, as the reference's worker closure does); "
-                   "the command line's file -> FASTA numbers are in profiles/r02ay_cli_e2e.txt")
+                   "the command line's file -> FASTA numbers (np2_job_create_bgzf: the records stay on the device) are in profiles/r02az_cli_e2e.txt")
     return res
 
 
