@@ -707,14 +707,14 @@ void np2_job::send_seq() {
         if (g_k0_serial && seq_path == 1) {  // one K0 at a time on the LINK; a device-to-device gather does not use it
             k0_chain_enter(ctx->device, c2);
             try {
-                gather_seq(src, d_src_off.p, d_dst_off.p, d_nbytes.p, d_blob.p, n, c2);
+                gather_seq(src, d_src_off.p, d_dst_off.p, d_nbytes.p, d_blob.p, n, c2, seq_path == 3);
             } catch (...) {
                 g_k0_chain[ctx->device & 15].mu.unlock();
                 throw;
             }
             k0_chain_leave(ctx->device, c2);
         } else {
-            gather_seq(src, d_src_off.p, d_dst_off.p, d_nbytes.p, d_blob.p, n, c2);
+            gather_seq(src, d_src_off.p, d_dst_off.p, d_nbytes.p, d_blob.p, n, c2, seq_path == 3);
         }
         timer.end(h);
         timer.s = s;

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(32) k_gather_seq_tma(const uint8_t *__restrict
 // the link; a CTA per read would fill every SM with waiting threads and lock out the kernels of the other contig
 // that is in flight on this GPU.
 void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
-                uint8_t *d_dst, uint32_t n_reads, cudaStream_t s) {
+                uint8_t *d_dst, uint32_t n_reads, cudaStream_t s, bool src_on_device) {
     static const uint32_t ctas = getenv("NP2_K0_CTAS") ? (uint32_t)atoi(getenv("NP2_K0_CTAS")) : 2 * 148;
     static const bool use_tma = !(getenv("NP2_K0_TMA") && atoi(getenv("NP2_K0_TMA")) == 0);
     if (n_reads && use_tma) {
@@ -394,7 +394,10 @@ void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint
         // 16 single-thread CTAs keep the link full (two 16 KB stages each); one per SM (148) measured the same alone and
         // 8 % slower with contigs in flight: a resident CTA pins its SM's shared-memory configuration for milliseconds
         static const uint32_t tma_ctas = getenv("NP2_K0_CTAS") ? ctas : 16;
-        NP2_K(k_gather_seq_tma)<<<std::min<uint32_t>(n_reads, std::max(1u, tma_ctas)), 32, 2 * kTmaStage, s>>>(
+        // records already on this device (np2_job_create_bgzf): the gather runs against HBM, not the link — a CTA pair
+        // per SM keeps enough 16 KB bulk copies in flight (16 CTAs: 0.80 ms for 165 MB, profiles/r02bc_bgzf_job_launches.txt)
+        const uint32_t want = src_on_device ? 2 * 148 : tma_ctas;
+        NP2_K(k_gather_seq_tma)<<<std::min<uint32_t>(n_reads, std::max(1u, want)), 32, 2 * kTmaStage, s>>>(
             src_mapped, d_src_off, d_dst_off, d_nbytes, d_dst, n_reads);
         return;
     }

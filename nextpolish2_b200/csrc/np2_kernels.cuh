@@ -104,7 +104,7 @@ struct ReadsDev {
 };
 // K0: pull the SEQ fields out of a page-locked (mapped) record buffer; dst_off[r] is 16-B aligned + (source address & 15)
 void gather_seq(const uint8_t *src_mapped, const uint64_t *d_src_off, const uint64_t *d_dst_off, const uint32_t *d_nbytes,
-                uint8_t *d_dst, uint32_t n_reads, cudaStream_t s);
+                uint8_t *d_dst, uint32_t n_reads, cudaStream_t s, bool src_on_device = false);
 // raw CIGAR words (in front of every read's SEQ in the blob) -> the 16-byte op records of the column-consuming ops
 void cigar_ops(const uint8_t *d_blob, const uint64_t *d_seq_off, const uint32_t *d_n_cig, const uint32_t *d_op_off,
                uint4 *d_ops, uint32_t n_reads, cudaStream_t s);
