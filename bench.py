@@ -570,13 +570,15 @@ def _run_ours(args):
             "wall_ms_per_step": round(m.wall / args.steps * 1e3, 3),
         }
     del m
-    for t in tables:
-        t.free()
     if rank == 0 and world == 1 and not args.no_bgzf_bench:  # the ingest step in front of the path, on the same records
         try:
-            line["bgzf_inflate"] = bgzf_bench(ctx, np2, contigs[0]["bam"], int(len(contigs[0]["contig"])), cores)
+            c0 = contigs[0]
+            line["bgzf_inflate"] = bgzf_bench(ctx, np2, c0["bam"], int(len(c0["contig"])), cores, contig=c0["contig"],
+                                              tables=tables, opts=opts, truth=c0["hap1"] if not len(c0["hap2"]) else None)
         except Exception as e:  # noqa: BLE001
             line["bgzf_inflate"] = {"error": repr(e)[:300]}
+    for t in tables:
+        t.free()
     del contigs, tabs
 
     # ---- the other configs, bounded (N = 1): same measurement, fewer steps
@@ -799,7 +801,7 @@ def strong_scaling(args, np2, torch, dist, ctx, local, rank, world, cores, barri
     return res
 
 
-def bgzf_bench(ctx, np2, bam_records, ref_len, cores):
+def bgzf_bench(ctx, np2, bam_records, ref_len, cores, contig=None, tables=None, opts=None, truth=None):
     """The ingest step in front of the hot path: the headline contig's records written as a BAM
     (BGZF level 1 and 6, the synthetic-input tool's writer), every member inflated on the device by np2_bgzf_inflate
     (a group of lanes per member) from a page-locked copy of the file into a page-locked record buffer.  Reported: the
@@ -847,6 +849,33 @@ def bgzf_bench(ctx, np2, bam_records, ref_len, cores):
             "kernel_ms": round(kms, 3), "kernel_GBps_out": round(total / kms / 1e6, 1), "kernel_GBps_in": round(len(buf) / kms / 1e6, 1),
             "call_ms_pinned_in_pinned_out": round(wms, 2), "h2d_bytes": int(len(buf)), "d2h_bytes": total,
             "host_zlib_ms": round(t_host * 1e3, 1), "host_threads": cores, "identical_to_zlib": bool(same)}
+        if level == 1 and tables is not None:
+            # file bytes -> polished bases through np2_job_create_bgzf (records inflated, walked and gathered on the
+            # device; only the record heads come down), one contig at a time on one context: what the command line
+            # runs per lane.  The result must be the contig the record path produces (= the truth haplotype here).
+            skip = want.find(bytes(bam_records[:4096]))
+            ref_job = np2.Job(ctx, contig, bam_records, tables, opts).upload().run()
+            ref_base = bytes(ref_job.bases()[2])
+            ref_job.destroy()
+            ts, same_job = [], None
+            for rep in range(4):
+                t0 = time.perf_counter()
+                job = np2.Job.from_bgzf(ctx, contig, pin_in, po, pl, iz, skip, len(bam_records), tables, opts).upload().run()
+                first, last, base = job.bases(copy=False)
+                n_base = len(base)
+                ts.append((time.perf_counter() - t0) * 1e3)
+                if rep == 0:
+                    same_job = bool(bytes(base) == ref_base)
+                    same_truth = None if truth is None else bool(ref_base == bytes(truth))
+                path = job.ingest_path
+                job.destroy()
+            res["job_from_members"] = {
+                "entry": "np2_job_create_bgzf -> np2_job_upload -> np2_job_run -> np2_job_get_consensus",
+                "ms_per_contig_one_at_a_time": round(float(np.median(ts[1:])), 2),
+                "Mbp_per_s_one_at_a_time": round(ref_len / 1e3 / float(np.median(ts[1:])), 1),
+                "h2d_bytes": int(len(buf)) + ref_len, "ingest_path": int(path),
+                "identical_to_job_from_records": same_job, "identical_to_truth_haplotype": same_truth,
+                "note": "three lanes of the command line overlap these steps: 11 ms per contig (profiles/r02az_cli_e2e.txt)"}
         pin_in.free()
         pin_out.free()
         del want, raw, buf
