@@ -176,3 +176,37 @@ def test_job_from_bgzf_reports_bad_records(ctx, tmp_path):
     ok.destroy()
     for t in tabs:
         t.free()
+
+
+def test_job_from_bgzf_fallback_walks_the_records_on_the_host(tmp_path):
+    """When the chunk join misses, the region is downloaded once and parsed by the host parser; the spans are still
+    gathered from the device's records.  NP2_BGZF_HOST_PARSE=1 forces that path (own process: the knob is read once)."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys, numpy as np
+sys.path[:0] = [%r, %r, %r]
+import common, bgzf as OB, oracle as O, nextpolish2_b200 as np2
+from nextpolish2_b200 import synth
+ds = common.dataset("clip120k")
+A, rec = ds["contig"], np.ascontiguousarray(ds["bam"], np.uint8)
+synth.write_bam(%r, ["ctg"], [len(A)], [rec], level=1)
+buf = np.fromfile(%r, np.uint8)
+po, pl, iz = np2.bgzf_members(buf)
+skip = OB.inflate_all(buf).find(bytes(rec[:4096]))
+ctx = np2.Context(0)
+tabs = common.gpu_tables(ctx, ds)
+j = np2.Job.from_bgzf(ctx, A, buf, po, pl, iz, skip, len(rec), tabs, np2.Opts(min_ctg_len=0))
+assert j.ingest_path == 3
+j.upload().run()
+pos, base = j.consensus()
+opos, obase = O.Job(A, rec, common.oracle_tables(ds), O.Opts(min_ctg_len=0)).consensus()
+assert np.array_equal(base, obase) and np.array_equal(pos, opos)
+print("fallback ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "f.bam")
+    r = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"), path, path)],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, NP2_BGZF_HOST_PARSE="1"))
+    assert r.returncode == 0 and "fallback ok" in r.stdout, r.stderr[-2000:]
