@@ -1,13 +1,16 @@
 // np2_inflate.cu — BGZF members inflated on the device (replaces htslib's bgzf_read_block +
 // zlib under bam::IndexedReader::fetch / records(), reference src/main.rs:1745-1757).
 //
-// A coordinate-sorted HiFi BAM holds ~700 independent <= 64 KiB DEFLATE members per Mbp of contig at 30x.  One WARP
-// takes one member: lane 0 runs the bit-serial part (np2_inflate.cuh infl_step: block headers, Huffman tables in shared
-// memory, symbol decode, literal bytes), and every time bytes have to be COPIED — an LZ77 match or a stored block — all 32
-// lanes do it, coalesced.  The serial part of a warp is latency bound (table look-up -> shift -> look-up), so the SM hides
-// it behind the other resident warps (one member each): throughput comes from the ~6000 members in flight, not from
-// any single one.  Output goes straight to its final place in the contig's record buffer (members are laid out back to
-// back by the caller's prefix sum of ISIZE), compressed input is read through the read-only path.
+// A coordinate-sorted HiFi BAM holds ~900 independent <= 64 KiB DEFLATE members per Mbp of contig at 30x.  A GROUP OF
+// LANES (16 by default, two members per warp) takes one member: the group's leader runs the bit-serial part
+// (np2_inflate.cuh infl_step: block headers, Huffman tables in shared memory, symbol decode, literal bytes, matches of up
+// to 8 bytes), and every time more bytes have to be COPIED — a longer LZ77 match or a stored block — the whole group does
+// it, coalesced.  One member's decode is a serial chain (table look-up -> shift -> look-up); the SM hides it behind the
+// other resident groups: throughput comes from the ~9000 members in flight, not from any single one, and once the grid
+// fills the SMs the kernel is bound by instruction issue (profiles/r02aw_inflate_ncu_summary.txt).  Output goes straight
+// to its final place in the contig's record buffer (members are laid out back to back by the caller's prefix sum of
+// ISIZE), compressed input is read through the read-only path.  The second half of the file finds the record boundaries
+// in the inflated bytes, so that the records can stay on the device (np2_job_create_bgzf).
 #include <algorithm>
 #include <cstdlib>
 
