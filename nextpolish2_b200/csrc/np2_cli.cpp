@@ -879,7 +879,13 @@ int main(int argc, char **argv) {
             // profiles/r01_cli_e2e.txt).  They, the contexts and the tables are NOT released when a lane or a GPU is done:
             // freeing page-locked memory or a pool synchronises the device and stalls the lanes still at work (100 ms
             // and more, profiles/r02av_cli_e2e.txt), and the process ends right after the last record is written.
-            const size_t want_lanes = getenv("NP2_CLI_LANES") ? (size_t)std::max(1, atoi(getenv("NP2_CLI_LANES"))) : 3;
+            // Contigs in flight per GPU.  With the records on the device a lane costs a context and its pool, no page-locked
+            // buffer, and its host share is small: five lanes on a 16-core host polish 10 Mbp contigs every 9.2 ms where
+            // three need 11.4 (profiles/r02bf_cli_lanes.txt); a third of the cores a GPU has, between 3 and 6.  The paths
+            // that bring the records to the host keep three (more only page-lock more memory, profiles/r02ay_cli_e2e.txt).
+            const size_t cores_per_gpu = std::max<size_t>(1, std::thread::hardware_concurrency() / (size_t)std::max(1, n_gpu));
+            const size_t auto_lanes = records_on_device ? std::min<size_t>(6, std::max<size_t>(3, cores_per_gpu / 3)) : 3;
+            const size_t want_lanes = getenv("NP2_CLI_LANES") ? (size_t)std::max(1, atoi(getenv("NP2_CLI_LANES"))) : auto_lanes;
             const size_t n_lanes = std::max<size_t>(1, std::min<size_t>(want_lanes, share[g].size()));
             std::vector<Blob *> blobs;
             for (size_t x = 0; x < n_lanes; x++) blobs.push_back(new Blob(!cli.host_inflate && !records_on_device));
@@ -894,7 +900,6 @@ int main(int argc, char **argv) {
                     if (!polish_one(c, tabs, tabs_ready, share[g][x], *blob)) break;
                 }
             };
-            // up to three contigs in flight per GPU (measured: 1.0 / 1.24 / 1.49 Gbp/s for 1 / 2 / 3 on 10 Mbp contigs)
             std::vector<np2_ctx *> extra;
             std::vector<std::thread> more;
             for (size_t x = 1; x < n_lanes; x++) {

@@ -1,6 +1,6 @@
 """End-to-end timing of the nextPolish2 command line on the GPU box: process start -> FASTA written, BAM (BGZF) decode
 and table loading included (SURVEY 8(d) metric (1)).
-usage: python profiles/cli_e2e.py [n_contigs] [contig_bp] [bgzf levels, e.g. 1,0] [n_distinct] [timing level]
+usage: python profiles/cli_e2e.py [n_contigs] [contig_bp] [bgzf levels, e.g. 1,0] [n_distinct] [timing level] [lanes]
 n_distinct < n_contigs: only that many contigs are synthesised, the others are copies under their own name / refID (the
 generator, not the command line, is what takes the time on the box)."""
 import os
@@ -60,8 +60,10 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
         modes = [("device inflate, records stay on the device (default)", [], {}),
                  ("device inflate, records come back to the host", [], {"NP2_CLI_RECORDS_ON_HOST": "1"}),
                  ("host inflate (zlib)", ["--host-inflate"], {})]
+        if len(sys.argv) > 6 and sys.argv[6] == "lanes":  # contigs in flight per GPU on the default path
+            modes = [("records stay on the device, %d lanes" % k, [], {"NP2_CLI_LANES": str(k)}) for k in (3, 4, 5, 6)]
         for label, mode, env in modes:
-            for rep in range(2):
+            for rep in range(1 if len(sys.argv) > 6 else 2):
                 out = os.path.join(d, "out.fa")
                 if os.path.exists(out):
                     os.remove(out)
