@@ -9,8 +9,8 @@
 // (the BAM is memory-mapped; a contig's BGZF members are inflated on the device by np2_bgzf_inflate, one
 // warp per member, or with --host-inflate by zlib on the host threads, in parallel and in place) that hand each contig's
 // raw alignment records to np2_polish_contig, and the orchestration
-// the reference does with three thread stages (main.rs:1698-1853): contigs are LPT-partitioned over the GPUs, up to
-// three host threads (contexts) per GPU share one set of tables, records are printed in INPUT order (= the reference
+// the reference does with three thread stages (main.rs:1698-1853): contigs are LPT-partitioned over the GPUs, three to
+// six host threads (contexts) per GPU share one set of tables, records are printed in INPUT order (= the reference
 // with -t 1).
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -724,7 +724,7 @@ int main(int argc, char **argv) {
                     if (rc != NP2_OK) die(np2_last_error());
                 }
         }
-        // Per GPU: the tables are staged once, then up to three host threads (one context + stream each, tables shared) take
+        // Per GPU: the tables are staged once, then three to six host threads (one context + stream each, tables shared) take
         // that GPU's contigs in input order, so BGZF decoding / record parsing / upload of one contig overlap the
         // kernels of the other.
         auto fail = [&](const std::string &m) {
