@@ -112,3 +112,24 @@ def test_corrupt_payloads_never_crash_and_agree_with_zlib(harness):
             assert ref == o
         elif ref is not None:  # zlib accepts: the only reason to refuse is an output beyond the member's ISIZE
             assert len(ref) > len(data)
+
+
+def test_member_walk_of_the_ctypes_mirror_matches_the_oracle(tmp_path):
+    """api.bgzf_members (what the tests and the bench hand to np2_bgzf_inflate / np2_job_create_bgzf) against the
+    oracle's walk, including the empty EOF member; garbage is refused."""
+    import nextpolish2_b200 as np2
+    A = synth.genome(31, 50_000)
+    c = synth.make_contig(32, A, depth=15, asm_err=1e-4, het=0.0, mean_len=5000, sd_len=800, min_len=2000, threads=2)
+    path = str(tmp_path / "m.bam")
+    synth.write_bam(path, ["ctg"], [len(A)], [c["bam"]], level=6)
+    buf = np.fromfile(path, np.uint8)
+    po, pl, iz = np2.bgzf_members(buf)
+    ms = OB.members(buf)
+    assert [int(x) for x in po] == [m[0] for m in ms]
+    assert [int(x) for x in pl] == [m[1] for m in ms]
+    assert [int(x) for x in iz] == [m[2] for m in ms]
+    assert iz[-1] == 0 and pl[-1] == 2  # the BGZF end-of-file marker: an empty fixed-Huffman block
+    with pytest.raises(ValueError):
+        np2.bgzf_members(buf[5:])
+    with pytest.raises(ValueError):
+        np2.bgzf_members(buf[:len(buf) - 9])
