@@ -94,11 +94,9 @@ void launch_inflate(const uint8_t *d_comp, const uint64_t *d_off, const uint32_t
                     cudaStream_t s) {
     constexpr uint32_t kPerCta = kInflThreads / G;
     constexpr int kSmem = (int)(kPerCta * sizeof(infl::Tabs));
-    static bool attr_set = false;
-    if (!attr_set) {
-        NP2_CUDA(cudaFuncSetAttribute(k_bgzf_inflate<G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_set = true;
-    }
+    // above the 48 KB every kernel may use without asking (8 lanes per member: 32 tables per CTA); the attribute belongs
+    // to the current device, so it is set at every launch rather than once per process
+    if (kSmem > 48 * 1024) NP2_CUDA(cudaFuncSetAttribute(k_bgzf_inflate<G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     NP2_K((k_bgzf_inflate<G, MINB>))<<<(n_members + kPerCta - 1) / kPerCta, kInflThreads, kSmem, s>>>(
         d_comp, d_off, d_clen, d_out_off, d_isize, n_members, d_out, d_bad, inline_max);
 }
